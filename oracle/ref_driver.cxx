@@ -1,0 +1,501 @@
+// C-ABI harness around the BOUT++ reference's own C++ API (TEST INFRASTRUCTURE ONLY).
+//
+// Linked with the reference sources compiled in place from /root/reference (see Makefile) into
+// oracle/_ref/libboutref.so.  It lets tests/ and bench.py's cpu_baseline leg feed raw arrays to the
+// reference's operators (DDX.., bracket, Delp2, Laplacian::solve, Mesh::communicate, boundary
+// conditions, RK solvers) and read raw arrays back.  Nothing in bout-dev_b200/ (the product) links,
+// imports or calls this file.
+//
+// All Field3D arrays are [LocalNx][LocalNy][LocalNz] doubles (z fastest) INCLUDING guard cells;
+// Field2D arrays are [LocalNx][LocalNy].
+
+#include <bout/bout.hxx>
+#include <bout/boundary_factory.hxx>
+#include <bout/boutcomm.hxx>
+#include <bout/coordinates_accessor.hxx>
+#include <bout/derivs.hxx>
+#include <bout/difops.hxx>
+#include <bout/fft.hxx>
+#include <bout/field_factory.hxx>
+#include <bout/invert_laplace.hxx>
+#include <bout/mpi_wrapper.hxx>
+#include <bout/optionsreader.hxx>
+#include <bout/physicsmodel.hxx>
+#include <bout/smoothing.hxx>
+#include <bout/solver.hxx>
+#include <bout/sys/timer.hxx>
+#include <bout/cyclic_reduction.hxx>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <string>
+#include <unistd.h>
+
+using bout::globals::mesh;
+
+namespace {
+std::string last_error;
+std::unique_ptr<Laplacian> lap;
+bool initialised = false;
+
+Field3D toField3D(const double* data) {
+  Field3D f(mesh);
+  f.allocate();
+  std::memcpy(&f(0, 0, 0), data,
+              sizeof(double) * mesh->LocalNx * mesh->LocalNy * mesh->LocalNz);
+  return f;
+}
+Field2D toField2D(const double* data) {
+  Field2D f(mesh);
+  f.allocate();
+  std::memcpy(&f(0, 0), data, sizeof(double) * mesh->LocalNx * mesh->LocalNy);
+  return f;
+}
+void fromField3D(const Field3D& f, double* out) {
+  std::memcpy(out, &f(0, 0, 0),
+              sizeof(double) * mesh->LocalNx * mesh->LocalNy * mesh->LocalNz);
+}
+void fromField2D(const Field2D& f, double* out) {
+  std::memcpy(out, &f(0, 0), sizeof(double) * mesh->LocalNx * mesh->LocalNy);
+}
+
+Coordinates::FieldMetric* metricByName(Coordinates* c, const std::string& n) {
+#define M(x)   \
+  if (n == #x) \
+    return &c->x;
+  M(dx) M(dy) M(dz) M(J) M(Bxy) M(g11) M(g22) M(g33) M(g12) M(g13) M(g23) M(g_11) M(g_22)
+      M(g_33) M(g_12) M(g_13) M(g_23) M(G1) M(G2) M(G3) M(d1_dx) M(d1_dy) M(d1_dz)
+          M(ShiftTorsion) M(IntShiftTorsion) M(G1_11) M(G1_22) M(G1_33) M(G1_12) M(G1_13)
+              M(G1_23) M(G2_11) M(G2_22) M(G2_33) M(G2_12) M(G2_13) M(G2_23) M(G3_11) M(G3_22)
+                  M(G3_33) M(G3_12) M(G3_13) M(G3_23)
+#undef M
+                      return nullptr;
+}
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    last_error = e.what();
+    return 1;
+  }
+}
+
+BRACKET_METHOD bracketMethod(const std::string& m) {
+  if (m == "ARAKAWA") {
+    return BRACKET_ARAKAWA;
+  }
+  if (m == "SIMPLE") {
+    return BRACKET_SIMPLE;
+  }
+  if (m == "CTU") {
+    return BRACKET_CTU;
+  }
+  return BRACKET_STD;
+}
+
+// One operator application. in[] are raw arrays (3D unless the op name says otherwise).
+Field3D applyOp(const std::string& op, const std::string& method, int nin, const double** in,
+                double scalar) {
+  const std::string m = method.empty() ? "DEFAULT" : method;
+  auto f0 = [&]() { return toField3D(in[0]); };
+  auto f1 = [&]() { return toField3D(in[1]); };
+  auto f2 = [&]() { return toField3D(in[2]); };
+  // --- index-space derivatives (index_derivs_interface.hxx:172-270)
+  if (op == "index_DDX") return bout::derivatives::index::DDX(f0(), CELL_DEFAULT, m);
+  if (op == "index_DDY") return bout::derivatives::index::DDY(f0(), CELL_DEFAULT, m);
+  if (op == "index_DDZ") return bout::derivatives::index::DDZ(f0(), CELL_DEFAULT, m);
+  if (op == "index_D2DX2") return bout::derivatives::index::D2DX2(f0(), CELL_DEFAULT, m);
+  if (op == "index_D2DY2") return bout::derivatives::index::D2DY2(f0(), CELL_DEFAULT, m);
+  if (op == "index_D2DZ2") return bout::derivatives::index::D2DZ2(f0(), CELL_DEFAULT, m);
+  if (op == "index_D4DX4") return bout::derivatives::index::D4DX4(f0(), CELL_DEFAULT, m);
+  if (op == "index_D4DY4") return bout::derivatives::index::D4DY4(f0(), CELL_DEFAULT, m);
+  if (op == "index_D4DZ4") return bout::derivatives::index::D4DZ4(f0(), CELL_DEFAULT, m);
+  if (op == "index_VDDX") return bout::derivatives::index::VDDX(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "index_VDDY") return bout::derivatives::index::VDDY(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "index_VDDZ") return bout::derivatives::index::VDDZ(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "index_FDDX") return bout::derivatives::index::FDDX(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "index_FDDY") return bout::derivatives::index::FDDY(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "index_FDDZ") return bout::derivatives::index::FDDZ(f0(), f1(), CELL_DEFAULT, m);
+  // --- coordinate derivatives (src/sys/derivs.cxx:57-352)
+  if (op == "DDX") return DDX(f0(), CELL_DEFAULT, m);
+  if (op == "DDY") return DDY(f0(), CELL_DEFAULT, m);
+  if (op == "DDZ") return DDZ(f0(), CELL_DEFAULT, m);
+  if (op == "D2DX2") return D2DX2(f0(), CELL_DEFAULT, m);
+  if (op == "D2DY2") return D2DY2(f0(), CELL_DEFAULT, m);
+  if (op == "D2DZ2") return D2DZ2(f0(), CELL_DEFAULT, m);
+  if (op == "D4DX4") return D4DX4(f0(), CELL_DEFAULT, m);
+  if (op == "D4DZ4") return D4DZ4(f0(), CELL_DEFAULT, m);
+  if (op == "D2DXDZ") return D2DXDZ(f0(), CELL_DEFAULT, m);
+  if (op == "VDDX") return VDDX(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "VDDY") return VDDY(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "VDDZ") return VDDZ(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "FDDX") return FDDX(f0(), f1(), CELL_DEFAULT, m);
+  if (op == "FDDZ") return FDDZ(f0(), f1(), CELL_DEFAULT, m);
+  // --- differential operators (src/mesh/difops.cxx)
+  if (op == "bracket") return bracket(f0(), f1(), bracketMethod(m));
+  if (op == "bracket_3d2d") return bracket(f0(), toField2D(in[1]), bracketMethod(m));
+  if (op == "bracket_2d3d") return bracket(toField2D(in[0]), f1(), bracketMethod(m));
+  if (op == "Delp2") return Delp2(f0(), CELL_DEFAULT, true);
+  if (op == "Delp2_fd") return Delp2(f0(), CELL_DEFAULT, false);
+  if (op == "Grad_par") return Grad_par(f0());
+  if (op == "Div_par") return Div_par(f0());
+  if (op == "Grad2_par2") return Grad2_par2(f0());
+  if (op == "b0xGrad_dot_Grad") return b0xGrad_dot_Grad(f0(), f1());
+  if (op == "b0xGrad_dot_Grad_3d2d") return b0xGrad_dot_Grad(f0(), toField2D(in[1]));
+  if (op == "b0xGrad_dot_Grad_2d3d") return b0xGrad_dot_Grad(toField2D(in[0]), f1());
+  // --- field algebra (src/field/generated_fieldops.cxx)
+  if (op == "add") return f0() + f1();
+  if (op == "sub") return f0() - f1();
+  if (op == "mul") return f0() * f1();
+  if (op == "div") return f0() / f1();
+  if (op == "mul_2d") return f0() * toField2D(in[1]);
+  if (op == "div_2d") return f0() / toField2D(in[1]);
+  if (op == "add_2d") return f0() + toField2D(in[1]);
+  if (op == "sub_2d") return f0() - toField2D(in[1]);
+  if (op == "mul_s") return f0() * scalar;
+  if (op == "div_s") return f0() / scalar;
+  if (op == "add_s") return f0() + scalar;
+  if (op == "sub_s") return f0() - scalar;
+  if (op == "s_sub") return scalar - f0();
+  if (op == "s_div") return scalar / f0();
+  if (op == "neg") return -f0();
+  if (op == "arith_2a_bc") return 2. * f0() + f1() * f2(); // examples/performance/arithmetic.cxx:52
+  if (op == "DC3d") {
+    Field3D r{emptyFrom(f0())};
+    r = DC(f0());
+    return r;
+  }
+  if (op == "averageY") return averageY(f0());
+  if (op == "averageY_DC") {
+    Field3D r{emptyFrom(f0())};
+    r = averageY(DC(f0()));
+    return r;
+  }
+  if (op == "smooth_x") return smooth_x(f0());
+  if (op == "filter") return filter(f0(), static_cast<int>(scalar));
+  if (op == "lowPass") return lowPass(f0(), static_cast<int>(scalar));
+  if (op == "shiftZ") {
+    Field3D a = f0();
+    shiftZ(a, scalar);
+    return a;
+  }
+  if (op == "sqrt") return sqrt(f0());
+  if (op == "exp") return exp(f0());
+  if (op == "abs") {
+    Field3D a = f0();
+    return abs(a);
+  }
+  throw BoutException("ref_driver: unknown op '{}' (nin={})", op, nin);
+}
+} // namespace
+
+extern "C" {
+
+const char* boutref_last_error() { return last_error.c_str(); }
+
+// Initialise mesh etc. from the text of a BOUT.inp file.
+int boutref_init(const char* ini_text) {
+  return guarded([&]() {
+    if (initialised) {
+      throw BoutException("boutref_init: already initialised; call boutref_finalise first");
+    }
+    static int argc = 1;
+    static char arg0[] = "boutref";
+    static char* argv_store[] = {arg0, nullptr};
+    static char** argv = argv_store;
+    BoutComm::setArgs(argc, argv);
+    (void)BoutComm::rank(); // triggers MPI_Init in the shim
+    output.disable();
+    output_info.disable();
+    output_progress.disable();
+    output_warn.disable();
+    output_verbose.disable();
+    output_debug.disable();
+
+    char tmpl[] = "/tmp/boutref_XXXXXX";
+    const int fd = mkstemp(tmpl);
+    if (fd < 0) {
+      throw BoutException("boutref_init: mkstemp failed");
+    }
+    const size_t n = std::strlen(ini_text);
+    if (write(fd, ini_text, n) != static_cast<ssize_t>(n)) {
+      close(fd);
+      throw BoutException("boutref_init: short write");
+    }
+    close(fd);
+    OptionsReader::getInstance()->read(Options::getRoot(), "{}", tmpl);
+    unlink(tmpl);
+    Options::root()["output"]["enabled"].force(false);
+    Options::root()["restart_files"]["enabled"].force(false);
+
+    bout::globals::mpi = new MpiWrapper();
+    bout::globals::mesh = Mesh::create();
+    bout::globals::mesh->load();
+    initialised = true;
+  });
+}
+
+void boutref_finalise() {
+  if (!initialised) {
+    return;
+  }
+  lap.reset();
+  delete bout::globals::mesh;
+  bout::globals::mesh = nullptr;
+  Laplacian::cleanup();
+  Array<BoutReal>::cleanup();
+  Array<dcomplex>::cleanup();
+  Array<fcmplx>::cleanup();
+  Array<int>::cleanup();
+  Array<unsigned long>::cleanup();
+  BoundaryFactory::cleanup();
+  CoordinatesAccessor::clear();
+  Timer::cleanup();
+  Options::cleanup();
+  OptionsReader::cleanup();
+  delete bout::globals::mpi;
+  bout::globals::mpi = nullptr;
+  initialised = false;
+}
+
+// v[0..11] = LocalNx, LocalNy, LocalNz, xstart, xend, ystart, yend, GlobalNx, GlobalNy, GlobalNz,
+//            periodicX, (unused)
+int boutref_mesh_info(int* v) {
+  return guarded([&]() {
+    v[0] = mesh->LocalNx;
+    v[1] = mesh->LocalNy;
+    v[2] = mesh->LocalNz;
+    v[3] = mesh->xstart;
+    v[4] = mesh->xend;
+    v[5] = mesh->ystart;
+    v[6] = mesh->yend;
+    v[7] = mesh->GlobalNx;
+    v[8] = mesh->GlobalNy;
+    v[9] = mesh->GlobalNz;
+    v[10] = mesh->periodicX ? 1 : 0;
+    v[11] = 0;
+  });
+}
+
+int boutref_get_metric(const char* name, double* out2d) {
+  return guarded([&]() {
+    auto* m = metricByName(mesh->getCoordinates(), name);
+    if (m == nullptr) {
+      throw BoutException("unknown metric '{}'", name);
+    }
+    fromField2D(*m, out2d);
+  });
+}
+
+int boutref_set_metric(const char* name, const double* in2d) {
+  return guarded([&]() {
+    auto* m = metricByName(mesh->getCoordinates(), name);
+    if (m == nullptr) {
+      throw BoutException("unknown metric '{}'", name);
+    }
+    *m = toField2D(in2d);
+  });
+}
+
+// Recompute Christoffel symbols, G1..G3, d1_dx.. from the current metric (coordinates.cxx:932).
+int boutref_geometry() {
+  return guarded([&]() { mesh->getCoordinates()->geometry(); });
+}
+
+// Evaluate a BOUT++ expression (FieldFactory) into a Field3D / Field2D array.
+int boutref_expr3d(const char* expr, double* out) {
+  return guarded([&]() { fromField3D(FieldFactory::get()->create3D(expr), out); });
+}
+int boutref_expr2d(const char* expr, double* out) {
+  return guarded([&]() { fromField2D(FieldFactory::get()->create2D(expr), out); });
+}
+
+int boutref_op(const char* op, const char* method, int nin, const double** in, double scalar,
+               double* out) {
+  return guarded([&]() {
+    // Pre-fill so cells the reference leaves unwritten are recognisable by the caller
+    Field3D r = applyOp(op, method, nin, in, scalar);
+    fromField3D(r, out);
+  });
+}
+
+// Seconds per call (mean over reps, after 1 warm-up), results discarded.
+double boutref_time_op(const char* op, const char* method, int nin, const double** in,
+                       double scalar, int reps) {
+  double result = -1.0;
+  guarded([&]() {
+    // Fields are built once outside the timed loop, as examples/performance/*/ do
+    std::vector<Field3D> f;
+    const std::string sop = op;
+    {
+      Field3D r = applyOp(sop, method, nin, in, scalar);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; ++i) {
+      Field3D r = applyOp(sop, method, nin, in, scalar);
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    result = std::chrono::duration<double>(t1 - t0).count() / reps;
+  });
+  return result;
+}
+
+// rfft / irfft (src/invert/fft_fftw.cxx:116-394); out has n/2+1 complex (interleaved re,im)
+int boutref_rfft(const double* in, int n, double* out) {
+  return guarded([&]() { bout::fft::rfft(in, n, reinterpret_cast<dcomplex*>(out)); });
+}
+int boutref_irfft(const double* in, int n, double* out) {
+  return guarded([&]() { bout::fft::irfft(reinterpret_cast<const dcomplex*>(in), n, out); });
+}
+
+// CyclicReduce<dcomplex> on nsys systems of length n (cyclic_reduction.hxx:119-637); arrays are
+// [nsys][n] interleaved complex.
+int boutref_cyclic_reduce(int nsys, int n, int periodic, const double* a, const double* b,
+                          const double* c, const double* rhs, double* x) {
+  return guarded([&]() {
+    CyclicReduce<dcomplex> cr(BoutComm::get(), n);
+    cr.setPeriodic(periodic != 0);
+    Matrix<dcomplex> A(nsys, n), B(nsys, n), C(nsys, n), R(nsys, n), X(nsys, n);
+    const auto* ca = reinterpret_cast<const dcomplex*>(a);
+    const auto* cb = reinterpret_cast<const dcomplex*>(b);
+    const auto* cc = reinterpret_cast<const dcomplex*>(c);
+    const auto* crhs = reinterpret_cast<const dcomplex*>(rhs);
+    for (int s = 0; s < nsys; ++s) {
+      for (int i = 0; i < n; ++i) {
+        A(s, i) = ca[s * n + i];
+        B(s, i) = cb[s * n + i];
+        C(s, i) = cc[s * n + i];
+        R(s, i) = crhs[s * n + i];
+      }
+    }
+    cr.setCoefs(A, B, C);
+    cr.solve(R, X);
+    auto* cx = reinterpret_cast<dcomplex*>(x);
+    for (int s = 0; s < nsys; ++s) {
+      for (int i = 0; i < n; ++i) {
+        cx[s * n + i] = X(s, i);
+      }
+    }
+  });
+}
+
+// Laplacian::tridagCoefs (invert_laplace.cxx:280-375) using the default instance (as Delp2 does);
+// abc = {a.re,a.im,b.re,b.im,c.re,c.im}. ccoef/d may be NULL.
+int boutref_tridag_coefs(int jx, int jy, int jz, const double* ccoef2d, const double* d2d,
+                         double* abc) {
+  return guarded([&]() {
+    dcomplex a, b, c;
+    Field2D cc, dd;
+    if (ccoef2d != nullptr) {
+      cc = toField2D(ccoef2d);
+    }
+    if (d2d != nullptr) {
+      dd = toField2D(d2d);
+    }
+    Laplacian::defaultInstance()->tridagCoefs(jx, jy, jz, a, b, c,
+                                              ccoef2d != nullptr ? &cc : nullptr,
+                                              d2d != nullptr ? &dd : nullptr);
+    abc[0] = a.real();
+    abc[1] = a.imag();
+    abc[2] = b.real();
+    abc[3] = b.imag();
+    abc[4] = c.real();
+    abc[5] = c.imag();
+  });
+}
+
+// --- Laplacian::create()->solve()
+int boutref_laplace_create(const char* section) {
+  return guarded([&]() {
+    lap.reset();
+    lap = Laplacian::create(&Options::root()[section]);
+  });
+}
+// which: 'A','C','D','1' (C1),'2' (C2); data is a Field2D array
+int boutref_laplace_set_coef(char which, const double* in2d) {
+  return guarded([&]() {
+    const Field2D f = toField2D(in2d);
+    switch (which) {
+    case 'A': lap->setCoefA(f); break;
+    case 'C': lap->setCoefC(f); break;
+    case 'D': lap->setCoefD(f); break;
+    case '1': lap->setCoefC1(f); break;
+    case '2': lap->setCoefC2(f); break;
+    default: throw BoutException("bad coefficient selector");
+    }
+  });
+}
+int boutref_laplace_set_flags(int global, int inner, int outer) {
+  return guarded([&]() {
+    lap->setGlobalFlags(global);
+    lap->setInnerBoundaryFlags(inner);
+    lap->setOuterBoundaryFlags(outer);
+  });
+}
+int boutref_laplace_solve(const double* b, const double* x0, double* out) {
+  return guarded([&]() {
+    Field3D r = (x0 != nullptr) ? lap->solve(toField3D(b), toField3D(x0))
+                                : lap->solve(toField3D(b));
+    fromField3D(r, out);
+  });
+}
+double boutref_time_laplace_solve(const double* b, int reps) {
+  double result = -1.0;
+  guarded([&]() {
+    const Field3D rhs = toField3D(b);
+    Field3D r = lap->solve(rhs);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; ++i) {
+      r = lap->solve(rhs);
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    result = std::chrono::duration<double>(t1 - t0).count() / reps;
+  });
+  return result;
+}
+
+// --- Mesh::communicate on nf fields in place (mesh.hxx:260, boutmesh.cxx:1221-1555)
+int boutref_communicate(int nf, double** fields) {
+  return guarded([&]() {
+    std::vector<Field3D> f;
+    f.reserve(nf);
+    FieldGroup g;
+    for (int i = 0; i < nf; ++i) {
+      f.push_back(toField3D(fields[i]));
+    }
+    for (int i = 0; i < nf; ++i) {
+      g.add(f[i]);
+    }
+    mesh->communicate(g);
+    for (int i = 0; i < nf; ++i) {
+      fromField3D(f[i], fields[i]);
+    }
+  });
+}
+
+// --- Field3D::applyBoundary("condition") in place (field3d.cxx, boundary_standard.cxx)
+int boutref_apply_boundary(double* field, const char* condition) {
+  return guarded([&]() {
+    Field3D f = toField3D(field);
+    f.applyBoundary(condition);
+    fromField3D(f, field);
+  });
+}
+
+// yup/ydown slices after communicate (ParallelTransform::calcParallelSlices)
+int boutref_parallel_slices(const double* field, double* yup, double* ydown) {
+  return guarded([&]() {
+    Field3D f = toField3D(field);
+    mesh->communicate(f);
+    fromField3D(f.yup(), yup);
+    fromField3D(f.ydown(), ydown);
+  });
+}
+} // extern "C"
