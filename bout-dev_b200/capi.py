@@ -1,0 +1,95 @@
+"""ctypes binding of include/bout_b200.h for the Python harness (tests/, bench.py).
+
+Torch is used for device memory, streams and torch.distributed only; every numerical operation
+below is a call into libbout_b200.so.  If the library is missing this module raises at import --
+there is deliberately no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbout_b200.so")
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(bout-dev_b200 has no CPU fallback)")
+lib = C.CDLL(LIB_PATH)
+lib.bout_b200_last_error.restype = C.c_char_p
+lib.bout_b200_launch_count.restype = C.c_ulonglong
+
+OPS = {
+    "DDX_C2": 0, "DDX_C4": 1, "DDX_W2": 2, "DDX_S2": 3, "DDX_W3": 4,
+    "D2DX2_C2": 10, "D2DX2_C4": 11, "D4DX4_C2": 12,
+    "VDDX_C2": 20, "VDDX_C4": 21, "VDDX_U1": 22, "VDDX_U2": 23, "VDDX_U3": 24, "VDDX_W3": 25,
+    "FDDX_U1": 30, "FDDX_U2": 31, "FDDX_C2": 32, "FDDX_C4": 33,
+}
+DIRS = {"X": 0, "Y": 1, "Z": 2}
+REGIONS = {"RGN_NOBNDRY": 0, "RGN_ALL": 1, "RGN_NOX": 2, "RGN_NOY": 3}
+
+
+class BoutB200Error(RuntimeError):
+    """Raised when a C-ABI call returns a negative status (the host layer throws BoutException)."""
+
+    def __init__(self, status):
+        self.status = status
+        super().__init__(f"bout_b200 status {status}: {lib.bout_b200_last_error().decode()}")
+
+
+class CGrid(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nx", "ny", "nz", "xstart", "xend", "ystart", "yend")]
+
+
+class Grid:
+    """Local grid, guard cells included (reference boutmesh.cxx:391-404)."""
+
+    def __init__(self, nx, ny, nz, mxg, myg):
+        self.nx, self.ny, self.nz, self.mxg, self.myg = nx, ny, nz, mxg, myg
+        self.xstart, self.xend = mxg, nx - mxg - 1
+        self.ystart, self.yend = myg, ny - myg - 1
+        self.c = CGrid(nx, ny, nz, self.xstart, self.xend, self.ystart, self.yend)
+        self.shape3 = (nx, ny, nz)
+        self.shape2 = (nx, ny)
+        self.n_interior = (self.xend - self.xstart + 1) * (self.yend - self.ystart + 1) * nz
+        self.interior = (slice(self.xstart, self.xend + 1), slice(self.ystart, self.yend + 1),
+                         slice(None))
+
+
+def _check(rc):
+    if rc != 0:
+        raise BoutB200Error(rc)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype in (torch.float64, torch.complex128) and t.is_contiguous(), \
+        "expected a contiguous fp64 CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(lib.bout_b200_launch_count())
+
+
+def stencil(g: Grid, op: str, direction: str, f, v=None, yup=None, ydown=None, scale1=None,
+            op2=None, scale2=None, out=None, region="RGN_NOBNDRY"):
+    out = torch.zeros_like(f) if out is None else out
+    _check(lib.bout_b200_stencil(C.byref(g.c), OPS[op], DIRS[direction], REGIONS[region], _ptr(v),
+                                 _ptr(f), _ptr(yup), _ptr(ydown), _ptr(scale1),
+                                 -1 if op2 is None else OPS[op2], _ptr(scale2), _ptr(out), _stream()))
+    return out
+
+
+def bracket_arakawa(g: Grid, f, gg, dx, dz, out=None):
+    out = torch.zeros_like(f) if out is None else out
+    fn = lib.bout_b200_bracket_arakawa if gg.dim() == 3 else lib.bout_b200_bracket_arakawa_3d2d
+    _check(fn(C.byref(g.c), _ptr(f), _ptr(gg), _ptr(dx), _ptr(dz), _ptr(out), _stream()))
+    return out
