@@ -93,3 +93,101 @@ def bracket_arakawa(g: Grid, f, gg, dx, dz, out=None):
     fn = lib.bout_b200_bracket_arakawa if gg.dim() == 3 else lib.bout_b200_bracket_arakawa_3d2d
     _check(fn(C.byref(g.c), _ptr(f), _ptr(gg), _ptr(dx), _ptr(dz), _ptr(out), _stream()))
     return out
+
+
+def ddz_fft(g: Grid, f, order=1, fft_filter=0.0, scale=None, out=None, region="RGN_NOBNDRY"):
+    out = torch.zeros_like(f) if out is None else out
+    _check(lib.bout_b200_ddz_fft(C.byref(g.c), order, C.c_double(fft_filter), REGIONS[region],
+                                 _ptr(f), _ptr(scale), _ptr(out), _stream()))
+    return out
+
+
+def zfilter(g: Grid, f, n0, out=None, region="RGN_ALL"):
+    out = torch.zeros_like(f) if out is None else out
+    _check(lib.bout_b200_zfilter(C.byref(g.c), REGIONS[region], n0, _ptr(f), _ptr(out), _stream()))
+    return out
+
+
+def zlowpass(g: Grid, f, zmax, keep_zonal=True, out=None, region="RGN_ALL"):
+    out = torch.zeros_like(f) if out is None else out
+    _check(lib.bout_b200_zlowpass(C.byref(g.c), REGIONS[region], zmax, int(keep_zonal), _ptr(f),
+                                  _ptr(out), _stream()))
+    return out
+
+
+def zshift(g: Grid, f, angle, zlength, out=None, region="RGN_ALL"):
+    """angle / zlength: python floats or Field2D tensors."""
+    out = torch.zeros_like(f) if out is None else out
+    a2 = angle if torch.is_tensor(angle) else None
+    z2 = zlength if torch.is_tensor(zlength) else None
+    _check(lib.bout_b200_zshift(C.byref(g.c), REGIONS[region], _ptr(f), _ptr(a2),
+                                C.c_double(0.0 if a2 is not None else angle), _ptr(z2),
+                                C.c_double(0.0 if z2 is not None else zlength), _ptr(out), _stream()))
+    return out
+
+
+def dc(g: Grid, f, out=None):
+    out = torch.zeros(g.shape2, dtype=torch.float64, device=f.device) if out is None else out
+    _check(lib.bout_b200_dc(C.byref(g.c), _ptr(f), _ptr(out), _stream()))
+    return out
+
+
+class CLaplace(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dx", "g11", "g33", "g13", "G1", "G3", "g_11", "g_22",
+                                          "A", "C1", "C2", "D")] + \
+               [("zlength", C.c_double)] + \
+               [(n, C.c_int) for n in ("all_terms", "nonuniform", "global_flags",
+                                       "inner_boundary_flags", "outer_boundary_flags", "maxmode",
+                                       "periodic_x", "first_x", "last_x", "include_yguards_lower",
+                                       "include_yguards_upper")]
+
+
+class Laplace:
+    """Host-side mirror of the Laplacian settings (reference invert_laplace.cxx:68-138)."""
+
+    def __init__(self, g: Grid, metric: dict, zlength, all_terms=True, nonuniform=True, flags=(0, 0, 0),
+                 maxmode=None, periodic_x=False, A=None, C1=None, C2=None, D=None):
+        self.g = g
+        self.keep = dict(metric)
+        self.keep.update(A=A, C1=C1, C2=C2, D=D)
+        c = CLaplace()
+        for n in ("dx", "g11", "g33", "g13", "G1", "G3", "g_11", "g_22", "A", "C1", "C2", "D"):
+            t = self.keep.get(n)
+            setattr(c, n, None if t is None else t.data_ptr())
+        c.zlength = zlength
+        c.all_terms, c.nonuniform = int(all_terms), int(nonuniform)
+        c.global_flags, c.inner_boundary_flags, c.outer_boundary_flags = flags
+        c.maxmode = g.nz // 2 if maxmode is None else maxmode
+        c.periodic_x, c.first_x, c.last_x = int(periodic_x), 1, 1
+        self.c = c
+        self.ws = None
+
+    def workspace(self, device):
+        lib.bout_b200_laplace_cyclic_workspace.restype = C.c_size_t
+        n = lib.bout_b200_laplace_cyclic_workspace(C.byref(self.g.c), C.byref(self.c))
+        if self.ws is None or self.ws.numel() < n:
+            self.ws = torch.empty(n, dtype=torch.uint8, device=device)
+        return self.ws
+
+    def solve(self, rhs, x0=None, out=None):
+        out = torch.zeros_like(rhs) if out is None else out
+        ws = self.workspace(rhs.device)
+        _check(lib.bout_b200_laplace_cyclic_solve(C.byref(self.g.c), C.byref(self.c), _ptr(rhs),
+                                                  _ptr(x0), _ptr(out), C.c_void_p(ws.data_ptr()),
+                                                  C.c_size_t(ws.numel()), _stream()))
+        return out
+
+    def status(self):
+        _check(lib.bout_b200_laplace_cyclic_status(C.c_void_p(self.ws.data_ptr()), _stream()))
+
+    def delp2(self, f, out=None):
+        out = torch.zeros_like(f) if out is None else out
+        _check(lib.bout_b200_delp2_fft(C.byref(self.g.c), C.byref(self.c), _ptr(f), _ptr(out), _stream()))
+        return out
+
+
+def delp2_fd(g: Grid, f, dx, dz, g11, g33, g13, G1, G3, d1_dx=None, out=None):
+    out = torch.zeros_like(f) if out is None else out
+    _check(lib.bout_b200_delp2_fd(C.byref(g.c), _ptr(f), _ptr(dx), _ptr(dz), _ptr(g11), _ptr(g33),
+                                  _ptr(g13), _ptr(G1), _ptr(G3), _ptr(d1_dx), _ptr(out), _stream()))
+    return out

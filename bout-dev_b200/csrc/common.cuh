@@ -69,7 +69,7 @@ inline int checkGrid(const bout_b200_grid* g) {
   return 0;
 }
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
 
 // ---- z-vectorised access: VEC = 2 uses 16-byte double2 transactions (nz even, base 16B aligned)
 template <int VEC>

@@ -1,0 +1,276 @@
+// Fused Delp2 kernels (subsystem 2b): one kernel per RHS term, no temporaries.
+//
+//  * bout_b200_delp2_fft : Coordinates::Delp2(Field3D, useFFT=true)
+//    (reference src/mesh/coordinates.cxx:1662-1699): rfft each x row, a*F[x-1] + b*F[x] + c*F[x+1]
+//    with Laplacian::tridagCoefs of the default instance, irfft.  A thread group marches along x
+//    keeping the spectra of rows x-1, x, x+1 in shared memory, so each row is transformed once.
+//  * bout_b200_delp2_fd  : the useFFT=false branch (coordinates.cxx:1701-1702) for C2 methods,
+//    G1 DDX + G3 DDZ + g11 D2DX2 + g33 D2DZ2 + 2 g13 D2DXDZ as one 9-point X-Z stencil pass
+//    (same arithmetic as include/bout/single_index_ops.hxx:222-246).
+#include "bracket.cuh"
+#include "laplace_coefs.cuh"
+
+namespace b200 {
+
+struct Delp2FftParams {
+  LapCoefs m;
+  const double* __restrict__ f;
+  double* __restrict__ out;
+  const cd* __restrict__ tw;
+  int nx, ny, nz, xs, xe, ys, ye;
+  int chunk, nchunks;
+  int tpr, rows, pow2;
+};
+
+__global__ void __launch_bounds__(128) k_delp2_fft(const Delp2FftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbuf = fftBufElems(p.nz);
+  const int rloc = threadIdx.x / p.tpr;
+  RowFFT r;
+  r.nz = p.nz;
+  r.N = p.nz / 2;
+  r.pow2 = p.pow2 != 0;
+  r.tpr = p.tpr;
+  r.lane = threadIdx.x % p.tpr;
+  cd* base = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(rloc) * 5 * nbuf;
+  r.A = base;
+  r.B = base + nbuf;
+  r.tw = p.tw;
+  cd* S[3] = {base + 2 * nbuf, base + 3 * nbuf, base + 4 * nbuf};
+
+  const int nyb = p.ye - p.ys + 1;
+  const long long ntasks = static_cast<long long>(nyb) * p.nchunks;
+  const long long task0 = static_cast<long long>(blockIdx.x) * p.rows + rloc;
+  const bool task_ok = task0 < ntasks;
+  const long long task = task_ok ? task0 : ntasks - 1;
+  const int y = p.ys + static_cast<int>(task / p.nchunks);
+  const int x0 = p.xs + static_cast<int>(task % p.nchunks) * p.chunk;
+  const int x1 = min(x0 + p.chunk - 1, p.xe);
+  const int nk = p.nz / 2 + 1;
+  const long long plane = static_cast<long long>(p.ny) * p.nz;
+  const double* __restrict__ col = p.f + static_cast<long long>(y) * p.nz;
+
+  auto forwardTo = [&](int x, cd* dst) {
+    // the CTA is synchronised on entry; on exit dst holds the spectrum and the CTA is synchronised
+    double* a = reinterpret_cast<double*>(r.A);
+    const double* __restrict__ src = col + x * plane;
+    if (p.nz % 2 == 0 && aligned16(src)) {
+      for (int j = r.lane; j < p.nz / 2; j += r.tpr) {
+        reinterpret_cast<double2*>(a)[j] = __ldg(reinterpret_cast<const double2*>(src) + j);
+      }
+    } else {
+      for (int j = r.lane; j < p.nz; j += r.tpr) {
+        a[j] = __ldg(src + j);
+      }
+    }
+    __syncthreads();
+    const cd* X = rfftForward(r);
+    for (int k = r.lane; k < nk; k += r.tpr) {
+      dst[k] = X[k];
+    }
+    __syncthreads();
+  };
+
+  forwardTo(x0 - 1, S[(x0 - 1) % 3]);
+  forwardTo(x0, S[x0 % 3]);
+  for (int it = 0; it < p.chunk; ++it) {
+    const int x = min(x0 + it, x1); // short chunks repeat their last row (never stored twice)
+    const bool store = task_ok && (x0 + it <= x1);
+    forwardTo(x + 1, S[(x + 1) % 3]);
+    const cd* Sm = S[(x + 2) % 3]; // (x - 1) mod 3
+    const cd* S0 = S[x % 3];
+    const cd* Sp = S[(x + 1) % 3];
+    for (int k = r.lane; k < nk; k += r.tpr) {
+      cd a, b, c;
+      const double kwave = k * 2.0 * M_PI / p.m.zlength; // invert_laplace.cxx:263
+      tridagCoefs(p.m, x, y, kwave, false, false, a, b, c);
+      r.A[k] = cadd(cadd(cmul(a, Sm[k]), cmul(b, S0[k])), cmul(c, Sp[k]));
+    }
+    __syncthreads();
+    const double* res = rfftBackward(r, r.A);
+    if (store) {
+      double* __restrict__ dst = p.out + x * plane + static_cast<long long>(y) * p.nz;
+      if (p.nz % 2 == 0 && aligned16(dst)) {
+        for (int j = r.lane; j < p.nz / 2; j += r.tpr) {
+          reinterpret_cast<double2*>(dst)[j] = reinterpret_cast<const double2*>(res)[j];
+        }
+      } else {
+        for (int j = r.lane; j < p.nz; j += r.tpr) {
+          dst[j] = res[j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct Delp2FdParams {
+  const double* __restrict__ f;
+  const double* __restrict__ dx;
+  const double* __restrict__ dz;
+  const double* __restrict__ g11;
+  const double* __restrict__ g33;
+  const double* __restrict__ g13;
+  const double* __restrict__ G1;
+  const double* __restrict__ G3;
+  const double* __restrict__ d1_dx; // NULL when the mesh is uniform (coords->non_uniform false)
+  double* __restrict__ out;
+  int nx, ny, nz, xs, xe, ys, ye, chunk;
+};
+
+// Per-point arithmetic, shared with the fused RHS kernels.  Term order follows
+// coordinates.cxx:1701-1702 with each operator as derivs.cxx defines it for C2.
+__device__ __forceinline__ double delp2FdPoint(const Row4& fm, const Row4& f0, const Row4& fp, int i,
+                                               double rdx, double rdz, double g11, double g33,
+                                               double g13, double G1, double G3, double d1_dx,
+                                               bool nonuni) {
+  const int zm = i, z = i + 1, zp = i + 2;
+  const double ddx = (0.5 * (fp.v[z] - fm.v[z])) * rdx;
+  const double ddz = (0.5 * (f0.v[zp] - f0.v[zm])) * rdz;
+  double d2dx2 = (fp.v[z] + fm.v[z] - 2. * f0.v[z]) * (rdx * rdx);
+  if (nonuni) {
+    d2dx2 += (d1_dx * (0.5 * (fp.v[z] - fm.v[z]))) * rdx;
+  }
+  const double d2dz2 = (f0.v[zp] + f0.v[zm] - 2. * f0.v[z]) * (rdz * rdz);
+  // D2DXDZ = DDZ(DDX(f))
+  const double ddx_zp = (0.5 * (fp.v[zp] - fm.v[zp])) * rdx;
+  const double ddx_zm = (0.5 * (fp.v[zm] - fm.v[zm])) * rdx;
+  const double d2dxdz = (0.5 * (ddx_zp - ddx_zm)) * rdz;
+  return G1 * ddx + G3 * ddz + g11 * d2dx2 + g33 * d2dz2 + 2 * g13 * d2dxdz;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_delp2_fd(const Delp2FdParams p) {
+  const int nzv = p.nz / VEC;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(p.ye - p.ys + 1) * nzv) {
+    return;
+  }
+  const int z = static_cast<int>(t % nzv) * VEC;
+  const int y = p.ys + static_cast<int>(t / nzv);
+  const int x0 = p.xs + blockIdx.y * p.chunk;
+  const int x1 = min(x0 + p.chunk - 1, p.xe);
+  const long long plane = static_cast<long long>(p.ny) * p.nz;
+  const long long rowoff = static_cast<long long>(y) * p.nz;
+  Row4 Fm, F0, Fp;
+  F0 = loadRow4<VEC>(p.f + (x0 - 1) * plane + rowoff, z, p.nz);
+  Fp = loadRow4<VEC>(p.f + x0 * plane + rowoff, z, p.nz);
+#pragma unroll 2
+  for (int x = x0; x <= x1; ++x) {
+    Fm = F0;
+    F0 = Fp;
+    Fp = loadRow4<VEC>(p.f + (x + 1) * plane + rowoff, z, p.nz);
+    const long long i2 = static_cast<long long>(x) * p.ny + y;
+    const double rdx = 1.0 / __ldg(p.dx + i2), rdz = 1.0 / __ldg(p.dz + i2);
+    const double g11 = __ldg(p.g11 + i2), g33 = __ldg(p.g33 + i2), g13 = __ldg(p.g13 + i2);
+    const double G1 = __ldg(p.G1 + i2), G3 = __ldg(p.G3 + i2);
+    const double d1 = p.d1_dx ? __ldg(p.d1_dx + i2) : 0.0;
+    Vz<VEC> r;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      r.v[i] = delp2FdPoint(Fm, F0, Fp, i, rdx, rdz, g11, g33, g13, G1, G3, d1, p.d1_dx != nullptr);
+    }
+    r.store(p.out + x * plane + rowoff + z);
+  }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int bout_b200_delp2_fft(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                   const double* f, double* out, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(L && f && out && f != out, BOUT_B200_ERR_ARG, "delp2_fft: bad argument");
+  B200_REQUIRE(L->dx && L->g11 && L->g33 && L->g13, BOUT_B200_ERR_ARG, "delp2_fft: metric missing");
+  B200_REQUIRE(!L->all_terms || (L->G1 && L->G3), BOUT_B200_ERR_ARG, "delp2_fft: all_terms needs G1, G3");
+  B200_REQUIRE(g->xstart >= 1 && g->xend <= g->nx - 2, BOUT_B200_ERR_GUARDS,
+               "delp2_fft: needs one x guard cell each side"); // ASSERT2(xstart > 0), coordinates.cxx:1657
+  cudaStream_t s = asStream(stream);
+  Delp2FftParams p{};
+  p.m.dx = L->dx;
+  p.m.g11 = L->g11;
+  p.m.g33 = L->g33;
+  p.m.g13 = L->g13;
+  p.m.G1 = L->G1;
+  p.m.G3 = L->G3;
+  p.m.zlength = L->zlength;
+  p.m.nx = g->nx;
+  p.m.ny = g->ny;
+  p.m.all_terms = L->all_terms;
+  p.m.nonuniform = L->nonuniform;
+  p.f = f;
+  p.out = out;
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.xs = g->xstart;
+  p.xe = g->xend;
+  p.ys = g->ystart;
+  p.ye = g->yend;
+  int st = 0;
+  p.tw = twiddleTable(g->nz, s, &st);
+  if (st != 0) {
+    return st;
+  }
+  RowGeom geo = rowGeometry(g->nz, 128);
+  geo.smemBytes = static_cast<size_t>(geo.rows) * 5 * fftBufElems(g->nz) * sizeof(cd);
+  p.tpr = geo.tpr;
+  p.rows = geo.rows;
+  p.pow2 = geo.pow2 ? 1 : 0;
+  B200_REQUIRE(geo.smemBytes <= 200 * 1024, BOUT_B200_ERR_UNSUPPORTED, "delp2_fft: nz=%d too large", g->nz);
+  if (geo.smemBytes > 48 * 1024) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_delp2_fft, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(geo.smemBytes)));
+  }
+  const int len = p.xe - p.xs + 1, nyb = p.ye - p.ys + 1;
+  // enough (y, chunk) tasks to fill 148 SMs a few times over, chunks no shorter than 8 rows
+  int chunk = 32;
+  while (chunk > 8 && static_cast<long long>(nyb) * ((len + chunk - 1) / chunk) < 148LL * 8 * geo.rows) {
+    chunk /= 2;
+  }
+  p.chunk = chunk;
+  p.nchunks = (len + chunk - 1) / chunk;
+  const long long ntasks = static_cast<long long>(nyb) * p.nchunks;
+  const unsigned blocks = static_cast<unsigned>((ntasks + geo.rows - 1) / geo.rows);
+  k_delp2_fft<<<blocks, 128, geo.smemBytes, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int bout_b200_delp2_fd(const bout_b200_grid* g, const double* f, const double* dx,
+                                  const double* dz, const double* g11, const double* g33,
+                                  const double* g13, const double* G1, const double* G3,
+                                  const double* d1_dx, double* out, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(f && dx && dz && g11 && g33 && g13 && G1 && G3 && out && f != out, BOUT_B200_ERR_ARG,
+               "delp2_fd: bad argument");
+  B200_REQUIRE(g->xstart >= 1 && g->xend <= g->nx - 2, BOUT_B200_ERR_GUARDS,
+               "delp2_fd: needs one x guard cell each side");
+  Delp2FdParams p{f, dx, dz, g11, g33, g13, G1, G3, d1_dx, out, g->nx, g->ny, g->nz,
+                  g->xstart, g->xend, g->ystart, g->yend, 16};
+  const bool vec2 = (g->nz % 2 == 0) && aligned16(f) && aligned16(out);
+  const int nzv = vec2 ? g->nz / 2 : g->nz;
+  const long long north = static_cast<long long>(p.ye - p.ys + 1) * nzv;
+  const int len = p.xe - p.xs + 1;
+  int chunk = 8;
+  for (int c : {64, 32, 16}) {
+    if (north * ((len + c - 1) / c) >= 148LL * 2048) {
+      chunk = c;
+      break;
+    }
+  }
+  p.chunk = chunk;
+  dim3 grid(static_cast<unsigned>((north + 255) / 256), static_cast<unsigned>((len + chunk - 1) / chunk));
+  if (vec2) {
+    k_delp2_fd<2><<<grid, 256, 0, asStream(stream)>>>(p);
+  } else {
+    k_delp2_fd<1><<<grid, 256, 0, asStream(stream)>>>(p);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,302 @@
+// z-FFT row operations: rfft -> per-mode multiplier -> irfft in ONE kernel (one read + one write
+// of the field; the spectrum never leaves shared memory).
+//
+// Replaces: FFTDerivativeType / FFT2ndDerivativeType (src/mesh/index_derivs.cxx:418-541),
+// filter / lowPass / shiftZ (src/field/field3d.cxx:620-741), and the phase-shift core of
+// ShiftedMetric::shiftZ (src/mesh/parallel/shiftedmetric.cxx:200-224).
+#include "fft.cuh"
+
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace b200 {
+
+const cd* twiddleTable(int nz, cudaStream_t stream, int* status) {
+  static std::mutex mtx;
+  static std::map<std::pair<int, int>, cd*> cache;
+  std::lock_guard<std::mutex> lock(mtx);
+  int dev = 0;
+  *status = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    *status = fail(BOUT_B200_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
+    return nullptr;
+  }
+  auto it = cache.find({dev, nz});
+  if (it != cache.end()) {
+    return it->second;
+  }
+  std::vector<cd> host(nz);
+  for (int k = 0; k < nz; ++k) {
+    const long double a = -2.0L * 3.141592653589793238462643383279502884L * k / nz;
+    host[k] = {static_cast<double>(cosl(a)), static_cast<double>(sinl(a))};
+  }
+  cd* devp = nullptr;
+  if (cudaMalloc(&devp, sizeof(cd) * nz) != cudaSuccess
+      || cudaMemcpyAsync(devp, host.data(), sizeof(cd) * nz, cudaMemcpyHostToDevice, stream) != cudaSuccess
+      || cudaStreamSynchronize(stream) != cudaSuccess) {
+    *status = fail(BOUT_B200_ERR_CUDA, "twiddle table upload failed: %s",
+                   cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  cache[{dev, nz}] = devp;
+  return devp;
+}
+
+enum ZMode { Z_DDZ1 = 0, Z_DDZ2 = 1, Z_FILTER = 2, Z_LOWPASS = 3, Z_SHIFT = 4 };
+
+struct ZfftParams {
+  const double* __restrict__ f;
+  const double* __restrict__ scale;  // Field2D output multiplier or NULL
+  const double* __restrict__ angle;  // Field2D shift angle (Z_SHIFT) or NULL -> angle0
+  const double* __restrict__ zlength; // Field2D zlength (Z_SHIFT) or NULL -> zlength0
+  double* __restrict__ out;
+  const cd* __restrict__ tw;
+  int nx, ny, nz, xs, xe, ys, ye;
+  int mode, kmax, n0, keep_zonal;
+  double angle0, zlength0;
+  int tpr, rows, pow2;
+};
+
+__global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbuf = fftBufElems(p.nz);
+  const int rloc = threadIdx.x / p.tpr;
+  RowFFT r;
+  r.nz = p.nz;
+  r.N = p.nz / 2;
+  r.pow2 = p.pow2 != 0;
+  r.tpr = p.tpr;
+  r.lane = threadIdx.x % p.tpr;
+  r.A = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(rloc) * 2 * nbuf;
+  r.B = r.A + nbuf;
+  r.tw = p.tw;
+
+  const int nyb = p.ye - p.ys + 1;
+  const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * nyb;
+  const long long rowid = static_cast<long long>(blockIdx.x) * p.rows + rloc;
+  const bool active = rowid < nrows;
+  const long long rid = active ? rowid : nrows - 1; // idle groups redo the last row, never store
+  const int x = p.xs + static_cast<int>(rid / nyb);
+  const int y = p.ys + static_cast<int>(rid % nyb);
+  const long long i2 = static_cast<long long>(x) * p.ny + y;
+  const double* __restrict__ src = p.f + i2 * p.nz;
+
+  // load the real row into A
+  double* a = reinterpret_cast<double*>(r.A);
+  if (p.nz % 2 == 0 && aligned16(src)) {
+    for (int j = r.lane; j < p.nz / 2; j += r.tpr) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(src) + j);
+      reinterpret_cast<double2*>(a)[j] = t;
+    }
+  } else {
+    for (int j = r.lane; j < p.nz; j += r.tpr) {
+      a[j] = __ldg(src + j);
+    }
+  }
+  __syncthreads();
+  cd* X = rfftForward(r);
+
+  const int nk = p.nz / 2;
+  const double kfac = 2.0 * M_PI / p.nz;
+  for (int k = r.lane; k <= nk; k += r.tpr) {
+    cd v = X[k];
+    switch (p.mode) {
+    case Z_DDZ1: {
+      if (k <= p.kmax) {
+        const double kw = k * kfac;
+        v = {-v.im * kw, v.re * kw}; // * (0, kwave)
+      } else {
+        v = {0.0, 0.0};
+      }
+      break;
+    }
+    case Z_DDZ2: {
+      const double kw = k * kfac;
+      const double m = -kw * kw;
+      v = {v.re * m, v.im * m};
+      break;
+    }
+    case Z_FILTER:
+      if (k != p.n0) {
+        v = {0.0, 0.0};
+      }
+      break;
+    case Z_LOWPASS:
+      if (k > p.kmax || (k == 0 && !p.keep_zonal)) {
+        v = {0.0, 0.0};
+      }
+      break;
+    case Z_SHIFT: {
+      if (k >= 1) {
+        const double zl = p.zlength ? __ldg(p.zlength + i2) : p.zlength0;
+        const double ang = p.angle ? __ldg(p.angle + i2) : p.angle0;
+        const double kwave = k * 2.0 * M_PI / zl;
+        double s, c;
+        sincos(kwave * ang, &s, &c);
+        v = cmul(v, cd{c, -s});
+      }
+      break;
+    }
+    default:
+      break;
+    }
+    X[k] = v;
+  }
+  __syncthreads();
+  const double* res = rfftBackward(r, X);
+  if (active) {
+    const double sc = p.scale ? __ldg(p.scale + i2) : 1.0;
+    double* __restrict__ dst = p.out + i2 * p.nz;
+    if (p.nz % 2 == 0 && aligned16(dst)) {
+      for (int j = r.lane; j < p.nz / 2; j += r.tpr) {
+        double2 t = reinterpret_cast<const double2*>(res)[j];
+        t.x *= sc;
+        t.y *= sc;
+        reinterpret_cast<double2*>(dst)[j] = t;
+      }
+    } else {
+      for (int j = r.lane; j < p.nz; j += r.tpr) {
+        dst[j] = res[j] * sc;
+      }
+    }
+  }
+}
+
+int launchZfft(const bout_b200_grid* g, int region, ZfftParams p, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(p.f && p.out, BOUT_B200_ERR_ARG, "zfft: null field");
+  Box b;
+  if (regionBox(g, region, &b) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  cudaStream_t s = asStream(stream);
+  int st = 0;
+  p.tw = twiddleTable(g->nz, s, &st);
+  if (st != 0) {
+    return st;
+  }
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.xs = b.xs;
+  p.xe = b.xe;
+  p.ys = b.ys;
+  p.ye = b.ye;
+  const RowGeom geo = rowGeometry(g->nz, 128);
+  p.tpr = geo.tpr;
+  p.rows = geo.rows;
+  p.pow2 = geo.pow2 ? 1 : 0;
+  B200_REQUIRE(geo.smemBytes <= 200 * 1024, BOUT_B200_ERR_UNSUPPORTED, "zfft: nz=%d too large", g->nz);
+  if (geo.smemBytes > 48 * 1024) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_zfft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(geo.smemBytes)));
+  }
+  const long long nrows = static_cast<long long>(b.xe - b.xs + 1) * (b.ye - b.ys + 1);
+  const unsigned blocks = static_cast<unsigned>((nrows + geo.rows - 1) / geo.rows);
+  k_zfft_rows<<<blocks, 128, geo.smemBytes, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ---- DC: z-mean of every (x,y) row (src/field/field3d.cxx:785-803) --------------------------
+__global__ void __launch_bounds__(256) k_dc(const double* __restrict__ f, double* __restrict__ out,
+                                            long long nrows, int nz) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= nrows) {
+    return;
+  }
+  const double* __restrict__ src = f + row * nz;
+  // sequential-order sum per lane then tree: differs from the reference's left-to-right sum only
+  // in rounding (<= nz * eps relative)
+  double acc = 0.0;
+  for (int j = lane; j < nz; j += 32) {
+    acc += __ldg(src + j);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  }
+  if (lane == 0) {
+    out[row] = acc / nz;
+  }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int bout_b200_ddz_fft(const bout_b200_grid* g, int order, double fft_filter, int region,
+                                 const double* f, const double* scale, double* out, void* stream) {
+  B200_REQUIRE(order == 1 || order == 2, BOUT_B200_ERR_ARG, "ddz_fft: order must be 1 or 2");
+  B200_REQUIRE(g != nullptr, BOUT_B200_ERR_ARG, "ddz_fft: null grid");
+  if (g->nz == 1) { // single point: zero field (index_derivs_interface.hxx:152-156)
+    B200_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * g->nx * g->ny * g->nz, asStream(stream)));
+    return 0;
+  }
+  ZfftParams p{};
+  p.f = f;
+  p.scale = scale;
+  p.out = out;
+  const int ncz = g->nz;
+  if (order == 1) { // index_derivs.cxx:435-444
+    int kfilter = static_cast<int>(fft_filter * ncz / 2);
+    kfilter = kfilter < 0 ? 0 : (kfilter > ncz / 2 ? ncz / 2 : kfilter);
+    p.kmax = ncz / 2 - kfilter;
+    p.mode = Z_DDZ1;
+  } else {
+    p.kmax = ncz / 2;
+    p.mode = Z_DDZ2;
+  }
+  return launchZfft(g, region, p, stream);
+}
+
+extern "C" int bout_b200_zfilter(const bout_b200_grid* g, int region, int n0, const double* f,
+                                 double* out, void* stream) {
+  ZfftParams p{};
+  p.f = f;
+  p.out = out;
+  p.mode = Z_FILTER;
+  p.n0 = n0;
+  return launchZfft(g, region, p, stream);
+}
+
+extern "C" int bout_b200_zlowpass(const bout_b200_grid* g, int region, int zmax, int keep_zonal,
+                                  const double* f, double* out, void* stream) {
+  ZfftParams p{};
+  p.f = f;
+  p.out = out;
+  p.mode = Z_LOWPASS;
+  p.kmax = zmax;
+  p.keep_zonal = keep_zonal;
+  return launchZfft(g, region, p, stream);
+}
+
+extern "C" int bout_b200_zshift(const bout_b200_grid* g, int region, const double* f,
+                                const double* angle2d, double angle0, const double* zlength2d,
+                                double zlength0, double* out, void* stream) {
+  ZfftParams p{};
+  p.f = f;
+  p.out = out;
+  p.mode = Z_SHIFT;
+  p.angle = angle2d;
+  p.angle0 = angle0;
+  p.zlength = zlength2d;
+  p.zlength0 = zlength0;
+  return launchZfft(g, region, p, stream);
+}
+
+extern "C" int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(f && out2d, BOUT_B200_ERR_ARG, "dc: null argument");
+  const long long nrows = static_cast<long long>(g->nx) * g->ny;
+  k_dc<<<static_cast<unsigned>((nrows + 7) / 8), 256, 0, asStream(stream)>>>(f, out2d, nrows, g->nz);
+  B200_LAUNCH_OK();
+  return 0;
+}

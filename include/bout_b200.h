@@ -96,6 +96,21 @@ int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region, cons
 int bout_b200_ddz_fft(const bout_b200_grid* g, int order, double fft_filter, int region,
                       const double* f, const double* scale, double* out, void* stream);
 
+/* filter(f, N0) (src/field/field3d.cxx:620-661): keep only z-mode n0. */
+int bout_b200_zfilter(const bout_b200_grid* g, int region, int n0, const double* f, double* out,
+                      void* stream);
+/* lowPass(f, zmax, keep_zonal) (src/field/field3d.cxx:664-710). */
+int bout_b200_zlowpass(const bout_b200_grid* g, int region, int zmax, int keep_zonal,
+                       const double* f, double* out, void* stream);
+/* shiftZ (src/field/field3d.cxx:715-741; ShiftedMetric::shiftZ src/mesh/parallel/shiftedmetric.cxx:200-224):
+ * multiply mode k by exp(-i k 2pi/zlength * angle); angle/zlength per (x,y) when the Field2D
+ * pointers are non-NULL, else the scalars.  out may alias f. */
+int bout_b200_zshift(const bout_b200_grid* g, int region, const double* f, const double* angle2d,
+                     double angle0, const double* zlength2d, double zlength0, double* out,
+                     void* stream);
+/* DC(f): z-mean of every (x,y) row, RGN_ALL (src/field/field3d.cxx:785-803). out2d is a Field2D. */
+int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* stream);
+
 /* ---- (2) fused Arakawa bracket -----------------------------------------------------------------
  * bracket(Field3D f, Field3D g, BRACKET_ARAKAWA) (src/mesh/difops.cxx:940-1041);
  * dx, dz Field2D spacings.  out = [f,g] on RGN_NOBNDRY. */
@@ -104,6 +119,58 @@ int bout_b200_bracket_arakawa(const bout_b200_grid* g, const double* f, const do
 /* bracket(Field3D f, Field2D g, BRACKET_ARAKAWA) (src/mesh/difops.cxx:693-765). */
 int bout_b200_bracket_arakawa_3d2d(const bout_b200_grid* g, const double* f, const double* g2d,
                                    const double* dx, const double* dz, double* out, void* stream);
+
+/* ---- (2b) fused Delp2 and (3) LaplaceCyclic -------------------------------------------------------
+ * Laplacian settings + the Field2D metric the coefficients are generated from on chip
+ * (reference Laplacian::Laplacian options src/invert/laplace/invert_laplace.cxx:68-138 and
+ * Laplacian::tridagCoefs :280-375).  All pointers are device Field2D arrays [nx][ny]; optional ones
+ * may be NULL. */
+typedef struct bout_b200_laplace {
+  const double* dx;
+  const double* g11;
+  const double* g33;
+  const double* g13;
+  const double* G1;   /* needed when all_terms */
+  const double* G3;   /* needed when all_terms */
+  const double* g_11; /* only for INVERT_{DC,AC}_GRAD combined with INVERT_SET / INVERT_RHS */
+  const double* g_22; /* only for INVERT_DC_GRADPAR(INV) */
+  const double* A;    /* setCoefA; NULL = 0 */
+  const double* C1;   /* setCoefC1 / setCoefC; NULL = 1 */
+  const double* C2;   /* setCoefC2 / setCoefC; NULL = 1 */
+  const double* D;    /* setCoefD; NULL = 1 */
+  double zlength;     /* Coordinates::zlength(), = dz * nz */
+  int all_terms;      /* laplace:all_terms (default true) */
+  int nonuniform;     /* laplace:nonuniform (default coords->non_uniform) */
+  int global_flags, inner_boundary_flags, outer_boundary_flags; /* invert_laplace.hxx:72-104 */
+  int maxmode;        /* laplace:maxmode / filter, clamped to [0, nz/2] */
+  int periodic_x;     /* mesh->periodicX */
+  int first_x, last_x;/* mesh->firstX(), lastX() (1,1 on a single rank in X) */
+  int include_yguards_lower, include_yguards_upper; /* laplace:include_yguards where a y boundary exists */
+} bout_b200_laplace;
+
+/* Coordinates::Delp2(Field3D, useFFT=true) (src/mesh/coordinates.cxx:1662-1699); uses
+ * dx,g11,g33,g13,G1,G3,zlength,all_terms,nonuniform of L (the default Laplacian instance). */
+int bout_b200_delp2_fft(const bout_b200_grid* g, const bout_b200_laplace* L, const double* f,
+                        double* out, void* stream);
+/* Coordinates::Delp2(Field3D, useFFT=false) with C2 methods (coordinates.cxx:1701-1702);
+ * d1_dx = NULL when coords->non_uniform is false. */
+int bout_b200_delp2_fd(const bout_b200_grid* g, const double* f, const double* dx, const double* dz,
+                       const double* g11, const double* g33, const double* g13, const double* G1,
+                       const double* G3, const double* d1_dx, double* out, void* stream);
+
+/* LaplaceCyclic::solve(Field3D rhs, Field3D x0)
+ * (src/invert/laplace/impls/cyclic/cyclic_laplace.cxx:187-290).  `workspace` is caller-owned device
+ * memory of at least bout_b200_laplace_cyclic_workspace() bytes, 16-byte aligned, reusable across
+ * calls (no allocation happens inside a solve).  x0 may be NULL unless INVERT_SET is used.
+ * out is written for x in [xs,xe] (boundary cells included on edge ranks unless periodic),
+ * y in the solved range; other cells are left untouched. */
+size_t bout_b200_laplace_cyclic_workspace(const bout_b200_grid* g, const bout_b200_laplace* L);
+int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                   const double* rhs, const double* x0, double* out,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+/* Synchronises `stream`; BOUT_B200_ERR_PIVOT if the last solve on this workspace met a zero pivot
+ * (reference throws BoutException, include/bout/cyclic_reduction.hxx:553). */
+int bout_b200_laplace_cyclic_status(void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

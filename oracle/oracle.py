@@ -276,6 +276,46 @@ class Port:
             return self.index_ddz_fft(g, 2, f) * (1.0 / m.dz ** 2)[:, :, None]
         return self.index_deriv(g, "D2DX2_" + method, "Z", f) * (1.0 / m.dz ** 2)[:, :, None]
 
+    def zrows(self, g, f, modify, region=None):
+        """rfft every (x,y) row in the region, let `modify(spectrum, x, y)` edit it, irfft back
+        (the common shape of filter/lowPass/shiftZ, src/field/field3d.cxx:620-741)."""
+        out = np.zeros(g.shape3)
+        xs, xe, ys, ye = region if region is not None else (0, g.nx - 1, 0, g.ny - 1)
+        for x in range(xs, xe + 1):
+            for y in range(ys, ye + 1):
+                spec = self.rfft(f[x, y])
+                modify(spec, x, y)
+                out[x, y] = self.irfft(spec, g.nz)
+        return out
+
+    def zfilter(self, g, f, n0):                       # field3d.cxx:620-661
+        def mod(s, x, y):
+            keep = s[n0] if 0 <= n0 < len(s) else 0.0
+            s[:] = 0.0
+            if 0 <= n0 < len(s):
+                s[n0] = keep
+        return self.zrows(g, f, mod)
+
+    def zlowpass(self, g, f, zmax, keep_zonal=True):   # field3d.cxx:664-710
+        if (zmax >= g.nz // 2 or zmax < 0) and keep_zonal:
+            return f.copy()
+        def mod(s, x, y):
+            s[zmax + 1:] = 0.0
+            if not keep_zonal:
+                s[0] = 0.0
+        return self.zrows(g, f, mod)
+
+    def zshift(self, g, f, angle, zlength):            # field3d.cxx:715-741
+        angle = np.broadcast_to(angle, g.shape2)
+        zlength = np.broadcast_to(zlength, g.shape2)
+        def mod(s, x, y):
+            for jz in range(1, g.nz // 2 + 1):
+                kwave = jz * 2.0 * np.pi / zlength[x, y]
+                s[jz] *= complex(np.cos(kwave * angle[x, y]), -np.sin(kwave * angle[x, y]))
+        if g.nz == 1:
+            return f.copy()
+        return self.zrows(g, f, mod)
+
     def rk4_final(self, start, dt, k1, k2, k3, k4):
         out = np.zeros_like(start)
         self.lib.bo_rk4_final(start.size, _p(start), dt, _p(k1), _p(k2), _p(k3), _p(k4), _p(out))

@@ -1,0 +1,136 @@
+"""GPU parity: Delp2 (FFT and FD) and LaplaceCyclic through the C-ABI vs the oracle.
+
+Tolerances from BASELINE.json north_star: Delp2 1e-12 relative, LaplaceCyclic solutions 1e-10
+relative.  Flag combinations follow the reference's own test (tests/integrated/test-laplace/
+test_laplace.cxx:19-100: flags 0, 3 (DC+AC grad), INVERT_SET inner/outer, with A, C, D coefficients).
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import make_metric, rel_err, seeded_fields
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_laplace(capi, g, m, **kw):
+    md = {n: dev(getattr(m, n)) for n in ("dx", "g11", "g33", "g13", "G1", "G3", "g_11", "g_22")}
+    for k in ("A", "C1", "C2", "D"):
+        if kw.get(k) is not None:
+            kw[k] = dev(kw[k])
+    return capi.Laplace(g, md, float(m.dz[0, 0]) * g.nz, **kw)
+
+
+GRIDS = [(20, 6, 32, 2, 1), (9, 5, 7, 2, 1), (12, 3, 16, 1, 1), (68, 4, 64, 2, 1)]
+
+
+@pytest.mark.parametrize("grid", GRIDS)
+@pytest.mark.parametrize("trivial", [True, False])
+def test_delp2_fft(capi, orc, port, grid, trivial):
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz, trivial=trivial)
+    (f,) = seeded_fields(g.shape3, 1)
+    for all_terms, nonuni in ((True, m.non_uniform), (False, False)):
+        want = port.delp2_fft(og, m, f, all_terms=all_terms, nonuniform=nonuni)
+        lap = gpu_laplace(capi, g, m, all_terms=all_terms, nonuniform=nonuni)
+        got = lap.delp2(dev(f)).cpu().numpy()
+        assert rel_err(got, want, g.interior) < 1e-12
+
+
+@pytest.mark.parametrize("grid", GRIDS)
+def test_delp2_fd_matches_composed_reference_operators(capi, orc, port, grid):
+    """useFFT=false branch: G1*DDX + G3*DDZ + g11*D2DX2 + g33*D2DZ2 + 2*g13*D2DXDZ
+    (coordinates.cxx:1701-1702) composed from the oracle's C2 operators."""
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz)
+    (f,) = seeded_fields(g.shape3, 1)
+    b = lambda a: a[:, :, None]
+    ddx = port.ddx(og, m, f, "C2")
+    d2dxdz = port.ddz(og, m, ddx, "C2")
+    want = (b(m.G1) * ddx + b(m.G3) * port.ddz(og, m, f, "C2") + b(m.g11) * port.d2dx2(og, m, f, "C2", "C2")
+            + b(m.g33) * port.d2dz2(og, m, f, "C2") + b(2 * m.g13) * d2dxdz)
+    got = capi.delp2_fd(g, dev(f), dev(m.dx), dev(m.dz), dev(m.g11), dev(m.g33), dev(m.g13), dev(m.G1),
+                        dev(m.G3), dev(m.d1_dx)).cpu().numpy()
+    assert rel_err(got, want, g.interior) < 1e-12
+
+
+FLAGSETS = [(0, 0, 0), (0, 3, 3), (0, 2, 0), (0, 0, 1), (1, 4, 64), (0, 16, 16), (0, 32 | 3, 32),
+            (4, 0, 0), (0, 128, 0), (0, 3 | 16, 3 | 32), (0, 1024, 0)]
+
+
+@pytest.mark.parametrize("grid", GRIDS)
+@pytest.mark.parametrize("flags", FLAGSETS)
+def test_laplace_cyclic_flags(capi, orc, port, grid, flags):
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz)
+    f, x0 = seeded_fields(g.shape3, 2)
+    want = port.laplace_cyclic(og, m, f, x0=x0, flags=flags)
+    lap = gpu_laplace(capi, g, m, flags=flags)
+    got = lap.solve(dev(f), dev(x0)).cpu().numpy()
+    lap.status()
+    region = (slice(None), slice(g.ystart, g.yend + 1), slice(None))
+    assert rel_err(got, want, region) < 1e-10
+
+
+@pytest.mark.parametrize("grid", GRIDS[:2])
+def test_laplace_cyclic_coefficients_and_filter(capi, orc, port, grid):
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz)
+    f, x0 = seeded_fields(g.shape3, 2)
+    X = (np.arange(g.nx)[:, None] + 0.5) / g.nx * np.ones(g.shape2)
+    A = np.ascontiguousarray(-0.1 - 0.05 * X)
+    D = np.ascontiguousarray(1 + 0.2 * X)
+    Cc = np.ascontiguousarray(1 + 0.3 * np.sin(3 * X))
+    region = (slice(None), slice(g.ystart, g.yend + 1), slice(None))
+    for kw in (dict(A=A), dict(A=A, D=D), dict(C1=Cc, C2=Cc), dict(A=A, C1=Cc, C2=Cc, D=D)):
+        for maxmode in (None, max(1, g.nz // 4)):
+            want = port.laplace_cyclic(og, m, f, x0=x0, maxmode=maxmode, **kw)
+            got = gpu_laplace(capi, g, m, maxmode=maxmode, **kw).solve(dev(f), dev(x0)).cpu().numpy()
+            assert rel_err(got, want, region) < 1e-10
+
+
+@pytest.mark.parametrize("grid", [(20, 1, 32, 2, 0), (36, 3, 16, 2, 1), (260, 1, 256, 2, 0)])
+def test_laplace_cyclic_periodic_x(capi, orc, port, grid):
+    """hasegawa-wakatani's configuration: periodicX, kz=0 pinned + mean removed
+    (invert_laplace.cxx:755-767, cyclic_laplace.cxx:266-287)."""
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz, trivial=True)
+    (f,) = seeded_fields(g.shape3, 1)
+    want = port.laplace_cyclic(og, m, f, periodic_x=True, nonuniform=False)
+    lap = gpu_laplace(capi, g, m, periodic_x=True, nonuniform=False)
+    got = lap.solve(dev(f)).cpu().numpy()
+    lap.status()
+    assert rel_err(got, want, g.interior) < 1e-10
+
+
+def test_laplace_residual_full_size(capi, orc):
+    """Size-independent property at a BASELINE-size grid (256x64x256): applying the forward
+    operator Delp2 (FFT form, same coefficients) to the solution returns the right-hand side in
+    the interior (the self-consistency check of tests/unit/invert/laplace/test_laplace_cyclic.cxx:36-63)."""
+    g = capi.Grid(260, 68, 256, 2, 2)
+    m = make_metric(orc, g.shape2, g.nz)
+    lap = gpu_laplace(capi, g, m)
+    rhs = torch.rand(g.shape3, dtype=torch.float64, device="cuda") - 0.5
+    x = lap.solve(rhs)
+    lap.status()
+    back = lap.delp2(x)
+    # rows next to the boundary rows use the Dirichlet-pinned guard values, still consistent
+    sl = (slice(g.xstart, g.xend + 1), slice(g.ystart, g.yend + 1), slice(None))
+    err = (back[sl] - rhs[sl]).abs().max() / rhs[sl].abs().max()
+    assert err.item() < 1e-9
+
+
+def test_zero_pivot_is_reported(capi, orc):
+    g = capi.Grid(12, 3, 8, 2, 1)
+    m = make_metric(orc, g.shape2, g.nz, trivial=True)
+    m.g11[:] = 0.0  # singular: b = 0 on the kz=0 interior rows
+    m.g33[:] = 0.0
+    lap = gpu_laplace(capi, g, m, nonuniform=False, all_terms=False, flags=(0, 1, 1))
+    lap.solve(torch.ones(g.shape3, dtype=torch.float64, device="cuda"))
+    with pytest.raises(capi.BoutB200Error) as e:
+        lap.status()
+    assert e.value.status == -4

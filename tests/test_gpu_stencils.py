@@ -40,7 +40,8 @@ def test_index_stencil_matches_oracle(capi, orc, port, op, direction, grid):
     needs_v = not op.startswith(("DDX", "D2DX2", "D4DX4"))
     want = port.index_deriv(og, op, direction, f, v=v if needs_v else None)
     got = capi.stencil(g, op, direction, dev(f), v=dev(v) if needs_v else None).cpu().numpy()
-    assert rel_err(got, want, g.interior) < TOL
+    # floor: e.g. W3 along z with nz=2 is analytically zero -> compare against |f| instead
+    assert rel_err(got, want, g.interior, floor=1e-3 * np.abs(f).max()) < TOL
     # cells outside the region are untouched (zeros from the harness allocation)
     mask = np.ones(g.shape3, bool)
     mask[g.interior] = False
