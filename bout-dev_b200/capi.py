@@ -191,3 +191,125 @@ def delp2_fd(g: Grid, f, dx, dz, g11, g33, g13, G1, G3, d1_dx=None, out=None):
     _check(lib.bout_b200_delp2_fd(C.byref(g.c), _ptr(f), _ptr(dx), _ptr(dz), _ptr(g11), _ptr(g33),
                                   _ptr(g13), _ptr(G1), _ptr(G3), _ptr(d1_dx), _ptr(out), _stream()))
     return out
+
+
+class CEwTerm(C.Structure):
+    _fields_ = [("coef", C.c_double), ("f1", C.c_void_p), ("f2", C.c_void_p), ("div", C.c_void_p),
+                ("f1_is2d", C.c_int), ("f2_is2d", C.c_int), ("div_is2d", C.c_int)]
+
+
+def elementwise(g: Grid, terms, out=None, region="RGN_ALL", like=None):
+    """terms: list of (coef, f1, f2, div) with tensors or None; 2-D tensors broadcast over z."""
+    arr = (CEwTerm * len(terms))()
+    ref = like
+    for i, t in enumerate(terms):
+        coef, f1, f2, dv = (list(t) + [None, None, None])[:4]
+        arr[i].coef = coef
+        for name, f in (("f1", f1), ("f2", f2), ("div", dv)):
+            setattr(arr[i], name, None if f is None else f.data_ptr())
+            setattr(arr[i], name + "_is2d", int(f is not None and f.dim() == 2))
+            if f is not None and f.dim() == 3 and ref is None:
+                ref = f
+    out = torch.zeros_like(ref) if out is None else out
+    _check(lib.bout_b200_elementwise(C.byref(g.c), REGIONS[region], len(terms), arr, _ptr(out), _stream()))
+    return out
+
+
+UNARY = {"neg": 0, "sqrt": 1, "abs": 2, "exp": 3, "log": 4, "sin": 5, "cos": 6, "tanh": 7, "sq": 8,
+         "pow": 9, "copy": 10}
+
+
+def unary(g: Grid, op, f, arg=0.0, out=None):
+    out = torch.empty_like(f) if out is None else out
+    _check(lib.bout_b200_unary(C.byref(g.c), UNARY[op], _ptr(f), C.c_double(arg), _ptr(out), _stream()))
+    return out
+
+
+def boundary(g: Grid, kind, side, f, value=0.0, spacing=None, lo=-1, hi=-1):
+    """In place.  kind: dirichlet | neumann | zero; side: xin | xout | ydown | yup."""
+    k = {"dirichlet": 0, "dirichlet_o2": 0, "neumann": 1, "zero": 2}[kind]
+    sd = {"xin": 0, "xout": 1, "ydown": 2, "yup": 3}[side]
+    _check(lib.bout_b200_boundary(C.byref(g.c), k, sd, C.c_double(value), _ptr(spacing), lo, hi, _ptr(f),
+                                  _stream()))
+    return f
+
+
+def _ptr_array(fields):
+    return (C.c_void_p * len(fields))(*[f.data_ptr() for f in fields])
+
+
+def halo_self(g: Grid, fields, periodic_x=False, periodic_y=True):
+    _check(lib.bout_b200_halo_self(C.byref(g.c), len(fields), _ptr_array(fields), int(periodic_x),
+                                   int(periodic_y), _stream()))
+
+
+def halo_pack_y(g: Grid, fields, y0, nrows, xlo, xhi, buf):
+    _check(lib.bout_b200_halo_pack_y(C.byref(g.c), len(fields), _ptr_array(fields), y0, nrows, xlo, xhi,
+                                     _ptr(buf), _stream()))
+
+
+def halo_unpack_y(g: Grid, fields, y0, nrows, xlo, xhi, buf):
+    _check(lib.bout_b200_halo_unpack_y(C.byref(g.c), len(fields), _ptr_array(fields), y0, nrows, xlo, xhi,
+                                       _ptr(buf), _stream()))
+
+
+def rk_stage(g: Grid, mode, dt, start, k1, k2=None, k3=None, k4=None, c=1.0, out=None,
+             region="RGN_NOBNDRY"):
+    m = {"axpy": 0, "rk4_final": 1, "rk3_stage2": 2, "rk3_stage3": 3}[mode]
+    out = torch.zeros_like(start) if out is None else out
+    _check(lib.bout_b200_rk_stage(C.byref(g.c), REGIONS[region], m, C.c_double(dt), C.c_double(c),
+                                  _ptr(start), _ptr(k1), _ptr(k2), _ptr(k3), _ptr(k4), _ptr(out), _stream()))
+    return out
+
+
+class CMetric(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dx", "dy", "dz", "J", "g_22", "g11", "g33", "g13", "G1", "G3",
+                                          "d1_dx")]
+
+
+class CRkEpilogue(C.Structure):
+    _fields_ = [("start", C.c_void_p * 2), ("acc_in", C.c_void_p * 2), ("state_out", C.c_void_p * 2),
+                ("acc_out", C.c_void_p * 2), ("a", C.c_double), ("b", C.c_double)]
+
+
+def make_metric(md: dict):
+    """md: name -> Field2D tensor (missing names become NULL).  Keeps the tensors alive."""
+    c = CMetric()
+    for n, _ in CMetric._fields_:
+        t = md.get(n)
+        setattr(c, n, None if t is None else t.data_ptr())
+    c._keep = md
+    return c
+
+
+def make_epilogue(start, acc_in, state_out, acc_out, a, b):
+    e = CRkEpilogue()
+    for name, pair in (("start", start), ("acc_in", acc_in), ("state_out", state_out), ("acc_out", acc_out)):
+        arr = getattr(e, name)
+        for i in range(2):
+            arr[i] = None if pair is None or pair[i] is None else pair[i].data_ptr()
+    e.a, e.b = a, b
+    e._keep = (start, acc_in, state_out, acc_out)
+    return e
+
+
+def fused_coef_workspace(g: Grid, device):
+    lib.bout_b200_fused_coef_doubles.restype = C.c_size_t
+    return torch.empty(lib.bout_b200_fused_coef_doubles(C.byref(g.c)), dtype=torch.float64, device=device)
+
+
+def hw3d_rhs(g: Grid, metric: CMetric, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n=None, ddt_vort=None,
+             epilogue=None, coef_ws=None):
+    coef_ws = fused_coef_workspace(g, n.device) if coef_ws is None else coef_ws
+    _check(lib.bout_b200_hw3d_rhs(C.byref(g.c), C.byref(metric), C.c_double(alpha), C.c_double(kappa),
+                                  C.c_double(Dn), C.c_double(Dvort), _ptr(n), _ptr(vort), _ptr(phi),
+                                  _ptr(ddt_n), _ptr(ddt_vort),
+                                  None if epilogue is None else C.byref(epilogue), _ptr(coef_ws), _stream()))
+
+
+def hw_convective(g: Grid, dx, dz, alpha, kappa, n, vort, phi, zonal_n=None, zonal_phi=None, ddt_n=None,
+                  ddt_vort=None, epilogue=None):
+    _check(lib.bout_b200_hw_convective(C.byref(g.c), _ptr(dx), _ptr(dz), C.c_double(alpha),
+                                       C.c_double(kappa), _ptr(n), _ptr(vort), _ptr(phi), _ptr(zonal_n),
+                                       _ptr(zonal_phi), _ptr(ddt_n), _ptr(ddt_vort),
+                                       None if epilogue is None else C.byref(epilogue), _stream()))

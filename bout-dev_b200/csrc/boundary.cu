@@ -1,0 +1,100 @@
+// Boundary conditions on guard cells (subsystem a15) for CELL_CENTRE Field3D with a constant value.
+// Reference: BoundaryDirichlet::apply standard case (src/mesh/boundary_standard.cxx:527-581):
+//   first guard = 2*val - f_inside, remaining guards = val;
+// BoundaryNeumann::apply CELL_CENTRE (:2167-2190): g1 = f_in + delta*val and, for width 2,
+//   g2 = f_in2 + 3*delta*val with delta = bx*dx + by*dy at the first guard cell;
+// apply_ddt (:591-600, :2201-2210): time derivative set to zero in the boundary cells.
+// X boundaries cover y = ystart..yend (src/mesh/impls/bout/boutmesh.cxx:1028-1037); Y boundaries
+// cover x = xlo..xhi as given (corner cells included by default, boutmesh.cxx:1057-1059).
+#include "common.cuh"
+
+namespace b200 {
+
+struct BndryParams {
+  double* __restrict__ f;
+  const double* __restrict__ spacing; // dx (x sides) or dy (y sides), Field2D; only for Neumann
+  double val;
+  int nx, ny, nz;
+  int kind; // 0 dirichlet, 1 neumann, 2 zero (apply_ddt)
+  int side; // 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper
+  int width;
+  int lo, hi; // range of the other index (y for x sides, x for y sides), inclusive
+  int first;  // first guard index along the boundary normal
+  int b;      // outward direction (-1 or +1)
+};
+
+__global__ void __launch_bounds__(256) k_boundary(const BndryParams p) {
+  const long long n = static_cast<long long>(p.hi - p.lo + 1) * p.nz;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n) {
+    return;
+  }
+  const int z = static_cast<int>(t % p.nz);
+  const int o = p.lo + static_cast<int>(t / p.nz);
+  const bool xside = p.side < 2;
+  auto idx3 = [&](int normal) -> long long {
+    const int x = xside ? normal : o;
+    const int y = xside ? o : normal;
+    return (static_cast<long long>(x) * p.ny + y) * p.nz + z;
+  };
+  if (p.kind == 2) {
+    for (int i = 0; i < p.width; ++i) {
+      p.f[idx3(p.first + i * p.b)] = 0.0;
+    }
+  } else if (p.kind == 0) {
+    p.f[idx3(p.first)] = 2 * p.val - p.f[idx3(p.first - p.b)];
+    for (int i = 1; i < p.width; ++i) {
+      p.f[idx3(p.first + i * p.b)] = p.val;
+    }
+  } else {
+    const int x = xside ? p.first : o;
+    const int y = xside ? o : p.first;
+    const double delta = p.b * __ldg(p.spacing + static_cast<long long>(x) * p.ny + y);
+    p.f[idx3(p.first)] = p.f[idx3(p.first - p.b)] + delta * p.val;
+    if (p.width == 2) {
+      p.f[idx3(p.first + p.b)] = p.f[idx3(p.first - 2 * p.b)] + 3.0 * delta * p.val;
+    }
+  }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value,
+                                  const double* spacing2d, int lo, int hi, double* f, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(f != nullptr && kind >= 0 && kind <= 2 && side >= 0 && side <= 3, BOUT_B200_ERR_ARG,
+               "boundary: bad argument");
+  B200_REQUIRE(kind != 1 || spacing2d != nullptr, BOUT_B200_ERR_ARG, "boundary: neumann needs the spacing");
+  BndryParams p{};
+  p.f = f;
+  p.spacing = spacing2d;
+  p.val = value;
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.kind = kind;
+  p.side = side;
+  switch (side) {
+  case 0: p.width = g->xstart; p.first = g->xstart - 1; p.b = -1; break;             // BoundaryRegionXIn
+  case 1: p.width = g->nx - g->xend - 1; p.first = g->nx - p.width; p.b = 1; break; // BoundaryRegionXOut
+  case 2: p.width = g->ystart; p.first = g->ystart - 1; p.b = -1; break;             // BoundaryRegionYDown
+  default: p.width = g->ny - g->yend - 1; p.first = g->ny - p.width; p.b = 1; break; // BoundaryRegionYUp
+  }
+  if (p.width <= 0) {
+    return 0; // no guard cells on this side
+  }
+  if (lo < 0 || hi < 0) { // default ranges
+    lo = side < 2 ? g->ystart : 0;
+    hi = side < 2 ? g->yend : g->nx - 1;
+  }
+  p.lo = lo;
+  p.hi = hi;
+  const long long n = static_cast<long long>(hi - lo + 1) * g->nz;
+  k_boundary<<<static_cast<unsigned>((n + 255) / 256), 256, 0, asStream(stream)>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}

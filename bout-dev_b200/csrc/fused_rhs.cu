@@ -1,0 +1,439 @@
+// Fused physics-model RHS kernels: "one kernel per RHS term set" with the explicit integrator's
+// stage update folded into the same pass (subsystems 2 + 4 of the hot path).
+//
+// The reference ships, next to each operator-at-a-time model, a hand-fused "outer loop" variant
+// that evaluates the whole right-hand side in one loop with single-index operators
+// (examples/hasegawa-wakatani-3d/hw.cxx:58-74, examples/blob2d-outerloop, examples/elm-pb-outerloop;
+// operators in include/bout/single_index_ops.hxx).  These kernels are the B200 statement of those
+// loops:
+//   * every thread owns a (y, z-pair) column and marches along x with the x-1, x, x+1 planes of
+//     each evolving field held in registers (z-1..z+2 of each), so n, vort and phi are read from
+//     L2/HBM once per chunk and feed both brackets, both Delp2 terms and DDZ;
+//   * y-neighbour values for the parallel term are read directly (L2 hits: the neighbouring
+//     CTAs stream the same rows);
+//   * all metric combinations that depend on (x,y) only are produced once by a small prologue
+//     kernel instead of per point (fp64 divisions are ~12-25 issue slots each on sm_100);
+//   * optional epilogue: the RK stage update state' = start + a*ddt, acc' = acc + b*ddt written in
+//     the same pass, so no separate axpy kernels run (reference RK4: rk4.cxx:172-210).
+#include "bracket.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// Per-(x,y) coefficients shared by the fused kernels
+// ------------------------------------------------------------------------------------------------
+enum { C_SF = 0,   // 1 / (12 dx dz)                         bracket spacing factor
+       C_RDZ2,     // 1 / (2 dz)                             DDZ
+       C_DPX,      // (G1 + d1_dx g11) / (2 dx)              Delp2: DDX coefficient
+       C_DPZ,      // G3 / (2 dz)
+       C_DPXX,     // g11 / dx^2
+       C_DPZZ,     // g33 / dz^2
+       C_DPXZ,     // 2 g13 / (4 dz dx)
+       C_UP,       // 2 (J + Jp) / ((dy + dyp)(g_22 + g_22p)) / (dy J)   Div_par_Grad_par upper flux
+       C_DN,       // same with the lower neighbour
+       C_NCOEF };
+
+struct CoefIn {
+  const double* dx;
+  const double* dy;
+  const double* dz;
+  const double* J;
+  const double* g_22;
+  const double* g11;
+  const double* g33;
+  const double* g13;
+  const double* G1;
+  const double* G3;
+  const double* d1_dx; // may be NULL (uniform mesh)
+  int nx, ny;
+};
+
+__global__ void __launch_bounds__(256) k_fused_coefs(const CoefIn m, double* __restrict__ coef, int with_par) {
+  const int n2 = m.nx * m.ny;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) {
+    return;
+  }
+  const int y = i % m.ny;
+  const double dx = m.dx[i], dz = m.dz[i];
+  coef[C_SF * n2 + i] = 1.0 / (12 * dx * dz);
+  coef[C_RDZ2 * n2 + i] = 1.0 / (2.0 * dz);
+  const double g11 = m.g11[i];
+  const double d1 = m.d1_dx ? m.d1_dx[i] : 0.0;
+  coef[C_DPX * n2 + i] = (m.G1[i] + d1 * g11) / (2.0 * dx);
+  coef[C_DPZ * n2 + i] = m.G3[i] / (2.0 * dz);
+  coef[C_DPXX * n2 + i] = g11 / (dx * dx);
+  coef[C_DPZZ * n2 + i] = m.g33[i] / (dz * dz);
+  coef[C_DPXZ * n2 + i] = 2 * m.g13[i] / (4. * dz * dx);
+  if (with_par && y >= 1 && y <= m.ny - 2) {
+    const double dy = m.dy[i], J = m.J[i], g22 = m.g_22[i];
+    const double up = 2. * (J + m.J[i + 1]) / ((dy + m.dy[i + 1]) * (g22 + m.g_22[i + 1]));
+    const double dn = 2. * (J + m.J[i - 1]) / ((dy + m.dy[i - 1]) * (g22 + m.g_22[i - 1]));
+    coef[C_UP * n2 + i] = up / (dy * J);
+    coef[C_DN * n2 + i] = dn / (dy * J);
+  } else {
+    coef[C_UP * n2 + i] = 0.0;
+    coef[C_DN * n2 + i] = 0.0;
+  }
+}
+
+// Delp2 of single_index_ops.hxx:222-246 from the three x-planes, with precombined coefficients
+__device__ __forceinline__ double delp2Point(const Row4& fm, const Row4& f0, const Row4& fp, int i,
+                                             double cx, double cz, double cxx, double czz, double cxz) {
+  const int zm = i, z = i + 1, zp = i + 2;
+  return cx * (fp.v[z] - fm.v[z]) + cz * (f0.v[zp] - f0.v[zm])
+         + cxx * (fp.v[z] - 2.0 * f0.v[z] + fm.v[z]) + czz * (f0.v[zp] - 2.0 * f0.v[z] + f0.v[zm])
+         + cxz * ((fp.v[zp] - fm.v[zp]) - (fp.v[zm] - fm.v[zm]));
+}
+
+struct RkEpilogue {
+  // For each evolving field e (0..1): state_out = start + a*ddt ; acc_out = acc_in + b*ddt.
+  // Any pointer may be NULL to skip that output.  In-place acc (acc_out == acc_in) is allowed.
+  const double* start[2];
+  const double* acc_in[2];
+  double* state_out[2];
+  double* acc_out[2];
+  double a, b;
+  int enabled;
+};
+
+template <int VEC>
+__device__ __forceinline__ void finishPoint(const RkEpilogue& ep, int e, long long idx, const Vz<VEC>& ddt,
+                                            double* __restrict__ ddt_out) {
+  if (ddt_out != nullptr) {
+    ddt.store(ddt_out + idx);
+  }
+  if (ep.enabled) {
+    const Vz<VEC> s = Vz<VEC>::load(ep.start[e] + idx);
+    if (ep.state_out[e] != nullptr) {
+      Vz<VEC> r;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        r.v[i] = s.v[i] + ep.a * ddt.v[i];
+      }
+      r.store(ep.state_out[e] + idx);
+    }
+    if (ep.acc_out[e] != nullptr) {
+      Vz<VEC> base = s;
+      if (ep.acc_in[e] != nullptr) {
+        base = Vz<VEC>::load(ep.acc_in[e] + idx);
+      }
+      Vz<VEC> r;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        r.v[i] = base.v[i] + ep.b * ddt.v[i];
+      }
+      r.store(ep.acc_out[e] + idx);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hasegawa-wakatani-3d (examples/hasegawa-wakatani-3d/hw.cxx:50-77)
+//   div_current = alpha * Div_par_Grad_par(phi - n)
+//   ddt(n)    = -[phi,n]    - div_current - kappa*DDZ(phi) + Dn   *Delp2(n)
+//   ddt(vort) = -[phi,vort] - div_current                  + Dvort*Delp2(vort)
+// ------------------------------------------------------------------------------------------------
+struct Hw3dParams {
+  const double* __restrict__ n;
+  const double* __restrict__ vort;
+  const double* __restrict__ phi;
+  const double* __restrict__ coef; // [C_NCOEF][nx*ny]
+  double* __restrict__ ddt_n;
+  double* __restrict__ ddt_vort;
+  RkEpilogue ep;
+  double alpha, kappa, Dn, Dvort;
+  int nx, ny, nz, xs, xe, ys, ye, chunk;
+  int with_par; // ny > 1
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(128) k_hw3d_rhs(const Hw3dParams p) {
+  const int nzv = p.nz / VEC;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(p.ye - p.ys + 1) * nzv) {
+    return;
+  }
+  const int z = static_cast<int>(t % nzv) * VEC;
+  const int y = p.ys + static_cast<int>(t / nzv);
+  const int x0 = p.xs + blockIdx.y * p.chunk;
+  const int x1 = min(x0 + p.chunk - 1, p.xe);
+  const long long plane = static_cast<long long>(p.ny) * p.nz;
+  const long long rowoff = static_cast<long long>(y) * p.nz;
+  const int n2 = p.nx * p.ny;
+
+  Row4 Nm, N0, Np, Vm, V0, Vp, Pm, P0, Pp;
+  N0 = loadRow4<VEC>(p.n + (x0 - 1) * plane + rowoff, z, p.nz);
+  Np = loadRow4<VEC>(p.n + x0 * plane + rowoff, z, p.nz);
+  V0 = loadRow4<VEC>(p.vort + (x0 - 1) * plane + rowoff, z, p.nz);
+  Vp = loadRow4<VEC>(p.vort + x0 * plane + rowoff, z, p.nz);
+  P0 = loadRow4<VEC>(p.phi + (x0 - 1) * plane + rowoff, z, p.nz);
+  Pp = loadRow4<VEC>(p.phi + x0 * plane + rowoff, z, p.nz);
+  for (int x = x0; x <= x1; ++x) {
+    Nm = N0; N0 = Np;
+    Vm = V0; V0 = Vp;
+    Pm = P0; P0 = Pp;
+    const long long nxt = (x + 1) * plane + rowoff;
+    Np = loadRow4<VEC>(p.n + nxt, z, p.nz);
+    Vp = loadRow4<VEC>(p.vort + nxt, z, p.nz);
+    Pp = loadRow4<VEC>(p.phi + nxt, z, p.nz);
+    const long long idx = x * plane + rowoff + z;
+    // y neighbours of (phi - n) at this x
+    Vz<VEC> pup, pdn, nup, ndn;
+    if (p.with_par) {
+      pup = Vz<VEC>::load(p.phi + idx + p.nz);
+      pdn = Vz<VEC>::load(p.phi + idx - p.nz);
+      nup = Vz<VEC>::load(p.n + idx + p.nz);
+      ndn = Vz<VEC>::load(p.n + idx - p.nz);
+    }
+    const int i2 = x * p.ny + y;
+    const double sf = __ldg(p.coef + C_SF * n2 + i2), rdz2 = __ldg(p.coef + C_RDZ2 * n2 + i2);
+    const double cx = __ldg(p.coef + C_DPX * n2 + i2), cz = __ldg(p.coef + C_DPZ * n2 + i2);
+    const double cxx = __ldg(p.coef + C_DPXX * n2 + i2), czz = __ldg(p.coef + C_DPZZ * n2 + i2);
+    const double cxz = __ldg(p.coef + C_DPXZ * n2 + i2);
+    const double cup = __ldg(p.coef + C_UP * n2 + i2), cdn = __ldg(p.coef + C_DN * n2 + i2);
+    Vz<VEC> dn_, dv_;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      double div_current = 0.0;
+      if (p.with_par) {
+        const double c = P0.v[i + 1] - N0.v[i + 1];
+        const double up = pup.v[i] - nup.v[i];
+        const double dn = pdn.v[i] - ndn.v[i];
+        div_current = p.alpha * (cup * (up - c) - cdn * (c - dn));
+      }
+      const double br_n = arakawaCore(Pm, P0, Pp, Nm, N0, Np, i) * sf;
+      const double br_v = arakawaCore(Pm, P0, Pp, Vm, V0, Vp, i) * sf;
+      const double ddz_phi = (P0.v[i + 2] - P0.v[i]) * rdz2;
+      const double d2n = delp2Point(Nm, N0, Np, i, cx, cz, cxx, czz, cxz);
+      const double d2v = delp2Point(Vm, V0, Vp, i, cx, cz, cxx, czz, cxz);
+      dn_.v[i] = -br_n - div_current - p.kappa * ddz_phi + p.Dn * d2n;
+      dv_.v[i] = -br_v - div_current + p.Dvort * d2v;
+    }
+    finishPoint<VEC>(p.ep, 0, idx, dn_, p.ddt_n);
+    finishPoint<VEC>(p.ep, 1, idx, dv_, p.ddt_vort);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hasegawa-wakatani convective part (examples/hasegawa-wakatani/hw.cxx:94-118), Arakawa bracket:
+//   ddt(n)    = -[phi,n]    + alpha*(nzphi - nzn) - kappa*DDZ(phi)
+//   ddt(vort) = -[phi,vort] + alpha*(nzphi - nzn)
+// with nzf = f - zonal[x,y] when `modified` (zonal = averageY(DC(f)), a Field2D) else f.
+// ------------------------------------------------------------------------------------------------
+struct HwConvParams {
+  const double* __restrict__ n;
+  const double* __restrict__ vort;
+  const double* __restrict__ phi;
+  const double* __restrict__ zonal_n;   // Field2D or NULL
+  const double* __restrict__ zonal_phi; // Field2D or NULL
+  const double* __restrict__ dx;
+  const double* __restrict__ dz;
+  double* __restrict__ ddt_n;
+  double* __restrict__ ddt_vort;
+  RkEpilogue ep;
+  double alpha, kappa;
+  int nx, ny, nz, xs, xe, ys, ye, chunk;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(128) k_hw_convective(const HwConvParams p) {
+  const int nzv = p.nz / VEC;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(p.ye - p.ys + 1) * nzv) {
+    return;
+  }
+  const int z = static_cast<int>(t % nzv) * VEC;
+  const int y = p.ys + static_cast<int>(t / nzv);
+  const int x0 = p.xs + blockIdx.y * p.chunk;
+  const int x1 = min(x0 + p.chunk - 1, p.xe);
+  const long long plane = static_cast<long long>(p.ny) * p.nz;
+  const long long rowoff = static_cast<long long>(y) * p.nz;
+  Row4 Nm, N0, Np, Vm, V0, Vp, Pm, P0, Pp;
+  N0 = loadRow4<VEC>(p.n + (x0 - 1) * plane + rowoff, z, p.nz);
+  Np = loadRow4<VEC>(p.n + x0 * plane + rowoff, z, p.nz);
+  V0 = loadRow4<VEC>(p.vort + (x0 - 1) * plane + rowoff, z, p.nz);
+  Vp = loadRow4<VEC>(p.vort + x0 * plane + rowoff, z, p.nz);
+  P0 = loadRow4<VEC>(p.phi + (x0 - 1) * plane + rowoff, z, p.nz);
+  Pp = loadRow4<VEC>(p.phi + x0 * plane + rowoff, z, p.nz);
+  for (int x = x0; x <= x1; ++x) {
+    Nm = N0; N0 = Np;
+    Vm = V0; V0 = Vp;
+    Pm = P0; P0 = Pp;
+    const long long nxt = (x + 1) * plane + rowoff;
+    Np = loadRow4<VEC>(p.n + nxt, z, p.nz);
+    Vp = loadRow4<VEC>(p.vort + nxt, z, p.nz);
+    Pp = loadRow4<VEC>(p.phi + nxt, z, p.nz);
+    const long long idx = x * plane + rowoff + z;
+    const long long i2 = static_cast<long long>(x) * p.ny + y;
+    const double dxv = __ldg(p.dx + i2), dzv = __ldg(p.dz + i2);
+    const double sf = 1.0 / (12 * dzv * dxv); // difops.cxx:950
+    const double rdz = 1.0 / dzv;             // DDZ = index * (1/dz), derivs.cxx:82-86
+    const double zn = p.zonal_n ? __ldg(p.zonal_n + i2) : 0.0;
+    const double zp = p.zonal_phi ? __ldg(p.zonal_phi + i2) : 0.0;
+    Vz<VEC> dn_, dv_;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const double br_n = arakawaCore(Pm, P0, Pp, Nm, N0, Np, i) * sf;
+      const double br_v = arakawaCore(Pm, P0, Pp, Vm, V0, Vp, i) * sf;
+      const double coupling = p.alpha * ((P0.v[i + 1] - zp) - (N0.v[i + 1] - zn));
+      const double ddz_phi = (0.5 * (P0.v[i + 2] - P0.v[i])) * rdz;
+      dn_.v[i] = (-1.0 * br_n + coupling) - p.kappa * ddz_phi;
+      dv_.v[i] = -1.0 * br_v + coupling;
+    }
+    finishPoint<VEC>(p.ep, 0, idx, dn_, p.ddt_n);
+    finishPoint<VEC>(p.ep, 1, idx, dv_, p.ddt_vort);
+  }
+}
+
+inline int pickChunk(long long north, int len) {
+  int chunk = 8;
+  for (int c : {64, 32, 16}) {
+    if (north * ((len + c - 1) / c) >= 148LL * 1024) {
+      chunk = c;
+      break;
+    }
+  }
+  return chunk;
+}
+
+inline RkEpilogue makeEpilogue(const bout_b200_rk_epilogue* e) {
+  RkEpilogue ep{};
+  if (e != nullptr) {
+    for (int i = 0; i < 2; ++i) {
+      ep.start[i] = e->start[i];
+      ep.acc_in[i] = e->acc_in[i];
+      ep.state_out[i] = e->state_out[i];
+      ep.acc_out[i] = e->acc_out[i];
+    }
+    ep.a = e->a;
+    ep.b = e->b;
+    ep.enabled = 1;
+  }
+  return ep;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" size_t bout_b200_fused_coef_doubles(const bout_b200_grid* g) {
+  return g ? static_cast<size_t>(C_NCOEF) * g->nx * g->ny : 0;
+}
+
+extern "C" int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, double alpha,
+                                  double kappa, double Dn, double Dvort, const double* n,
+                                  const double* vort, const double* phi, double* ddt_n,
+                                  double* ddt_vort, const bout_b200_rk_epilogue* epilogue,
+                                  double* coef_workspace, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(m && n && vort && phi && coef_workspace, BOUT_B200_ERR_ARG, "hw3d_rhs: null argument");
+  B200_REQUIRE((ddt_n && ddt_vort) || epilogue, BOUT_B200_ERR_ARG, "hw3d_rhs: no output requested");
+  B200_REQUIRE(m->dx && m->dy && m->dz && m->J && m->g_22 && m->g11 && m->g33 && m->g13 && m->G1 && m->G3,
+               BOUT_B200_ERR_ARG, "hw3d_rhs: metric missing");
+  B200_REQUIRE(g->xstart >= 1 && g->xend <= g->nx - 2, BOUT_B200_ERR_GUARDS, "hw3d_rhs: needs an x guard cell");
+  const int with_par = g->ny > 1 ? 1 : 0;
+  B200_REQUIRE(!with_par || (g->ystart >= 1 && g->yend <= g->ny - 2), BOUT_B200_ERR_GUARDS,
+               "hw3d_rhs: needs a y guard cell");
+  cudaStream_t s = asStream(stream);
+  CoefIn ci{m->dx, m->dy, m->dz, m->J, m->g_22, m->g11, m->g33, m->g13, m->G1, m->G3, m->d1_dx, g->nx, g->ny};
+  const int n2 = g->nx * g->ny;
+  k_fused_coefs<<<(n2 + 255) / 256, 256, 0, s>>>(ci, coef_workspace, with_par);
+  B200_LAUNCH_OK();
+  Hw3dParams p{};
+  p.n = n;
+  p.vort = vort;
+  p.phi = phi;
+  p.coef = coef_workspace;
+  p.ddt_n = ddt_n;
+  p.ddt_vort = ddt_vort;
+  p.ep = makeEpilogue(epilogue);
+  p.alpha = alpha;
+  p.kappa = kappa;
+  p.Dn = Dn;
+  p.Dvort = Dvort;
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.xs = g->xstart;
+  p.xe = g->xend;
+  p.ys = g->ystart;
+  p.ye = g->yend;
+  p.with_par = with_par;
+  bool vec2 = (g->nz % 2 == 0) && aligned16(n) && aligned16(vort) && aligned16(phi)
+              && (!ddt_n || aligned16(ddt_n)) && (!ddt_vort || aligned16(ddt_vort));
+  if (epilogue) {
+    for (int i = 0; i < 2; ++i) {
+      vec2 = vec2 && aligned16(epilogue->start[i]) && aligned16(epilogue->acc_in[i])
+             && aligned16(epilogue->state_out[i]) && aligned16(epilogue->acc_out[i]);
+    }
+  }
+  const int nzv = vec2 ? g->nz / 2 : g->nz;
+  const long long north = static_cast<long long>(p.ye - p.ys + 1) * nzv;
+  const int len = p.xe - p.xs + 1;
+  p.chunk = pickChunk(north, len);
+  dim3 grid(static_cast<unsigned>((north + 127) / 128), static_cast<unsigned>((len + p.chunk - 1) / p.chunk));
+  if (vec2) {
+    k_hw3d_rhs<2><<<grid, 128, 0, s>>>(p);
+  } else {
+    k_hw3d_rhs<1><<<grid, 128, 0, s>>>(p);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int bout_b200_hw_convective(const bout_b200_grid* g, const double* dx, const double* dz,
+                                       double alpha, double kappa, const double* n,
+                                       const double* vort, const double* phi, const double* zonal_n,
+                                       const double* zonal_phi, double* ddt_n, double* ddt_vort,
+                                       const bout_b200_rk_epilogue* epilogue, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(dx && dz && n && vort && phi, BOUT_B200_ERR_ARG, "hw_convective: null argument");
+  B200_REQUIRE((ddt_n && ddt_vort) || epilogue, BOUT_B200_ERR_ARG, "hw_convective: no output requested");
+  B200_REQUIRE(g->xstart >= 1 && g->xend <= g->nx - 2, BOUT_B200_ERR_GUARDS,
+               "hw_convective: needs an x guard cell");
+  HwConvParams p{};
+  p.n = n;
+  p.vort = vort;
+  p.phi = phi;
+  p.zonal_n = zonal_n;
+  p.zonal_phi = zonal_phi;
+  p.dx = dx;
+  p.dz = dz;
+  p.ddt_n = ddt_n;
+  p.ddt_vort = ddt_vort;
+  p.ep = makeEpilogue(epilogue);
+  p.alpha = alpha;
+  p.kappa = kappa;
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.xs = g->xstart;
+  p.xe = g->xend;
+  p.ys = g->ystart;
+  p.ye = g->yend;
+  bool vec2 = (g->nz % 2 == 0) && aligned16(n) && aligned16(vort) && aligned16(phi)
+              && (!ddt_n || aligned16(ddt_n)) && (!ddt_vort || aligned16(ddt_vort));
+  if (epilogue) {
+    for (int i = 0; i < 2; ++i) {
+      vec2 = vec2 && aligned16(epilogue->start[i]) && aligned16(epilogue->acc_in[i])
+             && aligned16(epilogue->state_out[i]) && aligned16(epilogue->acc_out[i]);
+    }
+  }
+  const int nzv = vec2 ? g->nz / 2 : g->nz;
+  const long long north = static_cast<long long>(p.ye - p.ys + 1) * nzv;
+  const int len = p.xe - p.xs + 1;
+  p.chunk = pickChunk(north, len);
+  dim3 grid(static_cast<unsigned>((north + 127) / 128), static_cast<unsigned>((len + p.chunk - 1) / p.chunk));
+  if (vec2) {
+    k_hw_convective<2><<<grid, 128, 0, asStream(stream)>>>(p);
+  } else {
+    k_hw_convective<1><<<grid, 128, 0, asStream(stream)>>>(p);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,99 @@
+// Explicit integrator stage updates (subsystem 4), applied field-by-field on device-resident SoA
+// fields over the evolving region (RGN_NOBNDRY): the reference's load_vars / save_derivs
+// gather-scatter through an interleaved state vector (src/solver/solver.cxx:1039-1309) is not
+// needed when fields stay in place.
+// Reference arithmetic: RK4Solver::take_step (src/solver/impls/rk4/rk4.cxx:172-210),
+// RK3SSP::take_step (src/solver/impls/rk3-ssp/rk3-ssp.cxx:100-129).
+#include "common.cuh"
+
+namespace b200 {
+
+enum RkMode { RK_AXPY = 0, RK4_FINAL = 1, RK3_STAGE2 = 2, RK3_STAGE3 = 3 };
+
+struct RkParams {
+  const double* a; // start
+  const double* k1;
+  const double* k2;
+  const double* k3;
+  const double* k4;
+  double* out;
+  double dt, c;
+  int mode;
+  int ny, nz, xs, xe, ys, ye;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_rk(const RkParams p) {
+  const int nzv = p.nz / VEC;
+  const int nyb = p.ye - p.ys + 1;
+  const long long total = static_cast<long long>(p.xe - p.xs + 1) * nyb * nzv;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int zv = static_cast<int>(t % nzv);
+    const long long xy = t / nzv;
+    const int y = p.ys + static_cast<int>(xy % nyb);
+    const int x = p.xs + static_cast<int>(xy / nyb);
+    const long long i = (static_cast<long long>(x) * p.ny + y) * p.nz + static_cast<long long>(zv) * VEC;
+    const Vz<VEC> s = Vz<VEC>::load(p.a + i);
+    Vz<VEC> r;
+    if (p.mode == RK_AXPY) { // k5 = start + c*dt*k   (rk4.cxx:179-200; rk3-ssp.cxx:107-109 with c = 1)
+      const Vz<VEC> k = Vz<VEC>::load(p.k1 + i);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        r.v[j] = s.v[j] + p.c * p.dt * k.v[j];
+      }
+    } else if (p.mode == RK4_FINAL) { // rk4.cxx:206-209
+      const Vz<VEC> a = Vz<VEC>::load(p.k1 + i), b = Vz<VEC>::load(p.k2 + i);
+      const Vz<VEC> c = Vz<VEC>::load(p.k3 + i), d = Vz<VEC>::load(p.k4 + i);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        r.v[j] = s.v[j] + (1. / 6.) * p.dt * (a.v[j] + 2. * b.v[j] + 2. * c.v[j] + d.v[j]);
+      }
+    } else if (p.mode == RK3_STAGE2) { // u2 = 0.75*start + 0.25*u1 + 0.25*dt*L
+      const Vz<VEC> u1 = Vz<VEC>::load(p.k1 + i), L = Vz<VEC>::load(p.k2 + i);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        r.v[j] = 0.75 * s.v[j] + 0.25 * u1.v[j] + 0.25 * p.dt * L.v[j];
+      }
+    } else { // result = (1/3)*start + (2/3)*(u2 + dt*L)
+      const Vz<VEC> u2 = Vz<VEC>::load(p.k1 + i), L = Vz<VEC>::load(p.k2 + i);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        r.v[j] = (1. / 3) * s.v[j] + (2. / 3.) * (u2.v[j] + p.dt * L.v[j]);
+      }
+    }
+    r.store(p.out + i);
+  }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int bout_b200_rk_stage(const bout_b200_grid* g, int region, int mode, double dt, double c,
+                                  const double* start, const double* k1, const double* k2,
+                                  const double* k3, const double* k4, double* out, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(start && k1 && out && mode >= 0 && mode <= 3, BOUT_B200_ERR_ARG, "rk_stage: bad argument");
+  B200_REQUIRE(mode == RK_AXPY || k2 != nullptr, BOUT_B200_ERR_ARG, "rk_stage: missing stage array");
+  B200_REQUIRE(mode != RK4_FINAL || (k3 && k4), BOUT_B200_ERR_ARG, "rk_stage: RK4 final needs k1..k4");
+  Box b;
+  if (regionBox(g, region, &b) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  RkParams p{start, k1, k2, k3, k4, out, dt, c, mode, g->ny, g->nz, b.xs, b.xe, b.ys, b.ye};
+  const bool vec2 = (g->nz % 2 == 0) && aligned16(start) && aligned16(k1) && aligned16(out)
+                    && (!k2 || aligned16(k2)) && (!k3 || aligned16(k3)) && (!k4 || aligned16(k4));
+  const long long total = static_cast<long long>(b.xe - b.xs + 1) * (b.ye - b.ys + 1) * (vec2 ? g->nz / 2 : g->nz);
+  const long long want = (total + 255) / 256;
+  const unsigned blocks = static_cast<unsigned>(want < 148LL * 64 ? (want < 1 ? 1 : want) : 148LL * 64);
+  if (vec2) {
+    k_rk<2><<<blocks, 256, 0, asStream(stream)>>>(p);
+  } else {
+    k_rk<1><<<blocks, 256, 0, asStream(stream)>>>(p);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}

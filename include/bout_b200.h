@@ -172,6 +172,94 @@ int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_lapl
  * (reference throws BoutException, include/bout/cyclic_reduction.hxx:553). */
 int bout_b200_laplace_cyclic_status(void* workspace, void* stream);
 
+/* ---- field algebra (a12) -----------------------------------------------------------------------------
+ * out[region] = sum_i coef_i * f1_i * f2_i [/ div_i]  in one pass (1..8 terms).  f1/f2/div may be NULL
+ * (factor 1); *_is2d marks a Field2D operand broadcast over z.  Every operator of
+ * src/field/generated_fieldops.cxx is one or two such terms: a*b -> {1,a,b}; a+b -> {1,a},{1,b};
+ * a-s -> {1,a},{-s}; a/b2d -> {1,a,div=b2d} (multiplies by 1/b2d as the reference, :253-274);
+ * 2.*a + b*c (examples/performance/arithmetic/arithmetic.cxx:52) -> {2,a},{1,b,c}. */
+typedef struct bout_b200_ewterm {
+  double coef;
+  const double* f1;
+  const double* f2;
+  const double* div;
+  int f1_is2d, f2_is2d, div_is2d;
+} bout_b200_ewterm;
+int bout_b200_elementwise(const bout_b200_grid* g, int region, int nterms,
+                          const bout_b200_ewterm* terms, double* out, void* stream);
+/* Unary functions over RGN_ALL (include/bout/field.hxx:527-634 FIELD_FUNC; field3d.cxx:581 unary minus):
+ * 0 neg, 1 sqrt, 2 abs, 3 exp, 4 log, 5 sin, 6 cos, 7 tanh, 8 SQ, 9 pow(f, arg), 10 copy. */
+int bout_b200_unary(const bout_b200_grid* g, int op, const double* f, double arg, double* out,
+                    void* stream);
+
+/* ---- boundary conditions (a15) ---------------------------------------------------------------------
+ * kind: 0 dirichlet / dirichlet_o2 (src/mesh/boundary_standard.cxx:527-581), 1 neumann (:2167-2190),
+ * 2 zero the cells (apply_ddt :591-600).  side: 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper.
+ * spacing2d: dx for x sides, dy for y sides (Neumann only).  lo/hi: range of the other index
+ * (y for x sides, x for y sides); pass -1,-1 for the reference's default (ystart..yend / all x). */
+int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value,
+                       const double* spacing2d, int lo, int hi, double* f, void* stream);
+
+/* ---- guard-cell exchange (a13, Mesh::communicate) ------------------------------------------------------
+ * Self exchange when the rank is its own neighbour (periodic Y with NYPE=1, periodicX with NXPE=1):
+ * Y first, then X with corners (src/mesh/mesh.cxx:351-362, boutmesh.cxx:1221-1555).  Up to 8 fields. */
+int bout_b200_halo_self(const bout_b200_grid* g, int nfields, double* const* fields, int periodic_x,
+                        int periodic_y, void* stream);
+/* y-guard rows y0..y0+nrows-1, x in [xlo,xhi] <-> contiguous buffer [field][x][y][z]
+ * (pack_data / unpack_data, boutmesh.cxx:2400-2466).  X guard planes need no packing. */
+int bout_b200_halo_pack_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0,
+                          int nrows, int xlo, int xhi, double* buf, void* stream);
+int bout_b200_halo_unpack_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0,
+                            int nrows, int xlo, int xhi, const double* buf, void* stream);
+
+/* ---- (4) explicit integrator stage updates --------------------------------------------------------
+ * mode 0: out = start + c*dt*k1                      (rk4.cxx:179-200; rk3-ssp.cxx:107 with c=1)
+ * mode 1: out = start + (1/6)*dt*(k1+2k2+2k3+k4)     (rk4.cxx:206-209)
+ * mode 2: out = 0.75*start + 0.25*k1 + 0.25*dt*k2    (rk3-ssp.cxx:115-117; k1=u1, k2=L)
+ * mode 3: out = (1/3)*start + (2/3)*(k1 + dt*k2)     (rk3-ssp.cxx:125-127; k1=u2, k2=L) */
+int bout_b200_rk_stage(const bout_b200_grid* g, int region, int mode, double dt, double c,
+                       const double* start, const double* k1, const double* k2, const double* k3,
+                       const double* k4, double* out, void* stream);
+
+/* ---- fused RHS kernels (2)+(4): whole model right-hand sides in one pass ---------------------------------
+ * Field2D metric bundle (reference include/bout/coordinates.hxx:83-116); unused members may be NULL. */
+typedef struct bout_b200_metric {
+  const double *dx, *dy, *dz;
+  const double *J, *g_22;
+  const double *g11, *g33, *g13;
+  const double *G1, *G3;
+  const double* d1_dx; /* NULL when coords->non_uniform is false */
+} bout_b200_metric;
+
+/* Optional stage update written by the fused kernel for its two evolving fields e = 0,1:
+ *   state_out[e] = start[e] + a*ddt_e      acc_out[e] = (acc_in[e] ? acc_in[e] : start[e]) + b*ddt_e
+ * over RGN_NOBNDRY; NULL outputs are skipped; acc_out may alias acc_in.  With
+ * (a,b) = (dt/2,dt/6), (dt/2,dt/3), (dt,dt/3), (-,dt/6) this is RK4 (rk4.cxx:172-210) with the final
+ * combination accumulated stage by stage. */
+typedef struct bout_b200_rk_epilogue {
+  const double* start[2];
+  const double* acc_in[2];
+  double* state_out[2];
+  double* acc_out[2];
+  double a, b;
+} bout_b200_rk_epilogue;
+
+size_t bout_b200_fused_coef_doubles(const bout_b200_grid* g);
+/* examples/hasegawa-wakatani-3d/hw.cxx:58-74 (single-index operators,
+ * include/bout/single_index_ops.hxx:93-128 bracket, :201-209 DDZ, :222-246 Delp2, :255-278
+ * Div_par_Grad_par): ddt(n), ddt(vort) from n, vort, phi.  ddt_* may be NULL when an epilogue is given.
+ * coef_workspace: bout_b200_fused_coef_doubles(g) doubles of device scratch. */
+int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, double alpha, double kappa,
+                       double Dn, double Dvort, const double* n, const double* vort,
+                       const double* phi, double* ddt_n, double* ddt_vort,
+                       const bout_b200_rk_epilogue* epilogue, double* coef_workspace, void* stream);
+/* examples/hasegawa-wakatani/hw.cxx:94-118 convective(), Arakawa bracket; zonal_* = averageY(DC(f))
+ * as Field2D when hw:modified, else NULL. */
+int bout_b200_hw_convective(const bout_b200_grid* g, const double* dx, const double* dz, double alpha,
+                            double kappa, const double* n, const double* vort, const double* phi,
+                            const double* zonal_n, const double* zonal_phi, double* ddt_n,
+                            double* ddt_vort, const bout_b200_rk_epilogue* epilogue, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

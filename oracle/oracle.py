@@ -452,6 +452,98 @@ class Ref:
         return f
 
 
+    # -- unchanged reference example models (examples/*/) through the reference's RK solvers
+    def model_create(self, name, solver="rk4"):
+        self._check(self.lib.boutref_model_create(name.encode(), solver.encode()))
+        self.lib.boutref_model_varname.restype = C.c_char_p
+        self.model_vars = [self.lib.boutref_model_varname(i).decode()
+                           for i in range(self.lib.boutref_model_nvars())]
+        return self.model_vars
+
+    def model_get(self, name):
+        out = np.zeros(self.grid.shape3)
+        self._check(self.lib.boutref_model_get(self.model_vars.index(name), _p(out)))
+        return out
+
+    def model_set(self, name, a):
+        self._check(self.lib.boutref_model_set(self.model_vars.index(name), _p(np.ascontiguousarray(a))))
+
+    def model_ddt(self, name):
+        out = np.zeros(self.grid.shape3)
+        self._check(self.lib.boutref_model_get_ddt(self.model_vars.index(name), _p(out)))
+        return out
+
+    def model_rhs(self, t=0.0):
+        self.lib.boutref_model_rhs.argtypes = [C.c_double]
+        self._check(self.lib.boutref_model_rhs(t))
+
+    def model_time_rhs(self, reps=3):
+        self.lib.boutref_model_time_rhs.restype = C.c_double
+        t = self.lib.boutref_model_time_rhs(reps)
+        if t < 0:
+            raise RuntimeError(self.lib.boutref_last_error().decode(errors="replace")[-2000:])
+        return t
+
+    def model_solve(self, nout, output_step):
+        self.lib.boutref_model_solve.argtypes = [C.c_int, C.c_double]
+        self._check(self.lib.boutref_model_solve(nout, output_step))
+
+
+# ---- numpy restatements of whole-model right-hand sides -------------------------------------------
+def _sh(f, dx=0, dy=0, dz=0):
+    """f shifted so that result[x,y,z] = f[x+dx, y+dy, z+dz] (z periodic; x,y edges wrap and are
+    never used: only interior points are compared)."""
+    return np.roll(f, (-dx, -dy, -dz), axis=(0, 1, 2))
+
+
+def si_bracket(f, g, dx, dz):
+    """bracket(FieldAccessor f, FieldAccessor g, i) -- include/bout/single_index_ops.hxx:93-128."""
+    Jpp = ((_sh(f, dz=1) - _sh(f, dz=-1)) * (_sh(g, dx=1) - _sh(g, dx=-1))
+           - (_sh(f, dx=1) - _sh(f, dx=-1)) * (_sh(g, dz=1) - _sh(g, dz=-1)))
+    Jpx = (_sh(g, dx=1) * (_sh(f, 1, 0, 1) - _sh(f, 1, 0, -1)) - _sh(g, dx=-1) * (_sh(f, -1, 0, 1) - _sh(f, -1, 0, -1))
+           - _sh(g, dz=1) * (_sh(f, 1, 0, 1) - _sh(f, -1, 0, 1)) + _sh(g, dz=-1) * (_sh(f, 1, 0, -1) - _sh(f, -1, 0, -1)))
+    Jxp = (_sh(g, 1, 0, 1) * (_sh(f, dz=1) - _sh(f, dx=1)) - _sh(g, -1, 0, -1) * (_sh(f, dx=-1) - _sh(f, dz=-1))
+           - _sh(g, -1, 0, 1) * (_sh(f, dz=1) - _sh(f, dx=-1)) + _sh(g, 1, 0, -1) * (_sh(f, dx=1) - _sh(f, dz=-1)))
+    return (Jpp + Jpx + Jxp) / (12 * dx[:, :, None] * dz[:, :, None])
+
+
+def si_ddz(f, dz):
+    """single_index_ops.hxx:201-209."""
+    return 0.5 * (_sh(f, dz=1) - _sh(f, dz=-1)) / dz[:, :, None]
+
+
+def si_delp2(f, m):
+    """single_index_ops.hxx:222-246 (non-uniform correction always included)."""
+    b = lambda a: a[:, :, None]
+    dx, dz = b(m.dx), b(m.dz)
+    return ((b(m.G1) + b(m.d1_dx) * b(m.g11)) * (_sh(f, dx=1) - _sh(f, dx=-1)) / (2.0 * dx)
+            + b(m.G3) * (_sh(f, dz=1) - _sh(f, dz=-1)) / (2.0 * dz)
+            + b(m.g11) * (_sh(f, dx=1) - 2.0 * f + _sh(f, dx=-1)) / dx ** 2
+            + b(m.g33) * (_sh(f, dz=1) - 2.0 * f + _sh(f, dz=-1)) / dz ** 2
+            + 2 * b(m.g13) * ((_sh(f, 1, 0, 1) - _sh(f, -1, 0, 1)) - (_sh(f, 1, 0, -1) - _sh(f, -1, 0, -1)))
+            / (4. * dz * dx))
+
+
+def si_div_par_grad_par(f, m):
+    """single_index_ops.hxx:255-278 with identity parallel transform (yup/ydown = the field)."""
+    b = lambda a: a[:, :, None]
+    s2 = lambda a, d: np.roll(a, -d, axis=1)
+    dy, J, g_22 = m.dy, m.J, m.g_22
+    gu = 2. * (_sh(f, dy=1) - f) / b(dy + s2(dy, 1))
+    fu = gu * b(J + s2(J, 1)) / b(g_22 + s2(g_22, 1))
+    gl = 2. * (f - _sh(f, dy=-1)) / b(dy + s2(dy, -1))
+    fl = gl * b(J + s2(J, -1)) / b(g_22 + s2(g_22, -1))
+    return (fu - fl) / b(dy * J)
+
+
+def hw3d_rhs(m, n, vort, phi, alpha, kappa, Dn, Dvort):
+    """examples/hasegawa-wakatani-3d/hw.cxx:65-74; valid on interior points."""
+    div_current = alpha * si_div_par_grad_par(phi - n, m) if n.shape[1] > 1 else 0.0
+    ddt_n = -si_bracket(phi, n, m.dx, m.dz) - div_current - kappa * si_ddz(phi, m.dz) + Dn * si_delp2(n, m)
+    ddt_v = -si_bracket(phi, vort, m.dx, m.dz) - div_current + Dvort * si_delp2(vort, m)
+    return ddt_n, ddt_v
+
+
 def make_ini(nx, ny, nz, mxg=2, myg=2, dx="0.2", dy="1.0", dz="0.2", periodic_x=False, extra="",
              mesh_extra=""):
     """BOUT.inp text for a mesh-from-options (reference: src/mesh/data/gridfromoptions.cxx)."""
@@ -469,3 +561,20 @@ dz = {dz}
 {mesh_extra}
 {extra}
 """
+
+
+def halo_self_reference(g: Grid, f, periodic_x=False, periodic_y=True):
+    """What Mesh::communicate leaves in the guard cells when the rank is its own neighbour
+    (BoutMesh::sendY/sendX/wait, src/mesh/impls/bout/boutmesh.cxx:1245-1555): Y first, then X with
+    the y-guard corners (src/mesh/mesh.cxx:351-362).  Pinned against the reference build in
+    tests/test_oracle_reference.py."""
+    f = f.copy()
+    if periodic_y and g.myg > 0:
+        ny_int = g.yend - g.ystart + 1
+        f[:, :g.ystart] = f[:, ny_int:ny_int + g.ystart]
+        f[:, g.yend + 1:] = f[:, g.ystart:g.ystart + (g.ny - g.yend - 1)]
+    if periodic_x and g.mxg > 0:
+        nx_int = g.xend - g.xstart + 1
+        f[:g.xstart] = f[nx_int:nx_int + g.xstart]
+        f[g.xend + 1:] = f[g.xstart:g.xstart + (g.nx - g.xend - 1)]
+    return f

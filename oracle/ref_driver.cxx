@@ -25,6 +25,8 @@
 #include <bout/solver.hxx>
 #include <bout/sys/timer.hxx>
 #include <bout/cyclic_reduction.hxx>
+#include "solver/impls/rk4/rk4.hxx"
+#include "solver/impls/rk3-ssp/rk3-ssp.hxx"
 
 #include <chrono>
 #include <cstdio>
@@ -37,7 +39,30 @@
 
 using bout::globals::mesh;
 
+std::unique_ptr<PhysicsModel> boutref_make_hw();
+std::unique_ptr<PhysicsModel> boutref_make_hw3d();
+std::unique_ptr<PhysicsModel> boutref_make_blob2d();
+
 namespace {
+// The reference's own RK4 solver with its (protected) variable registry made reachable, so the
+// harness can load states into an unchanged model and read ddt() back.
+template <class Base>
+class DriverSolver : public Base {
+public:
+  explicit DriverSolver(Options* opts) : Base(opts) {}
+  int nvars() const { return static_cast<int>(this->f3d.size()); }
+  const std::string& varName(int i) const { return this->f3d[i].name; }
+  Field3D& var(int i) { return *this->f3d[i].var; }
+  Field3D& ddtVar(int i) { return *this->f3d[i].F_var; }
+  int rhs(BoutReal t) { return this->run_rhs(t); }
+};
+using DriverRK4 = DriverSolver<RK4Solver>;
+using DriverRK3 = DriverSolver<RK3SSP>;
+std::unique_ptr<PhysicsModel> model;
+std::unique_ptr<DriverRK4> rk4;
+std::unique_ptr<DriverRK3> rk3;
+Solver* activeSolver() { return rk4 ? static_cast<Solver*>(rk4.get()) : static_cast<Solver*>(rk3.get()); }
+
 std::string last_error;
 std::unique_ptr<Laplacian> lap;
 bool initialised = false;
@@ -246,6 +271,9 @@ void boutref_finalise() {
   if (!initialised) {
     return;
   }
+  rk4.reset();
+  rk3.reset();
+  model.reset();
   lap.reset();
   delete bout::globals::mesh;
   bout::globals::mesh = nullptr;
@@ -496,6 +524,92 @@ int boutref_parallel_slices(const double* field, double* yup, double* ydown) {
     mesh->communicate(f);
     fromField3D(f.yup(), yup);
     fromField3D(f.ydown(), ydown);
+  });
+}
+
+// ---- unchanged example models driven through the reference's own RK solvers --------------------
+// name: "hw" (examples/hasegawa-wakatani), "hw3d" (examples/hasegawa-wakatani-3d), "blob2d";
+// solver: "rk4" or "rk3ssp" (options section [solver] of the ini text applies)
+int boutref_model_create(const char* name, const char* solver) {
+  return guarded([&]() {
+    rk4.reset();
+    rk3.reset();
+    model.reset();
+    const std::string n = name, s = solver;
+    Options* sopts = &Options::root()["solver"];
+    if (s == "rk3ssp") {
+      rk3 = std::make_unique<DriverRK3>(sopts);
+    } else {
+      rk4 = std::make_unique<DriverRK4>(sopts);
+    }
+    if (n == "hw") {
+      model = boutref_make_hw();
+    } else if (n == "hw3d") {
+      model = boutref_make_hw3d();
+    } else if (n == "blob2d") {
+      model = boutref_make_blob2d();
+    } else {
+      throw BoutException("unknown model '{}'", n);
+    }
+    activeSolver()->setModel(model.get());
+  });
+}
+int boutref_model_nvars() { return rk4 ? rk4->nvars() : (rk3 ? rk3->nvars() : 0); }
+const char* boutref_model_varname(int i) {
+  return rk4 ? rk4->varName(i).c_str() : rk3->varName(i).c_str();
+}
+int boutref_model_get(int i, double* out) {
+  return guarded([&]() { fromField3D(rk4 ? rk4->var(i) : rk3->var(i), out); });
+}
+int boutref_model_set(int i, const double* in) {
+  return guarded([&]() {
+    Field3D& f = rk4 ? rk4->var(i) : rk3->var(i);
+    f.allocate();
+    std::memcpy(&f(0, 0, 0), in, sizeof(double) * mesh->LocalNx * mesh->LocalNy * mesh->LocalNz);
+  });
+}
+int boutref_model_get_ddt(int i, double* out) {
+  return guarded([&]() { fromField3D(rk4 ? rk4->ddtVar(i) : rk3->ddtVar(i), out); });
+}
+// Solver::run_rhs (src/solver/solver.cxx:1380-1427): pre_rhs boundary conditions, the model's rhs
+// (or convective + diffusive for split-operator models), post_rhs.
+int boutref_model_rhs(double t) {
+  return guarded([&]() {
+    const int rc = rk4 ? rk4->rhs(t) : rk3->rhs(t);
+    if (rc != 0) {
+      throw BoutException("run_rhs returned {}", rc);
+    }
+  });
+}
+double boutref_model_time_rhs(int reps) {
+  double result = -1.0;
+  guarded([&]() {
+    if (rk4) {
+      rk4->rhs(0.0);
+    } else {
+      rk3->rhs(0.0);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; ++i) {
+      if (rk4) {
+        rk4->rhs(0.0);
+      } else {
+        rk3->rhs(0.0);
+      }
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    result = std::chrono::duration<double>(t1 - t0).count() / reps;
+  });
+  return result;
+}
+// Solver::solve (src/solver/solver.cxx:510-623) -> RK4Solver::run / RK3SSP::run for nout outputs of
+// `output_step` each, internal step solver:timestep.
+int boutref_model_solve(int nout, double output_step) {
+  return guarded([&]() {
+    const int rc = activeSolver()->solve(nout, output_step);
+    if (rc != 0) {
+      throw BoutException("solve returned {}", rc);
+    }
   });
 }
 } // extern "C"

@@ -58,8 +58,10 @@ def test_delp2_fd_matches_composed_reference_operators(capi, orc, port, grid):
     assert rel_err(got, want, g.interior) < 1e-12
 
 
-FLAGSETS = [(0, 0, 0), (0, 3, 3), (0, 2, 0), (0, 0, 1), (1, 4, 64), (0, 16, 16), (0, 32 | 3, 32),
-            (4, 0, 0), (0, 128, 0), (0, 3 | 16, 3 | 32), (0, 1024, 0)]
+# (global, inner, outer).  Neumann on BOTH sides with A = 0 is singular for kz = 0 (the reference
+# throws "Zero pivot"), so gradient conditions are one-sided here as in test-laplace.
+FLAGSETS = [(0, 0, 0), (0, 3, 0), (0, 0, 3), (0, 2, 2), (0, 0, 1), (1, 4, 64), (0, 16, 16), (0, 32 | 3, 32),
+            (4, 0, 0), (0, 128, 0), (0, 3 | 16, 32), (0, 1024, 0)]
 
 
 @pytest.mark.parametrize("grid", GRIDS)
@@ -115,6 +117,8 @@ def test_laplace_residual_full_size(capi, orc):
     m = make_metric(orc, g.shape2, g.nz)
     lap = gpu_laplace(capi, g, m)
     rhs = torch.rand(g.shape3, dtype=torch.float64, device="cuda") - 0.5
+    # drop the Nyquist mode: with g13, G3 != 0 its solution is complex and c2r keeps the real part only
+    rhs = capi.zlowpass(g, rhs, g.nz // 2 - 1, True)
     x = lap.solve(rhs)
     lap.status()
     back = lap.delp2(x)

@@ -111,11 +111,12 @@ def test_arakawa_bracket(capi, orc, port, grid):
     dx, dy, dz = metric_2d(g.shape2)
     want = port.bracket_arakawa(og, f, h, dx, dz)
     got = capi.bracket_arakawa(g, dev(f), dev(h), dev(dx), dev(dz)).cpu().numpy()
-    assert rel_err(got, want, g.interior) < TOL
+    floor = 1e-3 * np.abs(f).max() * np.abs(h).max() / (dx.min() * dz.min())  # nz=2: analytically 0
+    assert rel_err(got, want, g.interior, floor=floor) < TOL
     h2 = np.ascontiguousarray(h[:, :, 0])
     want = port.bracket_arakawa_3d2d(og, f, h2, dx, dz)
     got = capi.bracket_arakawa(g, dev(f), dev(h2), dev(dx), dev(dz)).cpu().numpy()
-    assert rel_err(got, want, g.interior) < TOL
+    assert rel_err(got, want, g.interior, floor=floor) < TOL
 
 
 def test_arakawa_antisymmetry_full_size(capi):
