@@ -73,7 +73,10 @@ def test_x_boundaries(capi, orc, port, grid, kind):
         F = dev(f)
         capi.boundary(g, kind, "xin", F, val, dev(dx))
         capi.boundary(g, kind, "xout", F, val, dev(dx))
-        assert np.array_equal(F.cpu().numpy(), want)
+        if kind == "dirichlet":  # 2*val - f is exact on both sides
+            assert np.array_equal(F.cpu().numpy(), want)
+        else:  # f + delta*val: the GPU contracts to an FMA, gcc does not -> 1 ulp
+            assert rel_err(F.cpu().numpy(), want, (slice(None),) * 3) < 1e-15
 
 
 def test_zero_boundary_apply_ddt(capi):
@@ -116,7 +119,7 @@ def test_rk_stage_updates(capi, orc, port):
     dt = 0.0371
     I = g.interior
     got = capi.rk_stage(g, "axpy", dt, dev(s), dev(k1), c=0.5).cpu().numpy()
-    assert np.array_equal(got[I], port.rk4_stage(s, k1, 0.5 * dt)[I])
+    assert rel_err(got, port.rk4_stage(s, k1, 0.5 * dt), I) < 1e-15  # FMA vs mul+add
     got = capi.rk_stage(g, "rk4_final", dt, dev(s), dev(k1), dev(k2), dev(k3), dev(k4)).cpu().numpy()
     assert rel_err(got, port.rk4_final(s, dt, k1, k2, k3, k4), I) < 1e-15
     got = capi.rk_stage(g, "rk3_stage2", dt, dev(s), dev(k1), dev(k2)).cpu().numpy()
