@@ -49,6 +49,10 @@ class Grid:
     mxg: int
     myg: int
 
+    def __post_init__(self):
+        for n in ("nx", "ny", "nz", "mxg", "myg"):
+            setattr(self, n, int(getattr(self, n)))
+
     @property
     def xstart(self): return self.mxg
     @property

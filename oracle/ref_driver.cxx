@@ -339,10 +339,12 @@ int boutref_geometry() {
 
 // Evaluate a BOUT++ expression (FieldFactory) into a Field3D / Field2D array.
 int boutref_expr3d(const char* expr, double* out) {
-  return guarded([&]() { fromField3D(FieldFactory::get()->create3D(expr), out); });
+  return guarded([&]() { FieldFactory ff{mesh};
+    fromField3D(ff.create3D(expr), out); });
 }
 int boutref_expr2d(const char* expr, double* out) {
-  return guarded([&]() { fromField2D(FieldFactory::get()->create2D(expr), out); });
+  return guarded([&]() { FieldFactory ff{mesh};
+    fromField2D(ff.create2D(expr), out); });
 }
 
 int boutref_op(const char* op, const char* method, int nin, const double** in, double scalar,

@@ -1,0 +1,363 @@
+"""Generates the golden fixtures in this directory from the BOUT++ reference itself.
+
+Run in the build container only (needs /root/reference and oracle/_ref/libboutref.so, i.e. the
+reference's own sources compiled in place by oracle/Makefile):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed; the GPU box has neither /root/reference nor needs the reference build):
+  laplace_benchmark.npz  the reference's golden file tests/integrated/test-laplace/data/benchmark.0.nc
+                         (float32, 16 LaplaceCyclic solutions) + the float64 inputs regenerated with the
+                         reference's expression parser + the float64 solutions of the reference build.
+  ops_small.npz          reference outputs of every operator on the hot path for one small grid with a
+                         non-trivial metric (stencils, brackets, Delp2, z-FFT ops, Laplace solves,
+                         boundaries, communicate, field algebra).
+  models.npz             unchanged example models (hasegawa-wakatani, hasegawa-wakatani-3d, blob2d) run
+                         through the reference's Solver::run_rhs and RK4 / RK3-SSP solvers: initial state,
+                         ddt after one RHS, state after a few steps.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+orc = ge.load_oracle()
+REF_ROOT = "/root/reference"
+
+LAPLACE_VARS = ["flag0", "flag3", "flag0a", "flag3a", "flag0ac", "flag3ac", "flag0ad", "flag3ad",
+                "flagis", "flagos", "flagisa", "flagosa", "flagisac", "flagosac", "flagisad", "flagosad"]
+
+TEST_LAPLACE_INI = """
+MZ = 32
+MXG = 2
+MYG = 2
+[mesh]
+symmetricGlobalX = false
+symmetricGlobalY = false
+nx = 12
+ny = 16
+ixseps1 = 6
+ixseps2 = 6
+jyseps1_1 = -1
+jyseps1_2 = 6
+jyseps2_1 = 6
+jyseps2_2 = 15
+dx = 1
+dy = 1
+[laplace]
+all_terms = false
+include_yguards = false
+filter = 0.2
+"""
+
+
+def laplace_benchmark():
+    """tests/integrated/test-laplace/test_laplace.cxx:19-100 replayed on the reference build."""
+    from scipy.io import netcdf_file
+    nc = netcdf_file(os.path.join(REF_ROOT, "tests/integrated/test-laplace/data/benchmark.0.nc"), "r", mmap=False)
+    bench = {k: nc.variables[k].data.copy() for k in LAPLACE_VARS + ["input", "a", "c", "d", "set_to"]}
+    r = orc.Ref(TEST_LAPLACE_INI)
+    g = r.grid
+    out = {"grid": np.array([g.nx, g.ny, g.nz, g.mxg, g.myg])}
+    out["input"] = r.expr3d("(1-gauss(x-0.5,0.2))*gauss(y-pi)*gauss(z-pi)")
+    e2 = lambda s: _expr2d(r, s)
+    out["a"] = e2("gauss(x) * sin(y)")
+    out["c"] = e2("sin(x) * gauss(x-0.5) * gauss(y-pi)")
+    out["d"] = e2("y - pi/2")
+    out["set_to"] = e2("cos(2*y)*(x - 0.5)")
+    for k in ("input",):
+        assert np.abs(out[k] - bench[k][:, :, :g.nz]).max() < 1e-7, k
+    for k in ("a", "c", "d", "set_to"):
+        assert np.abs(out[k] - bench[k]).max() < 1e-6, k
+    m = r.metric()
+    for n in orc.Metric.NAMES:
+        out["metric_" + n] = getattr(m, n)
+    set3 = np.ascontiguousarray(np.repeat(out["set_to"][:, :, None], g.nz, axis=2))
+    ones, zeros = np.ones(g.shape2), np.zeros(g.shape2)
+    DCAC = orc.INVERT_DC_GRAD + orc.INVERT_AC_GRAD
+    r.laplace_create()
+    ys = slice(g.ystart, g.yend + 1)
+
+    def run(name, A, C, D, inner, outer, x0=None):
+        r.laplace_set_coef("A", A)
+        r.laplace_set_coef("C", C)
+        r.laplace_set_coef("D", D)
+        r.laplace_set_flags(0, inner, outer)
+        sol = r.laplace_solve(out["input"], x0)
+        sol[:, :g.ystart] = 0.0   # include_yguards=false: y guards are not solved
+        sol[:, g.yend + 1:] = 0.0
+        err = np.abs(sol[:, ys] - bench[name][:, ys, :g.nz]).max()
+        assert err < 1e-6, (name, err)   # the reference's own tolerance (runtest:34)
+        out["ref64_" + name] = sol
+        out["bench32_" + name] = bench[name][:, ys, :g.nz].astype(np.float32)
+        print(f"  {name:9s} reference build vs benchmark.0.nc: {err:.2e}")
+
+    for suffix, A, C, D in (("", zeros, ones, ones), ("a", out["a"], ones, ones),
+                            ("ac", out["a"], out["c"], ones), ("ad", out["a"], ones, out["d"])):
+        run("flag0" + suffix, A, C, D, 0, 0)
+        run("flag3" + suffix, A, C, D, DCAC, 0)
+        run("flagis" + suffix, A, C, D, orc.INVERT_SET, 0, set3)
+        run("flagos" + suffix, A, C, D, 0, orc.INVERT_SET, set3)
+    r.close()
+    np.savez_compressed(os.path.join(HERE, "laplace_benchmark.npz"), **out)
+
+
+def _expr2d(r, s):
+    import ctypes as C
+    out = np.zeros(r.grid.shape2)
+    r._check(r.lib.boutref_expr2d(s.encode(), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+OPS_INI = orc.make_ini(12, 8, 16, mxg=2, myg=2, dx="0.2*(1+0.1*x)", dy="0.7+0.05*cos(2*pi*x)", dz="2*pi/16",
+                       mesh_extra="""
+g11 = 1 + 0.1*x
+g22 = 1.1 + 0.02*y
+g33 = 1.2 + 0.05*x
+g12 = 0.01
+g13 = 0.05 + 0.02*x
+g23 = 0.02
+ixseps1 = 12
+ixseps2 = 12
+""", extra="""
+[mesh:ddx]
+first = C2
+[laplace]
+include_yguards = false
+""")
+
+INDEX_METHODS = {
+    "DDX": ["C2", "C4", "W2", "S2", "W3"], "D2DX2": ["C2", "C4"], "D4DX4": ["C2"],
+    "VDDX": ["C2", "C4", "U1", "U2", "U3", "W3"], "FDDX": ["U1", "U2", "C2", "C4"],
+}
+
+
+def smooth_fields(g, n, seed):
+    rng = np.random.default_rng(seed)
+    X = (np.arange(g.nx)[:, None, None] + 0.5) / g.nx
+    Y = 2 * np.pi * np.arange(g.ny)[None, :, None] / g.ny
+    Z = 2 * np.pi * np.arange(g.nz)[None, None, :] / g.nz
+    return [np.ascontiguousarray(np.sin(2 * np.pi * (1 + i) * X) * np.cos((2 + i) * Z) * np.cos(Y)
+                                 + 0.1 * rng.uniform(-1, 1, g.shape3)) for i in range(n)]
+
+
+def ops_small():
+    r = orc.Ref(OPS_INI)
+    g = r.grid
+    out = {"grid": np.array([g.nx, g.ny, g.nz, g.mxg, g.myg])}
+    m = r.metric()
+    for n in orc.Metric.NAMES:
+        out["metric_" + n] = getattr(m, n)
+    f, h, v = smooth_fields(g, 3, 20261017)
+    v = v - 0.05  # sign-changing velocity for the upwind branches
+    f2 = np.ascontiguousarray(f[:, :, 0] + 1.5)
+    out.update(f=f, h=h, v=v, f2=f2)
+    for base, methods in INDEX_METHODS.items():
+        for d in "XYZ":
+            for meth in methods:
+                name = "index_" + base.replace("X", d)
+                if name in ("index_D4DY4",) and g.myg < 2:
+                    continue
+                ins = (v, f) if base in ("VDDX", "FDDX") else (f,)
+                if base == "FDDX" and d == "Y":
+                    pass
+                out[f"{name}_{meth}"] = r.op(name, *ins, method=meth)
+    out["index_DDZ_FFT"] = r.op("index_DDZ", f, method="FFT")
+    out["index_D2DZ2_FFT"] = r.op("index_D2DZ2", f, method="FFT")
+    for name in ("DDX", "DDY", "DDZ", "D2DX2", "D2DY2", "D2DZ2", "D2DXDZ"):
+        for meth in ("C2", "C4"):
+            out[f"{name}_{meth}"] = r.op(name, f, method=meth)
+    for name in ("VDDX", "VDDZ"):
+        for meth in ("U1", "W3"):
+            out[f"{name}_{meth}"] = r.op(name, v, f, method=meth)
+    out["bracket_arakawa"] = r.op("bracket", f, h, method="ARAKAWA")
+    out["bracket_arakawa_3d2d"] = r.op("bracket_3d2d", f, f2, method="ARAKAWA")
+    out["bracket_arakawa_2d3d"] = r.op("bracket_2d3d", f2, h, method="ARAKAWA")
+    out["Delp2_fft"] = r.op("Delp2", f)
+    out["Delp2_fd"] = r.op("Delp2_fd", f)
+    out["filter_3"] = r.op("filter", f, scalar=3)
+    out["lowPass_4"] = r.op("lowPass", f, scalar=4)
+    out["shiftZ_0.37"] = r.op("shiftZ", f, scalar=0.37)
+    out["DC3d"] = r.op("DC3d", f)
+    out["averageY_DC"] = r.op("averageY_DC", f)
+    out["arith_2a_bc"] = r.op("arith_2a_bc", f, h, v)
+    out["mul"] = r.op("mul", f, h)
+    out["div_2d"] = r.op("div_2d", f, f2)
+    out["s_sub"] = r.op("s_sub", f, scalar=0.25)
+    # Laplace solves: flags x coefficient sets (global, inner, outer)
+    r.laplace_create()
+    X = (np.arange(g.nx)[:, None] + 0.5) / g.nx * np.ones(g.shape2)
+    A = np.ascontiguousarray(-0.1 - 0.05 * X)
+    D = np.ascontiguousarray(1 + 0.2 * X)
+    Cc = np.ascontiguousarray(1 + 0.3 * np.sin(3 * X))
+    out.update(lap_A=A, lap_D=D, lap_C=Cc)
+    ones, zeros = np.ones(g.shape2), np.zeros(g.shape2)
+    flagsets = [(0, 0, 0), (0, 3, 0), (0, 0, 3), (0, 2, 2), (0, 0, 1), (1, 4, 64), (0, 16, 16), (0, 35, 32),
+                (4, 0, 0), (0, 128, 0), (0, 19, 32), (0, 1024, 0)]
+    out["lap_flagsets"] = np.array(flagsets)
+    for ci, (a_, c_, d_) in enumerate(((zeros, ones, ones), (A, Cc, D))):
+        r.laplace_set_coef("A", a_)
+        r.laplace_set_coef("C", c_)
+        r.laplace_set_coef("D", d_)
+        for fi, fl in enumerate(flagsets):
+            r.laplace_set_flags(*fl)
+            sol = r.laplace_solve(f, h)
+            sol[:, :g.ystart] = 0.0
+            sol[:, g.yend + 1:] = 0.0
+            out[f"lap_c{ci}_f{fi}"] = sol
+    # boundaries + communicate (ixseps = nx: y periodic on one rank)
+    for cond in ("dirichlet", "dirichlet_o2", "neumann", "dirichlet(0.7)", "neumann(0.7)"):
+        out["bndry_" + cond] = r.apply_boundary(f, cond)
+    out["communicate"] = r.communicate(f)[0]
+    r.close()
+    np.savez_compressed(os.path.join(HERE, "ops_small.npz"), **out)
+    print("  ops_small:", len(out), "arrays")
+
+
+HW_INI = orc.make_ini(36, 1, 32, mxg=2, myg=0, periodic_x=True, extra="""
+[hw]
+alpha = 1.0
+kappa = 0.5
+Dvort = 1e-4
+Dn = 1e-4
+modified = true
+bracket = 2
+[all]
+scale = 0.0
+bndry_all = dirichlet_o2
+[vort]
+scale = 0.1
+function = mixmode(2*pi*x) * mixmode(z)
+[n]
+scale = 0.05
+function = mixmode(2*pi*x + 1) * mixmode(z + 0.5)
+[solver]
+timestep = 0.01
+[input]
+error_on_unused_options = false
+""")
+
+HW3D_INI = orc.make_ini(20, 8, 16, mxg=2, myg=2, mesh_extra="ixseps1 = 20\nixseps2 = 20\n", extra="""
+[hw]
+alpha = 1.0
+kappa = 0.5
+Dvort = 0.001
+Dn = 0.001
+[all]
+scale = 0.0
+bndry_all = dirichlet_o2
+[vort]
+scale = 0.1
+function = mixmode(2*pi*x) * mixmode(z - y)
+[n]
+scale = 0.05
+function = mixmode(2*pi*x + 1) * mixmode(z + y)
+[solver]
+timestep = 0.01
+[input]
+error_on_unused_options = false
+""")
+
+BLOB_INI = orc.make_ini(36, 1, 32, mxg=2, myg=0, dx="0.3", dz="0.3", extra="""
+[mesh:ddx]
+first = C2
+second = C2
+upwind = W3
+[mesh:ddz]
+first = C2
+second = C2
+upwind = W3
+[model]
+Te0 = 5
+n0 = 2e18
+D_vort = 1e-6
+D_n = 1e-6
+R_c = 1.5
+L_par = 10
+B0 = 0.35
+compressible = false
+boussinesq = true
+sheath = true
+[phiBoussinesq]
+inner_boundary_flags = 0
+outer_boundary_flags = 0
+[phiSolver]
+inner_boundary_flags = 0
+[all]
+scale = 0.0
+bndry_all = neumann
+[n]
+scale = 1.0
+function = 1 + 0.5*exp(-((x-0.25)/0.1)^2 - ((z/(2*pi) - 0.5)/0.1)^2)
+[solver]
+timestep = 0.05
+[input]
+error_on_unused_options = false
+""")
+
+
+MODEL_CASES = {"hw": ("hw", HW_INI, "rk4", 5), "hw_rk3": ("hw", HW_INI, "rk3ssp", 5),
+               "hw3d": ("hw3d", HW3D_INI, "rk4", 5), "blob2d": ("blob2d", BLOB_INI, "rk4", 5)}
+
+
+def one_model(tag, path):
+    """One model case per process: the reference keeps static state that does not survive many
+    init/finalise cycles."""
+    name, ini, solver, nsteps = MODEL_CASES[tag]
+    out = {}
+    dt = float([l for l in ini.splitlines() if l.startswith("timestep")][0].split("=")[1])
+    # pass 1: Solver::solve with zero outputs = init + one run_rhs at the initial state
+    r = orc.Ref(ini)
+    g = r.grid
+    names = r.model_create(name, solver)
+    out[tag + "_grid"] = np.array([g.nx, g.ny, g.nz, g.mxg, g.myg])
+    m = r.metric()
+    for n in ("dx", "dy", "dz", "J", "g_22", "g11", "g33", "g13", "G1", "G3", "d1_dx", "g_11"):
+        out[f"{tag}_metric_{n}"] = getattr(m, n)
+    for v in names:
+        out[f"{tag}_init_{v}"] = r.model_get(v)
+    r.model_solve(0, dt)
+    for v in names:
+        out[f"{tag}_ddt_{v}"] = r.model_ddt(v)
+    r.close()
+    # pass 2: nsteps fixed steps of the reference's own RK solver
+    r = orc.Ref(ini)
+    r.model_create(name, solver)
+    r.model_solve(1, nsteps * dt)
+    for v in names:
+        out[f"{tag}_final_{v}"] = r.model_get(v)
+    out[tag + "_dt_nsteps"] = np.array([dt, nsteps])
+    print(f"  model {tag}: vars {names}, max|final| = {[float(np.abs(out[f'{tag}_final_{v}']).max()) for v in names]}")
+    np.savez(path, **out)
+
+
+def models():
+    import subprocess
+    import tempfile
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag in MODEL_CASES:
+            path = os.path.join(tmp, tag + ".npz")
+            subprocess.run([sys.executable, os.path.abspath(__file__), "model:" + tag, path], check=True)
+            out.update(dict(np.load(path)))
+    np.savez_compressed(os.path.join(HERE, "models.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["laplace", "ops", "models"]
+    if which[0].startswith("model:"):
+        one_model(which[0][6:], which[1])
+        sys.stdout.flush()
+        os._exit(0)
+    if "laplace" in which:
+        laplace_benchmark()
+    if "ops" in which:
+        ops_small()
+    if "models" in which:
+        models()
+    os._exit(0)  # the reference's static destructors are not exit-safe after repeated init/finalise
