@@ -7,3 +7,4 @@ library through ctypes and passes torch CUDA tensors' device pointers.  There is
 importing ``capi`` without the built library raises.
 """
 from . import capi  # noqa: F401
+from . import models  # noqa: F401

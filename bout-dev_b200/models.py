@@ -1,0 +1,73 @@
+"""Harness-side drivers of the fused model right-hand sides (Python over the C-ABI).
+
+These mirror what the reference does around PhysicsModel::rhs for the explicit RK solvers
+(Solver::run_rhs src/solver/solver.cxx:1380-1427: pre_rhs boundary conditions -> model rhs;
+RK4Solver::take_step src/solver/impls/rk4/rk4.cxx:172-210), with device-resident SoA fields: the
+load_vars / save_derivs gather-scatter passes of the reference do not exist here and the stage
+updates are written by the last RHS kernel (bout_b200_rk_epilogue).  Every numerical step is a
+C-ABI call; torch only owns the memory.  The C++ host layer (host/) drives the same entry points.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi
+
+
+class HW3D:
+    """examples/hasegawa-wakatani-3d/hw.cxx: rhs() lines 50-77, bndry_all = dirichlet_o2,
+    y periodic (ixseps = nx), identity parallel transform, LaplaceCyclic with default flags."""
+
+    def __init__(self, g: capi.Grid, metric: dict, alpha=1.0, kappa=0.5, Dn=1e-3, Dvort=1e-3,
+                 device="cuda", mesh=None):
+        self.g, self.dev = g, torch.device(device)
+        self.md = {k: v.to(self.dev) for k, v in metric.items()}
+        self.alpha, self.kappa, self.Dn, self.Dvort = alpha, kappa, Dn, Dvort
+        self.cm = capi.make_metric(self.md)
+        self.mesh = mesh  # None = single rank (self exchange)
+        zlength = float(self.md["dz"][0, 0].item()) * g.nz
+        self.lap = capi.Laplace(g, self.md, zlength, nonuniform=True)
+        self.lap.workspace(self.dev)
+        self.coef = capi.fused_coef_workspace(g, self.dev)
+        z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
+        self.n, self.vort, self.phi = z(), z(), z()
+        self.ddt_n, self.ddt_vort = z(), z()
+        # RK work fields: stage state (k5 in rk4.cxx) and the running combination
+        self.sn, self.sv, self.an, self.av = z(), z(), z(), z()
+
+    def set_state(self, n, vort):
+        self.n.copy_(n)
+        self.vort.copy_(vort)
+
+    # -- one right-hand side on (n, vort) held in fields fn, fv
+    def _pre_rhs(self, fn, fv):
+        g = self.g
+        if self.mesh is None or self.mesh.first_x:
+            capi.boundary(g, "dirichlet", "xin", fn)
+            capi.boundary(g, "dirichlet", "xin", fv)
+        if self.mesh is None or self.mesh.last_x:
+            capi.boundary(g, "dirichlet", "xout", fn)
+            capi.boundary(g, "dirichlet", "xout", fv)
+
+    def rhs(self, fn=None, fv=None, epilogue=None, ddt=True):
+        fn = self.n if fn is None else fn
+        fv = self.vort if fv is None else fv
+        self._pre_rhs(fn, fv)                                   # Solver::pre_rhs
+        self.lap.solve(fv, out=self.phi)                        # phi = phiSolver->solve(vort, phi)
+        if self.mesh is None:                                   # mesh->communicate(n, vort, phi, ...)
+            capi.halo_self(self.g, [fn, fv, self.phi], periodic_x=False, periodic_y=True)
+        else:
+            self.mesh.communicate([fn, fv, self.phi])
+        capi.hw3d_rhs(self.g, self.cm, self.alpha, self.kappa, self.Dn, self.Dvort, fn, fv, self.phi,
+                      self.ddt_n if ddt else None, self.ddt_vort if ddt else None, epilogue=epilogue,
+                      coef_ws=self.coef)
+
+    def rk4_step(self, dt):
+        """RK4Solver::take_step with the axpys folded into the RHS kernel:
+        stage i reads state_i, writes state_{i+1} = start + a_i dt k_i and acc += b_i dt k_i."""
+        n, v, sn, sv, an, av = self.n, self.vort, self.sn, self.sv, self.an, self.av
+        E = capi.make_epilogue
+        self.rhs(n, v, E((n, v), None, (sn, sv), (an, av), 0.5 * dt, dt / 6.0), ddt=False)
+        self.rhs(sn, sv, E((n, v), (an, av), (sn, sv), (an, av), 0.5 * dt, dt / 3.0), ddt=False)
+        self.rhs(sn, sv, E((n, v), (an, av), (sn, sv), (an, av), dt, dt / 3.0), ddt=False)
+        self.rhs(sn, sv, E((n, v), (an, av), (None, None), (n, v), 0.0, dt / 6.0), ddt=False)
