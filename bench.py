@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- RHS grid-points/s (fp64) of the BOUT++ physics-model RHS hot path on B200.
+
+Workload (BASELINE.json configs[3], the config the metric "RHS grid-pts/s fp64 at 1/2/4/8 B200" is
+quoted on): examples/hasegawa-wakatani-3d at 512x128x512 interior points PER GPU (516x132x512 with
+guard cells, MXG = MYG = 2, y periodic, bndry_all = dirichlet_o2), X-decomposed across N GPUs (weak
+scaling: global nx = 512*N + 4).  One "step" is one RK4 time step = 4 RHS evaluations, each
+  Solver::pre_rhs boundary conditions -> LaplaceCyclic solve (vort -> phi) -> Mesh::communicate(n, vort, phi)
+  -> fused RHS kernel (2 Arakawa brackets, Div_par_Grad_par, DDZ, 2 Delp2) with the RK stage update in
+  its epilogue;
+value = interior points * 4 * K / time.  Fields (279 MB each) are far larger than the 126 MB L2, so no
+L2 flush is needed between iterations (stated in config.l2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                        the reference's own CPU implementation of the
+                                                                same RHS (oracle/_ref, host cores, bounded slab)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MXSUB, MYSUB, MZ, MXG, MYG = 512, 128, 512, 2, 2
+HW = dict(alpha=1.0, kappa=0.5, Dn=1e-3, Dvort=1e-3)
+DT = 1e-3
+METRIC = "rhs_grid_points_per_s"
+UNIT = "grid-points/s"
+WORKLOAD = "hasegawa-wakatani-3d RHS, 512x128x512 interior points per GPU (516x132x512 with guards), RK4"
+# reference arm / cpu_baseline: same model and x-z extent, a y-slab of the workload
+REF_MY = 16
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def profile_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    ncu --set full capture (profiles/*.json), or None."""
+    p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("k_hw3d_rhs_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True,
+                                         bufsize=1)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        import datetime
+        for line in self.proc.stdout:
+            line = line.strip()
+            try:   # nvidia-smi's own sample time (the pipe may deliver lines late)
+                t = datetime.datetime.strptime(line.split(",")[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                t = time.time()
+            self.lines.append((t, line))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.3)
+        self.proc.terminate()
+        try:
+            self.thread.join(timeout=2.0)
+        except Exception:
+            pass
+        sm, smax, reasons, power = [], None, set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(",")][1:]
+            if len(f) < 7 or not (t0 - 0.03 <= t <= t1 + 0.03):
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
+
+
+def mixmode(a, seed=0.5):
+    """FieldMixmode (src/field/fieldgenerators.cxx:110-167): sum_i cos(i a + phase_i) / (1 + |i-4|)^2."""
+    import numpy as np
+
+    def gen_rand(s):
+        niter = 11 + (23 + int(round(s))) % 79
+        A, B = 0.01, 1.23456789
+        x = (A + s % B) / (B + 2 * A)
+        for _ in range(niter):
+            x = 3.99 * x * (1 - x)
+        return x
+    out = np.zeros_like(a)
+    for i in range(14):
+        out += np.cos(i * a + np.pi * (2 * gen_rand(seed + i) - 1)) / (1 + abs(i - 4)) ** 2
+    return out
+
+
+def initial_state(rank, world, torch, device):
+    """The shipped initial condition (examples/hasegawa-wakatani-3d/data/BOUT.inp): n = 0,
+    vort = 0.1 mixmode(2 pi x) mixmode(z - y), on this rank's X slab of the global grid.  Synthetic,
+    generated on the host once (setup, not timed)."""
+    import numpy as np
+    gnx = MXSUB * world
+    gx = np.arange(MXSUB + 2 * MXG) + rank * MXSUB          # global x index incl. guards
+    X = (0.5 + gx - MXG) / gnx                              # symmetricGlobalX (boutmesh.cxx:3159-3165)
+    Y = 2 * np.pi * (np.arange(MYSUB + 2 * MYG) - MYG + 0.5) / MYSUB
+    Z = 2 * np.pi * np.arange(MZ) / MZ
+    fx = mixmode(2 * np.pi * X)
+    zy = mixmode((Z[None, :] - Y[:, None]))
+    vort = 0.1 * fx[:, None, None] * zy[None, :, :]
+    return torch.zeros(vort.shape, dtype=torch.float64), torch.from_numpy(np.ascontiguousarray(vort))
+
+
+def run_ours(args):
+    import torch
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun as the driver would
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__),
+                   "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bout-dev_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pkg = ge.load_package()
+    capi, models = pkg.capi, pkg.models
+    mesh = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        mesh = pkg.mesh.BoutMesh(nxpe=world, nype=1, rank=rank, mxsub=MXSUB, mysub=MYSUB, mz=MZ, mxg=MXG, myg=MYG,
+                                 periodic_x=False, periodic_y=True, device=dev)
+
+    g = capi.Grid(MXSUB + 2 * MXG, MYSUB + 2 * MYG, MZ, MXG, MYG)
+    one = lambda v: torch.full(g.shape2, v, dtype=torch.float64, device=dev)
+    metric = dict(dx=one(0.2), dy=one(1.0), dz=one(0.2), J=one(1.0), g_22=one(1.0), g11=one(1.0), g33=one(1.0),
+                  g13=one(0.0), G1=one(0.0), G3=one(0.0), g_11=one(1.0))
+    model = models.HW3D(g, metric, device=dev, mesh=mesh, **HW)
+    n0, v0 = initial_state(rank, world, torch, dev)
+    hn, hv = n0.pin_memory(), v0.pin_memory()
+    hn_out, hv_out = torch.empty_like(hn).pin_memory(), torch.empty_like(hv).pin_memory()
+    model.set_state(hn.to(dev), hv.to(dev))
+    npts = MXSUB * MYSUB * MZ
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(args.warmup):
+        model.rk4_step(DT)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    model.kernel_events = []
+    l0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        model.rk4_step(DT)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    launches = capi.launch_count() - l0
+    secs = reduce_max(e0.elapsed_time(e1) * 1e-3)
+    kev = model.kernel_events
+    model.kernel_events = None
+    k_secs = sum(a.elapsed_time(b) for a, b in kev) * 1e-3 / len(kev)
+    finite = bool(torch.isfinite(model.n).all().item() and torch.isfinite(model.vort).all().item())
+
+    # ---- end to end through the public call with HOST buffers ------------------------------------
+    e2e_steps = args.steps
+    model.set_state(hn.to(dev), hv.to(dev))
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        model.n.copy_(hn, non_blocking=True)       # H2D of this step's state from pinned memory
+        model.vort.copy_(hv, non_blocking=True)
+        model.rk4_step(DT)
+        hn_out.copy_(model.n, non_blocking=True)   # D2H of the step's result
+        hv_out.copy_(model.vort, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_secs = reduce_max(e0.elapsed_time(e1) * 1e-3)
+    w2 = time.time()
+    clocks = sampler.stop(w0, w2) if rank == 0 else None   # samples over both timed regions
+    field_bytes = hn.numel() * 8
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    # fused kernel, algorithmic bytes per interior point per launch (DESIGN.md "k_hw3d_rhs"):
+    #   reads n, vort, phi (24) + start n, vort (16) + running combination in (16, stages 2-4)
+    #   writes next stage state (16, stages 1-3) + running combination out (16)   -> 72, 88, 88, 72
+    alg_bytes = (72 + 88 + 88 + 72) / 4.0 * npts
+    achieved = alg_bytes / k_secs / 1e9
+    value = npts * 4 * args.steps * world / secs
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (shipped closed-form initial condition, mixmode)",
+        "config": {"workload": WORKLOAD, "decomposition": f"NXPE={world} NYPE=1", "rhs_per_step": 4,
+                   "points_per_gpu": npts, "dt": DT,
+                   "l2": "inputs larger than L2 (each field 279 MB vs 126 MB L2); no flush needed"},
+        "gpu_launches": int(launches),
+        "finite": finite,
+        "e2e": {"value": npts * 4 * e2e_steps * world / e2e_secs, "unit": UNIT,
+                "h2d_bytes_per_step": 2 * field_bytes, "d2h_bytes_per_step": 2 * field_bytes,
+                "ms_per_step": e2e_secs / e2e_steps * 1e3,
+                "note": "state (n, vort) copied host->device from pinned memory and the result device->host every RK4 step"},
+        "roofline": {"bound": "hbm", "kernel": "k_hw3d_rhs<2> (fused RHS + RK stage update)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": profile_traffic(),
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_secs * 1e3,
+                     "kernel_share_of_step": 4 * k_secs / (secs / args.steps),
+                     "rhs_algorithmic_GBps": (56.0 + 64.0) * npts * 4 * args.steps / secs / 1e9,
+                     "rhs_bytes_per_point": "56 (solve 16 + fused 40, SURVEY 8d) + 64 RK stage update"},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(steps=3, warmup=1)
+    print(json.dumps(out), flush=True)
+
+
+# ---- reference arm: the reference's own CPU implementation (oracle/_ref/libboutref.so) ---------------
+def ref_ini():
+    import __graft_entry__ as ge
+    orc = ge.load_oracle()
+    nx = MXSUB + 2 * MXG
+    return orc, orc.make_ini(nx, REF_MY, MZ, mxg=MXG, myg=MYG, mesh_extra=f"ixseps1 = {nx}\nixseps2 = {nx}\n", extra=f"""
+[hw]
+alpha = {HW['alpha']}
+kappa = {HW['kappa']}
+Dvort = {HW['Dvort']}
+Dn = {HW['Dn']}
+[all]
+scale = 0.0
+bndry_all = dirichlet_o2
+[vort]
+scale = 0.1
+function = mixmode(2*pi*x) * mixmode(z - y)
+[solver]
+timestep = {DT}
+[input]
+error_on_unused_options = false
+""")
+
+
+def run_reference(args, as_baseline=False):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    orc, ini = ref_ini()
+    kind = "reference" if os.path.exists(orc.REF_SO) else None
+    if kind is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libboutref.so not built"}))
+        return
+    r = orc.Ref(ini)
+    r.model_create("hw3d", "rk4")
+    r.model_solve(0, DT)     # Solver::init + first run_rhs (the reference's own start-up)
+    npts = MXSUB * REF_MY * MZ
+    if args.warmup > 0:
+        r.model_time_rhs(reps=4 * args.warmup)
+    secs = r.model_time_rhs(reps=4 * args.steps) * 4 * args.steps
+    value = npts * 4 * args.steps / secs
+    sample = (f"unchanged examples/hasegawa-wakatani-3d/hw.cxx through the reference's Solver::run_rhs, "
+              f"y-slab 512x{REF_MY}x512 of the 512x128x512 workload, 4 run_rhs per step, OpenMP {cores} threads, "
+              f"single MPI rank (shim)")
+    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic (shipped closed-form initial condition, mixmode)",
+           "config": {"workload": WORKLOAD, "rhs_per_step": 4, "sample_points": npts},
+           "cpu_baseline": cb,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os._exit(0)  # the reference's static destructors are not exit-safe
+
+
+def cpu_baseline(steps, warmup):
+    """Runs the reference arm in a child process (it owns global state) and returns its cpu_baseline."""
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps),
+                            "--warmup", str(warmup)], capture_output=True, text=True, timeout=600,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        for line in reversed(p.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                d = json.loads(line)
+                return d.get("cpu_baseline", {"unavailable": d.get("unavailable")})
+        return {"unavailable": (p.stderr or "no output")[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

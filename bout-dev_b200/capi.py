@@ -298,10 +298,16 @@ def fused_coef_workspace(g: Grid, device):
     return torch.empty(lib.bout_b200_fused_coef_doubles(C.byref(g.c)), dtype=torch.float64, device=device)
 
 
-def hw3d_rhs(g: Grid, metric: CMetric, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n=None, ddt_vort=None,
+def fused_coefs(g: Grid, metric: CMetric, coef_ws):
+    _check(lib.bout_b200_fused_coefs(C.byref(g.c), C.byref(metric), _ptr(coef_ws), _stream()))
+    return coef_ws
+
+
+def hw3d_rhs(g: Grid, metric, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n=None, ddt_vort=None,
              epilogue=None, coef_ws=None):
     coef_ws = fused_coef_workspace(g, n.device) if coef_ws is None else coef_ws
-    _check(lib.bout_b200_hw3d_rhs(C.byref(g.c), C.byref(metric), C.c_double(alpha), C.c_double(kappa),
+    _check(lib.bout_b200_hw3d_rhs(C.byref(g.c), None if metric is None else C.byref(metric),
+                                  C.c_double(alpha), C.c_double(kappa),
                                   C.c_double(Dn), C.c_double(Dvort), _ptr(n), _ptr(vort), _ptr(phi),
                                   _ptr(ddt_n), _ptr(ddt_vort),
                                   None if epilogue is None else C.byref(epilogue), _ptr(coef_ws), _stream()))

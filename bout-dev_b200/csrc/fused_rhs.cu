@@ -321,6 +321,27 @@ extern "C" size_t bout_b200_fused_coef_doubles(const bout_b200_grid* g) {
   return g ? static_cast<size_t>(C_NCOEF) * g->nx * g->ny : 0;
 }
 
+static int launchFusedCoefs(const bout_b200_grid* g, const bout_b200_metric* m, double* coef_workspace,
+                            cudaStream_t s) {
+  B200_REQUIRE(m->dx && m->dy && m->dz && m->J && m->g_22 && m->g11 && m->g33 && m->g13 && m->G1 && m->G3,
+               BOUT_B200_ERR_ARG, "fused coefficients: metric missing");
+  const int with_par = g->ny > 1 ? 1 : 0;
+  CoefIn ci{m->dx, m->dy, m->dz, m->J, m->g_22, m->g11, m->g33, m->g13, m->G1, m->G3, m->d1_dx, g->nx, g->ny};
+  const int n2 = g->nx * g->ny;
+  k_fused_coefs<<<(n2 + 255) / 256, 256, 0, s>>>(ci, coef_workspace, with_par);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int bout_b200_fused_coefs(const bout_b200_grid* g, const bout_b200_metric* m,
+                                     double* coef_workspace, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(m && coef_workspace, BOUT_B200_ERR_ARG, "fused_coefs: null argument");
+  return launchFusedCoefs(g, m, coef_workspace, asStream(stream));
+}
+
 extern "C" int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, double alpha,
                                   double kappa, double Dn, double Dvort, const double* n,
                                   const double* vort, const double* phi, double* ddt_n,
@@ -329,19 +350,19 @@ extern "C" int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metri
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
-  B200_REQUIRE(m && n && vort && phi && coef_workspace, BOUT_B200_ERR_ARG, "hw3d_rhs: null argument");
+  B200_REQUIRE(n && vort && phi && coef_workspace, BOUT_B200_ERR_ARG, "hw3d_rhs: null argument");
   B200_REQUIRE((ddt_n && ddt_vort) || epilogue, BOUT_B200_ERR_ARG, "hw3d_rhs: no output requested");
-  B200_REQUIRE(m->dx && m->dy && m->dz && m->J && m->g_22 && m->g11 && m->g33 && m->g13 && m->G1 && m->G3,
-               BOUT_B200_ERR_ARG, "hw3d_rhs: metric missing");
   B200_REQUIRE(g->xstart >= 1 && g->xend <= g->nx - 2, BOUT_B200_ERR_GUARDS, "hw3d_rhs: needs an x guard cell");
   const int with_par = g->ny > 1 ? 1 : 0;
   B200_REQUIRE(!with_par || (g->ystart >= 1 && g->yend <= g->ny - 2), BOUT_B200_ERR_GUARDS,
                "hw3d_rhs: needs a y guard cell");
   cudaStream_t s = asStream(stream);
-  CoefIn ci{m->dx, m->dy, m->dz, m->J, m->g_22, m->g11, m->g33, m->g13, m->G1, m->G3, m->d1_dx, g->nx, g->ny};
-  const int n2 = g->nx * g->ny;
-  k_fused_coefs<<<(n2 + 255) / 256, 256, 0, s>>>(ci, coef_workspace, with_par);
-  B200_LAUNCH_OK();
+  if (m != nullptr) { // metric given: (re)build the per-(x,y) coefficients; NULL = already built
+    const int rc = launchFusedCoefs(g, m, coef_workspace, s);
+    if (rc != 0) {
+      return rc;
+    }
+  }
   Hw3dParams p{};
   p.n = n;
   p.vort = vort;

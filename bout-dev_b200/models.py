@@ -28,12 +28,13 @@ class HW3D:
         zlength = float(self.md["dz"][0, 0].item()) * g.nz
         self.lap = capi.Laplace(g, self.md, zlength, nonuniform=True)
         self.lap.workspace(self.dev)
-        self.coef = capi.fused_coef_workspace(g, self.dev)
+        self.coef = capi.fused_coefs(g, self.cm, capi.fused_coef_workspace(g, self.dev))
+        self.kernel_events = None  # bench.py: list collecting (start, end) CUDA events of the fused kernel
         z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
         self.n, self.vort, self.phi = z(), z(), z()
         self.ddt_n, self.ddt_vort = z(), z()
         # RK work fields: stage state (k5 in rk4.cxx) and the running combination
-        self.sn, self.sv, self.an, self.av = z(), z(), z(), z()
+        self.sn, self.sv, self.tn, self.tv, self.an, self.av = z(), z(), z(), z(), z(), z()
 
     def set_state(self, n, vort):
         self.n.copy_(n)
@@ -58,16 +59,23 @@ class HW3D:
             capi.halo_self(self.g, [fn, fv, self.phi], periodic_x=False, periodic_y=True)
         else:
             self.mesh.communicate([fn, fv, self.phi])
-        capi.hw3d_rhs(self.g, self.cm, self.alpha, self.kappa, self.Dn, self.Dvort, fn, fv, self.phi,
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        capi.hw3d_rhs(self.g, None, self.alpha, self.kappa, self.Dn, self.Dvort, fn, fv, self.phi,
                       self.ddt_n if ddt else None, self.ddt_vort if ddt else None, epilogue=epilogue,
                       coef_ws=self.coef)
+        if self.kernel_events is not None:
+            e1.record()
+            self.kernel_events.append((e0, e1))
 
     def rk4_step(self, dt):
         """RK4Solver::take_step with the axpys folded into the RHS kernel:
         stage i reads state_i, writes state_{i+1} = start + a_i dt k_i and acc += b_i dt k_i."""
-        n, v, sn, sv, an, av = self.n, self.vort, self.sn, self.sv, self.an, self.av
+        n, v, sn, sv, tn, tv, an, av = self.n, self.vort, self.sn, self.sv, self.tn, self.tv, self.an, self.av
         E = capi.make_epilogue
+        # the stage state a kernel writes must not be the one it reads (neighbour cells): ping-pong s/t
         self.rhs(n, v, E((n, v), None, (sn, sv), (an, av), 0.5 * dt, dt / 6.0), ddt=False)
-        self.rhs(sn, sv, E((n, v), (an, av), (sn, sv), (an, av), 0.5 * dt, dt / 3.0), ddt=False)
-        self.rhs(sn, sv, E((n, v), (an, av), (sn, sv), (an, av), dt, dt / 3.0), ddt=False)
+        self.rhs(sn, sv, E((n, v), (an, av), (tn, tv), (an, av), 0.5 * dt, dt / 3.0), ddt=False)
+        self.rhs(tn, tv, E((n, v), (an, av), (sn, sv), (an, av), dt, dt / 3.0), ddt=False)
         self.rhs(sn, sv, E((n, v), (an, av), (None, None), (n, v), 0.0, dt / 6.0), ddt=False)

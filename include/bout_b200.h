@@ -245,10 +245,15 @@ typedef struct bout_b200_rk_epilogue {
 } bout_b200_rk_epilogue;
 
 size_t bout_b200_fused_coef_doubles(const bout_b200_grid* g);
+/* Builds the per-(x,y) coefficient table the fused kernels use (spacing factors, Delp2 and
+ * Div_par_Grad_par coefficients) once; pass m = NULL to the fused kernels afterwards. */
+int bout_b200_fused_coefs(const bout_b200_grid* g, const bout_b200_metric* m, double* coef_workspace,
+                          void* stream);
 /* examples/hasegawa-wakatani-3d/hw.cxx:58-74 (single-index operators,
  * include/bout/single_index_ops.hxx:93-128 bracket, :201-209 DDZ, :222-246 Delp2, :255-278
  * Div_par_Grad_par): ddt(n), ddt(vort) from n, vort, phi.  ddt_* may be NULL when an epilogue is given.
- * coef_workspace: bout_b200_fused_coef_doubles(g) doubles of device scratch. */
+ * coef_workspace: bout_b200_fused_coef_doubles(g) doubles of device scratch, rebuilt from m by this
+ * call when m != NULL, used as already built by bout_b200_fused_coefs when m == NULL. */
 int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, double alpha, double kappa,
                        double Dn, double Dvort, const double* n, const double* vort,
                        const double* phi, double* ddt_n, double* ddt_vort,
