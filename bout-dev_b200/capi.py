@@ -146,7 +146,7 @@ class Laplace:
     """Host-side mirror of the Laplacian settings (reference invert_laplace.cxx:68-138)."""
 
     def __init__(self, g: Grid, metric: dict, zlength, all_terms=True, nonuniform=True, flags=(0, 0, 0),
-                 maxmode=None, periodic_x=False, A=None, C1=None, C2=None, D=None):
+                 maxmode=None, periodic_x=False, A=None, C1=None, C2=None, D=None, first_x=True, last_x=True):
         self.g = g
         self.keep = dict(metric)
         self.keep.update(A=A, C1=C1, C2=C2, D=D)
@@ -158,7 +158,7 @@ class Laplace:
         c.all_terms, c.nonuniform = int(all_terms), int(nonuniform)
         c.global_flags, c.inner_boundary_flags, c.outer_boundary_flags = flags
         c.maxmode = g.nz // 2 if maxmode is None else maxmode
-        c.periodic_x, c.first_x, c.last_x = int(periodic_x), 1, 1
+        c.periodic_x, c.first_x, c.last_x = int(periodic_x), int(first_x), int(last_x)
         self.c = c
         self.ws = None
 
@@ -175,6 +175,27 @@ class Laplace:
         _check(lib.bout_b200_laplace_cyclic_solve(C.byref(self.g.c), C.byref(self.c), _ptr(rhs),
                                                   _ptr(x0), _ptr(out), C.c_void_p(ws.data_ptr()),
                                                   C.c_size_t(ws.numel()), _stream()))
+        return out
+
+    # -- X-decomposed solve: reduce -> (all-gather of the interface records) -> finish
+    def iface_doubles(self):
+        lib.bout_b200_laplace_cyclic_iface_doubles.restype = C.c_size_t
+        return int(lib.bout_b200_laplace_cyclic_iface_doubles(C.byref(self.g.c), C.byref(self.c)))
+
+    def reduce(self, rhs, x0=None, iface=None):
+        ws = self.workspace(rhs.device)
+        if iface is None:
+            iface = torch.empty(self.iface_doubles(), dtype=torch.float64, device=rhs.device)
+        _check(lib.bout_b200_laplace_cyclic_reduce(C.byref(self.g.c), C.byref(self.c), _ptr(rhs), _ptr(x0),
+                                                   C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()),
+                                                   _ptr(iface), _stream()))
+        return iface
+
+    def finish(self, iface_all, nxpe, pe_xind, out):
+        ws = self.ws
+        _check(lib.bout_b200_laplace_cyclic_finish(C.byref(self.g.c), C.byref(self.c), _ptr(iface_all), nxpe,
+                                                   pe_xind, _ptr(out), C.c_void_p(ws.data_ptr()),
+                                                   C.c_size_t(ws.numel()), _stream()))
         return out
 
     def status(self):

@@ -36,9 +36,12 @@ struct LapCoefs {
   int all_terms, nonuniform;
 };
 
-// invert_laplace.cxx:280-375 (IncIntShear not supported: the option is off in every config)
-__device__ __forceinline__ void tridagCoefs(const LapCoefs& m, int jx, int jy, double kwave,
-                                            bool use_c, bool use_d, cd& a, cd& b, cd& c) {
+// invert_laplace.cxx:280-375 (IncIntShear not supported: the option is off in every config).
+// The kz-independent part: k[0] = coef1/dx^2, k[1] = coef2, k[2] = coef3/(2 dx), k[3] = coef4/(2 dx),
+// k[4] = coef5, from which a = (k0 - k3, -kwave k2), b = (-2 k0 - kwave^2 k1, kwave k4),
+// c = (k0 + k3, kwave k2).
+__device__ __forceinline__ void tridagCoef5(const LapCoefs& m, int jx, int jy, bool use_c, bool use_d,
+                                            double (&k)[5]) {
   const long long i = static_cast<long long>(jx) * m.ny + jy;
   const double dxi = __ldg(m.dx + i);
   const double g11 = __ldg(m.g11 + i);
@@ -73,9 +76,24 @@ __device__ __forceinline__ void tridagCoefs(const LapCoefs& m, int jx, int jy, d
   coef1 /= dxi * dxi;
   coef3 /= 2. * dxi;
   coef4 /= 2. * dxi;
-  a = {coef1 - coef4, -kwave * coef3};
-  b = {-2.0 * coef1 - kwave * kwave * coef2, kwave * coef5};
-  c = {coef1 + coef4, kwave * coef3};
+  k[0] = coef1;
+  k[1] = coef2;
+  k[2] = coef3;
+  k[3] = coef4;
+  k[4] = coef5;
+}
+
+__device__ __forceinline__ void coefsFromK(const double (&k)[5], double kwave, cd& a, cd& b, cd& c) {
+  a = {k[0] - k[3], -kwave * k[2]};
+  b = {-2.0 * k[0] - kwave * kwave * k[1], kwave * k[4]};
+  c = {k[0] + k[3], kwave * k[2]};
+}
+
+__device__ __forceinline__ void tridagCoefs(const LapCoefs& m, int jx, int jy, double kwave,
+                                            bool use_c, bool use_d, cd& a, cd& b, cd& c) {
+  double k[5];
+  tridagCoef5(m, jx, jy, use_c, use_d, k);
+  coefsFromK(k, kwave, a, b, c);
 }
 
 struct LapBndry {

@@ -4,23 +4,38 @@
 // Replaces LaplaceCyclic::solve(Field3D, Field3D)
 // (reference src/invert/laplace/impls/cyclic/cyclic_laplace.cxx:187-290), FFTTransform::forward /
 // backward (src/invert/laplace/common_transform.cxx:29-115), Laplacian::tridagMatrix
-// (src/invert/laplace/invert_laplace.cxx:416-768) and the single-rank path of CyclicReduce
-// (include/bout/cyclic_reduction.hxx:169-637).
+// (src/invert/laplace/invert_laplace.cxx:416-768) and CyclicReduce
+// (include/bout/cyclic_reduction.hxx:119-637), including its X-decomposed form.
 //
-// Data layout: the spectral work array is [x - xs][y - ys][kz] complex (kz fastest), i.e. the
+// Data layout: the spectral work arrays are [x - xs][y - ys][kz] complex (kz fastest), i.e. the
 // natural output order of the row FFTs.  The reference transposes to [y*nmode+kz][x] so that each
 // system is contiguous for its serial CPU solver; on the GPU one thread owns one (y,kz) system and
 // walks x, so at every x the 32 lanes of a warp read 32 consecutive kz -- fully coalesced with no
 // transpose at all.
 //
-// Tridiagonal algorithm: Thomas (forward elimination storing c', d'; back substitution).  For
-// periodic X the cyclic system is solved with the Sherman-Morrison correction (two right-hand
-// sides through the same sweeps).  The reference reduces to a 2x2 interface system first
-// (needed for its MPI decomposition); both are direct solvers for the same matrix and agree to
-// round-off (parity tolerance for this path: 1e-10 relative).
+// Tridiagonal algorithm.  A thread's walk along x is a serial dependency chain, so the kernels are
+// written to keep HBM latency off that chain: the kz-independent parts of a, b, c come from a
+// per-(x,y) table built once per solve (k_lap_table), the right-hand sides are read from a buffer
+// that is never written by the same kernel and are prefetched PF rows ahead into registers.
+//   * isolated systems (one rank in X, not periodic): Thomas; forward sweep stores c', d'; back
+//     substitution writes x.
+//   * coupled systems (X-decomposed over NXPE ranks and/or periodic in X): each rank eliminates
+//     downward AND upward in one pass (two independent chains per thread) keeping, per row,
+//         x_i + c'_i x_{i+1} + s_i x_L = d'_i          (x_L = last unknown of the rank below)
+//     and produces two interface equations in (x_L, x_first, x_last, x_R); the 6 complex
+//     coefficients per system and rank are exchanged (one all-gather -- the reference's
+//     CyclicReduce needs a gather and a scatter, cyclic_reduction.hxx:215-440), every rank solves
+//     the 2*NXPE-unknown interface system redundantly (dense, partial pivoting) and back-substitutes
+//     x_i = d'_i - c'_i x_{i+1} - s_i x_L.  Periodic X on one rank is the NXPE = 1 case (x_L = x_last,
+//     x_R = x_first).  Both are direct solvers for the reference's matrix and agree with it to
+//     round-off (parity tolerance for this path: 1e-10 relative).
 #include "laplace_coefs.cuh"
 
 namespace b200 {
+
+constexpr int LAP_NK = 6;     // table entries per (x,y): k0..k4 of tridagCoef5 and A
+constexpr int LAP_IFACE = 6;  // interface coefficients per system: sL, cL, dL, aU, cU, dU
+constexpr int LAP_MAXPE = 8;  // ranks in X
 
 struct LapParams {
   LapCoefs m;
@@ -28,9 +43,13 @@ struct LapParams {
   const double* __restrict__ rhs;
   const double* __restrict__ x0;
   double* __restrict__ out;
-  cd* __restrict__ spec;  // [nxs][nys][nmode]
+  double* __restrict__ table; // [nx][ny][LAP_NK]
+  cd* __restrict__ spec;   // [nxs][nys][nmode]  rhs spectrum in, solution spectrum out
   cd* __restrict__ cprime; // [nxs][nys][nmode]
-  cd* __restrict__ qwork;  // periodic only: [nxs][nys][nmode]
+  cd* __restrict__ dprime; // [nxs][nys][nmode]
+  cd* __restrict__ sprime; // coupled only: [nxs][nys][nmode]
+  cd* __restrict__ iface;  // coupled only: this rank's [LAP_IFACE][nsys]
+  const cd* __restrict__ iface_all; // coupled only: [nxpe][LAP_IFACE][nsys]
   int* __restrict__ status;
   const cd* __restrict__ tw;
   int nx, ny, nz;
@@ -39,6 +58,7 @@ struct LapParams {
   int zero_dc;
   int in_set, out_set;
   int tpr, rows, pow2;
+  int nxpe, pe_xind;
 };
 
 __device__ __forceinline__ RowFFT makeRow(const LapParams& p, unsigned char* smem_raw, int& rloc) {
@@ -100,10 +120,60 @@ __device__ __forceinline__ cd crecip(cd z) {
   const double d = 1.0 / (z.re * z.re + z.im * z.im);
   return {z.re * d, -z.im * d};
 }
+__device__ __forceinline__ cd ldcd(const cd* __restrict__ p) {
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  return {t.x, t.y};
+}
+__device__ __forceinline__ bool tiny(cd z) { return !((z.re * z.re + z.im * z.im) > 1e-300); }
 
-// K2: one thread per (y, kz) system, Thomas along x.
-template <bool PERIODIC>
-__global__ void __launch_bounds__(128) k_lap_tridiag(const LapParams p) {
+// K0: kz-independent coefficient table (Laplacian::tridagCoefs without the kwave factors, + A)
+__global__ void __launch_bounds__(256) k_lap_table(const LapParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.nx * p.ny) {
+    return;
+  }
+  double k[5];
+  tridagCoef5(p.m, i / p.ny, i % p.ny, true, true, k);
+  double* __restrict__ t = p.table + static_cast<long long>(i) * LAP_NK;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    t[j] = k[j];
+  }
+  t[5] = p.m.A != nullptr ? p.m.A[i] : 0.0;
+}
+
+// Row ix of the system (jy, kz): interior rows from the table, boundary rows (and the doubly
+// periodic kz = 0 pin) through the full tridagMatrix logic.
+__device__ __forceinline__ void lapRow(const LapParams& p, int ix, int jy, int kz, double kwave, cd& a,
+                                       cd& b, cd& c, cd& r) {
+  const int ncx = p.bd.xe - p.bd.xs;
+  const bool special = p.bd.periodic_x
+                           ? (kz == 0 && p.bd.first_x && ix == 0)
+                           : ((p.bd.first_x && ix < p.bd.inbndry) || (p.bd.last_x && (ncx - ix) < p.bd.outbndry));
+  if (special) {
+    tridagRow(p.m, p.bd, p.bd.xs + ix, jy, kz, kwave, a, b, c, r);
+    if (!p.bd.periodic_x) { // nothing lies beyond a physical boundary
+      if (p.bd.first_x && ix == 0) {
+        a = {0.0, 0.0};
+      }
+      if (p.bd.last_x && ix == ncx) {
+        c = {0.0, 0.0};
+      }
+    }
+    return;
+  }
+  const double2* __restrict__ t =
+      reinterpret_cast<const double2*>(p.table + (static_cast<long long>(p.bd.xs + ix) * p.ny + jy) * LAP_NK);
+  const double2 t01 = __ldg(t), t23 = __ldg(t + 1), t45 = __ldg(t + 2);
+  a = {t01.x - t23.y, -kwave * t23.x};
+  b = {-2.0 * t01.x - kwave * kwave * t01.y + t45.y, kwave * t45.x};
+  c = {t01.x + t23.y, kwave * t23.x};
+}
+
+constexpr int LAP_PF = 4; // rows of right-hand side prefetched ahead of the dependency chain
+
+// K2 (isolated systems): one thread per (y, kz) system, Thomas along x.
+__global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p) {
   const int nys = p.ye - p.ys + 1;
   const int nsys = nys * p.nmode;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,89 +183,294 @@ __global__ void __launch_bounds__(128) k_lap_tridiag(const LapParams p) {
   const int iyl = t / p.nmode, kz = t % p.nmode;
   const int jy = p.ys + iyl;
   const int n = p.bd.xe - p.bd.xs + 1;
-  const long long xstride = static_cast<long long>(nys) * p.nmode;
-  cd* __restrict__ d = p.spec + t;
+  const long long xs = static_cast<long long>(nys) * p.nmode;
+  const cd* __restrict__ rin = p.spec + t;
   cd* __restrict__ cp = p.cprime + t;
+  cd* __restrict__ dp = p.dprime + t;
   const double kwave = kz * 2.0 * M_PI / p.m.zlength; // common_transform.cxx:73
   bool bad = false;
 
-  if constexpr (!PERIODIC) {
-    cd cprev = {0, 0}, dprev = {0, 0};
-    for (int ix = 0; ix < n; ++ix) {
-      cd a, b, c, r = d[ix * xstride];
-      tridagRow(p.m, p.bd, p.bd.xs + ix, jy, kz, kwave, a, b, c, r);
-      const cd denom = csub(b, cmul(a, cprev));
-      bad = bad || !((denom.re * denom.re + denom.im * denom.im) > 1e-300);
-      const cd inv = crecip(denom);
-      cprev = cmul(c, inv);
-      dprev = cmul(csub(r, cmul(a, dprev)), inv);
-      cp[ix * xstride] = cprev;
-      d[ix * xstride] = dprev;
+  cd nxt[LAP_PF];
+#pragma unroll
+  for (int k = 0; k < LAP_PF; ++k) {
+    nxt[k] = ldcd(rin + static_cast<long long>(min(k, n - 1)) * xs);
+  }
+  cd cprev = {0, 0}, dprev = {0, 0};
+  for (int j0 = 0; j0 < n; j0 += LAP_PF) {
+    cd cur[LAP_PF];
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      cur[k] = nxt[k];
     }
-    cd x = dprev;
-    for (int ix = n - 2; ix >= 0; --ix) {
-      x = csub(d[ix * xstride], cmul(cp[ix * xstride], x));
-      d[ix * xstride] = x;
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      nxt[k] = ldcd(rin + static_cast<long long>(min(j0 + LAP_PF + k, n - 1)) * xs);
     }
-  } else {
-    // cyclic system: row 0 couples to x[n-1] through a0, row n-1 to x[0] through c_{n-1}
-    cd* __restrict__ q = p.qwork + t;
-    cd a0, b0, c0, r0 = d[0];
-    tridagRow(p.m, p.bd, p.bd.xs, jy, kz, kwave, a0, b0, c0, r0);
-    cd an, bn, cn, rn = d[(n - 1) * xstride];
-    tridagRow(p.m, p.bd, p.bd.xs + n - 1, jy, kz, kwave, an, bn, cn, rn);
-    const cd gamma = {-b0.re, -b0.im};
-    const cd vn = cmul(a0, crecip(gamma)); // v = (1, 0, ..., 0, a0/gamma)
-    cd cprev = {0, 0}, dprev = {0, 0}, qprev = {0, 0};
-    for (int ix = 0; ix < n; ++ix) {
-      cd a, b, c, r = d[ix * xstride];
-      tridagRow(p.m, p.bd, p.bd.xs + ix, jy, kz, kwave, a, b, c, r);
-      cd u = {0, 0};
-      if (ix == 0) {
-        b = csub(b, gamma);
-        u = gamma;
-        a = {0, 0};
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      const int ix = j0 + k;
+      if (ix < n) {
+        cd a, b, c, r = cur[k];
+        lapRow(p, ix, jy, kz, kwave, a, b, c, r);
+        const cd denom = csub(b, cmul(a, cprev));
+        bad = bad || tiny(denom);
+        const cd inv = crecip(denom);
+        cprev = cmul(c, inv);
+        dprev = cmul(csub(r, cmul(a, dprev)), inv);
+        cp[ix * xs] = cprev;
+        dp[ix * xs] = dprev;
       }
-      if (ix == n - 1) {
-        b = csub(b, cmul(cn, vn));
-        u = cadd(u, cn);
-        c = {0, 0};
+    }
+  }
+  // back substitution, reading c', d' (never written below) PF rows ahead
+  cd* __restrict__ xo = p.spec + t;
+  const cd* __restrict__ cpr = p.cprime + t;
+  const cd* __restrict__ dpr = p.dprime + t;
+  cd x = dprev;
+  xo[static_cast<long long>(n - 1) * xs] = x;
+  cd nc[LAP_PF], nd[LAP_PF];
+#pragma unroll
+  for (int k = 0; k < LAP_PF; ++k) {
+    const long long o = static_cast<long long>(max(n - 2 - k, 0)) * xs;
+    nc[k] = ldcd(cpr + o);
+    nd[k] = ldcd(dpr + o);
+  }
+  for (int j0 = n - 2; j0 >= 0; j0 -= LAP_PF) {
+    cd cc[LAP_PF], dd[LAP_PF];
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      cc[k] = nc[k];
+      dd[k] = nd[k];
+    }
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      const long long o = static_cast<long long>(max(j0 - LAP_PF - k, 0)) * xs;
+      nc[k] = ldcd(cpr + o);
+      nd[k] = ldcd(dpr + o);
+    }
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      const int ix = j0 - k;
+      if (ix >= 0) {
+        x = csub(dd[k], cmul(cc[k], x));
+        xo[ix * xs] = x;
       }
-      const cd denom = csub(b, cmul(a, cprev));
-      bad = bad || !((denom.re * denom.re + denom.im * denom.im) > 1e-300);
-      const cd inv = crecip(denom);
-      cprev = cmul(c, inv);
-      dprev = cmul(csub(r, cmul(a, dprev)), inv);
-      qprev = cmul(csub(u, cmul(a, qprev)), inv);
-      cp[ix * xstride] = cprev;
-      d[ix * xstride] = dprev;
-      q[ix * xstride] = qprev;
     }
-    cd y = dprev, qq = qprev;
-    const cd yn = y, qn = qq;
-    for (int ix = n - 2; ix >= 0; --ix) {
-      const cd cpi = cp[ix * xstride];
-      y = csub(d[ix * xstride], cmul(cpi, y));
-      qq = csub(q[ix * xstride], cmul(cpi, qq));
-      d[ix * xstride] = y;
-      q[ix * xstride] = qq;
+  }
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+
+// K2a (coupled systems): downward and upward elimination in one pass -> interface equations
+//   last row :  x_last  + sL x_L + cL x_R = dL      (downward sweep; also stores c', d', s per row)
+//   first row:  x_first + aU x_L + cU x_R = dU      (upward sweep, nothing stored)
+__global__ void __launch_bounds__(128) k_lap_reduce(const LapParams p) {
+  const int nys = p.ye - p.ys + 1;
+  const int nsys = nys * p.nmode;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsys) {
+    return;
+  }
+  const int iyl = t / p.nmode, kz = t % p.nmode;
+  const int jy = p.ys + iyl;
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const long long xs = static_cast<long long>(nys) * p.nmode;
+  const cd* __restrict__ rin = p.spec + t;
+  cd* __restrict__ cp = p.cprime + t;
+  cd* __restrict__ dp = p.dprime + t;
+  cd* __restrict__ sp = p.sprime + t;
+  const double kwave = kz * 2.0 * M_PI / p.m.zlength;
+  bool bad = false;
+
+  cd nd[LAP_PF], nu[LAP_PF];
+#pragma unroll
+  for (int k = 0; k < LAP_PF; ++k) {
+    nd[k] = ldcd(rin + static_cast<long long>(min(k, n - 1)) * xs);
+    nu[k] = ldcd(rin + static_cast<long long>(max(n - 1 - k, 0)) * xs);
+  }
+  cd cprev = {0, 0}, dprev = {0, 0}, sprev = {-1.0, 0};   // s_{-1} = -1 makes s_0 = a_0 / b_0
+  cd aup = {0, 0}, rup = {0, 0}, tup = {-1.0, 0};         // t_n = -1 makes t_{n-1} = c_{n-1} / b_{n-1}
+  for (int j0 = 0; j0 < n; j0 += LAP_PF) {
+    cd cd_[LAP_PF], cu_[LAP_PF];
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      cd_[k] = nd[k];
+      cu_[k] = nu[k];
     }
-    // y, qq now hold element 0
-    const cd num = cadd(y, cmul(vn, yn));
-    const cd den = cadd(cadd(cd{1.0, 0.0}, qq), cmul(vn, qn));
-    bad = bad || !((den.re * den.re + den.im * den.im) > 1e-300);
-    const cd fact = cmul(num, crecip(den));
-    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      const int j = j0 + LAP_PF + k;
+      nd[k] = ldcd(rin + static_cast<long long>(min(j, n - 1)) * xs);
+      nu[k] = ldcd(rin + static_cast<long long>(max(n - 1 - j, 0)) * xs);
+    }
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      const int j = j0 + k;
+      if (j < n) {
+        { // downward, row j
+          cd a, b, c, r = cd_[k];
+          lapRow(p, j, jy, kz, kwave, a, b, c, r);
+          const cd denom = csub(b, cmul(a, cprev));
+          bad = bad || tiny(denom);
+          const cd inv = crecip(denom);
+          cprev = cmul(c, inv);
+          dprev = cmul(csub(r, cmul(a, dprev)), inv);
+          const cd as = cmul(a, sprev);
+          sprev = cmul(cd{-as.re, -as.im}, inv);
+          cp[j * xs] = cprev;
+          dp[j * xs] = dprev;
+          sp[j * xs] = sprev;
+        }
+        { // upward, row n-1-j
+          const int i = n - 1 - j;
+          cd a, b, c, r = cu_[k];
+          lapRow(p, i, jy, kz, kwave, a, b, c, r);
+          const cd denom = csub(b, cmul(c, aup));
+          bad = bad || tiny(denom);
+          const cd inv = crecip(denom);
+          aup = cmul(a, inv);
+          rup = cmul(csub(r, cmul(c, rup)), inv);
+          const cd ct = cmul(c, tup);
+          tup = cmul(cd{-ct.re, -ct.im}, inv);
+        }
+      }
+    }
+  }
+  cd* __restrict__ f = p.iface + t;
+  f[0 * nsys] = sprev;
+  f[1 * nsys] = cprev;
+  f[2 * nsys] = dprev;
+  f[3 * nsys] = aup;
+  f[4 * nsys] = tup;
+  f[5 * nsys] = rup;
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+
+// K2b (coupled systems): interface system over the NXPE ranks (dense, partial pivoting), then back
+// substitution of this rank's rows.
+__global__ void __launch_bounds__(128) k_lap_finish(const LapParams p) {
+  const int nys = p.ye - p.ys + 1;
+  const int nsys = nys * p.nmode;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsys) {
+    return;
+  }
+  const int kz = t % p.nmode;
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const long long xs = static_cast<long long>(nys) * p.nmode;
+  const int P = p.nxpe, N2 = 2 * P;
+  const bool per = p.bd.periodic_x != 0;
+  bool bad = false;
+  // unknowns: z[2q] = first unknown of rank q, z[2q+1] = last unknown of rank q
+  cd M[2 * LAP_MAXPE][2 * LAP_MAXPE + 1];
+  for (int i = 0; i < N2; ++i) {
+    for (int j = 0; j <= N2; ++j) {
+      M[i][j] = {0.0, 0.0};
+    }
+  }
+  for (int q = 0; q < P; ++q) {
+    const cd* __restrict__ f = p.iface_all + (static_cast<long long>(q) * LAP_IFACE) * nsys + t;
+    const cd sL = ldcd(f), cL = ldcd(f + nsys), dL = ldcd(f + 2 * nsys);
+    const cd aU = ldcd(f + 3 * nsys), cU = ldcd(f + 4 * nsys), dU = ldcd(f + 5 * nsys);
+    const int prev = q > 0 ? q - 1 : (per ? P - 1 : -1);
+    const int next = q < P - 1 ? q + 1 : (per ? 0 : -1);
+    M[2 * q][2 * q].re += 1.0;
+    M[2 * q + 1][2 * q + 1].re += 1.0;
+    if (prev >= 0) {
+      M[2 * q][2 * prev + 1] = cadd(M[2 * q][2 * prev + 1], aU);
+      M[2 * q + 1][2 * prev + 1] = cadd(M[2 * q + 1][2 * prev + 1], sL);
+    }
+    if (next >= 0) {
+      M[2 * q][2 * next] = cadd(M[2 * q][2 * next], cU);
+      M[2 * q + 1][2 * next] = cadd(M[2 * q + 1][2 * next], cL);
+    }
+    M[2 * q][N2] = dU;
+    M[2 * q + 1][N2] = dL;
+  }
+  for (int col = 0; col < N2; ++col) { // Gaussian elimination, partial pivoting
+    int piv = col;
+    double best = M[col][col].re * M[col][col].re + M[col][col].im * M[col][col].im;
+    for (int r = col + 1; r < N2; ++r) {
+      const double v = M[r][col].re * M[r][col].re + M[r][col].im * M[r][col].im;
+      if (v > best) {
+        best = v;
+        piv = r;
+      }
+    }
+    bad = bad || !(best > 1e-300);
+    if (piv != col) {
+      for (int j = col; j <= N2; ++j) {
+        const cd tmp = M[col][j];
+        M[col][j] = M[piv][j];
+        M[piv][j] = tmp;
+      }
+    }
+    const cd inv = crecip(M[col][col]);
+    for (int j = col; j <= N2; ++j) {
+      M[col][j] = cmul(M[col][j], inv);
+    }
+    for (int r = 0; r < N2; ++r) {
+      if (r != col) {
+        const cd fct = M[r][col];
+        if (fct.re != 0.0 || fct.im != 0.0) {
+          for (int j = col; j <= N2; ++j) {
+            M[r][j] = csub(M[r][j], cmul(fct, M[col][j]));
+          }
+        }
+      }
+    }
+  }
+  const int q = p.pe_xind;
+  const int prev = q > 0 ? q - 1 : (per ? P - 1 : -1);
+  const cd xL = prev >= 0 ? M[2 * prev + 1][N2] : cd{0.0, 0.0};
+  cd x = M[2 * q + 1][N2]; // this rank's last unknown
+
+  cd* __restrict__ xo = p.spec + t;
+  const cd* __restrict__ cpr = p.cprime + t;
+  const cd* __restrict__ dpr = p.dprime + t;
+  const cd* __restrict__ spr = p.sprime + t;
+  xo[static_cast<long long>(n - 1) * xs] = x;
+  double sum = x.re;
+  cd nc[LAP_PF], ndd[LAP_PF], ns[LAP_PF];
+#pragma unroll
+  for (int k = 0; k < LAP_PF; ++k) {
+    const long long o = static_cast<long long>(max(n - 2 - k, 0)) * xs;
+    nc[k] = ldcd(cpr + o);
+    ndd[k] = ldcd(dpr + o);
+    ns[k] = ldcd(spr + o);
+  }
+  for (int j0 = n - 2; j0 >= 0; j0 -= LAP_PF) {
+    cd cc[LAP_PF], dd[LAP_PF], ss[LAP_PF];
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      cc[k] = nc[k];
+      dd[k] = ndd[k];
+      ss[k] = ns[k];
+    }
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      const long long o = static_cast<long long>(max(j0 - LAP_PF - k, 0)) * xs;
+      nc[k] = ldcd(cpr + o);
+      ndd[k] = ldcd(dpr + o);
+      ns[k] = ldcd(spr + o);
+    }
+#pragma unroll
+    for (int k = 0; k < LAP_PF; ++k) {
+      const int ix = j0 - k;
+      if (ix >= 0) {
+        x = csub(csub(dd[k], cmul(cc[k], x)), cmul(ss[k], xL));
+        xo[ix * xs] = x;
+        sum += x.re;
+      }
+    }
+  }
+  if (per && kz == 0 && P == 1) { // subtract the x-average of the kz=0 mode (cyclic_laplace.cxx:266-287)
+    const double avg = sum / static_cast<double>(n);
     for (int ix = 0; ix < n; ++ix) {
-      const cd x = csub(d[ix * xstride], cmul(fact, q[ix * xstride]));
-      d[ix * xstride] = x;
-      sum += x.re;
-    }
-    if (kz == 0) { // subtract the x-average of the kz=0 mode (cyclic_laplace.cxx:266-287)
-      const double avg = sum / static_cast<double>(n);
-      for (int ix = 0; ix < n; ++ix) {
-        d[ix * xstride].re -= avg;
-      }
+      xo[ix * xs].re -= avg;
     }
   }
   if (bad) {
@@ -258,32 +533,54 @@ static void lapBndryWidths(const bout_b200_grid* g, const bout_b200_laplace* L, 
   }
 }
 
+static bool lapCoupled(const bout_b200_laplace* L) {
+  return L->periodic_x || !L->first_x || !L->last_x;
+}
+
+static size_t roundUp(size_t n, size_t a) { return (n + a - 1) / a * a; }
+
 extern "C" size_t bout_b200_laplace_cyclic_workspace(const bout_b200_grid* g, const bout_b200_laplace* L) {
   if (g == nullptr || L == nullptr) {
     return 0;
   }
-  const size_t n = static_cast<size_t>(g->nx) * g->ny * (L->maxmode + 1) * sizeof(cd);
-  return 256 + n * (L->periodic_x ? 3 : 2);
+  const size_t nspec = static_cast<size_t>(g->nx) * g->ny * (L->maxmode + 1) * sizeof(cd);
+  const size_t table = roundUp(static_cast<size_t>(g->nx) * g->ny * LAP_NK * sizeof(double), 256);
+  size_t n = 256 + table + 3 * nspec;
+  if (lapCoupled(L)) {
+    n += nspec + static_cast<size_t>(LAP_IFACE) * g->ny * (L->maxmode + 1) * sizeof(cd);
+  }
+  return n;
 }
 
-extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_laplace* L,
-                                              const double* rhs, const double* x0, double* out,
-                                              void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" size_t bout_b200_laplace_cyclic_iface_doubles(const bout_b200_grid* g, const bout_b200_laplace* L) {
+  if (g == nullptr || L == nullptr) {
+    return 0;
+  }
+  const int ys = L->include_yguards_lower ? 0 : g->ystart;
+  const int ye = L->include_yguards_upper ? g->ny - 1 : g->yend;
+  return static_cast<size_t>(2 * LAP_IFACE) * (ye - ys + 1) * (L->maxmode + 1);
+}
+
+namespace {
+struct LapPlan {
+  LapParams p;
+  RowGeom geo;
+  unsigned rblocks;
+  int nsys;
+};
+
+int lapSetup(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspace, size_t workspace_bytes,
+             cudaStream_t s, LapPlan* plan) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
-  B200_REQUIRE(L && rhs && out && workspace, BOUT_B200_ERR_ARG, "laplace: null argument");
+  B200_REQUIRE(L && workspace, BOUT_B200_ERR_ARG, "laplace: null argument");
   B200_REQUIRE(L->dx && L->g11 && L->g33 && L->g13, BOUT_B200_ERR_ARG, "laplace: metric missing");
   B200_REQUIRE(!L->all_terms || (L->G1 && L->G3), BOUT_B200_ERR_ARG, "laplace: all_terms needs G1, G3");
   B200_REQUIRE(L->maxmode >= 0 && L->maxmode <= g->nz / 2, BOUT_B200_ERR_ARG, "laplace: bad maxmode");
   B200_REQUIRE(workspace_bytes >= bout_b200_laplace_cyclic_workspace(g, L), BOUT_B200_ERR_ARG,
                "laplace: workspace too small");
   B200_REQUIRE(aligned16(workspace), BOUT_B200_ERR_ARG, "laplace: workspace must be 16-byte aligned");
-  B200_REQUIRE(L->first_x && L->last_x, BOUT_B200_ERR_UNSUPPORTED,
-               "laplace: X-decomposed solves go through bout_b200_laplace_cyclic_reduce/_finish");
-  const int setflags = INV_SET;
-  B200_REQUIRE(!((L->inner_boundary_flags | L->outer_boundary_flags) & setflags) || x0 != nullptr,
-               BOUT_B200_ERR_ARG, "laplace: INVERT_SET needs x0");
   const int gradflags = INV_DC_GRAD | INV_AC_GRAD;
   if (((L->inner_boundary_flags | L->outer_boundary_flags) & gradflags)
       && ((L->inner_boundary_flags | L->outer_boundary_flags) & (INV_SET | INV_RHS))) {
@@ -292,9 +589,8 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
   if ((L->inner_boundary_flags | L->outer_boundary_flags) & (INV_DC_GRADPAR | INV_DC_GRADPARINV)) {
     B200_REQUIRE(L->g_22 != nullptr, BOUT_B200_ERR_ARG, "laplace: GRADPAR boundary needs g_22");
   }
-  cudaStream_t s = asStream(stream);
-
-  LapParams p{};
+  LapParams& p = plan->p;
+  p = LapParams{};
   p.m.dx = L->dx;
   p.m.g11 = L->g11;
   p.m.g33 = L->g33;
@@ -323,9 +619,6 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
   p.bd.xs = (L->first_x && !L->periodic_x) ? 0 : g->xstart;
   p.bd.xe = (L->last_x && !L->periodic_x) ? g->nx - 1 : g->xend;
   p.bd.nx_local = g->nx;
-  p.rhs = rhs;
-  p.x0 = x0;
-  p.out = out;
   p.nx = g->nx;
   p.ny = g->ny;
   p.nz = g->nz;
@@ -336,43 +629,141 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
   p.zero_dc = (L->global_flags & INV_ZERO_DC) ? 1 : 0;
   p.in_set = (L->first_x && (L->inner_boundary_flags & INV_SET)) ? 1 : 0;
   p.out_set = (L->last_x && (L->outer_boundary_flags & INV_SET)) ? 1 : 0;
+  p.nxpe = 1;
+  p.pe_xind = 0;
 
   const size_t nspec = static_cast<size_t>(g->nx) * g->ny * p.nmode;
+  const size_t table = roundUp(static_cast<size_t>(g->nx) * g->ny * LAP_NK * sizeof(double), 256);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   p.status = reinterpret_cast<int*>(ws);
-  p.spec = reinterpret_cast<cd*>(ws + 256);
+  p.table = reinterpret_cast<double*>(ws + 256);
+  p.spec = reinterpret_cast<cd*>(ws + 256 + table);
   p.cprime = p.spec + nspec;
-  p.qwork = L->periodic_x ? p.cprime + nspec : nullptr;
+  p.dprime = p.cprime + nspec;
+  if (lapCoupled(L)) {
+    p.sprime = p.dprime + nspec;
+    p.iface = p.sprime + nspec;
+  }
   int st = 0;
   p.tw = twiddleTable(g->nz, s, &st);
   if (st != 0) {
     return st;
   }
-  const RowGeom geo = rowGeometry(g->nz, 128);
-  p.tpr = geo.tpr;
-  p.rows = geo.rows;
-  p.pow2 = geo.pow2 ? 1 : 0;
-  B200_REQUIRE(geo.smemBytes <= 200 * 1024, BOUT_B200_ERR_UNSUPPORTED, "laplace: nz=%d too large", g->nz);
-  if (geo.smemBytes > 48 * 1024) {
+  plan->geo = rowGeometry(g->nz, 128);
+  p.tpr = plan->geo.tpr;
+  p.rows = plan->geo.rows;
+  p.pow2 = plan->geo.pow2 ? 1 : 0;
+  B200_REQUIRE(plan->geo.smemBytes <= 200 * 1024, BOUT_B200_ERR_UNSUPPORTED, "laplace: nz=%d too large", g->nz);
+  if (plan->geo.smemBytes > 48 * 1024) {
     B200_CUDA_OK(cudaFuncSetAttribute(k_lap_forward, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(geo.smemBytes)));
+                                      static_cast<int>(plan->geo.smemBytes)));
     B200_CUDA_OK(cudaFuncSetAttribute(k_lap_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(geo.smemBytes)));
+                                      static_cast<int>(plan->geo.smemBytes)));
   }
-  B200_CUDA_OK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
   const int nys = p.ye - p.ys + 1, nxs = p.bd.xe - p.bd.xs + 1;
   const long long nrows = static_cast<long long>(nxs) * nys;
-  const unsigned rblocks = static_cast<unsigned>((nrows + geo.rows - 1) / geo.rows);
-  k_lap_forward<<<rblocks, 128, geo.smemBytes, s>>>(p);
+  plan->rblocks = static_cast<unsigned>((nrows + plan->geo.rows - 1) / plan->geo.rows);
+  plan->nsys = nys * p.nmode;
+  return 0;
+}
+
+// table + forward FFT (+ status reset)
+int lapForward(const bout_b200_laplace* L, const double* rhs, const double* x0, LapPlan* plan, cudaStream_t s) {
+  LapParams& p = plan->p;
+  B200_REQUIRE(rhs != nullptr, BOUT_B200_ERR_ARG, "laplace: null rhs");
+  B200_REQUIRE(!((L->inner_boundary_flags | L->outer_boundary_flags) & INV_SET) || x0 != nullptr,
+               BOUT_B200_ERR_ARG, "laplace: INVERT_SET needs x0");
+  p.rhs = rhs;
+  p.x0 = x0;
+  B200_CUDA_OK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
+  const int n2 = p.nx * p.ny;
+  k_lap_table<<<(n2 + 255) / 256, 256, 0, s>>>(p);
   B200_LAUNCH_OK();
-  const int nsys = nys * p.nmode;
-  if (L->periodic_x) {
-    k_lap_tridiag<true><<<(nsys + 127) / 128, 128, 0, s>>>(p);
-  } else {
-    k_lap_tridiag<false><<<(nsys + 127) / 128, 128, 0, s>>>(p);
+  k_lap_forward<<<plan->rblocks, 128, plan->geo.smemBytes, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+} // namespace
+
+extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                              const double* rhs, const double* x0, double* out,
+                                              void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = asStream(stream);
+  LapPlan plan;
+  int rc = lapSetup(g, L, workspace, workspace_bytes, s, &plan);
+  if (rc != 0) {
+    return rc;
   }
+  B200_REQUIRE(out != nullptr, BOUT_B200_ERR_ARG, "laplace: null output");
+  B200_REQUIRE(L->first_x && L->last_x, BOUT_B200_ERR_UNSUPPORTED,
+               "laplace: X-decomposed solves go through bout_b200_laplace_cyclic_reduce/_finish");
+  rc = lapForward(L, rhs, x0, &plan, s);
+  if (rc != 0) {
+    return rc;
+  }
+  LapParams& p = plan.p;
+  p.out = out;
+  const unsigned sblocks = static_cast<unsigned>((plan.nsys + 127) / 128);
+  if (!lapCoupled(L)) {
+    k_lap_thomas<<<sblocks, 128, 0, s>>>(p);
+    B200_LAUNCH_OK();
+  } else { // periodic in X on a single rank: the NXPE = 1 case of the coupled algorithm
+    k_lap_reduce<<<sblocks, 128, 0, s>>>(p);
+    B200_LAUNCH_OK();
+    p.iface_all = p.iface;
+    k_lap_finish<<<sblocks, 128, 0, s>>>(p);
+    B200_LAUNCH_OK();
+  }
+  k_lap_backward<<<plan.rblocks, 128, plan.geo.smemBytes, s>>>(p);
   B200_LAUNCH_OK();
-  k_lap_backward<<<rblocks, 128, geo.smemBytes, s>>>(p);
+  return 0;
+}
+
+extern "C" int bout_b200_laplace_cyclic_reduce(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                               const double* rhs, const double* x0, void* workspace,
+                                               size_t workspace_bytes, double* iface_out, void* stream) {
+  cudaStream_t s = asStream(stream);
+  LapPlan plan;
+  int rc = lapSetup(g, L, workspace, workspace_bytes, s, &plan);
+  if (rc != 0) {
+    return rc;
+  }
+  B200_REQUIRE(iface_out != nullptr && aligned16(iface_out), BOUT_B200_ERR_ARG, "laplace reduce: bad iface_out");
+  B200_REQUIRE(lapCoupled(L), BOUT_B200_ERR_ARG, "laplace reduce: system is not coupled (use _solve)");
+  rc = lapForward(L, rhs, x0, &plan, s);
+  if (rc != 0) {
+    return rc;
+  }
+  plan.p.iface = reinterpret_cast<cd*>(iface_out);
+  k_lap_reduce<<<static_cast<unsigned>((plan.nsys + 127) / 128), 128, 0, s>>>(plan.p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int bout_b200_laplace_cyclic_finish(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                               const double* iface_all, int nxpe, int pe_xind, double* out,
+                                               void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = asStream(stream);
+  LapPlan plan;
+  int rc = lapSetup(g, L, workspace, workspace_bytes, s, &plan);
+  if (rc != 0) {
+    return rc;
+  }
+  B200_REQUIRE(out != nullptr && iface_all != nullptr && aligned16(iface_all), BOUT_B200_ERR_ARG,
+               "laplace finish: null argument");
+  B200_REQUIRE(nxpe >= 1 && nxpe <= LAP_MAXPE && pe_xind >= 0 && pe_xind < nxpe, BOUT_B200_ERR_ARG,
+               "laplace finish: NXPE must be 1..%d", LAP_MAXPE);
+  B200_REQUIRE(lapCoupled(L), BOUT_B200_ERR_ARG, "laplace finish: system is not coupled");
+  B200_REQUIRE(!(L->periodic_x && nxpe > 1), BOUT_B200_ERR_UNSUPPORTED,
+               "laplace: periodic X over several ranks is not supported yet (kz=0 mean needs a reduction)");
+  LapParams& p = plan.p;
+  p.out = out;
+  p.iface_all = reinterpret_cast<const cd*>(iface_all);
+  p.nxpe = nxpe;
+  p.pe_xind = pe_xind;
+  k_lap_finish<<<static_cast<unsigned>((plan.nsys + 127) / 128), 128, 0, s>>>(p);
+  B200_LAUNCH_OK();
+  k_lap_backward<<<plan.rblocks, 128, plan.geo.smemBytes, s>>>(p);
   B200_LAUNCH_OK();
   return 0;
 }

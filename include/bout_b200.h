@@ -168,6 +168,21 @@ size_t bout_b200_laplace_cyclic_workspace(const bout_b200_grid* g, const bout_b2
 int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_laplace* L,
                                    const double* rhs, const double* x0, double* out,
                                    void* workspace, size_t workspace_bytes, void* stream);
+/* X-decomposed solves (NXPE > 1; replaces the distributed part of CyclicReduce::solve,
+ * include/bout/cyclic_reduction.hxx:169-440).  Each rank calls _reduce on its slab (L->first_x /
+ * L->last_x say whether it owns a physical boundary): forward z-FFT, local elimination, and
+ * bout_b200_laplace_cyclic_iface_doubles() doubles of interface coefficients written to iface_out
+ * (device).  The ranks of one X row all-gather those records in PE_XIND order (NCCL; the only
+ * exchange of the solve) into iface_all = [nxpe][iface doubles], then each calls _finish: interface
+ * system, back substitution, inverse z-FFT into out.  The workspace carries state from _reduce to
+ * _finish. */
+size_t bout_b200_laplace_cyclic_iface_doubles(const bout_b200_grid* g, const bout_b200_laplace* L);
+int bout_b200_laplace_cyclic_reduce(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                    const double* rhs, const double* x0, void* workspace,
+                                    size_t workspace_bytes, double* iface_out, void* stream);
+int bout_b200_laplace_cyclic_finish(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                    const double* iface_all, int nxpe, int pe_xind, double* out,
+                                    void* workspace, size_t workspace_bytes, void* stream);
 /* Synchronises `stream`; BOUT_B200_ERR_PIVOT if the last solve on this workspace met a zero pivot
  * (reference throws BoutException, include/bout/cyclic_reduction.hxx:553). */
 int bout_b200_laplace_cyclic_status(void* workspace, void* stream);

@@ -138,3 +138,41 @@ def test_zero_pivot_is_reported(capi, orc):
     with pytest.raises(capi.BoutB200Error) as e:
         lap.status()
     assert e.value.status == -4
+
+
+@pytest.mark.parametrize("nxpe", [2, 3, 4, 8])
+@pytest.mark.parametrize("flags", [(0, 0, 0), (0, 3, 0), (0, 0, 3), (0, 16, 16), (1, 4, 64)])
+def test_laplace_x_decomposed_matches_single_rank(capi, orc, port, nxpe, flags):
+    """CyclicReduce across NXPE ranks (cyclic_reduction.hxx:169-440) emulated on one GPU: every
+    'rank' reduces its X slab, the interface records are concatenated as the NCCL all-gather would,
+    every rank finishes.  The reference's own criterion for its MPI solve is nproc-independence
+    (tests/integrated/test-laplace/runtest: nproc 1, 2, 4 against one benchmark)."""
+    mxsub, mxg, myg, ny, nz = 6, 2, 1, 3, 16
+    gnx = nxpe * mxsub + 2 * mxg
+    G, OG = capi.Grid(gnx, ny + 2 * myg, nz, mxg, myg), orc.Grid(gnx, ny + 2 * myg, nz, mxg, myg)
+    m = make_metric(orc, G.shape2, nz)
+    f, x0 = seeded_fields(G.shape3, 2)
+    X = (np.arange(gnx)[:, None] + 0.5) / gnx * np.ones(G.shape2)
+    A = np.ascontiguousarray(-0.1 - 0.05 * X)
+    D = np.ascontiguousarray(1 + 0.2 * X)
+    want = port.laplace_cyclic(OG, m, f, x0=x0, flags=flags, A=A, D=D)
+    g = capi.Grid(mxsub + 2 * mxg, ny + 2 * myg, nz, mxg, myg)
+    laps, ifaces = [], []
+    for p in range(nxpe):
+        sl = slice(p * mxsub, p * mxsub + g.nx)
+        md = {n: dev(getattr(m, n)[sl]) for n in ("dx", "g11", "g33", "g13", "G1", "G3", "g_11", "g_22")}
+        lap = capi.Laplace(g, md, float(m.dz[0, 0]) * nz, flags=flags, A=dev(A[sl]), D=dev(D[sl]),
+                           first_x=(p == 0), last_x=(p == nxpe - 1))
+        laps.append((lap, sl))
+        ifaces.append(lap.reduce(dev(f[sl]), dev(x0[sl])))
+    iface_all = torch.cat(ifaces)
+    got = np.zeros(G.shape3)
+    for p, (lap, sl) in enumerate(laps):
+        out = lap.finish(iface_all, nxpe, p, torch.zeros(g.shape3, dtype=torch.float64, device="cuda"))
+        lap.status()
+        o = out.cpu().numpy()
+        xs = 0 if p == 0 else g.xstart
+        xe = g.nx if p == nxpe - 1 else g.xend + 1
+        got[sl][xs:xe] = o[xs:xe]
+    region = (slice(None), slice(G.ystart, G.yend + 1), slice(None))
+    assert rel_err(got, want, region) < 1e-10
