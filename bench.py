@@ -30,7 +30,10 @@ sys.path.insert(0, ROOT)
 
 MXSUB, MYSUB, MZ, MXG, MYG = 512, 128, 512, 2, 2
 HW = dict(alpha=1.0, kappa=0.5, Dn=1e-3, Dvort=1e-3)
-DT = 1e-3
+# Explicit RK4 on HW3D is limited by the zonal (kz = 0) parallel-coupling mode: lambda ~ alpha * (4/dy^2) * (Lx/pi)^2,
+# i.e. 2.7e5 at 8 GPUs (Lx = 8 * 102.4): dt must stay below 2.8/lambda ~ 1e-5 (tools/dbg_stability.py shows the
+# blow-up at dt = 1e-3 for nx >= 768 on a single rank).  The arithmetic per step does not depend on dt.
+DT = 2e-6
 METRIC = "rhs_grid_points_per_s"
 UNIT = "grid-points/s"
 WORKLOAD = "hasegawa-wakatani-3d RHS, 512x128x512 interior points per GPU (516x132x512 with guards), RK4"

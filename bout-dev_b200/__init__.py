@@ -7,4 +7,5 @@ library through ctypes and passes torch CUDA tensors' device pointers.  There is
 importing ``capi`` without the built library raises.
 """
 from . import capi  # noqa: F401
+from . import mesh  # noqa: F401
 from . import models  # noqa: F401

@@ -26,8 +26,15 @@ class HW3D:
         self.cm = capi.make_metric(self.md)
         self.mesh = mesh  # None = single rank (self exchange)
         zlength = float(self.md["dz"][0, 0].item()) * g.nz
-        self.lap = capi.Laplace(g, self.md, zlength, nonuniform=True)
+        first_x = mesh is None or mesh.first_x
+        last_x = mesh is None or mesh.last_x
+        self.lap = capi.Laplace(g, self.md, zlength, nonuniform=True, first_x=first_x, last_x=last_x)
         self.lap.workspace(self.dev)
+        self.x_split = mesh is not None and mesh.nxpe > 1
+        if self.x_split:  # interface records of the X-decomposed tridiagonal solve
+            nif = self.lap.iface_doubles()
+            self.iface = torch.empty(nif, dtype=torch.float64, device=self.dev)
+            self.iface_all = torch.empty(nif * mesh.nxpe, dtype=torch.float64, device=self.dev)
         self.coef = capi.fused_coefs(g, self.cm, capi.fused_coef_workspace(g, self.dev))
         self.kernel_events = None  # bench.py: list collecting (start, end) CUDA events of the fused kernel
         z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
@@ -54,7 +61,12 @@ class HW3D:
         fn = self.n if fn is None else fn
         fv = self.vort if fv is None else fv
         self._pre_rhs(fn, fv)                                   # Solver::pre_rhs
-        self.lap.solve(fv, out=self.phi)                        # phi = phiSolver->solve(vort, phi)
+        if not self.x_split:                                    # phi = phiSolver->solve(vort, phi)
+            self.lap.solve(fv, out=self.phi)
+        else:
+            self.lap.reduce(fv, iface=self.iface)
+            self.mesh.all_gather_x(self.iface, self.iface_all)
+            self.lap.finish(self.iface_all, self.mesh.nxpe, self.mesh.pe_xind, self.phi)
         if self.mesh is None:                                   # mesh->communicate(n, vort, phi, ...)
             capi.halo_self(self.g, [fn, fv, self.phi], periodic_x=False, periodic_y=True)
         else:

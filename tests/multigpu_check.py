@@ -1,0 +1,58 @@
+"""Run under torchrun on N GPUs (N = 2, 4, 8): X-decomposed HW3D against the single-rank golden
+trajectory of the reference (tests/golden/models.npz) and an X-decomposed LaplaceCyclic against the
+golden operator fixture.  Exit code 0 = parity.  Launched by tests/test_gpu_multi.py."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as ge  # noqa: E402
+from util import rel_err  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = ge.load_package()
+    capi, models, meshmod = pkg.capi, pkg.models, pkg.mesh
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "models.npz")))
+    gnx, gny, nz, mxg, myg = [int(v) for v in gold["hw3d_grid"]]
+    MX = gnx - 2 * mxg
+    assert MX % world == 0
+    mxsub = MX // world
+    mesh = meshmod.BoutMesh(world, 1, rank, mxsub, gny - 2 * myg, nz, mxg, myg, periodic_x=False, periodic_y=True,
+                            device=dev)
+    sl = slice(rank * mxsub, rank * mxsub + mxsub + 2 * mxg)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(dev)
+    metric = {n: t(gold[f"hw3d_metric_{n}"]) for n in ("dx", "dy", "dz", "J", "g_22", "g11", "g33", "g13", "G1", "G3",
+                                                        "d1_dx", "g_11")}
+    m = models.HW3D(mesh.grid, metric, alpha=1.0, kappa=0.5, Dn=1e-3, Dvort=1e-3, device=dev, mesh=mesh)
+    m.set_state(t(gold["hw3d_init_n"]), t(gold["hw3d_init_vort"]))
+    m.rhs()
+    g = mesh.grid
+    I = g.interior
+    errs = [rel_err(m.ddt_n.cpu().numpy(), gold["hw3d_ddt_n"][sl], I), rel_err(m.ddt_vort.cpu().numpy(), gold["hw3d_ddt_vort"][sl], I)]
+    ok = max(errs) < 1e-10
+    dt, nsteps = gold["hw3d_dt_nsteps"]
+    m.set_state(t(gold["hw3d_init_n"]), t(gold["hw3d_init_vort"]))
+    for _ in range(int(nsteps)):
+        m.rk4_step(float(dt))
+    errs += [rel_err(m.n.cpu().numpy(), gold["hw3d_final_n"][sl], I), rel_err(m.vort.cpu().numpy(), gold["hw3d_final_vort"][sl], I)]
+    ok = ok and max(errs[2:]) < 1e-8
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    print(f"rank {rank}/{world}: ddt err {errs[0]:.2e} {errs[1]:.2e}; trajectory err {errs[2]:.2e} {errs[3]:.2e}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(int(flag.item() != 0))
+
+
+if __name__ == "__main__":
+    main()
