@@ -9,3 +9,4 @@ importing ``capi`` without the built library raises.
 from . import capi  # noqa: F401
 from . import mesh  # noqa: F401
 from . import models  # noqa: F401
+from . import host  # noqa: F401

@@ -29,3 +29,33 @@ extern "C" int bout_b200_version(void) { return 100; }
 extern "C" unsigned long long bout_b200_launch_count(void) {
   return b200::g_launches.load(std::memory_order_relaxed);
 }
+
+// ---- device memory for host layers that do not link the CUDA runtime themselves -------------------
+extern "C" int bout_b200_malloc(void** ptr, size_t bytes) {
+  B200_REQUIRE(ptr != nullptr, BOUT_B200_ERR_ARG, "malloc: null argument");
+  B200_CUDA_OK(cudaMalloc(ptr, bytes));
+  B200_CUDA_OK(cudaMemset(*ptr, 0, bytes));
+  return 0;
+}
+extern "C" int bout_b200_free(void* ptr) {
+  B200_CUDA_OK(cudaFree(ptr));
+  return 0;
+}
+extern "C" int bout_b200_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+  B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, b200::asStream(stream)));
+  B200_CUDA_OK(cudaStreamSynchronize(b200::asStream(stream)));
+  return 0;
+}
+extern "C" int bout_b200_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+  B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b200::asStream(stream)));
+  B200_CUDA_OK(cudaStreamSynchronize(b200::asStream(stream)));
+  return 0;
+}
+extern "C" int bout_b200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+  B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, b200::asStream(stream)));
+  return 0;
+}
+extern "C" int bout_b200_stream_sync(void* stream) {
+  B200_CUDA_OK(cudaStreamSynchronize(b200::asStream(stream)));
+  return 0;
+}

@@ -1,0 +1,1544 @@
+// Implementation of the C++17 host layer (see include/bout/b200_host.hxx) on the C-ABI of
+// include/bout_b200.h.  Set-up work (options, metric, initial profiles) runs once on the host, as in
+// the reference; everything inside a right-hand side or a time step is a kernel launch.
+#include "bout/b200_host.hxx"
+
+#include <algorithm>
+#include <cctype>
+#include <cstring>
+#include <stdexcept>
+
+Output output, output_info, output_warn, output_progress, output_error;
+
+namespace bout {
+namespace globals {
+Mesh* mesh = nullptr;
+}
+namespace b200 {
+
+void check(int status) {
+  if (status != BOUT_B200_OK) {
+    throw BoutException("bout_b200: {} (status {})", bout_b200_last_error(), status);
+  }
+}
+
+// ---- device block pool (reference Array<T> arena, include/bout/array.hxx:387-472) -------------------
+namespace {
+std::map<size_t, std::vector<double*>>& freeList() {
+  static std::map<size_t, std::vector<double*>> pool;
+  return pool;
+}
+size_t n_malloc = 0;
+} // namespace
+
+Block::~Block() {
+  if (ptr != nullptr) {
+    freeList()[count].push_back(ptr); // back to the pool, not to the driver
+  }
+}
+
+std::shared_ptr<Block> acquire(size_t count) {
+  auto blk = std::make_shared<Block>();
+  blk->count = count;
+  auto& bucket = freeList()[count];
+  if (!bucket.empty()) {
+    blk->ptr = bucket.back();
+    bucket.pop_back();
+  } else {
+    void* p = nullptr;
+    check(bout_b200_malloc(&p, count * sizeof(double)));
+    blk->ptr = static_cast<double*>(p);
+    ++n_malloc;
+  }
+  return blk;
+}
+
+void releasePool() {
+  for (auto& kv : freeList()) {
+    for (double* p : kv.second) {
+      bout_b200_free(p);
+    }
+  }
+  freeList().clear();
+}
+
+size_t poolAllocations() { return n_malloc; }
+
+// ---- small expression evaluator for option values and initial profiles ---------------------------------
+// (the reference's ExpressionParser / FieldFactory, src/sys/expressionparser.cxx, src/field/fieldgenerators.cxx,
+//  restated for the subset the example inputs use: + - * / ^ ( ) numbers, pi, x y z t, option references,
+//  sin cos tan exp log sqrt abs gauss mixmode tanh H)
+struct EvalContext {
+  double x = 0, y = 0, z = 0, t = 0;
+  Options* section = nullptr;
+  int depth = 0;
+};
+
+class Expr {
+public:
+  Expr(const std::string& s, const EvalContext& c) : src(s), ctx(c) {}
+  double eval() {
+    pos = 0;
+    const double v = sum();
+    skip();
+    if (pos != src.size()) {
+      throw BoutException("Cannot parse expression '{}' near position {}", src, pos);
+    }
+    return v;
+  }
+
+private:
+  std::string src;
+  EvalContext ctx;
+  size_t pos = 0;
+  void skip() {
+    while (pos < src.size() && std::isspace(static_cast<unsigned char>(src[pos]))) {
+      ++pos;
+    }
+  }
+  bool eat(char c) {
+    skip();
+    if (pos < src.size() && src[pos] == c) {
+      ++pos;
+      return true;
+    }
+    return false;
+  }
+  double sum() {
+    double v = product();
+    for (;;) {
+      if (eat('+')) {
+        v += product();
+      } else if (eat('-')) {
+        v -= product();
+      } else {
+        return v;
+      }
+    }
+  }
+  double product() {
+    double v = unary();
+    for (;;) {
+      if (eat('*')) {
+        v *= unary();
+      } else if (eat('/')) {
+        v /= unary();
+      } else {
+        return v;
+      }
+    }
+  }
+  double unary() {
+    if (eat('-')) {
+      return -unary();
+    }
+    if (eat('+')) {
+      return unary();
+    }
+    return power();
+  }
+  double power() {
+    const double base = atom();
+    if (eat('^')) {
+      return std::pow(base, unary());
+    }
+    return base;
+  }
+  static double genRand(double seed) { // FieldMixmode::genRand, fieldgenerators.cxx:148-167
+    if (seed < 0.0) {
+      seed *= -1;
+    }
+    const int niter = 11 + (23 + static_cast<int>(std::lround(seed))) % 79;
+    const double A = 0.01, B = 1.23456789;
+    double x = (A + std::fmod(seed, B)) / (B + 2. * A);
+    for (int i = 0; i != niter; ++i) {
+      x = 3.99 * x * (1. - x);
+    }
+    return x;
+  }
+  double call(const std::string& fn, const std::vector<double>& a) {
+    auto need = [&](size_t lo, size_t hi) {
+      if (a.size() < lo || a.size() > hi) {
+        throw BoutException("Wrong number of arguments to {} in '{}'", fn, src);
+      }
+    };
+    if (fn == "sin") { need(1, 1); return std::sin(a[0]); }
+    if (fn == "cos") { need(1, 1); return std::cos(a[0]); }
+    if (fn == "tan") { need(1, 1); return std::tan(a[0]); }
+    if (fn == "exp") { need(1, 1); return std::exp(a[0]); }
+    if (fn == "log") { need(1, 1); return std::log(a[0]); }
+    if (fn == "sqrt") { need(1, 1); return std::sqrt(a[0]); }
+    if (fn == "abs") { need(1, 1); return std::fabs(a[0]); }
+    if (fn == "tanh") { need(1, 1); return std::tanh(a[0]); }
+    if (fn == "h" || fn == "H") { need(1, 1); return a[0] > 0.0 ? 1.0 : 0.0; }
+    if (fn == "gauss") { // FieldGaussian, fieldgenerators.cxx:31-34
+      need(1, 2);
+      const double sigma = a.size() == 2 ? a[1] : 1.0;
+      return std::exp(-SQ(a[0] / sigma) / 2.) / (std::sqrt(TWOPI) * sigma);
+    }
+    if (fn == "mixmode") { // FieldMixmode, fieldgenerators.cxx:110-146
+      need(1, 2);
+      const double seed = a.size() == 2 ? a[1] : 0.5;
+      double result = 0.0;
+      for (int i = 0; i < 14; i++) {
+        const double phase = PI * (2. * genRand(seed + i) - 1.);
+        result += (1. / SQ(1. + std::abs(i - 4))) * std::cos(i * a[0] + phase);
+      }
+      return result;
+    }
+    if (fn == "min") { need(1, 8); return *std::min_element(a.begin(), a.end()); }
+    if (fn == "max") { need(1, 8); return *std::max_element(a.begin(), a.end()); }
+    if (fn == "power") { need(2, 2); return std::pow(a[0], a[1]); }
+    throw BoutException("Unknown function '{}' in expression '{}'", fn, src);
+  }
+  double lookup(const std::string& id) {
+    if (id == "pi" || id == "π") { return PI; }
+    if (id == "x") { return ctx.x; }
+    if (id == "y") { return ctx.y; }
+    if (id == "z") { return ctx.z; }
+    if (id == "t") { return ctx.t; }
+    // option reference: same section, then parents, "section:key" from the root
+    if (ctx.depth > 16) {
+      throw BoutException("Option reference loop while evaluating '{}'", src);
+    }
+    Options* found = nullptr;
+    const auto colon = id.find(':');
+    if (colon != std::string::npos) {
+      Options* o = &Options::root();
+      size_t start = 0;
+      for (;;) {
+        const auto c = id.find(':', start);
+        const std::string part = id.substr(start, c == std::string::npos ? std::string::npos : c - start);
+        if (c == std::string::npos) {
+          if (o->isSet(part)) {
+            found = &(*o)[part];
+          }
+          break;
+        }
+        o = &(*o)[part];
+        start = c + 1;
+      }
+    } else {
+      for (Options* o = ctx.section; o != nullptr; o = o->parent()) {
+        if (o->isSet(id)) {
+          found = &(*o)[id];
+          break;
+        }
+      }
+    }
+    if (found == nullptr) {
+      throw BoutException("Unknown symbol '{}' in expression '{}'", id, src);
+    }
+    EvalContext c = ctx;
+    c.section = found->parent();
+    c.depth = ctx.depth + 1;
+    return Expr(found->text(), c).eval();
+  }
+  double atom() {
+    skip();
+    if (pos >= src.size()) {
+      throw BoutException("Unexpected end of expression '{}'", src);
+    }
+    if (eat('(')) {
+      const double v = sum();
+      if (!eat(')')) {
+        throw BoutException("Missing ')' in '{}'", src);
+      }
+      return v;
+    }
+    const char c = src[pos];
+    if (std::isdigit(static_cast<unsigned char>(c)) || c == '.') {
+      size_t used = 0;
+      const double v = std::stod(src.substr(pos), &used);
+      pos += used;
+      return v;
+    }
+    if (std::isalpha(static_cast<unsigned char>(c)) || c == '_') {
+      size_t e = pos;
+      while (e < src.size() && (std::isalnum(static_cast<unsigned char>(src[e])) || src[e] == '_' || src[e] == ':')) {
+        ++e;
+      }
+      const std::string id = src.substr(pos, e - pos);
+      pos = e;
+      if (eat('(')) {
+        std::vector<double> args;
+        if (!eat(')')) {
+          do {
+            args.push_back(sum());
+          } while (eat(','));
+          if (!eat(')')) {
+            throw BoutException("Missing ')' after arguments of {} in '{}'", id, src);
+          }
+        }
+        return call(id, args);
+      }
+      return lookup(id);
+    }
+    throw BoutException("Unexpected character '{}' in expression '{}'", std::string(1, c), src);
+  }
+};
+
+double evalOption(Options& opt, double x = 0, double y = 0, double z = 0) {
+  EvalContext c;
+  c.x = x;
+  c.y = y;
+  c.z = z;
+  c.section = opt.parent();
+  return Expr(opt.text(), c).eval();
+}
+
+} // namespace b200
+} // namespace bout
+
+using bout::b200::check;
+
+// ======================================================================================================
+// Options
+// ======================================================================================================
+Options& Options::root() {
+  static Options* r = new Options();
+  return *r;
+}
+
+void Options::cleanup() {
+  Options& r = root();
+  r.children.clear();
+  r.has_value = false;
+  r.value.clear();
+}
+
+Options& Options::operator[](const std::string& key_in) {
+  const auto colon = key_in.find(':');
+  if (colon != std::string::npos) {
+    return (*this)[key_in.substr(0, colon)][key_in.substr(colon + 1)];
+  }
+  std::string key = key_in;
+  std::transform(key.begin(), key.end(), key.begin(), [](unsigned char c) { return std::tolower(c); });
+  auto it = children.find(key);
+  if (it == children.end()) {
+    it = children.emplace(key, Options()).first;
+    it->second.parent_ = this;
+    it->second.full_name = full_name.empty() ? key : full_name + ":" + key;
+  }
+  return it->second;
+}
+
+bool Options::isSet(const std::string& key_in) const {
+  std::string key = key_in;
+  std::transform(key.begin(), key.end(), key.begin(), [](unsigned char c) { return std::tolower(c); });
+  const auto it = children.find(key);
+  return it != children.end() && it->second.has_value;
+}
+
+template <>
+void Options::assignValue<std::string>(const std::string& v) { setText(v); }
+template <>
+void Options::assignValue<double>(const double& v) { char buf[64];
+  std::snprintf(buf, sizeof(buf), "%.17g", v);
+  setText(buf); }
+template <>
+void Options::assignValue<int>(const int& v) { setText(std::to_string(v)); }
+template <>
+void Options::assignValue<bool>(const bool& v) { setText(v ? "true" : "false"); }
+template <>
+void Options::assignValue<Field3D>(const Field3D& v) { field3d = &v; }
+
+template <>
+std::string Options::as<std::string>() const { return value; }
+template <>
+double Options::as<double>() const { return bout::b200::evalOption(const_cast<Options&>(*this)); }
+template <>
+int Options::as<int>() const {
+  const double v = bout::b200::evalOption(const_cast<Options&>(*this));
+  const int r = static_cast<int>(std::lround(v));
+  if (std::fabs(v - r) > 1e-3) {
+    throw BoutException("Value for option {} = {} is not an integer", full_name, v);
+  }
+  return r;
+}
+template <>
+bool Options::as<bool>() const {
+  std::string s = value;
+  std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return std::tolower(c); });
+  if (s == "true" || s == "yes" || s == "y" || s == "t" || s == "1") {
+    return true;
+  }
+  if (s == "false" || s == "no" || s == "n" || s == "f" || s == "0") {
+    return false;
+  }
+  throw BoutException("Value for option {} = '{}' cannot be converted to a bool", full_name, value);
+}
+
+Options& Options::assignRepeat(const Field3D& f, const std::string&, bool, const std::string&) {
+  field3d = &f;
+  return *this;
+}
+Options& Options::assignRepeat(const Field2D&, const std::string&, bool, const std::string&) { return *this; }
+Options& Options::setAttributes(std::initializer_list<std::pair<std::string, AttributeType>> attrs) {
+  for (const auto& a : attrs) {
+    attributes[a.first] = a.second;
+  }
+  return *this;
+}
+
+void readOptionsText(const std::string& ini_text, Options& root) {
+  std::istringstream in(ini_text);
+  std::string line;
+  Options* section = &root;
+  while (std::getline(in, line)) {
+    const auto hash = line.find_first_of("#;");
+    if (hash != std::string::npos) {
+      line.erase(hash);
+    }
+    auto trim = [](std::string s) {
+      const auto b = s.find_first_not_of(" \t\r\n");
+      if (b == std::string::npos) {
+        return std::string();
+      }
+      const auto e = s.find_last_not_of(" \t\r\n");
+      return s.substr(b, e - b + 1);
+    };
+    line = trim(line);
+    if (line.empty()) {
+      continue;
+    }
+    if (line.front() == '[') {
+      const auto close = line.find(']');
+      if (close == std::string::npos) {
+        throw BoutException("Options: missing ']' in line '{}'", line);
+      }
+      section = &root[trim(line.substr(1, close - 1))];
+      continue;
+    }
+    const auto eq = line.find('=');
+    if (eq == std::string::npos) {
+      throw BoutException("Options: expected key = value, got '{}'", line);
+    }
+    std::string val = trim(line.substr(eq + 1));
+    if (val.size() >= 2 && val.front() == '"' && val.back() == '"') {
+      val = val.substr(1, val.size() - 2);
+    }
+    (*section)[trim(line.substr(0, eq))].setText(val);
+  }
+}
+
+// ======================================================================================================
+// Fields
+// ======================================================================================================
+Mesh* FieldBase::getMesh() const { return fieldmesh != nullptr ? fieldmesh : bout::globals::mesh; }
+
+void FieldBase::makeUnique(size_t count) {
+  if (!data) {
+    data = bout::b200::acquire(count);
+  } else if (data.use_count() > 1) {
+    auto fresh = bout::b200::acquire(count);
+    check(bout_b200_memcpy_d2d(fresh->ptr, data->ptr, count * sizeof(double), nullptr));
+    data = fresh;
+  }
+}
+
+namespace {
+bout_b200_grid gridOf(const FieldBase& f) { return f.getMesh()->grid(); }
+
+bout_b200_ewterm term(double coef, const FieldBase* f1 = nullptr, bool f1_2d = false, const FieldBase* f2 = nullptr,
+                      bool f2_2d = false, const FieldBase* dv = nullptr, bool dv_2d = false) {
+  bout_b200_ewterm t{};
+  t.coef = coef;
+  t.f1 = f1 ? f1->dptr() : nullptr;
+  t.f2 = f2 ? f2->dptr() : nullptr;
+  t.div = dv ? dv->dptr() : nullptr;
+  t.f1_is2d = f1_2d;
+  t.f2_is2d = f2_2d;
+  t.div_is2d = dv_2d;
+  return t;
+}
+
+void requireData(const FieldBase& f, const char* what) {
+  if (!f.isAllocated()) {
+    throw BoutException("{}: field is not allocated", what);
+  }
+}
+
+// out (a fresh or in-place Field3D) = sum of terms over RGN_ALL
+void ew3(Field3D& out, std::initializer_list<bout_b200_ewterm> terms) {
+  const auto g = gridOf(out);
+  std::vector<bout_b200_ewterm> t(terms);
+  check(bout_b200_elementwise(&g, BOUT_B200_RGN_ALL, static_cast<int>(t.size()), t.data(), out.wptr(), nullptr));
+}
+
+// Field2D algebra runs through the same kernel on a grid with nz = 1
+void ew2(Field2D& out, std::initializer_list<bout_b200_ewterm> terms) {
+  Mesh* m = out.getMesh();
+  bout_b200_grid g{m->LocalNx, m->LocalNy, 1, m->xstart, m->xend, m->ystart, m->yend};
+  std::vector<bout_b200_ewterm> t(terms);
+  for (auto& e : t) { // every operand is a "3D" array with nz = 1 here
+    e.f1_is2d = e.f2_is2d = e.div_is2d = 0;
+  }
+  check(bout_b200_elementwise(&g, BOUT_B200_RGN_ALL, static_cast<int>(t.size()), t.data(), out.wptr(), nullptr));
+}
+} // namespace
+
+Field2D::Field2D(Mesh* m) { fieldmesh = m; }
+Field2D::Field2D(BoutReal v, Mesh* m) {
+  fieldmesh = m;
+  *this = v;
+}
+size_t Field2D::size() const {
+  Mesh* m = getMesh();
+  return static_cast<size_t>(m->LocalNx) * m->LocalNy;
+}
+Field2D& Field2D::allocate() {
+  makeUnique(size());
+  return *this;
+}
+double* Field2D::wptr() {
+  makeUnique(size());
+  return data->ptr;
+}
+Field2D& Field2D::operator=(BoutReal v) {
+  data = bout::b200::acquire(size());
+  Field2D& self = *this;
+  ew2(self, {term(v)});
+  return *this;
+}
+void Field2D::setHost(const std::vector<double>& v) {
+  if (v.size() != size()) {
+    throw BoutException("Field2D::setHost: expected {} values, got {}", size(), v.size());
+  }
+  data = bout::b200::acquire(size());
+  check(bout_b200_memcpy_h2d(data->ptr, v.data(), v.size() * sizeof(double), nullptr));
+}
+std::vector<double> Field2D::getHost() const {
+  requireData(*this, "Field2D::getHost");
+  std::vector<double> v(size());
+  check(bout_b200_memcpy_d2h(v.data(), data->ptr, v.size() * sizeof(double), nullptr));
+  return v;
+}
+Field2D& Field2D::operator+=(const Field2D& r) { return *this = *this + r; }
+Field2D& Field2D::operator-=(const Field2D& r) { return *this = *this - r; }
+Field2D& Field2D::operator*=(BoutReal s) { return *this = *this * s; }
+
+#define B200_F2_BINOP(OP, ...)                         \
+  Field2D operator OP(const Field2D& a, const Field2D& b) { \
+    requireData(a, "Field2D operator");                \
+    requireData(b, "Field2D operator");                \
+    Field2D r(a.getMesh());                            \
+    r.allocate();                                      \
+    ew2(r, {__VA_ARGS__});                             \
+    return r;                                          \
+  }
+B200_F2_BINOP(+, term(1.0, &a), term(1.0, &b))
+B200_F2_BINOP(-, term(1.0, &a), term(-1.0, &b))
+B200_F2_BINOP(*, term(1.0, &a, false, &b))
+B200_F2_BINOP(/, term(1.0, &a, false, nullptr, false, &b))
+Field2D operator*(const Field2D& a, BoutReal b) {
+  Field2D r(a.getMesh());
+  r.allocate();
+  ew2(r, {term(b, &a)});
+  return r;
+}
+Field2D operator*(BoutReal a, const Field2D& b) { return b * a; }
+Field2D operator/(const Field2D& a, BoutReal b) { return a * (1.0 / b); }
+Field2D operator/(BoutReal a, const Field2D& b) {
+  Field2D r(b.getMesh());
+  r.allocate();
+  ew2(r, {term(a, nullptr, false, nullptr, false, &b)});
+  return r;
+}
+Field2D operator+(const Field2D& a, BoutReal b) {
+  Field2D r(a.getMesh());
+  r.allocate();
+  ew2(r, {term(1.0, &a), term(b)});
+  return r;
+}
+Field2D operator-(const Field2D& a) { return a * (-1.0); }
+
+Field3D::Field3D(Mesh* m) { fieldmesh = m; }
+Field3D::Field3D(const Field3D& f) : FieldBase(f) { // shares the data block (field3d.cxx:74-84)
+  deriv = nullptr;
+}
+Field3D::Field3D(BoutReal v, Mesh* m) {
+  fieldmesh = m;
+  *this = v;
+}
+Field3D::~Field3D() { delete deriv; }
+size_t Field3D::size() const {
+  Mesh* m = getMesh();
+  return static_cast<size_t>(m->LocalNx) * m->LocalNy * m->LocalNz;
+}
+Field3D& Field3D::allocate() {
+  makeUnique(size());
+  return *this;
+}
+double* Field3D::wptr() {
+  makeUnique(size());
+  return data->ptr;
+}
+Field3D& Field3D::operator=(const Field3D& f) {
+  if (this != &f) {
+    data = f.data; // share; copy-on-write happens in wptr()
+    if (fieldmesh == nullptr) {
+      fieldmesh = f.fieldmesh;
+    }
+  }
+  return *this;
+}
+Field3D& Field3D::operator=(Field3D&& f) noexcept {
+  data = std::move(f.data);
+  if (fieldmesh == nullptr) {
+    fieldmesh = f.fieldmesh;
+  }
+  return *this;
+}
+Field3D& Field3D::operator=(const Field2D& f) {
+  requireData(f, "Field3D = Field2D");
+  data = bout::b200::acquire(size());
+  ew3(*this, {term(1.0, &f, true)});
+  return *this;
+}
+Field3D& Field3D::operator=(BoutReal v) {
+  data = bout::b200::acquire(size());
+  ew3(*this, {term(v)});
+  return *this;
+}
+void Field3D::setHost(const double* v) {
+  data = bout::b200::acquire(size());
+  check(bout_b200_memcpy_h2d(data->ptr, v, size() * sizeof(double), nullptr));
+}
+void Field3D::setHost(const std::vector<double>& v) {
+  if (v.size() != size()) {
+    throw BoutException("Field3D::setHost: expected {} values, got {}", size(), v.size());
+  }
+  setHost(v.data());
+}
+void Field3D::getHost(double* out) const {
+  requireData(*this, "Field3D::getHost");
+  check(bout_b200_memcpy_d2h(out, data->ptr, size() * sizeof(double), nullptr));
+}
+std::vector<double> Field3D::getHost() const {
+  std::vector<double> v(size());
+  getHost(v.data());
+  return v;
+}
+Field3D* Field3D::timeDeriv() {
+  if (deriv == nullptr) {
+    deriv = new Field3D(getMesh());
+  }
+  return deriv;
+}
+
+#define B200_F3_BINOP(OP, TB, ...)                          \
+  Field3D operator OP(const Field3D& a, const TB& b) {      \
+    requireData(a, "Field3D operator");                     \
+    requireData(b, "Field3D operator");                     \
+    Field3D r(a.getMesh());                                 \
+    r.allocate();                                           \
+    ew3(r, {__VA_ARGS__});                                  \
+    return r;                                               \
+  }
+B200_F3_BINOP(+, Field3D, term(1.0, &a), term(1.0, &b))
+B200_F3_BINOP(-, Field3D, term(1.0, &a), term(-1.0, &b))
+B200_F3_BINOP(*, Field3D, term(1.0, &a, false, &b))
+B200_F3_BINOP(/, Field3D, term(1.0, &a, false, nullptr, false, &b))
+B200_F3_BINOP(+, Field2D, term(1.0, &a), term(1.0, &b, true))
+B200_F3_BINOP(-, Field2D, term(1.0, &a), term(-1.0, &b, true))
+B200_F3_BINOP(*, Field2D, term(1.0, &a, false, &b, true))
+B200_F3_BINOP(/, Field2D, term(1.0, &a, false, nullptr, false, &b, true))
+Field3D operator+(const Field2D& a, const Field3D& b) { return b + a; }
+Field3D operator*(const Field2D& a, const Field3D& b) { return b * a; }
+Field3D operator-(const Field2D& a, const Field3D& b) {
+  Field3D r(b.getMesh());
+  r.allocate();
+  ew3(r, {term(1.0, &a, true), term(-1.0, &b)});
+  return r;
+}
+Field3D operator/(const Field2D& a, const Field3D& b) {
+  Field3D r(b.getMesh());
+  r.allocate();
+  ew3(r, {term(1.0, &a, true, nullptr, false, &b)});
+  return r;
+}
+#define B200_F3_SCALAR(NAME, ...)            \
+  {                                          \
+    requireData(f, "Field3D operator");      \
+    Field3D r(f.getMesh());                  \
+    r.allocate();                            \
+    ew3(r, {__VA_ARGS__});                   \
+    return r;                                \
+  }
+Field3D operator+(const Field3D& f, BoutReal s) B200_F3_SCALAR(add, term(1.0, &f), term(s))
+Field3D operator-(const Field3D& f, BoutReal s) B200_F3_SCALAR(sub, term(1.0, &f), term(-s))
+Field3D operator*(const Field3D& f, BoutReal s) B200_F3_SCALAR(mul, term(s, &f))
+Field3D operator/(const Field3D& f, BoutReal s) B200_F3_SCALAR(div, term(1.0 / s, &f)) // generated_fieldops.cxx:543-558
+Field3D operator+(BoutReal s, const Field3D& f) B200_F3_SCALAR(add, term(s), term(1.0, &f))
+Field3D operator-(BoutReal s, const Field3D& f) B200_F3_SCALAR(sub, term(s), term(-1.0, &f))
+Field3D operator*(BoutReal s, const Field3D& f) B200_F3_SCALAR(mul, term(s, &f))
+Field3D operator/(BoutReal s, const Field3D& f) B200_F3_SCALAR(div, term(s, nullptr, false, nullptr, false, &f))
+Field3D operator-(const Field3D& f) B200_F3_SCALAR(neg, term(-1.0, &f)) // field3d.cxx:581
+
+Field3D& Field3D::operator+=(const Field3D& r) { return *this = *this + r; }
+Field3D& Field3D::operator+=(const Field2D& r) { return *this = *this + r; }
+Field3D& Field3D::operator+=(BoutReal r) { return *this = *this + r; }
+Field3D& Field3D::operator-=(const Field3D& r) { return *this = *this - r; }
+Field3D& Field3D::operator-=(const Field2D& r) { return *this = *this - r; }
+Field3D& Field3D::operator-=(BoutReal r) { return *this = *this - r; }
+Field3D& Field3D::operator*=(const Field3D& r) { return *this = *this * r; }
+Field3D& Field3D::operator*=(const Field2D& r) { return *this = *this * r; }
+Field3D& Field3D::operator*=(BoutReal r) { return *this = *this * r; }
+Field3D& Field3D::operator/=(const Field3D& r) { return *this = *this / r; }
+Field3D& Field3D::operator/=(const Field2D& r) { return *this = *this / r; }
+Field3D& Field3D::operator/=(BoutReal r) { return *this = *this / r; }
+
+namespace {
+Field3D unaryOp(int op, const Field3D& f, double arg = 0.0) {
+  requireData(f, "Field3D function");
+  Field3D r(f.getMesh());
+  const auto g = gridOf(f);
+  check(bout_b200_unary(&g, op, f.dptr(), arg, r.wptr(), nullptr));
+  return r;
+}
+} // namespace
+Field3D sqrt(const Field3D& f) { return unaryOp(1, f); }
+Field3D abs(const Field3D& f) { return unaryOp(2, f); }
+Field3D exp(const Field3D& f) { return unaryOp(3, f); }
+Field3D log(const Field3D& f) { return unaryOp(4, f); }
+Field3D sin(const Field3D& f) { return unaryOp(5, f); }
+Field3D cos(const Field3D& f) { return unaryOp(6, f); }
+Field3D tanh(const Field3D& f) { return unaryOp(7, f); }
+Field3D SQ(const Field3D& f) { return unaryOp(8, f); }
+Field3D pow(const Field3D& f, BoutReal e) { return unaryOp(9, f, e); }
+
+Field2D DC(const Field3D& f) {
+  requireData(f, "DC");
+  Field2D r(f.getMesh());
+  const auto g = gridOf(f);
+  check(bout_b200_dc(&g, f.dptr(), r.wptr(), nullptr));
+  return r;
+}
+Field3D filter(const Field3D& f, int N0) {
+  Field3D r(f.getMesh());
+  const auto g = gridOf(f);
+  check(bout_b200_zfilter(&g, BOUT_B200_RGN_ALL, N0, f.dptr(), r.wptr(), nullptr));
+  return r;
+}
+Field3D lowPass(const Field3D& f, int zmax, bool keep_zonal) {
+  Field3D r(f.getMesh());
+  const auto g = gridOf(f);
+  check(bout_b200_zlowpass(&g, BOUT_B200_RGN_ALL, zmax, keep_zonal ? 1 : 0, f.dptr(), r.wptr(), nullptr));
+  return r;
+}
+
+// averageY (src/physics/smoothing.cxx:238-323): mean over ystart..yend broadcast to all y.  The y-mean of
+// a Field2D is a reduction over a few hundred numbers per x; it runs through the DC kernel by viewing
+// the Field2D [nx][ny] as a field with one "y" row per x and z = the interior y range.
+Field2D averageY(const Field2D& f) {
+  requireData(f, "averageY");
+  Mesh* m = f.getMesh();
+  const int nyint = m->yend - m->ystart + 1;
+  Field2D r(m);
+  if (nyint == m->LocalNy) { // no y guards: every row is one contiguous run
+    bout_b200_grid g{m->LocalNx, 1, m->LocalNy, 0, m->LocalNx - 1, 0, 0};
+    Field2D mean(m); // holds nx values in its first nx slots
+    check(bout_b200_dc(&g, f.dptr(), mean.wptr(), nullptr));
+    // broadcast: r[x][y] = mean[x] -> elementwise with f1 a "Field2D" on the (nx, 1, ny) grid
+    bout_b200_ewterm t{};
+    t.coef = 1.0;
+    t.f1 = mean.dptr();
+    t.f1_is2d = 1;
+    check(bout_b200_elementwise(&g, BOUT_B200_RGN_ALL, 1, &t, r.wptr(), nullptr));
+    return r;
+  }
+  // with y guards: gather the interior rows through the host-free path of a strided view is not
+  // available in the C-ABI; this is a set-up/diagnostic-sized array, reduce it on the host
+  std::vector<double> h = f.getHost(), out(h.size());
+  for (int x = 0; x < m->LocalNx; ++x) {
+    double s = 0.0;
+    for (int y = m->ystart; y <= m->yend; ++y) {
+      s += h[static_cast<size_t>(x) * m->LocalNy + y];
+    }
+    s /= nyint;
+    for (int y = 0; y < m->LocalNy; ++y) {
+      out[static_cast<size_t>(x) * m->LocalNy + y] = s;
+    }
+  }
+  r.setHost(out);
+  return r;
+}
+
+// ---- boundaries ---------------------------------------------------------------------------------------
+namespace {
+void applyOne(Field3D& f, const std::string& cond_in, int side) {
+  std::string cond = cond_in;
+  cond.erase(std::remove_if(cond.begin(), cond.end(), [](unsigned char c) { return std::isspace(c); }), cond.end());
+  std::transform(cond.begin(), cond.end(), cond.begin(), [](unsigned char c) { return std::tolower(c); });
+  if (cond.empty() || cond == "none") {
+    return;
+  }
+  double value = 0.0;
+  const auto paren = cond.find('(');
+  if (paren != std::string::npos) {
+    const std::string arg = cond.substr(paren + 1, cond.rfind(')') - paren - 1);
+    cond = cond.substr(0, paren);
+    if (!arg.empty()) {
+      bout::b200::EvalContext c;
+      value = bout::b200::Expr(arg, c).eval();
+    }
+  }
+  int kind;
+  if (cond == "dirichlet" || cond == "dirichlet_o2") {
+    kind = 0;
+  } else if (cond == "neumann" || cond == "neumann_o2") {
+    kind = 1;
+  } else {
+    throw BoutException("Boundary condition '{}' is not available in the B200 host layer", cond);
+  }
+  Mesh* m = f.getMesh();
+  Coordinates* c = m->getCoordinates();
+  const auto g = m->grid();
+  const double* spacing = side < 2 ? c->dx.dptr() : c->dy.dptr();
+  check(bout_b200_boundary(&g, kind, side, value, spacing, -1, -1, f.wptr(), nullptr));
+}
+bool hasBoundary(Mesh* m, int side) {
+  if (side < 2) {
+    return !m->periodicX;
+  }
+  return !m->periodicY;
+}
+} // namespace
+
+void Field3D::setBoundary(const std::string& var) {
+  static const char* keys[4] = {"bndry_xin", "bndry_xout", "bndry_ydown", "bndry_yup"};
+  bndry_conditions.assign(4, "");
+  Options& vo = Options::root()[var];
+  Options& all = Options::root()["all"];
+  for (int s = 0; s < 4; ++s) {
+    for (Options* o : {&vo, &all}) { // boundary_factory.cxx: [var] bndry_<region>, [var] bndry_all, then [all]
+      if (o->isSet(keys[s])) {
+        bndry_conditions[s] = (*o)[keys[s]].text();
+        break;
+      }
+      if (o->isSet("bndry_all")) {
+        bndry_conditions[s] = (*o)["bndry_all"].text();
+        break;
+      }
+    }
+  }
+}
+void Field3D::applyBoundary(bool) {
+  Mesh* m = getMesh();
+  for (int s = 0; s < 4 && s < static_cast<int>(bndry_conditions.size()); ++s) {
+    if (hasBoundary(m, s)) {
+      applyOne(*this, bndry_conditions[s], s);
+    }
+  }
+}
+void Field3D::applyBoundary(const std::string& condition) {
+  Mesh* m = getMesh();
+  for (int s = 0; s < 4; ++s) {
+    if (hasBoundary(m, s)) {
+      applyOne(*this, condition, s);
+    }
+  }
+}
+void Field3D::applyTDerivBoundary() {
+  Mesh* m = getMesh();
+  const auto g = m->grid();
+  for (int s = 0; s < 4; ++s) {
+    if (hasBoundary(m, s) && deriv != nullptr && deriv->isAllocated()) {
+      check(bout_b200_boundary(&g, 2, s, 0.0, nullptr, -1, -1, deriv->wptr(), nullptr));
+    }
+  }
+}
+
+Field3D averageY(const Field3D& f) {
+  // smoothing.cxx:272-323 on one rank: y-mean per (x,z) broadcast to every y
+  requireData(f, "averageY");
+  Mesh* m = f.getMesh();
+  if (m->LocalNy == 1) {
+    return f;
+  }
+  throw BoutException("averageY(Field3D) with ny > 1 is not available in the B200 host layer yet");
+}
+
+// ======================================================================================================
+// Mesh and Coordinates
+// ======================================================================================================
+Mesh* Mesh::create(Options* opts) { return new Mesh(opts != nullptr ? *opts : Options::root()["mesh"]); }
+
+Mesh::Mesh(Options& opts) : options(&opts) {
+  Options& root = Options::root();
+  const int nx = opts["nx"].withDefault(1), ny = opts["ny"].withDefault(1);
+  int nz = 1;
+  if (opts.isSet("nz")) {
+    nz = opts["nz"].as<int>();
+  } else if (root.isSet("mz")) {
+    nz = root["mz"].as<int>();
+  }
+  MXG = root.isSet("mxg") ? root["mxg"].as<int>() : opts["mxg"].withDefault(2);
+  MYG = root.isSet("myg") ? root["myg"].as<int>() : opts["myg"].withDefault(2);
+  if (ny == 1 && !root.isSet("myg") && !opts.isSet("myg")) {
+    MYG = 0; // boutmesh.cxx:509-517
+  }
+  periodicX = root.isSet("periodicx") ? root["periodicx"].as<bool>() : opts["periodicx"].withDefault(false);
+  const int ixseps1 = opts["ixseps1"].withDefault(nx), ixseps2 = opts["ixseps2"].withDefault(nx);
+  periodicY = (ixseps1 >= nx - MXG) && (ixseps2 >= nx - MXG); // closed field lines everywhere
+  if (!periodicY && ixseps1 > MXG) {
+    throw BoutException("B200 host layer: meshes with a separatrix (ixseps1 = {}) are not supported", ixseps1);
+  }
+  GlobalNx = nx;
+  GlobalNy = ny + 2 * MYG;
+  GlobalNz = nz;
+  LocalNx = nx;
+  LocalNy = ny + 2 * MYG;
+  LocalNz = nz;
+  xstart = MXG;
+  xend = nx - MXG - 1;
+  ystart = MYG;
+  yend = LocalNy - MYG - 1;
+  zend = nz - 1;
+  if (xend < xstart) {
+    throw BoutException("Mesh: nx = {} leaves no interior points with MXG = {}", nx, MXG);
+  }
+  // derivative method defaults (deriv_store.hxx:441-478) overridden by [mesh:ddx] first/second/upwind/flux
+  for (const char* dir : {"ddx", "ddy", "ddz"}) {
+    methods[std::string(dir) + ":first"] = "C2";
+    methods[std::string(dir) + ":second"] = "C2";
+    methods[std::string(dir) + ":fourth"] = "C2";
+    methods[std::string(dir) + ":upwind"] = "U1";
+    methods[std::string(dir) + ":flux"] = "U1";
+    for (const char* kind : {"first", "second", "fourth", "upwind", "flux"}) {
+      for (Options* sec : {&opts["diff"], &opts[dir]}) { // mesh:diff then mesh:ddx (deriv_store.hxx:308-389)
+        if (sec->isSet(kind)) {
+          std::string v = (*sec)[kind].text();
+          std::transform(v.begin(), v.end(), v.begin(), [](unsigned char c) { return std::toupper(c); });
+          methods[std::string(dir) + ":" + kind] = v;
+        }
+      }
+    }
+  }
+  bout::globals::mesh = this;
+  coords = std::make_unique<Coordinates>(this);
+}
+
+Mesh::~Mesh() {
+  if (bout::globals::mesh == this) {
+    bout::globals::mesh = nullptr;
+  }
+}
+
+std::string Mesh::method(char dir, const std::string& kind) const {
+  const std::string key = std::string("dd") + dir + ":" + kind;
+  const auto it = methods.find(key);
+  return it == methods.end() ? std::string("C2") : it->second;
+}
+
+// boutmesh.cxx:3159-3215 on one rank (symmetricGlobalX = symmetricGlobalY = true, no separatrix)
+BoutReal Mesh::GlobalX(int jx) const {
+  const int MX = GlobalNx - 2 * MXG;
+  return (0.5 + jx - (GlobalNx - MX) * 0.5) / static_cast<BoutReal>(MX);
+}
+BoutReal Mesh::GlobalY(int jy) const {
+  const int ny = GlobalNy - 2 * MYG;
+  return (jy - MYG + 0.5) / static_cast<BoutReal>(ny);
+}
+BoutReal Mesh::GlobalZ(int jz) const { return static_cast<BoutReal>(jz) / static_cast<BoutReal>(GlobalNz); }
+
+void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
+  const auto g = grid();
+  std::vector<double*> ptrs;
+  for (Field3D* f : fields) {
+    requireData(*f, "Mesh::communicate");
+    ptrs.push_back(f->wptr());
+  }
+  for (size_t i = 0; i < ptrs.size(); i += 8) { // the kernel takes up to 8 fields per launch
+    const int n = static_cast<int>(std::min<size_t>(8, ptrs.size() - i));
+    check(bout_b200_halo_self(&g, n, ptrs.data() + i, periodicX ? 1 : 0, (periodicY && MYG > 0) ? 1 : 0, nullptr));
+  }
+}
+
+namespace {
+Field2D field2DFromOption(Mesh* m, Options& sec, const std::string& key, double def) {
+  std::vector<double> v(static_cast<size_t>(m->LocalNx) * m->LocalNy, def);
+  if (sec.isSet(key)) {
+    Options& o = sec[key];
+    for (int x = 0; x < m->LocalNx; ++x) {
+      for (int y = 0; y < m->LocalNy; ++y) {
+        v[static_cast<size_t>(x) * m->LocalNy + y] =
+            bout::b200::evalOption(o, m->GlobalX(x), TWOPI * m->GlobalY(y), 0.0);
+      }
+    }
+  }
+  Field2D f(m);
+  f.setHost(v);
+  return f;
+}
+} // namespace
+
+Coordinates::Coordinates(Mesh* mesh) : localmesh(mesh) {
+  Options& o = *mesh->options;
+  dx = field2DFromOption(mesh, o, "dx", 1.0);
+  dy = field2DFromOption(mesh, o, "dy", 1.0);
+  // dz: mesh:dz, else from zperiod / ZMIN, ZMAX (coordinates.cxx:  zlength = (ZMAX - ZMIN) * 2 pi)
+  if (o.isSet("dz")) {
+    dz = field2DFromOption(mesh, o, "dz", 1.0);
+  } else {
+    Options& root = Options::root();
+    double zmin = root.isSet("zmin") ? root["zmin"].as<double>() : 0.0;
+    double zmax = root.isSet("zmax") ? root["zmax"].as<double>() : 1.0;
+    if (root.isSet("zperiod")) {
+      zmin = 0.0;
+      zmax = 1.0 / root["zperiod"].as<double>();
+    }
+    dz = Field2D((zmax - zmin) * TWOPI / mesh->LocalNz, mesh);
+  }
+  g11 = field2DFromOption(mesh, o, "g11", 1.0);
+  g22 = field2DFromOption(mesh, o, "g22", 1.0);
+  g33 = field2DFromOption(mesh, o, "g33", 1.0);
+  g12 = field2DFromOption(mesh, o, "g12", 0.0);
+  g13 = field2DFromOption(mesh, o, "g13", 0.0);
+  g23 = field2DFromOption(mesh, o, "g23", 0.0);
+  G1 = field2DFromOption(mesh, o, "G1", 0.0);
+  G2 = field2DFromOption(mesh, o, "G2", 0.0);
+  G3 = field2DFromOption(mesh, o, "G3", 0.0);
+  Bxy = field2DFromOption(mesh, o, "Bxy", 1.0);
+  geometry();
+}
+
+int Coordinates::geometry() {
+  // Covariant metric = inverse of the contravariant one, J = 1/sqrt(det g^ij) (coordinates.cxx:1210-1330),
+  // d1_dx = -DDX(dx)/dx^2 in index space (coordinates.cxx:1088-1099).  G1..G3 (Christoffel contractions)
+  // are taken from the options (0 by default): the configs in scope use metrics for which they vanish
+  // or supply them in the grid.
+  Mesh* m = localmesh;
+  const int nx = m->LocalNx, ny = m->LocalNy;
+  auto a11 = g11.getHost(), a22 = g22.getHost(), a33 = g33.getHost(), a12 = g12.getHost(), a13 = g13.getHost(),
+       a23 = g23.getHost(), hdx = dx.getHost(), hdy = dy.getHost(), hdz = dz.getHost();
+  const size_t n = a11.size();
+  std::vector<double> b11(n), b22(n), b33(n), b12(n), b13(n), b23(n), hJ(n), d1x(n, 0.0), d1y(n, 0.0);
+  for (size_t i = 0; i < n; ++i) {
+    const double det = a11[i] * (a22[i] * a33[i] - a23[i] * a23[i]) - a12[i] * (a12[i] * a33[i] - a23[i] * a13[i])
+                       + a13[i] * (a12[i] * a23[i] - a22[i] * a13[i]);
+    if (!(det > 0.0)) {
+      throw BoutException("Coordinates: metric is not positive definite at index {}", i);
+    }
+    b11[i] = (a22[i] * a33[i] - a23[i] * a23[i]) / det;
+    b22[i] = (a11[i] * a33[i] - a13[i] * a13[i]) / det;
+    b33[i] = (a11[i] * a22[i] - a12[i] * a12[i]) / det;
+    b12[i] = (a13[i] * a23[i] - a12[i] * a33[i]) / det;
+    b13[i] = (a12[i] * a23[i] - a13[i] * a22[i]) / det;
+    b23[i] = (a12[i] * a13[i] - a11[i] * a23[i]) / det;
+    hJ[i] = 1.0 / std::sqrt(det);
+  }
+  bool uniform = true;
+  for (int x = 1; x < nx - 1; ++x) {
+    for (int y = 0; y < ny; ++y) {
+      const size_t i = static_cast<size_t>(x) * ny + y;
+      const double d2x = 0.5 * (hdx[i + ny] - hdx[i - ny]);
+      d1x[i] = -d2x / (hdx[i] * hdx[i]);
+      uniform = uniform && d1x[i] == 0.0;
+    }
+  }
+  for (int y = 0; y < ny; ++y) { // extrapolate into the first/last x (interpolateAndExtrapolate)
+    if (nx > 2) {
+      d1x[y] = d1x[static_cast<size_t>(ny) + y];
+      d1x[static_cast<size_t>(nx - 1) * ny + y] = d1x[static_cast<size_t>(nx - 2) * ny + y];
+    }
+  }
+  g_11.setHost(b11);
+  g_22.setHost(b22);
+  g_33.setHost(b33);
+  g_12.setHost(b12);
+  g_13.setHost(b13);
+  g_23.setHost(b23);
+  if (localmesh->options->isSet("J")) {
+    J = field2DFromOption(m, *localmesh->options, "J", 1.0);
+  } else {
+    J.setHost(hJ);
+  }
+  d1_dx.setHost(d1x);
+  d1_dy.setHost(d1y);
+  non_uniform = localmesh->options->isSet("non_uniform") ? (*localmesh->options)["non_uniform"].as<bool>() : true;
+  zlength_ = hdz[0] * m->LocalNz;
+  cache.clear();
+  (void)uniform;
+  return 0;
+}
+
+const Field2D& Coordinates::recip(const std::string& which) {
+  auto it = cache.find(which);
+  if (it != cache.end()) {
+    return it->second;
+  }
+  Field2D r(localmesh);
+  if (which == "1/dx") { r = 1.0 / dx; }
+  else if (which == "1/dy") { r = 1.0 / dy; }
+  else if (which == "1/dz") { r = 1.0 / dz; }
+  else if (which == "1/dx2") { r = 1.0 / (dx * dx); }
+  else if (which == "1/dy2") { r = 1.0 / (dy * dy); }
+  else if (which == "1/dz2") { r = 1.0 / (dz * dz); }
+  else if (which == "d1_dx/dx") { r = d1_dx / dx; }
+  else if (which == "d1_dy/dy") { r = d1_dy / dy; }
+  else { throw BoutException("Coordinates::recip: unknown '{}'", which); }
+  return cache.emplace(which, r).first->second;
+}
+
+// ======================================================================================================
+// Derivatives, brackets, Delp2
+// ======================================================================================================
+namespace {
+int regionId(const std::string& r) {
+  if (r == "RGN_NOBNDRY") { return BOUT_B200_RGN_NOBNDRY; }
+  if (r == "RGN_ALL") { return BOUT_B200_RGN_ALL; }
+  if (r == "RGN_NOX") { return BOUT_B200_RGN_NOX; }
+  if (r == "RGN_NOY") { return BOUT_B200_RGN_NOY; }
+  throw BoutException("Unknown region '{}'", r);
+}
+int stencilOp(const std::string& family, const std::string& method) {
+  static const std::map<std::string, int> table = {
+      {"DDX_C2", BOUT_B200_DDX_C2}, {"DDX_C4", BOUT_B200_DDX_C4}, {"DDX_W2", BOUT_B200_DDX_W2},
+      {"DDX_S2", BOUT_B200_DDX_S2}, {"DDX_W3", BOUT_B200_DDX_W3}, {"D2DX2_C2", BOUT_B200_D2DX2_C2},
+      {"D2DX2_C4", BOUT_B200_D2DX2_C4}, {"D4DX4_C2", BOUT_B200_D4DX4_C2}, {"VDDX_C2", BOUT_B200_VDDX_C2},
+      {"VDDX_C4", BOUT_B200_VDDX_C4}, {"VDDX_U1", BOUT_B200_VDDX_U1}, {"VDDX_U2", BOUT_B200_VDDX_U2},
+      {"VDDX_U3", BOUT_B200_VDDX_U3}, {"VDDX_W3", BOUT_B200_VDDX_W3}, {"FDDX_U1", BOUT_B200_FDDX_U1},
+      {"FDDX_U2", BOUT_B200_FDDX_U2}, {"FDDX_C2", BOUT_B200_FDDX_C2}, {"FDDX_C4", BOUT_B200_FDDX_C4}};
+  const auto it = table.find(family + "_" + method);
+  if (it == table.end()) {
+    throw BoutException("Derivative method '{}' is not registered for {}", method, family);
+  }
+  return it->second;
+}
+std::string pick(Mesh* m, char dir, const std::string& kind, const std::string& method) {
+  std::string s = method;
+  std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return std::toupper(c); });
+  return (s == "DEFAULT" || s.empty()) ? m->method(dir, kind) : s;
+}
+// one fused kernel: out = scale1 * op(f) [+ scale2 * op2(f)]
+Field3D stencil(const Field3D& f, const Field3D* v, int op, int dir, const std::string& region, const Field2D* s1,
+                int op2 = -1, const Field2D* s2 = nullptr) {
+  requireData(f, "derivative");
+  Field3D r(f.getMesh());
+  const auto g = gridOf(f);
+  check(bout_b200_stencil(&g, op, dir, regionId(region), v ? v->dptr() : nullptr, f.dptr(), nullptr, nullptr,
+                          s1 ? s1->dptr() : nullptr, op2, s2 ? s2->dptr() : nullptr, r.wptr(), nullptr));
+  return r;
+}
+} // namespace
+
+Field3D DDX(const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, nullptr, stencilOp("DDX", pick(m, 'x', "first", method)), BOUT_B200_X, region,
+                 &m->getCoordinates()->recip("1/dx"));
+}
+Field3D DDY(const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, nullptr, stencilOp("DDX", pick(m, 'y', "first", method)), BOUT_B200_Y, region,
+                 &m->getCoordinates()->recip("1/dy"));
+}
+Field3D DDZ(const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  const std::string meth = pick(m, 'z', "first", method);
+  if (meth == "FFT") {
+    Field3D r(m);
+    const auto g = gridOf(f);
+    check(bout_b200_ddz_fft(&g, 1, 0.0, regionId(region), f.dptr(), m->getCoordinates()->recip("1/dz").dptr(), r.wptr(), nullptr));
+    return r;
+  }
+  return stencil(f, nullptr, stencilOp("DDX", meth), BOUT_B200_Z, region, &m->getCoordinates()->recip("1/dz"));
+}
+Field3D D2DX2(const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  Coordinates* c = m->getCoordinates();
+  const int op = stencilOp("D2DX2", pick(m, 'x', "second", method));
+  if (c->non_uniform) { // derivs.cxx:149-166: + d1_dx * DDX(f) / dx in the same pass
+    return stencil(f, nullptr, op, BOUT_B200_X, region, &c->recip("1/dx2"),
+                   stencilOp("DDX", m->method('x', "first")), &c->recip("d1_dx/dx"));
+  }
+  return stencil(f, nullptr, op, BOUT_B200_X, region, &c->recip("1/dx2"));
+}
+Field3D D2DY2(const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  Coordinates* c = m->getCoordinates();
+  const int op = stencilOp("D2DX2", pick(m, 'y', "second", method));
+  if (c->non_uniform) {
+    return stencil(f, nullptr, op, BOUT_B200_Y, region, &c->recip("1/dy2"),
+                   stencilOp("DDX", m->method('y', "first")), &c->recip("d1_dy/dy"));
+  }
+  return stencil(f, nullptr, op, BOUT_B200_Y, region, &c->recip("1/dy2"));
+}
+Field3D D2DZ2(const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  const std::string meth = pick(m, 'z', "second", method);
+  if (meth == "FFT") {
+    Field3D r(m);
+    const auto g = gridOf(f);
+    check(bout_b200_ddz_fft(&g, 2, 0.0, regionId(region), f.dptr(), m->getCoordinates()->recip("1/dz2").dptr(), r.wptr(), nullptr));
+    return r;
+  }
+  return stencil(f, nullptr, stencilOp("D2DX2", meth), BOUT_B200_Z, region, &m->getCoordinates()->recip("1/dz2"));
+}
+Field3D VDDX(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, &v, stencilOp("VDDX", pick(m, 'x', "upwind", method)), BOUT_B200_X, region,
+                 &m->getCoordinates()->recip("1/dx"));
+}
+Field3D VDDZ(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, &v, stencilOp("VDDX", pick(m, 'z', "upwind", method)), BOUT_B200_Z, region,
+                 &m->getCoordinates()->recip("1/dz"));
+}
+
+Field3D bracket(const Field3D& f, const Field3D& gfield, BRACKET_METHOD method, CELL_LOC, Solver*) {
+  if (method != BRACKET_ARAKAWA) {
+    throw BoutException("bracket: only BRACKET_ARAKAWA is implemented on the B200 path (method {})", static_cast<int>(method));
+  }
+  requireData(f, "bracket");
+  requireData(gfield, "bracket");
+  Mesh* m = f.getMesh();
+  Coordinates* c = m->getCoordinates();
+  Field3D r(m);
+  const auto g = m->grid();
+  check(bout_b200_bracket_arakawa(&g, f.dptr(), gfield.dptr(), c->dx.dptr(), c->dz.dptr(), r.wptr(), nullptr));
+  return r;
+}
+Field3D bracket(const Field3D& f, const Field2D& gfield, BRACKET_METHOD method, CELL_LOC, Solver*) {
+  if (method != BRACKET_ARAKAWA) {
+    throw BoutException("bracket: only BRACKET_ARAKAWA is implemented on the B200 path");
+  }
+  Mesh* m = f.getMesh();
+  Coordinates* c = m->getCoordinates();
+  Field3D r(m);
+  const auto g = m->grid();
+  check(bout_b200_bracket_arakawa_3d2d(&g, f.dptr(), gfield.dptr(), c->dx.dptr(), c->dz.dptr(), r.wptr(), nullptr));
+  return r;
+}
+Field3D bracket(const Field2D& f, const Field3D& g, BRACKET_METHOD method, CELL_LOC loc, Solver* s) {
+  return -bracket(g, f, method, loc, s); // difops.cxx:796-799
+}
+
+Field3D Delp2(const Field3D& f, CELL_LOC, bool useFFT) {
+  requireData(f, "Delp2");
+  Mesh* m = f.getMesh();
+  Coordinates* c = m->getCoordinates();
+  Field3D r(m);
+  const auto g = m->grid();
+  if (useFFT) { // coordinates.cxx:1662-1699 with the default Laplacian instance's settings
+    bout_b200_laplace L{};
+    Laplacian::defaultInstance()->fill(L);
+    check(bout_b200_delp2_fft(&g, &L, f.dptr(), r.wptr(), nullptr));
+  } else {
+    check(bout_b200_delp2_fd(&g, f.dptr(), c->dx.dptr(), c->dz.dptr(), c->g11.dptr(), c->g33.dptr(), c->g13.dptr(),
+                             c->G1.dptr(), c->G3.dptr(), c->non_uniform ? c->d1_dx.dptr() : nullptr, r.wptr(), nullptr));
+  }
+  return r;
+}
+
+// ======================================================================================================
+// Laplacian
+// ======================================================================================================
+std::unique_ptr<Laplacian> Laplacian::instance;
+
+Laplacian::Laplacian(Options* options, CELL_LOC, Mesh* mesh)
+    : localmesh(mesh != nullptr ? mesh : bout::globals::mesh), coords(localmesh->getCoordinates()) {
+  Options& o = options != nullptr ? *options : Options::root()["laplace"];
+  std::string type = o["type"].withDefault(std::string("cyclic"));
+  if (type != "cyclic") {
+    throw BoutException("Laplacian type '{}' is not available: the B200 path implements 'cyclic'", type);
+  }
+  // invert_laplace.cxx:68-138
+  const BoutReal filter = o["filter"].withDefault(0.0);
+  const int ncz = localmesh->LocalNz;
+  maxmode = o["maxmode"].withDefault(static_cast<int>(std::lround((1.0 - filter) * static_cast<BoutReal>(ncz) / 2.0)));
+  maxmode = std::max(0, std::min(maxmode, ncz / 2));
+  nonuniform = o["nonuniform"].withDefault(coords->non_uniform);
+  all_terms = o["all_terms"].withDefault(true);
+  global_flags = o["global_flags"].withDefault(0);
+  inner_boundary_flags = o["inner_boundary_flags"].withDefault(0);
+  outer_boundary_flags = o["outer_boundary_flags"].withDefault(0);
+  include_yguards = o["include_yguards"].withDefault(false);
+}
+
+Laplacian::~Laplacian() {
+  if (workspace != nullptr) {
+    bout_b200_free(workspace);
+  }
+}
+
+std::unique_ptr<Laplacian> Laplacian::create(Options* opts, CELL_LOC loc, Mesh* mesh, Solver*) {
+  return std::make_unique<Laplacian>(opts, loc, mesh);
+}
+Laplacian* Laplacian::defaultInstance() {
+  if (!instance) {
+    instance = create();
+  }
+  return instance.get();
+}
+void Laplacian::cleanup() { instance.reset(); }
+
+void Laplacian::fill(bout_b200_laplace& L) const {
+  L = bout_b200_laplace{};
+  L.dx = coords->dx.dptr();
+  L.g11 = coords->g11.dptr();
+  L.g33 = coords->g33.dptr();
+  L.g13 = coords->g13.dptr();
+  L.G1 = coords->G1.dptr();
+  L.G3 = coords->G3.dptr();
+  L.g_11 = coords->g_11.dptr();
+  L.g_22 = coords->g_22.dptr();
+  L.A = hasA ? A.dptr() : nullptr;
+  L.C1 = hasC ? C1.dptr() : nullptr;
+  L.C2 = hasC ? C2.dptr() : nullptr;
+  L.D = hasD ? D.dptr() : nullptr;
+  L.zlength = coords->zlength();
+  L.all_terms = all_terms ? 1 : 0;
+  L.nonuniform = nonuniform ? 1 : 0;
+  L.global_flags = global_flags;
+  L.inner_boundary_flags = inner_boundary_flags;
+  L.outer_boundary_flags = outer_boundary_flags;
+  L.maxmode = maxmode;
+  L.periodic_x = localmesh->periodicX ? 1 : 0;
+  L.first_x = 1;
+  L.last_x = 1;
+  // cyclic_laplace.cxx:216-232: y guards are only solved where a y boundary exists
+  L.include_yguards_lower = (include_yguards && !localmesh->periodicY) ? 1 : 0;
+  L.include_yguards_upper = L.include_yguards_lower;
+}
+
+Field3D Laplacian::solve(const Field3D& b, const Field3D& x0) {
+  requireData(b, "Laplacian::solve");
+  const auto g = localmesh->grid();
+  bout_b200_laplace L{};
+  fill(L);
+  const size_t need = bout_b200_laplace_cyclic_workspace(&g, &L);
+  if (need > workspace_bytes) {
+    if (workspace != nullptr) {
+      check(bout_b200_free(workspace));
+    }
+    check(bout_b200_malloc(&workspace, need));
+    workspace_bytes = need;
+  }
+  Field3D x(localmesh);
+  // cells the solve does not write keep the initial guess (cyclic_laplace.cxx:196 "x = x0" semantics
+  // for boundary/guard cells are emptyFrom in the reference; zero-initialised pool blocks here)
+  check(bout_b200_laplace_cyclic_solve(&g, &L, b.dptr(), x0.isAllocated() ? x0.dptr() : nullptr, x.wptr(), workspace,
+                                       workspace_bytes, nullptr));
+  return x;
+}
+
+// ======================================================================================================
+// Solver: rk4 and rk3ssp on device-resident fields
+// ======================================================================================================
+Solver::Solver(Options* opts) : options(opts != nullptr ? opts : &Options::root()["solver"]) {
+  Options& root = Options::root();
+  nout = (*options)["nout"].withDefault(root.isSet("nout") ? root["nout"].as<int>() : 1);
+  output_timestep = (*options)["output_step"].withDefault(root.isSet("timestep") ? root["timestep"].as<double>() : 1.0);
+  timestep = (*options)["timestep"].withDefault(output_timestep); // rk4.cxx:15-18
+}
+
+namespace {
+void initialProfile(const std::string& name, Field3D& var) { // initialprofiles.cxx:33-48 (+ VAROPTION fallback to [all])
+  Mesh* m = var.getMesh();
+  Options& vo = Options::root()[name];
+  Options& all = Options::root()["all"];
+  Options* fo = vo.isSet("function") ? &vo["function"] : (all.isSet("function") ? &all["function"] : nullptr);
+  double scale = 1.0;
+  if (vo.isSet("scale")) {
+    scale = vo["scale"].as<double>();
+  } else if (all.isSet("scale")) {
+    scale = all["scale"].as<double>();
+  }
+  std::vector<double> h(var.size(), 0.0);
+  if (fo != nullptr && scale != 0.0) {
+    for (int x = 0; x < m->LocalNx; ++x) {
+      for (int y = 0; y < m->LocalNy; ++y) {
+        for (int z = 0; z < m->LocalNz; ++z) {
+          h[(static_cast<size_t>(x) * m->LocalNy + y) * m->LocalNz + z] =
+              scale * bout::b200::evalOption(*fo, m->GlobalX(x), TWOPI * m->GlobalY(y), TWOPI * m->GlobalZ(z));
+        }
+      }
+    }
+  }
+  var.setHost(h);
+}
+} // namespace
+
+void Solver::add(Field3D& v, const std::string& name) {
+  if (initialised) {
+    throw BoutException("Error: Cannot add to solver after initialisation\n");
+  }
+  v.name = name;
+  initialProfile(name, v);
+  v.setBoundary(name);
+  v.applyBoundary(true);
+  Field3D* d = v.timeDeriv();
+  *d = 0.0;
+  f3d.push_back({&v, d, name});
+}
+
+void Solver::setModel(PhysicsModel* m) {
+  model = m;
+  m->initialise(this);
+}
+
+void PhysicsModel::initialise(Solver* s) {
+  solver = s;
+  mesh = bout::globals::mesh;
+  if (init(false) != 0) {
+    throw BoutException("Couldn't initialise physics model");
+  }
+}
+
+void Solver::pre_rhs() {
+  for (auto& f : f3d) {
+    f.var->applyBoundary();
+  }
+}
+void Solver::post_rhs() {
+  for (auto& f : f3d) {
+    if (!f.F_var->isAllocated()) {
+      throw BoutException("Time derivative for variable '{}' not set", f.name);
+    }
+  }
+}
+
+int Solver::run_rhs(BoutReal t) {
+  int status;
+  if (model->splitOperator()) { // solver.cxx:1391-1413 without the flat-array copies
+    pre_rhs();
+    status = model->runConvective(t);
+    post_rhs();
+    std::vector<Field3D> conv;
+    for (auto& f : f3d) {
+      conv.push_back(*f.F_var);
+    }
+    pre_rhs();
+    status = model->runDiffusive(t);
+    post_rhs();
+    for (size_t i = 0; i < f3d.size(); ++i) {
+      *f3d[i].F_var = conv[i] + *f3d[i].F_var;
+    }
+  } else {
+    pre_rhs();
+    status = model->runRHS(t);
+    post_rhs();
+  }
+  ++rhs_calls;
+  return status;
+}
+
+int Solver::solve(int nout_in, BoutReal output_step) {
+  if (nout_in >= 0) {
+    nout = nout_in;
+    output_timestep = output_step;
+  }
+  if (initialised) {
+    throw BoutException("ERROR: Solver is already initialised\n");
+  }
+  initialised = true;
+  if (run_rhs(simtime) != 0) { // solver.cxx:569
+    throw BoutException("Physics RHS call failed\n");
+  }
+  for (int s = 0; s < nout; ++s) { // rk4.cxx:75-165 (non-adaptive)
+    const BoutReal target = simtime + output_timestep;
+    bool running = true;
+    do {
+      BoutReal dt = timestep;
+      running = true;
+      if ((simtime + dt) >= target) {
+        dt = target - simtime;
+        running = false;
+      }
+      take_step(simtime, dt);
+      simtime += dt;
+    } while (running);
+    run_rhs(simtime); // rk4.cxx:157: extra variables at the output time
+  }
+  check(bout_b200_stream_sync(nullptr));
+  return 0;
+}
+
+namespace {
+void rkStage(Mesh* m, int mode, double dt, double c, const Field3D& start, const Field3D* k1, const Field3D* k2,
+             const Field3D* k3, const Field3D* k4, Field3D& out) {
+  const auto g = m->grid();
+  check(bout_b200_rk_stage(&g, BOUT_B200_RGN_NOBNDRY, mode, dt, c, start.dptr(), k1 ? k1->dptr() : nullptr,
+                           k2 ? k2->dptr() : nullptr, k3 ? k3->dptr() : nullptr, k4 ? k4->dptr() : nullptr, out.wptr(),
+                           nullptr));
+}
+
+class RK4Solver : public Solver {
+public:
+  using Solver::Solver;
+  void take_step(BoutReal t, BoutReal dt) override { // rk4.cxx:172-210 field by field
+    const size_t nv = f3d.size();
+    std::vector<Field3D> start(nv), k1(nv), k2(nv), k3(nv), k4(nv);
+    Mesh* m = f3d[0].var->getMesh();
+    for (size_t i = 0; i < nv; ++i) {
+      start[i] = *f3d[i].var;
+      start[i].allocate(); // a private copy: the variable is overwritten in place below
+    }
+    auto stage = [&](std::vector<Field3D>& k, BoutReal tt) {
+      run_rhs(tt);
+      for (size_t i = 0; i < nv; ++i) {
+        k[i] = *f3d[i].F_var;
+      }
+    };
+    auto advance = [&](const std::vector<Field3D>& k, BoutReal c) { // var(interior) = start + c dt k; guards kept
+      for (size_t i = 0; i < nv; ++i) {
+        rkStage(m, 0, dt, c, start[i], &k[i], nullptr, nullptr, nullptr, *f3d[i].var);
+      }
+    };
+    stage(k1, t);
+    advance(k1, 0.5);
+    stage(k2, t + 0.5 * dt);
+    advance(k2, 0.5);
+    stage(k3, t + 0.5 * dt);
+    advance(k3, 1.0);
+    stage(k4, t + dt);
+    for (size_t i = 0; i < nv; ++i) {
+      rkStage(m, 1, dt, 1.0, start[i], &k1[i], &k2[i], &k3[i], &k4[i], *f3d[i].var);
+    }
+  }
+};
+
+class RK3SSP : public Solver {
+public:
+  using Solver::Solver;
+  void take_step(BoutReal t, BoutReal dt) override { // rk3-ssp.cxx:100-129
+    const size_t nv = f3d.size();
+    std::vector<Field3D> start(nv), u(nv);
+    Mesh* m = f3d[0].var->getMesh();
+    for (size_t i = 0; i < nv; ++i) {
+      start[i] = *f3d[i].var;
+      start[i].allocate();
+    }
+    run_rhs(t);
+    for (size_t i = 0; i < nv; ++i) { // u1 = start + dt L
+      rkStage(m, 0, dt, 1.0, start[i], f3d[i].F_var, nullptr, nullptr, nullptr, *f3d[i].var);
+    }
+    run_rhs(t + dt);
+    for (size_t i = 0; i < nv; ++i) { // u2 = 3/4 start + 1/4 u1 + 1/4 dt L
+      u[i] = *f3d[i].var;
+      u[i].allocate();
+      rkStage(m, 2, dt, 1.0, start[i], &u[i], f3d[i].F_var, nullptr, nullptr, *f3d[i].var);
+    }
+    run_rhs(t + 0.5 * dt);
+    for (size_t i = 0; i < nv; ++i) { // result = 1/3 start + 2/3 (u2 + dt L)
+      u[i] = *f3d[i].var;
+      u[i].allocate();
+      rkStage(m, 3, dt, 1.0, start[i], &u[i], f3d[i].F_var, nullptr, nullptr, *f3d[i].var);
+    }
+  }
+};
+} // namespace
+
+std::unique_ptr<Solver> Solver::create(Options* opts) {
+  Options& o = opts != nullptr ? *opts : Options::root()["solver"];
+  const std::string type = o["type"].withDefault(std::string("rk4"));
+  if (type == "rk4") {
+    return std::make_unique<RK4Solver>(&o);
+  }
+  if (type == "rk3ssp") {
+    return std::make_unique<RK3SSP>(&o);
+  }
+  throw BoutException("Solver type '{}' is not available: the B200 path implements rk4 and rk3ssp", type);
+}

@@ -77,6 +77,17 @@ int bout_b200_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches counter). */
 unsigned long long bout_b200_launch_count(void);
 
+/* ---- device memory (Array<T> backing store, reference include/bout/array.hxx:61-139) ----------------
+ * For host layers that do not link the CUDA runtime: cudaMalloc (zero-filled) / cudaFree / copies.
+ * The host-side pool (bout-dev_b200/host) calls malloc only on a pool miss, so a steady-state time
+ * step allocates nothing.  h2d / d2h copies synchronise `stream` before returning. */
+int bout_b200_malloc(void** ptr, size_t bytes);
+int bout_b200_free(void* ptr);
+int bout_b200_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int bout_b200_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int bout_b200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int bout_b200_stream_sync(void* stream);
+
 /* ---- (1) index_derivs DerivativeStore stencils ------------------------------------------------
  * out[region] = scale1[x,y] * op(stencil of f along dir) (+ scale2[x,y] * op2(stencil))
  * Replaces DerivativeType::standard / upwindOrFlux (include/bout/index_derivs.hxx:84-116) over
