@@ -44,7 +44,17 @@ struct RowFFT {
   cd* A;         // smem buffer, N + 1 complex (holds the packed real row on entry)
   cd* B;         // smem buffer, N + 1 complex
   const cd* tw;  // global table exp(-2 pi i k / nz), k = 0..nz-1
+  bool wsync = false; // the row is owned by exactly one warp: synchronise with __syncwarp only
 };
+
+// Row-level barrier: rows owned by a single warp progress independently of the CTA's other rows.
+__device__ __forceinline__ void rowSync(const RowFFT& r) {
+  if (r.wsync) {
+    __syncwarp();
+  } else {
+    __syncthreads();
+  }
+}
 
 __host__ __device__ inline int fftBufElems(int nz) { return nz / 2 + 2; } // cd elements per buffer
 
@@ -80,7 +90,7 @@ __device__ __forceinline__ cd* cfftStockham(const RowFFT& r, cd* in, cd* out) {
       out[j0 + 2 * Ns] = csub(t0, t2);
       out[j0 + 3 * Ns] = csub(t1, t3);
     }
-    __syncthreads();
+    rowSync(r);
     cd* t = in;
     in = out;
     out = t;
@@ -100,7 +110,7 @@ __device__ __forceinline__ cd* cfftStockham(const RowFFT& r, cd* in, cd* out) {
       out[j0] = cadd(v0, v1);
       out[j0 + Ns] = csub(v0, v1);
     }
-    __syncthreads();
+    rowSync(r);
     cd* t = in;
     in = out;
     out = t;
@@ -127,7 +137,7 @@ __device__ __forceinline__ cd* rfftForward(const RowFFT& r) {
       const cd wk = (k == N) ? cd{-1.0, 0.0} : ldtw(r.tw, k);
       X[k] = cscale(cadd(e, cmul(wk, o)), inv);
     }
-    __syncthreads();
+    rowSync(r);
     return X;
   }
   // direct DFT
@@ -142,7 +152,7 @@ __device__ __forceinline__ cd* rfftForward(const RowFFT& r) {
     }
     r.B[k] = {re * inv, im * inv};
   }
-  __syncthreads();
+  rowSync(r);
   return r.B;
 }
 
@@ -165,7 +175,7 @@ __device__ __forceinline__ double* rfftBackward(const RowFFT& r, cd* X) {
       const cd d = cmul(wk, csub(xk, xc));
       other[k] = cadd(cadd(xk, xc), cd{-d.im, d.re}); // + i * wk * (xk - xc)
     }
-    __syncthreads();
+    rowSync(r);
     cd* z = cfftStockham<true>(r, other, X);
     return reinterpret_cast<double*>(z);
   }
@@ -181,7 +191,7 @@ __device__ __forceinline__ double* rfftBackward(const RowFFT& r, cd* X) {
     }
     out[j] = acc;
   }
-  __syncthreads();
+  rowSync(r);
   return out;
 }
 
@@ -194,12 +204,12 @@ struct RowGeom {
   bool pow2;
   size_t smemBytes;
 };
-inline RowGeom rowGeometry(int nz, int threads) {
+inline RowGeom rowGeometry(int nz, int threads, bool warp_rows = false) {
   RowGeom g;
   g.pow2 = nz >= 8 && (nz & (nz - 1)) == 0;
   int want = g.pow2 ? nz / 8 : 32; // N/4 butterflies per radix-4 stage
   int tpr = 32;
-  while (tpr < want && tpr < threads) {
+  while (!warp_rows && tpr < want && tpr < threads) {
     tpr *= 2;
   }
   g.tpr = tpr;

@@ -17,6 +17,8 @@
 //     the same pass, so no separate axpy kernels run (reference RK4: rk4.cxx:172-210).
 #include "bracket.cuh"
 
+#include <cstdlib>
+
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------------
@@ -216,6 +218,235 @@ __global__ void __launch_bounds__(128) k_hw3d_rhs(const Hw3dParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-pipelined variant of k_hw3d_rhs (the default on sm_100a).
+//
+// A CTA owns one y row and a chunk of x planes; thread t owns the z-pair (2t, 2t+1).  The three
+// stencil fields' rows (n, vort, phi at this y) of plane x+1, x+2, ... are brought into a ring of
+// NSLOT shared-memory slots by the TMA unit (cp.async.bulk, one 1-D bulk copy per field row, completion
+// on an mbarrier per slot), issued by one elected thread up to NSLOT-3 planes ahead of the plane
+// being computed.  Memory-level parallelism therefore comes from the copy engine's queue instead
+// of from registers or resident warps: the register-marching kernel above holds 9 x 4 neighbour
+// values per thread across iterations (158 registers, 12 warps/SM, 44 % of the HBM roofline).
+// Stencil neighbours are read from shared memory; the operands that are used exactly once per
+// point (y neighbours of n and phi, the RK epilogue's start / accumulator values) are ordinary
+// coalesced 16-byte global loads.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smemAddr(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smemAddr(dst)),
+               "l"(src), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned parity) {
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "B200_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra B200_DONE;\n"
+               "bra B200_WAIT;\n"
+               "B200_DONE:\n"
+               "}" ::"r"(smemAddr(bar)),
+               "r"(parity)
+               : "memory");
+}
+
+__device__ __forceinline__ Row4 ldsRow4(const double* row, int z, int nz) {
+  Row4 r;
+  const double2 c = *reinterpret_cast<const double2*>(row + z);
+  r.v[0] = row[z == 0 ? nz - 1 : z - 1];
+  r.v[1] = c.x;
+  r.v[2] = c.y;
+  r.v[3] = row[z + 2 == nz ? 0 : z + 2];
+  return r;
+}
+
+constexpr int HW3D_NS = 4; // stencil ring: planes x-1, x, x+1 resident + one in flight
+constexpr int HW3D_NA = 2; // once-used operand ring: plane x resident + plane x+1 in flight
+constexpr int HW3D_AUX = 8; // rows per aux slot: phi(y+1), phi(y-1), n(y+1), n(y-1), start n, start vort, acc n, acc vort
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_tma(const Hw3dParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nz = p.nz;
+  double* tile = reinterpret_cast<double*>(smem_raw);               // [NS][3 fields][nz]
+  double* aux = tile + static_cast<size_t>(HW3D_NS) * 3 * nz;        // [NA][AUX rows][nz]
+  __shared__ __align__(8) unsigned long long full[HW3D_NS];
+  __shared__ __align__(8) unsigned long long afull[HW3D_NA];
+  const int tid = threadIdx.x;
+  const int z = 2 * tid;
+  const int y = p.ys + blockIdx.x;
+  const int x0 = p.xs + blockIdx.y * p.chunk;
+  const int x1 = min(x0 + p.chunk - 1, p.xe);
+  const int nplanes = x1 - x0 + 3; // stencil planes x0-1 .. x1+1
+  const int ncentre = x1 - x0 + 1;
+  const long long plane = static_cast<long long>(p.ny) * nz;
+  const long long rowoff = static_cast<long long>(y) * nz;
+  const unsigned rowbytes = static_cast<unsigned>(nz) * 8u;
+  const int n2 = p.nx * p.ny;
+  const bool ep = p.ep.enabled != 0;
+  const bool has_acc0 = ep && p.ep.acc_in[0] != nullptr && p.ep.acc_out[0] != nullptr;
+  const bool has_acc1 = ep && p.ep.acc_in[1] != nullptr && p.ep.acc_out[1] != nullptr;
+  const unsigned aux_rows = (p.with_par ? 4u : 0u) + (ep ? 2u : 0u) + (has_acc0 ? 1u : 0u) + (has_acc1 ? 1u : 0u);
+
+  auto issue = [&](int j) { // stencil plane j (x = x0 - 1 + j) into slot j % NS
+    const int slot = j % HW3D_NS;
+    const long long off = static_cast<long long>(x0 - 1 + j) * plane + rowoff;
+    unsigned long long* bar = &full[slot];
+    mbarExpectTx(bar, 3u * rowbytes);
+    double* dst = tile + static_cast<size_t>(slot) * 3 * nz;
+    bulkLoad(dst, p.n + off, rowbytes, bar);
+    bulkLoad(dst + nz, p.vort + off, rowbytes, bar);
+    bulkLoad(dst + 2 * nz, p.phi + off, rowbytes, bar);
+  };
+  auto issueAux = [&](int ja) { // once-used rows of centre plane x = x0 + ja into slot ja % NA
+    if (aux_rows == 0) {
+      return;
+    }
+    const int slot = ja % HW3D_NA;
+    const long long off = static_cast<long long>(x0 + ja) * plane + rowoff;
+    unsigned long long* bar = &afull[slot];
+    mbarExpectTx(bar, aux_rows * rowbytes);
+    double* dst = aux + static_cast<size_t>(slot) * HW3D_AUX * nz;
+    if (p.with_par) {
+      bulkLoad(dst, p.phi + off + nz, rowbytes, bar);
+      bulkLoad(dst + nz, p.phi + off - nz, rowbytes, bar);
+      bulkLoad(dst + 2 * nz, p.n + off + nz, rowbytes, bar);
+      bulkLoad(dst + 3 * nz, p.n + off - nz, rowbytes, bar);
+    }
+    if (ep) {
+      bulkLoad(dst + 4 * nz, p.ep.start[0] + off, rowbytes, bar);
+      bulkLoad(dst + 5 * nz, p.ep.start[1] + off, rowbytes, bar);
+    }
+    if (has_acc0) {
+      bulkLoad(dst + 6 * nz, p.ep.acc_in[0] + off, rowbytes, bar);
+    }
+    if (has_acc1) {
+      bulkLoad(dst + 7 * nz, p.ep.acc_in[1] + off, rowbytes, bar);
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < HW3D_NS; ++s) {
+      mbarInit(&full[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < HW3D_NA; ++s) {
+      mbarInit(&afull[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int j = 0; j < min(HW3D_NS, nplanes); ++j) {
+      issue(j);
+    }
+    for (int ja = 0; ja < min(HW3D_NA, ncentre); ++ja) {
+      issueAux(ja);
+    }
+  }
+  mbarWait(&full[0], 0);
+  mbarWait(&full[1], 0);
+  for (int x = x0; x <= x1; ++x) {
+    const int j = x - x0 + 1; // centre stencil plane index
+    const int ja = x - x0;    // aux plane index
+    mbarWait(&full[(j + 1) % HW3D_NS], static_cast<unsigned>(((j + 1) / HW3D_NS) & 1));
+    if (aux_rows != 0) {
+      mbarWait(&afull[ja % HW3D_NA], static_cast<unsigned>((ja / HW3D_NA) & 1));
+    }
+    {
+      const long long idx = x * plane + rowoff + z;
+      const int i2 = x * p.ny + y;
+      const double sf = __ldg(p.coef + C_SF * n2 + i2), rdz2 = __ldg(p.coef + C_RDZ2 * n2 + i2);
+      const double cx = __ldg(p.coef + C_DPX * n2 + i2), cz = __ldg(p.coef + C_DPZ * n2 + i2);
+      const double cxx = __ldg(p.coef + C_DPXX * n2 + i2), czz = __ldg(p.coef + C_DPZZ * n2 + i2);
+      const double cxz = __ldg(p.coef + C_DPXZ * n2 + i2);
+      const double cup = __ldg(p.coef + C_UP * n2 + i2), cdn = __ldg(p.coef + C_DN * n2 + i2);
+      const double* sm = tile + static_cast<size_t>((j - 1) % HW3D_NS) * 3 * nz;
+      const double* s0 = tile + static_cast<size_t>(j % HW3D_NS) * 3 * nz;
+      const double* sp = tile + static_cast<size_t>((j + 1) % HW3D_NS) * 3 * nz;
+      const double* ax = aux + static_cast<size_t>(ja % HW3D_NA) * HW3D_AUX * nz;
+      const Row4 Pm = ldsRow4(sm + 2 * nz, z, nz), P0 = ldsRow4(s0 + 2 * nz, z, nz), Pp = ldsRow4(sp + 2 * nz, z, nz);
+      double dn_[2], dv_[2];
+      {
+        const Row4 Nm = ldsRow4(sm, z, nz), N0 = ldsRow4(s0, z, nz), Np = ldsRow4(sp, z, nz);
+        double2 pup = {0, 0}, pdn = {0, 0}, nup = {0, 0}, ndn = {0, 0};
+        if (p.with_par) {
+          pup = *reinterpret_cast<const double2*>(ax + z);
+          pdn = *reinterpret_cast<const double2*>(ax + nz + z);
+          nup = *reinterpret_cast<const double2*>(ax + 2 * nz + z);
+          ndn = *reinterpret_cast<const double2*>(ax + 3 * nz + z);
+        }
+        const double upv[2] = {pup.x - nup.x, pup.y - nup.y};
+        const double dnv[2] = {pdn.x - ndn.x, pdn.y - ndn.y};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          double div_current = 0.0;
+          if (p.with_par) {
+            const double c = P0.v[i + 1] - N0.v[i + 1];
+            div_current = p.alpha * (cup * (upv[i] - c) - cdn * (c - dnv[i]));
+          }
+          const double br_n = arakawaCore(Pm, P0, Pp, Nm, N0, Np, i) * sf;
+          const double ddz_phi = (P0.v[i + 2] - P0.v[i]) * rdz2;
+          const double d2n = delp2Point(Nm, N0, Np, i, cx, cz, cxx, czz, cxz);
+          dn_[i] = -br_n - div_current - p.kappa * ddz_phi + p.Dn * d2n;
+          dv_[i] = -div_current;
+        }
+      }
+      {
+        const Row4 Vm = ldsRow4(sm + nz, z, nz), V0 = ldsRow4(s0 + nz, z, nz), Vp = ldsRow4(sp + nz, z, nz);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double br_v = arakawaCore(Pm, P0, Pp, Vm, V0, Vp, i) * sf;
+          const double d2v = delp2Point(Vm, V0, Vp, i, cx, cz, cxx, czz, cxz);
+          dv_[i] = -br_v + dv_[i] + p.Dvort * d2v;
+        }
+      }
+      // outputs: ddt and/or the RK stage update (reads start / acc from the aux slot)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double* d = e == 0 ? dn_ : dv_;
+        double* ddt_out = e == 0 ? p.ddt_n : p.ddt_vort;
+        if (ddt_out != nullptr) {
+          *reinterpret_cast<double2*>(ddt_out + idx) = make_double2(d[0], d[1]);
+        }
+        if (ep) {
+          const double2 st = *reinterpret_cast<const double2*>(ax + (4 + e) * nz + z);
+          if (p.ep.state_out[e] != nullptr) {
+            *reinterpret_cast<double2*>(p.ep.state_out[e] + idx) = make_double2(st.x + p.ep.a * d[0], st.y + p.ep.a * d[1]);
+          }
+          if (p.ep.acc_out[e] != nullptr) {
+            double2 base = st;
+            if (p.ep.acc_in[e] != nullptr) {
+              base = *reinterpret_cast<const double2*>(ax + (6 + e) * nz + z);
+            }
+            *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx) = make_double2(base.x + p.ep.b * d[0], base.y + p.ep.b * d[1]);
+          }
+        }
+      }
+    }
+    __syncthreads(); // every thread is done with stencil plane j-1 and aux plane ja: refill their slots
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (j - 1 + HW3D_NS < nplanes) {
+        issue(j - 1 + HW3D_NS);
+      }
+      if (ja + HW3D_NA < ncentre) {
+        issueAux(ja + HW3D_NA);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // hasegawa-wakatani convective part (examples/hasegawa-wakatani/hw.cxx:94-118), Arakawa bracket:
 //   ddt(n)    = -[phi,n]    + alpha*(nzphi - nzn) - kappa*DDZ(phi)
 //   ddt(vort) = -[phi,vort] + alpha*(nzphi - nzn)
@@ -394,6 +625,34 @@ extern "C" int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metri
   const int nzv = vec2 ? g->nz / 2 : g->nz;
   const long long north = static_cast<long long>(p.ye - p.ys + 1) * nzv;
   const int len = p.xe - p.xs + 1;
+  static const bool no_tma = getenv("BOUT_B200_NO_TMA") != nullptr;
+  const int half = g->nz / 2;
+  if (vec2 && !no_tma && (half == 64 || half == 128 || half == 256 || half == 512)) {
+    // TMA-pipelined kernel: one CTA per (y, x-chunk); chunk sized for >= ~3 waves of resident CTAs
+    const int nyint = p.ye - p.ys + 1;
+    int chunk = 64;
+    while (chunk > 8 && static_cast<long long>(nyint) * ((len + chunk - 1) / chunk) < 148LL * 2 * 3) {
+      chunk /= 2;
+    }
+    p.chunk = chunk;
+    const size_t smem = static_cast<size_t>(HW3D_NS * 3 + HW3D_NA * HW3D_AUX) * g->nz * sizeof(double);
+    dim3 grid(static_cast<unsigned>(nyint), static_cast<unsigned>((len + chunk - 1) / chunk));
+#define B200_LAUNCH_TMA(T)                                                                               \
+  {                                                                                                      \
+    B200_CUDA_OK(cudaFuncSetAttribute(k_hw3d_rhs_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      static_cast<int>(smem)));                                          \
+    k_hw3d_rhs_tma<T><<<grid, T, smem, s>>>(p);                                                         \
+  }
+    switch (half) {
+    case 64: B200_LAUNCH_TMA(64) break;
+    case 128: B200_LAUNCH_TMA(128) break;
+    case 256: B200_LAUNCH_TMA(256) break;
+    default: B200_LAUNCH_TMA(512) break;
+    }
+#undef B200_LAUNCH_TMA
+    B200_LAUNCH_OK();
+    return 0;
+  }
   p.chunk = pickChunk(north, len);
   dim3 grid(static_cast<unsigned>((north + 127) / 128), static_cast<unsigned>((len + p.chunk - 1) / p.chunk));
   if (vec2) {

@@ -19,7 +19,9 @@ def gpu_metric(capi, m):
                                                               "g13", "G1", "G3", "d1_dx")})
 
 
-@pytest.mark.parametrize("grid", [(20, 8, 32, 2, 2), (9, 7, 7, 2, 1), (70, 6, 16, 2, 2), (14, 1, 16, 2, 0)])
+# nz = 128, 256, 1024 take the TMA-pipelined kernel (k_hw3d_rhs_tma), the others the register-marching one
+@pytest.mark.parametrize("grid", [(20, 8, 32, 2, 2), (9, 7, 7, 2, 1), (70, 6, 16, 2, 2), (14, 1, 16, 2, 0),
+                                  (12, 6, 128, 2, 2), (75, 5, 256, 2, 1), (9, 3, 1024, 2, 1), (10, 1, 128, 2, 0)])
 @pytest.mark.parametrize("trivial", [True, False])
 def test_hw3d_rhs(capi, orc, grid, trivial):
     g = capi.Grid(*grid)
@@ -33,8 +35,8 @@ def test_hw3d_rhs(capi, orc, grid, trivial):
     assert rel_err(dv.cpu().numpy(), want_v, g.interior) < 1e-12
 
 
-def test_hw3d_rhs_with_rk_epilogue(capi, orc):
-    grid = (20, 8, 32, 2, 2)
+@pytest.mark.parametrize("grid", [(20, 8, 32, 2, 2), (70, 5, 128, 2, 2), (11, 4, 512, 2, 1)])
+def test_hw3d_rhs_with_rk_epilogue(capi, orc, grid):
     g = capi.Grid(*grid)
     m = make_metric(orc, g.shape2, g.nz)
     n, vort, phi, sn, sv, an, av = seeded_fields(g.shape3, 7)
