@@ -245,6 +245,15 @@ def run_ours(args):
     clocks = sampler.stop(w0, w2) if rank == 0 else None   # samples over both timed regions
     field_bytes = hn.numel() * 8
 
+    # ---- per-phase breakdown of one RHS (separate short run; CUDA events between phases) -------------
+    model.phase_events = []
+    for _ in range(3):
+        model.rk4_step(DT)
+    torch.cuda.synchronize()
+    phases = model.phase_summary()
+    model.phase_events = None
+    if world > 1:
+        torch.distributed.barrier()
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -275,6 +284,7 @@ def run_ours(args):
                      "rhs_algorithmic_GBps": (56.0 + 64.0) * npts * 4 * args.steps / secs / 1e9,
                      "rhs_bytes_per_point": "56 (solve 16 + fused 40, SURVEY 8d) + 64 RK stage update"},
         "clocks": clocks,
+        "rhs_phase_ms": {k: round(v, 4) for k, v in phases.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(steps=3, warmup=1)

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbout_b200.so")
+LIB_PATH = os.environ.get("BOUT_B200_LIB") or os.path.join(_HERE, "csrc", "libbout_b200.so")  # env: A/B builds
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

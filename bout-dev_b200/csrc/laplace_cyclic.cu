@@ -43,7 +43,7 @@ struct LapParams {
   const double* __restrict__ rhs;
   const double* __restrict__ x0;
   double* __restrict__ out;
-  double* __restrict__ table; // [nx][ny][LAP_NK]
+  double* __restrict__ table; // [ny][nx][LAP_NK] (x contiguous for one y: a system's rows are one run)
   cd* __restrict__ spec;   // [nxs][nys][nmode]  rhs spectrum in, solution spectrum out
   cd* __restrict__ cprime; // [nxs][nys][nmode]
   cd* __restrict__ dprime; // [nxs][nys][nmode]
@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(256) k_lap_table(const LapParams p) {
     return;
   }
   double k[5];
-  tridagCoef5(p.m, i / p.ny, i % p.ny, true, true, k);
-  double* __restrict__ t = p.table + static_cast<long long>(i) * LAP_NK;
+  const int jx = i / p.ny, jy = i % p.ny;
+  tridagCoef5(p.m, jx, jy, true, true, k);
+  double* __restrict__ t = p.table + (static_cast<long long>(jy) * p.nx + jx) * LAP_NK;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     t[j] = k[j];
@@ -144,9 +145,10 @@ __global__ void __launch_bounds__(256) k_lap_table(const LapParams p) {
 }
 
 // Row ix of the system (jy, kz): interior rows from the table, boundary rows (and the doubly
-// periodic kz = 0 pin) through the full tridagMatrix logic.
-__device__ __forceinline__ void lapRow(const LapParams& p, int ix, int jy, int kz, double kwave, cd& a,
-                                       cd& b, cd& c, cd& r) {
+// periodic kz = 0 pin) through the full tridagMatrix logic.  `tab` is the table block of this
+// system's jy, indexed by the row number ix (either staged in shared memory or in global memory).
+__device__ __forceinline__ void lapRow(const LapParams& p, const double* tab, int ix, int jy, int kz,
+                                       double kwave, cd& a, cd& b, cd& c, cd& r) {
   const int ncx = p.bd.xe - p.bd.xs;
   const bool special = p.bd.periodic_x
                            ? (kz == 0 && p.bd.first_x && ix == 0)
@@ -163,27 +165,57 @@ __device__ __forceinline__ void lapRow(const LapParams& p, int ix, int jy, int k
     }
     return;
   }
-  const double2* __restrict__ t =
-      reinterpret_cast<const double2*>(p.table + (static_cast<long long>(p.bd.xs + ix) * p.ny + jy) * LAP_NK);
-  const double2 t01 = __ldg(t), t23 = __ldg(t + 1), t45 = __ldg(t + 2);
+  const double2* t = reinterpret_cast<const double2*>(tab + static_cast<long long>(ix) * LAP_NK);
+  const double2 t01 = t[0], t23 = t[1], t45 = t[2];
   a = {t01.x - t23.y, -kwave * t23.x};
   b = {-2.0 * t01.x - kwave * kwave * t01.y + t45.y, kwave * t45.x};
   c = {t01.x + t23.y, kwave * t23.x};
 }
 
-constexpr int LAP_PF = 4; // rows of right-hand side prefetched ahead of the dependency chain
+// Stages the table rows of the (at most two) jy values a CTA's systems belong to into shared memory
+// and returns this thread's block; falls back to global memory when the CTA spans more than two
+// jy (tiny nmode) -- `smem_ok` is decided by the host for the whole launch.
+__device__ __forceinline__ const double* stageTable(const LapParams& p, double* stab, int n, int t, int nsys,
+                                                    bool smem_ok) {
+  const int tc = min(t, nsys - 1);
+  const int jy = p.ys + tc / p.nmode;
+  const double* gtab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
+  if (!smem_ok) {
+    return gtab;
+  }
+  const int t0 = blockIdx.x * blockDim.x;
+  const int jy0 = p.ys + t0 / p.nmode;
+  const int jy1 = p.ys + min(t0 + static_cast<int>(blockDim.x) - 1, nsys - 1) / p.nmode;
+  const int per = n * LAP_NK; // doubles per jy block
+  for (int q = 0; q <= jy1 - jy0; ++q) {
+    const double2* src = reinterpret_cast<const double2*>(p.table + (static_cast<long long>(jy0 + q) * p.nx + p.bd.xs) * LAP_NK);
+    double2* dst = reinterpret_cast<double2*>(stab + static_cast<size_t>(q) * per);
+    for (int i = threadIdx.x; i < per / 2; i += blockDim.x) {
+      dst[i] = __ldg(src + i);
+    }
+  }
+  __syncthreads();
+  return stab + static_cast<size_t>(jy - jy0) * per;
+}
+
+#ifndef B200_LAP_PF
+#define B200_LAP_PF 8
+#endif
+constexpr int LAP_PF = B200_LAP_PF; // rows prefetched into registers ahead of the dependency chain
 
 // K2 (isolated systems): one thread per (y, kz) system, Thomas along x.
-__global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p) {
+__global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p, const bool smem_ok) {
+  extern __shared__ __align__(16) double stab[];
   const int nys = p.ye - p.ys + 1;
   const int nsys = nys * p.nmode;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const double* tab = stageTable(p, stab, n, t, nsys, smem_ok);
   if (t >= nsys) {
     return;
   }
   const int iyl = t / p.nmode, kz = t % p.nmode;
   const int jy = p.ys + iyl;
-  const int n = p.bd.xe - p.bd.xs + 1;
   const long long xs = static_cast<long long>(nys) * p.nmode;
   const cd* __restrict__ rin = p.spec + t;
   cd* __restrict__ cp = p.cprime + t;
@@ -212,7 +244,7 @@ __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p) {
       const int ix = j0 + k;
       if (ix < n) {
         cd a, b, c, r = cur[k];
-        lapRow(p, ix, jy, kz, kwave, a, b, c, r);
+        lapRow(p, tab, ix, jy, kz, kwave, a, b, c, r);
         const cd denom = csub(b, cmul(a, cprev));
         bad = bad || tiny(denom);
         const cd inv = crecip(denom);
@@ -263,19 +295,23 @@ __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p) {
   }
 }
 
+constexpr int LAP_PFC = 4; // coupled kernels carry two or three rings: keep them in registers
+
 // K2a (coupled systems): downward and upward elimination in one pass -> interface equations
 //   last row :  x_last  + sL x_L + cL x_R = dL      (downward sweep; also stores c', d', s per row)
 //   first row:  x_first + aU x_L + cU x_R = dU      (upward sweep, nothing stored)
-__global__ void __launch_bounds__(128) k_lap_reduce(const LapParams p) {
+__global__ void __launch_bounds__(128) k_lap_reduce(const LapParams p, const bool smem_ok) {
+  extern __shared__ __align__(16) double stab[];
   const int nys = p.ye - p.ys + 1;
   const int nsys = nys * p.nmode;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const double* tab = stageTable(p, stab, n, t, nsys, smem_ok);
   if (t >= nsys) {
     return;
   }
   const int iyl = t / p.nmode, kz = t % p.nmode;
   const int jy = p.ys + iyl;
-  const int n = p.bd.xe - p.bd.xs + 1;
   const long long xs = static_cast<long long>(nys) * p.nmode;
   const cd* __restrict__ rin = p.spec + t;
   cd* __restrict__ cp = p.cprime + t;
@@ -284,34 +320,34 @@ __global__ void __launch_bounds__(128) k_lap_reduce(const LapParams p) {
   const double kwave = kz * 2.0 * M_PI / p.m.zlength;
   bool bad = false;
 
-  cd nd[LAP_PF], nu[LAP_PF];
+  cd nd[LAP_PFC], nu[LAP_PFC];
 #pragma unroll
-  for (int k = 0; k < LAP_PF; ++k) {
+  for (int k = 0; k < LAP_PFC; ++k) {
     nd[k] = ldcd(rin + static_cast<long long>(min(k, n - 1)) * xs);
     nu[k] = ldcd(rin + static_cast<long long>(max(n - 1 - k, 0)) * xs);
   }
   cd cprev = {0, 0}, dprev = {0, 0}, sprev = {-1.0, 0};   // s_{-1} = -1 makes s_0 = a_0 / b_0
   cd aup = {0, 0}, rup = {0, 0}, tup = {-1.0, 0};         // t_n = -1 makes t_{n-1} = c_{n-1} / b_{n-1}
-  for (int j0 = 0; j0 < n; j0 += LAP_PF) {
-    cd cd_[LAP_PF], cu_[LAP_PF];
+  for (int j0 = 0; j0 < n; j0 += LAP_PFC) {
+    cd cd_[LAP_PFC], cu_[LAP_PFC];
 #pragma unroll
-    for (int k = 0; k < LAP_PF; ++k) {
+    for (int k = 0; k < LAP_PFC; ++k) {
       cd_[k] = nd[k];
       cu_[k] = nu[k];
     }
 #pragma unroll
-    for (int k = 0; k < LAP_PF; ++k) {
-      const int j = j0 + LAP_PF + k;
+    for (int k = 0; k < LAP_PFC; ++k) {
+      const int j = j0 + LAP_PFC + k;
       nd[k] = ldcd(rin + static_cast<long long>(min(j, n - 1)) * xs);
       nu[k] = ldcd(rin + static_cast<long long>(max(n - 1 - j, 0)) * xs);
     }
 #pragma unroll
-    for (int k = 0; k < LAP_PF; ++k) {
+    for (int k = 0; k < LAP_PFC; ++k) {
       const int j = j0 + k;
       if (j < n) {
         { // downward, row j
           cd a, b, c, r = cd_[k];
-          lapRow(p, j, jy, kz, kwave, a, b, c, r);
+          lapRow(p, tab, j, jy, kz, kwave, a, b, c, r);
           const cd denom = csub(b, cmul(a, cprev));
           bad = bad || tiny(denom);
           const cd inv = crecip(denom);
@@ -326,7 +362,7 @@ __global__ void __launch_bounds__(128) k_lap_reduce(const LapParams p) {
         { // upward, row n-1-j
           const int i = n - 1 - j;
           cd a, b, c, r = cu_[k];
-          lapRow(p, i, jy, kz, kwave, a, b, c, r);
+          lapRow(p, tab, i, jy, kz, kwave, a, b, c, r);
           const cd denom = csub(b, cmul(c, aup));
           bad = bad || tiny(denom);
           const cd inv = crecip(denom);
@@ -435,31 +471,31 @@ __global__ void __launch_bounds__(128) k_lap_finish(const LapParams p) {
   const cd* __restrict__ spr = p.sprime + t;
   xo[static_cast<long long>(n - 1) * xs] = x;
   double sum = x.re;
-  cd nc[LAP_PF], ndd[LAP_PF], ns[LAP_PF];
+  cd nc[LAP_PFC], ndd[LAP_PFC], ns[LAP_PFC];
 #pragma unroll
-  for (int k = 0; k < LAP_PF; ++k) {
+  for (int k = 0; k < LAP_PFC; ++k) {
     const long long o = static_cast<long long>(max(n - 2 - k, 0)) * xs;
     nc[k] = ldcd(cpr + o);
     ndd[k] = ldcd(dpr + o);
     ns[k] = ldcd(spr + o);
   }
-  for (int j0 = n - 2; j0 >= 0; j0 -= LAP_PF) {
-    cd cc[LAP_PF], dd[LAP_PF], ss[LAP_PF];
+  for (int j0 = n - 2; j0 >= 0; j0 -= LAP_PFC) {
+    cd cc[LAP_PFC], dd[LAP_PFC], ss[LAP_PFC];
 #pragma unroll
-    for (int k = 0; k < LAP_PF; ++k) {
+    for (int k = 0; k < LAP_PFC; ++k) {
       cc[k] = nc[k];
       dd[k] = ndd[k];
       ss[k] = ns[k];
     }
 #pragma unroll
-    for (int k = 0; k < LAP_PF; ++k) {
-      const long long o = static_cast<long long>(max(j0 - LAP_PF - k, 0)) * xs;
+    for (int k = 0; k < LAP_PFC; ++k) {
+      const long long o = static_cast<long long>(max(j0 - LAP_PFC - k, 0)) * xs;
       nc[k] = ldcd(cpr + o);
       ndd[k] = ldcd(dpr + o);
       ns[k] = ldcd(spr + o);
     }
 #pragma unroll
-    for (int k = 0; k < LAP_PF; ++k) {
+    for (int k = 0; k < LAP_PFC; ++k) {
       const int ix = j0 - k;
       if (ix >= 0) {
         x = csub(csub(dd[k], cmul(cc[k], x)), cmul(ss[k], xL));
@@ -568,6 +604,7 @@ struct LapPlan {
   RowGeom geo;
   unsigned rblocks;
   int nsys;
+  size_t tab_smem; // bytes of shared memory for the staged coefficient table (0 = read it from global memory)
 };
 
 int lapSetup(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspace, size_t workspace_bytes,
@@ -665,6 +702,18 @@ int lapSetup(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspac
   const long long nrows = static_cast<long long>(nxs) * nys;
   plan->rblocks = static_cast<unsigned>((nrows + plan->geo.rows - 1) / plan->geo.rows);
   plan->nsys = nys * p.nmode;
+  // a CTA of 128 consecutive systems spans at most two jy when nmode >= 127
+  plan->tab_smem = 0;
+  const size_t tab_bytes = static_cast<size_t>(2) * nxs * LAP_NK * sizeof(double);
+  if (p.nmode >= 127 && tab_bytes <= 160 * 1024) {
+    plan->tab_smem = tab_bytes;
+    if (tab_bytes > 48 * 1024) {
+      B200_CUDA_OK(cudaFuncSetAttribute(k_lap_thomas, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(tab_bytes)));
+      B200_CUDA_OK(cudaFuncSetAttribute(k_lap_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(tab_bytes)));
+    }
+  }
   return 0;
 }
 
@@ -706,10 +755,10 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
   p.out = out;
   const unsigned sblocks = static_cast<unsigned>((plan.nsys + 127) / 128);
   if (!lapCoupled(L)) {
-    k_lap_thomas<<<sblocks, 128, 0, s>>>(p);
+    k_lap_thomas<<<sblocks, 128, plan.tab_smem, s>>>(p, plan.tab_smem != 0);
     B200_LAUNCH_OK();
   } else { // periodic in X on a single rank: the NXPE = 1 case of the coupled algorithm
-    k_lap_reduce<<<sblocks, 128, 0, s>>>(p);
+    k_lap_reduce<<<sblocks, 128, plan.tab_smem, s>>>(p, plan.tab_smem != 0);
     B200_LAUNCH_OK();
     p.iface_all = p.iface;
     k_lap_finish<<<sblocks, 128, 0, s>>>(p);
@@ -736,7 +785,7 @@ extern "C" int bout_b200_laplace_cyclic_reduce(const bout_b200_grid* g, const bo
     return rc;
   }
   plan.p.iface = reinterpret_cast<cd*>(iface_out);
-  k_lap_reduce<<<static_cast<unsigned>((plan.nsys + 127) / 128), 128, 0, s>>>(plan.p);
+  k_lap_reduce<<<static_cast<unsigned>((plan.nsys + 127) / 128), 128, plan.tab_smem, s>>>(plan.p, plan.tab_smem != 0);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -36,6 +36,7 @@ class HW3D:
             self.iface = torch.empty(nif, dtype=torch.float64, device=self.dev)
             self.iface_all = torch.empty(nif * mesh.nxpe, dtype=torch.float64, device=self.dev)
         self.coef = capi.fused_coefs(g, self.cm, capi.fused_coef_workspace(g, self.dev))
+        self.phase_events = None
         self.kernel_events = None  # bench.py: list collecting (start, end) CUDA events of the fused kernel
         z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
         self.n, self.vort, self.phi = z(), z(), z()
@@ -57,20 +58,34 @@ class HW3D:
             capi.boundary(g, "dirichlet", "xout", fn)
             capi.boundary(g, "dirichlet", "xout", fv)
 
+    def _mark(self, name):
+        """bench.py / tools: optional per-phase CUDA events (None = off, no overhead)."""
+        if self.phase_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.phase_events.append((name, e))
+
     def rhs(self, fn=None, fv=None, epilogue=None, ddt=True):
         fn = self.n if fn is None else fn
         fv = self.vort if fv is None else fv
+        self._mark("start")
         self._pre_rhs(fn, fv)                                   # Solver::pre_rhs
+        self._mark("bc")
         if not self.x_split:                                    # phi = phiSolver->solve(vort, phi)
             self.lap.solve(fv, out=self.phi)
+            self._mark("solve")
         else:
             self.lap.reduce(fv, iface=self.iface)
+            self._mark("solve_reduce")
             self.mesh.all_gather_x(self.iface, self.iface_all)
+            self._mark("solve_allgather")
             self.lap.finish(self.iface_all, self.mesh.nxpe, self.mesh.pe_xind, self.phi)
+            self._mark("solve_finish")
         if self.mesh is None:                                   # mesh->communicate(n, vort, phi, ...)
             capi.halo_self(self.g, [fn, fv, self.phi], periodic_x=False, periodic_y=True)
         else:
             self.mesh.communicate([fn, fv, self.phi])
+        self._mark("halo")
         if self.kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -80,6 +95,18 @@ class HW3D:
         if self.kernel_events is not None:
             e1.record()
             self.kernel_events.append((e0, e1))
+        self._mark("fused")
+
+    def phase_summary(self):
+        """Mean milliseconds per phase from the recorded events (after torch.cuda.synchronize())."""
+        tot, cnt = {}, {}
+        ev = self.phase_events
+        for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+            if n1 == "start":
+                continue
+            tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        return {k: tot[k] / cnt[k] for k in tot}
 
     def rk4_step(self, dt):
         """RK4Solver::take_step with the axpys folded into the RHS kernel:
