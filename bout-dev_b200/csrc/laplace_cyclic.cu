@@ -30,6 +30,9 @@
 //     x_R = x_first).  Both are direct solvers for the reference's matrix and agree with it to
 //     round-off (parity tolerance for this path: 1e-10 relative).
 #include "laplace_coefs.cuh"
+#include "fft_fast.cuh"
+
+#include <cstdlib>
 
 namespace b200 {
 
@@ -114,6 +117,57 @@ __global__ void __launch_bounds__(128) k_lap_forward(const LapParams p) {
     for (int k = r.lane; k < p.nmode; k += r.tpr) {
       dst[k] = X[k];
     }
+  }
+}
+
+// K1 / K3, fast path (nz in {128, 256, 512, 1024}): persistent CTAs, register twiddles, swizzled buffers
+template <int N>
+__global__ void __launch_bounds__(128) k_lap_forward_fast(const LapParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TPR = FftShape<N>::TPR, ROWS = 128 / TPR;
+  const int rloc = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+  cd* A = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(rloc) * 2 * (N + 8);
+  cd* B = A + (N + 8);
+  FastTw<N> tw;
+  fastTwInit<N>(tw, p.tw, lane);
+  const int nys = p.ye - p.ys + 1;
+  const int nxs = p.bd.xe - p.bd.xs + 1;
+  const long long nrows = static_cast<long long>(nxs) * nys;
+  for (long long base = static_cast<long long>(blockIdx.x) * ROWS; base < nrows;
+       base += static_cast<long long>(gridDim.x) * ROWS) {
+    const long long rowid = base + rloc;
+    const bool active = rowid < nrows;
+    const long long rid = active ? rowid : nrows - 1;
+    const int ixl = static_cast<int>(rid / nys), iyl = static_cast<int>(rid % nys);
+    const int x = p.bd.xs + ixl, y = p.ys + iyl;
+    // common_transform.cxx:49-57
+    const bool from_x0 = ((x < p.bd.inbndry) && p.in_set) || ((p.nx - x - 1 < p.bd.outbndry) && p.out_set);
+    const double* __restrict__ src = (from_x0 ? p.x0 : p.rhs) + (static_cast<long long>(x) * p.ny + y) * p.nz;
+    rfftForwardFast<N>(src, p.spec + rid * p.nmode, p.nmode, active, A, B, tw, lane);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) k_lap_backward_fast(const LapParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TPR = FftShape<N>::TPR, ROWS = 128 / TPR;
+  const int rloc = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+  cd* A = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(rloc) * 2 * (N + 8);
+  cd* B = A + (N + 8);
+  FastTw<N> tw;
+  fastTwInit<N>(tw, p.tw, lane);
+  const int nys = p.ye - p.ys + 1;
+  const int nxs = p.bd.xe - p.bd.xs + 1;
+  const long long nrows = static_cast<long long>(nxs) * nys;
+  for (long long base = static_cast<long long>(blockIdx.x) * ROWS; base < nrows;
+       base += static_cast<long long>(gridDim.x) * ROWS) {
+    const long long rowid = base + rloc;
+    const bool active = rowid < nrows;
+    const long long rid = active ? rowid : nrows - 1;
+    const int ixl = static_cast<int>(rid / nys), iyl = static_cast<int>(rid % nys);
+    const int x = p.bd.xs + ixl, y = p.ys + iyl;
+    rfftBackwardFast<N>(p.spec + rid * p.nmode, p.out + (static_cast<long long>(x) * p.ny + y) * p.nz, p.nmode,
+                        p.zero_dc != 0, active, A, B, tw, lane);
   }
 }
 
@@ -717,6 +771,43 @@ int lapSetup(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspac
   return 0;
 }
 
+// FFT launches: fast path for nz in {128, 256, 512, 1024} with 16-byte aligned rows
+template <bool FORWARD>
+int launchFft(const LapPlan* plan, cudaStream_t s) {
+  const LapParams& p = plan->p;
+  const int N = p.nz / 2;
+  const bool aligned = FORWARD ? (aligned16(p.rhs) && (p.x0 == nullptr || aligned16(p.x0))) : aligned16(p.out);
+  static const bool no_fast = getenv("BOUT_B200_NO_FAST_FFT") != nullptr;
+  if (!no_fast && p.pow2 && aligned && (N == 64 || N == 128 || N == 256 || N == 512)) {
+    const int rows = 128 / (N / 4);
+    const long long nrows = static_cast<long long>(p.bd.xe - p.bd.xs + 1) * (p.ye - p.ys + 1);
+    const long long want = (nrows + rows - 1) / rows;
+    const unsigned blocks = static_cast<unsigned>(want < 148LL * 12 ? want : 148LL * 12);
+    const size_t smem = static_cast<size_t>(rows) * 2 * (N + 8) * sizeof(cd);
+#define B200_FFT_CASE(NN)                                                                              \
+  case NN:                                                                                             \
+    if (FORWARD) {                                                                                     \
+      k_lap_forward_fast<NN><<<blocks, 128, smem, s>>>(p);                                             \
+    } else {                                                                                           \
+      k_lap_backward_fast<NN><<<blocks, 128, smem, s>>>(p);                                            \
+    }                                                                                                  \
+    break;
+    switch (N) {
+      B200_FFT_CASE(64)
+      B200_FFT_CASE(128)
+      B200_FFT_CASE(256)
+      B200_FFT_CASE(512)
+    }
+#undef B200_FFT_CASE
+  } else if (FORWARD) {
+    k_lap_forward<<<plan->rblocks, 128, plan->geo.smemBytes, s>>>(p);
+  } else {
+    k_lap_backward<<<plan->rblocks, 128, plan->geo.smemBytes, s>>>(p);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 // table + forward FFT (+ status reset)
 int lapForward(const bout_b200_laplace* L, const double* rhs, const double* x0, LapPlan* plan, cudaStream_t s) {
   LapParams& p = plan->p;
@@ -729,9 +820,7 @@ int lapForward(const bout_b200_laplace* L, const double* rhs, const double* x0, 
   const int n2 = p.nx * p.ny;
   k_lap_table<<<(n2 + 255) / 256, 256, 0, s>>>(p);
   B200_LAUNCH_OK();
-  k_lap_forward<<<plan->rblocks, 128, plan->geo.smemBytes, s>>>(p);
-  B200_LAUNCH_OK();
-  return 0;
+  return launchFft<true>(plan, s);
 }
 } // namespace
 
@@ -764,9 +853,7 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
     k_lap_finish<<<sblocks, 128, 0, s>>>(p);
     B200_LAUNCH_OK();
   }
-  k_lap_backward<<<plan.rblocks, 128, plan.geo.smemBytes, s>>>(p);
-  B200_LAUNCH_OK();
-  return 0;
+  return launchFft<false>(&plan, s);
 }
 
 extern "C" int bout_b200_laplace_cyclic_reduce(const bout_b200_grid* g, const bout_b200_laplace* L,
@@ -813,9 +900,7 @@ extern "C" int bout_b200_laplace_cyclic_finish(const bout_b200_grid* g, const bo
   p.pe_xind = pe_xind;
   k_lap_finish<<<static_cast<unsigned>((plan.nsys + 127) / 128), 128, 0, s>>>(p);
   B200_LAUNCH_OK();
-  k_lap_backward<<<plan.rblocks, 128, plan.geo.smemBytes, s>>>(p);
-  B200_LAUNCH_OK();
-  return 0;
+  return launchFft<false>(&plan, s);
 }
 
 // Synchronises the stream and reports a zero pivot seen by the last solve that used `workspace`

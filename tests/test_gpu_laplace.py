@@ -25,7 +25,9 @@ def gpu_laplace(capi, g, m, **kw):
     return capi.Laplace(g, md, float(m.dz[0, 0]) * g.nz, **kw)
 
 
-GRIDS = [(20, 6, 32, 2, 1), (9, 5, 7, 2, 1), (12, 3, 16, 1, 1), (68, 4, 64, 2, 1)]
+# nz = 128 .. 1024 take the fast FFT kernels (fft_fast.cuh) and, with nmode >= 127, the shared-memory table
+GRIDS = [(20, 6, 32, 2, 1), (9, 5, 7, 2, 1), (12, 3, 16, 1, 1), (68, 4, 64, 2, 1), (20, 4, 128, 2, 1),
+         (14, 3, 256, 2, 1), (12, 3, 512, 2, 1), (10, 3, 1024, 2, 1)]
 
 
 @pytest.mark.parametrize("grid", GRIDS)
