@@ -1,6 +1,6 @@
 // C-ABI harness over the C++ host layer, for tests/ and bench.py (ctypes).  It plays the role of
 // BOUTMAIN's main() (reference include/bout/physicsmodel.hxx:429-452: BoutInitialise -> model -> solver
-// -> solve) with raw arrays in and out, and mirrors the calls of oracle/ref_driver.cxx so that the same
+// -> solve) with raw arrays in and out, and mirrors the calls of the reference-build test driver so that the same
 // test code can drive the reference build and this library side by side.
 #include "bout/b200_host.hxx"
 
