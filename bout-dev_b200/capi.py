@@ -177,6 +177,24 @@ class Laplace:
                                                   C.c_size_t(ws.numel()), _stream()))
         return out
 
+    def factor(self, device="cuda"):
+        """Compute the coefficient table and pivot reciprocals once; later solves with unchanged
+        coefficients reuse them.  Call again after changing the contents of any metric/coefficient array."""
+        ws = self.workspace(device)
+        _check(lib.bout_b200_laplace_cyclic_factor(C.byref(self.g.c), C.byref(self.c), C.c_void_p(ws.data_ptr()),
+                                                   C.c_size_t(ws.numel()), _stream()))
+        return self
+
+    def invalidate(self):
+        if self.ws is not None:
+            _check(lib.bout_b200_laplace_cyclic_invalidate(C.c_void_p(self.ws.data_ptr())))
+
+    def __del__(self):
+        try:
+            self.invalidate()   # the workspace address may be handed to another solver by the allocator
+        except Exception:
+            pass
+
     # -- X-decomposed solve: reduce -> (all-gather of the interface records) -> finish
     def iface_doubles(self):
         lib.bout_b200_laplace_cyclic_iface_doubles.restype = C.c_size_t

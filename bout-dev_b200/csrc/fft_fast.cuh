@@ -64,62 +64,126 @@ __device__ __forceinline__ void fastTwInit(FastTw<N>& t, const cd* __restrict__ 
   }
 }
 
-// Complex FFT of N points between the two swizzled buffers; returns the buffer holding the result.
-// CTA-level barriers: all rows of the CTA step through the stages together.
+// Barrier policies of the stage loop: the whole CTA, or only the first COUNT threads of it (named
+// barrier ID) when the CTA also holds threads that do not take part in the transform.
+struct SyncCta {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <int ID, int COUNT>
+struct SyncNamed {
+  static_assert(COUNT % 32 == 0 && ID > 0 && ID < 16, "named barrier: whole warps, id 1..15");
+  __device__ __forceinline__ void operator()() const {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+  }
+};
+
+// One radix-4 Stockham stage (stage index s, Ns = 4^s) of this thread's butterfly, in -> out.
 template <int N, bool INVERSE>
-__device__ __forceinline__ cd* cfftFast(cd* in, cd* out, const FastTw<N>& t, int lane) {
+__device__ __forceinline__ void radix4Stage(const cd* in, cd* out, const FastTw<N>& t, int lane, int s, int Ns) {
+  const int j = lane;
+  const int k = j & (Ns - 1);
+  cd v0 = in[fsw(j)], v1 = in[fsw(j + N / 4)], v2 = in[fsw(j + N / 2)], v3 = in[fsw(j + 3 * (N / 4))];
+  if (s > 0) {
+    cd w1 = t.w[s][0], w2 = t.w[s][1], w3 = t.w[s][2];
+    if (INVERSE) {
+      w1 = cconj(w1);
+      w2 = cconj(w2);
+      w3 = cconj(w3);
+    }
+    v1 = cmul(v1, w1);
+    v2 = cmul(v2, w2);
+    v3 = cmul(v3, w3);
+  }
+  const cd t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3);
+  const cd d = csub(v1, v3);
+  const cd t3 = INVERSE ? cd{-d.im, d.re} : cd{d.im, -d.re};
+  const int j0 = ((j - k) << 2) + k;
+  out[fsw(j0)] = cadd(t0, t2);
+  out[fsw(j0 + Ns)] = cadd(t1, t3);
+  out[fsw(j0 + 2 * Ns)] = csub(t0, t2);
+  out[fsw(j0 + 3 * Ns)] = csub(t1, t3);
+}
+
+// The trailing radix-2 stage (N = 128, 512): this thread's two butterflies, in -> out.
+template <int N, bool INVERSE>
+__device__ __forceinline__ void radix2Stage(const cd* in, cd* out, const FastTw<N>& t, int lane, int Ns) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + h * (N / 4);
+    const int k = j & (Ns - 1);
+    const cd v0 = in[fsw(j)];
+    cd w = t.w2[h];
+    if (INVERSE) {
+      w = cconj(w);
+    }
+    const cd v1 = cmul(in[fsw(j + N / 2)], w);
+    const int j0 = ((j - k) << 1) + k;
+    out[fsw(j0)] = cadd(v0, v1);
+    out[fsw(j0 + Ns)] = csub(v0, v1);
+  }
+}
+
+// Complex FFT of N points between the two swizzled buffers; returns the buffer holding the result.
+// All rows of the CTA step through the stages together (barrier = Sync).
+template <int N, bool INVERSE, class Sync = SyncCta>
+__device__ __forceinline__ cd* cfftFast(cd* in, cd* out, const FastTw<N>& t, int lane, Sync sync = Sync()) {
   int Ns = 1;
 #pragma unroll
   for (int s = 0; s < FftShape<N>::NST; ++s) {
-    const int j = lane;
-    const int k = j & (Ns - 1);
-    cd v0 = in[fsw(j)], v1 = in[fsw(j + N / 4)], v2 = in[fsw(j + N / 2)], v3 = in[fsw(j + 3 * (N / 4))];
-    if (s > 0) {
-      cd w1 = t.w[s][0], w2 = t.w[s][1], w3 = t.w[s][2];
-      if (INVERSE) {
-        w1 = cconj(w1);
-        w2 = cconj(w2);
-        w3 = cconj(w3);
-      }
-      v1 = cmul(v1, w1);
-      v2 = cmul(v2, w2);
-      v3 = cmul(v3, w3);
-    }
-    const cd t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3);
-    const cd d = csub(v1, v3);
-    const cd t3 = INVERSE ? cd{-d.im, d.re} : cd{d.im, -d.re};
-    const int j0 = ((j - k) << 2) + k;
-    out[fsw(j0)] = cadd(t0, t2);
-    out[fsw(j0 + Ns)] = cadd(t1, t3);
-    out[fsw(j0 + 2 * Ns)] = csub(t0, t2);
-    out[fsw(j0 + 3 * Ns)] = csub(t1, t3);
-    __syncthreads();
+    radix4Stage<N, INVERSE>(in, out, t, lane, s, Ns);
+    sync();
     cd* tmp = in;
     in = out;
     out = tmp;
     Ns *= 4;
   }
   if (FftShape<N>::R2) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = lane + h * (N / 4);
-      const int k = j & (Ns - 1);
-      const cd v0 = in[fsw(j)];
-      cd w = t.w2[h];
-      if (INVERSE) {
-        w = cconj(w);
-      }
-      const cd v1 = cmul(in[fsw(j + N / 2)], w);
-      const int j0 = ((j - k) << 1) + k;
-      out[fsw(j0)] = cadd(v0, v1);
-      out[fsw(j0 + Ns)] = csub(v0, v1);
-    }
-    __syncthreads();
+    radix2Stage<N, INVERSE>(in, out, t, lane, Ns);
+    sync();
     cd* tmp = in;
     in = out;
     out = tmp;
   }
   return in;
+}
+
+// Two rows per thread group (independent butterflies interleave in the pipeline) with a hook that
+// runs once per stage before the stage's barrier: the caller slots unrelated work (Thomas steps of
+// another batch) into the shadow of the shared-memory latency.  `live` = false skips the butterflies
+// but keeps the hooks and barriers.  Buffers swap every stage; fftSwaps<N>() tells where the result
+// is.  (Issuing all loads of a stage before the hook and the stores after it measured 7 % slower.)
+template <int N>
+__host__ __device__ constexpr int fftSwaps() {
+  return FftShape<N>::NST + (FftShape<N>::R2 ? 1 : 0);
+}
+template <int N, bool INVERSE, class Hook>
+__device__ __forceinline__ void cfftFast2(cd* a0, cd* b0, cd* a1, cd* b1, const FastTw<N>& t, int lane, bool live,
+                                          Hook hook) {
+  int Ns = 1;
+#pragma unroll
+  for (int s = 0; s < FftShape<N>::NST; ++s) {
+    if (live) {
+      radix4Stage<N, INVERSE>(a0, b0, t, lane, s, Ns);
+      radix4Stage<N, INVERSE>(a1, b1, t, lane, s, Ns);
+    }
+    hook(s);
+    __syncthreads();
+    cd* tmp = a0;
+    a0 = b0;
+    b0 = tmp;
+    tmp = a1;
+    a1 = b1;
+    b1 = tmp;
+    Ns *= 4;
+  }
+  if (FftShape<N>::R2) {
+    if (live) {
+      radix2Stage<N, INVERSE>(a0, b0, t, lane, Ns);
+      radix2Stage<N, INVERSE>(a1, b1, t, lane, Ns);
+    }
+    hook(FftShape<N>::NST);
+    __syncthreads();
+  }
 }
 
 // Forward: real row (global, nz doubles, 16-byte aligned) -> X[0 .. nmode-1] (global), scaled by 1/nz.
@@ -195,6 +259,56 @@ __device__ __forceinline__ void rfftBackwardFast(const cd* __restrict__ src, dou
     }
   }
   __syncthreads();
+}
+
+// ---- pieces for kernels that keep the spectrum on chip (fused LaplaceCyclic sweeps) ------------------
+// Split step of the forward transform: Z = complex FFT of the packed real row (swizzled buffer) ->
+// X[0 .. nmode-1] scaled by 1/nz, written to `dst` (shared or global memory).
+template <int N>
+__device__ __forceinline__ void rfftSplitTo(const cd* Z, cd* dst, int nmode, const FastTw<N>& t, int lane) {
+  constexpr double inv = 1.0 / (2 * N);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int k = lane + m * (N / 4);
+    if (k < nmode) {
+      const cd zk = Z[fsw(k)];
+      const cd zc = cconj(Z[fsw((N - k) & (N - 1))]);
+      const cd e = cscale(cadd(zk, zc), 0.5);
+      const cd dmi = csub(zk, zc);
+      const cd o = {0.5 * dmi.im, -0.5 * dmi.re};
+      dst[k] = cscale(cadd(e, cmul(t.wp[m], o)), inv);
+    }
+  }
+  if (lane == 0 && N < nmode) { // Nyquist bin k = N (w = -1)
+    const cd z0 = Z[fsw(0)];
+    dst[N] = {(z0.re - z0.im) * inv, 0.0};
+  }
+}
+
+// Merge step of the backward transform: X[0 .. nmode-1] from `src` (shared memory; zero beyond
+// nmode; DC dropped when zero_dc) -> packed complex input of the inverse FFT in swizzled buffer A.
+template <int N>
+__device__ __forceinline__ void rfftMergeFrom(const cd* src, cd* A, int nmode, bool zero_dc, const FastTw<N>& t,
+                                              int lane) {
+  auto load = [&](int k) -> cd {
+    if (k >= nmode || (k == 0 && zero_dc)) {
+      return cd{0.0, 0.0};
+    }
+    return src[k];
+  };
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int k = lane + m * (N / 4);
+    cd xk = load(k);
+    cd xc = cconj(load(N - k));
+    if (k == 0) { // imaginary parts of DC and Nyquist are ignored (FFTW c2r)
+      xk.im = 0.0;
+      xc.im = 0.0;
+    }
+    const cd wk = cconj(t.wp[m]);
+    const cd d = cmul(wk, csub(xk, xc));
+    A[fsw(k)] = cadd(cadd(xk, xc), cd{-d.im, d.re});
+  }
 }
 
 } // namespace b200

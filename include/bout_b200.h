@@ -179,6 +179,18 @@ size_t bout_b200_laplace_cyclic_workspace(const bout_b200_grid* g, const bout_b2
 int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_laplace* L,
                                    const double* rhs, const double* x0, double* out,
                                    void* workspace, size_t workspace_bytes, void* stream);
+/* Factorisation reuse.  The tridiagonal matrix of a solve depends on the metric, the A/C/D coefficients
+ * and the flags, not on the right-hand side; the reference rebuilds and re-eliminates it in every call
+ * (cyclic_laplace.cxx:236-250, cyclic_reduction.hxx:119-167).  _factor computes the coefficient table and
+ * the pivots' reciprocals once into `workspace`; every later _solve with the same grid, the same
+ * settings (all members of L equal, pointers compared by value) and the same workspace skips that half
+ * of the work.  The caller must call _factor again (or _invalidate) whenever it changes the CONTENTS of
+ * the metric / coefficient arrays (the host layer does so from setCoefA/C/D and the flag setters).
+ * Without a valid factorisation _solve computes one as part of the call (one-shot, reference semantics).
+ * Configurations that do not use the fused-sweep kernels ignore _factor (returns 0). */
+int bout_b200_laplace_cyclic_factor(const bout_b200_grid* g, const bout_b200_laplace* L,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+int bout_b200_laplace_cyclic_invalidate(void* workspace);
 /* X-decomposed solves (NXPE > 1; replaces the distributed part of CyclicReduce::solve,
  * include/bout/cyclic_reduction.hxx:169-440).  Each rank calls _reduce on its slab (L->first_x /
  * L->last_x say whether it owns a physical boundary): forward z-FFT, local elimination, and

@@ -178,3 +178,84 @@ def test_laplace_x_decomposed_matches_single_rank(capi, orc, port, nxpe, flags):
         got[sl][xs:xe] = o[xs:xe]
     region = (slice(None), slice(G.ystart, G.yend + 1), slice(None))
     assert rel_err(got, want, region) < 1e-10
+
+
+@pytest.mark.parametrize("grid", [(21, 5, 128, 2, 1), (14, 4, 256, 2, 1), (19, 3, 512, 2, 1), (10, 3, 1024, 2, 1),
+                                  (37, 3, 256, 2, 1)])
+@pytest.mark.parametrize("flags", [(0, 0, 0), (0, 3, 0), (4, 0, 0), (0, 16, 16), (0, 32 | 3, 32), (1, 4, 64)])
+@pytest.mark.parametrize("filt", [False, True])
+def test_laplace_fused_sweeps_match_three_kernel_path(capi, orc, port, grid, flags, filt, monkeypatch):
+    """The fused FFT+Thomas sweep kernels (one CTA per y row, spectrum kept on chip, pivots factored
+    once; opt-in through BOUT_B200_LAP_FUSED=1).  Same arithmetic as the row-parallel 3-kernel path
+    => equal to it to round-off (1e-13), and within 1e-10 of the oracle.  Row counts that
+    are not a multiple of the 8-row batch, truncated spectra (laplace:filter), INVERT_ZERO_DC and
+    INVERT_SET rows are covered; one-shot solves and solves on a held factorisation must agree."""
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz)
+    f, x0 = seeded_fields(g.shape3, 2)
+    maxmode = g.nz // 3 if filt else None
+    region = (slice(None), slice(g.ystart, g.yend + 1), slice(None))
+    lap = gpu_laplace(capi, g, m, flags=flags, maxmode=maxmode)
+    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "1")
+    n0 = capi.launch_count()
+    fused = lap.solve(dev(f), dev(x0)).cpu().numpy()
+    lap.status()
+    assert capi.launch_count() - n0 == 4      # one-shot: table + factor + forward sweep + backward sweep
+    lap.factor()
+    n0 = capi.launch_count()
+    held = lap.solve(dev(f), dev(x0)).cpu().numpy()
+    lap.status()
+    assert capi.launch_count() - n0 == 2      # forward sweep + backward sweep
+    assert np.array_equal(fused[region], held[region])
+    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "0")
+    n0 = capi.launch_count()
+    plain = lap.solve(dev(f), dev(x0)).cpu().numpy()
+    assert capi.launch_count() - n0 == 4      # table + rfft + Thomas + irfft
+    assert rel_err(fused, plain, region) < 1e-13
+    want = port.laplace_cyclic(og, m, f, x0=x0, flags=flags, maxmode=maxmode)
+    assert rel_err(fused, want, region) < 1e-10
+
+
+def test_laplace_factor_follows_coefficient_changes(capi, orc, port, monkeypatch):
+    """A held factorisation is tied to (grid, settings, workspace); re-factoring after the contents of
+    a coefficient array changed gives the new operator's solution, and a different settings struct on
+    the same workspace falls back to a one-shot solve."""
+    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "1")
+    grid = (21, 5, 128, 2, 1)
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz)
+    f, x0 = seeded_fields(g.shape3, 2)
+    region = (slice(None), slice(g.ystart, g.yend + 1), slice(None))
+    A = np.full(g.shape2, -0.1)
+    lap = gpu_laplace(capi, g, m, A=A).factor()
+    got = lap.solve(dev(f)).cpu().numpy()
+    assert rel_err(got, port.laplace_cyclic(og, m, f, A=A), region) < 1e-10
+    lap.keep["A"].fill_(-0.7)                 # same array, new contents
+    lap.factor()
+    got = lap.solve(dev(f)).cpu().numpy()
+    A2 = np.full(g.shape2, -0.7)
+    assert rel_err(got, port.laplace_cyclic(og, m, f, A=A2), region) < 1e-10
+    lap.c.inner_boundary_flags = 3            # settings no longer match the held factorisation
+    n0 = capi.launch_count()
+    got = lap.solve(dev(f)).cpu().numpy()
+    assert capi.launch_count() - n0 == 4
+    assert rel_err(got, port.laplace_cyclic(og, m, f, A=A2, flags=(0, 3, 0)), region) < 1e-10
+
+
+def test_laplace_fused_sweeps_full_size_residual(capi, orc, monkeypatch):
+    """BASELINE-size grid (516x132x512, the HW3D workload) through the fused sweeps: Delp2 of the
+    solution returns the right-hand side."""
+    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "1")
+    g = capi.Grid(516, 132, 512, 2, 2)
+    m = make_metric(orc, g.shape2, g.nz)
+    lap = gpu_laplace(capi, g, m).factor()
+    rhs = torch.rand(g.shape3, dtype=torch.float64, device="cuda") - 0.5
+    rhs = capi.zlowpass(g, rhs, g.nz // 2 - 1, True)
+    n0 = capi.launch_count()
+    x = lap.solve(rhs)
+    assert capi.launch_count() - n0 == 2
+    lap.status()
+    back = lap.delp2(x)
+    sl = (slice(g.xstart, g.xend + 1), slice(g.ystart, g.yend + 1), slice(None))
+    err = (back[sl] - rhs[sl]).abs().max() / rhs[sl].abs().max()
+    assert err.item() < 1e-9

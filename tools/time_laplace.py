@@ -23,9 +23,12 @@ for dims in ((516, 132, 512, 2, 2), (260, 68, 256, 2, 2), (1028, 1, 1024, 2, 0))
     md = dict(dx=one(0.2), g11=one(1.0), g33=one(1.0), g13=one(0.0), G1=one(0.0), G3=one(0.0), g_11=one(1.0), g_22=one(1.0))
     f = torch.rand(g.shape3, dtype=torch.float64, device=dev) - 0.5
     out = torch.zeros_like(f)
-    for per in (False, True):
+    for per, fused in ((False, "0"), (False, "1"), (False, "1+factor"), (True, "0")):
+        os.environ["BOUT_B200_LAP_FUSED"] = fused[0]
         lap = capi.Laplace(g, md, 0.2 * g.nz, periodic_x=per)
+        if "factor" in fused:
+            lap.factor()
         t = timeit(lambda: lap.solve(f, out=out))
         lap.status()
         npts = g.n_interior
-        print(f"{dims} periodic_x={per}: solve {t*1e3:8.1f} us  {npts/t/1e6:8.2f} Gpts/s  {16*npts/t/1e6:8.1f} GB/s algorithmic (16 B/pt)  {1e3/t:8.1f} solves/s", flush=True)
+        print(f"{dims} periodic_x={per} fused_sweeps={fused}: solve {t*1e3:8.1f} us  {npts/t/1e6:8.2f} Gpts/s  {16*npts/t/1e6:8.1f} GB/s algorithmic (16 B/pt)  {1e3/t:8.1f} solves/s", flush=True)
