@@ -135,15 +135,16 @@ def mixmode(a, seed=0.5):
     return out
 
 
-def initial_state(rank, world, torch, device):
+def initial_state(pe_xind, nxpe, pe_yind, nype, torch, device):
     """The shipped initial condition (examples/hasegawa-wakatani-3d/data/BOUT.inp): n = 0,
-    vort = 0.1 mixmode(2 pi x) mixmode(z - y), on this rank's X slab of the global grid.  Synthetic,
+    vort = 0.1 mixmode(2 pi x) mixmode(z - y), on this rank's slab of the global grid.  Synthetic,
     generated on the host once (setup, not timed)."""
     import numpy as np
-    gnx = MXSUB * world
-    gx = np.arange(MXSUB + 2 * MXG) + rank * MXSUB          # global x index incl. guards
+    gnx = MXSUB * nxpe
+    gx = np.arange(MXSUB + 2 * MXG) + pe_xind * MXSUB       # global x index incl. guards
     X = (0.5 + gx - MXG) / gnx                              # symmetricGlobalX (boutmesh.cxx:3159-3165)
-    Y = 2 * np.pi * (np.arange(MYSUB + 2 * MYG) - MYG + 0.5) / MYSUB
+    gy = np.arange(MYSUB + 2 * MYG) + pe_yind * MYSUB       # global y index incl. guards
+    Y = 2 * np.pi * (gy - MYG + 0.5) / (MYSUB * nype)
     Z = 2 * np.pi * np.arange(MZ) / MZ
     fx = mixmode(2 * np.pi * X)
     zy = mixmode((Z[None, :] - Y[:, None]))
@@ -162,7 +163,7 @@ def run_ours(args):
             # convenience: re-launch under torchrun as the driver would
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__),
-                   "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+                   "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--decomp", args.decomp]
             sys.exit(subprocess.call(cmd))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -172,18 +173,23 @@ def run_ours(args):
     pkg = ge.load_package()
     capi, models = pkg.capi, pkg.models
     mesh = None
+    # BoutMesh decomposition of the weak-scaled global grid (mesh:NXPE / mesh:NYPE of BOUT.inp): "y" splits
+    # the parallel direction (the tridiagonal solves stay rank-local), "x" the radial one (X-decomposed
+    # LaplaceCyclic: reduce + all-gather + finish), "xy" uses NXPE = 2.
+    nxpe, nype = {"x": (world, 1), "y": (1, world), "xy": (2 if world % 2 == 0 else 1, world // 2 if world % 2 == 0 else world)}[args.decomp]
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-        mesh = pkg.mesh.BoutMesh(nxpe=world, nype=1, rank=rank, mxsub=MXSUB, mysub=MYSUB, mz=MZ, mxg=MXG, myg=MYG,
+        mesh = pkg.mesh.BoutMesh(nxpe=nxpe, nype=nype, rank=rank, mxsub=MXSUB, mysub=MYSUB, mz=MZ, mxg=MXG, myg=MYG,
                                  periodic_x=False, periodic_y=True, device=dev)
+    pe_xind, pe_yind = rank % nxpe, rank // nxpe
 
     g = capi.Grid(MXSUB + 2 * MXG, MYSUB + 2 * MYG, MZ, MXG, MYG)
     one = lambda v: torch.full(g.shape2, v, dtype=torch.float64, device=dev)
     metric = dict(dx=one(0.2), dy=one(1.0), dz=one(0.2), J=one(1.0), g_22=one(1.0), g11=one(1.0), g33=one(1.0),
                   g13=one(0.0), G1=one(0.0), G3=one(0.0), g_11=one(1.0))
     model = models.HW3D(g, metric, device=dev, mesh=mesh, **HW)
-    n0, v0 = initial_state(rank, world, torch, dev)
+    n0, v0 = initial_state(pe_xind, nxpe, pe_yind, nype, torch, dev)
     hn, hv = n0.pin_memory(), v0.pin_memory()
     hn_out, hv_out = torch.empty_like(hn).pin_memory(), torch.empty_like(hv).pin_memory()
     model.set_state(hn.to(dev), hv.to(dev))
@@ -267,7 +273,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (shipped closed-form initial condition, mixmode)",
-        "config": {"workload": WORKLOAD, "decomposition": f"NXPE={world} NYPE=1", "rhs_per_step": 4,
+        "config": {"workload": WORKLOAD, "decomposition": f"NXPE={nxpe} NYPE={nype}", "rhs_per_step": 4,
                    "points_per_gpu": npts, "dt": DT,
                    "l2": "inputs larger than L2 (each field 279 MB vs 126 MB L2); no flush needed"},
         "gpu_launches": int(launches),
@@ -372,6 +378,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decomp", default=os.environ.get("BOUT_B200_DECOMP", "y"), choices=["x", "y", "xy"],
+                    help="BoutMesh decomposition at N > 1: NYPE=N (default), NXPE=N, or NXPE=2 x NYPE=N/2")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
