@@ -358,3 +358,82 @@ def hw_convective(g: Grid, dx, dz, alpha, kappa, n, vort, phi, zonal_n=None, zon
                                        C.c_double(kappa), _ptr(n), _ptr(vort), _ptr(phi), _ptr(zonal_n),
                                        _ptr(zonal_phi), _ptr(ddt_n), _ptr(ddt_vort),
                                        None if epilogue is None else C.byref(epilogue), _stream()))
+
+
+# ---- shifted-metric / elm-pb operator set -----------------------------------------------------------
+def stencil_yslices(g: Grid, op: str, f, yup, ydown, v=None, scale1=None, op2=None, scale2=None, out=None,
+                    region="RGN_NOBNDRY"):
+    """Y stencil whose neighbours come from parallel slices: yup / ydown are lists of 1 or 2 fields."""
+    out = torch.zeros_like(f) if out is None else out
+    _check(lib.bout_b200_stencil_yslices(C.byref(g.c), OPS[op], REGIONS[region], _ptr(v), _ptr(f), len(yup),
+                                         _ptr_array(yup), _ptr_array(ydown), _ptr(scale1),
+                                         -1 if op2 is None else OPS[op2], _ptr(scale2), _ptr(out), _stream()))
+    return out
+
+
+def parallel_slices(g: Grid, f, zshift, zlength, nslices=None, yup=None, ydown=None):
+    """ShiftedMetric::calcParallelSlices: returns (yup, ydown), lists of nslices fields (offsets +-1..)."""
+    n = g.myg if nslices is None else nslices
+    yup = [torch.zeros_like(f) for _ in range(n)] if yup is None else yup
+    ydown = [torch.zeros_like(f) for _ in range(n)] if ydown is None else ydown
+    _check(lib.bout_b200_parallel_slices(C.byref(g.c), _ptr(f), _ptr(zshift), C.c_double(zlength), n,
+                                         _ptr_array(yup), _ptr_array(ydown), _stream()))
+    return yup, ydown
+
+
+class CB0xGrad(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dx", "dy", "dz", "J", "g_22", "g_12", "g_23", "int_shift_torsion")] + \
+               [(n, C.c_int) for n in ("ddx_op", "ddy_op", "ddz_op", "vddx_op", "vddy_op", "vddz_op")]
+
+
+def make_b0xgrad(md: dict, first=("C4", "C2", "C4"), upwind=("W3", "C2", "W3"), int_shift_torsion=None):
+    """md: name -> Field2D tensor; first / upwind: (x, y, z) method names (mesh:dd?:first / :upwind)."""
+    c = CB0xGrad()
+    for n in ("dx", "dy", "dz", "J", "g_22", "g_12", "g_23"):
+        setattr(c, n, md[n].data_ptr())
+    c.int_shift_torsion = None if int_shift_torsion is None else int_shift_torsion.data_ptr()
+    c.ddx_op, c.ddy_op, c.ddz_op = (OPS["DDX_" + m] for m in first)
+    c.vddx_op, c.vddy_op, c.vddz_op = (OPS["VDDX_" + m] for m in upwind)
+    c._keep = (md, int_shift_torsion)
+    return c
+
+
+def b0xgrad_dot_grad(g: Grid, cfg, phi, A, phi_slices=None, a_slices=None, out=None, shifted=None):
+    """phi / A: Field3D or Field2D tensors; *_slices = (yup list, ydown list) or None (field itself).
+    shifted = (zShift, zlength) on a shifted-metric mesh: with a Field2D A the y-advection term is taken
+    through toFieldAligned / fromFieldAligned as the reference does."""
+    ref = phi if phi.dim() == 3 else A
+    out = torch.zeros_like(ref) if out is None else out
+    yterm = torch.zeros_like(ref) if (shifted is not None and A.dim() == 2) else None
+    pu, pd = phi_slices if phi_slices is not None else ([], [])
+    au, ad = a_slices if a_slices is not None else ([], [])
+    _check(lib.bout_b200_b0xgrad_dot_grad(
+        C.byref(g.c), C.byref(cfg), _ptr(phi), int(phi.dim() == 2), len(pu),
+        _ptr_array(pu) if pu else None, _ptr_array(pd) if pd else None, _ptr(A), int(A.dim() == 2), len(au),
+        _ptr_array(au) if au else None, _ptr_array(ad) if ad else None, _ptr(out), _ptr(yterm), _stream()))
+    if yterm is not None:
+        zs, zl = shifted
+        aligned = zshift(g, yterm, (-zs).contiguous(), zl, region="RGN_NOBNDRY")
+        back = zshift(g, aligned, zs, zl, region="RGN_NOBNDRY")
+        elementwise(g, [(1.0, out), (1.0, back)], out=out, region="RGN_NOBNDRY")
+    return out
+
+
+def average_y(g: Grid, f, out=None, y_group=None, nype=1):
+    """averageY(Field3D): local mean -> (SUM all-reduce over the Y communicator when NYPE > 1) -> broadcast."""
+    xz = torch.empty((g.nx, g.nz), dtype=torch.float64, device=f.device)
+    _check(lib.bout_b200_ymean(C.byref(g.c), _ptr(f), _ptr(xz), _stream()))
+    scale = 1.0
+    if nype > 1:
+        import torch.distributed as dist
+        dist.all_reduce(xz, group=y_group)
+        scale = 1.0 / nype
+    out = torch.empty_like(f) if out is None else out
+    _check(lib.bout_b200_yspread(C.byref(g.c), _ptr(xz), C.c_double(scale), _ptr(out), _stream()))
+    return out
+
+
+def smooth_x(g: Grid, f, out=None):
+    out = torch.empty_like(f) if out is None else out
+    _check(lib.bout_b200_smooth_x(C.byref(g.c), _ptr(f), _ptr(out), _stream()))
+    return out

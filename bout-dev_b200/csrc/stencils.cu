@@ -23,6 +23,8 @@ struct StencilParams {
   const double* __restrict__ f;
   const double* __restrict__ up;   // plane source for +direction neighbours (Y slices) or f
   const double* __restrict__ down; // plane source for -direction neighbours or f
+  const double* __restrict__ up2;  // second parallel slices (y + 2 / y - 2) when the op needs two
+  const double* __restrict__ down2;
   const double* __restrict__ scale1;
   const double* __restrict__ scale2;
   double* __restrict__ out;
@@ -107,9 +109,11 @@ __global__ void __launch_bounds__(256) k_stencil_march(const StencilParams p) {
     // were loaded as "up" for earlier centres must be re-read from the right source.
     if (p.up != p.f) {
       w[NG] = Vz<VEC>::load(p.f + col + m * stride);
-#pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        w[i] = Vz<VEC>::load(p.down + col + (m - NG + i) * stride);
+      w[NG - 1] = Vz<VEC>::load(p.down + col + (m - 1) * stride);
+      w[NG + 1] = Vz<VEC>::load(p.up + col + (m + 1) * stride);
+      if constexpr (NG == 2) { // each offset has its own slice field (Field3D::ynext(+-2))
+        w[0] = Vz<VEC>::load(p.down2 + col + (m - 2) * stride);
+        w[4] = Vz<VEC>::load(p.up2 + col + (m + 2) * stride);
       }
     }
     Vz<VEC> vc;
@@ -287,10 +291,9 @@ int launchStencilVec(const StencilParams& p, int dir, bool vec2, cudaStream_t st
 
 using namespace b200;
 
-extern "C" int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region,
-                                 const double* v, const double* f, const double* yup,
-                                 const double* ydown, const double* scale1, int op2,
-                                 const double* scale2, double* out, void* stream) {
+static int stencilImpl(const bout_b200_grid* g, int op, int dir, int region, const double* v, const double* f,
+                       const double* yup, const double* ydown, const double* yup2, const double* ydown2,
+                       const double* scale1, int op2, const double* scale2, double* out, void* stream) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
@@ -325,14 +328,18 @@ extern "C" int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int r
                  "stencil: Y region [%d,%d] needs %d guard cells (ny=%d)", b.ys, b.ye, ng, g->ny);
     B200_REQUIRE((yup == nullptr) == (ydown == nullptr), BOUT_B200_ERR_ARG,
                  "stencil: yup and ydown must be given together");
-    B200_REQUIRE(yup == nullptr || ng == 1, BOUT_B200_ERR_UNSUPPORTED,
-                 "stencil: parallel slices carry one point each side; op %d needs 2", op);
+    B200_REQUIRE(yup == nullptr || ng == 1 || (yup2 != nullptr && ydown2 != nullptr), BOUT_B200_ERR_ARG,
+                 "stencil: op %d needs two parallel slices each way", op);
+    B200_REQUIRE(yup == nullptr || kind != 2, BOUT_B200_ERR_UNSUPPORTED,
+                 "stencil: flux operators on parallel slices are not supported");
   }
   StencilParams p;
   p.v = v;
   p.f = f;
   p.up = (dir == BOUT_B200_Y && yup != nullptr) ? yup : f;
   p.down = (dir == BOUT_B200_Y && ydown != nullptr) ? ydown : f;
+  p.up2 = (dir == BOUT_B200_Y && yup != nullptr && yup2 != nullptr) ? yup2 : p.up;
+  p.down2 = (dir == BOUT_B200_Y && ydown != nullptr && ydown2 != nullptr) ? ydown2 : p.down;
   p.scale1 = scale1;
   p.scale2 = scale2;
   p.out = out;
@@ -345,7 +352,7 @@ extern "C" int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int r
   p.ye = b.ye;
   p.chunk = 16;
   const bool vec2 = (g->nz % 2 == 0) && aligned16(f) && aligned16(out) && (v == nullptr || aligned16(v))
-                    && aligned16(p.up) && aligned16(p.down);
+                    && aligned16(p.up) && aligned16(p.down) && aligned16(p.up2) && aligned16(p.down2);
 
 #define CASE1(OPC)                                                   \
   case OPC:                                                          \
@@ -387,4 +394,21 @@ extern "C" int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int r
 #undef CASE1
 #undef CASE2
   return fail(BOUT_B200_ERR_UNSUPPORTED, "stencil: unsupported op %d / op2 %d", op, op2);
+}
+
+extern "C" int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region,
+                                 const double* v, const double* f, const double* yup,
+                                 const double* ydown, const double* scale1, int op2,
+                                 const double* scale2, double* out, void* stream) {
+  return stencilImpl(g, op, dir, region, v, f, yup, ydown, nullptr, nullptr, scale1, op2, scale2, out, stream);
+}
+
+extern "C" int bout_b200_stencil_yslices(const bout_b200_grid* g, int op, int region, const double* v,
+                                         const double* f, int nslices, const double* const* yup,
+                                         const double* const* ydown, const double* scale1, int op2,
+                                         const double* scale2, double* out, void* stream) {
+  B200_REQUIRE(nslices >= 1 && nslices <= 2 && yup && ydown && yup[0] && ydown[0], BOUT_B200_ERR_ARG,
+               "stencil_yslices: 1 or 2 slices each way");
+  return stencilImpl(g, op, BOUT_B200_Y, region, v, f, yup[0], ydown[0], nslices > 1 ? yup[1] : nullptr,
+                     nslices > 1 ? ydown[1] : nullptr, scale1, op2, scale2, out, stream);
 }

@@ -44,7 +44,7 @@ const cd* twiddleTable(int nz, cudaStream_t stream, int* status) {
   return devp;
 }
 
-enum ZMode { Z_DDZ1 = 0, Z_DDZ2 = 1, Z_FILTER = 2, Z_LOWPASS = 3, Z_SHIFT = 4 };
+enum ZMode { Z_DDZ1 = 0, Z_DDZ2 = 1, Z_FILTER = 2, Z_LOWPASS = 3, Z_SHIFT = 4, Z_SLICE = 5 };
 
 struct ZfftParams {
   const double* __restrict__ f;
@@ -55,6 +55,7 @@ struct ZfftParams {
   const cd* __restrict__ tw;
   int nx, ny, nz, xs, xe, ys, ye;
   int mode, kmax, n0, keep_zonal;
+  int yoff; // Z_SLICE: this row is the y + yoff neighbour of the row whose frame it is shifted into
   double angle0, zlength0;
   int tpr, rows, pow2;
 };
@@ -139,6 +140,16 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
       }
       break;
     }
+    case Z_SLICE: { // ShiftedMetric::cachePhases, shiftedmetric.cxx:109-123: zShift(y) - zShift(y + offset)
+      if (k >= 1) {
+        const double ang = __ldg(p.angle + i2 - p.yoff) - __ldg(p.angle + i2);
+        const double kwave = k * 2.0 * M_PI / p.zlength0;
+        double s, c;
+        sincos(kwave * ang, &s, &c);
+        v = cmul(v, cd{c, -s});
+      }
+      break;
+    }
     default:
       break;
     }
@@ -164,13 +175,15 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
   }
 }
 
-int launchZfft(const bout_b200_grid* g, int region, ZfftParams p, void* stream) {
+int launchZfft(const bout_b200_grid* g, int region, ZfftParams p, void* stream, const Box* box = nullptr) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
   B200_REQUIRE(p.f && p.out, BOUT_B200_ERR_ARG, "zfft: null field");
   Box b;
-  if (regionBox(g, region, &b) != 0) {
+  if (box != nullptr) {
+    b = *box;
+  } else if (regionBox(g, region, &b) != 0) {
     return BOUT_B200_ERR_ARG;
   }
   cudaStream_t s = asStream(stream);
@@ -288,6 +301,44 @@ extern "C" int bout_b200_zshift(const bout_b200_grid* g, int region, const doubl
   p.zlength = zlength2d;
   p.zlength0 = zlength0;
   return launchZfft(g, region, p, stream);
+}
+
+// ShiftedMetric::calcParallelSlices (src/mesh/parallel/shiftedmetric.cxx:226-246): slice +-(i+1) holds,
+// at row y + offset, the field's own row y + offset shifted in z into the frame of row y.
+extern "C" int bout_b200_parallel_slices(const bout_b200_grid* g, const double* f, const double* zshift2d,
+                                         double zlength, int nslices, double* const* yup,
+                                         double* const* ydown, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(f && zshift2d && yup && ydown, BOUT_B200_ERR_ARG, "parallel_slices: null argument");
+  B200_REQUIRE(nslices >= 1 && nslices <= g->ystart && nslices <= g->ny - 1 - g->yend, BOUT_B200_ERR_GUARDS,
+               "parallel_slices: %d slices need as many y guard cells", nslices);
+  for (int i = 0; i < nslices; ++i) {
+    for (int sign = 1; sign >= -1; sign -= 2) {
+      double* out = sign > 0 ? yup[i] : ydown[i];
+      B200_REQUIRE(out != nullptr && out != f, BOUT_B200_ERR_ARG, "parallel_slices: bad slice pointer");
+      const int off = sign * (i + 1);
+      if (g->nz == 1) { // shifting does not change the values (shiftedmetric.cxx:159-163)
+        B200_CUDA_OK(cudaMemcpyAsync(out, f, sizeof(double) * g->nx * g->ny, cudaMemcpyDeviceToDevice,
+                                     asStream(stream)));
+        continue;
+      }
+      ZfftParams p{};
+      p.f = f;
+      p.out = out;
+      p.mode = Z_SLICE;
+      p.angle = zshift2d;
+      p.zlength0 = zlength;
+      p.yoff = off;
+      const Box b = {0, g->nx - 1, g->ystart + off, g->yend + off}; // RGN_NOY rows, displaced
+      const int rc = launchZfft(g, BOUT_B200_RGN_ALL, p, stream, &b);
+      if (rc != 0) {
+        return rc;
+      }
+    }
+  }
+  return 0;
 }
 
 extern "C" int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* stream) {

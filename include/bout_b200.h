@@ -102,6 +102,15 @@ int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region, cons
                       const double* scale1, int op2, const double* scale2, double* out,
                       void* stream);
 
+/* Y stencils on a mesh with a non-identity parallel transform: neighbour y +- k comes from the parallel
+ * slice field yup[k-1] / ydown[k-1] (Field3D::ynext(+-k), include/bout/field3d.hxx:265-300; stencil
+ * population include/bout/stencils.hxx:73-100), nslices = 1 or 2 as the operator needs.  Standard and
+ * upwind functors (the velocity is taken at the point). */
+int bout_b200_stencil_yslices(const bout_b200_grid* g, int op, int region, const double* v,
+                              const double* f, int nslices, const double* const* yup,
+                              const double* const* ydown, const double* scale1, int op2,
+                              const double* scale2, double* out, void* stream);
+
 /* FFT-in-Z derivative: order 1 (FFTDerivativeType, src/mesh/index_derivs.cxx:418-481, with
  * mesh:ddz:fft_filter) or order 2 (FFT2ndDerivativeType :483-541), times scale[x,y]. */
 int bout_b200_ddz_fft(const bout_b200_grid* g, int order, double fft_filter, int region,
@@ -119,6 +128,14 @@ int bout_b200_zlowpass(const bout_b200_grid* g, int region, int zmax, int keep_z
 int bout_b200_zshift(const bout_b200_grid* g, int region, const double* f, const double* angle2d,
                      double angle0, const double* zlength2d, double zlength0, double* out,
                      void* stream);
+/* ShiftedMetric::calcParallelSlices (src/mesh/parallel/shiftedmetric.cxx:54-124, 226-246): for k = 1..nslices
+ * yup[k-1](x, y+k, :) = f(x, y+k, :) shifted in z by zShift(x,y) - zShift(x,y+k) (mode jz multiplied by
+ * exp(-i jz 2pi/zlength * shift)), for y in ystart..yend and all x; ydown[k-1] likewise with y-k.
+ * Other cells of the slice fields are left untouched.  toFieldAligned / fromFieldAligned are
+ * bout_b200_zshift with angle2d = -zShift / +zShift. */
+int bout_b200_parallel_slices(const bout_b200_grid* g, const double* f, const double* zshift2d,
+                              double zlength, int nslices, double* const* yup, double* const* ydown,
+                              void* stream);
 /* DC(f): z-mean of every (x,y) row, RGN_ALL (src/field/field3d.cxx:785-803). out2d is a Field2D. */
 int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* stream);
 
@@ -130,6 +147,39 @@ int bout_b200_bracket_arakawa(const bout_b200_grid* g, const double* f, const do
 /* bracket(Field3D f, Field2D g, BRACKET_ARAKAWA) (src/mesh/difops.cxx:693-765). */
 int bout_b200_bracket_arakawa_3d2d(const bout_b200_grid* g, const double* f, const double* g2d,
                                    const double* dx, const double* dz, double* out, void* stream);
+
+/* b0xGrad_dot_Grad(phi, A) = bracket(phi, A, BRACKET_STD) * B (src/mesh/difops.cxx:455-601) in one pass:
+ * dphi/dx,y,z with the mesh's first-derivative functors, v = (g_22 dz - g_23 dy, g_23 dx - g_12 dz,
+ * g_12 dy - g_22 dx) [+ IntShiftTorsion vx on vz when mesh->IncIntShear], VDDX(vx,A) + VDDY(vy,A) +
+ * VDDZ(vz,A) with the mesh's upwind functors, divided by J sqrt(g_22).  Either operand may be a Field2D
+ * (*_is2d; its z derivative / advection term vanishes).  Y neighbours of a Field3D come from
+ * *_nslices (0, 1 or 2) parallel slices each way; 0 = the field itself (identity transform).
+ * yterm_out (optional): the VDDY(vy, A) / (J sqrt(g_22)) term is written there instead of being added
+ * to out.  With a Field2D A on a shifted-metric mesh the reference evaluates that term in field-aligned
+ * coordinates (the converted A carries no slices, include/bout/index_derivs_interface.hxx:360-390), i.e.
+ * out += fromFieldAligned(toFieldAligned(yterm)): two bout_b200_zshift passes and one _elementwise. */
+typedef struct bout_b200_b0xgrad {
+  const double *dx, *dy, *dz, *J, *g_22, *g_12, *g_23; /* Field2D */
+  const double* int_shift_torsion;                     /* NULL unless mesh->IncIntShear */
+  int ddx_op, ddy_op, ddz_op;                          /* BOUT_B200_DDX_* (mesh:ddx:first ...) */
+  int vddx_op, vddy_op, vddz_op;                       /* BOUT_B200_VDDX_* (mesh:ddx:upwind ...) */
+} bout_b200_b0xgrad;
+int bout_b200_b0xgrad_dot_grad(const bout_b200_grid* g, const bout_b200_b0xgrad* cfg,
+                               const double* phi, int phi_is2d, int phi_nslices,
+                               const double* const* phi_yup, const double* const* phi_ydown,
+                               const double* A, int a_is2d, int a_nslices,
+                               const double* const* a_yup, const double* const* a_ydown,
+                               double* out, double* yterm_out, void* stream);
+
+/* averageY(Field3D) (src/physics/smoothing.cxx:272-323) in two halves so that the all-reduce over the
+ * ranks of a Y communicator sits between them: xz[x][z] = mean over ystart..yend of f;
+ * out(x, y, z) = scale * xz[x][z] for every y (scale = 1/NYPE after a SUM all-reduce, else 1). */
+int bout_b200_ymean(const bout_b200_grid* g, const double* f, double* xz, void* stream);
+int bout_b200_yspread(const bout_b200_grid* g, const double* xz, double scale, double* out,
+                      void* stream);
+/* smooth_x (src/physics/smoothing.cxx:46-73): 1-2-1 filter in x over 0 < x < nx-1, edge planes copied;
+ * the caller communicates the result as the reference does. */
+int bout_b200_smooth_x(const bout_b200_grid* g, const double* f, double* out, void* stream);
 
 /* ---- (2b) fused Delp2 and (3) LaplaceCyclic -------------------------------------------------------
  * Laplacian settings + the Field2D metric the coefficients are generated from on chip

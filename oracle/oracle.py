@@ -392,6 +392,18 @@ class Ref:
         self._check(self.lib.boutref_op(name.encode(), method.encode(), len(ins), arr, scalar, _p(out)))
         return out
 
+    def parallel_slice(self, f, offset):
+        """Field3D::ynext(offset) after Mesh::communicate (ParallelTransform::calcParallelSlices)."""
+        out = np.zeros(self.grid.shape3)
+        self._check(self.lib.boutref_parallel_slice(_p(np.ascontiguousarray(f)), int(offset), _p(out)))
+        return out
+
+    def zshift(self):
+        out = np.zeros(self.grid.shape2)
+        zl = C.c_double(0.0)
+        self._check(self.lib.boutref_zshift(_p(out), C.byref(zl)))
+        return out, zl.value
+
     def time_op(self, name, *inputs, method="", scalar=0.0, reps=5):
         ins = [np.ascontiguousarray(a) for a in inputs]
         arr = (C.c_void_p * max(3, len(ins)))(*[a.ctypes.data for a in ins])

@@ -126,12 +126,27 @@ BRACKET_METHOD bracketMethod(const std::string& m) {
 }
 
 // One operator application. in[] are raw arrays (3D unless the op name says otherwise).
-Field3D applyOp(const std::string& op, const std::string& method, int nin, const double** in,
+Field3D applyOp(const std::string& op_in, const std::string& method, int nin, const double** in,
                 double scalar) {
   const std::string m = method.empty() ? "DEFAULT" : method;
-  auto f0 = [&]() { return toField3D(in[0]); };
-  auto f1 = [&]() { return toField3D(in[1]); };
-  auto f2 = [&]() { return toField3D(in[2]); };
+  // "name@comm": Mesh::communicate the Field3D inputs first, so that they carry parallel slices
+  // (the shifted-metric path of the Y operators); plain names take fields without slices.
+  std::string op = op_in;
+  bool comm = false;
+  if (op.size() > 5 && op.compare(op.size() - 5, 5, "@comm") == 0) {
+    comm = true;
+    op.resize(op.size() - 5);
+  }
+  auto mk = [&](int i) {
+    Field3D f = toField3D(in[i]);
+    if (comm) {
+      mesh->communicate(f);
+    }
+    return f;
+  };
+  auto f0 = [&]() { return mk(0); };
+  auto f1 = [&]() { return mk(1); };
+  auto f2 = [&]() { return mk(2); };
   // --- index-space derivatives (index_derivs_interface.hxx:172-270)
   if (op == "index_DDX") return bout::derivatives::index::DDX(f0(), CELL_DEFAULT, m);
   if (op == "index_DDY") return bout::derivatives::index::DDY(f0(), CELL_DEFAULT, m);
@@ -169,6 +184,13 @@ Field3D applyOp(const std::string& op, const std::string& method, int nin, const
   if (op == "bracket_2d3d") return bracket(toField2D(in[0]), f1(), bracketMethod(m));
   if (op == "Delp2") return Delp2(f0(), CELL_DEFAULT, true);
   if (op == "Delp2_fd") return Delp2(f0(), CELL_DEFAULT, false);
+  if (op == "toFieldAligned") return toFieldAligned(f0());
+  if (op == "fromFieldAligned") {
+    Field3D a = f0();
+    a.setDirectionY(YDirectionType::Aligned);
+    return fromFieldAligned(a);
+  }
+  if (op == "Vpar_Grad_par") return Vpar_Grad_par(f0(), f1());
   if (op == "Grad_par") return Grad_par(f0());
   if (op == "Div_par") return Div_par(f0());
   if (op == "Grad2_par2") return Grad2_par2(f0());
@@ -526,6 +548,25 @@ int boutref_parallel_slices(const double* field, double* yup, double* ydown) {
     mesh->communicate(f);
     fromField3D(f.yup(), yup);
     fromField3D(f.ydown(), ydown);
+  });
+}
+
+// one parallel slice (Field3D::ynext(offset)) after communicate
+int boutref_parallel_slice(const double* field, int offset, double* out) {
+  return guarded([&]() {
+    Field3D f = toField3D(field);
+    mesh->communicate(f);
+    fromField3D(f.ynext(offset), out);
+  });
+}
+
+// zShift as the ShiftedMetric holds it (guard cells fixed up, coordinates.cxx:1346-1375) and zlength
+int boutref_zshift(double* out2d, double* zlength) {
+  return guarded([&]() {
+    Options dump;
+    mesh->getCoordinates()->getParallelTransform().outputVars(dump);
+    fromField2D(dump["zShift"].as<Field2D>(), out2d);
+    *zlength = mesh->getCoordinates()->zlength()(0, 0);
   });
 }
 

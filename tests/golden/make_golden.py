@@ -12,6 +12,9 @@ Outputs (committed; the GPU box has neither /root/reference nor needs the refere
   ops_small.npz          reference outputs of every operator on the hot path for one small grid with a
                          non-trivial metric (stencils, brackets, Delp2, z-FFT ops, Laplace solves,
                          boundaries, communicate, field algebra).
+  ops_shifted.npz        the elm-pb operator vocabulary on a shifted-metric mesh with elm-pb's derivative
+                         methods: parallel slices, to/fromFieldAligned, Y operators on slices,
+                         b0xGrad_dot_Grad (3D3D, 3D2D, 2D3D), averageY, smooth_x.
   models.npz             unchanged example models (hasegawa-wakatani, hasegawa-wakatani-3d, blob2d) run
                          through the reference's Solver::run_rhs and RK4 / RK3-SSP solvers: initial state,
                          ddt after one RHS, state after a few steps.
@@ -227,6 +230,75 @@ MODEL_CASES = {"hw": ("hw", HW_INI, "rk4", 5), "hw_rk3": ("hw", HW_INI, "rk3ssp"
                "hw3d": ("hw3d", HW3D_INI, "rk4", 5), "blob2d": ("blob2d", BLOB_INI, "rk4", 5)}
 
 
+SHIFTED_INI = orc.make_ini(12, 8, 16, mxg=2, myg=2, dx="0.2*(1+0.1*x)", dy="0.7+0.05*cos(2*pi*x)", dz="2*pi/16",
+                           mesh_extra="""
+g11 = 1 + 0.1*x
+g22 = 1.1 + 0.02*cos(y)
+g33 = 1.2 + 0.05*x
+g12 = 0.01
+g13 = 0.05 + 0.02*x
+g23 = 0.02
+zShift = 0.4*(1+x)*sin(y) + 0.1*(1+x)*y
+ShiftAngle = 0.1*(1+x)*2*pi
+ixseps1 = 12
+ixseps2 = 12
+[mesh:paralleltransform]
+type = shifted
+""", extra="""
+[mesh:ddx]
+first = C4
+second = C4
+upwind = W3
+[mesh:ddy]
+first = C2
+second = C2
+upwind = C2
+flux = C2
+[mesh:ddz]
+first = C4
+second = C4
+upwind = W3
+""")
+
+
+def ops_shifted():
+    """elm-pb's operator vocabulary on a shifted-metric mesh with the derivative methods of
+    examples/elm-pb/data/BOUT.inp: parallel slices, field-aligned transforms, the Y operators on
+    slices (fields communicated first, '@comm'), b0xGrad_dot_Grad in its three operand mixes, averageY,
+    smooth_x."""
+    r = orc.Ref(SHIFTED_INI)
+    g = r.grid
+    out = {"grid": np.array([g.nx, g.ny, g.nz, g.mxg, g.myg])}
+    m = r.metric()
+    for n in orc.Metric.NAMES:
+        out["metric_" + n] = getattr(m, n)
+    zs, zl = r.zshift()
+    out["zShift"] = zs
+    out["zlength"] = np.array(zl)
+    f, h, v = smooth_fields(g, 3, 20261018)
+    v = v - 0.05
+    f2 = np.ascontiguousarray(f[:, :, 0] + 1.5)
+    # the reference communicates before it uses slices: hand both sides the communicated fields
+    f, h, v = r.communicate(f, h, v)
+    out.update(f=f, h=h, v=v, f2=f2)
+    for off in (1, 2, -1, -2):
+        out[f"slice_{off:+d}"] = r.parallel_slice(f, off)
+        out[f"slice_h_{off:+d}"] = r.parallel_slice(h, off)
+    out["toFieldAligned"] = r.op("toFieldAligned", f)
+    out["fromFieldAligned"] = r.op("fromFieldAligned", f)
+    for name in ("DDY", "D2DY2", "Grad_par", "Div_par", "Grad2_par2"):
+        out[name + "_slices"] = r.op(name + "@comm", f)
+    out["VDDY_slices"] = r.op("VDDY@comm", v, f)
+    out["Vpar_Grad_par_slices"] = r.op("Vpar_Grad_par@comm", v, f)
+    out["b0xGrad_dot_Grad"] = r.op("b0xGrad_dot_Grad@comm", f, h)
+    out["b0xGrad_dot_Grad_3d2d"] = r.op("b0xGrad_dot_Grad_3d2d@comm", f, f2)
+    out["b0xGrad_dot_Grad_2d3d"] = r.op("b0xGrad_dot_Grad_2d3d@comm", f2, h)
+    out["averageY"] = r.op("averageY", f)
+    out["smooth_x"] = r.op("smooth_x", f)
+    r.close()
+    np.savez_compressed(os.path.join(HERE, "ops_shifted.npz"), **out)
+
+
 def one_model(tag, path):
     """One model case per process: the reference keeps static state that does not survive many
     init/finalise cycles."""
@@ -271,7 +343,7 @@ def models():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["laplace", "ops", "models"]
+    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models"]
     if which[0].startswith("model:"):
         one_model(which[0][6:], which[1])
         sys.stdout.flush()
@@ -280,6 +352,8 @@ if __name__ == "__main__":
         laplace_benchmark()
     if "ops" in which:
         ops_small()
+    if "shifted" in which:
+        ops_shifted()
     if "models" in which:
         models()
     os._exit(0)  # the reference's static destructors are not exit-safe after repeated init/finalise
