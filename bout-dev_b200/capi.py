@@ -265,11 +265,19 @@ def unary(g: Grid, op, f, arg=0.0, out=None):
 
 
 def boundary(g: Grid, kind, side, f, value=0.0, spacing=None, lo=-1, hi=-1):
-    """In place.  kind: dirichlet | neumann | zero; side: xin | xout | ydown | yup."""
-    k = {"dirichlet": 0, "dirichlet_o2": 0, "neumann": 1, "zero": 2}[kind]
+    """In place.  kind: dirichlet | neumann | zero | extend; side: xin | xout | ydown | yup."""
+    k = {"dirichlet": 0, "dirichlet_o2": 0, "neumann": 1, "zero": 2, "extend": 3}[kind]
     sd = {"xin": 0, "xout": 1, "ydown": 2, "yup": 3}[side]
     _check(lib.bout_b200_boundary(C.byref(g.c), k, sd, C.c_double(value), _ptr(spacing), lo, hi, _ptr(f),
                                   _stream()))
+    return f
+
+
+def boundary_zerolaplace(g: Grid, side, f, dx, g11, g33, zlength, lo=-1, hi=-1):
+    """In place.  BoundaryZeroLaplace on the xin / xout guard cells."""
+    sd = {"xin": 0, "xout": 1}[side]
+    _check(lib.bout_b200_boundary_zerolaplace(C.byref(g.c), sd, _ptr(dx), _ptr(g11), _ptr(g33),
+                                              C.c_double(zlength), lo, hi, _ptr(f), _stream()))
     return f
 
 

@@ -15,7 +15,7 @@ struct BndryParams {
   const double* __restrict__ spacing; // dx (x sides) or dy (y sides), Field2D; only for Neumann
   double val;
   int nx, ny, nz;
-  int kind; // 0 dirichlet, 1 neumann, 2 zero (apply_ddt)
+  int kind; // 0 dirichlet, 1 neumann, 2 zero (apply_ddt), 3 extend (outer guards copy their inner neighbour)
   int side; // 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper
   int width;
   int lo, hi; // range of the other index (y for x sides, x for y sides), inclusive
@@ -40,6 +40,10 @@ __global__ void __launch_bounds__(256) k_boundary(const BndryParams p) {
   if (p.kind == 2) {
     for (int i = 0; i < p.width; ++i) {
       p.f[idx3(p.first + i * p.b)] = 0.0;
+    }
+  } else if (p.kind == 3) { // examples/elm-pb/elm_pb.cxx:1498-1516: phi(i) = phi(i+-1) beyond the first guard
+    for (int i = 1; i < p.width; ++i) {
+      p.f[idx3(p.first + i * p.b)] = p.f[idx3(p.first + (i - 1) * p.b)];
     }
   } else if (p.kind == 0) {
     p.f[idx3(p.first)] = 2 * p.val - p.f[idx3(p.first - p.b)];
@@ -66,7 +70,7 @@ extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, d
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
-  B200_REQUIRE(f != nullptr && kind >= 0 && kind <= 2 && side >= 0 && side <= 3, BOUT_B200_ERR_ARG,
+  B200_REQUIRE(f != nullptr && kind >= 0 && kind <= 3 && side >= 0 && side <= 3, BOUT_B200_ERR_ARG,
                "boundary: bad argument");
   B200_REQUIRE(kind != 1 || spacing2d != nullptr, BOUT_B200_ERR_ARG, "boundary: neumann needs the spacing");
   BndryParams p{};

@@ -44,7 +44,7 @@ const cd* twiddleTable(int nz, cudaStream_t stream, int* status) {
   return devp;
 }
 
-enum ZMode { Z_DDZ1 = 0, Z_DDZ2 = 1, Z_FILTER = 2, Z_LOWPASS = 3, Z_SHIFT = 4, Z_SLICE = 5 };
+enum ZMode { Z_DDZ1 = 0, Z_DDZ2 = 1, Z_FILTER = 2, Z_LOWPASS = 3, Z_SHIFT = 4, Z_SLICE = 5, Z_ZEROLAP = 6 };
 
 struct ZfftParams {
   const double* __restrict__ f;
@@ -56,6 +56,11 @@ struct ZfftParams {
   int nx, ny, nz, xs, xe, ys, ye;
   int mode, kmax, n0, keep_zonal;
   int yoff; // Z_SLICE: this row is the y + yoff neighbour of the row whose frame it is shifted into
+  // Z_ZEROLAP: guard rows are continued from the last interior row xin (outward direction bdir)
+  const double* __restrict__ m_dx;
+  const double* __restrict__ m_g11;
+  const double* __restrict__ m_g33;
+  int xin, bdir;
   double angle0, zlength0;
   int tpr, rows, pow2;
 };
@@ -82,7 +87,8 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
   const int x = p.xs + static_cast<int>(rid / nyb);
   const int y = p.ys + static_cast<int>(rid % nyb);
   const long long i2 = static_cast<long long>(x) * p.ny + y;
-  const double* __restrict__ src = p.f + i2 * p.nz;
+  const long long isrc2 = p.mode == Z_ZEROLAP ? static_cast<long long>(p.xin) * p.ny + y : i2;
+  const double* __restrict__ src = p.f + isrc2 * p.nz;
 
   // load the real row into A
   double* a = reinterpret_cast<double*>(r.A);
@@ -147,6 +153,31 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
         double s, c;
         sincos(kwave * ang, &s, &c);
         v = cmul(v, cd{c, -s});
+      }
+      break;
+    }
+    case Z_ZEROLAP: { // BoundaryZeroLaplace::apply(Field3D), boundary_standard.cxx:2630-2686
+      const int steps = (x - p.xin) * p.bdir;
+      if (k == 0) { // straight line through the last two interior z-means
+        const double* __restrict__ in2 = p.f + (static_cast<long long>(p.xin - p.bdir) * p.ny + y) * p.nz;
+        double m2 = 0.0;
+        for (int j = 0; j < p.nz; ++j) {
+          m2 += __ldg(in2 + j);
+        }
+        m2 /= p.nz;
+        const double grad = v.re - m2;
+        for (int s = 0; s < steps; ++s) {
+          v.re += grad;
+        }
+      } else { // decaying solution of g11 d2f/dx2 - g33 kz^2 f = 0, applied guard cell by guard cell
+        const double kwave = k * 2.0 * M_PI / p.zlength0;
+        for (int s = 1; s <= steps; ++s) {
+          const long long ig = static_cast<long long>(p.xin + s * p.bdir) * p.ny + y;
+          const double coef = -1.0 * sqrt(__ldg(p.m_g33 + ig) / __ldg(p.m_g11 + ig)) * __ldg(p.m_dx + ig);
+          const double e = exp(coef * kwave);
+          v.re *= e;
+          v.im *= e;
+        }
       }
       break;
     }
@@ -339,6 +370,39 @@ extern "C" int bout_b200_parallel_slices(const bout_b200_grid* g, const double* 
     }
   }
   return 0;
+}
+
+// BoundaryZeroLaplace::apply(Field3D) (src/mesh/boundary_standard.cxx:2630-2686) on the x-inner (side 0)
+// or x-outer (side 1) guard cells of rows y = lo..hi (default ystart..yend), in place.
+extern "C" int bout_b200_boundary_zerolaplace(const bout_b200_grid* g, int side, const double* dx2d,
+                                              const double* g11, const double* g33, double zlength, int lo,
+                                              int hi, double* f, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(f && dx2d && g11 && g33 && (side == 0 || side == 1), BOUT_B200_ERR_ARG,
+               "boundary_zerolaplace: bad argument (X boundaries only)");
+  const int width = side == 0 ? g->xstart : g->nx - 1 - g->xend;
+  if (width <= 0) {
+    return 0;
+  }
+  B200_REQUIRE(g->xend - g->xstart >= 1, BOUT_B200_ERR_GUARDS, "boundary_zerolaplace: needs 2 interior points");
+  if (lo < 0 || hi < 0) {
+    lo = g->ystart;
+    hi = g->yend;
+  }
+  ZfftParams p{};
+  p.f = f;
+  p.out = f;
+  p.mode = Z_ZEROLAP;
+  p.m_dx = dx2d;
+  p.m_g11 = g11;
+  p.m_g33 = g33;
+  p.zlength0 = zlength;
+  p.xin = side == 0 ? g->xstart : g->xend;
+  p.bdir = side == 0 ? -1 : 1;
+  const Box b = side == 0 ? Box{0, g->xstart - 1, lo, hi} : Box{g->xend + 1, g->nx - 1, lo, hi};
+  return launchZfft(g, BOUT_B200_RGN_ALL, p, stream, &b);
 }
 
 extern "C" int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* stream) {

@@ -118,3 +118,165 @@ class HW3D:
         self.rhs(sn, sv, E((n, v), (an, av), (tn, tv), (an, av), 0.5 * dt, dt / 3.0), ddt=False)
         self.rhs(tn, tv, E((n, v), (an, av), (sn, sv), (an, av), dt, dt / 3.0), ddt=False)
         self.rhs(sn, sv, E((n, v), (an, av), (None, None), (n, v), 0.0, dt / 6.0), ddt=False)
+
+
+class ELMpb:
+    """examples/elm-pb/elm_pb.cxx rhs() (lines 1240-2030) with the shipped [highbeta] switches
+    (examples/elm-pb/data/BOUT.inp): linear, evolve Psi, diamag + diamag_phi0, constn0, bm_*_flag = 0
+    (BRACKET_STD -> b0xGrad_dot_Grad), hyper-resistivity, smooth_j_x, filter_z + low_pass_z; shifted-metric
+    parallel transform, all-core grid (y periodic), methods C4 / C2 / C4 (first), W3 / C2 / W3 (upwind).
+
+    Inputs are the POST-INIT quantities of the model (init() is set-up time, not on the per-RHS path):
+    `md` the Coordinates Field2D set after ELMpb::init's metric assignment + geometry(); `eq` =
+    {J0, P0, phi0, B0, b0xcv_x, b0xcv_y, b0xcv_z (Field2D), eta (Field3D)}; scalars dnorm, hyperresist.
+    Every numerical step is a C-ABI call.  Evolving fields: U, P, Psi (solver order of SOLVE_FOR)."""
+
+    def __init__(self, g: capi.Grid, md: dict, eq: dict, zshift, zlength, dnorm, hyperresist,
+                 filter_z_mode=1, low_pass_z=16, zonal=(False, True, False), device="cuda"):
+        self.g, self.dev = g, torch.device(device)
+        dv = lambda t: t.to(self.dev).contiguous()
+        self.md = {k: dv(v) for k, v in md.items()}
+        self.eq = {k: dv(v) for k, v in eq.items()}
+        self.zs, self.zl = dv(zshift), float(zlength)
+        self.mzs = (-self.zs).contiguous()
+        self.dnorm, self.hyperresist = float(dnorm), float(hyperresist)
+        self.filter_z_mode, self.low_pass_z = int(filter_z_mode), int(low_pass_z)
+        self.zonal_flow, self.zonal_bkgd, self.zonal_field = zonal      # for ddt(U), ddt(P), ddt(Psi)
+        m = self.md
+        # phiSolver: [phiSolver] inner_boundary_flags = 4 (AC_LAP), outer = 1 + 4 (DC_GRAD + AC_LAP)
+        self.lap = capi.Laplace(g, m, self.zl, all_terms=True, nonuniform=True, flags=(0, 4, 5))
+        self.lap.workspace(self.dev)
+        self.delp = capi.Laplace(g, m, self.zl, all_terms=True, nonuniform=True)   # Delp2's default Laplacian
+        self.b0x = capi.make_b0xgrad(m, first=("C4", "C2", "C4"), upwind=("W3", "C2", "W3"))
+        self.rdx = (1.0 / m["dx"]).contiguous()
+        self.rdy = (1.0 / m["dy"]).contiguous()
+        self.rdz = (1.0 / m["dz"]).contiguous()
+        self.gradpar = (self.rdy / torch.sqrt(m["g_22"])).contiguous()       # DDY / dy * invSg
+        self.B0 = self.eq["B0"]
+        self.B0sq = (self.B0 * self.B0).contiguous()
+        z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
+        self.U, self.P, self.Psi = z(), z(), z()
+        self.phi, self.Jpar, self.Jpar2 = z(), z(), z()
+        self.ddt_U, self.ddt_P, self.ddt_Psi = z(), z(), z()
+        self.compute_jpar2 = True     # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
+
+    def set_state(self, U, P, Psi):
+        self.U.copy_(U), self.P.copy_(P), self.Psi.copy_(Psi)
+
+    def _slices(self, f):
+        return capi.parallel_slices(self.g, f, self.zs, self.zl, 1)
+
+    def _comm(self, fields):
+        """mesh->communicate(...) on one rank: y periodic self exchange; ShiftedMetric then builds the
+        parallel slices of each field (mesh.cxx:349-378)."""
+        capi.halo_self(self.g, fields, periodic_x=False, periodic_y=True)
+        return [self._slices(f) for f in fields]
+
+    def _bc_j(self, f):          # [J] bndry_core = neumann, rest dirichlet_o2
+        capi.boundary(self.g, "neumann", "xin", f, spacing=self.md["dx"])
+        capi.boundary(self.g, "dirichlet", "xout", f)
+
+    def _bc_psi(self, f):        # [Psi] zerolaplace on both X sides
+        m = self.md
+        capi.boundary_zerolaplace(self.g, "xin", f, m["dx"], m["g11"], m["g33"], self.zl)
+        capi.boundary_zerolaplace(self.g, "xout", f, m["dx"], m["g11"], m["g33"], self.zl)
+
+    def pre_rhs(self, U, P, Psi):
+        """Solver::pre_rhs (solver.cxx:1486-1500): boundary conditions of the evolving fields."""
+        g = self.g
+        capi.boundary(g, "dirichlet", "xin", U)
+        capi.boundary(g, "dirichlet", "xout", U)
+        capi.boundary(g, "neumann", "xin", P, spacing=self.md["dx"])      # [P] bndry_core = neumann
+        capi.boundary(g, "dirichlet", "xout", P)
+        self._bc_psi(Psi)
+
+    def _grad_par_noslices(self, f):
+        """Grad_par of a field WITHOUT parallel slices: DDY goes through toFieldAligned(RGN_NOX) ->
+        index DDY C2 -> fromFieldAligned (index_derivs_interface.hxx:205-211), / dy, * invSg."""
+        g = self.g
+        fa = capi.zshift(g, f, self.mzs, self.zl, region="RGN_NOX")
+        d = capi.stencil(g, "DDX_C2", "Y", fa, scale1=self.gradpar)
+        return capi.zshift(g, d, self.zs, self.zl, region="RGN_NOBNDRY")
+
+    def rhs(self, U=None, P=None, Psi=None):
+        g, m, eq = self.g, self.md, self.eq
+        U = self.U if U is None else U
+        P = self.P if P is None else P
+        Psi = self.Psi if Psi is None else Psi
+        ew = capi.elementwise
+        self.pre_rhs(U, P, Psi)
+        sU, sP, sPsi = self._comm([U, P, Psi])                               # mesh->communicate(comms)
+        # phi = phiSolver->solve(U) - 0.5 dnorm P / B0 (constn0, diamag)       elm_pb.cxx:1472-1477
+        self.lap.solve(U, out=self.phi)
+        ew(g, [(1.0, self.phi), (-0.5 * self.dnorm, P, None, self.B0)], out=self.phi)
+        (sphi,) = self._comm([self.phi])
+        capi.boundary(g, "extend", "xin", self.phi)                           # :1498-1516
+        capi.boundary(g, "extend", "xout", self.phi)
+        # Jpar = Delp2(Psi); BC; communicate; smooth_x; BC; communicate         :1518-1563
+        self.delp.delp2(Psi, out=self.Jpar)
+        self._bc_j(self.Jpar)
+        capi.halo_self(g, [self.Jpar], periodic_x=False, periodic_y=True)
+        sm = capi.smooth_x(g, self.Jpar)
+        capi.halo_self(g, [sm], periodic_x=False, periodic_y=True)            # smooth_x communicates its result
+        self.Jpar.copy_(sm)
+        self._bc_j(self.Jpar)
+        (sJ,) = self._comm([self.Jpar])
+        # Delp2(Jpar): Jpar2 (:1565-1572) and the hyper-resistivity term (:1717-1723) evaluate the same field
+        d2J = self.delp.delp2(self.Jpar)
+        if self.compute_jpar2:
+            self.Jpar2.copy_(d2J)
+            self._bc_j(self.Jpar2)
+            capi.halo_self(g, [self.Jpar2], periodic_x=False, periodic_y=True)
+        # ---- ddt(Psi) = -Grad_par(phi B0)/B0 + eta Jpar - bracket(phi0, Psi) B0 - eta hyperresist Delp2(Jpar)
+        # bracket(Field2D, Field3D, BRACKET_STD) = b0xGrad_dot_Grad / Bxy (difops.cxx:805-808)
+        phiB0 = ew(g, [(1.0, self.phi, self.B0)])
+        gp = self._grad_par_noslices(phiB0)
+        bg = capi.b0xgrad_dot_grad(g, self.b0x, eq["phi0"], Psi, None, sPsi)
+        ew(g, [(-1.0, gp, None, self.B0), (1.0, eq["eta"], self.Jpar), (-1.0, bg, self.B0, m["Bxy"]),
+               (-self.hyperresist, eq["eta"], d2J)], out=self.ddt_Psi, region="RGN_NOBNDRY")
+        # ---- ddt(U) = B0^2 b0xGrad_dot_Grad(Psi_loc, J0) + b0xcv . Grad(P) - B0^2 Grad_par(Jpar)
+        #               - b0xGrad_dot_Grad(phi0, U)                                         :1755-1775
+        # Psi_loc = Psi + the same zerolaplace boundary again (bitwise Psi); it keeps Psi's slices
+        t1 = capi.b0xgrad_dot_grad(g, self.b0x, Psi, eq["J0"], sPsi, None, shifted=(self.zs, self.zl))
+        dPx = capi.stencil(g, "DDX_C4", "X", P, scale1=self.rdx)
+        dPy = capi.stencil_yslices(g, "DDX_C2", P, sP[0], sP[1], scale1=self.rdy)
+        dPz = capi.stencil(g, "DDX_C4", "Z", P, scale1=self.rdz)
+        gpJ = capi.stencil_yslices(g, "DDX_C2", self.Jpar, sJ[0], sJ[1], scale1=self.gradpar)
+        t4 = capi.b0xgrad_dot_grad(g, self.b0x, eq["phi0"], U, None, sU)
+        ew(g, [(1.0, t1, self.B0sq), (1.0, dPx, eq["b0xcv_x"]), (1.0, dPy, eq["b0xcv_y"]),
+               (1.0, dPz, eq["b0xcv_z"]), (-1.0, gpJ, self.B0sq), (-1.0, t4)], out=self.ddt_U,
+           region="RGN_NOBNDRY")
+        # ---- ddt(P) = -b0xGrad_dot_Grad(phi, P0) - b0xGrad_dot_Grad(phi0, P)                :1869-1876
+        p1 = capi.b0xgrad_dot_grad(g, self.b0x, self.phi, eq["P0"], sphi, None, shifted=(self.zs, self.zl))
+        p2 = capi.b0xgrad_dot_grad(g, self.b0x, eq["phi0"], P, None, sP)
+        ew(g, [(-1.0, p1), (-1.0, p2)], out=self.ddt_P, region="RGN_NOBNDRY")
+        # ---- filter_z, low_pass_z                                                            :1931-1955
+        for f, zonal in ((self.ddt_Psi, self.zonal_field), (self.ddt_U, self.zonal_flow),
+                         (self.ddt_P, self.zonal_bkgd)):
+            capi.zfilter(g, f, self.filter_z_mode, out=f)
+            if self.low_pass_z > 0:
+                capi.zlowpass(g, f, self.low_pass_z, keep_zonal=zonal, out=f)
+
+    def rk4_step(self, dt):
+        """RK4Solver::take_step (rk4.cxx:172-210): stage combinations over the evolving region."""
+        g = self.g
+        state = (self.U, self.P, self.Psi)
+        if not hasattr(self, "_rk"):
+            self._rk = [[torch.zeros_like(self.U) for _ in range(3)] for _ in range(5)]   # k1..k4, stage state
+        k1, k2, k3, k4, st = self._rk
+        ddts = lambda: (self.ddt_U, self.ddt_P, self.ddt_Psi)
+
+        def stage(src, k, coef):
+            self.rhs(*src)
+            for i, d in enumerate(ddts()):
+                k[i].copy_(d)
+            if coef is not None:
+                for i in range(3):
+                    st[i].copy_(state[i])
+                    capi.rk_stage(g, "axpy", coef * dt, state[i], k[i], out=st[i])
+        stage(state, k1, 0.5)
+        stage(st, k2, 0.5)
+        stage(st, k3, 1.0)
+        stage(st, k4, None)
+        for i in range(3):
+            capi.rk_stage(g, "rk4_final", dt, state[i], k1[i], k2[i], k3[i], k4[i], out=state[i])

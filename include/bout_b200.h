@@ -282,11 +282,18 @@ int bout_b200_unary(const bout_b200_grid* g, int op, const double* f, double arg
 
 /* ---- boundary conditions (a15) ---------------------------------------------------------------------
  * kind: 0 dirichlet / dirichlet_o2 (src/mesh/boundary_standard.cxx:527-581), 1 neumann (:2167-2190),
- * 2 zero the cells (apply_ddt :591-600).  side: 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper.
+ * 2 zero the cells (apply_ddt :591-600), 3 extend: every guard cell beyond the first copies its inner
+ * neighbour (the phi guard loops of examples/elm-pb/elm_pb.cxx:1498-1516).  side: 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper.
  * spacing2d: dx for x sides, dy for y sides (Neumann only).  lo/hi: range of the other index
  * (y for x sides, x for y sides); pass -1,-1 for the reference's default (ystart..yend / all x). */
 int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value,
                        const double* spacing2d, int lo, int hi, double* f, void* stream);
+/* zerolaplace (BoundaryZeroLaplace::apply(Field3D), src/mesh/boundary_standard.cxx:2630-2686): guard rows
+ * continue the last interior row with the decaying solution of g11 d2f/dx2 - g33 kz^2 f = 0 per z mode and
+ * a straight line for kz = 0.  X sides only (side 0 or 1); dx2d, g11, g33 Field2D; lo/hi as above. */
+int bout_b200_boundary_zerolaplace(const bout_b200_grid* g, int side, const double* dx2d,
+                                   const double* g11, const double* g33, double zlength, int lo, int hi,
+                                   double* f, void* stream);
 
 /* ---- guard-cell exchange (a13, Mesh::communicate) ------------------------------------------------------
  * Self exchange when the rank is its own neighbour (periodic Y with NYPE=1, periodicX with NXPE=1):

@@ -500,6 +500,20 @@ class Ref:
             raise RuntimeError(self.lib.boutref_last_error().decode(errors="replace")[-2000:])
         return t
 
+    def elmpb_get(self, name):
+        """examples/elm-pb only: a post-init equilibrium field / scalar or a per-RHS auxiliary by name
+        (oracle/elmpb_export.cxx).  Returns a float for scalars."""
+        k = C.c_int(0)
+        self.lib.boutref_elmpb_get.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_int)]
+        if self.lib.boutref_elmpb_get(name.encode(), None, C.byref(k)) != 0:
+            raise KeyError(name)
+        if k.value == 0:
+            out = np.zeros(1)
+        else:
+            out = np.zeros(self.grid.shape2 if k.value == 2 else self.grid.shape3)
+        self._check(self.lib.boutref_elmpb_get(name.encode(), _p(out), C.byref(k)))
+        return float(out[0]) if k.value == 0 else out
+
     def model_solve(self, nout, output_step):
         self.lib.boutref_model_solve.argtypes = [C.c_int, C.c_double]
         self._check(self.lib.boutref_model_solve(nout, output_step))

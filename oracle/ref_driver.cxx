@@ -42,6 +42,8 @@ using bout::globals::mesh;
 std::unique_ptr<PhysicsModel> boutref_make_hw();
 std::unique_ptr<PhysicsModel> boutref_make_hw3d();
 std::unique_ptr<PhysicsModel> boutref_make_blob2d();
+std::unique_ptr<PhysicsModel> boutref_make_elmpb();
+int boutref_elmpb_get_impl(PhysicsModel* pm, const char* name, double* out, int* kind);
 
 namespace {
 // The reference's own RK4 solver with its (protected) variable registry made reachable, so the
@@ -591,11 +593,19 @@ int boutref_model_create(const char* name, const char* solver) {
       model = boutref_make_hw3d();
     } else if (n == "blob2d") {
       model = boutref_make_blob2d();
+    } else if (n == "elmpb") {
+      model = boutref_make_elmpb();
     } else {
       throw BoutException("unknown model '{}'", n);
     }
     activeSolver()->setModel(model.get());
   });
+}
+// examples/elm-pb only: equilibrium fields / scalars / per-RHS auxiliaries by name (elmpb_export.cxx)
+int boutref_elmpb_get(const char* name, double* out, int* kind) {
+  int rc = 0;
+  const int g = guarded([&]() { rc = boutref_elmpb_get_impl(model.get(), name, out, kind); });
+  return g != 0 ? 100 : rc;
 }
 int boutref_model_nvars() { return rk4 ? rk4->nvars() : (rk3 ? rk3->nvars() : 0); }
 const char* boutref_model_varname(int i) {

@@ -102,3 +102,141 @@ error_on_unused_options = false
 """)
 
 
+
+
+def elmpb_ini(nx, ny, nz, timestep="1e-3", extra_highbeta=""):
+    """examples/elm-pb/data/BOUT.inp (methods, solver flags, boundary conditions, [highbeta] switches as
+    shipped) on a SYNTHETIC closed-form circular-cross-section tokamak grid given as mesh options (the
+    shipped cbm18 grid file is NetCDF, which this build cannot read): all-core (ixseps = nx, y periodic),
+    shifted metric, zperiod = 15.  nx includes the 2*MXG guard cells; ny is the interior count."""
+    mx = nx - 4
+    return f"""
+MXG = 2
+MYG = 2
+zperiod = 15
+[mesh]
+staggergrids = false
+nx = {nx}
+ny = {ny}
+nz = {nz}
+ixseps1 = {nx}
+ixseps2 = {nx}
+rminor = 0.4 + 0.3*x
+qsafe = 1.2 + 2*x^2
+Rxy = 3 + mesh:rminor*cos(y)
+Btxy = 6/mesh:Rxy
+Bpxy = mesh:rminor*mesh:Btxy/(mesh:qsafe*mesh:Rxy)
+Bxy = sqrt(mesh:Btxy^2 + mesh:Bpxy^2)
+hthe = mesh:rminor*(1 + 0.05*cos(y))
+sinty = 1.5*x*(y - pi)
+psixy = x
+psi_axis = 0
+psi_bndry = 1
+bmag = 2.0
+rmag = 3.0
+dx = (0.15/{mx})*(1 + 0.2*x)
+dy = 2*pi/{ny}
+dz = 2*pi/15/{nz}
+zShift = mesh:qsafe*(y - pi + 0.2*mesh:rminor*sin(y))
+ShiftAngle = 2*pi*mesh:qsafe
+Jpar0 = 8e5*(1 - x^2)*(1 + 0.1*cos(y))
+pressure = 2e4*(1 - tanh((x - 0.6)/0.15)) + 500
+bxcvx = 0.02*sin(y)*(1 + 0.3*x)
+bxcvy = 0.003*cos(y)
+bxcvz = 0.05*cos(y) + 0.01*x
+[mesh:paralleltransform]
+type = shifted
+[mesh:ddx]
+first = C4
+second = C4
+upwind = W3
+[mesh:ddy]
+first = C2
+second = C2
+upwind = C2
+flux = C2
+[mesh:ddz]
+first = C4
+second = C4
+upwind = W3
+[solver]
+timestep = {timestep}
+[highbeta]
+density = 1e+19
+evolve_jpar = false
+evolve_pressure = true
+phi_constraint = false
+include_jpar0 = true
+include_curvature = true
+compress = false
+nonlinear = false
+diamag = true
+diamag_grad_t = false
+diamag_phi0 = true
+bm_exb_flag = 0
+bm_mag_flag = 0
+withflow = false
+eHall = false
+AA = 2.0
+noshear = false
+relax_j_vac = false
+filter_z = true
+filter_z_mode = 1
+low_pass_z = 16
+zonal_flow = false
+zonal_field = false
+zonal_bkgd = true
+smooth_j_x = true
+include_rmp = false
+vacuum_pressure = 0.02
+vacuum_trans = 0.01
+vac_lund = 1.e8
+core_lund = 1.e8
+hyperresist = 1.e-4
+damp_width = -1
+diffusion_par = -1.0
+diffusion_p4 = -1e-05
+diffusion_u4 = -1e-05
+diffusion_a4 = -1e-05
+heating_P = -1
+sink_P = -1
+sink_Ul = -10.0
+sink_Ur = -10.0
+viscos_par = -0.1
+viscos_perp = -1.0
+hyperviscos = -1.0
+phi_curv = true
+{extra_highbeta}
+[phiSolver]
+inner_boundary_flags = 4
+outer_boundary_flags = 5
+[aparSolver]
+inner_boundary_flags = 4
+outer_boundary_flags = 5
+[all]
+scale = 0.0
+bndry_all = dirichlet_o2
+[U]
+scale = 1e-05
+function = ballooning(gauss(x-0.5,0.1)*gauss(y-pi,0.6*pi)*sin(z),3)
+[P]
+bndry_core = neumann
+[Psi]
+bndry_xin = zerolaplace
+bndry_xout = zerolaplace
+[Psi_loc]
+bndry_xin = zerolaplace
+bndry_xout = zerolaplace
+bndry_yup = free_o3
+bndry_ydown = free_o3
+[J]
+bndry_core = neumann
+[phi]
+bndry_xin = none
+bndry_xout = none
+[input]
+error_on_unused_options = false
+"""
+
+
+ELMPB_INI = elmpb_ini(20, 8, 16, timestep="2e-3")

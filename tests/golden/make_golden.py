@@ -15,6 +15,10 @@ Outputs (committed; the GPU box has neither /root/reference nor needs the refere
   ops_shifted.npz        the elm-pb operator vocabulary on a shifted-metric mesh with elm-pb's derivative
                          methods: parallel slices, to/fromFieldAligned, Y operators on slices,
                          b0xGrad_dot_Grad (3D3D, 3D2D, 2D3D), averageY, smooth_x.
+  elmpb.npz              examples/elm-pb/elm_pb.cxx (unchanged, shipped [highbeta] switches) on the synthetic
+                         shifted-metric tokamak grid of cases.elmpb_ini: post-init equilibrium + metric, one
+                         Solver::run_rhs on a seeded (U, P, Psi) state (ddt + phi, Jpar, Jpar2), and a short
+                         RK4 trajectory.
   models.npz             unchanged example models (hasegawa-wakatani, hasegawa-wakatani-3d, blob2d) run
                          through the reference's Solver::run_rhs and RK4 / RK3-SSP solvers: initial state,
                          ddt after one RHS, state after a few steps.
@@ -223,7 +227,7 @@ def ops_small():
     print("  ops_small:", len(out), "arrays")
 
 
-from cases import HW_INI, HW3D_INI, BLOB_INI  # noqa: E402
+from cases import HW_INI, HW3D_INI, BLOB_INI, ELMPB_INI  # noqa: E402
 
 
 MODEL_CASES = {"hw": ("hw", HW_INI, "rk4", 5), "hw_rk3": ("hw", HW_INI, "rk3ssp", 5),
@@ -330,6 +334,64 @@ def one_model(tag, path):
     np.savez(path, **out)
 
 
+from elmpb_names import ELMPB_FIELDS, ELMPB_SCALARS  # noqa: E402
+ELMPB_DT, ELMPB_NSTEPS = 2e-3, 5
+
+
+def elmpb_states(g, U0):
+    """Seeded smooth (U, P, Psi) of elm-pb-like magnitudes for the single-RHS case."""
+    f, h, v = smooth_fields(g, 3, 20261019)
+    return U0 + 2e-6 * f, 3e-6 * h, 4e-7 * v
+
+
+def elmpb_case(which, path):
+    r = orc.Ref(ELMPB_INI)
+    g = r.grid
+    out = {}
+    names = r.model_create("elmpb", "rk4")
+    U0 = r.model_get("U")
+    U, P, Psi = elmpb_states(g, U0)
+    if which == "rhs":
+        out["grid"] = np.array([g.nx, g.ny, g.nz, g.mxg, g.myg])
+        m = r.metric()
+        for n in orc.Metric.NAMES:
+            out["metric_" + n] = getattr(m, n)
+        zs, zl = r.zshift()
+        out["zShift"], out["zlength"] = zs, np.array(zl)
+        for n in ELMPB_FIELDS:
+            out["eq_" + n] = r.elmpb_get(n)
+        out["scalars"] = np.array([r.elmpb_get(n) for n in ELMPB_SCALARS])
+        out["init_U"] = U0
+        out["rhs_in_U"], out["rhs_in_P"], out["rhs_in_Psi"] = U, P, Psi
+        r.model_set("U", U), r.model_set("P", P), r.model_set("Psi", Psi)
+        r.model_rhs(0.0)
+        for v in names:
+            out["rhs_ddt_" + v] = r.model_ddt(v)
+            out["rhs_bc_" + v] = r.model_get(v)      # the state after Solver::pre_rhs boundary conditions
+        for n in ("phi", "Jpar", "Jpar2", "Psi_loc"):
+            out["rhs_" + n] = r.elmpb_get(n)
+    else:
+        r.model_set("U", U), r.model_set("P", P), r.model_set("Psi", Psi)
+        r.model_solve(1, ELMPB_NSTEPS * ELMPB_DT)
+        for v in names:
+            out["final_" + v] = r.model_get(v)
+        out["dt_nsteps"] = np.array([ELMPB_DT, ELMPB_NSTEPS])
+        print("  elmpb trajectory: max|final| =", [float(np.abs(out["final_" + v]).max()) for v in names])
+    np.savez(path, **out)
+
+
+def elmpb():
+    import subprocess
+    import tempfile
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for which in ("rhs", "traj"):
+            path = os.path.join(tmp, which + ".npz")
+            subprocess.run([sys.executable, os.path.abspath(__file__), "elmpb:" + which, path], check=True)
+            out.update(dict(np.load(path)))
+    np.savez_compressed(os.path.join(HERE, "elmpb.npz"), **out)
+
+
 def models():
     import subprocess
     import tempfile
@@ -343,7 +405,11 @@ def models():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models"]
+    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb"]
+    if which[0].startswith("elmpb:"):
+        elmpb_case(which[0][6:], which[1])
+        sys.stdout.flush()
+        os._exit(0)
     if which[0].startswith("model:"):
         one_model(which[0][6:], which[1])
         sys.stdout.flush()
@@ -356,4 +422,6 @@ if __name__ == "__main__":
         ops_shifted()
     if "models" in which:
         models()
+    if "elmpb" in which:
+        elmpb()
     os._exit(0)  # the reference's static destructors are not exit-safe after repeated init/finalise
