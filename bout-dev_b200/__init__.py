@@ -10,3 +10,4 @@ from . import capi  # noqa: F401
 from . import mesh  # noqa: F401
 from . import models  # noqa: F401
 from . import host  # noqa: F401
+from . import elm_setup  # noqa: F401

@@ -115,6 +115,14 @@ def zlowpass(g: Grid, f, zmax, keep_zonal=True, out=None, region="RGN_ALL"):
     return out
 
 
+def zfilter_lowpass(g: Grid, f, n0, zmax, keep_zonal=True, out=None, region="RGN_ALL"):
+    """filter(f, n0) then lowPass(., zmax, keep_zonal) in one pass."""
+    out = torch.zeros_like(f) if out is None else out
+    _check(lib.bout_b200_zfilter_lowpass(C.byref(g.c), REGIONS[region], n0, zmax, int(keep_zonal), _ptr(f),
+                                         _ptr(out), _stream()))
+    return out
+
+
 def zshift(g: Grid, f, angle, zlength, out=None, region="RGN_ALL"):
     """angle / zlength: python floats or Field2D tensors."""
     out = torch.zeros_like(f) if out is None else out

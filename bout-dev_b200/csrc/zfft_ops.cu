@@ -5,6 +5,7 @@
 // filter / lowPass / shiftZ (src/field/field3d.cxx:620-741), and the phase-shift core of
 // ShiftedMetric::shiftZ (src/mesh/parallel/shiftedmetric.cxx:200-224).
 #include "fft.cuh"
+#include "fft_fast.cuh"
 
 #include <cmath>
 #include <map>
@@ -44,7 +45,8 @@ const cd* twiddleTable(int nz, cudaStream_t stream, int* status) {
   return devp;
 }
 
-enum ZMode { Z_DDZ1 = 0, Z_DDZ2 = 1, Z_FILTER = 2, Z_LOWPASS = 3, Z_SHIFT = 4, Z_SLICE = 5, Z_ZEROLAP = 6 };
+enum ZMode { Z_DDZ1 = 0, Z_DDZ2 = 1, Z_FILTER = 2, Z_LOWPASS = 3, Z_SHIFT = 4, Z_SLICE = 5, Z_ZEROLAP = 6,
+             Z_FILTER_LOWPASS = 7, Z_SLICE2 = 8 };
 
 struct ZfftParams {
   const double* __restrict__ f;
@@ -52,6 +54,7 @@ struct ZfftParams {
   const double* __restrict__ angle;  // Field2D shift angle (Z_SHIFT) or NULL -> angle0
   const double* __restrict__ zlength; // Field2D zlength (Z_SHIFT) or NULL -> zlength0
   double* __restrict__ out;
+  double* __restrict__ out2; // Z_SLICE2: ydown (out = yup)
   const cd* __restrict__ tw;
   int nx, ny, nz, xs, xe, ys, ye;
   int mode, kmax, n0, keep_zonal;
@@ -135,6 +138,11 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
         v = {0.0, 0.0};
       }
       break;
+    case Z_FILTER_LOWPASS:
+      if (k != p.n0 || k > p.kmax || (k == 0 && !p.keep_zonal)) {
+        v = {0.0, 0.0};
+      }
+      break;
     case Z_SHIFT: {
       if (k >= 1) {
         const double zl = p.zlength ? __ldg(p.zlength + i2) : p.zlength0;
@@ -206,6 +214,152 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
   }
 }
 
+
+// ---- fast path (nz in {128, 256, 512, 1024}, 16-byte aligned rows): fft_fast.cuh transforms, persistent
+// CTAs of 256 threads, the spectrum of a row held in shared memory between the forward and the one or two
+// backward transforms.  Z_SLICE2 produces both parallel slices (y+1 -> yup, y-1 -> ydown) of a source row
+// from ONE read and ONE forward transform of that row.
+template <int N>
+__device__ __forceinline__ void zmodSpectrum(const ZfftParams& p, const cd* S, cd* D, int lane, int mode, double ang,
+                                             double zl) {
+  constexpr int nz = 2 * N;
+  const double kfac = 2.0 * M_PI / nz;
+  for (int k = lane; k <= N; k += N / 4) {
+    cd v = S[k];
+    switch (mode) {
+    case Z_DDZ1:
+      if (k <= p.kmax) {
+        const double kw = k * kfac;
+        v = {-v.im * kw, v.re * kw};
+      } else {
+        v = {0.0, 0.0};
+      }
+      break;
+    case Z_DDZ2: {
+      const double kw = k * kfac;
+      const double m = -kw * kw;
+      v = {v.re * m, v.im * m};
+      break;
+    }
+    case Z_FILTER:
+      if (k != p.n0) {
+        v = {0.0, 0.0};
+      }
+      break;
+    case Z_LOWPASS:
+      if (k > p.kmax || (k == 0 && !p.keep_zonal)) {
+        v = {0.0, 0.0};
+      }
+      break;
+    case Z_FILTER_LOWPASS: // filter(f, n0) then lowPass(., kmax, keep_zonal)
+      if (k != p.n0 || k > p.kmax || (k == 0 && !p.keep_zonal)) {
+        v = {0.0, 0.0};
+      }
+      break;
+    default: // Z_SHIFT, Z_SLICE: multiply by exp(-i kwave ang)
+      if (k >= 1) {
+        const double kwave = k * 2.0 * M_PI / zl;
+        double sn, cs;
+        sincos(kwave * ang, &sn, &cs);
+        v = cmul(v, cd{cs, -sn});
+      }
+      break;
+    }
+    D[k] = v;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TPR = FftShape<N>::TPR, ROWS = 256 / TPR, STRIDE = 4 * (N + 8);
+  const int rloc = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+  cd* A = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(rloc) * STRIDE;
+  cd* B = A + (N + 8);
+  cd* S = B + (N + 8);   // spectrum of the row (N + 1 modes)
+  cd* D = S + (N + 8);   // modified spectrum
+  FastTw<N> tw;
+  fastTwInit<N>(tw, p.tw, lane);
+  const int nyb = p.ye - p.ys + 1;
+  const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * nyb;
+  for (long long base = static_cast<long long>(blockIdx.x) * ROWS; base < nrows;
+       base += static_cast<long long>(gridDim.x) * ROWS) {
+    const long long rowid = base + rloc;
+    const bool active = rowid < nrows;
+    const long long rid = active ? rowid : nrows - 1;
+    const int x = p.xs + static_cast<int>(rid / nyb);
+    const int y = p.ys + static_cast<int>(rid % nyb);
+    const long long i2 = static_cast<long long>(x) * p.ny + y;
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(p.f + i2 * p.nz);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + m * (N / 4);
+      const double2 v = __ldg(s2 + j);
+      A[fsw(j)] = {v.x, v.y};
+    }
+    __syncthreads();
+    const cd* Z = cfftFast<N, false>(A, B, tw, lane);
+    rfftSplitTo<N>(Z, S, N + 1, tw, lane);
+    __syncthreads();
+    const int nout = p.mode == Z_SLICE2 ? 2 : 1;
+    for (int o = 0; o < nout; ++o) {
+      double ang = 0.0, zl = p.zlength0;
+      int mode = p.mode;
+      bool store = active;
+      double* __restrict__ dstf = p.out;
+      if (p.mode == Z_SHIFT) {
+        zl = p.zlength ? __ldg(p.zlength + i2) : p.zlength0;
+        ang = p.angle ? __ldg(p.angle + i2) : p.angle0;
+      } else if (p.mode == Z_SLICE) {
+        ang = __ldg(p.angle + i2 - p.yoff) - __ldg(p.angle + i2);
+      } else if (p.mode == Z_SLICE2) {
+        // o = 0: this row is the y+1 neighbour of row y-1 (yup); o = 1: the y-1 neighbour of row y+1 (ydown)
+        const int yoff = o == 0 ? 1 : -1;
+        const int yt = y - yoff;                       // the row whose frame we shift into
+        const bool ok = yt >= p.n0 && yt <= p.kmax;    // n0..kmax = ystart..yend of the target rows
+        store = active && ok;
+        const int ytc = ok ? yt : y;
+        ang = __ldg(p.angle + static_cast<long long>(x) * p.ny + ytc) - __ldg(p.angle + i2);
+        mode = Z_SLICE;
+        dstf = o == 0 ? p.out : p.out2;
+      }
+      zmodSpectrum<N>(p, S, D, lane, mode, ang, zl);
+      __syncthreads();
+      rfftMergeFrom<N>(D, A, N + 1, false, tw, lane);
+      __syncthreads();
+      const cd* z = cfftFast<N, true>(A, B, tw, lane);
+      if (store) {
+        const double sc = p.scale ? __ldg(p.scale + i2) : 1.0;
+        double2* __restrict__ d2 = reinterpret_cast<double2*>(dstf + i2 * p.nz);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int j = lane + m * (N / 4);
+          const cd v = z[fsw(j)];
+          d2[j] = make_double2(v.re * sc, v.im * sc);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int N>
+int launchZrowsFast(const ZfftParams& p, long long nrows, cudaStream_t s) {
+  constexpr int ROWS = 256 / FftShape<N>::TPR;
+  const size_t smem = static_cast<size_t>(ROWS) * 4 * (N + 8) * sizeof(cd);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_zrows_fast<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const long long want = (nrows + ROWS - 1) / ROWS;
+  const unsigned blocks = static_cast<unsigned>(want < 148LL * 4 ? want : 148LL * 4);
+  k_zrows_fast<N><<<blocks, 256, smem, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 int launchZfft(const bout_b200_grid* g, int region, ZfftParams p, void* stream, const Box* box = nullptr) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
@@ -230,6 +384,19 @@ int launchZfft(const bout_b200_grid* g, int region, ZfftParams p, void* stream, 
   p.xe = b.xe;
   p.ys = b.ys;
   p.ye = b.ye;
+  const long long nrows_all = static_cast<long long>(b.xe - b.xs + 1) * (b.ye - b.ys + 1);
+  const int N = g->nz / 2;
+  const bool fast_ok = p.mode != Z_ZEROLAP && (g->nz == 128 || g->nz == 256 || g->nz == 512 || g->nz == 1024)
+                       && aligned16(p.f) && aligned16(p.out) && (p.out2 == nullptr || aligned16(p.out2));
+  if (fast_ok) {
+    switch (N) {
+    case 64: return launchZrowsFast<64>(p, nrows_all, s);
+    case 128: return launchZrowsFast<128>(p, nrows_all, s);
+    case 256: return launchZrowsFast<256>(p, nrows_all, s);
+    default: return launchZrowsFast<512>(p, nrows_all, s);
+    }
+  }
+  B200_REQUIRE(p.mode != Z_SLICE2, BOUT_B200_ERR_UNSUPPORTED, "zfft: dual-slice mode needs the fast path");
   const RowGeom geo = rowGeometry(g->nz, 128);
   p.tpr = geo.tpr;
   p.rows = geo.rows;
@@ -320,6 +487,19 @@ extern "C" int bout_b200_zlowpass(const bout_b200_grid* g, int region, int zmax,
   return launchZfft(g, region, p, stream);
 }
 
+/* filter(f, n0) followed by lowPass(., zmax, keep_zonal) in one pass (elm_pb.cxx:1931-1955). */
+extern "C" int bout_b200_zfilter_lowpass(const bout_b200_grid* g, int region, int n0, int zmax, int keep_zonal,
+                                         const double* f, double* out, void* stream) {
+  ZfftParams p{};
+  p.f = f;
+  p.out = out;
+  p.mode = Z_FILTER_LOWPASS;
+  p.n0 = n0;
+  p.kmax = zmax;
+  p.keep_zonal = keep_zonal;
+  return launchZfft(g, region, p, stream);
+}
+
 extern "C" int bout_b200_zshift(const bout_b200_grid* g, int region, const double* f,
                                 const double* angle2d, double angle0, const double* zlength2d,
                                 double zlength0, double* out, void* stream) {
@@ -345,6 +525,22 @@ extern "C" int bout_b200_parallel_slices(const bout_b200_grid* g, const double* 
   B200_REQUIRE(f && zshift2d && yup && ydown, BOUT_B200_ERR_ARG, "parallel_slices: null argument");
   B200_REQUIRE(nslices >= 1 && nslices <= g->ystart && nslices <= g->ny - 1 - g->yend, BOUT_B200_ERR_GUARDS,
                "parallel_slices: %d slices need as many y guard cells", nslices);
+  const bool fast_dual = nslices == 1 && (g->nz == 128 || g->nz == 256 || g->nz == 512 || g->nz == 1024)
+                         && aligned16(f) && yup[0] && ydown[0] && aligned16(yup[0]) && aligned16(ydown[0])
+                         && yup[0] != f && ydown[0] != f && g->ystart >= 1;
+  if (fast_dual) { // one read + one forward transform per source row, both slices written
+    ZfftParams p{};
+    p.f = f;
+    p.out = yup[0];
+    p.out2 = ydown[0];
+    p.mode = Z_SLICE2;
+    p.angle = zshift2d;
+    p.zlength0 = zlength;
+    p.n0 = g->ystart; // target rows ystart..yend
+    p.kmax = g->yend;
+    const Box b = {0, g->nx - 1, g->ystart - 1, g->yend + 1};
+    return launchZfft(g, BOUT_B200_RGN_ALL, p, stream, &b);
+  }
   for (int i = 0; i < nslices; ++i) {
     for (int sign = 1; sign >= -1; sign -= 2) {
       double* out = sign > 0 ? yup[i] : ydown[i];

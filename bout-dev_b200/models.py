@@ -160,6 +160,15 @@ class ELMpb:
         self.ddt_U, self.ddt_P, self.ddt_Psi = z(), z(), z()
         self.compute_jpar2 = True     # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
 
+    @classmethod
+    def from_setup(cls, s, device="cuda", **kw):
+        """Build from elm_setup.elmpb_setup(...) (numpy, set-up time)."""
+        g = capi.Grid(*s["grid"])
+        md = {k: torch.from_numpy(v) for k, v in s["md"].items()}
+        eq = {k: torch.from_numpy(v) for k, v in s["eq"].items()}
+        return cls(g, md, eq, torch.from_numpy(s["zShift"]), s["zlength"], s["dnorm"], s["hyperresist"],
+                   device=device, **kw)
+
     def set_state(self, U, P, Psi):
         self.U.copy_(U), self.P.copy_(P), self.Psi.copy_(Psi)
 
@@ -250,12 +259,13 @@ class ELMpb:
         p1 = capi.b0xgrad_dot_grad(g, self.b0x, self.phi, eq["P0"], sphi, None, shifted=(self.zs, self.zl))
         p2 = capi.b0xgrad_dot_grad(g, self.b0x, eq["phi0"], P, None, sP)
         ew(g, [(-1.0, p1), (-1.0, p2)], out=self.ddt_P, region="RGN_NOBNDRY")
-        # ---- filter_z, low_pass_z                                                            :1931-1955
+        # ---- filter_z, low_pass_z in one pass per field                                      :1931-1955
         for f, zonal in ((self.ddt_Psi, self.zonal_field), (self.ddt_U, self.zonal_flow),
                          (self.ddt_P, self.zonal_bkgd)):
-            capi.zfilter(g, f, self.filter_z_mode, out=f)
             if self.low_pass_z > 0:
-                capi.zlowpass(g, f, self.low_pass_z, keep_zonal=zonal, out=f)
+                capi.zfilter_lowpass(g, f, self.filter_z_mode, self.low_pass_z, keep_zonal=zonal, out=f)
+            else:
+                capi.zfilter(g, f, self.filter_z_mode, out=f)
 
     def rk4_step(self, dt):
         """RK4Solver::take_step (rk4.cxx:172-210): stage combinations over the evolving region."""
@@ -280,3 +290,18 @@ class ELMpb:
         stage(st, k4, None)
         for i in range(3):
             capi.rk_stage(g, "rk4_final", dt, state[i], k1[i], k2[i], k3[i], k4[i], out=state[i])
+
+
+def elmpb_initial_state(g: capi.Grid, device="cuda", amp=1e-5):
+    """Synthetic smooth (U, P, Psi) of elm-pb magnitudes: a gaussian-in-x, ballooning-like-in-y envelope times
+    the fundamental z harmonic plus weaker higher harmonics (the shipped [U] function is a ballooning transform
+    of gauss(x-0.5,0.1) gauss(y-pi,0.6pi) sin(z); examples/elm-pb/data/BOUT.inp)."""
+    x = ((torch.arange(g.nx, dtype=torch.float64, device=device) - g.xstart + 0.5) / (g.nx - 2 * g.xstart))[:, None, None]
+    y = (2 * torch.pi * (torch.arange(g.ny, dtype=torch.float64, device=device) - g.ystart + 0.5)
+         / (g.ny - 2 * g.ystart))[None, :, None]
+    z = (2 * torch.pi * torch.arange(g.nz, dtype=torch.float64, device=device) / g.nz)[None, None, :]
+    env = torch.exp(-((x - 0.5) / 0.1) ** 2) * torch.exp(-((y - torch.pi) / (0.6 * torch.pi)) ** 2)
+    U = amp * env * (torch.sin(z) + 0.2 * torch.cos(3 * z + y))
+    P = 0.3 * amp * env * (torch.cos(z) + 0.1 * torch.sin(2 * z - y))
+    Psi = 0.04 * amp * env * (torch.sin(z + 0.5) + 0.1 * torch.cos(4 * z))
+    return U.contiguous(), P.contiguous(), Psi.contiguous()

@@ -122,6 +122,10 @@ int bout_b200_zfilter(const bout_b200_grid* g, int region, int n0, const double*
 /* lowPass(f, zmax, keep_zonal) (src/field/field3d.cxx:664-710). */
 int bout_b200_zlowpass(const bout_b200_grid* g, int region, int zmax, int keep_zonal,
                        const double* f, double* out, void* stream);
+/* filter(f, n0) followed by lowPass(., zmax, keep_zonal) in ONE pass over the field (the ddt post-processing
+ * of examples/elm-pb/elm_pb.cxx:1931-1955: src/field/field3d.cxx:620-661 then :664-710). */
+int bout_b200_zfilter_lowpass(const bout_b200_grid* g, int region, int n0, int zmax, int keep_zonal,
+                              const double* f, double* out, void* stream);
 /* shiftZ (src/field/field3d.cxx:715-741; ShiftedMetric::shiftZ src/mesh/parallel/shiftedmetric.cxx:200-224):
  * multiply mode k by exp(-i k 2pi/zlength * angle); angle/zlength per (x,y) when the Field2D
  * pointers are non-NULL, else the scalars.  out may alias f. */

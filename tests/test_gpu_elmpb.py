@@ -82,3 +82,19 @@ def test_elmpb_rk4_trajectory(gold):
         got = f.cpu().numpy()
         assert np.isfinite(got).all()
         assert rel_err(got, gold["final_" + name], I) < 1e-8, name
+
+
+def test_elmpb_from_setup_matches_reference(gold):
+    """Same RHS with every equilibrium / metric array produced by the harness's own set-up restatement
+    (bout-dev_b200/elm_setup.py) instead of the reference's post-init arrays."""
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    nx, ny, nz, mxg, myg = [int(v) for v in gold["grid"]]
+    m = pkg.models.ELMpb.from_setup(pkg.elm_setup.elmpb_setup(nx, ny - 2 * myg, nz, mxg, myg))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    m.set_state(dev(gold["rhs_in_U"]), dev(gold["rhs_in_P"]), dev(gold["rhs_in_Psi"]))
+    m.rhs()
+    torch.cuda.synchronize()
+    I = m.g.interior
+    for name, f in (("Psi", m.ddt_Psi), ("U", m.ddt_U), ("P", m.ddt_P)):
+        assert rel_err(f.cpu().numpy(), gold["rhs_ddt_" + name], I) < 1e-10, name

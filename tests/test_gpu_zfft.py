@@ -9,7 +9,7 @@ from util import rel_err, seeded_fields
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
-GRIDS = [(8, 6, 64, 2, 2), (6, 5, 8, 1, 1), (6, 5, 9, 1, 1), (5, 4, 7, 1, 1), (6, 3, 256, 2, 1),
+GRIDS = [(8, 6, 64, 2, 2), (6, 5, 8, 1, 1), (6, 5, 9, 1, 1), (5, 4, 7, 1, 1), (6, 3, 256, 2, 1), (6, 4, 128, 2, 1),
          (5, 3, 512, 1, 1), (4, 3, 1024, 1, 1), (5, 3, 12, 1, 1), (5, 3, 16, 1, 1), (5, 3, 32, 1, 1)]
 
 
@@ -30,7 +30,7 @@ def test_fft_derivatives(capi, orc, port, grid):
     assert rel_err(got, want, g.interior) < TOL
 
 
-@pytest.mark.parametrize("grid", GRIDS[:6])
+@pytest.mark.parametrize("grid", GRIDS[:8])
 def test_filter_lowpass_shift(capi, orc, port, grid):
     g, og = capi.Grid(*grid), orc.Grid(*grid)
     (f,) = seeded_fields(g.shape3, 1)
@@ -68,3 +68,39 @@ def test_dc(capi, orc, port):
     got = capi.dc(g, dev(f)).cpu().numpy()
     want = port.dc(og, f)
     assert np.abs(got - want).max() / np.abs(want).max() < TOL
+
+
+@pytest.mark.parametrize("grid", [(6, 7, 256, 2, 2), (5, 6, 128, 1, 1), (5, 6, 16, 1, 1)])
+def test_filter_then_lowpass_one_pass(capi, orc, port, grid):
+    """bout_b200_zfilter_lowpass = lowPass(filter(f, n0), zmax, keep_zonal) (elm_pb.cxx:1931-1955)."""
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    (f,) = seeded_fields(g.shape3, 1)
+    allr = (slice(None),) * 3
+    for n0, zmax, kz in ((1, 16, False), (1, 16, True), (3, 2, True), (0, 4, False), (0, 4, True), (2, g.nz, False)):
+        want = port.zlowpass(og, port.zfilter(og, f, n0), zmax, kz)
+        got = capi.zfilter_lowpass(g, dev(f), n0, zmax, kz).cpu().numpy()
+        assert rel_err(got, want, allr, floor=1e-3) < TOL, (n0, zmax, kz)
+
+
+@pytest.mark.parametrize("grid", [(6, 9, 256, 2, 2), (5, 8, 128, 1, 2), (4, 7, 512, 1, 1)])
+def test_parallel_slices_dual_output_path(capi, grid):
+    """ShiftedMetric::calcParallelSlices (shiftedmetric.cxx:226-246, phases :109-123) on the fast path that
+    writes yup and ydown from one read of each source row, against a direct numpy restatement; the small-nz
+    generic path is pinned by tests/test_gpu_shifted.py against the reference's own output."""
+    g = capi.Grid(*grid)
+    (f,) = seeded_fields(g.shape3, 1)
+    rng = np.random.default_rng(7)
+    zs = np.cumsum(0.2 + 0.3 * rng.uniform(size=g.shape2), axis=1)
+    zl = 2 * np.pi / 5
+    k = np.arange(g.nz // 2 + 1) * 2 * np.pi / zl
+    yup, ydown = capi.parallel_slices(g, dev(f), dev(zs), zl, 1)
+    yup, ydown = yup[0].cpu().numpy(), ydown[0].cpu().numpy()
+    F = np.fft.rfft(f, axis=2)
+    for y in range(g.ystart, g.yend + 1):
+        for got, off in ((yup, 1), (ydown, -1)):
+            ang = (zs[:, y] - zs[:, y + off])[:, None]
+            ph = np.exp(-1j * k[None, :] * ang)
+            ph[:, 0] = 1.0
+            want = np.fft.irfft(F[:, y + off, :] * ph, n=g.nz, axis=1)
+            d = np.abs(got[:, y + off, :] - want).max() / np.abs(want).max()
+            assert d < TOL, (y, off, d)
