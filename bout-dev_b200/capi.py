@@ -435,6 +435,29 @@ def b0xgrad_dot_grad(g: Grid, cfg, phi, A, phi_slices=None, a_slices=None, out=N
     return out
 
 
+class CElmpbRhs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "dx", "dy", "dz", "J", "g_22", "g_12", "g_23", "Bxy", "B0", "J0", "P0", "phi0", "b0xcv_x", "b0xcv_y",
+        "b0xcv_z", "U", "P", "Psi", "phi", "Jpar", "d2Jpar", "eta", "U_up", "U_dn", "P_up", "P_dn", "Psi_up",
+        "Psi_dn", "phi_up", "phi_dn", "J_up", "J_dn")] + \
+        [("hyperresist", C.c_double), ("keep_U", C.c_double), ("keep_P", C.c_double), ("keep_Psi", C.c_double),
+         ("eta_is2d", C.c_int), ("filter_n0", C.c_int)] + \
+        [(n, C.c_void_p) for n in ("ddt_U", "ddt_P", "ddt_Psi")]
+
+
+def elmpb_rhs(g: Grid, fields: dict, hyperresist, filter_n0, keep=(1.0, 1.0, 1.0)):
+    """fields: name -> tensor for every pointer member of bout_b200_elmpb_rhs_args (eta may be 2-D)."""
+    c = CElmpbRhs()
+    for n, _t in CElmpbRhs._fields_:
+        if n in fields:
+            setattr(c, n, fields[n].data_ptr())
+    c.hyperresist = hyperresist
+    c.keep_U, c.keep_P, c.keep_Psi = keep
+    c.eta_is2d = int(fields["eta"].dim() == 2)
+    c.filter_n0 = filter_n0
+    _check(lib.bout_b200_elmpb_rhs(C.byref(g.c), C.byref(c), _stream()))
+
+
 def average_y(g: Grid, f, out=None, y_group=None, nype=1):
     """averageY(Field3D): local mean -> (SUM all-reduce over the Y communicator when NYPE > 1) -> broadcast."""
     xz = torch.empty((g.nx, g.nz), dtype=torch.float64, device=f.device)

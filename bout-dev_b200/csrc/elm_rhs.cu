@@ -1,0 +1,322 @@
+// Fused right-hand side of the elm-pb reduced-MHD model (examples/elm-pb/elm_pb.cxx:1674-1955) for the
+// shipped switch set: linear, evolve Psi, diamag + diamag_phi0, constn0, bm_exb_flag = bm_mag_flag = 0
+// (BRACKET_STD = b0xGrad_dot_Grad, difops.cxx:563-601), hyper-resistivity, filter_z (+ low_pass_z):
+//
+//   ddt(Psi) = -Grad_par(phi B0)/B0 + eta Jpar - b0xGrad_dot_Grad(phi0, Psi) B0/Bxy - eta hyperresist Delp2(Jpar)
+//   ddt(U)   = B0^2 b0xGrad_dot_Grad(Psi, J0) + b0xcv . Grad(P) - B0^2 Grad_par(Jpar) - b0xGrad_dot_Grad(phi0, U)
+//   ddt(P)   = -b0xGrad_dot_Grad(phi, P0) - b0xGrad_dot_Grad(phi0, P)
+//   ddt(.)   = lowPass(filter(ddt(.), n0), zmax, keep_zonal)
+//
+// ONE kernel instead of the reference's ~60 full-field passes (5 brackets of ~12 passes each, 5 first
+// derivatives, the axpys, 6 FFT filter passes): every input field is read once from HBM (x neighbours
+// of the four stencil fields come from L2), the three time derivatives are written once.
+// Methods are fixed to the shipped ones: first C4 / C2 / C4, upwind W3 / C2 / W3 in x / y / z.
+// Y neighbours come from the parallel slices (yup / ydown) of ShiftedMetric::calcParallelSlices.
+//
+// The z filter runs inside the kernel: a CTA owns whole z rows, so the one kept Fourier mode n0 is a
+// block-wide dot product with the twiddle table and the filtered row is written directly (the
+// reference's rfft -> zero all but n0 -> irfft, field3d.cxx:620-661, to round-off).
+//
+// Three terms are taken through field-aligned coordinates by the reference because their operand
+// carries no parallel slices (index_derivs_interface.hxx:205-211): Grad_par(phi*B0) and the y-advection
+// of the Field2D operands J0 and P0.  toFieldAligned/fromFieldAligned multiply z mode k by
+// exp(+-i k zShift), so on every mode except the Nyquist one the round trip equals the slice form used
+// here (yup/ydown hold exactly f(y+-1) shifted by zShift(y) - zShift(y+-1)); the Nyquist mode, whose
+// imaginary part c2r drops, is discarded by the filter (n0 != nz/2 is required).  Without filter_z the
+// harness uses the operator-by-operator path, which reproduces the Nyquist handling exactly.
+#include "fft.cuh"
+#include "stencil_ops.cuh"
+
+namespace b200 {
+
+const cd* twiddleTable(int nz, cudaStream_t stream, int* status); // zfft_ops.cu
+
+struct ElmParams {
+  bout_b200_elmpb_rhs_args a;
+  const cd* __restrict__ tw;
+  int nx, ny, nz, xs, xe, ys, ye;
+  int rows_per_cta;
+};
+
+struct Row2 { // the six z values z0-2 .. z0+3 of one (x, y) row around this thread's z pair
+  double v[6];
+};
+__device__ __forceinline__ Row2 loadRow6(const double* __restrict__ row, int z0, int nz) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(row + wrapz(z0 - 2, nz)));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(row + z0));
+  const double2 c = __ldg(reinterpret_cast<const double2*>(row + wrapz(z0 + 2, nz)));
+  return Row2{{a.x, a.y, b.x, b.y, c.x, c.y}};
+}
+__device__ __forceinline__ double2 ld2(const double* __restrict__ p) {
+  return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// x-stencil (5 rows) + z-stencil (centre row) + the two slices of a Field3D at this thread's z pair
+struct F3 {
+  double2 xmm, xm, xp, xpp, up, dn;
+  Row2 c;
+  __device__ __forceinline__ St sx(int j) const {
+    return j == 0 ? St{xmm.x, xm.x, c.v[2], xp.x, xpp.x} : St{xmm.y, xm.y, c.v[3], xp.y, xpp.y};
+  }
+  __device__ __forceinline__ St sz(int j) const { return St{c.v[j], c.v[j + 1], c.v[j + 2], c.v[j + 3], c.v[j + 4]}; }
+  __device__ __forceinline__ double yp(int j) const { return j == 0 ? up.x : up.y; }
+  __device__ __forceinline__ double ym(int j) const { return j == 0 ? dn.x : dn.y; }
+};
+__device__ __forceinline__ F3 loadF3(const double* __restrict__ f, const double* __restrict__ fup,
+                                     const double* __restrict__ fdn, long long i2, int ny, int nz, int z0) {
+  F3 r;
+  const long long plane = static_cast<long long>(ny) * nz;
+  const double* __restrict__ row = f + i2 * nz;
+  r.c = loadRow6(row, z0, nz);
+  r.xmm = ld2(row - 2 * plane + z0);
+  r.xm = ld2(row - plane + z0);
+  r.xp = ld2(row + plane + z0);
+  r.xpp = ld2(row + 2 * plane + z0);
+  r.up = ld2(fup + (i2 + 1) * nz + z0); // yup holds the y+1 neighbour at row y+1
+  r.dn = ld2(fdn + (i2 - 1) * nz + z0);
+  return r;
+}
+
+struct M2 { // per-(x,y) metric scalars
+  double rdx, rdy, rdz, g_22, g_23, g_12, rjs;
+};
+
+// b0xGrad_dot_Grad(f3d, A2d): A's x stencil ax and y neighbours are Field2D values
+__device__ __forceinline__ double b0x3d2d(const St& fx, double fyp, double fym, const St& fz, const St& ax,
+                                          double ayp, double aym, const M2& m) {
+  const double dpdx = applyStandard<BOUT_B200_DDX_C4>(fx) * m.rdx;
+  const double dpdy = 0.5 * (fyp - fym) * m.rdy;
+  const double dpdz = applyStandard<BOUT_B200_DDX_C4>(fz) * m.rdz;
+  const double vx = m.g_22 * dpdz - m.g_23 * dpdy;
+  const double vy = m.g_23 * dpdx - m.g_12 * dpdz;
+  double r = weno3(vx, ax) * m.rdx;
+  r += vy * 0.5 * (ayp - aym) * m.rdy;
+  return r * m.rjs;
+}
+// b0xGrad_dot_Grad(f2d, A3d): the velocity (vx, vy, vz) is a Field2D quantity
+__device__ __forceinline__ double b0x2d3d(double vx, double vy, double vz, const St& ax, double ayp, double aym,
+                                          const St& az, const M2& m) {
+  double r = weno3(vx, ax) * m.rdx;
+  r += vy * 0.5 * (ayp - aym) * m.rdy;
+  r += weno3(vz, az) * m.rdz;
+  return r * m.rjs;
+}
+
+__device__ __forceinline__ St st2dx(const double* __restrict__ f, long long i2, int ny) {
+  return St{__ldg(f + i2 - 2 * ny), __ldg(f + i2 - ny), __ldg(f + i2), __ldg(f + i2 + ny), __ldg(f + i2 + 2 * ny)};
+}
+
+// Sum of six doubles per thread over the `nthr` threads of one row group (all threads of the CTA call).
+__device__ __forceinline__ void rowReduce3(double (&acc)[6], double* red, int tin, int nthr, int rloc) {
+  if ((nthr & 31) == 0) { // whole warps: shuffle tree, then one partial per warp
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      }
+    }
+    const int nw = nthr >> 5, w = tin >> 5;
+    double* r = red + rloc * 6 * 32;
+    if ((tin & 31) == 0) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        r[q * 32 + w] = acc[q];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      double s = 0.0;
+      for (int i = 0; i < nw; ++i) {
+        s += r[q * 32 + i];
+      }
+      acc[q] = s;
+    }
+  } else { // short or odd rows (one row per CTA): every thread sums the row from shared memory
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      red[q * nthr + tin] = acc[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      double s = 0.0;
+      for (int i = 0; i < nthr; ++i) {
+        s += red[q * nthr + i];
+      }
+      acc[q] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_elmpb_rhs(const ElmParams p) {
+  __shared__ double red[8 * 6 * 32];
+  const bout_b200_elmpb_rhs_args& a = p.a;
+  const int nzp = p.nz / 2;                  // threads per row
+  const int rloc = threadIdx.x / nzp, tin = threadIdx.x % nzp;
+  const int nyb = p.ye - p.ys + 1;
+  const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * nyb;
+  const long long rowid = static_cast<long long>(blockIdx.x) * p.rows_per_cta + rloc;
+  const bool active = rowid < nrows;
+  const long long rid = active ? rowid : nrows - 1;
+  const int x = p.xs + static_cast<int>(rid / nyb);
+  const int y = p.ys + static_cast<int>(rid % nyb);
+  const long long i2 = static_cast<long long>(x) * p.ny + y;
+  const int z0 = 2 * tin;
+  const int ny = p.ny, nz = p.nz;
+
+  M2 m;
+  m.rdx = 1.0 / __ldg(a.dx + i2);
+  m.rdy = 1.0 / __ldg(a.dy + i2);
+  m.rdz = 1.0 / __ldg(a.dz + i2);
+  m.g_22 = __ldg(a.g_22 + i2);
+  m.g_23 = __ldg(a.g_23 + i2);
+  m.g_12 = __ldg(a.g_12 + i2);
+  const double sg = sqrt(m.g_22);
+  m.rjs = 1.0 / (__ldg(a.J + i2) * sg);
+  const double B0 = __ldg(a.B0 + i2), Bxy = __ldg(a.Bxy + i2);
+  const double B0sq = B0 * B0;
+  // velocity of the Field2D potential phi0 (difops.cxx:580-588 with DDZ(phi0) = 0)
+  const double d0x = applyStandard<BOUT_B200_DDX_C4>(st2dx(a.phi0, i2, ny)) * m.rdx;
+  const double d0y = 0.5 * (__ldg(a.phi0 + i2 + 1) - __ldg(a.phi0 + i2 - 1)) * m.rdy;
+  const double vx0 = m.g_22 * 0.0 - m.g_23 * d0y;
+  const double vy0 = m.g_23 * d0x - m.g_12 * 0.0;
+  const double vz0 = m.g_12 * d0y - m.g_22 * d0x;
+  const St J0x = st2dx(a.J0, i2, ny), P0x = st2dx(a.P0, i2, ny);
+  const double J0p = __ldg(a.J0 + i2 + 1), J0m = __ldg(a.J0 + i2 - 1);
+  const double P0p = __ldg(a.P0 + i2 + 1), P0m = __ldg(a.P0 + i2 - 1);
+  const double B0p = __ldg(a.B0 + i2 + 1), B0m = __ldg(a.B0 + i2 - 1);
+  const double gpar = m.rdy / sg; // Grad_par = DDY / dy * invSg (coordinates.cxx:1529-1535)
+  const double bcx = __ldg(a.b0xcv_x + i2), bcy = __ldg(a.b0xcv_y + i2), bcz = __ldg(a.b0xcv_z + i2);
+
+  const F3 U = loadF3(a.U, a.U_up, a.U_dn, i2, ny, nz, z0);
+  const F3 P = loadF3(a.P, a.P_up, a.P_dn, i2, ny, nz, z0);
+  const F3 Psi = loadF3(a.Psi, a.Psi_up, a.Psi_dn, i2, ny, nz, z0);
+  const F3 phi = loadF3(a.phi, a.phi_up, a.phi_dn, i2, ny, nz, z0);
+  const double2 J = ld2(a.Jpar + i2 * nz + z0);
+  const double2 Jup = ld2(a.J_up + (i2 + 1) * nz + z0), Jdn = ld2(a.J_dn + (i2 - 1) * nz + z0);
+  const double2 d2J = ld2(a.d2Jpar + i2 * nz + z0);
+  const double2 eta = a.eta_is2d ? make_double2(__ldg(a.eta + i2), __ldg(a.eta + i2)) : ld2(a.eta + i2 * nz + z0);
+
+  double tU[2], tP[2], tPsi[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double Jc = j == 0 ? J.x : J.y, Jp = j == 0 ? Jup.x : Jup.y, Jm = j == 0 ? Jdn.x : Jdn.y;
+    const double d2 = j == 0 ? d2J.x : d2J.y, et = j == 0 ? eta.x : eta.y;
+    // ---- ddt(Psi)
+    const double gp = 0.5 * (B0p * phi.yp(j) - B0m * phi.ym(j)) * gpar; // Grad_par(phi B0)
+    const double bg = b0x2d3d(vx0, vy0, vz0, Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m);
+    tPsi[j] = -1.0 * gp / B0 + et * Jc - bg * B0 / Bxy - a.hyperresist * et * d2;
+    // ---- ddt(U)
+    const double t1 = b0x3d2d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), J0x, J0p, J0m, m);
+    const double dPx = applyStandard<BOUT_B200_DDX_C4>(P.sx(j)) * m.rdx;
+    const double dPy = 0.5 * (P.yp(j) - P.ym(j)) * m.rdy;
+    const double dPz = applyStandard<BOUT_B200_DDX_C4>(P.sz(j)) * m.rdz;
+    const double gpJ = 0.5 * (Jp - Jm) * gpar;
+    const double t4 = b0x2d3d(vx0, vy0, vz0, U.sx(j), U.yp(j), U.ym(j), U.sz(j), m);
+    tU[j] = t1 * B0sq + dPx * bcx + dPy * bcy + dPz * bcz - gpJ * B0sq - t4;
+    // ---- ddt(P)
+    const double p1 = b0x3d2d(phi.sx(j), phi.yp(j), phi.ym(j), phi.sz(j), P0x, P0p, P0m, m);
+    const double p2 = b0x2d3d(vx0, vy0, vz0, P.sx(j), P.yp(j), P.ym(j), P.sz(j), m);
+    tP[j] = -1.0 * p1 - p2;
+  }
+
+  double* __restrict__ oU = a.ddt_U + i2 * nz + z0;
+  double* __restrict__ oP = a.ddt_P + i2 * nz + z0;
+  double* __restrict__ oPsi = a.ddt_Psi + i2 * nz + z0;
+  if (a.filter_n0 < 0) { // no filter: raw time derivatives
+    if (active) {
+      *reinterpret_cast<double2*>(oU) = make_double2(tU[0], tU[1]);
+      *reinterpret_cast<double2*>(oP) = make_double2(tP[0], tP[1]);
+      *reinterpret_cast<double2*>(oPsi) = make_double2(tPsi[0], tPsi[1]);
+    }
+    return;
+  }
+  // ---- filter(., n0): X = (1/nz) sum_j f_j exp(-2 pi i n0 j / nz); f_j <- (k = 0: X) / (else: 2 Re X exp(+...))
+  const int n0 = a.filter_n0;
+  const cd w0 = p.tw[(static_cast<long long>(n0) * z0) % nz];
+  const cd w1 = p.tw[(static_cast<long long>(n0) * (z0 + 1)) % nz];
+  double acc[6] = {tU[0] * w0.re + tU[1] * w1.re,     tU[0] * w0.im + tU[1] * w1.im,
+                   tP[0] * w0.re + tP[1] * w1.re,     tP[0] * w0.im + tP[1] * w1.im,
+                   tPsi[0] * w0.re + tPsi[1] * w1.re, tPsi[0] * w0.im + tPsi[1] * w1.im};
+  rowReduce3(acc, red, tin, nzp, rloc);
+  if (!active) {
+    return;
+  }
+  const double inv = 1.0 / nz;
+  const double mult = n0 == 0 ? 1.0 : 2.0;
+  auto back = [&](double xr, double xi, double keep, double* __restrict__ out) {
+    // Re(X conj(w)) with w = exp(-i theta): xr cos(theta) ... ; w.re = cos, w.im = -sin
+    const double s = keep * mult * inv;
+    const double v0 = s * (xr * w0.re + xi * w0.im);
+    const double v1 = s * (xr * w1.re + xi * w1.im);
+    *reinterpret_cast<double2*>(out) = make_double2(v0, v1);
+  };
+  back(acc[0], acc[1], a.keep_U, oU);
+  back(acc[2], acc[3], a.keep_P, oP);
+  back(acc[4], acc[5], a.keep_Psi, oPsi);
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmpb_rhs_args* args, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(args != nullptr, BOUT_B200_ERR_ARG, "elmpb_rhs: null arguments");
+  const bout_b200_elmpb_rhs_args& a = *args;
+  const void* ptrs[] = {a.dx, a.dy, a.dz, a.J, a.g_22, a.g_12, a.g_23, a.Bxy, a.B0, a.J0, a.P0, a.phi0, a.b0xcv_x,
+                        a.b0xcv_y, a.b0xcv_z, a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar, a.eta, a.U_up, a.U_dn,
+                        a.P_up, a.P_dn, a.Psi_up, a.Psi_dn, a.phi_up, a.phi_dn, a.J_up, a.J_dn, a.ddt_U, a.ddt_P,
+                        a.ddt_Psi};
+  for (const void* q : ptrs) {
+    B200_REQUIRE(q != nullptr, BOUT_B200_ERR_ARG, "elmpb_rhs: null field");
+  }
+  const void* vec[] = {a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar, a.U_up, a.U_dn, a.P_up, a.P_dn, a.Psi_up, a.Psi_dn,
+                       a.phi_up, a.phi_dn, a.J_up, a.J_dn, a.ddt_U, a.ddt_P, a.ddt_Psi};
+  for (const void* q : vec) {
+    B200_REQUIRE(aligned16(q), BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: fields must be 16-byte aligned");
+  }
+  B200_REQUIRE(a.eta_is2d || aligned16(a.eta), BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: eta must be 16-byte aligned");
+  B200_REQUIRE(g->nz % 2 == 0 && g->nz >= 4, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz must be even and >= 4");
+  B200_REQUIRE(g->xstart >= 2 && g->nx - 1 - g->xend >= 2 && g->ystart >= 1 && g->ny - 1 - g->yend >= 1,
+               BOUT_B200_ERR_GUARDS, "elmpb_rhs: needs 2 x guard cells and 1 y guard cell");
+  const int nzp = g->nz / 2;
+  B200_REQUIRE(a.filter_n0 < g->nz / 2, BOUT_B200_ERR_ARG,
+               "elmpb_rhs: the kept mode must be below the Nyquist mode (see the note on field-aligned terms)");
+  int threads, rows;
+  if (nzp <= 256) { // several short rows per CTA when whole warps divide evenly
+    rows = (nzp % 32 == 0) ? 256 / nzp : 1;
+    rows = rows > 8 ? 8 : rows;
+    threads = rows * nzp;
+  } else {
+    B200_REQUIRE(nzp <= 1024 && nzp % 32 == 0, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz too large");
+    rows = 1;
+    threads = nzp;
+  }
+  B200_REQUIRE(threads <= 256, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz > 512 not supported");
+  ElmParams p{};
+  p.a = a;
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.xs = g->xstart;
+  p.xe = g->xend;
+  p.ys = g->ystart;
+  p.ye = g->yend;
+  p.rows_per_cta = rows;
+  cudaStream_t s = asStream(stream);
+  int st = 0;
+  p.tw = twiddleTable(g->nz, s, &st);
+  if (st != 0) {
+    return st;
+  }
+  const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * (p.ye - p.ys + 1);
+  const unsigned blocks = static_cast<unsigned>((nrows + rows - 1) / rows);
+  k_elmpb_rhs<<<blocks, threads, 0, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -158,6 +158,8 @@ class ELMpb:
         self.U, self.P, self.Psi = z(), z(), z()
         self.phi, self.Jpar, self.Jpar2 = z(), z(), z()
         self.ddt_U, self.ddt_P, self.ddt_Psi = z(), z(), z()
+        self.fused = True             # one kernel for the three equations + filter (csrc/elm_rhs.cu)
+        self.kernel_events = None     # bench.py: (start, end) CUDA events of the fused kernel
         self.compute_jpar2 = True     # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
 
     @classmethod
@@ -207,35 +209,81 @@ class ELMpb:
         d = capi.stencil(g, "DDX_C2", "Y", fa, scale1=self.gradpar)
         return capi.zshift(g, d, self.zs, self.zl, region="RGN_NOBNDRY")
 
+    def _buffers(self):
+        if not hasattr(self, "_buf"):
+            z = lambda: torch.zeros(self.g.shape3, dtype=torch.float64, device=self.dev)
+            self._buf = {n: (z(), z()) for n in ("U", "P", "Psi", "phi", "J")}   # (yup, ydown) per field
+            self._buf["sm"] = z()
+            self._buf["d2J"] = z()
+        return self._buf
+
+    def _comm_into(self, fields, names):
+        """mesh->communicate(...) with the parallel slices written into preallocated buffers."""
+        capi.halo_self(self.g, fields, periodic_x=False, periodic_y=True)
+        out = []
+        for f, n in zip(fields, names):
+            up, dn = self._buffers()[n]
+            capi.parallel_slices(self.g, f, self.zs, self.zl, 1, yup=[up], ydown=[dn])
+            out.append(([up], [dn]))
+        return out
+
     def rhs(self, U=None, P=None, Psi=None):
         g, m, eq = self.g, self.md, self.eq
         U = self.U if U is None else U
         P = self.P if P is None else P
         Psi = self.Psi if Psi is None else Psi
         ew = capi.elementwise
+        buf = self._buffers()
         self.pre_rhs(U, P, Psi)
-        sU, sP, sPsi = self._comm([U, P, Psi])                               # mesh->communicate(comms)
+        sU, sP, sPsi = self._comm_into([U, P, Psi], ["U", "P", "Psi"])       # mesh->communicate(comms)
         # phi = phiSolver->solve(U) - 0.5 dnorm P / B0 (constn0, diamag)       elm_pb.cxx:1472-1477
         self.lap.solve(U, out=self.phi)
         ew(g, [(1.0, self.phi), (-0.5 * self.dnorm, P, None, self.B0)], out=self.phi)
-        (sphi,) = self._comm([self.phi])
+        (sphi,) = self._comm_into([self.phi], ["phi"])
         capi.boundary(g, "extend", "xin", self.phi)                           # :1498-1516
         capi.boundary(g, "extend", "xout", self.phi)
         # Jpar = Delp2(Psi); BC; communicate; smooth_x; BC; communicate         :1518-1563
         self.delp.delp2(Psi, out=self.Jpar)
         self._bc_j(self.Jpar)
         capi.halo_self(g, [self.Jpar], periodic_x=False, periodic_y=True)
-        sm = capi.smooth_x(g, self.Jpar)
+        sm = capi.smooth_x(g, self.Jpar, out=buf["sm"])
         capi.halo_self(g, [sm], periodic_x=False, periodic_y=True)            # smooth_x communicates its result
-        self.Jpar.copy_(sm)
+        buf["sm"], self.Jpar = self.Jpar, sm                                  # Jpar = smooth_x(Jpar)
         self._bc_j(self.Jpar)
-        (sJ,) = self._comm([self.Jpar])
+        (sJ,) = self._comm_into([self.Jpar], ["J"])
         # Delp2(Jpar): Jpar2 (:1565-1572) and the hyper-resistivity term (:1717-1723) evaluate the same field
-        d2J = self.delp.delp2(self.Jpar)
+        d2J = self.delp.delp2(self.Jpar, out=buf["d2J"])
         if self.compute_jpar2:
             self.Jpar2.copy_(d2J)
             self._bc_j(self.Jpar2)
             capi.halo_self(g, [self.Jpar2], periodic_x=False, periodic_y=True)
+        if self.fused and self.filter_z_mode >= 0 and self.filter_z_mode < g.nz // 2:
+            keep = [1.0, 1.0, 1.0]
+            if self.low_pass_z > 0:
+                for i, zonal in enumerate((self.zonal_flow, self.zonal_bkgd, self.zonal_field)):
+                    if self.filter_z_mode > self.low_pass_z or (self.filter_z_mode == 0 and not zonal):
+                        keep[i] = 0.0
+            fields = dict(m)
+            fields.update(eq)
+            fields.update(U=U, P=P, Psi=Psi, phi=self.phi, Jpar=self.Jpar, d2Jpar=d2J,
+                          U_up=sU[0][0], U_dn=sU[1][0], P_up=sP[0][0], P_dn=sP[1][0], Psi_up=sPsi[0][0],
+                          Psi_dn=sPsi[1][0], phi_up=sphi[0][0], phi_dn=sphi[1][0], J_up=sJ[0][0], J_dn=sJ[1][0],
+                          ddt_U=self.ddt_U, ddt_P=self.ddt_P, ddt_Psi=self.ddt_Psi)
+            if self.kernel_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            capi.elmpb_rhs(g, fields, self.hyperresist, self.filter_z_mode, keep=tuple(keep))
+            if self.kernel_events is not None:
+                e1.record()
+                self.kernel_events.append((e0, e1))
+        else:
+            self._rhs_terms(U, P, Psi, sU, sP, sPsi, sphi, sJ, d2J)
+
+    def _rhs_terms(self, U, P, Psi, sU, sP, sPsi, sphi, sJ, d2J):
+        """Operator-by-operator evaluation of the three equations (exact also without filter_z: the terms the
+        reference takes through field-aligned coordinates are taken through them here too)."""
+        g, m, eq = self.g, self.md, self.eq
+        ew = capi.elementwise
         # ---- ddt(Psi) = -Grad_par(phi B0)/B0 + eta Jpar - bracket(phi0, Psi) B0 - eta hyperresist Delp2(Jpar)
         # bracket(Field2D, Field3D, BRACKET_STD) = b0xGrad_dot_Grad / Bxy (difops.cxx:805-808)
         phiB0 = ew(g, [(1.0, self.phi, self.B0)])
@@ -260,6 +308,8 @@ class ELMpb:
         p2 = capi.b0xgrad_dot_grad(g, self.b0x, eq["phi0"], P, None, sP)
         ew(g, [(-1.0, p1), (-1.0, p2)], out=self.ddt_P, region="RGN_NOBNDRY")
         # ---- filter_z, low_pass_z in one pass per field                                      :1931-1955
+        if self.filter_z_mode < 0:
+            return
         for f, zonal in ((self.ddt_Psi, self.zonal_field), (self.ddt_U, self.zonal_flow),
                          (self.ddt_P, self.zonal_bkgd)):
             if self.low_pass_z > 0:

@@ -175,6 +175,30 @@ int bout_b200_b0xgrad_dot_grad(const bout_b200_grid* g, const bout_b200_b0xgrad*
                                const double* const* a_yup, const double* const* a_ydown,
                                double* out, double* yterm_out, void* stream);
 
+/* ---- fused elm-pb right-hand side (a18: examples/elm-pb/elm_pb.cxx:1674-1955, shipped switch set) --------
+ * ONE kernel for ddt(Psi), ddt(U), ddt(P) of the linear 3-field model incl. the final filter(., n0) +
+ * lowPass: five b0xGrad_dot_Grad brackets (3D x 2D and 2D x 3D, difops.cxx:563-601), b0xcv . Grad(P),
+ * Grad_par(phi B0) and Grad_par(Jpar), resistive + hyper-resistive terms.  Methods fixed to the shipped
+ * ones (first C4/C2/C4, upwind W3/C2/W3).  All Field3D inputs carry valid guard cells (2 in x, 1 in y);
+ * *_up / *_dn are the yup / ydown parallel slices (bout_b200_parallel_slices).  d2Jpar = Delp2(Jpar).
+ * filter_n0 >= 0 (and below the Nyquist mode): the kept z mode, filtered in-kernel; keep_* = 1.0, or 0.0 if
+ * the following lowPass removes that mode for the field (n0 > low_pass_z, or n0 = 0 without keep_zonal).
+ * filter_n0 < 0 writes the unfiltered sums (valid only up to the Nyquist-mode handling of the reference's
+ * field-aligned terms, see csrc/elm_rhs.cu).  Outputs cover RGN_NOBNDRY. */
+typedef struct bout_b200_elmpb_rhs_args {
+  const double *dx, *dy, *dz, *J, *g_22, *g_12, *g_23, *Bxy;                 /* Field2D metric */
+  const double *B0, *J0, *P0, *phi0, *b0xcv_x, *b0xcv_y, *b0xcv_z;           /* Field2D equilibrium */
+  const double *U, *P, *Psi, *phi, *Jpar, *d2Jpar;                           /* Field3D */
+  const double* eta;                                                         /* Field3D, or Field2D if eta_is2d */
+  const double *U_up, *U_dn, *P_up, *P_dn, *Psi_up, *Psi_dn, *phi_up, *phi_dn, *J_up, *J_dn;
+  double hyperresist;
+  double keep_U, keep_P, keep_Psi;
+  int eta_is2d;
+  int filter_n0;
+  double *ddt_U, *ddt_P, *ddt_Psi;
+} bout_b200_elmpb_rhs_args;
+int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmpb_rhs_args* args, void* stream);
+
 /* averageY(Field3D) (src/physics/smoothing.cxx:272-323) in two halves so that the all-reduce over the
  * ranks of a Y communicator sits between them: xz[x][z] = mean over ystart..yend of f;
  * out(x, y, z) = scale * xz[x][z] for every y (scale = 1/NYPE after a SUM all-reduce, else 1). */

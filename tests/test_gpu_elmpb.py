@@ -50,8 +50,10 @@ def make_model(gold):
     return g, model
 
 
-def test_elmpb_rhs_matches_reference(gold):
+@pytest.mark.parametrize("fused", [True, False])
+def test_elmpb_rhs_matches_reference(gold, fused):
     g, m = make_model(gold)
+    m.fused = fused
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     m.set_state(dev(gold["rhs_in_U"]), dev(gold["rhs_in_P"]), dev(gold["rhs_in_Psi"]))
     m.rhs()
@@ -69,8 +71,10 @@ def test_elmpb_rhs_matches_reference(gold):
         assert rel_err(f.cpu().numpy(), gold["rhs_ddt_" + name], I) < 1e-10, name
 
 
-def test_elmpb_rk4_trajectory(gold):
+@pytest.mark.parametrize("fused", [True, False])
+def test_elmpb_rk4_trajectory(gold, fused):
     g, m = make_model(gold)
+    m.fused = fused
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     m.set_state(dev(gold["rhs_in_U"]), dev(gold["rhs_in_P"]), dev(gold["rhs_in_Psi"]))
     dt, nsteps = gold["dt_nsteps"]
@@ -98,3 +102,25 @@ def test_elmpb_from_setup_matches_reference(gold):
     I = m.g.interior
     for name, f in (("Psi", m.ddt_Psi), ("U", m.ddt_U), ("P", m.ddt_P)):
         assert rel_err(f.cpu().numpy(), gold["rhs_ddt_" + name], I) < 1e-10, name
+
+
+def test_elmpb_fused_equals_operator_path_full_size():
+    """BASELINE C5 size (516 x 64 x 256): the fused kernel against the operator-by-operator path (itself pinned
+    to the reference above) on the same state; they differ only by round-off after the z filter."""
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    m = pkg.models.ELMpb.from_setup(pkg.elm_setup.elmpb_setup(516, 64, 256))
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    state = [s + 1e-7 * (torch.rand(s.shape, dtype=torch.float64, device="cuda", generator=gen) - 0.5)
+             for s in pkg.models.elmpb_initial_state(m.g)]
+    out = {}
+    for fused in (True, False):
+        m.fused = fused
+        m.set_state(*state)
+        m.rhs()
+        torch.cuda.synchronize()
+        out[fused] = [f.clone() for f in (m.ddt_U, m.ddt_P, m.ddt_Psi)]
+    I = m.g.interior
+    for a, b in zip(out[True], out[False]):
+        assert torch.isfinite(a[I]).all()
+        assert ((a[I] - b[I]).abs().max() / b[I].abs().max()).item() < 1e-10
