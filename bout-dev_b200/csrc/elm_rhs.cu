@@ -150,7 +150,7 @@ __device__ __forceinline__ void rowReduce3(double (&acc)[6], double* red, int ti
   }
 }
 
-__global__ void __launch_bounds__(256) k_elmpb_rhs(const ElmParams p) {
+__global__ void __launch_bounds__(256, 2) k_elmpb_rhs(const ElmParams p) {
   __shared__ double red[8 * 6 * 32];
   const bout_b200_elmpb_rhs_args& a = p.a;
   const int nzp = p.nz / 2;                  // threads per row
@@ -190,36 +190,56 @@ __global__ void __launch_bounds__(256) k_elmpb_rhs(const ElmParams p) {
   const double gpar = m.rdy / sg; // Grad_par = DDY / dy * invSg (coordinates.cxx:1529-1535)
   const double bcx = __ldg(a.b0xcv_x + i2), bcy = __ldg(a.b0xcv_y + i2), bcz = __ldg(a.b0xcv_z + i2);
 
-  const F3 U = loadF3(a.U, a.U_up, a.U_dn, i2, ny, nz, z0);
-  const F3 P = loadF3(a.P, a.P_up, a.P_dn, i2, ny, nz, z0);
-  const F3 Psi = loadF3(a.Psi, a.Psi_up, a.Psi_dn, i2, ny, nz, z0);
-  const F3 phi = loadF3(a.phi, a.phi_up, a.phi_dn, i2, ny, nz, z0);
-  const double2 J = ld2(a.Jpar + i2 * nz + z0);
-  const double2 Jup = ld2(a.J_up + (i2 + 1) * nz + z0), Jdn = ld2(a.J_dn + (i2 - 1) * nz + z0);
-  const double2 d2J = ld2(a.d2Jpar + i2 * nz + z0);
-  const double2 eta = a.eta_is2d ? make_double2(__ldg(a.eta + i2), __ldg(a.eta + i2)) : ld2(a.eta + i2 * nz + z0);
-
+  // One stencil field at a time (loads next to their use) so that at most one F3 is live: 128 registers,
+  // two CTAs per SM.  Field3D / Field2D multiplies by the reciprocal, as the reference does.
+  const double rB0 = 1.0 / B0, rBxy = 1.0 / Bxy;
   double tU[2], tP[2], tPsi[2];
+  {
+    const F3 phi = loadF3(a.phi, a.phi_up, a.phi_dn, i2, ny, nz, z0);
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const double Jc = j == 0 ? J.x : J.y, Jp = j == 0 ? Jup.x : Jup.y, Jm = j == 0 ? Jdn.x : Jdn.y;
-    const double d2 = j == 0 ? d2J.x : d2J.y, et = j == 0 ? eta.x : eta.y;
-    // ---- ddt(Psi)
-    const double gp = 0.5 * (B0p * phi.yp(j) - B0m * phi.ym(j)) * gpar; // Grad_par(phi B0)
-    const double bg = b0x2d3d(vx0, vy0, vz0, Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m);
-    tPsi[j] = -1.0 * gp / B0 + et * Jc - bg * B0 / Bxy - a.hyperresist * et * d2;
-    // ---- ddt(U)
-    const double t1 = b0x3d2d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), J0x, J0p, J0m, m);
-    const double dPx = applyStandard<BOUT_B200_DDX_C4>(P.sx(j)) * m.rdx;
-    const double dPy = 0.5 * (P.yp(j) - P.ym(j)) * m.rdy;
-    const double dPz = applyStandard<BOUT_B200_DDX_C4>(P.sz(j)) * m.rdz;
-    const double gpJ = 0.5 * (Jp - Jm) * gpar;
-    const double t4 = b0x2d3d(vx0, vy0, vz0, U.sx(j), U.yp(j), U.ym(j), U.sz(j), m);
-    tU[j] = t1 * B0sq + dPx * bcx + dPy * bcy + dPz * bcz - gpJ * B0sq - t4;
-    // ---- ddt(P)
-    const double p1 = b0x3d2d(phi.sx(j), phi.yp(j), phi.ym(j), phi.sz(j), P0x, P0p, P0m, m);
-    const double p2 = b0x2d3d(vx0, vy0, vz0, P.sx(j), P.yp(j), P.ym(j), P.sz(j), m);
-    tP[j] = -1.0 * p1 - p2;
+    for (int j = 0; j < 2; ++j) {
+      const double gp = 0.5 * (B0p * phi.yp(j) - B0m * phi.ym(j)) * gpar; // Grad_par(phi B0)
+      tPsi[j] = -1.0 * gp * rB0;
+      tP[j] = -1.0 * b0x3d2d(phi.sx(j), phi.yp(j), phi.ym(j), phi.sz(j), P0x, P0p, P0m, m);
+    }
+  }
+  {
+    const F3 P = loadF3(a.P, a.P_up, a.P_dn, i2, ny, nz, z0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double dPx = applyStandard<BOUT_B200_DDX_C4>(P.sx(j)) * m.rdx;
+      const double dPy = 0.5 * (P.yp(j) - P.ym(j)) * m.rdy;
+      const double dPz = applyStandard<BOUT_B200_DDX_C4>(P.sz(j)) * m.rdz;
+      tU[j] = dPx * bcx + dPy * bcy + dPz * bcz;
+      tP[j] -= b0x2d3d(vx0, vy0, vz0, P.sx(j), P.yp(j), P.ym(j), P.sz(j), m);
+    }
+  }
+  {
+    const F3 Psi = loadF3(a.Psi, a.Psi_up, a.Psi_dn, i2, ny, nz, z0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double bg = b0x2d3d(vx0, vy0, vz0, Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m);
+      tPsi[j] -= bg * B0 * rBxy;
+      const double t1 = b0x3d2d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), J0x, J0p, J0m, m);
+      tU[j] = t1 * B0sq + tU[j];
+    }
+  }
+  {
+    const F3 U = loadF3(a.U, a.U_up, a.U_dn, i2, ny, nz, z0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      tU[j] -= b0x2d3d(vx0, vy0, vz0, U.sx(j), U.yp(j), U.ym(j), U.sz(j), m);
+    }
+  }
+  {
+    const double2 J = ld2(a.Jpar + i2 * nz + z0);
+    const double2 Jup = ld2(a.J_up + (i2 + 1) * nz + z0), Jdn = ld2(a.J_dn + (i2 - 1) * nz + z0);
+    const double2 d2J = ld2(a.d2Jpar + i2 * nz + z0);
+    const double2 eta = a.eta_is2d ? make_double2(__ldg(a.eta + i2), __ldg(a.eta + i2)) : ld2(a.eta + i2 * nz + z0);
+    tPsi[0] += eta.x * J.x - a.hyperresist * eta.x * d2J.x;
+    tPsi[1] += eta.y * J.y - a.hyperresist * eta.y * d2J.y;
+    tU[0] -= 0.5 * (Jup.x - Jdn.x) * gpar * B0sq;
+    tU[1] -= 0.5 * (Jup.y - Jdn.y) * gpar * B0sq;
   }
 
   double* __restrict__ oU = a.ddt_U + i2 * nz + z0;

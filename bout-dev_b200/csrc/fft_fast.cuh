@@ -77,6 +77,20 @@ struct SyncNamed {
   }
 };
 
+// The threads of ONE row only (TPR consecutive threads, rows aligned to TPR): a warp-level barrier when a
+// row lives inside one warp, else a named barrier per row group (id 1 + row-in-CTA, at most 15 rows).
+// Rows of a CTA then run decoupled instead of stepping through every stage in lock-step.
+struct SyncGroup {
+  int id, count;
+  __device__ __forceinline__ void operator()() const {
+    if (count <= 32) {
+      __syncwarp();
+    } else {
+      asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+    }
+  }
+};
+
 // One radix-4 Stockham stage (stage index s, Ns = 4^s) of this thread's butterfly, in -> out.
 template <int N, bool INVERSE>
 __device__ __forceinline__ void radix4Stage(const cd* in, cd* out, const FastTw<N>& t, int lane, int s, int Ns) {
@@ -188,9 +202,10 @@ __device__ __forceinline__ void cfftFast2(cd* a0, cd* b0, cd* a1, cd* b1, const 
 
 // Forward: real row (global, nz doubles, 16-byte aligned) -> X[0 .. nmode-1] (global), scaled by 1/nz.
 // A, B: this row's swizzled buffers (N + 8 elements each).  All threads of the CTA call together.
-template <int N>
+template <int N, class Sync = SyncCta>
 __device__ __forceinline__ void rfftForwardFast(const double* __restrict__ src, cd* __restrict__ dst, int nmode,
-                                                bool active, cd* A, cd* B, const FastTw<N>& t, int lane) {
+                                                bool active, cd* A, cd* B, const FastTw<N>& t, int lane,
+                                                Sync sync = Sync()) {
   const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src);
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
@@ -198,8 +213,8 @@ __device__ __forceinline__ void rfftForwardFast(const double* __restrict__ src, 
     const double2 v = __ldg(s2 + j);
     A[fsw(j)] = {v.x, v.y};
   }
-  __syncthreads();
-  const cd* Z = cfftFast<N, false>(A, B, t, lane);
+  sync();
+  const cd* Z = cfftFast<N, false, Sync>(A, B, t, lane, sync);
   constexpr double inv = 1.0 / (2 * N);
   if (active) {
 #pragma unroll
@@ -219,14 +234,14 @@ __device__ __forceinline__ void rfftForwardFast(const double* __restrict__ src, 
       dst[N] = {(z0.re - z0.im) * inv, 0.0};
     }
   }
-  __syncthreads(); // the buffers are reused by the next row
+  sync(); // the buffers are reused by the next row
 }
 
 // Backward: X[0 .. nmode-1] (global; zero beyond nmode; DC dropped when zero_dc) -> real row (global).
-template <int N>
+template <int N, class Sync = SyncCta>
 __device__ __forceinline__ void rfftBackwardFast(const cd* __restrict__ src, double* __restrict__ dst, int nmode,
                                                  bool zero_dc, bool active, cd* A, cd* B, const FastTw<N>& t,
-                                                 int lane) {
+                                                 int lane, Sync sync = Sync()) {
   auto load = [&](int k) -> cd {
     if (k >= nmode || (k == 0 && zero_dc)) {
       return cd{0.0, 0.0};
@@ -247,8 +262,8 @@ __device__ __forceinline__ void rfftBackwardFast(const cd* __restrict__ src, dou
     const cd d = cmul(wk, csub(xk, xc));
     A[fsw(k)] = cadd(cadd(xk, xc), cd{-d.im, d.re});
   }
-  __syncthreads();
-  const cd* z = cfftFast<N, true>(A, B, t, lane);
+  sync();
+  const cd* z = cfftFast<N, true, Sync>(A, B, t, lane, sync);
   if (active) {
     double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
 #pragma unroll
@@ -258,7 +273,7 @@ __device__ __forceinline__ void rfftBackwardFast(const cd* __restrict__ src, dou
       d2[j] = make_double2(v.re, v.im);
     }
   }
-  __syncthreads();
+  sync();
 }
 
 // ---- pieces for kernels that keep the spectrum on chip (fused LaplaceCyclic sweeps) ------------------

@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(128) k_lap_forward_fast(const LapParams p) {
     // common_transform.cxx:49-57
     const bool from_x0 = ((x < p.bd.inbndry) && p.in_set) || ((p.nx - x - 1 < p.bd.outbndry) && p.out_set);
     const double* __restrict__ src = (from_x0 ? p.x0 : p.rhs) + (static_cast<long long>(x) * p.ny + y) * p.nz;
-    rfftForwardFast<N>(src, p.spec + rid * p.nmode, p.nmode, active, A, B, tw, lane);
+    rfftForwardFast<N, SyncGroup>(src, p.spec + rid * p.nmode, p.nmode, active, A, B, tw, lane,
+                                  SyncGroup{1 + rloc, TPR});
   }
 }
 
@@ -171,8 +172,8 @@ __global__ void __launch_bounds__(128) k_lap_backward_fast(const LapParams p) {
     const long long rid = active ? rowid : nrows - 1;
     const int ixl = static_cast<int>(rid / nys), iyl = static_cast<int>(rid % nys);
     const int x = p.bd.xs + ixl, y = p.ys + iyl;
-    rfftBackwardFast<N>(p.spec + rid * p.nmode, p.out + (static_cast<long long>(x) * p.ny + y) * p.nz, p.nmode,
-                        p.zero_dc != 0, active, A, B, tw, lane);
+    rfftBackwardFast<N, SyncGroup>(p.spec + rid * p.nmode, p.out + (static_cast<long long>(x) * p.ny + y) * p.nz,
+                                   p.nmode, p.zero_dc != 0, active, A, B, tw, lane, SyncGroup{1 + rloc, TPR});
   }
 }
 

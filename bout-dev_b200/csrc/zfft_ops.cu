@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
   cd* D = S + (N + 8);   // modified spectrum
   FastTw<N> tw;
   fastTwInit<N>(tw, p.tw, lane);
+  const SyncGroup sync{1 + rloc, TPR}; // rows of the CTA run decoupled
   const int nyb = p.ye - p.ys + 1;
   const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * nyb;
   for (long long base = static_cast<long long>(blockIdx.x) * ROWS; base < nrows;
@@ -297,10 +298,10 @@ __global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
       const double2 v = __ldg(s2 + j);
       A[fsw(j)] = {v.x, v.y};
     }
-    __syncthreads();
-    const cd* Z = cfftFast<N, false>(A, B, tw, lane);
+    sync();
+    const cd* Z = cfftFast<N, false, SyncGroup>(A, B, tw, lane, sync);
     rfftSplitTo<N>(Z, S, N + 1, tw, lane);
-    __syncthreads();
+    sync();
     const int nout = p.mode == Z_SLICE2 ? 2 : 1;
     for (int o = 0; o < nout; ++o) {
       double ang = 0.0, zl = p.zlength0;
@@ -324,10 +325,10 @@ __global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
         dstf = o == 0 ? p.out : p.out2;
       }
       zmodSpectrum<N>(p, S, D, lane, mode, ang, zl);
-      __syncthreads();
+      sync();
       rfftMergeFrom<N>(D, A, N + 1, false, tw, lane);
-      __syncthreads();
-      const cd* z = cfftFast<N, true>(A, B, tw, lane);
+      sync();
+      const cd* z = cfftFast<N, true, SyncGroup>(A, B, tw, lane, sync);
       if (store) {
         const double sc = p.scale ? __ldg(p.scale + i2) : 1.0;
         double2* __restrict__ d2 = reinterpret_cast<double2*>(dstf + i2 * p.nz);
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
           d2[j] = make_double2(v.re * sc, v.im * sc);
         }
       }
-      __syncthreads();
+      sync();
     }
   }
 }

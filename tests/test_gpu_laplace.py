@@ -180,8 +180,9 @@ def test_laplace_x_decomposed_matches_single_rank(capi, orc, port, nxpe, flags):
     assert rel_err(got, want, region) < 1e-10
 
 
-@pytest.mark.parametrize("grid", [(21, 5, 128, 2, 1), (14, 4, 256, 2, 1), (19, 3, 512, 2, 1), (10, 3, 1024, 2, 1),
-                                  (37, 3, 256, 2, 1)])
+# nz = 1024 is not in this list: its sweep buffers exceed one SM's shared memory (LapFusedShape<512>), so the
+# library keeps the 3-kernel path for it (covered by the parity tests above)
+@pytest.mark.parametrize("grid", [(21, 5, 128, 2, 1), (14, 4, 256, 2, 1), (19, 3, 512, 2, 1), (37, 3, 256, 2, 1)])
 @pytest.mark.parametrize("flags", [(0, 0, 0), (0, 3, 0), (4, 0, 0), (0, 16, 16), (0, 32 | 3, 32), (1, 4, 64)])
 @pytest.mark.parametrize("filt", [False, True])
 def test_laplace_fused_sweeps_match_three_kernel_path(capi, orc, port, grid, flags, filt, monkeypatch):
