@@ -12,6 +12,10 @@ value = interior points * 4 * K / time.  Fields (279 MB each) are far larger tha
 L2 flush is needed between iterations (stated in config.l2).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
+  python bench.py --workload elmpb [...]                        BASELINE configs[4]: elm-pb 3-field RHS, 512x64x256
+                                                                interior points per GPU (shifted metric), RK4
+The default (hw3d) line also carries "other": elm-pb RHS points/s at 1 GPU, LaplaceCyclic solves/s and the
+examples/performance microbenchmarks (BASELINE configs[1], 256x64x256) -- short extra measurements, N = 1 only.
   python bench.py --impl reference [...]                        the reference's own CPU implementation of the
                                                                 same RHS (oracle/_ref, host cores, bounded slab)
 """
@@ -48,13 +52,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def profile_traffic():
+def profile_traffic(key="k_hw3d_rhs_bytes_per_launch"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
     ncu --set full capture (profiles/*.json), or None."""
     p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("k_hw3d_rhs_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:
             return None
     return None
@@ -292,8 +296,232 @@ def run_ours(args):
         "clocks": clocks,
         "rhs_phase_ms": {k: round(v, 4) for k, v in phases.items()},
     }
+    if world == 1 and not args.no_other:
+        del model
+        torch.cuda.empty_cache()
+        try:
+            out["other"] = other_measurements(torch, pkg, dev, peak)
+        except Exception as e:  # noqa: BLE001 -- the extras never invalidate the main line
+            out["other"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(steps=3, warmup=1)
+    print(json.dumps(out), flush=True)
+
+
+
+ELM = dict(nx=516, ny=64, nz=256)   # BASELINE configs[4]: 516 x 64 x 256 (nx with guard cells)
+ELM_DT = 1e-3
+ELM_WORKLOAD = ("elm-pb linear 3-field reduced-MHD RHS (shipped [highbeta] switches), 512x64x256 interior points per "
+                "GPU (516x68x256 with guards), synthetic shifted-metric tokamak grid, zperiod 15, RK4")
+# Algorithmic bytes per interior point of the fused kernel k_elmpb_rhs: reads U, P, Psi, phi, Jpar,
+# Delp2(Jpar), eta (7 x 8) + the ten parallel slices (80), writes the three time derivatives (24)
+ELM_FUSED_BPP = 160.0
+# Whole elm-pb RHS pass list: slices 5 x 24, solve 16, phi update 24, Delp2 2 x 16,
+# smooth_x 16, Jpar2 copy 16, fused 160
+ELM_RHS_BPP = 5 * 24 + 16 + 24 + 2 * 16 + 16 + 16 + 160
+
+
+def event_time(torch, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def elmpb_model(pkg, dev):
+    m = pkg.models.ELMpb.from_setup(pkg.elm_setup.elmpb_setup(ELM["nx"], ELM["ny"], ELM["nz"]), device=dev)
+    m.set_state(*pkg.models.elmpb_initial_state(m.g, device=dev))
+    return m
+
+
+def other_measurements(torch, pkg, dev, peak):
+    """Short N = 1 extras for the default line: elm-pb RHS, LaplaceCyclic solves/s, configs[1] microbenchmarks."""
+    capi = pkg.capi
+    out = {}
+    # -- elm-pb RHS (configs[4])
+    m = elmpb_model(pkg, dev)
+    t = event_time(torch, m.rhs, reps=10)
+    m.kernel_events = []
+    for _ in range(5):
+        m.rhs()
+    torch.cuda.synchronize()
+    kt = sum(a.elapsed_time(b) for a, b in m.kernel_events) * 1e-3 / len(m.kernel_events)
+    m.kernel_events = None
+    npts = m.g.n_interior
+    out["elmpb_rhs"] = {"workload": ELM_WORKLOAD, "grid_points_per_s": npts / t, "ms_per_rhs": t * 1e3,
+                        "rhs_algorithmic_GBps": ELM_RHS_BPP * npts / t / 1e9,
+                        "rhs_frac_of_hbm_peak": ELM_RHS_BPP * npts / t / 1e9 / peak,
+                        "fused_kernel": {"name": "k_elmpb_rhs", "ms": kt * 1e3,
+                                         "achieved_GBps": ELM_FUSED_BPP * npts / kt / 1e9,
+                                         "frac": ELM_FUSED_BPP * npts / kt / 1e9 / peak},
+                        "finite": bool(all(torch.isfinite(f).all().item() for f in (m.ddt_U, m.ddt_P, m.ddt_Psi)))}
+    del m
+    # -- LaplaceCyclic solves/s (metric: "LaplaceCyclic solves/s"), 16 B/pt algorithmic
+    lap = {}
+    for name, dims in (("512x128x512", (516, 132, 512, 2, 2)), ("512x64x256", (516, 68, 256, 2, 2)),
+                       ("1024x1x1024", (1028, 1, 1024, 2, 0))):
+        g = capi.Grid(*dims)
+        one = lambda v: torch.full(g.shape2, v, dtype=torch.float64, device=dev)
+        md = dict(dx=one(0.2), g11=one(1.0), g33=one(1.0), g13=one(0.0), G1=one(0.0), G3=one(0.0), g_11=one(1.0),
+                  g_22=one(1.0))
+        f = torch.rand(g.shape3, dtype=torch.float64, device=dev) - 0.5
+        o = torch.zeros_like(f)
+        L = capi.Laplace(g, md, 0.2 * g.nz)
+        t = event_time(torch, lambda: L.solve(f, out=o), reps=20)
+        L.status()
+        lap[name] = {"solves_per_s": 1.0 / t, "us_per_solve": t * 1e6, "algorithmic_GBps": 16.0 * g.n_interior / t / 1e9,
+                     "frac_of_hbm_peak": 16.0 * g.n_interior / t / 1e9 / peak}
+        del L, f, o
+    out["laplace_cyclic"] = lap
+    # -- examples/performance microbenchmarks on a 256x64x256 Field3D (configs[1]); L2 flushed between launches
+    g = capi.Grid(260, 68, 256, 2, 2)
+    a, b, c = (torch.rand(g.shape3, dtype=torch.float64, device=dev) for _ in range(3))
+    o = torch.zeros_like(a)
+    dx = torch.full(g.shape2, 0.2, dtype=torch.float64, device=dev)
+    flush = torch.empty(40 * 1024 * 1024, dtype=torch.float64, device=dev)   # 320 MB > L2
+
+    def flushed(fn, reps=10):
+        fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.sort()
+        return ts[len(ts) // 2]
+    micro = {}
+    for name, fn, bpp in (
+            ("DDX_C2", lambda: capi.stencil(g, "DDX_C2", "X", a, scale1=dx, out=o), 16),
+            ("DDX_C4", lambda: capi.stencil(g, "DDX_C4", "X", a, scale1=dx, out=o), 16),
+            ("DDY_C2", lambda: capi.stencil(g, "DDX_C2", "Y", a, scale1=dx, out=o), 16),
+            ("DDZ_C2", lambda: capi.stencil(g, "DDX_C2", "Z", a, scale1=dx, out=o), 16),
+            ("DDZ_FFT", lambda: capi.ddz_fft(g, a, out=o), 16),
+            ("VDDX_U1", lambda: capi.stencil(g, "VDDX_U1", "X", a, v=b, scale1=dx, out=o), 24),
+            ("bracket_arakawa", lambda: capi.bracket_arakawa(g, a, b, dx, dx, out=o), 24),
+            ("arithmetic_2a_plus_bc", lambda: capi.elementwise(g, [(2.0, a), (1.0, b, c)], out=o), 32)):
+        t = flushed(fn)
+        micro[name] = {"us": t * 1e6, "grid_points_per_s": g.n_interior / t,
+                       "algorithmic_GBps": bpp * g.n_interior / t / 1e9, "frac_of_hbm_peak": bpp * g.n_interior / t / 1e9 / peak}
+    out["microbench_256x64x256"] = micro
+    return out
+
+
+def run_elmpb(args):
+    """--workload elmpb: BASELINE configs[4].  N > 1 runs N independent replicas of the per-GPU grid (the elm-pb
+    harness model is single-rank)."""
+    import torch
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__), "--gpus",
+                   str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", "elmpb"]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bout-dev_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pkg = ge.load_package()
+    capi = pkg.capi
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    m = elmpb_model(pkg, dev)
+    host = [f.cpu().pin_memory() for f in (m.U, m.P, m.Psi)]
+    host_out = [torch.empty_like(h).pin_memory() for h in host]
+    npts = m.g.n_interior
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        m.rk4_step(ELM_DT)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    m.kernel_events = []
+    l0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        m.rk4_step(ELM_DT)
+    e1.record()
+    barrier()
+    launches = capi.launch_count() - l0
+    secs = reduce_max(e0.elapsed_time(e1) * 1e-3)
+    kev = m.kernel_events
+    m.kernel_events = None
+    k_secs = sum(a.elapsed_time(b) for a, b in kev) * 1e-3 / len(kev)
+    finite = bool(all(torch.isfinite(f).all().item() for f in (m.U, m.P, m.Psi)))
+    # end to end: state from pinned host memory every step, result back
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        for f, h in zip((m.U, m.P, m.Psi), host):
+            f.copy_(h, non_blocking=True)
+        m.rk4_step(ELM_DT)
+        for f, h in zip((m.U, m.P, m.Psi), host_out):
+            h.copy_(f, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_secs = reduce_max(e0.elapsed_time(e1) * 1e-3)
+    w2 = time.time()
+    clocks = sampler.stop(w0, w2) if rank == 0 else None
+    if world > 1:
+        torch.distributed.barrier()
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    fb = host[0].numel() * 8
+    achieved = ELM_FUSED_BPP * npts / k_secs / 1e9
+    out = {
+        "metric": METRIC, "value": npts * 4 * args.steps * world / secs, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (closed-form tokamak grid and perturbation)",
+        "config": {"workload": ELM_WORKLOAD, "decomposition": "replicas only" if world > 1 else "NXPE=1 NYPE=1",
+                   "rhs_per_step": 4, "points_per_gpu": npts, "dt": ELM_DT,
+                   "l2": "the RHS streams ~25 fields of 72 MB each (1.8 GB per RHS) through the 126 MB L2; no flush needed"},
+        "gpu_launches": int(launches), "finite": finite,
+        "e2e": {"value": npts * 4 * args.steps * world / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": 3 * fb,
+                "d2h_bytes_per_step": 3 * fb, "ms_per_step": e2e_secs / args.steps * 1e3,
+                "note": "state (U, P, Psi) copied host->device from pinned memory and the result device->host every RK4 step"},
+        "roofline": {"bound": "hbm", "kernel": "k_elmpb_rhs (fused 3-equation RHS + z filter)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "traffic": profile_traffic("k_elmpb_rhs_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": ELM_FUSED_BPP * npts, "kernel_ms": k_secs * 1e3,
+                     "kernel_share_of_step": 4 * k_secs / (secs / args.steps),
+                     "rhs_algorithmic_GBps": ELM_RHS_BPP * npts * 4 * args.steps / secs / 1e9,
+                     "rhs_bytes_per_point": f"{ELM_RHS_BPP:.0f} (pass list in DESIGN.md section 3)"},
+        "clocks": clocks,
+    }
     print(json.dumps(out), flush=True)
 
 
@@ -378,11 +606,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the short extra measurements of the default line")
+    ap.add_argument("--workload", default="hw3d", choices=["hw3d", "elmpb"])
     ap.add_argument("--decomp", default=os.environ.get("BOUT_B200_DECOMP", "y"), choices=["x", "y", "xy"],
                     help="BoutMesh decomposition at N > 1: NYPE=N (default), NXPE=N, or NXPE=2 x NYPE=N/2")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "elmpb":
+        run_elmpb(args)
     else:
         run_ours(args)
 
