@@ -132,8 +132,14 @@ class ELMpb:
     Every numerical step is a C-ABI call.  Evolving fields: U, P, Psi (solver order of SOLVE_FOR)."""
 
     def __init__(self, g: capi.Grid, md: dict, eq: dict, zshift, zlength, dnorm, hyperresist,
-                 filter_z_mode=1, low_pass_z=16, zonal=(False, True, False), device="cuda"):
+                 filter_z_mode=1, low_pass_z=16, zonal=(False, True, False), device="cuda", mesh=None):
         self.g, self.dev = g, torch.device(device)
+        # mesh: a BoutMesh with NXPE = 1 (the domain split along Y only: every operator with X or Z coupling --
+        # LaplaceCyclic, Delp2, smooth_x, the z FFTs -- stays rank-local and only communicate() crosses ranks);
+        # g, md, eq, zshift are then this rank's slab.  None = single rank.
+        if mesh is not None and mesh.nxpe != 1:
+            raise ValueError("ELMpb: only NYPE decomposition (NXPE = 1) is implemented")
+        self.mesh = mesh
         dv = lambda t: t.to(self.dev).contiguous()
         self.md = {k: dv(v) for k, v in md.items()}
         self.eq = {k: dv(v) for k, v in eq.items()}
@@ -163,13 +169,23 @@ class ELMpb:
         self.compute_jpar2 = True     # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
 
     @classmethod
-    def from_setup(cls, s, device="cuda", **kw):
-        """Build from elm_setup.elmpb_setup(...) (numpy, set-up time)."""
-        g = capi.Grid(*s["grid"])
-        md = {k: torch.from_numpy(v) for k, v in s["md"].items()}
-        eq = {k: torch.from_numpy(v) for k, v in s["eq"].items()}
-        return cls(g, md, eq, torch.from_numpy(s["zShift"]), s["zlength"], s["dnorm"], s["hyperresist"],
-                   device=device, **kw)
+    def from_setup(cls, s, device="cuda", mesh=None, **kw):
+        """Build from elm_setup.elmpb_setup(...) of the GLOBAL grid (numpy, set-up time); with a mesh, each
+        rank keeps its own y slab (guard rows included) of every array."""
+        import numpy as np
+        nx, ny, nz, mxg, myg = s["grid"]
+        if mesh is None:
+            g, ysl = capi.Grid(*s["grid"]), slice(None)
+        else:
+            g = mesh.grid
+            if (ny - 2 * myg) != mesh.mysub * mesh.nype or g.nx != nx or g.nz != nz:
+                raise ValueError("ELMpb.from_setup: mesh does not tile the set-up grid")
+            ysl = slice(mesh.pe_yind * mesh.mysub, mesh.pe_yind * mesh.mysub + mesh.mysub + 2 * myg)
+        cut = lambda v: torch.from_numpy(np.ascontiguousarray(v[:, ysl]))
+        md = {k: cut(v) for k, v in s["md"].items()}
+        eq = {k: cut(v) for k, v in s["eq"].items()}
+        return cls(g, md, eq, cut(s["zShift"]), s["zlength"], s["dnorm"], s["hyperresist"], device=device,
+                   mesh=mesh, **kw)
 
     def set_state(self, U, P, Psi):
         self.U.copy_(U), self.P.copy_(P), self.Psi.copy_(Psi)
@@ -180,8 +196,15 @@ class ELMpb:
     def _comm(self, fields):
         """mesh->communicate(...) on one rank: y periodic self exchange; ShiftedMetric then builds the
         parallel slices of each field (mesh.cxx:349-378)."""
-        capi.halo_self(self.g, fields, periodic_x=False, periodic_y=True)
+        self._halo(fields)
         return [self._slices(f) for f in fields]
+
+    def _halo(self, fields):
+        """Guard-cell exchange of Mesh::communicate: y periodic (all-core grid), no X neighbours (NXPE = 1)."""
+        if self.mesh is None:
+            capi.halo_self(self.g, fields, periodic_x=False, periodic_y=True)
+        else:
+            self.mesh.communicate(fields)
 
     def _bc_j(self, f):          # [J] bndry_core = neumann, rest dirichlet_o2
         capi.boundary(self.g, "neumann", "xin", f, spacing=self.md["dx"])
@@ -219,7 +242,7 @@ class ELMpb:
 
     def _comm_into(self, fields, names):
         """mesh->communicate(...) with the parallel slices written into preallocated buffers."""
-        capi.halo_self(self.g, fields, periodic_x=False, periodic_y=True)
+        self._halo(fields)
         out = []
         for f, n in zip(fields, names):
             up, dn = self._buffers()[n]
@@ -245,9 +268,9 @@ class ELMpb:
         # Jpar = Delp2(Psi); BC; communicate; smooth_x; BC; communicate         :1518-1563
         self.delp.delp2(Psi, out=self.Jpar)
         self._bc_j(self.Jpar)
-        capi.halo_self(g, [self.Jpar], periodic_x=False, periodic_y=True)
+        self._halo([self.Jpar])
         sm = capi.smooth_x(g, self.Jpar, out=buf["sm"])
-        capi.halo_self(g, [sm], periodic_x=False, periodic_y=True)            # smooth_x communicates its result
+        self._halo([sm])                                                      # smooth_x communicates its result
         buf["sm"], self.Jpar = self.Jpar, sm                                  # Jpar = smooth_x(Jpar)
         self._bc_j(self.Jpar)
         (sJ,) = self._comm_into([self.Jpar], ["J"])
@@ -256,7 +279,7 @@ class ELMpb:
         if self.compute_jpar2:
             self.Jpar2.copy_(d2J)
             self._bc_j(self.Jpar2)
-            capi.halo_self(g, [self.Jpar2], periodic_x=False, periodic_y=True)
+            self._halo([self.Jpar2])
         if self.fused and self.filter_z_mode >= 0 and self.filter_z_mode < g.nz // 2:
             keep = [1.0, 1.0, 1.0]
             if self.low_pass_z > 0:
@@ -318,29 +341,32 @@ class ELMpb:
                 capi.zfilter(g, f, self.filter_z_mode, out=f)
 
     def rk4_step(self, dt):
-        """RK4Solver::take_step (rk4.cxx:172-210): stage combinations over the evolving region."""
+        """RK4Solver::take_step (rk4.cxx:172-210): stage combinations over the evolving region.  Each RHS
+        writes its time derivatives straight into that stage's k arrays and the stage states are built from
+        the interior only (their guard cells are filled by the next pre_rhs + communicate), so a step is
+        4 RHS + 9 axpy passes + the final combination, with no gather/scatter or copy passes."""
         g = self.g
         state = (self.U, self.P, self.Psi)
         if not hasattr(self, "_rk"):
             self._rk = [[torch.zeros_like(self.U) for _ in range(3)] for _ in range(5)]   # k1..k4, stage state
         k1, k2, k3, k4, st = self._rk
-        ddts = lambda: (self.ddt_U, self.ddt_P, self.ddt_Psi)
+        keep = (self.ddt_U, self.ddt_P, self.ddt_Psi)
 
         def stage(src, k, coef):
+            self.ddt_U, self.ddt_P, self.ddt_Psi = k
             self.rhs(*src)
-            for i, d in enumerate(ddts()):
-                k[i].copy_(d)
             if coef is not None:
                 for i in range(3):
-                    st[i].copy_(state[i])
                     capi.rk_stage(g, "axpy", coef * dt, state[i], k[i], out=st[i])
-        stage(state, k1, 0.5)
-        stage(st, k2, 0.5)
-        stage(st, k3, 1.0)
-        stage(st, k4, None)
+        try:
+            stage(state, k1, 0.5)
+            stage(st, k2, 0.5)
+            stage(st, k3, 1.0)
+            stage(st, k4, None)
+        finally:
+            self.ddt_U, self.ddt_P, self.ddt_Psi = keep
         for i in range(3):
             capi.rk_stage(g, "rk4_final", dt, state[i], k1[i], k2[i], k3[i], k4[i], out=state[i])
-
 
 def elmpb_initial_state(g: capi.Grid, device="cuda", amp=1e-5):
     """Synthetic smooth (U, P, Psi) of elm-pb magnitudes: a gaussian-in-x, ballooning-like-in-y envelope times

@@ -1,6 +1,7 @@
 """Run under torchrun on N GPUs (N = 2, 4, 8): X-decomposed HW3D against the single-rank golden
-trajectory of the reference (tests/golden/models.npz) and an X-decomposed LaplaceCyclic against the
-golden operator fixture.  Exit code 0 = parity.  Launched by tests/test_gpu_multi.py."""
+trajectory of the reference (tests/golden/models.npz), an X-decomposed LaplaceCyclic against the
+golden operator fixture, and the Y-decomposed elm-pb model against the reference's single-rank RHS and
+trajectory (tests/golden/elmpb.npz).  Exit code 0 = parity.  Launched by tests/test_gpu_multi.py."""
 import os
 import sys
 
@@ -46,12 +47,42 @@ def main():
         m.rk4_step(float(dt))
     errs += [rel_err(m.n.cpu().numpy(), gold["hw3d_final_n"][sl], I), rel_err(m.vort.cpu().numpy(), gold["hw3d_final_vort"][sl], I)]
     ok = ok and max(errs[2:]) < 1e-8
+    print(f"rank {rank}/{world}: ddt err {errs[0]:.2e} {errs[1]:.2e}; trajectory err {errs[2]:.2e} {errs[3]:.2e}", flush=True)
+    ok = elmpb_check(pkg, dev, rank, world) and ok
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
-    print(f"rank {rank}/{world}: ddt err {errs[0]:.2e} {errs[1]:.2e}; trajectory err {errs[2]:.2e} {errs[3]:.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(int(flag.item() != 0))
+
+
+def elmpb_check(pkg, dev, rank, world):
+    """elm-pb split along Y over all ranks (NXPE = 1, NYPE = world) vs the reference's single-rank golden."""
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "elmpb.npz")))
+    nx, ny, nz, mxg, myg = [int(v) for v in gold["grid"]]
+    my = ny - 2 * myg
+    if my % world != 0 or my // world < myg:
+        print(f"rank {rank}: elm-pb fixture (MY = {my}) does not split over {world} ranks; skipped", flush=True)
+        return True
+    mysub = my // world
+    mesh = pkg.mesh.BoutMesh(1, world, rank, nx - 2 * mxg, mysub, nz, mxg, myg, periodic_x=False, periodic_y=True,
+                             device=dev)
+    m = pkg.models.ELMpb.from_setup(pkg.elm_setup.elmpb_setup(nx, my, nz, mxg, myg), device=dev, mesh=mesh)
+    ysl = slice(rank * mysub, rank * mysub + mysub + 2 * myg)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[:, ysl])).to(dev)
+    state = [t(gold["rhs_in_" + n]) for n in ("U", "P", "Psi")]
+    I = mesh.grid.interior
+    m.set_state(*state)
+    m.rhs()
+    e1 = [rel_err(f.cpu().numpy(), gold["rhs_ddt_" + n][:, ysl], I)
+          for n, f in (("U", m.ddt_U), ("P", m.ddt_P), ("Psi", m.ddt_Psi))]
+    m.set_state(*state)
+    dt, nsteps = gold["dt_nsteps"]
+    for _ in range(int(nsteps)):
+        m.rk4_step(float(dt))
+    e2 = [rel_err(f.cpu().numpy(), gold["final_" + n][:, ysl], I) for n, f in (("U", m.U), ("P", m.P), ("Psi", m.Psi))]
+    print(f"rank {rank}/{world}: elm-pb NYPE={world} ddt err {max(e1):.2e}; trajectory err {max(e2):.2e}", flush=True)
+    return max(e1) < 1e-10 and max(e2) < 1e-8
 
 
 if __name__ == "__main__":
