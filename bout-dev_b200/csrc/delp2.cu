@@ -7,7 +7,10 @@
 //  * bout_b200_delp2_fd  : the useFFT=false branch (coordinates.cxx:1701-1702) for C2 methods,
 //    G1 DDX + G3 DDZ + g11 D2DX2 + g33 D2DZ2 + 2 g13 D2DXDZ as one 9-point X-Z stencil pass
 //    (same arithmetic as include/bout/single_index_ops.hxx:222-246).
+#include <cstdlib>
+
 #include "bracket.cuh"
+#include "fft_fast.cuh"
 #include "laplace_coefs.cuh"
 
 namespace b200 {
@@ -102,6 +105,104 @@ __global__ void __launch_bounds__(128) k_delp2_fft(const Delp2FftParams p) {
     }
     __syncthreads();
   }
+}
+
+
+// Fast path (nz in {128, 256, 512, 1024}, 16-byte aligned rows): same x-march, with the fft_fast.cuh
+// transforms (register twiddles, swizzled buffers), 256-thread CTAs and per-row barriers, so the row groups of
+// a CTA run decoupled.  Shared memory per row group: the two FFT buffers, the three spectra, the combination.
+template <int N>
+__global__ void __launch_bounds__(256) k_delp2_fast(const Delp2FftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TPR = FftShape<N>::TPR, ROWS = 256 / TPR, BUF = N + 8;
+  const int rloc = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+  cd* base = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(rloc) * 6 * BUF;
+  cd* A = base;
+  cd* B = base + BUF;
+  cd* S[3] = {base + 2 * BUF, base + 3 * BUF, base + 4 * BUF};
+  cd* D = base + 5 * BUF;
+  FastTw<N> tw;
+  fastTwInit<N>(tw, p.tw, lane);
+  const SyncGroup sync{1 + rloc, TPR};
+
+  const int nyb = p.ye - p.ys + 1;
+  const long long ntasks = static_cast<long long>(nyb) * p.nchunks;
+  const long long task0 = static_cast<long long>(blockIdx.x) * ROWS + rloc;
+  const bool task_ok = task0 < ntasks;
+  const long long task = task_ok ? task0 : ntasks - 1;
+  const int y = p.ys + static_cast<int>(task / p.nchunks);
+  const int x0 = p.xs + static_cast<int>(task % p.nchunks) * p.chunk;
+  const int x1 = min(x0 + p.chunk - 1, p.xe);
+  const long long plane = static_cast<long long>(p.ny) * p.nz;
+  const double* __restrict__ col = p.f + static_cast<long long>(y) * p.nz;
+
+  auto forwardTo = [&](int x, cd* dst) { // the row group is synchronised on entry and on exit
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(col + x * plane);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + m * (N / 4);
+      const double2 v = __ldg(s2 + j);
+      A[fsw(j)] = {v.x, v.y};
+    }
+    sync();
+    const cd* Z = cfftFast<N, false, SyncGroup>(A, B, tw, lane, sync);
+    rfftSplitTo<N>(Z, dst, N + 1, tw, lane);
+    sync();
+  };
+
+  forwardTo(x0 - 1, S[(x0 - 1) % 3]);
+  forwardTo(x0, S[x0 % 3]);
+  for (int it = 0; it < p.chunk; ++it) {
+    const int x = min(x0 + it, x1); // short chunks repeat their last row (never stored twice)
+    const bool store = task_ok && (x0 + it <= x1);
+    forwardTo(x + 1, S[(x + 1) % 3]);
+    const cd* Sm = S[(x + 2) % 3]; // (x - 1) mod 3
+    const cd* S0 = S[x % 3];
+    const cd* Sp = S[(x + 1) % 3];
+    for (int k = lane; k <= N; k += TPR) {
+      cd a, b, c;
+      const double kwave = k * 2.0 * M_PI / p.m.zlength; // invert_laplace.cxx:263
+      tridagCoefs(p.m, x, y, kwave, false, false, a, b, c);
+      D[k] = cadd(cadd(cmul(a, Sm[k]), cmul(b, S0[k])), cmul(c, Sp[k]));
+    }
+    sync();
+    rfftMergeFrom<N>(D, A, N + 1, false, tw, lane);
+    sync();
+    const cd* z = cfftFast<N, true, SyncGroup>(A, B, tw, lane, sync);
+    if (store) {
+      double2* __restrict__ d2 = reinterpret_cast<double2*>(p.out + x * plane + static_cast<long long>(y) * p.nz);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int j = lane + m * (N / 4);
+        const cd v = z[fsw(j)];
+        d2[j] = make_double2(v.re, v.im);
+      }
+    }
+    sync();
+  }
+}
+
+template <int N>
+int launchDelp2Fast(Delp2FftParams p, cudaStream_t s) {
+  constexpr int ROWS = 256 / FftShape<N>::TPR;
+  const size_t smem = static_cast<size_t>(ROWS) * 6 * (N + 8) * sizeof(cd);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_delp2_fast<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const int len = p.xe - p.xs + 1, nyb = p.ye - p.ys + 1;
+  int chunk = 32;
+  while (chunk > 8 && static_cast<long long>(nyb) * ((len + chunk - 1) / chunk) < 148LL * 4 * ROWS) {
+    chunk /= 2;
+  }
+  p.chunk = chunk;
+  p.nchunks = (len + chunk - 1) / chunk;
+  const long long ntasks = static_cast<long long>(nyb) * p.nchunks;
+  k_delp2_fast<N><<<static_cast<unsigned>((ntasks + ROWS - 1) / ROWS), 256, smem, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
 }
 
 struct Delp2FdParams {
@@ -214,6 +315,15 @@ extern "C" int bout_b200_delp2_fft(const bout_b200_grid* g, const bout_b200_lapl
   p.tw = twiddleTable(g->nz, s, &st);
   if (st != 0) {
     return st;
+  }
+  if ((g->nz == 128 || g->nz == 256 || g->nz == 512 || g->nz == 1024) && aligned16(f) && aligned16(out)
+      && getenv("BOUT_B200_NO_FAST_FFT") == nullptr) {
+    switch (g->nz / 2) {
+    case 64: return launchDelp2Fast<64>(p, s);
+    case 128: return launchDelp2Fast<128>(p, s);
+    case 256: return launchDelp2Fast<256>(p, s);
+    default: return launchDelp2Fast<512>(p, s);
+    }
   }
   RowGeom geo = rowGeometry(g->nz, 128);
   geo.smemBytes = static_cast<size_t>(geo.rows) * 5 * fftBufElems(g->nz) * sizeof(cd);

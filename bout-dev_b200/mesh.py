@@ -105,21 +105,22 @@ class BoutMesh:
             else:
                 n = nf * g.nx * self.myg * g.nz
                 ops, keep = [], []
+                tag = f"{nf}@{torch.cuda.current_stream().cuda_stream}" if fields[0].is_cuda else f"{nf}"
                 # Post order: send up, receive from below, send down, receive from above -- so that two
                 # messages between the same pair of ranks (NYPE = 2, periodic) match in order.
                 if self.yup is not None:
-                    sb = self._buf("s_up", n, fields[0])
+                    sb = self._buf("s_up" + tag, n, fields[0])
                     self.ops.pack_y(g, fields, g.yend - self.myg + 1, self.myg, sb)
                     ops.append(dist.P2POp(dist.isend, sb, self.yup))
                 if self.ydown is not None:
-                    rb = self._buf("r_dn", n, fields[0])
+                    rb = self._buf("r_dn" + tag, n, fields[0])
                     ops.append(dist.P2POp(dist.irecv, rb, self.ydown))
                     keep.append((rb, 0))
-                    sb = self._buf("s_dn", n, fields[0])
+                    sb = self._buf("s_dn" + tag, n, fields[0])
                     self.ops.pack_y(g, fields, g.ystart, self.myg, sb)
                     ops.append(dist.P2POp(dist.isend, sb, self.ydown))
                 if self.yup is not None:
-                    rb = self._buf("r_up", n, fields[0])
+                    rb = self._buf("r_up" + tag, n, fields[0])
                     ops.append(dist.P2POp(dist.irecv, rb, self.yup))
                     keep.append((rb, g.yend + 1))
                 if ops:

@@ -38,6 +38,12 @@ class HW3D:
         self.coef = capi.fused_coefs(g, self.cm, capi.fused_coef_workspace(g, self.dev))
         self.phase_events = None
         self.kernel_events = None  # bench.py: list collecting (start, end) CUDA events of the fused kernel
+        # NYPE > 1: the guard rows of n and vort travel on a second stream while the Laplacian solve runs on the
+        # main one (they do not depend on it); only phi's exchange stays on the critical path
+        import os
+        self.overlap = (mesh is not None and mesh.nxpe == 1 and mesh.nype > 1 and self.dev.type == "cuda"
+                        and os.environ.get("BOUT_B200_HALO_OVERLAP", "1") != "0")
+        self._comm_stream = None
         z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
         self.n, self.vort, self.phi = z(), z(), z()
         self.ddt_n, self.ddt_vort = z(), z()
@@ -71,6 +77,15 @@ class HW3D:
         self._mark("start")
         self._pre_rhs(fn, fv)                                   # Solver::pre_rhs
         self._mark("bc")
+        overlapped = False
+        if self.overlap and not self.x_split:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.dev)
+            main = torch.cuda.current_stream()
+            self._comm_stream.wait_stream(main)
+            with torch.cuda.stream(self._comm_stream):
+                self.mesh.communicate([fn, fv])
+            overlapped = True
         if not self.x_split:                                    # phi = phiSolver->solve(vort, phi)
             self.lap.solve(fv, out=self.phi)
             self._mark("solve")
@@ -83,6 +98,9 @@ class HW3D:
             self._mark("solve_finish")
         if self.mesh is None:                                   # mesh->communicate(n, vort, phi, ...)
             capi.halo_self(self.g, [fn, fv, self.phi], periodic_x=False, periodic_y=True)
+        elif overlapped:
+            self.mesh.communicate([self.phi])
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
         else:
             self.mesh.communicate([fn, fv, self.phi])
         self._mark("halo")

@@ -48,12 +48,41 @@ def main():
     errs += [rel_err(m.n.cpu().numpy(), gold["hw3d_final_n"][sl], I), rel_err(m.vort.cpu().numpy(), gold["hw3d_final_vort"][sl], I)]
     ok = ok and max(errs[2:]) < 1e-8
     print(f"rank {rank}/{world}: ddt err {errs[0]:.2e} {errs[1]:.2e}; trajectory err {errs[2]:.2e} {errs[3]:.2e}", flush=True)
+    ok = hw3d_y_check(pkg, dev, rank, world, gold) and ok
     ok = elmpb_check(pkg, dev, rank, world) and ok
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(int(flag.item() != 0))
+
+
+def hw3d_y_check(pkg, dev, rank, world, gold):
+    """HW3D split along Y (NXPE = 1, NYPE = world: bench.py's default decomposition, with the n / vort guard-row
+    exchange overlapped with the Laplacian solve) vs the reference's single-rank golden trajectory."""
+    gnx, gny, nz, mxg, myg = [int(v) for v in gold["hw3d_grid"]]
+    my = gny - 2 * myg
+    if my % world != 0 or my // world < myg:
+        print(f"rank {rank}: hw3d fixture (MY = {my}) does not split over {world} ranks; skipped", flush=True)
+        return True
+    mysub = my // world
+    mesh = pkg.mesh.BoutMesh(1, world, rank, gnx - 2 * mxg, mysub, nz, mxg, myg, periodic_x=False, periodic_y=True,
+                             device=dev)
+    ysl = slice(rank * mysub, rank * mysub + mysub + 2 * myg)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[:, ysl])).to(dev)
+    metric = {n: t(gold[f"hw3d_metric_{n}"]) for n in ("dx", "dy", "dz", "J", "g_22", "g11", "g33", "g13", "G1", "G3",
+                                                        "d1_dx", "g_11")}
+    m = pkg.models.HW3D(mesh.grid, metric, alpha=1.0, kappa=0.5, Dn=1e-3, Dvort=1e-3, device=dev, mesh=mesh)
+    assert m.overlap
+    m.set_state(t(gold["hw3d_init_n"]), t(gold["hw3d_init_vort"]))
+    dt, nsteps = gold["hw3d_dt_nsteps"]
+    for _ in range(int(nsteps)):
+        m.rk4_step(float(dt))
+    I = mesh.grid.interior
+    e = [rel_err(m.n.cpu().numpy(), gold["hw3d_final_n"][:, ysl], I),
+         rel_err(m.vort.cpu().numpy(), gold["hw3d_final_vort"][:, ysl], I)]
+    print(f"rank {rank}/{world}: hw3d NYPE={world} trajectory err {e[0]:.2e} {e[1]:.2e}", flush=True)
+    return max(e) < 1e-8
 
 
 def elmpb_check(pkg, dev, rank, world):
