@@ -308,6 +308,58 @@ def halo_unpack_y(g: Grid, fields, y0, nrows, xlo, xhi, buf):
                                        _ptr(buf), _stream()))
 
 
+# ---- Y exchange over NVLink peer memory (raw device addresses as python ints) -------------------------------
+def peer_alloc(nbytes):
+    p = C.c_void_p()
+    _check(lib.bout_b200_peer_alloc(C.c_size_t(nbytes), C.byref(p)))
+    return p.value
+
+
+def peer_export(ptr):
+    h = (C.c_ubyte * 64)()
+    _check(lib.bout_b200_peer_export(C.c_void_p(ptr), h))
+    return bytes(h)
+
+
+def peer_open(handle: bytes):
+    p = C.c_void_p()
+    h = (C.c_ubyte * 64).from_buffer_copy(handle)
+    _check(lib.bout_b200_peer_open(h, C.byref(p)))
+    return p.value
+
+
+def halo_push_y(g: Grid, fields, y0, nrows, xlo, xhi, peer_buf, peer_flag, value, counter):
+    _check(lib.bout_b200_halo_push_y(C.byref(g.c), len(fields), _ptr_array(fields), y0, nrows, xlo, xhi,
+                                     C.c_void_p(peer_buf), C.c_void_p(peer_flag), C.c_ulonglong(value),
+                                     C.c_void_p(counter), _stream()))
+
+
+def _xchg_args(y0, bufs, flags):
+    return ((C.c_int * 2)(*y0), (C.c_void_p * 2)(*[b or None for b in bufs]),
+            (C.c_void_p * 2)(*[f or None for f in flags]))
+
+
+def halo_push_y2(g: Grid, fields, nrows, y0, peer_bufs, peer_flags, value, counters):
+    a, b, f = _xchg_args(y0, peer_bufs, peer_flags)
+    _check(lib.bout_b200_halo_push_y2(C.byref(g.c), len(fields), _ptr_array(fields), nrows, a, b, f,
+                                      C.c_ulonglong(value), C.c_void_p(counters), _stream()))
+
+
+def halo_wait_unpack_y2(g: Grid, fields, nrows, y0, local_bufs, local_flags, value, status):
+    a, b, f = _xchg_args(y0, local_bufs, local_flags)
+    _check(lib.bout_b200_halo_wait_unpack_y2(C.byref(g.c), len(fields), _ptr_array(fields), nrows, a, b, f,
+                                             C.c_ulonglong(value), C.c_void_p(status), _stream()))
+
+
+def halo_wait(flag, value, status):
+    _check(lib.bout_b200_halo_wait(C.c_void_p(flag), C.c_ulonglong(value), C.c_void_p(status), _stream()))
+
+
+def halo_unpack_y_raw(g: Grid, fields, y0, nrows, xlo, xhi, buf):
+    _check(lib.bout_b200_halo_unpack_y(C.byref(g.c), len(fields), _ptr_array(fields), y0, nrows, xlo, xhi,
+                                       C.c_void_p(buf), _stream()))
+
+
 def rk_stage(g: Grid, mode, dt, start, k1, k2=None, k3=None, k4=None, c=1.0, out=None,
              region="RGN_NOBNDRY"):
     m = {"axpy": 0, "rk4_final": 1, "rk3_stage2": 2, "rk3_stage3": 3}[mode]

@@ -11,6 +11,15 @@
 //    out [field][x][y][z] as pack_data does.  X guard planes are already contiguous in memory
 //    (x is the slowest index), so X messages are sent straight from / received straight into the
 //    field with no pack step.
+//  * bout_b200_peer_* / bout_b200_halo_push_y / bout_b200_halo_wait : the same Y exchange WITHOUT a
+//    communication library -- the pack kernel stores the rows straight into the neighbour GPU's receive
+//    buffer over NVLink (CUDA IPC peer mapping) and its last block raises a flag in the neighbour's memory
+//    (writes -> __threadfence_system -> block counter -> flag, the threadfence-reduction pattern); the
+//    receiver spins on its own flag, then unpacks.  One hop per message, no rendezvous kernel on either
+//    side; receive buffers are double-buffered by the parity of the exchange counter, which is sufficient
+//    because a rank cannot start exchange c + 1 before it has waited for both neighbours' exchange c.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -58,6 +67,10 @@ struct PackYParams {
   int y0, nrows; // rows y0 .. y0+nrows-1
   int xlo, xhi;
   int unpack;
+  // push mode (buf is peer memory): the last block to finish stores `value` to *flag
+  unsigned long long* flag;
+  unsigned long long value;
+  unsigned int* done; // local block counter, reset by the last block
 };
 
 __global__ void __launch_bounds__(256) k_pack_y(const PackYParams p) {
@@ -79,6 +92,111 @@ __global__ void __launch_bounds__(256) k_pack_y(const PackYParams p) {
       p.buf[t] = *cell;
     }
   }
+  if (p.flag != nullptr) {
+    __threadfence_system(); // this thread's stores to the peer buffer are visible system-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(p.done, 1u);
+      if (prev == gridDim.x - 1) { // every block has fenced its stores
+        *p.done = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.flag), "l"(p.value) : "memory");
+      }
+    }
+  }
+}
+
+// Both directions of one Y exchange in ONE launch each way (blockIdx.y = direction), 16-byte transactions.
+struct PushY2Params {
+  double* f[kMaxHaloFields];
+  double* buf[2];               // peer receive buffers (push) / local receive buffers (unpack); NULL = no neighbour
+  unsigned long long* flag[2];  // peer flags (push) / local flags (unpack)
+  unsigned int* done;           // two local block counters (push)
+  int* status;                  // time-out word (unpack)
+  unsigned long long value;
+  int y0[2];
+  int nf, nx, ny, nz, nrows;
+};
+
+template <int VEC, bool UNPACK>
+__global__ void __launch_bounds__(256) k_xchg_y2(const PushY2Params p) {
+  const int d = blockIdx.y;
+  if (p.buf[d] == nullptr) {
+    return;
+  }
+  if (UNPACK) { // wait for the neighbour's rows to have landed in the local receive buffer
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      unsigned long long v;
+      ok = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.flag[d]) : "memory");
+        if (v >= p.value) {
+          ok = 1;
+          break;
+        }
+        __nanosleep(100);
+      } while (clock64() - t0 < 4000000000LL);
+      if (!ok) {
+        *p.status = 1;
+      }
+    }
+    __syncthreads();
+  }
+  const int nzv = p.nz / VEC;
+  const long long per_field = static_cast<long long>(p.nx) * p.nrows * nzv;
+  const long long total = per_field * p.nf;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int fi = static_cast<int>(t / per_field);
+    long long r = t % per_field;
+    const int zv = static_cast<int>(r % nzv);
+    r /= nzv;
+    const int yy = static_cast<int>(r % p.nrows);
+    const int x = static_cast<int>(r / p.nrows);
+    double* cell = p.f[fi] + (static_cast<long long>(x) * p.ny + (p.y0[d] + yy)) * p.nz + zv * VEC;
+    double* slot = p.buf[d] + t * VEC;
+    if (VEC == 2) {
+      if (UNPACK) {
+        *reinterpret_cast<double2*>(cell) = *reinterpret_cast<const double2*>(slot);
+      } else {
+        *reinterpret_cast<double2*>(slot) = *reinterpret_cast<const double2*>(cell);
+      }
+    } else {
+      if (UNPACK) {
+        *cell = *slot;
+      } else {
+        *slot = *cell;
+      }
+    }
+  }
+  if (!UNPACK) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(p.done + d, 1u);
+      if (prev == gridDim.x - 1) {
+        p.done[d] = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.flag[d]), "l"(p.value) : "memory");
+      }
+    }
+  }
+}
+
+// Receiver side: spin until the neighbour's flag reaches `value` (bounded: ~4e9 cycles, then status = 1).
+__global__ void k_flag_wait(const unsigned long long* flag, unsigned long long value, int* status) {
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= value) {
+      return;
+    }
+    __nanosleep(200);
+  } while (clock64() - t0 < 4000000000LL);
+  *status = 1;
 }
 
 } // namespace b200
@@ -127,7 +245,8 @@ extern "C" int bout_b200_halo_self(const bout_b200_grid* g, int nfields, double*
 }
 
 static int packY(const bout_b200_grid* g, int nfields, double* const* fields, int y0, int nrows,
-                 int xlo, int xhi, double* buf, int unpack, void* stream) {
+                 int xlo, int xhi, double* buf, int unpack, void* stream, unsigned long long* flag = nullptr,
+                 unsigned long long value = 0, unsigned int* done = nullptr) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
@@ -149,6 +268,9 @@ static int packY(const bout_b200_grid* g, int nfields, double* const* fields, in
   p.xlo = xlo;
   p.xhi = xhi;
   p.unpack = unpack;
+  p.flag = flag;
+  p.value = value;
+  p.done = done;
   const long long total = static_cast<long long>(xhi - xlo + 1) * nrows * g->nz * nfields;
   const long long want = (total + 255) / 256;
   const unsigned blocks = static_cast<unsigned>(want < 148LL * 32 ? want : 148LL * 32);
@@ -165,4 +287,115 @@ extern "C" int bout_b200_halo_unpack_y(const bout_b200_grid* g, int nfields, dou
                                        int y0, int nrows, int xlo, int xhi, const double* buf,
                                        void* stream) {
   return packY(g, nfields, fields, y0, nrows, xlo, xhi, const_cast<double*>(buf), 1, stream);
+}
+
+// ---- peer-memory exchange -------------------------------------------------------------------------------
+extern "C" int bout_b200_peer_alloc(size_t bytes, void** ptr) {
+  B200_REQUIRE(ptr != nullptr && bytes > 0, BOUT_B200_ERR_ARG, "peer_alloc: bad argument");
+  B200_CUDA_OK(cudaMalloc(ptr, bytes));
+  B200_CUDA_OK(cudaMemset(*ptr, 0, bytes));
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+extern "C" int bout_b200_peer_free(void* ptr) {
+  B200_CUDA_OK(cudaFree(ptr));
+  return 0;
+}
+extern "C" int bout_b200_peer_export(void* ptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  B200_REQUIRE(ptr && handle64, BOUT_B200_ERR_ARG, "peer_export: null argument");
+  cudaIpcMemHandle_t h;
+  B200_CUDA_OK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+extern "C" int bout_b200_peer_open(const unsigned char* handle64, void** ptr) {
+  B200_REQUIRE(ptr && handle64, BOUT_B200_ERR_ARG, "peer_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  B200_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+extern "C" int bout_b200_peer_close(void* ptr) {
+  B200_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+extern "C" int bout_b200_halo_push_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0,
+                                     int nrows, int xlo, int xhi, double* peer_buf,
+                                     unsigned long long* peer_flag, unsigned long long value,
+                                     unsigned int* local_counter, void* stream) {
+  B200_REQUIRE(peer_flag && local_counter, BOUT_B200_ERR_ARG, "halo_push_y: null flag");
+  return packY(g, nfields, fields, y0, nrows, xlo, xhi, peer_buf, 0, stream, peer_flag, value, local_counter);
+}
+extern "C" int bout_b200_halo_wait(const unsigned long long* local_flag, unsigned long long value, int* status,
+                                   void* stream) {
+  B200_REQUIRE(local_flag && status, BOUT_B200_ERR_ARG, "halo_wait: null argument");
+  k_flag_wait<<<1, 1, 0, asStream(stream)>>>(local_flag, value, status);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+static int xchgY2(const bout_b200_grid* g, int nfields, double* const* fields, int nrows, const int* y0,
+                  double* const* buf, unsigned long long* const* flag, unsigned long long value,
+                  unsigned int* counters, int* status, bool unpack, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(fields && y0 && buf && flag && nfields >= 1 && nfields <= kMaxHaloFields && nrows >= 1,
+               BOUT_B200_ERR_ARG, "halo exchange: bad argument");
+  PushY2Params p{};
+  bool vec2 = g->nz % 2 == 0;
+  for (int i = 0; i < nfields; ++i) {
+    B200_REQUIRE(fields[i] != nullptr, BOUT_B200_ERR_ARG, "halo exchange: null field");
+    p.f[i] = fields[i];
+    vec2 = vec2 && aligned16(fields[i]);
+  }
+  for (int d = 0; d < 2; ++d) {
+    p.buf[d] = buf[d];
+    p.flag[d] = flag[d];
+    p.y0[d] = y0[d];
+    B200_REQUIRE(buf[d] == nullptr || (flag[d] != nullptr && y0[d] >= 0 && y0[d] + nrows <= g->ny), BOUT_B200_ERR_ARG,
+                 "halo exchange: bad rows or missing flag");
+    vec2 = vec2 && (buf[d] == nullptr || aligned16(buf[d]));
+  }
+  p.done = counters;
+  p.status = status;
+  p.value = value;
+  p.nf = nfields;
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.nrows = nrows;
+  const long long total = static_cast<long long>(g->nx) * nrows * (vec2 ? g->nz / 2 : g->nz) * nfields;
+  const long long want = (total + 255) / 256;
+  const dim3 grid(static_cast<unsigned>(want < 148LL * 4 ? want : 148LL * 4), 2);
+  cudaStream_t s = asStream(stream);
+  if (unpack) {
+    if (vec2) {
+      k_xchg_y2<2, true><<<grid, 256, 0, s>>>(p);
+    } else {
+      k_xchg_y2<1, true><<<grid, 256, 0, s>>>(p);
+    }
+  } else {
+    if (vec2) {
+      k_xchg_y2<2, false><<<grid, 256, 0, s>>>(p);
+    } else {
+      k_xchg_y2<1, false><<<grid, 256, 0, s>>>(p);
+    }
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}
+extern "C" int bout_b200_halo_push_y2(const bout_b200_grid* g, int nfields, double* const* fields, int nrows,
+                                      const int* y0, double* const* peer_buf, unsigned long long* const* peer_flag,
+                                      unsigned long long value, unsigned int* local_counters, void* stream) {
+  B200_REQUIRE(local_counters != nullptr, BOUT_B200_ERR_ARG, "halo_push_y2: null counters");
+  return xchgY2(g, nfields, fields, nrows, y0, peer_buf, peer_flag, value, local_counters, nullptr, false, stream);
+}
+extern "C" int bout_b200_halo_wait_unpack_y2(const bout_b200_grid* g, int nfields, double* const* fields, int nrows,
+                                             const int* y0, double* const* local_buf,
+                                             unsigned long long* const* local_flag, unsigned long long value,
+                                             int* status, void* stream) {
+  B200_REQUIRE(status != nullptr, BOUT_B200_ERR_ARG, "halo_wait_unpack_y2: null status");
+  return xchgY2(g, nfields, fields, nrows, y0, local_buf, local_flag, value, nullptr, status, true, stream);
 }

@@ -34,6 +34,58 @@ class CudaHaloOps:
         self.capi.halo_unpack_y(g, fields, y0, nrows, 0, g.nx - 1, buf)
 
 
+class PeerYChannel:
+    """Y guard-row exchange through the neighbours' memory (bout_b200_halo_push_y / _wait): this rank owns
+    two double-buffered receive areas (rows arriving from below / from above), two arrival flags, two block
+    counters and a status word in ONE device allocation whose CUDA IPC handle every neighbour opens once."""
+
+    def __init__(self, mesh, nf, device):
+        from . import capi
+        self.capi, self.mesh, self.nf = capi, mesh, nf
+        g = mesh.grid
+        self.cap = nf * g.nx * mesh.myg * g.nz                      # doubles per message
+        self.flag_off = 4 * self.cap * 8                            # recv[parity][side][cap], then the flags
+        total = self.flag_off + 2 * 8 + 2 * 4 + 8
+        self.base = capi.peer_alloc(total)
+        mine = torch.tensor(list(capi.peer_export(self.base)), dtype=torch.uint8, device=device)
+        allh = torch.empty(dist.get_world_size() * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().tobytes()
+        self.peer = {}
+        for r in {mesh.yup, mesh.ydown} - {None, mesh.rank}:
+            self.peer[r] = capi.peer_open(allh[64 * r:64 * r + 64])
+        self.count = 0
+
+    def _recv(self, base, parity, side):
+        return base + ((parity * 2 + side) * self.cap) * 8
+
+    def exchange(self, fields):
+        capi, m, g = self.capi, self.mesh, self.mesh.grid
+        self.count += 1
+        c, par = self.count, self.count & 1
+        flags, counters = self.base + self.flag_off, self.base + self.flag_off + 16
+        status = self.base + self.flag_off + 24
+        up, dn = (self.peer[m.yup] if m.yup is not None else 0), (self.peer[m.ydown] if m.ydown is not None else 0)
+        # one launch: my top interior rows arrive "from below" (side 0) at the upper neighbour, my bottom
+        # interior rows "from above" (side 1) at the lower neighbour, each followed by that neighbour's flag
+        capi.halo_push_y2(g, fields, m.myg, (g.yend - m.myg + 1, g.ystart),
+                          (self._recv(up, par, 0) if up else 0, self._recv(dn, par, 1) if dn else 0),
+                          (up + self.flag_off if up else 0, dn + self.flag_off + 8 if dn else 0), c, counters)
+        # one launch: wait for my two flags, then unpack the lower / upper guard rows
+        capi.halo_wait_unpack_y2(g, fields, m.myg, (0, g.yend + 1),
+                                 (self._recv(self.base, par, 0) if dn else 0, self._recv(self.base, par, 1) if up else 0),
+                                 (flags, flags + 8), c, status)
+
+    def timed_out(self):
+        """True if a wait gave up (reads the status word after synchronising the device)."""
+        import ctypes as C
+        torch.cuda.synchronize()
+        v = C.c_int(0)
+        self.capi._check(self.capi.lib.bout_b200_memcpy_d2h(C.byref(v), C.c_void_p(self.base + self.flag_off + 24),
+                                                            C.c_size_t(4), None))
+        return v.value != 0
+
+
 def decompose(rank, nxpe, nype):
     """(PE_XIND, PE_YIND) of a rank (boutmesh.cxx:1041: MYPE = PE_YIND * NXPE + PE_XIND)."""
     if not 0 <= rank < nxpe * nype:
@@ -73,6 +125,12 @@ class BoutMesh:
         self.ops = ops
         self.grid = make_grid(mxsub + 2 * mxg, mysub + 2 * myg, mz, mxg, myg)
         self._ybuf = {}
+        # Y guard rows go through NVLink peer memory when the ranks are CUDA processes of one node
+        # (BOUT_B200_HALO=nccl keeps them on NCCL send/recv); X guard planes use NCCL
+        import os
+        self._peer_ok = (type(ops).__name__ == "CudaHaloOps" and dist.is_initialized() and nype > 1
+                         and os.environ.get("BOUT_B200_HALO", "peer") == "peer")
+        self._peer = {}
         # sub-communicator of this rank's X row (CyclicReduce's comm, boutmesh.cxx:668-760); every rank
         # must create every group
         self.x_group = None
@@ -102,6 +160,12 @@ class BoutMesh:
             if self.nype == 1:
                 if self.periodic_y:
                     self.ops.self_exchange(g, fields, False, True)
+            elif self._peer_ok and fields[0].is_cuda and self.rank not in (self.yup, self.ydown):
+                key = f"{nf}@{torch.cuda.current_stream().cuda_stream}"
+                ch = self._peer.get(key)
+                if ch is None:
+                    ch = self._peer[key] = PeerYChannel(self, nf, fields[0].device)
+                ch.exchange(fields)
             else:
                 n = nf * g.nx * self.myg * g.nz
                 ops, keep = [], []
@@ -148,6 +212,10 @@ class BoutMesh:
                 if ops:
                     for w in dist.batch_isend_irecv(ops):
                         w.wait()
+
+    def halo_timed_out(self):
+        """Peer-memory exchange only: did any wait on a neighbour's flag give up?  (Synchronises.)"""
+        return any(ch.timed_out() for ch in self._peer.values())
 
     def all_gather_x(self, local, out):
         """All-gather along this rank's X row in PE_XIND order (CyclicReduce interface exchange)."""

@@ -334,6 +334,31 @@ int bout_b200_halo_pack_y(const bout_b200_grid* g, int nfields, double* const* f
                           int nrows, int xlo, int xhi, double* buf, void* stream);
 int bout_b200_halo_unpack_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0,
                             int nrows, int xlo, int xhi, const double* buf, void* stream);
+/* The Y exchange over NVLink peer memory, no communication library on the data path (src/mesh/impls/bout/
+ * boutmesh.cxx:1245-1555 sendY/wait): buffers from bout_b200_peer_alloc are exported as 64-byte CUDA IPC handles
+ * (exchanged by the host out of band) and opened by the neighbour rank.  bout_b200_halo_push_y packs rows
+ * y0..y0+nrows-1 straight into the neighbour's receive buffer and then stores `value` to the neighbour's flag;
+ * bout_b200_halo_wait blocks the stream until this rank's own flag reaches `value` (bounded spin; *status = 1
+ * on time-out), after which bout_b200_halo_unpack_y reads the local receive buffer.  local_counter: one zeroed
+ * unsigned int per concurrent push. */
+int bout_b200_peer_alloc(size_t bytes, void** ptr);
+int bout_b200_peer_free(void* ptr);
+int bout_b200_peer_export(void* ptr, unsigned char* handle64);
+int bout_b200_peer_open(const unsigned char* handle64, void** ptr);
+int bout_b200_peer_close(void* ptr);
+int bout_b200_halo_push_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0, int nrows,
+                          int xlo, int xhi, double* peer_buf, unsigned long long* peer_flag,
+                          unsigned long long value, unsigned int* local_counter, void* stream);
+int bout_b200_halo_wait(const unsigned long long* local_flag, unsigned long long value, int* status,
+                        void* stream);
+/* The same, both directions per launch (index 0 / 1 of y0, buf, flag = the two neighbours; a NULL buffer skips
+ * that side): one push launch (pack + flag) and one receive launch (wait on the local flags + unpack) per exchange. */
+int bout_b200_halo_push_y2(const bout_b200_grid* g, int nfields, double* const* fields, int nrows, const int* y0,
+                           double* const* peer_buf, unsigned long long* const* peer_flag,
+                           unsigned long long value, unsigned int* local_counters, void* stream);
+int bout_b200_halo_wait_unpack_y2(const bout_b200_grid* g, int nfields, double* const* fields, int nrows,
+                                  const int* y0, double* const* local_buf, unsigned long long* const* local_flag,
+                                  unsigned long long value, int* status, void* stream);
 
 /* ---- (4) explicit integrator stage updates --------------------------------------------------------
  * mode 0: out = start + c*dt*k1                      (rk4.cxx:179-200; rk3-ssp.cxx:107 with c=1)
