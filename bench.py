@@ -527,6 +527,8 @@ def run_elmpb(args):
                      "rhs_bytes_per_point": f"{ELM_RHS_BPP:.0f} (pass list in DESIGN.md section 3)"},
         "clocks": clocks,
     }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(steps=2, warmup=1, workload="elmpb")
     print(json.dumps(out), flush=True)
 
 
@@ -554,12 +556,49 @@ error_on_unused_options = false
 """)
 
 
+def run_reference_elmpb(args, cores):
+    """Reference arm of --workload elmpb: the UNCHANGED examples/elm-pb/elm_pb.cxx through the reference's
+    Solver::run_rhs on a y-slab (512 x 8 x 256) of the workload's synthetic grid."""
+    import __graft_entry__ as ge
+    orc = ge.load_oracle()
+    if not os.path.exists(orc.REF_SO):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libboutref.so not built"}))
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from cases import elmpb_ini
+    my = 8
+    r = orc.Ref(elmpb_ini(ELM["nx"], my, ELM["nz"], timestep=str(ELM_DT)))
+    r.model_create("elmpb", "rk4")
+    r.model_rhs(0.0)
+    npts = (ELM["nx"] - 4) * my * ELM["nz"]
+    if args.warmup > 0:
+        r.model_time_rhs(reps=args.warmup)
+    reps = max(4 * args.steps, 4)
+    secs = r.model_time_rhs(reps=reps) * reps
+    value = npts * reps / secs
+    sample = (f"unchanged examples/elm-pb/elm_pb.cxx through the reference's Solver::run_rhs, y-slab 512x{my}x256 of the "
+              f"512x64x256 workload, {reps} run_rhs, OpenMP {cores} threads, single MPI rank (shim)")
+    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / reps * 4 * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic (closed-form tokamak grid and perturbation)",
+           "config": {"workload": ELM_WORKLOAD, "rhs_per_step": 4, "sample_points": npts},
+           "cpu_baseline": cb,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def run_reference(args, as_baseline=False):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if args.workload == "elmpb":
+        return run_reference_elmpb(args, cores)
     orc, ini = ref_ini()
     kind = "reference" if os.path.exists(orc.REF_SO) else None
     if kind is None:
@@ -589,11 +628,11 @@ def run_reference(args, as_baseline=False):
     os._exit(0)  # the reference's static destructors are not exit-safe
 
 
-def cpu_baseline(steps, warmup):
+def cpu_baseline(steps, warmup, workload="hw3d"):
     """Runs the reference arm in a child process (it owns global state) and returns its cpu_baseline."""
     try:
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps),
-                            "--warmup", str(warmup)], capture_output=True, text=True, timeout=600,
+                            "--warmup", str(warmup), "--workload", workload], capture_output=True, text=True, timeout=600,
                            env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
         for line in reversed(p.stdout.strip().splitlines()):
             if line.startswith("{"):

@@ -24,6 +24,8 @@
 // here (yup/ydown hold exactly f(y+-1) shifted by zShift(y) - zShift(y+-1)); the Nyquist mode, whose
 // imaginary part c2r drops, is discarded by the filter (n0 != nz/2 is required).  Without filter_z the
 // harness uses the operator-by-operator path, which reproduces the Nyquist handling exactly.
+#include <cstdlib>
+
 #include "fft.cuh"
 #include "stencil_ops.cuh"
 
@@ -77,28 +79,34 @@ __device__ __forceinline__ F3 loadF3(const double* __restrict__ f, const double*
   return r;
 }
 
-struct M2 { // per-(x,y) metric scalars
+// Per-(x,y) row constants, computed once per row by a few threads and kept in shared memory (every thread of
+// the row reads the same values: broadcast loads) so that they do not occupy registers.
+struct RowC {
   double rdx, rdy, rdz, g_22, g_23, g_12, rjs;
+  double B0sq, rB0, B0rBxy, B0p, B0m, gpar;
+  double vx0, vy0, vz0;                 // velocity of the Field2D potential phi0 (difops.cxx:580-588, DDZ(phi0) = 0)
+  double dJ0[2], dP0[2];                // WENO3 x-derivative factor of J0 / P0 for vx <= 0 ([0]) and vx > 0 ([1])
+  double dJ0y, dP0y;                    // J0(y+1) - J0(y-1), P0(y+1) - P0(y-1)
+  double bcx, bcy, bcz;
 };
 
-// b0xGrad_dot_Grad(f3d, A2d): A's x stencil ax and y neighbours are Field2D values
-__device__ __forceinline__ double b0x3d2d(const St& fx, double fyp, double fym, const St& fz, const St& ax,
-                                          double ayp, double aym, const M2& m) {
+// b0xGrad_dot_Grad(f3d, A2d): dAx = the two WENO3 factors of A's x stencil, dAy = A(y+1) - A(y-1)
+__device__ __forceinline__ double b0x3d2d(const St& fx, double fyp, double fym, const St& fz, const double (&dAx)[2],
+                                          double dAy, const RowC& m) {
   const double dpdx = applyStandard<BOUT_B200_DDX_C4>(fx) * m.rdx;
   const double dpdy = 0.5 * (fyp - fym) * m.rdy;
   const double dpdz = applyStandard<BOUT_B200_DDX_C4>(fz) * m.rdz;
   const double vx = m.g_22 * dpdz - m.g_23 * dpdy;
   const double vy = m.g_23 * dpdx - m.g_12 * dpdz;
-  double r = weno3(vx, ax) * m.rdx;
-  r += vy * 0.5 * (ayp - aym) * m.rdy;
+  double r = (vx * dAx[vx > 0.0 ? 1 : 0]) * m.rdx;
+  r += vy * 0.5 * dAy * m.rdy;
   return r * m.rjs;
 }
-// b0xGrad_dot_Grad(f2d, A3d): the velocity (vx, vy, vz) is a Field2D quantity
-__device__ __forceinline__ double b0x2d3d(double vx, double vy, double vz, const St& ax, double ayp, double aym,
-                                          const St& az, const M2& m) {
-  double r = weno3(vx, ax) * m.rdx;
-  r += vy * 0.5 * (ayp - aym) * m.rdy;
-  r += weno3(vz, az) * m.rdz;
+// b0xGrad_dot_Grad(f2d, A3d): the velocity (vx0, vy0, vz0) is a Field2D quantity
+__device__ __forceinline__ double b0x2d3d(const St& ax, double ayp, double aym, const St& az, const RowC& m) {
+  double r = weno3(m.vx0, ax) * m.rdx;
+  r += m.vy0 * 0.5 * (ayp - aym) * m.rdy;
+  r += weno3(m.vz0, az) * m.rdz;
   return r * m.rjs;
 }
 
@@ -150,7 +158,8 @@ __device__ __forceinline__ void rowReduce3(double (&acc)[6], double* red, int ti
   }
 }
 
-__global__ void __launch_bounds__(256, 2) k_elmpb_rhs(const ElmParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   __shared__ double red[8 * 6 * 32];
   const bout_b200_elmpb_rhs_args& a = p.a;
   const int nzp = p.nz / 2;                  // threads per row
@@ -166,41 +175,53 @@ __global__ void __launch_bounds__(256, 2) k_elmpb_rhs(const ElmParams p) {
   const int z0 = 2 * tin;
   const int ny = p.ny, nz = p.nz;
 
-  M2 m;
-  m.rdx = 1.0 / __ldg(a.dx + i2);
-  m.rdy = 1.0 / __ldg(a.dy + i2);
-  m.rdz = 1.0 / __ldg(a.dz + i2);
-  m.g_22 = __ldg(a.g_22 + i2);
-  m.g_23 = __ldg(a.g_23 + i2);
-  m.g_12 = __ldg(a.g_12 + i2);
-  const double sg = sqrt(m.g_22);
-  m.rjs = 1.0 / (__ldg(a.J + i2) * sg);
-  const double B0 = __ldg(a.B0 + i2), Bxy = __ldg(a.Bxy + i2);
-  const double B0sq = B0 * B0;
-  // velocity of the Field2D potential phi0 (difops.cxx:580-588 with DDZ(phi0) = 0)
-  const double d0x = applyStandard<BOUT_B200_DDX_C4>(st2dx(a.phi0, i2, ny)) * m.rdx;
-  const double d0y = 0.5 * (__ldg(a.phi0 + i2 + 1) - __ldg(a.phi0 + i2 - 1)) * m.rdy;
-  const double vx0 = m.g_22 * 0.0 - m.g_23 * d0y;
-  const double vy0 = m.g_23 * d0x - m.g_12 * 0.0;
-  const double vz0 = m.g_12 * d0y - m.g_22 * d0x;
-  const St J0x = st2dx(a.J0, i2, ny), P0x = st2dx(a.P0, i2, ny);
-  const double J0p = __ldg(a.J0 + i2 + 1), J0m = __ldg(a.J0 + i2 - 1);
-  const double P0p = __ldg(a.P0 + i2 + 1), P0m = __ldg(a.P0 + i2 - 1);
-  const double B0p = __ldg(a.B0 + i2 + 1), B0m = __ldg(a.B0 + i2 - 1);
-  const double gpar = m.rdy / sg; // Grad_par = DDY / dy * invSg (coordinates.cxx:1529-1535)
-  const double bcx = __ldg(a.b0xcv_x + i2), bcy = __ldg(a.b0xcv_y + i2), bcz = __ldg(a.b0xcv_z + i2);
+  __shared__ RowC rows[8];
+  if (tin == 0) {
+    RowC c;
+    c.rdx = 1.0 / __ldg(a.dx + i2);
+    c.rdy = 1.0 / __ldg(a.dy + i2);
+    c.rdz = 1.0 / __ldg(a.dz + i2);
+    c.g_22 = __ldg(a.g_22 + i2);
+    c.g_23 = __ldg(a.g_23 + i2);
+    c.g_12 = __ldg(a.g_12 + i2);
+    const double sg = sqrt(c.g_22);
+    c.rjs = 1.0 / (__ldg(a.J + i2) * sg);
+    const double B0 = __ldg(a.B0 + i2);
+    c.B0sq = B0 * B0;
+    c.rB0 = 1.0 / B0;                          // Field3D / Field2D multiplies by the reciprocal, as the reference does
+    c.B0rBxy = B0 * (1.0 / __ldg(a.Bxy + i2));
+    c.B0p = __ldg(a.B0 + i2 + 1);
+    c.B0m = __ldg(a.B0 + i2 - 1);
+    c.gpar = c.rdy / sg;                       // Grad_par = DDY / dy * invSg (coordinates.cxx:1529-1535)
+    const double d0x = applyStandard<BOUT_B200_DDX_C4>(st2dx(a.phi0, i2, ny)) * c.rdx;
+    const double d0y = 0.5 * (__ldg(a.phi0 + i2 + 1) - __ldg(a.phi0 + i2 - 1)) * c.rdy;
+    c.vx0 = c.g_22 * 0.0 - c.g_23 * d0y;
+    c.vy0 = c.g_23 * d0x - c.g_12 * 0.0;
+    c.vz0 = c.g_12 * d0y - c.g_22 * d0x;
+    const St J0x = st2dx(a.J0, i2, ny), P0x = st2dx(a.P0, i2, ny);
+    c.dJ0[0] = weno3Deriv(false, J0x);
+    c.dJ0[1] = weno3Deriv(true, J0x);
+    c.dP0[0] = weno3Deriv(false, P0x);
+    c.dP0[1] = weno3Deriv(true, P0x);
+    c.dJ0y = __ldg(a.J0 + i2 + 1) - __ldg(a.J0 + i2 - 1);
+    c.dP0y = __ldg(a.P0 + i2 + 1) - __ldg(a.P0 + i2 - 1);
+    c.bcx = __ldg(a.b0xcv_x + i2);
+    c.bcy = __ldg(a.b0xcv_y + i2);
+    c.bcz = __ldg(a.b0xcv_z + i2);
+    rows[rloc] = c;
+  }
+  __syncthreads();
+  const RowC& m = rows[rloc];
 
-  // One stencil field at a time (loads next to their use) so that at most one F3 is live: 128 registers,
-  // two CTAs per SM.  Field3D / Field2D multiplies by the reciprocal, as the reference does.
-  const double rB0 = 1.0 / B0, rBxy = 1.0 / Bxy;
+  // One stencil field at a time (loads next to their use) so that at most one F3 is live.
   double tU[2], tP[2], tPsi[2];
   {
     const F3 phi = loadF3(a.phi, a.phi_up, a.phi_dn, i2, ny, nz, z0);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const double gp = 0.5 * (B0p * phi.yp(j) - B0m * phi.ym(j)) * gpar; // Grad_par(phi B0)
-      tPsi[j] = -1.0 * gp * rB0;
-      tP[j] = -1.0 * b0x3d2d(phi.sx(j), phi.yp(j), phi.ym(j), phi.sz(j), P0x, P0p, P0m, m);
+      const double gp = 0.5 * (m.B0p * phi.yp(j) - m.B0m * phi.ym(j)) * m.gpar; // Grad_par(phi B0)
+      tPsi[j] = -1.0 * gp * m.rB0;
+      tP[j] = -1.0 * b0x3d2d(phi.sx(j), phi.yp(j), phi.ym(j), phi.sz(j), m.dP0, m.dP0y, m);
     }
   }
   {
@@ -210,25 +231,25 @@ __global__ void __launch_bounds__(256, 2) k_elmpb_rhs(const ElmParams p) {
       const double dPx = applyStandard<BOUT_B200_DDX_C4>(P.sx(j)) * m.rdx;
       const double dPy = 0.5 * (P.yp(j) - P.ym(j)) * m.rdy;
       const double dPz = applyStandard<BOUT_B200_DDX_C4>(P.sz(j)) * m.rdz;
-      tU[j] = dPx * bcx + dPy * bcy + dPz * bcz;
-      tP[j] -= b0x2d3d(vx0, vy0, vz0, P.sx(j), P.yp(j), P.ym(j), P.sz(j), m);
+      tU[j] = dPx * m.bcx + dPy * m.bcy + dPz * m.bcz;
+      tP[j] -= b0x2d3d(P.sx(j), P.yp(j), P.ym(j), P.sz(j), m);
     }
   }
   {
     const F3 Psi = loadF3(a.Psi, a.Psi_up, a.Psi_dn, i2, ny, nz, z0);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const double bg = b0x2d3d(vx0, vy0, vz0, Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m);
-      tPsi[j] -= bg * B0 * rBxy;
-      const double t1 = b0x3d2d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), J0x, J0p, J0m, m);
-      tU[j] = t1 * B0sq + tU[j];
+      const double bg = b0x2d3d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m);
+      tPsi[j] -= bg * m.B0rBxy;
+      const double t1 = b0x3d2d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m.dJ0, m.dJ0y, m);
+      tU[j] = t1 * m.B0sq + tU[j];
     }
   }
   {
     const F3 U = loadF3(a.U, a.U_up, a.U_dn, i2, ny, nz, z0);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      tU[j] -= b0x2d3d(vx0, vy0, vz0, U.sx(j), U.yp(j), U.ym(j), U.sz(j), m);
+      tU[j] -= b0x2d3d(U.sx(j), U.yp(j), U.ym(j), U.sz(j), m);
     }
   }
   {
@@ -238,8 +259,8 @@ __global__ void __launch_bounds__(256, 2) k_elmpb_rhs(const ElmParams p) {
     const double2 eta = a.eta_is2d ? make_double2(__ldg(a.eta + i2), __ldg(a.eta + i2)) : ld2(a.eta + i2 * nz + z0);
     tPsi[0] += eta.x * J.x - a.hyperresist * eta.x * d2J.x;
     tPsi[1] += eta.y * J.y - a.hyperresist * eta.y * d2J.y;
-    tU[0] -= 0.5 * (Jup.x - Jdn.x) * gpar * B0sq;
-    tU[1] -= 0.5 * (Jup.y - Jdn.y) * gpar * B0sq;
+    tU[0] -= 0.5 * (Jup.x - Jdn.x) * m.gpar * m.B0sq;
+    tU[1] -= 0.5 * (Jup.y - Jdn.y) * m.gpar * m.B0sq;
   }
 
   double* __restrict__ oU = a.ddt_U + i2 * nz + z0;
@@ -336,7 +357,12 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
   }
   const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * (p.ye - p.ys + 1);
   const unsigned blocks = static_cast<unsigned>((nrows + rows - 1) / rows);
-  k_elmpb_rhs<<<blocks, threads, 0, s>>>(p);
+  static const int minb = getenv("BOUT_B200_ELM_MINB") ? atoi(getenv("BOUT_B200_ELM_MINB")) : 3;
+  if (minb == 2) {
+    k_elmpb_rhs<2><<<blocks, threads, 0, s>>>(p);
+  } else {
+    k_elmpb_rhs<3><<<blocks, threads, 0, s>>>(p);
+  }
   B200_LAUNCH_OK();
   return 0;
 }

@@ -32,10 +32,11 @@ __device__ __forceinline__ double sq(double x) { return x * x; }
 // here w = b^2 / (b^2 + 2 a^2) -- the same number with ONE fp64 division instead of two (fp64
 // division is ~25 DFMA slots on sm_100 and made this stencil compute-bound); the two forms differ
 // by a few ulp, far inside the 1e-12 parity tolerance.
-__device__ __forceinline__ double weno3(double vc, const St& f) {
+// The derivative factor of VDDX_WENO3 for one upwind direction (positive = velocity > 0); weno3(vc, f) = vc * it.
+__device__ __forceinline__ double weno3Deriv(bool positive, const St& f) {
   double deriv, a;
   const double b = kWenoSmall + sq(f.p - 2.0 * f.c + f.m);
-  if (vc > 0.0) {
+  if (positive) {
     a = kWenoSmall + sq(f.c - 2.0 * f.m + f.mm);
     deriv = (-f.mm + 3. * f.m - 3. * f.c + f.p);
   } else {
@@ -44,9 +45,9 @@ __device__ __forceinline__ double weno3(double vc, const St& f) {
   }
   const double b2 = b * b;
   const double w = b2 / (b2 + 2.0 * a * a);
-  deriv = 0.5 * ((f.p - f.m) - w * deriv);
-  return vc * deriv;
+  return 0.5 * ((f.p - f.m) - w * deriv);
 }
+__device__ __forceinline__ double weno3(double vc, const St& f) { return vc * weno3Deriv(vc > 0.0, f); }
 
 template <int OP>
 __device__ __forceinline__ double applyStandard(const St& f) {
