@@ -138,14 +138,13 @@ __global__ void __launch_bounds__(256) k_delp2_fast(const Delp2FftParams p) {
 
   auto forwardTo = [&](int x, cd* dst) { // the row group is synchronised on entry and on exit
     const double2* __restrict__ s2 = reinterpret_cast<const double2*>(col + x * plane);
+    cd v[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const int j = lane + m * (N / 4);
-      const double2 v = __ldg(s2 + j);
-      A[fsw(j)] = {v.x, v.y};
+      const double2 q = __ldg(s2 + lane + m * (N / 4));
+      v[m] = {q.x, q.y};
     }
-    sync();
-    const cd* Z = cfftFast<N, false, SyncGroup>(A, B, tw, lane, sync);
+    const cd* Z = cfftFastFromRegs<N, false, SyncGroup>(v, A, B, tw, lane, sync);
     rfftSplitTo<N>(Z, dst, N + 1, tw, lane);
     sync();
   };
@@ -166,19 +165,16 @@ __global__ void __launch_bounds__(256) k_delp2_fast(const Delp2FftParams p) {
       D[k] = cadd(cadd(cmul(a, Sm[k]), cmul(b, S0[k])), cmul(c, Sp[k]));
     }
     sync();
-    rfftMergeFrom<N>(D, A, N + 1, false, tw, lane);
-    sync();
-    const cd* z = cfftFast<N, true, SyncGroup>(A, B, tw, lane, sync);
+    cd w[4], r[4];
+    rfftMergeRegs<N>([&](int k) -> cd { return D[k]; }, w, tw, lane);
+    cfftFastRegsToRegs<N, true, SyncGroup>(w, r, A, B, tw, lane, sync);
     if (store) {
       double2* __restrict__ d2 = reinterpret_cast<double2*>(p.out + x * plane + static_cast<long long>(y) * p.nz);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const int j = lane + m * (N / 4);
-        const cd v = z[fsw(j)];
-        d2[j] = make_double2(v.re, v.im);
+        d2[lane + m * (N / 4)] = make_double2(r[m].re, r[m].im);
       }
     }
-    sync();
   }
 }
 

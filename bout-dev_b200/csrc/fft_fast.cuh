@@ -200,6 +200,126 @@ __device__ __forceinline__ void cfftFast2(cd* a0, cd* b0, cd* a1, cd* b1, const 
   }
 }
 
+// ---- register shortcuts ----------------------------------------------------------------------------------
+// The first Stockham stage of thread `lane` reads elements lane + m N/4 (m = 0..3): exactly the four elements
+// that thread loads from global memory (or produces in the real-FFT merge step), so it can take them from
+// registers; and the outputs of the LAST stage of thread `lane` are again elements lane + m N/4, the ones
+// it stores to global memory.  Used together they save two shared-memory round trips of the row per transform.
+template <int N, bool INVERSE>
+__device__ __forceinline__ void radix4Stage0Regs(const cd (&v)[4], cd* out, int lane) {
+  const cd t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]);
+  const cd d = csub(v[1], v[3]);
+  const cd t3 = INVERSE ? cd{-d.im, d.re} : cd{d.im, -d.re};
+  const int j0 = lane << 2;
+  out[fsw(j0)] = cadd(t0, t2);
+  out[fsw(j0 + 1)] = cadd(t1, t3);
+  out[fsw(j0 + 2)] = csub(t0, t2);
+  out[fsw(j0 + 3)] = csub(t1, t3);
+}
+
+// Stages 1 .. of the transform whose stage 0 was radix4Stage0Regs(v, B): B -> A -> B ...; returns the buffer
+// holding the result (every stage through shared memory).
+template <int N, bool INVERSE, class Sync>
+__device__ __forceinline__ cd* cfftFastFromRegs(const cd (&v)[4], cd* A, cd* B, const FastTw<N>& t, int lane, Sync sync) {
+  radix4Stage0Regs<N, INVERSE>(v, B, lane);
+  sync();
+  cd* in = B;
+  cd* out = A;
+  int Ns = 4;
+#pragma unroll
+  for (int s = 1; s < FftShape<N>::NST; ++s) {
+    radix4Stage<N, INVERSE>(in, out, t, lane, s, Ns);
+    sync();
+    cd* tmp = in;
+    in = out;
+    out = tmp;
+    Ns *= 4;
+  }
+  if (FftShape<N>::R2) {
+    radix2Stage<N, INVERSE>(in, out, t, lane, Ns);
+    sync();
+    cd* tmp = in;
+    in = out;
+    out = tmp;
+  }
+  return in;
+}
+
+// The same with the last stage's outputs kept in registers: r[m] = element lane + m N/4 of the result.
+// Ends with a barrier so the buffers can be reused at once.
+template <int N, bool INVERSE, class Sync>
+__device__ __forceinline__ void cfftFastRegsToRegs(const cd (&v)[4], cd (&r)[4], cd* A, cd* B, const FastTw<N>& t, int lane,
+                                                   Sync sync) {
+  radix4Stage0Regs<N, INVERSE>(v, B, lane);
+  sync();
+  cd* in = B;
+  cd* out = A;
+  int Ns = 4;
+  constexpr int NLAST = FftShape<N>::R2 ? FftShape<N>::NST : FftShape<N>::NST - 1; // radix-4 stages through memory
+#pragma unroll
+  for (int s = 1; s < NLAST; ++s) {
+    radix4Stage<N, INVERSE>(in, out, t, lane, s, Ns);
+    sync();
+    cd* tmp = in;
+    in = out;
+    out = tmp;
+    Ns *= 4;
+  }
+  if (FftShape<N>::R2) { // last stage: radix 2 with Ns = N/2; butterfly j = lane + h N/4 yields elements j, j + N/2
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + h * (N / 4);
+      const cd v0 = in[fsw(j)];
+      cd w = t.w2[h];
+      if (INVERSE) {
+        w = cconj(w);
+      }
+      const cd v1 = cmul(in[fsw(j + N / 2)], w);
+      r[h] = cadd(v0, v1);      // element lane + h N/4
+      r[h + 2] = csub(v0, v1);  // element lane + h N/4 + N/2
+    }
+  } else { // last stage: radix 4 with Ns = N/4 (k = lane): yields elements lane + m N/4
+    constexpr int s = FftShape<N>::NST - 1;
+    const int j = lane;
+    cd v0 = in[fsw(j)], v1 = in[fsw(j + N / 4)], v2 = in[fsw(j + N / 2)], v3 = in[fsw(j + 3 * (N / 4))];
+    cd w1 = t.w[s][0], w2 = t.w[s][1], w3 = t.w[s][2];
+    if (INVERSE) {
+      w1 = cconj(w1);
+      w2 = cconj(w2);
+      w3 = cconj(w3);
+    }
+    v1 = cmul(v1, w1);
+    v2 = cmul(v2, w2);
+    v3 = cmul(v3, w3);
+    const cd t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3);
+    const cd d = csub(v1, v3);
+    const cd t3 = INVERSE ? cd{-d.im, d.re} : cd{d.im, -d.re};
+    r[0] = cadd(t0, t2);
+    r[1] = cadd(t1, t3);
+    r[2] = csub(t0, t2);
+    r[3] = csub(t1, t3);
+  }
+  sync();
+}
+
+// Merge step of the backward real transform into registers: v[m] = packed complex input element lane + m N/4.
+template <int N, class Load>
+__device__ __forceinline__ void rfftMergeRegs(Load load, cd (&v)[4], const FastTw<N>& t, int lane) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int k = lane + m * (N / 4);
+    cd xk = load(k);
+    cd xc = cconj(load(N - k));
+    if (k == 0) { // imaginary parts of DC and Nyquist are ignored (FFTW c2r)
+      xk.im = 0.0;
+      xc.im = 0.0;
+    }
+    const cd wk = cconj(t.wp[m]);
+    const cd d = cmul(wk, csub(xk, xc));
+    v[m] = cadd(cadd(xk, xc), cd{-d.im, d.re});
+  }
+}
+
 // Forward: real row (global, nz doubles, 16-byte aligned) -> X[0 .. nmode-1] (global), scaled by 1/nz.
 // A, B: this row's swizzled buffers (N + 8 elements each).  All threads of the CTA call together.
 template <int N, class Sync = SyncCta>
@@ -207,14 +327,13 @@ __device__ __forceinline__ void rfftForwardFast(const double* __restrict__ src, 
                                                 bool active, cd* A, cd* B, const FastTw<N>& t, int lane,
                                                 Sync sync = Sync()) {
   const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src);
+  cd v[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    const int j = lane + m * (N / 4);
-    const double2 v = __ldg(s2 + j);
-    A[fsw(j)] = {v.x, v.y};
+    const double2 q = __ldg(s2 + lane + m * (N / 4));
+    v[m] = {q.x, q.y};
   }
-  sync();
-  const cd* Z = cfftFast<N, false, Sync>(A, B, t, lane, sync);
+  const cd* Z = cfftFastFromRegs<N, false, Sync>(v, A, B, t, lane, sync);
   constexpr double inv = 1.0 / (2 * N);
   if (active) {
 #pragma unroll
@@ -249,31 +368,16 @@ __device__ __forceinline__ void rfftBackwardFast(const cd* __restrict__ src, dou
     const double2 v = __ldg(reinterpret_cast<const double2*>(src) + k);
     return cd{v.x, v.y};
   };
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const int k = lane + m * (N / 4);
-    cd xk = load(k);
-    cd xc = cconj(load(N - k));
-    if (k == 0) { // imaginary parts of DC and Nyquist are ignored (FFTW c2r)
-      xk.im = 0.0;
-      xc.im = 0.0;
-    }
-    const cd wk = cconj(t.wp[m]);
-    const cd d = cmul(wk, csub(xk, xc));
-    A[fsw(k)] = cadd(cadd(xk, xc), cd{-d.im, d.re});
-  }
-  sync();
-  const cd* z = cfftFast<N, true, Sync>(A, B, t, lane, sync);
+  cd v[4], r[4];
+  rfftMergeRegs<N>(load, v, t, lane);
+  cfftFastRegsToRegs<N, true, Sync>(v, r, A, B, t, lane, sync);
   if (active) {
     double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const int j = lane + m * (N / 4);
-      const cd v = z[fsw(j)];
-      d2[j] = make_double2(v.re, v.im);
+      d2[lane + m * (N / 4)] = make_double2(r[m].re, r[m].im);
     }
   }
-  sync();
 }
 
 // ---- pieces for kernels that keep the spectrum on chip (fused LaplaceCyclic sweeps) ------------------

@@ -292,14 +292,13 @@ __global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
     const int y = p.ys + static_cast<int>(rid % nyb);
     const long long i2 = static_cast<long long>(x) * p.ny + y;
     const double2* __restrict__ s2 = reinterpret_cast<const double2*>(p.f + i2 * p.nz);
+    cd v[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const int j = lane + m * (N / 4);
-      const double2 v = __ldg(s2 + j);
-      A[fsw(j)] = {v.x, v.y};
+      const double2 q = __ldg(s2 + lane + m * (N / 4));
+      v[m] = {q.x, q.y};
     }
-    sync();
-    const cd* Z = cfftFast<N, false, SyncGroup>(A, B, tw, lane, sync);
+    const cd* Z = cfftFastFromRegs<N, false, SyncGroup>(v, A, B, tw, lane, sync);
     rfftSplitTo<N>(Z, S, N + 1, tw, lane);
     sync();
     const int nout = p.mode == Z_SLICE2 ? 2 : 1;
@@ -326,20 +325,17 @@ __global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
       }
       zmodSpectrum<N>(p, S, D, lane, mode, ang, zl);
       sync();
-      rfftMergeFrom<N>(D, A, N + 1, false, tw, lane);
-      sync();
-      const cd* z = cfftFast<N, true, SyncGroup>(A, B, tw, lane, sync);
+      cd w[4], r[4];
+      rfftMergeRegs<N>([&](int k) -> cd { return D[k]; }, w, tw, lane);
+      cfftFastRegsToRegs<N, true, SyncGroup>(w, r, A, B, tw, lane, sync);
       if (store) {
         const double sc = p.scale ? __ldg(p.scale + i2) : 1.0;
         double2* __restrict__ d2 = reinterpret_cast<double2*>(dstf + i2 * p.nz);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const int j = lane + m * (N / 4);
-          const cd v = z[fsw(j)];
-          d2[j] = make_double2(v.re * sc, v.im * sc);
+          d2[lane + m * (N / 4)] = make_double2(r[m].re * sc, r[m].im * sc);
         }
       }
-      sync();
     }
   }
 }
