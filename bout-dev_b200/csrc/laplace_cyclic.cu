@@ -59,6 +59,7 @@ struct LapParams {
   cd* __restrict__ iface;  // coupled only: this rank's [LAP_IFACE][nsys]
   const cd* __restrict__ iface_all; // coupled only: [nxpe][LAP_IFACE][nsys]
   int* __restrict__ status;
+  int* __restrict__ ydep;  // 0 while no metric / coefficient array was seen to vary along y (k_lap_ycheck)
   const cd* __restrict__ tw;
   int nx, ny, nz;
   int ys, ye;     // y range solved
@@ -264,6 +265,32 @@ __device__ __forceinline__ const double* stageTable(const LapParams& p, double* 
 constexpr int LAP_PF = B200_LAP_PF; // rows prefetched into registers ahead of the dependency chain
 
 // K2 (isolated systems): one thread per (y, kz) system, Thomas along x.
+// Do the matrix coefficients depend on y?  When no metric / coefficient array does, the Thomas factors c' are the
+// same for every y and the sweeps keep ONE [x][kz] copy of them (2 MB at 516 x 257: L2-resident) instead of
+// streaming an [x][y][kz] array through HBM twice -- a third of the kernel's DRAM traffic.  Checked on the
+// device for every solve (the arrays are the caller's and may change between solves); bitwise comparison.
+__global__ void __launch_bounds__(256) k_lap_ycheck(const LapParams p) {
+  const int nys = p.ye - p.ys + 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.nx * nys) {
+    return;
+  }
+  const int x = t / nys, y = p.ys + t % nys;
+  const long long i = static_cast<long long>(x) * p.ny + y, i0 = static_cast<long long>(x) * p.ny + p.ys;
+  const double* arrs[12] = {p.m.dx, p.m.g11, p.m.g33, p.m.g13, p.m.G1, p.m.G3, p.m.g_11, p.m.g_22,
+                            p.m.A,  p.m.C1,  p.m.C2,  p.m.D};
+  bool differs = false;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    if (arrs[q] != nullptr) {
+      differs = differs || !(__ldg(arrs[q] + i) == __ldg(arrs[q] + i0));
+    }
+  }
+  if (differs) {
+    *p.ydep = 1;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p, const bool smem_ok) {
   extern __shared__ __align__(16) double stab[];
   const int nys = p.ye - p.ys + 1;
@@ -278,7 +305,10 @@ __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p, const boo
   const int jy = p.ys + iyl;
   const long long xs = static_cast<long long>(nys) * p.nmode;
   const cd* __restrict__ rin = p.spec + t;
-  cd* __restrict__ cp = p.cprime + t;
+  // y-independent matrix: every y of a kz writes (identical values) to / reads from one [x][kz] copy of c'
+  const bool yind = *p.ydep == 0;
+  const long long xsc = yind ? p.nmode : xs;
+  cd* __restrict__ cp = p.cprime + (yind ? kz : t);
   cd* __restrict__ dp = p.dprime + t;
   const double kwave = kz * 2.0 * M_PI / p.m.zlength; // common_transform.cxx:73
   bool bad = false;
@@ -310,23 +340,23 @@ __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p, const boo
         const cd inv = crecip(denom);
         cprev = cmul(c, inv);
         dprev = cmul(csub(r, cmul(a, dprev)), inv);
-        cp[ix * xs] = cprev;
+        cp[ix * xsc] = cprev;
         dp[ix * xs] = dprev;
       }
     }
   }
   // back substitution, reading c', d' (never written below) PF rows ahead
   cd* __restrict__ xo = p.spec + t;
-  const cd* __restrict__ cpr = p.cprime + t;
+  const cd* __restrict__ cpr = p.cprime + (yind ? kz : t);
   const cd* __restrict__ dpr = p.dprime + t;
   cd x = dprev;
   xo[static_cast<long long>(n - 1) * xs] = x;
   cd nc[LAP_PF], nd[LAP_PF];
 #pragma unroll
   for (int k = 0; k < LAP_PF; ++k) {
-    const long long o = static_cast<long long>(max(n - 2 - k, 0)) * xs;
-    nc[k] = ldcd(cpr + o);
-    nd[k] = ldcd(dpr + o);
+    const long long o = static_cast<long long>(max(n - 2 - k, 0));
+    nc[k] = ldcd(cpr + o * xsc);
+    nd[k] = ldcd(dpr + o * xs);
   }
   for (int j0 = n - 2; j0 >= 0; j0 -= LAP_PF) {
     cd cc[LAP_PF], dd[LAP_PF];
@@ -337,9 +367,9 @@ __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p, const boo
     }
 #pragma unroll
     for (int k = 0; k < LAP_PF; ++k) {
-      const long long o = static_cast<long long>(max(j0 - LAP_PF - k, 0)) * xs;
-      nc[k] = ldcd(cpr + o);
-      nd[k] = ldcd(dpr + o);
+      const long long o = static_cast<long long>(max(j0 - LAP_PF - k, 0));
+      nc[k] = ldcd(cpr + o * xsc);
+      nd[k] = ldcd(dpr + o * xs);
     }
 #pragma unroll
     for (int k = 0; k < LAP_PF; ++k) {
@@ -1113,6 +1143,7 @@ int lapSetup(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspac
   const size_t table = roundUp(static_cast<size_t>(g->nx) * g->ny * LAP_NK * sizeof(double), 256);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   p.status = reinterpret_cast<int*>(ws);
+  p.ydep = p.status + 1;
   p.table = reinterpret_cast<double*>(ws + 256);
   p.spec = reinterpret_cast<cd*>(ws + 256 + table);
   p.cprime = p.spec + nspec;
@@ -1320,10 +1351,15 @@ int lapForward(const bout_b200_laplace* L, const double* rhs, const double* x0, 
                BOUT_B200_ERR_ARG, "laplace: INVERT_SET needs x0");
   p.rhs = rhs;
   p.x0 = x0;
-  B200_CUDA_OK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
+  B200_CUDA_OK(cudaMemsetAsync(p.status, 0, 2 * sizeof(int), s)); // status and ydep
   const int n2 = p.nx * p.ny;
   k_lap_table<<<(n2 + 255) / 256, 256, 0, s>>>(p);
   B200_LAUNCH_OK();
+  const int nys = p.ye - p.ys + 1;
+  if (nys > 1) {
+    k_lap_ycheck<<<(p.nx * nys + 255) / 256, 256, 0, s>>>(p);
+    B200_LAUNCH_OK();
+  }
   return fft ? launchFft<true>(plan, s) : 0;
 }
 } // namespace
