@@ -9,6 +9,9 @@ C-ABI call; torch only owns the memory.  The C++ host layer (host/) drives the s
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 
 from . import capi
@@ -183,6 +186,8 @@ class ELMpb:
         self.phi, self.Jpar, self.Jpar2 = z(), z(), z()
         self.ddt_U, self.ddt_P, self.ddt_Psi = z(), z(), z()
         self.fused = True             # one kernel for the three equations + filter (csrc/elm_rhs.cu)
+        self.two_streams = os.environ.get("BOUT_B200_ELM_STREAMS", "2") != "1"
+        self._side = None
         self.kernel_events = None     # bench.py: (start, end) CUDA events of the fused kernel
         self.compute_jpar2 = True     # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
 
@@ -258,15 +263,15 @@ class ELMpb:
             self._buf["d2J"] = z()
         return self._buf
 
+    def _slices_into(self, f, name):
+        up, dn = self._buffers()[name]
+        capi.parallel_slices(self.g, f, self.zs, self.zl, 1, yup=[up], ydown=[dn])
+        return ([up], [dn])
+
     def _comm_into(self, fields, names):
         """mesh->communicate(...) with the parallel slices written into preallocated buffers."""
         self._halo(fields)
-        out = []
-        for f, n in zip(fields, names):
-            up, dn = self._buffers()[n]
-            capi.parallel_slices(self.g, f, self.zs, self.zl, 1, yup=[up], ydown=[dn])
-            out.append(([up], [dn]))
-        return out
+        return [self._slices_into(f, n) for f, n in zip(fields, names)]
 
     def rhs(self, U=None, P=None, Psi=None):
         g, m, eq = self.g, self.md, self.eq
@@ -276,13 +281,24 @@ class ELMpb:
         ew = capi.elementwise
         buf = self._buffers()
         self.pre_rhs(U, P, Psi)
-        sU, sP, sPsi = self._comm_into([U, P, Psi], ["U", "P", "Psi"])       # mesh->communicate(comms)
-        # phi = phiSolver->solve(U) - 0.5 dnorm P / B0 (constn0, diamag)       elm_pb.cxx:1472-1477
-        self.lap.solve(U, out=self.phi)
-        ew(g, [(1.0, self.phi), (-0.5 * self.dnorm, P, None, self.B0)], out=self.phi)
-        (sphi,) = self._comm_into([self.phi], ["phi"])
-        capi.boundary(g, "extend", "xin", self.phi)                           # :1498-1516
-        capi.boundary(g, "extend", "xout", self.phi)
+        self._halo([U, P, Psi])                                               # mesh->communicate(comms)
+        # The potential chain (LaplaceCyclic -> phi update -> communicate -> slices) runs on a second stream: its
+        # Thomas kernel has only ny * (nz/2 + 1) systems (65 CTAs at 64 x 129) and its small launches leave SMs
+        # idle, which the slice / Delp2 kernels of the main stream fill.  Both streams only READ U, P, Psi.
+        two = self.two_streams and self.dev.type == "cuda"
+        main = torch.cuda.current_stream() if two else None
+        if two:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            self._side.wait_stream(main)
+        with (torch.cuda.stream(self._side) if two else contextlib.nullcontext()):
+            # phi = phiSolver->solve(U) - 0.5 dnorm P / B0 (constn0, diamag)       elm_pb.cxx:1472-1477
+            self.lap.solve(U, out=self.phi)
+            ew(g, [(1.0, self.phi), (-0.5 * self.dnorm, P, None, self.B0)], out=self.phi)
+            (sphi,) = self._comm_into([self.phi], ["phi"])
+            capi.boundary(g, "extend", "xin", self.phi)                           # :1498-1516
+            capi.boundary(g, "extend", "xout", self.phi)
+        sU, sP, sPsi = [self._slices_into(f, n) for f, n in ((U, "U"), (P, "P"), (Psi, "Psi"))]
         # Jpar = Delp2(Psi); BC; communicate; smooth_x; BC; communicate         :1518-1563
         self.delp.delp2(Psi, out=self.Jpar)
         self._bc_j(self.Jpar)
@@ -298,6 +314,8 @@ class ELMpb:
             self.Jpar2.copy_(d2J)
             self._bc_j(self.Jpar2)
             self._halo([self.Jpar2])
+        if two:
+            main.wait_stream(self._side)
         if self.fused and self.filter_z_mode >= 0 and self.filter_z_mode < g.nz // 2:
             keep = [1.0, 1.0, 1.0]
             if self.low_pass_z > 0:
