@@ -316,9 +316,12 @@ ELM_WORKLOAD = ("elm-pb linear 3-field reduced-MHD RHS (shipped [highbeta] switc
 # Algorithmic bytes per interior point of the fused kernel k_elmpb_rhs: reads U, P, Psi, phi, Jpar,
 # Delp2(Jpar), eta (7 x 8) + the ten parallel slices (80), writes the three time derivatives (24)
 ELM_FUSED_BPP = 160.0
+# inside an RK4 step three of the four launches also read the step's start state and write the next stage state
+# (3 fields x 16 B): (3 * 208 + 160) / 4
+ELM_FUSED_BPP_RK4 = (3 * 208.0 + 160.0) / 4
 # Whole elm-pb RHS pass list: slices 5 x 24, solve 16, phi update 24, Delp2 2 x 16,
 # smooth_x 16, Jpar2 copy 16, fused 160
-ELM_RHS_BPP = 5 * 24 + 16 + 24 + 2 * 16 + 16 + 16 + 160
+ELM_RHS_BPP = 5 * 24 + 16 + 24 + 2 * 16 + 16 + 16 + 160   # = 404; + 36 per RHS of RK stage traffic inside a step
 
 
 def event_time(torch, fn, reps, warm=2):
@@ -505,7 +508,7 @@ def run_elmpb(args):
         return
     peak, peak_src = peaks()
     fb = host[0].numel() * 8
-    achieved = ELM_FUSED_BPP * npts / k_secs / 1e9
+    achieved = ELM_FUSED_BPP_RK4 * npts / k_secs / 1e9
     out = {
         "metric": METRIC, "value": npts * 4 * args.steps * world / secs, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
@@ -518,13 +521,14 @@ def run_elmpb(args):
         "e2e": {"value": npts * 4 * args.steps * world / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": 3 * fb,
                 "d2h_bytes_per_step": 3 * fb, "ms_per_step": e2e_secs / args.steps * 1e3,
                 "note": "state (U, P, Psi) copied host->device from pinned memory and the result device->host every RK4 step"},
-        "roofline": {"bound": "hbm", "kernel": "k_elmpb_rhs (fused 3-equation RHS + z filter)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "k_elmpb_rhs (fused 3-equation RHS + z filter + RK stage update)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "traffic": profile_traffic("k_elmpb_rhs_bytes_per_launch"),
-                     "algorithmic_bytes_per_launch": ELM_FUSED_BPP * npts, "kernel_ms": k_secs * 1e3,
+                     "algorithmic_bytes_per_launch": ELM_FUSED_BPP_RK4 * npts, "kernel_ms": k_secs * 1e3,
                      "kernel_share_of_step": 4 * k_secs / (secs / args.steps),
-                     "rhs_algorithmic_GBps": ELM_RHS_BPP * npts * 4 * args.steps / secs / 1e9,
-                     "rhs_bytes_per_point": f"{ELM_RHS_BPP:.0f} (pass list in DESIGN.md section 3)"},
+                     "rhs_algorithmic_GBps": (ELM_RHS_BPP + 36.0 + 36.0) * npts * 4 * args.steps / secs / 1e9,
+                     "rhs_bytes_per_point": f"{ELM_RHS_BPP:.0f} (pass list in DESIGN.md section 3) + 36 RK stage states "
+                                            f"+ 36 final combination (3 fields x 48 B per step / 4)"},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

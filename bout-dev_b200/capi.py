@@ -494,15 +494,23 @@ class CElmpbRhs(C.Structure):
         "Psi_dn", "phi_up", "phi_dn", "J_up", "J_dn")] + \
         [("hyperresist", C.c_double), ("keep_U", C.c_double), ("keep_P", C.c_double), ("keep_Psi", C.c_double),
          ("eta_is2d", C.c_int), ("filter_n0", C.c_int)] + \
-        [(n, C.c_void_p) for n in ("ddt_U", "ddt_P", "ddt_Psi")]
+        [(n, C.c_void_p) for n in ("ddt_U", "ddt_P", "ddt_Psi", "rk_start_U", "rk_start_P", "rk_start_Psi",
+                                   "rk_stage_U", "rk_stage_P", "rk_stage_Psi")] + [("rk_cdt", C.c_double)]
 
 
-def elmpb_rhs(g: Grid, fields: dict, hyperresist, filter_n0, keep=(1.0, 1.0, 1.0)):
-    """fields: name -> tensor for every pointer member of bout_b200_elmpb_rhs_args (eta may be 2-D)."""
+def elmpb_rhs(g: Grid, fields: dict, hyperresist, filter_n0, keep=(1.0, 1.0, 1.0), rk=None):
+    """fields: name -> tensor for every pointer member of bout_b200_elmpb_rhs_args (eta may be 2-D).
+    rk = (start fields (U, P, Psi), stage-state fields (U, P, Psi), c * dt) or None."""
     c = CElmpbRhs()
     for n, _t in CElmpbRhs._fields_:
         if n in fields:
             setattr(c, n, fields[n].data_ptr())
+    if rk is not None:
+        start, stage, cdt = rk
+        for nm, a, b in zip(("U", "P", "Psi"), start, stage):
+            setattr(c, "rk_start_" + nm, a.data_ptr())
+            setattr(c, "rk_stage_" + nm, b.data_ptr())
+        c.rk_cdt = cdt
     c.hyperresist = hyperresist
     c.keep_U, c.keep_P, c.keep_Psi = keep
     c.eta_is2d = int(fields["eta"].dim() == 2)

@@ -287,16 +287,22 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   }
   const double inv = 1.0 / nz;
   const double mult = n0 == 0 ? 1.0 : 2.0;
-  auto back = [&](double xr, double xi, double keep, double* __restrict__ out) {
+  const long long i3 = i2 * nz + z0;
+  auto back = [&](double xr, double xi, double keep, double* __restrict__ out, const double* __restrict__ start,
+                  double* __restrict__ stage) {
     // Re(X conj(w)) with w = exp(-i theta): xr cos(theta) ... ; w.re = cos, w.im = -sin
     const double s = keep * mult * inv;
     const double v0 = s * (xr * w0.re + xi * w0.im);
     const double v1 = s * (xr * w1.re + xi * w1.im);
     *reinterpret_cast<double2*>(out) = make_double2(v0, v1);
+    if (stage != nullptr) { // explicit RK stage state: start + (c dt) ddt   (rk4.cxx:179-200)
+      const double2 st = ld2(start + i3);
+      *reinterpret_cast<double2*>(stage + i3) = make_double2(st.x + a.rk_cdt * v0, st.y + a.rk_cdt * v1);
+    }
   };
-  back(acc[0], acc[1], a.keep_U, oU);
-  back(acc[2], acc[3], a.keep_P, oP);
-  back(acc[4], acc[5], a.keep_Psi, oPsi);
+  back(acc[0], acc[1], a.keep_U, oU, a.rk_start_U, a.rk_stage_U);
+  back(acc[2], acc[3], a.keep_P, oP, a.rk_start_P, a.rk_stage_P);
+  back(acc[4], acc[5], a.keep_Psi, oPsi, a.rk_start_Psi, a.rk_stage_Psi);
 }
 
 } // namespace b200
@@ -322,6 +328,16 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
     B200_REQUIRE(aligned16(q), BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: fields must be 16-byte aligned");
   }
   B200_REQUIRE(a.eta_is2d || aligned16(a.eta), BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: eta must be 16-byte aligned");
+  const void* rk[] = {a.rk_start_U, a.rk_start_P, a.rk_start_Psi, a.rk_stage_U, a.rk_stage_P, a.rk_stage_Psi};
+  int nrk = 0;
+  for (const void* q : rk) {
+    nrk += q != nullptr;
+    B200_REQUIRE(aligned16(q), BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: RK fields must be 16-byte aligned");
+  }
+  B200_REQUIRE(nrk == 0 || (nrk == 6 && a.filter_n0 >= 0), BOUT_B200_ERR_ARG,
+               "elmpb_rhs: the RK stage epilogue needs all six rk_* fields and the in-kernel filter");
+  B200_REQUIRE(a.rk_stage_U != a.U && a.rk_stage_P != a.P && a.rk_stage_Psi != a.Psi, BOUT_B200_ERR_ARG,
+               "elmpb_rhs: a stage state must not be a field this launch reads neighbours of");
   B200_REQUIRE(g->nz % 2 == 0 && g->nz >= 4, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz must be even and >= 4");
   B200_REQUIRE(g->xstart >= 2 && g->nx - 1 - g->xend >= 2 && g->ystart >= 1 && g->ny - 1 - g->yend >= 1,
                BOUT_B200_ERR_GUARDS, "elmpb_rhs: needs 2 x guard cells and 1 y guard cell");
@@ -360,6 +376,8 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
   static const int minb = getenv("BOUT_B200_ELM_MINB") ? atoi(getenv("BOUT_B200_ELM_MINB")) : 3;
   if (minb == 2) {
     k_elmpb_rhs<2><<<blocks, threads, 0, s>>>(p);
+  } else if (minb == 4) {
+    k_elmpb_rhs<4><<<blocks, threads, 0, s>>>(p);
   } else {
     k_elmpb_rhs<3><<<blocks, threads, 0, s>>>(p);
   }

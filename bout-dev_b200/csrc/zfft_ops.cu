@@ -107,6 +107,16 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
   }
   __syncthreads();
   cd* X = rfftForward(r);
+  __shared__ double zsum[128];
+  if (p.mode == Z_ZEROLAP) { // z-sum of the second interior row, all threads of the row group (uniform branch)
+    const double* __restrict__ in2 = p.f + (static_cast<long long>(p.xin - p.bdir) * p.ny + y) * p.nz;
+    double part = 0.0;
+    for (int j = r.lane; j < p.nz; j += r.tpr) {
+      part += __ldg(in2 + j);
+    }
+    zsum[threadIdx.x] = part;
+    __syncthreads();
+  }
 
   const int nk = p.nz / 2;
   const double kfac = 2.0 * M_PI / p.nz;
@@ -167,10 +177,9 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
     case Z_ZEROLAP: { // BoundaryZeroLaplace::apply(Field3D), boundary_standard.cxx:2630-2686
       const int steps = (x - p.xin) * p.bdir;
       if (k == 0) { // straight line through the last two interior z-means
-        const double* __restrict__ in2 = p.f + (static_cast<long long>(p.xin - p.bdir) * p.ny + y) * p.nz;
         double m2 = 0.0;
-        for (int j = 0; j < p.nz; ++j) {
-          m2 += __ldg(in2 + j);
+        for (int j = 0; j < p.tpr; ++j) {
+          m2 += zsum[rloc * p.tpr + j];
         }
         m2 /= p.nz;
         const double grad = v.re - m2;

@@ -273,7 +273,8 @@ class ELMpb:
         self._halo(fields)
         return [self._slices_into(f, n) for f, n in zip(fields, names)]
 
-    def rhs(self, U=None, P=None, Psi=None):
+    def rhs(self, U=None, P=None, Psi=None, rk=None):
+        """rk = (start (U, P, Psi), stage state (U, P, Psi), c * dt): also form the next RK stage state."""
         g, m, eq = self.g, self.md, self.eq
         U = self.U if U is None else U
         P = self.P if P is None else P
@@ -331,12 +332,16 @@ class ELMpb:
             if self.kernel_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            capi.elmpb_rhs(g, fields, self.hyperresist, self.filter_z_mode, keep=tuple(keep))
+            capi.elmpb_rhs(g, fields, self.hyperresist, self.filter_z_mode, keep=tuple(keep), rk=rk)
+            rk = None
             if self.kernel_events is not None:
                 e1.record()
                 self.kernel_events.append((e0, e1))
         else:
             self._rhs_terms(U, P, Psi, sU, sP, sPsi, sphi, sJ, d2J)
+        if rk is not None:   # operator path: the stage update is its own pass
+            for st0, st1, k in zip(rk[0], rk[1], (self.ddt_U, self.ddt_P, self.ddt_Psi)):
+                capi.rk_stage(g, "axpy", rk[2], st0, k, out=st1)
 
     def _rhs_terms(self, U, P, Psi, sU, sP, sPsi, sphi, sJ, d2J):
         """Operator-by-operator evaluation of the three equations (exact also without filter_z: the terms the
@@ -380,7 +385,8 @@ class ELMpb:
         """RK4Solver::take_step (rk4.cxx:172-210): stage combinations over the evolving region.  Each RHS
         writes its time derivatives straight into that stage's k arrays and the stage states are built from
         the interior only (their guard cells are filled by the next pre_rhs + communicate), so a step is
-        4 RHS + 9 axpy passes + the final combination, with no gather/scatter or copy passes."""
+        4 RHS (the stage states are written by the fused RHS kernel's epilogue) + the final combination, with no
+        gather/scatter, copy or axpy passes."""
         g = self.g
         state = (self.U, self.P, self.Psi)
         if not hasattr(self, "_rk"):
@@ -388,17 +394,19 @@ class ELMpb:
         k1, k2, k3, k4, st = self._rk
         keep = (self.ddt_U, self.ddt_P, self.ddt_Psi)
 
-        def stage(src, k, coef):
+        if not hasattr(self, "_rk2"):
+            self._rk2 = [torch.zeros_like(self.U) for _ in range(3)]   # second stage state (ping-pong)
+        su = self._rk2
+
+        def stage(src, k, coef, dst):
+            # the stage state a kernel writes must not be the one it reads neighbours of: ping-pong st / su
             self.ddt_U, self.ddt_P, self.ddt_Psi = k
-            self.rhs(*src)
-            if coef is not None:
-                for i in range(3):
-                    capi.rk_stage(g, "axpy", coef * dt, state[i], k[i], out=st[i])
+            self.rhs(*src, rk=None if coef is None else (state, dst, coef * dt))
         try:
-            stage(state, k1, 0.5)
-            stage(st, k2, 0.5)
-            stage(st, k3, 1.0)
-            stage(st, k4, None)
+            stage(state, k1, 0.5, st)
+            stage(st, k2, 0.5, su)
+            stage(su, k3, 1.0, st)
+            stage(st, k4, None, None)
         finally:
             self.ddt_U, self.ddt_P, self.ddt_Psi = keep
         for i in range(3):

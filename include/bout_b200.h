@@ -184,7 +184,8 @@ int bout_b200_b0xgrad_dot_grad(const bout_b200_grid* g, const bout_b200_b0xgrad*
  * filter_n0 >= 0 (and below the Nyquist mode): the kept z mode, filtered in-kernel; keep_* = 1.0, or 0.0 if
  * the following lowPass removes that mode for the field (n0 > low_pass_z, or n0 = 0 without keep_zonal).
  * filter_n0 < 0 writes the unfiltered sums (valid only up to the Nyquist-mode handling of the reference's
- * field-aligned terms, see csrc/elm_rhs.cu).  Outputs cover RGN_NOBNDRY. */
+ * field-aligned terms, see csrc/elm_rhs.cu).  Outputs cover RGN_NOBNDRY.  With the rk_* members set the kernel
+ * also writes the next explicit-RK stage state, so a stage costs no extra pass. */
 typedef struct bout_b200_elmpb_rhs_args {
   const double *dx, *dy, *dz, *J, *g_22, *g_12, *g_23, *Bxy;                 /* Field2D metric */
   const double *B0, *J0, *P0, *phi0, *b0xcv_x, *b0xcv_y, *b0xcv_z;           /* Field2D equilibrium */
@@ -196,6 +197,11 @@ typedef struct bout_b200_elmpb_rhs_args {
   int eta_is2d;
   int filter_n0;
   double *ddt_U, *ddt_P, *ddt_Psi;
+  /* optional explicit-RK epilogue (all six or none): rk_stage_X = rk_start_X + rk_cdt * ddt_X on RGN_NOBNDRY, the
+   * `k5 = start + c dt k` loops of RK4Solver::take_step (src/solver/impls/rk4/rk4.cxx:179-200) */
+  const double *rk_start_U, *rk_start_P, *rk_start_Psi;
+  double *rk_stage_U, *rk_stage_P, *rk_stage_Psi;
+  double rk_cdt;
 } bout_b200_elmpb_rhs_args;
 int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmpb_rhs_args* args, void* stream);
 
