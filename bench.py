@@ -418,7 +418,52 @@ def other_measurements(torch, pkg, dev, peak):
         micro[name] = {"us": t * 1e6, "grid_points_per_s": g.n_interior / t,
                        "algorithmic_GBps": bpp * g.n_interior / t / 1e9, "frac_of_hbm_peak": bpp * g.n_interior / t / 1e9 / peak}
     out["microbench_256x64x256"] = micro
+    del a, b, c, o, flush
+    torch.cuda.empty_cache()
+    # -- UNCHANGED reference model sources through the C++ host layer (bout-dev_b200/host: BOUT++'s own API on the
+    #    C-ABI): examples/blob2d scaled to 1024 x 1024 (configs[2]) and examples/hasegawa-wakatani as shipped
+    #    (configs[0], 256 x 256, periodic X); wall clock around Solver::solve, all host overheads included
+    try:
+        out["host_layer_models"] = host_layer_models(pkg)
+    except Exception as e:  # noqa: BLE001
+        out["host_layer_models"] = {"error": repr(e)[:300]}
     return out
+
+
+def host_layer_models(pkg):
+    """Wall time of Solver::solve for two step counts (after a discarded warm-up instance): the slope is the
+    per-RHS cost with every host overhead of the C++ layer in it; the intercept is start-up."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    import numpy as np
+    res = {}
+    blob_extra = cases.BLOB_INI[cases.BLOB_INI.index("[mesh:ddx]"):]
+    hw_extra = cases.HW_INI[cases.HW_INI.index("[hw]"):]
+    for tag, model, ini, steps in (
+            ("blob2d_1024x1x1024", "blob2d", cases.make_ini(1028, 1, 1024, mxg=2, myg=0, dx="0.3", dz="0.3", extra=blob_extra), (5, 20, 60)),
+            ("hasegawa-wakatani_256x1x256", "hw", cases.make_ini(260, 1, 256, mxg=2, myg=0, periodic_x=True, extra=hw_extra), (5, 50, 150))):
+        dt = float([ln for ln in ini.splitlines() if ln.startswith("timestep")][0].split("=")[1])
+        pts = []
+        for nsteps in steps:
+            h = pkg.host.Host(ini)
+            try:
+                names = h.model_create(model, "rk4")
+                h.model_rhs(0.0)
+                h.model_get(names[0])
+                c0 = h.rhs_calls()
+                t0 = time.time()
+                h.model_solve(1, nsteps * dt)
+                final = h.model_get(names[0])             # device -> host read: the solve has completed
+                pts.append((h.rhs_calls() - c0, time.time() - t0, bool(np.isfinite(final).all()), h.pool_allocations()))
+                nx, ny, nz = h.shape3
+            finally:
+                h.close()
+        (n1, t1, _, _), (n2, t2, fin, pool) = pts[1], pts[2]
+        per = (t2 - t1) / (n2 - n1)
+        npts = (nx - 4) * max(ny, 1) * nz
+        res[tag] = {"us_per_rhs": per * 1e6, "grid_points_per_s": npts / per, "rhs_calls": [n1, n2],
+                    "wall_ms": [t1 * 1e3, t2 * 1e3], "finite": fin, "steady_state_pool_allocations": pool}
+    return res
 
 
 def run_elmpb(args):

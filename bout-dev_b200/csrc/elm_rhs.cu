@@ -40,42 +40,52 @@ struct ElmParams {
   int rows_per_cta;
 };
 
-struct Row2 { // the six z values z0-2 .. z0+3 of one (x, y) row around this thread's z pair
-  double v[6];
-};
-__device__ __forceinline__ Row2 loadRow6(const double* __restrict__ row, int z0, int nz) {
-  const double2 a = __ldg(reinterpret_cast<const double2*>(row + wrapz(z0 - 2, nz)));
-  const double2 b = __ldg(reinterpret_cast<const double2*>(row + z0));
-  const double2 c = __ldg(reinterpret_cast<const double2*>(row + wrapz(z0 + 2, nz)));
-  return Row2{{a.x, a.y, b.x, b.y, c.x, c.y}};
-}
 __device__ __forceinline__ double2 ld2(const double* __restrict__ p) {
   return __ldg(reinterpret_cast<const double2*>(p));
 }
 
-// x-stencil (5 rows) + z-stencil (centre row) + the two slices of a Field3D at this thread's z pair
+// x-stencil (5 rows) + z-stencil (centre row) + the two slices of a Field3D at this thread's V consecutive z points
+// (V = 2: 16-byte transactions; V = 1: half the registers, twice the warps per SM).
+template <int V>
 struct F3 {
-  double2 xmm, xm, xp, xpp, up, dn;
-  Row2 c;
-  __device__ __forceinline__ St sx(int j) const {
-    return j == 0 ? St{xmm.x, xm.x, c.v[2], xp.x, xpp.x} : St{xmm.y, xm.y, c.v[3], xp.y, xpp.y};
-  }
-  __device__ __forceinline__ St sz(int j) const { return St{c.v[j], c.v[j + 1], c.v[j + 2], c.v[j + 3], c.v[j + 4]}; }
-  __device__ __forceinline__ double yp(int j) const { return j == 0 ? up.x : up.y; }
-  __device__ __forceinline__ double ym(int j) const { return j == 0 ? dn.x : dn.y; }
+  double xmm[V], xm[V], xp[V], xpp[V], up[V], dn[V];
+  double c[4 + V]; // z0-2 .. z0+V+1
+  __device__ __forceinline__ St sx(int j) const { return St{xmm[j], xm[j], c[2 + j], xp[j], xpp[j]}; }
+  __device__ __forceinline__ St sz(int j) const { return St{c[j], c[j + 1], c[j + 2], c[j + 3], c[j + 4]}; }
+  __device__ __forceinline__ double yp(int j) const { return up[j]; }
+  __device__ __forceinline__ double ym(int j) const { return dn[j]; }
 };
-__device__ __forceinline__ F3 loadF3(const double* __restrict__ f, const double* __restrict__ fup,
-                                     const double* __restrict__ fdn, long long i2, int ny, int nz, int z0) {
-  F3 r;
+template <int V>
+__device__ __forceinline__ void ldv(const double* __restrict__ p, double (&out)[V]) {
+  if constexpr (V == 2) {
+    const double2 t = ld2(p);
+    out[0] = t.x;
+    out[1] = t.y;
+  } else {
+    out[0] = __ldg(p);
+  }
+}
+template <int V>
+__device__ __forceinline__ F3<V> loadF3(const double* __restrict__ f, const double* __restrict__ fup,
+                                        const double* __restrict__ fdn, long long i2, int ny, int nz, int z0) {
+  F3<V> r;
   const long long plane = static_cast<long long>(ny) * nz;
   const double* __restrict__ row = f + i2 * nz;
-  r.c = loadRow6(row, z0, nz);
-  r.xmm = ld2(row - 2 * plane + z0);
-  r.xm = ld2(row - plane + z0);
-  r.xp = ld2(row + plane + z0);
-  r.xpp = ld2(row + 2 * plane + z0);
-  r.up = ld2(fup + (i2 + 1) * nz + z0); // yup holds the y+1 neighbour at row y+1
-  r.dn = ld2(fdn + (i2 - 1) * nz + z0);
+  if constexpr (V == 2) {
+    const double2 a = ld2(row + wrapz(z0 - 2, nz)), b = ld2(row + z0), c = ld2(row + wrapz(z0 + 2, nz));
+    r.c[0] = a.x, r.c[1] = a.y, r.c[2] = b.x, r.c[3] = b.y, r.c[4] = c.x, r.c[5] = c.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      r.c[q] = __ldg(row + wrapz(z0 - 2 + q, nz));
+    }
+  }
+  ldv<V>(row - 2 * plane + z0, r.xmm);
+  ldv<V>(row - plane + z0, r.xm);
+  ldv<V>(row + plane + z0, r.xp);
+  ldv<V>(row + 2 * plane + z0, r.xpp);
+  ldv<V>(fup + (i2 + 1) * nz + z0, r.up); // yup holds the y+1 neighbour at row y+1
+  ldv<V>(fdn + (i2 - 1) * nz + z0, r.dn);
   return r;
 }
 
@@ -158,11 +168,11 @@ __device__ __forceinline__ void rowReduce3(double (&acc)[6], double* red, int ti
   }
 }
 
-template <int MINB>
+template <int MINB, int V>
 __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   __shared__ double red[8 * 6 * 32];
   const bout_b200_elmpb_rhs_args& a = p.a;
-  const int nzp = p.nz / 2;                  // threads per row
+  const int nzp = p.nz / V;                  // threads per row
   const int rloc = threadIdx.x / nzp, tin = threadIdx.x % nzp;
   const int nyb = p.ye - p.ys + 1;
   const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * nyb;
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   const int x = p.xs + static_cast<int>(rid / nyb);
   const int y = p.ys + static_cast<int>(rid % nyb);
   const long long i2 = static_cast<long long>(x) * p.ny + y;
-  const int z0 = 2 * tin;
+  const int z0 = V * tin;
   const int ny = p.ny, nz = p.nz;
 
   __shared__ RowC rows[8];
@@ -214,20 +224,20 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   const RowC& m = rows[rloc];
 
   // One stencil field at a time (loads next to their use) so that at most one F3 is live.
-  double tU[2], tP[2], tPsi[2];
+  double tU[V], tP[V], tPsi[V];
   {
-    const F3 phi = loadF3(a.phi, a.phi_up, a.phi_dn, i2, ny, nz, z0);
+    const F3<V> phi = loadF3<V>(a.phi, a.phi_up, a.phi_dn, i2, ny, nz, z0);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < V; ++j) {
       const double gp = 0.5 * (m.B0p * phi.yp(j) - m.B0m * phi.ym(j)) * m.gpar; // Grad_par(phi B0)
       tPsi[j] = -1.0 * gp * m.rB0;
       tP[j] = -1.0 * b0x3d2d(phi.sx(j), phi.yp(j), phi.ym(j), phi.sz(j), m.dP0, m.dP0y, m);
     }
   }
   {
-    const F3 P = loadF3(a.P, a.P_up, a.P_dn, i2, ny, nz, z0);
+    const F3<V> P = loadF3<V>(a.P, a.P_up, a.P_dn, i2, ny, nz, z0);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < V; ++j) {
       const double dPx = applyStandard<BOUT_B200_DDX_C4>(P.sx(j)) * m.rdx;
       const double dPy = 0.5 * (P.yp(j) - P.ym(j)) * m.rdy;
       const double dPz = applyStandard<BOUT_B200_DDX_C4>(P.sz(j)) * m.rdz;
@@ -236,9 +246,9 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
     }
   }
   {
-    const F3 Psi = loadF3(a.Psi, a.Psi_up, a.Psi_dn, i2, ny, nz, z0);
+    const F3<V> Psi = loadF3<V>(a.Psi, a.Psi_up, a.Psi_dn, i2, ny, nz, z0);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < V; ++j) {
       const double bg = b0x2d3d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m);
       tPsi[j] -= bg * m.B0rBxy;
       const double t1 = b0x3d2d(Psi.sx(j), Psi.yp(j), Psi.ym(j), Psi.sz(j), m.dJ0, m.dJ0y, m);
@@ -246,63 +256,92 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
     }
   }
   {
-    const F3 U = loadF3(a.U, a.U_up, a.U_dn, i2, ny, nz, z0);
+    const F3<V> U = loadF3<V>(a.U, a.U_up, a.U_dn, i2, ny, nz, z0);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < V; ++j) {
       tU[j] -= b0x2d3d(U.sx(j), U.yp(j), U.ym(j), U.sz(j), m);
     }
   }
   {
-    const double2 J = ld2(a.Jpar + i2 * nz + z0);
-    const double2 Jup = ld2(a.J_up + (i2 + 1) * nz + z0), Jdn = ld2(a.J_dn + (i2 - 1) * nz + z0);
-    const double2 d2J = ld2(a.d2Jpar + i2 * nz + z0);
-    const double2 eta = a.eta_is2d ? make_double2(__ldg(a.eta + i2), __ldg(a.eta + i2)) : ld2(a.eta + i2 * nz + z0);
-    tPsi[0] += eta.x * J.x - a.hyperresist * eta.x * d2J.x;
-    tPsi[1] += eta.y * J.y - a.hyperresist * eta.y * d2J.y;
-    tU[0] -= 0.5 * (Jup.x - Jdn.x) * m.gpar * m.B0sq;
-    tU[1] -= 0.5 * (Jup.y - Jdn.y) * m.gpar * m.B0sq;
+    double J[V], Jup[V], Jdn[V], d2J[V], eta[V];
+    ldv<V>(a.Jpar + i2 * nz + z0, J);
+    ldv<V>(a.J_up + (i2 + 1) * nz + z0, Jup);
+    ldv<V>(a.J_dn + (i2 - 1) * nz + z0, Jdn);
+    ldv<V>(a.d2Jpar + i2 * nz + z0, d2J);
+    if (a.eta_is2d) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        eta[j] = __ldg(a.eta + i2);
+      }
+    } else {
+      ldv<V>(a.eta + i2 * nz + z0, eta);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      tPsi[j] += eta[j] * J[j] - a.hyperresist * eta[j] * d2J[j];
+      tU[j] -= 0.5 * (Jup[j] - Jdn[j]) * m.gpar * m.B0sq;
+    }
   }
 
-  double* __restrict__ oU = a.ddt_U + i2 * nz + z0;
-  double* __restrict__ oP = a.ddt_P + i2 * nz + z0;
-  double* __restrict__ oPsi = a.ddt_Psi + i2 * nz + z0;
+  const long long i3 = i2 * nz + z0;
+  auto stv = [&](double* __restrict__ q, const double (&v)[V]) {
+    if constexpr (V == 2) {
+      *reinterpret_cast<double2*>(q) = make_double2(v[0], v[1]);
+    } else {
+      *q = v[0];
+    }
+  };
   if (a.filter_n0 < 0) { // no filter: raw time derivatives
     if (active) {
-      *reinterpret_cast<double2*>(oU) = make_double2(tU[0], tU[1]);
-      *reinterpret_cast<double2*>(oP) = make_double2(tP[0], tP[1]);
-      *reinterpret_cast<double2*>(oPsi) = make_double2(tPsi[0], tPsi[1]);
+      stv(a.ddt_U + i3, tU);
+      stv(a.ddt_P + i3, tP);
+      stv(a.ddt_Psi + i3, tPsi);
     }
     return;
   }
   // ---- filter(., n0): X = (1/nz) sum_j f_j exp(-2 pi i n0 j / nz); f_j <- (k = 0: X) / (else: 2 Re X exp(+...))
   const int n0 = a.filter_n0;
-  const cd w0 = p.tw[(static_cast<long long>(n0) * z0) % nz];
-  const cd w1 = p.tw[(static_cast<long long>(n0) * (z0 + 1)) % nz];
-  double acc[6] = {tU[0] * w0.re + tU[1] * w1.re,     tU[0] * w0.im + tU[1] * w1.im,
-                   tP[0] * w0.re + tP[1] * w1.re,     tP[0] * w0.im + tP[1] * w1.im,
-                   tPsi[0] * w0.re + tPsi[1] * w1.re, tPsi[0] * w0.im + tPsi[1] * w1.im};
+  cd w[V];
+  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    w[j] = p.tw[(static_cast<long long>(n0) * (z0 + j)) % nz];
+    acc[0] += tU[j] * w[j].re;
+    acc[1] += tU[j] * w[j].im;
+    acc[2] += tP[j] * w[j].re;
+    acc[3] += tP[j] * w[j].im;
+    acc[4] += tPsi[j] * w[j].re;
+    acc[5] += tPsi[j] * w[j].im;
+  }
   rowReduce3(acc, red, tin, nzp, rloc);
   if (!active) {
     return;
   }
   const double inv = 1.0 / nz;
   const double mult = n0 == 0 ? 1.0 : 2.0;
-  const long long i3 = i2 * nz + z0;
   auto back = [&](double xr, double xi, double keep, double* __restrict__ out, const double* __restrict__ start,
                   double* __restrict__ stage) {
-    // Re(X conj(w)) with w = exp(-i theta): xr cos(theta) ... ; w.re = cos, w.im = -sin
+    // Re(X conj(w)) with w = exp(-i theta): w.re = cos(theta), w.im = -sin(theta)
     const double s = keep * mult * inv;
-    const double v0 = s * (xr * w0.re + xi * w0.im);
-    const double v1 = s * (xr * w1.re + xi * w1.im);
-    *reinterpret_cast<double2*>(out) = make_double2(v0, v1);
+    double v[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j] = s * (xr * w[j].re + xi * w[j].im);
+    }
+    stv(out + i3, v);
     if (stage != nullptr) { // explicit RK stage state: start + (c dt) ddt   (rk4.cxx:179-200)
-      const double2 st = ld2(start + i3);
-      *reinterpret_cast<double2*>(stage + i3) = make_double2(st.x + a.rk_cdt * v0, st.y + a.rk_cdt * v1);
+      double st[V];
+      ldv<V>(start + i3, st);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        st[j] += a.rk_cdt * v[j];
+      }
+      stv(stage + i3, st);
     }
   };
-  back(acc[0], acc[1], a.keep_U, oU, a.rk_start_U, a.rk_stage_U);
-  back(acc[2], acc[3], a.keep_P, oP, a.rk_start_P, a.rk_stage_P);
-  back(acc[4], acc[5], a.keep_Psi, oPsi, a.rk_start_Psi, a.rk_stage_Psi);
+  back(acc[0], acc[1], a.keep_U, a.ddt_U, a.rk_start_U, a.rk_stage_U);
+  back(acc[2], acc[3], a.keep_P, a.ddt_P, a.rk_start_P, a.rk_stage_P);
+  back(acc[4], acc[5], a.keep_Psi, a.ddt_Psi, a.rk_start_Psi, a.rk_stage_Psi);
 }
 
 } // namespace b200
@@ -341,20 +380,21 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
   B200_REQUIRE(g->nz % 2 == 0 && g->nz >= 4, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz must be even and >= 4");
   B200_REQUIRE(g->xstart >= 2 && g->nx - 1 - g->xend >= 2 && g->ystart >= 1 && g->ny - 1 - g->yend >= 1,
                BOUT_B200_ERR_GUARDS, "elmpb_rhs: needs 2 x guard cells and 1 y guard cell");
-  const int nzp = g->nz / 2;
+  // V = 2 z points per thread (16-byte transactions, 80 registers, 24 warps/SM) or V = 1 (8-byte transactions, fewer
+  // registers, more warps in flight); BOUT_B200_ELM_VEC overrides the default
+  static const int vec_env = getenv("BOUT_B200_ELM_VEC") ? atoi(getenv("BOUT_B200_ELM_VEC")) : 0;
+  int V = vec_env == 1 ? 1 : 2;
+  if (g->nz / V > 256 && V == 1) {
+    V = 2;
+  }
+  const int nzp = g->nz / V;
   B200_REQUIRE(a.filter_n0 < g->nz / 2, BOUT_B200_ERR_ARG,
                "elmpb_rhs: the kept mode must be below the Nyquist mode (see the note on field-aligned terms)");
   int threads, rows;
-  if (nzp <= 256) { // several short rows per CTA when whole warps divide evenly
-    rows = (nzp % 32 == 0) ? 256 / nzp : 1;
-    rows = rows > 8 ? 8 : rows;
-    threads = rows * nzp;
-  } else {
-    B200_REQUIRE(nzp <= 1024 && nzp % 32 == 0, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz too large");
-    rows = 1;
-    threads = nzp;
-  }
-  B200_REQUIRE(threads <= 256, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz > 512 not supported");
+  B200_REQUIRE(nzp <= 256, BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: nz > 512 not supported");
+  rows = (nzp % 32 == 0) ? 256 / nzp : 1; // several short rows per CTA when whole warps divide evenly
+  rows = rows > 8 ? 8 : rows;
+  threads = rows * nzp;
   ElmParams p{};
   p.a = a;
   p.nx = g->nx;
@@ -373,13 +413,19 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
   }
   const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * (p.ye - p.ys + 1);
   const unsigned blocks = static_cast<unsigned>((nrows + rows - 1) / rows);
-  static const int minb = getenv("BOUT_B200_ELM_MINB") ? atoi(getenv("BOUT_B200_ELM_MINB")) : 3;
-  if (minb == 2) {
-    k_elmpb_rhs<2><<<blocks, threads, 0, s>>>(p);
+  static const int minb = getenv("BOUT_B200_ELM_MINB") ? atoi(getenv("BOUT_B200_ELM_MINB")) : 0;
+  if (V == 1) {
+    if (minb == 3) {
+      k_elmpb_rhs<3, 1><<<blocks, threads, 0, s>>>(p);
+    } else {
+      k_elmpb_rhs<4, 1><<<blocks, threads, 0, s>>>(p);
+    }
+  } else if (minb == 2) {
+    k_elmpb_rhs<2, 2><<<blocks, threads, 0, s>>>(p);
   } else if (minb == 4) {
-    k_elmpb_rhs<4><<<blocks, threads, 0, s>>>(p);
+    k_elmpb_rhs<4, 2><<<blocks, threads, 0, s>>>(p);
   } else {
-    k_elmpb_rhs<3><<<blocks, threads, 0, s>>>(p);
+    k_elmpb_rhs<3, 2><<<blocks, threads, 0, s>>>(p);
   }
   B200_LAUNCH_OK();
   return 0;
