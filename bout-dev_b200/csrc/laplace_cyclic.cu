@@ -385,6 +385,117 @@ __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p, const boo
   }
 }
 
+// ---- few long systems (2-D models: ny = 1, e.g. blob2d 1024 x 1024 has 513 systems of 1028 rows) ----------------
+// One thread per system leaves the GPU empty and is bound by the 1000-step dependency chain.  Here ONE CTA
+// solves ONE system by parallel cyclic reduction in shared memory: ceil(log2 n) steps, in each of which every
+// row i eliminates its couplings to rows i -+ s (s = 1, 2, 4, ...), after which x_i = d_i / b_i.  Same rows
+// (lapRow) as the Thomas kernel; a different but equally stable elimination order for these diagonally dominant
+// systems, so solutions agree with the reference's CyclicReduce to round-off (tests: 1e-10).  Periodic-X systems
+// (one rank, n a power of two) wrap the row indices; after the last step (s = n/2) a row's a and c refer to
+// x_i itself.
+__global__ void __launch_bounds__(256) k_lap_pcr(const LapParams p) {
+  extern __shared__ __align__(16) unsigned char pcr_raw[];
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const bool periodic = p.bd.periodic_x != 0; // single rank, n a power of two (checked by the host)
+  cd* buf[2][4]; // [ping-pong][a, b, c, d]
+  for (int h = 0; h < 2; ++h) {
+    for (int q = 0; q < 4; ++q) {
+      buf[h][q] = reinterpret_cast<cd*>(pcr_raw) + static_cast<size_t>(h * 4 + q) * n;
+    }
+  }
+  const int nys = p.ye - p.ys + 1;
+  const int t = blockIdx.x; // system index
+  const int iyl = t / p.nmode, kz = t % p.nmode;
+  const int jy = p.ys + iyl;
+  const long long xs = static_cast<long long>(nys) * p.nmode;
+  const double kwave = kz * 2.0 * M_PI / p.m.zlength;
+  const double* tab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
+  cd* __restrict__ sp = p.spec + t;
+  for (int ix = threadIdx.x; ix < n; ix += blockDim.x) {
+    cd a, b, c, r = ldcd(sp + ix * xs);
+    lapRow(p, tab, ix, jy, kz, kwave, a, b, c, r);
+    if (!periodic && ix == 0) {
+      a = {0.0, 0.0};
+    }
+    if (!periodic && ix == n - 1) {
+      c = {0.0, 0.0};
+    }
+    buf[0][0][ix] = a;
+    buf[0][1][ix] = b;
+    buf[0][2][ix] = c;
+    buf[0][3][ix] = r;
+  }
+  __syncthreads();
+  bool bad = false;
+  int cur = 0;
+  for (int sft = 1; sft < n; sft <<= 1) {
+    cd* const* in = buf[cur];
+    cd* const* out = buf[cur ^ 1];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const cd a = in[0][i], c = in[2][i];
+      cd b = in[1][i], d = in[3][i];
+      cd an = {0.0, 0.0}, cn = {0.0, 0.0};
+      int im = i - sft, ip = i + sft;
+      if (periodic) { // n is a power of two: rows wrap around
+        im &= n - 1;
+        ip &= n - 1;
+      }
+      if (im >= 0) {
+        const cd bm = in[1][im];
+        bad = bad || tiny(bm);
+        const cd k1 = cmul(a, crecip(bm));
+        an = cmul(in[0][im], k1);
+        an = {-an.re, -an.im};
+        b = csub(b, cmul(in[2][im], k1));
+        d = csub(d, cmul(in[3][im], k1));
+      }
+      if (ip < n) {
+        const cd bp = in[1][ip];
+        bad = bad || tiny(bp);
+        const cd k2 = cmul(c, crecip(bp));
+        cn = cmul(in[2][ip], k2);
+        cn = {-cn.re, -cn.im};
+        b = csub(b, cmul(in[0][ip], k2));
+        d = csub(d, cmul(in[3][ip], k2));
+      }
+      out[0][i] = an;
+      out[1][i] = b;
+      out[2][i] = cn;
+      out[3][i] = d;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  // every row is now decoupled: its remaining a and c multiply x_i itself (periodic, s = n) or are zero
+  __shared__ double psum[256];
+  double part = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const cd b = cadd(cadd(buf[cur][0][i], buf[cur][1][i]), buf[cur][2][i]);
+    bad = bad || tiny(b);
+    const cd x = cmul(buf[cur][3][i], crecip(b));
+    buf[cur][3][i] = x;
+    part += x.re;
+  }
+  double avg = 0.0;
+  if (periodic && kz == 0) { // subtract the x-average of the kz = 0 mode (cyclic_laplace.cxx:266-287); uniform branch
+    psum[threadIdx.x] = part;
+    __syncthreads();
+    double sum = 0.0;
+    for (int q = 0; q < static_cast<int>(blockDim.x); ++q) {
+      sum += psum[q];
+    }
+    avg = sum / static_cast<double>(n);
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { // rows this thread wrote itself
+    cd x = buf[cur][3][i];
+    x.re -= avg;
+    sp[i * xs] = x;
+  }
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+
 // ---- isolated systems, fused sweeps: the spectrum never visits HBM -----------------------------------
 // The Thomas recurrence c'_i = c_i / (b_i - a_i c'_{i-1}) depends on the matrix only, not on the
 // right-hand side: k_lap_factor stores inv_i = 1 / (b_i - a_i c'_{i-1}) per (x, y, kz) once
@@ -1401,7 +1512,20 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
     return rc;
   }
   const unsigned sblocks = static_cast<unsigned>((plan.nsys + 127) / 128);
-  if (!lapCoupled(L)) {
+  const int nrows_sys = p.bd.xe - p.bd.xs + 1;
+  const size_t pcr_smem = static_cast<size_t>(8) * nrows_sys * sizeof(cd);
+  static const bool no_pcr = getenv("BOUT_B200_LAP_NO_PCR") != nullptr;
+  const bool pcr_shape = !lapCoupled(L) || (L->periodic_x && (nrows_sys & (nrows_sys - 1)) == 0);
+  if (pcr_shape && !no_pcr && plan.nsys <= 2048 && nrows_sys >= 8 && pcr_smem <= 200 * 1024) {
+    static size_t pcr_attr = 0;
+    if (pcr_smem > 48 * 1024 && pcr_smem > pcr_attr) {
+      B200_CUDA_OK(cudaFuncSetAttribute(k_lap_pcr, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(pcr_smem)));
+      pcr_attr = pcr_smem;
+    }
+    k_lap_pcr<<<static_cast<unsigned>(plan.nsys), 256, pcr_smem, s>>>(p);
+    B200_LAUNCH_OK();
+  } else if (!lapCoupled(L)) {
     k_lap_thomas<<<sblocks, 128, plan.tab_smem, s>>>(p, plan.tab_smem != 0);
     B200_LAUNCH_OK();
   } else { // periodic in X on a single rank: the NXPE = 1 case of the coupled algorithm

@@ -213,7 +213,7 @@ def test_laplace_fused_sweeps_match_three_kernel_path(capi, orc, port, grid, fla
     plain = lap.solve(dev(f), dev(x0)).cpu().numpy()
     # table + (y-dependence check of the coefficients when more than one y row is solved) + rfft + Thomas + irfft
     assert capi.launch_count() - n0 == 4 + int(g.yend > g.ystart)
-    assert rel_err(fused, plain, region) < 1e-13
+    assert rel_err(fused, plain, region) < 1e-12   # plain = cyclic reduction per system (few systems) or Thomas
     want = port.laplace_cyclic(og, m, f, x0=x0, flags=flags, maxmode=maxmode)
     assert rel_err(fused, want, region) < 1e-10
 
