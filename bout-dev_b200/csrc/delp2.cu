@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(128) k_delp2_fft(const Delp2FftParams p) {
 template <int N>
 __global__ void __launch_bounds__(256) k_delp2_fast(const Delp2FftParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int TPR = FftShape<N>::TPR, ROWS = 256 / TPR, BUF = N + 8;
+  constexpr int TPR = FftShape<N>::TPR, BUF = N + 8;
+  const int ROWS = blockDim.x / TPR; // row groups (tasks) per CTA: 256 / TPR, fewer when there are few tasks
   const int rloc = threadIdx.x / TPR, lane = threadIdx.x % TPR;
   cd* base = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(rloc) * 6 * BUF;
   cd* A = base;
@@ -180,23 +181,31 @@ __global__ void __launch_bounds__(256) k_delp2_fast(const Delp2FftParams p) {
 
 template <int N>
 int launchDelp2Fast(Delp2FftParams p, cudaStream_t s) {
-  constexpr int ROWS = 256 / FftShape<N>::TPR;
-  const size_t smem = static_cast<size_t>(ROWS) * 6 * (N + 8) * sizeof(cd);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(k_delp2_fast<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-    attr_set = true;
-  }
+  constexpr int TPR = FftShape<N>::TPR, ROWS_MAX = 256 / TPR;
   const int len = p.xe - p.xs + 1, nyb = p.ye - p.ys + 1;
+  // (y, x-chunk) tasks: enough of them to occupy the SMs; each chunk costs two extra forward transforms, so
+  // chunks shrink (down to 2 rows) only for small problems, where latency, not throughput, is the limit
   int chunk = 32;
-  while (chunk > 8 && static_cast<long long>(nyb) * ((len + chunk - 1) / chunk) < 148LL * 4 * ROWS) {
+  while (chunk > 2 && static_cast<long long>(nyb) * ((len + chunk - 1) / chunk) < 148LL * 4 * ROWS_MAX) {
     chunk /= 2;
   }
   p.chunk = chunk;
   p.nchunks = (len + chunk - 1) / chunk;
   const long long ntasks = static_cast<long long>(nyb) * p.nchunks;
-  k_delp2_fast<N><<<static_cast<unsigned>((ntasks + ROWS - 1) / ROWS), 256, smem, s>>>(p);
+  int rows = ROWS_MAX; // tasks per CTA: spread few tasks over many SMs
+  while (rows > 1 && (ntasks + rows - 1) / rows < 148LL * 2) {
+    rows /= 2;
+  }
+  const int threads = rows * TPR < 32 ? 32 : rows * TPR;
+  const int rows_eff = threads / TPR;
+  const size_t smem = static_cast<size_t>(rows_eff) * 6 * (N + 8) * sizeof(cd);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_delp2_fast<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    attr = smem;
+  }
+  k_delp2_fast<N><<<static_cast<unsigned>((ntasks + rows_eff - 1) / rows_eff), threads, smem, s>>>(p);
   B200_LAUNCH_OK();
   return 0;
 }
