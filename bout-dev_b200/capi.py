@@ -491,14 +491,22 @@ class CElmpbRhs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "dx", "dy", "dz", "J", "g_22", "g_12", "g_23", "Bxy", "B0", "J0", "P0", "phi0", "b0xcv_x", "b0xcv_y",
         "b0xcv_z", "U", "P", "Psi", "phi", "Jpar", "d2Jpar", "eta", "U_up", "U_dn", "P_up", "P_dn", "Psi_up",
-        "Psi_dn", "phi_up", "phi_dn", "J_up", "J_dn")] + \
-        [("hyperresist", C.c_double), ("keep_U", C.c_double), ("keep_P", C.c_double), ("keep_Psi", C.c_double),
+        "Psi_dn", "phi_up", "phi_dn", "J_up", "J_dn", "U_mode", "P_mode", "J_mode", "zShift")] + \
+        [("zlength", C.c_double), ("hyperresist", C.c_double), ("keep_U", C.c_double), ("keep_P", C.c_double), ("keep_Psi", C.c_double),
          ("eta_is2d", C.c_int), ("filter_n0", C.c_int)] + \
         [(n, C.c_void_p) for n in ("ddt_U", "ddt_P", "ddt_Psi", "rk_start_U", "rk_start_P", "rk_start_Psi",
                                    "rk_stage_U", "rk_stage_P", "rk_stage_Psi")] + [("rk_cdt", C.c_double)]
 
 
-def elmpb_rhs(g: Grid, fields: dict, hyperresist, filter_n0, keep=(1.0, 1.0, 1.0), rk=None):
+def row_mode(g: Grid, fields, n0, out=None):
+    """One Fourier coefficient per (x,y) row: list of complex [nx][ny] tensors (stored as float64 [nx][ny][2])."""
+    if out is None:
+        out = [torch.zeros(g.shape2 + (2,), dtype=torch.float64, device=fields[0].device) for _ in fields]
+    _check(lib.bout_b200_row_mode(C.byref(g.c), len(fields), _ptr_array(fields), n0, _ptr_array(out), _stream()))
+    return out
+
+
+def elmpb_rhs(g: Grid, fields: dict, hyperresist, filter_n0, keep=(1.0, 1.0, 1.0), rk=None, zlength=0.0):
     """fields: name -> tensor for every pointer member of bout_b200_elmpb_rhs_args (eta may be 2-D).
     rk = (start fields (U, P, Psi), stage-state fields (U, P, Psi), c * dt) or None."""
     c = CElmpbRhs()
@@ -512,6 +520,7 @@ def elmpb_rhs(g: Grid, fields: dict, hyperresist, filter_n0, keep=(1.0, 1.0, 1.0
             setattr(c, "rk_stage_" + nm, b.data_ptr())
         c.rk_cdt = cdt
     c.hyperresist = hyperresist
+    c.zlength = zlength
     c.keep_U, c.keep_P, c.keep_Psi = keep
     c.eta_is2d = int(fields["eta"].dim() == 2)
     c.filter_n0 = filter_n0

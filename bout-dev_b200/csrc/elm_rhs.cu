@@ -84,8 +84,16 @@ __device__ __forceinline__ F3<V> loadF3(const double* __restrict__ f, const doub
   ldv<V>(row - plane + z0, r.xm);
   ldv<V>(row + plane + z0, r.xp);
   ldv<V>(row + 2 * plane + z0, r.xpp);
-  ldv<V>(fup + (i2 + 1) * nz + z0, r.up); // yup holds the y+1 neighbour at row y+1
-  ldv<V>(fdn + (i2 - 1) * nz + z0, r.dn);
+  if (fup != nullptr) { // (no slices: their y-derivative terms are added in mode space, see RowC::x*)
+    ldv<V>(fup + (i2 + 1) * nz + z0, r.up); // yup holds the y+1 neighbour at row y+1
+    ldv<V>(fdn + (i2 - 1) * nz + z0, r.dn);
+  } else {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      r.up[j] = 0.0;
+      r.dn[j] = 0.0;
+    }
+  }
   return r;
 }
 
@@ -98,6 +106,7 @@ struct RowC {
   double dJ0[2], dP0[2];                // WENO3 x-derivative factor of J0 / P0 for vx <= 0 ([0]) and vx > 0 ([1])
   double dJ0y, dP0y;                    // J0(y+1) - J0(y-1), P0(y+1) - P0(y-1)
   double bcx, bcy, bcz;
+  double xU[2], xP[2]; // mode-space additions to the row sums of ddt(U), ddt(P) (re, im), zero on the slice path
 };
 
 // b0xGrad_dot_Grad(f3d, A2d): dAx = the two WENO3 factors of A's x stencil, dAy = A(y+1) - A(y-1)
@@ -218,6 +227,30 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
     c.bcx = __ldg(a.b0xcv_x + i2);
     c.bcy = __ldg(a.b0xcv_y + i2);
     c.bcz = __ldg(a.b0xcv_z + i2);
+    c.xU[0] = c.xU[1] = c.xP[0] = c.xP[1] = 0.0;
+    if (a.U_mode != nullptr) {
+      // mode n0 of the slice pair of a field: M(y+1) exp(-i k (zs(y) - zs(y+1))) - M(y-1) exp(-i k (zs(y) - zs(y-1)))
+      const double kwave = a.filter_n0 * 2.0 * M_PI / a.zlength;
+      const double zs0 = __ldg(a.zShift + i2);
+      double sn, cs;
+      sincos(kwave * (zs0 - __ldg(a.zShift + i2 + 1)), &sn, &cs);
+      const cd pu = {cs, -sn};
+      sincos(kwave * (zs0 - __ldg(a.zShift + i2 - 1)), &sn, &cs);
+      const cd pd = {cs, -sn};
+      auto diff = [&](const double* __restrict__ mode) {
+        const cd mu = {__ldg(mode + 2 * (i2 + 1)), __ldg(mode + 2 * (i2 + 1) + 1)};
+        const cd md = {__ldg(mode + 2 * (i2 - 1)), __ldg(mode + 2 * (i2 - 1) + 1)};
+        return csub(cmul(mu, pu), cmul(md, pd));
+      };
+      const cd dU = diff(a.U_mode), dP = diff(a.P_mode), dJ = diff(a.J_mode);
+      const double cy = c.vy0 * 0.5 * c.rdy * c.rjs;     // y-advection by the phi0 velocity (b0x2d3d)
+      const double cP = 0.5 * c.rdy * c.bcy;             // b0xcv.y DDY(P)
+      const double cJ = 0.5 * c.gpar * c.B0sq;           // B0^2 Grad_par(Jpar)
+      c.xU[0] = -cy * dU.re + cP * dP.re - cJ * dJ.re;
+      c.xU[1] = -cy * dU.im + cP * dP.im - cJ * dJ.im;
+      c.xP[0] = -cy * dP.re;
+      c.xP[1] = -cy * dP.im;
+    }
     rows[rloc] = c;
   }
   __syncthreads();
@@ -265,8 +298,15 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   {
     double J[V], Jup[V], Jdn[V], d2J[V], eta[V];
     ldv<V>(a.Jpar + i2 * nz + z0, J);
-    ldv<V>(a.J_up + (i2 + 1) * nz + z0, Jup);
-    ldv<V>(a.J_dn + (i2 - 1) * nz + z0, Jdn);
+    if (a.J_up != nullptr) {
+      ldv<V>(a.J_up + (i2 + 1) * nz + z0, Jup);
+      ldv<V>(a.J_dn + (i2 - 1) * nz + z0, Jdn);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        Jup[j] = Jdn[j] = 0.0;
+      }
+    }
     ldv<V>(a.d2Jpar + i2 * nz + z0, d2J);
     if (a.eta_is2d) {
 #pragma unroll
@@ -317,6 +357,10 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   if (!active) {
     return;
   }
+  acc[0] += m.xU[0];
+  acc[1] += m.xU[1];
+  acc[2] += m.xP[0];
+  acc[3] += m.xP[1];
   const double inv = 1.0 / nz;
   const double mult = n0 == 0 ? 1.0 : 2.0;
   auto back = [&](double xr, double xi, double keep, double* __restrict__ out, const double* __restrict__ start,
@@ -355,11 +399,20 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
   B200_REQUIRE(args != nullptr, BOUT_B200_ERR_ARG, "elmpb_rhs: null arguments");
   const bout_b200_elmpb_rhs_args& a = *args;
   const void* ptrs[] = {a.dx, a.dy, a.dz, a.J, a.g_22, a.g_12, a.g_23, a.Bxy, a.B0, a.J0, a.P0, a.phi0, a.b0xcv_x,
-                        a.b0xcv_y, a.b0xcv_z, a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar, a.eta, a.U_up, a.U_dn,
-                        a.P_up, a.P_dn, a.Psi_up, a.Psi_dn, a.phi_up, a.phi_dn, a.J_up, a.J_dn, a.ddt_U, a.ddt_P,
-                        a.ddt_Psi};
+                        a.b0xcv_y, a.b0xcv_z, a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar, a.eta,
+                        a.Psi_up, a.Psi_dn, a.phi_up, a.phi_dn, a.ddt_U, a.ddt_P, a.ddt_Psi};
   for (const void* q : ptrs) {
     B200_REQUIRE(q != nullptr, BOUT_B200_ERR_ARG, "elmpb_rhs: null field");
+  }
+  const bool modes = a.U_mode != nullptr;
+  if (modes) {
+    B200_REQUIRE(a.P_mode && a.J_mode && a.zShift && a.zlength > 0.0 && a.filter_n0 >= 0, BOUT_B200_ERR_ARG,
+                 "elmpb_rhs: the mode path needs U_mode, P_mode, J_mode, zShift, zlength and the in-kernel filter");
+    B200_REQUIRE(!a.U_up && !a.U_dn && !a.P_up && !a.P_dn && !a.J_up && !a.J_dn, BOUT_B200_ERR_ARG,
+                 "elmpb_rhs: give either the U, P, Jpar slices or their modes, not both");
+  } else {
+    B200_REQUIRE(a.U_up && a.U_dn && a.P_up && a.P_dn && a.J_up && a.J_dn, BOUT_B200_ERR_ARG,
+                 "elmpb_rhs: null slice");
   }
   const void* vec[] = {a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar, a.U_up, a.U_dn, a.P_up, a.P_dn, a.Psi_up, a.Psi_dn,
                        a.phi_up, a.phi_dn, a.J_up, a.J_dn, a.ddt_U, a.ddt_P, a.ddt_Psi};

@@ -419,6 +419,44 @@ int launchZfft(const bout_b200_grid* g, int region, ZfftParams p, void* stream, 
   return 0;
 }
 
+// ---- one Fourier mode of every (x,y) row: M = sum_j f_j exp(-2 pi i n0 j / nz) (unnormalised) ---------------
+// Where a term is linear in a field with z-independent coefficients and the result is filtered to the single
+// mode n0 afterwards (elm-pb: the y-derivative terms of U, P, Jpar), only this one coefficient of each row is
+// needed instead of the field's full parallel slices.
+struct RowModeParams {
+  const double* f[4];
+  double* out[4];
+  const cd* __restrict__ tw;
+  long long nrows;
+  int nf, nz, n0;
+};
+__global__ void __launch_bounds__(256) k_row_mode(const RowModeParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (w >= p.nrows * p.nf) {
+    return;
+  }
+  const int fi = static_cast<int>(w / p.nrows);
+  const long long row = w % p.nrows;
+  const double* __restrict__ src = p.f[fi] + row * p.nz;
+  double re = 0.0, im = 0.0;
+  for (int j = lane; j < p.nz; j += 32) {
+    const cd t = p.tw[(static_cast<long long>(p.n0) * j) % p.nz];
+    const double v = __ldg(src + j);
+    re += v * t.re;
+    im += v * t.im;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if (lane == 0) {
+    p.out[fi][2 * row] = re;
+    p.out[fi][2 * row + 1] = im;
+  }
+}
+
 // ---- DC: z-mean of every (x,y) row (src/field/field3d.cxx:785-803) --------------------------
 __global__ void __launch_bounds__(256) k_dc(const double* __restrict__ f, double* __restrict__ out,
                                             long long nrows, int nz) {
@@ -605,6 +643,35 @@ extern "C" int bout_b200_boundary_zerolaplace(const bout_b200_grid* g, int side,
   p.bdir = side == 0 ? -1 : 1;
   const Box b = side == 0 ? Box{0, g->xstart - 1, lo, hi} : Box{g->xend + 1, g->nx - 1, lo, hi};
   return launchZfft(g, BOUT_B200_RGN_ALL, p, stream, &b);
+}
+
+extern "C" int bout_b200_row_mode(const bout_b200_grid* g, int nfields, const double* const* fields, int n0,
+                                  double* const* out_complex2d, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(fields && out_complex2d && nfields >= 1 && nfields <= 4 && n0 >= 0 && n0 <= g->nz / 2,
+               BOUT_B200_ERR_ARG, "row_mode: bad argument");
+  RowModeParams p{};
+  for (int i = 0; i < nfields; ++i) {
+    B200_REQUIRE(fields[i] && out_complex2d[i], BOUT_B200_ERR_ARG, "row_mode: null field");
+    p.f[i] = fields[i];
+    p.out[i] = out_complex2d[i];
+  }
+  cudaStream_t s = asStream(stream);
+  int st = 0;
+  p.tw = twiddleTable(g->nz, s, &st);
+  if (st != 0) {
+    return st;
+  }
+  p.nrows = static_cast<long long>(g->nx) * g->ny;
+  p.nf = nfields;
+  p.nz = g->nz;
+  p.n0 = n0;
+  const long long warps = p.nrows * nfields;
+  k_row_mode<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
 }
 
 extern "C" int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* stream) {

@@ -187,6 +187,7 @@ class ELMpb:
         self.ddt_U, self.ddt_P, self.ddt_Psi = z(), z(), z()
         self.fused = True             # one kernel for the three equations + filter (csrc/elm_rhs.cu)
         self.two_streams = os.environ.get("BOUT_B200_ELM_STREAMS", "2") != "1"
+        self.mode_slices = os.environ.get("BOUT_B200_ELM_MODES", "1") != "0"
         self._side = None
         self.kernel_events = None     # bench.py: (start, end) CUDA events of the fused kernel
         self.compute_jpar2 = True     # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
@@ -261,6 +262,8 @@ class ELMpb:
             self._buf = {n: (z(), z()) for n in ("U", "P", "Psi", "phi", "J")}   # (yup, ydown) per field
             self._buf["sm"] = z()
             self._buf["d2J"] = z()
+            for n in ("mU", "mP", "mJ"):   # one Fourier coefficient per (x,y) row, complex
+                self._buf[n] = torch.zeros(self.g.shape2 + (2,), dtype=torch.float64, device=self.dev)
         return self._buf
 
     def _slices_into(self, f, name):
@@ -281,6 +284,9 @@ class ELMpb:
         Psi = self.Psi if Psi is None else Psi
         ew = capi.elementwise
         buf = self._buffers()
+        fused = self.fused and 0 <= self.filter_z_mode < g.nz // 2
+        # y-derivative terms of U, P, Jpar in mode space (one Fourier coefficient per row) instead of full slices
+        modes = fused and self.mode_slices
         self.pre_rhs(U, P, Psi)
         self._halo([U, P, Psi])                                               # mesh->communicate(comms)
         # The potential chain (LaplaceCyclic -> phi update -> communicate -> slices) runs on a second stream: its
@@ -299,7 +305,12 @@ class ELMpb:
             (sphi,) = self._comm_into([self.phi], ["phi"])
             capi.boundary(g, "extend", "xin", self.phi)                           # :1498-1516
             capi.boundary(g, "extend", "xout", self.phi)
-        sU, sP, sPsi = [self._slices_into(f, n) for f, n in ((U, "U"), (P, "P"), (Psi, "Psi"))]
+        if modes:
+            sPsi = self._slices_into(Psi, "Psi")
+            capi.row_mode(g, [U, P], self.filter_z_mode, out=[buf["mU"], buf["mP"]])
+            sU = sP = None
+        else:
+            sU, sP, sPsi = [self._slices_into(f, n) for f, n in ((U, "U"), (P, "P"), (Psi, "Psi"))]
         # Jpar = Delp2(Psi); BC; communicate; smooth_x; BC; communicate         :1518-1563
         self.delp.delp2(Psi, out=self.Jpar)
         self._bc_j(self.Jpar)
@@ -308,7 +319,12 @@ class ELMpb:
         self._halo([sm])                                                      # smooth_x communicates its result
         buf["sm"], self.Jpar = self.Jpar, sm                                  # Jpar = smooth_x(Jpar)
         self._bc_j(self.Jpar)
-        (sJ,) = self._comm_into([self.Jpar], ["J"])
+        if modes:
+            self._halo([self.Jpar])
+            capi.row_mode(g, [self.Jpar], self.filter_z_mode, out=[buf["mJ"]])
+            sJ = None
+        else:
+            (sJ,) = self._comm_into([self.Jpar], ["J"])
         # Delp2(Jpar): Jpar2 (:1565-1572) and the hyper-resistivity term (:1717-1723) evaluate the same field
         d2J = self.delp.delp2(self.Jpar, out=buf["d2J"])
         if self.compute_jpar2:
@@ -317,7 +333,7 @@ class ELMpb:
             self._halo([self.Jpar2])
         if two:
             main.wait_stream(self._side)
-        if self.fused and self.filter_z_mode >= 0 and self.filter_z_mode < g.nz // 2:
+        if fused:
             keep = [1.0, 1.0, 1.0]
             if self.low_pass_z > 0:
                 for i, zonal in enumerate((self.zonal_flow, self.zonal_bkgd, self.zonal_field)):
@@ -325,14 +341,17 @@ class ELMpb:
                         keep[i] = 0.0
             fields = dict(m)
             fields.update(eq)
-            fields.update(U=U, P=P, Psi=Psi, phi=self.phi, Jpar=self.Jpar, d2Jpar=d2J,
-                          U_up=sU[0][0], U_dn=sU[1][0], P_up=sP[0][0], P_dn=sP[1][0], Psi_up=sPsi[0][0],
-                          Psi_dn=sPsi[1][0], phi_up=sphi[0][0], phi_dn=sphi[1][0], J_up=sJ[0][0], J_dn=sJ[1][0],
+            fields.update(U=U, P=P, Psi=Psi, phi=self.phi, Jpar=self.Jpar, d2Jpar=d2J, Psi_up=sPsi[0][0],
+                          Psi_dn=sPsi[1][0], phi_up=sphi[0][0], phi_dn=sphi[1][0],
                           ddt_U=self.ddt_U, ddt_P=self.ddt_P, ddt_Psi=self.ddt_Psi)
+            if modes:
+                fields.update(U_mode=buf["mU"], P_mode=buf["mP"], J_mode=buf["mJ"], zShift=self.zs)
+            else:
+                fields.update(U_up=sU[0][0], U_dn=sU[1][0], P_up=sP[0][0], P_dn=sP[1][0], J_up=sJ[0][0], J_dn=sJ[1][0])
             if self.kernel_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            capi.elmpb_rhs(g, fields, self.hyperresist, self.filter_z_mode, keep=tuple(keep), rk=rk)
+            capi.elmpb_rhs(g, fields, self.hyperresist, self.filter_z_mode, keep=tuple(keep), rk=rk, zlength=self.zl)
             rk = None
             if self.kernel_events is not None:
                 e1.record()

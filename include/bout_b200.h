@@ -175,6 +175,11 @@ int bout_b200_b0xgrad_dot_grad(const bout_b200_grid* g, const bout_b200_b0xgrad*
                                const double* const* a_yup, const double* const* a_ydown,
                                double* out, double* yterm_out, void* stream);
 
+/* One Fourier coefficient per (x,y) row of up to 4 fields: out[f][x][y] = sum_j f(x,y,j) exp(-2 pi i n0 j / nz)
+ * (complex, interleaved re/im, unnormalised), RGN_ALL. */
+int bout_b200_row_mode(const bout_b200_grid* g, int nfields, const double* const* fields, int n0,
+                       double* const* out_complex2d, void* stream);
+
 /* ---- fused elm-pb right-hand side (a18: examples/elm-pb/elm_pb.cxx:1674-1955, shipped switch set) --------
  * ONE kernel for ddt(Psi), ddt(U), ddt(P) of the linear 3-field model incl. the final filter(., n0) +
  * lowPass: five b0xGrad_dot_Grad brackets (3D x 2D and 2D x 3D, difops.cxx:563-601), b0xcv . Grad(P),
@@ -192,6 +197,13 @@ typedef struct bout_b200_elmpb_rhs_args {
   const double *U, *P, *Psi, *phi, *Jpar, *d2Jpar;                           /* Field3D */
   const double* eta;                                                         /* Field3D, or Field2D if eta_is2d */
   const double *U_up, *U_dn, *P_up, *P_dn, *Psi_up, *Psi_dn, *phi_up, *phi_dn, *J_up, *J_dn;
+  /* Alternative to the U, P, Jpar slices (all three or none; needs filter_n0 >= 0): their y-derivative terms are
+   * linear with z-independent coefficients, so after the filter only mode filter_n0 of each neighbour row
+   * matters: U_mode / P_mode / J_mode = bout_b200_row_mode(., filter_n0) of the communicated fields (complex
+   * [nx][ny]), shifted between the rows' frames with zShift / zlength as ShiftedMetric does.  With these set
+   * the six *_up / *_dn pointers of U, P, Jpar may be NULL. */
+  const double *U_mode, *P_mode, *J_mode, *zShift;
+  double zlength;
   double hyperresist;
   double keep_U, keep_P, keep_Psi;
   int eta_is2d;

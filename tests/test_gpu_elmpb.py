@@ -50,10 +50,13 @@ def make_model(gold):
     return g, model
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, "slices", False])
 def test_elmpb_rhs_matches_reference(gold, fused):
+    """fused = True: one kernel, y-derivative terms of U, P, Jpar in mode space; "slices": one kernel with the full
+    parallel slices of all five fields; False: operator by operator."""
     g, m = make_model(gold)
-    m.fused = fused
+    m.fused = bool(fused)
+    m.mode_slices = fused is True
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     m.set_state(dev(gold["rhs_in_U"]), dev(gold["rhs_in_P"]), dev(gold["rhs_in_Psi"]))
     m.rhs()
