@@ -313,15 +313,15 @@ ELM = dict(nx=516, ny=64, nz=256)   # BASELINE configs[4]: 516 x 64 x 256 (nx wi
 ELM_DT = 1e-3
 ELM_WORKLOAD = ("elm-pb linear 3-field reduced-MHD RHS (shipped [highbeta] switches), 512x64x256 interior points per "
                 "GPU (516x68x256 with guards), synthetic shifted-metric tokamak grid, zperiod 15, RK4")
-# Algorithmic bytes per interior point of the fused kernel k_elmpb_rhs: reads U, P, Psi, phi, Jpar,
-# Delp2(Jpar), eta (7 x 8) + the parallel slices of Psi and phi (32), writes the three time derivatives (24)
-ELM_FUSED_BPP = 112.0
+# Algorithmic bytes per interior point of the fused kernel k_elmpb_rhs: reads U, P, Psi, phi, Jpar
+# (5 x 8) + the parallel slices of Psi and phi (32), writes the three time derivatives (24)
+ELM_FUSED_BPP = 96.0
 # inside an RK4 step three of the four launches also read the step's start state and write the next stage state
-# (3 fields x 16 B): (3 * 160 + 112) / 4
-ELM_FUSED_BPP_RK4 = (3 * 160.0 + 112.0) / 4
+# (3 fields x 16 B): (3 * 144 + 96) / 4
+ELM_FUSED_BPP_RK4 = (3 * 144.0 + 96.0) / 4
 # Whole elm-pb RHS pass list: slices of Psi, phi 2 x 24, row modes of U, P, Jpar 3 x 8,
-# solve 16, phi update 24, Delp2 2 x 16, smooth_x 16, Jpar2 copy 16, fused 112
-ELM_RHS_BPP = 2 * 24 + 3 * 8 + 16 + 24 + 2 * 16 + 16 + 16 + 112   # = 288; + 36 per RHS of RK stage traffic in a step
+# solve 16, phi update 24, Delp2(Psi) 16, smooth_x 16, fused 96
+ELM_RHS_BPP = 2 * 24 + 3 * 8 + 16 + 24 + 16 + 16 + 96   # = 240; + 36 per RHS of RK stage traffic in a step
 
 
 def event_time(torch, fn, reps, warm=2):

@@ -491,8 +491,10 @@ class CElmpbRhs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "dx", "dy", "dz", "J", "g_22", "g_12", "g_23", "Bxy", "B0", "J0", "P0", "phi0", "b0xcv_x", "b0xcv_y",
         "b0xcv_z", "U", "P", "Psi", "phi", "Jpar", "d2Jpar", "eta", "U_up", "U_dn", "P_up", "P_dn", "Psi_up",
-        "Psi_dn", "phi_up", "phi_dn", "J_up", "J_dn", "U_mode", "P_mode", "J_mode", "zShift")] + \
-        [("zlength", C.c_double), ("hyperresist", C.c_double), ("keep_U", C.c_double), ("keep_P", C.c_double), ("keep_Psi", C.c_double),
+        "Psi_dn", "phi_up", "phi_dn", "J_up", "J_dn", "U_mode", "P_mode", "J_mode", "zShift",
+        "g11", "g33", "g13", "G1", "G3")] + \
+        [("delp2_all_terms", C.c_int), ("delp2_nonuniform", C.c_int), ("zlength", C.c_double),
+         ("hyperresist", C.c_double), ("keep_U", C.c_double), ("keep_P", C.c_double), ("keep_Psi", C.c_double),
          ("eta_is2d", C.c_int), ("filter_n0", C.c_int)] + \
         [(n, C.c_void_p) for n in ("ddt_U", "ddt_P", "ddt_Psi", "rk_start_U", "rk_start_P", "rk_start_Psi",
                                    "rk_stage_U", "rk_stage_P", "rk_stage_Psi")] + [("rk_cdt", C.c_double)]
@@ -521,6 +523,7 @@ def elmpb_rhs(g: Grid, fields: dict, hyperresist, filter_n0, keep=(1.0, 1.0, 1.0
         c.rk_cdt = cdt
     c.hyperresist = hyperresist
     c.zlength = zlength
+    c.delp2_all_terms, c.delp2_nonuniform = 1, 1     # the default Laplacian instance Delp2 uses
     c.keep_U, c.keep_P, c.keep_Psi = keep
     c.eta_is2d = int(fields["eta"].dim() == 2)
     c.filter_n0 = filter_n0

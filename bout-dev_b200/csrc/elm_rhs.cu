@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "fft.cuh"
+#include "laplace_coefs.cuh"
 #include "stencil_ops.cuh"
 
 namespace b200 {
@@ -107,6 +108,7 @@ struct RowC {
   double dJ0y, dP0y;                    // J0(y+1) - J0(y-1), P0(y+1) - P0(y-1)
   double bcx, bcy, bcz;
   double xU[2], xP[2]; // mode-space additions to the row sums of ddt(U), ddt(P) (re, im), zero on the slice path
+  double xPsi[2];      // likewise ddt(Psi): -hyperresist eta Delp2(Jpar) evaluated on the row modes of Jpar
 };
 
 // b0xGrad_dot_Grad(f3d, A2d): dAx = the two WENO3 factors of A's x stencil, dAy = A(y+1) - A(y-1)
@@ -227,7 +229,30 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
     c.bcx = __ldg(a.b0xcv_x + i2);
     c.bcy = __ldg(a.b0xcv_y + i2);
     c.bcz = __ldg(a.b0xcv_z + i2);
-    c.xU[0] = c.xU[1] = c.xP[0] = c.xP[1] = 0.0;
+    c.xU[0] = c.xU[1] = c.xP[0] = c.xP[1] = c.xPsi[0] = c.xPsi[1] = 0.0;
+    if (a.U_mode != nullptr && a.d2Jpar == nullptr) {
+      // Delp2(Jpar) of mode n0 straight from the row modes (Coordinates::Delp2, coordinates.cxx:1662-1699:
+      // a J(x-1) + b J(x) + c J(x+1) with Laplacian::tridagCoefs); eta is a Field2D on this path
+      LapCoefs L{};
+      L.dx = a.dx;
+      L.g11 = a.g11;
+      L.g33 = a.g33;
+      L.g13 = a.g13;
+      L.G1 = a.G1;
+      L.G3 = a.G3;
+      L.zlength = a.zlength;
+      L.nx = p.nx;
+      L.ny = ny;
+      L.all_terms = a.delp2_all_terms;
+      L.nonuniform = a.delp2_nonuniform;
+      cd ca, cb, cc;
+      tridagCoefs(L, x, y, a.filter_n0 * 2.0 * M_PI / a.zlength, false, false, ca, cb, cc);
+      auto md = [&](long long q) { return cd{__ldg(a.J_mode + 2 * q), __ldg(a.J_mode + 2 * q + 1)}; };
+      const cd d2 = cadd(cadd(cmul(ca, md(i2 - ny)), cmul(cb, md(i2))), cmul(cc, md(i2 + ny)));
+      const double he = a.hyperresist * __ldg(a.eta + i2);
+      c.xPsi[0] = -he * d2.re;
+      c.xPsi[1] = -he * d2.im;
+    }
     if (a.U_mode != nullptr) {
       // mode n0 of the slice pair of a field: M(y+1) exp(-i k (zs(y) - zs(y+1))) - M(y-1) exp(-i k (zs(y) - zs(y-1)))
       const double kwave = a.filter_n0 * 2.0 * M_PI / a.zlength;
@@ -298,6 +323,14 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   {
     double J[V], Jup[V], Jdn[V], d2J[V], eta[V];
     ldv<V>(a.Jpar + i2 * nz + z0, J);
+    if (a.d2Jpar != nullptr) {
+      ldv<V>(a.d2Jpar + i2 * nz + z0, d2J);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        d2J[j] = 0.0;
+      }
+    }
     if (a.J_up != nullptr) {
       ldv<V>(a.J_up + (i2 + 1) * nz + z0, Jup);
       ldv<V>(a.J_dn + (i2 - 1) * nz + z0, Jdn);
@@ -307,7 +340,6 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
         Jup[j] = Jdn[j] = 0.0;
       }
     }
-    ldv<V>(a.d2Jpar + i2 * nz + z0, d2J);
     if (a.eta_is2d) {
 #pragma unroll
       for (int j = 0; j < V; ++j) {
@@ -361,6 +393,8 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   acc[1] += m.xU[1];
   acc[2] += m.xP[0];
   acc[3] += m.xP[1];
+  acc[4] += m.xPsi[0];
+  acc[5] += m.xPsi[1];
   const double inv = 1.0 / nz;
   const double mult = n0 == 0 ? 1.0 : 2.0;
   auto back = [&](double xr, double xi, double keep, double* __restrict__ out, const double* __restrict__ start,
@@ -399,12 +433,17 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
   B200_REQUIRE(args != nullptr, BOUT_B200_ERR_ARG, "elmpb_rhs: null arguments");
   const bout_b200_elmpb_rhs_args& a = *args;
   const void* ptrs[] = {a.dx, a.dy, a.dz, a.J, a.g_22, a.g_12, a.g_23, a.Bxy, a.B0, a.J0, a.P0, a.phi0, a.b0xcv_x,
-                        a.b0xcv_y, a.b0xcv_z, a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar, a.eta,
+                        a.b0xcv_y, a.b0xcv_z, a.U, a.P, a.Psi, a.phi, a.Jpar, a.eta,
                         a.Psi_up, a.Psi_dn, a.phi_up, a.phi_dn, a.ddt_U, a.ddt_P, a.ddt_Psi};
   for (const void* q : ptrs) {
     B200_REQUIRE(q != nullptr, BOUT_B200_ERR_ARG, "elmpb_rhs: null field");
   }
   const bool modes = a.U_mode != nullptr;
+  if (a.d2Jpar == nullptr) {
+    B200_REQUIRE(modes && a.eta_is2d && a.g11 && a.g33 && a.g13 && (!a.delp2_all_terms || (a.G1 && a.G3)),
+                 BOUT_B200_ERR_ARG,
+                 "elmpb_rhs: without d2Jpar the mode path, a Field2D eta and the Delp2 metric (g11, g33, g13, G1, G3) are needed");
+  }
   if (modes) {
     B200_REQUIRE(a.P_mode && a.J_mode && a.zShift && a.zlength > 0.0 && a.filter_n0 >= 0, BOUT_B200_ERR_ARG,
                  "elmpb_rhs: the mode path needs U_mode, P_mode, J_mode, zShift, zlength and the in-kernel filter");
@@ -414,7 +453,7 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
     B200_REQUIRE(a.U_up && a.U_dn && a.P_up && a.P_dn && a.J_up && a.J_dn, BOUT_B200_ERR_ARG,
                  "elmpb_rhs: null slice");
   }
-  const void* vec[] = {a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar, a.U_up, a.U_dn, a.P_up, a.P_dn, a.Psi_up, a.Psi_dn,
+  const void* vec[] = {a.U, a.P, a.Psi, a.phi, a.Jpar, a.d2Jpar /* may be NULL */, a.U_up, a.U_dn, a.P_up, a.P_dn, a.Psi_up, a.Psi_dn,
                        a.phi_up, a.phi_dn, a.J_up, a.J_dn, a.ddt_U, a.ddt_P, a.ddt_Psi};
   for (const void* q : vec) {
     B200_REQUIRE(aligned16(q), BOUT_B200_ERR_UNSUPPORTED, "elmpb_rhs: fields must be 16-byte aligned");

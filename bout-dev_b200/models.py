@@ -190,7 +190,9 @@ class ELMpb:
         self.mode_slices = os.environ.get("BOUT_B200_ELM_MODES", "1") != "0"
         self._side = None
         self.kernel_events = None     # bench.py: (start, end) CUDA events of the fused kernel
-        self.compute_jpar2 = True     # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
+        e3 = self.eq["eta"]
+        self.eta2d = e3[:, :, 0].contiguous() if (e3.dim() == 3 and bool((e3 == e3[:, :, :1]).all())) else None
+        self.compute_jpar2 = False    # the reference evaluates Jpar2 = Delp2(Jpar) although no shipped term reads it
 
     @classmethod
     def from_setup(cls, s, device="cuda", mesh=None, **kw):
@@ -325,8 +327,12 @@ class ELMpb:
             sJ = None
         else:
             (sJ,) = self._comm_into([self.Jpar], ["J"])
-        # Delp2(Jpar): Jpar2 (:1565-1572) and the hyper-resistivity term (:1717-1723) evaluate the same field
-        d2J = self.delp.delp2(self.Jpar, out=buf["d2J"])
+        # Delp2(Jpar): Jpar2 (:1565-1572) and the hyper-resistivity term (:1717-1723) evaluate the same field.
+        # With a z-independent eta the term is linear with z-independent coefficients, so (after filter_z) the
+        # fused kernel forms mode n0 of Delp2(Jpar) from the row modes of Jpar and the full-field pass is skipped
+        # unless Jpar2 itself is wanted (no shipped term reads it and it is not an output).
+        skip_d2j = modes and self.eta2d is not None and not self.compute_jpar2
+        d2J = None if skip_d2j else self.delp.delp2(self.Jpar, out=buf["d2J"])
         if self.compute_jpar2:
             self.Jpar2.copy_(d2J)
             self._bc_j(self.Jpar2)
@@ -341,7 +347,11 @@ class ELMpb:
                         keep[i] = 0.0
             fields = dict(m)
             fields.update(eq)
-            fields.update(U=U, P=P, Psi=Psi, phi=self.phi, Jpar=self.Jpar, d2Jpar=d2J, Psi_up=sPsi[0][0],
+            if d2J is not None:
+                fields["d2Jpar"] = d2J
+            else:
+                fields["eta"] = self.eta2d
+            fields.update(U=U, P=P, Psi=Psi, phi=self.phi, Jpar=self.Jpar, Psi_up=sPsi[0][0],
                           Psi_dn=sPsi[1][0], phi_up=sphi[0][0], phi_dn=sphi[1][0],
                           ddt_U=self.ddt_U, ddt_P=self.ddt_P, ddt_Psi=self.ddt_Psi)
             if modes:

@@ -203,6 +203,11 @@ typedef struct bout_b200_elmpb_rhs_args {
    * [nx][ny]), shifted between the rows' frames with zShift / zlength as ShiftedMetric does.  With these set
    * the six *_up / *_dn pointers of U, P, Jpar may be NULL. */
   const double *U_mode, *P_mode, *J_mode, *zShift;
+  /* With the modes AND a Field2D eta, d2Jpar may be NULL: Delp2(Jpar) of mode filter_n0 is then formed from
+   * J_mode inside the kernel with Laplacian::tridagCoefs of the default Laplacian (its all_terms / nonuniform
+   * settings below and the Field2D metric g11, g33, g13, G1, G3), and no Delp2(Jpar) pass is needed. */
+  const double *g11, *g33, *g13, *G1, *G3;
+  int delp2_all_terms, delp2_nonuniform;
   double zlength;
   double hyperresist;
   double keep_U, keep_P, keep_Psi;
