@@ -493,7 +493,7 @@ class CElmpbRhs(C.Structure):
         "b0xcv_z", "U", "P", "Psi", "phi", "Jpar", "d2Jpar", "eta", "U_up", "U_dn", "P_up", "P_dn", "Psi_up",
         "Psi_dn", "phi_up", "phi_dn", "J_up", "J_dn", "U_mode", "P_mode", "J_mode", "zShift",
         "g11", "g33", "g13", "G1", "G3")] + \
-        [("delp2_all_terms", C.c_int), ("delp2_nonuniform", C.c_int), ("zlength", C.c_double),
+        [("delp2_all_terms", C.c_int), ("delp2_nonuniform", C.c_int), ("rowc_ws", C.c_void_p), ("zlength", C.c_double),
          ("hyperresist", C.c_double), ("keep_U", C.c_double), ("keep_P", C.c_double), ("keep_Psi", C.c_double),
          ("eta_is2d", C.c_int), ("filter_n0", C.c_int)] + \
         [(n, C.c_void_p) for n in ("ddt_U", "ddt_P", "ddt_Psi", "rk_start_U", "rk_start_P", "rk_start_Psi",

@@ -179,6 +179,112 @@ __device__ __forceinline__ void rowReduce3(double (&acc)[6], double* red, int ti
   }
 }
 
+// All per-row constants of row (x, y) (a few dozen dependent loads, two sincos, one tridagCoefs): evaluated by
+// k_elm_rowc for every row ahead of the main kernel when the caller provides rowc_ws, else by one thread of the row.
+__device__ __forceinline__ RowC elmRowConstants(const ElmParams& p, int x, int y) {
+  const bout_b200_elmpb_rhs_args& a = p.a;
+  const int ny = p.ny;
+  const long long i2 = static_cast<long long>(x) * p.ny + y;
+  RowC c;
+  c.rdx = 1.0 / __ldg(a.dx + i2);
+  c.rdy = 1.0 / __ldg(a.dy + i2);
+  c.rdz = 1.0 / __ldg(a.dz + i2);
+  c.g_22 = __ldg(a.g_22 + i2);
+  c.g_23 = __ldg(a.g_23 + i2);
+  c.g_12 = __ldg(a.g_12 + i2);
+  const double sg = sqrt(c.g_22);
+  c.rjs = 1.0 / (__ldg(a.J + i2) * sg);
+  const double B0 = __ldg(a.B0 + i2);
+  c.B0sq = B0 * B0;
+  c.rB0 = 1.0 / B0;                          // Field3D / Field2D multiplies by the reciprocal, as the reference does
+  c.B0rBxy = B0 * (1.0 / __ldg(a.Bxy + i2));
+  c.B0p = __ldg(a.B0 + i2 + 1);
+  c.B0m = __ldg(a.B0 + i2 - 1);
+  c.gpar = c.rdy / sg;                       // Grad_par = DDY / dy * invSg (coordinates.cxx:1529-1535)
+  const double d0x = applyStandard<BOUT_B200_DDX_C4>(st2dx(a.phi0, i2, ny)) * c.rdx;
+  const double d0y = 0.5 * (__ldg(a.phi0 + i2 + 1) - __ldg(a.phi0 + i2 - 1)) * c.rdy;
+  c.vx0 = c.g_22 * 0.0 - c.g_23 * d0y;
+  c.vy0 = c.g_23 * d0x - c.g_12 * 0.0;
+  c.vz0 = c.g_12 * d0y - c.g_22 * d0x;
+  const St J0x = st2dx(a.J0, i2, ny), P0x = st2dx(a.P0, i2, ny);
+  c.dJ0[0] = weno3Deriv(false, J0x);
+  c.dJ0[1] = weno3Deriv(true, J0x);
+  c.dP0[0] = weno3Deriv(false, P0x);
+  c.dP0[1] = weno3Deriv(true, P0x);
+  c.dJ0y = __ldg(a.J0 + i2 + 1) - __ldg(a.J0 + i2 - 1);
+  c.dP0y = __ldg(a.P0 + i2 + 1) - __ldg(a.P0 + i2 - 1);
+  c.bcx = __ldg(a.b0xcv_x + i2);
+  c.bcy = __ldg(a.b0xcv_y + i2);
+  c.bcz = __ldg(a.b0xcv_z + i2);
+  c.xU[0] = c.xU[1] = c.xP[0] = c.xP[1] = c.xPsi[0] = c.xPsi[1] = 0.0;
+  if (a.U_mode != nullptr && a.d2Jpar == nullptr) {
+    // Delp2(Jpar) of mode n0 straight from the row modes (Coordinates::Delp2, coordinates.cxx:1662-1699:
+    // a J(x-1) + b J(x) + c J(x+1) with Laplacian::tridagCoefs); eta is a Field2D on this path
+    LapCoefs L{};
+    L.dx = a.dx;
+    L.g11 = a.g11;
+    L.g33 = a.g33;
+    L.g13 = a.g13;
+    L.G1 = a.G1;
+    L.G3 = a.G3;
+    L.zlength = a.zlength;
+    L.nx = p.nx;
+    L.ny = ny;
+    L.all_terms = a.delp2_all_terms;
+    L.nonuniform = a.delp2_nonuniform;
+    cd ca, cb, cc;
+    tridagCoefs(L, x, y, a.filter_n0 * 2.0 * M_PI / a.zlength, false, false, ca, cb, cc);
+    auto md = [&](long long q) { return cd{__ldg(a.J_mode + 2 * q), __ldg(a.J_mode + 2 * q + 1)}; };
+    const cd d2 = cadd(cadd(cmul(ca, md(i2 - ny)), cmul(cb, md(i2))), cmul(cc, md(i2 + ny)));
+    const double he = a.hyperresist * __ldg(a.eta + i2);
+    c.xPsi[0] = -he * d2.re;
+    c.xPsi[1] = -he * d2.im;
+  }
+  if (a.U_mode != nullptr) {
+    // mode n0 of the slice pair of a field: M(y+1) exp(-i k (zs(y) - zs(y+1))) - M(y-1) exp(-i k (zs(y) - zs(y-1)))
+    const double kwave = a.filter_n0 * 2.0 * M_PI / a.zlength;
+    const double zs0 = __ldg(a.zShift + i2);
+    double sn, cs;
+    sincos(kwave * (zs0 - __ldg(a.zShift + i2 + 1)), &sn, &cs);
+    const cd pu = {cs, -sn};
+    sincos(kwave * (zs0 - __ldg(a.zShift + i2 - 1)), &sn, &cs);
+    const cd pd = {cs, -sn};
+    auto diff = [&](const double* __restrict__ mode) {
+      const cd mu = {__ldg(mode + 2 * (i2 + 1)), __ldg(mode + 2 * (i2 + 1) + 1)};
+      const cd md = {__ldg(mode + 2 * (i2 - 1)), __ldg(mode + 2 * (i2 - 1) + 1)};
+      return csub(cmul(mu, pu), cmul(md, pd));
+    };
+    const cd dU = diff(a.U_mode), dP = diff(a.P_mode), dJ = diff(a.J_mode);
+    const double cy = c.vy0 * 0.5 * c.rdy * c.rjs;     // y-advection by the phi0 velocity (b0x2d3d)
+    const double cP = 0.5 * c.rdy * c.bcy;             // b0xcv.y DDY(P)
+    const double cJ = 0.5 * c.gpar * c.B0sq;           // B0^2 Grad_par(Jpar)
+    c.xU[0] = -cy * dU.re + cP * dP.re - cJ * dJ.re;
+    c.xU[1] = -cy * dU.im + cP * dP.im - cJ * dJ.im;
+    c.xP[0] = -cy * dP.re;
+    c.xP[1] = -cy * dP.im;
+  }
+  return c;
+}
+
+constexpr int kRowCDoubles = static_cast<int>(sizeof(RowC) / sizeof(double));
+
+__global__ void __launch_bounds__(128) k_elm_rowc(const ElmParams p) {
+  const int nyb = p.ye - p.ys + 1;
+  const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * nyb;
+  const long long rid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (rid >= nrows) {
+    return;
+  }
+  const int x = p.xs + static_cast<int>(rid / nyb), y = p.ys + static_cast<int>(rid % nyb);
+  const RowC c = elmRowConstants(p, x, y);
+  double* __restrict__ dst = p.a.rowc_ws + rid * kRowCDoubles;
+  const double* src = reinterpret_cast<const double*>(&c);
+#pragma unroll
+  for (int q = 0; q < kRowCDoubles; ++q) {
+    dst[q] = src[q];
+  }
+}
+
 template <int MINB, int V>
 __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   __shared__ double red[8 * 6 * 32];
@@ -197,86 +303,14 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
   const int ny = p.ny, nz = p.nz;
 
   __shared__ RowC rows[8];
-  if (tin == 0) {
-    RowC c;
-    c.rdx = 1.0 / __ldg(a.dx + i2);
-    c.rdy = 1.0 / __ldg(a.dy + i2);
-    c.rdz = 1.0 / __ldg(a.dz + i2);
-    c.g_22 = __ldg(a.g_22 + i2);
-    c.g_23 = __ldg(a.g_23 + i2);
-    c.g_12 = __ldg(a.g_12 + i2);
-    const double sg = sqrt(c.g_22);
-    c.rjs = 1.0 / (__ldg(a.J + i2) * sg);
-    const double B0 = __ldg(a.B0 + i2);
-    c.B0sq = B0 * B0;
-    c.rB0 = 1.0 / B0;                          // Field3D / Field2D multiplies by the reciprocal, as the reference does
-    c.B0rBxy = B0 * (1.0 / __ldg(a.Bxy + i2));
-    c.B0p = __ldg(a.B0 + i2 + 1);
-    c.B0m = __ldg(a.B0 + i2 - 1);
-    c.gpar = c.rdy / sg;                       // Grad_par = DDY / dy * invSg (coordinates.cxx:1529-1535)
-    const double d0x = applyStandard<BOUT_B200_DDX_C4>(st2dx(a.phi0, i2, ny)) * c.rdx;
-    const double d0y = 0.5 * (__ldg(a.phi0 + i2 + 1) - __ldg(a.phi0 + i2 - 1)) * c.rdy;
-    c.vx0 = c.g_22 * 0.0 - c.g_23 * d0y;
-    c.vy0 = c.g_23 * d0x - c.g_12 * 0.0;
-    c.vz0 = c.g_12 * d0y - c.g_22 * d0x;
-    const St J0x = st2dx(a.J0, i2, ny), P0x = st2dx(a.P0, i2, ny);
-    c.dJ0[0] = weno3Deriv(false, J0x);
-    c.dJ0[1] = weno3Deriv(true, J0x);
-    c.dP0[0] = weno3Deriv(false, P0x);
-    c.dP0[1] = weno3Deriv(true, P0x);
-    c.dJ0y = __ldg(a.J0 + i2 + 1) - __ldg(a.J0 + i2 - 1);
-    c.dP0y = __ldg(a.P0 + i2 + 1) - __ldg(a.P0 + i2 - 1);
-    c.bcx = __ldg(a.b0xcv_x + i2);
-    c.bcy = __ldg(a.b0xcv_y + i2);
-    c.bcz = __ldg(a.b0xcv_z + i2);
-    c.xU[0] = c.xU[1] = c.xP[0] = c.xP[1] = c.xPsi[0] = c.xPsi[1] = 0.0;
-    if (a.U_mode != nullptr && a.d2Jpar == nullptr) {
-      // Delp2(Jpar) of mode n0 straight from the row modes (Coordinates::Delp2, coordinates.cxx:1662-1699:
-      // a J(x-1) + b J(x) + c J(x+1) with Laplacian::tridagCoefs); eta is a Field2D on this path
-      LapCoefs L{};
-      L.dx = a.dx;
-      L.g11 = a.g11;
-      L.g33 = a.g33;
-      L.g13 = a.g13;
-      L.G1 = a.G1;
-      L.G3 = a.G3;
-      L.zlength = a.zlength;
-      L.nx = p.nx;
-      L.ny = ny;
-      L.all_terms = a.delp2_all_terms;
-      L.nonuniform = a.delp2_nonuniform;
-      cd ca, cb, cc;
-      tridagCoefs(L, x, y, a.filter_n0 * 2.0 * M_PI / a.zlength, false, false, ca, cb, cc);
-      auto md = [&](long long q) { return cd{__ldg(a.J_mode + 2 * q), __ldg(a.J_mode + 2 * q + 1)}; };
-      const cd d2 = cadd(cadd(cmul(ca, md(i2 - ny)), cmul(cb, md(i2))), cmul(cc, md(i2 + ny)));
-      const double he = a.hyperresist * __ldg(a.eta + i2);
-      c.xPsi[0] = -he * d2.re;
-      c.xPsi[1] = -he * d2.im;
+  if (a.rowc_ws != nullptr) { // precomputed by k_elm_rowc: one coalesced load per row
+    const double* __restrict__ src = a.rowc_ws + rid * kRowCDoubles;
+    double* dst = reinterpret_cast<double*>(&rows[rloc]);
+    for (int q = tin; q < kRowCDoubles; q += nzp) {
+      dst[q] = __ldg(src + q);
     }
-    if (a.U_mode != nullptr) {
-      // mode n0 of the slice pair of a field: M(y+1) exp(-i k (zs(y) - zs(y+1))) - M(y-1) exp(-i k (zs(y) - zs(y-1)))
-      const double kwave = a.filter_n0 * 2.0 * M_PI / a.zlength;
-      const double zs0 = __ldg(a.zShift + i2);
-      double sn, cs;
-      sincos(kwave * (zs0 - __ldg(a.zShift + i2 + 1)), &sn, &cs);
-      const cd pu = {cs, -sn};
-      sincos(kwave * (zs0 - __ldg(a.zShift + i2 - 1)), &sn, &cs);
-      const cd pd = {cs, -sn};
-      auto diff = [&](const double* __restrict__ mode) {
-        const cd mu = {__ldg(mode + 2 * (i2 + 1)), __ldg(mode + 2 * (i2 + 1) + 1)};
-        const cd md = {__ldg(mode + 2 * (i2 - 1)), __ldg(mode + 2 * (i2 - 1) + 1)};
-        return csub(cmul(mu, pu), cmul(md, pd));
-      };
-      const cd dU = diff(a.U_mode), dP = diff(a.P_mode), dJ = diff(a.J_mode);
-      const double cy = c.vy0 * 0.5 * c.rdy * c.rjs;     // y-advection by the phi0 velocity (b0x2d3d)
-      const double cP = 0.5 * c.rdy * c.bcy;             // b0xcv.y DDY(P)
-      const double cJ = 0.5 * c.gpar * c.B0sq;           // B0^2 Grad_par(Jpar)
-      c.xU[0] = -cy * dU.re + cP * dP.re - cJ * dJ.re;
-      c.xU[1] = -cy * dU.im + cP * dP.im - cJ * dJ.im;
-      c.xP[0] = -cy * dP.re;
-      c.xP[1] = -cy * dP.im;
-    }
-    rows[rloc] = c;
+  } else if (tin == 0) {
+    rows[rloc] = elmRowConstants(p, x, y);
   }
   __syncthreads();
   const RowC& m = rows[rloc];
@@ -426,6 +460,8 @@ __global__ void __launch_bounds__(256, MINB) k_elmpb_rhs(const ElmParams p) {
 
 using namespace b200;
 
+extern "C" int bout_b200_elmpb_rowc_doubles(void) { return kRowCDoubles; }
+
 extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmpb_rhs_args* args, void* stream) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
@@ -505,6 +541,10 @@ extern "C" int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmp
   }
   const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * (p.ye - p.ys + 1);
   const unsigned blocks = static_cast<unsigned>((nrows + rows - 1) / rows);
+  if (a.rowc_ws != nullptr) {
+    k_elm_rowc<<<static_cast<unsigned>((nrows + 127) / 128), 128, 0, s>>>(p);
+    B200_LAUNCH_OK();
+  }
   static const int minb = getenv("BOUT_B200_ELM_MINB") ? atoi(getenv("BOUT_B200_ELM_MINB")) : 0;
   if (V == 1) {
     if (minb == 3) {

@@ -264,6 +264,8 @@ class ELMpb:
             self._buf = {n: (z(), z()) for n in ("U", "P", "Psi", "phi", "J")}   # (yup, ydown) per field
             self._buf["sm"] = z()
             self._buf["d2J"] = z()
+            nrc = capi.lib.bout_b200_elmpb_rowc_doubles()
+            self._buf["rowc_ws"] = torch.zeros(self.g.nx * self.g.ny * nrc, dtype=torch.float64, device=self.dev)
             for n in ("mU", "mP", "mJ"):   # one Fourier coefficient per (x,y) row, complex
                 self._buf[n] = torch.zeros(self.g.shape2 + (2,), dtype=torch.float64, device=self.dev)
         return self._buf
@@ -354,6 +356,7 @@ class ELMpb:
             fields.update(U=U, P=P, Psi=Psi, phi=self.phi, Jpar=self.Jpar, Psi_up=sPsi[0][0],
                           Psi_dn=sPsi[1][0], phi_up=sphi[0][0], phi_dn=sphi[1][0],
                           ddt_U=self.ddt_U, ddt_P=self.ddt_P, ddt_Psi=self.ddt_Psi)
+            fields["rowc_ws"] = buf["rowc_ws"]
             if modes:
                 fields.update(U_mode=buf["mU"], P_mode=buf["mP"], J_mode=buf["mJ"], zShift=self.zs)
             else:

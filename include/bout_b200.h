@@ -208,6 +208,9 @@ typedef struct bout_b200_elmpb_rhs_args {
    * settings below and the Field2D metric g11, g33, g13, G1, G3), and no Delp2(Jpar) pass is needed. */
   const double *g11, *g33, *g13, *G1, *G3;
   int delp2_all_terms, delp2_nonuniform;
+  /* optional scratch of bout_b200_elmpb_rowc_doubles() * nx * ny doubles: the per-row constants are then evaluated
+   * by a small kernel ahead of the main one instead of by one thread of every row */
+  double* rowc_ws;
   double zlength;
   double hyperresist;
   double keep_U, keep_P, keep_Psi;
@@ -221,6 +224,7 @@ typedef struct bout_b200_elmpb_rhs_args {
   double rk_cdt;
 } bout_b200_elmpb_rhs_args;
 int bout_b200_elmpb_rhs(const bout_b200_grid* g, const bout_b200_elmpb_rhs_args* args, void* stream);
+int bout_b200_elmpb_rowc_doubles(void);
 
 /* averageY(Field3D) (src/physics/smoothing.cxx:272-323) in two halves so that the all-reduce over the
  * ranks of a Y communicator sits between them: xz[x][z] = mean over ystart..yend of f;
