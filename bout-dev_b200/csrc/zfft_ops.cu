@@ -440,11 +440,33 @@ __global__ void __launch_bounds__(256) k_row_mode(const RowModeParams p) {
   const long long row = w % p.nrows;
   const double* __restrict__ src = p.f[fi] + row * p.nz;
   double re = 0.0, im = 0.0;
-  for (int j = lane; j < p.nz; j += 32) {
-    const cd t = p.tw[(static_cast<long long>(p.n0) * j) % p.nz];
-    const double v = __ldg(src + j);
-    re += v * t.re;
-    im += v * t.im;
+  if (p.nz % 64 == 0 && aligned16(src)) { // 16-byte loads; twiddle indices advance without a division
+    int i0 = static_cast<int>((static_cast<long long>(p.n0) * 2 * lane) % p.nz);
+    int i1 = (i0 + p.n0) % p.nz;
+    const int step = static_cast<int>((static_cast<long long>(p.n0) * 64) % p.nz);
+    double re1 = 0.0, im1 = 0.0;
+#pragma unroll 4
+    for (int j = 2 * lane; j < p.nz; j += 64) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(src + j));
+      const cd t0 = p.tw[i0], t1 = p.tw[i1];
+      re += v.x * t0.re;
+      im += v.x * t0.im;
+      re1 += v.y * t1.re;
+      im1 += v.y * t1.im;
+      i0 += step;
+      i0 -= i0 >= p.nz ? p.nz : 0;
+      i1 += step;
+      i1 -= i1 >= p.nz ? p.nz : 0;
+    }
+    re += re1;
+    im += im1;
+  } else {
+    for (int j = lane; j < p.nz; j += 32) {
+      const cd t = p.tw[(static_cast<long long>(p.n0) * j) % p.nz];
+      const double v = __ldg(src + j);
+      re += v * t.re;
+      im += v * t.im;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
