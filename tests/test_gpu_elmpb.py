@@ -130,3 +130,39 @@ def test_elmpb_fused_equals_operator_path_full_size():
     for a, b in zip(out[True], out[False]):
         assert torch.isfinite(a[I]).all()
         assert ((a[I] - b[I]).abs().max() / b[I].abs().max()).item() < 1e-10
+
+
+@pytest.mark.parametrize("dims", [(36, 12, 32), (24, 6, 64)])
+def test_elmpb_rhs_vs_numpy_oracle_on_other_grids(orc, port, dims):
+    """Beyond the one golden state: the CUDA RHS against the numpy restatement oracle/elm_oracle.py (itself pinned to
+    the reference on CPU by tests/test_elm_oracle.py) on other grid sizes and a seeded state with every z mode."""
+    import importlib.util
+    import __graft_entry__ as ge
+    spec = importlib.util.spec_from_file_location("elm_oracle", os.path.join(os.path.dirname(HERE), "oracle", "elm_oracle.py"))
+    eo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(eo)
+    pkg = ge.load_package()
+    nx, nyi, nz = dims
+    s = pkg.elm_setup.elmpb_setup(nx, nyi, nz)
+    m = pkg.models.ELMpb.from_setup(s)
+    g = m.g
+    rng = np.random.default_rng(20261018)
+    X = (np.arange(g.nx)[:, None, None] + 0.5) / g.nx
+    Y = 2 * np.pi * np.arange(g.ny)[None, :, None] / g.ny
+    Z = 2 * np.pi * np.arange(g.nz)[None, None, :] / g.nz
+    mk = lambda a, i: np.ascontiguousarray(a * (np.sin(2 * np.pi * (1 + i) * X) * np.cos((1 + i) * Z + Y)
+                                                + 0.1 * rng.uniform(-1, 1, g.shape3)))
+    U, P, Psi = mk(1e-5, 0), mk(3e-6, 1), mk(4e-7, 2)
+    og = orc.Grid(g.nx, g.ny, g.nz, g.mxg, g.myg)
+    md = dict(s["md"])
+    for n in orc.Metric.NAMES:          # fields the set-up does not produce are not read by these operators
+        md.setdefault(n, np.zeros(g.shape2))
+    metric = orc.Metric(**{n: md[n] for n in orc.Metric.NAMES})
+    want = eo.elmpb_rhs(port, og, metric, md, s["eq"], s["zShift"], s["zlength"], s["dnorm"], s["hyperresist"], U, P, Psi)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    m.set_state(dev(U), dev(P), dev(Psi))
+    m.rhs()
+    torch.cuda.synchronize()
+    I = g.interior
+    for name, f in (("Psi", m.ddt_Psi), ("U", m.ddt_U), ("P", m.ddt_P)):
+        assert rel_err(f.cpu().numpy(), want["ddt_" + name], I) < 1e-10, name
