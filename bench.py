@@ -351,7 +351,7 @@ def run_ours(args):
         del model
         torch.cuda.empty_cache()
         try:
-            out["other"] = other_measurements(torch, pkg, dev, peak)
+            out["other"] = other_measurements(torch, pkg, dev, peak, with_cpu=not args.no_cpu_baseline)
         except Exception as e:  # noqa: BLE001 -- the extras never invalidate the main line
             out["other"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
@@ -396,7 +396,7 @@ def elmpb_model(pkg, dev, mesh=None, nype=1):
     return m
 
 
-def other_measurements(torch, pkg, dev, peak):
+def other_measurements(torch, pkg, dev, peak, with_cpu=False):
     """Short N = 1 extras for the default line: elm-pb RHS, LaplaceCyclic solves/s, configs[1] microbenchmarks."""
     capi = pkg.capi
     out = {}
@@ -475,24 +475,20 @@ def other_measurements(torch, pkg, dev, peak):
     #    C-ABI): examples/blob2d scaled to 1024 x 1024 (configs[2]) and examples/hasegawa-wakatani as shipped
     #    (configs[0], 256 x 256, periodic X); wall clock around Solver::solve, all host overheads included
     try:
-        out["host_layer_models"] = host_layer_models(pkg)
+        out["host_layer_models"] = host_layer_models(pkg, with_cpu=with_cpu)
     except Exception as e:  # noqa: BLE001
         out["host_layer_models"] = {"error": repr(e)[:300]}
     return out
 
 
-def host_layer_models(pkg):
+def host_layer_models(pkg, with_cpu=False):
     """Wall time of Solver::solve for two step counts (after a discarded warm-up instance): the slope is the
     per-RHS cost with every host overhead of the C++ layer in it; the intercept is start-up."""
-    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-    import cases
     import numpy as np
     res = {}
-    blob_extra = cases.BLOB_INI[cases.BLOB_INI.index("[mesh:ddx]"):]
-    hw_extra = cases.HW_INI[cases.HW_INI.index("[hw]"):]
     for tag, model, ini, steps in (
-            ("blob2d_1024x1x1024", "blob2d", cases.make_ini(1028, 1, 1024, mxg=2, myg=0, dx="0.3", dz="0.3", extra=blob_extra), (5, 20, 60)),
-            ("hasegawa-wakatani_256x1x256", "hw", cases.make_ini(260, 1, 256, mxg=2, myg=0, periodic_x=True, extra=hw_extra), (5, 50, 150))):
+            ("blob2d_1024x1x1024", "blob2d", model_2d_ini("blob2d")[0], (5, 20, 60)),
+            ("hasegawa-wakatani_256x1x256", "hw", model_2d_ini("hw")[0], (5, 50, 150))):
         dt = float([ln for ln in ini.splitlines() if ln.startswith("timestep")][0].split("=")[1])
         pts = []
         for nsteps in steps:
@@ -514,6 +510,8 @@ def host_layer_models(pkg):
         npts = (nx - 4) * max(ny, 1) * nz
         res[tag] = {"us_per_rhs": per * 1e6, "grid_points_per_s": npts / per, "rhs_calls": [n1, n2],
                     "wall_ms": [t1 * 1e3, t2 * 1e3], "finite": fin, "steady_state_pool_allocations": pool}
+        if with_cpu:   # the reference's own CPU run of the same unchanged source, beside it (cpu_baseline leg)
+            res[tag]["cpu_baseline"] = cpu_baseline(steps=2, warmup=0, workload=model)
     return res
 
 
@@ -690,6 +688,41 @@ def run_reference_elmpb(args, cores):
     os._exit(0)
 
 
+def model_2d_ini(tag):
+    """BOUT.inp of the two 2-D model cases timed through the host layer (and through the reference beside them)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    if tag == "blob2d":
+        extra = cases.BLOB_INI[cases.BLOB_INI.index("[mesh:ddx]"):]
+        return cases.make_ini(1028, 1, 1024, mxg=2, myg=0, dx="0.3", dz="0.3", extra=extra), (1024, 1, 1024)
+    extra = cases.HW_INI[cases.HW_INI.index("[hw]"):]
+    return cases.make_ini(260, 1, 256, mxg=2, myg=0, periodic_x=True, extra=extra), (256, 1, 256)
+
+
+def run_reference_2d(args, cores):
+    """Reference arm for the 2-D model cases of the default line's extras: the unchanged example source through
+    the reference's Solver::run_rhs at the full grid (blob2d 1024 x 1024, hasegawa-wakatani 256 x 256)."""
+    import __graft_entry__ as ge
+    orc = ge.load_oracle()
+    if not os.path.exists(orc.REF_SO):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libboutref.so not built"}))
+        return
+    ini, (mx, my, mz) = model_2d_ini(args.workload)
+    r = orc.Ref(ini)
+    r.model_create("blob2d" if args.workload == "blob2d" else "hw", "rk4")
+    dt = float([ln for ln in ini.splitlines() if ln.startswith("timestep")][0].split("=")[1])
+    r.model_solve(0, dt)     # Solver::init + first run_rhs (the reference's own start-up)
+    reps = max(4 * args.steps, 4)
+    secs = r.model_time_rhs(reps=reps)
+    value = mx * my * mz / secs
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "us_per_rhs": secs * 1e6,
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                                       "sample": f"unchanged examples/{args.workload} source, {mx}x{my}x{mz}, {reps} run_rhs, "
+                                                 f"OpenMP {cores} threads"}}), flush=True)
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def run_reference(args, as_baseline=False):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -698,6 +731,8 @@ def run_reference(args, as_baseline=False):
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     if args.workload == "elmpb":
         return run_reference_elmpb(args, cores)
+    if args.workload in ("blob2d", "hw"):
+        return run_reference_2d(args, cores)
     orc, ini = ref_ini()
     kind = "reference" if os.path.exists(orc.REF_SO) else None
     if kind is None:
@@ -750,7 +785,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short extra measurements of the default line")
-    ap.add_argument("--workload", default="hw3d", choices=["hw3d", "elmpb"])
+    ap.add_argument("--workload", default="hw3d", choices=["hw3d", "elmpb", "blob2d", "hw"],
+                    help="blob2d / hw: reference arm only (the CPU numbers beside the host-layer extras)")
     ap.add_argument("--decomp", default=os.environ.get("BOUT_B200_DECOMP", "y"), choices=["x", "y", "xy"],
                     help="BoutMesh decomposition at N > 1: NYPE=N (default), NXPE=N, or NXPE=2 x NYPE=N/2")
     args = ap.parse_args()
@@ -758,6 +794,9 @@ def main():
         run_reference(args)
     elif args.workload == "elmpb":
         run_elmpb(args)
+    elif args.workload != "hw3d":
+        raise SystemExit("--workload blob2d / hw exist for --impl reference only; our arm reports them in the default "
+                         "line's other.host_layer_models")
     else:
         run_ours(args)
 
