@@ -251,3 +251,59 @@ def elmpb_rhs(port, og, metric, md, eq, zshift, zlength, dnorm, hyperresist, U, 
         out[name] = f
     out.update(phi=phi, Jpar=Jpar, Jpar2=Jpar2, U=U, P=P, Psi=Psi)
     return out
+
+
+# ---- Y operators on parallel slices (the remaining elm-pb / 6-field vocabulary) ----------------------------------
+def _b3(a):
+    return a[:, :, None] if a.ndim == 2 else a
+
+
+def ddy_slices(md, f, sl):
+    """DDY on a field with parallel slices: index DDY_C2 (YOrthogonal, index_derivs_interface.hxx:199-203) / dy
+    (coordinates.cxx:1488-1499)."""
+    up, dn = sl
+    return 0.5 * (_sh(up, 1, 1) - _sh(dn, 1, -1)) / _b3(md["dy"])
+
+
+def d2dy2_slices(md, f, sl):
+    """D2DY2 (src/sys/derivs.cxx:194-213): index D2DY2_C2 / dy^2 + d1_dy * index DDY_C2 / dy (non-uniform mesh)."""
+    up, dn = sl
+    dy = _b3(md["dy"])
+    second = (_sh(up, 1, 1) + _sh(dn, 1, -1) - 2.0 * f) / (dy * dy)
+    return second + _b3(md["d1_dy"]) * (0.5 * (_sh(up, 1, 1) - _sh(dn, 1, -1))) / dy
+
+
+def grad_par(md, f, sl):                          # coordinates.cxx:1529-1535
+    return ddy_slices(md, f, sl) / np.sqrt(_b3(md["g_22"]))
+
+
+def vddy_slices(md, v, f, sl):                    # VDDY_C2 (index_derivs.cxx:148) / dy
+    up, dn = sl
+    return v * 0.5 * (_sh(up, 1, 1) - _sh(dn, 1, -1)) / _b3(md["dy"])
+
+
+def vpar_grad_par(md, v, f, sl):                  # coordinates.cxx:1541-1566
+    return vddy_slices(md, v, f, sl) / np.sqrt(_b3(md["g_22"]))
+
+
+def div_par(md, f, sl):
+    """Div_par (coordinates.cxx:1571-1594): Bxy * Grad_par(f / Bxy), the slices divided by Bxy at their own rows."""
+    B = _b3(md["Bxy"])
+    up, dn = sl
+    return B * grad_par(md, f / B, (up / B, dn / B))
+
+
+def grad2_par2(md, f, sl):
+    """Grad2_par2 (coordinates.cxx:1611-1628, coefficient :1889-1905):
+    DDY(1/sqrt(g_22)) / sqrt(g_22) * DDY(f) + D2DY2(f) / g_22."""
+    g_22 = md["g_22"]
+    sg = 1.0 / np.sqrt(g_22)
+    dsg = np.zeros_like(sg)
+    dsg[:, 1:-1] = 0.5 * (sg[:, 2:] - sg[:, :-2])
+    coef = dsg / md["dy"] * sg
+    return _b3(coef) * ddy_slices(md, f, sl) + d2dy2_slices(md, f, sl) / _b3(g_22)
+
+
+def average_y(f, myg):                            # src/physics/smoothing.cxx:272-323 (one rank in y)
+    mean = f[:, myg:f.shape[1] - myg].mean(axis=1, keepdims=True)
+    return np.broadcast_to(mean, f.shape).copy()
