@@ -62,3 +62,22 @@ def test_compute_call_without_gpu_fails_loudly():
     rc = lib.bout_b200_unary(C.byref(g), 10, buf, C.c_double(0.0), buf, None)
     assert rc == -2, rc   # BOUT_B200_ERR_CUDA
     assert b"" != lib.bout_b200_last_error()
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/bout_b200.h must compile as C99 (no C++/torch types)."""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "bout_b200.h"\nint main(void) { bout_b200_elmpb_rhs_args a; bout_b200_laplace l; (void)a; (void)l; return 0; }\n')
+        path = f.name
+    try:
+        p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                            "-fsyntax-only", path], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+    finally:
+        os.unlink(path)
