@@ -369,6 +369,34 @@ def rk_stage(g: Grid, mode, dt, start, k1, k2=None, k3=None, k4=None, c=1.0, out
     return out
 
 
+def lincomb(g: Grid, coefs, fields, out, region="RGN_NOBNDRY"):
+    """out[region] = sum_j coefs[j] * fields[j] (1..8 terms; out must not alias a field): the state / output
+    loops of euler, rkgeneric and splitrk (bout_b200_lincomb)."""
+    n = len(coefs)
+    assert n == len(fields)
+    cs = (C.c_double * n)(*[float(c) for c in coefs])
+    for f in fields:
+        _ptr(f)
+    _check(lib.bout_b200_lincomb(C.byref(g.c), REGIONS[region], n, cs, _ptr_array(fields), _ptr(out), _stream()))
+    return out
+
+
+lib.bout_b200_err_sum_scratch_doubles.restype = C.c_size_t
+
+
+def err_sum(g: Grid, a, b, atol, accumulate_onto=None, region="RGN_NOBNDRY"):
+    """sum over region of |a-b| / (|a|+|b|+atol) (bout_b200_err_sum; rkscheme.cxx:150-156), returned as a float.
+    accumulate_onto: a previous sum to add to on the device (the per-field accumulation of a state)."""
+    n = int(lib.bout_b200_err_sum_scratch_doubles())
+    scratch = torch.empty(n + 1, dtype=torch.float64, device=a.device)
+    result = scratch[n:]
+    if accumulate_onto is not None:
+        result.fill_(float(accumulate_onto))
+    _check(lib.bout_b200_err_sum(C.byref(g.c), REGIONS[region], _ptr(a), _ptr(b), C.c_double(atol), _ptr(scratch),
+                                 0 if accumulate_onto is None else 1, C.c_void_p(result.data_ptr()), _stream()))
+    return float(result.item())
+
+
 class CMetric(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dx", "dy", "dz", "J", "g_22", "g11", "g33", "g13", "G1", "G3",
                                           "d1_dx")]

@@ -187,3 +187,17 @@ extern "C" int bout_b200_unary(const bout_b200_grid* g, int op, const double* f,
   B200_LAUNCH_OK();
   return 0;
 }
+
+// Linear combination of fields, the stage / output-state loops of the explicit integrators beyond rk4 and rk3ssp
+// (euler.cxx:178-181, rkscheme.cxx:57-84 and :173-190, split-rk.cxx:226-300): one pass through k_elementwise.
+extern "C" int bout_b200_lincomb(const bout_b200_grid* g, int region, int n, const double* coef,
+                                 const double* const* x, double* out, void* stream) {
+  B200_REQUIRE(coef != nullptr && x != nullptr && n >= 1 && n <= kMaxTerms, BOUT_B200_ERR_ARG,
+               "lincomb: 1..%d terms", kMaxTerms);
+  bout_b200_ewterm terms[kMaxTerms];
+  for (int i = 0; i < n; ++i) {
+    B200_REQUIRE(x[i] != nullptr && x[i] != out, BOUT_B200_ERR_ARG, "lincomb: operand %d is null or aliases out", i);
+    terms[i] = {coef[i], x[i], nullptr, nullptr, 0, 0, 0};
+  }
+  return bout_b200_elementwise(g, region, n, terms, out, stream);
+}

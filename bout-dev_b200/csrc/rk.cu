@@ -97,3 +97,93 @@ extern "C" int bout_b200_rk_stage(const bout_b200_grid* g, int region, int mode,
   B200_LAUNCH_OK();
   return 0;
 }
+
+// ---- error norm of the adaptive integrators -----------------------------------------------------------
+// sum over the evolving region of |a - b| / (|a| + |b| + atol): RK4Solver::run (rk4.cxx:103-106),
+// RKScheme::getErr (src/solver/impls/rkgeneric/rkscheme.cxx:150-156), SplitRK::run (split-rk.cxx:128-133).
+// The reference reduces with an OpenMP `reduction(+)` (order not fixed); here the order is fixed: every CTA owns a
+// grid-stride subsequence and writes one partial, one CTA then adds the partials in index order.
+namespace b200 {
+
+constexpr int kErrThreads = 256;
+constexpr int kErrMaxBlocks = 148 * 8;
+
+__device__ __forceinline__ double blockSum(double v, double* sh) { // all kErrThreads threads call; result in thread 0
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[warp] = v;
+  }
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < kErrThreads / 32; ++w) {
+      r += sh[w];
+    }
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(kErrThreads) k_err_partial(const double* __restrict__ a, const double* __restrict__ b,
+                                                             double atol, double* __restrict__ partial, int ny, int nz,
+                                                             int xs, int xe, int ys, int ye) {
+  __shared__ double sh[kErrThreads / 32];
+  const int nyb = ye - ys + 1;
+  const long long total = static_cast<long long>(xe - xs + 1) * nyb * nz;
+  double acc = 0.0;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int z = static_cast<int>(t % nz);
+    const long long xy = t / nz;
+    const int y = ys + static_cast<int>(xy % nyb);
+    const int x = xs + static_cast<int>(xy / nyb);
+    const long long i = (static_cast<long long>(x) * ny + y) * nz + z;
+    const double va = __ldg(a + i), vb = __ldg(b + i);
+    acc += fabs(va - vb) / (fabs(va) + fabs(vb) + atol);
+  }
+  const double s = blockSum(acc, sh);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kErrThreads) k_err_final(const double* __restrict__ partial, int n, int accumulate,
+                                                           double* __restrict__ result) {
+  __shared__ double sh[kErrThreads / 32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += kErrThreads) {
+    acc += partial[i];
+  }
+  const double s = blockSum(acc, sh);
+  if (threadIdx.x == 0) {
+    result[0] = (accumulate != 0 ? result[0] : 0.0) + s;
+  }
+}
+
+} // namespace b200
+
+extern "C" size_t bout_b200_err_sum_scratch_doubles(void) { return static_cast<size_t>(kErrMaxBlocks); }
+
+extern "C" int bout_b200_err_sum(const bout_b200_grid* g, int region, const double* a, const double* b, double atol,
+                                 double* scratch, int accumulate, double* result, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(a && b && scratch && result, BOUT_B200_ERR_ARG, "err_sum: null argument");
+  Box bx;
+  if (regionBox(g, region, &bx) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  const long long total = static_cast<long long>(bx.xe - bx.xs + 1) * (bx.ye - bx.ys + 1) * g->nz;
+  const long long want = (total + kErrThreads - 1) / kErrThreads;
+  const int blocks = static_cast<int>(want < kErrMaxBlocks ? (want < 1 ? 1 : want) : kErrMaxBlocks);
+  k_err_partial<<<blocks, kErrThreads, 0, asStream(stream)>>>(a, b, atol, scratch, g->ny, g->nz, bx.xs, bx.xe, bx.ys,
+                                                              bx.ye);
+  B200_LAUNCH_OK();
+  k_err_final<<<1, kErrThreads, 0, asStream(stream)>>>(scratch, blocks, accumulate, result);
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -491,12 +491,21 @@ class Solver {
 public:
   explicit Solver(Options* opts);
   virtual ~Solver() = default;
-  static std::unique_ptr<Solver> create(Options* opts = nullptr); ///< solver:type = rk4 | rk3ssp
+  /// solver:type = rk4 | rk3ssp | euler | rkgeneric (solver:scheme = rkf45 | cashkarp | rk4 | rkf34) | splitrk
+  static std::unique_ptr<Solver> create(Options* opts = nullptr);
   void add(Field3D& v, const std::string& name); ///< solver.cxx:210: initial profile + boundary set-up
   void setModel(PhysicsModel* m);
   int solve(int nout = -1, BoutReal output_step = 0.0); ///< solver.cxx:510-623
   int run_rhs(BoutReal t); ///< solver.cxx:1380-1427 incl. the split-operator path
-  virtual void take_step(BoutReal t, BoutReal dt) = 0;
+  int run_convective(BoutReal t); ///< solver.cxx:1430-1458
+  int run_diffusive(BoutReal t);  ///< solver.cxx:1460-1484
+  /// One fixed step of the non-adaptive integrators (rk4, rk3ssp); the others override run_output_step
+  virtual void take_step(BoutReal t, BoutReal dt);
+  /// Advances simtime to `target` (one output step): the body of the reference solvers' run() loops
+  virtual void run_output_step(BoutReal target);
+  /// Called once from solve() before the first step (the reference solvers' init())
+  virtual void init_solver() {}
+  virtual void setMaxTimestep(BoutReal) {} ///< solver.hxx:369; EulerSolver / RKGenericSolver override
   struct Var {
     Field3D* var;
     Field3D* F_var;
@@ -504,7 +513,9 @@ public:
   };
   std::vector<Var> f3d;
   BoutReal simtime = 0.0;
-  int rhs_calls = 0;
+  int rhs_calls = 0;   ///< run_rhs + run_convective (rhs_ncalls, solver.cxx:1425,1455)
+  int rhs_calls_i = 0; ///< run_diffusive (rhs_ncalls_i, solver.cxx:1482)
+  BoutReal getCurrentTimestep() const { return timestep; }
 
 protected:
   PhysicsModel* model = nullptr;
@@ -512,6 +523,7 @@ protected:
   BoutReal timestep, output_timestep;
   int nout;
   bool initialised = false;
+  bool is_nonsplit_model_diffusive = true; ///< solver.cxx:97-101
   void pre_rhs();
   void post_rhs();
 };

@@ -1332,6 +1332,7 @@ Solver::Solver(Options* opts) : options(opts != nullptr ? opts : &Options::root(
   nout = (*options)["nout"].withDefault(root.isSet("nout") ? root["nout"].as<int>() : 1);
   output_timestep = (*options)["output_step"].withDefault(root.isSet("timestep") ? root["timestep"].as<double>() : 1.0);
   timestep = (*options)["timestep"].withDefault(output_timestep); // rk4.cxx:15-18
+  is_nonsplit_model_diffusive = (*options)["is_nonsplit_model_diffusive"].withDefault(true); // solver.cxx:97-101
 }
 
 namespace {
@@ -1425,6 +1426,58 @@ int Solver::run_rhs(BoutReal t) {
   return status;
 }
 
+int Solver::run_convective(BoutReal t) { // solver.cxx:1430-1458
+  int status = 0;
+  pre_rhs();
+  if (model->splitOperator()) {
+    status = model->runConvective(t);
+  } else if (!is_nonsplit_model_diffusive) {
+    status = model->runRHS(t);
+  } else {
+    for (auto& f : f3d) {
+      *f.F_var = 0.0;
+    }
+  }
+  post_rhs();
+  ++rhs_calls;
+  return status;
+}
+
+int Solver::run_diffusive(BoutReal t) { // solver.cxx:1460-1484
+  int status = 0;
+  pre_rhs();
+  if (model->splitOperator()) {
+    status = model->runDiffusive(t);
+    post_rhs();
+  } else if (is_nonsplit_model_diffusive) {
+    status = model->runRHS(t);
+  } else {
+    for (auto& f : f3d) {
+      *f.F_var = 0.0;
+    }
+  }
+  ++rhs_calls_i;
+  return status;
+}
+
+void Solver::take_step(BoutReal, BoutReal) {
+  throw BoutException("Solver::take_step: this integrator advances through run_output_step only");
+}
+
+void Solver::run_output_step(BoutReal target) { // rk4.cxx:75-152 (non-adaptive), rk3-ssp.cxx:66-93
+  bool running = true;
+  do {
+    BoutReal dt = timestep;
+    running = true;
+    if ((simtime + dt) >= target) {
+      dt = target - simtime;
+      running = false;
+    }
+    take_step(simtime, dt);
+    simtime += dt;
+  } while (running);
+}
+
 int Solver::solve(int nout_in, BoutReal output_step) {
   if (nout_in >= 0) {
     nout = nout_in;
@@ -1433,23 +1486,16 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   if (initialised) {
     throw BoutException("ERROR: Solver is already initialised\n");
   }
+  if (f3d.empty()) {
+    throw BoutException("Solver::solve: no evolving variables were added");
+  }
   initialised = true;
+  init_solver();
   if (run_rhs(simtime) != 0) { // solver.cxx:569
     throw BoutException("Physics RHS call failed\n");
   }
-  for (int s = 0; s < nout; ++s) { // rk4.cxx:75-165 (non-adaptive)
-    const BoutReal target = simtime + output_timestep;
-    bool running = true;
-    do {
-      BoutReal dt = timestep;
-      running = true;
-      if ((simtime + dt) >= target) {
-        dt = target - simtime;
-        running = false;
-      }
-      take_step(simtime, dt);
-      simtime += dt;
-    } while (running);
+  for (int s = 0; s < nout; ++s) {
+    run_output_step(simtime + output_timestep);
     run_rhs(simtime); // rk4.cxx:157: extra variables at the output time
   }
   check(bout_b200_stream_sync(nullptr));
@@ -1465,39 +1511,42 @@ void rkStage(Mesh* m, int mode, double dt, double c, const Field3D& start, const
                            nullptr));
 }
 
+void rk4Step(Solver& s, BoutReal t, BoutReal dt) { // rk4.cxx:172-210 field by field
+  auto& f3d = s.f3d;
+  const size_t nv = f3d.size();
+  std::vector<Field3D> start(nv), k1(nv), k2(nv), k3(nv), k4(nv);
+  Mesh* m = f3d[0].var->getMesh();
+  for (size_t i = 0; i < nv; ++i) {
+    start[i] = *f3d[i].var;
+    start[i].allocate(); // a private copy: the variable is overwritten in place below
+  }
+  auto stage = [&](std::vector<Field3D>& k, BoutReal tt) {
+    s.run_rhs(tt);
+    for (size_t i = 0; i < nv; ++i) {
+      k[i] = *f3d[i].F_var;
+    }
+  };
+  auto advance = [&](const std::vector<Field3D>& k, BoutReal c) { // var(interior) = start + c dt k; guards kept
+    for (size_t i = 0; i < nv; ++i) {
+      rkStage(m, 0, dt, c, start[i], &k[i], nullptr, nullptr, nullptr, *f3d[i].var);
+    }
+  };
+  stage(k1, t);
+  advance(k1, 0.5);
+  stage(k2, t + 0.5 * dt);
+  advance(k2, 0.5);
+  stage(k3, t + 0.5 * dt);
+  advance(k3, 1.0);
+  stage(k4, t + dt);
+  for (size_t i = 0; i < nv; ++i) {
+    rkStage(m, 1, dt, 1.0, start[i], &k1[i], &k2[i], &k3[i], &k4[i], *f3d[i].var);
+  }
+}
+
 class RK4Solver : public Solver {
 public:
   using Solver::Solver;
-  void take_step(BoutReal t, BoutReal dt) override { // rk4.cxx:172-210 field by field
-    const size_t nv = f3d.size();
-    std::vector<Field3D> start(nv), k1(nv), k2(nv), k3(nv), k4(nv);
-    Mesh* m = f3d[0].var->getMesh();
-    for (size_t i = 0; i < nv; ++i) {
-      start[i] = *f3d[i].var;
-      start[i].allocate(); // a private copy: the variable is overwritten in place below
-    }
-    auto stage = [&](std::vector<Field3D>& k, BoutReal tt) {
-      run_rhs(tt);
-      for (size_t i = 0; i < nv; ++i) {
-        k[i] = *f3d[i].F_var;
-      }
-    };
-    auto advance = [&](const std::vector<Field3D>& k, BoutReal c) { // var(interior) = start + c dt k; guards kept
-      for (size_t i = 0; i < nv; ++i) {
-        rkStage(m, 0, dt, c, start[i], &k[i], nullptr, nullptr, nullptr, *f3d[i].var);
-      }
-    };
-    stage(k1, t);
-    advance(k1, 0.5);
-    stage(k2, t + 0.5 * dt);
-    advance(k2, 0.5);
-    stage(k3, t + 0.5 * dt);
-    advance(k3, 1.0);
-    stage(k4, t + dt);
-    for (size_t i = 0; i < nv; ++i) {
-      rkStage(m, 1, dt, 1.0, start[i], &k1[i], &k2[i], &k3[i], &k4[i], *f3d[i].var);
-    }
-  }
+  void take_step(BoutReal t, BoutReal dt) override { rk4Step(*this, t, dt); }
 };
 
 class RK3SSP : public Solver {
@@ -1529,16 +1578,589 @@ public:
     }
   }
 };
+
+// ------------------------------------------------------------------------------------------------------
+// Other explicit integrators: euler, rkgeneric (rkf45 / cashkarp / rk4 / rkf34), splitrk.
+// A "state" is one Field3D handle per evolving variable.  New states are always formed INTO the evolving
+// variables themselves (bout_b200_lincomb over RGN_NOBNDRY through the copy-on-write handle, so guard cells carry
+// over exactly as with the reference's load_vars, solver.cxx:1039-1140, which writes the evolving region only);
+// keeping or re-loading a state is a handle copy, not a pass over memory.
+// ------------------------------------------------------------------------------------------------------
+using State = std::vector<Field3D>;
+struct Term {
+  double c;
+  const Field3D* f;
+};
+
+// out(RGN_NOBNDRY) = sum_j c_j f_j, terms added left to right; operands may share storage with `out`
+void combine(Field3D& out, const std::vector<Term>& terms) {
+  Mesh* m = out.getMesh();
+  const auto g = m->grid();
+  std::vector<double> c;
+  std::vector<const double*> x;
+  for (const auto& t : terms) {
+    if (t.c == 0.0) {
+      continue; // rkscheme.cxx:179 skips zero coefficients; also keeps never-written stage fields out
+    }
+    if (!t.f->isAllocated()) {
+      throw BoutException("Solver: state field used before it was set");
+    }
+    c.push_back(t.c);
+    x.push_back(t.f->dptr()); // taken BEFORE un-sharing `out`: an operand that shares out's block keeps reading the old block
+  }
+  if (c.empty()) {
+    throw BoutException("Solver: empty linear combination");
+  }
+  Field3D keep;
+  for (const double* xp : x) {
+    if (xp == out.dptr()) {
+      keep = out; // an operand IS out's block: keep it alive and force the un-share below
+    }
+  }
+  double* w = out.wptr(); // fresh block with the old contents (guards included) whenever the block was shared
+  constexpr size_t kMax = 8; // bout_b200_lincomb takes up to 8 terms; longer sums continue from the partial result
+  if (c.size() <= kMax) {
+    check(bout_b200_lincomb(&g, BOUT_B200_RGN_NOBNDRY, static_cast<int>(c.size()), c.data(), x.data(), w, nullptr));
+    return;
+  }
+  Field3D partial = emptyFrom(out), next;
+  size_t done = 0;
+  check(bout_b200_lincomb(&g, BOUT_B200_RGN_NOBNDRY, static_cast<int>(kMax), c.data(), x.data(), partial.wptr(), nullptr));
+  done = kMax;
+  while (done < c.size()) {
+    const size_t n = std::min(kMax - 1, c.size() - done);
+    std::vector<double> cc{1.0};
+    std::vector<const double*> xx{partial.dptr()};
+    cc.insert(cc.end(), c.begin() + done, c.begin() + done + n);
+    xx.insert(xx.end(), x.begin() + done, x.begin() + done + n);
+    done += n;
+    if (done == c.size()) {
+      check(bout_b200_lincomb(&g, BOUT_B200_RGN_NOBNDRY, static_cast<int>(cc.size()), cc.data(), xx.data(), w, nullptr));
+    } else {
+      next = emptyFrom(out);
+      check(bout_b200_lincomb(&g, BOUT_B200_RGN_NOBNDRY, static_cast<int>(cc.size()), cc.data(), xx.data(), next.wptr(), nullptr));
+      partial = next;
+    }
+  }
+}
+
+// Local error sum of the adaptive integrators on the device, one number back to the host
+class ErrorNorm {
+public:
+  // sum_i sum_{RGN_NOBNDRY} |a_i - b_i| / (|a_i| + |b_i| + atol) / neq  (rkscheme.cxx:139-168, split-rk.cxx:127-144)
+  double operator()(const State& a, const State& b, double atol) {
+    Mesh* m = a.at(0).getMesh();
+    const auto g = m->grid();
+    if (!scratch) {
+      scratch = bout::b200::acquire(bout_b200_err_sum_scratch_doubles() + 2);
+    }
+    double* result = scratch->ptr + bout_b200_err_sum_scratch_doubles();
+    for (size_t i = 0; i < a.size(); ++i) {
+      check(bout_b200_err_sum(&g, BOUT_B200_RGN_NOBNDRY, a[i].dptr(), b[i].dptr(), atol, scratch->ptr, i == 0 ? 0 : 1,
+                              result, nullptr));
+    }
+    double host = 0.0;
+    check(bout_b200_memcpy_d2h(&host, result, sizeof(double), nullptr));
+    check(bout_b200_stream_sync(nullptr));
+    const double neq = static_cast<double>(a.size()) * (g.xend - g.xstart + 1) * (g.yend - g.ystart + 1) * g.nz;
+    return host / neq;
+  }
+
+private:
+  std::shared_ptr<bout::b200::Block> scratch;
+};
+
+class StateSolver : public Solver {
+public:
+  using Solver::Solver;
+
+protected:
+  size_t nv() const { return f3d.size(); }
+  State current() const { // handles of the evolving variables (no copy)
+    State s(nv());
+    for (size_t i = 0; i < nv(); ++i) {
+      s[i] = *f3d[i].var;
+    }
+    return s;
+  }
+  State derivs() const {
+    State s(nv());
+    for (size_t i = 0; i < nv(); ++i) {
+      s[i] = *f3d[i].F_var;
+    }
+    return s;
+  }
+  void load(const State& s) { // load_vars
+    for (size_t i = 0; i < nv(); ++i) {
+      if (f3d[i].var->dptr() != s[i].dptr()) {
+        *f3d[i].var = s[i];
+      }
+    }
+  }
+  /// variables <- sum_j c_j states_j (per variable)
+  void form(const std::vector<std::pair<double, const State*>>& terms) {
+    for (size_t i = 0; i < nv(); ++i) {
+      std::vector<Term> t;
+      for (const auto& p : terms) {
+        t.push_back({p.first, &(*p.second)[i]});
+      }
+      combine(*f3d[i].var, t);
+    }
+  }
+};
+
+// ---- euler (src/solver/impls/euler/euler.cxx) ---------------------------------------------------------------
+class EulerSolver : public StateSolver {
+public:
+  explicit EulerSolver(Options* opts) : StateSolver(opts) {
+    mxstep = (*options)["mxstep"].withDefault(500);
+    cfl_factor = (*options)["cfl_factor"].withDefault(2.);
+  }
+  void setMaxTimestep(BoutReal dt) override { // euler.cxx:28-36
+    if (dt >= cfl_factor * timestep) {
+      return;
+    }
+    timestep = dt * 0.99 / cfl_factor;
+    timestep_reduced = true;
+  }
+  void run_output_step(BoutReal target) override { // euler.cxx:67-135
+    bool running = true;
+    int internal_steps = 0;
+    do {
+      BoutReal dt_limit = timestep;
+      if ((simtime + timestep) >= target) {
+        timestep = target - simtime;
+        running = false;
+      }
+      const BoutReal old_timestep = timestep;
+      const State start = current();
+      timestep_reduced = false;
+      eulerStep(simtime, timestep, start);
+      if (timestep_reduced && timestep < old_timestep) { // the model lowered the limit during the RHS: redo
+        eulerStep(simtime, timestep, start);
+        dt_limit = timestep;
+        running = true;
+      }
+      simtime += timestep;
+      if (++internal_steps > mxstep) {
+        throw BoutException("ERROR: MXSTEP exceeded. simtime={:e}, timestep = {:e}\n", simtime, timestep);
+      }
+      timestep = dt_limit;
+    } while (running);
+  }
+
+private:
+  int mxstep;
+  BoutReal cfl_factor;
+  bool timestep_reduced = false;
+  void eulerStep(BoutReal t, BoutReal dt, const State& start) { // euler.cxx:138-182: result = start + dt * F(start)
+    load(start);
+    run_rhs(t);
+    const State k = derivs();
+    form({{1.0, &start}, {dt, &k}});
+  }
+};
+
+// ---- rkgeneric (src/solver/impls/rkgeneric/rkgeneric.cxx, rkscheme.cxx and impls/*) ------------------------------
+struct RKTableau {
+  std::string label;
+  int stages = 0, order = 0;
+  std::vector<double> stage;  // [stages][stages]
+  std::vector<double> result; // [stages][2]: column 0 / 1 as in RKScheme::resultCoeffs
+  std::vector<double> time;   // [stages]
+  double a(int i, int j) const { return stage[static_cast<size_t>(i) * stages + j]; }
+  double b(int i, int k) const { return result[static_cast<size_t>(i) * 2 + k]; }
+};
+
+RKTableau makeTableau(const std::string& name) {
+  RKTableau t;
+  auto size = [&](int n, int order) {
+    t.stages = n;
+    t.order = order;
+    t.stage.assign(static_cast<size_t>(n) * n, 0.0);
+    t.result.assign(static_cast<size_t>(n) * 2, 0.0);
+    t.time.assign(n, 0.0);
+  };
+  auto A = [&](int i, int j) -> double& { return t.stage[static_cast<size_t>(i) * t.stages + j]; };
+  auto B = [&](int i, int k) -> double& { return t.result[static_cast<size_t>(i) * 2 + k]; };
+  t.label = name;
+  if (name == "rkf45") { // Fehlberg 4(5): impls/rkf45/rkf45.cxx:27-88
+    size(6, 4);
+    A(1, 0) = 1.0 / 4.0;
+    A(2, 0) = 3.0 / 32.0, A(2, 1) = 9.0 / 32.0;
+    A(3, 0) = 1932.0 / 2197.0, A(3, 1) = -7200.0 / 2197.0, A(3, 2) = 7296.0 / 2197.0;
+    A(4, 0) = 439.0 / 216.0, A(4, 1) = -8.0, A(4, 2) = 3680.0 / 513.0, A(4, 3) = -845.0 / 4104.0;
+    A(5, 0) = -8.0 / 27.0, A(5, 1) = 2.0, A(5, 2) = -3544.0 / 2565.0, A(5, 3) = 1859.0 / 4104.0, A(5, 4) = -11.0 / 40.0;
+    B(0, 0) = 16.0 / 135.0, B(0, 1) = 25.0 / 216.0;
+    B(2, 0) = 6656.0 / 12825.0, B(2, 1) = 1408.0 / 2565.0;
+    B(3, 0) = 28561.0 / 56430.0, B(3, 1) = 2197.0 / 4104.0;
+    B(4, 0) = -9.0 / 50.0, B(4, 1) = -1.0 / 5.0;
+    B(5, 0) = 2.0 / 55.0;
+    t.time = {0.0, 1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
+  } else if (name == "cashkarp") { // impls/cashkarp/cashkarp.cxx:27-88
+    size(6, 4);
+    A(1, 0) = 1.0 / 5.0;
+    A(2, 0) = 3.0 / 40.0, A(2, 1) = 9.0 / 40.0;
+    A(3, 0) = 3.0 / 10.0, A(3, 1) = -9.0 / 10.0, A(3, 2) = 6.0 / 5.0;
+    A(4, 0) = -11.0 / 54.0, A(4, 1) = 5.0 / 2.0, A(4, 2) = -70.0 / 27.0, A(4, 3) = 35.0 / 27.0;
+    A(5, 0) = 1631.0 / 55296.0, A(5, 1) = 175.0 / 512.0, A(5, 2) = 575.0 / 13824.0, A(5, 3) = 44275.0 / 110592.0,
+         A(5, 4) = 253.0 / 4096.0;
+    B(0, 0) = 37.0 / 378.0, B(0, 1) = 2825.0 / 27648.0;
+    B(2, 0) = 250.0 / 621.0, B(2, 1) = 18575.0 / 48384.0;
+    B(3, 0) = 125.0 / 594.0, B(3, 1) = 13525.0 / 55296.0;
+    B(4, 1) = 277.0 / 14336.0;
+    B(5, 0) = 512.0 / 1771.0, B(5, 1) = 1.0 / 4.0;
+    t.time = {0.0, 1.0 / 5.0, 3.0 / 10.0, 3.0 / 5.0, 1.0, 7.0 / 8.0};
+  } else if (name == "rkf34") { // impls/rkf34/rkf34.cxx:33-83
+    size(5, 3);
+    A(1, 0) = 1.0 / 4.0;
+    A(2, 0) = 4.0 / 81.0, A(2, 1) = 32.0 / 81.0;
+    A(3, 0) = 57.0 / 98.0, A(3, 1) = -432.0 / 343.0, A(3, 2) = 1053.0 / 686.0;
+    A(4, 0) = 1.0 / 6.0, A(4, 2) = 27.0 / 52.0, A(4, 3) = 49.0 / 156.0;
+    B(0, 0) = 43.0 / 288.0, B(0, 1) = 1.0 / 6.0;
+    B(2, 0) = 243.0 / 416.0, B(2, 1) = 27.0 / 52.0;
+    B(3, 0) = 343.0 / 1872.0, B(3, 1) = 49.0 / 156.0;
+    B(4, 0) = 1.0 / 12.0;
+    t.time = {0.0, 1.0 / 4.0, 4.0 / 9.0, 6.0 / 7.0, 1.0};
+  } else if (name == "rk4") { // one RK4 step against two half steps: impls/rk4simple/rk4simple.cxx:27-116
+    size(11, 4);
+    A(1, 0) = 1.0 / 2.0, A(2, 1) = 1.0 / 2.0, A(3, 2) = 1.0;
+    A(4, 0) = 1.0 / 4.0, A(5, 4) = 1.0 / 4.0, A(6, 5) = 1.0 / 2.0;
+    for (int i = 7; i <= 10; ++i) { // the state after the first half step
+      A(i, 0) = 1.0 / 12.0, A(i, 4) = 1.0 / 6.0, A(i, 5) = 1.0 / 6.0, A(i, 6) = 1.0 / 12.0;
+    }
+    A(8, 7) = 1.0 / 4.0, A(9, 8) = 1.0 / 4.0, A(10, 9) = 1.0 / 2.0;
+    B(0, 1) = 1.0 / 6.0, B(1, 1) = 1.0 / 3.0, B(2, 1) = 1.0 / 3.0, B(3, 1) = 1.0 / 6.0;
+    B(0, 0) = 1.0 / 12.0, B(4, 0) = 1.0 / 6.0, B(5, 0) = 1.0 / 6.0, B(6, 0) = 1.0 / 12.0;
+    B(7, 0) = 1.0 / 12.0, B(8, 0) = 1.0 / 6.0, B(9, 0) = 1.0 / 6.0, B(10, 0) = 1.0 / 12.0;
+    t.time = {0.0, 0.5, 0.5, 1.0, 0.25, 0.25, 0.5, 0.5, 0.75, 0.75, 1.0};
+  } else {
+    throw BoutException("RKScheme '{}' is not available: rkf45, cashkarp, rk4, rkf34", name);
+  }
+  return t;
+}
+
+class RKGenericSolver : public StateSolver {
+public:
+  explicit RKGenericSolver(Options* opts) : StateSolver(opts) { // rkgeneric.cxx:9-24, rkscheme.cxx:19-25
+    atol = (*options)["atol"].withDefault(1.e-5);
+    rtol = (*options)["rtol"].withDefault(1.e-3);
+    max_timestep = (*options)["max_timestep"].withDefault(output_timestep);
+    timestep = (*options)["timestep"].withDefault(max_timestep);
+    mxstep = (*options)["mxstep"].withDefault(500);
+    adaptive = (*options)["adaptive"].withDefault(true);
+    tab = makeTableau((*options)["scheme"].withDefault(std::string("rkf45")));
+    followHighOrder = (*options)["followHighOrder"].withDefault(false);
+    dtfac = (*options)["dtfac"].withDefault(1.0);
+    if (tab.label == "rkf34") {
+      dtfac = 0.9; // impls/rkf34/rkf34.cxx:10-14 overrides the option
+    }
+  }
+  void setMaxTimestep(BoutReal dt) override { // rkgeneric.cxx:26-34
+    if (dt > timestep) {
+      return;
+    }
+    if (adaptive) {
+      timestep = dt;
+    }
+  }
+  void run_output_step(BoutReal target) override { // rkgeneric.cxx:82-160
+    bool running = true;
+    int internal_steps = 0;
+    do {
+      BoutReal dt;
+      const State start = current();
+      do {
+        dt = timestep;
+        running = true;
+        if ((simtime + dt) >= target) {
+          dt = target - simtime;
+          running = false;
+        }
+        const BoutReal err = rkStep(simtime, dt, start);
+        if (!adaptive) {
+          break;
+        }
+        if (++internal_steps > mxstep) {
+          throw BoutException("ERROR: MXSTEP exceeded. timestep = {:e}, err={:e}\n", timestep, err);
+        }
+        if ((err > rtol) || ((err < 0.1 * rtol) && running)) {
+          timestep = dtfac * dt * std::pow(rtol / (2.0 * err), 1.0 / (tab.order + 1.0)); // rkscheme.cxx:129-131
+          if ((max_timestep > 0) && (timestep > max_timestep)) {
+            timestep = max_timestep;
+          }
+        }
+        if (err < rtol) {
+          break;
+        }
+      } while (true);
+      simtime += dt; // the accepted result already sits in the evolving variables
+    } while (running);
+  }
+
+private:
+  BoutReal atol, rtol, max_timestep, dtfac;
+  int mxstep;
+  bool adaptive, followHighOrder;
+  RKTableau tab;
+  ErrorNorm errnorm;
+
+  // rkgeneric.cxx:163-180 + rkscheme.cxx:52-127: stages, then the followed result into the variables
+  BoutReal rkStep(BoutReal t, BoutReal dt, const State& start) {
+    std::vector<State> k(tab.stages);
+    for (int s = 0; s < tab.stages; ++s) {
+      std::vector<std::pair<double, const State*>> terms{{1.0, &start}};
+      for (int j = 0; j < s; ++j) {
+        if (std::abs(tab.a(s, j)) < atol) { // rkscheme.cxx:74 (sic: compared with atol)
+          continue;
+        }
+        terms.push_back({tab.a(s, j) * dt, &k[j]});
+      }
+      if (terms.size() == 1) {
+        load(start);
+      } else {
+        form(terms);
+      }
+      run_rhs(t + dt * tab.time[s]);
+      k[s] = derivs();
+    }
+    const int follow = followHighOrder ? 0 : 1, alt = followHighOrder ? 1 : 0;
+    auto output = [&](int col) {
+      std::vector<std::pair<double, const State*>> terms{{1.0, &start}};
+      for (int s = 0; s < tab.stages; ++s) {
+        terms.push_back({dt * tab.b(s, col), &k[s]}); // zero coefficients are dropped by combine()
+      }
+      form(terms);
+    };
+    if (!adaptive) {
+      output(follow);
+      return 0.0;
+    }
+    output(alt);
+    const State resultAlt = current();
+    output(follow);
+    return errnorm(current(), resultAlt, atol);
+  }
+};
+
+// ---- splitrk (src/solver/impls/split-rk/split-rk.cxx): Strang split, RK-Legendre diffusive + SSP-RK3 advective ---
+class SplitRK : public StateSolver {
+public:
+  explicit SplitRK(Options* opts) : StateSolver(opts) { // split-rk.cxx:18-52
+    nstages = (*options)["nstages"].withDefault(10);
+    adaptive = (*options)["adaptive"].withDefault(true);
+    atol = (*options)["atol"].withDefault(1e-10);
+    rtol = (*options)["rtol"].withDefault(1e-5);
+    max_timestep = (*options)["max_timestep"].withDefault(output_timestep);
+    max_timestep_change = (*options)["max_timestep_change"].withDefault(2.0);
+    mxstep = (*options)["mxstep"].withDefault(1000);
+    adapt_period = (*options)["adapt_period"].withDefault(1);
+    if (!(max_timestep_change > 1.0) || mxstep <= 0 || nstages <= 1 || adapt_period <= 0) {
+      throw BoutException("splitrk: need max_timestep_change > 1, mxstep > 0, nstages > 1, adapt_period > 0");
+    }
+  }
+  void init_solver() override { // split-rk.cxx:90-94
+    const int ninternal_steps = static_cast<int>(std::ceil(output_timestep / timestep));
+    if (ninternal_steps <= 0) {
+      throw BoutException("splitrk: output step / timestep must be positive");
+    }
+    timestep = output_timestep / ninternal_steps;
+  }
+  void run_output_step(BoutReal target) override { // split-rk.cxx:99-207
+    BoutReal dt;
+    bool running = true;
+    int internal_steps = 0;
+    do {
+      if (adaptive && (internal_steps % adapt_period == 0)) {
+        const State state = current();
+        do {
+          dt = timestep;
+          running = true;
+          if ((simtime + dt) >= target) {
+            dt = target - simtime;
+            running = false;
+          }
+          load(state); // two half steps
+          splitStep(simtime, 0.5 * dt);
+          splitStep(simtime + 0.5 * dt, 0.5 * dt);
+          const State state2 = current();
+          load(state); // one full step
+          splitStep(simtime, dt);
+          const State state1 = current();
+          const BoutReal err = errnorm(state2, state1, atol);
+          if (++internal_steps > mxstep) {
+            throw BoutException("ERROR: MXSTEP exceeded. timestep = {:e}, err={:e}\n", timestep, err);
+          }
+          if ((err > rtol) || (err < 0.1 * rtol)) { // error ~ dt^2
+            BoutReal factor = std::pow((0.5 * rtol) / err, 1. / 3);
+            if (factor > max_timestep_change) {
+              factor = max_timestep_change;
+            } else if (factor < 1. / max_timestep_change) {
+              factor = 1. / max_timestep_change;
+            }
+            timestep *= factor;
+            if ((max_timestep > 0) && (timestep > max_timestep)) {
+              timestep = max_timestep;
+            }
+          }
+          if (err < rtol) {
+            load(state2);
+            break;
+          }
+        } while (true);
+      } else {
+        dt = timestep;
+        running = true;
+        if ((simtime + dt) >= target) {
+          dt = target - simtime;
+          running = false;
+        }
+        splitStep(simtime, timestep); // split-rk.cxx:192 (sic: the un-clipped timestep)
+        internal_steps++;
+      }
+      simtime += dt;
+    } while (running);
+  }
+
+private:
+  int nstages, mxstep, adapt_period;
+  bool adaptive;
+  BoutReal atol, rtol, max_timestep, max_timestep_change;
+  ErrorNorm errnorm;
+
+  void splitStep(BoutReal t, BoutReal dt) { // split-rk.cxx:209-219, on the state held by the variables
+    diffusionStep(t, 0.5 * dt);
+    advectionStep(t, dt);
+    diffusionStep(t + 0.5 * dt, 0.5 * dt);
+  }
+
+  void diffusionStep(BoutReal t, BoutReal dt) { // Runge-Kutta-Legendre, split-rk.cxx:221-283
+    const BoutReal weight = dt * 4. / (SQ(static_cast<BoutReal>(nstages)) + nstages - 2);
+    const State start = current();
+    run_diffusive(t);
+    const State dydt = derivs();
+    form({{1.0, &start}, {weight / 3.0, &dydt}}); // y_1
+    State u2 = current();
+    run_diffusive(t + (weight / 3.0) * dt);
+    State f = derivs();
+    // y_2 = 1.5 (u2 + weight f(u2)) - 0.5 start - weight dydt
+    form({{1.5, &u2}, {1.5 * weight, &f}, {-0.5, &start}, {-weight, &dydt}});
+    State u1 = current();
+    BoutReal b_jm2 = 1. / 3, b_jm1 = 1. / 3;
+    for (int j = 3; j <= nstages; ++j) {
+      const BoutReal b_j = (SQ(static_cast<BoutReal>(j)) + j - 2.0) / (2. * j * (j + 1.));
+      const BoutReal mu = (2. * j - 1.) / j * b_j / b_jm1;
+      const BoutReal nu = -(j - 1.) / j * b_j / b_jm2;
+      const BoutReal a_jm1 = 1. - b_jm1;
+      run_diffusive(t); // the variables hold u1
+      f = derivs();
+      // mu (u1 + weight (f - a_jm1 dydt)) + nu u2 + (1 - mu - nu) start
+      form({{mu, &u1}, {mu * weight, &f}, {-mu * weight * a_jm1, &dydt}, {nu, &u2}, {1. - mu - nu, &start}});
+      b_jm2 = b_jm1;
+      b_jm1 = b_j;
+      u2 = u1;
+      u1 = current();
+    }
+  }
+
+  void advectionStep(BoutReal t, BoutReal dt) { // SSP-RK3, split-rk.cxx:285-318
+    const State start = current();
+    run_convective(t);
+    State k = derivs();
+    form({{1.0, &start}, {dt, &k}});
+    const State u1 = current();
+    run_convective(t + dt);
+    k = derivs();
+    form({{0.75, &start}, {0.25, &u1}, {0.25 * dt, &k}});
+    const State u2 = current();
+    run_convective(t + 0.5 * dt);
+    k = derivs();
+    form({{1. / 3, &start}, {2. / 3., &u2}, {(2. / 3.) * dt, &k}});
+  }
+};
+
+// ---- rk4 with solver:adaptive = true (rk4.cxx:84-140): two half steps against one full step ---------------------
+class RK4Adaptive : public StateSolver {
+public:
+  explicit RK4Adaptive(Options* opts) : StateSolver(opts) { // rk4.cxx:11-25
+    atol = (*options)["atol"].withDefault(1.e-5);
+    rtol = (*options)["rtol"].withDefault(1.e-3);
+    max_timestep = (*options)["max_timestep"].withDefault(output_timestep);
+    timestep = (*options)["timestep"].withDefault(max_timestep);
+    mxstep = (*options)["mxstep"].withDefault(500);
+  }
+  void setMaxTimestep(BoutReal dt) override { // rk4.cxx:27-35
+    if (dt <= timestep) {
+      timestep = dt;
+    }
+  }
+  void run_output_step(BoutReal target) override {
+    bool running = true;
+    int internal_steps = 0;
+    do {
+      BoutReal dt;
+      const State f0 = current();
+      do {
+        dt = timestep;
+        running = true;
+        if ((simtime + dt) >= target) {
+          dt = target - simtime;
+          running = false;
+        }
+        load(f0);
+        rk4Step(*this, simtime, 0.5 * dt);
+        rk4Step(*this, simtime + 0.5 * dt, 0.5 * dt);
+        const State f2 = current();
+        load(f0);
+        rk4Step(*this, simtime, dt);
+        const State f1 = current();
+        const BoutReal err = errnorm(f2, f1, atol);
+        if (++internal_steps > mxstep) {
+          throw BoutException("ERROR: MXSTEP exceeded. timestep = {:e}, err={:e}\n", timestep, err);
+        }
+        if ((err > rtol) || (err < 0.1 * rtol)) { // error ~ dt^5
+          timestep /= std::pow(err / (0.5 * rtol), 0.2);
+          if ((max_timestep > 0) && (timestep > max_timestep)) {
+            timestep = max_timestep;
+          }
+        }
+        if (err < rtol) {
+          load(f2);
+          break;
+        }
+      } while (true);
+      simtime += dt;
+    } while (running);
+  }
+
+private:
+  BoutReal atol, rtol, max_timestep;
+  int mxstep;
+  ErrorNorm errnorm;
+};
 } // namespace
 
 std::unique_ptr<Solver> Solver::create(Options* opts) {
   Options& o = opts != nullptr ? *opts : Options::root()["solver"];
   const std::string type = o["type"].withDefault(std::string("rk4"));
   if (type == "rk4") {
+    if (o["adaptive"].withDefault(false)) {
+      return std::make_unique<RK4Adaptive>(&o);
+    }
     return std::make_unique<RK4Solver>(&o);
   }
   if (type == "rk3ssp") {
     return std::make_unique<RK3SSP>(&o);
   }
-  throw BoutException("Solver type '{}' is not available: the B200 path implements rk4 and rk3ssp", type);
+  if (type == "euler") {
+    return std::make_unique<EulerSolver>(&o);
+  }
+  if (type == "rkgeneric") {
+    return std::make_unique<RKGenericSolver>(&o);
+  }
+  if (type == "splitrk") {
+    return std::make_unique<SplitRK>(&o);
+  }
+  throw BoutException("Solver type '{}' is not available: the B200 path implements rk4, rk3ssp, euler, rkgeneric and splitrk",
+                      type);
 }

@@ -396,6 +396,21 @@ int bout_b200_rk_stage(const bout_b200_grid* g, int region, int mode, double dt,
                        const double* start, const double* k1, const double* k2, const double* k3,
                        const double* k4, double* out, void* stream);
 
+/* out[region] = sum_{j<n} coef[j] * x[j]  (1 <= n <= 8, terms added left to right; out must not alias an x[j]):
+ * the state and output loops of the other explicit integrators, one pass instead of one per term --
+ * EulerSolver::take_step (src/solver/impls/euler/euler.cxx:178-181), RKScheme::setCurState / constructOutput
+ * (src/solver/impls/rkgeneric/rkscheme.cxx:57-84, :173-190), SplitRK::take_diffusion_step / take_advection_step
+ * (src/solver/impls/split-rk/split-rk.cxx:226-300). */
+int bout_b200_lincomb(const bout_b200_grid* g, int region, int n, const double* coef,
+                      const double* const* x, double* out, void* stream);
+/* result[0] (+)= sum over region of |a-b| / (|a| + |b| + atol): the local error sum of the adaptive integrators
+ * (rk4.cxx:103-106, rkscheme.cxx:150-156, split-rk.cxx:128-133); the caller divides by the number of evolving
+ * values.  scratch: bout_b200_err_sum_scratch_doubles() doubles of device memory; result: one device double
+ * (accumulate != 0 adds to it, so the fields of a state sum into one number).  The summation order is fixed. */
+size_t bout_b200_err_sum_scratch_doubles(void);
+int bout_b200_err_sum(const bout_b200_grid* g, int region, const double* a, const double* b, double atol,
+                      double* scratch, int accumulate, double* result, void* stream);
+
 /* ---- fused RHS kernels (2)+(4): whole model right-hand sides in one pass ---------------------------------
  * Field2D metric bundle (reference include/bout/coordinates.hxx:83-116); unused members may be NULL. */
 typedef struct bout_b200_metric {

@@ -514,6 +514,10 @@ class Ref:
         self._check(self.lib.boutref_elmpb_get(name.encode(), _p(out), C.byref(k)))
         return float(out[0]) if k.value == 0 else out
 
+    def model_rhs_calls(self):
+        """Solver::resetRHSCounter (src/solver/solver.cxx:946): run_rhs + run_convective calls since the last query."""
+        return int(self.lib.boutref_model_rhs_calls())
+
     def model_solve(self, nout, output_step):
         self.lib.boutref_model_solve.argtypes = [C.c_int, C.c_double]
         self._check(self.lib.boutref_model_solve(nout, output_step))

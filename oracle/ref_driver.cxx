@@ -27,6 +27,10 @@
 #include <bout/cyclic_reduction.hxx>
 #include "solver/impls/rk4/rk4.hxx"
 #include "solver/impls/rk3-ssp/rk3-ssp.hxx"
+#include "solver/impls/euler/euler.hxx"
+#include "solver/impls/rkgeneric/rkgeneric.hxx"
+#include "solver/impls/split-rk/split-rk.hxx"
+#include "solver/impls/adams_bashforth/adams_bashforth.hxx"
 
 #include <chrono>
 #include <cstdio>
@@ -43,27 +47,37 @@ std::unique_ptr<PhysicsModel> boutref_make_hw();
 std::unique_ptr<PhysicsModel> boutref_make_hw3d();
 std::unique_ptr<PhysicsModel> boutref_make_blob2d();
 std::unique_ptr<PhysicsModel> boutref_make_elmpb();
+std::unique_ptr<PhysicsModel> boutref_make_ode_pair(); // tests/models/ode_pair.cxx (this repository's test model)
 int boutref_elmpb_get_impl(PhysicsModel* pm, const char* name, double* out, int* kind);
 
 namespace {
-// The reference's own RK4 solver with its (protected) variable registry made reachable, so the
+// The reference's own solvers with their (protected) variable registry made reachable, so the
 // harness can load states into an unchanged model and read ddt() back.
+struct DriverIface {
+  virtual ~DriverIface() = default;
+  virtual int nvars() const = 0;
+  virtual const std::string& varName(int i) const = 0;
+  virtual Field3D& var(int i) = 0;
+  virtual Field3D& ddtVar(int i) = 0;
+  virtual int rhs(BoutReal t) = 0;
+  virtual int rhsCalls() = 0;
+  virtual Solver* solver() = 0;
+};
 template <class Base>
-class DriverSolver : public Base {
+class DriverSolver : public Base, public DriverIface {
 public:
   explicit DriverSolver(Options* opts) : Base(opts) {}
-  int nvars() const { return static_cast<int>(this->f3d.size()); }
-  const std::string& varName(int i) const { return this->f3d[i].name; }
-  Field3D& var(int i) { return *this->f3d[i].var; }
-  Field3D& ddtVar(int i) { return *this->f3d[i].F_var; }
-  int rhs(BoutReal t) { return this->run_rhs(t); }
+  int nvars() const override { return static_cast<int>(this->f3d.size()); }
+  const std::string& varName(int i) const override { return this->f3d[i].name; }
+  Field3D& var(int i) override { return *this->f3d[i].var; }
+  Field3D& ddtVar(int i) override { return *this->f3d[i].F_var; }
+  int rhs(BoutReal t) override { return this->run_rhs(t); }
+  int rhsCalls() override { return this->resetRHSCounter(); } // calls since the last query
+  Solver* solver() override { return this; }
 };
-using DriverRK4 = DriverSolver<RK4Solver>;
-using DriverRK3 = DriverSolver<RK3SSP>;
 std::unique_ptr<PhysicsModel> model;
-std::unique_ptr<DriverRK4> rk4;
-std::unique_ptr<DriverRK3> rk3;
-Solver* activeSolver() { return rk4 ? static_cast<Solver*>(rk4.get()) : static_cast<Solver*>(rk3.get()); }
+std::unique_ptr<DriverIface> drv;
+Solver* activeSolver() { return drv ? drv->solver() : nullptr; }
 
 std::string last_error;
 std::unique_ptr<Laplacian> lap;
@@ -295,8 +309,7 @@ void boutref_finalise() {
   if (!initialised) {
     return;
   }
-  rk4.reset();
-  rk3.reset();
+  drv.reset();
   model.reset();
   lap.reset();
   delete bout::globals::mesh;
@@ -574,18 +587,27 @@ int boutref_zshift(double* out2d, double* zlength) {
 
 // ---- unchanged example models driven through the reference's own RK solvers --------------------
 // name: "hw" (examples/hasegawa-wakatani), "hw3d" (examples/hasegawa-wakatani-3d), "blob2d";
-// solver: "rk4" or "rk3ssp" (options section [solver] of the ini text applies)
+// solver: "rk4", "rk3ssp", "euler", "rkgeneric", "splitrk" or "adams-bashforth" (options section [solver] of the ini text applies)
 int boutref_model_create(const char* name, const char* solver) {
   return guarded([&]() {
-    rk4.reset();
-    rk3.reset();
+    drv.reset();
     model.reset();
     const std::string n = name, s = solver;
     Options* sopts = &Options::root()["solver"];
     if (s == "rk3ssp") {
-      rk3 = std::make_unique<DriverRK3>(sopts);
+      drv = std::make_unique<DriverSolver<RK3SSP>>(sopts);
+    } else if (s == "euler") {
+      drv = std::make_unique<DriverSolver<EulerSolver>>(sopts);
+    } else if (s == "rkgeneric") {
+      drv = std::make_unique<DriverSolver<RKGenericSolver>>(sopts);
+    } else if (s == "splitrk") {
+      drv = std::make_unique<DriverSolver<SplitRK>>(sopts);
+    } else if (s == "adams-bashforth") {
+      drv = std::make_unique<DriverSolver<AdamsBashforthSolver>>(sopts);
+    } else if (s == "rk4") {
+      drv = std::make_unique<DriverSolver<RK4Solver>>(sopts);
     } else {
-      rk4 = std::make_unique<DriverRK4>(sopts);
+      throw BoutException("ref_driver: unknown solver '{}'", s);
     }
     if (n == "hw") {
       model = boutref_make_hw();
@@ -595,6 +617,8 @@ int boutref_model_create(const char* name, const char* solver) {
       model = boutref_make_blob2d();
     } else if (n == "elmpb") {
       model = boutref_make_elmpb();
+    } else if (n == "ode_pair") {
+      model = boutref_make_ode_pair();
     } else {
       throw BoutException("unknown model '{}'", n);
     }
@@ -607,28 +631,29 @@ int boutref_elmpb_get(const char* name, double* out, int* kind) {
   const int g = guarded([&]() { rc = boutref_elmpb_get_impl(model.get(), name, out, kind); });
   return g != 0 ? 100 : rc;
 }
-int boutref_model_nvars() { return rk4 ? rk4->nvars() : (rk3 ? rk3->nvars() : 0); }
+int boutref_model_nvars() { return drv ? drv->nvars() : 0; }
+int boutref_model_rhs_calls() { return drv ? drv->rhsCalls() : 0; }
 const char* boutref_model_varname(int i) {
-  return rk4 ? rk4->varName(i).c_str() : rk3->varName(i).c_str();
+  return drv->varName(i).c_str();
 }
 int boutref_model_get(int i, double* out) {
-  return guarded([&]() { fromField3D(rk4 ? rk4->var(i) : rk3->var(i), out); });
+  return guarded([&]() { fromField3D(drv->var(i), out); });
 }
 int boutref_model_set(int i, const double* in) {
   return guarded([&]() {
-    Field3D& f = rk4 ? rk4->var(i) : rk3->var(i);
+    Field3D& f = drv->var(i);
     f.allocate();
     std::memcpy(&f(0, 0, 0), in, sizeof(double) * mesh->LocalNx * mesh->LocalNy * mesh->LocalNz);
   });
 }
 int boutref_model_get_ddt(int i, double* out) {
-  return guarded([&]() { fromField3D(rk4 ? rk4->ddtVar(i) : rk3->ddtVar(i), out); });
+  return guarded([&]() { fromField3D(drv->ddtVar(i), out); });
 }
 // Solver::run_rhs (src/solver/solver.cxx:1380-1427): pre_rhs boundary conditions, the model's rhs
 // (or convective + diffusive for split-operator models), post_rhs.
 int boutref_model_rhs(double t) {
   return guarded([&]() {
-    const int rc = rk4 ? rk4->rhs(t) : rk3->rhs(t);
+    const int rc = drv->rhs(t);
     if (rc != 0) {
       throw BoutException("run_rhs returned {}", rc);
     }
@@ -637,18 +662,10 @@ int boutref_model_rhs(double t) {
 double boutref_model_time_rhs(int reps) {
   double result = -1.0;
   guarded([&]() {
-    if (rk4) {
-      rk4->rhs(0.0);
-    } else {
-      rk3->rhs(0.0);
-    }
+    drv->rhs(0.0);
     const auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < reps; ++i) {
-      if (rk4) {
-        rk4->rhs(0.0);
-      } else {
-        rk3->rhs(0.0);
-      }
+      drv->rhs(0.0);
     }
     const auto t1 = std::chrono::steady_clock::now();
     result = std::chrono::duration<double>(t1 - t0).count() / reps;

@@ -1,0 +1,171 @@
+/* TEST DOUBLE, never shipped and never loaded by the product: a host-memory stand-in for the handful of C-ABI
+ * entry points (include/bout_b200.h) that the C++ host layer's explicit integrators go through.  tests/
+ * LD_PRELOADs it in a child process so that the HOST LOGIC of bout-dev_b200/host (Solver::create, the euler /
+ * rkgeneric / splitrk control flow, copy-on-write states) can be compared with the reference build on a box
+ * without a GPU.  Every other entry point still resolves to the real library and fails with BOUT_B200_ERR_CUDA.
+ * The GPU tests run the same cases through the real kernels. */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "bout_b200.h"
+
+const char* bout_b200_last_error(void) { return "fake device (tests/fake_device/fake_b200.c)"; }
+int bout_b200_malloc(void** ptr, size_t bytes) {
+  *ptr = calloc(bytes ? bytes : 1, 1);
+  return *ptr ? 0 : BOUT_B200_ERR_CUDA;
+}
+int bout_b200_free(void* ptr) {
+  free(ptr);
+  return 0;
+}
+int bout_b200_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+  (void)stream;
+  memmove(dst, src, bytes);
+  return 0;
+}
+int bout_b200_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+  (void)stream;
+  memmove(dst, src, bytes);
+  return 0;
+}
+int bout_b200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+  (void)stream;
+  memmove(dst, src, bytes);
+  return 0;
+}
+int bout_b200_stream_sync(void* stream) {
+  (void)stream;
+  return 0;
+}
+
+static int box(const bout_b200_grid* g, int region, int* xs, int* xe, int* ys, int* ye) {
+  switch (region) {
+  case BOUT_B200_RGN_NOBNDRY: *xs = g->xstart, *xe = g->xend, *ys = g->ystart, *ye = g->yend; return 0;
+  case BOUT_B200_RGN_ALL: *xs = 0, *xe = g->nx - 1, *ys = 0, *ye = g->ny - 1; return 0;
+  case BOUT_B200_RGN_NOX: *xs = g->xstart, *xe = g->xend, *ys = 0, *ye = g->ny - 1; return 0;
+  case BOUT_B200_RGN_NOY: *xs = 0, *xe = g->nx - 1, *ys = g->ystart, *ye = g->yend; return 0;
+  default: return BOUT_B200_ERR_ARG;
+  }
+}
+
+int bout_b200_elementwise(const bout_b200_grid* g, int region, int nterms, const bout_b200_ewterm* t, double* out,
+                          void* stream) {
+  int xs, xe, ys, ye;
+  (void)stream;
+  if (nterms < 1 || nterms > 8 || box(g, region, &xs, &xe, &ys, &ye) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  for (int x = xs; x <= xe; ++x) {
+    for (int y = ys; y <= ye; ++y) {
+      const long long i2 = (long long)x * g->ny + y;
+      for (int z = 0; z < g->nz; ++z) {
+        const long long i3 = i2 * g->nz + z;
+        double acc = 0.0;
+        for (int k = 0; k < nterms; ++k) {
+          double v = t[k].coef;
+          if (t[k].f1) {
+            v *= t[k].f1_is2d ? t[k].f1[i2] : t[k].f1[i3];
+          }
+          if (t[k].f2) {
+            v *= t[k].f2_is2d ? t[k].f2[i2] : t[k].f2[i3];
+          }
+          if (t[k].div) {
+            v = t[k].div_is2d ? v * (1.0 / t[k].div[i2]) : v / t[k].div[i3];
+          }
+          acc = (k == 0) ? v : acc + v;
+        }
+        out[i3] = acc;
+      }
+    }
+  }
+  return 0;
+}
+
+int bout_b200_lincomb(const bout_b200_grid* g, int region, int n, const double* coef, const double* const* x,
+                      double* out, void* stream) {
+  bout_b200_ewterm t[8];
+  if (n < 1 || n > 8) {
+    return BOUT_B200_ERR_ARG;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (x[i] == NULL || x[i] == out) {
+      return BOUT_B200_ERR_ARG;
+    }
+    memset(&t[i], 0, sizeof(t[i]));
+    t[i].coef = coef[i];
+    t[i].f1 = x[i];
+  }
+  return bout_b200_elementwise(g, region, n, t, out, stream);
+}
+
+int bout_b200_unary(const bout_b200_grid* g, int op, const double* f, double arg, double* out, void* stream) {
+  const long long n = (long long)g->nx * g->ny * g->nz;
+  (void)stream;
+  for (long long i = 0; i < n; ++i) {
+    const double v = f[i];
+    double r;
+    switch (op) {
+    case 0: r = -1.0 * v; break;
+    case 1: r = sqrt(v); break;
+    case 2: r = fabs(v); break;
+    case 3: r = exp(v); break;
+    case 4: r = log(v); break;
+    case 5: r = sin(v); break;
+    case 6: r = cos(v); break;
+    case 7: r = tanh(v); break;
+    case 8: r = v * v; break;
+    case 9: r = pow(v, arg); break;
+    case 10: r = v; break;
+    default: return BOUT_B200_ERR_ARG;
+    }
+    out[i] = r;
+  }
+  return 0;
+}
+
+int bout_b200_rk_stage(const bout_b200_grid* g, int region, int mode, double dt, double c, const double* start,
+                       const double* k1, const double* k2, const double* k3, const double* k4, double* out,
+                       void* stream) {
+  int xs, xe, ys, ye;
+  (void)stream;
+  if (box(g, region, &xs, &xe, &ys, &ye) != 0 || mode < 0 || mode > 3) {
+    return BOUT_B200_ERR_ARG;
+  }
+  for (int x = xs; x <= xe; ++x) {
+    for (int y = ys; y <= ye; ++y) {
+      for (int z = 0; z < g->nz; ++z) {
+        const long long i = ((long long)x * g->ny + y) * g->nz + z;
+        switch (mode) {
+        case 0: out[i] = start[i] + c * dt * k1[i]; break;
+        case 1: out[i] = start[i] + (1. / 6.) * dt * (k1[i] + 2. * k2[i] + 2. * k3[i] + k4[i]); break;
+        case 2: out[i] = 0.75 * start[i] + 0.25 * k1[i] + 0.25 * dt * k2[i]; break;
+        default: out[i] = (1. / 3) * start[i] + (2. / 3.) * (k1[i] + dt * k2[i]); break;
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+size_t bout_b200_err_sum_scratch_doubles(void) { return 16; }
+int bout_b200_err_sum(const bout_b200_grid* g, int region, const double* a, const double* b, double atol,
+                      double* scratch, int accumulate, double* result, void* stream) {
+  int xs, xe, ys, ye;
+  double s = 0.0;
+  (void)stream;
+  (void)scratch;
+  if (box(g, region, &xs, &xe, &ys, &ye) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  for (int x = xs; x <= xe; ++x) {
+    for (int y = ys; y <= ye; ++y) {
+      for (int z = 0; z < g->nz; ++z) {
+        const long long i = ((long long)x * g->ny + y) * g->nz + z;
+        s += fabs(a[i] - b[i]) / (fabs(a[i]) + fabs(b[i]) + atol);
+      }
+    }
+  }
+  result[0] = (accumulate ? result[0] : 0.0) + s;
+  return 0;
+}

@@ -240,3 +240,64 @@ error_on_unused_options = false
 
 
 ELMPB_INI = elmpb_ini(20, 8, 16, timestep="2e-3")
+
+
+# ---- explicit integrators beyond rk4 / rk3ssp on tests/models/ode_pair.cxx (tests/golden/integrators.npz) --------
+def ode_ini(solver_opts, split, nout, output_step):
+    """12x1x8 periodic-X mesh without boundaries; [solver] options per case; root nout / timestep = the
+    arguments later given to Solver::solve, so option defaults that derive from them agree on both sides."""
+    return f"nout = {nout}\ntimestep = {output_step}\n" + make_ini(12, 1, 8, mxg=2, myg=0, periodic_x=True, extra=f"""
+[ode]
+damp = 0.3
+split = {'true' if split else 'false'}
+[all]
+scale = 0.0
+[f]
+scale = 1.0
+function = 1 + 0.5*sin(2*pi*x)*cos(z)
+[g]
+scale = 1.0
+function = 0.3*cos(2*pi*x) + 0.2*sin(z)
+[solver]
+{solver_opts}
+[input]
+error_on_unused_options = false
+""")
+
+
+# tag: (solver type, [solver] options, split-operator model?, nout, output_step)
+INTEGRATOR_CASES = {
+    "rk4_fixed": ("rk4", "timestep = 0.07", False, 2, 0.5),
+    "rk4_adaptive": ("rk4", "adaptive = true\ntimestep = 0.25\nmax_timestep = 0.5\natol = 1e-8\nrtol = 1e-7", False, 2, 0.5),
+    "rk3ssp_split": ("rk3ssp", "timestep = 0.07", True, 1, 0.5),
+    "euler": ("euler", "timestep = 0.01\nmxstep = 1000", False, 2, 0.1),
+    "euler_split": ("euler", "timestep = 0.03\nmxstep = 1000", True, 1, 0.1),
+    "rkf45_adaptive": ("rkgeneric", "timestep = 0.2\nmax_timestep = 0.5\natol = 1e-8\nrtol = 1e-6", False, 2, 0.5),
+    "rkf45_follow_high": ("rkgeneric", "timestep = 0.2\nmax_timestep = 0.5\natol = 1e-8\nrtol = 1e-6\nfollowHighOrder = true",
+                          False, 1, 0.5),
+    "cashkarp_fixed": ("rkgeneric", "scheme = cashkarp\nadaptive = false\ntimestep = 0.07\nmax_timestep = 0.5", False, 1, 0.5),
+    "cashkarp_adaptive": ("rkgeneric", "scheme = cashkarp\ntimestep = 0.25\nmax_timestep = 0.5\natol = 1e-9\nrtol = 1e-7",
+                          True, 1, 0.5),
+    "rk4simple_adaptive": ("rkgeneric", "scheme = rk4\ntimestep = 0.25\nmax_timestep = 0.5\natol = 1e-8\nrtol = 1e-6\n"
+                           "followHighOrder = true", False, 1, 0.5),
+    "rkf34_adaptive": ("rkgeneric", "scheme = rkf34\ntimestep = 0.25\nmax_timestep = 0.5\natol = 1e-8\nrtol = 1e-5", False, 1, 0.5),
+    "splitrk_fixed": ("splitrk", "adaptive = false\ntimestep = 0.06\nnstages = 5", True, 1, 0.5),
+    "splitrk_adaptive": ("splitrk", "timestep = 0.25\nmax_timestep = 0.5\nrtol = 1e-4\natol = 1e-10\nnstages = 6", True, 2, 0.5),
+    "splitrk_nonsplit_model": ("splitrk", "adaptive = false\ntimestep = 0.1\nnstages = 4", False, 1, 0.5),
+}
+
+
+# the same integrators on the UNCHANGED examples/hasegawa-wakatani/hw.cxx (a split-operator model; GPU tests only)
+def hw_integrator_ini(solver_opts, nout, output_step):
+    assert "[solver]\ntimestep = 0.01" in HW_INI
+    return f"nout = {nout}\ntimestep = {output_step}\n" + HW_INI.replace("[solver]\ntimestep = 0.01", "[solver]\n" + solver_opts)
+
+
+# tag: (solver type, [solver] options, nout, output_step) -- fixed-step settings, so the comparison does not hinge on
+# an accept / reject decision taken at rounding level (the controllers are pinned by INTEGRATOR_CASES)
+HW_INTEGRATOR_CASES = {
+    "hw_euler": ("euler", "timestep = 0.005\nmxstep = 1000", 1, 0.05),
+    "hw_cashkarp_fixed": ("rkgeneric", "scheme = cashkarp\nadaptive = false\ntimestep = 0.01\nmax_timestep = 0.05", 1, 0.05),
+    "hw_rkf45_fixed": ("rkgeneric", "adaptive = false\ntimestep = 0.01\nmax_timestep = 0.05", 1, 0.05),
+    "hw_splitrk_fixed": ("splitrk", "adaptive = false\ntimestep = 0.01\nnstages = 4", 1, 0.05),
+}

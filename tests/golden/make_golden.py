@@ -22,6 +22,9 @@ Outputs (committed; the GPU box has neither /root/reference nor needs the refere
   models.npz             unchanged example models (hasegawa-wakatani, hasegawa-wakatani-3d, blob2d) run
                          through the reference's Solver::run_rhs and RK4 / RK3-SSP solvers: initial state,
                          ddt after one RHS, state after a few steps.
+  integrators.npz        this repository's test model tests/models/ode_pair.cxx through the reference's own
+                         euler, rkgeneric (rkf45, cashkarp, rk4, rkf34; adaptive and fixed) and splitrk solvers
+                         (cases.INTEGRATOR_CASES): final state and number of RHS calls.
 """
 import os
 import sys
@@ -334,6 +337,40 @@ def one_model(tag, path):
     np.savez(path, **out)
 
 
+def one_integrator(tag, path):
+    """tests/models/ode_pair.cxx through the reference's own euler / rkgeneric / splitrk solvers."""
+    from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
+    if tag in HW_INTEGRATOR_CASES:   # unchanged examples/hasegawa-wakatani/hw.cxx
+        solver, opts, nout, step = HW_INTEGRATOR_CASES[tag]
+        r = orc.Ref(hw_integrator_ini(opts, nout, step))
+        names = r.model_create("hw", solver)
+    else:
+        solver, opts, split, nout, step = INTEGRATOR_CASES[tag]
+        r = orc.Ref(ode_ini(opts, split, nout, step))
+        names = r.model_create("ode_pair", solver)
+    out = {f"{tag}_init_{v}": r.model_get(v) for v in names}
+    r.model_solve(nout, step)
+    for v in names:
+        out[f"{tag}_final_{v}"] = r.model_get(v)
+    out[f"{tag}_rhs_calls"] = np.array(r.model_rhs_calls())
+    print(f"  integrator {tag}: rhs calls {int(out[f'{tag}_rhs_calls'])}, max|final| = "
+          f"{[float(np.abs(out[f'{tag}_final_{v}']).max()) for v in names]}")
+    np.savez(path, **out)
+
+
+def integrators():
+    import subprocess
+    import tempfile
+    from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag in list(INTEGRATOR_CASES) + list(HW_INTEGRATOR_CASES):
+            path = os.path.join(tmp, tag + ".npz")
+            subprocess.run([sys.executable, os.path.abspath(__file__), "integrator:" + tag, path], check=True)
+            out.update(dict(np.load(path)))
+    np.savez_compressed(os.path.join(HERE, "integrators.npz"), **out)
+
+
 from elmpb_names import ELMPB_FIELDS, ELMPB_SCALARS  # noqa: E402
 ELMPB_DT, ELMPB_NSTEPS = 2e-3, 5
 
@@ -405,9 +442,13 @@ def models():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb"]
+    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb", "integrators"]
     if which[0].startswith("elmpb:"):
         elmpb_case(which[0][6:], which[1])
+        sys.stdout.flush()
+        os._exit(0)
+    if which[0].startswith("integrator:"):
+        one_integrator(which[0][11:], which[1])
         sys.stdout.flush()
         os._exit(0)
     if which[0].startswith("model:"):
@@ -424,4 +465,6 @@ if __name__ == "__main__":
         models()
     if "elmpb" in which:
         elmpb()
+    if "integrators" in which:
+        integrators()
     os._exit(0)  # the reference's static destructors are not exit-safe after repeated init/finalise

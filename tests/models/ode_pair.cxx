@@ -1,0 +1,44 @@
+// Test model of this repository (NOT from the reference): two coupled nonlinear ODEs in every cell, written
+// against the public BOUT++ API only (PhysicsModel, SOLVE_FOR, ddt, Field3D algebra).  It is compiled twice from
+// this one source -- against the reference build (oracle/Makefile -> oracle/_ref/libboutref.so) and against the
+// B200 host layer (bout-dev_b200/host/Makefile -> host/models/ode_pair.so) -- so that every explicit integrator of
+// the host layer can be checked against the reference's own integrator on the same model:
+//   rhs:        ddt(f) = g - damp f^3,   ddt(g) = -f - damp g
+//   convective: ddt(f) = g,              ddt(g) = -f
+//   diffusive:  ddt(f) = -damp f^3,      ddt(g) = -damp g         ([ode] split = true)
+#include <bout/physicsmodel.hxx>
+
+class OdePair : public PhysicsModel {
+private:
+  Field3D f, g;
+  BoutReal damp;
+
+protected:
+  int init(bool) override {
+    auto& options = Options::root()["ode"];
+    damp = options["damp"].withDefault(0.3);
+    const bool split = options["split"].withDefault(false);
+    SOLVE_FOR(f, g);
+    if (split) {
+      setSplitOperator();
+    }
+    return 0;
+  }
+  int rhs(BoutReal) override {
+    ddt(f) = g - damp * f * f * f;
+    ddt(g) = -1.0 * f - damp * g;
+    return 0;
+  }
+  int convective(BoutReal) override {
+    ddt(f) = g;
+    ddt(g) = -1.0 * f;
+    return 0;
+  }
+  int diffusive(BoutReal) override {
+    ddt(f) = -damp * f * f * f;
+    ddt(g) = -damp * g;
+    return 0;
+  }
+};
+
+BOUTMAIN(OdePair)

@@ -1,0 +1,90 @@
+"""CPU: host logic of the explicit integrators in the C++ host layer (bout-dev_b200/host: rk4 fixed/adaptive, rk3ssp,
+euler, rkgeneric with rkf45 / cashkarp / rk4 / rkf34, splitrk) against the reference's own solvers on
+tests/models/ode_pair.cxx (tests/golden/integrators.npz, made by tests/golden/make_golden.py integrators).
+
+There is no CPU compute path in the product, so the child process LD_PRELOADs tests/fake_device/fake_b200.c, a
+host-memory test double of the few C-ABI entry points the integrators call.  What this pins: Solver::create, the
+accept / reject control flow (same number of RHS evaluations as the reference), the stage and output formulas, the
+copy-on-write state handling.  The same cases run through the real kernels in tests/test_zz_gpu_integrators.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from cases import INTEGRATOR_CASES  # noqa: E402
+
+HOST_LIB = os.path.join(ROOT, "bout-dev_b200", "host", "libbout_b200_host.so")
+MODEL = os.path.join(ROOT, "bout-dev_b200", "host", "models", "ode_pair.so")
+
+
+@pytest.fixture(scope="module")
+def fake_device(tmp_path_factory):
+    for p in (HOST_LIB, MODEL):
+        if not os.path.exists(p):
+            pytest.fail(f"{p} missing: run python -c 'import __graft_entry__ as g; g.build()'")
+    so = str(tmp_path_factory.mktemp("fake") / "libfake_b200.so")
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                    "-o", so, os.path.join(HERE, "fake_device", "fake_b200.c"), "-lm"], check=True)
+    return so
+
+
+@pytest.fixture(scope="module")
+def results(fake_device):
+    """All cases in ONE child process (one torch import)."""
+    env = dict(os.environ, LD_PRELOAD=fake_device)
+    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py")] + sorted(INTEGRATOR_CASES), env=env,
+                       capture_output=True, text=True, timeout=600)
+    out = {}
+    for line in p.stdout.splitlines():
+        if line.startswith("{"):
+            r = json.loads(line)
+            out[r["tag"]] = r
+    assert out, p.stdout[-2000:] + p.stderr[-2000:]
+    return out
+
+
+@pytest.mark.parametrize("tag", sorted(INTEGRATOR_CASES))
+def test_integrator_matches_reference_solver(results, tag):
+    res = results[tag]
+    assert "error" not in res, res
+    assert res["rhs_calls"] == res["ref_rhs_calls"], res
+    assert res["ok"] and res["tol"] <= 1e-10, res
+
+
+def test_without_the_test_double_the_host_layer_fails_loudly():
+    """No GPU and no test double: the first device allocation must raise, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py"), "euler"], capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode != 0
+    assert "HostError" in p.stdout and "error" in p.stdout, p.stdout[-1500:] + p.stderr[-1500:]
+
+
+def test_unknown_solver_and_scheme_are_rejected(fake_device):
+    code = (
+        "import sys, os\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(HERE, 'golden')!r})\n"
+        "import __graft_entry__ as ge\n"
+        "from cases import ode_ini\n"
+        "hostmod = ge.load_package().host\n"
+        "for solver, opts in (('cvode', ''), ('rkgeneric', 'scheme = dopri5')):\n"
+        "    h = hostmod.Host(ode_ini(opts, False, 1, 0.1))\n"
+        "    try:\n"
+        "        h.model_create('ode_pair', solver)\n"
+        "    except hostmod.HostError as e:\n"
+        "        print('rejected:', e)\n"
+        "    else:\n"
+        "        sys.exit(3)\n"
+        "    finally:\n"
+        "        h.close()\n")
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LD_PRELOAD=fake_device), capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("rejected:") == 2

@@ -1,0 +1,86 @@
+"""GPU: the explicit integrators of the C++ host layer through the real kernels (bout_b200_lincomb = k_elementwise,
+bout_b200_err_sum = k_err_partial + k_err_final, bout_b200_rk_stage) against the reference's own solvers
+(tests/golden/integrators.npz), plus the error-sum kernel against numpy.  Tolerance 1e-10 relative on the final
+state; identical RHS-evaluation counts."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def results(capi):
+    env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}
+    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py")] + sorted(INTEGRATOR_CASES)
+                       + sorted(HW_INTEGRATOR_CASES), env=env,
+                       capture_output=True, text=True, timeout=900)
+    out = {}
+    for line in p.stdout.splitlines():
+        if line.startswith("{"):
+            r = json.loads(line)
+            out[r["tag"]] = r
+    assert out, p.stdout[-2000:] + p.stderr[-2000:]
+    return out
+
+
+@pytest.mark.parametrize("tag", sorted(INTEGRATOR_CASES))
+def test_integrator_on_device_matches_reference_solver(results, tag):
+    res = results[tag]
+    assert "error" not in res, res
+    assert res["rhs_calls"] == res["ref_rhs_calls"], res
+    assert res["ok"] and res["tol"] <= 1e-10, res
+
+
+@pytest.mark.parametrize("tag", sorted(HW_INTEGRATOR_CASES))
+def test_unchanged_hw_model_with_the_other_integrators(results, tag):
+    """examples/hasegawa-wakatani/hw.cxx (split-operator model, Arakawa brackets + LaplaceCyclic per RHS) stepped by
+    euler / rkgeneric / splitrk of the host layer against the reference's solvers: 1e-8 on the final state."""
+    res = results[tag]
+    assert "error" not in res, res
+    assert res["rhs_calls"] == res["ref_rhs_calls"], res
+    assert res["ok"] and res["tol"] <= 1e-8, res
+
+
+@pytest.mark.parametrize("shape,guards", [((12, 1, 8), (2, 0)), ((20, 9, 16), (2, 2)), ((68, 36, 130), (2, 2)),
+                                          ((260, 68, 256), (2, 2)), ((7, 5, 3), (1, 1))])
+def test_err_sum_and_lincomb_kernels(capi, shape, guards):
+    """sum |a-b| / (|a|+|b|+atol) over RGN_NOBNDRY (rkscheme.cxx:150-156) and out = sum_j c_j x_j."""
+    import torch
+    nx, ny, nz = shape
+    mxg, myg = guards
+    g = capi.Grid(nx, ny, nz, mxg, myg)
+    rng = np.random.default_rng(nx * 1000 + nz)
+    a, b = rng.standard_normal(shape), rng.standard_normal(shape)
+    a[0, 0, 0] = np.nan   # guard cells must not enter the sum (myg = 0: x guard)
+    I = (slice(mxg, nx - mxg), slice(myg, ny - myg), slice(None))
+    atol = 1e-3
+    want = float((np.abs(a[I] - b[I]) / (np.abs(a[I]) + np.abs(b[I]) + atol)).sum())
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    got = capi.err_sum(g, da, db, atol)
+    assert abs(got - want) <= 1e-12 * abs(want)
+    assert capi.err_sum(g, da, db, atol) == got                      # fixed summation order
+    assert abs(capi.err_sum(g, da, db, atol, accumulate_onto=got) - 2 * want) <= 1e-12 * abs(want)
+    xs = [torch.from_numpy(rng.standard_normal(shape)).cuda() for _ in range(8)]
+    cs = [float(c) for c in rng.standard_normal(8)]
+    for n in (1, 3, 8):
+        out = torch.full(shape, 7.0, dtype=torch.float64, device="cuda")
+        capi.lincomb(g, cs[:n], xs[:n], out)
+        ref = np.zeros(shape)
+        for c, x in zip(cs[:n], xs[:n]):
+            ref = ref + c * x.cpu().numpy() if ref.any() else c * x.cpu().numpy()
+        o = out.cpu().numpy()
+        assert np.abs(o[I] - ref[I]).max() <= 4e-16 * n * max(1.0, np.abs(ref[I]).max())
+        mask = np.ones(shape, bool)
+        mask[I] = False
+        assert (o[mask] == 7.0).all()                                # guards untouched
+    with pytest.raises(capi.BoutB200Error):
+        capi.lincomb(g, [1.0, 2.0], [xs[0], xs[1]], xs[1])           # out must not alias an operand
