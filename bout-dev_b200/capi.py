@@ -397,6 +397,18 @@ def err_sum(g: Grid, a, b, atol, accumulate_onto=None, region="RGN_NOBNDRY"):
     return float(result.item())
 
 
+def err_max(g: Grid, a, b, accumulate_onto=None, region="RGN_NOBNDRY"):
+    """max over region of |a-b| (bout_b200_err_max; adams_bashforth.cxx:229-253), returned as a float."""
+    n = int(lib.bout_b200_err_sum_scratch_doubles())
+    scratch = torch.empty(n + 1, dtype=torch.float64, device=a.device)
+    result = scratch[n:]
+    if accumulate_onto is not None:
+        result.fill_(float(accumulate_onto))
+    _check(lib.bout_b200_err_max(C.byref(g.c), REGIONS[region], _ptr(a), _ptr(b), _ptr(scratch),
+                                 0 if accumulate_onto is None else 1, C.c_void_p(result.data_ptr()), _stream()))
+    return float(result.item())
+
+
 class CMetric(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dx", "dy", "dz", "J", "g_22", "g11", "g33", "g13", "G1", "G3",
                                           "d1_dx")]

@@ -98,35 +98,44 @@ extern "C" int bout_b200_rk_stage(const bout_b200_grid* g, int region, int mode,
   return 0;
 }
 
-// ---- error norm of the adaptive integrators -----------------------------------------------------------
-// sum over the evolving region of |a - b| / (|a| + |b| + atol): RK4Solver::run (rk4.cxx:103-106),
-// RKScheme::getErr (src/solver/impls/rkgeneric/rkscheme.cxx:150-156), SplitRK::run (split-rk.cxx:128-133).
+// ---- error norms of the adaptive integrators ----------------------------------------------------------
+// MODE 0: sum over the evolving region of |a - b| / (|a| + |b| + atol): RK4Solver::run (rk4.cxx:103-106),
+//         RKScheme::getErr (src/solver/impls/rkgeneric/rkscheme.cxx:150-156), SplitRK::run (split-rk.cxx:128-133).
+// MODE 1: max over the evolving region of |a - b|: get_error of the Adams-Bashforth solver
+//         (src/solver/impls/adams_bashforth/adams_bashforth.cxx:229-253).
 // The reference reduces with an OpenMP `reduction(+)` (order not fixed); here the order is fixed: every CTA owns a
-// grid-stride subsequence and writes one partial, one CTA then adds the partials in index order.
+// grid-stride subsequence and writes one partial, one CTA then combines the partials in index order.
 namespace b200 {
 
 constexpr int kErrThreads = 256;
 constexpr int kErrMaxBlocks = 148 * 8;
 
-__device__ __forceinline__ double blockSum(double v, double* sh) { // all kErrThreads threads call; result in thread 0
+template <int MODE>
+__device__ __forceinline__ double errCombine(double x, double y) {
+  return MODE == 0 ? x + y : fmax(x, y);
+}
+
+template <int MODE>
+__device__ __forceinline__ double blockReduce(double v, double* sh) { // all kErrThreads threads call; result in thread 0
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    v += __shfl_down_sync(0xffffffffu, v, o);
+    v = errCombine<MODE>(v, __shfl_down_sync(0xffffffffu, v, o));
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) {
     sh[warp] = v;
   }
   __syncthreads();
-  double r = 0.0;
+  double r = 0.0; // both norms are >= 0, so 0 is the identity of either reduction
   if (threadIdx.x == 0) {
     for (int w = 0; w < kErrThreads / 32; ++w) {
-      r += sh[w];
+      r = errCombine<MODE>(r, sh[w]);
     }
   }
   return r;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kErrThreads) k_err_partial(const double* __restrict__ a, const double* __restrict__ b,
                                                              double atol, double* __restrict__ partial, int ny, int nz,
                                                              int xs, int xe, int ys, int ye) {
@@ -142,25 +151,52 @@ __global__ void __launch_bounds__(kErrThreads) k_err_partial(const double* __res
     const int x = xs + static_cast<int>(xy / nyb);
     const long long i = (static_cast<long long>(x) * ny + y) * nz + z;
     const double va = __ldg(a + i), vb = __ldg(b + i);
-    acc += fabs(va - vb) / (fabs(va) + fabs(vb) + atol);
+    if (MODE == 0) {
+      acc += fabs(va - vb) / (fabs(va) + fabs(vb) + atol);
+    } else {
+      acc = fmax(acc, fabs(va - vb));
+    }
   }
-  const double s = blockSum(acc, sh);
+  const double s = blockReduce<MODE>(acc, sh);
   if (threadIdx.x == 0) {
     partial[blockIdx.x] = s;
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kErrThreads) k_err_final(const double* __restrict__ partial, int n, int accumulate,
                                                            double* __restrict__ result) {
   __shared__ double sh[kErrThreads / 32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += kErrThreads) {
-    acc += partial[i];
+    acc = errCombine<MODE>(acc, partial[i]);
   }
-  const double s = blockSum(acc, sh);
+  const double s = blockReduce<MODE>(acc, sh);
   if (threadIdx.x == 0) {
-    result[0] = (accumulate != 0 ? result[0] : 0.0) + s;
+    result[0] = accumulate != 0 ? errCombine<MODE>(result[0], s) : s;
   }
+}
+
+template <int MODE>
+int errNorm(const bout_b200_grid* g, int region, const double* a, const double* b, double atol, double* scratch,
+            int accumulate, double* result, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(a && b && scratch && result, BOUT_B200_ERR_ARG, "error norm: null argument");
+  Box bx;
+  if (regionBox(g, region, &bx) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  const long long total = static_cast<long long>(bx.xe - bx.xs + 1) * (bx.ye - bx.ys + 1) * g->nz;
+  const long long want = (total + kErrThreads - 1) / kErrThreads;
+  const int blocks = static_cast<int>(want < kErrMaxBlocks ? (want < 1 ? 1 : want) : kErrMaxBlocks);
+  k_err_partial<MODE><<<blocks, kErrThreads, 0, asStream(stream)>>>(a, b, atol, scratch, g->ny, g->nz, bx.xs, bx.xe,
+                                                                    bx.ys, bx.ye);
+  B200_LAUNCH_OK();
+  k_err_final<MODE><<<1, kErrThreads, 0, asStream(stream)>>>(scratch, blocks, accumulate, result);
+  B200_LAUNCH_OK();
+  return 0;
 }
 
 } // namespace b200
@@ -169,21 +205,10 @@ extern "C" size_t bout_b200_err_sum_scratch_doubles(void) { return static_cast<s
 
 extern "C" int bout_b200_err_sum(const bout_b200_grid* g, int region, const double* a, const double* b, double atol,
                                  double* scratch, int accumulate, double* result, void* stream) {
-  if (checkGrid(g) != 0) {
-    return BOUT_B200_ERR_ARG;
-  }
-  B200_REQUIRE(a && b && scratch && result, BOUT_B200_ERR_ARG, "err_sum: null argument");
-  Box bx;
-  if (regionBox(g, region, &bx) != 0) {
-    return BOUT_B200_ERR_ARG;
-  }
-  const long long total = static_cast<long long>(bx.xe - bx.xs + 1) * (bx.ye - bx.ys + 1) * g->nz;
-  const long long want = (total + kErrThreads - 1) / kErrThreads;
-  const int blocks = static_cast<int>(want < kErrMaxBlocks ? (want < 1 ? 1 : want) : kErrMaxBlocks);
-  k_err_partial<<<blocks, kErrThreads, 0, asStream(stream)>>>(a, b, atol, scratch, g->ny, g->nz, bx.xs, bx.xe, bx.ys,
-                                                              bx.ye);
-  B200_LAUNCH_OK();
-  k_err_final<<<1, kErrThreads, 0, asStream(stream)>>>(scratch, blocks, accumulate, result);
-  B200_LAUNCH_OK();
-  return 0;
+  return errNorm<0>(g, region, a, b, atol, scratch, accumulate, result, stream);
+}
+
+extern "C" int bout_b200_err_max(const bout_b200_grid* g, int region, const double* a, const double* b,
+                                 double* scratch, int accumulate, double* result, void* stream) {
+  return errNorm<1>(g, region, a, b, 0.0, scratch, accumulate, result, stream);
 }

@@ -491,7 +491,8 @@ class Solver {
 public:
   explicit Solver(Options* opts);
   virtual ~Solver() = default;
-  /// solver:type = rk4 | rk3ssp | euler | rkgeneric (solver:scheme = rkf45 | cashkarp | rk4 | rkf34) | splitrk
+  /// solver:type = rk4 | rk3ssp | euler | rkgeneric (solver:scheme = rkf45 | cashkarp | rk4 | rkf34) | splitrk |
+  /// adams-bashforth
   static std::unique_ptr<Solver> create(Options* opts = nullptr);
   void add(Field3D& v, const std::string& name); ///< solver.cxx:210: initial profile + boundary set-up
   void setModel(PhysicsModel* m);

@@ -3,6 +3,8 @@
 // the reference; everything inside a right-hand side or a time step is a kernel launch.
 #include "bout/b200_host.hxx"
 
+#include <deque>
+
 #include <algorithm>
 #include <cctype>
 #include <cstring>
@@ -1666,6 +1668,24 @@ public:
     return host / neq;
   }
 
+  // max_i max_{RGN_NOBNDRY} |a_i - b_i|  (adams_bashforth.cxx:229-253)
+  double maxAbsDiff(const State& a, const State& b) {
+    Mesh* m = a.at(0).getMesh();
+    const auto g = m->grid();
+    if (!scratch) {
+      scratch = bout::b200::acquire(bout_b200_err_sum_scratch_doubles() + 2);
+    }
+    double* result = scratch->ptr + bout_b200_err_sum_scratch_doubles();
+    for (size_t i = 0; i < a.size(); ++i) {
+      check(bout_b200_err_max(&g, BOUT_B200_RGN_NOBNDRY, a[i].dptr(), b[i].dptr(), scratch->ptr, i == 0 ? 0 : 1, result,
+                              nullptr));
+    }
+    double host = 0.0;
+    check(bout_b200_memcpy_d2h(&host, result, sizeof(double), nullptr));
+    check(bout_b200_stream_sync(nullptr));
+    return host;
+  }
+
 private:
   std::shared_ptr<bout::b200::Block> scratch;
 };
@@ -2138,6 +2158,194 @@ private:
   int mxstep;
   ErrorNorm errnorm;
 };
+
+// ---- adams-bashforth (src/solver/impls/adams_bashforth/adams_bashforth.cxx): variable-step, variable-order ------
+// Coefficient of history point `position` for the advance from points[0] to `next`: the Lagrange basis polynomial
+// through the first `order` time points, integrated with the closed Newton-Cotes rule on order + 1 nodes (exact for
+// that degree) -- adams_bashforth.cxx:10-186.  Host scalar arithmetic only.
+double abCoefficient(double next, const std::deque<double>& points, int position, int order) {
+  static const std::vector<std::vector<double>> weights = {
+      {1., 1.},
+      {1., 4., 1.},
+      {1., 3., 3., 1.},
+      {7., 32., 12., 32., 7.},
+      {19., 75., 50., 50., 75., 19.},
+      {41., 216., 27., 272., 27., 216., 41.},
+      {751., 3577., 1323., 2989., 2989., 1323., 3577., 751.},
+      {989., 5888., -928., 10496., -4540., 10496., -928., 5888., 989.}};
+  static const double scale[] = {1.0 / 2.0, 1.0 / 3.0, 3.0 / 8.0, 2.0 / 45.0, 5.0 / 288.0, 1.0 / 140.0, 7.0 / 17280.0,
+                                 4.0 / 14175.0};
+  const int rule = std::min(std::max(order, 1), 8) - 1; // order 1 -> trapezium ... order >= 8 -> 9-point rule
+  const auto& w = weights[rule];
+  const int npts = static_cast<int>(w.size()) - 1; // basis points entering the products (:149-166)
+  const double start = points[0];
+  const double step = (next - start) / (static_cast<double>(w.size()) - 1.0);
+  double sum = 0.0;
+  for (size_t i = 0; i < w.size(); ++i) {
+    const double x = start + i * step;
+    double num = 1.0;
+    for (int k = 0; k < npts; ++k) {
+      num *= (k != position) ? (x - points[k]) : 1.0;
+    }
+    sum += (w[i] * scale[rule]) * num;
+  }
+  double den = 1.0;
+  for (int k = 0; k < npts; ++k) {
+    den /= (k != position) ? (points[position] - points[k]) : 1.0;
+  }
+  return step * sum * den;
+}
+
+class AdamsBashforthSolver : public StateSolver {
+public:
+  explicit AdamsBashforthSolver(Options* opts) : StateSolver(opts) { // adams_bashforth.cxx:256-285
+    atol = (*options)["atol"].withDefault(1.e-5);
+    rtol = (*options)["rtol"].withDefault(1.e-5);
+    mxstep = (*options)["mxstep"].withDefault(50000);
+    adaptive = (*options)["adaptive"].withDefault(true);
+    adaptive_order = (*options)["adaptive_order"].withDefault(true);
+    followHighOrder = (*options)["followHighOrder"].withDefault(true);
+    dtFac = (*options)["dtFac"].withDefault(0.75);
+    maximum_order = (*options)["order"].withDefault(5);
+    max_timestep = (*options)["max_timestep"].withDefault(output_timestep);
+    timestep = (*options)["timestep"].withDefault(max_timestep);
+    if (maximum_order < 1) {
+      throw BoutException("adams-bashforth: order must be >= 1");
+    }
+  }
+  void setMaxTimestep(BoutReal dt) override { // :289-300
+    if (dt <= timestep && adaptive) {
+      timestep = dt;
+    }
+  }
+  void init_solver() override { // :320-336
+    if (!adaptive && (output_timestep / timestep > mxstep)) {
+      throw BoutException("ERROR: Requested timestep would lead to MXSTEP being exceeded. timestep = {:e}, MXSTEP={:d}\n",
+                          timestep, mxstep);
+    }
+    current_order = 1;
+  }
+  void run_output_step(BoutReal target) override { // :352-540
+    bool running = true;
+    int internal_steps = 0;
+    while (running) {
+      run_rhs(simtime); // the derivative at the current time joins the history once per step
+      history.push_front(derivs());
+      times.push_front(simtime);
+      const State state = current();
+      State nextState;
+      bool use_lower = false;
+      BoutReal dt;
+      while (true) {
+        timestep = std::min(timestep, max_timestep);
+        dt = timestep;
+        running = true;
+        if ((simtime + dt) >= target) {
+          dt = target - simtime;
+          running = false;
+        }
+        const BoutReal err = abStep(simtime, dt, current_order, state, nextState);
+        if (!adaptive) {
+          break;
+        }
+        if (++internal_steps > mxstep) {
+          throw BoutException("ERROR: MXSTEP exceeded. timestep = {:e}, err={:e}\n", timestep, err);
+        }
+        BoutReal dt_lim = dt * timestepLimit(err, rtol, current_order);
+        if (err < rtol) {
+          if (adaptive_order && current_order > 1) { // would one order lower allow a longer step?
+            State lowerNextState;
+            const BoutReal lowerErr = abStep(simtime, dt, current_order - 1, state, lowerNextState);
+            const BoutReal lower_dt_lim = dt * timestepLimit(lowerErr, rtol, current_order - 1);
+            use_lower = lower_dt_lim > dt_lim;
+            if (use_lower) {
+              dt_lim = lower_dt_lim;
+              nextState = lowerNextState;
+              current_order = current_order - 1;
+            }
+          }
+          timestep = std::min(timestep * 1.1, dt_lim);
+          break;
+        }
+        timestep = 0.9 * dt_lim;
+      }
+      if (times.size() == static_cast<size_t>(maximum_order)) {
+        times.pop_back();
+      }
+      if (history.size() == static_cast<size_t>(maximum_order)) {
+        history.pop_back();
+      }
+      if (current_order < maximum_order && !use_lower) {
+        current_order++;
+      }
+      simtime += dt;
+      load(nextState);
+    }
+  }
+
+private:
+  BoutReal atol, rtol, dtFac, max_timestep;
+  int mxstep, maximum_order, current_order = 1;
+  bool adaptive, adaptive_order, followHighOrder;
+  std::deque<State> history;
+  std::deque<BoutReal> times;
+  ErrorNorm errnorm;
+
+  static BoutReal timestepLimit(BoutReal error, BoutReal tolerance, int order) { // :221-224
+    return std::exp(-std::log(error / tolerance) / order);
+  }
+
+  /// sum_j coef_j history_j (+ base) for the advance from times[0] to `next` (:189-218)
+  State integrate(BoutReal next, int order, const State* base) {
+    std::vector<double> c(order);
+    for (int j = 0; j < order; ++j) {
+      c[j] = abCoefficient(next, times, j, order);
+    }
+    State update(nv());
+    for (size_t i = 0; i < nv(); ++i) {
+      std::vector<Term> t;
+      if (base != nullptr) {
+        t.push_back({1.0, &(*base)[i]});
+      }
+      for (int j = 0; j < order; ++j) {
+        t.push_back({c[j], &history[j][i]});
+      }
+      update[i] = emptyFrom(*f3d[i].var);
+      combine(update[i], t);
+    }
+    return update;
+  }
+
+  // :556-641.  Forms the next state (as handles in `result`) and returns max |full - two-half-steps| of the updates
+  BoutReal abStep(BoutReal timeIn, BoutReal dt, int order, const State& cur, State& result) {
+    const State full_update = integrate(timeIn + dt, order, nullptr);
+    if (!(adaptive && followHighOrder)) {
+      form({{1.0, &cur}, {1.0, &full_update}});
+      result = current();
+    }
+    if (!adaptive) {
+      return 0.0;
+    }
+    constexpr BoutReal firstPart = 0.5;
+    State half_update = integrate(timeIn + dt * firstPart, order, nullptr);
+    times.push_front(timeIn + dt * firstPart);
+    if (order == current_order) { // derivative at the half point (:604-621)
+      form({{1.0, &cur}, {1.0, &half_update}});
+      run_rhs(timeIn + firstPart * dt);
+      load(cur);
+    } // else: the lower-order trial re-uses the half-point derivative still held by the ddt fields (:598-603)
+    history.push_front(derivs());
+    half_update = integrate(timeIn + dt, order, &half_update);
+    history.pop_front();
+    times.pop_front();
+    if (followHighOrder) {
+      form({{1.0, &cur}, {1.0, &half_update}});
+      result = current();
+    }
+    load(cur);
+    return errnorm.maxAbsDiff(full_update, half_update);
+  }
+};
 } // namespace
 
 std::unique_ptr<Solver> Solver::create(Options* opts) {
@@ -2161,6 +2369,9 @@ std::unique_ptr<Solver> Solver::create(Options* opts) {
   if (type == "splitrk") {
     return std::make_unique<SplitRK>(&o);
   }
-  throw BoutException("Solver type '{}' is not available: the B200 path implements rk4, rk3ssp, euler, rkgeneric and splitrk",
+  if (type == "adams-bashforth") {
+    return std::make_unique<AdamsBashforthSolver>(&o);
+  }
+  throw BoutException("Solver type '{}' is not available: the B200 path implements rk4, rk3ssp, euler, rkgeneric, splitrk and adams-bashforth",
                       type);
 }

@@ -410,6 +410,10 @@ int bout_b200_lincomb(const bout_b200_grid* g, int region, int n, const double* 
 size_t bout_b200_err_sum_scratch_doubles(void);
 int bout_b200_err_sum(const bout_b200_grid* g, int region, const double* a, const double* b, double atol,
                       double* scratch, int accumulate, double* result, void* stream);
+/* result[0] = max over region of |a-b| (accumulate != 0: max with the value already there): get_error of the
+ * Adams-Bashforth solver (src/solver/impls/adams_bashforth/adams_bashforth.cxx:229-253).  Same scratch as above. */
+int bout_b200_err_max(const bout_b200_grid* g, int region, const double* a, const double* b,
+                      double* scratch, int accumulate, double* result, void* stream);
 
 /* ---- fused RHS kernels (2)+(4): whole model right-hand sides in one pass ---------------------------------
  * Field2D metric bundle (reference include/bout/coordinates.hxx:83-116); unused members may be NULL. */

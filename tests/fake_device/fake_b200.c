@@ -169,3 +169,24 @@ int bout_b200_err_sum(const bout_b200_grid* g, int region, const double* a, cons
   result[0] = (accumulate ? result[0] : 0.0) + s;
   return 0;
 }
+
+int bout_b200_err_max(const bout_b200_grid* g, int region, const double* a, const double* b, double* scratch,
+                      int accumulate, double* result, void* stream) {
+  int xs, xe, ys, ye;
+  double s = 0.0;
+  (void)stream;
+  (void)scratch;
+  if (box(g, region, &xs, &xe, &ys, &ye) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  for (int x = xs; x <= xe; ++x) {
+    for (int y = ys; y <= ye; ++y) {
+      for (int z = 0; z < g->nz; ++z) {
+        const long long i = ((long long)x * g->ny + y) * g->nz + z;
+        s = fmax(s, fabs(a[i] - b[i]));
+      }
+    }
+  }
+  result[0] = accumulate ? fmax(result[0], s) : s;
+  return 0;
+}

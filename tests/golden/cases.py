@@ -283,6 +283,13 @@ INTEGRATOR_CASES = {
     "rkf34_adaptive": ("rkgeneric", "scheme = rkf34\ntimestep = 0.25\nmax_timestep = 0.5\natol = 1e-8\nrtol = 1e-5", False, 1, 0.5),
     "splitrk_fixed": ("splitrk", "adaptive = false\ntimestep = 0.06\nnstages = 5", True, 1, 0.5),
     "splitrk_adaptive": ("splitrk", "timestep = 0.25\nmax_timestep = 0.5\nrtol = 1e-4\natol = 1e-10\nnstages = 6", True, 2, 0.5),
+    # fixed-step Adams-Bashforth: binary-exact timesteps, so that no rounding-sized last step (two history times 1e-17
+    # apart make the reference's own Lagrange coefficients ill-conditioned) enters the comparison
+    "ab_fixed_order3": ("adams-bashforth", "adaptive = false\ntimestep = 0.0625\nmax_timestep = 0.5\norder = 3", False, 2, 0.5),
+    "ab_fixed_order8": ("adams-bashforth", "adaptive = false\ntimestep = 0.03125\nmax_timestep = 0.5\norder = 8", True, 1, 0.5),
+    "ab_adaptive": ("adams-bashforth", "timestep = 0.05\nmax_timestep = 0.5\nrtol = 1e-6", False, 2, 0.5),
+    "ab_adaptive_follow_low": ("adams-bashforth", "timestep = 0.05\nmax_timestep = 0.5\nrtol = 1e-6\norder = 4\n"
+                               "followHighOrder = false\nadaptive_order = false", True, 1, 0.5),
     "splitrk_nonsplit_model": ("splitrk", "adaptive = false\ntimestep = 0.1\nnstages = 4", False, 1, 0.5),
 }
 

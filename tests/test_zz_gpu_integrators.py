@@ -69,6 +69,9 @@ def test_err_sum_and_lincomb_kernels(capi, shape, guards):
     assert abs(got - want) <= 1e-12 * abs(want)
     assert capi.err_sum(g, da, db, atol) == got                      # fixed summation order
     assert abs(capi.err_sum(g, da, db, atol, accumulate_onto=got) - 2 * want) <= 1e-12 * abs(want)
+    assert capi.err_max(g, da, db) == float(np.abs(a[I] - b[I]).max())   # max |a-b| (adams_bashforth.cxx:229-253): exact
+    assert capi.err_max(g, da, db, accumulate_onto=1e9) == 1e9
+    assert capi.err_max(g, da, da.clone()) == 0.0 or np.isnan(a[I]).any()
     xs = [torch.from_numpy(rng.standard_normal(shape)).cuda() for _ in range(8)]
     cs = [float(c) for c in rng.standard_normal(8)]
     for n in (1, 3, 8):
