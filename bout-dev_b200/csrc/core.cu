@@ -59,3 +59,48 @@ extern "C" int bout_b200_stream_sync(void* stream) {
   B200_CUDA_OK(cudaStreamSynchronize(b200::asStream(stream)));
   return 0;
 }
+
+// ---- streams and page-locked staging for the output step --------------------------------------
+// The RK loop runs on the caller's stream; a dump snapshot is copied device -> host on a second, non-blocking
+// stream into page-locked memory while the next steps compute (PhysicsModelMonitor::call,
+// src/physics/physicsmodel.cxx:241-268, writes synchronously from host-resident fields).
+extern "C" int bout_b200_stream_create(void** stream) {
+  B200_REQUIRE(stream != nullptr, BOUT_B200_ERR_ARG, "stream_create: null argument");
+  cudaStream_t s = nullptr;
+  B200_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = reinterpret_cast<void*>(s);
+  return 0;
+}
+extern "C" int bout_b200_stream_destroy(void* stream) {
+  B200_REQUIRE(stream != nullptr, BOUT_B200_ERR_ARG, "stream_destroy: the default stream cannot be destroyed");
+  B200_CUDA_OK(cudaStreamDestroy(b200::asStream(stream)));
+  return 0;
+}
+// Work queued on `waiter` after this call starts only when everything queued on `signaller` so far has finished
+extern "C" int bout_b200_stream_wait(void* waiter, void* signaller) {
+  cudaEvent_t ev = nullptr;
+  B200_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t err = cudaEventRecord(ev, b200::asStream(signaller));
+  if (err == cudaSuccess) {
+    err = cudaStreamWaitEvent(b200::asStream(waiter), ev, 0);
+  }
+  cudaEventDestroy(ev); // released by the runtime once the recorded work has completed
+  if (err != cudaSuccess) {
+    return b200::fail(BOUT_B200_ERR_CUDA, "stream_wait failed: %s", cudaGetErrorString(err));
+  }
+  return 0;
+}
+extern "C" int bout_b200_host_alloc(void** ptr, size_t bytes) {
+  B200_REQUIRE(ptr != nullptr, BOUT_B200_ERR_ARG, "host_alloc: null argument");
+  B200_CUDA_OK(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return 0;
+}
+extern "C" int bout_b200_host_free(void* ptr) {
+  B200_CUDA_OK(cudaFreeHost(ptr));
+  return 0;
+}
+// Queues the copy and returns; the caller synchronises `stream` before reading dst (dst from bout_b200_host_alloc)
+extern "C" int bout_b200_memcpy_d2h_async(void* dst, const void* src, size_t bytes, void* stream) {
+  B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b200::asStream(stream)));
+  return 0;
+}

@@ -17,6 +17,7 @@
 #include <functional>
 #include <initializer_list>
 #include <map>
+#include <future>
 #include <memory>
 #include <sstream>
 #include <type_traits>
@@ -484,6 +485,53 @@ private:
   size_t workspace_bytes = 0;
   static std::unique_ptr<Laplacian> instance;
 };
+
+// ---- output step: dump file + device -> host -> disk pipeline (src/dump_writer.cxx) ------------------
+namespace bout {
+namespace b200 {
+/// NetCDF classic (CDF-2) dump file: dims t (record), x, y, z; integer scalars; t_array, iteration, one (t,x,y,z)
+/// double variable per field -- readable with scipy.io.netcdf_file / boutdata.collect like BOUT.dmp.<rank>.nc
+class DumpFile {
+public:
+  DumpFile(const std::string& path, int nx, int ny, int nz, const std::vector<std::pair<std::string, int>>& scalars,
+           const std::vector<std::string>& fields);
+  ~DumpFile();
+  void append(double t, int iteration, const std::vector<const double*>& host_fields); ///< one record, host data
+  int records() const;
+
+private:
+  struct Impl;
+  std::unique_ptr<Impl> impl;
+};
+
+/// Snapshots leave the device on a second stream while the solver keeps stepping; records reach the file in order
+class OutputPipeline {
+public:
+  OutputPipeline(const std::string& path, Mesh* mesh, const std::vector<std::string>& names);
+  ~OutputPipeline();
+  void snapshot(double time, int iteration, const std::vector<const Field3D*>& fields);
+  void finish(); ///< drains both stages; every snapshot is on disk afterwards
+  int recordsWritten() const;
+
+private:
+  struct Slot {
+    double* staging = nullptr;  ///< page-locked, nfields * count doubles
+    std::vector<Field3D> held;  ///< handles that keep the snapshot's device blocks alive during the copy
+    std::future<void> writing;  ///< host thread appending this slot's record
+    bool copying = false;
+    double time = 0.0;
+    int iteration = 0;
+  };
+  void retire(Slot& s);
+  void handOver(Slot& s);
+  std::unique_ptr<DumpFile> file;
+  void* copy_stream = nullptr;
+  Slot slots[2];
+  size_t nfields, count = 0;
+  unsigned next = 0;
+};
+} // namespace b200
+} // namespace bout
 
 // ---- Solver / PhysicsModel ---------------------------------------------------------------------------------
 class PhysicsModel;

@@ -1496,9 +1496,39 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   if (run_rhs(simtime) != 0) { // solver.cxx:569
     throw BoutException("Physics RHS call failed\n");
   }
+  // Output step ([output] path = <file>): evolving variables (Solver::outputVars, solver.cxx:694-724) and the fields
+  // the model registers in outputVars(), one record at the start (call_monitors(simtime, -1, NOUT), solver.cxx:580)
+  // and one per output step; device -> host -> disk overlaps the following steps (src/dump_writer.cxx).
+  std::unique_ptr<bout::b200::OutputPipeline> dump;
+  std::vector<const Field3D*> dump_fields;
+  Options& oo = Options::root()["output"];
+  if (oo.isSet("path")) {
+    std::vector<std::string> names;
+    for (const auto& f : f3d) {
+      names.push_back(f.name);
+      dump_fields.push_back(f.var);
+    }
+    Options registered;
+    model->outputVars(registered);
+    for (auto& kv : registered.sections()) {
+      const bool evolving = std::find(names.begin(), names.end(), kv.first) != names.end();
+      if (kv.second.field3d != nullptr && !evolving) {
+        names.push_back(kv.first);
+        dump_fields.push_back(kv.second.field3d);
+      }
+    }
+    dump = std::make_unique<bout::b200::OutputPipeline>(oo["path"].as<std::string>(), f3d[0].var->getMesh(), names);
+    dump->snapshot(simtime, -1, dump_fields);
+  }
   for (int s = 0; s < nout; ++s) {
     run_output_step(simtime + output_timestep);
     run_rhs(simtime); // rk4.cxx:157: extra variables at the output time
+    if (dump) {
+      dump->snapshot(simtime, s, dump_fields);
+    }
+  }
+  if (dump) {
+    dump->finish();
   }
   check(bout_b200_stream_sync(nullptr));
   return 0;

@@ -87,6 +87,16 @@ int bout_b200_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream)
 int bout_b200_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
 int bout_b200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 int bout_b200_stream_sync(void* stream);
+/* Output step (reference PhysicsModelMonitor::call, src/physics/physicsmodel.cxx:241-268): a second,
+ * non-blocking stream and page-locked staging so that a dump snapshot leaves the device while the next steps compute.
+ * _stream_wait: work queued on `waiter` afterwards starts once everything queued on `signaller` so far is done.
+ * _memcpy_d2h_async only queues the copy; synchronise `stream` before reading dst. */
+int bout_b200_stream_create(void** stream);
+int bout_b200_stream_destroy(void* stream);
+int bout_b200_stream_wait(void* waiter, void* signaller);
+int bout_b200_host_alloc(void** ptr, size_t bytes);
+int bout_b200_host_free(void* ptr);
+int bout_b200_memcpy_d2h_async(void* dst, const void* src, size_t bytes, void* stream);
 
 /* ---- (1) index_derivs DerivativeStore stencils ------------------------------------------------
  * out[region] = scale1[x,y] * op(stencil of f along dir) (+ scale2[x,y] * op2(stencil))

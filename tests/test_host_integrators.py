@@ -88,3 +88,13 @@ def test_unknown_solver_and_scheme_are_rejected(fake_device):
                        text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("rejected:") == 2
+
+
+def test_output_step_writes_a_readable_dump_file(fake_device, tmp_path):
+    """[output] path: NetCDF classic dump file (dims, scalars, t_array, iteration, one record per output incl. the
+    initial state); record k of a 3-output run == final state of a k-output run (tests/output_check.py)."""
+    p = subprocess.run([sys.executable, os.path.join(HERE, "output_check.py"), str(tmp_path)],
+                       env=dict(os.environ, LD_PRELOAD=fake_device), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["ok"] and res["records"] == 4, res

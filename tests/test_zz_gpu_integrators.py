@@ -87,3 +87,14 @@ def test_err_sum_and_lincomb_kernels(capi, shape, guards):
         assert (o[mask] == 7.0).all()                                # guards untouched
     with pytest.raises(capi.BoutB200Error):
         capi.lincomb(g, [1.0, 2.0], [xs[0], xs[1]], xs[1])           # out must not alias an operand
+
+
+@pytest.mark.parametrize("mode", ["ode_pair", "hw"])
+def test_output_step_on_device(capi, tmp_path, mode):
+    """Dump snapshots leave the device on a second stream (page-locked staging) while the solver keeps stepping:
+    every record must equal the state at its output time (tests/output_check.py)."""
+    env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}
+    args = [sys.executable, os.path.join(HERE, "output_check.py"), str(tmp_path)] + (["hw"] if mode == "hw" else [])
+    p = subprocess.run(args, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
