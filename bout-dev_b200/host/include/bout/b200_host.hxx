@@ -491,10 +491,21 @@ namespace bout {
 namespace b200 {
 /// NetCDF classic (CDF-2) dump file: dims t (record), x, y, z; integer scalars; t_array, iteration, one (t,x,y,z)
 /// double variable per field -- readable with scipy.io.netcdf_file / boutdata.collect like BOUT.dmp.<rank>.nc
+struct DumpScalar { ///< written once: int or double
+  std::string name;
+  bool is_double;
+  int i;
+  double d;
+};
+struct DumpOnceField { ///< written once: (x, y) or (x, y, z) doubles, host data
+  std::string name;
+  bool is3d;
+  std::vector<double> data;
+};
 class DumpFile {
 public:
-  DumpFile(const std::string& path, int nx, int ny, int nz, const std::vector<std::pair<std::string, int>>& scalars,
-           const std::vector<std::string>& fields);
+  DumpFile(const std::string& path, int nx, int ny, int nz, const std::vector<DumpScalar>& scalars,
+           const std::vector<DumpOnceField>& once, const std::vector<std::string>& fields);
   ~DumpFile();
   void append(double t, int iteration, const std::vector<const double*>& host_fields); ///< one record, host data
   int records() const;
@@ -507,7 +518,8 @@ private:
 /// Snapshots leave the device on a second stream while the solver keeps stepping; records reach the file in order
 class OutputPipeline {
 public:
-  OutputPipeline(const std::string& path, Mesh* mesh, const std::vector<std::string>& names);
+  OutputPipeline(const std::string& path, Mesh* mesh, const std::vector<std::string>& names,
+                 std::vector<DumpScalar> extra_scalars = {}, const std::vector<DumpOnceField>& once = {});
   ~OutputPipeline();
   void snapshot(double time, int iteration, const std::vector<const Field3D*>& fields);
   void finish(); ///< drains both stages; every snapshot is on disk afterwards
@@ -577,11 +589,32 @@ protected:
   void post_rhs();
 };
 
+/// `dump` member of PhysicsModel behind SAVE_REPEAT / SAVE_ONCE (reference bout::DataFileFacade,
+/// include/bout/physicsmodel.hxx:91-137): registers variables for the output step; nothing is written unless
+/// `[output] path` is set.
+class DataFileFacade {
+public:
+  void addRepeat(Field3D& f, const std::string& name) { repeat3d.push_back({name, &f}); }
+  void addRepeat(Field2D&, const std::string& name) { unsupported.push_back(name); }
+  void addRepeat(BoutReal&, const std::string& name) { unsupported.push_back(name); }
+  void addRepeat(int&, const std::string& name) { unsupported.push_back(name); }
+  void addOnce(Field3D& f, const std::string& name) { once3d.push_back({name, &f}); }
+  void addOnce(Field2D& f, const std::string& name) { once2d.push_back({name, &f}); }
+  void addOnce(BoutReal& v, const std::string& name) { once_real.push_back({name, &v}); }
+  void addOnce(int& v, const std::string& name) { once_int.push_back({name, &v}); }
+  std::vector<std::pair<std::string, Field3D*>> repeat3d, once3d;
+  std::vector<std::pair<std::string, Field2D*>> once2d;
+  std::vector<std::pair<std::string, BoutReal*>> once_real;
+  std::vector<std::pair<std::string, int*>> once_int;
+  std::vector<std::string> unsupported; ///< repeated scalars / Field2D: rejected when the output step is enabled
+};
+
 class PhysicsModel {
 public:
   virtual ~PhysicsModel() = default;
   Mesh* mesh = nullptr;
   Solver* solver = nullptr;
+  DataFileFacade dump;
   void initialise(Solver* s);
   int runRHS(BoutReal t) { return rhs(t); }
   int runConvective(BoutReal t) { return convective(t); }
@@ -611,8 +644,14 @@ protected:
 #define SOLVE_FOR(...) { B200_FOR_EACH(B200_SOLVE_FOR1, __VA_ARGS__) }
 #define SOLVE_FOR2(a, b) SOLVE_FOR(a, b)
 #define SOLVE_FOR3(a, b, c) SOLVE_FOR(a, b, c)
-#define SAVE_REPEAT(...)
-#define SAVE_ONCE(...)
+#define B200_SAVE_REPEAT1(var) dump.addRepeat(var, #var);
+#define B200_SAVE_ONCE1(var) dump.addOnce(var, #var);
+#define SAVE_REPEAT(...) { B200_FOR_EACH(B200_SAVE_REPEAT1, __VA_ARGS__) }
+#define SAVE_ONCE(...) { B200_FOR_EACH(B200_SAVE_ONCE1, __VA_ARGS__) }
+#define SAVE_REPEAT2(a, b) SAVE_REPEAT(a, b)
+#define SAVE_REPEAT3(a, b, c) SAVE_REPEAT(a, b, c)
+#define SAVE_ONCE2(a, b) SAVE_ONCE(a, b)
+#define SAVE_ONCE3(a, b, c) SAVE_ONCE(a, b, c)
 
 /// Model factory used by the harness instead of main(): BOUTMAIN(Model) defines it
 #ifndef B200_MODEL_FACTORY

@@ -1517,7 +1517,36 @@ int Solver::solve(int nout_in, BoutReal output_step) {
         dump_fields.push_back(kv.second.field3d);
       }
     }
-    dump = std::make_unique<bout::b200::OutputPipeline>(oo["path"].as<std::string>(), f3d[0].var->getMesh(), names);
+    const DataFileFacade& reg = model->dump; // SAVE_REPEAT / SAVE_ONCE registrations
+    if (!reg.unsupported.empty()) {
+      throw BoutException("Output step: SAVE_REPEAT of scalar / Field2D variable '{}' is not supported", reg.unsupported[0]);
+    }
+    for (const auto& kv : reg.repeat3d) {
+      if (std::find(names.begin(), names.end(), kv.first) == names.end()) {
+        names.push_back(kv.first);
+        dump_fields.push_back(kv.second);
+      }
+    }
+    std::vector<bout::b200::DumpScalar> scalars;
+    std::vector<bout::b200::DumpOnceField> once;
+    for (const auto& kv : reg.once_int) {
+      scalars.push_back({kv.first, false, *kv.second, 0.0});
+    }
+    for (const auto& kv : reg.once_real) {
+      scalars.push_back({kv.first, true, 0, *kv.second});
+    }
+    for (const auto& kv : reg.once2d) {
+      if (kv.second->isAllocated()) {
+        once.push_back({kv.first, false, kv.second->getHost()});
+      }
+    }
+    for (const auto& kv : reg.once3d) {
+      if (kv.second->isAllocated()) {
+        once.push_back({kv.first, true, kv.second->getHost()});
+      }
+    }
+    dump = std::make_unique<bout::b200::OutputPipeline>(oo["path"].as<std::string>(), f3d[0].var->getMesh(), names, scalars,
+                                                        once);
     dump->snapshot(simtime, -1, dump_fields);
   }
   for (int s = 0; s < nout; ++s) {

@@ -59,14 +59,22 @@ struct DumpFile::Impl {
   std::vector<unsigned char> scratch;
 };
 
-DumpFile::DumpFile(const std::string& path, int nx, int ny, int nz,
-                   const std::vector<std::pair<std::string, int>>& scalars, const std::vector<std::string>& fields)
+DumpFile::DumpFile(const std::string& path, int nx, int ny, int nz, const std::vector<DumpScalar>& scalars,
+                   const std::vector<DumpOnceField>& once, const std::vector<std::string>& fields)
     : impl(new Impl) {
   impl->path = path;
   impl->field_count = static_cast<size_t>(nx) * ny * nz;
   std::vector<VarDesc> vars;
   for (const auto& s : scalars) {
-    vars.push_back({s.first, {}, NC_INT, 4});
+    vars.push_back({s.name, {}, s.is_double ? NC_DOUBLE : NC_INT, s.is_double ? 8 : 4});
+  }
+  for (const auto& f : once) { // written once (SAVE_ONCE of a Field2D / Field3D): (x, y) or (x, y, z), no record dimension
+    const size_t n = static_cast<size_t>(nx) * ny * (f.is3d ? nz : 1);
+    if (f.data.size() != n) {
+      throw BoutException("DumpFile: '{}' has {} values, expected {}", f.name, f.data.size(), n);
+    }
+    vars.push_back({f.name, f.is3d ? std::vector<int>{1, 2, 3} : std::vector<int>{1, 2}, NC_DOUBLE,
+                    static_cast<std::int64_t>(n) * 8});
   }
   const size_t first_record_var = vars.size();
   vars.push_back({"t_array", {0}, NC_DOUBLE, 8});
@@ -130,8 +138,22 @@ DumpFile::DumpFile(const std::string& path, int nx, int ny, int nz,
   if (impl->fp == nullptr) {
     throw BoutException("Could not open output file '{}'", path);
   }
+  auto putDouble = [&](double v) {
+    std::uint64_t u;
+    std::memcpy(&u, &v, 8);
+    put64(h, static_cast<std::int64_t>(u));
+  };
   for (const auto& s : scalars) {
-    put32(h, s.second);
+    if (s.is_double) {
+      putDouble(s.d);
+    } else {
+      put32(h, s.i);
+    }
+  }
+  for (const auto& f : once) {
+    for (double v : f.data) {
+      putDouble(v);
+    }
   }
   if (std::fwrite(h.data(), 1, h.size(), impl->fp) != h.size()) {
     throw BoutException("Short write to '{}'", path);
@@ -181,13 +203,20 @@ void DumpFile::append(double t, int iteration, const std::vector<const double*>&
 }
 
 // ---- the pipeline ------------------------------------------------------------------------------------------
-OutputPipeline::OutputPipeline(const std::string& path, Mesh* mesh, const std::vector<std::string>& names) : nfields(names.size()) {
+OutputPipeline::OutputPipeline(const std::string& path, Mesh* mesh, const std::vector<std::string>& names,
+                               std::vector<DumpScalar> extra_scalars, const std::vector<DumpOnceField>& once)
+    : nfields(names.size()) {
   const auto g = mesh->grid();
   count = static_cast<size_t>(g.nx) * g.ny * g.nz;
-  const std::vector<std::pair<std::string, int>> scalars = {
+  std::vector<DumpScalar> scalars;
+  const std::pair<const char*, int> ints[] = {
       {"NXPE", 1}, {"NYPE", 1}, {"MXSUB", g.xend - g.xstart + 1}, {"MYSUB", g.yend - g.ystart + 1},
       {"MXG", mesh->MXG}, {"MYG", mesh->MYG}, {"MZ", g.nz}, {"nx", g.nx}, {"ny", g.yend - g.ystart + 1}, {"nz", g.nz}};
-  file = std::make_unique<DumpFile>(path, g.nx, g.ny, g.nz, scalars, names);
+  for (const auto& kv : ints) {
+    scalars.push_back({kv.first, false, kv.second, 0.0});
+  }
+  scalars.insert(scalars.end(), extra_scalars.begin(), extra_scalars.end());
+  file = std::make_unique<DumpFile>(path, g.nx, g.ny, g.nz, scalars, once, names);
   check(bout_b200_stream_create(&copy_stream));
   for (auto& s : slots) {
     void* p = nullptr;

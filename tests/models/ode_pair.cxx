@@ -6,12 +6,15 @@
 //   rhs:        ddt(f) = g - damp f^3,   ddt(g) = -f - damp g
 //   convective: ddt(f) = g,              ddt(g) = -f
 //   diffusive:  ddt(f) = -damp f^3,      ddt(g) = -damp g         ([ode] split = true)
+// It also registers output variables the way models do: SAVE_REPEAT(energy), SAVE_ONCE(damp, answer, f_initial).
 #include <bout/physicsmodel.hxx>
 
 class OdePair : public PhysicsModel {
 private:
   Field3D f, g;
+  Field3D energy, f_initial; // diagnostics: written every output / once
   BoutReal damp;
+  int answer = 42;
 
 protected:
   int init(bool) override {
@@ -19,6 +22,10 @@ protected:
     damp = options["damp"].withDefault(0.3);
     const bool split = options["split"].withDefault(false);
     SOLVE_FOR(f, g);
+    f_initial = f;
+    energy = 0.5 * (f * f + g * g);
+    SAVE_REPEAT(energy);
+    SAVE_ONCE(damp, answer, f_initial);
     if (split) {
       setSplitOperator();
     }
@@ -27,11 +34,13 @@ protected:
   int rhs(BoutReal) override {
     ddt(f) = g - damp * f * f * f;
     ddt(g) = -1.0 * f - damp * g;
+    energy = 0.5 * (f * f + g * g);
     return 0;
   }
   int convective(BoutReal) override {
     ddt(f) = g;
     ddt(g) = -1.0 * f;
+    energy = 0.5 * (f * f + g * g);
     return 0;
   }
   int diffusive(BoutReal) override {

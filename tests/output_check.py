@@ -59,6 +59,14 @@ def main(workdir):
         check("t_array", np.array_equal(nc.variables["t_array"][:], [0.0, 0.25, 0.5, 0.75]))
         check("iteration", np.array_equal(nc.variables["iteration"][:], [-1, 0, 1, 2]))
         recs = {v: np.array(nc.variables[v][:]) for v in ("f", "g")}
+        # SAVE_REPEAT(energy), SAVE_ONCE(damp, answer, f_initial) of tests/models/ode_pair.cxx
+        check("once_scalars", float(nc.variables["damp"].getValue()) == 0.3 and int(nc.variables["answer"].getValue()) == 42)
+        check("once_field", np.array_equal(np.array(nc.variables["f_initial"][:]), init["f"])
+              and nc.variables["f_initial"].dimensions == ("x", "y", "z"))
+        en = np.array(nc.variables["energy"][:])
+        I = (slice(None), slice(xstart, xend + 1), slice(ystart, yend + 1), slice(None))
+        want = 0.5 * (recs["f"] * recs["f"] + recs["g"] * recs["g"])
+        check("repeat_field", en.shape == (4, nx, ny, nz) and np.abs(en[I] - want[I]).max() <= 1e-15 * np.abs(want[I]).max())
     for v in ("f", "g"):
         check(f"shape_{v}", recs[v].shape == (4, nx, ny, nz))
         check(f"initial_{v}", np.array_equal(recs[v][0], init[v]))
