@@ -478,6 +478,21 @@ def other_measurements(torch, pkg, dev, peak, with_cpu=False):
         out["host_layer_models"] = host_layer_models(pkg, with_cpu=with_cpu)
     except Exception as e:  # noqa: BLE001
         out["host_layer_models"] = {"error": repr(e)[:300]}
+    # -- SURVEY 8(f)2/(f)3 through the host layer: the other explicit integrators and the output step on blob2d
+    #    1024 x 1024, in a child process with a time limit (tools/bench_host_extras.py)
+    try:
+        import subprocess
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_host_extras.py")], capture_output=True,
+                               text=True, timeout=120)
+            stdout, stderr = p.stdout, p.stderr
+        except subprocess.TimeoutExpired as te:   # keep what the child had finished
+            stdout = te.stdout.decode() if isinstance(te.stdout, bytes) else (te.stdout or "")
+            stderr = "time limit"
+        lines = [ln for ln in stdout.splitlines() if ln.startswith("{") and ln.endswith("}")]
+        out["host_layer_extras"] = json.loads(lines[-1]) if lines else {"error": (stderr or "no output")[-300:]}
+    except Exception as e:  # noqa: BLE001
+        out["host_layer_extras"] = {"error": repr(e)[:300]}
     return out
 
 
