@@ -273,8 +273,8 @@ def unary(g: Grid, op, f, arg=0.0, out=None):
 
 
 def boundary(g: Grid, kind, side, f, value=0.0, spacing=None, lo=-1, hi=-1):
-    """In place.  kind: dirichlet | neumann | zero | extend; side: xin | xout | ydown | yup."""
-    k = {"dirichlet": 0, "dirichlet_o2": 0, "neumann": 1, "zero": 2, "extend": 3}[kind]
+    """In place.  kind: dirichlet | neumann | zero | extend | free_o2 | free_o3; side: xin | xout | ydown | yup."""
+    k = {"dirichlet": 0, "dirichlet_o2": 0, "neumann": 1, "zero": 2, "extend": 3, "free_o2": 4, "free_o3": 5}[kind]
     sd = {"xin": 0, "xout": 1, "ydown": 2, "yup": 3}[side]
     _check(lib.bout_b200_boundary(C.byref(g.c), k, sd, C.c_double(value), _ptr(spacing), lo, hi, _ptr(f),
                                   _stream()))

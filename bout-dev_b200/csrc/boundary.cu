@@ -3,7 +3,9 @@
 //   first guard = 2*val - f_inside, remaining guards = val;
 // BoundaryNeumann::apply CELL_CENTRE (:2167-2190): g1 = f_in + delta*val and, for width 2,
 //   g2 = f_in2 + 3*delta*val with delta = bx*dx + by*dy at the first guard cell;
-// apply_ddt (:591-600, :2201-2210): time derivative set to zero in the boundary cells.
+// apply_ddt (:591-600, :2201-2210): time derivative set to zero in the boundary cells;
+// BoundaryFree_O2::apply / BoundaryFree_O3::apply standard case (:3281-3293, :3545-3558): every guard cell, outwards,
+//   g = 2 f(-1) - f(-2)  /  g = 3 f(-1) - 3 f(-2) + f(-3), f(-k) being k cells inwards along the boundary normal.
 // X boundaries cover y = ystart..yend (src/mesh/impls/bout/boutmesh.cxx:1028-1037); Y boundaries
 // cover x = xlo..xhi as given (corner cells included by default, boutmesh.cxx:1057-1059).
 #include "common.cuh"
@@ -15,7 +17,8 @@ struct BndryParams {
   const double* __restrict__ spacing; // dx (x sides) or dy (y sides), Field2D; only for Neumann
   double val;
   int nx, ny, nz;
-  int kind; // 0 dirichlet, 1 neumann, 2 zero (apply_ddt), 3 extend (outer guards copy their inner neighbour)
+  int kind; // 0 dirichlet, 1 neumann, 2 zero (apply_ddt), 3 extend (outer guards copy their inner neighbour),
+            // 4 free_o2, 5 free_o3 (extrapolation)
   int side; // 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper
   int width;
   int lo, hi; // range of the other index (y for x sides, x for y sides), inclusive
@@ -45,6 +48,16 @@ __global__ void __launch_bounds__(256) k_boundary(const BndryParams p) {
     for (int i = 1; i < p.width; ++i) {
       p.f[idx3(p.first + i * p.b)] = p.f[idx3(p.first + (i - 1) * p.b)];
     }
+  } else if (p.kind == 4) {
+    for (int i = 0; i < p.width; ++i) {
+      const int n0 = p.first + i * p.b;
+      p.f[idx3(n0)] = 2 * p.f[idx3(n0 - p.b)] - p.f[idx3(n0 - 2 * p.b)];
+    }
+  } else if (p.kind == 5) {
+    for (int i = 0; i < p.width; ++i) {
+      const int n0 = p.first + i * p.b;
+      p.f[idx3(n0)] = 3.0 * p.f[idx3(n0 - p.b)] - 3.0 * p.f[idx3(n0 - 2 * p.b)] + p.f[idx3(n0 - 3 * p.b)];
+    }
   } else if (p.kind == 0) {
     p.f[idx3(p.first)] = 2 * p.val - p.f[idx3(p.first - p.b)];
     for (int i = 1; i < p.width; ++i) {
@@ -70,8 +83,13 @@ extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, d
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
-  B200_REQUIRE(f != nullptr && kind >= 0 && kind <= 3 && side >= 0 && side <= 3, BOUT_B200_ERR_ARG,
+  B200_REQUIRE(f != nullptr && kind >= 0 && kind <= 5 && side >= 0 && side <= 3, BOUT_B200_ERR_ARG,
                "boundary: bad argument");
+  {
+    const int interior = side < 2 ? g->xend - g->xstart + 1 : g->yend - g->ystart + 1;
+    B200_REQUIRE(kind < 4 || interior >= (kind == 4 ? 2 : 3), BOUT_B200_ERR_GUARDS,
+                 "boundary: free_o%d needs %d interior cells along the normal", kind - 2, kind - 2);
+  }
   B200_REQUIRE(kind != 1 || spacing2d != nullptr, BOUT_B200_ERR_ARG, "boundary: neumann needs the spacing");
   BndryParams p{};
   p.f = f;

@@ -791,6 +791,10 @@ void applyOne(Field3D& f, const std::string& cond_in, int side) {
     kind = 0;
   } else if (cond == "neumann" || cond == "neumann_o2") {
     kind = 1;
+  } else if (cond == "free_o2") {
+    kind = 4;
+  } else if (cond == "free_o3") {
+    kind = 5;
   } else {
     throw BoutException("Boundary condition '{}' is not available in the B200 host layer", cond);
   }

@@ -348,7 +348,9 @@ int bout_b200_unary(const bout_b200_grid* g, int op, const double* f, double arg
 /* ---- boundary conditions (a15) ---------------------------------------------------------------------
  * kind: 0 dirichlet / dirichlet_o2 (src/mesh/boundary_standard.cxx:527-581), 1 neumann (:2167-2190),
  * 2 zero the cells (apply_ddt :591-600), 3 extend: every guard cell beyond the first copies its inner
- * neighbour (the phi guard loops of examples/elm-pb/elm_pb.cxx:1498-1516).  side: 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper.
+ * neighbour (the phi guard loops of examples/elm-pb/elm_pb.cxx:1498-1516), 4 free_o2 / 5 free_o3: every guard cell,
+ * outwards, extrapolated from the 2 / 3 cells inside it (boundary_standard.cxx:3281-3293, :3545-3558; elm-pb's shipped
+ * bndry_yup/ydown = free_o3).  side: 0 x-inner, 1 x-outer, 2 y-lower, 3 y-upper.
  * spacing2d: dx for x sides, dy for y sides (Neumann only).  lo/hi: range of the other index
  * (y for x sides, x for y sides); pass -1,-1 for the reference's default (ystart..yend / all x). */
 int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value,

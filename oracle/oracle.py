@@ -245,7 +245,7 @@ class Port:
     def bndry_x(self, g, kind, side, f, dx, val=0.0):
         gc = g.c()
         self.lib.bo_bndry_x.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
-        self.lib.bo_bndry_x(C.byref(gc), {"dirichlet": 0, "neumann": 1}[kind], side, val, _p(dx), _p(f))
+        self.lib.bo_bndry_x(C.byref(gc), {"dirichlet": 0, "neumann": 1, "free_o2": 2, "free_o3": 3}[kind], side, val, _p(dx), _p(f))
         return f
 
     def dc(self, g, f):

@@ -22,6 +22,7 @@ Outputs (committed; the GPU box has neither /root/reference nor needs the refere
   models.npz             unchanged example models (hasegawa-wakatani, hasegawa-wakatani-3d, blob2d) run
                          through the reference's Solver::run_rhs and RK4 / RK3-SSP solvers: initial state,
                          ddt after one RHS, state after a few steps.
+  bndry_free.npz         free_o2 / free_o3 boundary conditions on the ops_small grid and field.
   integrators.npz        this repository's test model tests/models/ode_pair.cxx through the reference's own
                          euler, rkgeneric (rkf45, cashkarp, rk4, rkf34; adaptive and fixed) and splitrk solvers
                          (cases.INTEGRATOR_CASES): final state and number of RHS calls.
@@ -337,6 +338,16 @@ def one_model(tag, path):
     np.savez(path, **out)
 
 
+def bndry_free():
+    """free_o2 / free_o3 (BoundaryFree_O2/O3::apply) on the ops_small grid and field: tests/golden/bndry_free.npz."""
+    ops = np.load(os.path.join(HERE, "ops_small.npz"))
+    r = orc.Ref(OPS_INI)
+    out = {"bndry_" + cond: r.apply_boundary(ops["f"], cond) for cond in ("free_o2", "free_o3")}
+    r.close()
+    np.savez_compressed(os.path.join(HERE, "bndry_free.npz"), **out)
+    print("  bndry_free:", {k: float(np.abs(v - ops["f"]).max()) for k, v in out.items()})
+
+
 def one_integrator(tag, path):
     """tests/models/ode_pair.cxx through the reference's own euler / rkgeneric / splitrk solvers."""
     from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
@@ -442,7 +453,7 @@ def models():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb", "integrators"]
+    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb", "integrators", "bndry_free"]
     if which[0].startswith("elmpb:"):
         elmpb_case(which[0][6:], which[1])
         sys.stdout.flush()
@@ -467,4 +478,6 @@ if __name__ == "__main__":
         elmpb()
     if "integrators" in which:
         integrators()
+    if "bndry_free" in which:
+        bndry_free()
     os._exit(0)  # the reference's static destructors are not exit-safe after repeated init/finalise

@@ -193,6 +193,19 @@ def test_boundaries_and_communicate_match_reference(port, orc, ops):
     assert np.array_equal(orc.halo_self_reference(g, f, periodic_x=False, periodic_y=True), ops["communicate"])
 
 
+def test_free_boundaries_match_reference(port, orc, ops):
+    """BoundaryFree_O2 / BoundaryFree_O3 (src/mesh/boundary_standard.cxx:3281-3293, :3545-3558) against the
+    reference build's output on the same field (tests/golden/bndry_free.npz)."""
+    gold = np.load(os.path.join(GOLD, "bndry_free.npz"))
+    g, m, f = _grid(orc, ops), metric_from(orc, ops), ops["f"]
+    for kind in ("free_o2", "free_o3"):
+        got = f.copy()
+        port.bndry_x(g, kind, -1, got, m.dx)
+        port.bndry_x(g, kind, +1, got, m.dx)
+        # 5e-15 (a few ulp, amplified x3 into the second guard cell): the reference build contracts the three-term sum into FMAs (-march=x86-64-v3), the port does not
+        assert np.abs(got - gold["bndry_" + kind]).max() <= 5e-15, kind
+
+
 def test_field_algebra_matches_reference(ops):
     """generated_fieldops.cxx arithmetic restated in numpy with the reference's operation order."""
     f, h, v, f2 = ops["f"], ops["h"], ops["v"], ops["f2"]

@@ -98,3 +98,35 @@ def test_output_step_on_device(capi, tmp_path, mode):
     p = subprocess.run(args, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
+def test_free_boundaries_on_device(capi):
+    """free_o2 / free_o3 (kinds 4, 5 of bout_b200_boundary) on the x sides against the reference build's output
+    (tests/golden/bndry_free.npz) and on the y sides against the closed form (boundary_standard.cxx:3281-3293,
+    :3545-3558: every guard cell, outwards, from the 2 / 3 cells inside it)."""
+    import torch
+    ops = np.load(os.path.join(HERE, "golden", "ops_small.npz"))
+    gold = np.load(os.path.join(HERE, "golden", "bndry_free.npz"))
+    nx, ny, nz, mxg, myg = [int(v) for v in ops["grid"]]
+    g = capi.Grid(nx, ny, nz, mxg, myg)
+    for kind in ("free_o2", "free_o3"):
+        F = torch.from_numpy(np.ascontiguousarray(ops["f"])).cuda()
+        capi.boundary(g, kind, "xin", F)
+        capi.boundary(g, kind, "xout", F)
+        assert np.abs(F.cpu().numpy() - gold["bndry_" + kind]).max() <= 5e-15, kind
+        F = torch.from_numpy(np.ascontiguousarray(ops["f"])).cuda()
+        capi.boundary(g, kind, "ydown", F)
+        capi.boundary(g, kind, "yup", F)
+        w = ops["f"].copy()
+        for i in range(myg):
+            lo, hi = myg - 1 - i, ny - myg + i
+            if kind == "free_o2":
+                w[:, lo] = 2 * w[:, lo + 1] - w[:, lo + 2]
+                w[:, hi] = 2 * w[:, hi - 1] - w[:, hi - 2]
+            else:
+                w[:, lo] = 3.0 * w[:, lo + 1] - 3.0 * w[:, lo + 2] + w[:, lo + 3]
+                w[:, hi] = 3.0 * w[:, hi - 1] - 3.0 * w[:, hi - 2] + w[:, hi - 3]
+        assert np.abs(F.cpu().numpy() - w).max() <= 5e-15, kind + " y"
+    tiny = capi.Grid(6, 6, 4, 2, 2)   # 2 interior cells: free_o3 needs 3
+    with pytest.raises(capi.BoutB200Error):
+        capi.boundary(tiny, "free_o3", "xin", torch.zeros(6, 6, 4, dtype=torch.float64, device="cuda"))
