@@ -85,11 +85,6 @@ extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, d
   }
   B200_REQUIRE(f != nullptr && kind >= 0 && kind <= 5 && side >= 0 && side <= 3, BOUT_B200_ERR_ARG,
                "boundary: bad argument");
-  {
-    const int interior = side < 2 ? g->xend - g->xstart + 1 : g->yend - g->ystart + 1;
-    B200_REQUIRE(kind < 4 || interior >= (kind == 4 ? 2 : 3), BOUT_B200_ERR_GUARDS,
-                 "boundary: free_o%d needs %d interior cells along the normal", kind - 2, kind - 2);
-  }
   B200_REQUIRE(kind != 1 || spacing2d != nullptr, BOUT_B200_ERR_ARG, "boundary: neumann needs the spacing");
   BndryParams p{};
   p.f = f;
@@ -108,6 +103,11 @@ extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, d
   }
   if (p.width <= 0) {
     return 0; // no guard cells on this side
+  }
+  {
+    const int interior = side < 2 ? g->xend - g->xstart + 1 : g->yend - g->ystart + 1;
+    B200_REQUIRE(kind < 4 || interior >= (kind == 4 ? 2 : 3), BOUT_B200_ERR_GUARDS,
+                 "boundary: free_o%d needs %d interior cells along the normal", kind - 2, kind - 2);
   }
   if (lo < 0 || hi < 0) { // default ranges
     lo = side < 2 ? g->ystart : 0;
