@@ -776,6 +776,22 @@ void applyOne(Field3D& f, const std::string& cond_in, int side) {
   if (cond.empty() || cond == "none") {
     return;
   }
+  if (cond.rfind("relax(", 0) == 0 && cond.back() == ')') {
+    // relax(op[, rate]) (BoundaryRelax, boundary_standard.cxx:3599-3637): apply() is the wrapped condition's; the
+    // relaxation only enters apply_ddt, which the solver calls for evolve_bndry = true (not supported here)
+    const std::string inner = cond.substr(6, cond.size() - 7);
+    int depth = 0;
+    size_t cut = inner.size();
+    for (size_t i = 0; i < inner.size(); ++i) {
+      depth += inner[i] == '(' ? 1 : (inner[i] == ')' ? -1 : 0);
+      if (inner[i] == ',' && depth == 0) {
+        cut = i;
+        break;
+      }
+    }
+    applyOne(f, inner.substr(0, cut), side);
+    return;
+  }
   double value = 0.0;
   const auto paren = cond.find('(');
   if (paren != std::string::npos) {

@@ -218,3 +218,53 @@ int bout_b200_memcpy_d2h_async(void* dst, const void* src, size_t bytes, void* s
   memmove(dst, src, bytes);
   return 0;
 }
+
+/* boundary conditions (kinds as in include/bout_b200.h; 3 "extend" is elm-pb specific and not needed by the host logic) */
+int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value, const double* spacing2d, int lo,
+                       int hi, double* f, void* stream) {
+  int width, first, b;
+  (void)stream;
+  if (kind < 0 || kind > 5 || kind == 3 || side < 0 || side > 3) {
+    return BOUT_B200_ERR_UNSUPPORTED;
+  }
+  switch (side) {
+  case 0: width = g->xstart; first = g->xstart - 1; b = -1; break;
+  case 1: width = g->nx - g->xend - 1; first = g->nx - width; b = 1; break;
+  case 2: width = g->ystart; first = g->ystart - 1; b = -1; break;
+  default: width = g->ny - g->yend - 1; first = g->ny - width; b = 1; break;
+  }
+  if (width <= 0) {
+    return 0;
+  }
+  if (lo < 0 || hi < 0) {
+    lo = side < 2 ? g->ystart : 0;
+    hi = side < 2 ? g->yend : g->nx - 1;
+  }
+#define AT(n, o, z) f[(((long long)(side < 2 ? (n) : (o))) * g->ny + (side < 2 ? (o) : (n))) * g->nz + (z)]
+  for (int o = lo; o <= hi; ++o) {
+    for (int z = 0; z < g->nz; ++z) {
+      for (int i = 0; i < width; ++i) {
+        const int n = first + i * b;
+        if (kind == 2) {
+          AT(n, o, z) = 0.0;
+        } else if (kind == 4) {
+          AT(n, o, z) = 2 * AT(n - b, o, z) - AT(n - 2 * b, o, z);
+        } else if (kind == 5) {
+          AT(n, o, z) = 3.0 * AT(n - b, o, z) - 3.0 * AT(n - 2 * b, o, z) + AT(n - 3 * b, o, z);
+        } else if (kind == 0) {
+          AT(n, o, z) = (i == 0) ? 2 * value - AT(n - b, o, z) : value;
+        } else { /* neumann */
+          const int x = side < 2 ? first : o, y = side < 2 ? o : first;
+          const double delta = b * spacing2d[(long long)x * g->ny + y];
+          if (i == 0) {
+            AT(n, o, z) = AT(n - b, o, z) + delta * value;
+          } else if (i == 1 && width == 2) {
+            AT(n, o, z) = AT(first - 2 * b, o, z) + 3.0 * delta * value;
+          }
+        }
+      }
+    }
+  }
+#undef AT
+  return 0;
+}

@@ -243,15 +243,16 @@ ELMPB_INI = elmpb_ini(20, 8, 16, timestep="2e-3")
 
 
 # ---- explicit integrators beyond rk4 / rk3ssp on tests/models/ode_pair.cxx (tests/golden/integrators.npz) --------
-def ode_ini(solver_opts, split, nout, output_step):
+def ode_ini(solver_opts, split, nout, output_step, bndry=None):
     """12x1x8 periodic-X mesh without boundaries; [solver] options per case; root nout / timestep = the
     arguments later given to Solver::solve, so option defaults that derive from them agree on both sides."""
-    return f"nout = {nout}\ntimestep = {output_step}\n" + make_ini(12, 1, 8, mxg=2, myg=0, periodic_x=True, extra=f"""
+    return f"nout = {nout}\ntimestep = {output_step}\n" + make_ini(12, 1, 8, mxg=2, myg=0, periodic_x=bndry is None, extra=f"""
 [ode]
 damp = 0.3
 split = {'true' if split else 'false'}
 [all]
 scale = 0.0
+{bndry or ''}
 [f]
 scale = 1.0
 function = 1 + 0.5*sin(2*pi*x)*cos(z)
@@ -265,8 +266,13 @@ error_on_unused_options = false
 """)
 
 
-# tag: (solver type, [solver] options, split-operator model?, nout, output_step)
+# tag: (solver type, [solver] options, split-operator model?, nout, output_step[, boundary options of [all]])
+# The "bc_" cases have X boundaries (periodicX = false): the comparison then covers the guard cells as well, i.e. the
+# boundary-condition names, arguments and the relax() modifier as Solver::pre_rhs applies them.
 INTEGRATOR_CASES = {
+    "bc_dirichlet_neumann": ("rk4", "timestep = 0.0625", False, 1, 0.25, "bndry_xin = dirichlet(0.5)\nbndry_xout = neumann(0.2)"),
+    "bc_free_relax": ("rk3ssp", "timestep = 0.0625", True, 1, 0.25, "bndry_xin = free_o3\nbndry_xout = relax(dirichlet_o2(0.25), 10)"),
+    "bc_free_o2_all": ("euler", "timestep = 0.0625", False, 1, 0.25, "bndry_all = free_o2"),
     "rk4_fixed": ("rk4", "timestep = 0.07", False, 2, 0.5),
     "rk4_adaptive": ("rk4", "adaptive = true\ntimestep = 0.25\nmax_timestep = 0.5\natol = 1e-8\nrtol = 1e-7", False, 2, 0.5),
     "rk3ssp_split": ("rk3ssp", "timestep = 0.07", True, 1, 0.5),

@@ -356,8 +356,8 @@ def one_integrator(tag, path):
         r = orc.Ref(hw_integrator_ini(opts, nout, step))
         names = r.model_create("hw", solver)
     else:
-        solver, opts, split, nout, step = INTEGRATOR_CASES[tag]
-        r = orc.Ref(ode_ini(opts, split, nout, step))
+        solver, opts, split, nout, step, *bndry = INTEGRATOR_CASES[tag]
+        r = orc.Ref(ode_ini(opts, split, nout, step, *bndry))
         names = r.model_create("ode_pair", solver)
     out = {f"{tag}_init_{v}": r.model_get(v) for v in names}
     r.model_solve(nout, step)
