@@ -518,8 +518,11 @@ private:
 /// Snapshots leave the device on a second stream while the solver keeps stepping; records reach the file in order
 class OutputPipeline {
 public:
+  /// path: dump file ("" = none); restart_path: restart file rewritten at every snapshot from its first n_evolving
+  /// fields ("" = none)
   OutputPipeline(const std::string& path, Mesh* mesh, const std::vector<std::string>& names,
-                 std::vector<DumpScalar> extra_scalars = {}, const std::vector<DumpOnceField>& once = {});
+                 std::vector<DumpScalar> extra_scalars = {}, const std::vector<DumpOnceField>& once = {},
+                 const std::string& restart_path = "", size_t n_evolving = 0);
   ~OutputPipeline();
   void snapshot(double time, int iteration, const std::vector<const Field3D*>& fields);
   void finish(); ///< drains both stages; every snapshot is on disk afterwards
@@ -541,7 +544,21 @@ private:
   Slot slots[2];
   size_t nfields, count = 0;
   unsigned next = 0;
+  std::string restart_path;
+  size_t n_evolving = 0;
+  std::vector<std::string> field_names;
+  int dims[3] = {0, 0, 0};
 };
+
+/// Variables without a record dimension of a NetCDF classic file (CDF-1 / CDF-2), ints widened to double
+struct NcVariable {
+  std::vector<int> shape;
+  std::vector<double> data;
+  bool is_int = false;
+};
+std::map<std::string, NcVariable> readNcFixedVariables(const std::string& path);
+void writeRestartFile(const std::string& path, int nx, int ny, int nz, double time, int iteration,
+                      const std::vector<std::string>& names, const std::vector<const double*>& host_fields);
 } // namespace b200
 } // namespace bout
 

@@ -1512,6 +1512,29 @@ int Solver::solve(int nout_in, BoutReal output_step) {
     throw BoutException("Solver::solve: no evolving variables were added");
   }
   initialised = true;
+  // Restart (`restart = true`, file `[restart] path`): evolving variables, time and iteration of the latest output of
+  // an earlier run (reference: Solver::add reads them from the restart options, solver.cxx:240-262; tt / hist_hi :694-697)
+  Options& ro = Options::root()["restart_file"];
+  const std::string restart_path = ro.isSet("path") ? ro["path"].as<std::string>() : std::string();
+  int iteration0 = 0;
+  if (Options::root()["restart"].withDefault(false)) {
+    if (restart_path.empty()) {
+      throw BoutException("restart = true needs [restart_file] path");
+    }
+    const auto vars = bout::b200::readNcFixedVariables(restart_path);
+    for (auto& f : f3d) {
+      const auto it = vars.find(f.name);
+      if (it == vars.end() || it->second.data.size() != f.var->size()) {
+        throw BoutException("Restart file '{}' has no variable '{}' of the mesh's size", restart_path, f.name);
+      }
+      f.var->setHost(it->second.data);
+    }
+    if (vars.count("tt") == 0 || vars.count("hist_hi") == 0) {
+      throw BoutException("Restart file '{}' lacks tt / hist_hi", restart_path);
+    }
+    simtime = vars.at("tt").data.at(0);
+    iteration0 = static_cast<int>(vars.at("hist_hi").data.at(0)) + 1;
+  }
   init_solver();
   if (run_rhs(simtime) != 0) { // solver.cxx:569
     throw BoutException("Physics RHS call failed\n");
@@ -1522,7 +1545,7 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   std::unique_ptr<bout::b200::OutputPipeline> dump;
   std::vector<const Field3D*> dump_fields;
   Options& oo = Options::root()["output"];
-  if (oo.isSet("path")) {
+  if (oo.isSet("path") || !restart_path.empty()) {
     std::vector<std::string> names;
     for (const auto& f : f3d) {
       names.push_back(f.name);
@@ -1565,15 +1588,16 @@ int Solver::solve(int nout_in, BoutReal output_step) {
         once.push_back({kv.first, true, kv.second->getHost()});
       }
     }
-    dump = std::make_unique<bout::b200::OutputPipeline>(oo["path"].as<std::string>(), f3d[0].var->getMesh(), names, scalars,
-                                                        once);
-    dump->snapshot(simtime, -1, dump_fields);
+    dump = std::make_unique<bout::b200::OutputPipeline>(oo.isSet("path") ? oo["path"].as<std::string>() : std::string(),
+                                                        f3d[0].var->getMesh(), names, scalars, once, restart_path,
+                                                        f3d.size());
+    dump->snapshot(simtime, iteration0 - 1, dump_fields);
   }
   for (int s = 0; s < nout; ++s) {
     run_output_step(simtime + output_timestep);
     run_rhs(simtime); // rk4.cxx:157: extra variables at the output time
     if (dump) {
-      dump->snapshot(simtime, s, dump_fields);
+      dump->snapshot(simtime, iteration0 + s, dump_fields);
     }
   }
   if (dump) {

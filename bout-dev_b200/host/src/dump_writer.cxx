@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 
 namespace bout {
 namespace b200 {
@@ -202,11 +203,151 @@ void DumpFile::append(double t, int iteration, const std::vector<const double*>&
   std::fflush(impl->fp);
 }
 
+// ---- reading the non-record variables of such a file back (restart) ------------------------------------------
+namespace {
+struct Cursor {
+  const std::vector<unsigned char>& b;
+  size_t pos = 0;
+  std::int64_t get(int bytes) {
+    if (pos + bytes > b.size()) {
+      throw BoutException("NetCDF header is truncated");
+    }
+    std::uint64_t v = 0;
+    for (int i = 0; i < bytes; ++i) {
+      v = (v << 8) | b[pos++];
+    }
+    return bytes == 4 ? static_cast<std::int64_t>(static_cast<std::int32_t>(v)) : static_cast<std::int64_t>(v);
+  }
+  std::string name() {
+    const auto n = static_cast<size_t>(get(4));
+    if (pos + n > b.size()) {
+      throw BoutException("NetCDF header is truncated");
+    }
+    std::string s(b.begin() + pos, b.begin() + pos + n);
+    pos += (n + 3) / 4 * 4;
+    return s;
+  }
+  void skipAttributes() { // tag + count, then name, type, nelems, values padded to 4 bytes
+    const auto tag = get(4);
+    const auto n = get(4);
+    if (tag == 0 && n == 0) {
+      return;
+    }
+    static const int size_of[] = {0, 1, 1, 2, 4, 4, 8};
+    for (std::int64_t i = 0; i < n; ++i) {
+      name();
+      const auto type = get(4);
+      const auto nel = get(4);
+      if (type < 1 || type > 6) {
+        throw BoutException("NetCDF attribute of unknown type {}", type);
+      }
+      pos += (static_cast<size_t>(nel) * size_of[type] + 3) / 4 * 4;
+    }
+  }
+};
+} // namespace
+
+std::map<std::string, NcVariable> readNcFixedVariables(const std::string& path) {
+  std::FILE* fp = std::fopen(path.c_str(), "rb");
+  if (fp == nullptr) {
+    throw BoutException("Could not open '{}'", path);
+  }
+  std::vector<unsigned char> all;
+  unsigned char chunk[1 << 16];
+  size_t got;
+  while ((got = std::fread(chunk, 1, sizeof(chunk), fp)) > 0) {
+    all.insert(all.end(), chunk, chunk + got);
+  }
+  std::fclose(fp);
+  if (all.size() < 8 || all[0] != 'C' || all[1] != 'D' || all[2] != 'F' || (all[3] != 1 && all[3] != 2)) {
+    throw BoutException("'{}' is not a NetCDF classic file", path);
+  }
+  const int offset_bytes = all[3] == 2 ? 8 : 4;
+  Cursor c{all, 4};
+  c.get(4); // numrecs
+  std::vector<std::int64_t> dim_len;
+  {
+    const auto tag = c.get(4);
+    const auto n = c.get(4);
+    if (tag != 0 || n != 0) {
+      for (std::int64_t i = 0; i < n; ++i) {
+        c.name();
+        dim_len.push_back(c.get(4));
+      }
+    }
+  }
+  c.skipAttributes();
+  std::map<std::string, NcVariable> out;
+  const auto tag = c.get(4);
+  const auto nvars = c.get(4);
+  if (tag == 0 && nvars == 0) {
+    return out;
+  }
+  for (std::int64_t i = 0; i < nvars; ++i) {
+    const std::string name = c.name();
+    const auto nd = c.get(4);
+    NcVariable v;
+    bool record = false;
+    size_t count = 1;
+    for (std::int64_t d = 0; d < nd; ++d) {
+      const auto id = c.get(4);
+      const auto len = dim_len.at(static_cast<size_t>(id));
+      record = record || len == 0;
+      v.shape.push_back(static_cast<int>(len));
+      count *= static_cast<size_t>(len);
+    }
+    c.skipAttributes();
+    const auto type = c.get(4);
+    c.get(4); // vsize
+    const auto begin = static_cast<size_t>(c.get(offset_bytes));
+    if (record || (type != NC_INT && type != NC_DOUBLE)) {
+      continue; // record variables and other types are not needed for a restart
+    }
+    const size_t width = type == NC_INT ? 4 : 8;
+    if (begin + count * width > all.size()) {
+      throw BoutException("'{}': variable '{}' extends past the end of the file", path, name);
+    }
+    v.is_int = type == NC_INT;
+    v.data.resize(count);
+    Cursor d{all, begin};
+    for (size_t k = 0; k < count; ++k) {
+      if (v.is_int) {
+        v.data[k] = static_cast<double>(d.get(4));
+      } else {
+        const auto bits = static_cast<std::uint64_t>(d.get(8));
+        std::memcpy(&v.data[k], &bits, 8);
+      }
+    }
+    out[name] = std::move(v);
+  }
+  return out;
+}
+
+// Restart file: the evolving variables at the latest output plus tt (time) and hist_hi (iteration), as
+// Solver::outputVars(restart_options, false) (solver.cxx:694-724); written to <path>.tmp and renamed.
+void writeRestartFile(const std::string& path, int nx, int ny, int nz, double time, int iteration,
+                      const std::vector<std::string>& names, const std::vector<const double*>& host_fields) {
+  std::vector<DumpOnceField> once;
+  const size_t count = static_cast<size_t>(nx) * ny * nz;
+  for (size_t f = 0; f < names.size(); ++f) {
+    once.push_back({names[f], true, std::vector<double>(host_fields[f], host_fields[f] + count)});
+  }
+  const std::string tmp = path + ".tmp";
+  {
+    DumpFile file(tmp, nx, ny, nz, {{"hist_hi", false, iteration, 0.0}, {"tt", true, 0, time}}, once, {});
+  }
+  if (std::rename(tmp.c_str(), path.c_str()) != 0) {
+    throw BoutException("Could not move '{}' to '{}'", tmp, path);
+  }
+}
+
 // ---- the pipeline ------------------------------------------------------------------------------------------
 OutputPipeline::OutputPipeline(const std::string& path, Mesh* mesh, const std::vector<std::string>& names,
-                               std::vector<DumpScalar> extra_scalars, const std::vector<DumpOnceField>& once)
-    : nfields(names.size()) {
+                               std::vector<DumpScalar> extra_scalars, const std::vector<DumpOnceField>& once,
+                               const std::string& restart_path_in, size_t n_evolving_in)
+    : nfields(names.size()), restart_path(restart_path_in), n_evolving(n_evolving_in), field_names(names) {
   const auto g = mesh->grid();
+  dims[0] = g.nx, dims[1] = g.ny, dims[2] = g.nz;
   count = static_cast<size_t>(g.nx) * g.ny * g.nz;
   std::vector<DumpScalar> scalars;
   const std::pair<const char*, int> ints[] = {
@@ -216,7 +357,9 @@ OutputPipeline::OutputPipeline(const std::string& path, Mesh* mesh, const std::v
     scalars.push_back({kv.first, false, kv.second, 0.0});
   }
   scalars.insert(scalars.end(), extra_scalars.begin(), extra_scalars.end());
-  file = std::make_unique<DumpFile>(path, g.nx, g.ny, g.nz, scalars, once, names);
+  if (!path.empty()) {
+    file = std::make_unique<DumpFile>(path, g.nx, g.ny, g.nz, scalars, once, names);
+  }
   check(bout_b200_stream_create(&copy_stream));
   for (auto& s : slots) {
     void* p = nullptr;
@@ -260,7 +403,16 @@ void OutputPipeline::handOver(Slot& s) { // device -> host copy done: release th
   DumpFile* out = file.get();
   const double t = s.time;
   const int it = s.iteration;
-  s.writing = std::async(std::launch::async, [out, t, it, ptrs]() { out->append(t, it, ptrs); });
+  s.writing = std::async(std::launch::async, [this, out, t, it, ptrs]() {
+    if (out != nullptr) {
+      out->append(t, it, ptrs);
+    }
+    if (!restart_path.empty()) { // the evolving variables come first in every snapshot
+      const std::vector<std::string> names(field_names.begin(), field_names.begin() + n_evolving);
+      const std::vector<const double*> fields(ptrs.begin(), ptrs.begin() + n_evolving);
+      writeRestartFile(restart_path, dims[0], dims[1], dims[2], t, it, names, fields);
+    }
+  });
 }
 
 void OutputPipeline::snapshot(double time, int iteration, const std::vector<const Field3D*>& fields) {
@@ -287,9 +439,6 @@ void OutputPipeline::snapshot(double time, int iteration, const std::vector<cons
 }
 
 void OutputPipeline::finish() {
-  if (!file) {
-    return;
-  }
   for (int k = 0; k < 2; ++k) { // oldest first
     Slot& s = slots[(next + k) % 2];
     if (s.copying) {
@@ -302,7 +451,7 @@ void OutputPipeline::finish() {
   }
 }
 
-int OutputPipeline::recordsWritten() const { return file->records(); }
+int OutputPipeline::recordsWritten() const { return file ? file->records() : 0; }
 
 } // namespace b200
 } // namespace bout

@@ -7,7 +7,8 @@ tests/models/ode_pair.cxx with `[output] path = <file>` and checks the dump file
 Checks: the file parses as NetCDF classic; dimensions / scalars as in BOUT.dmp.<rank>.nc; t_array and iteration per
 record (the first record is the initial state, iteration -1, as Solver::solve's call_monitors(simtime, -1, NOUT));
 record k of a 3-output run equals, bit for bit, the final state of a separate k-output run (fixed binary-exact
-timestep), i.e. a snapshot is not disturbed by the steps that run while it is copied and written.
+timestep), i.e. a snapshot is not disturbed by the steps that run while it is copied and written; a run restarted
+from the restart file of a 2-output run (`restart = true`, `[restart_file] path`) ends bit-equal to the 3-output run.
 Prints one JSON line; exit code 0 iff all checks pass."""
 import json
 import os
@@ -23,11 +24,13 @@ SOLVER_OPTS = "timestep = 0.0625"
 STEP = 0.25
 
 
-def run(hostmod, nout, path=None):
+def run(hostmod, nout, path=None, restart_path=None, restart=False):
     from cases import ode_ini
-    ini = ode_ini(SOLVER_OPTS, False, nout, STEP)
+    ini = ("restart = true\n" if restart else "") + ode_ini(SOLVER_OPTS, False, nout, STEP)
     if path is not None:
         ini += f"\n[output]\npath = {path}\n"
+    if restart_path is not None:
+        ini += f"\n[restart_file]\npath = {restart_path}\n"
     h = hostmod.Host(ini)
     try:
         names = h.model_create("ode_pair", "rk4")
@@ -75,6 +78,21 @@ def main(workdir):
         _, fin_k, _ = run(hostmod, k)
         for v in ("f", "g"):
             check(f"record{k}_{v}", np.array_equal(recs[v][k], fin_k[v]))
+    # restart: two outputs with a restart file, then a restarted run of one more output == the straight 3-output run
+    rpath = os.path.join(workdir, "BOUT.restart.0.nc")
+    _, fin2, _ = run(hostmod, 2, restart_path=rpath)
+    with netcdf_file(rpath, "r", mmap=False) as nc:
+        check("restart_file", float(nc.variables["tt"].getValue()) == 0.5 and int(nc.variables["hist_hi"].getValue()) == 1
+              and np.array_equal(np.array(nc.variables["f"][:]), fin2["f"]) and np.array_equal(np.array(nc.variables["g"][:]), fin2["g"]))
+    path2 = os.path.join(workdir, "BOUT.dmp.restarted.nc")
+    _, fin3, _ = run(hostmod, 1, path=path2, restart_path=rpath, restart=True)
+    for v in ("f", "g"):
+        check(f"restarted_{v}", np.array_equal(fin3[v], final[v]))
+    with netcdf_file(path2, "r", mmap=False) as nc:
+        check("restarted_times", np.array_equal(nc.variables["t_array"][:], [0.5, 0.75])
+              and np.array_equal(nc.variables["iteration"][:], [1, 2]))
+    with netcdf_file(rpath, "r", mmap=False) as nc:
+        check("restart_file_advanced", float(nc.variables["tt"].getValue()) == 0.75 and int(nc.variables["hist_hi"].getValue()) == 2)
     res["ok"] = all(ok for _, ok in res["checks"])
     print(json.dumps(res), flush=True)
     return 0 if res["ok"] else 1
