@@ -564,6 +564,21 @@ void writeRestartFile(const std::string& path, int nx, int ny, int nz, double ti
 
 // ---- Solver / PhysicsModel ---------------------------------------------------------------------------------
 class PhysicsModel;
+class Solver;
+/// Output monitor (reference include/bout/monitor.hxx:28-75).  Only the default period (every output step) exists here.
+class Monitor {
+public:
+  explicit Monitor(BoutReal timestep_ = -1) : timestep(timestep_) {}
+  virtual ~Monitor() = default;
+  virtual int call(Solver* solver, BoutReal time, int iter, int nout) = 0;
+  virtual void cleanup() {}
+  BoutReal getTimestep() const { return timestep; }
+
+private:
+  BoutReal timestep;
+};
+enum class MonitorPosition { BACK, FRONT };
+
 class Solver {
 public:
   explicit Solver(Options* opts);
@@ -584,6 +599,10 @@ public:
   /// Called once from solve() before the first step (the reference solvers' init())
   virtual void init_solver() {}
   virtual void setMaxTimestep(BoutReal) {} ///< solver.hxx:369; EulerSolver / RKGenericSolver override
+  /// solver.cxx:840-867; called at the start (iter = -1) and after every output step, in order; a non-zero return
+  /// stops the run with a BoutException as in Solver::call_monitors (solver.cxx:874-900)
+  void addMonitor(Monitor* monitor, MonitorPosition pos = MonitorPosition::BACK);
+  void removeMonitor(Monitor* monitor);
   struct Var {
     Field3D* var;
     Field3D* F_var;
@@ -602,6 +621,8 @@ protected:
   int nout;
   bool initialised = false;
   bool is_nonsplit_model_diffusive = true; ///< solver.cxx:97-101
+  std::vector<Monitor*> monitors;
+  void call_monitors(BoutReal t, int iter, int nout_total);
   void pre_rhs();
   void post_rhs();
 };
@@ -638,6 +659,9 @@ public:
   int runDiffusive(BoutReal t) { return diffusive(t); }
   bool splitOperator() const { return splitop; }
   virtual void outputVars(Options&) {}
+  /// physicsmodel.hxx:299-308: called by the solver at every output (after the model's variables are up to date)
+  virtual int outputMonitor(BoutReal, int, int) { return 0; }
+  virtual int timestepMonitor(BoutReal, BoutReal) { return 0; }
 
 protected:
   virtual int init(bool restarting) = 0;

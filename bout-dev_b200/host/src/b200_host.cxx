@@ -1482,6 +1482,44 @@ int Solver::run_diffusive(BoutReal t) { // solver.cxx:1460-1484
   return status;
 }
 
+void Solver::addMonitor(Monitor* monitor, MonitorPosition pos) {
+  if (monitor->getTimestep() > 0 && monitor->getTimestep() != output_timestep) {
+    throw BoutException("Solver::addMonitor: monitors with their own timestep are not supported by the B200 host layer");
+  }
+  if (pos == MonitorPosition::FRONT) {
+    monitors.insert(monitors.begin(), monitor);
+  } else {
+    monitors.push_back(monitor);
+  }
+}
+void Solver::removeMonitor(Monitor* monitor) {
+  monitors.erase(std::remove(monitors.begin(), monitors.end(), monitor), monitors.end());
+}
+void Solver::call_monitors(BoutReal t, int iter, int nout_total) { // solver.cxx:874-935
+  try {
+    for (Monitor* m : monitors) {
+      const int ret = m->call(this, t, iter, nout_total);
+      if (ret != 0) {
+        throw BoutException("Monitor signalled to quit (return code {})", ret);
+      }
+    }
+    const int ret = model->outputMonitor(t, iter, nout_total); // PhysicsModelMonitor::call, physicsmodel.cxx:255
+    if (ret != 0) {
+      throw BoutException("Monitor signalled to quit (return code {})", ret);
+    }
+  } catch (const BoutException&) {
+    for (Monitor* m : monitors) {
+      m->cleanup();
+    }
+    throw;
+  }
+  if (iter == nout_total) {
+    for (Monitor* m : monitors) {
+      m->cleanup();
+    }
+  }
+}
+
 void Solver::take_step(BoutReal, BoutReal) {
   throw BoutException("Solver::take_step: this integrator advances through run_output_step only");
 }
@@ -1593,12 +1631,14 @@ int Solver::solve(int nout_in, BoutReal output_step) {
                                                         f3d.size());
     dump->snapshot(simtime, iteration0 - 1, dump_fields);
   }
+  call_monitors(simtime, -1, nout); // solver.cxx:580
   for (int s = 0; s < nout; ++s) {
     run_output_step(simtime + output_timestep);
     run_rhs(simtime); // rk4.cxx:157: extra variables at the output time
     if (dump) {
       dump->snapshot(simtime, iteration0 + s, dump_fields);
     }
+    call_monitors(simtime, s, nout);
   }
   if (dump) {
     dump->finish();

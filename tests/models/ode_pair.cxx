@@ -15,12 +15,14 @@ private:
   Field3D energy, f_initial; // diagnostics: written every output / once
   BoutReal damp;
   int answer = 42;
+  int quit_at = -1; // [ode] quit_at = <iteration>: outputMonitor asks the solver to stop there
 
 protected:
   int init(bool) override {
     auto& options = Options::root()["ode"];
     damp = options["damp"].withDefault(0.3);
     const bool split = options["split"].withDefault(false);
+    quit_at = options["quit_at"].withDefault(-1);
     SOLVE_FOR(f, g);
     f_initial = f;
     energy = 0.5 * (f * f + g * g);
@@ -43,6 +45,7 @@ protected:
     energy = 0.5 * (f * f + g * g);
     return 0;
   }
+  int outputMonitor(BoutReal, int iter, int) override { return (quit_at >= 0 && iter == quit_at) ? 7 : 0; }
   int diffusive(BoutReal) override {
     ddt(f) = -damp * f * f * f;
     ddt(g) = -damp * g;

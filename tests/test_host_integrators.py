@@ -98,3 +98,33 @@ def test_output_step_writes_a_readable_dump_file(fake_device, tmp_path):
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     res = json.loads(p.stdout.strip().splitlines()[-1])
     assert res["ok"] and res["records"] == 4, res
+
+
+def test_output_monitor_can_stop_the_run(fake_device, tmp_path):
+    """PhysicsModel::outputMonitor returning non-zero ends Solver::solve with the reference's exception text
+    (Solver::call_monitors, src/solver/solver.cxx:893-896); the records written so far stay in the dump file."""
+    path = str(tmp_path / "BOUT.dmp.0.nc")
+    code = (
+        "import sys, os\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(HERE, 'golden')!r})\n"
+        "import __graft_entry__ as ge\n"
+        "from cases import ode_ini\n"
+        "hostmod = ge.load_package().host\n"
+        f"ini = ode_ini('timestep = 0.0625', False, 4, 0.25).replace('[ode]', '[ode]\\nquit_at = 1') + '\\n[output]\\npath = {path}\\n'\n"
+        "h = hostmod.Host(ini)\n"
+        "h.model_create('ode_pair', 'rk4')\n"
+        "try:\n"
+        "    h.model_solve(4, 0.25)\n"
+        "except hostmod.HostError as e:\n"
+        "    print('stopped:', e)\n"
+        "else:\n"
+        "    sys.exit(3)\n"
+        "finally:\n"
+        "    h.close()\n")
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LD_PRELOAD=fake_device), capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Monitor signalled to quit (return code 7)" in p.stdout
+    from scipy.io import netcdf_file
+    with netcdf_file(path, "r", mmap=False) as nc:
+        assert list(nc.variables["iteration"][:]) == [-1, 0, 1]
