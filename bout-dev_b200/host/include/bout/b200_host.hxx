@@ -92,6 +92,20 @@ using BoutReal = double;
 #define UNUSED(x)
 constexpr BoutReal PI = 3.141592653589793238462643383279502884;
 constexpr BoutReal TWOPI = 2 * PI;
+/// Physical constants in SI units, the values models normalise with (reference include/bout/constants.hxx:17-30)
+namespace SI {
+constexpr BoutReal c = 299792458;
+constexpr BoutReal mu0 = 4.e-7 * PI;
+constexpr BoutReal e0 = 1 / (c * c * mu0);
+constexpr BoutReal qe = 1.602176634e-19;
+constexpr BoutReal Me = 9.10938356e-31;
+constexpr BoutReal Mp = 1.672621898e-27;
+constexpr BoutReal kb = 1.38064852e-23;
+constexpr BoutReal amu = 1.660539040e-27;
+constexpr BoutReal M_Hydrogen = 1.008 * amu;
+constexpr BoutReal M_Deuterium = 2.01410178 * amu;
+constexpr BoutReal M_Tritium = 3.0160492 * amu;
+} // namespace SI
 
 enum CELL_LOC { CELL_DEFAULT = 0, CELL_CENTRE = 1, CELL_CENTER = 1, CELL_XLOW = 2, CELL_YLOW = 3, CELL_ZLOW = 4 };
 enum BRACKET_METHOD { BRACKET_STD = 0, BRACKET_SIMPLE = 1, BRACKET_ARAKAWA = 2, BRACKET_CTU = 3, BRACKET_ARAKAWA_OLD = 4 };
