@@ -255,6 +255,12 @@ namespace b200 {
 struct Block {
   double* ptr = nullptr;
   size_t count = 0;
+  /// Host mirror behind element access from host code (f(x,y,z), f[i]): filled on first use, uploaded again at the
+  /// next device access of the block (FieldBase::dptr / wptr are the synchronisation points).
+  std::vector<double> host;
+  enum Mirror { none = 0, synced = 1, host_newer = 2 } mirror = none;
+  void syncToHost();   ///< device -> host if the mirror is not current
+  void syncToDevice(); ///< host -> device if host code wrote through the mirror
   ~Block();
 };
 /// Block of `count` doubles from the size-keyed pool (cudaMalloc only on a pool miss; zero-filled then)
@@ -273,13 +279,56 @@ extern Mesh* mesh;
 }
 } // namespace bout
 
+// ---- indices and regions for host-side loops (reference include/bout/region.hxx:168-326, 491-) -------------------
+struct Ind3D {
+  int ind = 0, ny = 1, nz = 1;
+  int x() const { return ind / (ny * nz); }
+  int y() const { return (ind / nz) % ny; }
+  int z() const { return ind % nz; }
+  Ind3D offset(int dx, int dy, int dz) const { // z wraps (region.hxx:297-310); x, y must stay inside the local array
+    const int zz = ((z() + dz) % nz + nz) % nz;
+    return {((x() + dx) * ny + (y() + dy)) * nz + zz, ny, nz};
+  }
+  Ind3D xp(int d = 1) const { return offset(d, 0, 0); }
+  Ind3D xm(int d = 1) const { return offset(-d, 0, 0); }
+  Ind3D yp(int d = 1) const { return offset(0, d, 0); }
+  Ind3D ym(int d = 1) const { return offset(0, -d, 0); }
+  Ind3D zp(int d = 1) const { return offset(0, 0, d); }
+  Ind3D zm(int d = 1) const { return offset(0, 0, -d); }
+};
+struct Ind2D {
+  int ind = 0, ny = 1;
+  int x() const { return ind / ny; }
+  int y() const { return ind % ny; }
+};
+template <class I>
+class Region {
+public:
+  std::vector<I> indices;
+  typename std::vector<I>::const_iterator begin() const { return indices.begin(); }
+  typename std::vector<I>::const_iterator end() const { return indices.end(); }
+  size_t size() const { return indices.size(); }
+};
+/// Host loops over a region (reference BOUT_FOR / BOUT_FOR_SERIAL, region.hxx:124-139): element access goes through the
+/// host mirror of the fields touched
+#define BOUT_FOR(index, region) for (const auto& index : (region))
+#define BOUT_FOR_SERIAL(index, region) for (const auto& index : (region))
+
 // ---- Field2D / Field3D ------------------------------------------------------------------------------
 class FieldBase {
 public:
   Mesh* getMesh() const;
   CELL_LOC getLocation() const { return CELL_CENTRE; }
   bool isAllocated() const { return static_cast<bool>(data); }
-  const double* dptr() const { return data ? data->ptr : nullptr; } ///< device pointer
+  const double* dptr() const { ///< device pointer for reading (uploads pending host-side element writes first)
+    if (!data) {
+      return nullptr;
+    }
+    if (data->mirror == bout::b200::Block::host_newer) {
+      data->syncToDevice();
+    }
+    return data->ptr;
+  }
   std::string name;
 
 protected:
@@ -298,6 +347,15 @@ public:
   size_t size() const;
   void setHost(const std::vector<double>& v); ///< upload [nx][ny]
   std::vector<double> getHost() const;
+  /// element access from host code (field2d.hxx:186-258); the z argument of the 3-index form is ignored as there
+  BoutReal& operator()(int x, int y);
+  const BoutReal& operator()(int x, int y) const;
+  BoutReal& operator()(int x, int y, int) { return (*this)(x, y); }
+  const BoutReal& operator()(int x, int y, int) const { return (*this)(x, y); }
+  BoutReal& operator[](const Ind2D& i);
+  const BoutReal& operator[](const Ind2D& i) const;
+  BoutReal& operator[](const Ind3D& i) { return (*this)(i.x(), i.y()); }
+  const BoutReal& operator[](const Ind3D& i) const { return (*this)(i.x(), i.y()); }
   Field2D& operator+=(const Field2D& r);
   Field2D& operator-=(const Field2D& r);
   Field2D& operator*=(BoutReal s);
@@ -320,6 +378,13 @@ public:
   void setHost(const double* v);
   std::vector<double> getHost() const;
   void getHost(double* out) const;
+  /// element access from host code (field3d.hxx:349-420): served from a host mirror of the block; the next device
+  /// operation on the field uploads what was written (no arithmetic is done on the host by the library)
+  BoutReal& operator()(int x, int y, int z);
+  const BoutReal& operator()(int x, int y, int z) const;
+  BoutReal& operator[](const Ind3D& i);
+  const BoutReal& operator[](const Ind3D& i) const;
+  const Region<Ind3D>& getRegion(const std::string& name) const; ///< RGN_ALL | RGN_NOBNDRY | RGN_NOX | RGN_NOY
 
   Field3D* timeDeriv(); ///< ddt(), created on first use and owned by this field (field3d.cxx:133-138)
   void applyBoundary(bool init = false);          ///< the field's own boundary ops (set by Solver::add)
@@ -441,6 +506,8 @@ public:
     communicateFields(v);
   }
   void communicateFields(const std::vector<Field3D*>& fields); ///< mesh.cxx:349-378
+  const Region<Ind3D>& getRegion3D(const std::string& name); ///< mesh.cxx:650-665
+  const Region<Ind3D>& getRegion(const std::string& name) { return getRegion3D(name); }
   /// default derivative methods per direction: mesh:ddx:first etc. (deriv_store.hxx:308-389, 441-478)
   std::string method(char dir, const std::string& kind) const;
   Options* options;
@@ -448,6 +515,7 @@ public:
 private:
   std::unique_ptr<Coordinates> coords;
   std::map<std::string, std::string> methods;
+  std::map<std::string, Region<Ind3D>> regions3d;
 };
 
 // ---- derivatives and differential operators -------------------------------------------------------------

@@ -33,6 +33,20 @@ std::map<size_t, std::vector<double*>>& freeList() {
 size_t n_malloc = 0;
 } // namespace
 
+void Block::syncToHost() {
+  if (mirror == none) {
+    host.resize(count);
+    check(bout_b200_memcpy_d2h(host.data(), ptr, count * sizeof(double), nullptr));
+    mirror = synced;
+  }
+}
+void Block::syncToDevice() {
+  if (mirror == host_newer) {
+    check(bout_b200_memcpy_h2d(ptr, host.data(), count * sizeof(double), nullptr));
+    mirror = synced;
+  }
+}
+
 Block::~Block() {
   if (ptr != nullptr) {
     freeList()[count].push_back(ptr); // back to the pool, not to the driver
@@ -433,11 +447,26 @@ void FieldBase::makeUnique(size_t count) {
   if (!data) {
     data = bout::b200::acquire(count);
   } else if (data.use_count() > 1) {
+    data->syncToDevice(); // pending host-side element writes belong to the contents being copied
     auto fresh = bout::b200::acquire(count);
     check(bout_b200_memcpy_d2d(fresh->ptr, data->ptr, count * sizeof(double), nullptr));
     data = fresh;
   }
 }
+
+namespace {
+// Host mirror of a field's block for element access: writable = the caller may store through the pointer
+double* mirrorOf(const std::shared_ptr<bout::b200::Block>& data, bool writable, const char* what) {
+  if (!data) {
+    throw BoutException("{}: field has no data", what);
+  }
+  data->syncToHost();
+  if (writable) {
+    data->mirror = bout::b200::Block::host_newer;
+  }
+  return data->host.data();
+}
+} // namespace
 
 namespace {
 bout_b200_grid gridOf(const FieldBase& f) { return f.getMesh()->grid(); }
@@ -495,8 +524,22 @@ Field2D& Field2D::allocate() {
 }
 double* Field2D::wptr() {
   makeUnique(size());
+  data->syncToDevice();
+  data->mirror = bout::b200::Block::none; // the device copy is about to change
   return data->ptr;
 }
+BoutReal& Field2D::operator()(int x, int y) {
+  makeUnique(size());
+  return mirrorOf(data, true, "Field2D(x,y)")[static_cast<size_t>(x) * getMesh()->LocalNy + y];
+}
+const BoutReal& Field2D::operator()(int x, int y) const {
+  return mirrorOf(data, false, "Field2D(x,y)")[static_cast<size_t>(x) * getMesh()->LocalNy + y];
+}
+BoutReal& Field2D::operator[](const Ind2D& i) {
+  makeUnique(size());
+  return mirrorOf(data, true, "Field2D[i]")[i.ind];
+}
+const BoutReal& Field2D::operator[](const Ind2D& i) const { return mirrorOf(data, false, "Field2D[i]")[i.ind]; }
 Field2D& Field2D::operator=(BoutReal v) {
   data = bout::b200::acquire(size());
   Field2D& self = *this;
@@ -513,7 +556,7 @@ void Field2D::setHost(const std::vector<double>& v) {
 std::vector<double> Field2D::getHost() const {
   requireData(*this, "Field2D::getHost");
   std::vector<double> v(size());
-  check(bout_b200_memcpy_d2h(v.data(), data->ptr, v.size() * sizeof(double), nullptr));
+  check(bout_b200_memcpy_d2h(v.data(), dptr(), v.size() * sizeof(double), nullptr));
   return v;
 }
 Field2D& Field2D::operator+=(const Field2D& r) { return *this = *this + r; }
@@ -574,8 +617,25 @@ Field3D& Field3D::allocate() {
 }
 double* Field3D::wptr() {
   makeUnique(size());
+  data->syncToDevice();
+  data->mirror = bout::b200::Block::none; // the device copy is about to change
   return data->ptr;
 }
+BoutReal& Field3D::operator()(int x, int y, int z) {
+  makeUnique(size());
+  Mesh* m = getMesh();
+  return mirrorOf(data, true, "Field3D(x,y,z)")[(static_cast<size_t>(x) * m->LocalNy + y) * m->LocalNz + z];
+}
+const BoutReal& Field3D::operator()(int x, int y, int z) const {
+  Mesh* m = getMesh();
+  return mirrorOf(data, false, "Field3D(x,y,z)")[(static_cast<size_t>(x) * m->LocalNy + y) * m->LocalNz + z];
+}
+BoutReal& Field3D::operator[](const Ind3D& i) {
+  makeUnique(size());
+  return mirrorOf(data, true, "Field3D[i]")[i.ind];
+}
+const BoutReal& Field3D::operator[](const Ind3D& i) const { return mirrorOf(data, false, "Field3D[i]")[i.ind]; }
+const Region<Ind3D>& Field3D::getRegion(const std::string& name) const { return getMesh()->getRegion3D(name); }
 Field3D& Field3D::operator=(const Field3D& f) {
   if (this != &f) {
     data = f.data; // share; copy-on-write happens in wptr()
@@ -615,7 +675,7 @@ void Field3D::setHost(const std::vector<double>& v) {
 }
 void Field3D::getHost(double* out) const {
   requireData(*this, "Field3D::getHost");
-  check(bout_b200_memcpy_d2h(out, data->ptr, size() * sizeof(double), nullptr));
+  check(bout_b200_memcpy_d2h(out, dptr(), size() * sizeof(double), nullptr));
 }
 std::vector<double> Field3D::getHost() const {
   std::vector<double> v(size());
@@ -885,6 +945,34 @@ Field3D averageY(const Field3D& f) {
 // ======================================================================================================
 // Mesh and Coordinates
 // ======================================================================================================
+const Region<Ind3D>& Mesh::getRegion3D(const std::string& name) { // mesh.cxx:650-665
+  auto it = regions3d.find(name);
+  if (it != regions3d.end()) {
+    return it->second;
+  }
+  int xs = 0, xe = LocalNx - 1, ys = 0, ye = LocalNy - 1;
+  if (name == "RGN_NOBNDRY" || name == "RGN_NOX") {
+    xs = xstart;
+    xe = xend;
+  }
+  if (name == "RGN_NOBNDRY" || name == "RGN_NOY") {
+    ys = ystart;
+    ye = yend;
+  }
+  if (name != "RGN_ALL" && name != "RGN_NOBNDRY" && name != "RGN_NOX" && name != "RGN_NOY") {
+    throw BoutException("Couldn't find region {:s} in regionMap3D", name);
+  }
+  Region<Ind3D> r;
+  for (int x = xs; x <= xe; ++x) {
+    for (int y = ys; y <= ye; ++y) {
+      for (int z = 0; z < LocalNz; ++z) {
+        r.indices.push_back({(x * LocalNy + y) * LocalNz + z, LocalNy, LocalNz});
+      }
+    }
+  }
+  return regions3d.emplace(name, std::move(r)).first->second;
+}
+
 Mesh* Mesh::create(Options* opts) { return new Mesh(opts != nullptr ? *opts : Options::root()["mesh"]); }
 
 Mesh::Mesh(Options& opts) : options(&opts) {

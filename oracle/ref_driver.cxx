@@ -48,6 +48,7 @@ std::unique_ptr<PhysicsModel> boutref_make_hw3d();
 std::unique_ptr<PhysicsModel> boutref_make_blob2d();
 std::unique_ptr<PhysicsModel> boutref_make_elmpb();
 std::unique_ptr<PhysicsModel> boutref_make_ode_pair(); // tests/models/ode_pair.cxx (this repository's test model)
+std::unique_ptr<PhysicsModel> boutref_make_elem_access(); // tests/models/elem_access.cxx
 int boutref_elmpb_get_impl(PhysicsModel* pm, const char* name, double* out, int* kind);
 
 namespace {
@@ -619,6 +620,8 @@ int boutref_model_create(const char* name, const char* solver) {
       model = boutref_make_elmpb();
     } else if (n == "ode_pair") {
       model = boutref_make_ode_pair();
+    } else if (n == "elem_access") {
+      model = boutref_make_elem_access();
     } else {
       throw BoutException("unknown model '{}'", n);
     }

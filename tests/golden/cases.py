@@ -314,3 +314,10 @@ HW_INTEGRATOR_CASES = {
     "hw_rkf45_fixed": ("rkgeneric", "adaptive = false\ntimestep = 0.01\nmax_timestep = 0.05", 1, 0.05),
     "hw_splitrk_fixed": ("splitrk", "adaptive = false\ntimestep = 0.01\nnstages = 4", 1, 0.05),
 }
+
+
+# host-side element access (tests/models/elem_access.cxx): tag: (solver type, [solver] options, nout, output_step)
+ELEM_CASES = {
+    "elem_rk4": ("rk4", "timestep = 0.0625", 2, 0.25),
+    "elem_rkf45": ("rkgeneric", "timestep = 0.1\nmax_timestep = 0.25\natol = 1e-9\nrtol = 1e-7", 1, 0.25),
+}

@@ -350,11 +350,15 @@ def bndry_free():
 
 def one_integrator(tag, path):
     """tests/models/ode_pair.cxx through the reference's own euler / rkgeneric / splitrk solvers."""
-    from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
+    from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
     if tag in HW_INTEGRATOR_CASES:   # unchanged examples/hasegawa-wakatani/hw.cxx
         solver, opts, nout, step = HW_INTEGRATOR_CASES[tag]
         r = orc.Ref(hw_integrator_ini(opts, nout, step))
         names = r.model_create("hw", solver)
+    elif tag in ELEM_CASES:         # tests/models/elem_access.cxx
+        solver, opts, nout, step = ELEM_CASES[tag]
+        r = orc.Ref(ode_ini(opts, False, nout, step))
+        names = r.model_create("elem_access", solver)
     else:
         solver, opts, split, nout, step, *bndry = INTEGRATOR_CASES[tag]
         r = orc.Ref(ode_ini(opts, split, nout, step, *bndry))
@@ -372,10 +376,10 @@ def one_integrator(tag, path):
 def integrators():
     import subprocess
     import tempfile
-    from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES
+    from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for tag in list(INTEGRATOR_CASES) + list(HW_INTEGRATOR_CASES):
+        for tag in list(INTEGRATOR_CASES) + list(HW_INTEGRATOR_CASES) + list(ELEM_CASES):
             path = os.path.join(tmp, tag + ".npz")
             subprocess.run([sys.executable, os.path.abspath(__file__), "integrator:" + tag, path], check=True)
             out.update(dict(np.load(path)))

@@ -24,12 +24,15 @@ TOL = 1e-10
 
 def run(tag):
     import __graft_entry__ as ge
-    from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
+    from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
     hostmod = ge.load_package().host
     gold = np.load(os.path.join(HERE, "golden", "integrators.npz"))
     if tag in HW_INTEGRATOR_CASES:   # unchanged examples/hasegawa-wakatani/hw.cxx (needs the real device)
         solver, opts, nout, step = HW_INTEGRATOR_CASES[tag]
         model, ini, tol = "hw", hw_integrator_ini(opts, nout, step), 1e-8
+    elif tag in ELEM_CASES:         # tests/models/elem_access.cxx: host-side element access
+        solver, opts, nout, step = ELEM_CASES[tag]
+        model, ini, tol = "elem_access", ode_ini(opts, False, nout, step), TOL
     else:
         solver, opts, split, nout, step, *bndry = INTEGRATOR_CASES[tag]
         model, ini, tol = "ode_pair", ode_ini(opts, split, nout, step, *bndry), TOL

@@ -16,15 +16,18 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from cases import INTEGRATOR_CASES  # noqa: E402
+from cases import ELEM_CASES, INTEGRATOR_CASES  # noqa: E402
+
+ALL_CASES = sorted(INTEGRATOR_CASES) + sorted(ELEM_CASES)
 
 HOST_LIB = os.path.join(ROOT, "bout-dev_b200", "host", "libbout_b200_host.so")
 MODEL = os.path.join(ROOT, "bout-dev_b200", "host", "models", "ode_pair.so")
+MODEL2 = os.path.join(ROOT, "bout-dev_b200", "host", "models", "elem_access.so")
 
 
 @pytest.fixture(scope="module")
 def fake_device(tmp_path_factory):
-    for p in (HOST_LIB, MODEL):
+    for p in (HOST_LIB, MODEL, MODEL2):
         if not os.path.exists(p):
             pytest.fail(f"{p} missing: run python -c 'import __graft_entry__ as g; g.build()'")
     so = str(tmp_path_factory.mktemp("fake") / "libfake_b200.so")
@@ -37,7 +40,7 @@ def fake_device(tmp_path_factory):
 def results(fake_device):
     """All cases in ONE child process (one torch import)."""
     env = dict(os.environ, LD_PRELOAD=fake_device)
-    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py")] + sorted(INTEGRATOR_CASES), env=env,
+    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py")] + ALL_CASES, env=env,
                        capture_output=True, text=True, timeout=600)
     out = {}
     for line in p.stdout.splitlines():
@@ -48,8 +51,10 @@ def results(fake_device):
     return out
 
 
-@pytest.mark.parametrize("tag", sorted(INTEGRATOR_CASES))
+@pytest.mark.parametrize("tag", ALL_CASES)
 def test_integrator_matches_reference_solver(results, tag):
+    """INTEGRATOR_CASES: every solver / scheme / controller and the boundary-condition names on ode_pair.cxx;
+    ELEM_CASES: host-side element access (f(x,y,z), f[i], BOUT_FOR, Ind3D::zp) mixed with device operations."""
     res = results[tag]
     assert "error" not in res, res
     assert res["rhs_calls"] == res["ref_rhs_calls"], res

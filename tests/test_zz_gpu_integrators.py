@@ -12,7 +12,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from cases import HW_INTEGRATOR_CASES, INTEGRATOR_CASES  # noqa: E402
+from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 def results(capi):
     env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}
     p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py")] + sorted(INTEGRATOR_CASES)
-                       + sorted(HW_INTEGRATOR_CASES), env=env,
+                       + sorted(ELEM_CASES) + sorted(HW_INTEGRATOR_CASES), env=env,
                        capture_output=True, text=True, timeout=900)
     out = {}
     for line in p.stdout.splitlines():
@@ -32,7 +32,7 @@ def results(capi):
     return out
 
 
-@pytest.mark.parametrize("tag", sorted(INTEGRATOR_CASES))
+@pytest.mark.parametrize("tag", sorted(INTEGRATOR_CASES) + sorted(ELEM_CASES))
 def test_integrator_on_device_matches_reference_solver(results, tag):
     res = results[tag]
     assert "error" not in res, res
