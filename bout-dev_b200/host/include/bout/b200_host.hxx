@@ -411,6 +411,7 @@ private:
 };
 
 inline Field3D& ddt(Field3D& f) { return *f.timeDeriv(); }
+template <> Field3D Options::as<Field3D>() const; ///< the option's expression evaluated over the mesh
 
 // element-wise algebra (src/field/generated_fieldops.cxx); one kernel per operator
 Field3D operator+(const Field3D& a, const Field3D& b);

@@ -132,14 +132,28 @@ private:
       }
     }
   }
+  // A number directly followed by a symbol multiplies it ("2π", "3x"): the reference's lexer inserts '*' there
+  // (src/sys/expressionparser.cxx:682-687), with the precedence of an ordinary product
+  bool after_number = false;
+  static bool identStart(char c) {
+    return std::isalpha(static_cast<unsigned char>(c)) || c == '_' || static_cast<unsigned char>(c) >= 0x80;
+  }
+  bool symbolAhead() {
+    skip();
+    return pos < src.size() && identStart(src[pos]);
+  }
   double product() {
     double v = unary();
     for (;;) {
-      if (eat('*')) {
+      if (after_number && symbolAhead()) {
+        after_number = false;
+        v *= unary();
+      } else if (eat('*')) {
         v *= unary();
       } else if (eat('/')) {
         v /= unary();
       } else {
+        after_number = false;
         return v;
       }
     }
@@ -252,6 +266,7 @@ private:
   }
   double atom() {
     skip();
+    after_number = false;
     if (pos >= src.size()) {
       throw BoutException("Unexpected end of expression '{}'", src);
     }
@@ -267,11 +282,13 @@ private:
       size_t used = 0;
       const double v = std::stod(src.substr(pos), &used);
       pos += used;
+      after_number = true;
       return v;
     }
-    if (std::isalpha(static_cast<unsigned char>(c)) || c == '_') {
+    if (identStart(c)) { // symbols may hold any non-reserved character, UTF-8 included (expressionparser.cxx:679-720)
       size_t e = pos;
-      while (e < src.size() && (std::isalnum(static_cast<unsigned char>(src[e])) || src[e] == '_' || src[e] == ':')) {
+      while (e < src.size() && (std::isalnum(static_cast<unsigned char>(src[e])) || src[e] == '_' || src[e] == ':'
+                                || static_cast<unsigned char>(src[e]) >= 0x80)) {
         ++e;
       }
       const std::string id = src.substr(pos, e - pos);
@@ -358,6 +375,28 @@ template <>
 void Options::assignValue<bool>(const bool& v) { setText(v ? "true" : "false"); }
 template <>
 void Options::assignValue<Field3D>(const Field3D& v) { field3d = &v; }
+
+// A field-valued option is an expression of x, y, z evaluated over the mesh (reference Options::as<Field3D>,
+// src/sys/options.cxx:563-610 -> FieldFactory::create3D; coordinates as in initialProfile below)
+template <>
+Field3D Options::as<Field3D>() const {
+  Mesh* m = bout::globals::mesh;
+  if (m == nullptr) {
+    throw BoutException("Option {}: a Field3D value needs a mesh", full_name);
+  }
+  Field3D f(m);
+  std::vector<double> h(static_cast<size_t>(m->LocalNx) * m->LocalNy * m->LocalNz);
+  for (int x = 0; x < m->LocalNx; ++x) {
+    for (int y = 0; y < m->LocalNy; ++y) {
+      for (int z = 0; z < m->LocalNz; ++z) {
+        h[(static_cast<size_t>(x) * m->LocalNy + y) * m->LocalNz + z] = bout::b200::evalOption(
+            const_cast<Options&>(*this), m->GlobalX(x), TWOPI * m->GlobalY(y), TWOPI * m->GlobalZ(z));
+      }
+    }
+  }
+  f.setHost(h);
+  return f;
+}
 
 template <>
 std::string Options::as<std::string>() const { return value; }

@@ -321,3 +321,50 @@ ELEM_CASES = {
     "elem_rk4": ("rk4", "timestep = 0.0625", 2, 0.25),
     "elem_rkf45": ("rkgeneric", "timestep = 0.1\nmax_timestep = 0.25\natol = 1e-9\nrtol = 1e-7", 1, 0.25),
 }
+
+
+# examples/IMEX/advection-diffusion (unchanged imex.cxx, a split-operator model) with its SHIPPED data/BOUT.inp
+# (solver type = splitrk, nstages = 9, adapt_period = 5, W3 upwinding, C4 second derivatives); the text below is that
+# file's content with comments dropped, restated here because /root/reference does not exist on the GPU box.
+# Only nout is reduced (50 -> 2).
+IMEX_INI = """
+nout = 2
+periodicX = true
+MYG = 0
+[mesh]
+nx = 132
+ny = 1
+nz = 128
+dx = 1 / nx
+dz = 1 / (nz-4)
+[mesh:ddx]
+first = C4
+second = C4
+upwind = W3
+flux = U1
+[mesh:ddy]
+first = C4
+second = C4
+upwind = W3
+flux = U1
+[mesh:ddz]
+first = C4
+second = C4
+upwind = W3
+flux = U1
+[solver]
+type = splitrk
+timestep = 0.0001
+nstages = 9
+adapt_period = 5
+output_step = 0.01
+[imex]
+Vx = 2.0
+Dz = 1.0
+[U]
+zs = z / (2π)
+function = exp(-((x-0.5)/0.1)^2 - ((zs-0.5)/0.1)^2)
+[input]
+error_on_unused_options = false
+"""
+IMEX_NOUT, IMEX_STEP = 2, 0.01

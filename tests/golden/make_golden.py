@@ -355,6 +355,11 @@ def one_integrator(tag, path):
         solver, opts, nout, step = HW_INTEGRATOR_CASES[tag]
         r = orc.Ref(hw_integrator_ini(opts, nout, step))
         names = r.model_create("hw", solver)
+    elif tag == "imex_shipped":     # unchanged examples/IMEX/advection-diffusion/imex.cxx, shipped input
+        from cases import IMEX_INI, IMEX_NOUT, IMEX_STEP
+        solver, nout, step = "splitrk", IMEX_NOUT, IMEX_STEP
+        r = orc.Ref(IMEX_INI)
+        names = r.model_create("imex", solver)
     elif tag in ELEM_CASES:         # tests/models/elem_access.cxx
         solver, opts, nout, step = ELEM_CASES[tag]
         r = orc.Ref(ode_ini(opts, False, nout, step))
@@ -379,7 +384,7 @@ def integrators():
     from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for tag in list(INTEGRATOR_CASES) + list(HW_INTEGRATOR_CASES) + list(ELEM_CASES):
+        for tag in list(INTEGRATOR_CASES) + list(HW_INTEGRATOR_CASES) + list(ELEM_CASES) + ["imex_shipped"]:
             path = os.path.join(tmp, tag + ".npz")
             subprocess.run([sys.executable, os.path.abspath(__file__), "integrator:" + tag, path], check=True)
             out.update(dict(np.load(path)))

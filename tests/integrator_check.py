@@ -30,6 +30,10 @@ def run(tag):
     if tag in HW_INTEGRATOR_CASES:   # unchanged examples/hasegawa-wakatani/hw.cxx (needs the real device)
         solver, opts, nout, step = HW_INTEGRATOR_CASES[tag]
         model, ini, tol = "hw", hw_integrator_ini(opts, nout, step), 1e-8
+    elif tag == "imex_shipped":     # unchanged examples/IMEX/advection-diffusion/imex.cxx with its shipped input
+        from cases import IMEX_INI, IMEX_NOUT, IMEX_STEP
+        solver, nout, step = "splitrk", IMEX_NOUT, IMEX_STEP
+        model, ini, tol = "imex", IMEX_INI, 1e-8
     elif tag in ELEM_CASES:         # tests/models/elem_access.cxx: host-side element access
         solver, opts, nout, step = ELEM_CASES[tag]
         model, ini, tol = "elem_access", ode_ini(opts, False, nout, step), TOL
@@ -46,6 +50,12 @@ def run(tag):
         res = {"tag": tag}
         for v in names:
             assert np.abs(h.model_get(v)[I] - gold[f"{tag}_init_{v}"][I]).max() < 1e-13, "initial profile " + v
+        if tag == "imex_shipped":   # mesh expressions of the shipped input: dx = 1 / nx, dz = 1 / (nz-4)
+            assert np.allclose(h.metric("dx"), 1.0 / 132, rtol=1e-15) and np.allclose(h.metric("dz"), 1.0 / 124, rtol=1e-15)
+        if os.environ.get("B200_CHECK_INIT_ONLY") == "1":   # CPU: options, mesh and initial profile only
+            res.update(ok=True, init_only=True, tol=tol)
+            print(json.dumps(res), flush=True)
+            return 0
         h.model_solve(nout, step)
         for v in names:
             a, b = h.model_get(v)[I], gold[f"{tag}_final_{v}"][I]

@@ -133,3 +133,18 @@ def test_output_monitor_can_stop_the_run(fake_device, tmp_path):
     from scipy.io import netcdf_file
     with netcdf_file(path, "r", mmap=False) as nc:
         assert list(nc.variables["iteration"][:]) == [-1, 0, 1]
+
+
+def test_shipped_imex_input_parses_and_initialises(fake_device):
+    """examples/IMEX/advection-diffusion/data/BOUT.inp as shipped (solver type = splitrk; `zs = z / (2π)`: a UTF-8
+    symbol after a number, i.e. the reference lexer's implicit multiplication; sibling option references; mesh
+    expressions) through Options -> Mesh -> Solver::create -> initial profile of the unchanged imex.cxx: the initial
+    state equals the reference's.  The trajectory needs the stencil kernels: tests/test_zz_gpu_integrators.py."""
+    if not os.path.exists(os.path.join(ROOT, "bout-dev_b200", "host", "models", "imex.so")):
+        pytest.skip("host/models/imex.so not built (needs the reference's example source at build time)")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py"), "imex_shipped"],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_CHECK_INIT_ONLY="1"), capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res.get("ok") and res.get("init_only"), res
