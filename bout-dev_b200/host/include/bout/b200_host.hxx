@@ -645,6 +645,14 @@ void writeRestartFile(const std::string& path, int nx, int ny, int nz, double ti
 } // namespace b200
 } // namespace bout
 
+/// Sets a variable from the [name] (or [all]) `function` / `scale` options (reference src/field/initialprofiles.cxx:33-48)
+void initial_profile(const std::string& name, Field3D& var);
+
+/// OpenMP wrappers of the reference (include/bout/openmpwrap.hxx): host loops of a model are serial here
+#define BOUT_OMP(...)
+#define BOUT_OMP_SAFE(...)
+#define BOUT_OMP_PERF(...)
+
 // ---- Solver / PhysicsModel ---------------------------------------------------------------------------------
 class PhysicsModel;
 class Solver;

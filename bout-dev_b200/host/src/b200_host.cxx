@@ -1511,6 +1511,13 @@ void initialProfile(const std::string& name, Field3D& var) { // initialprofiles.
 }
 } // namespace
 
+void initial_profile(const std::string& name, Field3D& var) {
+  if (var.getMesh() == nullptr) {
+    var = Field3D(bout::globals::mesh);
+  }
+  initialProfile(name, var);
+}
+
 void Solver::add(Field3D& v, const std::string& name) {
   if (initialised) {
     throw BoutException("Error: Cannot add to solver after initialisation\n");
