@@ -56,9 +56,9 @@ def main():
               "rk3ssp": ("rk3ssp", f"timestep = {dt}"),
               "euler": ("euler", f"timestep = {dt}\nmxstep = 100000"),
               "rkgeneric_cashkarp_fixed": ("rkgeneric", f"scheme = cashkarp\nadaptive = false\ntimestep = {dt}\nmax_timestep = 100"),
-              "rkgeneric_rkf45_adaptive": ("rkgeneric", f"timestep = {dt}\nmax_timestep = 100\nrtol = 1e-5\natol = 1e-10\nmxstep = 100000"),
+              "rkgeneric_rkf45_adaptive": ("rkgeneric", f"timestep = {dt}\nmax_timestep = 100\nrtol = 1e-5\natol = 1e-10\nmxstep = 2000"),
               "splitrk_fixed": ("splitrk", f"adaptive = false\ntimestep = {dt}\nnstages = 4"),
-              "adams_bashforth_adaptive": ("adams-bashforth", f"timestep = {dt}\nmax_timestep = 100\nrtol = 1e-5\nmxstep = 100000")}
+              "adams_bashforth_adaptive": ("adams-bashforth", f"timestep = {dt}\nmax_timestep = 100\nrtol = 1e-5\nmxstep = 4000")}
     solve(hostmod, blob_ini(cases_["rk4"][1]), "rk4", 1, 5 * dt)   # warm-up instance (library load, pool)
     try:
         nout, per = 8, 5
