@@ -120,59 +120,86 @@ private:
     }
     return false;
   }
-  double sum() {
-    double v = product();
-    for (;;) {
-      if (eat('+')) {
-        v += product();
-      } else if (eat('-')) {
-        v -= product();
-      } else {
-        return v;
-      }
-    }
-  }
-  // A number directly followed by a symbol multiplies it ("2π", "3x"): the reference's lexer inserts '*' there
-  // (src/sys/expressionparser.cxx:682-687), with the precedence of an ordinary product
+  // Binary operators by precedence climbing with the reference's table and quirks (src/sys/expressionparser.cxx:
+  // 256-264 precedences, :554-608 parseBinOpRHS, all operators left-associative; :530-534 a '-' where an operand is
+  // expected yields an implicit 0 and stays a BINARY minus, so "a * -b" is (a * 0) - b as in the reference;
+  // :682-687 a number directly followed by a symbol multiplies it, "2π").
   bool after_number = false;
   static bool identStart(char c) {
     return std::isalpha(static_cast<unsigned char>(c)) || c == '_' || static_cast<unsigned char>(c) >= 0x80;
   }
-  bool symbolAhead() {
+  static int precedence(char op) {
+    switch (op) {
+    case '|': return 3;
+    case '&': return 5;
+    case '<':
+    case '>': return 7;
+    case '+':
+    case '-': return 10;
+    case '*':
+    case '/': return 20;
+    case '^': return 30;
+    default: return -1;
+    }
+  }
+  static bool toBool(double v, const std::string& where) { // expressionparser.cxx:196-206
+    if (std::fabs(v - 1.0) < 1e-5) {
+      return true;
+    }
+    if (std::fabs(v) < 1e-5) {
+      return false;
+    }
+    throw BoutException("Boolean operator argument {} is not a bool in '{}'", v, where);
+  }
+  // next binary operator without consuming it: 0 = none; 'i' = the implicit '*' after a number
+  char peekOp() {
     skip();
-    return pos < src.size() && identStart(src[pos]);
+    if (pos >= src.size()) {
+      return 0;
+    }
+    const char c = src[pos];
+    if (after_number && identStart(c)) {
+      return 'i';
+    }
+    return precedence(c) >= 0 ? c : 0;
   }
-  double product() {
-    double v = unary();
+  double apply(char op, double l, double r) const {
+    switch (op) {
+    case '|': return (toBool(l, src) || toBool(r, src)) ? 1.0 : 0.0;
+    case '&': return (toBool(l, src) && toBool(r, src)) ? 1.0 : 0.0;
+    case '>': return l > r ? 1.0 : 0.0;
+    case '<': return l < r ? 1.0 : 0.0;
+    case '+': return l + r;
+    case '-': return l - r;
+    case '/': return l / r;
+    case '^': return std::pow(l, r);
+    default: return l * r; // '*' and the implicit product
+    }
+  }
+  double binopRHS(int exprPrec, double lhs) {
     for (;;) {
-      if (after_number && symbolAhead()) {
-        after_number = false;
-        v *= unary();
-      } else if (eat('*')) {
-        v *= unary();
-      } else if (eat('/')) {
-        v /= unary();
-      } else {
-        after_number = false;
-        return v;
+      const char op = peekOp();
+      if (op == 0) {
+        return lhs;
       }
+      const int prec = precedence(op == 'i' ? '*' : op);
+      if (prec < exprPrec) {
+        return lhs;
+      }
+      if (op != 'i') {
+        ++pos;
+      }
+      double rhs = atom();
+      const char next = peekOp();
+      if (next != 0 && prec < precedence(next == 'i' ? '*' : next)) {
+        rhs = binopRHS(prec + 1, rhs);
+      }
+      lhs = apply(op, lhs, rhs);
     }
   }
-  double unary() {
-    if (eat('-')) {
-      return -unary();
-    }
-    if (eat('+')) {
-      return unary();
-    }
-    return power();
-  }
-  double power() {
-    const double base = atom();
-    if (eat('^')) {
-      return std::pow(base, unary());
-    }
-    return base;
+  double sum() { // a whole expression
+    const double lhs = atom();
+    return binopRHS(0, lhs);
   }
   static double genRand(double seed) { // FieldMixmode::genRand, fieldgenerators.cxx:148-167
     if (seed < 0.0) {
@@ -219,10 +246,26 @@ private:
     if (fn == "min") { need(1, 8); return *std::min_element(a.begin(), a.end()); }
     if (fn == "max") { need(1, 8); return *std::max_element(a.begin(), a.end()); }
     if (fn == "power") { need(2, 2); return std::pow(a[0], a[1]); }
+    if (fn == "sinh") { need(1, 1); return std::sinh(a[0]); }
+    if (fn == "cosh") { need(1, 1); return std::cosh(a[0]); }
+    if (fn == "asin") { need(1, 1); return std::asin(a[0]); }
+    if (fn == "acos") { need(1, 1); return std::acos(a[0]); }
+    if (fn == "atan") { need(1, 2); return a.size() == 1 ? std::atan(a[0]) : std::atan2(a[0], a[1]); } // fieldgenerators.hxx:103-108
+    if (fn == "erf") { need(1, 1); return std::erf(a[0]); }
+    if (fn == "fmod") { need(2, 2); return std::fmod(a[0], a[1]); }
+    if (fn == "clamp") { need(3, 3); return a[0] < a[1] ? a[1] : (a[0] > a[2] ? a[2] : a[0]); } // fieldgenerators.hxx:219-231
+    if (fn == "round") { need(1, 1); return static_cast<int>(a[0] > 0.0 ? a[0] + 0.5 : a[0] - 0.5); } // :249-255
+    if (fn == "tanhhat") { // FieldTanhHat (X, width, centre, steepness), fieldgenerators.cxx:198-206
+      need(4, 4);
+      return 0.5 * (std::tanh(a[3] * (a[0] - (a[2] - 0.5 * a[1]))) - std::tanh(a[3] * (a[0] - (a[2] + 0.5 * a[1]))));
+    }
+    if (fn == "where") { need(3, 3); return a[0] > 0.0 ? a[1] : a[2]; } // FieldWhere, fieldgenerators.cxx:208-214
     throw BoutException("Unknown function '{}' in expression '{}'", fn, src);
   }
   double lookup(const std::string& id) {
     if (id == "pi" || id == "π") { return PI; }
+    if (id == "true" || id == "True") { return 1.0; } // field_factory.cxx:120-123
+    if (id == "false" || id == "False") { return 0.0; }
     if (id == "x") { return ctx.x; }
     if (id == "y") { return ctx.y; }
     if (id == "z") { return ctx.z; }
@@ -269,6 +312,12 @@ private:
     after_number = false;
     if (pos >= src.size()) {
       throw BoutException("Unexpected end of expression '{}'", src);
+    }
+    if (src[pos] == '-' || src[pos] == '+') {
+      return 0.0; // implicit zero; the sign is then read as a binary operator (expressionparser.cxx:530-534)
+    }
+    if (eat('!')) {
+      return toBool(atom(), src) ? 0.0 : 1.0;
     }
     if (eat('(')) {
       const double v = sum();

@@ -368,3 +368,18 @@ function = exp(-((x-0.5)/0.1)^2 - ((zs-0.5)/0.1)^2)
 error_on_unused_options = false
 """
 IMEX_NOUT, IMEX_STEP = 2, 0.01
+
+
+# Expressions evaluated by the reference's FieldFactory (tests/golden/expressions.npz) and by the host layer's
+# evaluator: operators with the reference's precedences and quirks ("a * -b" is (a*0) - b, "2^-1*x" is 2^0 - 1*x, all
+# operators left-associative), implicit product after a number, UTF-8 symbols, every generator of field_factory.cxx
+# except ballooning / is_periodic_y.
+EXPR_INI = make_ini(12, 6, 8, mxg=2, myg=1, mesh_extra="ixseps1 = 12\nixseps2 = 12\n")
+EXPRESSIONS = [
+    "sin(2*pi*x) + cos(z - y)", "2π*x", "3x + 2 z", "exp(-((x-0.5)/0.1)^2)", "gauss(x-0.5, 0.1)", "gauss(z-pi)",
+    "mixmode(2*pi*x)*mixmode(z)", "mixmode(y, 3.5)", "H(x-0.5)", "tanh(3*(x-0.5))", "abs(x-0.5)^1.5", "sqrt(x+1)",
+    "min(x, 0.3, z/10)", "max(x,y)", "power(x+1, 2.5)", "log(x+1)", "sinh(x) + cosh(z)", "erf(2*x-1)", "round(3.6*x)",
+    "-x^2", "2^-1 * x", "1e-3*x + 1.5E2", "atan(x)", "atan(x-0.5, z+1)", "x - -y", "tan(x)", "asin(x/2) + acos(x/2)",
+    "1/2π", "2x^2", "fmod(z, 1.5)", "tanhhat(x, 0.3, 0.5, 0.1)", "clamp(x, 0.2, 0.7)", "where(x - 0.5, y, z)", "x * -y",
+    "2^3^2", "x < 0.5 | z > 3", "!(x > 0.5) & true", "2 - 3 - 4 * 2 / 4 ^ 2", "(x + 1)^2 * 3 - 1", "-(x+1)", "1 - -(y)",
+]

@@ -22,6 +22,7 @@ Outputs (committed; the GPU box has neither /root/reference nor needs the refere
   models.npz             unchanged example models (hasegawa-wakatani, hasegawa-wakatani-3d, blob2d) run
                          through the reference's Solver::run_rhs and RK4 / RK3-SSP solvers: initial state,
                          ddt after one RHS, state after a few steps.
+  expressions.npz        cases.EXPRESSIONS evaluated by the reference's expression parser / FieldFactory.
   bndry_free.npz         free_o2 / free_o3 boundary conditions on the ops_small grid and field.
   integrators.npz        this repository's test model tests/models/ode_pair.cxx through the reference's own
                          euler, rkgeneric (rkf45, cashkarp, rk4, rkf34; adaptive and fixed) and splitrk solvers
@@ -348,6 +349,16 @@ def bndry_free():
     print("  bndry_free:", {k: float(np.abs(v - ops["f"]).max()) for k, v in out.items()})
 
 
+def expressions():
+    """cases.EXPRESSIONS through the reference's FieldFactory::create3D: tests/golden/expressions.npz."""
+    from cases import EXPR_INI, EXPRESSIONS
+    r = orc.Ref(EXPR_INI)
+    out = {str(i): r.expr3d(e) for i, e in enumerate(EXPRESSIONS)}
+    r.close()
+    np.savez_compressed(os.path.join(HERE, "expressions.npz"), **out)
+    print("  expressions:", len(out))
+
+
 def one_integrator(tag, path):
     """tests/models/ode_pair.cxx through the reference's own euler / rkgeneric / splitrk solvers."""
     from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
@@ -462,7 +473,7 @@ def models():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb", "integrators", "bndry_free"]
+    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb", "integrators", "bndry_free", "expressions"]
     if which[0].startswith("elmpb:"):
         elmpb_case(which[0][6:], which[1])
         sys.stdout.flush()
@@ -489,4 +500,6 @@ if __name__ == "__main__":
         integrators()
     if "bndry_free" in which:
         bndry_free()
+    if "expressions" in which:
+        expressions()
     os._exit(0)  # the reference's static destructors are not exit-safe after repeated init/finalise

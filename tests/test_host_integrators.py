@@ -148,3 +148,13 @@ def test_shipped_imex_input_parses_and_initialises(fake_device):
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     res = json.loads(p.stdout.strip().splitlines()[-1])
     assert res.get("ok") and res.get("init_only"), res
+
+
+def test_expression_evaluator_and_model_setup_match_reference(fake_device):
+    """tests/host_parser_check.py: 41 expressions against the reference's FieldFactory (precedence quirks, implicit
+    product, UTF-8 symbols, all generators but ballooning) and the set-up of the unchanged hw.cxx / blob2d.cxx
+    (initial profiles, metrics) against the reference build."""
+    p = subprocess.run([sys.executable, os.path.join(HERE, "host_parser_check.py")], env=dict(os.environ, LD_PRELOAD=fake_device),
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
