@@ -394,8 +394,7 @@ Options& Options::operator[](const std::string& key_in) {
   if (colon != std::string::npos) {
     return (*this)[key_in.substr(0, colon)][key_in.substr(colon + 1)];
   }
-  std::string key = key_in;
-  std::transform(key.begin(), key.end(), key.begin(), [](unsigned char c) { return std::tolower(c); });
+  const std::string& key = key_in; // names are case-sensitive (reference src/sys/options.cxx:109-143)
   auto it = children.find(key);
   if (it == children.end()) {
     it = children.emplace(key, Options()).first;
@@ -406,9 +405,7 @@ Options& Options::operator[](const std::string& key_in) {
 }
 
 bool Options::isSet(const std::string& key_in) const {
-  std::string key = key_in;
-  std::transform(key.begin(), key.end(), key.begin(), [](unsigned char c) { return std::tolower(c); });
-  const auto it = children.find(key);
+  const auto it = children.find(key_in);
   return it != children.end() && it->second.has_value;
 }
 
@@ -489,20 +486,33 @@ void readOptionsText(const std::string& ini_text, Options& root) {
   std::istringstream in(ini_text);
   std::string line;
   Options* section = &root;
-  while (std::getline(in, line)) {
-    const auto hash = line.find_first_of("#;");
-    if (hash != std::string::npos) {
-      line.erase(hash);
+  auto trim = [](std::string s) {
+    const auto b = s.find_first_not_of(" \t\r\n");
+    if (b == std::string::npos) {
+      return std::string();
     }
-    auto trim = [](std::string s) {
-      const auto b = s.find_first_not_of(" \t\r\n");
-      if (b == std::string::npos) {
-        return std::string();
-      }
-      const auto e = s.find_last_not_of(" \t\r\n");
-      return s.substr(b, e - b + 1);
-    };
-    line = trim(line);
+    const auto e = s.find_last_not_of(" \t\r\n");
+    return s.substr(b, e - b + 1);
+  };
+  auto nextLine = [&](std::string& out) { // stripped of comments and surrounding blanks (options_ini.cxx:179-187)
+    if (!std::getline(in, out)) {
+      return false;
+    }
+    const auto hash = out.find_first_of("#;");
+    if (hash != std::string::npos) {
+      out.erase(hash);
+    }
+    out = trim(out);
+    return true;
+  };
+  auto openBrackets = [](const std::string& t) { // options_ini.cxx:121-132
+    int n = 0;
+    for (char ch : t) {
+      n += (ch == '(' || ch == '[') ? 1 : ((ch == ')' || ch == ']') ? -1 : 0);
+    }
+    return n;
+  };
+  while (nextLine(line)) {
     if (line.empty()) {
       continue;
     }
@@ -515,10 +525,19 @@ void readOptionsText(const std::string& ini_text, Options& root) {
       continue;
     }
     const auto eq = line.find('=');
-    if (eq == std::string::npos) {
-      throw BoutException("Options: expected key = value, got '{}'", line);
+    if (eq == std::string::npos) { // a bare key is a flag set to true (options_ini.cxx:194-201)
+      (*section)[line].setText("true");
+      continue;
     }
     std::string val = trim(line.substr(eq + 1));
+    for (int open = openBrackets(val); open > 0;) { // a value continues over lines until its brackets balance (:134-150)
+      std::string more;
+      if (!nextLine(more)) {
+        throw BoutException("Options: unbalanced brackets in the value starting '{}'", val);
+      }
+      open += openBrackets(more);
+      val += more;
+    }
     if (val.size() >= 2 && val.front() == '"' && val.back() == '"') {
       val = val.substr(1, val.size() - 2);
     }
@@ -1069,15 +1088,15 @@ Mesh::Mesh(Options& opts) : options(&opts) {
   int nz = 1;
   if (opts.isSet("nz")) {
     nz = opts["nz"].as<int>();
-  } else if (root.isSet("mz")) {
-    nz = root["mz"].as<int>();
+  } else if (root.isSet("MZ")) {
+    nz = root["MZ"].as<int>();
   }
-  MXG = root.isSet("mxg") ? root["mxg"].as<int>() : opts["mxg"].withDefault(2);
-  MYG = root.isSet("myg") ? root["myg"].as<int>() : opts["myg"].withDefault(2);
-  if (ny == 1 && !root.isSet("myg") && !opts.isSet("myg")) {
+  MXG = root.isSet("MXG") ? root["MXG"].as<int>() : opts["MXG"].withDefault(2);
+  MYG = root.isSet("MYG") ? root["MYG"].as<int>() : opts["MYG"].withDefault(2);
+  if (ny == 1 && !root.isSet("MYG") && !opts.isSet("MYG")) {
     MYG = 0; // boutmesh.cxx:509-517
   }
-  periodicX = root.isSet("periodicx") ? root["periodicx"].as<bool>() : opts["periodicx"].withDefault(false);
+  periodicX = root.isSet("periodicX") ? root["periodicX"].as<bool>() : opts["periodicX"].withDefault(false);
   const int ixseps1 = opts["ixseps1"].withDefault(nx), ixseps2 = opts["ixseps2"].withDefault(nx);
   periodicY = (ixseps1 >= nx - MXG) && (ixseps2 >= nx - MXG); // closed field lines everywhere
   if (!periodicY && ixseps1 > MXG) {
@@ -1181,8 +1200,8 @@ Coordinates::Coordinates(Mesh* mesh) : localmesh(mesh) {
     dz = field2DFromOption(mesh, o, "dz", 1.0);
   } else {
     Options& root = Options::root();
-    double zmin = root.isSet("zmin") ? root["zmin"].as<double>() : 0.0;
-    double zmax = root.isSet("zmax") ? root["zmax"].as<double>() : 1.0;
+    double zmin = root.isSet("ZMIN") ? root["ZMIN"].as<double>() : 0.0;
+    double zmax = root.isSet("ZMAX") ? root["ZMAX"].as<double>() : 1.0;
     if (root.isSet("zperiod")) {
       zmin = 0.0;
       zmax = 1.0 / root["zperiod"].as<double>();

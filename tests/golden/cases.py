@@ -383,3 +383,29 @@ EXPRESSIONS = [
     "1/2π", "2x^2", "fmod(z, 1.5)", "tanhhat(x, 0.3, 0.5, 0.1)", "clamp(x, 0.2, 0.7)", "where(x - 0.5, y, z)", "x * -y",
     "2^3^2", "x < 0.5 | z > 3", "!(x > 0.5) & true", "2 - 3 - 4 * 2 / 4 ^ 2", "(x + 1)^2 * 3 - 1", "-(x+1)", "1 - -(y)",
 ]
+
+
+# Options-file syntax seen through option references in expressions (tests/golden/options_probe.json, values from the
+# reference's OptionINI reader + FieldFactory; "ERR" = the reference throws): comments, blanks, multi-line values with
+# open brackets, bare flags, sections, case-sensitive names, parent-section lookup.
+OPTIONS_PROBE_INI = make_ini(8, 4, 4, mxg=1, myg=1, mesh_extra="ixseps1 = 8\nixseps2 = 8\n", extra="""
+[sec]
+a = 1.5   # comment
+b = 2*a
+k = 1e-2
+neg = -a
+flag
+[other]
+g = sec:b^2
+h = 2 * (sec:a
+   + 1)
+hash = 7 # trailing
+semi = 8 ; also
+[CaseSec]
+Val = 9
+[ws]
+  spaced   =    10
+tabbed	=	11
+""")
+OPTIONS_PROBE_EXPRS = ["sec:a", "sec:b", "sec:k", "sec:neg", "sec:flag", "other:g", "other:h", "other:hash", "other:semi",
+                       "CaseSec:Val", "ws:spaced", "ws:tabbed", "casesec:val", "sec:A", "sec:missing"]

@@ -359,6 +359,22 @@ def expressions():
     print("  expressions:", len(out))
 
 
+def options_probe():
+    """cases.OPTIONS_PROBE_EXPRS through the reference: tests/golden/options_probe.json."""
+    import json
+    from cases import OPTIONS_PROBE_EXPRS, OPTIONS_PROBE_INI
+    r = orc.Ref(OPTIONS_PROBE_INI)
+    res = {}
+    for e in OPTIONS_PROBE_EXPRS:
+        try:
+            res[e] = float(r.expr3d(e)[2, 2, 1])
+        except Exception:  # noqa: BLE001 -- the reference rejects the reference
+            res[e] = "ERR"
+    r.close()
+    json.dump(res, open(os.path.join(HERE, "options_probe.json"), "w"), indent=1)
+    print("  options_probe:", res)
+
+
 def one_integrator(tag, path):
     """tests/models/ode_pair.cxx through the reference's own euler / rkgeneric / splitrk solvers."""
     from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES, hw_integrator_ini, ode_ini
@@ -473,7 +489,7 @@ def models():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb", "integrators", "bndry_free", "expressions"]
+    which = sys.argv[1:] or ["laplace", "ops", "shifted", "models", "elmpb", "integrators", "bndry_free", "expressions", "options_probe"]
     if which[0].startswith("elmpb:"):
         elmpb_case(which[0][6:], which[1])
         sys.stdout.flush()
@@ -502,4 +518,6 @@ if __name__ == "__main__":
         bndry_free()
     if "expressions" in which:
         expressions()
+    if "options_probe" in which:
+        options_probe()
     os._exit(0)  # the reference's static destructors are not exit-safe after repeated init/finalise

@@ -1,5 +1,7 @@
 """Host-side set-up logic of the C++ host layer against the reference (run with LD_PRELOAD=<test double> on CPU):
  * the expression evaluator on cases.EXPRESSIONS against tests/golden/expressions.npz (reference FieldFactory);
+ * the options-file reader (comments, multi-line bracketed values, bare flags, case-sensitive names) through option
+   references against tests/golden/options_probe.json;
  * Options -> Mesh -> model init() -> Solver::add of the unchanged hw.cxx / blob2d.cxx: initial profiles and metrics
    against tests/golden/models.npz.
 Prints one JSON line; exit code 0 iff everything matches."""
@@ -31,6 +33,18 @@ def main():
                 e = f"{e}: {ex}"
             if not ok:
                 bad.append(e)
+    finally:
+        h.close()
+    probe = json.load(open(os.path.join(HERE, "golden", "options_probe.json")))
+    h = hostmod.Host(cases.OPTIONS_PROBE_INI)
+    try:
+        for e in cases.OPTIONS_PROBE_EXPRS:
+            try:
+                v = float(h.expr3d(e)[2, 2, 1])
+            except hostmod.HostError:
+                v = "ERR"
+            if v != probe[e]:
+                bad.append(f"option reference {e}: {v} (reference {probe[e]})")
     finally:
         h.close()
     gold = np.load(os.path.join(HERE, "golden", "models.npz"))
