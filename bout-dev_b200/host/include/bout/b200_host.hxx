@@ -494,6 +494,7 @@ public:
   int xstart, xend, ystart, yend, zstart = 0, zend;
   int MXG, MYG;
   bool periodicX = false, periodicY = true; ///< periodicY: ixseps >= nx (all core)
+  bool symmetricGlobalX = true, symmetricGlobalY = true; ///< mesh:symmetricGlobalX / Y (boutmesh.cxx:72-75)
   bool firstX() const { return true; }
   bool lastX() const { return true; }
   BoutReal GlobalX(int jx) const;

@@ -1097,6 +1097,8 @@ Mesh::Mesh(Options& opts) : options(&opts) {
     MYG = 0; // boutmesh.cxx:509-517
   }
   periodicX = root.isSet("periodicX") ? root["periodicX"].as<bool>() : opts["periodicX"].withDefault(false);
+  symmetricGlobalX = opts["symmetricGlobalX"].withDefault(true);
+  symmetricGlobalY = opts["symmetricGlobalY"].withDefault(true);
   const int ixseps1 = opts["ixseps1"].withDefault(nx), ixseps2 = opts["ixseps2"].withDefault(nx);
   periodicY = (ixseps1 >= nx - MXG) && (ixseps2 >= nx - MXG); // closed field lines everywhere
   if (!periodicY && ixseps1 > MXG) {
@@ -1149,13 +1151,19 @@ std::string Mesh::method(char dir, const std::string& kind) const {
   return it == methods.end() ? std::string("C2") : it->second;
 }
 
-// boutmesh.cxx:3159-3215 on one rank (symmetricGlobalX = symmetricGlobalY = true, no separatrix)
+// boutmesh.cxx:3159-3215 on one rank, all-core topology (jyseps1_1 = -1, no separatrix)
 BoutReal Mesh::GlobalX(int jx) const {
   const int MX = GlobalNx - 2 * MXG;
+  if (!symmetricGlobalX) {
+    return static_cast<BoutReal>(jx) / static_cast<BoutReal>(MX);
+  }
   return (0.5 + jx - (GlobalNx - MX) * 0.5) / static_cast<BoutReal>(MX);
 }
 BoutReal Mesh::GlobalY(int jy) const {
   const int ny = GlobalNy - 2 * MYG;
+  if (!symmetricGlobalY) {
+    return static_cast<BoutReal>(jy - MYG) / static_cast<BoutReal>(ny);
+  }
   return (jy - MYG + 0.5) / static_cast<BoutReal>(ny);
 }
 BoutReal Mesh::GlobalZ(int jz) const { return static_cast<BoutReal>(jz) / static_cast<BoutReal>(GlobalNz); }
