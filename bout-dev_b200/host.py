@@ -7,6 +7,7 @@ example sources) with raw arrays in and out, the same way the test harness drive
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 
@@ -41,13 +42,17 @@ class Host:
         self.shape3 = tuple(v[0:3])
         self.shape2 = tuple(v[0:2])
         self.model_vars = []
+        self._open = True
+        atexit.register(self.close)   # the library's static objects must not outlive the mesh at interpreter exit
 
     def _check(self, rc):
         if rc != 0:
             raise HostError(self.lib.b200host_last_error().decode(errors="replace"))
 
     def close(self):
-        self.lib.b200host_finalise()
+        if self._open:
+            self._open = False
+            self.lib.b200host_finalise()
 
     def metric(self, name):
         a = np.zeros(self.shape2)

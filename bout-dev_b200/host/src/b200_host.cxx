@@ -1199,6 +1199,90 @@ Field2D field2DFromOption(Mesh* m, Options& sec, const std::string& key, double 
 }
 } // namespace
 
+namespace {
+// interpolateAndExtrapolate(f, CELL_CENTRE, extrapolate, extrapolate) on one rank (src/mesh/coordinates.cxx:32-125):
+// communicate first (periodic directions wrap), then -- only where the caller extrapolates (the derived G1..G3; mesh
+// quantities that come from options are valid in the boundary cells and are NOT extrapolated, :394-397) -- every
+// boundary guard cell, outwards, from the three cells inside it (a copy with fewer than 3 interior cells).  X regions
+// cover ystart..yend, Y regions xstart..xend (boutmesh.cxx:1028-1059 defaults).
+void fixGuards2D(Mesh* m, std::vector<double>& f, bool extrapolate) {
+  const int nx = m->LocalNx, ny = m->LocalNy;
+  auto at = [&](int x, int y) -> double& { return f[static_cast<size_t>(x) * ny + y]; };
+  const int mx = m->xend - m->xstart + 1, my = m->yend - m->ystart + 1;
+  if (m->periodicY && m->MYG > 0) { // Y first, then X with the y guards included (mesh.cxx:351-362)
+    for (int x = 0; x < nx; ++x) {
+      for (int i = 0; i < m->ystart; ++i) {
+        at(x, i) = at(x, i + my);
+        at(x, m->yend + 1 + i) = at(x, m->ystart + i);
+      }
+    }
+  }
+  if (m->periodicX && m->MXG > 0) {
+    for (int y = 0; y < ny; ++y) {
+      for (int i = 0; i < m->xstart; ++i) {
+        at(i, y) = at(i + mx, y);
+        at(m->xend + 1 + i, y) = at(m->xstart + i, y);
+      }
+    }
+  }
+  if (!extrapolate) {
+    return; // options-defined quantities are valid in the boundary cells (GridFromOptions::hasXBoundaryGuards)
+  }
+  auto outward = [&](bool xdir, int first, int b, int width, int interior, int lo, int hi) {
+    for (int o = lo; o <= hi; ++o) {
+      for (int i = 0; i < width; ++i) {
+        const int n = first + i * b;
+        auto v = [&](int k) -> double& { return xdir ? at(k, o) : at(o, k); };
+        v(n) = interior >= 3 ? 3.0 * v(n - b) - 3.0 * v(n - 2 * b) + v(n - 3 * b) : v(first - b);
+      }
+    }
+  };
+  if (!m->periodicX && m->MXG > 0) {
+    outward(true, m->xstart - 1, -1, m->xstart, mx, m->ystart, m->yend);
+    outward(true, m->xend + 1, 1, nx - m->xend - 1, mx, m->ystart, m->yend);
+  }
+  if (!m->periodicY && m->MYG > 0) {
+    outward(false, m->ystart - 1, -1, m->ystart, my, m->xstart, m->xend);
+    outward(false, m->yend + 1, 1, ny - m->yend - 1, my, m->xstart, m->xend);
+  }
+}
+
+// Index-space first derivative of a 2-D array along x or y with the mesh's default method, interior points only
+// (index_derivs.cxx:70-78 C2 / C4), divided by the spacing (Coordinates::DDX / DDY, coordinates.cxx:1467-1490)
+std::vector<double> ddIndex2D(Mesh* m, const std::vector<double>& f, const std::vector<double>& spacing, char dir) {
+  const int nx = m->LocalNx, ny = m->LocalNy;
+  std::vector<double> r(f.size(), 0.0);
+  const int guards = dir == 'x' ? m->MXG : m->MYG;
+  if (guards == 0) {
+    return r; // no variation represented along this direction
+  }
+  const std::string method = m->method(dir, "first");
+  const size_t st = dir == 'x' ? static_cast<size_t>(ny) : 1;
+  if (method != "C2" && method != "C4") { // any consistent stencil gives 0 for a quantity that does not vary
+    for (int x = m->xstart; x <= m->xend; ++x) {
+      for (int y = m->ystart; y <= m->yend; ++y) {
+        const size_t i = static_cast<size_t>(x) * ny + y;
+        if (f[i + st] != f[i] || f[i - st] != f[i]) {
+          throw BoutException("Coordinates: metric derivatives support mesh:dd{}:first = C2 or C4, not '{}'", dir, method);
+        }
+      }
+    }
+    return r;
+  }
+  const bool c4 = method == "C4" && guards >= 2;
+  for (int x = m->xstart; x <= m->xend; ++x) {
+    for (int y = m->ystart; y <= m->yend; ++y) {
+      const size_t i = static_cast<size_t>(x) * ny + y;
+      const double d = c4 ? (8. * f[i + st] - 8. * f[i - st] + f[i - 2 * st] - f[i + 2 * st]) / 12.
+                          : 0.5 * (f[i + st] - f[i - st]);
+      r[i] = d / spacing[i];
+    }
+  }
+  (void)nx;
+  return r;
+}
+} // namespace
+
 Coordinates::Coordinates(Mesh* mesh) : localmesh(mesh) {
   Options& o = *mesh->options;
   dx = field2DFromOption(mesh, o, "dx", 1.0);
@@ -1231,13 +1315,18 @@ Coordinates::Coordinates(Mesh* mesh) : localmesh(mesh) {
 
 int Coordinates::geometry() {
   // Covariant metric = inverse of the contravariant one, J = 1/sqrt(det g^ij) (coordinates.cxx:1210-1330),
-  // d1_dx = -DDX(dx)/dx^2 in index space (coordinates.cxx:1088-1099).  G1..G3 (Christoffel contractions)
-  // are taken from the options (0 by default): the configs in scope use metrics for which they vanish
-  // or supply them in the grid.
+  // d1_dx = -DDX(dx)/dx^2 in index space (coordinates.cxx:1088-1099), the Christoffel contractions G1..G3 and Bxy.
+  // Set-up arithmetic on the host, once per mesh, as in the reference.
   Mesh* m = localmesh;
-  const int nx = m->LocalNx, ny = m->LocalNy;
   auto a11 = g11.getHost(), a22 = g22.getHost(), a33 = g33.getHost(), a12 = g12.getHost(), a13 = g13.getHost(),
        a23 = g23.getHost(), hdx = dx.getHost(), hdy = dy.getHost(), hdz = dz.getHost();
+  // mesh quantities read from options carry no boundary guard cells: the reference wraps / extrapolates them
+  // (extrapolate_x / extrapolate_y default to true for such sources, coordinates.cxx:394-470)
+  for (auto* a : {&a11, &a22, &a33, &a12, &a13, &a23, &hdx, &hdy}) {
+    fixGuards2D(m, *a, false);
+  }
+  g11.setHost(a11), g22.setHost(a22), g33.setHost(a33), g12.setHost(a12), g13.setHost(a13), g23.setHost(a23);
+  dx.setHost(hdx), dy.setHost(hdy);
   const size_t n = a11.size();
   std::vector<double> b11(n), b22(n), b33(n), b12(n), b13(n), b23(n), hJ(n), d1x(n, 0.0), d1y(n, 0.0);
   for (size_t i = 0; i < n; ++i) {
@@ -1254,20 +1343,54 @@ int Coordinates::geometry() {
     b23[i] = (a12[i] * a13[i] - a11[i] * a23[i]) / det;
     hJ[i] = 1.0 / std::sqrt(det);
   }
-  bool uniform = true;
-  for (int x = 1; x < nx - 1; ++x) {
-    for (int y = 0; y < ny; ++y) {
-      const size_t i = static_cast<size_t>(x) * ny + y;
-      const double d2x = 0.5 * (hdx[i + ny] - hdx[i - ny]);
-      d1x[i] = -d2x / (hdx[i] * hdx[i]);
-      uniform = uniform && d1x[i] == 0.0;
+  // non-uniform corrections (coordinates.cxx:1085-1110, no d2x / d2y in the source): d1_dx = index-space DDX(1/dx),
+  // d1_dy = DDY(1/dy) (sic: the coordinate derivative, i.e. divided by dy once more), both extrapolated into guards
+  {
+    std::vector<double> inv_dx(n), inv_dy(n), ones(n, 1.0);
+    for (size_t i = 0; i < n; ++i) {
+      inv_dx[i] = 1.0 / hdx[i];
+      inv_dy[i] = 1.0 / hdy[i];
     }
+    d1x = ddIndex2D(m, inv_dx, ones, 'x');
+    d1y = ddIndex2D(m, inv_dy, hdy, 'y');
+    fixGuards2D(m, d1x, true);
+    fixGuards2D(m, d1y, true);
   }
-  for (int y = 0; y < ny; ++y) { // extrapolate into the first/last x (interpolateAndExtrapolate)
-    if (nx > 2) {
-      d1x[y] = d1x[static_cast<size_t>(ny) + y];
-      d1x[static_cast<size_t>(nx - 1) * ny + y] = d1x[static_cast<size_t>(nx - 2) * ny + y];
+  for (auto* a : {&b11, &b22, &b33, &b12, &b13, &b23, &hJ}) { // coordinates.cxx:500-530
+    fixGuards2D(m, *a, false);
+  }
+  // Christoffel contractions G^i = (d_x(J g^i1) + d_y(J g^i2)) / J for z-independent metrics (coordinates.cxx:1018-1026,
+  // then :1066-1068), unless the options give them; Bxy = sqrt(g_22) / J unless given (:547)
+  auto contraction = [&](const std::vector<double>& gi1, const std::vector<double>& gi2) {
+    std::vector<double> p(n), q(n);
+    for (size_t i = 0; i < n; ++i) {
+      p[i] = hJ[i] * gi1[i];
+      q[i] = hJ[i] * gi2[i];
     }
+    const auto dpx = ddIndex2D(m, p, hdx, 'x'), dqy = ddIndex2D(m, q, hdy, 'y');
+    std::vector<double> G(n, 0.0);
+    for (size_t i = 0; i < n; ++i) {
+      G[i] = (dpx[i] + dqy[i]) / hJ[i];
+    }
+    fixGuards2D(m, G, true); // coordinates.cxx:1066-1068 extrapolate in x and y
+    return G;
+  };
+  if (!localmesh->options->isSet("G1")) {
+    G1.setHost(contraction(a11, a12));
+  }
+  if (!localmesh->options->isSet("G2")) {
+    G2.setHost(contraction(a12, a22));
+  }
+  if (!localmesh->options->isSet("G3")) {
+    G3.setHost(contraction(a13, a23));
+  }
+  if (!localmesh->options->isSet("Bxy")) {
+    std::vector<double> hb(n);
+    for (size_t i = 0; i < n; ++i) {
+      hb[i] = std::sqrt(b22[i]) / hJ[i];
+    }
+    fixGuards2D(m, hb, false);
+    Bxy.setHost(hb);
   }
   g_11.setHost(b11);
   g_22.setHost(b22);
@@ -1285,7 +1408,6 @@ int Coordinates::geometry() {
   non_uniform = localmesh->options->isSet("non_uniform") ? (*localmesh->options)["non_uniform"].as<bool>() : true;
   zlength_ = hdz[0] * m->LocalNz;
   cache.clear();
-  (void)uniform;
   return 0;
 }
 

@@ -409,3 +409,23 @@ tabbed	=	11
 """)
 OPTIONS_PROBE_EXPRS = ["sec:a", "sec:b", "sec:k", "sec:neg", "sec:flag", "other:g", "other:h", "other:hash", "other:semi",
                        "CaseSec:Val", "ws:spaced", "ws:tabbed", "casesec:val", "sec:A", "sec:missing"]
+
+
+# The mesh of tests/golden/ops_small.npz (make_golden.OPS_INI: non-uniform dx, x-dependent dy, full non-orthogonal,
+# x- and y-dependent metric): the host layer's Coordinates (covariant metric, J, Bxy, Christoffel contractions G1..G3,
+# non-uniform corrections, guard-cell treatment) is compared with the reference's on it.
+OPS_MESH_INI = make_ini(12, 8, 16, mxg=2, myg=2, dx="0.2*(1+0.1*x)", dy="0.7+0.05*cos(2*pi*x)", dz="2*pi/16", mesh_extra="""
+g11 = 1 + 0.1*x
+g22 = 1.1 + 0.02*y
+g33 = 1.2 + 0.05*x
+g12 = 0.01
+g13 = 0.05 + 0.02*x
+g23 = 0.02
+ixseps1 = 12
+ixseps2 = 12
+""", extra="""
+[mesh:ddx]
+first = C2
+[mesh:ddy]
+first = C2
+""")

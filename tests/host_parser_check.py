@@ -2,6 +2,7 @@
  * the expression evaluator on cases.EXPRESSIONS against tests/golden/expressions.npz (reference FieldFactory);
  * the options-file reader (comments, multi-line bracketed values, bare flags, case-sensitive names) through option
    references against tests/golden/options_probe.json;
+ * Coordinates (covariant metric, J, Bxy, G1..G3, d1_dx, guard cells) of a general metric against ops_small.npz;
  * Options -> Mesh -> model init() -> Solver::add of the unchanged hw.cxx / blob2d.cxx: initial profiles and metrics
    against tests/golden/models.npz.
 Prints one JSON line; exit code 0 iff everything matches."""
@@ -45,6 +46,22 @@ def main():
                 v = "ERR"
             if v != probe[e]:
                 bad.append(f"option reference {e}: {v} (reference {probe[e]})")
+    finally:
+        h.close()
+    # Coordinates of a non-orthogonal, x- and y-dependent metric against the reference's (tests/golden/ops_small.npz)
+    ops = np.load(os.path.join(HERE, "golden", "ops_small.npz"))
+    h = hostmod.Host(cases.OPS_MESH_INI)
+    try:
+        nx, ny, nz, mxg, myg = [int(v) for v in ops["grid"]]
+        nocorners = np.ones((nx, ny), bool)
+        for xs in (slice(0, mxg), slice(nx - mxg, nx)):
+            for ys in (slice(0, myg), slice(ny - myg, ny)):
+                nocorners[xs, ys] = False   # corner cells of derived quantities are never written by the reference
+        for n in ("dx", "dy", "dz", "g11", "g22", "g33", "g12", "g13", "g23", "g_11", "g_22", "g_33", "g_12", "g_13", "g_23",
+                  "J", "Bxy", "G1", "G2", "G3", "d1_dx", "d1_dy"):
+            a, b = h.metric(n), ops["metric_" + n]
+            if np.abs(a - b)[nocorners].max() > 1e-13 * max(1.0, np.abs(b).max()):
+                bad.append(f"metric {n}: {np.abs(a - b)[nocorners].max():.3e}")
     finally:
         h.close()
     gold = np.load(os.path.join(HERE, "golden", "models.npz"))
