@@ -1,7 +1,7 @@
 """ctypes binding of the C++ host layer's harness (host/src/host_driver.cxx -> libbout_b200_host.so).
 
 The host layer is the product's C++17 side: BOUT++'s public API (Field3D, DDX.., bracket, Delp2,
-Laplacian, Mesh::communicate, PhysicsModel, rk4 / rk3ssp) implemented on the C-ABI.  This module lets
+Laplacian, Mesh::communicate, PhysicsModel, the explicit solvers, dump / restart files) implemented on the C-ABI.  This module lets
 tests/ and bench.py run UNCHANGED reference models (host/models/*.so, compiled from the reference's
 example sources) with raw arrays in and out, the same way the test harness drives the reference build.
 """

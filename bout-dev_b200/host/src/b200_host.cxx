@@ -1672,7 +1672,7 @@ Field3D Laplacian::solve(const Field3D& b, const Field3D& x0) {
 }
 
 // ======================================================================================================
-// Solver: rk4 and rk3ssp on device-resident fields
+// Solver: explicit integrators on device-resident fields (rk4, rk3ssp; euler, rkgeneric, splitrk, adams-bashforth below)
 // ======================================================================================================
 Solver::Solver(Options* opts) : options(opts != nullptr ? opts : &Options::root()["solver"]) {
   Options& root = Options::root();

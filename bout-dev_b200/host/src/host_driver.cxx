@@ -94,7 +94,7 @@ int b200host_set_metric(const char* name, const double* in2d) {
 }
 
 // Loads a model shared object built from an UNCHANGED BOUT++ model source (BOUTMAIN -> factory) and
-// attaches it to a solver ("rk4" or "rk3ssp").
+// attaches it to a solver (any solver:type of Solver::create: rk4, rk3ssp, euler, rkgeneric, splitrk, adams-bashforth).
 int b200host_model_create(const char* model_so, const char* solver_type) {
   return guarded([&]() {
     solver.reset();
