@@ -296,6 +296,8 @@ INTEGRATOR_CASES = {
     "ab_adaptive": ("adams-bashforth", "timestep = 0.05\nmax_timestep = 0.5\nrtol = 1e-6", False, 2, 0.5),
     "ab_adaptive_follow_low": ("adams-bashforth", "timestep = 0.05\nmax_timestep = 0.5\nrtol = 1e-6\norder = 4\n"
                                "followHighOrder = false\nadaptive_order = false", True, 1, 0.5),
+    "splitrk_adapt_period3": ("splitrk", "timestep = 0.05\nmax_timestep = 0.5\nrtol = 1e-4\natol = 1e-10\nnstages = 5\n"
+                              "adapt_period = 3", True, 2, 0.5),
     "splitrk_nonsplit_model": ("splitrk", "adaptive = false\ntimestep = 0.1\nnstages = 4", False, 1, 0.5),
 }
 
