@@ -2,8 +2,11 @@
  * entry points (include/bout_b200.h) that the C++ host layer's explicit integrators go through.  tests/
  * LD_PRELOADs it in a child process so that the HOST LOGIC of bout-dev_b200/host (Solver::create, the euler /
  * rkgeneric / splitrk control flow, copy-on-write states) can be compared with the reference build on a box
- * without a GPU.  Every other entry point still resolves to the real library and fails with BOUT_B200_ERR_CUDA.
+ * without a GPU.  Stencils and the self halo are forwarded to the oracle's C restatement when
+ * $B200_FAKE_ORACLE_PORT names it.  Every other entry point still resolves to the real library and fails with
+ * BOUT_B200_ERR_CUDA.
  * The GPU tests run the same cases through the real kernels. */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -266,5 +269,91 @@ int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value
     }
   }
 #undef AT
+  return 0;
+}
+
+/* stencils and the self halo: forwarded to the oracle's plain-C restatement (oracle/_ref/liboracle_port.so, path in
+ * $B200_FAKE_ORACLE_PORT) -- tests may use the oracle, the product never does.  Lets the CPU suite run whole
+ * derivative-based models (examples/IMEX/advection-diffusion) through the host layer to check its dispatch
+ * (method names -> operator ids, 1/dx factors, communicate) against the reference build. */
+#include <dlfcn.h>
+typedef int (*bo_index_deriv_fn)(const void* g, int op, int dir, const double* v, const double* f, const double* yup,
+                                 const double* ydown, double* out);
+static bo_index_deriv_fn oracle_index_deriv(void) {
+  static bo_index_deriv_fn fn = NULL;
+  if (fn == NULL) {
+    const char* path = getenv("B200_FAKE_ORACLE_PORT");
+    void* lib = path ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : NULL;
+    fn = lib ? (bo_index_deriv_fn)dlsym(lib, "bo_index_deriv") : NULL;
+  }
+  return fn;
+}
+
+int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region, const double* v, const double* f,
+                      const double* yup, const double* ydown, const double* scale1, int op2, const double* scale2,
+                      double* out, void* stream) {
+  const long long n = (long long)g->nx * g->ny * g->nz;
+  bo_index_deriv_fn deriv = oracle_index_deriv();
+  (void)stream;
+  if (deriv == NULL || region != BOUT_B200_RGN_NOBNDRY) {
+    return BOUT_B200_ERR_UNSUPPORTED;
+  }
+  double* t1 = (double*)calloc((size_t)n, sizeof(double));
+  double* t2 = (double*)calloc((size_t)n, sizeof(double));
+  int rc = deriv(g, op, dir, v, f, yup, ydown, t1); /* bo_grid has the layout of bout_b200_grid */
+  if (rc == 0 && op2 >= 0) {
+    rc = deriv(g, op2, dir, v, f, yup, ydown, t2);
+  }
+  for (int x = g->xstart; rc == 0 && x <= g->xend; ++x) {
+    for (int y = g->ystart; y <= g->yend; ++y) {
+      const long long i2 = (long long)x * g->ny + y;
+      for (int z = 0; z < g->nz; ++z) {
+        const long long i = i2 * g->nz + z;
+        double r = (scale1 ? scale1[i2] : 1.0) * t1[i];
+        if (op2 >= 0) {
+          r += (scale2 ? scale2[i2] : 1.0) * t2[i];
+        }
+        out[i] = r;
+      }
+    }
+  }
+  free(t1);
+  free(t2);
+  return rc == 0 ? 0 : BOUT_B200_ERR_ARG;
+}
+
+int bout_b200_halo_self(const bout_b200_grid* g, int nfields, double* const* fields, int periodic_x, int periodic_y,
+                        void* stream) {
+  const int mx = g->xend - g->xstart + 1, my = g->yend - g->ystart + 1;
+  (void)stream;
+  for (int k = 0; k < nfields; ++k) {
+    double* f = fields[k];
+#define F3(x, y, z) f[(((long long)(x)) * g->ny + (y)) * g->nz + (z)]
+    if (periodic_y) { /* Y first, then X with the y guards (src/mesh/mesh.cxx:351-362) */
+      for (int x = 0; x < g->nx; ++x) {
+        for (int z = 0; z < g->nz; ++z) {
+          for (int i = 0; i < g->ystart; ++i) {
+            F3(x, i, z) = F3(x, i + my, z);
+          }
+          for (int i = 0; i < g->ny - g->yend - 1; ++i) {
+            F3(x, g->yend + 1 + i, z) = F3(x, g->ystart + i, z);
+          }
+        }
+      }
+    }
+    if (periodic_x) {
+      for (int y = 0; y < g->ny; ++y) {
+        for (int z = 0; z < g->nz; ++z) {
+          for (int i = 0; i < g->xstart; ++i) {
+            F3(i, y, z) = F3(i + mx, y, z);
+          }
+          for (int i = 0; i < g->nx - g->xend - 1; ++i) {
+            F3(g->xend + 1 + i, y, z) = F3(g->xstart + i, y, z);
+          }
+        }
+      }
+    }
+#undef F3
+  }
   return 0;
 }
