@@ -431,3 +431,34 @@ first = C2
 [mesh:ddy]
 first = C2
 """)
+
+
+# examples/eigen-box (unchanged eigen-box.cxx: a wave equation, D2DX2 + communicate) with its shipped data/BOUT.inp
+# restated without comments; the shipped solver type is slepc (an eigenvalue solver, out of scope), so the run uses
+# rk4 with the input's own timestep / output_step / nout.  nz = 1, MXG = 1, mesh sizes given as expressions of MXG.
+EIGENBOX_INI = """
+MXG = 1
+MYG = 0
+dump_on_restart = false
+[mesh]
+length = 1
+nx = 32 + 2*MXG
+ny = 1
+nz = 1
+dx = length / (nx - 2*MXG)
+dy = 1
+[solver]
+type = "slepc"
+timestep = 0.01
+output_step = 0.2
+nout = 1
+[f]
+bndry_all = dirichlet_o2
+scale = 1
+function = sin(2*pi*x)
+[g]
+bndry_all = none
+scale = 0.0
+[input]
+error_on_unused_options = false
+"""

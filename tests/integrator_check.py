@@ -34,6 +34,10 @@ def run(tag):
         from cases import IMEX_INI, IMEX_NOUT, IMEX_STEP
         solver, nout, step = "splitrk", IMEX_NOUT, IMEX_STEP
         model, ini, tol = "imex", IMEX_INI, 1e-8
+    elif tag == "eigenbox_shipped":  # unchanged examples/eigen-box/eigen-box.cxx with its shipped input, rk4
+        from cases import EIGENBOX_INI
+        solver, nout, step = "rk4", 1, 0.2
+        model, ini, tol = "eigenbox", EIGENBOX_INI, 1e-10
     elif tag in ELEM_CASES:         # tests/models/elem_access.cxx: host-side element access
         solver, opts, nout, step = ELEM_CASES[tag]
         model, ini, tol = "elem_access", ode_ini(opts, False, nout, step), TOL
@@ -44,7 +48,8 @@ def run(tag):
     try:
         names = h.model_create(model, solver)
         nx, ny, nz = h.shape3
-        I = (slice(2, nx - 2), slice(None), slice(None))
+        mxg = h.info[3]
+        I = (slice(mxg, nx - mxg), slice(None), slice(None))
         if tag.startswith("bc_"):   # X boundaries: guard cells are set by the boundary conditions and compared too
             I = (slice(None), slice(None), slice(None))
         res = {"tag": tag}
