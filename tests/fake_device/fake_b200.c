@@ -357,3 +357,107 @@ int bout_b200_halo_self(const bout_b200_grid* g, int nfields, double* const* fie
   }
   return 0;
 }
+
+/* Arakawa brackets, Delp2 (FFT branch), LaplaceCyclic and DC forwarded to the oracle port as well: the unchanged
+ * examples/hasegawa-wakatani/hw.cxx then runs on CPU through the host layer (Laplacian options and flags,
+ * split-operator RHS, the integrators) against the reference build. */
+typedef struct {
+  const double *dx, *dz, *g11, *g33, *g13, *g_11, *g_22, *G1, *G3, *IntShiftTorsion;
+  double zlength;
+  int all_terms, nonuniform, inc_int_shear, periodic_x, first_x, last_x;
+} fake_lapl_metric; /* layout of bo_lapl_metric (oracle/bout_oracle.c) */
+typedef struct {
+  int global, inner, outer;
+} fake_lapl_flags;
+
+static void* oracle_symbol(const char* name) {
+  static void* lib = NULL;
+  if (lib == NULL) {
+    const char* path = getenv("B200_FAKE_ORACLE_PORT");
+    lib = path ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : NULL;
+  }
+  return lib ? dlsym(lib, name) : NULL;
+}
+
+static double* constant2d(const bout_b200_grid* g, double v) {
+  const long long n = (long long)g->nx * g->ny;
+  double* a = (double*)malloc((size_t)n * sizeof(double));
+  for (long long i = 0; i < n; ++i) {
+    a[i] = v;
+  }
+  return a;
+}
+
+static fake_lapl_metric to_metric(const bout_b200_grid* g, const bout_b200_laplace* L, double* dz) {
+  fake_lapl_metric m;
+  memset(&m, 0, sizeof(m));
+  m.dx = L->dx, m.dz = dz, m.g11 = L->g11, m.g33 = L->g33, m.g13 = L->g13, m.g_11 = L->g_11, m.g_22 = L->g_22;
+  m.G1 = L->G1, m.G3 = L->G3, m.zlength = L->zlength, m.all_terms = L->all_terms, m.nonuniform = L->nonuniform;
+  m.periodic_x = L->periodic_x, m.first_x = L->first_x, m.last_x = L->last_x;
+  (void)g;
+  return m;
+}
+
+int bout_b200_bracket_arakawa(const bout_b200_grid* g, const double* f, const double* gg, const double* dx,
+                              const double* dz, double* out, void* stream) {
+  typedef int (*fn_t)(const void*, const double*, const double*, const double*, const double*, double*);
+  fn_t fn = (fn_t)oracle_symbol("bo_bracket_arakawa");
+  (void)stream;
+  return fn ? fn(g, f, gg, dx, dz, out) : BOUT_B200_ERR_UNSUPPORTED;
+}
+int bout_b200_bracket_arakawa_3d2d(const bout_b200_grid* g, const double* f, const double* g2d, const double* dx,
+                                   const double* dz, double* out, void* stream) {
+  typedef int (*fn_t)(const void*, const double*, const double*, const double*, const double*, double*);
+  fn_t fn = (fn_t)oracle_symbol("bo_bracket_arakawa_3d2d");
+  (void)stream;
+  return fn ? fn(g, f, g2d, dx, dz, out) : BOUT_B200_ERR_UNSUPPORTED;
+}
+int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* stream) {
+  typedef int (*fn_t)(const void*, const double*, double*);
+  fn_t fn = (fn_t)oracle_symbol("bo_dc");
+  (void)stream;
+  return fn ? fn(g, f, out2d) : BOUT_B200_ERR_UNSUPPORTED;
+}
+int bout_b200_delp2_fft(const bout_b200_grid* g, const bout_b200_laplace* L, const double* f, double* out,
+                        void* stream) {
+  typedef int (*fn_t)(const void*, const void*, const double*, double*);
+  fn_t fn = (fn_t)oracle_symbol("bo_delp2_fft");
+  (void)stream;
+  if (fn == NULL) {
+    return BOUT_B200_ERR_UNSUPPORTED;
+  }
+  double* dz = constant2d(g, L->zlength / g->nz);
+  fake_lapl_metric m = to_metric(g, L, dz);
+  const int rc = fn(g, &m, f, out);
+  free(dz);
+  return rc;
+}
+size_t bout_b200_laplace_cyclic_workspace(const bout_b200_grid* g, const bout_b200_laplace* L) {
+  (void)g;
+  (void)L;
+  return 64;
+}
+int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_laplace* L, const double* rhs,
+                                   const double* x0, double* out, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  typedef int (*fn_t)(const void*, const void*, const void*, int, const double*, const double*, const double*,
+                      const double*, const double*, const double*, double*);
+  fn_t fn = (fn_t)oracle_symbol("bo_laplace_cyclic");
+  (void)workspace;
+  (void)workspace_bytes;
+  (void)stream;
+  if (fn == NULL || L->include_yguards_lower || L->include_yguards_upper) {
+    return BOUT_B200_ERR_UNSUPPORTED;
+  }
+  double* dz = constant2d(g, L->zlength / g->nz);
+  double* zeros = constant2d(g, 0.0);
+  double* ones = constant2d(g, 1.0);
+  fake_lapl_metric m = to_metric(g, L, dz);
+  fake_lapl_flags fl = {L->global_flags, L->inner_boundary_flags, L->outer_boundary_flags};
+  const int rc = fn(g, &m, &fl, L->maxmode, L->A ? L->A : zeros, L->C1 ? L->C1 : ones, L->C2 ? L->C2 : ones,
+                    L->D ? L->D : ones, rhs, x0 ? x0 : rhs, out);
+  free(dz);
+  free(zeros);
+  free(ones);
+  return rc == 0 ? 0 : BOUT_B200_ERR_PIVOT;
+}

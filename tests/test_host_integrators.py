@@ -16,7 +16,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from cases import ELEM_CASES, INTEGRATOR_CASES  # noqa: E402
+from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES  # noqa: E402
 
 ALL_CASES = sorted(INTEGRATOR_CASES) + sorted(ELEM_CASES)
 
@@ -176,5 +176,49 @@ def test_expression_evaluator_and_model_setup_match_reference(fake_device):
     (initial profiles, metrics) against the reference build."""
     p = subprocess.run([sys.executable, os.path.join(HERE, "host_parser_check.py")], env=dict(os.environ, LD_PRELOAD=fake_device),
                        capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
+PORT = os.path.join(ROOT, "oracle", "_ref", "liboracle_port.so")
+
+
+@pytest.fixture(scope="module")
+def hw_results(fake_device):
+    """cases.HW_INTEGRATOR_CASES in one child process; stencils, brackets, Delp2, LaplaceCyclic served by the oracle
+    port behind the test double."""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py")] + sorted(HW_INTEGRATOR_CASES),
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT), capture_output=True, text=True,
+                       timeout=900)
+    out = {}
+    for line in p.stdout.splitlines():
+        if line.startswith("{"):
+            r = json.loads(line)
+            out[r["tag"]] = r
+    assert out, p.stdout[-2000:] + p.stderr[-2000:]
+    return out
+
+
+@pytest.mark.parametrize("tag", sorted(HW_INTEGRATOR_CASES))
+def test_unchanged_hw_model_with_the_other_integrators_host_logic(hw_results, tag):
+    """examples/hasegawa-wakatani/hw.cxx (split-operator, Arakawa brackets, Delp2, LaplaceCyclic per RHS) stepped by
+    euler / rkgeneric / splitrk of the host layer: final state vs the reference's own solver run, same RHS count."""
+    res = hw_results[tag]
+    assert "error" not in res, res
+    assert res["ok"] and res["rhs_calls"] == res["ref_rhs_calls"], res
+
+
+def test_unchanged_hw_and_blob2d_through_the_host_layer_host_logic(fake_device):
+    """tests/host_models_check.py: the checks of tests/test_gpu_models.py (one run_rhs at 1e-10, 5-step RK4 / RK3-SSP
+    trajectories at 1e-8 against tests/golden/models.npz) on CPU -- options, mesh, Laplacian flags, boundary
+    conditions, method dispatch and split-operator handling of the host layer with the device replaced by the
+    oracle port."""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "host_models_check.py")],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT), capture_output=True, text=True,
+                       timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
