@@ -1535,8 +1535,12 @@ Field3D VDDZ(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& me
 }
 
 Field3D bracket(const Field3D& f, const Field3D& gfield, BRACKET_METHOD method, CELL_LOC, Solver*) {
+  if (method == BRACKET_SIMPLE) { // difops.cxx:1042-1046: a subset of terms, built from the upwind operators
+    return VDDX(DDZ(f), gfield) + VDDZ(-DDX(f), gfield);
+  }
   if (method != BRACKET_ARAKAWA) {
-    throw BoutException("bracket: only BRACKET_ARAKAWA is implemented on the B200 path (method {})", static_cast<int>(method));
+    throw BoutException("bracket: BRACKET_ARAKAWA and BRACKET_SIMPLE are implemented in the B200 host layer (method {})",
+                        static_cast<int>(method));
   }
   requireData(f, "bracket");
   requireData(gfield, "bracket");

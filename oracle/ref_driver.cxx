@@ -49,6 +49,7 @@ std::unique_ptr<PhysicsModel> boutref_make_blob2d();
 std::unique_ptr<PhysicsModel> boutref_make_elmpb();
 std::unique_ptr<PhysicsModel> boutref_make_imex(); // examples/IMEX/advection-diffusion/imex.cxx
 std::unique_ptr<PhysicsModel> boutref_make_eigenbox(); // examples/eigen-box/eigen-box.cxx
+std::unique_ptr<PhysicsModel> boutref_make_advreact(); // examples/IMEX/advection-reaction/split_operator.cxx
 std::unique_ptr<PhysicsModel> boutref_make_ode_pair(); // tests/models/ode_pair.cxx (this repository's test model)
 std::unique_ptr<PhysicsModel> boutref_make_elem_access(); // tests/models/elem_access.cxx
 int boutref_elmpb_get_impl(PhysicsModel* pm, const char* name, double* out, int* kind);
@@ -624,6 +625,8 @@ int boutref_model_create(const char* name, const char* solver) {
       model = boutref_make_imex();
     } else if (n == "eigenbox") {
       model = boutref_make_eigenbox();
+    } else if (n == "advreact") {
+      model = boutref_make_advreact();
     } else if (n == "ode_pair") {
       model = boutref_make_ode_pair();
     } else if (n == "elem_access") {

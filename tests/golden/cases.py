@@ -462,3 +462,43 @@ scale = 0.0
 [input]
 error_on_unused_options = false
 """
+
+
+# examples/IMEX/advection-reaction (unchanged split_operator.cxx: bracket(phi, U, BRACKET_SIMPLE) advection + a reaction
+# term, split operator, SAVE_ONCE, initial_profile).  Its shipped input reads the mesh from simple_xz.nc (NetCDF,
+# unreadable in this image on either side), so the mesh is given as options here; derivative methods, solver type and
+# profiles are the shipped ones; rate is non-zero so that the diffusive half does something; nout reduced.
+ADVREACT_INI = """
+MZ = 64
+periodicX = true
+MYG = 0
+[mesh]
+nx = 68
+ny = 1
+dx = 1 / 64
+dz = 2*pi / 64
+[mesh:ddx]
+first = C4
+second = C4
+upwind = W3
+flux = U1
+[mesh:ddz]
+first = C4
+second = C4
+upwind = W3
+flux = U1
+[solver]
+type = splitrk
+timestep = 0.0001
+output_step = 0.01
+[split]
+rate = 0.5
+[U]
+scale = 1.0
+function = sin(4*pi*x) * sin(3*z)
+[phi]
+scale = 1.0
+function = sin(2*pi*x) * sin(z)
+[input]
+error_on_unused_options = false
+"""

@@ -387,6 +387,11 @@ def one_integrator(tag, path):
         solver, nout, step = "splitrk", IMEX_NOUT, IMEX_STEP
         r = orc.Ref(IMEX_INI)
         names = r.model_create("imex", solver)
+    elif tag == "advreact":          # unchanged examples/IMEX/advection-reaction/split_operator.cxx
+        from cases import ADVREACT_INI
+        solver, nout, step = "splitrk", 1, 0.01
+        r = orc.Ref(ADVREACT_INI)
+        names = r.model_create("advreact", solver)
     elif tag == "eigenbox_shipped":  # unchanged examples/eigen-box/eigen-box.cxx, shipped input, rk4
         from cases import EIGENBOX_INI
         solver, nout, step = "rk4", 1, 0.2
@@ -416,7 +421,7 @@ def integrators():
     from cases import ELEM_CASES, HW_INTEGRATOR_CASES, INTEGRATOR_CASES
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for tag in list(INTEGRATOR_CASES) + list(HW_INTEGRATOR_CASES) + list(ELEM_CASES) + ["imex_shipped", "eigenbox_shipped"]:
+        for tag in list(INTEGRATOR_CASES) + list(HW_INTEGRATOR_CASES) + list(ELEM_CASES) + ["imex_shipped", "eigenbox_shipped", "advreact"]:
             path = os.path.join(tmp, tag + ".npz")
             subprocess.run([sys.executable, os.path.abspath(__file__), "integrator:" + tag, path], check=True)
             out.update(dict(np.load(path)))

@@ -34,6 +34,10 @@ def run(tag):
         from cases import IMEX_INI, IMEX_NOUT, IMEX_STEP
         solver, nout, step = "splitrk", IMEX_NOUT, IMEX_STEP
         model, ini, tol = "imex", IMEX_INI, 1e-8
+    elif tag == "advreact":          # unchanged examples/IMEX/advection-reaction/split_operator.cxx (BRACKET_SIMPLE)
+        from cases import ADVREACT_INI
+        solver, nout, step = "splitrk", 1, 0.01
+        model, ini, tol = "advreact", ADVREACT_INI, 1e-8
     elif tag == "eigenbox_shipped":  # unchanged examples/eigen-box/eigen-box.cxx with its shipped input, rk4
         from cases import EIGENBOX_INI
         solver, nout, step = "rk4", 1, 0.2

@@ -170,6 +170,22 @@ def test_unchanged_eigen_box_example_with_its_shipped_input(fake_device):
     assert res["ok"] and res["rhs_calls"] == res["ref_rhs_calls"], res
 
 
+def test_unchanged_advection_reaction_example(fake_device):
+    """examples/IMEX/advection-reaction/split_operator.cxx unchanged (bracket(phi, U, BRACKET_SIMPLE), split operator,
+    initial_profile(), SAVE_ONCE, nz from the root option MZ) with the shipped methods / solver (splitrk) and profiles
+    on a mesh given as options (the shipped grid file is NetCDF): 1e-8 of the reference's run, same RHS count."""
+    port = os.path.join(ROOT, "oracle", "_ref", "liboracle_port.so")
+    for need in (os.path.join(ROOT, "bout-dev_b200", "host", "models", "advreact.so"), port):
+        if not os.path.exists(need):
+            pytest.skip(f"{need} not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py"), "advreact"],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=port), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["ok"] and res["rhs_calls"] == res["ref_rhs_calls"], res
+
+
 def test_expression_evaluator_and_model_setup_match_reference(fake_device):
     """tests/host_parser_check.py: 41 expressions against the reference's FieldFactory (precedence quirks, implicit
     product, UTF-8 symbols, all generators but ballooning) and the set-up of the unchanged hw.cxx / blob2d.cxx
