@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 def results(capi):
     env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}
     p = subprocess.run([sys.executable, os.path.join(HERE, "integrator_check.py")] + sorted(INTEGRATOR_CASES)
-                       + sorted(ELEM_CASES) + sorted(HW_INTEGRATOR_CASES) + ["imex_shipped"], env=env,
+                       + sorted(ELEM_CASES) + sorted(HW_INTEGRATOR_CASES) + ["imex_shipped", "advreact"], env=env,
                        capture_output=True, text=True, timeout=900)
     out = {}
     for line in p.stdout.splitlines():
@@ -54,6 +54,14 @@ def test_unchanged_imex_example_with_its_shipped_input(results):
     """examples/IMEX/advection-diffusion: imex.cxx and data/BOUT.inp as shipped (splitrk, nstages 9, adapt_period 5,
     W3 upwinding, C4 second derivative; nout reduced to 2) against the reference's own run: 1e-8 on the final state."""
     res = results["imex_shipped"]
+    assert "error" not in res, res
+    assert res["ok"] and res["tol"] <= 1e-8, res
+
+
+def test_unchanged_advection_reaction_example_on_device(results):
+    """examples/IMEX/advection-reaction/split_operator.cxx (bracket SIMPLE = VDDX(DDZ f, g) + VDDZ(-DDX f, g), W3 / C4,
+    splitrk) on the device against the reference's run: 1e-8."""
+    res = results["advreact"]
     assert "error" not in res, res
     assert res["ok"] and res["tol"] <= 1e-8, res
 
