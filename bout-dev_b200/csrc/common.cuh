@@ -69,6 +69,15 @@ inline int checkGrid(const bout_b200_grid* g) {
   return 0;
 }
 
+// Functions shared by the kernels and the host-side emulation of tests/emul/ (which steps simulated threads
+// through the same code): callable from both sides, read-only loads through the non-coherent path on the device.
+#define B200_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define B200_LDG(p) __ldg(p)
+#else
+#define B200_LDG(p) (*(p))
+#endif
+
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
 
 // ---- z-vectorised access: VEC = 2 uses 16-byte double2 transactions (nz even, base 16B aligned)

@@ -23,15 +23,15 @@ struct cd { // complex double, 16-byte aligned so it moves as one 128-bit transa
 };
 static_assert(sizeof(cd) == 16, "cd must be 16 bytes");
 
-__device__ __forceinline__ cd cmul(cd a, cd b) {
+B200_HD cd cmul(cd a, cd b) {
   return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
 }
-__device__ __forceinline__ cd cadd(cd a, cd b) { return {a.re + b.re, a.im + b.im}; }
-__device__ __forceinline__ cd csub(cd a, cd b) { return {a.re - b.re, a.im - b.im}; }
-__device__ __forceinline__ cd cconj(cd a) { return {a.re, -a.im}; }
-__device__ __forceinline__ cd cscale(cd a, double s) { return {a.re * s, a.im * s}; }
-__device__ __forceinline__ cd ldtw(const cd* __restrict__ tw, int i) {
-  const double2 t = __ldg(reinterpret_cast<const double2*>(tw) + i);
+B200_HD cd cadd(cd a, cd b) { return {a.re + b.re, a.im + b.im}; }
+B200_HD cd csub(cd a, cd b) { return {a.re - b.re, a.im - b.im}; }
+B200_HD cd cconj(cd a) { return {a.re, -a.im}; }
+B200_HD cd cscale(cd a, double s) { return {a.re * s, a.im * s}; }
+B200_HD cd ldtw(const cd* __restrict__ tw, int i) {
+  const double2 t = B200_LDG(reinterpret_cast<const double2*>(tw) + i);
   return {t.x, t.y};
 }
 

@@ -40,20 +40,20 @@ struct LapCoefs {
 // The kz-independent part: k[0] = coef1/dx^2, k[1] = coef2, k[2] = coef3/(2 dx), k[3] = coef4/(2 dx),
 // k[4] = coef5, from which a = (k0 - k3, -kwave k2), b = (-2 k0 - kwave^2 k1, kwave k4),
 // c = (k0 + k3, kwave k2).
-__device__ __forceinline__ void tridagCoef5(const LapCoefs& m, int jx, int jy, bool use_c, bool use_d,
+B200_HD void tridagCoef5(const LapCoefs& m, int jx, int jy, bool use_c, bool use_d,
                                             double (&k)[5]) {
   const long long i = static_cast<long long>(jx) * m.ny + jy;
-  const double dxi = __ldg(m.dx + i);
-  const double g11 = __ldg(m.g11 + i);
-  double coef1 = g11, coef2 = __ldg(m.g33 + i);
-  const double g13 = __ldg(m.g13 + i);
+  const double dxi = B200_LDG(m.dx + i);
+  const double g11 = B200_LDG(m.g11 + i);
+  double coef1 = g11, coef2 = B200_LDG(m.g33 + i);
+  const double g13 = B200_LDG(m.g13 + i);
   double coef3 = 2. * g13, coef4 = 0.0, coef5 = 0.0;
   if (m.all_terms) {
-    coef4 = __ldg(m.G1 + i);
-    coef5 = __ldg(m.G3 + i);
+    coef4 = B200_LDG(m.G1 + i);
+    coef5 = B200_LDG(m.G3 + i);
   }
   if (use_d && m.D != nullptr) {
-    const double d = __ldg(m.D + i);
+    const double d = B200_LDG(m.D + i);
     coef1 *= d;
     coef2 *= d;
     coef3 *= d;
@@ -62,13 +62,13 @@ __device__ __forceinline__ void tridagCoef5(const LapCoefs& m, int jx, int jy, b
   }
   if (m.nonuniform) {
     if ((jx != 0) && (jx != (m.nx - 1))) {
-      coef4 -= 0.5 * ((__ldg(m.dx + i + m.ny) - __ldg(m.dx + i - m.ny)) / (dxi * dxi)) * coef1;
+      coef4 -= 0.5 * ((B200_LDG(m.dx + i + m.ny) - B200_LDG(m.dx + i - m.ny)) / (dxi * dxi)) * coef1;
     }
   }
   if (use_c && m.C1 != nullptr) {
     if ((jx > 0) && (jx < (m.nx - 1))) {
       const double dc2dx_over_c1 =
-          (__ldg(m.C2 + i + m.ny) - __ldg(m.C2 + i - m.ny)) / (2. * dxi * __ldg(m.C1 + i));
+          (B200_LDG(m.C2 + i + m.ny) - B200_LDG(m.C2 + i - m.ny)) / (2. * dxi * B200_LDG(m.C1 + i));
       coef4 += g11 * dc2dx_over_c1;
       coef5 += g13 * dc2dx_over_c1;
     }
@@ -83,13 +83,13 @@ __device__ __forceinline__ void tridagCoef5(const LapCoefs& m, int jx, int jy, b
   k[4] = coef5;
 }
 
-__device__ __forceinline__ void coefsFromK(const double (&k)[5], double kwave, cd& a, cd& b, cd& c) {
+B200_HD void coefsFromK(const double (&k)[5], double kwave, cd& a, cd& b, cd& c) {
   a = {k[0] - k[3], -kwave * k[2]};
   b = {-2.0 * k[0] - kwave * kwave * k[1], kwave * k[4]};
   c = {k[0] + k[3], kwave * k[2]};
 }
 
-__device__ __forceinline__ void tridagCoefs(const LapCoefs& m, int jx, int jy, double kwave,
+B200_HD void tridagCoefs(const LapCoefs& m, int jx, int jy, double kwave,
                                             bool use_c, bool use_d, cd& a, cd& b, cd& c) {
   double k[5];
   tridagCoef5(m, jx, jy, use_c, use_d, k);
@@ -106,11 +106,11 @@ struct LapBndry {
 
 // One matrix row of the system for (x, jy, kz) including the boundary rows; `rhs` is modified
 // where tridagMatrix zeroes it.  Row index within the system is x - xs.
-__device__ __forceinline__ void tridagRow(const LapCoefs& m, const LapBndry& bd, int x, int jy,
+B200_HD void tridagRow(const LapCoefs& m, const LapBndry& bd, int x, int jy,
                                           int kz, double kwave, cd& a, cd& b, cd& c, cd& rhs) {
   tridagCoefs(m, x, jy, kwave, true, true, a, b, c);
   if (m.A != nullptr) {
-    b.re += __ldg(m.A + static_cast<long long>(x) * m.ny + jy);
+    b.re += B200_LDG(m.A + static_cast<long long>(x) * m.ny + jy);
   }
   const int ix = x - bd.xs;
   const int ncx = bd.xe - bd.xs;
@@ -125,38 +125,38 @@ __device__ __forceinline__ void tridagRow(const LapCoefs& m, const LapBndry& bd,
       double A = 0.0, B = 0.5, C = 0.5;
       if (kz == 0) {
         if ((fl & INV_DC_GRAD) && setrhs) {
-          B = -1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
-          C = 1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
+          B = -1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
+          C = 1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
         } else if (fl & INV_DC_GRAD) {
           B = -1.;
           C = 1.;
         } else if (fl & INV_DC_GRADPAR) {
-          B = 1.0 / sqrt(__ldg(m.g_22 + i));
-          C = -1.0 / sqrt(__ldg(m.g_22 + i + m.ny));
+          B = 1.0 / sqrt(B200_LDG(m.g_22 + i));
+          C = -1.0 / sqrt(B200_LDG(m.g_22 + i + m.ny));
         } else if (fl & INV_DC_GRADPARINV) {
-          B = sqrt(__ldg(m.g_22 + i));
-          C = -sqrt(__ldg(m.g_22 + i + m.ny));
+          B = sqrt(B200_LDG(m.g_22 + i));
+          C = -sqrt(B200_LDG(m.g_22 + i + m.ny));
         } else if (fl & INV_DC_LAP) {
           double k = 0.0;
           if (m.A != nullptr) {
-            k = sqrt(-__ldg(m.A + static_cast<long long>(bd.inbndry) * m.ny + jy));
+            k = sqrt(-B200_LDG(m.A + static_cast<long long>(bd.inbndry) * m.ny + jy));
           }
           B = 1.;
-          C = -exp(-k * __ldg(m.dx + i) / sqrt(__ldg(m.g11 + i)));
+          C = -exp(-k * B200_LDG(m.dx + i) / sqrt(B200_LDG(m.g11 + i)));
         } else if (fl & INV_IN_CYLINDER) {
           B = 1.;
           C = -1.;
         }
       } else {
         if ((fl & INV_AC_GRAD) && setrhs) {
-          B = -1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
-          C = 1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
+          B = -1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
+          C = 1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
         } else if (fl & INV_AC_GRAD) {
           B = -1.;
           C = 1.;
         } else if (fl & INV_AC_LAP) {
           B = 1.0;
-          C = -exp(-1.0 * sqrt(__ldg(m.g33 + i) / __ldg(m.g11 + i)) * kwave * __ldg(m.dx + i));
+          C = -exp(-1.0 * sqrt(B200_LDG(m.g33 + i) / B200_LDG(m.g11 + i)) * kwave * B200_LDG(m.dx + i));
         } else if (fl & INV_IN_CYLINDER) {
           B = 1.;
           C = ((kz % 2) == 0) ? -1. : 1.;
@@ -178,8 +178,8 @@ __device__ __forceinline__ void tridagRow(const LapCoefs& m, const LapBndry& bd,
       bool write = true;
       if (kz == 0) {
         if ((fl & INV_DC_GRAD) && setrhs) {
-          A = -1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
-          B = 1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
+          A = -1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
+          B = 1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
         } else if (fl & INV_DC_GRAD) {
           A = 1.;
           B = -1.;
@@ -187,29 +187,29 @@ __device__ __forceinline__ void tridagRow(const LapCoefs& m, const LapBndry& bd,
           // the reference loops these three outer cases over inbndry (invert_laplace.cxx:673-703)
           write = k_from_edge < bd.inbndry;
           if (fl & INV_DC_GRADPAR) {
-            A = 1.0 / sqrt(__ldg(m.g_22 + i - m.ny));
-            B = -1.0 / sqrt(__ldg(m.g_22 + i));
+            A = 1.0 / sqrt(B200_LDG(m.g_22 + i - m.ny));
+            B = -1.0 / sqrt(B200_LDG(m.g_22 + i));
           } else if (fl & INV_DC_GRADPARINV) {
-            A = sqrt(__ldg(m.g_22 + i - m.ny));
-            B = -sqrt(__ldg(m.g_22 + i));
+            A = sqrt(B200_LDG(m.g_22 + i - m.ny));
+            B = -sqrt(B200_LDG(m.g_22 + i));
           } else {
             double k = 0.0;
             if (m.A != nullptr) {
-              k = sqrt(-__ldg(m.A + static_cast<long long>(bd.inbndry) * m.ny + jy));
+              k = sqrt(-B200_LDG(m.A + static_cast<long long>(bd.inbndry) * m.ny + jy));
             }
             B = 1.;
-            A = -exp(-k * __ldg(m.dx + i) / sqrt(__ldg(m.g11 + i)));
+            A = -exp(-k * B200_LDG(m.dx + i) / sqrt(B200_LDG(m.g11 + i)));
           }
         }
       } else {
         if ((fl & INV_AC_GRAD) && setrhs) {
-          A = -1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
-          B = 1. / sqrt(__ldg(m.g_11 + i)) / __ldg(m.dx + i);
+          A = -1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
+          B = 1. / sqrt(B200_LDG(m.g_11 + i)) / B200_LDG(m.dx + i);
         } else if (fl & INV_AC_GRAD) {
           A = 1.;
           B = -1.;
         } else if (fl & INV_AC_LAP) {
-          A = -exp(-1.0 * sqrt(__ldg(m.g33 + i) / __ldg(m.g11 + i)) * kwave * __ldg(m.dx + i));
+          A = -exp(-1.0 * sqrt(B200_LDG(m.g33 + i) / B200_LDG(m.g11 + i)) * kwave * B200_LDG(m.dx + i));
           B = 1.0;
         }
       }

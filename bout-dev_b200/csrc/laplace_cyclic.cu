@@ -29,7 +29,7 @@
 //     x_i = d'_i - c'_i x_{i+1} - s_i x_L.  Periodic X on one rank is the NXPE = 1 case (x_L = x_last,
 //     x_R = x_first).  Both are direct solvers for the reference's matrix and agree with it to
 //     round-off (parity tolerance for this path: 1e-10 relative).
-#include "laplace_coefs.cuh"
+#include "laplace_block.cuh"
 #include "fft_fast.cuh"
 
 #include <cstdlib>
@@ -38,37 +38,6 @@
 #include <unordered_map>
 
 namespace b200 {
-
-constexpr int LAP_NK = 6;     // table entries per (x,y): k0..k4 of tridagCoef5 and A
-constexpr int LAP_IFACE = 6;  // interface coefficients per system: sL, cL, dL, aU, cU, dU
-constexpr int LAP_MAXPE = 8;  // ranks in X
-
-struct LapParams {
-  LapCoefs m;
-  LapBndry bd;
-  const double* __restrict__ rhs;
-  const double* __restrict__ x0;
-  double* __restrict__ out;
-  double* __restrict__ table; // [ny][nx][LAP_NK] (x contiguous for one y: a system's rows are one run)
-  cd* __restrict__ spec;   // [nxs][nys][nmode]  rhs spectrum in, solution spectrum out
-  cd* __restrict__ cprime; // [nxs][nys][nmode]
-  cd* __restrict__ dprime; // [nxs][nys][nmode]
-  cd* __restrict__ sprime; // coupled only: [nxs][nys][nmode]
-  cd* __restrict__ inv;    // fused sweeps: 1 / (b_i - a_i c'_{i-1}), [nxs][nys][nmode]
-  cd* __restrict__ bnd;    // fused sweeps: a, c of the boundary rows, [inbndry+outbndry][nys][nmode][2]
-  cd* __restrict__ iface;  // coupled only: this rank's [LAP_IFACE][nsys]
-  const cd* __restrict__ iface_all; // coupled only: [nxpe][LAP_IFACE][nsys]
-  int* __restrict__ status;
-  int* __restrict__ ydep;  // 0 while no metric / coefficient array was seen to vary along y (k_lap_ycheck)
-  const cd* __restrict__ tw;
-  int nx, ny, nz;
-  int ys, ye;     // y range solved
-  int nmode;
-  int zero_dc;
-  int in_set, out_set;
-  int tpr, rows, pow2;
-  int nxpe, pe_xind;
-};
 
 __device__ __forceinline__ RowFFT makeRow(const LapParams& p, unsigned char* smem_raw, int& rloc) {
   const int nbuf = fftBufElems(p.nz);
@@ -178,59 +147,12 @@ __global__ void __launch_bounds__(128) k_lap_backward_fast(const LapParams p) {
   }
 }
 
-__device__ __forceinline__ cd crecip(cd z) {
-  const double d = 1.0 / (z.re * z.re + z.im * z.im);
-  return {z.re * d, -z.im * d};
-}
-__device__ __forceinline__ cd ldcd(const cd* __restrict__ p) {
-  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
-  return {t.x, t.y};
-}
-__device__ __forceinline__ bool tiny(cd z) { return !((z.re * z.re + z.im * z.im) > 1e-300); }
-
 // K0: kz-independent coefficient table (Laplacian::tridagCoefs without the kwave factors, + A)
 __global__ void __launch_bounds__(256) k_lap_table(const LapParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.nx * p.ny) {
-    return;
+  if (i < p.nx * p.ny) {
+    lapTableEntry(p, i);
   }
-  double k[5];
-  const int jx = i / p.ny, jy = i % p.ny;
-  tridagCoef5(p.m, jx, jy, true, true, k);
-  double* __restrict__ t = p.table + (static_cast<long long>(jy) * p.nx + jx) * LAP_NK;
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    t[j] = k[j];
-  }
-  t[5] = p.m.A != nullptr ? p.m.A[i] : 0.0;
-}
-
-// Row ix of the system (jy, kz): interior rows from the table, boundary rows (and the doubly
-// periodic kz = 0 pin) through the full tridagMatrix logic.  `tab` is the table block of this
-// system's jy, indexed by the row number ix (either staged in shared memory or in global memory).
-__device__ __forceinline__ void lapRow(const LapParams& p, const double* tab, int ix, int jy, int kz,
-                                       double kwave, cd& a, cd& b, cd& c, cd& r) {
-  const int ncx = p.bd.xe - p.bd.xs;
-  const bool special = p.bd.periodic_x
-                           ? (kz == 0 && p.bd.first_x && ix == 0)
-                           : ((p.bd.first_x && ix < p.bd.inbndry) || (p.bd.last_x && (ncx - ix) < p.bd.outbndry));
-  if (special) {
-    tridagRow(p.m, p.bd, p.bd.xs + ix, jy, kz, kwave, a, b, c, r);
-    if (!p.bd.periodic_x) { // nothing lies beyond a physical boundary
-      if (p.bd.first_x && ix == 0) {
-        a = {0.0, 0.0};
-      }
-      if (p.bd.last_x && ix == ncx) {
-        c = {0.0, 0.0};
-      }
-    }
-    return;
-  }
-  const double2* t = reinterpret_cast<const double2*>(tab + static_cast<long long>(ix) * LAP_NK);
-  const double2 t01 = t[0], t23 = t[1], t45 = t[2];
-  a = {t01.x - t23.y, -kwave * t23.x};
-  b = {-2.0 * t01.x - kwave * kwave * t01.y + t45.y, kwave * t45.x};
-  c = {t01.x + t23.y, kwave * t23.x};
 }
 
 // Stages the table rows of the (at most two) jy values a CTA's systems belong to into shared memory
@@ -496,384 +418,6 @@ __global__ void __launch_bounds__(256) k_lap_pcr(const LapParams p) {
   }
 }
 
-// ---- isolated systems, fused sweeps: the spectrum never visits HBM -----------------------------------
-// The Thomas recurrence c'_i = c_i / (b_i - a_i c'_{i-1}) depends on the matrix only, not on the
-// right-hand side: k_lap_factor stores inv_i = 1 / (b_i - a_i c'_{i-1}) per (x, y, kz) once
-// (bout_b200_laplace_cyclic_factor; every later solve with unchanged coefficients reuses it), which
-// takes the division and a 16-deep dependency chain out of every solve.  Two sweep kernels remain.
-// One CTA owns one y index (all kz systems of that y share the same input rows) and marches along x
-// in batches of eight rows:
-//   forward  : rows (x..x+7, y, :) --rfft in shared memory--> 8 x nmode spectrum values on chip;
-//              thread kz advances d'_i = (r_i - a_i d'_{i-1}) inv_i and stores d' (the only write);
-//   backward : thread kz back-substitutes x_i = d'_i - (c_i inv_i) x_{i+1} into the on-chip spectrum
-//              --irfft--> output rows.
-// The transform of one batch and the Thomas steps of the neighbouring batch are interleaved stage
-// by stage in the same threads (cfftFast2's hook), so the recurrence runs in the shadow of the
-// shared-memory latency of the butterflies; row data, inv and d' are register-prefetched one batch
-// ahead.  HBM traffic per point: 8 (rhs) + 8 (inv) + 8 (d' out) and 8 (inv) + 8 (d' in) + 8 (out)
-// = 48 B (32 B when the coefficients do not depend on y: inv is then served by L2), instead of the
-// 3-kernel path's 80 B.  Every row's arithmetic is the same code as the 3-kernel path: results are
-// equal to it to round-off (FMA contraction may differ).  Opt-in, see lapFusedEligible.
-// CTA = N threads (N = nz/2): four row groups of N/4 threads, each transforming two rows of the
-// batch; Thomas thread kz = tid; thread 0 also carries the Nyquist system kz = N, whose inv / d'
-// values are staged through shared memory by the last eight threads.
-constexpr int LAPF_ROWS = 8;
-
-template <int N>
-struct LapFusedShape {
-  static constexpr int NT = N;
-  static constexpr int SROW = N + 2; // spectrum row pitch (N + 1 modes)
-  static constexpr int NSLOT = fftSwaps<N>();                          // hook calls per batch
-  static constexpr int RPS = (LAPF_ROWS + NSLOT - 1) / NSLOT;          // Thomas rows per hook call
-  static constexpr size_t fftElems = static_cast<size_t>(LAPF_ROWS) * 2 * (N + 8);
-  static constexpr size_t specElems = static_cast<size_t>(2) * LAPF_ROWS * SROW; // double buffered
-  static constexpr size_t nyqElems = static_cast<size_t>(2) * 2 * LAPF_ROWS;     // [2][inv, d'][row]
-  static size_t smemBytes(int n) {
-    return (fftElems + specElems + nyqElems) * sizeof(cd) + static_cast<size_t>(n) * LAP_NK * sizeof(double);
-  }
-};
-
-// Boundary rows are rare (inbndry + outbndry of n) but their coefficient logic is long: k_lap_factor
-// stores their a and c per (boundary row, y, kz) in `bnd`, the sweeps read them back, and the
-// unrolled hot loops only carry the interior-row formula.  `r` is zeroed where tridagMatrix does.
-__device__ __forceinline__ int lapBndRow(const LapParams& p, int ix, bool& inner, bool& outer) {
-  const int ncx = p.bd.xe - p.bd.xs;
-  inner = p.bd.first_x && ix < p.bd.inbndry;
-  outer = p.bd.last_x && (ncx - ix) < p.bd.outbndry;
-  return outer ? p.bd.inbndry + (ix - (ncx - p.bd.outbndry + 1)) : ix;
-}
-__device__ __forceinline__ void lapRowFused(const LapParams& p, const double* tab, int ix, int iyl, int kz,
-                                            double kwave, cd& a, cd& c, cd& r) {
-  bool inner, outer;
-  const int sr = lapBndRow(p, ix, inner, outer);
-  if (inner || outer) {
-    const int nys = p.ye - p.ys + 1;
-    const cd* q = p.bnd + ((static_cast<long long>(sr) * nys + iyl) * p.nmode + kz) * 2;
-    a = ldcd(q);
-    c = ldcd(q + 1);
-    const int fl = outer ? p.bd.outer_flags : p.bd.inner_flags;
-    if (!(fl & (INV_RHS | INV_SET))) {
-      r = {0.0, 0.0};
-    }
-    return;
-  }
-  const double2* t = reinterpret_cast<const double2*>(tab + static_cast<long long>(ix) * LAP_NK);
-  const double2 t01 = t[0], t23 = t[1];
-  a = {t01.x - t23.y, -kwave * t23.x};
-  c = {t01.x + t23.y, kwave * t23.x};
-}
-
-// inv_i for every row of every (y, kz) system (the matrix-only half of the Thomas forward sweep)
-__global__ void __launch_bounds__(128) k_lap_factor(const LapParams p, const bool smem_ok) {
-  extern __shared__ __align__(16) double stab[];
-  const int nys = p.ye - p.ys + 1;
-  const int nsys = nys * p.nmode;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = p.bd.xe - p.bd.xs + 1;
-  const double* tab = stageTable(p, stab, n, t, nsys, smem_ok);
-  if (t >= nsys) {
-    return;
-  }
-  const int iyl = t / p.nmode, kz = t % p.nmode;
-  const int jy = p.ys + iyl;
-  const long long xs = static_cast<long long>(nys) * p.nmode;
-  const double kwave = kz * 2.0 * M_PI / p.m.zlength;
-  cd* __restrict__ ip = p.inv + t;
-  cd cprev = {0, 0};
-  bool bad = false;
-  for (int ix = 0; ix < n; ++ix) {
-    cd a, b, c, r = {0.0, 0.0};
-    lapRow(p, tab, ix, jy, kz, kwave, a, b, c, r);
-    const cd denom = csub(b, cmul(a, cprev));
-    bad = bad || tiny(denom);
-    const cd inv = crecip(denom);
-    cprev = cmul(c, inv);
-    ip[ix * xs] = inv;
-    bool inner, outer;
-    const int sr = lapBndRow(p, ix, inner, outer);
-    if (inner || outer) {
-      cd* q = p.bnd + ((static_cast<long long>(sr) * nys + iyl) * p.nmode + kz) * 2;
-      q[0] = a;
-      q[1] = c;
-    }
-  }
-  if (bad) {
-    atomicExch(p.status, 1);
-  }
-}
-
-template <int N>
-struct LapFusedCtx {
-  cd *a0, *b0, *a1, *b1; // transform buffers of this thread group's two rows
-  cd* S;                 // [2][LAPF_ROWS][SROW]
-  cd* nyq;               // [2][2][LAPF_ROWS]
-  double* stab;
-  int grp, lane;
-};
-template <int N>
-__device__ __forceinline__ LapFusedCtx<N> lapFusedCtx(unsigned char* smem_raw) {
-  using Sh = LapFusedShape<N>;
-  LapFusedCtx<N> c;
-  c.grp = threadIdx.x / (N / 4);
-  c.lane = threadIdx.x % (N / 4);
-  cd* bufs = reinterpret_cast<cd*>(smem_raw);
-  c.a0 = bufs + static_cast<size_t>(c.grp) * 2 * (N + 8);
-  c.b0 = c.a0 + (N + 8);
-  c.a1 = bufs + static_cast<size_t>(c.grp + 4) * 2 * (N + 8);
-  c.b1 = c.a1 + (N + 8);
-  c.S = bufs + Sh::fftElems;
-  c.nyq = c.S + Sh::specElems;
-  c.stab = reinterpret_cast<double*>(c.nyq + Sh::nyqElems);
-  return c;
-}
-
-template <int N>
-__global__ void __launch_bounds__(N, 1) k_lap_fused_forward(const LapParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Sh = LapFusedShape<N>;
-  constexpr int TPR = N / 4, SROW = Sh::SROW, R = LAPF_ROWS, RPS = Sh::RPS;
-  const int tid = threadIdx.x;
-  const LapFusedCtx<N> cx = lapFusedCtx<N>(smem_raw);
-  const int lane = cx.lane;
-  const int nys = p.ye - p.ys + 1;
-  const int n = p.bd.xe - p.bd.xs + 1;
-  const int nb = (n + R - 1) / R;
-  const int iyl = blockIdx.x, jy = p.ys + iyl;
-  { // this y's coefficient table rows
-    const double2* src = reinterpret_cast<const double2*>(p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK);
-    double2* dst = reinterpret_cast<double2*>(cx.stab);
-    for (int i = tid; i < n * (LAP_NK / 2); i += Sh::NT) {
-      dst[i] = __ldg(src + i);
-    }
-  }
-  FastTw<N> tw;
-  fastTwInit<N>(tw, p.tw, lane);
-
-  const bool sys = tid < p.nmode;
-  const bool nyqt = tid == 0 && p.nmode > N;          // second chain of thread 0: kz = N
-  const bool nyql = tid >= N - R && p.nmode > N;      // loader of the Nyquist system's inv values
-  const double kwave = tid * 2.0 * M_PI / p.m.zlength; // common_transform.cxx:73
-  const double kwaveN = N * 2.0 * M_PI / p.m.zlength;
-  const long long xs = static_cast<long long>(nys) * p.nmode;
-  const long long t0 = static_cast<long long>(iyl) * p.nmode;
-  const cd* __restrict__ ivp = p.inv + t0 + tid;
-  cd* __restrict__ dp = p.dprime + t0 + tid;
-
-  double2 pre[2][4]; // the two rows of batch b this thread group transforms
-  cd pinv[R];        // inv of batch b for this thread's system (consumed in iteration b + 1)
-  cd pnq = {0.0, 0.0};
-  auto prefetch = [&](int b) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ix = b * R + cx.grp + 4 * h;
-      if (b < nb && ix < n) {
-        const int x = p.bd.xs + ix;
-        // common_transform.cxx:49-57
-        const bool from_x0 = ((x < p.bd.inbndry) && p.in_set) || ((p.nx - x - 1 < p.bd.outbndry) && p.out_set);
-        const double2* __restrict__ s2 = reinterpret_cast<const double2*>(
-            (from_x0 ? p.x0 : p.rhs) + (static_cast<long long>(x) * p.ny + jy) * p.nz);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          pre[h][m] = __ldg(s2 + lane + m * TPR);
-        }
-      } else {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          pre[h][m] = make_double2(0.0, 0.0);
-        }
-      }
-    }
-  };
-  auto prefetchInv = [&](int b) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int ix = b * R + r;
-      pinv[r] = (sys && b < nb && ix < n) ? ldcd(ivp + ix * xs) : cd{0.0, 0.0};
-    }
-    if (nyql) {
-      const int ix = b * R + (tid - (N - R));
-      pnq = (b < nb && ix < n) ? ldcd(p.inv + t0 + N + ix * xs) : cd{0.0, 0.0};
-    }
-  };
-  prefetch(0);
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    pinv[r] = {0.0, 0.0};
-  }
-  cd dprev = {0, 0}, dprevN = {0, 0};
-
-  for (int b = 0; b <= nb; ++b) { // iteration b: transform batch b, Thomas steps of batch b - 1
-    cd cinv[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cinv[r] = pinv[r];
-    }
-    if (nyql) {
-      cx.nyq[(b & 1) * 2 * R + (tid - (N - R))] = pnq; // batch b - 1, read after the barrier below
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      cx.a0[fsw(lane + m * TPR)] = {pre[0][m].x, pre[0][m].y};
-      cx.a1[fsw(lane + m * TPR)] = {pre[1][m].x, pre[1][m].y};
-    }
-    prefetch(b + 1);
-    prefetchInv(b);
-    __syncthreads(); // rows staged (first time round: the table too); spectrum of batch b - 1 visible
-    const cd* Sp = cx.S + ((b - 1) & 1) * R * SROW;
-    const cd* nq = cx.nyq + (b & 1) * 2 * R;
-    cfftFast2<N, false>(cx.a0, cx.b0, cx.a1, cx.b1, tw, lane, b < nb, [&](int slot) {
-      if (b > 0) {
-#pragma unroll
-        for (int q = 0; q < RPS; ++q) {
-          const int r = slot * RPS + q;
-          const int ix = (b - 1) * R + r;
-          if (r < R && ix < n) {
-            if (sys) {
-              cd a, c, rr = Sp[r * SROW + tid];
-              lapRowFused(p, cx.stab, ix, iyl, tid, kwave, a, c, rr);
-              dprev = cmul(csub(rr, cmul(a, dprev)), cinv[r]);
-              dp[ix * xs] = dprev;
-            }
-            if (nyqt) {
-              cd a, c, rr = Sp[r * SROW + N];
-              lapRowFused(p, cx.stab, ix, iyl, N, kwaveN, a, c, rr);
-              dprevN = cmul(csub(rr, cmul(a, dprevN)), nq[r]);
-              p.dprime[t0 + N + ix * xs] = dprevN;
-            }
-          }
-        }
-      }
-    });
-    if (b < nb) {
-      constexpr bool inB = (fftSwaps<N>() % 2) != 0;
-      cd* Sc = cx.S + (b & 1) * R * SROW;
-      rfftSplitTo<N>(inB ? cx.b0 : cx.a0, Sc + cx.grp * SROW, p.nmode, tw, lane);
-      rfftSplitTo<N>(inB ? cx.b1 : cx.a1, Sc + (cx.grp + 4) * SROW, p.nmode, tw, lane);
-      if (!inB) {
-        __syncthreads(); // the split read buffer A, which the next batch's rows are staged into
-      }
-    }
-  }
-}
-
-template <int N>
-__global__ void __launch_bounds__(N, 1) k_lap_fused_backward(const LapParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Sh = LapFusedShape<N>;
-  constexpr int TPR = N / 4, SROW = Sh::SROW, R = LAPF_ROWS, RPS = Sh::RPS;
-  const int tid = threadIdx.x;
-  const LapFusedCtx<N> cx = lapFusedCtx<N>(smem_raw);
-  const int lane = cx.lane;
-  const int nys = p.ye - p.ys + 1;
-  const int n = p.bd.xe - p.bd.xs + 1;
-  const int nb = (n + R - 1) / R;
-  const int iyl = blockIdx.x, jy = p.ys + iyl;
-  {
-    const double2* src = reinterpret_cast<const double2*>(p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK);
-    double2* dst = reinterpret_cast<double2*>(cx.stab);
-    for (int i = tid; i < n * (LAP_NK / 2); i += Sh::NT) {
-      dst[i] = __ldg(src + i);
-    }
-  }
-  FastTw<N> tw;
-  fastTwInit<N>(tw, p.tw, lane);
-
-  const bool sys = tid < p.nmode;
-  const bool nyqt = tid == 0 && p.nmode > N;
-  const bool nyql = tid >= N - 2 * R && p.nmode > N; // loaders: R inv values, then R d' values
-  const double kwave = tid * 2.0 * M_PI / p.m.zlength;
-  const double kwaveN = N * 2.0 * M_PI / p.m.zlength;
-  const long long xs = static_cast<long long>(nys) * p.nmode;
-  const long long t0 = static_cast<long long>(iyl) * p.nmode;
-  const cd* __restrict__ ivp = p.inv + t0 + tid;
-  const cd* __restrict__ dpr = p.dprime + t0 + tid;
-
-  cd pinv[R], pd[R];
-  cd pnq = {0.0, 0.0};
-  auto prefetch = [&](int b) { // batch b of this thread's system
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int ix = b * R + r;
-      const bool ok = sys && b >= 0 && ix < n;
-      pinv[r] = ok ? ldcd(ivp + ix * xs) : cd{0.0, 0.0};
-      pd[r] = ok ? ldcd(dpr + ix * xs) : cd{0.0, 0.0};
-    }
-    if (nyql) {
-      const int q = tid - (N - 2 * R);
-      const int ix = b * R + (q % R);
-      const cd* src = (q < R ? p.inv : p.dprime) + t0 + N;
-      pnq = (b >= 0 && ix < n) ? ldcd(src + ix * xs) : cd{0.0, 0.0};
-    }
-  };
-  prefetch(nb - 1);
-  cd x = {0.0, 0.0}, xN = {0.0, 0.0}; // x_n = 0: the last row of an isolated system has c = 0
-
-  for (int i = 0; i <= nb; ++i) { // iteration i: Thomas steps of batch nb-1-i, inverse transform of batch nb-i
-    const int bt = nb - 1 - i, bf = nb - i;
-    cd cinv[R], cdp[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cinv[r] = pinv[r];
-      cdp[r] = pd[r];
-    }
-    if (nyql) {
-      cx.nyq[(i & 1) * 2 * R + (tid - (N - 2 * R))] = pnq;
-    }
-    prefetch(bt - 1);
-    if (i > 0) { // solution spectrum of batch bf (complete since the last barrier of iteration i - 1)
-      const cd* Sp = cx.S + ((i - 1) & 1) * R * SROW;
-      rfftMergeFrom<N>(Sp + cx.grp * SROW, cx.a0, p.nmode, p.zero_dc != 0, tw, lane);
-      rfftMergeFrom<N>(Sp + (cx.grp + 4) * SROW, cx.a1, p.nmode, p.zero_dc != 0, tw, lane);
-    }
-    __syncthreads();
-    cd* Sc = cx.S + (i & 1) * R * SROW;
-    const cd* nq = cx.nyq + (i & 1) * 2 * R;
-    cfftFast2<N, true>(cx.a0, cx.b0, cx.a1, cx.b1, tw, lane, i > 0, [&](int slot) {
-      if (bt >= 0) {
-#pragma unroll
-        for (int q = 0; q < RPS; ++q) {
-          const int r = R - 1 - (slot * RPS + q);
-          const int ix = bt * R + r;
-          if (r >= 0 && ix < n) {
-            if (sys) {
-              cd a, c, rr = {0.0, 0.0};
-              lapRowFused(p, cx.stab, ix, iyl, tid, kwave, a, c, rr);
-              x = csub(cdp[r], cmul(cmul(c, cinv[r]), x));
-              Sc[r * SROW + tid] = x;
-            }
-            if (nyqt) {
-              cd a, c, rr = {0.0, 0.0};
-              lapRowFused(p, cx.stab, ix, iyl, N, kwaveN, a, c, rr);
-              xN = csub(nq[R + r], cmul(cmul(c, nq[r]), xN));
-              Sc[r * SROW + N] = xN;
-            }
-          }
-        }
-      }
-    });
-    if (i > 0) {
-      constexpr bool inB = (fftSwaps<N>() % 2) != 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ix = bf * R + cx.grp + 4 * h;
-        if (ix < n) {
-          const cd* z = h == 0 ? (inB ? cx.b0 : cx.a0) : (inB ? cx.b1 : cx.a1);
-          double2* __restrict__ d2 = reinterpret_cast<double2*>(
-              p.out + (static_cast<long long>(p.bd.xs + ix) * p.ny + jy) * p.nz);
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int j = lane + m * TPR;
-            const cd v = z[fsw(j)];
-            d2[j] = make_double2(v.re, v.im);
-          }
-        }
-      }
-    }
-    // no barrier: the next merge writes buffer A at exactly the positions this thread read above
-    // (or the result sits in buffer B), and S[(i+1)&1] was last read by the merge of iteration i
-  }
-}
-
 constexpr int LAP_PFC = 4; // coupled kernels carry two or three rings: keep them in registers
 
 // K2a (coupled systems): downward and upward elimination in one pass -> interface equations
@@ -1132,41 +676,118 @@ __global__ void __launch_bounds__(128) k_lap_backward(const LapParams p) {
   }
 }
 
+
+// ---- block path (laplace_block.cuh) ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lapb_prepare(const LapParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.nx * p.ny) {
+    lapbPrepareThread(p, i);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_lapb_factor1(const LapParams p) {
+  if (!lapbDirty(p)) {
+    return;
+  }
+  const long long total = static_cast<long long>(p.ye - p.ys + 1) * p.bP * p.nmode;
+  bool bad = false;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    bad = lapbFactor1Thread(p, idx) || bad;
+  }
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_lapb_factor2(const LapParams p) {
+  if (!lapbDirty(p)) {
+    return;
+  }
+  const int total = (p.ye - p.ys + 1) * p.nmode;
+  bool bad = false;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    bad = lapbFactor2Thread(p, idx) || bad;
+  }
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+
+__global__ void __launch_bounds__(64) k_lapb_reduced(const LapParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (p.ye - p.ys + 1) * p.nmode) {
+    lapbReducedThread(p, idx);
+  }
+}
+
+// rows kernels: CTA = (NBLK consecutive blocks of one y row); the phases of laplace_block.cuh / fft_reg.cuh
+// with their barriers.  A row is owned by T lanes of one warp, so the transform phases only need __syncwarp.
+template <int N, int MODE>
+__global__ void __launch_bounds__(256, 2) k_lapb_rows(const LapParams p) {
+  using Sh = LapbShape<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* S = reinterpret_cast<cd*>(smem_raw);
+  double* ktab = reinterpret_cast<double*>(S + Sh::ROWS * Sh::SROW);
+  const int tid = threadIdx.x, t = tid % Sh::T;
+  const LapbCta c = lapbCta<N>(p, blockIdx.x);
+  cd* row = S + (tid / Sh::T) * Sh::SROW;
+  cd v[Sh::B];
+  lapbLoadRow<N, MODE>(p, c, tid, v);
+  if (MODE == LAPB_SOLVE) {
+    lapbStageTable<N>(p, c, tid, ktab);
+  }
+  regfftStage1<N, false>(v, p.tw, t);
+  regfftXchgWrite<N>(v, row, t);
+  __syncwarp();
+  regfftStage2<N, false>(v, row, t);
+  __syncwarp();
+  regfftSplitWriteZ<N>(v, row, t);
+  __syncwarp();
+  {
+    cd pc[Sh::B / 2 + 1];
+    regfftSplitReadPartners<N>(pc, row, t);
+    __syncwarp();
+    regfftSplitWriteX<N>(v, pc, row, p.tw, t);
+  }
+  __syncthreads();
+  const int blk = tid / N, kz = tid % N;
+  if (kz < p.nmode) {
+    if (MODE == LAPB_DOTS) {
+      lapbDotsThread<N>(p, c, blk, kz, S);
+    } else {
+      lapbSolveThread<N>(p, c, blk, kz, S, ktab);
+    }
+  }
+  if (p.nmode > N && kz == 0) { // the Nyquist system of this block
+    if (MODE == LAPB_DOTS) {
+      lapbDotsThread<N>(p, c, blk, N, S);
+    } else {
+      lapbSolveThread<N>(p, c, blk, N, S, ktab);
+    }
+  }
+  if (MODE == LAPB_DOTS) {
+    return;
+  }
+  __syncthreads();
+  regfftMergeRead<N>(v, row, p.nmode, p.zero_dc != 0, p.tw, t);
+  __syncwarp();
+  regfftStage1<N, true>(v, p.tw, t);
+  regfftXchgWrite<N>(v, row, t);
+  __syncwarp();
+  regfftStage2<N, true>(v, row, t);
+  lapbStoreRow<N>(p, c, tid, v);
+}
+
 } // namespace b200
 
 using namespace b200;
-
-static void lapBndryWidths(const bout_b200_grid* g, const bout_b200_laplace* L, int* inb, int* outb) {
-  *inb = *outb = g->xstart;
-  if ((L->global_flags & INV_BOTH_BNDRY_ONE) || g->xstart < 2) {
-    *inb = *outb = 1;
-  }
-  if (L->inner_boundary_flags & INV_BNDRY_ONE) {
-    *inb = 1;
-  }
-  if (L->outer_boundary_flags & INV_BNDRY_ONE) {
-    *outb = 1;
-  }
-}
-
-static bool lapCoupled(const bout_b200_laplace* L) {
-  return L->periodic_x || !L->first_x || !L->last_x;
-}
-
-static size_t roundUp(size_t n, size_t a) { return (n + a - 1) / a * a; }
 
 extern "C" size_t bout_b200_laplace_cyclic_workspace(const bout_b200_grid* g, const bout_b200_laplace* L) {
   if (g == nullptr || L == nullptr) {
     return 0;
   }
-  const size_t nspec = static_cast<size_t>(g->nx) * g->ny * (L->maxmode + 1) * sizeof(cd);
-  const size_t table = roundUp(static_cast<size_t>(g->nx) * g->ny * LAP_NK * sizeof(double), 256);
-  const size_t nbnd = static_cast<size_t>(4) * g->xstart * g->ny * (L->maxmode + 1) * sizeof(cd); // boundary rows' a, c
-  size_t n = 256 + table + 4 * nspec + nbnd; // spec, c', d', inv
-  if (lapCoupled(L)) {
-    n += nspec + static_cast<size_t>(LAP_IFACE) * g->ny * (L->maxmode + 1) * sizeof(cd);
-  }
-  return n;
+  return lapLayout(g, L).total;
 }
 
 extern "C" size_t bout_b200_laplace_cyclic_iface_doubles(const bout_b200_grid* g, const bout_b200_laplace* L) {
@@ -1208,63 +829,7 @@ int lapSetup(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspac
     B200_REQUIRE(L->g_22 != nullptr, BOUT_B200_ERR_ARG, "laplace: GRADPAR boundary needs g_22");
   }
   LapParams& p = plan->p;
-  p = LapParams{};
-  p.m.dx = L->dx;
-  p.m.g11 = L->g11;
-  p.m.g33 = L->g33;
-  p.m.g13 = L->g13;
-  p.m.G1 = L->G1;
-  p.m.G3 = L->G3;
-  p.m.g_11 = L->g_11;
-  p.m.g_22 = L->g_22;
-  p.m.A = L->A;
-  p.m.C1 = L->C1;
-  p.m.C2 = L->C2;
-  p.m.D = L->D;
-  p.m.zlength = L->zlength;
-  p.m.nx = g->nx;
-  p.m.ny = g->ny;
-  p.m.all_terms = L->all_terms;
-  p.m.nonuniform = L->nonuniform;
-  p.bd.inner_flags = L->inner_boundary_flags;
-  p.bd.outer_flags = L->outer_boundary_flags;
-  p.bd.global_flags = L->global_flags;
-  lapBndryWidths(g, L, &p.bd.inbndry, &p.bd.outbndry);
-  p.bd.periodic_x = L->periodic_x;
-  p.bd.first_x = L->first_x;
-  p.bd.last_x = L->last_x;
-  // cyclic_laplace.cxx:88-101
-  p.bd.xs = (L->first_x && !L->periodic_x) ? 0 : g->xstart;
-  p.bd.xe = (L->last_x && !L->periodic_x) ? g->nx - 1 : g->xend;
-  p.bd.nx_local = g->nx;
-  p.nx = g->nx;
-  p.ny = g->ny;
-  p.nz = g->nz;
-  // cyclic_laplace.cxx:216-232 (include_yguards only matters where a y boundary exists)
-  p.ys = L->include_yguards_lower ? 0 : g->ystart;
-  p.ye = L->include_yguards_upper ? g->ny - 1 : g->yend;
-  p.nmode = L->maxmode + 1;
-  p.zero_dc = (L->global_flags & INV_ZERO_DC) ? 1 : 0;
-  p.in_set = (L->first_x && (L->inner_boundary_flags & INV_SET)) ? 1 : 0;
-  p.out_set = (L->last_x && (L->outer_boundary_flags & INV_SET)) ? 1 : 0;
-  p.nxpe = 1;
-  p.pe_xind = 0;
-
-  const size_t nspec = static_cast<size_t>(g->nx) * g->ny * p.nmode;
-  const size_t table = roundUp(static_cast<size_t>(g->nx) * g->ny * LAP_NK * sizeof(double), 256);
-  unsigned char* ws = static_cast<unsigned char*>(workspace);
-  p.status = reinterpret_cast<int*>(ws);
-  p.ydep = p.status + 1;
-  p.table = reinterpret_cast<double*>(ws + 256);
-  p.spec = reinterpret_cast<cd*>(ws + 256 + table);
-  p.cprime = p.spec + nspec;
-  p.dprime = p.cprime + nspec;
-  p.inv = p.dprime + nspec;
-  p.bnd = p.inv + nspec;
-  if (lapCoupled(L)) {
-    p.sprime = p.bnd + static_cast<size_t>(4) * g->xstart * g->ny * p.nmode;
-    p.iface = p.sprime + nspec;
-  }
+  lapFillParams(g, L, workspace, &p);
   int st = 0;
   p.tw = twiddleTable(g->nz, s, &st);
   if (st != 0) {
@@ -1337,45 +902,10 @@ int launchFft(const LapPlan* plan, cudaStream_t s) {
   return 0;
 }
 
-// Fused sweeps (k_lap_fused_forward / _backward): one CTA per solved y row, so the path needs enough
-// y rows to occupy the SMs; below the threshold the row-parallel 3-kernel path is faster.
-// BOUT_B200_LAP_FUSED=0 / 1 forces the choice (tests run both).
-template <int N>
-int lapFusedFits(int n) {
-  return LapFusedShape<N>::smemBytes(n) <= 220 * 1024;
-}
-bool lapFusedEligible(const LapPlan* plan, const bout_b200_laplace* L) {
-  const LapParams& p = plan->p;
-  const int N = p.nz / 2, n = p.bd.xe - p.bd.xs + 1, nys = p.ye - p.ys + 1;
-  if (lapCoupled(L) || !p.pow2 || !(N == 64 || N == 128 || N == 256 || N == 512)
-      || n <= p.bd.inbndry + p.bd.outbndry) {
-    return false;
-  }
-  const bool fits = N == 64 ? lapFusedFits<64>(n) : N == 128 ? lapFusedFits<128>(n)
-                  : N == 256 ? lapFusedFits<256>(n) : lapFusedFits<512>(n);
-  if (!fits) {
-    return false;
-  }
-  // Measured on B200 at 516x132x512 (tools/time_laplace.py): 3-kernel path 592 us; fused sweeps 650 us
-  // on a held factorisation, 785 us one-shot.  One CTA of 8 warps per SM leaves the butterflies and
-  // the recurrence latency-bound (issue slots 25 % busy, FP64 pipe 17 %), which costs more than the
-  // 40 % of HBM traffic the sweeps save -- so the path is opt-in (BOUT_B200_LAP_FUSED=1) until it
-  // runs >= 16 warps per SM.
-  (void)nys;
-  const char* env = getenv("BOUT_B200_LAP_FUSED");
-  return env != nullptr && env[0] == '1';
-}
-bool lapUseFused(const LapPlan* plan, const bout_b200_laplace* L) {
-  const LapParams& p = plan->p;
-  if (!aligned16(p.rhs) || (p.x0 != nullptr && !aligned16(p.x0)) || !aligned16(p.out)) {
-    return false;
-  }
-  return lapFusedEligible(plan, L);
-}
-
-// Factorisations held in caller workspaces (bout_b200_laplace_cyclic_factor): workspace -> the grid
-// and settings it was computed for.  Pointer members are compared by value: the caller vouches for
-// the contents of the metric / coefficient arrays being unchanged (it re-factors when it changes them).
+// Factorisations held in caller workspaces (block path): workspace -> the grid and settings its tables were
+// computed for.  Pointer members are compared by value; the CONTENTS of the arrays they point to are compared
+// on the device by k_lapb_prepare in every solve, so a caller that rewrites a coefficient array in place gets
+// a new factorisation without having to say so.
 struct FactorKey {
   bout_b200_grid g;
   bout_b200_laplace L;
@@ -1383,6 +913,7 @@ struct FactorKey {
 };
 std::mutex g_factor_mutex;
 std::unordered_map<const void*, FactorKey> g_factors;
+std::atomic<unsigned> g_lapb_gen{0};
 
 bool factorMatches(const void* ws, const bout_b200_grid* g, const bout_b200_laplace* L, size_t bytes) {
   std::lock_guard<std::mutex> lock(g_factor_mutex);
@@ -1390,67 +921,107 @@ bool factorMatches(const void* ws, const bout_b200_grid* g, const bout_b200_lapl
   if (it == g_factors.end()) {
     return false;
   }
-  FactorKey k{};
-  k.g = *g;
-  k.L = *L;
-  k.bytes = bytes;
-  return it->second.bytes == bytes && memcmp(&it->second.g, &k.g, sizeof(k.g)) == 0
-         && it->second.L.dx == L->dx && it->second.L.g11 == L->g11 && it->second.L.g33 == L->g33
-         && it->second.L.g13 == L->g13 && it->second.L.G1 == L->G1 && it->second.L.G3 == L->G3
-         && it->second.L.g_11 == L->g_11 && it->second.L.g_22 == L->g_22 && it->second.L.A == L->A
-         && it->second.L.C1 == L->C1 && it->second.L.C2 == L->C2 && it->second.L.D == L->D
-         && it->second.L.zlength == L->zlength && it->second.L.all_terms == L->all_terms
-         && it->second.L.nonuniform == L->nonuniform && it->second.L.global_flags == L->global_flags
-         && it->second.L.inner_boundary_flags == L->inner_boundary_flags
-         && it->second.L.outer_boundary_flags == L->outer_boundary_flags && it->second.L.maxmode == L->maxmode
-         && it->second.L.periodic_x == L->periodic_x && it->second.L.first_x == L->first_x
-         && it->second.L.last_x == L->last_x
-         && it->second.L.include_yguards_lower == L->include_yguards_lower
-         && it->second.L.include_yguards_upper == L->include_yguards_upper;
+  const bout_b200_laplace& K = it->second.L;
+  return it->second.bytes == bytes && memcmp(&it->second.g, g, sizeof(*g)) == 0 && K.dx == L->dx && K.g11 == L->g11
+         && K.g33 == L->g33 && K.g13 == L->g13 && K.G1 == L->G1 && K.G3 == L->G3 && K.g_11 == L->g_11
+         && K.g_22 == L->g_22 && K.A == L->A && K.C1 == L->C1 && K.C2 == L->C2 && K.D == L->D
+         && K.zlength == L->zlength && K.all_terms == L->all_terms && K.nonuniform == L->nonuniform
+         && K.global_flags == L->global_flags && K.inner_boundary_flags == L->inner_boundary_flags
+         && K.outer_boundary_flags == L->outer_boundary_flags && K.maxmode == L->maxmode
+         && K.periodic_x == L->periodic_x && K.first_x == L->first_x && K.last_x == L->last_x
+         && K.include_yguards_lower == L->include_yguards_lower
+         && K.include_yguards_upper == L->include_yguards_upper;
+}
+void factorForget(const void* ws) {
+  std::lock_guard<std::mutex> lock(g_factor_mutex);
+  g_factors.erase(ws);
 }
 
-// status reset + coefficient table + inv (the matrix-only half of the solve)
-int lapFactor(LapPlan* plan, cudaStream_t s) {
-  LapParams& p = plan->p;
-  B200_CUDA_OK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
-  const int n2 = p.nx * p.ny;
-  k_lap_table<<<(n2 + 255) / 256, 256, 0, s>>>(p);
-  B200_LAUNCH_OK();
-  if (plan->tab_smem > 48 * 1024) {
-    B200_CUDA_OK(cudaFuncSetAttribute(k_lap_factor, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(plan->tab_smem)));
-  }
-  k_lap_factor<<<static_cast<unsigned>((plan->nsys + 127) / 128), 128, plan->tab_smem, s>>>(p, plan->tab_smem != 0);
-  B200_LAUNCH_OK();
-  return 0;
-}
-
-template <int N>
-int launchFusedT(const LapPlan* plan, cudaStream_t s) {
+// Is this solve served by the block path?  Isolated systems, nz in {128, 256, 512}, 16-byte aligned rows.
+// BOUT_B200_LAP_BLOCK=0 keeps the three-kernel paths (tests compare the two).
+bool lapUseBlock(const LapPlan* plan, const bout_b200_laplace* L, bool with_fields) {
   const LapParams& p = plan->p;
-  const int n = p.bd.xe - p.bd.xs + 1, nys = p.ye - p.ys + 1;
-  const size_t smem = LapFusedShape<N>::smemBytes(n);
-  static size_t attr = 0; // largest size the two kernels have been configured for
-  if (smem > 48 * 1024 && smem > attr) {
-    B200_CUDA_OK(cudaFuncSetAttribute(k_lap_fused_forward<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-    B200_CUDA_OK(cudaFuncSetAttribute(k_lap_fused_backward<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-    attr = smem;
+  if (lapCoupled(L) || !lapbShapeOk(p.nz)) {
+    return false;
   }
-  k_lap_fused_forward<N><<<nys, N, smem, s>>>(p);
-  B200_LAUNCH_OK();
-  k_lap_fused_backward<N><<<nys, N, smem, s>>>(p);
+  if (with_fields && (!aligned16(p.rhs) || (p.x0 != nullptr && !aligned16(p.x0)) || !aligned16(p.out))) {
+    return false;
+  }
+  const char* env = getenv("BOUT_B200_LAP_BLOCK");
+  return env == nullptr || env[0] != '0';
+}
+
+template <int N, int MODE>
+int launchRows(const LapParams& p, cudaStream_t s) {
+  using Sh = LapbShape<N>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_lapb_rows<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(Sh::smemBytes)));
+    configured = true;
+  }
+  const int n = p.bd.xe - p.bd.xs + 1, nys = p.ye - p.ys + 1;
+  const unsigned blocks = static_cast<unsigned>(nys) * ((n + Sh::ROWS - 1) / Sh::ROWS);
+  k_lapb_rows<N, MODE><<<blocks, Sh::NT, Sh::smemBytes, s>>>(p);
   B200_LAUNCH_OK();
   return 0;
 }
-int launchFused(const LapPlan* plan, cudaStream_t s) {
-  switch (plan->p.nz / 2) {
-  case 64: return launchFusedT<64>(plan, s);
-  case 128: return launchFusedT<128>(plan, s);
-  case 256: return launchFusedT<256>(plan, s);
-  default: return launchFusedT<512>(plan, s);
+template <int MODE>
+int launchRowsN(const LapParams& p, cudaStream_t s) {
+  switch (p.nz) {
+  case 128: return launchRows<64, MODE>(p, s);
+  case 256: return launchRows<128, MODE>(p, s);
+  default: return launchRows<256, MODE>(p, s);
   }
+}
+
+// prepare + (conditional) factorisation; leaves p.gen / p.force set for the solve kernels
+int lapBlockFactor(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspace, size_t workspace_bytes,
+                   LapPlan* plan, bool force, cudaStream_t s) {
+  LapParams& p = plan->p;
+  unsigned gen = 0;
+  while (gen == 0) {
+    gen = ++g_lapb_gen;
+  }
+  p.gen = gen;
+  p.force = (force || !factorMatches(workspace, g, L, workspace_bytes)) ? 1 : 0;
+  {
+    FactorKey k{};
+    k.g = *g;
+    k.L = *L;
+    k.bytes = workspace_bytes;
+    std::lock_guard<std::mutex> lock(g_factor_mutex);
+    g_factors[workspace] = k;
+  }
+  const int n2 = p.nx * p.ny;
+  k_lapb_prepare<<<(n2 + 255) / 256, 256, 0, s>>>(p);
+  B200_LAUNCH_OK();
+  const long long t1 = static_cast<long long>(p.ye - p.ys + 1) * p.bP * p.nmode;
+  const unsigned b1 = static_cast<unsigned>(t1 + 127) / 128 < 148u * 8 ? static_cast<unsigned>((t1 + 127) / 128) : 148u * 8;
+  k_lapb_factor1<<<b1, 128, 0, s>>>(p);
+  B200_LAUNCH_OK();
+  if (p.bP > 1) {
+    const int t2 = (p.ye - p.ys + 1) * p.nmode;
+    const unsigned b2 = static_cast<unsigned>((t2 + 127) / 128) < 148u * 4 ? static_cast<unsigned>((t2 + 127) / 128) : 148u * 4;
+    k_lapb_factor2<<<b2, 128, 0, s>>>(p);
+    B200_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int lapBlockSolve(const LapPlan* plan, cudaStream_t s) {
+  const LapParams& p = plan->p;
+  int rc = 0;
+  if (p.bP > 1) {
+    rc = launchRowsN<LAPB_DOTS>(p, s);
+    if (rc != 0) {
+      return rc;
+    }
+    const int t = (p.ye - p.ys + 1) * p.nmode;
+    k_lapb_reduced<<<(t + 63) / 64, 64, 0, s>>>(p);
+    B200_LAUNCH_OK();
+  }
+  return launchRowsN<LAPB_SOLVE>(p, s);
 }
 
 // status reset + coefficient table (+ forward FFT of the 3-kernel paths)
@@ -1491,22 +1062,17 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
   p.rhs = rhs;
   p.x0 = x0;
   p.out = out;
-  if (lapUseFused(&plan, L)) {
+  if (lapUseBlock(&plan, L, true)) {
     B200_REQUIRE(rhs != nullptr, BOUT_B200_ERR_ARG, "laplace: null rhs");
     B200_REQUIRE(!((L->inner_boundary_flags | L->outer_boundary_flags) & INV_SET) || x0 != nullptr,
                  BOUT_B200_ERR_ARG, "laplace: INVERT_SET needs x0");
-    if (!factorMatches(workspace, g, L, workspace_bytes)) { // one-shot: factor as part of this solve
-      rc = lapFactor(&plan, s);
-      if (rc != 0) {
-        return rc;
-      }
+    rc = lapBlockFactor(g, L, workspace, workspace_bytes, &plan, false, s);
+    if (rc != 0) {
+      return rc;
     }
-    return launchFused(&plan, s);
+    return lapBlockSolve(&plan, s);
   }
-  {
-    std::lock_guard<std::mutex> lock(g_factor_mutex);
-    g_factors.erase(workspace); // the 3-kernel paths overwrite the table and status
-  }
+  factorForget(workspace); // the three-kernel paths overwrite the regions the block path keeps its tables in
   rc = lapForward(L, rhs, x0, &plan, s);
   if (rc != 0) {
     return rc;
@@ -1538,6 +1104,8 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
   return launchFft<false>(&plan, s);
 }
 
+// Builds the matrix-only tables of the block path now (they are otherwise built by the first solve and
+// rebuilt by any solve that finds an input array changed).  A no-op for configurations on the other paths.
 extern "C" int bout_b200_laplace_cyclic_factor(const bout_b200_grid* g, const bout_b200_laplace* L,
                                                void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t s = asStream(stream);
@@ -1546,29 +1114,15 @@ extern "C" int bout_b200_laplace_cyclic_factor(const bout_b200_grid* g, const bo
   if (rc != 0) {
     return rc;
   }
-  {
-    std::lock_guard<std::mutex> lock(g_factor_mutex);
-    g_factors.erase(workspace);
+  if (!lapUseBlock(&plan, L, false)) {
+    factorForget(workspace);
+    return 0;
   }
-  if (!lapFusedEligible(&plan, L)) {
-    return 0; // this configuration regenerates its coefficients inside every solve
-  }
-  rc = lapFactor(&plan, s);
-  if (rc != 0) {
-    return rc;
-  }
-  FactorKey k{};
-  k.g = *g;
-  k.L = *L;
-  k.bytes = workspace_bytes;
-  std::lock_guard<std::mutex> lock(g_factor_mutex);
-  g_factors[workspace] = k;
-  return 0;
+  return lapBlockFactor(g, L, workspace, workspace_bytes, &plan, true, s);
 }
 
 extern "C" int bout_b200_laplace_cyclic_invalidate(void* workspace) {
-  std::lock_guard<std::mutex> lock(g_factor_mutex);
-  g_factors.erase(workspace);
+  factorForget(workspace);
   return 0;
 }
 

@@ -180,50 +180,48 @@ def test_laplace_x_decomposed_matches_single_rank(capi, orc, port, nxpe, flags):
     assert rel_err(got, want, region) < 1e-10
 
 
-# nz = 1024 is not in this list: its sweep buffers exceed one SM's shared memory (LapFusedShape<512>), so the
-# library keeps the 3-kernel path for it (covered by the parity tests above)
-@pytest.mark.parametrize("grid", [(21, 5, 128, 2, 1), (14, 4, 256, 2, 1), (19, 3, 512, 2, 1), (37, 3, 256, 2, 1)])
+# nz = 128, 256, 512 with isolated systems take the block-partitioned path (csrc/laplace_block.cuh); row counts
+# cover a single block, a trailing separator-only block (n = 16 k + 1), short last blocks and several CTAs per y
+BLOCK_GRIDS = [(12, 3, 128, 2, 1), (17, 4, 128, 2, 1), (40, 5, 128, 2, 1), (33, 3, 256, 2, 1), (70, 4, 256, 2, 1),
+               (20, 3, 512, 2, 1), (49, 4, 512, 2, 1), (36, 4, 512, 1, 1)]
+
+
+@pytest.mark.parametrize("grid", BLOCK_GRIDS)
 @pytest.mark.parametrize("flags", [(0, 0, 0), (0, 3, 0), (4, 0, 0), (0, 16, 16), (0, 32 | 3, 32), (1, 4, 64)])
 @pytest.mark.parametrize("filt", [False, True])
-def test_laplace_fused_sweeps_match_three_kernel_path(capi, orc, port, grid, flags, filt, monkeypatch):
-    """The fused FFT+Thomas sweep kernels (one CTA per y row, spectrum kept on chip, pivots factored
-    once; opt-in through BOUT_B200_LAP_FUSED=1).  Same arithmetic as the row-parallel 3-kernel path
-    => equal to it to round-off (1e-13), and within 1e-10 of the oracle.  Row counts that
-    are not a multiple of the 8-row batch, truncated spectra (laplace:filter), INVERT_ZERO_DC and
-    INVERT_SET rows are covered; one-shot solves and solves on a held factorisation must agree."""
+def test_laplace_block_path_matches_three_kernel_path(capi, orc, port, grid, flags, filt, monkeypatch):
+    """The block-partitioned path (rows kernels with the spectrum on chip + separator system; default for these
+    shapes) against the rfft -> Thomas / PCR -> irfft path (BOUT_B200_LAP_BLOCK=0) and against the oracle.
+    Truncated spectra (laplace:filter), INVERT_ZERO_DC and INVERT_SET rows are covered; the second solve on the
+    same workspace must not re-factor and must give the same bits."""
     g, og = capi.Grid(*grid), orc.Grid(*grid)
     m = make_metric(orc, g.shape2, g.nz)
     f, x0 = seeded_fields(g.shape3, 2)
     maxmode = g.nz // 3 if filt else None
     region = (slice(None), slice(g.ystart, g.yend + 1), slice(None))
     lap = gpu_laplace(capi, g, m, flags=flags, maxmode=maxmode)
-    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "1")
+    nblocks = -(-g.nx // (8 if g.nz == 128 else 16))
     n0 = capi.launch_count()
-    fused = lap.solve(dev(f), dev(x0)).cpu().numpy()
+    first = lap.solve(dev(f), dev(x0)).cpu().numpy()
     lap.status()
-    assert capi.launch_count() - n0 == 4      # one-shot: table + factor + forward sweep + backward sweep
-    lap.factor()
-    n0 = capi.launch_count()
-    held = lap.solve(dev(f), dev(x0)).cpu().numpy()
+    # prepare + factor (+ separator factor) + [dots + reduced] + solve
+    assert capi.launch_count() - n0 == (6 if nblocks > 1 else 3)
+    again = lap.solve(dev(f), dev(x0)).cpu().numpy()
     lap.status()
-    assert capi.launch_count() - n0 == 2      # forward sweep + backward sweep
-    assert np.array_equal(fused[region], held[region])
-    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "0")
-    n0 = capi.launch_count()
+    assert np.array_equal(first[region], again[region])
+    monkeypatch.setenv("BOUT_B200_LAP_BLOCK", "0")
     plain = lap.solve(dev(f), dev(x0)).cpu().numpy()
-    # table + (y-dependence check of the coefficients when more than one y row is solved) + rfft + Thomas + irfft
-    assert capi.launch_count() - n0 == 4 + int(g.yend > g.ystart)
-    assert rel_err(fused, plain, region) < 1e-12   # plain = cyclic reduction per system (few systems) or Thomas
+    lap.status()
+    assert rel_err(first, plain, region) < 1e-11
     want = port.laplace_cyclic(og, m, f, x0=x0, flags=flags, maxmode=maxmode)
-    assert rel_err(fused, want, region) < 1e-10
+    assert rel_err(first, want, region) < 1e-10
 
 
-def test_laplace_factor_follows_coefficient_changes(capi, orc, port, monkeypatch):
-    """A held factorisation is tied to (grid, settings, workspace); re-factoring after the contents of
-    a coefficient array changed gives the new operator's solution, and a different settings struct on
-    the same workspace falls back to a one-shot solve."""
-    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "1")
-    grid = (21, 5, 128, 2, 1)
+def test_laplace_block_path_follows_coefficient_changes(capi, orc, port):
+    """The matrix-only tables are kept in the workspace between solves; every solve compares the Field2D inputs
+    with the copy taken at factorisation time on the device, so a coefficient array rewritten IN PLACE (setCoefA
+    of the host layer), changed settings on the same workspace, or an explicit factor() all give the new operator."""
+    grid = (40, 5, 128, 2, 1)
     g, og = capi.Grid(*grid), orc.Grid(*grid)
     m = make_metric(orc, g.shape2, g.nz)
     f, x0 = seeded_fields(g.shape3, 2)
@@ -232,32 +230,62 @@ def test_laplace_factor_follows_coefficient_changes(capi, orc, port, monkeypatch
     lap = gpu_laplace(capi, g, m, A=A).factor()
     got = lap.solve(dev(f)).cpu().numpy()
     assert rel_err(got, port.laplace_cyclic(og, m, f, A=A), region) < 1e-10
-    lap.keep["A"].fill_(-0.7)                 # same array, new contents
-    lap.factor()
+    lap.keep["A"].fill_(-0.7)                 # same array, new contents, no factor() call
     got = lap.solve(dev(f)).cpu().numpy()
     A2 = np.full(g.shape2, -0.7)
     assert rel_err(got, port.laplace_cyclic(og, m, f, A=A2), region) < 1e-10
     lap.c.inner_boundary_flags = 3            # settings no longer match the held factorisation
-    n0 = capi.launch_count()
     got = lap.solve(dev(f)).cpu().numpy()
-    assert capi.launch_count() - n0 == 4
+    assert rel_err(got, port.laplace_cyclic(og, m, f, A=A2, flags=(0, 3, 0)), region) < 1e-10
+    lap.keep["A"][7, 2] = float("nan")        # a NaN input must not read as "unchanged" for ever after
+    lap.solve(dev(f))
+    lap.keep["A"].fill_(-0.7)
+    got = lap.solve(dev(f)).cpu().numpy()
     assert rel_err(got, port.laplace_cyclic(og, m, f, A=A2, flags=(0, 3, 0)), region) < 1e-10
 
 
-def test_laplace_fused_sweeps_full_size_residual(capi, orc, monkeypatch):
-    """BASELINE-size grid (516x132x512, the HW3D workload) through the fused sweeps: Delp2 of the
-    solution returns the right-hand side."""
-    monkeypatch.setenv("BOUT_B200_LAP_FUSED", "1")
-    g = capi.Grid(516, 132, 512, 2, 2)
+def test_laplace_block_path_y_independent_tables(capi, orc, port):
+    """No coefficient array varies along y: one [x][kz] table serves every y (the HW3D configuration)."""
+    grid = (70, 6, 256, 2, 2)
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz, trivial=True)
+    f, x0 = seeded_fields(g.shape3, 2)
+    region = (slice(None), slice(g.ystart, g.yend + 1), slice(None))
+    A = np.full(g.shape2, -0.3)
+    for flags in ((0, 0, 0), (0, 3, 0), (0, 16, 16)):
+        want = port.laplace_cyclic(og, m, f, x0=x0, flags=flags, A=A, nonuniform=False)
+        got = gpu_laplace(capi, g, m, flags=flags, A=A, nonuniform=False).solve(dev(f), dev(x0)).cpu().numpy()
+        assert rel_err(got, want, region) < 1e-10
+
+
+def test_zero_pivot_is_reported_by_the_block_path(capi, orc):
+    g = capi.Grid(20, 3, 128, 2, 1)
+    m = make_metric(orc, g.shape2, g.nz, trivial=True)
+    m.g11[:] = 0.0
+    m.g33[:] = 0.0
+    lap = gpu_laplace(capi, g, m, nonuniform=False, all_terms=False, flags=(0, 1, 1))
+    lap.solve(torch.ones(g.shape3, dtype=torch.float64, device="cuda"))
+    with pytest.raises(capi.BoutB200Error) as e:
+        lap.status()
+    assert e.value.status == -4
+
+
+@pytest.mark.parametrize("dims", [(516, 132, 512, 2, 2), (516, 68, 256, 2, 2)])
+def test_laplace_block_path_full_size(capi, orc, dims, monkeypatch):
+    """BASELINE-size grids (the HW3D and elm-pb workloads): Delp2 of the solution returns the right-hand side, and
+    the block path agrees with the three-kernel path to round-off."""
+    g = capi.Grid(*dims)
     m = make_metric(orc, g.shape2, g.nz)
-    lap = gpu_laplace(capi, g, m).factor()
+    lap = gpu_laplace(capi, g, m)
     rhs = torch.rand(g.shape3, dtype=torch.float64, device="cuda") - 0.5
     rhs = capi.zlowpass(g, rhs, g.nz // 2 - 1, True)
-    n0 = capi.launch_count()
     x = lap.solve(rhs)
-    assert capi.launch_count() - n0 == 2
     lap.status()
     back = lap.delp2(x)
     sl = (slice(g.xstart, g.xend + 1), slice(g.ystart, g.yend + 1), slice(None))
     err = (back[sl] - rhs[sl]).abs().max() / rhs[sl].abs().max()
     assert err.item() < 1e-9
+    monkeypatch.setenv("BOUT_B200_LAP_BLOCK", "0")
+    y = lap.solve(rhs)
+    region = (slice(None), slice(g.ystart, g.yend + 1), slice(None))
+    assert ((x[region] - y[region]).abs().max() / y[region].abs().max()).item() < 1e-11
