@@ -72,6 +72,7 @@ inline int checkGrid(const bout_b200_grid* g) {
 // Functions shared by the kernels and the host-side emulation of tests/emul/ (which steps simulated threads
 // through the same code): callable from both sides, read-only loads through the non-coherent path on the device.
 #define B200_HD __host__ __device__ __forceinline__
+#define B200_HD_COLD __host__ __device__ __noinline__ // rare paths kept out of the unrolled hot loops
 #ifdef __CUDA_ARCH__
 #define B200_LDG(p) __ldg(p)
 #else

@@ -49,8 +49,8 @@ constexpr int LAP_NK = 6;     // table entries per (x,y): k0..k4 of tridagCoef5 
 constexpr int LAP_IFACE = 6;  // interface coefficients per system: sL, cL, dL, aU, cU, dU
 constexpr int LAP_MAXPE = 8;  // ranks in X
 constexpr int LAP_NFP = 12;   // Field2D inputs of a solve (fingerprinted by the block path)
-constexpr int LAPB_NRED = 9;  // reduced-system arrays: RA, RBU, RBD, RC (assembly), RINV, RAI, RCP, RAS, RCS
-enum { LAPB_RA = 0, LAPB_RBU, LAPB_RBD, LAPB_RC, LAPB_RINV, LAPB_RAI, LAPB_RCP, LAPB_RAS, LAPB_RCS };
+constexpr int LAPB_NRED = 10; // per-block / per-separator arrays: RA, RBU, RBD, RC (assembly), the factored system, MID
+enum { LAPB_RA = 0, LAPB_RBU, LAPB_RBD, LAPB_RC, LAPB_RINV, LAPB_RAI, LAPB_RCP, LAPB_ASI, LAPB_CSI, LAPB_MID };
 enum { LAPW_STATUS = 0, LAPW_YDEP = 1, LAPW_YDEP_GEN = 2, LAPW_DIRTY_GEN = 3 }; // 32-bit words at the workspace start
 
 struct LapParams {
@@ -80,13 +80,19 @@ struct LapParams {
   int nxpe, pe_xind;
   // block path
   double* __restrict__ fpcopy; // [LAP_NFP][nx*ny] inputs as of the last factorisation
-  cd* __restrict__ bif;        // [nys][P][3][nmode]  yF, yL, r_s
+  cd* __restrict__ bif;        // [nys][P][2][nmode]  F0 (scaled separator right-hand side), F1 = yL
   cd* __restrict__ bxs;        // [nys][P][nmode]     separator values
-  cd* __restrict__ bds;        // [nys][P][nmode]     d' of the reduced forward sweep
   cd* __restrict__ bred;       // [LAPB_NRED][nys][P][nmode]
+  double* __restrict__ bnq;    // [nys][n]      Nyquist mode kz = nz/2: Re of the rhs spectrum in, of the solution out
+  cd* __restrict__ bnqd;       // [nys][n]      its sweep values
+  cd* __restrict__ bnqt;       // [nys][n + 1][3] its pivots and multipliers (row n: the meeting-point factor)
+  double kscale;               // 2 pi / zlength: kwave = kz * kscale (common_transform.cxx:73)
   unsigned gen;                // generation of this solve (ydep / dirty words hold the generation that set them)
   int force;                   // settings changed on the host side: factor regardless of the comparison
-  int bP, bMB;                 // blocks per system, rows per block
+  int bP, bMB, bNT;            // blocks per system, rows per block, threads per CTA of the rows kernels
+  int bPD;                     // rows kernels: CTA b prefetches the rows of CTA b + bPD into L2 (0 = off)
+  int dbg;                     // timing ablations (BOUT_B200_LAPB_DBG; results are wrong when set): 1 = no per-mode
+                               // phase, 2 = no inverse transform, 4 = no forward transform, 8 = no row loads
 };
 
 B200_HD cd crecip(cd z) {
@@ -150,31 +156,54 @@ B200_HD void lapTableEntry(const LapParams& p, int i) {
 }
 
 // ---- geometry of the block path -----------------------------------------------------------------------------
-template <int N>
+// A CTA of NT threads transforms ROWS = NT / T rows at once and then turns into one thread per kz mode.
+//   NT >= N: NBLK = NT / N blocks per CTA, thread tid -> (block tid / N, mode tid % N), one chain per thread;
+//   NT <  N: one block per CTA, KPT = N / NT modes per thread (independent chains, interleaved).
+// Rows per block MB = ROWS / NBLK.  The Nyquist mode kz = N of a block is one more chain of the block's thread 0.
+template <int N, int NT>
 struct LapbShape {
   using F = RegFft<N>;
-  static constexpr int NT = 256;          // threads per CTA
   static constexpr int T = F::T, B = F::B, SROW = F::SROW;
-  static constexpr int ROWS = NT / T;     // rows per CTA (16, 32, 32)
-  static constexpr int NBLK = NT / N;     // blocks per CTA (1, 2, 4): thread tid -> block tid / N, mode tid % N
-  static constexpr int MB = ROWS / NBLK;  // rows per block (16, 16, 8)
-  static_assert(MB == B, "rows per block = points per thread");
-  static constexpr size_t smemBytes = static_cast<size_t>(ROWS) * SROW * sizeof(cd) + ROWS * LAP_NK * sizeof(double);
+  static constexpr int ROWS = NT / T;
+  static constexpr int NBLK = NT >= N ? NT / N : 1;
+  static constexpr int KPT = NT >= N ? 1 : N / NT;
+  static constexpr int MB = ROWS / NBLK;
+  static constexpr int NRC = 4; // staged per-row constants: k0 - k3, k0 + k3, k2 (+ padding to 32 bytes)
+  static constexpr size_t smemBytes = static_cast<size_t>(ROWS) * SROW * sizeof(cd) + ROWS * NRC * sizeof(double);
 };
-__host__ __device__ inline int lapbRowsPerBlock(int nz) { return nz == 128 ? 8 : 16; }
+// rows per block for a row length and CTA size (the two are tied by the shapes above)
+__host__ __device__ inline int lapbRowsPerBlock(int nz, int nt) { return nz == 512 ? nt / 16 : (nz == 256 ? 16 : 8); }
+// The rows of a block (local indices li0 .. cnt-1 after its separator) split into a top half swept downward and a
+// bottom half swept upward.  Boundary rows of tridagMatrix (the first inbndry / last outbndry rows of the whole
+// system) have their own coefficient logic: [ra, rb) is the run of regular rows, leading boundary rows always fall
+// into the top half and trailing ones into the bottom half, so the unrolled sweeps only ever see regular rows.
+struct LapbSplit {
+  int ra, rb, mid; // regular rows [ra, rb); top half [li0, mid), bottom half [mid, cnt)
+};
+B200_HD LapbSplit lapbSplit(const LapBndry& bd, int n, int r0, int li0, int cnt) {
+  LapbSplit sp;
+  const int inb = bd.first_x ? bd.inbndry : 0, outb = bd.last_x ? bd.outbndry : 0;
+  sp.ra = max(li0, min(cnt, inb - r0));
+  sp.rb = min(cnt, max(sp.ra, n - outb - r0));
+  sp.mid = sp.ra + (sp.rb - sp.ra + 1) / 2;
+  return sp;
+}
 
 struct LapbCta {
   int iyl, jy; // y row of this CTA (local to the solved range / mesh index)
   int row0;    // first system row of this CTA
   int ysel;    // y index into the matrix-only tables
 };
-template <int N>
+template <int N, int NT>
 B200_HD LapbCta lapbCta(const LapParams& p, int bid) {
-  const int nys = p.ye - p.ys + 1;
+  // x tile fastest: CTAs in flight together then read DIFFERENT slices of the shared matrix tables (with the y row
+  // fastest, ~128 CTAs ask the same few L2 lines for their pivots at the same moment)
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const int ntile = (n + LapbShape<N, NT>::ROWS - 1) / LapbShape<N, NT>::ROWS;
   LapbCta c;
-  c.iyl = bid % nys;
+  c.iyl = bid / ntile;
   c.jy = p.ys + c.iyl;
-  c.row0 = (bid / nys) * LapbShape<N>::ROWS;
+  c.row0 = (bid % ntile) * LapbShape<N, NT>::ROWS;
   c.ysel = (static_cast<unsigned>(p.status[LAPW_YDEP_GEN]) == p.gen) ? c.iyl : 0;
   return c;
 }
@@ -186,7 +215,7 @@ B200_HD long long lapbRedIndex(const LapParams& p, int which, int ysel, int jb, 
   const int nys = p.ye - p.ys + 1;
   return ((static_cast<long long>(which) * nys + ysel) * p.bP + jb) * p.nmode + kz;
 }
-B200_HD long long lapbSysIndex(const LapParams& p, int iyl, int jb, int kz) { // bxs, bds
+B200_HD long long lapbSysIndex(const LapParams& p, int iyl, int jb, int kz) { // bxs
   return (static_cast<long long>(iyl) * p.bP + jb) * p.nmode + kz;
 }
 B200_HD long long lapbBndIndex(const LapParams& p, int sr, int ysel, int kz) {
@@ -203,25 +232,31 @@ B200_HD long long bitsOf(double v) {
 #endif
 }
 
-// ---- prepare: K-table, y-dependence of the matrix, change detection -------------------------------------------
-// thread i of nx*ny
-B200_HD void lapbPrepareThread(const LapParams& p, int i) {
-  lapTableEntry(p, i);
+// ---- prepare: y-dependence of the matrix, change detection ----------------------------------------------------
+// element i of nx*ny.  Every load is issued before any is used (one memory round trip, not twelve).
+B200_HD void lapbCompareThread(const LapParams& p, int i) {
   const int jx = i / p.ny, jy = i % p.ny;
   const long long i0 = static_cast<long long>(jx) * p.ny + p.ys;
   const bool solved = jy >= p.ys && jy <= p.ye;
   const double* arrs[LAP_NFP] = {p.m.dx, p.m.g11, p.m.g33, p.m.g13, p.m.G1, p.m.G3, p.m.g_11, p.m.g_22,
                                  p.m.A,  p.m.C1,  p.m.C2,  p.m.D};
   const long long n2 = static_cast<long long>(p.nx) * p.ny;
-  bool ydiff = false, changed = false;
+  double v[LAP_NFP], v0[LAP_NFP], old[LAP_NFP];
 #pragma unroll
   for (int q = 0; q < LAP_NFP; ++q) {
-    if (arrs[q] != nullptr) {
-      const double v = B200_LDG(arrs[q] + i);
-      ydiff = ydiff || (solved && !(v == B200_LDG(arrs[q] + i0)));
-      double* cp = p.fpcopy + q * n2 + i;
-      changed = changed || bitsOf(*cp) != bitsOf(v);
-      *cp = v;
+    const bool have = arrs[q] != nullptr;
+    v[q] = have ? B200_LDG(arrs[q] + i) : 0.0;
+    v0[q] = have ? B200_LDG(arrs[q] + i0) : 0.0;
+    old[q] = have ? p.fpcopy[q * n2 + i] : 0.0;
+  }
+  int ydiff = 0, changed = 0;
+#pragma unroll
+  for (int q = 0; q < LAP_NFP; ++q) {
+    ydiff |= (solved && !(v[q] == v0[q])) ? 1 : 0;
+    const bool ch = bitsOf(old[q]) != bitsOf(v[q]);
+    changed |= ch ? 1 : 0;
+    if (ch && arrs[q] != nullptr) {
+      p.fpcopy[q * n2 + i] = v[q];
     }
   }
   unsigned* w = reinterpret_cast<unsigned*>(p.status);
@@ -237,7 +272,10 @@ B200_HD bool lapbDirty(const LapParams& p) { return static_cast<unsigned>(p.stat
 B200_HD bool lapbYdep(const LapParams& p) { return static_cast<unsigned>(p.status[LAPW_YDEP_GEN]) == p.gen; }
 
 // ---- factor 1: thread (ysel, block, kz): pivots, gF, gL, boundary-row coefficients, reduced-row pieces --------
-// Returns true when a pivot vanished.
+// The pivot table serves the two-sided elimination of the SOLVE kernel: rows of the top half of a block
+// (local index < lapbMid) hold the reciprocal pivots of the downward elimination started below the block's
+// separator, rows of the bottom half those of the upward elimination started above the next separator; MID
+// closes the 2x2 system where the two meet.  Returns true when a pivot vanished.
 B200_HD bool lapbFactor1Thread(const LapParams& p, long long idx) {
   const int n = p.bd.xe - p.bd.xs + 1, nys = p.ye - p.ys + 1, nmode = p.nmode, P = p.bP, MB = p.bMB;
   const int ysel = static_cast<int>(idx / (static_cast<long long>(P) * nmode));
@@ -247,9 +285,10 @@ B200_HD bool lapbFactor1Thread(const LapParams& p, long long idx) {
   const int jb = static_cast<int>((idx / nmode) % P), kz = static_cast<int>(idx % nmode);
   const int jy = p.ys + ysel;
   const double* tab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
-  const double kwave = kz * 2.0 * M_PI / p.m.zlength; // common_transform.cxx:73
+  const double kwave = kz * p.kscale; // common_transform.cxx:73
   const int r0 = jb * MB, cnt = min(MB, n - r0);
-  const int lo = r0 + (jb > 0 ? 1 : 0), hi = r0 + cnt - 1;
+  const int li0 = jb > 0 ? 1 : 0;
+  const int lo = r0 + li0, hi = r0 + cnt - 1, mid = r0 + lapbSplit(p.bd, n, r0, li0, cnt).mid;
   cd* __restrict__ INV = p.inv;
   cd* __restrict__ GF = p.cprime;
   cd* __restrict__ GL = p.dprime;
@@ -261,19 +300,23 @@ B200_HD bool lapbFactor1Thread(const LapParams& p, long long idx) {
     GF[o] = {0.0, 0.0};
     GL[o] = {0.0, 0.0};
   }
+  p.bred[lapbRedIndex(p, LAPB_MID, ysel, jb, kz)] = {1.0, 0.0};
   if (hi < lo) { // a trailing block that is a separator only
     p.bred[lapbRedIndex(p, LAPB_RBD, ysel, jb, kz)] = {0.0, 0.0};
     p.bred[lapbRedIndex(p, LAPB_RC, ysel, jb, kz)] = {0.0, 0.0};
     return false;
   }
   // downward elimination inside the block (c' of the row above the block is 0)
-  cd cprev = {0.0, 0.0};
+  cd cprev = {0.0, 0.0}, cp_above_mid = {0.0, 0.0};
   for (int i = lo; i <= hi; ++i) {
     lapRow(p, tab, i, jy, kz, kwave, a, b, c, r);
     const cd denom = csub(b, cmul(a, cprev));
     bad = bad || tiny(denom);
     const cd inv = crecip(denom);
     cprev = cmul(c, inv);
+    if (i == mid - 1) {
+      cp_above_mid = cprev;
+    }
     INV[lapbTabIndex(p, ysel, i, kz)] = inv;
     bool inner, outer;
     const int sr = lapBndRow(p, i, inner, outer);
@@ -291,7 +334,9 @@ B200_HD bool lapbFactor1Thread(const LapParams& p, long long idx) {
     g = cneg(cmul(cmul(a, INV[lapbTabIndex(p, ysel, k, kz)]), g));
     GL[lapbTabIndex(p, ysel, k, kz)] = g;
   }
-  // upward elimination: invU_k = 1 / (b_k - c_k a_{k+1} invU_{k+1}), kept in GF for the next loop
+  const cd mLF = GL[lapbTabIndex(p, ysel, lo, kz)], mLL = GL[lapbTabIndex(p, ysel, hi, kz)];
+  // upward elimination: invU_k = 1 / (b_k - c_k a_{k+1} invU_{k+1}), kept in GF for the next loop; the
+  // bottom-half rows of the pivot table take these
   cd e = {0.0, 0.0};
   for (int k = hi; k >= lo; --k) {
     lapRow(p, tab, k, jy, kz, kwave, a, b, c, r);
@@ -300,6 +345,14 @@ B200_HD bool lapbFactor1Thread(const LapParams& p, long long idx) {
     const cd inv = crecip(denom);
     e = cmul(a, inv);
     GF[lapbTabIndex(p, ysel, k, kz)] = inv;
+    if (k >= mid) {
+      INV[lapbTabIndex(p, ysel, k, kz)] = inv;
+    }
+    if (k == mid) { // x_mid = (u_mid - a'_mid d'_{mid-1}) / (1 - a'_mid c'_{mid-1})
+      const cd den = csub(cd{1.0, 0.0}, cmul(e, cp_above_mid));
+      bad = bad || tiny(den);
+      p.bred[lapbRedIndex(p, LAPB_MID, ysel, jb, kz)] = crecip(den);
+    }
   }
   // gF = first row of the inverse: gF_lo = invU_lo, gF_k = -c_{k-1} invU_k gF_{k-1}
   g = GF[lapbTabIndex(p, ysel, lo, kz)];
@@ -309,7 +362,6 @@ B200_HD bool lapbFactor1Thread(const LapParams& p, long long idx) {
     GF[lapbTabIndex(p, ysel, k, kz)] = g;
   }
   // pieces of the reduced rows of the separators above and below this block
-  const cd mLF = GL[lapbTabIndex(p, ysel, lo, kz)], mLL = GL[lapbTabIndex(p, ysel, hi, kz)];
   const cd mFF = GF[lapbTabIndex(p, ysel, lo, kz)], mFL = GF[lapbTabIndex(p, ysel, hi, kz)];
   lapRow(p, tab, lo, jy, kz, kwave, a, b, c, r);
   const cd a_lo = a;
@@ -329,6 +381,8 @@ B200_HD bool lapbFactor1Thread(const LapParams& p, long long idx) {
 }
 
 // ---- factor 2: thread (ysel, kz): Thomas factors of the separator system --------------------------------------
+// Row j:  A_j x_{j-1} + B_j x_j + C_j x_{j+1} = r_s - a_s yL_{j-1} - c_s yF_j.  Stored scaled by the pivot:
+// RINV, CSI = c_s rinv (DOTS forms F0 = r_s rinv - CSI yF), ASI = a_s rinv, RAI = A rinv, RCP = C rinv.
 B200_HD bool lapbFactor2Thread(const LapParams& p, int idx) {
   const int nys = p.ye - p.ys + 1, nmode = p.nmode, P = p.bP, MB = p.bMB;
   const int ysel = idx / nmode, kz = idx % nmode;
@@ -337,7 +391,7 @@ B200_HD bool lapbFactor2Thread(const LapParams& p, int idx) {
   }
   const int jy = p.ys + ysel;
   const double* tab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
-  const double kwave = kz * 2.0 * M_PI / p.m.zlength;
+  const double kwave = kz * p.kscale;
   bool bad = false;
   cd cprev = {0.0, 0.0};
   for (int j = 1; j < P; ++j) {
@@ -353,62 +407,90 @@ B200_HD bool lapbFactor2Thread(const LapParams& p, int idx) {
     p.bred[lapbRedIndex(p, LAPB_RINV, ysel, j, kz)] = rinv;
     p.bred[lapbRedIndex(p, LAPB_RAI, ysel, j, kz)] = cmul(RA, rinv);
     p.bred[lapbRedIndex(p, LAPB_RCP, ysel, j, kz)] = cprev;
-    p.bred[lapbRedIndex(p, LAPB_RAS, ysel, j, kz)] = a;
-    p.bred[lapbRedIndex(p, LAPB_RCS, ysel, j, kz)] = c;
+    p.bred[lapbRedIndex(p, LAPB_ASI, ysel, j, kz)] = cmul(a, rinv);
+    p.bred[lapbRedIndex(p, LAPB_CSI, ysel, j, kz)] = cmul(c, rinv);
   }
   return bad;
 }
 
 // ---- reduced: thread (iyl, kz): the separator values of one system --------------------------------------------
-B200_HD void lapbReducedThread(const LapParams& p, int idx) {
+//   d_j = F0_j - F1_{j-1} - RAI_j d_{j-1},   x_j = d_j - RCP_j x_{j+1}
+// with F0_j = (r_s - c_s yF_j) rinv_j and F1_{j-1} = a_s rinv_j yL_{j-1} from the DOTS kernel.
+// D: this thread's scratch column (P entries, stride dstride): shared memory on the device.
+constexpr int LAPB_PF = 8; // steps whose operands are fetched together
+B200_HD void lapbReducedThread(const LapParams& p, int idx, cd* D, int dstride) {
   const int nmode = p.nmode, P = p.bP;
   const int iyl = idx / nmode, kz = idx % nmode;
   const int ysel = lapbYdep(p) ? iyl : 0;
-  const cd* __restrict__ IF = p.bif;
-  const cd* __restrict__ red = p.bred;
-  cd* DS = p.bds; // written and read back by this thread: plain loads and stores
+  const cd* __restrict__ IF = p.bif + static_cast<long long>(iyl) * P * 2 * nmode + kz; // [j][2][nmode]
+  const cd* __restrict__ rai = p.bred + lapbRedIndex(p, LAPB_RAI, ysel, 0, kz);
+  const cd* __restrict__ rcp = p.bred + lapbRedIndex(p, LAPB_RCP, ysel, 0, kz);
   cd dp = {0.0, 0.0};
-#pragma unroll 4
-  for (int j = 1; j < P; ++j) {
-    const long long f = (static_cast<long long>(iyl) * P + j) * 3 * nmode + kz;
-    const cd yLprev = ldcd(IF + f - 2 * nmode); // [iyl][j-1][1]
-    const cd yF = ldcd(IF + f), rs = ldcd(IF + f + 2 * nmode);
-    const cd as = ldcd(red + lapbRedIndex(p, LAPB_RAS, ysel, j, kz));
-    const cd cs = ldcd(red + lapbRedIndex(p, LAPB_RCS, ysel, j, kz));
-    const cd R = csub(csub(rs, cmul(as, yLprev)), cmul(cs, yF));
-    const cd d = csub(cmul(R, ldcd(red + lapbRedIndex(p, LAPB_RINV, ysel, j, kz))),
-                      cmul(ldcd(red + lapbRedIndex(p, LAPB_RAI, ysel, j, kz)), dp));
-    DS[lapbSysIndex(p, iyl, j, kz)] = d;
-    dp = d;
+  for (int j0 = 1; j0 < P; j0 += LAPB_PF) {
+    cd f0[LAPB_PF], f1[LAPB_PF], ra[LAPB_PF];
+#pragma unroll
+    for (int k = 0; k < LAPB_PF; ++k) {
+      const int j = min(j0 + k, P - 1);
+      f0[k] = ldcd(IF + static_cast<long long>(j) * 2 * nmode);
+      f1[k] = ldcd(IF + (static_cast<long long>(j - 1) * 2 + 1) * nmode);
+      ra[k] = ldcd(rai + static_cast<long long>(j) * nmode);
+    }
+#pragma unroll
+    for (int k = 0; k < LAPB_PF; ++k) {
+      if (j0 + k < P) {
+        dp = csub(csub(f0[k], f1[k]), cmul(ra[k], dp));
+        D[(j0 + k) * dstride] = dp;
+      }
+    }
   }
   cd x = {0.0, 0.0};
-#pragma unroll 4
-  for (int j = P - 1; j >= 1; --j) {
-    x = csub(DS[lapbSysIndex(p, iyl, j, kz)], cmul(ldcd(red + lapbRedIndex(p, LAPB_RCP, ysel, j, kz)), x));
-    p.bxs[lapbSysIndex(p, iyl, j, kz)] = x;
+  cd* __restrict__ xs = p.bxs + lapbSysIndex(p, iyl, 0, kz);
+  for (int j0 = P - 1; j0 >= 1; j0 -= LAPB_PF) {
+    cd rc[LAPB_PF];
+#pragma unroll
+    for (int k = 0; k < LAPB_PF; ++k) {
+      rc[k] = ldcd(rcp + static_cast<long long>(max(j0 - k, 1)) * nmode);
+    }
+#pragma unroll
+    for (int k = 0; k < LAPB_PF; ++k) {
+      const int j = j0 - k;
+      if (j >= 1) {
+        x = csub(D[j * dstride], cmul(rc[k], x));
+        xs[static_cast<long long>(j) * nmode] = x;
+      }
+    }
   }
 }
 
 // ---- rows kernels: per-thread phases --------------------------------------------------------------------------
 enum { LAPB_DOTS = 0, LAPB_SOLVE = 1 };
 
-// this thread's part of the CTA's K-table rows -> shared memory
-template <int N>
-B200_HD void lapbStageTable(const LapParams& p, const LapbCta& c, int tid, double* ktab) {
-  using Sh = LapbShape<N>;
-  const int n = p.bd.xe - p.bd.xs + 1;
-  for (int i = tid; i < Sh::ROWS * LAP_NK; i += Sh::NT) {
-    const int r = i / LAP_NK;
-    ktab[i] = (c.row0 + r < n)
-                  ? B200_LDG(p.table + (static_cast<long long>(c.jy) * p.nx + p.bd.xs + c.row0 + r) * LAP_NK + i % LAP_NK)
-                  : 0.0;
+// per-row constants of the CTA's rows -> shared memory (threads tid < ROWS): k0 - k3, k0 + k3, k2, boundary flag
+template <int N, int NT>
+B200_HD void lapbStageRows(const LapParams& p, const LapbCta& c, int tid, double* rowc) {
+  using Sh = LapbShape<N, NT>;
+  if (tid >= Sh::ROWS) {
+    return;
   }
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const int ix = c.row0 + tid;
+  double* rc = rowc + tid * Sh::NRC;
+  if (ix >= n) {
+    rc[0] = rc[1] = rc[2] = rc[3] = 0.0;
+    return;
+  }
+  const double2* t = reinterpret_cast<const double2*>(p.table + (static_cast<long long>(c.jy) * p.nx + p.bd.xs + ix) * LAP_NK);
+  const double2 t01 = B200_LDG(t), t23 = B200_LDG(t + 1);
+  rc[0] = t01.x - t23.y;
+  rc[1] = t01.x + t23.y;
+  rc[2] = t23.x;
+  rc[3] = 0.0;
 }
 
 // the row of this thread's group as packed complex numbers: v[n2] = (row[2 (t + T n2)], row[2 (t + T n2) + 1])
-template <int N, int MODE>
+template <int N, int NT, int MODE>
 B200_HD void lapbLoadRow(const LapParams& p, const LapbCta& c, int tid, cd (&v)[RegFft<N>::B]) {
-  using Sh = LapbShape<N>;
+  using Sh = LapbShape<N, NT>;
   const int grp = tid / Sh::T, t = tid % Sh::T;
   const int n = p.bd.xe - p.bd.xs + 1, ncx = n - 1;
   const int ix = c.row0 + grp;
@@ -439,9 +521,9 @@ B200_HD void lapbLoadRow(const LapParams& p, const LapbCta& c, int tid, cd (&v)[
   }
 }
 
-template <int N>
+template <int N, int NT>
 B200_HD void lapbStoreRow(const LapParams& p, const LapbCta& c, int tid, const cd (&v)[RegFft<N>::B]) {
-  using Sh = LapbShape<N>;
+  using Sh = LapbShape<N, NT>;
   const int grp = tid / Sh::T, t = tid % Sh::T;
   const int n = p.bd.xe - p.bd.xs + 1;
   const int ix = c.row0 + grp;
@@ -456,107 +538,565 @@ B200_HD void lapbStoreRow(const LapParams& p, const LapbCta& c, int tid, const c
   }
 }
 
-// a, c of local row r of the CTA for mode kz: boundary rows from the bnd array, interior rows from the staged table
-template <int N>
-B200_HD void lapbRowAC(const LapParams& p, const LapbCta& c, const double* ktab, int r, int kz, double kwave, cd& a,
-                       cd& cc) {
-  const int ix = c.row0 + r;
-  bool inner, outer;
-  const int sr = lapBndRow(p, ix, inner, outer);
-  if (inner || outer) {
-    const cd* q = p.bnd + lapbBndIndex(p, sr, c.ysel, kz);
-    a = ldcd(q);
-    cc = ldcd(q + 1);
-    return;
+// ---- per-mode phase --------------------------------------------------------------------------------------------
+// A chain = one kz mode of one block, owned by one thread.  on[ch] = false marks an idle chain (kz beyond the
+// kept modes, or a lane that has no second-pass chain): it reads mode 0's operands and stores nothing.
+//
+// DOTS: yF = gF . r and yL = gL . r over the block's interior rows (gF / gL: first / last row of the inverse of the
+// block's interior matrix, so yF, yL are the first / last interior values of the block's solution with zero
+// separator values), then F0 = (r_s - c_s yF) rinv for this block's separator row of the reduced system and
+// F1 = a_s' rinv' yL for the next one's.  No dependency chain at all.  The first LAPB_DB rows' table entries and
+// the scaling factors are fetched before the CTA barrier that ends the transform phase.
+constexpr int LAPB_DB = 8; // rows per batch of table fetches
+template <int NCH>
+struct LapbDots {
+  cd gf[NCH][LAPB_DB], gl[NCH][LAPB_DB];
+  cd rinv[NCH], csi[NCH], asi[NCH];
+};
+template <int N, int NT, int NCH>
+B200_HD void lapbDotsFetch(const LapParams& p, const LapbCta& c, int blk, const int (&kzs)[NCH], int l0,
+                           LapbDots<NCH>& st) {
+  using Sh = LapbShape<N, NT>;
+  const int n = p.bd.xe - p.bd.xs + 1, nmode = p.nmode;
+  const int r0 = c.row0 + blk * Sh::MB;
+  const int cnt = max(min(Sh::MB, n - r0), 1);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int kz = kzs[ch] < nmode ? kzs[ch] : 0;
+    const long long o = lapbTabIndex(p, c.ysel, min(r0, n - 1), kz);
+#pragma unroll
+    for (int k = 0; k < LAPB_DB; ++k) {
+      const long long ro = static_cast<long long>(min(l0 + k, cnt - 1)) * nmode; // rows past the end weigh nothing
+      st.gf[ch][k] = ldcd(p.cprime + o + ro);
+      st.gl[ch][k] = ldcd(p.dprime + o + ro);
+    }
   }
-  const double* t = ktab + r * LAP_NK;
-  a = {t[0] - t[3], -kwave * t[2]};
-  cc = {t[0] + t[3], kwave * t[2]};
 }
-
-// DOTS, thread (blk, kz): yF, yL over the block's interior rows and the separator row's spectrum
-template <int N>
-B200_HD void lapbDotsThread(const LapParams& p, const LapbCta& c, int blk, int kz, const cd* S) {
-  using Sh = LapbShape<N>;
-  const int n = p.bd.xe - p.bd.xs + 1;
+template <int N, int NT, int NCH>
+B200_HD void lapbDotsFetchScale(const LapParams& p, const LapbCta& c, int blk, const int (&kzs)[NCH], LapbDots<NCH>& st) {
+  using Sh = LapbShape<N, NT>;
+  const int n = p.bd.xe - p.bd.xs + 1, nmode = p.nmode;
+  const int r0 = c.row0 + blk * Sh::MB, jb = min(r0 / Sh::MB, p.bP - 1);
+  const bool next = r0 + Sh::MB < n;
+  const cd zero = {0.0, 0.0};
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int kz = kzs[ch] < nmode ? kzs[ch] : 0;
+    st.rinv[ch] = jb > 0 ? ldcd(p.bred + lapbRedIndex(p, LAPB_RINV, c.ysel, jb, kz)) : zero;
+    st.csi[ch] = jb > 0 ? ldcd(p.bred + lapbRedIndex(p, LAPB_CSI, c.ysel, jb, kz)) : zero;
+    st.asi[ch] = next ? ldcd(p.bred + lapbRedIndex(p, LAPB_ASI, c.ysel, jb + 1, kz)) : zero;
+  }
+}
+B200_HD void cfma(cd& acc, cd a, cd b) { // acc += a b, four fused multiply-adds
+  acc.re = fma(a.re, b.re, acc.re);
+  acc.re = fma(-a.im, b.im, acc.re);
+  acc.im = fma(a.re, b.im, acc.im);
+  acc.im = fma(a.im, b.re, acc.im);
+}
+// st holds batch 0 on entry
+template <int N, int NT, int NCH>
+B200_HD void lapbDotsRun(const LapParams& p, const LapbCta& c, int blk, const int (&kzs)[NCH], const bool (&on)[NCH],
+                         LapbDots<NCH>& st, const cd* S) {
+  using Sh = LapbShape<N, NT>;
+  const int n = p.bd.xe - p.bd.xs + 1, nmode = p.nmode;
   const int r0 = c.row0 + blk * Sh::MB, jb = r0 / Sh::MB;
   const int cnt = min(Sh::MB, n - r0);
   if (cnt <= 0) {
     return;
   }
   const int li0 = jb > 0 ? 1 : 0;
-  const cd* __restrict__ GF = p.cprime;
-  const cd* __restrict__ GL = p.dprime;
-  const cd* Sb = S + static_cast<size_t>(blk) * Sh::MB * Sh::SROW + kz;
-  cd yF = {0.0, 0.0}, yL = {0.0, 0.0};
+  const cd* Sb[NCH];
+  cd yF[NCH], yL[NCH];
 #pragma unroll
-  for (int li = 0; li < Sh::MB; ++li) {
-    if (li >= li0 && li < cnt) {
-      const long long o = lapbTabIndex(p, c.ysel, r0 + li, kz);
-      const cd s = Sb[li * Sh::SROW];
-      yF = cadd(yF, cmul(ldcd(GF + o), s));
-      yL = cadd(yL, cmul(ldcd(GL + o), s));
+  for (int ch = 0; ch < NCH; ++ch) {
+    Sb[ch] = S + static_cast<size_t>(blk) * Sh::MB * Sh::SROW + (on[ch] ? kzs[ch] : 0);
+    yF[ch] = yL[ch] = {0.0, 0.0};
+  }
+#pragma unroll
+  for (int l0 = 0; l0 < Sh::MB; l0 += LAPB_DB) {
+    if (l0 > 0) {
+      lapbDotsFetch<N, NT, NCH>(p, c, blk, kzs, l0, st);
+    }
+#pragma unroll
+    for (int k = 0; k < LAPB_DB; ++k) {
+      const int li = l0 + k;
+      if (li < Sh::MB) {
+        const bool act = li >= li0 && li < cnt;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const cd s = act ? Sb[ch][li * Sh::SROW] : cd{0.0, 0.0};
+          cfma(yF[ch], st.gf[ch][k], s);
+          cfma(yL[ch], st.gl[ch][k], s);
+        }
+      }
     }
   }
-  cd* __restrict__ f = p.bif + (static_cast<long long>(c.iyl) * p.bP + jb) * 3 * p.nmode + kz;
-  f[0] = yF;
-  f[p.nmode] = yL;
-  f[2 * p.nmode] = jb > 0 ? Sb[0] : cd{0.0, 0.0};
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (on[ch]) {
+      cd* __restrict__ f = p.bif + (static_cast<long long>(c.iyl) * p.bP + jb) * 2 * nmode + kzs[ch];
+      f[0] = jb > 0 ? csub(cmul(Sb[ch][0], st.rinv[ch]), cmul(st.csi[ch], yF[ch])) : cd{0.0, 0.0};
+      f[nmode] = cmul(st.asi[ch], yL[ch]);
+    }
+  }
 }
 
-// SOLVE, thread (blk, kz): Thomas inside the block between the known separator values; S: rhs spectrum in,
-// solution spectrum out.
-template <int N>
-B200_HD void lapbSolveThread(const LapParams& p, const LapbCta& c, int blk, int kz, cd* S, const double* ktab) {
-  using Sh = LapbShape<N>;
+// SOLVE: two-sided elimination between the known separator values.  Top half: d_i = (r_i - a_i d_{i-1}) inv_i
+// downward from d = x_s; bottom half: u_i = (r_i - c_i u_{i+1}) inv_i upward from u = x_{s+1}; where they meet
+// x_mid = (u_mid - a'_mid d_{mid-1}) MID; then x_i = d_i - c'_i x_{i+1} upward through the top half and
+// x_i = u_i - a'_i x_{i-1} downward through the bottom half.  The two sweeps (and the NCH modes of a thread) are
+// independent dependency chains.  S: rhs spectrum in, solution spectrum out.  The operands from global memory are
+// fetched by lapbChainLoad before the CTA barrier that ends the transform phase.
+template <int MB, int NCH>
+struct LapbChain {
+  cd w[NCH][MB]; // pivot reciprocals, replaced row by row by c' (top half) / a' (bottom half)
+  cd xs[NCH];    // x_s
+  cd xn[NCH];    // x_{s+1}
+  cd midinv[NCH];
+};
+
+template <int N, int NT, int NCH>
+B200_HD void lapbChainLoad(const LapParams& p, const LapbCta& c, int blk, const int (&kzs)[NCH],
+                           LapbChain<LapbShape<N, NT>::MB, NCH>& st) {
+  using Sh = LapbShape<N, NT>;
+  constexpr int MB = Sh::MB;
+  const int n = p.bd.xe - p.bd.xs + 1, nmode = p.nmode;
+  const int r0 = c.row0 + blk * MB, jb = min(r0 / MB, p.bP - 1);
+  const int cnt = max(min(MB, n - r0), 1);
+  const bool next = r0 + MB < n; // a separator follows this block
+  const cd zero = {0.0, 0.0};
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int kz = kzs[ch] < nmode ? kzs[ch] : 0;
+    const cd* ip = p.inv + lapbTabIndex(p, c.ysel, min(r0, n - 1), kz);
+#pragma unroll
+    for (int li = 0; li < MB; ++li) {
+      st.w[ch][li] = ldcd(ip + static_cast<long long>(min(li, cnt - 1)) * nmode);
+    }
+    st.midinv[ch] = ldcd(p.bred + lapbRedIndex(p, LAPB_MID, c.ysel, jb, kz));
+    st.xs[ch] = jb > 0 ? ldcd(p.bxs + lapbSysIndex(p, c.iyl, jb, kz)) : zero;
+    st.xn[ch] = next ? ldcd(p.bxs + lapbSysIndex(p, c.iyl, jb + 1, kz)) : zero;
+  }
+}
+
+// The boundary rows of a block's sweeps, outside the unrolled loops (they exist in the first and the last block of
+// a system only).  Sc: this mode's column of the block in S.  phase 0: top-half rows [li0, ra) downward (carry =
+// d); 1: bottom-half rows [rb, cnt) upward (carry = u; amid = a' of row mid when that is a boundary row);
+// 2: bottom-half rows after mid, downward substitution (carry = x); 3: top-half rows [li0, ra) upward (carry = x).
+B200_HD_COLD void lapbEdgeRows(const LapParams& p, int ysel, int r0, int li0, int cnt, LapbSplit sp, int srow, int kz,
+                               bool on, int phase, cd* Sc, cd* carry, cd* amid) {
+  const int first = phase == 0 ? li0 : (phase == 1 ? cnt - 1 : (phase == 2 ? max(sp.rb, sp.mid + 1) : sp.ra - 1));
+  const int last = phase == 0 ? sp.ra - 1 : (phase == 1 ? sp.rb : (phase == 2 ? cnt - 1 : li0));
+  const int step = (phase == 0 || phase == 2) ? 1 : -1;
+  cd x = *carry;
+  for (int li = first; step > 0 ? li <= last : li >= last; li += step) {
+    bool inner, outer;
+    const int sr = lapBndRow(p, r0 + li, inner, outer);
+    const cd* q = p.bnd + lapbBndIndex(p, sr, ysel, kz);
+    const cd a = ldcd(q), cc = ldcd(q + 1);
+    const cd inv = ldcd(p.inv + lapbTabIndex(p, ysel, r0 + li, kz));
+    const cd s = Sc[li * srow];
+    if (phase == 0) {
+      x = csub(cmul(s, inv), cmul(cmul(a, inv), x));
+    } else if (phase == 1) {
+      x = csub(cmul(s, inv), cmul(cmul(cc, inv), x));
+      if (li == sp.mid) {
+        *amid = cmul(a, inv);
+      }
+    } else if (phase == 2) {
+      x = csub(s, cmul(cmul(a, inv), x));
+    } else {
+      x = csub(s, cmul(cmul(cc, inv), x));
+    }
+    if (on) {
+      Sc[li * srow] = x;
+    }
+  }
+  *carry = x;
+}
+
+// The common case -- a full block of regular rows behind a separator (every block but the first and the last of
+// a system) -- with every bound a compile-time constant: straight-line code.  The shared-memory operands of row
+// s + 1 are read before row s is computed and stored (the compiler keeps shared loads behind earlier shared stores,
+// which would put a full load latency into every step of the recurrences).
+template <int N, int NT, int NCH>
+B200_HD void lapbChainRunFull(const LapParams& p, int blk, const int (&kzs)[NCH], const bool (&on)[NCH],
+                              LapbChain<LapbShape<N, NT>::MB, NCH>& st, cd* S, const double* rowc) {
+  using Sh = LapbShape<N, NT>;
+  constexpr int MB = Sh::MB, MID = 1 + MB / 2, NTOP = MID - 1, NBOT = MB - MID, SR = Sh::SROW;
+  const double* rc0 = rowc + blk * MB * Sh::NRC;
+  double kw[NCH];
+  cd* Sb[NCH];
+  cd dt[NCH], ub[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int kz = on[ch] ? kzs[ch] : 0;
+    kw[ch] = kz * p.kscale; // common_transform.cxx:73
+    Sb[ch] = S + static_cast<size_t>(blk) * MB * SR + kz;
+    dt[ch] = st.xs[ch];
+    ub[ch] = st.xn[ch];
+  }
+  struct RowIn {
+    double2 r01;
+    double k2;
+    cd s[NCH];
+  };
+  auto fetch = [&](int li) {
+    RowIn in;
+    in.r01 = *reinterpret_cast<const double2*>(rc0 + li * Sh::NRC);
+    in.k2 = rc0[li * Sh::NRC + 2];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      in.s[ch] = Sb[ch][li * SR];
+    }
+    return in;
+  };
+  RowIn tn = fetch(1), bn = fetch(MB - 1);
+#pragma unroll
+  for (int s = 0; s < NTOP; ++s) {
+    const RowIn tc = tn, bc = bn;
+    if (s + 1 < NTOP) {
+      tn = fetch(2 + s);
+    }
+    if (s + 1 < NBOT) {
+      bn = fetch(MB - 2 - s);
+    }
+    { // top half, downward: d_i = (r_i - a_i d_{i-1}) inv_i
+      const int li = 1 + s;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const double im = kw[ch] * tc.k2;
+        const cd a = {tc.r01.x, -im}, cc = {tc.r01.y, im};
+        const cd inv = st.w[ch][li];
+        const cd ri = cmul(tc.s[ch], inv);
+        const cd ai = cmul(a, inv);
+        st.w[ch][li] = cmul(cc, inv);
+        dt[ch] = csub(ri, cmul(ai, dt[ch]));
+        if (on[ch]) {
+          Sb[ch][li * SR] = dt[ch];
+        }
+      }
+    }
+    if (s < NBOT) { // bottom half, upward: u_i = (r_i - c_i u_{i+1}) inv_i
+      const int li = MB - 1 - s;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const double im = kw[ch] * bc.k2;
+        const cd a = {bc.r01.x, -im}, cc = {bc.r01.y, im};
+        const cd inv = st.w[ch][li];
+        const cd ri = cmul(bc.s[ch], inv);
+        const cd ci = cmul(cc, inv);
+        st.w[ch][li] = cmul(a, inv);
+        ub[ch] = csub(ri, cmul(ci, ub[ch]));
+        if (on[ch] && li != MID) {
+          Sb[ch][li * SR] = ub[ch];
+        }
+      }
+    }
+  }
+  // the second sweeps read back what this thread stored above; again one row ahead of the stores
+  cd xt[NCH], xb[NCH], tnx[NCH], bnx[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    tnx[ch] = dt[ch]; // d of row MID - 1 is still in a register
+    bnx[ch] = NBOT > 1 ? Sb[ch][(MID + 1) * SR] : cd{0.0, 0.0};
+    const cd xm = cmul(csub(ub[ch], cmul(st.w[ch][MID], dt[ch])), st.midinv[ch]);
+    xt[ch] = xm;
+    xb[ch] = xm;
+  }
+#pragma unroll
+  for (int s = 0; s < NTOP; ++s) {
+    cd tcx[NCH], bcx[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      tcx[ch] = tnx[ch];
+      bcx[ch] = bnx[ch];
+      if (s + 1 < NTOP) {
+        tnx[ch] = Sb[ch][(MID - 2 - s) * SR];
+      }
+      if (s + 1 < NBOT - 1) {
+        bnx[ch] = Sb[ch][(MID + 2 + s) * SR];
+      }
+    }
+    { // top half, upward: x_i = d_i - c'_i x_{i+1}
+      const int li = MID - 1 - s;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        xt[ch] = csub(tcx[ch], cmul(st.w[ch][li], xt[ch]));
+        if (on[ch]) {
+          Sb[ch][li * SR] = xt[ch];
+        }
+      }
+    }
+    if (s < NBOT - 1) { // bottom half, downward: x_i = u_i - a'_i x_{i-1}
+      const int li = MID + 1 + s;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        xb[ch] = csub(bcx[ch], cmul(st.w[ch][li], xb[ch]));
+        if (on[ch]) {
+          Sb[ch][li * SR] = xb[ch];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (on[ch]) {
+      Sb[ch][MID * SR] = xb[ch] = cmul(csub(ub[ch], cmul(st.w[ch][MID], dt[ch])), st.midinv[ch]);
+      Sb[ch][0] = st.xs[ch];
+    }
+  }
+}
+
+template <int N, int NT, int NCH>
+B200_HD void lapbChainRun(const LapParams& p, const LapbCta& c, int blk, const int (&kzs)[NCH], const bool (&on)[NCH],
+                          LapbChain<LapbShape<N, NT>::MB, NCH>& st, cd* S, const double* rowc) {
+  using Sh = LapbShape<N, NT>;
+  constexpr int MB = Sh::MB;
   const int n = p.bd.xe - p.bd.xs + 1;
-  const int r0 = c.row0 + blk * Sh::MB, jb = r0 / Sh::MB;
-  const int cnt = min(Sh::MB, n - r0);
+  const int r0 = c.row0 + blk * MB, jb = r0 / MB;
+  const int cnt = min(MB, n - r0);
   if (cnt <= 0) {
     return;
   }
   const int li0 = jb > 0 ? 1 : 0;
-  const double kwave = kz * 2.0 * M_PI / p.m.zlength; // common_transform.cxx:73
-  cd* Sb = S + static_cast<size_t>(blk) * Sh::MB * Sh::SROW + kz;
-  cd inv[Sh::MB];
-#pragma unroll
-  for (int li = 0; li < Sh::MB; ++li) {
-    inv[li] = li < cnt ? ldcd(p.inv + lapbTabIndex(p, c.ysel, r0 + li, kz)) : cd{1.0, 0.0};
+  const LapbSplit sp = lapbSplit(p.bd, n, r0, li0, cnt);
+  const bool edges = sp.ra > li0 || sp.rb < cnt; // boundary rows in this block (uniform over the CTA's block)
+  if (jb > 0 && cnt == MB && !edges) {
+    lapbChainRunFull<N, NT, NCH>(p, blk, kzs, on, st, S, rowc);
+    return;
   }
-  const cd xs = jb > 0 ? ldcd(p.bxs + lapbSysIndex(p, c.iyl, jb, kz)) : cd{0.0, 0.0};
-  cd x = (r0 + cnt < n) ? ldcd(p.bxs + lapbSysIndex(p, c.iyl, jb + 1, kz)) : cd{0.0, 0.0};
-  cd dprev = xs;
+  int ra = sp.ra, rb = sp.rb, mid = sp.mid;
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+r"(ra), "+r"(rb), "+r"(mid)); // fixed registers: the unrolled rows only compare against them
+#endif
+  const double* rc0 = rowc + blk * MB * Sh::NRC;
+  int kz[NCH];
+  double kw[NCH];
+  cd* Sb[NCH];
+  cd dt[NCH], ub[NCH], amid[NCH];
 #pragma unroll
-  for (int li = 0; li < Sh::MB; ++li) {
-    if (li >= li0 && li < cnt) {
-      cd a, cc;
-      lapbRowAC<N>(p, c, ktab, blk * Sh::MB + li, kz, kwave, a, cc);
-      const cd ri = cmul(Sb[li * Sh::SROW], inv[li]);
-      const cd ai = cmul(a, inv[li]);
-      dprev = csub(ri, cmul(ai, dprev));
-      Sb[li * Sh::SROW] = dprev;
+  for (int ch = 0; ch < NCH; ++ch) {
+    kz[ch] = on[ch] ? kzs[ch] : 0;
+    kw[ch] = kz[ch] * p.kscale; // common_transform.cxx:73
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(kw[ch])); // keep it in a register (the compiler otherwise re-derives it in every row)
+#endif
+    Sb[ch] = S + static_cast<size_t>(blk) * MB * Sh::SROW + kz[ch];
+    dt[ch] = st.xs[ch];
+    ub[ch] = st.xn[ch];
+    amid[ch] = {0.0, 0.0};
+  }
+  if (edges) { // (through copies: the sweeps' own variables must not have their address taken)
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      cd t0 = dt[ch], t1 = ub[ch], t2 = amid[ch];
+      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 0, Sb[ch], &t0, &t2);
+      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 1, Sb[ch], &t1, &t2);
+      dt[ch] = t0;
+      ub[ch] = t1;
+      amid[ch] = t2;
     }
   }
 #pragma unroll
-  for (int li = Sh::MB - 1; li >= 0; --li) {
-    if (li >= li0 && li < cnt) {
-      cd a, cc;
-      lapbRowAC<N>(p, c, ktab, blk * Sh::MB + li, kz, kwave, a, cc);
-      x = csub(Sb[li * Sh::SROW], cmul(cmul(cc, inv[li]), x));
-      Sb[li * Sh::SROW] = x;
+  for (int s = 0; s < MB; ++s) {
+    { // top half, downward: row s
+      const int li = s;
+      if (li >= ra && li < mid) {
+        const double2 r01 = *reinterpret_cast<const double2*>(rc0 + li * Sh::NRC);
+        const double k2 = rc0[li * Sh::NRC + 2];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const double im = kw[ch] * k2;
+          const cd a = {r01.x, -im}, cc = {r01.y, im};
+          const cd inv = st.w[ch][li];
+          const cd ri = cmul(Sb[ch][li * Sh::SROW], inv);
+          const cd ai = cmul(a, inv);
+          st.w[ch][li] = cmul(cc, inv);
+          dt[ch] = csub(ri, cmul(ai, dt[ch]));
+          if (on[ch]) {
+            Sb[ch][li * Sh::SROW] = dt[ch];
+          }
+        }
+      }
+    }
+    { // bottom half, upward: row MB - 1 - s
+      const int li = MB - 1 - s;
+      if (li >= mid && li < rb) {
+        const double2 r01 = *reinterpret_cast<const double2*>(rc0 + li * Sh::NRC);
+        const double k2 = rc0[li * Sh::NRC + 2];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const double im = kw[ch] * k2;
+          const cd a = {r01.x, -im}, cc = {r01.y, im};
+          const cd inv = st.w[ch][li];
+          const cd ri = cmul(Sb[ch][li * Sh::SROW], inv);
+          const cd ci = cmul(cc, inv);
+          st.w[ch][li] = cmul(a, inv);
+          if (li == mid) {
+            amid[ch] = st.w[ch][li];
+          }
+          ub[ch] = csub(ri, cmul(ci, ub[ch]));
+          if (on[ch]) {
+            Sb[ch][li * Sh::SROW] = ub[ch];
+          }
+        }
+      }
+    }
+  }
+  // the meeting point.  dt = d_{mid-1}; ub = u_mid (or, with an empty bottom half, the next separator's value)
+  cd xt[NCH], xb[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    cd xm = ub[ch];
+    if (mid < cnt) {
+      xm = cmul(csub(ub[ch], cmul(amid[ch], dt[ch])), st.midinv[ch]);
+      if (on[ch]) {
+        Sb[ch][mid * Sh::SROW] = xm;
+      }
+    }
+    xt[ch] = xm;
+    xb[ch] = xm;
+  }
+#pragma unroll
+  for (int s = 0; s < MB; ++s) {
+    { // top half, upward: x_i = d_i - c'_i x_{i+1}
+      const int li = MB - 1 - s;
+      if (li >= ra && li < mid) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          xt[ch] = csub(Sb[ch][li * Sh::SROW], cmul(st.w[ch][li], xt[ch]));
+          if (on[ch]) {
+            Sb[ch][li * Sh::SROW] = xt[ch];
+          }
+        }
+      }
+    }
+    { // bottom half, downward: x_i = u_i - a'_i x_{i-1}
+      const int li = s;
+      if (li > mid && li < rb) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          xb[ch] = csub(Sb[ch][li * Sh::SROW], cmul(st.w[ch][li], xb[ch]));
+          if (on[ch]) {
+            Sb[ch][li * Sh::SROW] = xb[ch];
+          }
+        }
+      }
+    }
+  }
+  if (edges) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      cd t0 = xb[ch], t1 = xt[ch], t2 = amid[ch];
+      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 2, Sb[ch], &t0, &t2);
+      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 3, Sb[ch], &t1, &t2);
     }
   }
   if (jb > 0) {
-    Sb[0] = xs;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (on[ch]) {
+        Sb[ch][0] = st.xs[ch];
+      }
+    }
   }
+}
+
+// ---- the Nyquist mode kz = nz/2 ----------------------------------------------------------------------------------
+// N + 1 modes do not divide over the N per-mode threads of a block, and a second pass for one mode would hold the
+// whole CTA at its barrier.  The mode's right-hand side is real and only the real part of its solution is used
+// (c2r ignores Im X[nz/2]), so it travels as one double per row: the DOTS kernel exports Re X[N] of every row, the
+// (tiny) systems -- one per y -- are solved next to the separator systems in k_lapb_reduced by a two-sided sweep
+// over the WHOLE row range (no blocks), and the SOLVE kernel puts the result into X[N] before its inverse
+// transform.  Table row i: e0 = pivot reciprocal, e1 = sweep multiplier, e2 = substitution multiplier (top half
+// i < mid: downward pivots, e1 = a inv, e2 = c inv; bottom half: upward pivots, e1 = c inv, e2 = a inv).
+B200_HD int lapbNyqMid(int n) { return (n + 1) / 2; }
+B200_HD bool lapbNyquistFactorThread(const LapParams& p, int ysel) {
+  const int n = p.bd.xe - p.bd.xs + 1, kz = p.nz / 2, mid = lapbNyqMid(n);
+  const int jy = p.ys + ysel;
+  const double* tab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
+  const double kwave = kz * p.kscale;
+  cd* __restrict__ T = p.bnqt + static_cast<long long>(ysel) * (n + 1) * 3;
+  bool bad = false;
+  cd a, b, c, r = {0.0, 0.0};
+  cd cprev = {0.0, 0.0};
+  for (int i = 0; i < mid; ++i) {
+    lapRow(p, tab, i, jy, kz, kwave, a, b, c, r);
+    const cd denom = csub(b, cmul(a, cprev));
+    bad = bad || tiny(denom);
+    const cd inv = crecip(denom);
+    cprev = cmul(c, inv);
+    T[i * 3] = inv;
+    T[i * 3 + 1] = cmul(a, inv);
+    T[i * 3 + 2] = cprev;
+  }
+  cd e = {0.0, 0.0};
+  for (int i = n - 1; i >= mid; --i) {
+    lapRow(p, tab, i, jy, kz, kwave, a, b, c, r);
+    const cd denom = csub(b, cmul(c, e));
+    bad = bad || tiny(denom);
+    const cd inv = crecip(denom);
+    e = cmul(a, inv);
+    T[i * 3] = inv;
+    T[i * 3 + 1] = cmul(c, inv);
+    T[i * 3 + 2] = e;
+  }
+  cd midinv = {1.0, 0.0};
+  if (mid < n) {
+    const cd den = csub(cd{1.0, 0.0}, cmul(e, cprev)); // 1 - a'_mid c'_{mid-1}
+    bad = bad || tiny(den);
+    midinv = crecip(den);
+  }
+  T[n * 3] = midinv;
+  return bad;
+}
+// one sweep (rows from .. to, step +-1): d_i = r_i e0_i - e1_i d_prev; stores d_i, returns the last one
+B200_HD cd lapbNyqSweep(const cd* T, const double* r, cd* D, int from, int to, int step) {
+  cd d = {0.0, 0.0};
+  for (int i = from; step > 0 ? i <= to : i >= to; i += step) {
+    d = csub(cscale(T[i * 3], r[i]), cmul(T[i * 3 + 1], d));
+    D[i] = d;
+  }
+  return d;
+}
+// outward substitution x_i = d_i - e2_i x_prev from the meeting point; writes Re x_i
+B200_HD void lapbNyqSubst(const cd* T, const cd* D, double* xout, int from, int to, int step, cd x) {
+  for (int i = from; step > 0 ? i <= to : i >= to; i += step) {
+    x = csub(D[i], cmul(T[i * 3 + 2], x));
+    xout[i] = x.re;
+  }
+}
+// x_mid from the two sweep ends (dt = d_{mid-1}, ub = u_mid)
+B200_HD cd lapbNyqMeet(const cd* T, int n, cd dt, cd ub) {
+  const int mid = lapbNyqMid(n);
+  return mid < n ? cmul(csub(ub, cmul(T[mid * 3 + 2], dt)), T[n * 3]) : cd{0.0, 0.0};
+}
+
+// the modes of thread tid in the per-mode phase, and the block they belong to
+template <int N, int NT>
+B200_HD int lapbModes(int tid, int (&kzs)[LapbShape<N, NT>::KPT]) {
+  using Sh = LapbShape<N, NT>;
+#pragma unroll
+  for (int ch = 0; ch < Sh::KPT; ++ch) {
+    kzs[ch] = (NT >= N ? tid % N : tid) + ch * NT;
+  }
+  return NT >= N ? tid / N : 0;
 }
 
 // ---- host side: is this configuration served by the block path, and how large are its arrays? ---------------
 inline bool lapbShapeOk(int nz) { return nz == 128 || nz == 256 || nz == 512; }
-inline int lapbBlocks(int n, int nz) { return (n + lapbRowsPerBlock(nz) - 1) / lapbRowsPerBlock(nz); }
-// complex elements of the per-solve / reduced arrays: bif (3) + bxs + bds + bred (LAPB_NRED)
-inline size_t lapbSmallElems(int nx, int ny, int nz, int nmode) {
-  return static_cast<size_t>(3 + 2 + LAPB_NRED) * ny * lapbBlocks(nx, nz) * nmode;
+inline int lapbBlocks(int n, int mb) { return (n + mb - 1) / mb; }
+// complex elements of the per-solve / per-separator arrays: bif (2) + bxs + bred (LAPB_NRED), for the smallest
+// block size (8 rows) any CTA size uses
+inline size_t lapbSmallElems(int nx, int ny, int nmode) {
+  return static_cast<size_t>(2 + 1 + LAPB_NRED) * ny * lapbBlocks(nx, 8) * nmode;
+}
+// threads per CTA of the rows kernels for nz = 512 (256: blocks of 16 rows; 128: blocks of 8 rows, two modes per
+// thread).  Other row lengths always use 256.
+inline int& lapbThreads512() {
+  static int nt = 256;
+  return nt;
 }
 
 // ---- host side: workspace layout and the parameter block (no CUDA calls: shared with tests/emul/) -------------
@@ -579,7 +1119,7 @@ inline void lapBndryWidths(const bout_b200_grid* g, const bout_b200_laplace* L, 
 // Byte offsets of the workspace regions.  The block path overlays its matrix-only tables on the regions the
 // three-kernel paths use for c', d' (gF, gL) and keeps its small per-solve arrays where they keep the spectrum.
 struct LapLayout {
-  size_t table, fpcopy, spec, cprime, dprime, inv, bnd, sprime, iface, total;
+  size_t table, fpcopy, spec, cprime, dprime, inv, bnd, nyq, sprime, iface, total;
   size_t nspec; // complex elements of one spectral array
 };
 inline LapLayout lapLayout(const bout_b200_grid* g, const bout_b200_laplace* L) {
@@ -589,7 +1129,7 @@ inline LapLayout lapLayout(const bout_b200_grid* g, const bout_b200_laplace* L) 
   const size_t n2 = static_cast<size_t>(g->nx) * g->ny;
   size_t spec_elems = l.nspec;
   if (lapbShapeOk(g->nz)) {
-    const size_t small = lapbSmallElems(g->nx, g->ny, g->nz, static_cast<int>(nmode));
+    const size_t small = lapbSmallElems(g->nx, g->ny, static_cast<int>(nmode));
     spec_elems = small > spec_elems ? small : spec_elems;
   }
   size_t o = 256;
@@ -607,6 +1147,8 @@ inline LapLayout lapLayout(const bout_b200_grid* g, const bout_b200_laplace* L) 
   o += lapRoundUp(l.nspec * sizeof(cd), 256);
   l.bnd = o;
   o += lapRoundUp(static_cast<size_t>(4) * (g->xstart > 1 ? g->xstart : 1) * g->ny * nmode * sizeof(cd), 256);
+  l.nyq = o; // block path, Nyquist mode: values (8 B), sweep values (16 B), table (48 B) per (x, y) + one table row per y
+  o += lapRoundUp(n2 * 72 + static_cast<size_t>(g->ny) * 48, 256);
   if (lapCoupled(L)) {
     l.sprime = o;
     o += lapRoundUp(l.nspec * sizeof(cd), 256);
@@ -661,6 +1203,7 @@ inline void lapFillParams(const bout_b200_grid* g, const bout_b200_laplace* L, v
   p.out_set = (L->last_x && (L->outer_boundary_flags & INV_SET)) ? 1 : 0;
   p.nxpe = 1;
   p.pe_xind = 0;
+  p.kscale = 2.0 * M_PI / L->zlength;
 
   const LapLayout l = lapLayout(g, L);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -679,13 +1222,17 @@ inline void lapFillParams(const bout_b200_grid* g, const bout_b200_laplace* L, v
   }
   if (lapbShapeOk(g->nz)) {
     const int n = p.bd.xe - p.bd.xs + 1;
-    p.bMB = lapbRowsPerBlock(g->nz);
-    p.bP = lapbBlocks(n, g->nz);
+    p.bNT = g->nz == 512 ? lapbThreads512() : 256;
+    p.bMB = lapbRowsPerBlock(g->nz, p.bNT);
+    p.bP = lapbBlocks(n, p.bMB);
     const size_t per = static_cast<size_t>(p.ye - p.ys + 1) * p.bP * p.nmode;
     p.bif = p.spec;
-    p.bxs = p.bif + 3 * per;
-    p.bds = p.bxs + per;
-    p.bred = p.bds + per;
+    p.bxs = p.bif + 2 * per;
+    p.bred = p.bxs + per;
+    const size_t n2 = static_cast<size_t>(g->nx) * g->ny;
+    p.bnqt = reinterpret_cast<cd*>(ws + l.nyq);
+    p.bnqd = p.bnqt + n2 * 3 + static_cast<size_t>(g->ny) * 3;
+    p.bnq = reinterpret_cast<double*>(p.bnqd + n2);
   }
 }
 

@@ -32,12 +32,23 @@
 #include "laplace_block.cuh"
 #include "fft_fast.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
 
+namespace cg = cooperative_groups;
+
 namespace b200 {
+
+// clock read that memory operations are not moved across (phase traces)
+__device__ __forceinline__ long long clockFenced() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
 
 __device__ __forceinline__ RowFFT makeRow(const LapParams& p, unsigned char* smem_raw, int& rloc) {
   const int nbuf = fftBufElems(p.nz);
@@ -678,105 +689,235 @@ __global__ void __launch_bounds__(128) k_lap_backward(const LapParams p) {
 
 
 // ---- block path (laplace_block.cuh) ---------------------------------------------------------------------------
+// One cooperative kernel per solve decides whether the matrix-only tables are still valid and rebuilds them when
+// not: compare the Field2D inputs with the copy of the last factorisation -> grid barrier -> (only when something
+// changed) K-table -> barrier -> block factors -> barrier -> separator-system factors.
 __global__ void __launch_bounds__(256) k_lapb_prepare(const LapParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < p.nx * p.ny) {
-    lapbPrepareThread(p, i);
+  cg::grid_group grid = cg::this_grid();
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int n2 = p.nx * p.ny;
+  for (long long i = tid; i < n2; i += nth) {
+    lapbCompareThread(p, static_cast<int>(i));
   }
-}
-
-__global__ void __launch_bounds__(128) k_lapb_factor1(const LapParams p) {
+  grid.sync();
   if (!lapbDirty(p)) {
     return;
   }
-  const long long total = static_cast<long long>(p.ye - p.ys + 1) * p.bP * p.nmode;
+  for (long long i = tid; i < n2; i += nth) {
+    lapTableEntry(p, static_cast<int>(i));
+  }
+  grid.sync();
   bool bad = false;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long t1 = static_cast<long long>(p.ye - p.ys + 1) * p.bP * p.nmode;
+  for (long long idx = tid; idx < t1; idx += nth) {
     bad = lapbFactor1Thread(p, idx) || bad;
   }
+  grid.sync();
+  if (p.bP > 1) {
+    const long long t2 = static_cast<long long>(p.ye - p.ys + 1) * p.nmode;
+    for (long long idx = tid; idx < t2; idx += nth) {
+      bad = lapbFactor2Thread(p, static_cast<int>(idx)) || bad;
+    }
+  }
+  if (p.nmode > p.nz / 2) { // the Nyquist mode's own (unblocked) factors: one thread per table row in y, from the far end
+    const int ny_tab = lapbYdep(p) ? p.ye - p.ys + 1 : 1;
+    const long long rid = nth - 1 - tid;
+    if (rid < ny_tab) {
+      bad = lapbNyquistFactorThread(p, static_cast<int>(rid)) || bad;
+    }
+  }
   if (bad) {
     atomicExch(p.status, 1);
   }
 }
 
-__global__ void __launch_bounds__(128) k_lapb_factor2(const LapParams p) {
-  if (!lapbDirty(p)) {
+constexpr int LAPB_RED_NT = 64;
+// Separator systems: one thread per (y, kz < N).  The CTAs after those solve the Nyquist systems, one per y:
+// tables and right-hand side staged in shared memory, lane 0 sweeps the top half downward while lane 1 sweeps
+// the bottom half upward, they meet and substitute outward.
+__global__ void __launch_bounds__(LAPB_RED_NT) k_lapb_reduced(const LapParams p, const int nred_ctas) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nys = p.ye - p.ys + 1, nk = min(p.nmode, p.nz / 2);
+  if (static_cast<int>(blockIdx.x) < nred_ctas) {
+    cd* D = reinterpret_cast<cd*>(smem_raw); // [P][LAPB_RED_NT]: a thread's column is conflict-free
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < nys * nk) {
+      lapbReducedThread(p, (idx / nk) * p.nmode + idx % nk, D + threadIdx.x, LAPB_RED_NT);
+    }
     return;
   }
-  const int total = (p.ye - p.ys + 1) * p.nmode;
-  bool bad = false;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    bad = lapbFactor2Thread(p, idx) || bad;
+  const int iyl = blockIdx.x - nred_ctas, n = p.bd.xe - p.bd.xs + 1, mid = lapbNyqMid(n);
+  const int ysel = lapbYdep(p) ? iyl : 0;
+  cd* T = reinterpret_cast<cd*>(smem_raw);  // [n + 1][3]
+  cd* D = T + (n + 1) * 3;                  // [n]
+  double* r = reinterpret_cast<double*>(D + n); // [n]
+  const cd* __restrict__ Tg = p.bnqt + static_cast<long long>(ysel) * (n + 1) * 3;
+  double* __restrict__ rg = p.bnq + static_cast<long long>(iyl) * n;
+  for (int i = threadIdx.x; i < (n + 1) * 3; i += blockDim.x) {
+    T[i] = ldcd(Tg + i);
   }
-  if (bad) {
-    atomicExch(p.status, 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    r[i] = rg[i];
   }
-}
-
-__global__ void __launch_bounds__(64) k_lapb_reduced(const LapParams p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < (p.ye - p.ys + 1) * p.nmode) {
-    lapbReducedThread(p, idx);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    cd e = {0.0, 0.0};
+    if (lane == 0) {
+      e = lapbNyqSweep(T, r, D, 0, mid - 1, 1);
+    } else if (lane == 1) {
+      e = lapbNyqSweep(T, r, D, n - 1, mid, -1);
+    }
+    const cd dt = {__shfl_sync(0xffffffffu, e.re, 0), __shfl_sync(0xffffffffu, e.im, 0)};
+    const cd ub = {__shfl_sync(0xffffffffu, e.re, 1), __shfl_sync(0xffffffffu, e.im, 1)};
+    const cd xm = lapbNyqMeet(T, n, dt, ub);
+    if (lane == 0) {
+      lapbNyqSubst(T, D, r, mid - 1, 0, -1, xm);
+    } else if (lane == 1 && mid < n) {
+      r[mid] = xm.re;
+      lapbNyqSubst(T, D, r, mid + 1, n - 1, 1, xm);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    rg[i] = r[i];
   }
 }
 
 // rows kernels: CTA = (NBLK consecutive blocks of one y row); the phases of laplace_block.cuh / fft_reg.cuh
 // with their barriers.  A row is owned by T lanes of one warp, so the transform phases only need __syncwarp.
-template <int N, int MODE>
-__global__ void __launch_bounds__(256, 2) k_lapb_rows(const LapParams p) {
-  using Sh = LapbShape<N>;
+// While a CTA works, the rows of the CTA that will take its place (block index + bPD) are pulled into L2 by
+// the bulk-prefetch unit: DRAM latency then overlaps the transforms without costing registers or shared memory.
+template <int N, int NT, int MODE>
+__global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
+  using Sh = LapbShape<N, NT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* S = reinterpret_cast<cd*>(smem_raw);
-  double* ktab = reinterpret_cast<double*>(S + Sh::ROWS * Sh::SROW);
+  double* rowc = reinterpret_cast<double*>(S + Sh::ROWS * Sh::SROW);
   const int tid = threadIdx.x, t = tid % Sh::T;
-  const LapbCta c = lapbCta<N>(p, blockIdx.x);
+  const bool trace = (p.dbg & 32) && (blockIdx.x % 1000 == 500) && (tid % 32 == 0); // phase clocks of a few CTAs
+  long long tk[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (trace) tk[0] = clockFenced();
+  const LapbCta c = lapbCta<N, NT>(p, blockIdx.x);
+  if (p.bPD > 0 && tid < Sh::ROWS && blockIdx.x + p.bPD < gridDim.x) {
+    const LapbCta cn = lapbCta<N, NT>(p, blockIdx.x + p.bPD);
+    const int ix = cn.row0 + tid;
+    if (ix <= p.bd.xe - p.bd.xs) {
+      const double* src = p.rhs + (static_cast<long long>(p.bd.xs + ix) * p.ny + cn.jy) * p.nz;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(p.nz * 8) : "memory");
+    }
+  }
   cd* row = S + (tid / Sh::T) * Sh::SROW;
   cd v[Sh::B];
-  lapbLoadRow<N, MODE>(p, c, tid, v);
+  if (!(p.dbg & 8)) {
+    lapbLoadRow<N, NT, MODE>(p, c, tid, v);
+  } else {
+#pragma unroll
+    for (int q = 0; q < Sh::B; ++q) {
+      v[q] = {1.0 + tid, 2.0 + q};
+    }
+  }
   if (MODE == LAPB_SOLVE) {
-    lapbStageTable<N>(p, c, tid, ktab);
+    lapbStageRows<N, NT>(p, c, tid, rowc);
   }
-  regfftStage1<N, false>(v, p.tw, t);
-  regfftXchgWrite<N>(v, row, t);
-  __syncwarp();
-  regfftStage2<N, false>(v, row, t);
-  __syncwarp();
-  regfftSplitWriteZ<N>(v, row, t);
-  __syncwarp();
-  {
-    cd pc[Sh::B / 2 + 1];
-    regfftSplitReadPartners<N>(pc, row, t);
+  if (trace) tk[1] = clockFenced();
+  if (!(p.dbg & 4)) {
+    regfftStage1<N, false>(v, p.tw, t);
+    regfftXchgWrite<N>(v, row, t);
     __syncwarp();
-    regfftSplitWriteX<N>(v, pc, row, p.tw, t);
+    regfftStage2<N, false>(v, row, t);
+    __syncwarp();
+    regfftSplitWriteZ<N>(v, row, t);
+    __syncwarp();
+    {
+      cd pc[Sh::B / 2 + 1];
+      regfftSplitReadPartners<N>(pc, row, t);
+      __syncwarp();
+      regfftSplitWriteX<N>(v, pc, row, p.tw, t);
+    }
+  } else {
+    regfftSplitWriteZ<N>(v, row, t);
   }
-  __syncthreads();
-  const int blk = tid / N, kz = tid % N;
-  if (kz < p.nmode) {
+  if (trace) tk[2] = clockFenced();
+  const bool nyquist = p.nmode > N;
+  if (nyquist && t == 0 && c.row0 + tid / Sh::T <= p.bd.xe - p.bd.xs) { // this thread wrote X[N] of its row itself
+    double* q = p.bnq + static_cast<long long>(c.iyl) * (p.bd.xe - p.bd.xs + 1) + c.row0 + tid / Sh::T;
     if (MODE == LAPB_DOTS) {
-      lapbDotsThread<N>(p, c, blk, kz, S);
+      *q = row[N].re;
     } else {
-      lapbSolveThread<N>(p, c, blk, kz, S, ktab);
+      row[N] = {*q, 0.0};
     }
   }
-  if (p.nmode > N && kz == 0) { // the Nyquist system of this block
-    if (MODE == LAPB_DOTS) {
-      lapbDotsThread<N>(p, c, blk, N, S);
-    } else {
-      lapbSolveThread<N>(p, c, blk, N, S, ktab);
+  if (!(p.dbg & 1)) { // per-mode phase; its operands are fetched on this side of the barrier
+    int kzs[Sh::KPT];
+    bool on[Sh::KPT];
+    const int blk = lapbModes<N, NT>(tid, kzs);
+#pragma unroll
+    for (int ch = 0; ch < Sh::KPT; ++ch) {
+      on[ch] = kzs[ch] < p.nmode;
     }
+    if (MODE == LAPB_DOTS) {
+      LapbDots<Sh::KPT> st;
+      lapbDotsFetch<N, NT, Sh::KPT>(p, c, blk, kzs, 0, st);
+      lapbDotsFetchScale<N, NT, Sh::KPT>(p, c, blk, kzs, st);
+      if (trace) tk[5] = clockFenced();
+      __syncthreads();
+      if (trace) tk[3] = clockFenced();
+      lapbDotsRun<N, NT, Sh::KPT>(p, c, blk, kzs, on, st, S);
+    } else {
+      LapbChain<Sh::MB, Sh::KPT> st;
+      if (!(p.dbg & 64)) {
+        lapbChainLoad<N, NT, Sh::KPT>(p, c, blk, kzs, st);
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < Sh::KPT; ++ch) {
+#pragma unroll
+          for (int li = 0; li < Sh::MB; ++li) {
+            st.w[ch][li] = {0.5 + tid, 0.25};
+          }
+          st.xs[ch] = st.xn[ch] = st.midinv[ch] = {0.1, 0.2};
+        }
+      }
+      if (trace) tk[6] = clockFenced();
+      __syncthreads();
+      if (trace) tk[3] = clockFenced();
+      lapbChainRun<N, NT, Sh::KPT>(p, c, blk, kzs, on, st, S, rowc);
+    }
+  } else {
+    __syncthreads();
   }
   if (MODE == LAPB_DOTS) {
+    if (trace) {
+      tk[4] = clockFenced();
+      printf("DOTS cta %d warp %d: load %lld fft %lld fetch %lld bar1 %lld permode %lld total %lld\n", blockIdx.x, tid / 32,
+             tk[1] - tk[0], tk[2] - tk[1], tk[5] - tk[2], tk[3] - tk[5], tk[4] - tk[3], tk[4] - tk[0]);
+    }
     return;
   }
+  if (trace) tk[4] = clockFenced();
   __syncthreads();
-  regfftMergeRead<N>(v, row, p.nmode, p.zero_dc != 0, p.tw, t);
-  __syncwarp();
-  regfftStage1<N, true>(v, p.tw, t);
-  regfftXchgWrite<N>(v, row, t);
-  __syncwarp();
-  regfftStage2<N, true>(v, row, t);
-  lapbStoreRow<N>(p, c, tid, v);
+  if (trace) tk[5] = clockFenced();
+  if (!(p.dbg & 2)) {
+    regfftMergeRead<N>(v, row, p.nmode, p.zero_dc != 0, p.tw, t);
+    __syncwarp();
+    regfftStage1<N, true>(v, p.tw, t);
+    regfftXchgWrite<N>(v, row, t);
+    __syncwarp();
+    regfftStage2<N, true>(v, row, t);
+  } else {
+#pragma unroll
+    for (int q = 0; q < Sh::B; ++q) {
+      v[q] = row[t + Sh::T * q];
+    }
+  }
+  lapbStoreRow<N, NT>(p, c, tid, v);
+  if (trace) {
+    const long long te = clockFenced();
+    printf("SOLVE cta %d warp %d: load %lld fft %lld fetch %lld bar1 %lld permode %lld bar2 %lld ifft+store %lld total %lld\n",
+           blockIdx.x, tid / 32, tk[1] - tk[0], tk[2] - tk[1], tk[6] - tk[2], tk[3] - tk[6], tk[4] - tk[3], tk[5] - tk[4],
+           te - tk[5], te - tk[0]);
+  }
 }
 
 } // namespace b200
@@ -829,7 +970,17 @@ int lapSetup(const bout_b200_grid* g, const bout_b200_laplace* L, void* workspac
     B200_REQUIRE(L->g_22 != nullptr, BOUT_B200_ERR_ARG, "laplace: GRADPAR boundary needs g_22");
   }
   LapParams& p = plan->p;
+  if (const char* env = getenv("BOUT_B200_LAPB_NT")) { // rows-kernel CTA size at nz = 512: 256 (default) or 128
+    lapbThreads512() = atoi(env) == 128 ? 128 : 256;
+  }
   lapFillParams(g, L, workspace, &p);
+  if (const char* env = getenv("BOUT_B200_LAPB_DBG")) {
+    p.dbg = atoi(env);
+  }
+  p.bPD = 2 * 148; // CTAs in flight: 2 per SM
+  if (const char* env = getenv("BOUT_B200_LAPB_PD")) {
+    p.bPD = atoi(env);
+  }
   int st = 0;
   p.tw = twiddleTable(g->nz, s, &st);
   if (st != 0) {
@@ -951,27 +1102,27 @@ bool lapUseBlock(const LapPlan* plan, const bout_b200_laplace* L, bool with_fiel
   return env == nullptr || env[0] != '0';
 }
 
-template <int N, int MODE>
+template <int N, int NT, int MODE>
 int launchRows(const LapParams& p, cudaStream_t s) {
-  using Sh = LapbShape<N>;
+  using Sh = LapbShape<N, NT>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(k_lapb_rows<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA_OK(cudaFuncSetAttribute(k_lapb_rows<N, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(Sh::smemBytes)));
     configured = true;
   }
   const int n = p.bd.xe - p.bd.xs + 1, nys = p.ye - p.ys + 1;
   const unsigned blocks = static_cast<unsigned>(nys) * ((n + Sh::ROWS - 1) / Sh::ROWS);
-  k_lapb_rows<N, MODE><<<blocks, Sh::NT, Sh::smemBytes, s>>>(p);
+  k_lapb_rows<N, NT, MODE><<<blocks, NT, Sh::smemBytes, s>>>(p);
   B200_LAUNCH_OK();
   return 0;
 }
 template <int MODE>
 int launchRowsN(const LapParams& p, cudaStream_t s) {
   switch (p.nz) {
-  case 128: return launchRows<64, MODE>(p, s);
-  case 256: return launchRows<128, MODE>(p, s);
-  default: return launchRows<256, MODE>(p, s);
+  case 128: return launchRows<64, 256, MODE>(p, s);
+  case 256: return launchRows<128, 256, MODE>(p, s);
+  default: return p.bNT == 128 ? launchRows<256, 128, MODE>(p, s) : launchRows<256, 256, MODE>(p, s);
   }
 }
 
@@ -993,32 +1144,44 @@ int lapBlockFactor(const bout_b200_grid* g, const bout_b200_laplace* L, void* wo
     std::lock_guard<std::mutex> lock(g_factor_mutex);
     g_factors[workspace] = k;
   }
-  const int n2 = p.nx * p.ny;
-  k_lapb_prepare<<<(n2 + 255) / 256, 256, 0, s>>>(p);
-  B200_LAUNCH_OK();
-  const long long t1 = static_cast<long long>(p.ye - p.ys + 1) * p.bP * p.nmode;
-  const unsigned b1 = static_cast<unsigned>(t1 + 127) / 128 < 148u * 8 ? static_cast<unsigned>((t1 + 127) / 128) : 148u * 8;
-  k_lapb_factor1<<<b1, 128, 0, s>>>(p);
-  B200_LAUNCH_OK();
-  if (p.bP > 1) {
-    const int t2 = (p.ye - p.ys + 1) * p.nmode;
-    const unsigned b2 = static_cast<unsigned>((t2 + 127) / 128) < 148u * 4 ? static_cast<unsigned>((t2 + 127) / 128) : 148u * 4;
-    k_lapb_factor2<<<b2, 128, 0, s>>>(p);
-    B200_LAUNCH_OK();
+  static int coop_blocks = 0; // co-resident CTAs of the cooperative kernel on this device
+  if (coop_blocks == 0) {
+    int dev = 0, sms = 0, per = 0;
+    B200_CUDA_OK(cudaGetDevice(&dev));
+    B200_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B200_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lapb_prepare, 256, 0));
+    B200_REQUIRE(per >= 1, BOUT_B200_ERR_CUDA, "laplace: the prepare kernel does not fit on an SM");
+    coop_blocks = sms * (per < 2 ? per : 2);
   }
+  void* args[] = {&p};
+  B200_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_lapb_prepare), dim3(coop_blocks), dim3(256), args, 0, s));
+  countLaunch();
   return 0;
 }
 
 int lapBlockSolve(const LapPlan* plan, cudaStream_t s) {
   const LapParams& p = plan->p;
   int rc = 0;
-  if (p.bP > 1) {
+  if (p.bP > 1 || p.nmode > p.nz / 2) { // separators and / or the Nyquist mode to be solved between the two passes
     rc = launchRowsN<LAPB_DOTS>(p, s);
     if (rc != 0) {
       return rc;
     }
-    const int t = (p.ye - p.ys + 1) * p.nmode;
-    k_lapb_reduced<<<(t + 63) / 64, 64, 0, s>>>(p);
+    const int nys = p.ye - p.ys + 1, nk = p.nmode < p.nz / 2 ? p.nmode : p.nz / 2, n = p.bd.xe - p.bd.xs + 1;
+    const int nred = (nys * nk + LAPB_RED_NT - 1) / LAPB_RED_NT;
+    const bool nyquist = p.nmode > p.nz / 2;
+    size_t dsm = static_cast<size_t>(p.bP) * LAPB_RED_NT * sizeof(cd);
+    const size_t nsm = static_cast<size_t>(n + 1) * 3 * sizeof(cd) + static_cast<size_t>(n) * (sizeof(cd) + sizeof(double));
+    if (nyquist && nsm > dsm) {
+      dsm = nsm;
+    }
+    B200_REQUIRE(dsm <= 200 * 1024, BOUT_B200_ERR_UNSUPPORTED, "laplace: nx = %d too large for the block path", p.nx);
+    static size_t dsm_attr = 48 * 1024;
+    if (dsm > dsm_attr) {
+      B200_CUDA_OK(cudaFuncSetAttribute(k_lapb_reduced, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dsm)));
+      dsm_attr = dsm;
+    }
+    k_lapb_reduced<<<nred + (nyquist ? nys : 0), LAPB_RED_NT, dsm, s>>>(p, nred);
     B200_LAUNCH_OK();
   }
   return launchRowsN<LAPB_SOLVE>(p, s);

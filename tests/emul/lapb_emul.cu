@@ -17,69 +17,80 @@ std::vector<unsigned char> g_ws;
 std::vector<cd> g_tw;
 unsigned g_gen = 0;
 
-template <int N, int MODE>
+template <int N, int NT, int MODE>
 void emulRows(const LapParams& p) {
-  using Sh = LapbShape<N>;
+  using Sh = LapbShape<N, NT>;
   const int n = p.bd.xe - p.bd.xs + 1, nys = p.ye - p.ys + 1;
   const int nblocks = nys * ((n + Sh::ROWS - 1) / Sh::ROWS);
   std::vector<cd> S(static_cast<size_t>(Sh::ROWS) * Sh::SROW);
-  std::vector<double> ktab(Sh::ROWS * LAP_NK);
-  static cd v[Sh::NT][Sh::B];
-  static cd pc[Sh::NT][Sh::B / 2 + 1];
+  std::vector<double> rowc(Sh::ROWS * Sh::NRC);
+  static cd v[NT][Sh::B];
+  static cd pc[NT][Sh::B / 2 + 1];
   for (int bid = 0; bid < nblocks; ++bid) {
-    const LapbCta c = lapbCta<N>(p, bid);
+    const LapbCta c = lapbCta<N, NT>(p, bid);
     auto row = [&](int tid) { return S.data() + (tid / Sh::T) * Sh::SROW; };
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       const int t = tid % Sh::T;
-      lapbLoadRow<N, MODE>(p, c, tid, v[tid]);
+      lapbLoadRow<N, NT, MODE>(p, c, tid, v[tid]);
       if (MODE == LAPB_SOLVE) {
-        lapbStageTable<N>(p, c, tid, ktab.data());
+        lapbStageRows<N, NT>(p, c, tid, rowc.data());
       }
       regfftStage1<N, false>(v[tid], p.tw, t);
       regfftXchgWrite<N>(v[tid], row(tid), t);
     }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       regfftStage2<N, false>(v[tid], row(tid), tid % Sh::T);
     }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       regfftSplitWriteZ<N>(v[tid], row(tid), tid % Sh::T);
     }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       regfftSplitReadPartners<N>(pc[tid], row(tid), tid % Sh::T);
     }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       regfftSplitWriteX<N>(v[tid], pc[tid], row(tid), p.tw, tid % Sh::T);
-    }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
-      const int blk = tid / N, kz = tid % N;
-      if (kz < p.nmode) {
+      if (p.nmode > N && tid % Sh::T == 0 && c.row0 + tid / Sh::T <= p.bd.xe - p.bd.xs) {
+        double* q = p.bnq + static_cast<long long>(c.iyl) * (p.bd.xe - p.bd.xs + 1) + c.row0 + tid / Sh::T;
         if (MODE == LAPB_DOTS) {
-          lapbDotsThread<N>(p, c, blk, kz, S.data());
+          *q = row(tid)[N].re;
         } else {
-          lapbSolveThread<N>(p, c, blk, kz, S.data(), ktab.data());
+          row(tid)[N] = {*q, 0.0};
         }
       }
-      if (p.nmode > N && kz == 0) {
-        if (MODE == LAPB_DOTS) {
-          lapbDotsThread<N>(p, c, blk, N, S.data());
-        } else {
-          lapbSolveThread<N>(p, c, blk, N, S.data(), ktab.data());
-        }
+    }
+    // per-mode phase.  The fetches of pass 0 sit before the CTA barrier in the kernel; they read global memory
+    // only, so a simulated thread may do them right before its run
+    for (int tid = 0; tid < NT; ++tid) {
+      int kzs[Sh::KPT];
+      bool on[Sh::KPT];
+      const int blk = lapbModes<N, NT>(tid, kzs);
+      for (int ch = 0; ch < Sh::KPT; ++ch) {
+        on[ch] = kzs[ch] < p.nmode;
+      }
+      if (MODE == LAPB_DOTS) {
+        LapbDots<Sh::KPT> st;
+        lapbDotsFetch<N, NT, Sh::KPT>(p, c, blk, kzs, 0, st);
+        lapbDotsFetchScale<N, NT, Sh::KPT>(p, c, blk, kzs, st);
+        lapbDotsRun<N, NT, Sh::KPT>(p, c, blk, kzs, on, st, S.data());
+      } else {
+        LapbChain<Sh::MB, Sh::KPT> st;
+        lapbChainLoad<N, NT, Sh::KPT>(p, c, blk, kzs, st);
+        lapbChainRun<N, NT, Sh::KPT>(p, c, blk, kzs, on, st, S.data(), rowc.data());
       }
     }
     if (MODE == LAPB_DOTS) {
       continue;
     }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       regfftMergeRead<N>(v[tid], row(tid), p.nmode, p.zero_dc != 0, p.tw, tid % Sh::T);
     }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       regfftStage1<N, true>(v[tid], p.tw, tid % Sh::T);
       regfftXchgWrite<N>(v[tid], row(tid), tid % Sh::T);
     }
-    for (int tid = 0; tid < Sh::NT; ++tid) {
+    for (int tid = 0; tid < NT; ++tid) {
       regfftStage2<N, true>(v[tid], row(tid), tid % Sh::T);
-      lapbStoreRow<N>(p, c, tid, v[tid]);
+      lapbStoreRow<N, NT>(p, c, tid, v[tid]);
     }
   }
 }
@@ -87,9 +98,15 @@ void emulRows(const LapParams& p) {
 template <int MODE>
 void emulRowsN(const LapParams& p) {
   switch (p.nz) {
-  case 128: emulRows<64, MODE>(p); break;
-  case 256: emulRows<128, MODE>(p); break;
-  default: emulRows<256, MODE>(p); break;
+  case 128: emulRows<64, 256, MODE>(p); break;
+  case 256: emulRows<128, 256, MODE>(p); break;
+  default:
+    if (p.bNT == 128) {
+      emulRows<256, 128, MODE>(p);
+    } else {
+      emulRows<256, 256, MODE>(p);
+    }
+    break;
   }
 }
 } // namespace
@@ -97,10 +114,15 @@ void emulRowsN(const LapParams& p) {
 // All pointers are HOST pointers.  Returns bit 0 = zero pivot seen, bit 1 = the factorisation was rebuilt,
 // bit 2 = the tables are per-y; -1 when the configuration is not served by the block path.
 // `fresh` != 0 drops the emulated workspace first (a new solver object).
+// `nt512`: CTA size of the rows kernels at nz = 512 (256 or 128).
 extern "C" int lapb_emul_solve(const bout_b200_grid* g, const bout_b200_laplace* L, const double* rhs,
-                               const double* x0, double* out, int fresh, int force) {
+                               const double* x0, double* out, int fresh, int force, int nt512) {
   if (lapCoupled(L) || !lapbShapeOk(g->nz)) {
     return -1;
+  }
+  if (lapbThreads512() != nt512) {
+    lapbThreads512() = nt512;
+    fresh = 1;
   }
   const size_t need = lapLayout(g, L).total;
   if (fresh || g_ws.size() != need) {
@@ -123,11 +145,14 @@ extern "C" int lapb_emul_solve(const bout_b200_grid* g, const bout_b200_laplace*
   p.gen = ++g_gen;
   p.force = force;
   for (int i = 0; i < p.nx * p.ny; ++i) {
-    lapbPrepareThread(p, i);
+    lapbCompareThread(p, i);
   }
   int flags = 0;
   if (lapbDirty(p)) {
     flags |= 2;
+    for (int i = 0; i < p.nx * p.ny; ++i) {
+      lapTableEntry(p, i);
+    }
     bool bad = false;
     const long long t1 = static_cast<long long>(p.ye - p.ys + 1) * p.bP * p.nmode;
     for (long long idx = 0; idx < t1; ++idx) {
@@ -138,6 +163,11 @@ extern "C" int lapb_emul_solve(const bout_b200_grid* g, const bout_b200_laplace*
         bad = lapbFactor2Thread(p, idx) || bad;
       }
     }
+    if (p.nmode > p.nz / 2) {
+      for (int ysel = 0; ysel < (lapbYdep(p) ? p.ye - p.ys + 1 : 1); ++ysel) {
+        bad = lapbNyquistFactorThread(p, ysel) || bad;
+      }
+    }
     if (bad) {
       p.status[LAPW_STATUS] = 1;
     }
@@ -145,10 +175,28 @@ extern "C" int lapb_emul_solve(const bout_b200_grid* g, const bout_b200_laplace*
   if (lapbYdep(p)) {
     flags |= 4;
   }
-  if (p.bP > 1) {
+  if (p.bP > 1 || p.nmode > p.nz / 2) {
     emulRowsN<LAPB_DOTS>(p);
-    for (int idx = 0; idx < (p.ye - p.ys + 1) * p.nmode; ++idx) {
-      lapbReducedThread(p, idx);
+    std::vector<cd> D(p.bP);
+    const int nys = p.ye - p.ys + 1, nk = p.nmode < p.nz / 2 ? p.nmode : p.nz / 2;
+    for (int idx = 0; idx < nys * nk; ++idx) {
+      lapbReducedThread(p, (idx / nk) * p.nmode + idx % nk, D.data(), 1);
+    }
+    if (p.nmode > p.nz / 2) {
+      const int n = p.bd.xe - p.bd.xs + 1, mid = lapbNyqMid(n);
+      std::vector<cd> Dn(n);
+      for (int iyl = 0; iyl < nys; ++iyl) {
+        const cd* T = p.bnqt + static_cast<long long>(lapbYdep(p) ? iyl : 0) * (n + 1) * 3;
+        double* r = p.bnq + static_cast<long long>(iyl) * n;
+        const cd dt = lapbNyqSweep(T, r, Dn.data(), 0, mid - 1, 1);
+        const cd ub = lapbNyqSweep(T, r, Dn.data(), n - 1, mid, -1);
+        const cd xm = lapbNyqMeet(T, n, dt, ub);
+        lapbNyqSubst(T, Dn.data(), r, mid - 1, 0, -1, xm);
+        if (mid < n) {
+          r[mid] = xm.re;
+          lapbNyqSubst(T, Dn.data(), r, mid + 1, n - 1, 1, xm);
+        }
+      }
     }
   }
   emulRowsN<LAPB_SOLVE>(p);

@@ -204,8 +204,8 @@ def test_laplace_block_path_matches_three_kernel_path(capi, orc, port, grid, fla
     n0 = capi.launch_count()
     first = lap.solve(dev(f), dev(x0)).cpu().numpy()
     lap.status()
-    # prepare + factor (+ separator factor) + [dots + reduced] + solve
-    assert capi.launch_count() - n0 == (6 if nblocks > 1 else 3)
+    # prepare / factor (one cooperative kernel) + [dots + reduced: separators and / or the Nyquist mode] + solve
+    assert capi.launch_count() - n0 == (4 if (nblocks > 1 or not filt) else 2)
     again = lap.solve(dev(f), dev(x0)).cpu().numpy()
     lap.status()
     assert np.array_equal(first[region], again[region])
