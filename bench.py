@@ -3,13 +3,17 @@
 
 Workload (BASELINE.json configs[3], the config the metric "RHS grid-pts/s fp64 at 1/2/4/8 B200" is
 quoted on): examples/hasegawa-wakatani-3d at 512x128x512 interior points PER GPU (516x132x512 with
-guard cells, MXG = MYG = 2, y periodic, bndry_all = dirichlet_o2), X-decomposed across N GPUs (weak
-scaling: global nx = 512*N + 4).  One "step" is one RK4 time step = 4 RHS evaluations, each
+guard cells, MXG = MYG = 2, y periodic, bndry_all = dirichlet_o2).  At N GPUs the BoutMesh decomposition is
+NYPE = N by default (weak scaling: global ny = 128*N; --decomp x gives NXPE = N, global nx = 512*N + 4, with the
+X-decomposed LaplaceCyclic; --decomp xy gives NXPE = 2).  One "step" is one RK4 time step = 4 RHS evaluations, each
   Solver::pre_rhs boundary conditions -> LaplaceCyclic solve (vort -> phi) -> Mesh::communicate(n, vort, phi)
   -> fused RHS kernel (2 Arakawa brackets, Div_par_Grad_par, DDZ, 2 Delp2) with the RK stage update in
   its epilogue;
 value = interior points * 4 * K / time.  Fields (279 MB each) are far larger than the 126 MB L2, so no
-L2 flush is needed between iterations (stated in config.l2).
+L2 flush is needed between iterations (stated in config.l2).  Before anything is timed the arm must pass a
+full-size parity gate: one RHS on the reference arm's own 512x16x512 slab state against the reference's output
+(<= 1e-10, N = 1), and at N > 1 every rank's slab of a decomposed 512x16Nx512 (or 512Nx16x512) problem against
+the same problem computed on one rank (<= 1e-12).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
   python bench.py --workload elmpb [...]                        BASELINE configs[4]: elm-pb 3-field RHS, 512x64x256
@@ -190,7 +194,7 @@ def mixmode(a, seed=0.5):
     return out
 
 
-def initial_state(pe_xind, nxpe, pe_yind, nype, torch, device):
+def initial_state(pe_xind, nxpe, pe_yind, nype, torch, device, MXSUB=MXSUB, MYSUB=MYSUB):
     """The shipped initial condition (examples/hasegawa-wakatani-3d/data/BOUT.inp): n = 0,
     vort = 0.1 mixmode(2 pi x) mixmode(z - y), on this rank's slab of the global grid.  Synthetic,
     generated on the host once (setup, not timed)."""
@@ -205,6 +209,80 @@ def initial_state(pe_xind, nxpe, pe_yind, nype, torch, device):
     zy = mixmode((Z[None, :] - Y[:, None]))
     vort = 0.1 * fx[:, None, None] * zy[None, :, :]
     return torch.zeros(vort.shape, dtype=torch.float64), torch.from_numpy(np.ascontiguousarray(vort))
+
+
+def hw3d_metric(torch, g, dev):
+    one = lambda v: torch.full(g.shape2, v, dtype=torch.float64, device=dev)
+    return dict(dx=one(0.2), dy=one(1.0), dz=one(0.2), J=one(1.0), g_22=one(1.0), g11=one(1.0), g33=one(1.0),
+                g13=one(0.0), G1=one(0.0), G3=one(0.0), g_11=one(1.0))
+
+
+def rel_err_interior(torch, got, want, sl):
+    return float(((got[sl] - want[sl]).abs().max() / want[sl].abs().max().clamp_min(1e-300)).item())
+
+
+def parity_gate_reference(torch, pkg, dev):
+    """N = 1, before anything is timed: the reference arm's own 512x16x512 slab state through ONE RHS of our arm
+    against the reference's Solver::run_rhs output for that state (the unchanged hw.cxx; <= 1e-10 relative)."""
+    import tempfile
+    import numpy as np
+    path = os.path.join(tempfile.mkdtemp(prefix="b200_gate_"), "slab.npz")
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--dump-rhs", path],
+                           capture_output=True, text=True, timeout=900,
+                           env={k: v for k, v in os.environ.items()
+                                if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS", "OMP_PROC_BIND")})
+    except Exception as e:  # noqa: BLE001
+        return {"ok": None, "skipped": repr(e)[:200]}
+    if not os.path.exists(path):
+        return {"ok": None, "skipped": ("reference arm gave no slab: " + (p.stdout + p.stderr)[-200:])}
+    d = np.load(path)
+    capi = pkg.capi
+    g = capi.Grid(MXSUB + 2 * MXG, REF_MY + 2 * MYG, MZ, MXG, MYG)
+    m = pkg.models.HW3D(g, hw3d_metric(torch, g, dev), device=dev, **HW)
+    m.set_state(torch.from_numpy(d["n"]).to(dev), torch.from_numpy(d["vort"]).to(dev))
+    m.rhs()
+    torch.cuda.synchronize()
+    errs = {nm: rel_err_interior(torch, f, torch.from_numpy(d["ddt_" + nm]).to(dev), g.interior)
+            for nm, f in (("n", m.ddt_n), ("vort", m.ddt_vort))}
+    tol = 1e-10
+    return {"ok": bool(max(errs.values()) <= tol), "tolerance": tol, "rel_err": errs,
+            "what": f"one RHS on the reference arm's 512x{REF_MY}x512 slab state vs the reference's Solver::run_rhs"}
+
+
+def parity_gate_decomposed(torch, pkg, dev, rank, nxpe, nype):
+    """N > 1, before anything is timed: this rank's slab of ONE RHS of a decomposed 512*NXPE x 16*NYPE x 512
+    problem (same kernels, exchanges and X-decomposed solve as the workload) against the same problem computed on
+    one rank by the same GPU (<= 1e-12 relative)."""
+    capi, models = pkg.capi, pkg.models
+    my = REF_MY
+    mesh = pkg.mesh.BoutMesh(nxpe=nxpe, nype=nype, rank=rank, mxsub=MXSUB, mysub=my, mz=MZ, mxg=MXG, myg=MYG,
+                             periodic_x=False, periodic_y=True, device=dev)
+    pe_x, pe_y = rank % nxpe, rank // nxpe
+    g = capi.Grid(MXSUB + 2 * MXG, my + 2 * MYG, MZ, MXG, MYG)
+    md = models.HW3D(g, hw3d_metric(torch, g, dev), device=dev, mesh=mesh, **HW)
+    n0, v0 = initial_state(pe_x, nxpe, pe_y, nype, torch, dev, MYSUB=my)
+    md.set_state(n0.to(dev), v0.to(dev))
+    md.rhs()
+    G = capi.Grid(MXSUB * nxpe + 2 * MXG, my * nype + 2 * MYG, MZ, MXG, MYG)
+    mg = models.HW3D(G, hw3d_metric(torch, G, dev), device=dev, **HW)
+    N0, V0 = initial_state(0, 1, 0, 1, torch, dev, MXSUB=MXSUB * nxpe, MYSUB=my * nype)
+    mg.set_state(N0.to(dev), V0.to(dev))
+    mg.rhs()
+    torch.cuda.synchronize()
+    sl = (slice(MXG + pe_x * MXSUB, MXG + (pe_x + 1) * MXSUB), slice(MYG + pe_y * my, MYG + (pe_y + 1) * my), slice(None))
+    errs = {}
+    for nm, fd, fg in (("n", md.ddt_n, mg.ddt_n), ("vort", md.ddt_vort, mg.ddt_vort)):
+        want = fg[sl]
+        errs[nm] = float(((fd[g.interior] - want).abs().max() / want.abs().max().clamp_min(1e-300)).item())
+    worst = torch.tensor([max(errs.values())], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(worst, op=torch.distributed.ReduceOp.MAX)
+    tol = 1e-12
+    del md, mg
+    torch.cuda.empty_cache()
+    return {"ok": bool(worst.item() <= tol), "tolerance": tol, "rel_err_max_over_ranks": float(worst.item()),
+            "what": f"one RHS of a {MXSUB * nxpe}x{my * nype}x{MZ} problem decomposed NXPE={nxpe} NYPE={nype} vs the same "
+                    f"problem on one rank"}
 
 
 def run_ours(args):
@@ -239,10 +317,20 @@ def run_ours(args):
                                  periodic_x=False, periodic_y=True, device=dev)
     pe_xind, pe_yind = rank % nxpe, rank // nxpe
 
+    # ---- parity gate (nothing is timed before it passes) ------------------------------------------
+    if args.no_parity_gate:
+        gate = {"ok": None, "skipped": "--no-parity-gate"}
+    elif world == 1:
+        gate = parity_gate_reference(torch, pkg, dev)
+    else:
+        gate = parity_gate_decomposed(torch, pkg, dev, rank, nxpe, nype)
+    if gate.get("ok") is False:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": None, "error": "parity gate failed", "parity_gate": gate}), flush=True)
+        raise SystemExit(3)
+
     g = capi.Grid(MXSUB + 2 * MXG, MYSUB + 2 * MYG, MZ, MXG, MYG)
-    one = lambda v: torch.full(g.shape2, v, dtype=torch.float64, device=dev)
-    metric = dict(dx=one(0.2), dy=one(1.0), dz=one(0.2), J=one(1.0), g_22=one(1.0), g11=one(1.0), g33=one(1.0),
-                  g13=one(0.0), G1=one(0.0), G3=one(0.0), g_11=one(1.0))
+    metric = hw3d_metric(torch, g, dev)
     model = models.HW3D(g, metric, device=dev, mesh=mesh, **HW)
     n0, v0 = initial_state(pe_xind, nxpe, pe_yind, nype, torch, dev)
     hn, hv = n0.pin_memory(), v0.pin_memory()
@@ -317,10 +405,10 @@ def run_ours(args):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    # fused kernel, algorithmic bytes per interior point per launch (DESIGN.md "k_hw3d_rhs"):
-    #   reads n, vort, phi (24) + start n, vort (16) + running combination in (16, stages 2-4)
-    #   writes next stage state (16, stages 1-3) + running combination out (16)   -> 72, 88, 88, 72
-    alg_bytes = (72 + 88 + 88 + 72) / 4.0 * npts
+    # fused kernel, compulsory bytes per interior point per launch (DESIGN.md "k_hw3d_rhs"):
+    #   reads n, vort, phi (24) + start n, vort (16; in stage 1 they ARE the input rows: 0) + running combination
+    #   in (16, stages 2-4); writes next stage state (16, stages 1-3) + running combination out (16) -> 56, 88, 88, 72
+    alg_bytes = (56 + 88 + 88 + 72) / 4.0 * npts
     achieved = alg_bytes / k_secs / 1e9
     value = npts * 4 * args.steps * world / secs
     out = {
@@ -343,7 +431,11 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_secs * 1e3,
                      "kernel_share_of_step": 4 * k_secs / (secs / args.steps),
                      "rhs_algorithmic_GBps": (56.0 + 64.0) * npts * 4 * args.steps / secs / 1e9,
-                     "rhs_bytes_per_point": "56 (solve 16 + fused 40, SURVEY 8d) + 64 RK stage update"},
+                     "rhs_bytes_per_point": "56 (solve 16 + fused 40, SURVEY 8d) + 64 RK stage update",
+                     "rhs_frac_of_hbm_peak": (56.0 + 64.0) * npts * 4 * args.steps / secs / 1e9 / peak,
+                     "rhs_frac_of_survey_ceiling": 56.0 * npts * 4 * args.steps / secs / 1e9 / peak,
+                     "survey_ceiling_points_per_s": peak * 1e9 / 56.0},
+        "parity_gate": gate,
         "clocks": clocks,
         "rhs_phase_ms": {k: round(v, 4) for k, v in phases.items()},
     }
@@ -688,9 +780,12 @@ def run_reference_elmpb(args, cores):
     reps = max(4 * args.steps, 4)
     secs = r.model_time_rhs(reps=reps) * reps
     value = npts * reps / secs
+    threads = r.omp_threads()
     sample = (f"unchanged examples/elm-pb/elm_pb.cxx through the reference's Solver::run_rhs, y-slab 512x{my}x256 of the "
-              f"512x64x256 workload, {reps} run_rhs, OpenMP {cores} threads, single MPI rank (shim)")
-    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
+              f"512x64x256 workload, {reps} run_rhs, OpenMP {threads} threads (omp_get_max_threads; {cores} host cores), "
+              f"single MPI rank (shim)")
+    cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample, "same_config": False,
+          "host_cores": cores}
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / reps * 4 * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -731,9 +826,9 @@ def run_reference_2d(args, cores):
     secs = r.model_time_rhs(reps=reps)
     value = mx * my * mz / secs
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "us_per_rhs": secs * 1e6,
-                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": r.omp_threads(), "kind": "reference",
                                        "sample": f"unchanged examples/{args.workload} source, {mx}x{my}x{mz}, {reps} run_rhs, "
-                                                 f"OpenMP {cores} threads"}}), flush=True)
+                                                 f"OpenMP {r.omp_threads()} threads"}}), flush=True)
     sys.stdout.flush()
     os._exit(0)
 
@@ -743,7 +838,10 @@ def run_reference(args, as_baseline=False):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit that.  It runs on rank 0 only
+    # (one process, every host core of the box, whatever N is) -- the reference build here is single-rank (MPI shim).
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.pop("OMP_PROC_BIND", None)
     if args.workload == "elmpb":
         return run_reference_elmpb(args, cores)
     if args.workload in ("blob2d", "hw"):
@@ -754,17 +852,27 @@ def run_reference(args, as_baseline=False):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libboutref.so not built"}))
         return
     r = orc.Ref(ini)
-    r.model_create("hw3d", "rk4")
+    names = r.model_create("hw3d", "rk4")
     r.model_solve(0, DT)     # Solver::init + first run_rhs (the reference's own start-up)
+    threads = r.omp_threads()
+    if args.dump_rhs:        # state + one Solver::run_rhs of it, for the parity gate of our arm
+        import numpy as np
+        state = {nm: r.model_get(nm) for nm in names}
+        r.model_rhs(0.0)
+        np.savez(args.dump_rhs, **state, **{"ddt_" + nm: r.model_ddt(nm) for nm in names})
+        print(json.dumps({"impl": "reference", "dumped": args.dump_rhs, "vars": names}), flush=True)
+        sys.stdout.flush()
+        os._exit(0)
     npts = MXSUB * REF_MY * MZ
     if args.warmup > 0:
         r.model_time_rhs(reps=4 * args.warmup)
     secs = r.model_time_rhs(reps=4 * args.steps) * 4 * args.steps
     value = npts * 4 * args.steps / secs
     sample = (f"unchanged examples/hasegawa-wakatani-3d/hw.cxx through the reference's Solver::run_rhs, "
-              f"y-slab 512x{REF_MY}x512 of the 512x128x512 workload, 4 run_rhs per step, OpenMP {cores} threads, "
-              f"single MPI rank (shim)")
-    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
+              f"y-slab 512x{REF_MY}x512 of the 512x128x512 workload, 4 run_rhs per step, OpenMP {threads} threads "
+              f"(omp_get_max_threads; {cores} host cores), single MPI rank (shim); one CPU process whatever --gpus is")
+    cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+          "same_config": False, "host_cores": cores}
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -782,7 +890,8 @@ def cpu_baseline(steps, warmup, workload="hw3d"):
     try:
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps),
                             "--warmup", str(warmup), "--workload", workload], capture_output=True, text=True, timeout=600,
-                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+                           env={k: v for k, v in os.environ.items()
+                                if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS", "OMP_PROC_BIND")})
         for line in reversed(p.stdout.strip().splitlines()):
             if line.startswith("{"):
                 d = json.loads(line)
@@ -795,10 +904,13 @@ def cpu_baseline(steps, warmup, workload="hw3d"):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50, help="RK4 steps timed (4 RHS each: the default is 200 RHS)")
+    ap.add_argument("--warmup", type=int, default=5, help="untimed RK4 steps first (default: 20 RHS)")
+    ap.add_argument("--dump-rhs", default=None, help="reference arm: write the slab state and its RHS to this .npz "
+                                                     "(the parity gate of our arm reads it)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true", help="skip the full-size parity gate (profiling runs)")
     ap.add_argument("--no-other", action="store_true", help="skip the short extra measurements of the default line")
     ap.add_argument("--workload", default="hw3d", choices=["hw3d", "elmpb", "blob2d", "hw"],
                     help="blob2d / hw: reference arm only (the CPU numbers beside the host-layer extras)")

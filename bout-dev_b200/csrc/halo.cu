@@ -22,6 +22,8 @@
 
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b200 {
 
 constexpr int kMaxHaloFields = 8;
@@ -113,6 +115,7 @@ struct PushY2Params {
   unsigned long long* flag[2];  // peer flags (push) / local flags (unpack)
   unsigned int* done;           // two local block counters (push)
   int* status;                  // time-out word (unpack)
+  long long timeout;            // cycles the receiver waits for its neighbour before giving up (unpack)
   unsigned long long value;
   int y0[2];
   int nf, nx, ny, nz, nrows;
@@ -137,12 +140,19 @@ __global__ void __launch_bounds__(256) k_xchg_y2(const PushY2Params p) {
           break;
         }
         __nanosleep(100);
-      } while (clock64() - t0 < 4000000000LL);
+      } while (clock64() - t0 < p.timeout);
       if (!ok) {
         *p.status = 1;
       }
     }
     __syncthreads();
+    if (!ok) {
+      // The neighbour never signalled: the receive buffer holds stale or partial rows.  Nothing is unpacked, the
+      // status word says why, and the trap makes every later call on this context fail (BOUT_B200_ERR_CUDA) --
+      // a run must not continue on guard cells that never arrived.
+      __threadfence_system();
+      __trap();
+    }
   }
   const int nzv = p.nz / VEC;
   const long long per_field = static_cast<long long>(p.nx) * p.nrows * nzv;
@@ -185,8 +195,8 @@ __global__ void __launch_bounds__(256) k_xchg_y2(const PushY2Params p) {
   }
 }
 
-// Receiver side: spin until the neighbour's flag reaches `value` (bounded: ~4e9 cycles, then status = 1).
-__global__ void k_flag_wait(const unsigned long long* flag, unsigned long long value, int* status) {
+// Receiver side: spin until the neighbour's flag reaches `value` (bounded; then status = 1 and the context traps).
+__global__ void k_flag_wait(const unsigned long long* flag, unsigned long long value, int* status, long long timeout) {
   const long long t0 = clock64();
   unsigned long long v;
   do {
@@ -195,8 +205,21 @@ __global__ void k_flag_wait(const unsigned long long* flag, unsigned long long v
       return;
     }
     __nanosleep(200);
-  } while (clock64() - t0 < 4000000000LL);
+  } while (clock64() - t0 < timeout);
   *status = 1;
+  __threadfence_system();
+  __trap();
+}
+
+// Cycles a receiver waits: BOUT_B200_HALO_TIMEOUT_S seconds (default 60: first-call IPC mapping, module loads, a
+// neighbour busy writing output are all far below it; a dead neighbour is not) at the 1.965 GHz B200 clock.
+static long long haloTimeoutCycles() {
+  static const long long cycles = [] {
+    const char* env = getenv("BOUT_B200_HALO_TIMEOUT_S");
+    const double secs = env != nullptr && atof(env) > 0.0 ? atof(env) : 60.0;
+    return static_cast<long long>(secs * 1.965e9);
+  }();
+  return cycles;
 }
 
 } // namespace b200
@@ -330,7 +353,7 @@ extern "C" int bout_b200_halo_push_y(const bout_b200_grid* g, int nfields, doubl
 extern "C" int bout_b200_halo_wait(const unsigned long long* local_flag, unsigned long long value, int* status,
                                    void* stream) {
   B200_REQUIRE(local_flag && status, BOUT_B200_ERR_ARG, "halo_wait: null argument");
-  k_flag_wait<<<1, 1, 0, asStream(stream)>>>(local_flag, value, status);
+  k_flag_wait<<<1, 1, 0, asStream(stream)>>>(local_flag, value, status, haloTimeoutCycles());
   B200_LAUNCH_OK();
   return 0;
 }
@@ -360,6 +383,7 @@ static int xchgY2(const bout_b200_grid* g, int nfields, double* const* fields, i
   }
   p.done = counters;
   p.status = status;
+  p.timeout = haloTimeoutCycles();
   p.value = value;
   p.nf = nfields;
   p.nx = g->nx;

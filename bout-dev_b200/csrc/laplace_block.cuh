@@ -84,8 +84,6 @@ struct LapParams {
   cd* __restrict__ bxs;        // [nys][P][nmode]     separator values
   cd* __restrict__ bred;       // [LAPB_NRED][nys][P][nmode]
   double* __restrict__ bnq;    // [nys][n]      Nyquist mode kz = nz/2: Re of the rhs spectrum in, of the solution out
-  cd* __restrict__ bnqd;       // [nys][n]      its sweep values
-  cd* __restrict__ bnqt;       // [nys][n + 1][3] its pivots and multipliers (row n: the meeting-point factor)
   double kscale;               // 2 pi / zlength: kwave = kz * kscale (common_transform.cxx:73)
   unsigned gen;                // generation of this solve (ydep / dirty words hold the generation that set them)
   int force;                   // settings changed on the host side: factor regardless of the comparison
@@ -683,19 +681,29 @@ B200_HD void lapbChainLoad(const LapParams& p, const LapbCta& c, int blk, const 
 // a system only).  Sc: this mode's column of the block in S.  phase 0: top-half rows [li0, ra) downward (carry =
 // d); 1: bottom-half rows [rb, cnt) upward (carry = u; amid = a' of row mid when that is a boundary row);
 // 2: bottom-half rows after mid, downward substitution (carry = x); 3: top-half rows [li0, ra) upward (carry = x).
-B200_HD_COLD void lapbEdgeRows(const LapParams& p, int ysel, int r0, int li0, int cnt, LapbSplit sp, int srow, int kz,
-                               bool on, int phase, cd* Sc, cd* carry, cd* amid) {
-  const int first = phase == 0 ? li0 : (phase == 1 ? cnt - 1 : (phase == 2 ? max(sp.rb, sp.mid + 1) : sp.ra - 1));
-  const int last = phase == 0 ? sp.ra - 1 : (phase == 1 ? sp.rb : (phase == 2 ? cnt - 1 : li0));
+struct LapbEdge { // what lapbEdgeRows needs of the parameter block, by value (a reference to the kernel's parameter
+                  // struct would make the compiler copy all of it to local memory in every thread)
+  const cd* bnd;
+  const cd* inv;
+  long long inv0;  // index of (ysel, row r0, kz) in the pivot table
+  long long bnd0;  // index of (slot 0, ysel, kz) in bnd
+  long long bnd_slot; // index stride between boundary-row slots
+  int nmode, r0, li0, cnt, srow;
+  int ncx, inbndry, outbndry, first_x, last_x;
+};
+B200_HD_COLD void lapbEdgeRows(LapbEdge e, LapbSplit sp, bool on, int phase, cd* Sc, cd* carry, cd* amid) {
+  const int first = phase == 0 ? e.li0 : (phase == 1 ? e.cnt - 1 : (phase == 2 ? max(sp.rb, sp.mid + 1) : sp.ra - 1));
+  const int last = phase == 0 ? sp.ra - 1 : (phase == 1 ? sp.rb : (phase == 2 ? e.cnt - 1 : e.li0));
   const int step = (phase == 0 || phase == 2) ? 1 : -1;
   cd x = *carry;
   for (int li = first; step > 0 ? li <= last : li >= last; li += step) {
-    bool inner, outer;
-    const int sr = lapBndRow(p, r0 + li, inner, outer);
-    const cd* q = p.bnd + lapbBndIndex(p, sr, ysel, kz);
+    const int ix = e.r0 + li;
+    const bool outer = e.last_x && (e.ncx - ix) < e.outbndry;
+    const int sr = outer ? e.inbndry + (ix - (e.ncx - e.outbndry + 1)) : ix; // lapBndRow
+    const cd* q = e.bnd + e.bnd0 + sr * e.bnd_slot;
     const cd a = ldcd(q), cc = ldcd(q + 1);
-    const cd inv = ldcd(p.inv + lapbTabIndex(p, ysel, r0 + li, kz));
-    const cd s = Sc[li * srow];
+    const cd inv = ldcd(e.inv + e.inv0 + static_cast<long long>(li) * e.nmode);
+    const cd s = Sc[li * e.srow];
     if (phase == 0) {
       x = csub(cmul(s, inv), cmul(cmul(a, inv), x));
     } else if (phase == 1) {
@@ -709,7 +717,7 @@ B200_HD_COLD void lapbEdgeRows(const LapParams& p, int ysel, int r0, int li0, in
       x = csub(s, cmul(cmul(cc, inv), x));
     }
     if (on) {
-      Sc[li * srow] = x;
+      Sc[li * e.srow] = x;
     }
   }
   *carry = x;
@@ -848,6 +856,26 @@ B200_HD void lapbChainRunFull(const LapParams& p, int blk, const int (&kzs)[NCH]
   }
 }
 
+B200_HD LapbEdge lapbEdgeOf(const LapParams& p, int ysel, int r0, int li0, int cnt, int srow, int kz) {
+  LapbEdge e;
+  e.bnd = p.bnd;
+  e.inv = p.inv;
+  e.inv0 = lapbTabIndex(p, ysel, r0, kz);
+  e.bnd0 = lapbBndIndex(p, 0, ysel, kz);
+  e.bnd_slot = lapbBndIndex(p, 1, ysel, kz) - e.bnd0;
+  e.nmode = p.nmode;
+  e.r0 = r0;
+  e.li0 = li0;
+  e.cnt = cnt;
+  e.srow = srow;
+  e.ncx = p.bd.xe - p.bd.xs;
+  e.inbndry = p.bd.inbndry;
+  e.outbndry = p.bd.outbndry;
+  e.first_x = p.bd.first_x;
+  e.last_x = p.bd.last_x;
+  return e;
+}
+
 template <int N, int NT, int NCH>
 B200_HD void lapbChainRun(const LapParams& p, const LapbCta& c, int blk, const int (&kzs)[NCH], const bool (&on)[NCH],
                           LapbChain<LapbShape<N, NT>::MB, NCH>& st, cd* S, const double* rowc) {
@@ -891,8 +919,9 @@ B200_HD void lapbChainRun(const LapParams& p, const LapbCta& c, int blk, const i
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       cd t0 = dt[ch], t1 = ub[ch], t2 = amid[ch];
-      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 0, Sb[ch], &t0, &t2);
-      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 1, Sb[ch], &t1, &t2);
+      const LapbEdge e = lapbEdgeOf(p, c.ysel, r0, li0, cnt, Sh::SROW, kz[ch]);
+      lapbEdgeRows(e, sp, on[ch], 0, Sb[ch], &t0, &t2);
+      lapbEdgeRows(e, sp, on[ch], 1, Sb[ch], &t1, &t2);
       dt[ch] = t0;
       ub[ch] = t1;
       amid[ch] = t2;
@@ -989,8 +1018,9 @@ B200_HD void lapbChainRun(const LapParams& p, const LapbCta& c, int blk, const i
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       cd t0 = xb[ch], t1 = xt[ch], t2 = amid[ch];
-      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 2, Sb[ch], &t0, &t2);
-      lapbEdgeRows(p, c.ysel, r0, li0, cnt, sp, Sh::SROW, kz[ch], on[ch], 3, Sb[ch], &t1, &t2);
+      const LapbEdge e = lapbEdgeOf(p, c.ysel, r0, li0, cnt, Sh::SROW, kz[ch]);
+      lapbEdgeRows(e, sp, on[ch], 2, Sb[ch], &t0, &t2);
+      lapbEdgeRows(e, sp, on[ch], 3, Sb[ch], &t1, &t2);
     }
   }
   if (jb > 0) {
@@ -1007,70 +1037,174 @@ B200_HD void lapbChainRun(const LapParams& p, const LapbCta& c, int blk, const i
 // N + 1 modes do not divide over the N per-mode threads of a block, and a second pass for one mode would hold the
 // whole CTA at its barrier.  The mode's right-hand side is real and only the real part of its solution is used
 // (c2r ignores Im X[nz/2]), so it travels as one double per row: the DOTS kernel exports Re X[N] of every row, the
-// (tiny) systems -- one per y -- are solved next to the separator systems in k_lapb_reduced by a two-sided sweep
-// over the WHOLE row range (no blocks), and the SOLVE kernel puts the result into X[N] before its inverse
-// transform.  Table row i: e0 = pivot reciprocal, e1 = sweep multiplier, e2 = substitution multiplier (top half
-// i < mid: downward pivots, e1 = a inv, e2 = c inv; bottom half: upward pivots, e1 = c inv, e2 = a inv).
-B200_HD int lapbNyqMid(int n) { return (n + 1) / 2; }
-B200_HD bool lapbNyquistFactorThread(const LapParams& p, int ysel) {
-  const int n = p.bd.xe - p.bd.xs + 1, kz = p.nz / 2, mid = lapbNyqMid(n);
-  const int jy = p.ys + ysel;
-  const double* tab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
-  const double kwave = kz * p.kscale;
-  cd* __restrict__ T = p.bnqt + static_cast<long long>(ysel) * (n + 1) * 3;
-  bool bad = false;
-  cd a, b, c, r = {0.0, 0.0};
-  cd cprev = {0.0, 0.0};
-  for (int i = 0; i < mid; ++i) {
-    lapRow(p, tab, i, jy, kz, kwave, a, b, c, r);
-    const cd denom = csub(b, cmul(a, cprev));
-    bad = bad || tiny(denom);
-    const cd inv = crecip(denom);
-    cprev = cmul(c, inv);
-    T[i * 3] = inv;
-    T[i * 3 + 1] = cmul(a, inv);
-    T[i * 3 + 2] = cprev;
-  }
-  cd e = {0.0, 0.0};
-  for (int i = n - 1; i >= mid; --i) {
-    lapRow(p, tab, i, jy, kz, kwave, a, b, c, r);
-    const cd denom = csub(b, cmul(c, e));
-    bad = bad || tiny(denom);
-    const cd inv = crecip(denom);
-    e = cmul(a, inv);
-    T[i * 3] = inv;
-    T[i * 3 + 1] = cmul(c, inv);
-    T[i * 3 + 2] = e;
-  }
-  cd midinv = {1.0, 0.0};
-  if (mid < n) {
-    const cd den = csub(cd{1.0, 0.0}, cmul(e, cprev)); // 1 - a'_mid c'_{mid-1}
-    bad = bad || tiny(den);
-    midinv = crecip(den);
-  }
-  T[n * 3] = midinv;
-  return bad;
+// (tiny) systems -- one per y -- are solved next to the separator systems in k_lapb_reduced, and the SOLVE kernel
+// puts the result into X[N] before its inverse transform.  One warp solves one system with the SAME block
+// algorithm and tables (column kz = N of inv, gF, gL and of the separator factors): lane = block for the dot
+// products, one lane for the separator sweep, lane = block for the two-sided block solves; everything staged in
+// shared memory first.
+struct LapbNyq {
+  double* r;    // [n]   Re X[N]: right-hand side in, solution out
+  cd* D;        // [n]   sweep values
+  double* ktab; // [n][LAP_NK] K-table rows of this y
+  cd* inv;      // [n]   column N of the pivot table
+  cd* gf;       // [n]
+  cd* gl;       // [n]
+  cd* f0;       // [P]   separator right-hand sides, then separator values
+  cd* f1;       // [P]
+  cd* rai;      // [P]
+  cd* rcp;      // [P]
+  cd* bac;      // [LAPB_NQB][2] a, c of the boundary rows
+};
+constexpr int LAPB_NQB = 16; // boundary rows (inbndry + outbndry) whose a, c are staged; more are read from global memory
+inline size_t lapbNyqBytes(int n, int P) {
+  return static_cast<size_t>(n) * (sizeof(double) * (1 + LAP_NK) + sizeof(cd) * 4)
+         + (static_cast<size_t>(P) * 4 + 2 * LAPB_NQB) * sizeof(cd);
 }
-// one sweep (rows from .. to, step +-1): d_i = r_i e0_i - e1_i d_prev; stores d_i, returns the last one
-B200_HD cd lapbNyqSweep(const cd* T, const double* r, cd* D, int from, int to, int step) {
+B200_HD LapbNyq lapbNyqCarve(void* mem, int n, int P) {
+  LapbNyq w;
+  w.D = reinterpret_cast<cd*>(mem);
+  w.inv = w.D + n;
+  w.gf = w.inv + n;
+  w.gl = w.gf + n;
+  w.f0 = w.gl + n;
+  w.f1 = w.f0 + P;
+  w.rai = w.f1 + P;
+  w.rcp = w.rai + P;
+  w.bac = w.rcp + P;
+  w.ktab = reinterpret_cast<double*>(w.bac + 2 * LAPB_NQB);
+  w.r = w.ktab + static_cast<size_t>(n) * LAP_NK;
+  return w;
+}
+B200_HD void lapbNyqStage(const LapParams& p, int iyl, int ysel, int tid, int nt, const LapbNyq& w) {
+  const int n = p.bd.xe - p.bd.xs + 1, kz = p.nz / 2, jy = p.ys + iyl;
+  const long long o0 = lapbTabIndex(p, ysel, 0, kz);
+#pragma unroll 8
+  for (int i = tid; i < n; i += nt) {
+    const long long o = o0 + static_cast<long long>(i) * p.nmode;
+    w.r[i] = p.bnq[static_cast<long long>(iyl) * n + i];
+    w.inv[i] = ldcd(p.inv + o);
+    w.gf[i] = ldcd(p.cprime + o);
+    w.gl[i] = ldcd(p.dprime + o);
+  }
+  const double* tg = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
+#pragma unroll 8
+  for (int i = tid; i < n * LAP_NK; i += nt) {
+    w.ktab[i] = B200_LDG(tg + i);
+  }
+  for (int j = tid; j < p.bP; j += nt) {
+    w.rai[j] = j > 0 ? ldcd(p.bred + lapbRedIndex(p, LAPB_RAI, ysel, j, kz)) : cd{0.0, 0.0};
+    w.rcp[j] = j > 0 ? ldcd(p.bred + lapbRedIndex(p, LAPB_RCP, ysel, j, kz)) : cd{0.0, 0.0};
+  }
+  const int nb = (p.bd.first_x ? p.bd.inbndry : 0) + (p.bd.last_x ? p.bd.outbndry : 0);
+  for (int q = tid; q < 2 * min(nb, LAPB_NQB); q += nt) {
+    w.bac[q] = ldcd(p.bnd + lapbBndIndex(p, q / 2, ysel, kz) + q % 2);
+  }
+}
+// block jb: F0 = (r_s - c_s yF) rinv, F1 = a_s' rinv' yL
+B200_HD void lapbNyqDots(const LapParams& p, int ysel, int jb, const LapbNyq& w) {
+  const int n = p.bd.xe - p.bd.xs + 1, kz = p.nz / 2, MB = p.bMB;
+  const int r0 = jb * MB, cnt = min(MB, n - r0), li0 = jb > 0 ? 1 : 0;
+  const int jc = max(jb, 1), jn = min(jb + 1, p.bP - 1); // (clamped: the loads below are issued before the loop)
+  const cd rinv = ldcd(p.bred + lapbRedIndex(p, LAPB_RINV, ysel, jc, kz));
+  const cd csi = ldcd(p.bred + lapbRedIndex(p, LAPB_CSI, ysel, jc, kz));
+  const cd asi = ldcd(p.bred + lapbRedIndex(p, LAPB_ASI, ysel, max(jn, 1), kz));
+  cd yF = {0.0, 0.0}, yL = {0.0, 0.0};
+  for (int li = li0; li < cnt; ++li) {
+    yF = cadd(yF, cscale(w.gf[r0 + li], w.r[r0 + li]));
+    yL = cadd(yL, cscale(w.gl[r0 + li], w.r[r0 + li]));
+  }
+  cd f0 = {0.0, 0.0}, f1 = {0.0, 0.0};
+  if (jb > 0) {
+    f0 = csub(cscale(rinv, w.r[r0]), cmul(csi, yF));
+  }
+  if (jb + 1 < p.bP) {
+    f1 = cmul(asi, yL);
+  }
+  w.f0[jb] = f0;
+  w.f1[jb] = f1;
+}
+// the separator sweep (one thread): f0[j] becomes the value of separator j
+B200_HD void lapbNyqSeparators(const LapParams& p, const LapbNyq& w) {
+  const int P = p.bP;
   cd d = {0.0, 0.0};
-  for (int i = from; step > 0 ? i <= to : i >= to; i += step) {
-    d = csub(cscale(T[i * 3], r[i]), cmul(T[i * 3 + 1], d));
-    D[i] = d;
+  for (int j = 1; j < P; ++j) {
+    d = csub(csub(w.f0[j], w.f1[j - 1]), cmul(w.rai[j], d));
+    w.f0[j] = d;
   }
-  return d;
-}
-// outward substitution x_i = d_i - e2_i x_prev from the meeting point; writes Re x_i
-B200_HD void lapbNyqSubst(const cd* T, const cd* D, double* xout, int from, int to, int step, cd x) {
-  for (int i = from; step > 0 ? i <= to : i >= to; i += step) {
-    x = csub(D[i], cmul(T[i * 3 + 2], x));
-    xout[i] = x.re;
+  cd x = {0.0, 0.0};
+  for (int j = P - 1; j >= 1; --j) {
+    x = csub(w.f0[j], cmul(w.rcp[j], x));
+    w.f0[j] = x;
   }
 }
-// x_mid from the two sweep ends (dt = d_{mid-1}, ub = u_mid)
-B200_HD cd lapbNyqMeet(const cd* T, int n, cd dt, cd ub) {
-  const int mid = lapbNyqMid(n);
-  return mid < n ? cmul(csub(ub, cmul(T[mid * 3 + 2], dt)), T[n * 3]) : cd{0.0, 0.0};
+// a, c of row i for the Nyquist mode: boundary rows from the bnd array (filled by the factor kernel), others from the
+// staged K-table
+B200_HD void lapbNyqAC(const LapParams& p, int ysel, const LapbNyq& w, int i, double kwave, cd& a, cd& c) {
+  bool inner, outer;
+  const int sr = lapBndRow(p, i, inner, outer);
+  if (inner || outer) {
+    if (sr < LAPB_NQB) {
+      a = w.bac[2 * sr];
+      c = w.bac[2 * sr + 1];
+    } else {
+      const cd* q = p.bnd + lapbBndIndex(p, sr, ysel, p.nz / 2);
+      a = ldcd(q);
+      c = ldcd(q + 1);
+    }
+    return;
+  }
+  const double* t = w.ktab + static_cast<size_t>(i) * LAP_NK;
+  a = {t[0] - t[3], -kwave * t[2]};
+  c = {t[0] + t[3], kwave * t[2]};
+}
+// block jb between its separator values: two-sided sweeps with the shared pivot table; writes Re x into r
+B200_HD void lapbNyqBlock(const LapParams& p, int ysel, int jb, const LapbNyq& w) {
+  const int n = p.bd.xe - p.bd.xs + 1, kz = p.nz / 2, MB = p.bMB;
+  const int r0 = jb * MB, cnt = min(MB, n - r0), li0 = jb > 0 ? 1 : 0;
+  const double kwave = kz * p.kscale;
+  const LapbSplit sp = lapbSplit(p.bd, n, r0, li0, cnt);
+  const cd midinv = ldcd(p.bred + lapbRedIndex(p, LAPB_MID, ysel, jb, kz));
+  const cd xs = jb > 0 ? w.f0[jb] : cd{0.0, 0.0};
+  const cd xn = jb + 1 < p.bP ? w.f0[jb + 1] : cd{0.0, 0.0};
+  cd a, c;
+  cd dt = xs, ub = xn, amid = {0.0, 0.0};
+  for (int li = li0; li < sp.mid; ++li) { // top half, downward
+    const int i = r0 + li;
+    lapbNyqAC(p, ysel, w, i, kwave, a, c);
+    dt = cmul(csub(cd{w.r[i], 0.0}, cmul(a, dt)), w.inv[i]);
+    w.D[i] = dt;
+  }
+  for (int li = cnt - 1; li >= sp.mid; --li) { // bottom half, upward
+    const int i = r0 + li;
+    lapbNyqAC(p, ysel, w, i, kwave, a, c);
+    ub = cmul(csub(cd{w.r[i], 0.0}, cmul(c, ub)), w.inv[i]);
+    w.D[i] = ub;
+    if (li == sp.mid) {
+      amid = cmul(a, w.inv[i]);
+    }
+  }
+  cd xm = ub;
+  if (sp.mid < cnt) {
+    xm = cmul(csub(ub, cmul(amid, dt)), midinv);
+    w.r[r0 + sp.mid] = xm.re;
+  }
+  cd x = xm;
+  for (int li = sp.mid - 1; li >= li0; --li) { // top half, upward
+    const int i = r0 + li;
+    lapbNyqAC(p, ysel, w, i, kwave, a, c);
+    x = csub(w.D[i], cmul(cmul(c, w.inv[i]), x));
+    w.r[i] = x.re;
+  }
+  x = xm;
+  for (int li = sp.mid + 1; li < cnt; ++li) { // bottom half, downward
+    const int i = r0 + li;
+    lapbNyqAC(p, ysel, w, i, kwave, a, c);
+    x = csub(w.D[i], cmul(cmul(a, w.inv[i]), x));
+    w.r[i] = x.re;
+  }
+  if (jb > 0) {
+    w.r[r0] = xs.re;
+  }
 }
 
 // the modes of thread tid in the per-mode phase, and the block they belong to
@@ -1147,8 +1281,8 @@ inline LapLayout lapLayout(const bout_b200_grid* g, const bout_b200_laplace* L) 
   o += lapRoundUp(l.nspec * sizeof(cd), 256);
   l.bnd = o;
   o += lapRoundUp(static_cast<size_t>(4) * (g->xstart > 1 ? g->xstart : 1) * g->ny * nmode * sizeof(cd), 256);
-  l.nyq = o; // block path, Nyquist mode: values (8 B), sweep values (16 B), table (48 B) per (x, y) + one table row per y
-  o += lapRoundUp(n2 * 72 + static_cast<size_t>(g->ny) * 48, 256);
+  l.nyq = o; // block path, Nyquist mode: one double per (x, y)
+  o += lapRoundUp(n2 * sizeof(double), 256);
   if (lapCoupled(L)) {
     l.sprime = o;
     o += lapRoundUp(l.nspec * sizeof(cd), 256);
@@ -1229,10 +1363,7 @@ inline void lapFillParams(const bout_b200_grid* g, const bout_b200_laplace* L, v
     p.bif = p.spec;
     p.bxs = p.bif + 2 * per;
     p.bred = p.bxs + per;
-    const size_t n2 = static_cast<size_t>(g->nx) * g->ny;
-    p.bnqt = reinterpret_cast<cd*>(ws + l.nyq);
-    p.bnqd = p.bnqt + n2 * 3 + static_cast<size_t>(g->ny) * 3;
-    p.bnq = reinterpret_cast<double*>(p.bnqd + n2);
+    p.bnq = reinterpret_cast<double*>(ws + l.nyq);
   }
 }
 

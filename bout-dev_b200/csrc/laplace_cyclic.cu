@@ -43,13 +43,6 @@ namespace cg = cooperative_groups;
 
 namespace b200 {
 
-// clock read that memory operations are not moved across (phase traces)
-__device__ __forceinline__ long long clockFenced() {
-  long long t;
-  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
-  return t;
-}
-
 __device__ __forceinline__ RowFFT makeRow(const LapParams& p, unsigned char* smem_raw, int& rloc) {
   const int nbuf = fftBufElems(p.nz);
   rloc = threadIdx.x / p.tpr;
@@ -720,22 +713,14 @@ __global__ void __launch_bounds__(256) k_lapb_prepare(const LapParams p) {
       bad = lapbFactor2Thread(p, static_cast<int>(idx)) || bad;
     }
   }
-  if (p.nmode > p.nz / 2) { // the Nyquist mode's own (unblocked) factors: one thread per table row in y, from the far end
-    const int ny_tab = lapbYdep(p) ? p.ye - p.ys + 1 : 1;
-    const long long rid = nth - 1 - tid;
-    if (rid < ny_tab) {
-      bad = lapbNyquistFactorThread(p, static_cast<int>(rid)) || bad;
-    }
-  }
   if (bad) {
     atomicExch(p.status, 1);
   }
 }
 
 constexpr int LAPB_RED_NT = 64;
-// Separator systems: one thread per (y, kz < N).  The CTAs after those solve the Nyquist systems, one per y:
-// tables and right-hand side staged in shared memory, lane 0 sweeps the top half downward while lane 1 sweeps
-// the bottom half upward, they meet and substitute outward.
+// Separator systems: one thread per (y, kz < N).  The CTAs after those solve the Nyquist systems, one per y, with
+// the block algorithm on one warp (laplace_block.cuh).
 __global__ void __launch_bounds__(LAPB_RED_NT) k_lapb_reduced(const LapParams p, const int nred_ctas) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nys = p.ye - p.ys + 1, nk = min(p.nmode, p.nz / 2);
@@ -747,41 +732,31 @@ __global__ void __launch_bounds__(LAPB_RED_NT) k_lapb_reduced(const LapParams p,
     }
     return;
   }
-  const int iyl = blockIdx.x - nred_ctas, n = p.bd.xe - p.bd.xs + 1, mid = lapbNyqMid(n);
+  if (p.dbg & 256) {
+    return;
+  }
+  const int iyl = blockIdx.x - nred_ctas, n = p.bd.xe - p.bd.xs + 1;
   const int ysel = lapbYdep(p) ? iyl : 0;
-  cd* T = reinterpret_cast<cd*>(smem_raw);  // [n + 1][3]
-  cd* D = T + (n + 1) * 3;                  // [n]
-  double* r = reinterpret_cast<double*>(D + n); // [n]
-  const cd* __restrict__ Tg = p.bnqt + static_cast<long long>(ysel) * (n + 1) * 3;
-  double* __restrict__ rg = p.bnq + static_cast<long long>(iyl) * n;
-  for (int i = threadIdx.x; i < (n + 1) * 3; i += blockDim.x) {
-    T[i] = ldcd(Tg + i);
-  }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    r[i] = rg[i];
-  }
+  const LapbNyq w = lapbNyqCarve(smem_raw, n, p.bP);
+  lapbNyqStage(p, iyl, ysel, threadIdx.x, blockDim.x, w);
   __syncthreads();
   if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    cd e = {0.0, 0.0};
-    if (lane == 0) {
-      e = lapbNyqSweep(T, r, D, 0, mid - 1, 1);
-    } else if (lane == 1) {
-      e = lapbNyqSweep(T, r, D, n - 1, mid, -1);
+    for (int jb = threadIdx.x; jb < p.bP; jb += 32) {
+      lapbNyqDots(p, ysel, jb, w);
     }
-    const cd dt = {__shfl_sync(0xffffffffu, e.re, 0), __shfl_sync(0xffffffffu, e.im, 0)};
-    const cd ub = {__shfl_sync(0xffffffffu, e.re, 1), __shfl_sync(0xffffffffu, e.im, 1)};
-    const cd xm = lapbNyqMeet(T, n, dt, ub);
-    if (lane == 0) {
-      lapbNyqSubst(T, D, r, mid - 1, 0, -1, xm);
-    } else if (lane == 1 && mid < n) {
-      r[mid] = xm.re;
-      lapbNyqSubst(T, D, r, mid + 1, n - 1, 1, xm);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+      lapbNyqSeparators(p, w);
+    }
+    __syncwarp();
+    for (int jb = threadIdx.x; jb < p.bP; jb += 32) {
+      lapbNyqBlock(p, ysel, jb, w);
     }
   }
   __syncthreads();
+  double* __restrict__ rg = p.bnq + static_cast<long long>(iyl) * n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    rg[i] = r[i];
+    rg[i] = w.r[i];
   }
 }
 
@@ -796,9 +771,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
   cd* S = reinterpret_cast<cd*>(smem_raw);
   double* rowc = reinterpret_cast<double*>(S + Sh::ROWS * Sh::SROW);
   const int tid = threadIdx.x, t = tid % Sh::T;
-  const bool trace = (p.dbg & 32) && (blockIdx.x % 1000 == 500) && (tid % 32 == 0); // phase clocks of a few CTAs
-  long long tk[7] = {0, 0, 0, 0, 0, 0, 0};
-  if (trace) tk[0] = clockFenced();
   const LapbCta c = lapbCta<N, NT>(p, blockIdx.x);
   if (p.bPD > 0 && tid < Sh::ROWS && blockIdx.x + p.bPD < gridDim.x) {
     const LapbCta cn = lapbCta<N, NT>(p, blockIdx.x + p.bPD);
@@ -821,7 +793,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
   if (MODE == LAPB_SOLVE) {
     lapbStageRows<N, NT>(p, c, tid, rowc);
   }
-  if (trace) tk[1] = clockFenced();
   if (!(p.dbg & 4)) {
     regfftStage1<N, false>(v, p.tw, t);
     regfftXchgWrite<N>(v, row, t);
@@ -839,7 +810,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
   } else {
     regfftSplitWriteZ<N>(v, row, t);
   }
-  if (trace) tk[2] = clockFenced();
   const bool nyquist = p.nmode > N;
   if (nyquist && t == 0 && c.row0 + tid / Sh::T <= p.bd.xe - p.bd.xs) { // this thread wrote X[N] of its row itself
     double* q = p.bnq + static_cast<long long>(c.iyl) * (p.bd.xe - p.bd.xs + 1) + c.row0 + tid / Sh::T;
@@ -861,9 +831,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
       LapbDots<Sh::KPT> st;
       lapbDotsFetch<N, NT, Sh::KPT>(p, c, blk, kzs, 0, st);
       lapbDotsFetchScale<N, NT, Sh::KPT>(p, c, blk, kzs, st);
-      if (trace) tk[5] = clockFenced();
       __syncthreads();
-      if (trace) tk[3] = clockFenced();
       lapbDotsRun<N, NT, Sh::KPT>(p, c, blk, kzs, on, st, S);
     } else {
       LapbChain<Sh::MB, Sh::KPT> st;
@@ -879,25 +847,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
           st.xs[ch] = st.xn[ch] = st.midinv[ch] = {0.1, 0.2};
         }
       }
-      if (trace) tk[6] = clockFenced();
       __syncthreads();
-      if (trace) tk[3] = clockFenced();
       lapbChainRun<N, NT, Sh::KPT>(p, c, blk, kzs, on, st, S, rowc);
     }
   } else {
     __syncthreads();
   }
   if (MODE == LAPB_DOTS) {
-    if (trace) {
-      tk[4] = clockFenced();
-      printf("DOTS cta %d warp %d: load %lld fft %lld fetch %lld bar1 %lld permode %lld total %lld\n", blockIdx.x, tid / 32,
-             tk[1] - tk[0], tk[2] - tk[1], tk[5] - tk[2], tk[3] - tk[5], tk[4] - tk[3], tk[4] - tk[0]);
-    }
     return;
   }
-  if (trace) tk[4] = clockFenced();
   __syncthreads();
-  if (trace) tk[5] = clockFenced();
   if (!(p.dbg & 2)) {
     regfftMergeRead<N>(v, row, p.nmode, p.zero_dc != 0, p.tw, t);
     __syncwarp();
@@ -912,12 +871,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
     }
   }
   lapbStoreRow<N, NT>(p, c, tid, v);
-  if (trace) {
-    const long long te = clockFenced();
-    printf("SOLVE cta %d warp %d: load %lld fft %lld fetch %lld bar1 %lld permode %lld bar2 %lld ifft+store %lld total %lld\n",
-           blockIdx.x, tid / 32, tk[1] - tk[0], tk[2] - tk[1], tk[6] - tk[2], tk[3] - tk[6], tk[4] - tk[3], tk[5] - tk[4],
-           te - tk[5], te - tk[0]);
-  }
 }
 
 } // namespace b200
@@ -1095,6 +1048,10 @@ bool lapUseBlock(const LapPlan* plan, const bout_b200_laplace* L, bool with_fiel
   if (lapCoupled(L) || !lapbShapeOk(p.nz)) {
     return false;
   }
+  // k_lapb_reduced keeps P sweep values per thread, and one whole Nyquist system with its tables, on chip
+  if (static_cast<size_t>(p.bP) * 64 * sizeof(cd) > 160 * 1024 || lapbNyqBytes(p.bd.xe - p.bd.xs + 1, p.bP) > 160 * 1024) {
+    return false;
+  }
   if (with_fields && (!aligned16(p.rhs) || (p.x0 != nullptr && !aligned16(p.x0)) || !aligned16(p.out))) {
     return false;
   }
@@ -1171,7 +1128,7 @@ int lapBlockSolve(const LapPlan* plan, cudaStream_t s) {
     const int nred = (nys * nk + LAPB_RED_NT - 1) / LAPB_RED_NT;
     const bool nyquist = p.nmode > p.nz / 2;
     size_t dsm = static_cast<size_t>(p.bP) * LAPB_RED_NT * sizeof(cd);
-    const size_t nsm = static_cast<size_t>(n + 1) * 3 * sizeof(cd) + static_cast<size_t>(n) * (sizeof(cd) + sizeof(double));
+    const size_t nsm = lapbNyqBytes(n, p.bP);
     if (nyquist && nsm > dsm) {
       dsm = nsm;
     }

@@ -940,7 +940,7 @@ void applyOne(Field3D& f, const std::string& cond_in, int side) {
   std::string cond = cond_in;
   cond.erase(std::remove_if(cond.begin(), cond.end(), [](unsigned char c) { return std::isspace(c); }), cond.end());
   std::transform(cond.begin(), cond.end(), cond.begin(), [](unsigned char c) { return std::tolower(c); });
-  if (cond.empty() || cond == "none") {
+  if (cond.empty() || cond == "none" || cond == "null") {
     return;
   }
   if (cond.rfind("relax(", 0) == 0 && cond.back() == ')') {
@@ -996,18 +996,27 @@ bool hasBoundary(Mesh* m, int side) {
 } // namespace
 
 void Field3D::setBoundary(const std::string& var) {
-  static const char* keys[4] = {"bndry_xin", "bndry_xout", "bndry_ydown", "bndry_yup"};
-  bndry_conditions.assign(4, "");
+  // BoundaryFactory::createFromOptions (src/mesh/boundary_factory.cxx:228-340): per boundary region the keys
+  // bndry_<region label>, bndry_<side>, bndry_all are tried in [var], then the same three in [all]; a region for
+  // which nothing is set gets "dirichlet" (to prevent undefined guard cells; "none" switches a side off).
+  // Region labels of BoutMesh on the default (all-core) topology (boutmesh.cxx:1019-1078): the inner x boundary is
+  // "core", the outer one "sol", the y boundaries "lower_target" / "upper_target".
+  static const char* labels[4] = {"core", "sol", "lower_target", "upper_target"};
+  static const char* sides[4] = {"xin", "xout", "ydown", "yup"};
+  bndry_conditions.assign(4, "dirichlet");
   Options& vo = Options::root()[var];
   Options& all = Options::root()["all"];
   for (int s = 0; s < 4; ++s) {
-    for (Options* o : {&vo, &all}) { // boundary_factory.cxx: [var] bndry_<region>, [var] bndry_all, then [all]
-      if (o->isSet(keys[s])) {
-        bndry_conditions[s] = (*o)[keys[s]].text();
-        break;
+    bool found = false;
+    for (Options* o : {&vo, &all}) {
+      for (const std::string key : {std::string("bndry_") + labels[s], std::string("bndry_") + sides[s], std::string("bndry_all")}) {
+        if (o->isSet(key)) {
+          bndry_conditions[s] = (*o)[key].text();
+          found = true;
+          break;
+        }
       }
-      if (o->isSet("bndry_all")) {
-        bndry_conditions[s] = (*o)["bndry_all"].text();
+      if (found) {
         break;
       }
     }

@@ -514,6 +514,10 @@ class Ref:
         self._check(self.lib.boutref_elmpb_get(name.encode(), _p(out), C.byref(k)))
         return float(out[0]) if k.value == 0 else out
 
+    def omp_threads(self):
+        """OpenMP threads the reference build uses in this process."""
+        return int(self.lib.boutref_omp_threads())
+
     def model_rhs_calls(self):
         """Solver::resetRHSCounter (src/solver/solver.cxx:946): run_rhs + run_convective calls since the last query."""
         return int(self.lib.boutref_model_rhs_calls())

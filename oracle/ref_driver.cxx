@@ -33,6 +33,9 @@
 #include "solver/impls/adams_bashforth/adams_bashforth.hxx"
 
 #include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -642,6 +645,14 @@ int boutref_elmpb_get(const char* name, double* out, int* kind) {
   int rc = 0;
   const int g = guarded([&]() { rc = boutref_elmpb_get_impl(model.get(), name, out, kind); });
   return g != 0 ? 100 : rc;
+}
+// OpenMP threads the reference's BOUT_FOR loops run on in this process (bench.py reports what was USED)
+int boutref_omp_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
 }
 int boutref_model_nvars() { return drv ? drv->nvars() : 0; }
 int boutref_model_rhs_calls() { return drv ? drv->rhsCalls() : 0; }

@@ -49,6 +49,8 @@ void emulRows(const LapParams& p) {
     }
     for (int tid = 0; tid < NT; ++tid) {
       regfftSplitWriteX<N>(v[tid], pc[tid], row(tid), p.tw, tid % Sh::T);
+    }
+    for (int tid = 0; tid < NT; ++tid) {
       if (p.nmode > N && tid % Sh::T == 0 && c.row0 + tid / Sh::T <= p.bd.xe - p.bd.xs) {
         double* q = p.bnq + static_cast<long long>(c.iyl) * (p.bd.xe - p.bd.xs + 1) + c.row0 + tid / Sh::T;
         if (MODE == LAPB_DOTS) {
@@ -163,11 +165,6 @@ extern "C" int lapb_emul_solve(const bout_b200_grid* g, const bout_b200_laplace*
         bad = lapbFactor2Thread(p, idx) || bad;
       }
     }
-    if (p.nmode > p.nz / 2) {
-      for (int ysel = 0; ysel < (lapbYdep(p) ? p.ye - p.ys + 1 : 1); ++ysel) {
-        bad = lapbNyquistFactorThread(p, ysel) || bad;
-      }
-    }
     if (bad) {
       p.status[LAPW_STATUS] = 1;
     }
@@ -183,18 +180,23 @@ extern "C" int lapb_emul_solve(const bout_b200_grid* g, const bout_b200_laplace*
       lapbReducedThread(p, (idx / nk) * p.nmode + idx % nk, D.data(), 1);
     }
     if (p.nmode > p.nz / 2) {
-      const int n = p.bd.xe - p.bd.xs + 1, mid = lapbNyqMid(n);
-      std::vector<cd> Dn(n);
+      const int n = p.bd.xe - p.bd.xs + 1;
+      std::vector<unsigned char> mem(lapbNyqBytes(n, p.bP) + 64);
+      const LapbNyq w = lapbNyqCarve(mem.data(), n, p.bP);
       for (int iyl = 0; iyl < nys; ++iyl) {
-        const cd* T = p.bnqt + static_cast<long long>(lapbYdep(p) ? iyl : 0) * (n + 1) * 3;
-        double* r = p.bnq + static_cast<long long>(iyl) * n;
-        const cd dt = lapbNyqSweep(T, r, Dn.data(), 0, mid - 1, 1);
-        const cd ub = lapbNyqSweep(T, r, Dn.data(), n - 1, mid, -1);
-        const cd xm = lapbNyqMeet(T, n, dt, ub);
-        lapbNyqSubst(T, Dn.data(), r, mid - 1, 0, -1, xm);
-        if (mid < n) {
-          r[mid] = xm.re;
-          lapbNyqSubst(T, Dn.data(), r, mid + 1, n - 1, 1, xm);
+        const int ysel = lapbYdep(p) ? iyl : 0;
+        for (int tid = 0; tid < 64; ++tid) {
+          lapbNyqStage(p, iyl, ysel, tid, 64, w);
+        }
+        for (int jb = 0; jb < p.bP; ++jb) {
+          lapbNyqDots(p, ysel, jb, w);
+        }
+        lapbNyqSeparators(p, w);
+        for (int jb = 0; jb < p.bP; ++jb) {
+          lapbNyqBlock(p, ysel, jb, w);
+        }
+        for (int i = 0; i < n; ++i) {
+          p.bnq[static_cast<long long>(iyl) * n + i] = w.r[i];
         }
       }
     }

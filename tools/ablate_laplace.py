@@ -24,8 +24,8 @@ md = dict(dx=one(0.2), g11=one(1.0), g33=one(1.0), g13=one(0.0), G1=one(0.0), G3
 f = torch.rand(g.shape3, dtype=torch.float64, device="cuda") - 0.5
 out = torch.zeros_like(f)
 lap = capi.Laplace(g, md, 0.2 * g.nz)
-for dbg in (0, 1, 64, 128, 192, 2, 4, 8, 7, 15):
+for dbg in (0, 256, 1, 64, 2, 4, 8, 7, 15):
     os.environ["BOUT_B200_LAPB_DBG"] = str(dbg)
     t = timeit(lambda: lap.solve(f, out=out))
-    off = [n for b, n in ((1, "per-mode"), (2, "inverse fft"), (4, "forward fft"), (8, "row loads"), (64, "SOLVE table loads"), (128, "Nyquist pass")) if dbg & b]
+    off = [n for b, n in ((1, "per-mode"), (2, "inverse fft"), (4, "forward fft"), (8, "row loads"), (64, "SOLVE table loads"), (256, "Nyquist systems")) if dbg & b]
     print(f"dbg={dbg:2d} off: {', '.join(off) or '-':45s} solve {t*1e3:8.1f} us", flush=True)
