@@ -202,8 +202,11 @@ B200_HD LapbCta lapbCta(const LapParams& p, int bid) {
   c.iyl = bid / ntile;
   c.jy = p.ys + c.iyl;
   c.row0 = (bid % ntile) * LapbShape<N, NT>::ROWS;
-  c.ysel = (static_cast<unsigned>(p.status[LAPW_YDEP_GEN]) == p.gen) ? c.iyl : 0;
+  c.ysel = 0; // set by lapbSetYsel once the prepare kernel's verdict may be read
   return c;
+}
+B200_HD void lapbSetYsel(const LapParams& p, LapbCta& c) {
+  c.ysel = (static_cast<unsigned>(p.status[LAPW_YDEP_GEN]) == p.gen) ? c.iyl : 0;
 }
 B200_HD long long lapbTabIndex(const LapParams& p, int ysel, int row, int kz) {
   const int n = p.bd.xe - p.bd.xs + 1;
@@ -1054,11 +1057,12 @@ struct LapbNyq {
   cd* rai;      // [P]
   cd* rcp;      // [P]
   cd* bac;      // [LAPB_NQB][2] a, c of the boundary rows
+  cd* ends;     // [P][3] a block's two sweep ends and a' of its row mid
 };
 constexpr int LAPB_NQB = 16; // boundary rows (inbndry + outbndry) whose a, c are staged; more are read from global memory
 inline size_t lapbNyqBytes(int n, int P) {
   return static_cast<size_t>(n) * (sizeof(double) * (1 + LAP_NK) + sizeof(cd) * 4)
-         + (static_cast<size_t>(P) * 4 + 2 * LAPB_NQB) * sizeof(cd);
+         + (static_cast<size_t>(P) * 7 + 2 * LAPB_NQB) * sizeof(cd);
 }
 B200_HD LapbNyq lapbNyqCarve(void* mem, int n, int P) {
   LapbNyq w;
@@ -1071,7 +1075,8 @@ B200_HD LapbNyq lapbNyqCarve(void* mem, int n, int P) {
   w.rai = w.f1 + P;
   w.rcp = w.rai + P;
   w.bac = w.rcp + P;
-  w.ktab = reinterpret_cast<double*>(w.bac + 2 * LAPB_NQB);
+  w.ends = w.bac + 2 * LAPB_NQB;
+  w.ktab = reinterpret_cast<double*>(w.ends + 3 * P);
   w.r = w.ktab + static_cast<size_t>(n) * LAP_NK;
   return w;
 }
@@ -1157,53 +1162,71 @@ B200_HD void lapbNyqAC(const LapParams& p, int ysel, const LapbNyq& w, int i, do
   a = {t[0] - t[3], -kwave * t[2]};
   c = {t[0] + t[3], kwave * t[2]};
 }
-// block jb between its separator values: two-sided sweeps with the shared pivot table; writes Re x into r
-B200_HD void lapbNyqBlock(const LapParams& p, int ysel, int jb, const LapbNyq& w) {
+// block jb between its separator values: two-sided sweeps with the shared pivot table, one thread per half
+// (half 0: top rows downward, half 1: bottom rows upward).  Sweep: stores the sweep values, leaves the half's end
+// value (and a' of row mid) in `ends`; after a barrier, Subst: both halves form x_mid and substitute outward,
+// writing Re x into r.
+B200_HD void lapbNyqSweepHalf(const LapParams& p, int ysel, int jb, int half, const LapbNyq& w, cd* ends) {
   const int n = p.bd.xe - p.bd.xs + 1, kz = p.nz / 2, MB = p.bMB;
   const int r0 = jb * MB, cnt = min(MB, n - r0), li0 = jb > 0 ? 1 : 0;
   const double kwave = kz * p.kscale;
   const LapbSplit sp = lapbSplit(p.bd, n, r0, li0, cnt);
-  const cd midinv = ldcd(p.bred + lapbRedIndex(p, LAPB_MID, ysel, jb, kz));
-  const cd xs = jb > 0 ? w.f0[jb] : cd{0.0, 0.0};
-  const cd xn = jb + 1 < p.bP ? w.f0[jb + 1] : cd{0.0, 0.0};
   cd a, c;
-  cd dt = xs, ub = xn, amid = {0.0, 0.0};
-  for (int li = li0; li < sp.mid; ++li) { // top half, downward
-    const int i = r0 + li;
-    lapbNyqAC(p, ysel, w, i, kwave, a, c);
-    dt = cmul(csub(cd{w.r[i], 0.0}, cmul(a, dt)), w.inv[i]);
-    w.D[i] = dt;
-  }
-  for (int li = cnt - 1; li >= sp.mid; --li) { // bottom half, upward
-    const int i = r0 + li;
-    lapbNyqAC(p, ysel, w, i, kwave, a, c);
-    ub = cmul(csub(cd{w.r[i], 0.0}, cmul(c, ub)), w.inv[i]);
-    w.D[i] = ub;
-    if (li == sp.mid) {
-      amid = cmul(a, w.inv[i]);
+  if (half == 0) {
+    cd dt = jb > 0 ? w.f0[jb] : cd{0.0, 0.0};
+    for (int li = li0; li < sp.mid; ++li) {
+      const int i = r0 + li;
+      lapbNyqAC(p, ysel, w, i, kwave, a, c);
+      dt = cmul(csub(cd{w.r[i], 0.0}, cmul(a, dt)), w.inv[i]);
+      w.D[i] = dt;
     }
+    ends[jb * 3] = dt;
+  } else {
+    cd ub = jb + 1 < p.bP ? w.f0[jb + 1] : cd{0.0, 0.0}, amid = {0.0, 0.0};
+    for (int li = cnt - 1; li >= sp.mid; --li) {
+      const int i = r0 + li;
+      lapbNyqAC(p, ysel, w, i, kwave, a, c);
+      ub = cmul(csub(cd{w.r[i], 0.0}, cmul(c, ub)), w.inv[i]);
+      w.D[i] = ub;
+      if (li == sp.mid) {
+        amid = cmul(a, w.inv[i]);
+      }
+    }
+    ends[jb * 3 + 1] = ub;
+    ends[jb * 3 + 2] = amid;
   }
+}
+B200_HD void lapbNyqSubstHalf(const LapParams& p, int ysel, int jb, int half, const LapbNyq& w, const cd* ends) {
+  const int n = p.bd.xe - p.bd.xs + 1, kz = p.nz / 2, MB = p.bMB;
+  const int r0 = jb * MB, cnt = min(MB, n - r0), li0 = jb > 0 ? 1 : 0;
+  const double kwave = kz * p.kscale;
+  const LapbSplit sp = lapbSplit(p.bd, n, r0, li0, cnt);
+  const cd dt = ends[jb * 3], ub = ends[jb * 3 + 1], amid = ends[jb * 3 + 2];
   cd xm = ub;
   if (sp.mid < cnt) {
-    xm = cmul(csub(ub, cmul(amid, dt)), midinv);
-    w.r[r0 + sp.mid] = xm.re;
+    xm = cmul(csub(ub, cmul(amid, dt)), ldcd(p.bred + lapbRedIndex(p, LAPB_MID, ysel, jb, kz)));
   }
-  cd x = xm;
-  for (int li = sp.mid - 1; li >= li0; --li) { // top half, upward
-    const int i = r0 + li;
-    lapbNyqAC(p, ysel, w, i, kwave, a, c);
-    x = csub(w.D[i], cmul(cmul(c, w.inv[i]), x));
-    w.r[i] = x.re;
-  }
-  x = xm;
-  for (int li = sp.mid + 1; li < cnt; ++li) { // bottom half, downward
-    const int i = r0 + li;
-    lapbNyqAC(p, ysel, w, i, kwave, a, c);
-    x = csub(w.D[i], cmul(cmul(a, w.inv[i]), x));
-    w.r[i] = x.re;
-  }
-  if (jb > 0) {
-    w.r[r0] = xs.re;
+  cd a, c, x = xm;
+  if (half == 0) {
+    for (int li = sp.mid - 1; li >= li0; --li) { // top half, upward
+      const int i = r0 + li;
+      lapbNyqAC(p, ysel, w, i, kwave, a, c);
+      x = csub(w.D[i], cmul(cmul(c, w.inv[i]), x));
+      w.r[i] = x.re;
+    }
+    if (jb > 0) {
+      w.r[r0] = w.f0[jb].re;
+    }
+  } else {
+    if (sp.mid < cnt) {
+      w.r[r0 + sp.mid] = xm.re;
+    }
+    for (int li = sp.mid + 1; li < cnt; ++li) { // bottom half, downward
+      const int i = r0 + li;
+      lapbNyqAC(p, ysel, w, i, kwave, a, c);
+      x = csub(w.D[i], cmul(cmul(a, w.inv[i]), x));
+      w.r[i] = x.re;
+    }
   }
 }
 

@@ -686,6 +686,8 @@ __global__ void __launch_bounds__(128) k_lap_backward(const LapParams p) {
 // not: compare the Field2D inputs with the copy of the last factorisation -> grid barrier -> (only when something
 // changed) K-table -> barrier -> block factors -> barrier -> separator-system factors.
 __global__ void __launch_bounds__(256) k_lapb_prepare(const LapParams p) {
+  // the DOTS kernel may start now: it reads only the right-hand side until it waits for this grid to finish
+  asm volatile("griddepcontrol.launch_dependents;");
   cg::grid_group grid = cg::this_grid();
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -718,17 +720,23 @@ __global__ void __launch_bounds__(256) k_lapb_prepare(const LapParams p) {
   }
 }
 
-constexpr int LAPB_RED_NT = 64;
-// Separator systems: one thread per (y, kz < N).  The CTAs after those solve the Nyquist systems, one per y, with
-// the block algorithm on one warp (laplace_block.cuh).
-__global__ void __launch_bounds__(LAPB_RED_NT) k_lapb_reduced(const LapParams p, const int nred_ctas) {
+constexpr int LAPB_RED_NT = 64;   // separator systems per CTA
+constexpr int LAPB_RED_CTA = 256; // threads per CTA (the Nyquist CTAs use them all)
+// Separator systems: one thread per (y, kz < N), LAPB_RED_NT per CTA (the other threads leave at once).  The CTAs
+// after those solve the Nyquist systems, one per y, with the block algorithm (laplace_block.cuh): staging by all
+// threads, dot products by one thread per block, the separator sweep by one thread, the block solves by one thread
+// per half block.
+__global__ void __launch_bounds__(LAPB_RED_CTA) k_lapb_reduced(const LapParams p, const int nred_ctas) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // the SOLVE kernel may start now: its row loads and forward transforms do not depend on this grid
+  asm volatile("griddepcontrol.launch_dependents;");
   const int nys = p.ye - p.ys + 1, nk = min(p.nmode, p.nz / 2);
+  const int tid = threadIdx.x;
   if (static_cast<int>(blockIdx.x) < nred_ctas) {
     cd* D = reinterpret_cast<cd*>(smem_raw); // [P][LAPB_RED_NT]: a thread's column is conflict-free
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < nys * nk) {
-      lapbReducedThread(p, (idx / nk) * p.nmode + idx % nk, D + threadIdx.x, LAPB_RED_NT);
+    const int idx = blockIdx.x * LAPB_RED_NT + tid;
+    if (tid < LAPB_RED_NT && idx < nys * nk) {
+      lapbReducedThread(p, (idx / nk) * p.nmode + idx % nk, D + tid, LAPB_RED_NT);
     }
     return;
   }
@@ -738,24 +746,26 @@ __global__ void __launch_bounds__(LAPB_RED_NT) k_lapb_reduced(const LapParams p,
   const int iyl = blockIdx.x - nred_ctas, n = p.bd.xe - p.bd.xs + 1;
   const int ysel = lapbYdep(p) ? iyl : 0;
   const LapbNyq w = lapbNyqCarve(smem_raw, n, p.bP);
-  lapbNyqStage(p, iyl, ysel, threadIdx.x, blockDim.x, w);
+  lapbNyqStage(p, iyl, ysel, tid, LAPB_RED_CTA, w);
   __syncthreads();
-  if (threadIdx.x < 32) {
-    for (int jb = threadIdx.x; jb < p.bP; jb += 32) {
-      lapbNyqDots(p, ysel, jb, w);
-    }
-    __syncwarp();
-    if (threadIdx.x == 0) {
-      lapbNyqSeparators(p, w);
-    }
-    __syncwarp();
-    for (int jb = threadIdx.x; jb < p.bP; jb += 32) {
-      lapbNyqBlock(p, ysel, jb, w);
-    }
+  for (int jb = tid; jb < p.bP; jb += LAPB_RED_CTA) {
+    lapbNyqDots(p, ysel, jb, w);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    lapbNyqSeparators(p, w);
+  }
+  __syncthreads();
+  for (int q = tid; q < 2 * p.bP; q += LAPB_RED_CTA) {
+    lapbNyqSweepHalf(p, ysel, q >> 1, q & 1, w, w.ends);
+  }
+  __syncthreads();
+  for (int q = tid; q < 2 * p.bP; q += LAPB_RED_CTA) {
+    lapbNyqSubstHalf(p, ysel, q >> 1, q & 1, w, w.ends);
   }
   __syncthreads();
   double* __restrict__ rg = p.bnq + static_cast<long long>(iyl) * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = tid; i < n; i += LAPB_RED_CTA) {
     rg[i] = w.r[i];
   }
 }
@@ -771,7 +781,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
   cd* S = reinterpret_cast<cd*>(smem_raw);
   double* rowc = reinterpret_cast<double*>(S + Sh::ROWS * Sh::SROW);
   const int tid = threadIdx.x, t = tid % Sh::T;
-  const LapbCta c = lapbCta<N, NT>(p, blockIdx.x);
+  LapbCta c = lapbCta<N, NT>(p, blockIdx.x);
   if (p.bPD > 0 && tid < Sh::ROWS && blockIdx.x + p.bPD < gridDim.x) {
     const LapbCta cn = lapbCta<N, NT>(p, blockIdx.x + p.bPD);
     const int ix = cn.row0 + tid;
@@ -790,9 +800,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
       v[q] = {1.0 + tid, 2.0 + q};
     }
   }
-  if (MODE == LAPB_SOLVE) {
-    lapbStageRows<N, NT>(p, c, tid, rowc);
-  }
   if (!(p.dbg & 4)) {
     regfftStage1<N, false>(v, p.tw, t);
     regfftXchgWrite<N>(v, row, t);
@@ -809,6 +816,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
     }
   } else {
     regfftSplitWriteZ<N>(v, row, t);
+  }
+  // Everything above read the right-hand side only.  From here on the results of the previous kernel in the stream
+  // are needed (DOTS: the matrix tables of k_lapb_prepare; SOLVE: the separator and Nyquist values of
+  // k_lapb_reduced): this grid was launched with programmatic stream serialisation and waits for them here.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  lapbSetYsel(p, c);
+  if (MODE == LAPB_SOLVE) {
+    lapbStageRows<N, NT>(p, c, tid, rowc);
   }
   const bool nyquist = p.nmode > N;
   if (nyquist && t == 0 && c.row0 + tid / Sh::T <= p.bd.xe - p.bd.xs) { // this thread wrote X[N] of its row itself
@@ -1070,8 +1085,18 @@ int launchRows(const LapParams& p, cudaStream_t s) {
   }
   const int n = p.bd.xe - p.bd.xs + 1, nys = p.ye - p.ys + 1;
   const unsigned blocks = static_cast<unsigned>(nys) * ((n + Sh::ROWS - 1) / Sh::ROWS);
-  k_lapb_rows<N, NT, MODE><<<blocks, NT, Sh::smemBytes, s>>>(p);
-  B200_LAUNCH_OK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = Sh::smemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; // may start while the previous kernel still runs
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, k_lapb_rows<N, NT, MODE>, p));
+  countLaunch();
   return 0;
 }
 template <int MODE>
@@ -1138,7 +1163,7 @@ int lapBlockSolve(const LapPlan* plan, cudaStream_t s) {
       B200_CUDA_OK(cudaFuncSetAttribute(k_lapb_reduced, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dsm)));
       dsm_attr = dsm;
     }
-    k_lapb_reduced<<<nred + (nyquist ? nys : 0), LAPB_RED_NT, dsm, s>>>(p, nred);
+    k_lapb_reduced<<<nred + (nyquist ? nys : 0), LAPB_RED_CTA, dsm, s>>>(p, nred);
     B200_LAUNCH_OK();
   }
   return launchRowsN<LAPB_SOLVE>(p, s);

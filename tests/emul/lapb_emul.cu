@@ -27,7 +27,8 @@ void emulRows(const LapParams& p) {
   static cd v[NT][Sh::B];
   static cd pc[NT][Sh::B / 2 + 1];
   for (int bid = 0; bid < nblocks; ++bid) {
-    const LapbCta c = lapbCta<N, NT>(p, bid);
+    LapbCta c = lapbCta<N, NT>(p, bid);
+    lapbSetYsel(p, c);
     auto row = [&](int tid) { return S.data() + (tid / Sh::T) * Sh::SROW; };
     for (int tid = 0; tid < NT; ++tid) {
       const int t = tid % Sh::T;
@@ -192,8 +193,11 @@ extern "C" int lapb_emul_solve(const bout_b200_grid* g, const bout_b200_laplace*
           lapbNyqDots(p, ysel, jb, w);
         }
         lapbNyqSeparators(p, w);
-        for (int jb = 0; jb < p.bP; ++jb) {
-          lapbNyqBlock(p, ysel, jb, w);
+        for (int q = 0; q < 2 * p.bP; ++q) {
+          lapbNyqSweepHalf(p, ysel, q >> 1, q & 1, w, w.ends);
+        }
+        for (int q = 0; q < 2 * p.bP; ++q) {
+          lapbNyqSubstHalf(p, ysel, q >> 1, q & 1, w, w.ends);
         }
         for (int i = 0; i < n; ++i) {
           p.bnq[static_cast<long long>(iyl) * n + i] = w.r[i];
