@@ -6,8 +6,10 @@
 // ShiftedMetric::shiftZ (src/mesh/parallel/shiftedmetric.cxx:200-224).
 #include "fft.cuh"
 #include "fft_fast.cuh"
+#include "fft_reg.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -349,6 +351,167 @@ __global__ void __launch_bounds__(256) k_zrows_fast(const ZfftParams p) {
   }
 }
 
+// ---- register path (nz in {128, 256, 512}): fft_reg.cuh transforms ---------------------------------------------
+// A row is owned by T lanes of ONE warp holding 16 (8) points each in registers; a transform passes through shared
+// memory once; there is no CTA-wide barrier anywhere, so the warps of a CTA run decoupled.  The spectrum of the row
+// sits in the row's buffer X between the forward and the backward transform; TWO = Z_SLICE2 keeps it there for the
+// second output and modifies into a second buffer.  The phase factors exp(-i k theta) of the shift modes are built
+// by repeated multiplication from two sincos per thread (round 1 called sincos for every mode of every row).
+template <int N, bool TWO>
+__global__ void __launch_bounds__(128, 4) k_zrows_reg(const ZfftParams p) {
+  using F = RegFft<N>;
+  constexpr int T = F::T, B = F::B, SROW = F::SROW, ROWS = 128 / T, NBUF = TWO ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, grp = tid / T, t = tid % T;
+  cd* X = reinterpret_cast<cd*>(smem_raw) + static_cast<size_t>(grp) * NBUF * SROW;
+  cd* D = TWO ? X + SROW : X; // modified spectrum and exchange area of the backward transform
+  const int nyb = p.ye - p.ys + 1;
+  const long long nrows = static_cast<long long>(p.xe - p.xs + 1) * nyb;
+  constexpr double kfac = 2.0 * M_PI / (2 * N);
+  for (long long base = static_cast<long long>(blockIdx.x) * ROWS; base < nrows;
+       base += static_cast<long long>(gridDim.x) * ROWS) {
+    const long long rowid = base + grp;
+    const bool active = rowid < nrows;
+    const long long rid = active ? rowid : nrows - 1; // idle groups redo the last row, never store
+    const int x = p.xs + static_cast<int>(rid / nyb);
+    const int y = p.ys + static_cast<int>(rid % nyb);
+    const long long i2 = static_cast<long long>(x) * p.ny + y;
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(p.f + i2 * p.nz);
+    cd v[B];
+#pragma unroll
+    for (int n2 = 0; n2 < B; ++n2) {
+      const double2 q = __ldg(s2 + t + T * n2);
+      v[n2] = {q.x, q.y};
+    }
+    regfftStage1<N, false>(v, p.tw, t);
+    regfftXchgWrite<N>(v, X, t);
+    __syncwarp();
+    regfftStage2<N, false>(v, X, t);
+    __syncwarp();
+    regfftSplitWriteZ<N>(v, X, t);
+    __syncwarp();
+    {
+      cd pc[B / 2 + 1];
+      regfftSplitReadPartners<N>(pc, X, t);
+      __syncwarp();
+      regfftSplitWriteX<N>(v, pc, X, p.tw, t);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 0; o < NBUF; ++o) {
+      double ang = 0.0, zl = p.zlength0;
+      int mode = p.mode;
+      bool store = active;
+      double* __restrict__ dstf = p.out;
+      if (p.mode == Z_SHIFT) {
+        zl = p.zlength ? __ldg(p.zlength + i2) : p.zlength0;
+        ang = p.angle ? __ldg(p.angle + i2) : p.angle0;
+      } else if (p.mode == Z_SLICE) {
+        ang = __ldg(p.angle + i2 - p.yoff) - __ldg(p.angle + i2);
+      } else if (TWO) {
+        // o = 0: this row is the y+1 neighbour of row y-1 (yup); o = 1: the y-1 neighbour of row y+1 (ydown)
+        const int yoff = o == 0 ? 1 : -1;
+        const int yt = y - yoff;                       // the row whose frame we shift into
+        const bool ok = yt >= p.n0 && yt <= p.kmax;    // n0..kmax = ystart..yend of the target rows
+        store = active && ok;
+        const int ytc = ok ? yt : y;
+        ang = __ldg(p.angle + static_cast<long long>(x) * p.ny + ytc) - __ldg(p.angle + i2);
+        mode = Z_SLICE;
+        dstf = o == 0 ? p.out : p.out2;
+      }
+      // this thread's bins k = t + T q (and the Nyquist bin for t = 0): X -> D
+      if (mode == Z_SHIFT || mode == Z_SLICE) { // * exp(-i kwave ang), kwave = 2 pi k / zl
+        const double th = 2.0 * M_PI / zl * ang;
+        double sn, cs;
+        sincos(th * t, &sn, &cs);
+        cd ph = {cs, -sn};            // exp(-i t th)
+        sincos(th * T, &sn, &cs);
+        const cd rot = {cs, -sn};     // exp(-i T th)
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          const int k = t + T * q;
+          D[k] = cmul(X[k], ph);     // (k = 0: ph = 1 exactly)
+          ph = cmul(ph, rot);
+        }
+        if (t == 0) {
+          D[N] = cmul(X[N], ph);     // ph = exp(-i N th) after B steps
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q <= B; ++q) {
+          const int k = q < B ? t + T * q : N;
+          if (q < B || t == 0) {
+            cd w = X[k];
+            const double kw = k * kfac;
+            switch (mode) {
+            case Z_DDZ1:
+              w = k <= p.kmax ? cd{-w.im * kw, w.re * kw} : cd{0.0, 0.0};
+              break;
+            case Z_DDZ2:
+              w = cscale(w, -kw * kw);
+              break;
+            case Z_FILTER:
+              if (k != p.n0) {
+                w = {0.0, 0.0};
+              }
+              break;
+            case Z_LOWPASS:
+              if (k > p.kmax || (k == 0 && !p.keep_zonal)) {
+                w = {0.0, 0.0};
+              }
+              break;
+            default: // Z_FILTER_LOWPASS: filter(f, n0) then lowPass(., kmax, keep_zonal)
+              if (k != p.n0 || k > p.kmax || (k == 0 && !p.keep_zonal)) {
+                w = {0.0, 0.0};
+              }
+              break;
+            }
+            D[k] = w;
+          }
+        }
+      }
+      __syncwarp();
+      regfftMergeRead<N>(v, D, N + 1, false, p.tw, t);
+      __syncwarp();
+      regfftStage1<N, true>(v, p.tw, t);
+      regfftXchgWrite<N>(v, D, t);
+      __syncwarp();
+      regfftStage2<N, true>(v, D, t);
+      if (store) {
+        const double sc = p.scale ? __ldg(p.scale + i2) : 1.0;
+        double2* __restrict__ d2 = reinterpret_cast<double2*>(dstf + i2 * p.nz);
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          d2[t + T * q] = make_double2(v[q].re * sc, v[q].im * sc);
+        }
+      }
+      __syncwarp(); // the next output (or row) reuses the buffers
+    }
+  }
+}
+
+template <int N, bool TWO>
+int launchZrowsRegT(const ZfftParams& p, long long nrows, cudaStream_t s) {
+  using F = RegFft<N>;
+  constexpr int ROWS = 128 / F::T;
+  const size_t smem = static_cast<size_t>(ROWS) * (TWO ? 2 : 1) * F::SROW * sizeof(cd);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_zrows_reg<N, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const long long want = (nrows + ROWS - 1) / ROWS;
+  const unsigned blocks = static_cast<unsigned>(want < 148LL * 12 ? want : 148LL * 12);
+  k_zrows_reg<N, TWO><<<blocks, 128, smem, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+template <int N>
+int launchZrowsReg(const ZfftParams& p, long long nrows, cudaStream_t s) {
+  return p.mode == Z_SLICE2 ? launchZrowsRegT<N, true>(p, nrows, s) : launchZrowsRegT<N, false>(p, nrows, s);
+}
+
 template <int N>
 int launchZrowsFast(const ZfftParams& p, long long nrows, cudaStream_t s) {
   constexpr int ROWS = 256 / FftShape<N>::TPR;
@@ -394,6 +557,14 @@ int launchZfft(const bout_b200_grid* g, int region, ZfftParams p, void* stream, 
   const int N = g->nz / 2;
   const bool fast_ok = p.mode != Z_ZEROLAP && (g->nz == 128 || g->nz == 256 || g->nz == 512 || g->nz == 1024)
                        && aligned16(p.f) && aligned16(p.out) && (p.out2 == nullptr || aligned16(p.out2));
+  static const bool no_reg = getenv("BOUT_B200_ZROWS_REG") != nullptr && getenv("BOUT_B200_ZROWS_REG")[0] == '0';
+  if (fast_ok && !no_reg && N <= 256) { // nz = 128, 256, 512: register-resident transforms
+    switch (N) {
+    case 64: return launchZrowsReg<64>(p, nrows_all, s);
+    case 128: return launchZrowsReg<128>(p, nrows_all, s);
+    default: return launchZrowsReg<256>(p, nrows_all, s);
+    }
+  }
   if (fast_ok) {
     switch (N) {
     case 64: return launchZrowsFast<64>(p, nrows_all, s);
