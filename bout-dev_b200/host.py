@@ -98,6 +98,9 @@ class Host:
     def model_solve(self, nout, output_step):
         self._check(self.lib.b200host_model_solve(nout, output_step))
 
+    def stream_sync(self):
+        self._check(self.lib.b200host_stream_sync())
+
     def rhs_calls(self):
         return int(self.lib.b200host_rhs_calls())
 

@@ -259,6 +259,18 @@ struct Block {
   /// next device access of the block (FieldBase::dptr / wptr are the synchronisation points).
   std::vector<double> host;
   enum Mirror { none = 0, synced = 1, host_newer = 2 } mirror = none;
+  /// Stamped from a global counter at creation and at every write intent (FieldBase::makeUnique): (address, version)
+  /// names one state of one block's contents.
+  unsigned long long version = 0;
+  /// How the contents were made, kept while it stays true: op = 1 means contents == a - b element-wise over the whole
+  /// array, a and b being the blocks that carried versions a_ver / b_ver.  The single-index loop dispatcher
+  /// (single_index_ops.hxx) uses it to see that hw.cxx's phi_minus_n is phi - n without reading any data.
+  struct Recipe {
+    int op = 0;
+    const Block* a = nullptr;
+    const Block* b = nullptr;
+    unsigned long long a_ver = 0, b_ver = 0;
+  } recipe;
   void syncToHost();   ///< device -> host if the mirror is not current
   void syncToDevice(); ///< host -> device if host code wrote through the mirror
   ~Block();
@@ -267,6 +279,7 @@ struct Block {
 std::shared_ptr<Block> acquire(size_t count);
 void releasePool();
 size_t poolAllocations(); ///< number of cudaMalloc calls so far (steady state: constant)
+unsigned long long nextVersion();
 } // namespace b200
 } // namespace bout
 
@@ -330,6 +343,7 @@ public:
     return data->ptr;
   }
   std::string name;
+  bout::b200::Block* block() const { return data.get(); }
 
 protected:
   std::shared_ptr<bout::b200::Block> data;

@@ -2,8 +2,10 @@
 // include/bout_b200.h.  Set-up work (options, metric, initial profiles) runs once on the host, as in
 // the reference; everything inside a right-hand side or a time step is a kernel launch.
 #include "bout/b200_host.hxx"
+#include "bout/field_accessor.hxx"
 
 #include <deque>
+#include <thread>
 
 #include <algorithm>
 #include <cctype>
@@ -53,9 +55,15 @@ Block::~Block() {
   }
 }
 
+unsigned long long nextVersion() {
+  static unsigned long long v = 0;
+  return ++v;
+}
+
 std::shared_ptr<Block> acquire(size_t count) {
   auto blk = std::make_shared<Block>();
   blk->count = count;
+  blk->version = nextVersion();
   auto& bucket = freeList()[count];
   if (!bucket.empty()) {
     blk->ptr = bucket.back();
@@ -236,10 +244,18 @@ private:
     if (fn == "mixmode") { // FieldMixmode, fieldgenerators.cxx:110-146
       need(1, 2);
       const double seed = a.size() == 2 ? a[1] : 0.5;
+      // the 14 phases depend on the seed only: kept from the previous call (a field is filled point by point)
+      thread_local double cached_seed = std::nan("");
+      thread_local double phase[14];
+      if (!(cached_seed == seed)) {
+        for (int i = 0; i < 14; i++) {
+          phase[i] = PI * (2. * genRand(seed + i) - 1.);
+        }
+        cached_seed = seed;
+      }
       double result = 0.0;
       for (int i = 0; i < 14; i++) {
-        const double phase = PI * (2. * genRand(seed + i) - 1.);
-        result += (1. / SQ(1. + std::abs(i - 4))) * std::cos(i * a[0] + phase);
+        result += (1. / SQ(1. + std::abs(i - 4))) * std::cos(i * a[0] + phase[i]);
       }
       return result;
     }
@@ -360,6 +376,40 @@ private:
   }
 };
 
+// Fills of whole fields from an expression (initial profiles, field-valued options) run the x planes on the host's
+// cores: fn(x) for x in [0, nx), exceptions rethrown on the calling thread.
+void forEachPlane(int nx, const std::function<void(int)>& fn) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nt = std::max(1, std::min<int>(nx, hw == 0 ? 1 : static_cast<int>(hw)));
+  if (nt == 1) {
+    for (int x = 0; x < nx; ++x) {
+      fn(x);
+    }
+    return;
+  }
+  std::vector<std::thread> pool;
+  std::vector<std::exception_ptr> errs(nt);
+  for (int t = 0; t < nt; ++t) {
+    pool.emplace_back([&, t]() {
+      try {
+        for (int x = t; x < nx; x += nt) {
+          fn(x);
+        }
+      } catch (...) {
+        errs[t] = std::current_exception();
+      }
+    });
+  }
+  for (auto& th : pool) {
+    th.join();
+  }
+  for (auto& e : errs) {
+    if (e) {
+      std::rethrow_exception(e);
+    }
+  }
+}
+
 double evalOption(Options& opt, double x = 0, double y = 0, double z = 0) {
   EvalContext c;
   c.x = x;
@@ -432,14 +482,14 @@ Field3D Options::as<Field3D>() const {
   }
   Field3D f(m);
   std::vector<double> h(static_cast<size_t>(m->LocalNx) * m->LocalNy * m->LocalNz);
-  for (int x = 0; x < m->LocalNx; ++x) {
+  bout::b200::forEachPlane(m->LocalNx, [&](int x) {
     for (int y = 0; y < m->LocalNy; ++y) {
       for (int z = 0; z < m->LocalNz; ++z) {
         h[(static_cast<size_t>(x) * m->LocalNy + y) * m->LocalNz + z] = bout::b200::evalOption(
             const_cast<Options&>(*this), m->GlobalX(x), TWOPI * m->GlobalY(y), TWOPI * m->GlobalZ(z));
       }
     }
-  }
+  });
   f.setHost(h);
   return f;
 }
@@ -559,6 +609,9 @@ void FieldBase::makeUnique(size_t count) {
     check(bout_b200_memcpy_d2d(fresh->ptr, data->ptr, count * sizeof(double), nullptr));
     data = fresh;
   }
+  // every caller is about to write: the contents get a new identity and lose their recipe
+  data->version = bout::b200::nextVersion();
+  data->recipe = bout::b200::Block::Recipe{};
 }
 
 namespace {
@@ -806,7 +859,22 @@ Field3D* Field3D::timeDeriv() {
     return r;                                               \
   }
 B200_F3_BINOP(+, Field3D, term(1.0, &a), term(1.0, &b))
-B200_F3_BINOP(-, Field3D, term(1.0, &a), term(-1.0, &b))
+Field3D operator-(const Field3D& a, const Field3D& b) {
+  requireData(a, "Field3D operator");
+  requireData(b, "Field3D operator");
+  Field3D r(a.getMesh());
+  r.allocate();
+  ew3(r, {term(1.0, &a), term(-1.0, &b)});
+  // remembered for the single-index loop dispatcher: r == a - b while a and b keep these versions
+  bout::b200::Block::Recipe rec;
+  rec.op = 1;
+  rec.a = a.block();
+  rec.b = b.block();
+  rec.a_ver = a.block()->version;
+  rec.b_ver = b.block()->version;
+  r.block()->recipe = rec;
+  return r;
+}
 B200_F3_BINOP(*, Field3D, term(1.0, &a, false, &b))
 B200_F3_BINOP(/, Field3D, term(1.0, &a, false, nullptr, false, &b))
 B200_F3_BINOP(+, Field2D, term(1.0, &a), term(1.0, &b, true))
@@ -1009,7 +1077,7 @@ void Field3D::setBoundary(const std::string& var) {
   for (int s = 0; s < 4; ++s) {
     bool found = false;
     for (Options* o : {&vo, &all}) {
-      for (const std::string key : {std::string("bndry_") + labels[s], std::string("bndry_") + sides[s], std::string("bndry_all")}) {
+      for (const std::string& key : {std::string("bndry_") + labels[s], std::string("bndry_") + sides[s], std::string("bndry_all")}) {
         if (o->isSet(key)) {
           bndry_conditions[s] = (*o)[key].text();
           found = true;
@@ -1180,13 +1248,47 @@ BoutReal Mesh::GlobalZ(int jz) const { return static_cast<BoutReal>(jz) / static
 void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
   const auto g = grid();
   std::vector<double*> ptrs;
+  // A guard-cell exchange copies cells, so a field that was the difference of two others communicated in the same
+  // call still is afterwards: carry such recipes over to the blocks' new versions.
+  struct Kept {
+    Field3D* f;
+    Field3D* a;
+    Field3D* b;
+  };
+  std::vector<Kept> kept;
   for (Field3D* f : fields) {
     requireData(*f, "Mesh::communicate");
+    const auto& rec = f->block()->recipe;
+    if (rec.op == 1) {
+      Field3D *fa = nullptr, *fb = nullptr;
+      for (Field3D* o : fields) {
+        if (o->block() == rec.a && o->block()->version == rec.a_ver) {
+          fa = o;
+        }
+        if (o->block() == rec.b && o->block()->version == rec.b_ver) {
+          fb = o;
+        }
+      }
+      if (fa != nullptr && fb != nullptr) {
+        kept.push_back({f, fa, fb});
+      }
+    }
+  }
+  for (Field3D* f : fields) {
     ptrs.push_back(f->wptr());
   }
   for (size_t i = 0; i < ptrs.size(); i += 8) { // the kernel takes up to 8 fields per launch
     const int n = static_cast<int>(std::min<size_t>(8, ptrs.size() - i));
     check(bout_b200_halo_self(&g, n, ptrs.data() + i, periodicX ? 1 : 0, (periodicY && MYG > 0) ? 1 : 0, nullptr));
+  }
+  for (const Kept& k : kept) {
+    bout::b200::Block::Recipe rec;
+    rec.op = 1;
+    rec.a = k.a->block();
+    rec.b = k.b->block();
+    rec.a_ver = rec.a->version;
+    rec.b_ver = rec.b->version;
+    k.f->block()->recipe = rec;
   }
 }
 
@@ -1593,6 +1695,286 @@ Field3D Delp2(const Field3D& f, CELL_LOC, bool useFFT) {
 }
 
 // ======================================================================================================
+// Single-index loops (BOUT_FOR_RAJA): dispatch of a recorded loop body (include/bout/field_accessor.hxx)
+// ======================================================================================================
+namespace bout {
+namespace b200 {
+namespace si {
+Recorder& Recorder::get() {
+  static Recorder r;
+  return r;
+}
+
+namespace {
+struct Term { // coef * prim(f, g); prim = CONST means the constant coef itself
+  double coef;
+  Kind prim;
+  const Field3D* f;
+  const Field3D* g;
+};
+
+bool constantValue(const std::vector<Node>& nodes, int id, double* v) {
+  const Node& n = nodes[id];
+  double a = 0.0, b = 0.0;
+  switch (n.kind) {
+  case CONST: *v = n.value; return true;
+  case NEG:
+    if (!constantValue(nodes, n.a, &a)) {
+      return false;
+    }
+    *v = -a;
+    return true;
+  case ADD:
+  case SUB:
+  case MUL:
+  case DIV:
+    if (!constantValue(nodes, n.a, &a) || !constantValue(nodes, n.b, &b)) {
+      return false;
+    }
+    *v = n.kind == ADD ? a + b : (n.kind == SUB ? a - b : (n.kind == MUL ? a * b : a / b));
+    return true;
+  default: return false;
+  }
+}
+
+// the expression as a sum of coef * primitive terms; products of two field-dependent factors are not linear
+void linearise(const std::vector<Node>& nodes, int id, double scale, std::vector<Term>& out) {
+  const Node& n = nodes[id];
+  double c = 0.0;
+  switch (n.kind) {
+  case CONST: out.push_back({scale * n.value, CONST, nullptr, nullptr}); return;
+  case ADD:
+    linearise(nodes, n.a, scale, out);
+    linearise(nodes, n.b, scale, out);
+    return;
+  case SUB:
+    linearise(nodes, n.a, scale, out);
+    linearise(nodes, n.b, -scale, out);
+    return;
+  case NEG: linearise(nodes, n.a, -scale, out); return;
+  case MUL:
+    if (constantValue(nodes, n.a, &c)) {
+      linearise(nodes, n.b, scale * c, out);
+    } else if (constantValue(nodes, n.b, &c)) {
+      linearise(nodes, n.a, scale * c, out);
+    } else {
+      throw BoutException("BOUT_FOR_RAJA: a product of two field terms in a single-index loop is not implemented on the B200 path");
+    }
+    return;
+  case DIV:
+    if (!constantValue(nodes, n.b, &c)) {
+      throw BoutException("BOUT_FOR_RAJA: division by a field term in a single-index loop is not implemented on the B200 path");
+    }
+    linearise(nodes, n.a, scale / c, out);
+    return;
+  default: out.push_back({scale, n.kind, n.f, n.g}); return;
+  }
+}
+
+// same primitive on the same fields: coefficients add
+std::vector<Term> merged(const std::vector<Term>& in) {
+  std::vector<Term> out;
+  for (const Term& t : in) {
+    bool found = false;
+    for (Term& o : out) {
+      if (o.prim == t.prim && o.f == t.f && o.g == t.g) {
+        o.coef += t.coef;
+        found = true;
+        break;
+      }
+    }
+    if (!found) {
+      out.push_back(t);
+    }
+  }
+  return out;
+}
+
+const Term* findTerm(const std::vector<Term>& ts, Kind prim, const Field3D* f = nullptr, const Field3D* g = nullptr) {
+  for (const Term& t : ts) {
+    if (t.prim == prim && (f == nullptr || t.f == f) && (g == nullptr || t.g == g)) {
+      return &t;
+    }
+  }
+  return nullptr;
+}
+
+// is x's block the difference a - b, still valid?
+bool isDifference(const Field3D* x, const Field3D* a, const Field3D* b) {
+  const Block* xb = x->block();
+  if (xb == nullptr || a->block() == nullptr || b->block() == nullptr) {
+    return false;
+  }
+  const Block::Recipe& r = xb->recipe;
+  return r.op == 1 && r.a == a->block() && r.a_ver == a->block()->version && r.b == b->block()
+         && r.b_ver == b->block()->version;
+}
+
+bout_b200_metric metricOf(Coordinates* c) {
+  bout_b200_metric m{};
+  m.dx = c->dx.dptr();
+  m.dy = c->dy.dptr();
+  m.dz = c->dz.dptr();
+  m.J = c->J.dptr();
+  m.g_22 = c->g_22.dptr();
+  m.g11 = c->g11.dptr();
+  m.g33 = c->g33.dptr();
+  m.g13 = c->g13.dptr();
+  m.G1 = c->G1.dptr();
+  m.G3 = c->G3.dptr();
+  m.d1_dx = c->non_uniform ? c->d1_dx.dptr() : nullptr;
+  return m;
+}
+
+// examples/hasegawa-wakatani-3d/hw.cxx:58-74:
+//   ddt(n)    = -[phi, n]    - alpha Div_par_Grad_par(phi - n) - kappa DDZ(phi) + Dn Delp2(n)
+//   ddt(vort) = -[phi, vort] - alpha Div_par_Grad_par(phi - n)                  + Dvort Delp2(vort)
+// Recognised from the recorded terms, whatever the order or grouping they were written in.
+bool tryHw3d(Mesh* mesh, const std::vector<std::pair<Field3D*, std::vector<Term>>>& eqs) {
+  if (eqs.size() != 2) {
+    return false;
+  }
+  for (int swap = 0; swap < 2; ++swap) {
+    Field3D* n = eqs[swap].first;
+    Field3D* vort = eqs[1 - swap].first;
+    const std::vector<Term>& tn = eqs[swap].second;
+    const std::vector<Term>& tv = eqs[1 - swap].second;
+    const Term* bn = findTerm(tn, BRACKET, nullptr, n);
+    const Term* bv = findTerm(tv, BRACKET, nullptr, vort);
+    if (bn == nullptr || bv == nullptr || bn->f != bv->f || bn->coef != -1.0 || bv->coef != -1.0) {
+      continue;
+    }
+    const Field3D* phi = bn->f;
+    const Term* dn = findTerm(tn, DIV_PAR_GRAD_PAR);
+    const Term* dv = findTerm(tv, DIV_PAR_GRAD_PAR);
+    if (dn == nullptr || dv == nullptr || dn->f != dv->f || dn->coef != dv->coef || !isDifference(dn->f, phi, n)) {
+      continue;
+    }
+    const Term* zn = findTerm(tn, DDZ, phi);
+    const Term* ln = findTerm(tn, DELP2, n);
+    const Term* lv = findTerm(tv, DELP2, vort);
+    const size_t used_n = 2 + (zn != nullptr) + (ln != nullptr), used_v = 2 + (lv != nullptr);
+    if (tn.size() != used_n || tv.size() != used_v) {
+      continue; // some other term is present
+    }
+    // scratch for the per-(x,y) coefficient table of the fused kernel (rebuilt from the metric by every call)
+    const auto g = mesh->grid();
+    const size_t need = bout_b200_fused_coef_doubles(&g);
+    static std::map<Mesh*, std::shared_ptr<Block>> ws_blocks;
+    std::shared_ptr<Block>& wb = ws_blocks[mesh];
+    if (!wb || wb->count < need) {
+      wb = acquire(need);
+    }
+    const bout_b200_metric m = metricOf(mesh->getCoordinates());
+    Field3D* dtn = n->timeDeriv();
+    Field3D* dtv = vort->timeDeriv();
+    if (!dtn->isAllocated()) {
+      dtn->allocate();
+    }
+    if (!dtv->isAllocated()) {
+      dtv->allocate();
+    }
+    check(bout_b200_hw3d_rhs(&g, &m, -dn->coef, zn != nullptr ? -zn->coef : 0.0, ln != nullptr ? ln->coef : 0.0,
+                             lv != nullptr ? lv->coef : 0.0, n->dptr(), vort->dptr(), phi->dptr(), dtn->wptr(),
+                             dtv->wptr(), nullptr, wb->ptr, nullptr));
+    return true;
+  }
+  return false;
+}
+
+// one kernel per operator: every primitive becomes a field, the assignment a linear combination over the region
+Field3D primitiveField(const Term& t) {
+  switch (t.prim) {
+  case FIELD: return *t.f;
+  case BRACKET: return ::bracket(*t.f, *t.g, BRACKET_ARAKAWA);
+  case DDX: return ::DDX(*t.f, CELL_DEFAULT, "C2");
+  case DDZ: return ::DDZ(*t.f, CELL_DEFAULT, "C2");
+  case DELP2: return ::Delp2(*t.f, CELL_DEFAULT, false);
+  default:
+    throw BoutException("BOUT_FOR_RAJA: this single-index operator is only implemented inside the fused "
+                        "hasegawa-wakatani-3d pattern on the B200 path (operator {})", static_cast<int>(t.prim));
+  }
+}
+} // namespace
+
+void dispatch(const Region<Ind3D>& region) {
+  Recorder& rec = Recorder::get();
+  if (rec.assigns.empty()) {
+    return;
+  }
+  Mesh* mesh = rec.assigns.front().target->getMesh();
+  if (&region != &mesh->getRegion3D("RGN_NOBNDRY")) {
+    throw BoutException("BOUT_FOR_RAJA: only RGN_NOBNDRY loops are implemented on the B200 path");
+  }
+  // one term list per assigned field, in order of first assignment (a later plain assignment replaces, += adds)
+  std::vector<std::pair<Field3D*, std::vector<Term>>> eqs;
+  for (const Assignment& a : rec.assigns) {
+    std::vector<Term> ts;
+    linearise(rec.nodes, a.node, 1.0, ts);
+    auto it = eqs.begin();
+    for (; it != eqs.end(); ++it) {
+      if (it->first == a.target) {
+        break;
+      }
+    }
+    if (it == eqs.end()) {
+      if (a.accumulate) {
+        throw BoutException("BOUT_FOR_RAJA: ddt(f)[i] += ... before any assignment to it");
+      }
+      eqs.push_back({a.target, ts});
+    } else if (a.accumulate) {
+      it->second.insert(it->second.end(), ts.begin(), ts.end());
+    } else {
+      it->second = ts;
+    }
+  }
+  for (auto& e : eqs) {
+    e.second = merged(e.second);
+  }
+  if (tryHw3d(mesh, eqs)) {
+    return;
+  }
+  const auto g = mesh->grid();
+  for (auto& e : eqs) {
+    std::vector<Field3D> held;
+    std::vector<double> coef;
+    double constant = 0.0;
+    for (const Term& t : e.second) {
+      if (t.prim == CONST) {
+        constant += t.coef;
+      } else {
+        held.push_back(primitiveField(t));
+        coef.push_back(t.coef);
+      }
+    }
+    if (constant != 0.0) {
+      held.push_back(Field3D(constant, mesh));
+      coef.push_back(1.0);
+    }
+    Field3D* dt = e.first->timeDeriv();
+    if (!dt->isAllocated()) {
+      dt->allocate();
+    }
+    if (held.empty()) {
+      *dt = 0.0;
+      continue;
+    }
+    if (held.size() > 8) {
+      throw BoutException("BOUT_FOR_RAJA: more than 8 terms in one assignment");
+    }
+    std::vector<const double*> x;
+    for (const Field3D& f : held) {
+      x.push_back(f.dptr());
+    }
+    check(bout_b200_lincomb(&g, BOUT_B200_RGN_NOBNDRY, static_cast<int>(coef.size()), coef.data(), x.data(), dt->wptr(),
+                            nullptr));
+  }
+}
+} // namespace si
+} // namespace b200
+} // namespace bout
+
+// ======================================================================================================
 // Laplacian
 // ======================================================================================================
 std::unique_ptr<Laplacian> Laplacian::instance;
@@ -1709,14 +2091,14 @@ void initialProfile(const std::string& name, Field3D& var) { // initialprofiles.
   }
   std::vector<double> h(var.size(), 0.0);
   if (fo != nullptr && scale != 0.0) {
-    for (int x = 0; x < m->LocalNx; ++x) {
+    bout::b200::forEachPlane(m->LocalNx, [&](int x) {
       for (int y = 0; y < m->LocalNy; ++y) {
         for (int z = 0; z < m->LocalNz; ++z) {
           h[(static_cast<size_t>(x) * m->LocalNy + y) * m->LocalNz + z] =
               scale * bout::b200::evalOption(*fo, m->GlobalX(x), TWOPI * m->GlobalY(y), TWOPI * m->GlobalZ(z));
         }
       }
-    }
+    });
   }
   var.setHost(h);
 }

@@ -143,6 +143,10 @@ int b200host_model_solve(int nout, double output_step) {
     }
   });
 }
+/// Waits for the device work queued so far (timing brackets around b200host_model_solve)
+int b200host_stream_sync() {
+  return guarded([&]() { bout::b200::check(bout_b200_stream_sync(nullptr)); });
+}
 int b200host_rhs_calls() { return solver ? solver->rhs_calls : 0; }
 unsigned long long b200host_pool_allocations() { return bout::b200::poolAllocations(); }
 

@@ -461,3 +461,75 @@ int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_lapl
   free(ones);
   return rc == 0 ? 0 : BOUT_B200_ERR_PIVOT;
 }
+
+/* ---- fused hasegawa-wakatani-3d right-hand side (host-logic tests of the single-index loop dispatcher) --------
+ * Brackets through the oracle port; DDZ, Delp2 and Div_par_Grad_par restated from the reference's
+ * include/bout/single_index_ops.hxx:201-209, :222-246, :255-278 (identity parallel transform: yup / ydown are the
+ * field itself), as oracle/oracle.py::hw3d_rhs does in numpy. */
+size_t bout_b200_fused_coef_doubles(const bout_b200_grid* g) { return (size_t)g->nx * g->ny * 16; }
+int bout_b200_fused_coefs(const bout_b200_grid* g, const bout_b200_metric* m, double* ws, void* stream) {
+  (void)g, (void)m, (void)ws, (void)stream;
+  return 0;
+}
+int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, double alpha, double kappa, double Dn,
+                       double Dvort, const double* n, const double* vort, const double* phi, double* ddt_n,
+                       double* ddt_vort, const bout_b200_rk_epilogue* epilogue, double* coef_workspace, void* stream) {
+  (void)coef_workspace, (void)stream;
+  if (m == NULL || epilogue != NULL || ddt_n == NULL || ddt_vort == NULL) {
+    return BOUT_B200_ERR_UNSUPPORTED;
+  }
+  const size_t n3 = (size_t)g->nx * g->ny * g->nz;
+  double* bn = (double*)malloc(n3 * sizeof(double));
+  double* bv = (double*)malloc(n3 * sizeof(double));
+  int rc = bout_b200_bracket_arakawa(g, phi, n, m->dx, m->dz, bn, NULL);
+  if (rc == 0) {
+    rc = bout_b200_bracket_arakawa(g, phi, vort, m->dx, m->dz, bv, NULL);
+  }
+  if (rc != 0) {
+    free(bn);
+    free(bv);
+    return rc;
+  }
+  const int ny = g->ny, nz = g->nz;
+#define AT(f, x, y, z) (f)[((size_t)(x) * ny + (y)) * nz + (((z) % nz + nz) % nz)]
+#define M2(a, x, y) (a)[(size_t)(x) * ny + (y)]
+  for (int x = g->xstart; x <= g->xend; ++x) {
+    for (int y = g->ystart; y <= g->yend; ++y) {
+      const double dx = M2(m->dx, x, y), dz = M2(m->dz, x, y), dy = M2(m->dy, x, y), J = M2(m->J, x, y);
+      const double d1 = m->d1_dx ? M2(m->d1_dx, x, y) : 0.0;
+      for (int z = 0; z < nz; ++z) {
+        double lap[2];
+        const double* fl[2] = {n, vort};
+        for (int q = 0; q < 2; ++q) {
+          const double* f = fl[q];
+          lap[q] = (M2(m->G1, x, y) + d1 * M2(m->g11, x, y)) * (AT(f, x + 1, y, z) - AT(f, x - 1, y, z)) / (2.0 * dx)
+                   + M2(m->G3, x, y) * (AT(f, x, y, z + 1) - AT(f, x, y, z - 1)) / (2.0 * dz)
+                   + M2(m->g11, x, y) * (AT(f, x + 1, y, z) - 2.0 * AT(f, x, y, z) + AT(f, x - 1, y, z)) / (dx * dx)
+                   + M2(m->g33, x, y) * (AT(f, x, y, z + 1) - 2.0 * AT(f, x, y, z) + AT(f, x, y, z - 1)) / (dz * dz)
+                   + 2 * M2(m->g13, x, y)
+                         * ((AT(f, x + 1, y, z + 1) - AT(f, x - 1, y, z + 1))
+                            - (AT(f, x + 1, y, z - 1) - AT(f, x - 1, y, z - 1)))
+                         / (4. * dz * dx);
+        }
+        double div = 0.0;
+        if (ny > 1) {
+#define PMN(x, y, z) (AT(phi, x, y, z) - AT(n, x, y, z))
+          const double gu = 2. * (PMN(x, y + 1, z) - PMN(x, y, z)) / (dy + M2(m->dy, x, y + 1));
+          const double fu = gu * (J + M2(m->J, x, y + 1)) / (M2(m->g_22, x, y) + M2(m->g_22, x, y + 1));
+          const double gl = 2. * (PMN(x, y, z) - PMN(x, y - 1, z)) / (dy + M2(m->dy, x, y - 1));
+          const double fd = gl * (J + M2(m->J, x, y - 1)) / (M2(m->g_22, x, y) + M2(m->g_22, x, y - 1));
+          div = alpha * (fu - fd) / (dy * J);
+#undef PMN
+        }
+        const double ddz = 0.5 * (AT(phi, x, y, z + 1) - AT(phi, x, y, z - 1)) / dz;
+        AT(ddt_n, x, y, z) = -AT(bn, x, y, z) - div - kappa * ddz + Dn * lap[0];
+        AT(ddt_vort, x, y, z) = -AT(bv, x, y, z) - div + Dvort * lap[1];
+      }
+    }
+  }
+#undef AT
+#undef M2
+  free(bn);
+  free(bv);
+  return 0;
+}

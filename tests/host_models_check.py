@@ -1,4 +1,5 @@
-"""The unchanged examples/hasegawa-wakatani/hw.cxx and examples/blob2d/blob2d.cxx through the C++ host layer against
+"""The unchanged examples/hasegawa-wakatani/hw.cxx, examples/blob2d/blob2d.cxx and examples/hasegawa-wakatani-3d/hw.cxx
+(its BOUT_FOR_RAJA single-index loop recorded and dispatched to the fused kernel) through the C++ host layer against
 the reference build (tests/golden/models.npz): initial profiles, one Solver::run_rhs, a 5-step RK trajectory -- the
 checks of tests/test_gpu_models.py::test_unchanged_model_through_host_layer, runnable on CPU with the test double
 (LD_PRELOAD=<libfake_b200.so> B200_FAKE_ORACLE_PORT=<liboracle_port.so>), where they pin the HOST logic: options,
@@ -26,7 +27,8 @@ def main():
     gold = np.load(os.path.join(HERE, "golden", "models.npz"))
     res, bad = {}, []
     for tag, model, solver, ini in (("hw", "hw", "rk4", cases.HW_INI), ("hw_rk3", "hw", "rk3ssp", cases.HW_INI),
-                                    ("blob2d", "blob2d", "rk4", cases.BLOB_INI)):
+                                    ("blob2d", "blob2d", "rk4", cases.BLOB_INI),
+                                    ("hw3d", "hw3d", "rk4", cases.HW3D_INI)):
         h = hostmod.Host(ini)
         try:
             names = h.model_create(model, solver)

@@ -60,13 +60,16 @@ def _cases():
     return cases
 
 
-@pytest.mark.parametrize("tag,model,solver", [("hw", "hw", "rk4"), ("hw_rk3", "hw", "rk3ssp"), ("blob2d", "blob2d", "rk4")])
+@pytest.mark.parametrize("tag,model,solver", [("hw", "hw", "rk4"), ("hw_rk3", "hw", "rk3ssp"), ("blob2d", "blob2d", "rk4"),
+                                              ("hw3d", "hw3d", "rk4")])
 def test_unchanged_model_through_host_layer(hostmod, gold, tag, model, solver):
-    """examples/hasegawa-wakatani/hw.cxx and examples/blob2d/blob2d.cxx, compiled unchanged against
+    """examples/hasegawa-wakatani/hw.cxx, examples/blob2d/blob2d.cxx and examples/hasegawa-wakatani-3d/hw.cxx (the
+    headline workload: its single-index BOUT_FOR_RAJA loop is recorded and dispatched to bout_b200_hw3d_rhs), compiled
+    unchanged against
     bout-dev_b200/host/include/bout/*.hxx, run device-resident: initial profiles, one Solver::run_rhs
     and a 5-step RK trajectory against the reference build."""
     cases = _cases()
-    ini = {"hw": cases.HW_INI, "hw_rk3": cases.HW_INI, "blob2d": cases.BLOB_INI}[tag]
+    ini = {"hw": cases.HW_INI, "hw_rk3": cases.HW_INI, "blob2d": cases.BLOB_INI, "hw3d": cases.HW3D_INI}[tag]
     h = hostmod.Host(ini)
     try:
         names = h.model_create(model, solver)
@@ -107,3 +110,13 @@ def test_host_layer_pool_reaches_steady_state(hostmod, gold):
         assert h.pool_allocations() == a0
     finally:
         h.close()
+
+
+def test_single_index_loop_generic_dispatch():
+    """tests/models/si_loop.cxx: a BOUT_FOR_RAJA loop outside the fused hw3d pattern, dispatched operator by operator
+    on the device, against the same expression with whole-field operators (tests/si_loop_check.py)."""
+    import json, os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, os.path.join(here, "si_loop_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]

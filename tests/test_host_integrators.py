@@ -238,3 +238,16 @@ def test_unchanged_hw_and_blob2d_through_the_host_layer_host_logic(fake_device):
                        timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
+def test_single_index_loop_generic_dispatch_host_logic(fake_device):
+    """tests/si_loop_check.py on CPU: the recorder behind BOUT_FOR_RAJA / FieldAccessor / single_index_ops.hxx
+    (NaN-boxed intermediates, += assignments, integer constants) and its one-kernel-per-operator dispatch give the
+    same ddt as the whole-field operators."""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "si_loop_check.py")],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
