@@ -171,11 +171,7 @@ int b200host_expr3d(const char* expr, double* out) {
     o["scale"].setText("1.0");
     Field3D f(bout::globals::mesh);
     f.name = "b200host_tmp";
-    Solver* none = nullptr;
-    (void)none;
-    // reuse the initial-profile path
-    std::unique_ptr<Solver> s = Solver::create();
-    s->add(f, "b200host_tmp");
+    initial_profile("b200host_tmp", f); // the initial-profile path without Solver::add's boundary conditions
     f.getHost(out);
   });
 }
