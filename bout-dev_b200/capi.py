@@ -150,6 +150,74 @@ class CLaplace(C.Structure):
                                        "include_yguards_upper")]
 
 
+class CLaplaceXZ(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("A", "B", "J", "g11", "g33", "dx")] + [
+        ("zlength", C.c_double), ("inner_boundary_flags", C.c_int), ("outer_boundary_flags", C.c_int)]
+
+
+class CInvertPar(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("A", "B", "C", "D", "E", "sg", "g_22", "dy", "d1_dy", "twist_shift")] + [
+        ("zlength", C.c_double), ("closed", C.c_int)]
+
+
+class LaplaceXZ:
+    """LaplaceXZ "cyclic" (reference src/invert/laplacexz/impls/cyclic/laplacexz-cyclic.cxx): setCoefs(A, B), solve."""
+
+    def __init__(self, g: Grid, metric: dict, zlength, A, B, inner_boundary_flags=0, outer_boundary_flags=0):
+        self.g = g
+        self.keep = dict(A=A, B=B, J=metric["J"], g11=metric["g11"], g33=metric["g33"], dx=metric["dx"])
+        c = CLaplaceXZ()
+        for n, t in self.keep.items():
+            setattr(c, n, t.data_ptr())
+        c.zlength = zlength
+        c.inner_boundary_flags, c.outer_boundary_flags = inner_boundary_flags, outer_boundary_flags
+        self.c, self.ws = c, None
+
+    def solve(self, rhs, x0=None, out=None):
+        out = torch.zeros_like(rhs) if out is None else out
+        lib.bout_b200_laplacexz_workspace.restype = C.c_size_t
+        n = lib.bout_b200_laplacexz_workspace(C.byref(self.g.c))
+        if self.ws is None or self.ws.numel() < n:
+            self.ws = torch.empty(n, dtype=torch.uint8, device=rhs.device)
+        _check(lib.bout_b200_laplacexz_solve(C.byref(self.g.c), C.byref(self.c), _ptr(rhs), _ptr(x0), _ptr(out),
+                                             C.c_void_p(self.ws.data_ptr()), C.c_size_t(self.ws.numel()), _stream()))
+        return out
+
+
+class InvertPar:
+    """InvertPar "cyclic" (reference src/invert/parderiv/impls/cyclic/cyclic.cxx) on a field-aligned input.  sg is
+    formed as the reference's constructor does, with the 2nd-order central DDY of a Field2D."""
+
+    def __init__(self, g: Grid, metric: dict, zlength, A=None, B=None, Cc=None, D=None, E=None, closed=True,
+                 nonuniform=True, twist_shift=None):
+        self.g = g
+        g22, dy = metric["g_22"], metric["dy"]
+        r = 1.0 / torch.sqrt(g22)
+        ddy = torch.zeros_like(r)
+        if closed:   # guard rows hold the periodic images
+            ddy[:, 1:-1] = 0.5 * (r[:, 2:] - r[:, :-2]) / dy[:, 1:-1]
+        else:
+            ddy[:, 1:-1] = 0.5 * (r[:, 2:] - r[:, :-2]) / dy[:, 1:-1]
+        sg = (ddy / torch.sqrt(g22)).contiguous()
+        self.keep = dict(A=A, B=B, C=Cc, D=D, E=E, sg=sg, g_22=g22, dy=dy,
+                         d1_dy=metric["d1_dy"] if nonuniform else None, twist_shift=twist_shift)
+        c = CInvertPar()
+        for n, t in self.keep.items():
+            setattr(c, n, None if t is None else t.data_ptr())
+        c.zlength, c.closed = zlength, int(closed)
+        self.c, self.ws = c, None
+
+    def solve(self, f, out=None):
+        out = torch.zeros_like(f) if out is None else out
+        lib.bout_b200_invert_par_workspace.restype = C.c_size_t
+        n = lib.bout_b200_invert_par_workspace(C.byref(self.g.c))
+        if self.ws is None or self.ws.numel() < n:
+            self.ws = torch.empty(n, dtype=torch.uint8, device=f.device)
+        _check(lib.bout_b200_invert_par_solve(C.byref(self.g.c), C.byref(self.c), _ptr(f), _ptr(out),
+                                              C.c_void_p(self.ws.data_ptr()), C.c_size_t(self.ws.numel()), _stream()))
+        return out
+
+
 class Laplace:
     """Host-side mirror of the Laplacian settings (reference invert_laplace.cxx:68-138)."""
 

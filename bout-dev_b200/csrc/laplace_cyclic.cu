@@ -1330,3 +1330,384 @@ extern "C" int bout_b200_laplace_cyclic_status(void* workspace, void* stream) {
   }
   return 0;
 }
+
+// =====================================================================================================================
+// LaplaceXZ (cyclic) and InvertPar (cyclic) on the same machinery -- row rfft (k_lap_forward), one thread
+// per (line, kz) tridiagonal system with the coefficients formed on the fly, row irfft (k_lap_backward).
+// =====================================================================================================================
+namespace b200 {
+struct XzParams {
+  const double *A, *B, *J, *g11, *g33, *dx;
+  double kscale;
+  int inner, outer;
+  int ny, xstart, xend, ys, nys, nmode;
+  cd* spec;          // [row = x - (xstart - 1)][iyl][kz]: right-hand side in, solution out
+  cd* cp;            // c' of the sweep, same layout
+  const cd* x0spec;  // INVERT_SET on the inner boundary: spectra of x0 at x = xstart - 1, xstart ([2][iyl][kz])
+  int* status;
+};
+
+// laplacexz-cyclic.cxx:63-143 (coefficients), :146-250 (right-hand side), CyclicReduce -> Thomas here
+__global__ void __launch_bounds__(128) k_xz_thomas(const XzParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.nys * p.nmode) {
+    return;
+  }
+  const int iyl = t / p.nmode, kz = t % p.nmode, y = p.ys + iyl;
+  const double kwave = kz * p.kscale;
+  const long long rs = static_cast<long long>(p.nys) * p.nmode; // row stride
+  const int n = p.xend - p.xstart + 3;
+  cd* __restrict__ S = p.spec + t;
+  cd* __restrict__ CP = p.cp + t;
+  const bool grad_in = (kz == 0 && (p.inner & INV_DC_GRAD)) || (kz != 0 && (p.inner & INV_AC_GRAD));
+  const bool grad_out = (kz == 0 && (p.outer & INV_DC_GRAD)) || (kz != 0 && (p.outer & INV_AC_GRAD));
+  auto at = [&](const double* f, int x) { return __ldg(f + static_cast<long long>(x) * p.ny + y); };
+  // row 0: x = xstart - 1
+  double b0 = grad_in ? 1.0 : 0.5, c0 = grad_in ? -1.0 : 0.5;
+  cd r0 = {0.0, 0.0};
+  if (p.inner & INV_SET) {
+    const cd u = p.x0spec[t], v = p.x0spec[rs + t];
+    r0 = {b0 * u.re + c0 * v.re, b0 * u.im + c0 * v.im};
+  } else if (p.inner & INV_RHS) {
+    const cd u = S[0], v = S[rs];
+    r0 = {b0 * u.re + c0 * v.re, b0 * u.im + c0 * v.im};
+  }
+  bool bad = b0 == 0.0;
+  double cprev = c0 / b0;
+  cd dprev = {r0.re / b0, r0.im / b0};
+  CP[0] = {cprev, 0.0};
+  S[0] = dprev;
+  for (int i = 1; i < n; ++i) {
+    double a, b, c;
+    cd r;
+    if (i < n - 1) {
+      const int x = p.xstart - 1 + i;
+      const double Jc = at(p.J, x), dxc = at(p.dx, x), Ac = at(p.A, x), gc = at(p.g11, x);
+      const double vp = (0.5 * (Ac + at(p.A, x + 1))) * (0.5 * (Jc + at(p.J, x + 1))) * (0.5 * (gc + at(p.g11, x + 1)))
+                        / (Jc * (0.5 * (dxc + at(p.dx, x + 1))) * dxc);
+      const double vm = (0.5 * (Ac + at(p.A, x - 1))) * (0.5 * (Jc + at(p.J, x - 1))) * (0.5 * (gc + at(p.g11, x - 1)))
+                        / (Jc * (0.5 * (dxc + at(p.dx, x - 1))) * dxc);
+      a = vm;
+      c = vp;
+      b = at(p.B, x) - vp - vm - Ac * kwave * kwave * at(p.g33, x);
+      r = S[i * rs];
+    } else { // x = xend + 1; its right-hand side is always zeroed (laplacexz-cyclic.cxx:237-239)
+      a = grad_out ? -1.0 : 0.5;
+      b = grad_out ? 1.0 : 0.5;
+      c = 0.0;
+      r = {0.0, 0.0};
+    }
+    const double den = b - a * cprev;
+    bad = bad || !(fabs(den) > 1e-300);
+    const double inv = 1.0 / den;
+    cprev = c * inv;
+    dprev = {(r.re - a * dprev.re) * inv, (r.im - a * dprev.im) * inv};
+    CP[i * rs] = {cprev, 0.0};
+    S[i * rs] = dprev;
+  }
+  cd x = dprev;
+  for (int i = n - 2; i >= 0; --i) {
+    const double cpi = CP[i * rs].re;
+    const cd d = S[i * rs];
+    x = {d.re - cpi * x.re, d.im - cpi * x.im};
+    S[i * rs] = x;
+  }
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+
+struct ParParams {
+  const double *A, *B, *C, *D, *E, *sg, *g_22, *dy, *d1_dy, *twist;
+  double kscale;
+  int closed;
+  int ny, xs, nxs, ystart, yend, nmode;
+  int ys, nys;   // y range transformed (closed: the interior rows; open: every row)
+  cd *spec, *cp, *zs;
+  int* status;
+};
+
+// parderiv/impls/cyclic/cyclic.cxx:60-245.  Closed field lines: periodic system with the twist-shift phases on its
+// two corner elements, solved by Thomas + the Sherman-Morrison correction; open: boundary rows in the y guard cells.
+__global__ void __launch_bounds__(128) k_par_thomas(const ParParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.nxs * p.nmode) {
+    return;
+  }
+  const int ixl = t / p.nmode, kz = t % p.nmode, x = p.xs + ixl;
+  const double kwave = kz * p.kscale;
+  const long long rs = p.nmode;
+  const long long base = static_cast<long long>(ixl) * p.nys * p.nmode + kz;
+  cd* __restrict__ S = p.spec + base;
+  cd* __restrict__ CP = p.cp + base;
+  cd* __restrict__ Z = p.zs + base;
+  const int n = p.nys;
+  auto rowOf = [&](int j, cd& a, cd& b, cd& c) { // row j <-> y = ys + j
+    const int y = p.ys + j;
+    if (!p.closed && y < p.ystart) {
+      a = {0.0, 0.0}, b = {1.0, 0.0}, c = {-1.0, 0.0};
+      return false;
+    }
+    if (!p.closed && y > p.yend) {
+      a = {-1.0, 0.0}, b = {1.0, 0.0}, c = {0.0, 0.0};
+      return false;
+    }
+    const long long i2 = static_cast<long long>(x) * p.ny + y;
+    const double Bv = p.B ? __ldg(p.B + i2) : 0.0, dy = __ldg(p.dy + i2);
+    const double acoef = p.A ? __ldg(p.A + i2) : 1.0;
+    double bcoef = Bv / __ldg(p.g_22 + i2);
+    double ccoef = p.C ? __ldg(p.C + i2) : 0.0;
+    const double dcoef = p.D ? __ldg(p.D + i2) : 0.0;
+    double ecoef = (p.E ? __ldg(p.E + i2) : 0.0) + __ldg(p.sg + i2) * Bv;
+    if (p.d1_dy != nullptr) {
+      ecoef += bcoef * __ldg(p.d1_dy + i2);
+    }
+    bcoef /= dy * dy;
+    ccoef /= dy;
+    ecoef /= dy;
+    a = {bcoef - 0.5 * ecoef, -0.5 * kwave * ccoef};
+    b = {acoef - 2. * bcoef - kwave * kwave * dcoef, 0.0};
+    c = {bcoef + 0.5 * ecoef, 0.5 * kwave * ccoef};
+    return true;
+  };
+  bool bad = false;
+  cd a, b, c;
+  if (!p.closed) {
+    cd cprev = {0.0, 0.0}, dprev = {0.0, 0.0};
+    for (int j = 0; j < n; ++j) {
+      const bool interior = rowOf(j, a, b, c);
+      const cd r = interior ? S[j * rs] : cd{0.0, 0.0};
+      const cd den = j == 0 ? b : csub(b, cmul(a, cprev));
+      bad = bad || tiny(den);
+      const cd inv = crecip(den);
+      cprev = cmul(c, inv);
+      dprev = cmul(j == 0 ? r : csub(r, cmul(a, dprev)), inv);
+      CP[j * rs] = cprev;
+      S[j * rs] = dprev;
+    }
+    cd xv = dprev;
+    for (int j = n - 2; j >= 0; --j) {
+      xv = csub(S[j * rs], cmul(CP[j * rs], xv));
+      S[j * rs] = xv;
+    }
+  } else {
+    const double ts = p.twist ? __ldg(p.twist + x) : 0.0;
+    double sn, cs;
+    sincos(kwave * ts, &sn, &cs);
+    // corner elements: row 0 couples to x_{n-1} through a_0 exp(-i k ts), row n-1 to x_0 through c_{n-1} exp(+i k ts)
+    rowOf(0, a, b, c);
+    const cd beta = cmul(a, cd{cs, -sn});
+    const cd gamma = cneg(b);
+    cd an, bn, cn;
+    rowOf(n - 1, an, bn, cn);
+    const cd alpha = cmul(cn, cd{cs, sn});
+    bad = bad || tiny(gamma);
+    const cd ginv = crecip(gamma);
+    // T' = T - u v^T with u = (gamma, 0, .., 0, alpha), v = (1, 0, .., 0, beta / gamma)
+    cd den = csub(b, gamma);
+    bad = bad || tiny(den);
+    cd inv = crecip(den);
+    cd cprev = cmul(c, inv), dprev = cmul(S[0], inv), zprev = cmul(gamma, inv);
+    CP[0] = cprev;
+    S[0] = dprev;
+    Z[0] = zprev;
+    for (int j = 1; j < n; ++j) {
+      rowOf(j, a, b, c);
+      cd u = {0.0, 0.0};
+      if (j == n - 1) {
+        b = csub(b, cmul(cmul(alpha, beta), ginv));
+        u = alpha;
+      }
+      den = csub(b, cmul(a, cprev));
+      bad = bad || tiny(den);
+      inv = crecip(den);
+      cprev = cmul(c, inv);
+      dprev = cmul(csub(S[j * rs], cmul(a, dprev)), inv);
+      zprev = cmul(csub(u, cmul(a, zprev)), inv);
+      CP[j * rs] = cprev;
+      S[j * rs] = dprev;
+      Z[j * rs] = zprev;
+    }
+    cd yv = dprev, zv = zprev;
+    const cd ylast = yv, zlast = zv;
+    for (int j = n - 2; j >= 0; --j) {
+      const cd cpj = CP[j * rs];
+      yv = csub(S[j * rs], cmul(cpj, yv));
+      zv = csub(Z[j * rs], cmul(cpj, zv));
+      S[j * rs] = yv;
+      Z[j * rs] = zv;
+    }
+    const cd bg = cmul(beta, ginv);
+    const cd num = cadd(yv, cmul(bg, ylast));
+    const cd dn = cadd(cadd(cd{1.0, 0.0}, zv), cmul(bg, zlast));
+    bad = bad || tiny(dn);
+    const cd fact = cmul(num, crecip(dn));
+    for (int j = 0; j < n; ++j) {
+      S[j * rs] = csub(S[j * rs], cmul(fact, Z[j * rs]));
+    }
+  }
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+} // namespace b200
+
+namespace {
+// LapParams for the generic row transforms over [xs, xe] x [ys, ye], every mode kept
+int rowTransformPlan(const bout_b200_grid* g, int xs, int xe, int ys, int ye, cd* spec, cudaStream_t s, LapParams* pp,
+                     RowGeom* geo, unsigned* blocks) {
+  LapParams& p = *pp;
+  p = LapParams{};
+  p.nx = g->nx;
+  p.ny = g->ny;
+  p.nz = g->nz;
+  p.bd.xs = xs;
+  p.bd.xe = xe;
+  p.ys = ys;
+  p.ye = ye;
+  p.nmode = g->nz / 2 + 1;
+  p.spec = spec;
+  int st = 0;
+  p.tw = twiddleTable(g->nz, s, &st);
+  if (st != 0) {
+    return st;
+  }
+  *geo = rowGeometry(g->nz, 128);
+  p.tpr = geo->tpr;
+  p.rows = geo->rows;
+  p.pow2 = geo->pow2 ? 1 : 0;
+  B200_REQUIRE(geo->smemBytes <= 200 * 1024, BOUT_B200_ERR_UNSUPPORTED, "row transform: nz=%d too large", g->nz);
+  if (geo->smemBytes > 48 * 1024) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_lap_forward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(geo->smemBytes)));
+    B200_CUDA_OK(cudaFuncSetAttribute(k_lap_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(geo->smemBytes)));
+  }
+  const long long nrows = static_cast<long long>(xe - xs + 1) * (ye - ys + 1);
+  *blocks = static_cast<unsigned>((nrows + geo->rows - 1) / geo->rows);
+  return 0;
+}
+size_t specBytes(const bout_b200_grid* g, int nrows_x, int nrows_y) {
+  return lapRoundUp(static_cast<size_t>(nrows_x) * nrows_y * (g->nz / 2 + 1) * sizeof(cd), 256);
+}
+} // namespace
+
+extern "C" size_t bout_b200_laplacexz_workspace(const bout_b200_grid* g) {
+  if (g == nullptr) {
+    return 0;
+  }
+  const int nrx = g->xend - g->xstart + 3, nys = g->yend - g->ystart + 1;
+  return 256 + 2 * specBytes(g, nrx, nys) + specBytes(g, 2, nys);
+}
+
+extern "C" int bout_b200_laplacexz_solve(const bout_b200_grid* g, const bout_b200_laplacexz* xz, const double* rhs,
+                                         const double* x0, double* out, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  cudaStream_t s = asStream(stream);
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(xz && rhs && out && workspace, BOUT_B200_ERR_ARG, "laplacexz: null argument");
+  B200_REQUIRE(xz->A && xz->B && xz->J && xz->g11 && xz->g33 && xz->dx, BOUT_B200_ERR_ARG, "laplacexz: coefficient or metric missing");
+  B200_REQUIRE(g->xstart >= 1 && g->xend + 1 < g->nx, BOUT_B200_ERR_GUARDS, "laplacexz: needs one guard cell in x");
+  B200_REQUIRE(!(xz->inner_boundary_flags & INV_SET) || x0 != nullptr, BOUT_B200_ERR_ARG, "laplacexz: INVERT_SET needs x0");
+  B200_REQUIRE(workspace_bytes >= bout_b200_laplacexz_workspace(g), BOUT_B200_ERR_ARG, "laplacexz: workspace too small");
+  B200_REQUIRE(aligned16(workspace), BOUT_B200_ERR_ARG, "laplacexz: workspace must be 16-byte aligned");
+  const int nrx = g->xend - g->xstart + 3, nys = g->yend - g->ystart + 1;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  XzParams q{};
+  q.status = reinterpret_cast<int*>(ws);
+  q.spec = reinterpret_cast<cd*>(ws + 256);
+  q.cp = reinterpret_cast<cd*>(ws + 256 + specBytes(g, nrx, nys));
+  cd* x0spec = reinterpret_cast<cd*>(ws + 256 + 2 * specBytes(g, nrx, nys));
+  q.x0spec = x0spec;
+  B200_CUDA_OK(cudaMemsetAsync(q.status, 0, sizeof(int), s));
+  LapParams p;
+  RowGeom geo;
+  unsigned blocks = 0;
+  int rc = rowTransformPlan(g, g->xstart - 1, g->xend + 1, g->ystart, g->yend, q.spec, s, &p, &geo, &blocks);
+  if (rc != 0) {
+    return rc;
+  }
+  p.rhs = rhs;
+  p.out = out;
+  k_lap_forward<<<blocks, 128, geo.smemBytes, s>>>(p);
+  B200_LAUNCH_OK();
+  if (xz->inner_boundary_flags & INV_SET) {
+    LapParams p0;
+    RowGeom geo0;
+    unsigned blocks0 = 0;
+    rc = rowTransformPlan(g, g->xstart - 1, g->xstart, g->ystart, g->yend, x0spec, s, &p0, &geo0, &blocks0);
+    if (rc != 0) {
+      return rc;
+    }
+    p0.rhs = x0;
+    k_lap_forward<<<blocks0, 128, geo0.smemBytes, s>>>(p0);
+    B200_LAUNCH_OK();
+  }
+  q.A = xz->A, q.B = xz->B, q.J = xz->J, q.g11 = xz->g11, q.g33 = xz->g33, q.dx = xz->dx;
+  q.kscale = 2.0 * M_PI / xz->zlength;
+  q.inner = xz->inner_boundary_flags;
+  q.outer = xz->outer_boundary_flags;
+  q.ny = g->ny, q.xstart = g->xstart, q.xend = g->xend, q.ys = g->ystart, q.nys = nys, q.nmode = p.nmode;
+  const int nsys = nys * p.nmode;
+  k_xz_thomas<<<(nsys + 127) / 128, 128, 0, s>>>(q);
+  B200_LAUNCH_OK();
+  k_lap_backward<<<blocks, 128, geo.smemBytes, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" size_t bout_b200_invert_par_workspace(const bout_b200_grid* g) {
+  if (g == nullptr) {
+    return 0;
+  }
+  return 256 + 3 * specBytes(g, g->xend - g->xstart + 1, g->ny);
+}
+
+extern "C" int bout_b200_invert_par_solve(const bout_b200_grid* g, const bout_b200_invert_par* ip, const double* f,
+                                          double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = asStream(stream);
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(ip && f && out && workspace, BOUT_B200_ERR_ARG, "invert_par: null argument");
+  B200_REQUIRE(ip->g_22 && ip->dy && ip->sg, BOUT_B200_ERR_ARG, "invert_par: metric missing");
+  B200_REQUIRE(workspace_bytes >= bout_b200_invert_par_workspace(g), BOUT_B200_ERR_ARG, "invert_par: workspace too small");
+  B200_REQUIRE(aligned16(workspace), BOUT_B200_ERR_ARG, "invert_par: workspace must be 16-byte aligned");
+  const int nxs = g->xend - g->xstart + 1;
+  const int ys = ip->closed ? g->ystart : 0, ye = ip->closed ? g->yend : g->ny - 1;
+  const int nys = ye - ys + 1;
+  B200_REQUIRE(nys >= 3, BOUT_B200_ERR_ARG, "invert_par: needs at least 3 rows in y");
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const size_t sb = specBytes(g, nxs, g->ny);
+  ParParams q{};
+  q.status = reinterpret_cast<int*>(ws);
+  q.spec = reinterpret_cast<cd*>(ws + 256);
+  q.cp = reinterpret_cast<cd*>(ws + 256 + sb);
+  q.zs = reinterpret_cast<cd*>(ws + 256 + 2 * sb);
+  B200_CUDA_OK(cudaMemsetAsync(q.status, 0, sizeof(int), s));
+  LapParams p;
+  RowGeom geo;
+  unsigned blocks = 0;
+  int rc = rowTransformPlan(g, g->xstart, g->xend, ys, ye, q.spec, s, &p, &geo, &blocks);
+  if (rc != 0) {
+    return rc;
+  }
+  p.rhs = f;
+  p.out = out;
+  k_lap_forward<<<blocks, 128, geo.smemBytes, s>>>(p);
+  B200_LAUNCH_OK();
+  q.A = ip->A, q.B = ip->B, q.C = ip->C, q.D = ip->D, q.E = ip->E, q.sg = ip->sg;
+  q.g_22 = ip->g_22, q.dy = ip->dy, q.d1_dy = ip->d1_dy, q.twist = ip->twist_shift;
+  q.kscale = 2.0 * M_PI / ip->zlength;
+  q.closed = ip->closed ? 1 : 0;
+  q.ny = g->ny, q.xs = g->xstart, q.nxs = nxs, q.ystart = g->ystart, q.yend = g->yend, q.nmode = p.nmode;
+  q.ys = ys, q.nys = nys;
+  const int nsys = nxs * p.nmode;
+  k_par_thomas<<<(nsys + 127) / 128, 128, 0, s>>>(q);
+  B200_LAUNCH_OK();
+  k_lap_backward<<<blocks, 128, geo.smemBytes, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}

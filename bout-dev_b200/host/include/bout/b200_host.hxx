@@ -579,9 +579,60 @@ private:
   bool hasA = false, hasC = false, hasD = false;
   int global_flags, inner_boundary_flags, outer_boundary_flags, maxmode;
   bool all_terms, nonuniform, include_yguards;
+  bool pcr_thomas = false;
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   static std::unique_ptr<Laplacian> instance;
+};
+
+// ---- LaplaceXZ (reference include/bout/invert/laplacexz.hxx, impls/cyclic) ------------------------------------------
+class LaplaceXZ {
+public:
+  LaplaceXZ(Mesh* m, Options* options, CELL_LOC loc);
+  ~LaplaceXZ();
+  static std::unique_ptr<LaplaceXZ> create(Mesh* m = nullptr, Options* opt = nullptr, CELL_LOC loc = CELL_CENTRE);
+  void setCoefs(const Field2D& A, const Field2D& B);
+  void setCoefs(const Field3D& A, const Field3D& B) { setCoefs(DC(A), DC(B)); }
+  Field3D solve(const Field3D& b, const Field3D& x0);
+
+private:
+  Mesh* localmesh;
+  Field2D A, B;
+  int inner_boundary_flags = 0, outer_boundary_flags = 0;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+};
+
+// ---- InvertPar (reference include/bout/invert_parderiv.hxx, parderiv/impls/cyclic) ---------------------------------
+class InvertPar {
+public:
+  InvertPar(Options* options, CELL_LOC loc, Mesh* m);
+  ~InvertPar();
+  static std::unique_ptr<InvertPar> create(Options* opt = nullptr, CELL_LOC loc = CELL_CENTRE, Mesh* m = nullptr);
+  Field3D solve(const Field3D& f);
+  Field3D solve(const Field3D& f, const Field3D&) { return solve(f); }
+  void setCoefA(const Field2D& f) { A = f; hasA = true; }
+  void setCoefB(const Field2D& f) { B = f; hasB = true; }
+  void setCoefC(const Field2D& f) { C = f; hasC = true; }
+  void setCoefD(const Field2D& f) { D = f; hasD = true; }
+  void setCoefE(const Field2D& f) { E = f; hasE = true; }
+  void setCoefA(const Field3D& f) { setCoefA(DC(f)); }
+  void setCoefB(const Field3D& f) { setCoefB(DC(f)); }
+  void setCoefC(const Field3D& f) { setCoefC(DC(f)); }
+  void setCoefD(const Field3D& f) { setCoefD(DC(f)); }
+  void setCoefE(const Field3D& f) { setCoefE(DC(f)); }
+  void setCoefA(BoutReal v) { setCoefA(Field2D(v, localmesh)); }
+  void setCoefB(BoutReal v) { setCoefB(Field2D(v, localmesh)); }
+  void setCoefC(BoutReal v) { setCoefC(Field2D(v, localmesh)); }
+  void setCoefD(BoutReal v) { setCoefD(Field2D(v, localmesh)); }
+  void setCoefE(BoutReal v) { setCoefE(Field2D(v, localmesh)); }
+
+private:
+  Mesh* localmesh;
+  Field2D A, B, C, D, E, sg;
+  bool hasA = false, hasB = false, hasC = false, hasD = false, hasE = false;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
 };
 
 // ---- output step: dump file + device -> host -> disk pipeline (src/dump_writer.cxx) ------------------

@@ -471,6 +471,43 @@ int bout_b200_hw_convective(const bout_b200_grid* g, const double* dx, const dou
                             const double* zonal_n, const double* zonal_phi, double* ddt_n,
                             double* ddt_vort, const bout_b200_rk_epilogue* epilogue, void* stream);
 
+/* ---- the sibling inversions on the batched tridiagonal core ---------------------------------------
+ * Laplacian types "pcr" and "pcr_thomas" (src/invert/laplace/impls/pcr/pcr.cxx, impls/pcr_thomas/pcr_thomas.cxx) solve
+ * the systems of LaplaceCyclic -- same FFTTransform, same tridagMatrix -- with a different MPI elimination order: their
+ * factory entries bind bout_b200_laplace_cyclic_solve.  (tests/golden/invert.npz pins that against each solver's OWN
+ * reference output; the reference's pcr_thomas with INVERT_BNDRY_ONE and two guard cells leaves the outer guard row
+ * out of its boundary elimination and differs from cyclic / pcr there: not reproduced.)
+ *
+ * LaplaceXZ "cyclic" (src/invert/laplacexz/impls/cyclic/laplacexz-cyclic.cxx:63-277): Div(A Grad_perp f) + B f = rhs
+ * in X-Z with g13 = 0; rows x = xstart-1 .. xend+1 of every interior y are solved and written, other cells of `out`
+ * are left as they are.  A, B and the metric are Field2D arrays. */
+typedef struct bout_b200_laplacexz {
+  const double *A, *B;
+  const double *J, *g11, *g33, *dx;
+  double zlength;
+  int inner_boundary_flags, outer_boundary_flags; /* INVERT_DC_GRAD | INVERT_AC_GRAD | INVERT_SET | INVERT_RHS */
+} bout_b200_laplacexz;
+size_t bout_b200_laplacexz_workspace(const bout_b200_grid* g);
+int bout_b200_laplacexz_solve(const bout_b200_grid* g, const bout_b200_laplacexz* xz, const double* rhs,
+                              const double* x0, double* out, void* workspace, size_t workspace_bytes, void* stream);
+/* InvertPar "cyclic" (src/invert/parderiv/impls/cyclic/cyclic.cxx:48-245):
+ *   A f + B d2f/dy2 + C d2f/dydz + D d2f/dz2 + E df/dy = rhs   along y for every interior x and kz,
+ * on a FIELD-ALIGNED input (the caller applies toFieldAligned / fromFieldAligned; identity for the identity
+ * transform).  Coefficient pointers may be NULL (A = 1, the others 0).  sg = DDY(1/sqrt(g_22)) / sqrt(g_22) as the
+ * reference's constructor forms it (:55-56).  closed != 0: periodic in y with the twist-shift phase per x
+ * (twist_shift NULL = 0), rows ystart..yend written; closed == 0: open field lines, boundary rows in the y guard
+ * cells (:208-229), every y written.  d1_dy NULL when coords->non_uniform is false. */
+typedef struct bout_b200_invert_par {
+  const double *A, *B, *C, *D, *E;
+  const double *sg, *g_22, *dy, *d1_dy;
+  const double* twist_shift; /* [nx] */
+  double zlength;
+  int closed;
+} bout_b200_invert_par;
+size_t bout_b200_invert_par_workspace(const bout_b200_grid* g);
+int bout_b200_invert_par_solve(const bout_b200_grid* g, const bout_b200_invert_par* ip, const double* f, double* out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -443,6 +443,34 @@ class Ref:
     def laplace_set_flags(self, global_=0, inner=0, outer=0):
         self._check(self.lib.boutref_laplace_set_flags(global_, inner, outer))
 
+    def laplacexz_solve(self, section, A2d, B2d, b, x0):
+        """LaplaceXZ::create(mesh, &options[section]) -> setCoefs(A, B) -> solve(b, x0); unwritten cells are 0."""
+        out = np.zeros_like(b)
+        self.lib.boutref_laplacexz_solve.argtypes = [C.c_char_p] + [C.c_void_p] * 5
+        self._check(self.lib.boutref_laplacexz_solve(section.encode(), _p(np.ascontiguousarray(A2d)),
+                                                     _p(np.ascontiguousarray(B2d)), _p(np.ascontiguousarray(b)),
+                                                     _p(np.ascontiguousarray(x0)), _p(out)))
+        return out
+
+    def invert_par_solve(self, section, f, A=None, B=None, Cc=None, D=None, E=None):
+        """InvertPar::create(&options[section]) -> setCoefA..E -> solve(f); unwritten cells are 0."""
+        out = np.zeros_like(f)
+        keep = [None if a is None else np.ascontiguousarray(a) for a in (A, B, Cc, D, E)]
+        self.lib.boutref_invert_par_solve.argtypes = [C.c_char_p] + [C.c_void_p] * 7
+        self._check(self.lib.boutref_invert_par_solve(section.encode(), *[None if a is None else _p(a) for a in keep],
+                                                      _p(np.ascontiguousarray(f)), _p(out)))
+        return out
+
+    def invert_par_solve_all_y(self, section, f, A=None, B=None, Cc=None, D=None, E=None):
+        """As invert_par_solve, returning every y of the interior x range (open field lines: the solver writes the y
+        guard cells too)."""
+        out = np.zeros_like(f)
+        keep = [None if a is None else np.ascontiguousarray(a) for a in (A, B, Cc, D, E)]
+        self.lib.boutref_invert_par_solve_all_y.argtypes = [C.c_char_p] + [C.c_void_p] * 7
+        self._check(self.lib.boutref_invert_par_solve_all_y(section.encode(), *[None if a is None else _p(a) for a in keep],
+                                                            _p(np.ascontiguousarray(f)), _p(out)))
+        return out
+
     def laplace_solve(self, b, x0=None):
         out = np.zeros(self.grid.shape3)
         self._check(self.lib.boutref_laplace_solve(_p(np.ascontiguousarray(b)),

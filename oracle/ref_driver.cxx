@@ -18,6 +18,8 @@
 #include <bout/fft.hxx>
 #include <bout/field_factory.hxx>
 #include <bout/invert_laplace.hxx>
+#include <bout/invert/laplacexz.hxx>
+#include <bout/invert_parderiv.hxx>
 #include <bout/mpi_wrapper.hxx>
 #include <bout/optionsreader.hxx>
 #include <bout/physicsmodel.hxx>
@@ -533,6 +535,76 @@ double boutref_time_laplace_solve(const double* b, int reps) {
     result = std::chrono::duration<double>(t1 - t0).count() / reps;
   });
   return result;
+}
+
+// --- LaplaceXZ::create(mesh, &options[section])->setCoefs(A, B); solve(b, x0)
+//     (src/invert/laplacexz/impls/cyclic/laplacexz-cyclic.cxx)
+int boutref_laplacexz_solve(const char* section, const double* A2d, const double* B2d, const double* b,
+                            const double* x0, double* out) {
+  return guarded([&]() {
+    auto xz = LaplaceXZ::create(bout::globals::mesh, &Options::root()[section]);
+    xz->setCoefs(toField2D(A2d), toField2D(B2d));
+    Field3D r = xz->solve(toField3D(b), toField3D(x0));
+    // cells the solver does not write are uninitialised: report them as 0
+    Field3D full = 0.0;
+    const int xs = bout::globals::mesh->xstart - 1, xe = bout::globals::mesh->xend + 1;
+    for (int x = xs; x <= xe; ++x) {
+      for (int y = bout::globals::mesh->ystart; y <= bout::globals::mesh->yend; ++y) {
+        for (int z = 0; z < bout::globals::mesh->LocalNz; ++z) {
+          full(x, y, z) = r(x, y, z);
+        }
+      }
+    }
+    fromField3D(full, out);
+  });
+}
+// --- InvertPar::create(&options[section])->setCoefA..E; solve(f)
+//     (src/invert/parderiv/impls/cyclic/cyclic.cxx); coefficient pointers may be null (left at their defaults)
+int boutref_invert_par_solve(const char* section, const double* A, const double* B, const double* C,
+                             const double* D, const double* E, const double* f, double* out) {
+  return guarded([&]() {
+    auto inv = InvertPar::create(&Options::root()[section]);
+    if (A != nullptr) { inv->setCoefA(toField2D(A)); }
+    if (B != nullptr) { inv->setCoefB(toField2D(B)); }
+    if (C != nullptr) { inv->setCoefC(toField2D(C)); }
+    if (D != nullptr) { inv->setCoefD(toField2D(D)); }
+    if (E != nullptr) { inv->setCoefE(toField2D(E)); }
+    const Field3D r = inv->solve(toField3D(f));
+    Field3D full = 0.0;
+    Mesh* m = bout::globals::mesh;
+    for (int x = m->xstart; x <= m->xend; ++x) {
+      for (int y = m->ystart; y <= m->yend; ++y) {
+        for (int z = 0; z < m->LocalNz; ++z) {
+          full(x, y, z) = r(x, y, z);
+        }
+      }
+    }
+    fromField3D(full, out);
+  });
+}
+
+// the same, every y of the interior x range (open field lines: the y guard cells are part of the solve)
+int boutref_invert_par_solve_all_y(const char* section, const double* A, const double* B, const double* C,
+                                   const double* D, const double* E, const double* f, double* out) {
+  return guarded([&]() {
+    auto inv = InvertPar::create(&Options::root()[section]);
+    if (A != nullptr) { inv->setCoefA(toField2D(A)); }
+    if (B != nullptr) { inv->setCoefB(toField2D(B)); }
+    if (C != nullptr) { inv->setCoefC(toField2D(C)); }
+    if (D != nullptr) { inv->setCoefD(toField2D(D)); }
+    if (E != nullptr) { inv->setCoefE(toField2D(E)); }
+    const Field3D r = inv->solve(toField3D(f));
+    Field3D full = 0.0;
+    Mesh* m = bout::globals::mesh;
+    for (int x = m->xstart; x <= m->xend; ++x) {
+      for (int y = 0; y < m->LocalNy; ++y) {
+        for (int z = 0; z < m->LocalNz; ++z) {
+          full(x, y, z) = r(x, y, z);
+        }
+      }
+    }
+    fromField3D(full, out);
+  });
 }
 
 // --- Mesh::communicate on nf fields in place (mesh.hxx:260, boutmesh.cxx:1221-1555)

@@ -502,3 +502,34 @@ function = sin(2*pi*x) * sin(z)
 [input]
 error_on_unused_options = false
 """
+
+
+# SURVEY 8(f)4: Laplacian types pcr / pcr_thomas, LaplaceXZ cyclic, InvertPar cyclic (tests/golden/make_golden_invert.py).
+# 16 interior x points (the reference's pcr needs a power of two), x- and y-dependent metric with g13 = 0 (LaplaceXZ
+# cyclic asserts it), y periodic.
+INVERT_GRID = (20, 8, 16)
+INVERT_LAP_FLAGS = [(0, 0, 0), (0, 3, 0), (0, 0, 3), (0, 16, 16), (0, 32, 32), (1, 0, 0), (0, 1, 2)]
+INVERT_XZ_FLAGS = [(0, 0), (3, 0), (0, 3), (16, 16), (32, 32), (1, 2)]
+INVERT_LAP_INI = make_ini(20, 8, 16, mxg=2, myg=2, dx="0.2*(1+0.1*x)", dy="0.7+0.05*cos(2*pi*x)", dz="2*pi/16", mesh_extra="""
+g11 = 1 + 0.1*x
+g22 = 1.1 + 0.02*cos(y)
+g33 = 1.2 + 0.05*x
+ixseps1 = 20
+ixseps2 = 20
+""", extra="""
+[mesh:ddx]
+first = C2
+[mesh:ddy]
+first = C2
+[lap_cyclic]
+type = cyclic
+[lap_pcr]
+type = pcr
+[lap_pcr_thomas]
+type = pcr_thomas
+[parderiv]
+type = cyclic
+""" + "".join(f"[xz{i}]\ntype = cyclic\ninner_boundary_flags = {a}\nouter_boundary_flags = {b}\n"
+              for i, (a, b) in enumerate(INVERT_XZ_FLAGS)))
+# the same mesh with open field lines everywhere (y boundaries): InvertPar's boundary rows in the y guard cells
+INVERT_OPEN_INI = INVERT_LAP_INI.replace("ixseps1 = 20", "ixseps1 = 0").replace("ixseps2 = 20", "ixseps2 = 0")
