@@ -150,6 +150,12 @@ class CLaplace(C.Structure):
                                        "include_yguards_upper")]
 
 
+def copy_xz(g, jy, field3d, perp, to_perp=True):
+    """sliceXZ (to_perp) / Field3D = FieldPerp (not to_perp): plane jy of a Field3D <-> an [nx][nz] array."""
+    _check(lib.bout_b200_copy_xz(C.byref(g.c), int(jy), _ptr(field3d), _ptr(perp), int(bool(to_perp)), _stream()))
+    return perp if to_perp else field3d
+
+
 class CLaplaceXZ(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("A", "B", "J", "g11", "g33", "dx")] + [
         ("zlength", C.c_double), ("inner_boundary_flags", C.c_int), ("outer_boundary_flags", C.c_int)]
@@ -251,6 +257,18 @@ class Laplace:
         _check(lib.bout_b200_laplace_cyclic_solve(C.byref(self.g.c), C.byref(self.c), _ptr(rhs),
                                                   _ptr(x0), _ptr(out), C.c_void_p(ws.data_ptr()),
                                                   C.c_size_t(ws.numel()), _stream()))
+        return out
+
+    def solve_perp(self, jy, rhs, x0=None, out=None):
+        """LaplaceCyclic::solve(FieldPerp, FieldPerp): rhs, x0, out are [nx][nz] planes belonging to y index jy."""
+        out = torch.zeros_like(rhs) if out is None else out
+        lib.bout_b200_laplace_cyclic_workspace_perp.restype = C.c_size_t
+        n = lib.bout_b200_laplace_cyclic_workspace_perp(C.byref(self.g.c), C.byref(self.c))
+        if getattr(self, "ws_perp", None) is None or self.ws_perp.numel() < n:
+            self.ws_perp = torch.empty(n, dtype=torch.uint8, device=rhs.device)
+        _check(lib.bout_b200_laplace_cyclic_solve_perp(C.byref(self.g.c), C.byref(self.c), int(jy), _ptr(rhs), _ptr(x0),
+                                                       _ptr(out), C.c_void_p(self.ws_perp.data_ptr()),
+                                                       C.c_size_t(self.ws_perp.numel()), _stream()))
         return out
 
     def factor(self, device="cuda"):

@@ -1711,3 +1711,70 @@ extern "C" int bout_b200_invert_par_solve(const bout_b200_grid* g, const bout_b2
   B200_LAUNCH_OK();
   return 0;
 }
+
+// =====================================================================================================================
+// FieldPerp (one x-z plane at a y index): slice copies and LaplaceCyclic::solve(const FieldPerp&, const FieldPerp&)
+// (reference include/bout/fieldperp.hxx:54-330, src/field/fieldperp.cxx sliceXZ, cyclic_laplace.cxx:120-185)
+// =====================================================================================================================
+extern "C" int bout_b200_copy_xz(const bout_b200_grid* g, int jy, double* field3d, double* perp, int to_perp,
+                                 void* stream) {
+  cudaStream_t s = asStream(stream);
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(field3d && perp, BOUT_B200_ERR_ARG, "copy_xz: null argument");
+  B200_REQUIRE(jy >= 0 && jy < g->ny, BOUT_B200_ERR_ARG, "copy_xz: y index %d outside 0..%d", jy, g->ny - 1);
+  const size_t row = static_cast<size_t>(g->nz) * sizeof(double), pitch = row * g->ny;
+  double* plane = field3d + static_cast<size_t>(jy) * g->nz;
+  if (to_perp) {
+    B200_CUDA_OK(cudaMemcpy2DAsync(perp, row, plane, pitch, row, g->nx, cudaMemcpyDeviceToDevice, s));
+  } else {
+    B200_CUDA_OK(cudaMemcpy2DAsync(plane, pitch, perp, row, row, g->nx, cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+namespace {
+constexpr int kPerpFields = 12;
+bout_b200_grid perpGrid(const bout_b200_grid* g) { return bout_b200_grid{g->nx, 1, g->nz, g->xstart, g->xend, 0, 0}; }
+size_t perpHead(const bout_b200_grid* g) { return lapRoundUp(static_cast<size_t>(kPerpFields) * g->nx * sizeof(double), 256); }
+} // namespace
+
+extern "C" size_t bout_b200_laplace_cyclic_workspace_perp(const bout_b200_grid* g, const bout_b200_laplace* L) {
+  if (g == nullptr || L == nullptr) {
+    return 0;
+  }
+  const bout_b200_grid g1 = perpGrid(g);
+  return perpHead(g) + bout_b200_laplace_cyclic_workspace(&g1, L);
+}
+
+extern "C" int bout_b200_laplace_cyclic_solve_perp(const bout_b200_grid* g, const bout_b200_laplace* L, int jy,
+                                                   const double* rhs, const double* x0, double* out, void* workspace,
+                                                   size_t workspace_bytes, void* stream) {
+  cudaStream_t s = asStream(stream);
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(L && rhs && out && workspace, BOUT_B200_ERR_ARG, "laplace (FieldPerp): null argument");
+  B200_REQUIRE(jy >= 0 && jy < g->ny, BOUT_B200_ERR_ARG, "laplace (FieldPerp): y index %d outside 0..%d", jy, g->ny - 1);
+  B200_REQUIRE(workspace_bytes >= bout_b200_laplace_cyclic_workspace_perp(g, L), BOUT_B200_ERR_ARG,
+               "laplace (FieldPerp): workspace too small");
+  // the y = jy row of every Field2D input, as [nx][1] arrays at the head of the workspace
+  bout_b200_laplace L1 = *L;
+  const double** src[kPerpFields] = {&L1.dx, &L1.g11, &L1.g33, &L1.g13, &L1.G1, &L1.G3,
+                                     &L1.g_11, &L1.g_22, &L1.A, &L1.C1, &L1.C2, &L1.D};
+  double* head = static_cast<double*>(workspace);
+  for (int q = 0; q < kPerpFields; ++q) {
+    if (*src[q] == nullptr) {
+      continue;
+    }
+    double* dst = head + static_cast<size_t>(q) * g->nx;
+    B200_CUDA_OK(cudaMemcpy2DAsync(dst, sizeof(double), *src[q] + jy, static_cast<size_t>(g->ny) * sizeof(double),
+                                   sizeof(double), g->nx, cudaMemcpyDeviceToDevice, s));
+    *src[q] = dst;
+  }
+  L1.include_yguards_lower = L1.include_yguards_upper = 0;
+  const bout_b200_grid g1 = perpGrid(g);
+  unsigned char* tail = static_cast<unsigned char*>(workspace) + perpHead(g);
+  return bout_b200_laplace_cyclic_solve(&g1, &L1, rhs, x0, out, tail, workspace_bytes - perpHead(g), stream);
+}

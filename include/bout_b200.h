@@ -508,6 +508,18 @@ size_t bout_b200_invert_par_workspace(const bout_b200_grid* g);
 int bout_b200_invert_par_solve(const bout_b200_grid* g, const bout_b200_invert_par* ip, const double* f, double* out,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- FieldPerp: one x-z plane [nx][nz] at a y index (include/bout/fieldperp.hxx:54-330) ---------------------------
+ * sliceXZ (src/field/fieldperp.cxx) and Field3D::operator=(const FieldPerp&): to_perp != 0 copies plane jy of field3d
+ * into perp, to_perp == 0 copies perp into plane jy of field3d.  Element-wise FieldPerp algebra is
+ * bout_b200_elementwise on a grid with ny = 1. */
+int bout_b200_copy_xz(const bout_b200_grid* g, int jy, double* field3d, double* perp, int to_perp, void* stream);
+/* LaplaceCyclic::solve(const FieldPerp& rhs, const FieldPerp& x0) (cyclic_laplace.cxx:120-185): the systems of row jy
+ * only; rhs, x0, out are [nx][nz] planes, the Field2D inputs of L stay full [nx][ny] arrays (row jy is used). */
+size_t bout_b200_laplace_cyclic_workspace_perp(const bout_b200_grid* g, const bout_b200_laplace* L);
+int bout_b200_laplace_cyclic_solve_perp(const bout_b200_grid* g, const bout_b200_laplace* L, int jy, const double* rhs,
+                                        const double* x0, double* out, void* workspace, size_t workspace_bytes,
+                                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

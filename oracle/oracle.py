@@ -471,6 +471,13 @@ class Ref:
                                                             _p(np.ascontiguousarray(f)), _p(out)))
         return out
 
+    def laplace_solve_perp(self, jy, b, x0):
+        """Laplacian::solve(FieldPerp, FieldPerp) on the y = jy slices of two Field3D arrays -> [nx][nz]."""
+        out = np.zeros((b.shape[0], b.shape[2]))
+        self.lib.boutref_laplace_solve_perp.argtypes = [C.c_int] + [C.c_void_p] * 3
+        self._check(self.lib.boutref_laplace_solve_perp(jy, _p(np.ascontiguousarray(b)), _p(np.ascontiguousarray(x0)), _p(out)))
+        return out
+
     def laplace_solve(self, b, x0=None):
         out = np.zeros(self.grid.shape3)
         self._check(self.lib.boutref_laplace_solve(_p(np.ascontiguousarray(b)),

@@ -522,6 +522,17 @@ int boutref_laplace_solve(const double* b, const double* x0, double* out) {
     fromField3D(r, out);
   });
 }
+// LaplaceCyclic::solve(const FieldPerp&, const FieldPerp&) (cyclic_laplace.cxx:120-185) on the y = jy slices of b, x0
+int boutref_laplace_solve_perp(int jy, const double* b, const double* x0, double* out_perp) {
+  return guarded([&]() {
+    const FieldPerp r = lap->solve(sliceXZ(toField3D(b), jy), sliceXZ(toField3D(x0), jy));
+    for (int x = 0; x < mesh->LocalNx; ++x) {
+      for (int z = 0; z < mesh->LocalNz; ++z) {
+        out_perp[x * mesh->LocalNz + z] = r(x, z);
+      }
+    }
+  });
+}
 double boutref_time_laplace_solve(const double* b, int reps) {
   double result = -1.0;
   guarded([&]() {

@@ -37,6 +37,15 @@ for i, flags in enumerate(cases.INVERT_LAP_FLAGS):
         r.laplace_set_coef("C", Cc)
         out[f"{sec}_{i}"] = r.laplace_solve(b, x0)
 
+# LaplaceCyclic::solve(FieldPerp) (cyclic_laplace.cxx:120-185) on two y slices, Dirichlet and INVERT_SET + Neumann flags
+for i, flags in enumerate(((0, 0, 0), (0, 16, 3))):
+    r.laplace_create("lap_cyclic")
+    r.laplace_set_flags(*flags)
+    r.laplace_set_coef("A", A)
+    r.laplace_set_coef("C", Cc)
+    for jy in (3, 6):
+        out[f"perp_{i}_{jy}"] = r.laplace_solve_perp(jy, b, x0)
+
 # ---- LaplaceXZ cyclic (src/invert/laplacexz/impls/cyclic/laplacexz-cyclic.cxx) ------------------------------------
 A2 = 1.0 + 0.3 * rng.uniform(size=(nx, ny))
 B2 = -0.5 - 0.2 * rng.uniform(size=(nx, ny))
