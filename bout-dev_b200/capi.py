@@ -147,7 +147,7 @@ class CLaplace(C.Structure):
                [(n, C.c_int) for n in ("all_terms", "nonuniform", "global_flags",
                                        "inner_boundary_flags", "outer_boundary_flags", "maxmode",
                                        "periodic_x", "first_x", "last_x", "include_yguards_lower",
-                                       "include_yguards_upper")]
+                                       "include_yguards_upper", "wrap_yguards")]
 
 
 def copy_xz(g, jy, field3d, perp, to_perp=True):
@@ -228,7 +228,8 @@ class Laplace:
     """Host-side mirror of the Laplacian settings (reference invert_laplace.cxx:68-138)."""
 
     def __init__(self, g: Grid, metric: dict, zlength, all_terms=True, nonuniform=True, flags=(0, 0, 0),
-                 maxmode=None, periodic_x=False, A=None, C1=None, C2=None, D=None, first_x=True, last_x=True):
+                 maxmode=None, periodic_x=False, A=None, C1=None, C2=None, D=None, first_x=True, last_x=True,
+                 wrap_yguards=False):
         self.g = g
         self.keep = dict(metric)
         self.keep.update(A=A, C1=C1, C2=C2, D=D)
@@ -241,6 +242,7 @@ class Laplace:
         c.global_flags, c.inner_boundary_flags, c.outer_boundary_flags = flags
         c.maxmode = g.nz // 2 if maxmode is None else maxmode
         c.periodic_x, c.first_x, c.last_x = int(periodic_x), int(first_x), int(last_x)
+        c.wrap_yguards = int(wrap_yguards)   # single rank, periodic y: the solve also writes the y guard rows
         self.c = c
         self.ws = None
 
@@ -536,14 +538,26 @@ def fused_coefs(g: Grid, metric: CMetric, coef_ws):
     return coef_ws
 
 
+class CGuardFill(C.Structure):
+    _fields_ = [("value", C.c_double), ("x_inner", C.c_int), ("x_outer", C.c_int), ("wrap_y", C.c_int),
+                ("ystart", C.c_int), ("yend", C.c_int)]
+
+
+def make_guard_fill(g: Grid, value=0.0, x_inner=True, x_outer=True, wrap_y=True):
+    """Guard cells written by the kernel that produces the next stage state (bout_b200_guard_fill): constant-value
+    Dirichlet on the x sides, periodic y copies on a single rank; g is the MESH's grid (its ystart / yend)."""
+    return CGuardFill(float(value), int(x_inner), int(x_outer), int(wrap_y), g.c.ystart, g.c.yend)
+
+
 def hw3d_rhs(g: Grid, metric, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n=None, ddt_vort=None,
-             epilogue=None, coef_ws=None):
+             epilogue=None, coef_ws=None, guards=None):
     coef_ws = fused_coef_workspace(g, n.device) if coef_ws is None else coef_ws
-    _check(lib.bout_b200_hw3d_rhs(C.byref(g.c), None if metric is None else C.byref(metric),
-                                  C.c_double(alpha), C.c_double(kappa),
-                                  C.c_double(Dn), C.c_double(Dvort), _ptr(n), _ptr(vort), _ptr(phi),
-                                  _ptr(ddt_n), _ptr(ddt_vort),
-                                  None if epilogue is None else C.byref(epilogue), _ptr(coef_ws), _stream()))
+    _check(lib.bout_b200_hw3d_rhs_guards(C.byref(g.c), None if metric is None else C.byref(metric),
+                                         C.c_double(alpha), C.c_double(kappa),
+                                         C.c_double(Dn), C.c_double(Dvort), _ptr(n), _ptr(vort), _ptr(phi),
+                                         _ptr(ddt_n), _ptr(ddt_vort),
+                                         None if epilogue is None else C.byref(epilogue),
+                                         None if guards is None else C.byref(guards), _ptr(coef_ws), _stream()))
 
 
 def hw_convective(g: Grid, dx, dz, alpha, kappa, n, vort, phi, zonal_n=None, zonal_phi=None, ddt_n=None,

@@ -136,6 +136,32 @@ __device__ __forceinline__ void finishPoint(const RkEpilogue& ep, int e, long lo
 //   ddt(n)    = -[phi,n]    - div_current - kappa*DDZ(phi) + Dn   *Delp2(n)
 //   ddt(vort) = -[phi,vort] - div_current                  + Dvort*Delp2(vort)
 // ------------------------------------------------------------------------------------------------
+// Guard cells of the next stage state written by the kernel that produces it (bout_b200_guard_fill): the constant-value
+// Dirichlet condition Solver::pre_rhs would apply on the x sides (boundary_standard.cxx:527-581: first guard
+// 2 val - f_inside, the others val; rows ystart..yend) and the y guard rows a single-rank periodic
+// Mesh::communicate would copy (x guard cells of those rows included).
+struct GuardFill {
+  double val;
+  int xin, xout, wrapy;
+  int ys, ye; // the mesh's ystart / yend (the launch may cover fewer rows)
+};
+// the y guard rows the point (x, y, z..z+1) wraps to (and the point itself when `self`)
+__device__ __forceinline__ void storeWrapY(const GuardFill& gf, double* __restrict__ out, int ny, int nz, int x, int y,
+                                           int z, double2 v, bool self) {
+  double* q = out + (static_cast<long long>(x) * ny + y) * nz + z;
+  if (self) {
+    *reinterpret_cast<double2*>(q) = v;
+  }
+  if (gf.wrapy) {
+    const int nyint = gf.ye - gf.ys + 1;
+    if (y - gf.ys < ny - 1 - gf.ye) {
+      *reinterpret_cast<double2*>(q + static_cast<long long>(nyint) * nz) = v;
+    }
+    if (gf.ye - y < gf.ys) {
+      *reinterpret_cast<double2*>(q - static_cast<long long>(nyint) * nz) = v;
+    }
+  }
+}
 struct Hw3dParams {
   const double* __restrict__ n;
   const double* __restrict__ vort;
@@ -147,6 +173,7 @@ struct Hw3dParams {
   double alpha, kappa, Dn, Dvort;
   int nx, ny, nz, xs, xe, ys, ye, chunk;
   int with_par; // ny > 1
+  GuardFill gf;
 };
 
 template <int VEC>
@@ -269,11 +296,40 @@ __device__ __forceinline__ Row4 ldsRow4(const double* row, int z, int nz) {
   return r;
 }
 
+// x0..x1: the planes this CTA marched over at row y; thread = z pair.  Dirichlet x guard cells and their y-wrapped copies.
+__device__ __noinline__ void guardPass(const GuardFill gf, double* f0, double* f1, int nx, int ny, int nz, int xs, int xe,
+                                       int x0, int x1, int y, int z) {
+  const bool xin = gf.xin && x0 == xs, xout = gf.xout && x1 == xe;
+  if (!xin && !xout) {
+    return;
+  }
+  for (int e = 0; e < 2; ++e) {
+    double* f = e == 0 ? f0 : f1;
+    if (f == nullptr) {
+      continue;
+    }
+    if (xin) {
+      const double2 v = *reinterpret_cast<const double2*>(f + (static_cast<long long>(xs) * ny + y) * nz + z);
+      storeWrapY(gf, f, ny, nz, xs - 1, y, z, make_double2(2 * gf.val - v.x, 2 * gf.val - v.y), true);
+      for (int gx = xs - 2; gx >= 0; --gx) {
+        storeWrapY(gf, f, ny, nz, gx, y, z, make_double2(gf.val, gf.val), true);
+      }
+    }
+    if (xout) {
+      const double2 v = *reinterpret_cast<const double2*>(f + (static_cast<long long>(xe) * ny + y) * nz + z);
+      storeWrapY(gf, f, ny, nz, xe + 1, y, z, make_double2(2 * gf.val - v.x, 2 * gf.val - v.y), true);
+      for (int gx = xe + 2; gx < nx; ++gx) {
+        storeWrapY(gf, f, ny, nz, gx, y, z, make_double2(gf.val, gf.val), true);
+      }
+    }
+  }
+}
+
 constexpr int HW3D_NS = 4; // stencil ring: planes x-1, x, x+1 resident + one in flight
 constexpr int HW3D_NA = 2; // once-used operand ring: plane x resident + plane x+1 in flight
 constexpr int HW3D_AUX = 8; // rows per aux slot: phi(y+1), phi(y-1), n(y+1), n(y-1), start n, start vort, acc n, acc vort
 
-template <int THREADS>
+template <int THREADS, bool GUARDS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_tma(const Hw3dParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nz = p.nz;
@@ -296,6 +352,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
   const bool has_acc0 = ep && p.ep.acc_in[0] != nullptr && p.ep.acc_out[0] != nullptr;
   const bool has_acc1 = ep && p.ep.acc_in[1] != nullptr && p.ep.acc_out[1] != nullptr;
   const unsigned aux_rows = (p.with_par ? 4u : 0u) + (ep ? 2u : 0u) + (has_acc0 ? 1u : 0u) + (has_acc1 ? 1u : 0u);
+  // GUARDS: y guard rows this CTA's row is the periodic image of (0 = none), offsets in doubles
+  const long long wrap_rows = static_cast<long long>(p.gf.ye - p.gf.ys + 1) * nz;
+  const long long wrap_up = (GUARDS && p.gf.wrapy && y - p.gf.ys < p.ny - 1 - p.gf.ye) ? wrap_rows : 0;
+  const long long wrap_dn = (GUARDS && p.gf.wrapy && p.gf.ye - y < p.gf.ys) ? wrap_rows : 0;
 
   auto issue = [&](int j) { // stencil plane j (x = x0 - 1 + j) into slot j % NS
     const int slot = j % HW3D_NS;
@@ -420,15 +480,33 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
         }
         if (ep) {
           const double2 st = *reinterpret_cast<const double2*>(ax + (4 + e) * nz + z);
+          // GUARDS: the field the next right-hand side reads (the stage state; after the last stage the combination)
+          // also goes to the y guard rows this row is the periodic image of
           if (p.ep.state_out[e] != nullptr) {
-            *reinterpret_cast<double2*>(p.ep.state_out[e] + idx) = make_double2(st.x + p.ep.a * d[0], st.y + p.ep.a * d[1]);
+            const double2 r = make_double2(st.x + p.ep.a * d[0], st.y + p.ep.a * d[1]);
+            *reinterpret_cast<double2*>(p.ep.state_out[e] + idx) = r;
+            if (GUARDS && wrap_up != 0) {
+              *reinterpret_cast<double2*>(p.ep.state_out[e] + idx + wrap_up) = r;
+            }
+            if (GUARDS && wrap_dn != 0) {
+              *reinterpret_cast<double2*>(p.ep.state_out[e] + idx - wrap_dn) = r;
+            }
           }
           if (p.ep.acc_out[e] != nullptr) {
             double2 base = st;
             if (p.ep.acc_in[e] != nullptr) {
               base = *reinterpret_cast<const double2*>(ax + (6 + e) * nz + z);
             }
-            *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx) = make_double2(base.x + p.ep.b * d[0], base.y + p.ep.b * d[1]);
+            const double2 r = make_double2(base.x + p.ep.b * d[0], base.y + p.ep.b * d[1]);
+            *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx) = r;
+            if (GUARDS && p.ep.state_out[e] == nullptr) {
+              if (wrap_up != 0) {
+                *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx + wrap_up) = r;
+              }
+              if (wrap_dn != 0) {
+                *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx - wrap_dn) = r;
+              }
+            }
           }
         }
       }
@@ -443,6 +521,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
         issueAux(ja + HW3D_NA);
       }
     }
+  }
+  // x guard cells of the field the next right-hand side reads, from the edge-plane values this thread has just written
+  if (GUARDS && ep) {
+    guardPass(p.gf, p.ep.state_out[0] != nullptr ? p.ep.state_out[0] : p.ep.acc_out[0],
+              p.ep.state_out[1] != nullptr ? p.ep.state_out[1] : p.ep.acc_out[1], p.nx, p.ny, nz, p.xs, p.xe, x0, x1, y, z);
   }
 }
 
@@ -578,8 +661,26 @@ extern "C" int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metri
                                   const double* vort, const double* phi, double* ddt_n,
                                   double* ddt_vort, const bout_b200_rk_epilogue* epilogue,
                                   double* coef_workspace, void* stream) {
+  return bout_b200_hw3d_rhs_guards(g, m, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n, ddt_vort, epilogue, nullptr,
+                                   coef_workspace, stream);
+}
+
+extern "C" int bout_b200_hw3d_rhs_guards(const bout_b200_grid* g, const bout_b200_metric* m, double alpha,
+                                         double kappa, double Dn, double Dvort, const double* n,
+                                         const double* vort, const double* phi, double* ddt_n,
+                                         double* ddt_vort, const bout_b200_rk_epilogue* epilogue,
+                                         const bout_b200_guard_fill* guards, double* coef_workspace, void* stream) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
+  }
+  const bool fill = guards != nullptr && (guards->x_inner || guards->x_outer || guards->wrap_y);
+  if (fill) {
+    B200_REQUIRE(epilogue != nullptr, BOUT_B200_ERR_ARG, "hw3d_rhs: guard cells are filled on the epilogue's output");
+    B200_REQUIRE(guards->ystart >= 0 && guards->ystart <= g->ystart && guards->yend >= g->yend && guards->yend < g->ny,
+                 BOUT_B200_ERR_ARG, "hw3d_rhs: the rows of this launch lie outside the guard fill's ystart..yend");
+    B200_REQUIRE(!guards->wrap_y || (guards->yend - guards->ystart + 1 >= guards->ystart
+                                     && guards->yend - guards->ystart + 1 >= g->ny - 1 - guards->yend),
+                 BOUT_B200_ERR_GUARDS, "hw3d_rhs: fewer interior rows than y guard rows");
   }
   B200_REQUIRE(n && vort && phi && coef_workspace, BOUT_B200_ERR_ARG, "hw3d_rhs: null argument");
   B200_REQUIRE((ddt_n && ddt_vort) || epilogue, BOUT_B200_ERR_ARG, "hw3d_rhs: no output requested");
@@ -627,21 +728,75 @@ extern "C" int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metri
   const int len = p.xe - p.xs + 1;
   static const bool no_tma = getenv("BOUT_B200_NO_TMA") != nullptr;
   const int half = g->nz / 2;
-  if (vec2 && !no_tma && (half == 64 || half == 128 || half == 256 || half == 512)) {
-    // TMA-pipelined kernel: one CTA per (y, x-chunk); chunk sized for >= ~3 waves of resident CTAs
+  const bool tma = vec2 && !no_tma && (half == 64 || half == 128 || half == 256 || half == 512);
+  if (fill && tma) {
+    p.gf = GuardFill{guards->value, guards->x_inner, guards->x_outer, guards->wrap_y, guards->ystart, guards->yend};
+  }
+  if (fill && !tma) { // the register-marching kernel writes interior cells only: the guard cells by their own kernels
+    const int rc = bout_b200_hw3d_rhs_guards(g, nullptr, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n, ddt_vort, epilogue,
+                                             nullptr, coef_workspace, stream);
+    if (rc != 0) {
+      return rc;
+    }
+    bout_b200_grid gm = *g;
+    gm.ystart = guards->ystart;
+    gm.yend = guards->yend;
+    double* outs[2];
+    int nout = 0;
+    for (int e = 0; e < 2; ++e) {
+      double* f = epilogue->state_out[e] != nullptr ? epilogue->state_out[e] : epilogue->acc_out[e];
+      if (f == nullptr) {
+        continue;
+      }
+      outs[nout++] = f;
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? guards->x_inner : guards->x_outer) {
+          const int rb = bout_b200_boundary(&gm, 0, side, guards->value, nullptr, g->ystart, g->yend, f, stream);
+          if (rb != 0) {
+            return rb;
+          }
+        }
+      }
+    }
+    // (a launch over a subset of the rows re-copies rows other launches own: harmless, the values are final
+    // only once every row's launch is done, which is also when the caller may read them)
+    return (guards->wrap_y && nout > 0) ? bout_b200_halo_self(&gm, nout, outs, 0, 1, stream) : 0;
+  }
+  if (tma) {
+    // TMA-pipelined kernel: one CTA per (y, x-chunk).  All CTAs run for about the same time (chunk planes + the
+    // pipeline fill), so the chunk length is chosen for whole waves of resident CTAs: 512 planes x 128 rows in
+    // chunks of 64 are 1024 CTAs = 3.46 waves of 2 x 148 (measured 0.507 ms), in chunks of 57 they are 1152 = 3.9
+    // waves (0.474 ms).
     const int nyint = p.ye - p.ys + 1;
+    const long long slots = 148LL * (half <= 256 ? 2 : 1);
     int chunk = 64;
-    while (chunk > 8 && static_cast<long long>(nyint) * ((len + chunk - 1) / chunk) < 148LL * 2 * 3) {
-      chunk /= 2;
+    long long best = -1;
+    for (int c = 8; c <= 128; ++c) {
+      const long long ncta = static_cast<long long>(nyint) * ((len + c - 1) / c);
+      const long long cost = ((ncta + slots - 1) / slots) * (c + 4);
+      if (best < 0 || cost <= best) {
+        best = cost;
+        chunk = c;
+      }
+    }
+    static const int chunk_env = getenv("BOUT_B200_HW3D_CHUNK") ? atoi(getenv("BOUT_B200_HW3D_CHUNK")) : 0;
+    if (chunk_env > 0) {
+      chunk = chunk_env;
     }
     p.chunk = chunk;
     const size_t smem = static_cast<size_t>(HW3D_NS * 3 + HW3D_NA * HW3D_AUX) * g->nz * sizeof(double);
     dim3 grid(static_cast<unsigned>(nyint), static_cast<unsigned>((len + chunk - 1) / chunk));
 #define B200_LAUNCH_TMA(T)                                                                               \
   {                                                                                                      \
-    B200_CUDA_OK(cudaFuncSetAttribute(k_hw3d_rhs_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                      static_cast<int>(smem)));                                          \
-    k_hw3d_rhs_tma<T><<<grid, T, smem, s>>>(p);                                                         \
+    if (fill) {                                                                                          \
+      B200_CUDA_OK(cudaFuncSetAttribute(k_hw3d_rhs_tma<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        static_cast<int>(smem)));                                        \
+      k_hw3d_rhs_tma<T, true><<<grid, T, smem, s>>>(p);                                                  \
+    } else {                                                                                             \
+      B200_CUDA_OK(cudaFuncSetAttribute(k_hw3d_rhs_tma<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        static_cast<int>(smem)));                                        \
+      k_hw3d_rhs_tma<T, false><<<grid, T, smem, s>>>(p);                                                 \
+    }                                                                                                    \
   }
     switch (half) {
     case 64: B200_LAUNCH_TMA(64) break;

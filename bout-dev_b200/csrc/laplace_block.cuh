@@ -89,6 +89,7 @@ struct LapParams {
   int force;                   // settings changed on the host side: factor regardless of the comparison
   int bP, bMB, bNT;            // blocks per system, rows per block, threads per CTA of the rows kernels
   int bPD;                     // rows kernels: CTA b prefetches the rows of CTA b + bPD into L2 (0 = off)
+  int wrapy, mys, mye;         // wrap_yguards: rows also stored into the y guard rows (mesh ystart / yend in mys / mye)
   int dbg;                     // timing ablations (BOUT_B200_LAPB_DBG; results are wrong when set): 1 = no per-mode
                                // phase, 2 = no inverse transform, 4 = no forward transform, 8 = no row loads
 };
@@ -536,6 +537,21 @@ B200_HD void lapbStoreRow(const LapParams& p, const LapbCta& c, int tid, const c
 #pragma unroll
   for (int q = 0; q < Sh::B; ++q) {
     d2[t + Sh::T * q] = make_double2(v[q].re, v[q].im);
+  }
+  if (p.wrapy) { // the y guard rows this row is the periodic image of
+    const long long wrap = static_cast<long long>(p.mye - p.mys + 1) * (p.nz / 2);
+    if (c.jy - p.mys < p.ny - 1 - p.mye) {
+#pragma unroll
+      for (int q = 0; q < Sh::B; ++q) {
+        d2[wrap + t + Sh::T * q] = make_double2(v[q].re, v[q].im);
+      }
+    }
+    if (p.mye - c.jy < p.mys) {
+#pragma unroll
+      for (int q = 0; q < Sh::B; ++q) {
+        d2[t + Sh::T * q - wrap] = make_double2(v[q].re, v[q].im);
+      }
+    }
   }
 }
 
@@ -1354,6 +1370,9 @@ inline void lapFillParams(const bout_b200_grid* g, const bout_b200_laplace* L, v
   // cyclic_laplace.cxx:216-232 (include_yguards only matters where a y boundary exists)
   p.ys = L->include_yguards_lower ? 0 : g->ystart;
   p.ye = L->include_yguards_upper ? g->ny - 1 : g->yend;
+  p.wrapy = (L->wrap_yguards && !L->include_yguards_lower && !L->include_yguards_upper) ? 1 : 0;
+  p.mys = g->ystart;
+  p.mye = g->yend;
   p.nmode = L->maxmode + 1;
   p.zero_dc = (L->global_flags & INV_ZERO_DC) ? 1 : 0;
   p.in_set = (L->first_x && (L->inner_boundary_flags & INV_SET)) ? 1 : 0;

@@ -1246,7 +1246,12 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
     k_lap_finish<<<sblocks, 128, 0, s>>>(p);
     B200_LAUNCH_OK();
   }
-  return launchFft<false>(&plan, s);
+  rc = launchFft<false>(&plan, s);
+  if (rc == 0 && p.wrapy) { // the block path stores the wrapped rows itself; here they are copied afterwards
+    double* f[1] = {out};
+    rc = bout_b200_halo_self(g, 1, f, 0, 1, stream);
+  }
+  return rc;
 }
 
 // Builds the matrix-only tables of the block path now (they are otherwise built by the first solve and

@@ -31,8 +31,20 @@ class HW3D:
         zlength = float(self.md["dz"][0, 0].item()) * g.nz
         first_x = mesh is None or mesh.first_x
         last_x = mesh is None or mesh.last_x
-        self.lap = capi.Laplace(g, self.md, zlength, nonuniform=True, first_x=first_x, last_x=last_x)
+        # Guard cells without separate passes (BOUT_B200_GUARD_FILL=0 keeps one launch per boundary / exchange):
+        # the fused kernel's epilogue writes the x guard cells of the stage state it produces (the Dirichlet condition
+        # Solver::pre_rhs would apply) and, on a single rank, its periodic y guard rows; the Laplacian solve writes
+        # phi's y guard rows.  An RHS then is: solve (3 launches) + fused kernel.
+        self.guard_fill = (not (mesh is not None and mesh.nxpe > 1) and self.dev.type == "cuda"
+                           and os.environ.get("BOUT_B200_GUARD_FILL", "1") != "0")
+        single = mesh is None
+        self.lap = capi.Laplace(g, self.md, zlength, nonuniform=True, first_x=first_x, last_x=last_x,
+                                wrap_yguards=single and self.guard_fill)
         self.lap.workspace(self.dev)
+        self.gf = capi.make_guard_fill(g, 0.0, first_x, last_x, wrap_y=single) if self.guard_fill else None
+        # (n, vort) pairs whose guard cells were written by the kernel that produced them: data pointers -> tensor
+        # versions at that moment (any later in-place torch operation on them bumps the version and voids the entry)
+        self._ready = {}
         self.x_split = mesh is not None and mesh.nxpe > 1
         if self.x_split:  # interface records of the X-decomposed tridiagonal solve
             nif = self.lap.iface_doubles()
@@ -42,10 +54,18 @@ class HW3D:
         self.phase_events = None
         self.kernel_events = None  # bench.py: list collecting (start, end) CUDA events of the fused kernel
         # NYPE > 1: the guard rows of n and vort travel on a second stream while the Laplacian solve runs on the
-        # main one (they do not depend on it); only phi's exchange stays on the critical path
-        import os
+        # main one (they do not depend on it); phi's rows travel while the fused kernel works on the rows that do not
+        # need them (all but the first and the last interior row), which then follow on the second stream
         self.overlap = (mesh is not None and mesh.nxpe == 1 and mesh.nype > 1 and self.dev.type == "cuda"
                         and os.environ.get("BOUT_B200_HALO_OVERLAP", "1") != "0")
+        self.overlap_phi = self.overlap and g.yend - g.ystart >= 2 and os.environ.get("BOUT_B200_PHI_OVERLAP", "1") != "0"
+        if self.overlap_phi:
+            self.g_mid = capi.Grid(g.nx, g.ny, g.nz, g.mxg, g.myg)
+            self.g_lo = capi.Grid(g.nx, g.ny, g.nz, g.mxg, g.myg)
+            self.g_hi = capi.Grid(g.nx, g.ny, g.nz, g.mxg, g.myg)
+            for gg, (a, b) in ((self.g_mid, (g.ystart + 1, g.yend - 1)), (self.g_lo, (g.ystart, g.ystart)),
+                               (self.g_hi, (g.yend, g.yend))):
+                gg.c.ystart, gg.c.yend = a, b
         self._comm_stream = None
         z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
         self.n, self.vort, self.phi = z(), z(), z()
@@ -56,6 +76,7 @@ class HW3D:
     def set_state(self, n, vort):
         self.n.copy_(n)
         self.vort.copy_(vort)
+        self._ready.clear()
 
     # -- one right-hand side on (n, vort) held in fields fn, fv
     def _pre_rhs(self, fn, fv):
@@ -74,16 +95,25 @@ class HW3D:
             e.record()
             self.phase_events.append((name, e))
 
+    def _fused(self, gsel, fn, fv, epilogue, ddt, guards):
+        capi.hw3d_rhs(gsel, None, self.alpha, self.kappa, self.Dn, self.Dvort, fn, fv, self.phi,
+                      self.ddt_n if ddt else None, self.ddt_vort if ddt else None, epilogue=epilogue,
+                      coef_ws=self.coef, guards=guards)
+
     def rhs(self, fn=None, fv=None, epilogue=None, ddt=True):
         fn = self.n if fn is None else fn
         fv = self.vort if fv is None else fv
+        # were the guard cells of this state written by the kernel that produced it?
+        ready = self._ready.get((fn.data_ptr(), fv.data_ptr())) == (fn._version, fv._version)
+        guards = self.gf if (self.guard_fill and epilogue is not None) else None
         self._mark("start")
-        self._pre_rhs(fn, fv)                                   # Solver::pre_rhs
+        if not ready:
+            self._pre_rhs(fn, fv)                               # Solver::pre_rhs
         self._mark("bc")
         overlapped = False
         if self.overlap and not self.x_split:
             if self._comm_stream is None:
-                self._comm_stream = torch.cuda.Stream(device=self.dev)
+                self._comm_stream = torch.cuda.Stream(device=self.dev, priority=-1)
             main = torch.cuda.current_stream()
             self._comm_stream.wait_stream(main)
             with torch.cuda.stream(self._comm_stream):
@@ -99,8 +129,13 @@ class HW3D:
             self._mark("solve_allgather")
             self.lap.finish(self.iface_all, self.mesh.nxpe, self.mesh.pe_xind, self.phi)
             self._mark("solve_finish")
+        split_rows = False
         if self.mesh is None:                                   # mesh->communicate(n, vort, phi, ...)
-            capi.halo_self(self.g, [fn, fv, self.phi], periodic_x=False, periodic_y=True)
+            need = ([] if ready else [fn, fv]) + ([] if self.lap.c.wrap_yguards else [self.phi])
+            if need:
+                capi.halo_self(self.g, need, periodic_x=False, periodic_y=True)
+        elif overlapped and self.overlap_phi:
+            split_rows = True
         elif overlapped:
             self.mesh.communicate([self.phi])
             torch.cuda.current_stream().wait_stream(self._comm_stream)
@@ -110,13 +145,30 @@ class HW3D:
         if self.kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        capi.hw3d_rhs(self.g, None, self.alpha, self.kappa, self.Dn, self.Dvort, fn, fv, self.phi,
-                      self.ddt_n if ddt else None, self.ddt_vort if ddt else None, epilogue=epilogue,
-                      coef_ws=self.coef)
+        if split_rows:
+            # the rows that need no y guard row start at once; phi's rows travel meanwhile on the second (high
+            # priority) stream, followed there by the first and the last interior row
+            main = torch.cuda.current_stream()
+            self._comm_stream.wait_stream(main)
+            self._fused(self.g_mid, fn, fv, epilogue, ddt, guards)
+            with torch.cuda.stream(self._comm_stream):
+                self.mesh.communicate([self.phi])
+                self._fused(self.g_lo, fn, fv, epilogue, ddt, guards)
+                self._fused(self.g_hi, fn, fv, epilogue, ddt, guards)
+            main.wait_stream(self._comm_stream)
+        else:
+            self._fused(self.g, fn, fv, epilogue, ddt, guards)
         if self.kernel_events is not None:
             e1.record()
             self.kernel_events.append((e0, e1))
         self._mark("fused")
+        if guards is not None:  # the field the next right-hand side reads now has its guard cells
+            e = epilogue
+            nxt = tuple((e._keep[2][i] if e._keep[2] is not None and e._keep[2][i] is not None else e._keep[3][i])
+                        for i in range(2))
+            if nxt[0] is not None and nxt[1] is not None:
+                # x guard cells always; the y guard rows only on a single rank (otherwise they are exchanged anyway)
+                self._ready[(nxt[0].data_ptr(), nxt[1].data_ptr())] = (nxt[0]._version, nxt[1]._version)
 
     def phase_summary(self):
         """Mean milliseconds per phase from the recorded events (after torch.cuda.synchronize())."""

@@ -272,6 +272,9 @@ typedef struct bout_b200_laplace {
   int periodic_x;     /* mesh->periodicX */
   int first_x, last_x;/* mesh->firstX(), lastX() (1,1 on a single rank in X) */
   int include_yguards_lower, include_yguards_upper; /* laplace:include_yguards where a y boundary exists */
+  int wrap_yguards;   /* single rank, periodic y: the solve also writes each solution row into the y guard row it
+                         wraps to -- what the Mesh::communicate(phi) that follows the solve in a model's rhs() would
+                         copy (boutmesh.cxx:1221-1555); 0 = the reference's behaviour (guard rows untouched) */
 } bout_b200_laplace;
 
 /* Coordinates::Delp2(Field3D, useFFT=true) (src/mesh/coordinates.cxx:1662-1699); uses
@@ -464,6 +467,26 @@ int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, doubl
                        double Dn, double Dvort, const double* n, const double* vort,
                        const double* phi, double* ddt_n, double* ddt_vort,
                        const bout_b200_rk_epilogue* epilogue, double* coef_workspace, void* stream);
+/* The same with the guard cells of the epilogue's output written by the kernel that produces the interior values
+ * (the field the next right-hand side reads: state_out, or acc_out where state_out is NULL), so that no
+ * separate boundary / exchange pass runs between two stages:
+ *   x_inner / x_outer: the constant-value Dirichlet condition Solver::pre_rhs would apply to the evolving fields
+ *     before the next rhs() (src/solver/solver.cxx:1380-1400, BoundaryDirichlet::apply src/mesh/
+ *     boundary_standard.cxx:527-581: first guard 2 value - f_inside, the others value; rows ystart..yend);
+ *   wrap_y: the y guard rows Mesh::communicate copies on a single rank with periodic y (boutmesh.cxx:1221-1555),
+ *     x guard cells of those rows included.
+ * ystart / yend are the MESH's interior rows; g may select fewer rows (g->ystart..g->yend inside them), e.g. the
+ * interior rows while an exchange of phi is in flight and the edge rows after it. */
+typedef struct bout_b200_guard_fill {
+  double value;
+  int x_inner, x_outer, wrap_y;
+  int ystart, yend;
+} bout_b200_guard_fill;
+int bout_b200_hw3d_rhs_guards(const bout_b200_grid* g, const bout_b200_metric* m, double alpha, double kappa,
+                              double Dn, double Dvort, const double* n, const double* vort,
+                              const double* phi, double* ddt_n, double* ddt_vort,
+                              const bout_b200_rk_epilogue* epilogue, const bout_b200_guard_fill* guards,
+                              double* coef_workspace, void* stream);
 /* examples/hasegawa-wakatani/hw.cxx:94-118 convective(), Arakawa bracket; zonal_* = averageY(DC(f))
  * as Field2D when hw:modified, else NULL. */
 int bout_b200_hw_convective(const bout_b200_grid* g, const double* dx, const double* dz, double alpha,

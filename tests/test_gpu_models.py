@@ -46,6 +46,45 @@ def test_hw3d_rhs_and_rk4_trajectory(capi, gold):
     assert rel_err(m.vort.cpu().numpy(), gold["hw3d_final_vort"], I) < 1e-8
 
 
+@pytest.mark.parametrize("nz", [16, 128])
+def test_hw3d_guard_cells_written_by_the_producing_kernels(capi, gold, nz, monkeypatch):
+    """bout_b200_hw3d_rhs_guards / bout_b200_laplace.wrap_yguards: the x guard cells (Dirichlet of Solver::pre_rhs) and
+    periodic y guard rows (single-rank Mesh::communicate) written by the fused kernel's epilogue and by the solve are
+    bitwise what the separate boundary / exchange launches give (nz = 16: register-marching kernel + three-kernel
+    solve, guard cells by the fall-back launches; nz = 128: bulk-copy kernel + block solve, in-kernel)."""
+    import __graft_entry__ as ge
+    models = ge.load_package().models
+    g = capi.Grid(20, 9, nz, 2, 2)
+    one = lambda v: torch.full(g.shape2, v, dtype=torch.float64, device="cuda")
+    md = dict(dx=one(0.3), dy=one(0.7), dz=one(0.2), J=one(1.0), g_22=one(1.0), g11=one(1.0), g33=one(1.0), g13=one(0.0),
+              G1=one(0.0), G3=one(0.0), d1_dx=one(0.0), g_11=one(1.0))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    n0 = torch.rand(g.shape3, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    v0 = torch.rand(g.shape3, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    res = {}
+    for fill in ("0", "1"):
+        monkeypatch.setenv("BOUT_B200_GUARD_FILL", fill)
+        m = models.HW3D(g, md, alpha=1.0, kappa=0.5, Dn=1e-3, Dvort=1e-3)
+        assert m.guard_fill == (fill == "1")
+        m.set_state(n0, v0)
+        launches = capi.launch_count()
+        for _ in range(3):
+            m.rk4_step(1e-3)
+        launches = capi.launch_count() - launches
+        phi = m.phi.clone()
+        n, v = m.n.clone(), m.vort.clone()
+        if fill == "0":   # what the next right-hand side's pre_rhs + communicate would make of them
+            m._pre_rhs(n, v)
+            capi.halo_self(g, [n, v], periodic_x=False, periodic_y=True)
+            capi.halo_self(g, [phi], periodic_x=False, periodic_y=True)
+        res[fill] = (n, v, phi, launches)
+    for a, b, name in zip(res["0"][:3], res["1"][:3], ("n", "vort", "phi")):
+        assert torch.equal(a, b), name
+    assert torch.isfinite(res["1"][0]).all() and float(res["1"][0].abs().max()) > 0.1
+    if nz == 128:
+        assert res["1"][3] < res["0"][3] - 40   # no boundary / exchange launches between the stages
+
+
 # ---- UNCHANGED reference models compiled against the C++ host layer -----------------------------------
 @pytest.fixture(scope="module")
 def hostmod():
