@@ -389,7 +389,11 @@ def run_ours(args):
     model.set_state(hn.to(dev), hv.to(dev))
     model.rk4_step(DT)
     torch.cuda.synchronize()
-    e2e_ok = bool(torch.equal(model.n.cpu(), hn_out) and torch.equal(model.vort.cpu(), hv_out))
+    # (interior points: the guard cells of an output state are not part of it -- the next right-hand side's boundary
+    # conditions / exchange set them, and whether the last kernel has already written them depends on where the
+    # output buffer lives)
+    I = g.interior
+    e2e_ok = bool(torch.equal(model.n.cpu()[I], hn_out[I]) and torch.equal(model.vort.cpu()[I], hv_out[I]))
     clocks = sampler.stop(w0, w2) if rank == 0 else None   # samples over both timed regions
     field_bytes = hn.numel() * 8
 

@@ -147,7 +147,7 @@ class CLaplace(C.Structure):
                [(n, C.c_int) for n in ("all_terms", "nonuniform", "global_flags",
                                        "inner_boundary_flags", "outer_boundary_flags", "maxmode",
                                        "periodic_x", "first_x", "last_x", "include_yguards_lower",
-                                       "include_yguards_upper", "wrap_yguards")]
+                                       "include_yguards_upper", "wrap_yguards")] + [("ypeer", C.c_void_p)]
 
 
 def copy_xz(g, jy, field3d, perp, to_perp=True):
@@ -245,6 +245,11 @@ class Laplace:
         c.wrap_yguards = int(wrap_yguards)   # single rank, periodic y: the solve also writes the y guard rows
         self.c = c
         self.ws = None
+
+    def set_ypeer(self, ypeer):
+        """bout_b200_laplace.ypeer for the next solves (a CYPeer, or None)."""
+        self._ypeer = ypeer
+        self.c.ypeer = None if ypeer is None else C.addressof(ypeer)
 
     def workspace(self, device):
         lib.bout_b200_laplace_cyclic_workspace.restype = C.c_size_t
@@ -397,6 +402,17 @@ def halo_unpack_y(g: Grid, fields, y0, nrows, xlo, xhi, buf):
 
 
 # ---- Y exchange over NVLink peer memory (raw device addresses as python ints) -------------------------------
+class _RawCuda:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+def tensor_from_ptr(ptr, shape, device):
+    """A torch view (fp64, contiguous) of device memory this library allocated (bout_b200_peer_alloc)."""
+    return torch.as_tensor(_RawCuda(ptr, shape), device=device)
+
+
 def peer_alloc(nbytes):
     p = C.c_void_p()
     _check(lib.bout_b200_peer_alloc(C.c_size_t(nbytes), C.byref(p)))
@@ -538,15 +554,40 @@ def fused_coefs(g: Grid, metric: CMetric, coef_ws):
     return coef_ws
 
 
+class CYPeer(C.Structure):
+    """bout_b200_ypeer: Y guard rows delivered by the producing kernel into the neighbours' mapped arenas."""
+    _fields_ = [("delta", C.c_longlong * 2), ("peer_flag", C.c_void_p * 2), ("signal", C.c_ulonglong),
+                ("counters", C.c_void_p), ("wait_flag", (C.c_void_p * 2) * 2), ("wait_value", (C.c_ulonglong * 2) * 2),
+                ("status", C.c_void_p)]
+
+
+def make_ypeer(delta, peer_flag, signal, counters, status, waits=None):
+    """delta / peer_flag: (lower, upper) neighbour; waits[d] = up to two (flag address, value) the CTAs next to side d
+    wait for.  None entries = nothing on that side."""
+    y = CYPeer()
+    for d in range(2):
+        y.delta[d] = int(delta[d] or 0)
+        y.peer_flag[d] = peer_flag[d]
+        for k, w in enumerate((waits[d] if waits is not None else ())[:2]):
+            if w is not None:
+                y.wait_flag[d][k], y.wait_value[d][k] = w
+    y.signal, y.counters, y.status = int(signal), counters, status
+    return y
+
+
 class CGuardFill(C.Structure):
     _fields_ = [("value", C.c_double), ("x_inner", C.c_int), ("x_outer", C.c_int), ("wrap_y", C.c_int),
-                ("ystart", C.c_int), ("yend", C.c_int)]
+                ("ystart", C.c_int), ("yend", C.c_int), ("ypeer", C.c_void_p)]
 
 
-def make_guard_fill(g: Grid, value=0.0, x_inner=True, x_outer=True, wrap_y=True):
+def make_guard_fill(g: Grid, value=0.0, x_inner=True, x_outer=True, wrap_y=True, ypeer=None):
     """Guard cells written by the kernel that produces the next stage state (bout_b200_guard_fill): constant-value
-    Dirichlet on the x sides, periodic y copies on a single rank; g is the MESH's grid (its ystart / yend)."""
-    return CGuardFill(float(value), int(x_inner), int(x_outer), int(wrap_y), g.c.ystart, g.c.yend)
+    Dirichlet on the x sides, periodic y copies on a single rank or delivery to the Y neighbours (ypeer: a CYPeer);
+    g is the MESH's grid (its ystart / yend)."""
+    gf = CGuardFill(float(value), int(x_inner), int(x_outer), int(wrap_y), g.c.ystart, g.c.yend,
+                    None if ypeer is None else C.addressof(ypeer))
+    gf._keep = ypeer
+    return gf
 
 
 def hw3d_rhs(g: Grid, metric, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n=None, ddt_vort=None,

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/bout_b200.h"
@@ -112,6 +113,17 @@ struct Vz<2> {
 __device__ __forceinline__ int wrapz(int z, int nz) {
   // z in [-nz, 2nz)
   return z < 0 ? z + nz : (z >= nz ? z - nz : z);
+}
+
+// Cycles a receiver waits: BOUT_B200_HALO_TIMEOUT_S seconds (default 60: first-call IPC mapping, module loads, a
+// neighbour busy writing output are all far below it; a dead neighbour is not) at the 1.965 GHz B200 clock.
+inline long long haloTimeoutCycles() {
+  static const long long cycles = [] {
+    const char* env = getenv("BOUT_B200_HALO_TIMEOUT_S");
+    const double secs = env != nullptr && atof(env) > 0.0 ? atof(env) : 60.0;
+    return static_cast<long long>(secs * 1.965e9);
+  }();
+  return cycles;
 }
 
 } // namespace b200

@@ -17,6 +17,7 @@
 //     the same pass, so no separate axpy kernels run (reference RK4: rk4.cxx:172-210).
 #include "bracket.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace b200 {
@@ -142,26 +143,65 @@ __device__ __forceinline__ void finishPoint(const RkEpilogue& ep, int e, long lo
 // Mesh::communicate would copy (x guard cells of those rows included).
 struct GuardFill {
   double val;
-  int xin, xout, wrapy;
+  int xin, xout;
   int ys, ye; // the mesh's ystart / yend (the launch may cover fewer rows)
+  // Images of the edge rows.  The bottom rows (y - ys < upper guard rows) go to the upper guard rows of: this field
+  // (single rank, periodic y) or the same field in the LOWER neighbour's mapped arena; the top rows to the lower guard
+  // rows of this field / of the UPPER neighbour.  off = row shift + arena offset, in doubles; on = 0 disables a side.
+  long long off_up, off_dn;
+  int on_up, on_dn;
+  // Y neighbours on other GPUs (bout_b200_ypeer): flags raised once all rows of a side are delivered, flags awaited by
+  // the CTAs of the edge rows before they touch anything
+  unsigned long long* peer_flag[2];
+  const unsigned long long* wait_flag[2][2];
+  unsigned long long wait_value[2][2];
+  unsigned long long signal;
+  unsigned int* counters;
+  unsigned int expect[2]; // CTAs that deliver to the lower / upper neighbour in this launch
+  int* status;
+  long long timeout;
 };
-// the y guard rows the point (x, y, z..z+1) wraps to (and the point itself when `self`)
+__device__ __forceinline__ bool imageUp(const GuardFill& gf, int ny, int y) { return gf.on_up && y - gf.ys < ny - 1 - gf.ye; }
+__device__ __forceinline__ bool imageDn(const GuardFill& gf, int y) { return gf.on_dn && gf.ye - y < gf.ys; }
+// the images of the point (x, y, z..z+1) (and the point itself when `self`)
 __device__ __forceinline__ void storeWrapY(const GuardFill& gf, double* __restrict__ out, int ny, int nz, int x, int y,
                                            int z, double2 v, bool self) {
   double* q = out + (static_cast<long long>(x) * ny + y) * nz + z;
   if (self) {
     *reinterpret_cast<double2*>(q) = v;
   }
-  if (gf.wrapy) {
-    const int nyint = gf.ye - gf.ys + 1;
-    if (y - gf.ys < ny - 1 - gf.ye) {
-      *reinterpret_cast<double2*>(q + static_cast<long long>(nyint) * nz) = v;
-    }
-    if (gf.ye - y < gf.ys) {
-      *reinterpret_cast<double2*>(q - static_cast<long long>(nyint) * nz) = v;
-    }
+  if (imageUp(gf, ny, y)) {
+    *reinterpret_cast<double2*>(q + gf.off_up) = v;
+  }
+  if (imageDn(gf, y)) {
+    *reinterpret_cast<double2*>(q + gf.off_dn) = v;
   }
 }
+// bounded spin on a flag another GPU raises; a time-out is fatal (cf. k_xchg_y2 in halo.cu)
+__device__ __noinline__ void waitFlag(const unsigned long long* flag, unsigned long long value, int* status, long long timeout) {
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= value) {
+      return;
+    }
+    __nanosleep(64);
+  } while (clock64() - t0 < timeout);
+  *status = 1;
+  __threadfence_system();
+  __trap();
+}
+// one thread per CTA, after the CTA's remote stores are fenced: the last CTA of a side raises the neighbour's flag
+__device__ __forceinline__ void signalSide(const GuardFill& gf, int d) {
+  const unsigned int prev = atomicAdd(gf.counters + d, 1u);
+  if (prev == gf.expect[d] - 1) {
+    gf.counters[d] = 0;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(gf.peer_flag[d]), "l"(gf.signal) : "memory");
+  }
+}
+
 struct Hw3dParams {
   const double* __restrict__ n;
   const double* __restrict__ vort;
@@ -297,7 +337,7 @@ __device__ __forceinline__ Row4 ldsRow4(const double* row, int z, int nz) {
 }
 
 // x0..x1: the planes this CTA marched over at row y; thread = z pair.  Dirichlet x guard cells and their y-wrapped copies.
-__device__ __noinline__ void guardPass(const GuardFill gf, double* f0, double* f1, int nx, int ny, int nz, int xs, int xe,
+__device__ __forceinline__ void guardPass(const GuardFill& gf, double* f0, double* f1, int nx, int ny, int nz, int xs, int xe,
                                        int x0, int x1, int y, int z) {
   const bool xin = gf.xin && x0 == xs, xout = gf.xout && x1 == xe;
   if (!xin && !xout) {
@@ -329,8 +369,13 @@ constexpr int HW3D_NS = 4; // stencil ring: planes x-1, x, x+1 resident + one in
 constexpr int HW3D_NA = 2; // once-used operand ring: plane x resident + plane x+1 in flight
 constexpr int HW3D_AUX = 8; // rows per aux slot: phi(y+1), phi(y-1), n(y+1), n(y-1), start n, start vort, acc n, acc vort
 
-template <int THREADS, bool GUARDS>
+// GMODE: 0 = interior cells only; 1 = + the Dirichlet x guard cells of the epilogue's output, written after the march by
+// the CTAs of the first / last x chunk (rows whose y images nobody needs); 2 = + the y images of the rows (periodic
+// wrap or delivery to the Y neighbours with its waits and flags) -- for the few edge rows, launched on their own so
+// that the march of all the other rows keeps the register budget of the plain kernel.
+template <int THREADS, int GMODE>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_tma(const Hw3dParams p) {
+  constexpr bool GUARDS = GMODE == 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nz = p.nz;
   double* tile = reinterpret_cast<double*>(smem_raw);               // [NS][3 fields][nz]
@@ -352,10 +397,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
   const bool has_acc0 = ep && p.ep.acc_in[0] != nullptr && p.ep.acc_out[0] != nullptr;
   const bool has_acc1 = ep && p.ep.acc_in[1] != nullptr && p.ep.acc_out[1] != nullptr;
   const unsigned aux_rows = (p.with_par ? 4u : 0u) + (ep ? 2u : 0u) + (has_acc0 ? 1u : 0u) + (has_acc1 ? 1u : 0u);
-  // GUARDS: y guard rows this CTA's row is the periodic image of (0 = none), offsets in doubles
-  const long long wrap_rows = static_cast<long long>(p.gf.ye - p.gf.ys + 1) * nz;
-  const long long wrap_up = (GUARDS && p.gf.wrapy && y - p.gf.ys < p.ny - 1 - p.gf.ye) ? wrap_rows : 0;
-  const long long wrap_dn = (GUARDS && p.gf.wrapy && p.gf.ye - y < p.gf.ys) ? wrap_rows : 0;
+  // GUARDS: does this CTA's row have an image (a y guard row of this field, or of the field in a neighbour's arena)?
+  const bool has_up = GUARDS && imageUp(p.gf, p.ny, y), has_dn = GUARDS && imageDn(p.gf, y);
 
   auto issue = [&](int j) { // stencil plane j (x = x0 - 1 + j) into slot j % NS
     const int slot = j % HW3D_NS;
@@ -405,6 +448,22 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (GUARDS && tid == 0) { // rows next to a neighbour on another GPU: its rows must have arrived, and it must be done
+                            // with the guard rows this CTA is about to overwrite (bout_b200_ypeer)
+    const int width = max(p.gf.ys, p.ny - 1 - p.gf.ye);
+    const bool lo = y - p.gf.ys < width, hi = p.gf.ye - y < width;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (lo && p.gf.wait_flag[0][k] != nullptr) {
+        waitFlag(p.gf.wait_flag[0][k], p.gf.wait_value[0][k], p.gf.status, p.gf.timeout);
+      }
+      if (hi && p.gf.wait_flag[1][k] != nullptr) {
+        waitFlag(p.gf.wait_flag[1][k], p.gf.wait_value[1][k], p.gf.status, p.gf.timeout);
+      }
+    }
+    // rows another GPU wrote (generic proxy, acquired above) are read by the bulk-copy unit
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
   if (tid == 0) {
     for (int j = 0; j < min(HW3D_NS, nplanes); ++j) {
       issue(j);
@@ -485,11 +544,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
           if (p.ep.state_out[e] != nullptr) {
             const double2 r = make_double2(st.x + p.ep.a * d[0], st.y + p.ep.a * d[1]);
             *reinterpret_cast<double2*>(p.ep.state_out[e] + idx) = r;
-            if (GUARDS && wrap_up != 0) {
-              *reinterpret_cast<double2*>(p.ep.state_out[e] + idx + wrap_up) = r;
+            if (GUARDS && has_up) {
+              *reinterpret_cast<double2*>(p.ep.state_out[e] + idx + p.gf.off_up) = r;
             }
-            if (GUARDS && wrap_dn != 0) {
-              *reinterpret_cast<double2*>(p.ep.state_out[e] + idx - wrap_dn) = r;
+            if (GUARDS && has_dn) {
+              *reinterpret_cast<double2*>(p.ep.state_out[e] + idx + p.gf.off_dn) = r;
             }
           }
           if (p.ep.acc_out[e] != nullptr) {
@@ -500,11 +559,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
             const double2 r = make_double2(base.x + p.ep.b * d[0], base.y + p.ep.b * d[1]);
             *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx) = r;
             if (GUARDS && p.ep.state_out[e] == nullptr) {
-              if (wrap_up != 0) {
-                *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx + wrap_up) = r;
+              if (has_up) {
+                *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx + p.gf.off_up) = r;
               }
-              if (wrap_dn != 0) {
-                *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx - wrap_dn) = r;
+              if (has_dn) {
+                *reinterpret_cast<double2*>(p.ep.acc_out[e] + idx + p.gf.off_dn) = r;
               }
             }
           }
@@ -523,9 +582,24 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) k_hw3d_rhs_
     }
   }
   // x guard cells of the field the next right-hand side reads, from the edge-plane values this thread has just written
-  if (GUARDS && ep) {
+  if (GMODE >= 1 && ep) {
     guardPass(p.gf, p.ep.state_out[0] != nullptr ? p.ep.state_out[0] : p.ep.acc_out[0],
               p.ep.state_out[1] != nullptr ? p.ep.state_out[1] : p.ep.acc_out[1], p.nx, p.ny, nz, p.xs, p.xe, x0, x1, y, z);
+  }
+  if (GUARDS && ep) {
+    const bool to_lower = has_up && p.gf.peer_flag[0] != nullptr, to_upper = has_dn && p.gf.peer_flag[1] != nullptr;
+    if (to_lower || to_upper) { // every thread's remote stores are visible system-wide before the flag can rise
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        if (to_lower) {
+          signalSide(p.gf, 0);
+        }
+        if (to_upper) {
+          signalSide(p.gf, 1);
+        }
+      }
+    }
   }
 }
 
@@ -673,9 +747,16 @@ extern "C" int bout_b200_hw3d_rhs_guards(const bout_b200_grid* g, const bout_b20
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
-  const bool fill = guards != nullptr && (guards->x_inner || guards->x_outer || guards->wrap_y);
+  const bout_b200_ypeer* yp = guards != nullptr ? guards->ypeer : nullptr;
+  const bool fill = guards != nullptr && (guards->x_inner || guards->x_outer || guards->wrap_y || yp != nullptr);
+  if (yp != nullptr) {
+    B200_REQUIRE(!guards->wrap_y, BOUT_B200_ERR_ARG, "hw3d_rhs: wrap_y and ypeer exclude each other");
+    B200_REQUIRE(yp->counters != nullptr && yp->status != nullptr, BOUT_B200_ERR_ARG, "hw3d_rhs: ypeer without counters / status");
+  }
   if (fill) {
-    B200_REQUIRE(epilogue != nullptr, BOUT_B200_ERR_ARG, "hw3d_rhs: guard cells are filled on the epilogue's output");
+    const bool writes = guards->x_inner || guards->x_outer || guards->wrap_y
+                        || (yp != nullptr && (yp->peer_flag[0] != nullptr || yp->peer_flag[1] != nullptr));
+    B200_REQUIRE(!writes || epilogue != nullptr, BOUT_B200_ERR_ARG, "hw3d_rhs: guard cells are filled on the epilogue's output");
     B200_REQUIRE(guards->ystart >= 0 && guards->ystart <= g->ystart && guards->yend >= g->yend && guards->yend < g->ny,
                  BOUT_B200_ERR_ARG, "hw3d_rhs: the rows of this launch lie outside the guard fill's ystart..yend");
     B200_REQUIRE(!guards->wrap_y || (guards->yend - guards->ystart + 1 >= guards->ystart
@@ -730,8 +811,42 @@ extern "C" int bout_b200_hw3d_rhs_guards(const bout_b200_grid* g, const bout_b20
   const int half = g->nz / 2;
   const bool tma = vec2 && !no_tma && (half == 64 || half == 128 || half == 256 || half == 512);
   if (fill && tma) {
-    p.gf = GuardFill{guards->value, guards->x_inner, guards->x_outer, guards->wrap_y, guards->ystart, guards->yend};
+    GuardFill& gf = p.gf;
+    gf.val = guards->value;
+    gf.xin = guards->x_inner;
+    gf.xout = guards->x_outer;
+    gf.ys = guards->ystart;
+    gf.ye = guards->yend;
+    const long long image = static_cast<long long>(gf.ye - gf.ys + 1) * g->nz; // interior rows of the mesh, in doubles
+    if (guards->wrap_y) {
+      gf.on_up = gf.on_dn = 1;
+      gf.off_up = image;
+      gf.off_dn = -image;
+    }
+    if (yp != nullptr) {
+      if (yp->peer_flag[0] != nullptr) {
+        gf.on_up = 1;
+        gf.off_up = image + yp->delta[0];
+      }
+      if (yp->peer_flag[1] != nullptr) {
+        gf.on_dn = 1;
+        gf.off_dn = -image + yp->delta[1];
+      }
+      for (int d = 0; d < 2; ++d) {
+        gf.peer_flag[d] = yp->peer_flag[d];
+        for (int k = 0; k < 2; ++k) {
+          gf.wait_flag[d][k] = yp->wait_flag[d][k];
+          gf.wait_value[d][k] = yp->wait_value[d][k];
+        }
+      }
+      gf.signal = yp->signal;
+      gf.counters = yp->counters;
+      gf.status = yp->status;
+      gf.timeout = haloTimeoutCycles();
+    }
   }
+  B200_REQUIRE(yp == nullptr || tma, BOUT_B200_ERR_UNSUPPORTED,
+               "hw3d_rhs: rows are delivered to Y neighbours by the bulk-copy kernel only (nz = 128 .. 1024, aligned fields)");
   if (fill && !tma) { // the register-marching kernel writes interior cells only: the guard cells by their own kernels
     const int rc = bout_b200_hw3d_rhs_guards(g, nullptr, alpha, kappa, Dn, Dvort, n, vort, phi, ddt_n, ddt_vort, epilogue,
                                              nullptr, coef_workspace, stream);
@@ -786,16 +901,37 @@ extern "C" int bout_b200_hw3d_rhs_guards(const bout_b200_grid* g, const bout_b20
     p.chunk = chunk;
     const size_t smem = static_cast<size_t>(HW3D_NS * 3 + HW3D_NA * HW3D_AUX) * g->nz * sizeof(double);
     dim3 grid(static_cast<unsigned>(nyint), static_cast<unsigned>((len + chunk - 1) / chunk));
+    // which variant: do any of this launch's rows have a y image or wait for a neighbour?
+    int gmode = 0;
+    if (fill) {
+      const int width = std::max(p.gf.ys, g->ny - 1 - p.gf.ye);
+      const bool edge_rows = (p.gf.on_up || p.gf.on_dn || yp != nullptr)
+                             && (p.ys - p.gf.ys < width || p.gf.ye - p.ye < width);
+      gmode = edge_rows ? 2 : 1;
+      if (yp != nullptr) { // CTAs of this launch that deliver rows to the lower / upper neighbour
+        int rows_lo = 0, rows_hi = 0;
+        for (int y = p.ys; y <= p.ye; ++y) {
+          rows_lo += (y - p.gf.ys < g->ny - 1 - p.gf.ye) ? 1 : 0;
+          rows_hi += (p.gf.ye - y < p.gf.ys) ? 1 : 0;
+        }
+        p.gf.expect[0] = static_cast<unsigned>(rows_lo) * grid.y;
+        p.gf.expect[1] = static_cast<unsigned>(rows_hi) * grid.y;
+      }
+    }
+#define B200_LAUNCH_TMA_M(T, M)                                                                          \
+  {                                                                                                      \
+    B200_CUDA_OK(cudaFuncSetAttribute(k_hw3d_rhs_tma<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      static_cast<int>(smem)));                                          \
+    k_hw3d_rhs_tma<T, M><<<grid, T, smem, s>>>(p);                                                       \
+  }
 #define B200_LAUNCH_TMA(T)                                                                               \
   {                                                                                                      \
-    if (fill) {                                                                                          \
-      B200_CUDA_OK(cudaFuncSetAttribute(k_hw3d_rhs_tma<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        static_cast<int>(smem)));                                        \
-      k_hw3d_rhs_tma<T, true><<<grid, T, smem, s>>>(p);                                                  \
+    if (gmode == 2) {                                                                                    \
+      B200_LAUNCH_TMA_M(T, 2)                                                                            \
+    } else if (gmode == 1) {                                                                             \
+      B200_LAUNCH_TMA_M(T, 1)                                                                            \
     } else {                                                                                             \
-      B200_CUDA_OK(cudaFuncSetAttribute(k_hw3d_rhs_tma<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        static_cast<int>(smem)));                                        \
-      k_hw3d_rhs_tma<T, false><<<grid, T, smem, s>>>(p);                                                 \
+      B200_LAUNCH_TMA_M(T, 0)                                                                            \
     }                                                                                                    \
   }
     switch (half) {
@@ -805,6 +941,7 @@ extern "C" int bout_b200_hw3d_rhs_guards(const bout_b200_grid* g, const bout_b20
     default: B200_LAUNCH_TMA(512) break;
     }
 #undef B200_LAUNCH_TMA
+#undef B200_LAUNCH_TMA_M
     B200_LAUNCH_OK();
     return 0;
   }

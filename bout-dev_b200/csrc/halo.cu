@@ -211,17 +211,6 @@ __global__ void k_flag_wait(const unsigned long long* flag, unsigned long long v
   __trap();
 }
 
-// Cycles a receiver waits: BOUT_B200_HALO_TIMEOUT_S seconds (default 60: first-call IPC mapping, module loads, a
-// neighbour busy writing output are all far below it; a dead neighbour is not) at the 1.965 GHz B200 clock.
-static long long haloTimeoutCycles() {
-  static const long long cycles = [] {
-    const char* env = getenv("BOUT_B200_HALO_TIMEOUT_S");
-    const double secs = env != nullptr && atof(env) > 0.0 ? atof(env) : 60.0;
-    return static_cast<long long>(secs * 1.965e9);
-  }();
-  return cycles;
-}
-
 } // namespace b200
 
 using namespace b200;

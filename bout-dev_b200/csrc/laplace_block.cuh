@@ -89,7 +89,15 @@ struct LapParams {
   int force;                   // settings changed on the host side: factor regardless of the comparison
   int bP, bMB, bNT;            // blocks per system, rows per block, threads per CTA of the rows kernels
   int bPD;                     // rows kernels: CTA b prefetches the rows of CTA b + bPD into L2 (0 = off)
-  int wrapy, mys, mye;         // wrap_yguards: rows also stored into the y guard rows (mesh ystart / yend in mys / mye)
+  // images of the solution's edge rows (mesh ystart / yend in mys / mye): the bottom rows also go to the upper guard rows
+  // of `out` (wrap_yguards) or of the lower Y neighbour's mapped arena (ypeer), the top rows to the lower guard rows of
+  // `out` / of the upper neighbour; offsets in doubles, on = 0 disables a side
+  int mys, mye, on_up, on_dn;
+  long long off_up, off_dn;
+  unsigned long long* peer_flag[2]; // ypeer: raised to `signal` by the last CTA that delivered rows to that neighbour
+  unsigned long long signal;
+  unsigned int* counters;
+  unsigned int expect[2];
   int dbg;                     // timing ablations (BOUT_B200_LAPB_DBG; results are wrong when set): 1 = no per-mode
                                // phase, 2 = no inverse transform, 4 = no forward transform, 8 = no row loads
 };
@@ -538,19 +546,18 @@ B200_HD void lapbStoreRow(const LapParams& p, const LapbCta& c, int tid, const c
   for (int q = 0; q < Sh::B; ++q) {
     d2[t + Sh::T * q] = make_double2(v[q].re, v[q].im);
   }
-  if (p.wrapy) { // the y guard rows this row is the periodic image of
-    const long long wrap = static_cast<long long>(p.mye - p.mys + 1) * (p.nz / 2);
-    if (c.jy - p.mys < p.ny - 1 - p.mye) {
+  if (p.on_up && c.jy - p.mys < p.ny - 1 - p.mye) { // images of this row (see LapParams)
+    double2* __restrict__ u2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(d2) + p.off_up);
 #pragma unroll
-      for (int q = 0; q < Sh::B; ++q) {
-        d2[wrap + t + Sh::T * q] = make_double2(v[q].re, v[q].im);
-      }
+    for (int q = 0; q < Sh::B; ++q) {
+      u2[t + Sh::T * q] = make_double2(v[q].re, v[q].im);
     }
-    if (p.mye - c.jy < p.mys) {
+  }
+  if (p.on_dn && p.mye - c.jy < p.mys) {
+    double2* __restrict__ l2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(d2) + p.off_dn);
 #pragma unroll
-      for (int q = 0; q < Sh::B; ++q) {
-        d2[t + Sh::T * q - wrap] = make_double2(v[q].re, v[q].im);
-      }
+    for (int q = 0; q < Sh::B; ++q) {
+      l2[t + Sh::T * q] = make_double2(v[q].re, v[q].im);
     }
   }
 }
@@ -1370,9 +1377,30 @@ inline void lapFillParams(const bout_b200_grid* g, const bout_b200_laplace* L, v
   // cyclic_laplace.cxx:216-232 (include_yguards only matters where a y boundary exists)
   p.ys = L->include_yguards_lower ? 0 : g->ystart;
   p.ye = L->include_yguards_upper ? g->ny - 1 : g->yend;
-  p.wrapy = (L->wrap_yguards && !L->include_yguards_lower && !L->include_yguards_upper) ? 1 : 0;
   p.mys = g->ystart;
   p.mye = g->yend;
+  if (!L->include_yguards_lower && !L->include_yguards_upper) {
+    const long long image = static_cast<long long>(g->yend - g->ystart + 1) * g->nz;
+    if (L->wrap_yguards) {
+      p.on_up = p.on_dn = 1;
+      p.off_up = image;
+      p.off_dn = -image;
+    } else if (L->ypeer != nullptr) {
+      const bout_b200_ypeer* yp = L->ypeer;
+      if (yp->peer_flag[0] != nullptr) {
+        p.on_up = 1;
+        p.off_up = image + yp->delta[0];
+      }
+      if (yp->peer_flag[1] != nullptr) {
+        p.on_dn = 1;
+        p.off_dn = -image + yp->delta[1];
+      }
+      p.peer_flag[0] = yp->peer_flag[0];
+      p.peer_flag[1] = yp->peer_flag[1];
+      p.signal = yp->signal;
+      p.counters = yp->counters;
+    }
+  }
   p.nmode = L->maxmode + 1;
   p.zero_dc = (L->global_flags & INV_ZERO_DC) ? 1 : 0;
   p.in_set = (L->first_x && (L->inner_boundary_flags & INV_SET)) ? 1 : 0;

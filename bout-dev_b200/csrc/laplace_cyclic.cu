@@ -886,6 +886,27 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_lapb_rows(const LapParams p) {
     }
   }
   lapbStoreRow<N, NT>(p, c, tid, v);
+  // rows delivered to a Y neighbour on another GPU (bout_b200_ypeer): fenced system-wide, then the last CTA of that
+  // side raises the neighbour's flag
+  const bool to_lower = p.peer_flag[0] != nullptr && p.on_up && c.jy - p.mys < p.ny - 1 - p.mye;
+  const bool to_upper = p.peer_flag[1] != nullptr && p.on_dn && p.mye - c.jy < p.mys;
+  if (to_lower || to_upper) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        if (d == 0 ? to_lower : to_upper) {
+          const unsigned int prev = atomicAdd(p.counters + d, 1u);
+          if (prev == p.expect[d] - 1) {
+            p.counters[d] = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flag[d]), "l"(p.signal) : "memory");
+          }
+        }
+      }
+    }
+  }
 }
 
 } // namespace b200
@@ -1075,8 +1096,20 @@ bool lapUseBlock(const LapPlan* plan, const bout_b200_laplace* L, bool with_fiel
 }
 
 template <int N, int NT, int MODE>
-int launchRows(const LapParams& p, cudaStream_t s) {
+int launchRows(const LapParams& p_in, cudaStream_t s) {
   using Sh = LapbShape<N, NT>;
+  LapParams p = p_in;
+  if (MODE == LAPB_SOLVE && (p.peer_flag[0] != nullptr || p.peer_flag[1] != nullptr)) {
+    // CTAs that deliver rows to the lower / upper Y neighbour: every x tile of the bottom / top rows
+    const unsigned ntile = static_cast<unsigned>((p.bd.xe - p.bd.xs + 1 + Sh::ROWS - 1) / Sh::ROWS);
+    int rows_lo = 0, rows_hi = 0;
+    for (int y = p.ys; y <= p.ye; ++y) {
+      rows_lo += (y - p.mys < p.ny - 1 - p.mye) ? 1 : 0;
+      rows_hi += (p.mye - y < p.mys) ? 1 : 0;
+    }
+    p.expect[0] = static_cast<unsigned>(rows_lo) * ntile;
+    p.expect[1] = static_cast<unsigned>(rows_hi) * ntile;
+  }
   static bool configured = false;
   if (!configured) {
     B200_CUDA_OK(cudaFuncSetAttribute(k_lapb_rows<N, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1246,8 +1279,10 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
     k_lap_finish<<<sblocks, 128, 0, s>>>(p);
     B200_LAUNCH_OK();
   }
+  B200_REQUIRE(L->ypeer == nullptr, BOUT_B200_ERR_UNSUPPORTED,
+               "laplace: rows are delivered to Y neighbours by the block path only (isolated systems, nz = 128 / 256 / 512)");
   rc = launchFft<false>(&plan, s);
-  if (rc == 0 && p.wrapy) { // the block path stores the wrapped rows itself; here they are copied afterwards
+  if (rc == 0 && L->wrap_yguards && p.on_up) { // the block path stores the wrapped rows itself; here they are copied afterwards
     double* f[1] = {out};
     rc = bout_b200_halo_self(g, 1, f, 0, 1, stream);
   }

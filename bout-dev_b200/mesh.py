@@ -86,6 +86,56 @@ class PeerYChannel:
         return v.value != 0
 
 
+class PeerFieldArena:
+    """Fields whose Y guard rows are written by the NEIGHBOURS' kernels (bout_b200_ypeer): all of them live at the same
+    offsets of one device allocation per rank, which the two Y neighbours map with CUDA IPC, followed by the arrival
+    flags [channel][side] (side 0: rows from the lower neighbour have arrived, side 1: from the upper one), two block
+    counters per channel and a status word."""
+
+    NCH = 2  # channels: 0 = evolving-field stage states, 1 = phi
+
+    def __init__(self, mesh, nfields, device):
+        from . import capi
+        self.capi, self.mesh = capi, mesh
+        g = mesh.grid
+        self.fbytes = (g.nx * g.ny * g.nz * 8 + 255) // 256 * 256
+        self.flag_off = nfields * self.fbytes
+        self.base = capi.peer_alloc(self.flag_off + 256)
+        mine = torch.tensor(list(capi.peer_export(self.base)), dtype=torch.uint8, device=device)
+        allh = torch.empty(dist.get_world_size() * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().tobytes()
+        opened = {r: capi.peer_open(allh[64 * r:64 * r + 64]) for r in {mesh.yup, mesh.ydown} - {None, mesh.rank}}
+        self.peer = [opened.get(mesh.ydown), opened.get(mesh.yup)]          # lower, upper neighbour's arena (or None)
+        self.fields = [capi.tensor_from_ptr(self.base + i * self.fbytes, g.shape3, device) for i in range(nfields)]
+        self.ptrs = {f.data_ptr() for f in self.fields}
+        self.counters = [self.base + self.flag_off + 8 * 2 * self.NCH + 8 * ch for ch in range(self.NCH)]
+        self.status = self.base + self.flag_off + 8 * 2 * self.NCH + 8 * self.NCH
+
+    def flag(self, ch, side, base=None):
+        return (self.base if base is None else base) + self.flag_off + 8 * (2 * ch + side)
+
+    def ypeer(self, ch, signal, deliver=True, waits=None):
+        """A CYPeer for a launch on channel ch that raises the neighbours' flags to `signal`: this rank is the UPPER
+        neighbour of its lower neighbour (raises that one's side-1 flag) and the lower neighbour of its upper one."""
+        pf = [None, None]
+        delta = [0, 0]
+        if deliver:
+            for d in range(2):
+                if self.peer[d] is not None:
+                    pf[d] = self.flag(ch, 1 - d, self.peer[d])
+                    assert (self.peer[d] - self.base) % 8 == 0
+                    delta[d] = (self.peer[d] - self.base) // 8
+        return self.capi.make_ypeer(delta, pf, signal, self.counters[ch], self.status, waits)
+
+    def timed_out(self):
+        import ctypes as C
+        torch.cuda.synchronize()
+        v = C.c_int(0)
+        self.capi._check(self.capi.lib.bout_b200_memcpy_d2h(C.byref(v), C.c_void_p(self.status), C.c_size_t(4), None))
+        return v.value != 0
+
+
 def decompose(rank, nxpe, nype):
     """(PE_XIND, PE_YIND) of a rank (boutmesh.cxx:1041: MYPE = PE_YIND * NXPE + PE_XIND)."""
     if not 0 <= rank < nxpe * nype:

@@ -59,19 +59,43 @@ class HW3D:
         self.overlap = (mesh is not None and mesh.nxpe == 1 and mesh.nype > 1 and self.dev.type == "cuda"
                         and os.environ.get("BOUT_B200_HALO_OVERLAP", "1") != "0")
         self.overlap_phi = self.overlap and g.yend - g.ystart >= 2 and os.environ.get("BOUT_B200_PHI_OVERLAP", "1") != "0"
-        if self.overlap_phi:
+        # row ranges of the fused kernel's launches: the rows within `w` of an end (they have y images / wait for a
+        # neighbour) and all the others
+        w = max(g.myg, 1) if self.guard_fill else 1
+        self.edge_w = w
+        self.split_ok = g.yend - g.ystart + 1 >= 2 * w + 1
+        if self.split_ok:
             self.g_mid = capi.Grid(g.nx, g.ny, g.nz, g.mxg, g.myg)
             self.g_lo = capi.Grid(g.nx, g.ny, g.nz, g.mxg, g.myg)
             self.g_hi = capi.Grid(g.nx, g.ny, g.nz, g.mxg, g.myg)
-            for gg, (a, b) in ((self.g_mid, (g.ystart + 1, g.yend - 1)), (self.g_lo, (g.ystart, g.ystart)),
-                               (self.g_hi, (g.yend, g.yend))):
+            for gg, (a, b) in ((self.g_mid, (g.ystart + w, g.yend - w)), (self.g_lo, (g.ystart, g.ystart + w - 1)),
+                               (self.g_hi, (g.yend - w + 1, g.yend))):
                 gg.c.ystart, gg.c.yend = a, b
+        self.overlap_phi = self.overlap_phi and self.split_ok
         self._comm_stream = None
         z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
-        self.n, self.vort, self.phi = z(), z(), z()
+        # NYPE > 1 on one node (BOUT_B200_YPEER=0 keeps the exchange kernels): no exchange pass at all -- the fused
+        # kernel and the Laplacian solve store the rows a neighbour needs straight into its guard rows over NVLink
+        # (bout_b200_ypeer) and raise its flags; only the CTAs of the edge rows, launched last, ever wait.  The fields
+        # that take part live in a peer-mapped arena; phi alternates between two buffers so that a neighbour that is
+        # one solve ahead does not overwrite guard rows this rank's fused kernel is still reading.
+        self.ypeer = (self.overlap and self.guard_fill and g.nz in (128, 256, 512) and getattr(mesh, "_peer_ok", False)
+                      and mesh.rank not in (mesh.yup, mesh.ydown) and g.yend - g.ystart + 1 >= 2 * max(g.ystart, 1)
+                      and os.environ.get("BOUT_B200_YPEER", "1") != "0")
+        if self.ypeer:
+            from .mesh import PeerFieldArena
+            self.arena = PeerFieldArena(mesh, 8, self.dev)
+            self.n, self.vort, self.sn, self.sv, self.tn, self.tv, ph0, ph1 = self.arena.fields
+            self.phis = [ph0, ph1]
+            self.phi = ph0
+            self.an, self.av = z(), z()
+            self._cstate = self._cphi = 0   # deliveries so far on the two channels (the same on every rank)
+            self.overlap_phi = False
+        else:
+            self.n, self.vort, self.phi = z(), z(), z()
+            # RK work fields: stage state (k5 in rk4.cxx) and the running combination
+            self.sn, self.sv, self.tn, self.tv, self.an, self.av = z(), z(), z(), z(), z(), z()
         self.ddt_n, self.ddt_vort = z(), z()
-        # RK work fields: stage state (k5 in rk4.cxx) and the running combination
-        self.sn, self.sv, self.tn, self.tv, self.an, self.av = z(), z(), z(), z(), z(), z()
 
     def set_state(self, n, vort):
         self.n.copy_(n)
@@ -95,14 +119,75 @@ class HW3D:
             e.record()
             self.phase_events.append((name, e))
 
+    def _fused_split(self, fn, fv, epilogue, ddt, guards):
+        """The fused kernel as three launches: the few edge rows (y images, waits for neighbour GPUs: the full guard
+        variant of the kernel, short x chunks) on a second, high-priority stream beside all the other rows (the plain
+        march + x guard cells) on this one."""
+        if not self.split_ok:
+            return self._fused(self.g, fn, fv, epilogue, ddt, guards)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        main, side = torch.cuda.current_stream(), self._comm_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._fused(self.g_lo, fn, fv, epilogue, ddt, guards)
+            self._fused(self.g_hi, fn, fv, epilogue, ddt, guards)
+        self._fused(self.g_mid, fn, fv, epilogue, ddt, guards)
+        main.wait_stream(side)
+
     def _fused(self, gsel, fn, fv, epilogue, ddt, guards):
         capi.hw3d_rhs(gsel, None, self.alpha, self.kappa, self.Dn, self.Dvort, fn, fv, self.phi,
                       self.ddt_n if ddt else None, self.ddt_vort if ddt else None, epilogue=epilogue,
                       coef_ws=self.coef, guards=guards)
 
+    def _rhs_ypeer(self, fn, fv, epilogue, ddt):
+        """One right-hand side with the Y guard rows delivered by the producing kernels (bout_b200_ypeer)."""
+        A = self.arena
+        ready = self._ready.get((fn.data_ptr(), fv.data_ptr())) == (fn._version, fv._version)
+        self._mark("start")
+        if not ready:   # a state set from outside: boundary conditions and one ordinary exchange
+            self._pre_rhs(fn, fv)
+            self.mesh.communicate([fn, fv])
+        self._mark("bc")
+        self.phi = self.phis[self._cphi % 2]
+        self._cphi += 1
+        self.lap.set_ypeer(A.ypeer(1, self._cphi))
+        self.lap.solve(fv, out=self.phi)
+        self._mark("solve")
+        self._mark("halo")
+        nxt = None
+        if epilogue is not None:
+            k = epilogue._keep
+            nxt = tuple((k[2][i] if k[2] is not None and k[2][i] is not None else k[3][i]) for i in range(2))
+        deliver = nxt is not None and all(t is not None and t.data_ptr() in A.ptrs for t in nxt)
+        # edge rows wait for: the neighbour's rows of this state (when they were delivered by its kernel, not by the
+        # exchange above) and its rows of phi
+        waits = [[(A.flag(0, d), self._cstate) if ready else None, (A.flag(1, d), self._cphi)] for d in range(2)]
+        for d, nb in enumerate((self.mesh.ydown, self.mesh.yup)):
+            if nb is None:
+                waits[d] = [None, None]
+        yp = A.ypeer(0, self._cstate + 1, deliver=deliver, waits=waits)
+        gf = capi.make_guard_fill(self.g, 0.0, self.gf.x_inner and epilogue is not None, self.gf.x_outer and epilogue is not None,
+                                  wrap_y=False, ypeer=yp)
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._fused_split(fn, fv, epilogue, ddt, gf)
+        if self.kernel_events is not None:
+            e1.record()
+            self.kernel_events.append((e0, e1))
+        self._mark("fused")
+        if deliver:
+            self._cstate += 1
+            self._ready = {(nxt[0].data_ptr(), nxt[1].data_ptr()): (nxt[0]._version, nxt[1]._version)}
+        elif nxt is not None and nxt[0] is not None and nxt[1] is not None:
+            self._ready.pop((nxt[0].data_ptr(), nxt[1].data_ptr()), None)
+
     def rhs(self, fn=None, fv=None, epilogue=None, ddt=True):
         fn = self.n if fn is None else fn
         fv = self.vort if fv is None else fv
+        if self.ypeer:
+            return self._rhs_ypeer(fn, fv, epilogue, ddt)
         # were the guard cells of this state written by the kernel that produced it?
         ready = self._ready.get((fn.data_ptr(), fv.data_ptr())) == (fn._version, fv._version)
         guards = self.gf if (self.guard_fill and epilogue is not None) else None
@@ -156,6 +241,8 @@ class HW3D:
                 self._fused(self.g_lo, fn, fv, epilogue, ddt, guards)
                 self._fused(self.g_hi, fn, fv, epilogue, ddt, guards)
             main.wait_stream(self._comm_stream)
+        elif guards is not None:
+            self._fused_split(fn, fv, epilogue, ddt, guards)
         else:
             self._fused(self.g, fn, fv, epilogue, ddt, guards)
         if self.kernel_events is not None:

@@ -251,6 +251,25 @@ int bout_b200_smooth_x(const bout_b200_grid* g, const double* f, double* out, vo
  * (reference Laplacian::Laplacian options src/invert/laplace/invert_laplace.cxx:68-138 and
  * Laplacian::tridagCoefs :280-375).  All pointers are device Field2D arrays [nx][ny]; optional ones
  * may be NULL. */
+/* ---- Y guard rows delivered by the kernel that produces them, over NVLink peer memory --------------------------------
+ * Mesh::communicate's Y exchange (sendY / wait, src/mesh/impls/bout/boutmesh.cxx:1245-1555) without pack, send or
+ * unpack passes: every field that takes part lives at the same offset of a per-rank arena (bout_b200_peer_alloc) which
+ * the two Y neighbours map with CUDA IPC; the CTAs that produce the top / bottom MYG interior rows of a field also store
+ * them straight into the neighbour's guard rows (x guard cells of those rows included), and the last of them raises a
+ * flag in the neighbour's arena.  The CTAs that read (or remotely write) next to side d first wait for up to two local
+ * flags -- e.g. "the neighbour's rows of the state have arrived" and "its rows of phi have arrived".  Used by
+ * bout_b200_hw3d_rhs_guards (through bout_b200_guard_fill) and by the block path of bout_b200_laplace_cyclic_solve
+ * (bout_b200_laplace.ypeer; no waits there).  A wait that times out (BOUT_B200_HALO_TIMEOUT_S) sets *status and traps. */
+typedef struct bout_b200_ypeer {
+  long long delta[2];               /* [0] lower, [1] upper neighbour: (its mapped arena - this rank's arena) in doubles */
+  unsigned long long* peer_flag[2]; /* flag in that neighbour's arena, raised to `signal`; NULL = no neighbour there */
+  unsigned long long signal;
+  unsigned int* counters;           /* two local block counters, zero between launches */
+  const unsigned long long* wait_flag[2][2]; /* local flags the CTAs next to side d wait for (NULL = none) ... */
+  unsigned long long wait_value[2][2];       /* ... to reach this value */
+  int* status;
+} bout_b200_ypeer;
+
 typedef struct bout_b200_laplace {
   const double* dx;
   const double* g11;
@@ -275,6 +294,8 @@ typedef struct bout_b200_laplace {
   int wrap_yguards;   /* single rank, periodic y: the solve also writes each solution row into the y guard row it
                          wraps to -- what the Mesh::communicate(phi) that follows the solve in a model's rhs() would
                          copy (boutmesh.cxx:1221-1555); 0 = the reference's behaviour (guard rows untouched) */
+  const bout_b200_ypeer* ypeer; /* Y-decomposed ranks: the solve delivers the top / bottom MYG solution rows into the
+                         neighbours' y guard rows and raises their flags (block path only); NULL = off */
 } bout_b200_laplace;
 
 /* Coordinates::Delp2(Field3D, useFFT=true) (src/mesh/coordinates.cxx:1662-1699); uses
@@ -481,6 +502,7 @@ typedef struct bout_b200_guard_fill {
   double value;
   int x_inner, x_outer, wrap_y;
   int ystart, yend;
+  const struct bout_b200_ypeer* ypeer; /* Y-decomposed ranks: deliver the rows to the neighbours instead (wrap_y = 0) */
 } bout_b200_guard_fill;
 int bout_b200_hw3d_rhs_guards(const bout_b200_grid* g, const bout_b200_metric* m, double alpha, double kappa,
                               double Dn, double Dvort, const double* n, const double* vort,

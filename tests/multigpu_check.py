@@ -49,12 +49,49 @@ def main():
     ok = ok and max(errs[2:]) < 1e-8
     print(f"rank {rank}/{world}: ddt err {errs[0]:.2e} {errs[1]:.2e}; trajectory err {errs[2]:.2e} {errs[3]:.2e}", flush=True)
     ok = hw3d_y_check(pkg, dev, rank, world, gold) and ok
+    ok = hw3d_ypeer_check(pkg, dev, rank, world) and ok
     ok = elmpb_check(pkg, dev, rank, world) and ok
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(int(flag.item() != 0))
+
+
+def hw3d_ypeer_check(pkg, dev, rank, world):
+    """Y guard rows delivered by the producing kernels over peer memory (bout_b200_ypeer: fused RHS epilogue + the
+    Laplacian solve write the neighbours' guard rows, edge CTAs wait on flags) against the exchange kernels
+    (BOUT_B200_YPEER=0) on the same NYPE = world decomposition: bitwise, after 3 RK4 steps and one more RHS."""
+    capi, models, meshmod = pkg.capi, pkg.models, pkg.mesh
+    mxsub, mysub, nz, mxg, myg = 24, 6, 128, 2, 2
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["BOUT_B200_YPEER"] = mode
+        mesh = meshmod.BoutMesh(1, world, rank, mxsub, mysub, nz, mxg, myg, periodic_x=False, periodic_y=True, device=dev)
+        g = mesh.grid
+        one = lambda v: torch.full(g.shape2, v, dtype=torch.float64, device=dev)
+        md = dict(dx=one(0.3), dy=one(0.7), dz=one(0.2), J=one(1.0), g_22=one(1.0), g11=one(1.0), g33=one(1.0),
+                  g13=one(0.0), G1=one(0.0), G3=one(0.0), d1_dx=one(0.0), g_11=one(1.0))
+        gen = torch.Generator(device=dev).manual_seed(11 + rank)
+        n0 = torch.rand(g.shape3, dtype=torch.float64, device=dev, generator=gen) - 0.5
+        v0 = torch.rand(g.shape3, dtype=torch.float64, device=dev, generator=gen) - 0.5
+        m = models.HW3D(g, md, alpha=1.0, kappa=0.5, Dn=1e-3, Dvort=1e-3, device=dev, mesh=mesh)
+        assert m.ypeer == (mode == "1"), (mode, m.ypeer)
+        m.set_state(n0, v0)
+        for _ in range(3):
+            m.rk4_step(1e-3)
+        m.rhs()
+        torch.cuda.synchronize()
+        dist.barrier()
+        I = g.interior
+        res[mode] = [t[I].clone() for t in (m.n, m.vort, m.phi, m.ddt_n, m.ddt_vort)]
+        if mode == "1":
+            assert not m.arena.timed_out()
+    os.environ.pop("BOUT_B200_YPEER", None)
+    same = all(torch.equal(a, b) for a, b in zip(res["0"], res["1"]))
+    big = float(res["1"][0].abs().max())
+    print(f"rank {rank}/{world} (ypeer vs exchange kernels, NYPE={world}): bitwise equal {same}, max |n| {big:.3f}", flush=True)
+    return same and big > 0.1 and all(bool(torch.isfinite(t).all()) for t in res["1"])
 
 
 def hw3d_y_check(pkg, dev, rank, world, gold):
