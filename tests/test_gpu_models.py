@@ -82,7 +82,9 @@ def test_hw3d_guard_cells_written_by_the_producing_kernels(capi, gold, nz, monke
         assert torch.equal(a, b), name
     assert torch.isfinite(res["1"][0]).all() and float(res["1"][0].abs().max()) > 0.1
     if nz == 128:
-        assert res["1"][3] < res["0"][3] - 40   # no boundary / exchange launches between the stages
+        # no boundary / exchange launches between the stages (the fused kernel itself is three launches: the edge
+        # rows apart from the rest)
+        assert res["1"][3] < res["0"][3] - 20
 
 
 # ---- UNCHANGED reference models compiled against the C++ host layer -----------------------------------

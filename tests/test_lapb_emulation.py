@@ -30,7 +30,7 @@ class CLaplace(C.Structure):
                [(n, C.c_int) for n in ("all_terms", "nonuniform", "global_flags",
                                        "inner_boundary_flags", "outer_boundary_flags", "maxmode",
                                        "periodic_x", "first_x", "last_x", "include_yguards_lower",
-                                       "include_yguards_upper")]
+                                       "include_yguards_upper", "wrap_yguards")] + [("ypeer", C.c_void_p)]
 
 
 @pytest.fixture(scope="module")
