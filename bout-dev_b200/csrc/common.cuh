@@ -115,6 +115,31 @@ __device__ __forceinline__ int wrapz(int z, int nz) {
   return z < 0 ? z + nz : (z >= nz ? z - nz : z);
 }
 
+// Flat work-item index t -> (z-vector zv < nzv, row yb < nyb, plane xb): 32-bit unsigned arithmetic whenever t fits
+// (a 64-bit division by a run-time value is ~100 instructions on sm_100: four of them per element made the
+// element-wise kernels integer-bound), a mask / shift when nzv is a power of two (nz almost always is).
+__device__ __forceinline__ void splitIndex(long long t, int nzv, int nyb, int& zv, int& yb, int& xb) {
+  if (t <= 0x7fffffffLL) {
+    const unsigned u = static_cast<unsigned>(t), n = static_cast<unsigned>(nzv), m = static_cast<unsigned>(nyb);
+    unsigned xy;
+    if ((n & (n - 1)) == 0) {
+      xy = u >> (__ffs(static_cast<int>(n)) - 1);
+      zv = static_cast<int>(u & (n - 1));
+    } else {
+      xy = u / n;
+      zv = static_cast<int>(u - xy * n);
+    }
+    const unsigned xq = xy / m;
+    yb = static_cast<int>(xy - xq * m);
+    xb = static_cast<int>(xq);
+  } else {
+    zv = static_cast<int>(t % nzv);
+    const long long xy = t / nzv;
+    yb = static_cast<int>(xy % nyb);
+    xb = static_cast<int>(xy / nyb);
+  }
+}
+
 // Cycles a receiver waits: BOUT_B200_HALO_TIMEOUT_S seconds (default 60: first-call IPC mapping, module loads, a
 // neighbour busy writing output are all far below it; a dead neighbour is not) at the 1.965 GHz B200 clock.
 inline long long haloTimeoutCycles() {

@@ -34,10 +34,9 @@ __global__ void __launch_bounds__(256) k_elementwise(const EwParams p) {
   const long long total = static_cast<long long>(p.xe - p.xs + 1) * nyb * nzv;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int zv = static_cast<int>(t % nzv);
-    const long long xy = t / nzv;
-    const int y = p.ys + static_cast<int>(xy % nyb);
-    const int x = p.xs + static_cast<int>(xy / nyb);
+    int zv, yb_, xb_;
+    splitIndex(t, nzv, nyb, zv, yb_, xb_);
+    const int y = p.ys + yb_, x = p.xs + xb_;
     const long long i2 = static_cast<long long>(x) * p.ny + y;
     const long long i3 = i2 * p.nz + static_cast<long long>(zv) * VEC;
     Vz<VEC> acc;

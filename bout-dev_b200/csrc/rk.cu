@@ -29,10 +29,9 @@ __global__ void __launch_bounds__(256) k_rk(const RkParams p) {
   const long long total = static_cast<long long>(p.xe - p.xs + 1) * nyb * nzv;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int zv = static_cast<int>(t % nzv);
-    const long long xy = t / nzv;
-    const int y = p.ys + static_cast<int>(xy % nyb);
-    const int x = p.xs + static_cast<int>(xy / nyb);
+    int zv, yb_, xb_;
+    splitIndex(t, nzv, nyb, zv, yb_, xb_);
+    const int y = p.ys + yb_, x = p.xs + xb_;
     const long long i = (static_cast<long long>(x) * p.ny + y) * p.nz + static_cast<long long>(zv) * VEC;
     const Vz<VEC> s = Vz<VEC>::load(p.a + i);
     Vz<VEC> r;
@@ -145,10 +144,9 @@ __global__ void __launch_bounds__(kErrThreads) k_err_partial(const double* __res
   double acc = 0.0;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int z = static_cast<int>(t % nz);
-    const long long xy = t / nz;
-    const int y = ys + static_cast<int>(xy % nyb);
-    const int x = xs + static_cast<int>(xy / nyb);
+    int z, yb_, xb_;
+    splitIndex(t, nz, nyb, z, yb_, xb_);
+    const int y = ys + yb_, x = xs + xb_;
     const long long i = (static_cast<long long>(x) * ny + y) * nz + z;
     const double va = __ldg(a + i), vb = __ldg(b + i);
     if (MODE == 0) {

@@ -159,10 +159,9 @@ __global__ void __launch_bounds__(256) k_stencil_z(const StencilParams p) {
   if (t >= total) {
     return;
   }
-  const int zv = static_cast<int>(t % nzv);
-  const long long xy = t / nzv;
-  const int y = p.ys + static_cast<int>(xy % nyb);
-  const int x = p.xs + static_cast<int>(xy / nyb);
+  int zv, yb_, xb_;
+  splitIndex(t, nzv, nyb, zv, yb_, xb_);
+  const int y = p.ys + yb_, x = p.xs + xb_;
   const long long row2 = static_cast<long long>(x) * p.ny + y;
   const long long row = row2 * p.nz;
   const int z = zv * VEC;
@@ -268,6 +267,10 @@ int launchStencil(const StencilParams& p, int dir, cudaStream_t stream) {
         chunk = c;
         break;
       }
+    }
+    static const int chunk_env = getenv("BOUT_B200_MARCH_CHUNK") ? atoi(getenv("BOUT_B200_MARCH_CHUNK")) : 0;
+    if (chunk_env > 0) {
+      chunk = chunk_env;
     }
     StencilParams q = p;
     q.chunk = chunk;

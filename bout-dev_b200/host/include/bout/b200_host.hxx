@@ -375,6 +375,7 @@ public:
   Field2D& operator*=(BoutReal s);
 };
 
+class FieldPerp;
 class Field3D : public FieldBase {
 public:
   Field3D(Mesh* m = nullptr);
@@ -385,6 +386,7 @@ public:
   Field3D& operator=(const Field3D& f);
   Field3D& operator=(Field3D&& f) noexcept;
   Field3D& operator=(const Field2D& f);
+  Field3D& operator=(const FieldPerp& p); ///< sets plane y = p.getIndex() only (field3d.cxx:293-310)
   Field3D& operator=(BoutReal v);
   double* wptr();
   size_t size() const;
@@ -426,6 +428,66 @@ private:
 
 inline Field3D& ddt(Field3D& f) { return *f.timeDeriv(); }
 template <> Field3D Options::as<Field3D>() const; ///< the option's expression evaluated over the mesh
+
+// ---- FieldPerp: one x-z plane [nx][nz] at a y index (reference include/bout/fieldperp.hxx:54-330) ---------------------
+// Device-resident like the other fields (a pooled block of LocalNx * LocalNz doubles); algebra is bout_b200_elementwise
+// on a grid with ny = 1, slicing and Field3D = FieldPerp are bout_b200_copy_xz, the Laplacian inversion of one plane is
+// bout_b200_laplace_cyclic_solve_perp.
+class FieldPerp : public FieldBase {
+public:
+  FieldPerp(Mesh* m = nullptr, CELL_LOC loc = CELL_CENTRE, int yindex_in = -1);
+  FieldPerp(BoutReal v, Mesh* m = nullptr);
+  FieldPerp& allocate();
+  FieldPerp& operator=(BoutReal v);
+  int getIndex() const { return yindex; }          ///< fieldperp.hxx:118
+  FieldPerp& setIndex(int y) { yindex = y; return *this; }
+  int getNx() const;
+  int getNy() const { return 1; }
+  int getNz() const;
+  double* wptr();
+  size_t size() const;
+  void setHost(const double* v);                   ///< upload [nx][nz]
+  std::vector<double> getHost() const;
+  /// element access from host code (fieldperp.hxx:166-216) through the block's host mirror, as for Field3D
+  BoutReal& operator()(int x, int z);
+  const BoutReal& operator()(int x, int z) const;
+  BoutReal& operator()(int x, int, int z) { return (*this)(x, z); }
+  const BoutReal& operator()(int x, int, int z) const { return (*this)(x, z); }
+  FieldPerp& operator+=(const FieldPerp& r);
+  FieldPerp& operator-=(const FieldPerp& r);
+  FieldPerp& operator*=(const FieldPerp& r);
+  FieldPerp& operator/=(const FieldPerp& r);
+  FieldPerp& operator+=(BoutReal r);
+  FieldPerp& operator-=(BoutReal r);
+  FieldPerp& operator*=(BoutReal r);
+  FieldPerp& operator/=(BoutReal r);
+
+private:
+  int yindex = -1;
+};
+FieldPerp sliceXZ(const Field3D& f, int y);        ///< src/field/fieldperp.cxx:150-165
+FieldPerp operator+(const FieldPerp& a, const FieldPerp& b);
+FieldPerp operator-(const FieldPerp& a, const FieldPerp& b);
+FieldPerp operator*(const FieldPerp& a, const FieldPerp& b);
+FieldPerp operator/(const FieldPerp& a, const FieldPerp& b);
+// FieldPerp (op) Field3D / Field2D use the operand's values at the FieldPerp's y index (generated_fieldops.cxx)
+FieldPerp operator+(const FieldPerp& a, const Field3D& b);
+FieldPerp operator-(const FieldPerp& a, const Field3D& b);
+FieldPerp operator*(const FieldPerp& a, const Field3D& b);
+FieldPerp operator/(const FieldPerp& a, const Field3D& b);
+FieldPerp operator+(const FieldPerp& a, BoutReal b);
+FieldPerp operator-(const FieldPerp& a, BoutReal b);
+FieldPerp operator*(const FieldPerp& a, BoutReal b);
+FieldPerp operator/(const FieldPerp& a, BoutReal b);
+FieldPerp operator+(BoutReal a, const FieldPerp& b);
+FieldPerp operator-(BoutReal a, const FieldPerp& b);
+FieldPerp operator*(BoutReal a, const FieldPerp& b);
+FieldPerp operator/(BoutReal a, const FieldPerp& b);
+FieldPerp operator-(const FieldPerp& a);
+FieldPerp sqrt(const FieldPerp& f);
+FieldPerp abs(const FieldPerp& f);
+FieldPerp exp(const FieldPerp& f);
+FieldPerp SQ(const FieldPerp& f);
 
 // element-wise algebra (src/field/generated_fieldops.cxx); one kernel per operator
 Field3D operator+(const Field3D& a, const Field3D& b);
@@ -570,6 +632,8 @@ public:
   void setOuterBoundaryFlags(int f) { outer_boundary_flags = f; }
   Field3D solve(const Field3D& b) { return solve(b, b); }
   Field3D solve(const Field3D& b, const Field3D& x0);
+  FieldPerp solve(const FieldPerp& b) { return solve(b, b); }   ///< invert_laplace.hxx:246
+  FieldPerp solve(const FieldPerp& b, const FieldPerp& x0);     ///< cyclic_laplace.cxx:120-185
   void fill(bout_b200_laplace& L) const;
 
 private:
@@ -582,6 +646,8 @@ private:
   bool pcr_thomas = false;
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
+  void* workspace_perp = nullptr; ///< FieldPerp solves keep their own (the factorisation cache is keyed by workspace)
+  size_t workspace_perp_bytes = 0;
   static std::unique_ptr<Laplacian> instance;
 };
 

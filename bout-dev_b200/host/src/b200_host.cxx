@@ -926,6 +926,138 @@ Field3D& Field3D::operator/=(const Field3D& r) { return *this = *this / r; }
 Field3D& Field3D::operator/=(const Field2D& r) { return *this = *this / r; }
 Field3D& Field3D::operator/=(BoutReal r) { return *this = *this / r; }
 
+// ======================================================================================================
+// FieldPerp (reference include/bout/fieldperp.hxx, src/field/fieldperp.cxx, generated_fieldops.cxx)
+// ======================================================================================================
+namespace {
+bout_b200_grid perpGridOf(const FieldBase& f) {
+  Mesh* m = f.getMesh();
+  return bout_b200_grid{m->LocalNx, 1, m->LocalNz, m->xstart, m->xend, 0, 0};
+}
+// out = sum of terms over the whole plane; every operand is an [nx][nz] array (a "3D" field with ny = 1)
+void ewp(FieldPerp& out, std::initializer_list<bout_b200_ewterm> terms) {
+  const auto g = perpGridOf(out);
+  std::vector<bout_b200_ewterm> t(terms);
+  check(bout_b200_elementwise(&g, BOUT_B200_RGN_ALL, static_cast<int>(t.size()), t.data(), out.wptr(), nullptr));
+}
+FieldPerp perpLike(const FieldPerp& a) {
+  FieldPerp r(a.getMesh(), CELL_CENTRE, a.getIndex());
+  r.allocate();
+  return r;
+}
+} // namespace
+
+FieldPerp::FieldPerp(Mesh* m, CELL_LOC, int yindex_in) : yindex(yindex_in) { fieldmesh = m; }
+FieldPerp::FieldPerp(BoutReal v, Mesh* m) {
+  fieldmesh = m;
+  *this = v;
+}
+int FieldPerp::getNx() const { return getMesh()->LocalNx; }
+int FieldPerp::getNz() const { return getMesh()->LocalNz; }
+size_t FieldPerp::size() const { return static_cast<size_t>(getNx()) * getNz(); }
+FieldPerp& FieldPerp::allocate() {
+  makeUnique(size());
+  return *this;
+}
+double* FieldPerp::wptr() {
+  makeUnique(size());
+  data->syncToDevice();
+  data->mirror = bout::b200::Block::none; // the device copy is about to change
+  return data->ptr;
+}
+FieldPerp& FieldPerp::operator=(BoutReal v) {
+  data = bout::b200::acquire(size());
+  ewp(*this, {term(v)});
+  return *this;
+}
+void FieldPerp::setHost(const double* v) {
+  data = bout::b200::acquire(size());
+  check(bout_b200_memcpy_h2d(data->ptr, v, size() * sizeof(double), nullptr));
+}
+std::vector<double> FieldPerp::getHost() const {
+  requireData(*this, "FieldPerp::getHost");
+  std::vector<double> v(size());
+  check(bout_b200_memcpy_d2h(v.data(), dptr(), size() * sizeof(double), nullptr));
+  return v;
+}
+BoutReal& FieldPerp::operator()(int x, int z) {
+  makeUnique(size());
+  return mirrorOf(data, true, "FieldPerp(x,z)")[static_cast<size_t>(x) * getNz() + z];
+}
+const BoutReal& FieldPerp::operator()(int x, int z) const {
+  return mirrorOf(data, false, "FieldPerp(x,z)")[static_cast<size_t>(x) * getNz() + z];
+}
+
+FieldPerp sliceXZ(const Field3D& f, int y) {
+  requireData(f, "sliceXZ");
+  FieldPerp r(f.getMesh(), CELL_CENTRE, y);
+  const auto g = gridOf(f);
+  check(bout_b200_copy_xz(&g, y, const_cast<double*>(f.dptr()), r.wptr(), 1, nullptr));
+  return r;
+}
+Field3D& Field3D::operator=(const FieldPerp& p) {
+  requireData(p, "Field3D = FieldPerp");
+  const auto g = gridOf(*this);
+  check(bout_b200_copy_xz(&g, p.getIndex(), wptr(), const_cast<double*>(p.dptr()), 0, nullptr));
+  return *this;
+}
+
+#define B200_FP_BINOP(OP, ...)                                  \
+  FieldPerp operator OP(const FieldPerp& a, const FieldPerp& b) { \
+    requireData(a, "FieldPerp operator");                       \
+    requireData(b, "FieldPerp operator");                       \
+    FieldPerp r = perpLike(a);                                  \
+    ewp(r, {__VA_ARGS__});                                      \
+    return r;                                                   \
+  }
+B200_FP_BINOP(+, term(1.0, &a), term(1.0, &b))
+B200_FP_BINOP(-, term(1.0, &a), term(-1.0, &b))
+B200_FP_BINOP(*, term(1.0, &a, false, &b))
+B200_FP_BINOP(/, term(1.0, &a, false, nullptr, false, &b))
+#undef B200_FP_BINOP
+FieldPerp operator+(const FieldPerp& a, const Field3D& b) { return a + sliceXZ(b, a.getIndex()); }
+FieldPerp operator-(const FieldPerp& a, const Field3D& b) { return a - sliceXZ(b, a.getIndex()); }
+FieldPerp operator*(const FieldPerp& a, const Field3D& b) { return a * sliceXZ(b, a.getIndex()); }
+FieldPerp operator/(const FieldPerp& a, const Field3D& b) { return a / sliceXZ(b, a.getIndex()); }
+#define B200_FP_SCALAR(...)                 \
+  {                                         \
+    requireData(f, "FieldPerp operator");   \
+    FieldPerp r = perpLike(f);              \
+    ewp(r, {__VA_ARGS__});                  \
+    return r;                               \
+  }
+FieldPerp operator+(const FieldPerp& f, BoutReal s) B200_FP_SCALAR(term(1.0, &f), term(s))
+FieldPerp operator-(const FieldPerp& f, BoutReal s) B200_FP_SCALAR(term(1.0, &f), term(-s))
+FieldPerp operator*(const FieldPerp& f, BoutReal s) B200_FP_SCALAR(term(s, &f))
+FieldPerp operator/(const FieldPerp& f, BoutReal s) B200_FP_SCALAR(term(1.0 / s, &f)) // generated_fieldops.cxx: * (1 / rhs)
+FieldPerp operator+(BoutReal s, const FieldPerp& f) B200_FP_SCALAR(term(s), term(1.0, &f))
+FieldPerp operator-(BoutReal s, const FieldPerp& f) B200_FP_SCALAR(term(s), term(-1.0, &f))
+FieldPerp operator*(BoutReal s, const FieldPerp& f) B200_FP_SCALAR(term(s, &f))
+FieldPerp operator/(BoutReal s, const FieldPerp& f) B200_FP_SCALAR(term(s, nullptr, false, nullptr, false, &f))
+FieldPerp operator-(const FieldPerp& f) B200_FP_SCALAR(term(-1.0, &f))
+#undef B200_FP_SCALAR
+FieldPerp& FieldPerp::operator+=(const FieldPerp& r) { return *this = *this + r; }
+FieldPerp& FieldPerp::operator-=(const FieldPerp& r) { return *this = *this - r; }
+FieldPerp& FieldPerp::operator*=(const FieldPerp& r) { return *this = *this * r; }
+FieldPerp& FieldPerp::operator/=(const FieldPerp& r) { return *this = *this / r; }
+FieldPerp& FieldPerp::operator+=(BoutReal r) { return *this = *this + r; }
+FieldPerp& FieldPerp::operator-=(BoutReal r) { return *this = *this - r; }
+FieldPerp& FieldPerp::operator*=(BoutReal r) { return *this = *this * r; }
+FieldPerp& FieldPerp::operator/=(BoutReal r) { return *this = *this / r; }
+namespace {
+FieldPerp unaryPerp(int op, const FieldPerp& f, double arg = 0.0) {
+  requireData(f, "FieldPerp function");
+  FieldPerp r = perpLike(f);
+  const auto g = perpGridOf(f);
+  check(bout_b200_unary(&g, op, f.dptr(), arg, r.wptr(), nullptr));
+  return r;
+}
+} // namespace
+FieldPerp sqrt(const FieldPerp& f) { return unaryPerp(1, f); }
+FieldPerp abs(const FieldPerp& f) { return unaryPerp(2, f); }
+FieldPerp exp(const FieldPerp& f) { return unaryPerp(3, f); }
+FieldPerp SQ(const FieldPerp& f) { return unaryPerp(8, f); }
+
 namespace {
 Field3D unaryOp(int op, const Field3D& f, double arg = 0.0) {
   requireData(f, "Field3D function");
@@ -2123,6 +2255,9 @@ Laplacian::~Laplacian() {
   if (workspace != nullptr) {
     bout_b200_free(workspace);
   }
+  if (workspace_perp != nullptr) {
+    bout_b200_free(workspace_perp);
+  }
 }
 
 std::unique_ptr<Laplacian> Laplacian::create(Options* opts, CELL_LOC loc, Mesh* mesh, Solver*) {
@@ -2190,6 +2325,29 @@ Field3D Laplacian::solve(const Field3D& b, const Field3D& x0) {
   // for boundary/guard cells are emptyFrom in the reference; zero-initialised pool blocks here)
   check(bout_b200_laplace_cyclic_solve(&g, &L, b.dptr(), x0.isAllocated() ? x0.dptr() : nullptr, x.wptr(), workspace,
                                        workspace_bytes, nullptr));
+  return x;
+}
+
+FieldPerp Laplacian::solve(const FieldPerp& b, const FieldPerp& x0) {
+  requireData(b, "Laplacian::solve(FieldPerp)");
+  const int jy = b.getIndex();
+  if (jy < 0 || jy >= localmesh->LocalNy) {
+    throw BoutException("Laplacian::solve(FieldPerp): the FieldPerp has no y index");
+  }
+  const auto g = localmesh->grid();
+  bout_b200_laplace L{};
+  fill(L);
+  const size_t need = bout_b200_laplace_cyclic_workspace_perp(&g, &L);
+  if (need > workspace_perp_bytes) {
+    if (workspace_perp != nullptr) {
+      check(bout_b200_free(workspace_perp));
+    }
+    check(bout_b200_malloc(&workspace_perp, need));
+    workspace_perp_bytes = need;
+  }
+  FieldPerp x(localmesh, CELL_CENTRE, jy);
+  check(bout_b200_laplace_cyclic_solve_perp(&g, &L, jy, b.dptr(), x0.isAllocated() ? x0.dptr() : nullptr, x.wptr(),
+                                            workspace_perp, workspace_perp_bytes, nullptr));
   return x;
 }
 

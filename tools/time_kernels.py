@@ -43,6 +43,10 @@ def main():
             rows.append((f"{op}/{d}", t, bpp))
         t = timeit(lambda: capi.bracket_arakawa(g, f, h, dx, dz, out=out), flush=flush)
         rows.append(("bracket_arakawa", t, 24))
+        t = timeit(lambda: capi.elementwise(g, [(2.0, f), (1.0, h, v)], out=out), flush=flush)
+        rows.append(("2a + b*c", t, 32))
+        t = timeit(lambda: capi.ddz_fft(g, f, out=out), flush=flush)
+        rows.append(("DDZ_FFT", t, 16))
         t = timeit(lambda: out.copy_(f), flush=flush)
         rows.append(("torch copy_", t, 16 * f.numel() / npts))
         print(f"== {name}: {npts/1e6:.2f} M interior points")
