@@ -596,3 +596,115 @@ def elmpb_initial_state(g: capi.Grid, device="cuda", amp=1e-5):
     P = 0.3 * amp * env * (torch.cos(z) + 0.1 * torch.sin(2 * z - y))
     Psi = 0.04 * amp * env * (torch.sin(z + 0.5) + 0.1 * torch.cos(4 * z))
     return U.contiguous(), P.contiguous(), Psi.contiguous()
+
+
+class Blob2D:
+    """examples/blob2d/blob2d.cxx rhs() (lines 165-213) with the shipped switches (boussinesq, sheath, not compressible;
+    [all] bndry_all = neumann, mesh:ddz first = C2, Delp2 through FFTs, LaplaceCyclic with the [phiBoussinesq] flags),
+    on a BoutMesh decomposed in X (BASELINE configs[2]): X guard planes of n, omega and phi travel through
+    Mesh::communicate, the tridiagonal solves through reduce -> all-gather of the interface rows -> finish
+    (CyclicReduce across NXPE ranks, cyclic_reduction.hxx:215-440)."""
+
+    def __init__(self, g: capi.Grid, metric: dict, Te0=5.0, B0=0.35, D_n=1e-6, D_vort=1e-6, R_c=1.5, L_par=10.0,
+                 e=1.602e-19, m_i=2 * 1.667e-27, flags=(0, 0, 0), device="cuda", mesh=None):
+        self.g, self.dev, self.mesh = g, torch.device(device), mesh
+        self.md = {k: v.to(self.dev) for k, v in metric.items()}
+        Omega_i = e * B0 / m_i                     # blob2d.cxx:80-82
+        c_s = (e * Te0 / m_i) ** 0.5
+        self.rho_s = c_s / Omega_i
+        self.D_n, self.D_vort, self.R_c, self.L_par = D_n, D_vort, R_c, L_par
+        self.first_x = mesh is None or mesh.first_x
+        self.last_x = mesh is None or mesh.last_x
+        self.x_split = mesh is not None and mesh.nxpe > 1
+        zl = float(self.md["dz"][0, 0].item()) * g.nz
+        self.lap = capi.Laplace(g, self.md, zl, all_terms=True, nonuniform=True, flags=flags,
+                                first_x=self.first_x, last_x=self.last_x)
+        self.lap.workspace(self.dev)
+        self.delp = capi.Laplace(g, self.md, zl, all_terms=True, nonuniform=True)   # Delp2's default Laplacian
+        self.rdz = (1.0 / self.md["dz"]).contiguous()
+        if self.x_split:
+            nif = self.lap.iface_doubles()
+            self.iface = torch.empty(nif, dtype=torch.float64, device=self.dev)
+            self.iface_all = torch.empty(nif * mesh.nxpe, dtype=torch.float64, device=self.dev)
+        z = lambda: torch.zeros(g.shape3, dtype=torch.float64, device=self.dev)
+        self.n, self.omega, self.phi = z(), z(), z()
+        self.ddt_n, self.ddt_omega = z(), z()
+        self._t = [z() for _ in range(5)]      # bracket x 2, DDZ(n), Delp2 x 2
+
+    def set_state(self, n, omega):
+        self.n.copy_(n)
+        self.omega.copy_(omega)
+
+    def _bc(self, f):                          # bndry_all = neumann (Solver::pre_rhs)
+        if self.first_x:
+            capi.boundary(self.g, "neumann", "xin", f, spacing=self.md["dx"])
+        if self.last_x:
+            capi.boundary(self.g, "neumann", "xout", f, spacing=self.md["dx"])
+
+    def _comm(self, fields):
+        if self.mesh is not None:
+            self.mesh.communicate(fields)      # ny = 1, MYG = 0: X guard planes only
+
+    def rhs(self, n=None, omega=None):
+        g = self.g
+        n = self.n if n is None else n
+        omega = self.omega if omega is None else omega
+        ew = capi.elementwise
+        self._bc(n)
+        self._bc(omega)
+        self._comm([n, omega])                                            # :169
+        if not self.x_split:                                              # phi = phiSolver->solve(omega)  :181
+            self.lap.solve(omega, out=self.phi)
+        else:
+            self.lap.reduce(omega, iface=self.iface)
+            self.mesh.all_gather_x(self.iface, self.iface_all)
+            self.lap.finish(self.iface_all, self.mesh.nxpe, self.mesh.pe_xind, self.phi)
+        self._comm([self.phi])                                            # :184
+        bn, bo, dzn, d2n, d2o = self._t
+        dx, dz = self.md["dx"], self.md["dz"]
+        capi.bracket_arakawa(g, self.phi, n, dx, dz, out=bn)
+        capi.bracket_arakawa(g, self.phi, omega, dx, dz, out=bo)
+        capi.stencil(g, "DDX_C2", "Z", n, scale1=self.rdz, out=dzn)
+        self.delp.delp2(n, out=d2n)
+        self.delp.delp2(omega, out=d2o)
+        curv, sh = 2.0 * self.rho_s / self.R_c, self.rho_s / self.L_par
+        # ddt(n) = -bracket(phi, n) + 2 DDZ(n) rho_s/R_c + D_n Delp2(n) + n phi rho_s/L_par          :189-200
+        ew(g, [(-1.0, bn), (curv, dzn), (self.D_n, d2n), (sh, n, self.phi)], out=self.ddt_n, region="RGN_NOBNDRY")
+        # ddt(omega) = -bracket(phi, omega) + 2 DDZ(n) rho_s/R_c / n + D_vort Delp2(omega) / n + phi rho_s/L_par
+        ew(g, [(-1.0, bo), (curv, dzn, None, n), (self.D_vort, d2o, None, n), (sh, self.phi)], out=self.ddt_omega,
+           region="RGN_NOBNDRY")
+
+    def rk4_step(self, dt):
+        """RK4Solver::take_step (rk4.cxx:172-210)."""
+        g = self.g
+        if not hasattr(self, "_rk"):
+            self._rk = [[torch.zeros_like(self.n) for _ in range(2)] for _ in range(5)]   # k1..k4, stage state
+        k1, k2, k3, k4, st = self._rk
+        state = (self.n, self.omega)
+        keep = (self.ddt_n, self.ddt_omega)
+        try:
+            for src, k, coef in ((state, k1, 0.5), (st, k2, 0.5), (st, k3, 1.0), (st, k4, None)):
+                self.ddt_n, self.ddt_omega = k
+                self.rhs(*src)
+                if coef is not None:
+                    for i in range(2):
+                        capi.rk_stage(g, "axpy", coef * dt, state[i], k[i], out=st[i])
+        finally:
+            self.ddt_n, self.ddt_omega = keep
+        for i in range(2):
+            capi.rk_stage(g, "rk4_final", dt, state[i], k1[i], k2[i], k3[i], k4[i], out=state[i])
+
+
+def blob2d_initial_state(g: capi.Grid, mesh=None, device="cuda", height=0.5, width=0.05, gnx=None):
+    """[n] function = 1 + height exp(-((x-0.25)/width)^2 - ((z/(2 pi) - 0.5)/width)^2), omega = 0
+    (examples/blob2d/delta_1/BOUT.inp); x = GlobalX of the decomposed mesh."""
+    jx = torch.arange(g.nx, dtype=torch.float64, device=device)
+    if mesh is not None:
+        jx = jx + mesh.pe_xind * mesh.mxsub
+        gnx = mesh.nxpe * mesh.mxsub + 2 * mesh.mxg
+    gnx = g.nx if gnx is None else gnx
+    x = ((jx - g.xstart + 0.5) / (gnx - 2 * g.xstart))[:, None, None]
+    z = (torch.arange(g.nz, dtype=torch.float64, device=device) / g.nz)[None, None, :]
+    n = 1.0 + height * torch.exp(-((x - 0.25) / width) ** 2 - ((z - 0.5) / width) ** 2)
+    n = n.expand(g.nx, g.ny, g.nz).contiguous()
+    return n, torch.zeros_like(n)

@@ -51,6 +51,7 @@ def main():
     ok = hw3d_y_check(pkg, dev, rank, world, gold) and ok
     ok = hw3d_ypeer_check(pkg, dev, rank, world) and ok
     ok = elmpb_check(pkg, dev, rank, world) and ok
+    ok = blob2d_x_check(pkg, dev, rank, world, gold) and ok
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.barrier()
@@ -92,6 +93,39 @@ def hw3d_ypeer_check(pkg, dev, rank, world):
     big = float(res["1"][0].abs().max())
     print(f"rank {rank}/{world} (ypeer vs exchange kernels, NYPE={world}): bitwise equal {same}, max |n| {big:.3f}", flush=True)
     return same and big > 0.1 and all(bool(torch.isfinite(t).all()) for t in res["1"])
+
+
+def blob2d_x_check(pkg, dev, rank, world, gold):
+    """BASELINE configs[2]: models.Blob2D on NXPE = N ranks (X guard planes through Mesh::communicate, the tridiagonal
+    solves through reduce -> all-gather -> finish) against the reference's single-rank run of the unchanged
+    examples/blob2d source: one RHS (1e-10) and the 5-step RK4 trajectory (1e-8)."""
+    capi, models, meshmod = pkg.capi, pkg.models, pkg.mesh
+    gnx, gny, nz, mxg, myg = [int(v) for v in gold["blob2d_grid"]]
+    MX = gnx - 2 * mxg
+    if MX % world != 0 or MX // world < mxg:
+        return True
+    mxsub = MX // world
+    mesh = meshmod.BoutMesh(world, 1, rank, mxsub, gny - 2 * myg, nz, mxg, myg, periodic_x=False, periodic_y=True, device=dev)
+    sl = slice(rank * mxsub, rank * mxsub + mxsub + 2 * mxg)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(dev)
+    metric = {n: t(gold[f"blob2d_metric_{n}"]) for n in ("dx", "dy", "dz", "J", "g_22", "g11", "g33", "g13", "G1", "G3",
+                                                          "d1_dx", "g_11")}
+    m = models.Blob2D(mesh.grid, metric, Te0=5.0, B0=0.35, D_n=1e-6, D_vort=1e-6, R_c=1.5, L_par=10.0, device=dev, mesh=mesh)
+    I = mesh.grid.interior
+    n0, _ = models.blob2d_initial_state(mesh.grid, mesh=mesh, device=dev, height=0.5, width=0.1)
+    e0 = rel_err(n0.cpu().numpy(), gold["blob2d_init_n"][sl], I)
+    m.set_state(t(gold["blob2d_init_n"]), t(gold["blob2d_init_omega"]))
+    m.rhs()
+    errs = [rel_err(m.ddt_n.cpu().numpy(), gold["blob2d_ddt_n"][sl], I), rel_err(m.ddt_omega.cpu().numpy(), gold["blob2d_ddt_omega"][sl], I)]
+    dt, nsteps = gold["blob2d_dt_nsteps"]
+    m.set_state(t(gold["blob2d_init_n"]), t(gold["blob2d_init_omega"]))
+    for _ in range(int(nsteps)):
+        m.rk4_step(float(dt))
+    errs += [rel_err(m.n.cpu().numpy(), gold["blob2d_final_n"][sl], I), rel_err(m.omega.cpu().numpy(), gold["blob2d_final_omega"][sl], I)]
+    ok = e0 < 1e-13 and max(errs[:2]) < 1e-10 and max(errs[2:]) < 1e-8
+    print(f"rank {rank}/{world}: blob2d NXPE={world}: init {e0:.1e}; ddt err {errs[0]:.2e} {errs[1]:.2e}; trajectory err "
+          f"{errs[2]:.2e} {errs[3]:.2e}", flush=True)
+    return ok
 
 
 def hw3d_y_check(pkg, dev, rank, world, gold):

@@ -46,6 +46,29 @@ def test_hw3d_rhs_and_rk4_trajectory(capi, gold):
     assert rel_err(m.vort.cpu().numpy(), gold["hw3d_final_vort"], I) < 1e-8
 
 
+def test_blob2d_harness_rhs_and_rk4_trajectory(capi, gold):
+    """models.Blob2D (the operator sequence of examples/blob2d/blob2d.cxx:165-213 through the C-ABI; the model bench.py
+    decomposes in X for configs[2]) against the reference build's run of the unchanged source: initial profile,
+    one Solver::run_rhs (1e-10) and the 5-step RK4 trajectory (1e-8)."""
+    import __graft_entry__ as ge
+    models = ge.load_package().models
+    g = capi.Grid(*[int(v) for v in gold["blob2d_grid"]])
+    m = models.Blob2D(g, metric(gold, "blob2d"), Te0=5.0, B0=0.35, D_n=1e-6, D_vort=1e-6, R_c=1.5, L_par=10.0)
+    I = (slice(g.xstart, g.xend + 1), slice(g.ystart, g.yend + 1), slice(None))
+    n0, o0 = models.blob2d_initial_state(g, height=0.5, width=0.1)
+    assert rel_err(n0.cpu().numpy(), gold["blob2d_init_n"], I) < 1e-13
+    m.set_state(dev(gold["blob2d_init_n"]), dev(gold["blob2d_init_omega"]))
+    m.rhs()
+    assert rel_err(m.ddt_n.cpu().numpy(), gold["blob2d_ddt_n"], I) < 1e-10
+    assert rel_err(m.ddt_omega.cpu().numpy(), gold["blob2d_ddt_omega"], I) < 1e-10
+    dt, nsteps = gold["blob2d_dt_nsteps"]
+    m.set_state(dev(gold["blob2d_init_n"]), dev(gold["blob2d_init_omega"]))
+    for _ in range(int(nsteps)):
+        m.rk4_step(float(dt))
+    assert rel_err(m.n.cpu().numpy(), gold["blob2d_final_n"], I) < 1e-8
+    assert rel_err(m.omega.cpu().numpy(), gold["blob2d_final_omega"], I) < 1e-8
+
+
 @pytest.mark.parametrize("nz", [16, 128])
 def test_hw3d_guard_cells_written_by_the_producing_kernels(capi, gold, nz, monkeypatch):
     """bout_b200_hw3d_rhs_guards / bout_b200_laplace.wrap_yguards: the x guard cells (Dirichlet of Solver::pre_rhs) and
