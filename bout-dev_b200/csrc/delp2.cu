@@ -11,6 +11,7 @@
 
 #include "bracket.cuh"
 #include "fft_fast.cuh"
+#include "fft_reg.cuh"
 #include "laplace_coefs.cuh"
 
 namespace b200 {
@@ -210,6 +211,113 @@ int launchDelp2Fast(Delp2FftParams p, cudaStream_t s) {
   return 0;
 }
 
+// Register-transform path (nz in {128, 256, 512}): no march.  A CTA takes ROWS = NT / T consecutive x rows of one y
+// (the first and the last are the x - 1 / x + 1 neighbours of the ROWS - 2 rows it produces), every row group of T
+// threads transforms its row in registers (fft_reg.cuh: one shared-memory exchange per transform) and leaves the
+// spectrum in the row's buffer; after ONE CTA barrier each group forms the packed input of its inverse transform
+// straight from the three neighbouring spectra, a X[x-1] + b X[x] + c X[x+1] for bins k and N - k, and transforms
+// back.  2 / ROWS of the forward transforms are redundant (6 % at nz = 256); shared memory holds only the spectra.
+template <int N, int NT>
+__global__ void __launch_bounds__(NT) k_delp2_reg(const Delp2FftParams p) {
+  using F = RegFft<N>;
+  constexpr int T = F::T, B = F::B, SROW = F::SROW, ROWS = NT / T, OUTR = ROWS - 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* S = reinterpret_cast<cd*>(smem_raw);
+  const int tid = threadIdx.x, grp = tid / T, t = tid % T;
+  const int ntile = p.nchunks;
+  const int y = p.ys + blockIdx.x / ntile;
+  const int x = p.xs + (blockIdx.x % ntile) * OUTR - 1 + grp; // this group's row
+  const bool have = x <= p.xe + 1;
+  cd* row = S + grp * SROW;
+  const long long plane = static_cast<long long>(p.ny) * p.nz;
+  cd v[B];
+  if (have) {
+    const double2* __restrict__ s2 =
+        reinterpret_cast<const double2*>(p.f + x * plane + static_cast<long long>(y) * p.nz);
+#pragma unroll
+    for (int n2 = 0; n2 < B; ++n2) {
+      const double2 q = B200_LDG(s2 + t + T * n2);
+      v[n2] = {q.x, q.y};
+    }
+  } else {
+#pragma unroll
+    for (int n2 = 0; n2 < B; ++n2) {
+      v[n2] = {0.0, 0.0};
+    }
+  }
+  regfftStage1<N, false>(v, p.tw, t);
+  regfftXchgWrite<N>(v, row, t);
+  __syncwarp();
+  regfftStage2<N, false>(v, row, t);
+  __syncwarp();
+  regfftSplitWriteZ<N>(v, row, t);
+  __syncwarp();
+  {
+    cd pc[B / 2 + 1];
+    regfftSplitReadPartners<N>(pc, row, t);
+    __syncwarp();
+    regfftSplitWriteX<N>(v, pc, row, p.tw, t);
+  }
+  __syncthreads();
+  const bool produce = grp >= 1 && grp <= OUTR && x <= p.xe;
+  if (produce) {
+    double k5[5];
+    tridagCoef5(p.m, x, y, false, false, k5);
+    const double kscale = 2.0 * M_PI / p.m.zlength; // invert_laplace.cxx:263
+    const cd *Xm = row - SROW, *X0 = row, *Xp = row + SROW;
+    auto bin = [&](int k) -> cd {
+      cd a, b, c;
+      coefsFromK(k5, k * kscale, a, b, c);
+      return cadd(cadd(cmul(a, Xm[k]), cmul(b, X0[k])), cmul(c, Xp[k]));
+    };
+    const cd ws = ldtw(p.tw, t);
+#pragma unroll
+    for (int n2 = 0; n2 < B; ++n2) { // regfftMergeRead with the combined spectrum as its input
+      const int k = t + T * n2;
+      cd xk = bin(k);
+      cd xc = cconj(bin(N - k));
+      if (k == 0) { // imaginary parts of DC and Nyquist are ignored (FFTW c2r)
+        xk.im = 0.0;
+        xc.im = 0.0;
+      }
+      const cd wk = cconj(regfftSplitTw<N>(ws, n2));
+      const cd d = cmul(wk, csub(xk, xc));
+      v[n2] = cadd(cadd(xk, xc), cd{-d.im, d.re});
+    }
+  }
+  __syncthreads(); // every group has read its neighbours' spectra: the buffers become exchange areas again
+  if (!produce) {
+    return;
+  }
+  regfftStage1<N, true>(v, p.tw, t);
+  regfftXchgWrite<N>(v, row, t);
+  __syncwarp();
+  regfftStage2<N, true>(v, row, t);
+  double2* __restrict__ d2 = reinterpret_cast<double2*>(p.out + x * plane + static_cast<long long>(y) * p.nz);
+#pragma unroll
+  for (int q = 0; q < B; ++q) {
+    d2[t + T * q] = make_double2(v[q].re, v[q].im);
+  }
+}
+
+template <int N, int NT>
+int launchDelp2Reg(Delp2FftParams p, cudaStream_t s) {
+  using F = RegFft<N>;
+  constexpr int ROWS = NT / F::T, OUTR = ROWS - 2;
+  const int len = p.xe - p.xs + 1, nyb = p.ye - p.ys + 1;
+  p.nchunks = (len + OUTR - 1) / OUTR;
+  const size_t smem = static_cast<size_t>(ROWS) * F::SROW * sizeof(cd);
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k_delp2_reg<N, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    configured = true;
+  }
+  k_delp2_reg<N, NT><<<static_cast<unsigned>(nyb) * p.nchunks, NT, smem, s>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 struct Delp2FdParams {
   const double* __restrict__ f;
   const double* __restrict__ dx;
@@ -321,8 +429,19 @@ extern "C" int bout_b200_delp2_fft(const bout_b200_grid* g, const bout_b200_lapl
   if (st != 0) {
     return st;
   }
-  if ((g->nz == 128 || g->nz == 256 || g->nz == 512 || g->nz == 1024) && aligned16(f) && aligned16(out)
-      && getenv("BOUT_B200_NO_FAST_FFT") == nullptr) {
+  const bool fast_ok = aligned16(f) && aligned16(out) && getenv("BOUT_B200_NO_FAST_FFT") == nullptr;
+  static const bool no_reg = getenv("BOUT_B200_DELP2_REG") != nullptr && getenv("BOUT_B200_DELP2_REG")[0] == '0';
+  // enough (y, x-tile) CTAs for the machine: the register path has no march, so 2-D (ny = 1) problems keep the
+  // marching kernel, whose tasks shrink with the problem
+  if (fast_ok && !no_reg && (g->nz == 128 || g->nz == 256 || g->nz == 512)
+      && static_cast<long long>(g->yend - g->ystart + 1) * (g->xend - g->xstart + 1) >= 148LL * 30) {
+    switch (g->nz / 2) {
+    case 64: return launchDelp2Reg<64, 256>(p, s);
+    case 128: return launchDelp2Reg<128, 256>(p, s);
+    default: return launchDelp2Reg<256, 256>(p, s);
+    }
+  }
+  if ((g->nz == 128 || g->nz == 256 || g->nz == 512 || g->nz == 1024) && fast_ok) {
     switch (g->nz / 2) {
     case 64: return launchDelp2Fast<64>(p, s);
     case 128: return launchDelp2Fast<128>(p, s);

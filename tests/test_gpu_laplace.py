@@ -43,6 +43,24 @@ def test_delp2_fft(capi, orc, port, grid, trivial):
         assert rel_err(got, want, g.interior) < 1e-12
 
 
+# enough (x, y) rows for the register-transform kernel (k_delp2_reg: tiles of 30 / 14 / 30 produced rows per CTA, so
+# these row counts leave a partly filled last tile), checked against the marching kernel as well
+@pytest.mark.parametrize("grid", [(156, 40, 128, 2, 2), (131, 44, 256, 2, 2), (321, 18, 512, 2, 1)])
+def test_delp2_fft_register_transform_path(capi, orc, port, grid, monkeypatch):
+    g, og = capi.Grid(*grid), orc.Grid(*grid)
+    m = make_metric(orc, g.shape2, g.nz)
+    (f,) = seeded_fields(g.shape3, 1)
+    for all_terms, nonuni in ((True, m.non_uniform), (False, False)):
+        want = port.delp2_fft(og, m, f, all_terms=all_terms, nonuniform=nonuni)
+        lap = gpu_laplace(capi, g, m, all_terms=all_terms, nonuniform=nonuni)
+        out = torch.full(g.shape3, 7.0, dtype=torch.float64, device="cuda")
+        got = lap.delp2(dev(f), out=out).cpu().numpy()
+        assert rel_err(got, want, g.interior) < 1e-12
+        guard = np.ones(g.shape3, dtype=bool)
+        guard[g.interior] = False
+        assert np.all(got[guard] == 7.0)          # nothing outside the region is written
+
+
 @pytest.mark.parametrize("grid", GRIDS)
 def test_delp2_fd_matches_composed_reference_operators(capi, orc, port, grid):
     """useFFT=false branch: G1*DDX + G3*DDZ + g11*D2DX2 + g33*D2DZ2 + 2*g13*D2DXDZ
