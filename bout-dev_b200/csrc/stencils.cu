@@ -261,8 +261,10 @@ int launchStencil(const StencilParams& p, int dir, cudaStream_t stream) {
     const long long north =
         static_cast<long long>(dir == BOUT_B200_X ? (p.ye - p.ys + 1) : (p.xe - p.xs + 1)) * nzv;
     // chunk: as long as possible (less halo re-read) while still filling the machine
-    int chunk = 8;
-    for (int c : {64, 32, 16}) {
+    // (measured at 256x64x256, profiles/r02ah_micro_chunk.log: chunks of 4 beat 8 -- two waves of CTAs instead of a
+    // partial one -- while 16 and 32 lose 20-40 %)
+    int chunk = 4;
+    for (int c : {64, 32, 16, 8}) {
       if (north * ((len + c - 1) / c) >= 148LL * 2048) {
         chunk = c;
         break;
