@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) k_bracket_arakawa(const BracketParams p) 
       Gp = loadRow4<VEC>(p.g + (x + 1) * plane + rowoff, z, p.nz);
     }
     const long long i2 = static_cast<long long>(x) * p.ny + y;
-    const double spacingFactor = 1.0 / (12 * __ldg(p.dz + i2) * __ldg(p.dx + i2));
+    // 1 / (12 dz dx), difops.cxx:961: dx, dz > 0, so the Newton-refined hardware reciprocal applies (<= 2 ulp)
+    const double spacingFactor = rcpPositive(12 * __ldg(p.dz + i2) * __ldg(p.dx + i2));
     Vz<VEC> r;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -89,8 +90,8 @@ int launchBracket(const bout_b200_grid* g, const double* f, const double* gg, co
   const int nzv = vec2 ? g->nz / 2 : g->nz;
   const long long north = static_cast<long long>(p.ye - p.ys + 1) * nzv;
   const int len = p.xe - p.xs + 1;
-  int chunk = 8;
-  for (int c : {64, 32, 16}) {
+  int chunk = 4;
+  for (int c : {64, 32, 16, 8}) {
     if (north * ((len + c - 1) / c) >= 148LL * 2048) {
       chunk = c;
       break;

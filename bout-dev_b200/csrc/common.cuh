@@ -151,4 +151,16 @@ inline long long haloTimeoutCycles() {
   return cycles;
 }
 
+// Reciprocal of a normal, non-zero double (the callers' arguments are bounded away from 0 by construction): hardware
+// seed (rcp.approx.ftz.f64, the upper word only) + two Newton steps = 1 MUFU + 4 DFMA, <= 2 ulp, instead of the IEEE
+// division sequence with its special-case path (~25 issue slots).
+__device__ __forceinline__ double rcpPositive(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
 } // namespace b200

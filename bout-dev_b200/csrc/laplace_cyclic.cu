@@ -319,7 +319,14 @@ __global__ void __launch_bounds__(128) k_lap_thomas(const LapParams p, const boo
 // systems, so solutions agree with the reference's CyclicReduce to round-off (tests: 1e-10).  Periodic-X systems
 // (one rank, n a power of two) wrap the row indices; after the last step (s = n/2) a row's a and c refer to
 // x_i itself.
-__global__ void __launch_bounds__(256) k_lap_pcr(const LapParams p) {
+constexpr int LAP_PCR_NT = 512; // the 8 n complex numbers of a system allow one CTA per SM anyway: make it a wide one
+// 1 / z through the Newton-refined hardware reciprocal (common.cuh): each row inverts two pivots in each of the
+// log2 n steps
+__device__ __forceinline__ cd crecipFast(cd z) {
+  const double d = rcpPositive(z.re * z.re + z.im * z.im);
+  return {z.re * d, -z.im * d};
+}
+__global__ void __launch_bounds__(LAP_PCR_NT) k_lap_pcr(const LapParams p) {
   extern __shared__ __align__(16) unsigned char pcr_raw[];
   const int n = p.bd.xe - p.bd.xs + 1;
   const bool periodic = p.bd.periodic_x != 0; // single rank, n a power of two (checked by the host)
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(256) k_lap_pcr(const LapParams p) {
       if (im >= 0) {
         const cd bm = in[1][im];
         bad = bad || tiny(bm);
-        const cd k1 = cmul(a, crecip(bm));
+        const cd k1 = cmul(a, tiny(bm) ? crecip(bm) : crecipFast(bm));
         an = cmul(in[0][im], k1);
         an = {-an.re, -an.im};
         b = csub(b, cmul(in[2][im], k1));
@@ -378,7 +385,7 @@ __global__ void __launch_bounds__(256) k_lap_pcr(const LapParams p) {
       if (ip < n) {
         const cd bp = in[1][ip];
         bad = bad || tiny(bp);
-        const cd k2 = cmul(c, crecip(bp));
+        const cd k2 = cmul(c, tiny(bp) ? crecip(bp) : crecipFast(bp));
         cn = cmul(in[2][ip], k2);
         cn = {-cn.re, -cn.im};
         b = csub(b, cmul(in[0][ip], k2));
@@ -393,7 +400,7 @@ __global__ void __launch_bounds__(256) k_lap_pcr(const LapParams p) {
     cur ^= 1;
   }
   // every row is now decoupled: its remaining a and c multiply x_i itself (periodic, s = n) or are zero
-  __shared__ double psum[256];
+  __shared__ double psum[LAP_PCR_NT];
   double part = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const cd b = cadd(cadd(buf[cur][0][i], buf[cur][1][i]), buf[cur][2][i]);
@@ -1267,7 +1274,7 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
                                         static_cast<int>(pcr_smem)));
       pcr_attr = pcr_smem;
     }
-    k_lap_pcr<<<static_cast<unsigned>(plan.nsys), 256, pcr_smem, s>>>(p);
+    k_lap_pcr<<<static_cast<unsigned>(plan.nsys), nrows_sys > 256 ? LAP_PCR_NT : 256, pcr_smem, s>>>(p);
     B200_LAUNCH_OK();
   } else if (!lapCoupled(L)) {
     k_lap_thomas<<<sblocks, 128, plan.tab_smem, s>>>(p, plan.tab_smem != 0);

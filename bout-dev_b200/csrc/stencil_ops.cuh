@@ -32,17 +32,7 @@ __device__ __forceinline__ double sq(double x) { return x * x; }
 // here w = b^2 / (b^2 + 2 a^2) -- the same number with ONE fp64 division instead of two (fp64
 // division is ~25 DFMA slots on sm_100 and made this stencil compute-bound); the two forms differ
 // by a few ulp, far inside the 1e-12 parity tolerance.
-// That one division is a reciprocal of a positive normal number (>= kWenoSmall^2): hardware seed
-// (rcp.approx.ftz.f64, the upper word only) + two Newton steps = 1 MUFU + 4 DFMA, <= 2 ulp, instead of
-// the IEEE division sequence with its special-case path (the fused elm-pb kernel evaluates six of these per point).
-__device__ __forceinline__ double rcpPositive(double d) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  return fma(r, e, r);
-}
+// That one division goes through rcpPositive (common.cuh): the fused elm-pb kernel evaluates six of these per point.
 // The derivative factor of VDDX_WENO3 for one upwind direction (positive = velocity > 0); weno3(vc, f) = vc * it.
 __device__ __forceinline__ double weno3Deriv(bool positive, const St& f) {
   double deriv, a;
