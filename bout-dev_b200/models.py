@@ -328,6 +328,8 @@ class ELMpb:
         self.two_streams = os.environ.get("BOUT_B200_ELM_STREAMS", "2") != "1"
         self.mode_slices = os.environ.get("BOUT_B200_ELM_MODES", "1") != "0"
         self._side = None
+        self._side2 = None
+        self.three_streams = os.environ.get("BOUT_B200_ELM_STREAMS", "2") == "3"   # measured: 1.003 ms vs 0.966 ms with two
         self.kernel_events = None     # bench.py: (start, end) CUDA events of the fused kernel
         e3 = self.eq["eta"]
         self.eta2d = e3[:, :, 0].contiguous() if (e3.dim() == 3 and bool((e3 == e3[:, :, :1]).all())) else None
@@ -448,26 +450,36 @@ class ELMpb:
             (sphi,) = self._comm_into([self.phi], ["phi"])
             capi.boundary(g, "extend", "xin", self.phi)                           # :1498-1516
             capi.boundary(g, "extend", "xout", self.phi)
+        # The current chain (Delp2(Psi) -> BC -> communicate -> smooth_x -> ... -> row mode of Jpar: nine short launches
+        # that depend on each other) is issued first; BOUT_B200_ELM_STREAMS=3 puts it on a third stream beside the
+        # slice / row-mode kernels of the main one (no gain measured: the GPU is busy, not waiting)
+        three = two and modes and self.three_streams
+        if three:
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=self.dev)
+            self._side2.wait_stream(main)
+        with (torch.cuda.stream(self._side2) if three else contextlib.nullcontext()):
+            # Jpar = Delp2(Psi); BC; communicate; smooth_x; BC; communicate         :1518-1563
+            self.delp.delp2(Psi, out=self.Jpar)
+            self._bc_j(self.Jpar)
+            self._halo([self.Jpar])
+            sm = capi.smooth_x(g, self.Jpar, out=buf["sm"])
+            self._halo([sm])                                                      # smooth_x communicates its result
+            buf["sm"], self.Jpar = self.Jpar, sm                                  # Jpar = smooth_x(Jpar)
+            self._bc_j(self.Jpar)
+            if modes:
+                self._halo([self.Jpar])
+                capi.row_mode(g, [self.Jpar], self.filter_z_mode, out=[buf["mJ"]])
+                sJ = None
         if modes:
             sPsi = self._slices_into(Psi, "Psi")
             capi.row_mode(g, [U, P], self.filter_z_mode, out=[buf["mU"], buf["mP"]])
             sU = sP = None
         else:
             sU, sP, sPsi = [self._slices_into(f, n) for f, n in ((U, "U"), (P, "P"), (Psi, "Psi"))]
-        # Jpar = Delp2(Psi); BC; communicate; smooth_x; BC; communicate         :1518-1563
-        self.delp.delp2(Psi, out=self.Jpar)
-        self._bc_j(self.Jpar)
-        self._halo([self.Jpar])
-        sm = capi.smooth_x(g, self.Jpar, out=buf["sm"])
-        self._halo([sm])                                                      # smooth_x communicates its result
-        buf["sm"], self.Jpar = self.Jpar, sm                                  # Jpar = smooth_x(Jpar)
-        self._bc_j(self.Jpar)
-        if modes:
-            self._halo([self.Jpar])
-            capi.row_mode(g, [self.Jpar], self.filter_z_mode, out=[buf["mJ"]])
-            sJ = None
-        else:
             (sJ,) = self._comm_into([self.Jpar], ["J"])
+        if three:
+            main.wait_stream(self._side2)
         # Delp2(Jpar): Jpar2 (:1565-1572) and the hyper-resistivity term (:1717-1723) evaluate the same field.
         # With a z-independent eta the term is linear with z-independent coefficients, so (after filter_z) the
         # fused kernel forms mode n0 of Delp2(Jpar) from the row modes of Jpar and the full-field pass is skipped
