@@ -271,6 +271,26 @@ struct Block {
     const Block* b = nullptr;
     unsigned long long a_ver = 0, b_ver = 0;
   } recipe;
+  /// Expression fusion: the result of Field3D algebra is not computed when the operator returns.  The block keeps the
+  /// combination it stands for, contents == sum_i coef_i * f1_i * f2_i / dv_i over the whole array (the term form of
+  /// bout_b200_elementwise), with handles on the operand blocks; a following operator that can absorb those terms
+  /// builds a longer combination instead of reading this block, and the ONE kernel launch happens when the device
+  /// pointer of a block is first asked for (FieldBase::dptr / wptr, the host mirror).  `ddt(n) = -bracket(phi, n)
+  /// + 2 * DDZ(n) * c + D * Delp2(n)` is then one pass over its three operator results instead of five passes with
+  /// four temporaries (the reference: one loop per operator, src/field/generated_fieldops.cxx).
+  struct LazyTerm {
+    double coef = 0.0;
+    std::shared_ptr<Block> f1, f2, dv;
+    bool f1_2d = false, f2_2d = false, dv_2d = false;
+  };
+  std::vector<LazyTerm> pending;
+  /// Blocks whose pending combination reads this one.  They are launched before this block is written (makeUnique), so
+  /// that they see the contents they were built from and their handles do not force a copy-on-write of a block that
+  /// is about to be updated in place (Mesh::communicate, boundary conditions, the integrators' stage updates).
+  std::vector<std::weak_ptr<Block>> dependents;
+  void launchDependents();
+  int pgrid[7] = {0, 0, 0, 0, 0, 0, 0}; ///< bout_b200_grid of the pending launch
+  void ensure();       ///< launch the pending combination, if any (operands first)
   void syncToHost();   ///< device -> host if the mirror is not current
   void syncToDevice(); ///< host -> device if host code wrote through the mirror
   ~Block();
@@ -337,6 +357,9 @@ public:
     if (!data) {
       return nullptr;
     }
+    if (!data->pending.empty()) {
+      data->ensure();
+    }
     if (data->mirror == bout::b200::Block::host_newer) {
       data->syncToDevice();
     }
@@ -344,6 +367,7 @@ public:
   }
   std::string name;
   bout::b200::Block* block() const { return data.get(); }
+  const std::shared_ptr<bout::b200::Block>& shared() const { return data; }
 
 protected:
   std::shared_ptr<bout::b200::Block> data;

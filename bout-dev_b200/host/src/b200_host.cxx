@@ -49,6 +49,49 @@ void Block::syncToDevice() {
   }
 }
 
+void Block::ensure() {
+  if (pending.empty()) {
+    return;
+  }
+  std::vector<LazyTerm> terms;
+  terms.swap(pending); // (an operand can never be this block: it was created after all of them)
+  std::vector<bout_b200_ewterm> t(terms.size());
+  auto devptr = [](const std::shared_ptr<Block>& b) -> const double* {
+    if (!b) {
+      return nullptr;
+    }
+    b->ensure();
+    b->syncToDevice();
+    return b->ptr;
+  };
+  for (size_t i = 0; i < terms.size(); ++i) {
+    t[i] = bout_b200_ewterm{};
+    t[i].coef = terms[i].coef;
+    t[i].f1 = devptr(terms[i].f1);
+    t[i].f2 = devptr(terms[i].f2);
+    t[i].div = devptr(terms[i].dv);
+    t[i].f1_is2d = terms[i].f1_2d;
+    t[i].f2_is2d = terms[i].f2_2d;
+    t[i].div_is2d = terms[i].dv_2d;
+  }
+  const bout_b200_grid g{pgrid[0], pgrid[1], pgrid[2], pgrid[3], pgrid[4], pgrid[5], pgrid[6]};
+  check(bout_b200_elementwise(&g, BOUT_B200_RGN_ALL, static_cast<int>(t.size()), t.data(), ptr, nullptr));
+  mirror = none;
+}
+
+void Block::launchDependents() {
+  if (dependents.empty()) {
+    return;
+  }
+  std::vector<std::weak_ptr<Block>> deps;
+  deps.swap(dependents);
+  for (auto& w : deps) {
+    if (auto d = w.lock()) {
+      d->ensure();
+    }
+  }
+}
+
 Block::~Block() {
   if (ptr != nullptr) {
     freeList()[count].push_back(ptr); // back to the pool, not to the driver
@@ -601,14 +644,19 @@ void readOptionsText(const std::string& ini_text, Options& root) {
 Mesh* FieldBase::getMesh() const { return fieldmesh != nullptr ? fieldmesh : bout::globals::mesh; }
 
 void FieldBase::makeUnique(size_t count) {
+  if (data) {
+    data->launchDependents();
+  }
   if (!data) {
     data = bout::b200::acquire(count);
   } else if (data.use_count() > 1) {
+    data->ensure();       // a combination that was never launched is the contents being copied
     data->syncToDevice(); // pending host-side element writes belong to the contents being copied
     auto fresh = bout::b200::acquire(count);
     check(bout_b200_memcpy_d2d(fresh->ptr, data->ptr, count * sizeof(double), nullptr));
     data = fresh;
   }
+  data->ensure(); // a partial write lands on the values the block stands for
   // every caller is about to write: the contents get a new identity and lose their recipe
   data->version = bout::b200::nextVersion();
   data->recipe = bout::b200::Block::Recipe{};
@@ -620,6 +668,7 @@ double* mirrorOf(const std::shared_ptr<bout::b200::Block>& data, bool writable, 
   if (!data) {
     throw BoutException("{}: field has no data", what);
   }
+  data->ensure();
   data->syncToHost();
   if (writable) {
     data->mirror = bout::b200::Block::host_newer;
@@ -849,69 +898,229 @@ Field3D* Field3D::timeDeriv() {
   return deriv;
 }
 
-#define B200_F3_BINOP(OP, TB, ...)                          \
-  Field3D operator OP(const Field3D& a, const TB& b) {      \
-    requireData(a, "Field3D operator");                     \
-    requireData(b, "Field3D operator");                     \
-    Field3D r(a.getMesh());                                 \
-    r.allocate();                                           \
-    ew3(r, {__VA_ARGS__});                                  \
-    return r;                                               \
+// ---- Field3D algebra: deferred, fused (bout::b200::Block::pending) ------------------------------------------------
+namespace {
+using LazyTerm = bout::b200::Block::LazyTerm;
+using Terms = std::vector<LazyTerm>;
+constexpr size_t kMaxTerms = 8; // bout_b200_elementwise takes 1..8 terms
+
+bool lazyAlgebra() { // BOUT_B200_LAZY=0: every operator launches its own kernel as it returns
+  static const bool on = [] {
+    const char* e = getenv("BOUT_B200_LAZY");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+LazyTerm fieldTerm(const FieldBase& f, bool is2d, double coef = 1.0) {
+  LazyTerm t;
+  t.coef = coef;
+  t.f1 = f.shared();
+  t.f1_2d = is2d;
+  return t;
+}
+LazyTerm constTerm(double v) {
+  LazyTerm t;
+  t.coef = v;
+  return t;
+}
+// the combination a Field3D stands for: its own pending terms while they were not launched, else the field itself
+Terms exprOf(const Field3D& f, bool inline_pending = true) {
+  const auto* b = f.block();
+  if (inline_pending && lazyAlgebra() && !b->pending.empty()) {
+    return b->pending;
   }
-B200_F3_BINOP(+, Field3D, term(1.0, &a), term(1.0, &b))
-Field3D operator-(const Field3D& a, const Field3D& b) {
-  requireData(a, "Field3D operator");
-  requireData(b, "Field3D operator");
-  Field3D r(a.getMesh());
+  return {fieldTerm(f, false)};
+}
+bool pureField(const Terms& t) { // coef * f1 and nothing else
+  return t.size() == 1 && t[0].f1 && !t[0].f2 && !t[0].dv;
+}
+Field3D lazyResult(Mesh* m, Terms&& terms) {
+  Field3D r(m);
   r.allocate();
-  ew3(r, {term(1.0, &a), term(-1.0, &b)});
-  // remembered for the single-index loop dispatcher: r == a - b while a and b keep these versions
-  bout::b200::Block::Recipe rec;
-  rec.op = 1;
-  rec.a = a.block();
-  rec.b = b.block();
-  rec.a_ver = a.block()->version;
-  rec.b_ver = b.block()->version;
-  r.block()->recipe = rec;
+  auto* b = r.block();
+  const auto g = m->grid();
+  const int gi[7] = {g.nx, g.ny, g.nz, g.xstart, g.xend, g.ystart, g.yend};
+  std::copy(gi, gi + 7, b->pgrid);
+  b->pending = std::move(terms);
+  if (!lazyAlgebra()) {
+    b->ensure();
+    return r;
+  }
+  for (const auto& t : b->pending) {
+    for (const auto* op : {&t.f1, &t.f2, &t.dv}) {
+      if (*op) {
+        auto& deps = (*op)->dependents;
+        if (deps.size() >= 16) { // forget the ones that are gone or were launched meanwhile
+          deps.erase(std::remove_if(deps.begin(), deps.end(),
+                                    [](const std::weak_ptr<bout::b200::Block>& w) {
+                                      auto d = w.lock();
+                                      return !d || d->pending.empty();
+                                    }),
+                     deps.end());
+        }
+        deps.push_back(r.shared());
+      }
+    }
+  }
   return r;
 }
-B200_F3_BINOP(*, Field3D, term(1.0, &a, false, &b))
-B200_F3_BINOP(/, Field3D, term(1.0, &a, false, nullptr, false, &b))
-B200_F3_BINOP(+, Field2D, term(1.0, &a), term(1.0, &b, true))
-B200_F3_BINOP(-, Field2D, term(1.0, &a), term(-1.0, &b, true))
-B200_F3_BINOP(*, Field2D, term(1.0, &a, false, &b, true))
-B200_F3_BINOP(/, Field2D, term(1.0, &a, false, nullptr, false, &b, true))
+// a + sign * b with as many of the operands' pending terms absorbed as fit into one launch
+Field3D lazySum(const Field3D& a, const Terms& ea_all, Terms eb, double sign, Mesh* m) {
+  Terms ea = ea_all;
+  if (ea.size() + eb.size() > kMaxTerms) { // keep the longer combination a launch of its own
+    if (ea.size() >= eb.size()) {
+      ea = exprOf(a, false);
+    }
+    if (ea.size() + eb.size() > kMaxTerms) {
+      return Field3D(); // caller falls back to single terms
+    }
+  }
+  for (auto& t : eb) {
+    t.coef *= sign;
+    ea.push_back(std::move(t));
+  }
+  return lazyResult(m, std::move(ea));
+}
+Field3D addSub(const Field3D& a, const Field3D& b, double sign) {
+  requireData(a, "Field3D operator");
+  requireData(b, "Field3D operator");
+  Field3D r = lazySum(a, exprOf(a), exprOf(b), sign, a.getMesh());
+  if (!r.isAllocated()) {
+    Terms eb = exprOf(b, false);
+    r = lazySum(a, exprOf(a), eb, sign, a.getMesh());
+    if (!r.isAllocated()) {
+      r = lazySum(a, exprOf(a, false), exprOf(b, false), sign, a.getMesh());
+    }
+  }
+  return r;
+}
+// every term of `e` times (div = false) or divided by (div = true) the field g (3-D or 2-D): possible while each term
+// has the slot free; otherwise e is launched on its own first
+Field3D mulDiv(const Field3D& a, const FieldBase& gfield, bool g2d, bool div) {
+  requireData(a, "Field3D operator");
+  requireData(gfield, "Field3D operator");
+  Terms e = exprOf(a);
+  auto fits = [&](const Terms& ts) {
+    for (const auto& t : ts) {
+      if (div ? static_cast<bool>(t.dv) : (t.f1 && t.f2)) {
+        return false;
+      }
+    }
+    return true;
+  };
+  if (!fits(e)) {
+    e = exprOf(a, false);
+  }
+  for (auto& t : e) {
+    if (div) {
+      t.dv = gfield.shared();
+      t.dv_2d = g2d;
+    } else if (!t.f1) {
+      t.f1 = gfield.shared();
+      t.f1_2d = g2d;
+    } else {
+      t.f2 = gfield.shared();
+      t.f2_2d = g2d;
+    }
+  }
+  return lazyResult(a.getMesh(), std::move(e));
+}
+Field3D scaled(const Field3D& f, double s) {
+  requireData(f, "Field3D operator");
+  Terms e = exprOf(f);
+  for (auto& t : e) {
+    t.coef *= s;
+  }
+  return lazyResult(f.getMesh(), std::move(e));
+}
+Field3D plusConst(const Field3D& f, double fs, double c) { // fs * f + c
+  requireData(f, "Field3D operator");
+  Terms e = exprOf(f);
+  if (e.size() + 1 > kMaxTerms) {
+    e = exprOf(f, false);
+  }
+  for (auto& t : e) {
+    t.coef *= fs;
+  }
+  e.push_back(constTerm(c));
+  return lazyResult(f.getMesh(), std::move(e));
+}
+} // namespace
+
+Field3D operator+(const Field3D& a, const Field3D& b) { return addSub(a, b, 1.0); }
+Field3D operator-(const Field3D& a, const Field3D& b) {
+  // remembered for the single-index loop dispatcher: r == a - b while a and b keep these versions
+  const bool plain = a.isAllocated() && b.isAllocated() && a.block()->pending.empty() && b.block()->pending.empty();
+  Field3D r = addSub(a, b, -1.0);
+  if (plain) {
+    bout::b200::Block::Recipe rec;
+    rec.op = 1;
+    rec.a = a.block();
+    rec.b = b.block();
+    rec.a_ver = a.block()->version;
+    rec.b_ver = b.block()->version;
+    r.block()->recipe = rec;
+  }
+  return r;
+}
+Field3D operator*(const Field3D& a, const Field3D& b) {
+  requireData(a, "Field3D operator");
+  requireData(b, "Field3D operator");
+  // the operand that is a plain field multiplies the other one's terms
+  if (!b.block()->pending.empty() && a.block()->pending.empty()) {
+    return mulDiv(b, a, false, false);
+  }
+  return mulDiv(a, b, false, false); // (b is launched first when it is a pending combination itself: dptr in ensure)
+}
+Field3D operator/(const Field3D& a, const Field3D& b) { return mulDiv(a, b, false, true); }
+Field3D operator+(const Field3D& a, const Field2D& b) {
+  requireData(b, "Field3D operator");
+  Field3D r = lazySum(a, exprOf(a), {fieldTerm(b, true)}, 1.0, a.getMesh());
+  return r.isAllocated() ? r : lazySum(a, exprOf(a, false), {fieldTerm(b, true)}, 1.0, a.getMesh());
+}
+Field3D operator-(const Field3D& a, const Field2D& b) {
+  requireData(b, "Field3D operator");
+  Field3D r = lazySum(a, exprOf(a), {fieldTerm(b, true)}, -1.0, a.getMesh());
+  return r.isAllocated() ? r : lazySum(a, exprOf(a, false), {fieldTerm(b, true)}, -1.0, a.getMesh());
+}
+Field3D operator*(const Field3D& a, const Field2D& b) { return mulDiv(a, b, true, false); }
+Field3D operator/(const Field3D& a, const Field2D& b) { return mulDiv(a, b, true, true); }
 Field3D operator+(const Field2D& a, const Field3D& b) { return b + a; }
 Field3D operator*(const Field2D& a, const Field3D& b) { return b * a; }
 Field3D operator-(const Field2D& a, const Field3D& b) {
-  Field3D r(b.getMesh());
-  r.allocate();
-  ew3(r, {term(1.0, &a, true), term(-1.0, &b)});
-  return r;
+  requireData(a, "Field3D operator");
+  requireData(b, "Field3D operator");
+  Terms e = exprOf(b);
+  if (e.size() + 1 > kMaxTerms) {
+    e = exprOf(b, false);
+  }
+  for (auto& t : e) {
+    t.coef = -t.coef;
+  }
+  e.insert(e.begin(), fieldTerm(a, true));
+  return lazyResult(b.getMesh(), std::move(e));
 }
 Field3D operator/(const Field2D& a, const Field3D& b) {
-  Field3D r(b.getMesh());
-  r.allocate();
-  ew3(r, {term(1.0, &a, true, nullptr, false, &b)});
-  return r;
+  requireData(a, "Field3D operator");
+  requireData(b, "Field3D operator");
+  LazyTerm t = fieldTerm(a, true);
+  t.dv = b.shared(); // (a pending b is launched first)
+  return lazyResult(b.getMesh(), {t});
 }
-#define B200_F3_SCALAR(NAME, ...)            \
-  {                                          \
-    requireData(f, "Field3D operator");      \
-    Field3D r(f.getMesh());                  \
-    r.allocate();                            \
-    ew3(r, {__VA_ARGS__});                   \
-    return r;                                \
-  }
-Field3D operator+(const Field3D& f, BoutReal s) B200_F3_SCALAR(add, term(1.0, &f), term(s))
-Field3D operator-(const Field3D& f, BoutReal s) B200_F3_SCALAR(sub, term(1.0, &f), term(-s))
-Field3D operator*(const Field3D& f, BoutReal s) B200_F3_SCALAR(mul, term(s, &f))
-Field3D operator/(const Field3D& f, BoutReal s) B200_F3_SCALAR(div, term(1.0 / s, &f)) // generated_fieldops.cxx:543-558
-Field3D operator+(BoutReal s, const Field3D& f) B200_F3_SCALAR(add, term(s), term(1.0, &f))
-Field3D operator-(BoutReal s, const Field3D& f) B200_F3_SCALAR(sub, term(s), term(-1.0, &f))
-Field3D operator*(BoutReal s, const Field3D& f) B200_F3_SCALAR(mul, term(s, &f))
-Field3D operator/(BoutReal s, const Field3D& f) B200_F3_SCALAR(div, term(s, nullptr, false, nullptr, false, &f))
-Field3D operator-(const Field3D& f) B200_F3_SCALAR(neg, term(-1.0, &f)) // field3d.cxx:581
+Field3D operator+(const Field3D& f, BoutReal s) { return plusConst(f, 1.0, s); }
+Field3D operator-(const Field3D& f, BoutReal s) { return plusConst(f, 1.0, -s); }
+Field3D operator*(const Field3D& f, BoutReal s) { return scaled(f, s); }
+Field3D operator/(const Field3D& f, BoutReal s) { return scaled(f, 1.0 / s); } // generated_fieldops.cxx:543-558
+Field3D operator+(BoutReal s, const Field3D& f) { return plusConst(f, 1.0, s); }
+Field3D operator-(BoutReal s, const Field3D& f) { return plusConst(f, -1.0, s); }
+Field3D operator*(BoutReal s, const Field3D& f) { return scaled(f, s); }
+Field3D operator/(BoutReal s, const Field3D& f) {
+  requireData(f, "Field3D operator");
+  LazyTerm t = constTerm(s);
+  t.dv = f.shared();
+  return lazyResult(f.getMesh(), {t});
+}
+Field3D operator-(const Field3D& f) { return scaled(f, -1.0); } // field3d.cxx:581
 
 Field3D& Field3D::operator+=(const Field3D& r) { return *this = *this + r; }
 Field3D& Field3D::operator+=(const Field2D& r) { return *this = *this + r; }
