@@ -184,3 +184,18 @@ def test_single_index_loop_generic_dispatch():
     p = subprocess.run([sys.executable, os.path.join(here, "si_loop_check.py")], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
+@pytest.mark.parametrize("lazy", ["1", "0"])
+def test_deferred_fused_field_algebra_on_device(lazy):
+    """tests/models/lazy_ops.cxx on the device (tests/lazy_ops_check.py): deferred, fused Field3D algebra of the host layer
+    against the element-wise formulas; with fusion the 21 operators of the model's rhs() are at most 10 launches."""
+    import json, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, os.path.join(here, "lazy_ops_check.py")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, BOUT_B200_LAZY=lazy))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["ok"]
+    if lazy == "1":
+        assert 0 < res["launches"] <= 10, res

@@ -253,6 +253,20 @@ def test_single_index_loop_generic_dispatch_host_logic(fake_device):
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
 
 
+@pytest.mark.parametrize("lazy", ["1", "0"])
+def test_deferred_fused_field_algebra_host_logic(fake_device, lazy):
+    """tests/lazy_ops_check.py on CPU: the host layer's deferred, fused Field3D algebra (absorbed combinations, an operand
+    written in place after an expression that reads it was built, pending multipliers / divisors, more than eight
+    terms) and the one-launch-per-operator mode give the element-wise formulas of the statements, in statement order."""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "lazy_ops_check.py")],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT, BOUT_B200_LAZY=lazy),
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
 def test_fieldperp_through_the_host_layer_host_logic(fake_device):
     """tests/perp_ops_check.py on CPU: the host layer's FieldPerp (sliceXZ, algebra, element access,
     Laplacian::solve(FieldPerp), Field3D = FieldPerp) against the same model source run by the reference build."""
