@@ -295,6 +295,20 @@ struct Block {
   void syncToDevice(); ///< host -> device if host code wrote through the mirror
   ~Block();
 };
+/// Stage update a solver asks the next right-hand side to carry out itself ("axpys fused into the last RHS
+/// kernel"): for every evolving variable e,  state_out = start + a ddt_e,  acc_out = (acc_in ? acc_in : start) + b ddt_e
+/// over RGN_NOBNDRY.  A fused whole-model kernel that recognises the variables (the hasegawa-wakatani-3d dispatch)
+/// passes it on as its bout_b200_rk_epilogue and sets `consumed`; otherwise the solver applies it with its own passes.
+struct StageFusion {
+  bool active = false, consumed = false;
+  std::vector<class ::Field3D*> vars, start, acc_in, state_out, acc_out; ///< per variable; null entries = absent
+  double a = 0.0, b = 0.0;
+  /// set by the consumer: the time-derivative blocks (not written by the fused kernel) as they were at that moment; a
+  /// model that goes on to modify ddt() after its fused loop is detected by the solver through them
+  std::vector<const Block*> ddt_blocks;
+  std::vector<unsigned long long> ddt_versions;
+};
+StageFusion& stageFusion();
 /// Block of `count` doubles from the size-keyed pool (cudaMalloc only on a pool miss; zero-filled then)
 std::shared_ptr<Block> acquire(size_t count);
 void releasePool();
@@ -868,6 +882,9 @@ protected:
   int nout;
   bool initialised = false;
   bool is_nonsplit_model_diffusive = true; ///< solver.cxx:97-101
+public:
+  int stage_fusion = -1; ///< rk4: -1 not tried yet, 1 the model's fused kernel takes the stage updates, 0 it does not
+protected:
   std::vector<Monitor*> monitors;
   void call_monitors(BoutReal t, int iter, int nout_total);
   void pre_rhs();

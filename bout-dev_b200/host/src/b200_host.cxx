@@ -98,6 +98,11 @@ Block::~Block() {
   }
 }
 
+StageFusion& stageFusion() {
+  static StageFusion f;
+  return f;
+}
+
 unsigned long long nextVersion() {
   static unsigned long long v = 0;
   return ++v;
@@ -1615,8 +1620,32 @@ void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
       }
     }
   }
+  // ... and while such a difference is still a pending combination (never launched) it needs no exchange of its own:
+  // evaluated later over the whole array from the exchanged a and b it has exactly the guard cells an exchange would
+  // have given it.  It is taken off its operands' dependents for the duration, so that un-sharing them for the
+  // exchange does not launch it.
+  std::vector<Field3D*> deferred;
+  for (const Kept& k : kept) {
+    if (!k.f->block()->pending.empty()) {
+      deferred.push_back(k.f);
+      for (Field3D* o : {k.a, k.b}) {
+        auto& deps = o->block()->dependents;
+        deps.erase(std::remove_if(deps.begin(), deps.end(),
+                                  [&](const std::weak_ptr<bout::b200::Block>& w) { return w.lock().get() == k.f->block(); }),
+                   deps.end());
+      }
+    }
+  }
   for (Field3D* f : fields) {
-    ptrs.push_back(f->wptr());
+    if (std::find(deferred.begin(), deferred.end(), f) == deferred.end()) {
+      ptrs.push_back(f->wptr());
+    }
+  }
+  for (const Kept& k : kept) {
+    if (std::find(deferred.begin(), deferred.end(), k.f) != deferred.end()) {
+      k.a->block()->dependents.push_back(k.f->shared());
+      k.b->block()->dependents.push_back(k.f->shared());
+    }
   }
   for (size_t i = 0; i < ptrs.size(); i += 8) { // the kernel takes up to 8 fields per launch
     const int n = static_cast<int>(std::min<size_t>(8, ptrs.size() - i));
@@ -2332,9 +2361,46 @@ bool tryHw3d(Mesh* mesh, const std::vector<std::pair<Field3D*, std::vector<Term>
     if (!dtv->isAllocated()) {
       dtv->allocate();
     }
+    // a stage update the solver asked for (StageFusion) becomes the kernel's epilogue when it is about these two fields
+    bout_b200_rk_epilogue ep{};
+    bool fuse = false;
+    StageFusion& sf = stageFusion();
+    if (sf.active && !sf.consumed && sf.vars.size() == 2) {
+      int idx[2] = {-1, -1};
+      for (int e = 0; e < 2; ++e) {
+        if (sf.vars[e] == n) {
+          idx[0] = e;
+        }
+        if (sf.vars[e] == vort) {
+          idx[1] = e;
+        }
+      }
+      if (idx[0] >= 0 && idx[1] >= 0) {
+        fuse = true;
+        for (int e = 0; e < 2; ++e) {
+          const int j = idx[e];
+          ep.start[e] = sf.start[j] != nullptr ? sf.start[j]->dptr() : nullptr;
+          ep.acc_in[e] = sf.acc_in[j] != nullptr ? sf.acc_in[j]->dptr() : nullptr;
+        }
+        for (int e = 0; e < 2; ++e) { // (write pointers last: acc_out may be the block acc_in / start read from)
+          const int j = idx[e];
+          ep.state_out[e] = sf.state_out[j] != nullptr ? sf.state_out[j]->wptr() : nullptr;
+          ep.acc_out[e] = sf.acc_out[j] != nullptr ? sf.acc_out[j]->wptr() : nullptr;
+        }
+        ep.a = sf.a;
+        ep.b = sf.b;
+      }
+    }
     check(bout_b200_hw3d_rhs(&g, &m, -dn->coef, zn != nullptr ? -zn->coef : 0.0, ln != nullptr ? ln->coef : 0.0,
-                             lv != nullptr ? lv->coef : 0.0, n->dptr(), vort->dptr(), phi->dptr(), dtn->wptr(),
-                             dtv->wptr(), nullptr, wb->ptr, nullptr));
+                             lv != nullptr ? lv->coef : 0.0, n->dptr(), vort->dptr(), phi->dptr(),
+                             fuse ? nullptr : dtn->wptr(), fuse ? nullptr : dtv->wptr(), fuse ? &ep : nullptr, wb->ptr,
+                             nullptr));
+    if (fuse) {
+      sf.consumed = true;
+      sf.ddt_blocks = {dtn->block(), dtv->block()};
+      sf.ddt_versions = {dtn->block()->version, dtv->block()->version};
+      sf.vars = {n, vort};
+    }
     return true;
   }
   return false;
@@ -2877,17 +2943,139 @@ void rkStage(Mesh* m, int mode, double dt, double c, const Field3D& start, const
                            nullptr));
 }
 
+// RK4 with the stage updates carried by the right-hand side itself (StageFusion): stage j reads the state in the
+// model's own variables, and its kernel writes the next stage state (start + a_j dt k_j) and the running result
+// (start + sum b_i dt k_i) -- no k arrays, no axpy passes, no final combination (rk4.cxx:172-210 accumulated stage by
+// stage, as bout_b200_rk_epilogue documents).  Stage states move between the variables and two work fields as block
+// handles.  Returns false, having evaluated the first right-hand side, when the model's kernel did not take the stage.
+bool rk4StepFused(Solver& s, BoutReal t, BoutReal dt) {
+  auto& f3d = s.f3d;
+  const size_t nv = f3d.size();
+  Mesh* m = f3d[0].var->getMesh();
+  bout::b200::StageFusion& sf = bout::b200::stageFusion();
+  std::vector<Field3D> y0(nv), sa(nv), sb(nv), acc(nv);
+  for (size_t i = 0; i < nv; ++i) {
+    sa[i] = Field3D(m);
+    sa[i].allocate();
+    acc[i] = Field3D(m);
+    acc[i].allocate();
+  }
+  auto ptrs = [&](std::vector<Field3D>& v) {
+    std::vector<Field3D*> p(nv);
+    for (size_t i = 0; i < nv; ++i) {
+      p[i] = &v[i];
+    }
+    return p;
+  };
+  const std::vector<Field3D*> none(nv, nullptr);
+  std::vector<Field3D*> vars(nv);
+  for (size_t i = 0; i < nv; ++i) {
+    vars[i] = f3d[i].var;
+  }
+  // one stage: returns whether the model's kernel applied the update; if not, it is applied here from ddt
+  auto stage = [&](BoutReal tt, const std::vector<Field3D*>& start, const std::vector<Field3D*>& acc_in,
+                   const std::vector<Field3D*>& state_out, const std::vector<Field3D*>& acc_out, double a, double b,
+                   bool may_fall_back) {
+    sf = bout::b200::StageFusion{};
+    sf.active = true;
+    sf.vars = vars;
+    sf.start = start;
+    sf.acc_in = acc_in;
+    sf.state_out = state_out;
+    sf.acc_out = acc_out;
+    sf.a = a;
+    sf.b = b;
+    try {
+      s.run_rhs(tt);
+    } catch (...) {
+      sf = bout::b200::StageFusion{};
+      throw;
+    }
+    const bool consumed = sf.consumed;
+    if (consumed) { // ddt() was not written by the kernel: nothing may have been added to it afterwards
+      for (size_t e = 0; e < sf.ddt_blocks.size(); ++e) {
+        const Field3D* d = sf.vars[e]->timeDeriv();
+        if (d->block() != sf.ddt_blocks[e] || d->block()->version != sf.ddt_versions[e]) {
+          sf = bout::b200::StageFusion{};
+          throw BoutException("rk4: the model changed ddt() after its fused right-hand-side loop, which the fused stage "
+                              "update cannot see; run with BOUT_B200_RK_FUSE=0");
+        }
+      }
+    }
+    sf = bout::b200::StageFusion{};
+    if (consumed || may_fall_back) {
+      return consumed;
+    }
+    for (size_t i = 0; i < nv; ++i) { // the same update from ddt, variable by variable
+      const Field3D k = *f3d[i].F_var;
+      const Field3D& base = acc_in[i] != nullptr ? *acc_in[i] : *start[i];
+      if (state_out[i] != nullptr) {
+        rkStage(m, 0, a, 1.0, *start[i], &k, nullptr, nullptr, nullptr, *state_out[i]);
+      }
+      if (acc_out[i] != nullptr) {
+        if (acc_out[i] == acc_in[i] || acc_out[i] == start[i]) { // in place: through a private handle on the operand
+          const Field3D keep = base;
+          rkStage(m, 0, b, 1.0, keep, &k, nullptr, nullptr, nullptr, *acc_out[i]);
+        } else {
+          rkStage(m, 0, b, 1.0, base, &k, nullptr, nullptr, nullptr, *acc_out[i]);
+        }
+      }
+    }
+    return false;
+  };
+  // stage 1 reads the variables themselves as `start` (boundary conditions / exchanges only touch their guard cells)
+  if (!stage(t, vars, none, ptrs(sa), ptrs(acc), 0.5 * dt, dt / 6.0, s.stage_fusion < 0) && s.stage_fusion < 0) {
+    return false;
+  }
+  for (size_t i = 0; i < nv; ++i) {
+    y0[i] = std::move(*f3d[i].var);
+    *f3d[i].var = std::move(sa[i]);
+    sb[i] = Field3D(m);
+    sb[i].allocate();
+  }
+  stage(t + 0.5 * dt, ptrs(y0), ptrs(acc), ptrs(sb), ptrs(acc), 0.5 * dt, dt / 3.0, false);
+  for (size_t i = 0; i < nv; ++i) {
+    sa[i] = std::move(*f3d[i].var);
+    *f3d[i].var = std::move(sb[i]);
+  }
+  stage(t + 0.5 * dt, ptrs(y0), ptrs(acc), ptrs(sa), ptrs(acc), dt, dt / 3.0, false);
+  for (size_t i = 0; i < nv; ++i) {
+    sb[i] = std::move(*f3d[i].var);
+    *f3d[i].var = std::move(sa[i]);
+  }
+  stage(t + dt, ptrs(y0), ptrs(acc), none, ptrs(y0), 0.0, dt / 6.0, false); // the result lands in the start block
+  for (size_t i = 0; i < nv; ++i) {
+    *f3d[i].var = std::move(y0[i]);
+  }
+  return true;
+}
+
 void rk4Step(Solver& s, BoutReal t, BoutReal dt) { // rk4.cxx:172-210 field by field
   auto& f3d = s.f3d;
   const size_t nv = f3d.size();
   std::vector<Field3D> start(nv), k1(nv), k2(nv), k3(nv), k4(nv);
   Mesh* m = f3d[0].var->getMesh();
+  static const bool fuse_env = [] {
+    const char* e = getenv("BOUT_B200_RK_FUSE");
+    return e == nullptr || e[0] != '0';
+  }();
+  bool have_k1 = false;
+  if (fuse_env && nv == 2 && s.stage_fusion != 0) {
+    if (rk4StepFused(s, t, dt)) {
+      s.stage_fusion = 1;
+      return;
+    }
+    s.stage_fusion = 0; // the first right-hand side was evaluated the ordinary way: carry on from its ddt
+    have_k1 = true;
+  }
   for (size_t i = 0; i < nv; ++i) {
     start[i] = *f3d[i].var;
     start[i].allocate(); // a private copy: the variable is overwritten in place below
   }
   auto stage = [&](std::vector<Field3D>& k, BoutReal tt) {
-    s.run_rhs(tt);
+    if (!(have_k1 && &k == &k1)) {
+      s.run_rhs(tt);
+    }
     for (size_t i = 0; i < nv; ++i) {
       k[i] = *f3d[i].F_var;
     }
