@@ -597,6 +597,13 @@ public:
 private:
   Mesh* localmesh;
   std::map<std::string, Field2D> cache;
+  /// (block, version) of the two source fields each cached entry was formed from: an entry is rebuilt when the model
+  /// assigned or modified dx / dy / dz / d1_dx / d1_dy since (no geometry() call needed)
+  struct CacheKey {
+    const bout::b200::Block* blk[2] = {nullptr, nullptr};
+    unsigned long long ver[2] = {0, 0};
+  };
+  std::map<std::string, CacheKey> cache_key;
 };
 
 class Mesh {

@@ -1381,6 +1381,17 @@ void applyOne(Field3D& f, const std::string& cond_in, int side) {
     if (!arg.empty()) {
       bout::b200::EvalContext c;
       value = bout::b200::Expr(arg, c).eval();
+      // the reference evaluates the argument per boundary cell and per time (FieldGenerator); here it must be a constant
+      bout::b200::EvalContext c2;
+      c2.x = 0.37;
+      c2.y = 1.1;
+      c2.z = 2.3;
+      c2.t = 0.7;
+      const double v2 = bout::b200::Expr(arg, c2).eval();
+      if (!(v2 == value) && !(std::isnan(v2) && std::isnan(value))) {
+        throw BoutException("Boundary condition '{}': a value that depends on x, y, z or t is not available in the B200 "
+                            "host layer (constant values only)", cond_in);
+      }
     }
   }
   int kind;
@@ -1893,10 +1904,29 @@ int Coordinates::geometry() {
 }
 
 const Field2D& Coordinates::recip(const std::string& which) {
+  // which metric fields the entry depends on
+  const Field2D* src[2] = {nullptr, nullptr};
+  if (which == "1/dx" || which == "1/dx2") { src[0] = &dx; }
+  else if (which == "1/dy" || which == "1/dy2") { src[0] = &dy; }
+  else if (which == "1/dz" || which == "1/dz2") { src[0] = &dz; }
+  else if (which == "d1_dx/dx") { src[0] = &d1_dx; src[1] = &dx; }
+  else if (which == "d1_dy/dy") { src[0] = &d1_dy; src[1] = &dy; }
+  CacheKey key;
+  for (int i = 0; i < 2; ++i) {
+    if (src[i] != nullptr && src[i]->block() != nullptr) {
+      key.blk[i] = src[i]->block();
+      key.ver[i] = src[i]->block()->version;
+    }
+  }
   auto it = cache.find(which);
   if (it != cache.end()) {
-    return it->second;
+    const CacheKey& k = cache_key[which];
+    if (k.blk[0] == key.blk[0] && k.blk[1] == key.blk[1] && k.ver[0] == key.ver[0] && k.ver[1] == key.ver[1]) {
+      return it->second;
+    }
+    cache.erase(it); // a source field was assigned or written since: rebuild
   }
+  cache_key[which] = key;
   Field2D r(localmesh);
   if (which == "1/dx") { r = 1.0 / dx; }
   else if (which == "1/dy") { r = 1.0 / dy; }

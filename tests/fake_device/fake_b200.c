@@ -513,10 +513,19 @@ int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, doubl
                        double Dvort, const double* n, const double* vort, const double* phi, double* ddt_n,
                        double* ddt_vort, const bout_b200_rk_epilogue* epilogue, double* coef_workspace, void* stream) {
   (void)coef_workspace, (void)stream;
-  if (m == NULL || epilogue != NULL || ddt_n == NULL || ddt_vort == NULL) {
+  if (m == NULL || (epilogue == NULL && (ddt_n == NULL || ddt_vort == NULL))) {
     return BOUT_B200_ERR_UNSUPPORTED;
   }
   const size_t n3 = (size_t)g->nx * g->ny * g->nz;
+  /* with an epilogue the time derivatives may be omitted: they are formed in scratch arrays and the stage update
+   * state_out = start + a ddt, acc_out = (acc_in ? acc_in : start) + b ddt (include/bout_b200.h) follows below */
+  double* own[2] = {NULL, NULL};
+  if (ddt_n == NULL) {
+    ddt_n = own[0] = (double*)calloc(n3, sizeof(double));
+  }
+  if (ddt_vort == NULL) {
+    ddt_vort = own[1] = (double*)calloc(n3, sizeof(double));
+  }
   double* bn = (double*)malloc(n3 * sizeof(double));
   double* bv = (double*)malloc(n3 * sizeof(double));
   int rc = bout_b200_bracket_arakawa(g, phi, n, m->dx, m->dz, bn, NULL);
@@ -565,9 +574,31 @@ int bout_b200_hw3d_rhs(const bout_b200_grid* g, const bout_b200_metric* m, doubl
       }
     }
   }
+  if (epilogue != NULL) {
+    double* k[2] = {ddt_n, ddt_vort};
+    for (int e = 0; e < 2; ++e) {
+      const double* base = epilogue->acc_in[e] ? epilogue->acc_in[e] : epilogue->start[e];
+      for (int x = g->xstart; x <= g->xend; ++x) {
+        for (int y = g->ystart; y <= g->yend; ++y) {
+          for (int z = 0; z < nz; ++z) {
+            const double d = AT(k[e], x, y, z);
+            const double st = AT(epilogue->start[e], x, y, z), ac = AT(base, x, y, z);
+            if (epilogue->state_out[e]) {
+              AT(epilogue->state_out[e], x, y, z) = st + epilogue->a * d;
+            }
+            if (epilogue->acc_out[e]) {
+              AT(epilogue->acc_out[e], x, y, z) = ac + epilogue->b * d;
+            }
+          }
+        }
+      }
+    }
+  }
 #undef AT
 #undef M2
   free(bn);
   free(bv);
+  free(own[0]);
+  free(own[1]);
   return 0;
 }
