@@ -5,6 +5,8 @@
 // Each thread owns a (y, z-pair) column and marches along x with the three x-planes of f and g
 // held in registers (z-1, z, z+1, z+2 of each), so f and g are each read once per chunk; the
 // z-neighbour scalars come out of L1.  Algorithmic traffic: 2 reads + 1 write = 24 B/point.
+#include <cstdlib>
+
 #include "bracket.cuh"
 
 namespace b200 {
@@ -18,8 +20,8 @@ struct BracketParams {
   int nx, ny, nz, xs, xe, ys, ye, chunk;
 };
 
-template <int VEC, bool G2D>
-__global__ void __launch_bounds__(256) k_bracket_arakawa(const BracketParams p) {
+template <int VEC, bool G2D, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_bracket_arakawa(const BracketParams p) {
   const int nzv = p.nz / VEC;
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(p.ye - p.ys + 1) * nzv) {
@@ -99,10 +101,14 @@ int launchBracket(const bout_b200_grid* g, const double* f, const double* gg, co
   }
   p.chunk = chunk;
   dim3 grid(static_cast<unsigned>((north + 255) / 256), static_cast<unsigned>((len + chunk - 1) / chunk));
-  if (vec2) {
-    k_bracket_arakawa<2, G2D><<<grid, 256, 0, asStream(stream)>>>(p);
+  // 80 registers (3 CTAs per SM) unless asked otherwise: BOUT_B200_BRACKET_MINB=4 caps at 64 with a few spills
+  static const int minb = getenv("BOUT_B200_BRACKET_MINB") ? atoi(getenv("BOUT_B200_BRACKET_MINB")) : 3;
+  if (vec2 && minb == 4) {
+    k_bracket_arakawa<2, G2D, 4><<<grid, 256, 0, asStream(stream)>>>(p);
+  } else if (vec2) {
+    k_bracket_arakawa<2, G2D, 3><<<grid, 256, 0, asStream(stream)>>>(p);
   } else {
-    k_bracket_arakawa<1, G2D><<<grid, 256, 0, asStream(stream)>>>(p);
+    k_bracket_arakawa<1, G2D, 3><<<grid, 256, 0, asStream(stream)>>>(p);
   }
   B200_LAUNCH_OK();
   return 0;

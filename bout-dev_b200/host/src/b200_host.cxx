@@ -1635,10 +1635,17 @@ void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
   // evaluated later over the whole array from the exchanged a and b it has exactly the guard cells an exchange would
   // have given it.  It is taken off its operands' dependents for the duration, so that un-sharing them for the
   // exchange does not launch it.
+  // Its handles on a and b are dropped for the duration as well (they would make the exchange un-share, i.e. copy,
+  // both operands) and the combination is rebuilt from the same fields afterwards.
   std::vector<Field3D*> deferred;
   for (const Kept& k : kept) {
-    if (!k.f->block()->pending.empty()) {
+    auto& pend = k.f->block()->pending;
+    const bool plain_difference = pend.size() == 2 && pend[0].coef == 1.0 && pend[1].coef == -1.0
+                                  && pend[0].f1.get() == k.a->block() && pend[1].f1.get() == k.b->block() && !pend[0].f2
+                                  && !pend[0].dv && !pend[1].f2 && !pend[1].dv && k.f != k.a && k.f != k.b;
+    if (plain_difference) {
       deferred.push_back(k.f);
+      pend.clear();
       for (Field3D* o : {k.a, k.b}) {
         auto& deps = o->block()->dependents;
         deps.erase(std::remove_if(deps.begin(), deps.end(),
@@ -1647,13 +1654,20 @@ void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
       }
     }
   }
+  auto isDeferred = [&](const Field3D* f) { return std::find(deferred.begin(), deferred.end(), f) != deferred.end(); };
   for (Field3D* f : fields) {
-    if (std::find(deferred.begin(), deferred.end(), f) == deferred.end()) {
+    if (!isDeferred(f)) {
       ptrs.push_back(f->wptr());
     }
   }
   for (const Kept& k : kept) {
-    if (std::find(deferred.begin(), deferred.end(), k.f) != deferred.end()) {
+    if (isDeferred(k.f)) {
+      bout::b200::Block::LazyTerm ta, tb;
+      ta.coef = 1.0;
+      ta.f1 = k.a->shared();
+      tb.coef = -1.0;
+      tb.f1 = k.b->shared();
+      k.f->block()->pending = {ta, tb};
       k.a->block()->dependents.push_back(k.f->shared());
       k.b->block()->dependents.push_back(k.f->shared());
     }
