@@ -365,6 +365,17 @@ def unary(g: Grid, op, f, arg=0.0, out=None):
     return out
 
 
+def where(g: Grid, test, gt0, le0, out=None):
+    """where(test, gt0, le0): test > 0 ? gt0 : le0; test 3-D or 2-D, gt0 / le0 tensors or numbers."""
+    ref = gt0 if torch.is_tensor(gt0) else (le0 if torch.is_tensor(le0) else None)
+    out = torch.empty(g.shape3, dtype=torch.float64, device=test.device) if out is None else out
+    a, av = (gt0, 0.0) if torch.is_tensor(gt0) else (None, float(gt0))
+    b, bv = (le0, 0.0) if torch.is_tensor(le0) else (None, float(le0))
+    _check(lib.bout_b200_where(C.byref(g.c), _ptr(test), int(test.dim() == 2), _ptr(a), C.c_double(av), _ptr(b),
+                               C.c_double(bv), _ptr(out), _stream()))
+    return out
+
+
 def boundary(g: Grid, kind, side, f, value=0.0, spacing=None, lo=-1, hi=-1):
     """In place.  kind: dirichlet | neumann | zero | extend | free_o2 | free_o3; side: xin | xout | ydown | yup."""
     k = {"dirichlet": 0, "dirichlet_o2": 0, "neumann": 1, "zero": 2, "extend": 3, "free_o2": 4, "free_o3": 5}[kind]

@@ -187,6 +187,32 @@ extern "C" int bout_b200_unary(const bout_b200_grid* g, int op, const double* f,
   return 0;
 }
 
+namespace b200 {
+__global__ void __launch_bounds__(256) k_where(const double* __restrict__ test, int test_is2d, const double* __restrict__ a,
+                                               double av, const double* __restrict__ b, double bv, double* __restrict__ out,
+                                               long long n, int nz) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double t = __ldg(test + (test_is2d ? i / nz : i));
+    out[i] = t > 0.0 ? (a != nullptr ? __ldg(a + i) : av) : (b != nullptr ? __ldg(b + i) : bv);
+  }
+}
+} // namespace b200
+
+extern "C" int bout_b200_where(const bout_b200_grid* g, const double* test, int test_is2d, const double* gt0,
+                               double gt0_value, const double* le0, double le0_value, double* out, void* stream) {
+  if (checkGrid(g) != 0) {
+    return BOUT_B200_ERR_ARG;
+  }
+  B200_REQUIRE(test && out && out != test, BOUT_B200_ERR_ARG, "where: bad argument");
+  const long long n = static_cast<long long>(g->nx) * g->ny * g->nz;
+  const long long want = (n + 255) / 256;
+  const unsigned blocks = static_cast<unsigned>(want < 148LL * 64 ? want : 148LL * 64);
+  b200::k_where<<<blocks, 256, 0, asStream(stream)>>>(test, test_is2d, gt0, gt0_value, le0, le0_value, out, n, g->nz);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 // Linear combination of fields, the stage / output-state loops of the explicit integrators beyond rk4 and rk3ssp
 // (euler.cxx:178-181, rkscheme.cxx:57-84 and :173-190, split-rk.cxx:226-300): one pass through k_elementwise.
 extern "C" int bout_b200_lincomb(const bout_b200_grid* g, int region, int n, const double* coef,

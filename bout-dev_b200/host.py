@@ -33,6 +33,7 @@ class Host:
         L.b200host_last_error.restype = C.c_char_p
         L.b200host_model_varname.restype = C.c_char_p
         L.b200host_pool_allocations.restype = C.c_ulonglong
+        L.b200host_cow_copies.restype = C.c_ulonglong
         L.b200host_model_rhs.argtypes = [C.c_double]
         L.b200host_model_solve.argtypes = [C.c_int, C.c_double]
         self._check(L.b200host_init(ini_text.encode()))
@@ -106,3 +107,7 @@ class Host:
 
     def pool_allocations(self):
         return int(self.lib.b200host_pool_allocations())
+
+    def cow_copies(self):
+        """Whole-block device copies made by copy-on-write so far (each is a pass over a field that no kernel list shows)."""
+        return int(self.lib.b200host_cow_copies())

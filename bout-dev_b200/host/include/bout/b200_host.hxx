@@ -313,6 +313,7 @@ StageFusion& stageFusion();
 std::shared_ptr<Block> acquire(size_t count);
 void releasePool();
 size_t poolAllocations(); ///< number of cudaMalloc calls so far (steady state: constant)
+size_t cowCopies();       ///< whole-block device copies made by copy-on-write so far (FieldBase::makeUnique)
 unsigned long long nextVersion();
 } // namespace b200
 } // namespace bout
@@ -575,6 +576,14 @@ Field3D lowPass(const Field3D& f, int zmax, bool keep_zonal = true); ///< field3
 Field2D averageY(const Field2D& f);             ///< smoothing.cxx:238-270
 Field3D averageY(const Field3D& f);             ///< smoothing.cxx:272-323
 inline Field3D emptyFrom(const Field3D& f) { return Field3D(f.getMesh()).allocate(); }
+/// where(test, gt0, le0): test > 0 ? gt0 : le0, element by element (reference include/bout/where.hxx:41-91)
+Field3D where(const Field3D& test, const Field3D& gt0, const Field3D& le0);
+Field3D where(const Field3D& test, const Field3D& gt0, BoutReal le0);
+Field3D where(const Field3D& test, BoutReal gt0, const Field3D& le0);
+Field3D where(const Field3D& test, BoutReal gt0, BoutReal le0);
+Field3D where(const Field2D& test, const Field3D& gt0, const Field3D& le0);
+Field3D where(const Field2D& test, const Field3D& gt0, BoutReal le0);
+Field3D where(const Field2D& test, BoutReal gt0, const Field3D& le0);
 
 // ---- Coordinates / Mesh ---------------------------------------------------------------------------
 class Coordinates {

@@ -1,0 +1,2 @@
+#pragma once
+#include "b200_vectors.hxx"

@@ -135,6 +135,9 @@ void releasePool() {
 }
 
 size_t poolAllocations() { return n_malloc; }
+static size_t n_cow = 0;
+size_t cowCopies() { return n_cow; }
+void countCowCopy() { ++n_cow; }
 
 // ---- small expression evaluator for option values and initial profiles ---------------------------------
 // (the reference's ExpressionParser / FieldFactory, src/sys/expressionparser.cxx, src/field/fieldgenerators.cxx,
@@ -659,6 +662,7 @@ void FieldBase::makeUnique(size_t count) {
     data->syncToDevice(); // pending host-side element writes belong to the contents being copied
     auto fresh = bout::b200::acquire(count);
     check(bout_b200_memcpy_d2d(fresh->ptr, data->ptr, count * sizeof(double), nullptr));
+    bout::b200::countCowCopy();
     data = fresh;
   }
   data->ensure(); // a partial write lands on the values the block stands for
@@ -1126,6 +1130,25 @@ Field3D operator/(BoutReal s, const Field3D& f) {
   return lazyResult(f.getMesh(), {t});
 }
 Field3D operator-(const Field3D& f) { return scaled(f, -1.0); } // field3d.cxx:581
+
+namespace {
+Field3D whereImpl(const FieldBase& test, bool test2d, const Field3D* gt0, double gv, const Field3D* le0, double lv, Mesh* m) {
+  requireData(test, "where");
+  Field3D r(m);
+  const auto g = m->grid();
+  const double* a = gt0 != nullptr ? gt0->dptr() : nullptr;
+  const double* b = le0 != nullptr ? le0->dptr() : nullptr;
+  check(bout_b200_where(&g, test.dptr(), test2d ? 1 : 0, a, gv, b, lv, r.wptr(), nullptr));
+  return r;
+}
+} // namespace
+Field3D where(const Field3D& t, const Field3D& a, const Field3D& b) { return whereImpl(t, false, &a, 0.0, &b, 0.0, t.getMesh()); }
+Field3D where(const Field3D& t, const Field3D& a, BoutReal b) { return whereImpl(t, false, &a, 0.0, nullptr, b, t.getMesh()); }
+Field3D where(const Field3D& t, BoutReal a, const Field3D& b) { return whereImpl(t, false, nullptr, a, &b, 0.0, t.getMesh()); }
+Field3D where(const Field3D& t, BoutReal a, BoutReal b) { return whereImpl(t, false, nullptr, a, nullptr, b, t.getMesh()); }
+Field3D where(const Field2D& t, const Field3D& a, const Field3D& b) { return whereImpl(t, true, &a, 0.0, &b, 0.0, a.getMesh()); }
+Field3D where(const Field2D& t, const Field3D& a, BoutReal b) { return whereImpl(t, true, &a, 0.0, nullptr, b, a.getMesh()); }
+Field3D where(const Field2D& t, BoutReal a, const Field3D& b) { return whereImpl(t, true, nullptr, a, &b, 0.0, b.getMesh()); }
 
 Field3D& Field3D::operator+=(const Field3D& r) { return *this = *this + r; }
 Field3D& Field3D::operator+=(const Field2D& r) { return *this = *this + r; }

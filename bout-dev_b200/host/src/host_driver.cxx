@@ -149,6 +149,7 @@ int b200host_stream_sync() {
 }
 int b200host_rhs_calls() { return solver ? solver->rhs_calls : 0; }
 unsigned long long b200host_pool_allocations() { return bout::b200::poolAllocations(); }
+unsigned long long b200host_cow_copies() { return bout::b200::cowCopies(); }
 
 // Diagnostic field registered by the model's outputVars() (e.g. "phi")
 int b200host_model_output(const char* name, double* out) {

@@ -368,6 +368,11 @@ int bout_b200_elementwise(const bout_b200_grid* g, int region, int nterms,
  * 0 neg, 1 sqrt, 2 abs, 3 exp, 4 log, 5 sin, 6 cos, 7 tanh, 8 SQ, 9 pow(f, arg), 10 copy. */
 int bout_b200_unary(const bout_b200_grid* g, int op, const double* f, double arg, double* out,
                     void* stream);
+/* where(test, gt0, le0) over RGN_ALL (reference include/bout/where.hxx:41-91): out = test > 0 ? gt0 : le0 element by
+ * element.  test is a Field3D, or a Field2D broadcast over z (test_is2d); gt0 / le0 are Field3D arrays, or NULL for
+ * the constants gt0_value / le0_value. */
+int bout_b200_where(const bout_b200_grid* g, const double* test, int test_is2d, const double* gt0, double gt0_value,
+                    const double* le0, double le0_value, double* out, void* stream);
 
 /* ---- boundary conditions (a15) ---------------------------------------------------------------------
  * kind: 0 dirichlet / dirichlet_o2 (src/mesh/boundary_standard.cxx:527-581), 1 neumann (:2167-2190),

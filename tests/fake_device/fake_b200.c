@@ -222,6 +222,17 @@ int bout_b200_memcpy_d2h_async(void* dst, const void* src, size_t bytes, void* s
   return 0;
 }
 
+int bout_b200_where(const bout_b200_grid* g, const double* test, int test_is2d, const double* gt0, double gt0_value,
+                    const double* le0, double le0_value, double* out, void* stream) {
+  const long long n = (long long)g->nx * g->ny * g->nz;
+  (void)stream;
+  for (long long i = 0; i < n; ++i) {
+    const double t = test[test_is2d ? i / g->nz : i];
+    out[i] = t > 0.0 ? (gt0 ? gt0[i] : gt0_value) : (le0 ? le0[i] : le0_value);
+  }
+  return 0;
+}
+
 /* boundary conditions (kinds as in include/bout_b200.h; 3 "extend" is elm-pb specific and not needed by the host logic) */
 int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value, const double* spacing2d, int lo,
                        int hi, double* f, void* stream) {

@@ -199,3 +199,29 @@ def test_deferred_fused_field_algebra_on_device(lazy):
     assert res["ok"]
     if lazy == "1":
         assert 0 < res["launches"] <= 10, res
+
+
+def test_vectors_grad_where_through_the_host_layer():
+    """tests/models/vec_ops.cxx on the device (tests/vec_ops_check.py): Vector2D / Vector3D, Grad, dot products,
+    toContravariant, where (bout_b200_where), interp_to against the reference build's run of the same source (1e-12)."""
+    import json, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, os.path.join(here, "vec_ops_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
+def test_where_kernel(capi):
+    """bout_b200_where against numpy (reference include/bout/where.hxx: test > 0 ? gt0 : le0), 3-D and 2-D tests,
+    field and constant branches; bit-exact (a selection)."""
+    g = capi.Grid(9, 6, 10, 2, 1)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    t3 = torch.rand(g.shape3, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    t3[2, 3, 4] = 0.0                      # the boundary case takes the le0 branch
+    t2 = torch.rand(g.shape2, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    a = torch.rand(g.shape3, dtype=torch.float64, device="cuda", generator=gen)
+    b = torch.rand(g.shape3, dtype=torch.float64, device="cuda", generator=gen)
+    assert torch.equal(capi.where(g, t3, a, b), torch.where(t3 > 0, a, b))
+    assert torch.equal(capi.where(g, t3, 2.5, b), torch.where(t3 > 0, torch.full_like(b, 2.5), b))
+    assert torch.equal(capi.where(g, t3, a, -1.0), torch.where(t3 > 0, a, torch.full_like(a, -1.0)))
+    assert torch.equal(capi.where(g, t2, a, b), torch.where(t2[:, :, None] > 0, a, b))

@@ -267,6 +267,19 @@ def test_deferred_fused_field_algebra_host_logic(fake_device, lazy):
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
 
 
+def test_vectors_grad_where_through_the_host_layer_host_logic(fake_device):
+    """tests/vec_ops_check.py on CPU: the host layer's Vector2D / Vector3D, Grad, dot products (components / through the
+    metric), toContravariant, where and interp_to against the same model source run by the reference build on a
+    non-orthogonal metric."""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "vec_ops_check.py")],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
 def test_fieldperp_through_the_host_layer_host_logic(fake_device):
     """tests/perp_ops_check.py on CPU: the host layer's FieldPerp (sliceXZ, algebra, element access,
     Laplacian::solve(FieldPerp), Field3D = FieldPerp) against the same model source run by the reference build."""

@@ -8,5 +8,5 @@ h = pkg.host.Host(bench.hw3d_host_ini())
 h.model_create("hw3d", "rk4")
 h.model_solve(1, (int(sys.argv[1]) if len(sys.argv) > 1 else 3) * bench.DT)
 h.stream_sync()
-print("rhs calls", h.rhs_calls(), "pool allocations", h.pool_allocations())
+print("rhs calls", h.rhs_calls(), "pool allocations", h.pool_allocations(), "copy-on-write copies", h.cow_copies())
 h.close()
