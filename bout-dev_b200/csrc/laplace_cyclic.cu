@@ -330,12 +330,12 @@ __global__ void __launch_bounds__(LAP_PCR_NT) k_lap_pcr(const LapParams p) {
   extern __shared__ __align__(16) unsigned char pcr_raw[];
   const int n = p.bd.xe - p.bd.xs + 1;
   const bool periodic = p.bd.periodic_x != 0; // single rank, n a power of two (checked by the host)
-  cd* buf[2][4]; // [ping-pong][a, b, c, d]
-  for (int h = 0; h < 2; ++h) {
-    for (int q = 0; q < 4; ++q) {
-      buf[h][q] = reinterpret_cast<cd*>(pcr_raw) + static_cast<size_t>(h * 4 + q) * n;
-    }
-  }
+  // Rows are kept NORMALISED, (a, c, d) / b, so that a step reads nine and writes three complex numbers per row
+  // (twelve and four with b carried along) and inverts one pivot instead of two: the load/store pipe bounds this
+  // kernel.  [ping-pong][a, c, d][n], addressed by arithmetic on one base pointer (an array of pointers indexed by the
+  // ping-pong bit would live in local memory: six more loads per row and step through the same pipe).
+  cd* const base = reinterpret_cast<cd*>(pcr_raw);
+  auto arr = [&](int h, int q) { return base + static_cast<size_t>(h * 3 + q) * n; };
   const int nys = p.ye - p.ys + 1;
   const int t = blockIdx.x; // system index
   const int iyl = t / p.nmode, kz = t % p.nmode;
@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(LAP_PCR_NT) k_lap_pcr(const LapParams p) {
   const double kwave = kz * 2.0 * M_PI / p.m.zlength;
   const double* tab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
   cd* __restrict__ sp = p.spec + t;
+  bool bad = false;
   for (int ix = threadIdx.x; ix < n; ix += blockDim.x) {
     cd a, b, c, r = ldcd(sp + ix * xs);
     lapRow(p, tab, ix, jy, kz, kwave, a, b, c, r);
@@ -353,48 +354,45 @@ __global__ void __launch_bounds__(LAP_PCR_NT) k_lap_pcr(const LapParams p) {
     if (!periodic && ix == n - 1) {
       c = {0.0, 0.0};
     }
-    buf[0][0][ix] = a;
-    buf[0][1][ix] = b;
-    buf[0][2][ix] = c;
-    buf[0][3][ix] = r;
+    bad = bad || tiny(b);
+    const cd ib = crecip(b);
+    arr(0, 0)[ix] = cmul(a, ib);
+    arr(0, 1)[ix] = cmul(c, ib);
+    arr(0, 2)[ix] = cmul(r, ib);
   }
   __syncthreads();
-  bool bad = false;
   int cur = 0;
   for (int sft = 1; sft < n; sft <<= 1) {
-    cd* const* in = buf[cur];
-    cd* const* out = buf[cur ^ 1];
+    const cd* const ina = arr(cur, 0);
+    const cd* const inc = arr(cur, 1);
+    const cd* const ind = arr(cur, 2);
+    cd* const outa = arr(cur ^ 1, 0);
+    cd* const outc = arr(cur ^ 1, 1);
+    cd* const outd = arr(cur ^ 1, 2);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const cd a = in[0][i], c = in[2][i];
-      cd b = in[1][i], d = in[3][i];
-      cd an = {0.0, 0.0}, cn = {0.0, 0.0};
+      // x_i + a_i x_{i-s} + c_i x_{i+s} = d_i; rows i -+ s eliminate those two couplings.  A coupling that would
+      // leave the system is exactly zero (a_0 = c_{n-1} = 0 and a step multiplies a_i by a_{i-s}), so the
+      // neighbour index may simply be clamped: whatever it reads is multiplied by that zero.
       int im = i - sft, ip = i + sft;
       if (periodic) { // n is a power of two: rows wrap around
         im &= n - 1;
         ip &= n - 1;
+      } else {
+        im = max(im, 0);
+        ip = min(ip, n - 1);
       }
-      if (im >= 0) {
-        const cd bm = in[1][im];
-        bad = bad || tiny(bm);
-        const cd k1 = cmul(a, tiny(bm) ? crecip(bm) : crecipFast(bm));
-        an = cmul(in[0][im], k1);
-        an = {-an.re, -an.im};
-        b = csub(b, cmul(in[2][im], k1));
-        d = csub(d, cmul(in[3][im], k1));
-      }
-      if (ip < n) {
-        const cd bp = in[1][ip];
-        bad = bad || tiny(bp);
-        const cd k2 = cmul(c, tiny(bp) ? crecip(bp) : crecipFast(bp));
-        cn = cmul(in[2][ip], k2);
-        cn = {-cn.re, -cn.im};
-        b = csub(b, cmul(in[0][ip], k2));
-        d = csub(d, cmul(in[3][ip], k2));
-      }
-      out[0][i] = an;
-      out[1][i] = b;
-      out[2][i] = cn;
-      out[3][i] = d;
+      const cd a = ina[i], c = inc[i], d = ind[i];
+      const cd am = ina[im], cm = inc[im], dm = ind[im];
+      const cd ap = ina[ip], cp = inc[ip], dp = ind[ip];
+      const cd bb = csub(csub(cd{1.0, 0.0}, cmul(a, cm)), cmul(c, ap));
+      bad = bad || tiny(bb);
+      const cd ib = tiny(bb) ? crecip(bb) : crecipFast(bb);
+      const cd an = cmul(cmul(a, am), ib);
+      const cd cn = cmul(cmul(c, cp), ib);
+      const cd dn = cmul(csub(csub(d, cmul(a, dm)), cmul(c, dp)), ib);
+      outa[i] = {-an.re, -an.im};
+      outc[i] = {-cn.re, -cn.im};
+      outd[i] = dn;
     }
     __syncthreads();
     cur ^= 1;
@@ -403,10 +401,10 @@ __global__ void __launch_bounds__(LAP_PCR_NT) k_lap_pcr(const LapParams p) {
   __shared__ double psum[LAP_PCR_NT];
   double part = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const cd b = cadd(cadd(buf[cur][0][i], buf[cur][1][i]), buf[cur][2][i]);
+    const cd b = cadd(cadd(arr(cur, 0)[i], cd{1.0, 0.0}), arr(cur, 1)[i]);
     bad = bad || tiny(b);
-    const cd x = cmul(buf[cur][3][i], crecip(b));
-    buf[cur][3][i] = x;
+    const cd x = cmul(arr(cur, 2)[i], crecip(b));
+    arr(cur, 2)[i] = x;
     part += x.re;
   }
   double avg = 0.0;
@@ -420,7 +418,7 @@ __global__ void __launch_bounds__(LAP_PCR_NT) k_lap_pcr(const LapParams p) {
     avg = sum / static_cast<double>(n);
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) { // rows this thread wrote itself
-    cd x = buf[cur][3][i];
+    cd x = arr(cur, 2)[i];
     x.re -= avg;
     sp[i * xs] = x;
   }
@@ -1264,7 +1262,7 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
   }
   const unsigned sblocks = static_cast<unsigned>((plan.nsys + 127) / 128);
   const int nrows_sys = p.bd.xe - p.bd.xs + 1;
-  const size_t pcr_smem = static_cast<size_t>(8) * nrows_sys * sizeof(cd);
+  const size_t pcr_smem = static_cast<size_t>(6) * nrows_sys * sizeof(cd); // [2][a, c, d][n]
   static const bool no_pcr = getenv("BOUT_B200_LAP_NO_PCR") != nullptr;
   const bool pcr_shape = !lapCoupled(L) || (L->periodic_x && (nrows_sys & (nrows_sys - 1)) == 0);
   if (pcr_shape && !no_pcr && plan.nsys <= 2048 && nrows_sys >= 8 && pcr_smem <= 200 * 1024) {
@@ -1274,7 +1272,14 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
                                         static_cast<int>(pcr_smem)));
       pcr_attr = pcr_smem;
     }
-    k_lap_pcr<<<static_cast<unsigned>(plan.nsys), nrows_sys > 256 ? LAP_PCR_NT : 256, pcr_smem, s>>>(p);
+    // two 256-thread CTAs per SM while two systems fit into shared memory (measured at 1028 rows: 93 us per solve
+    // against 107 us with one 512-thread CTA), one wide CTA beyond that; BOUT_B200_PCR_NT overrides
+    static const int pcr_env = getenv("BOUT_B200_PCR_NT") ? atoi(getenv("BOUT_B200_PCR_NT")) : 0;
+    int pcr_nt = 2 * (pcr_smem + 1024) <= 220 * 1024 ? 256 : LAP_PCR_NT;
+    if (pcr_env == 256 || pcr_env == LAP_PCR_NT) {
+      pcr_nt = pcr_env;
+    }
+    k_lap_pcr<<<static_cast<unsigned>(plan.nsys), pcr_nt, pcr_smem, s>>>(p);
     B200_LAUNCH_OK();
   } else if (!lapCoupled(L)) {
     k_lap_thomas<<<sblocks, 128, plan.tab_smem, s>>>(p, plan.tab_smem != 0);
