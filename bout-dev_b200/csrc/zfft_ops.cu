@@ -609,7 +609,10 @@ __global__ void __launch_bounds__(256) k_row_mode(const RowModeParams p) {
   }
   const int fi = static_cast<int>(w / p.nrows);
   const long long row = w % p.nrows;
-  const double* __restrict__ src = p.f[fi] + row * p.nz;
+  // (selected without indexing the parameter arrays by a run-time value: that copies the struct to local memory)
+  const double* __restrict__ fsel = fi == 0 ? p.f[0] : (fi == 1 ? p.f[1] : (fi == 2 ? p.f[2] : p.f[3]));
+  double* __restrict__ osel = fi == 0 ? p.out[0] : (fi == 1 ? p.out[1] : (fi == 2 ? p.out[2] : p.out[3]));
+  const double* __restrict__ src = fsel + row * p.nz;
   double re = 0.0, im = 0.0;
   if (p.nz % 64 == 0 && aligned16(src)) {
     // 16-byte loads; three table reads per lane (its two starting factors and the common rotation by n0 * 64
@@ -648,8 +651,8 @@ __global__ void __launch_bounds__(256) k_row_mode(const RowModeParams p) {
     im += __shfl_xor_sync(0xffffffffu, im, o);
   }
   if (lane == 0) {
-    p.out[fi][2 * row] = re;
-    p.out[fi][2 * row + 1] = im;
+    osel[2 * row] = re;
+    osel[2 * row + 1] = im;
   }
 }
 
