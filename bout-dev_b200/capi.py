@@ -385,6 +385,28 @@ def boundary(g: Grid, kind, side, f, value=0.0, spacing=None, lo=-1, hi=-1):
     return f
 
 
+class CBndrySpec(C.Structure):
+    _fields_ = [("f", C.c_void_p), ("kind", C.c_int), ("side", C.c_int), ("value", C.c_double), ("spacing2d", C.c_void_p),
+                ("lo", C.c_int), ("hi", C.c_int)]
+
+
+def boundary_batch(g: Grid, entries):
+    """Several boundary conditions in one launch: entries = [(kind, side, f[, value[, spacing]]), ...]; entries must
+    not depend on each other (bout_b200_boundary_batch)."""
+    kinds = {"dirichlet": 0, "dirichlet_o2": 0, "neumann": 1, "zero": 2, "extend": 3, "free_o2": 4, "free_o3": 5}
+    sides = {"xin": 0, "xout": 1, "ydown": 2, "yup": 3}
+    arr = (CBndrySpec * len(entries))()
+    for i, e in enumerate(entries):
+        kind, side, f = e[0], e[1], e[2]
+        value = e[3] if len(e) > 3 else 0.0
+        spacing = e[4] if len(e) > 4 else None
+        arr[i].f = f.data_ptr()
+        arr[i].kind, arr[i].side, arr[i].value = kinds[kind], sides[side], value
+        arr[i].spacing2d = None if spacing is None else spacing.data_ptr()
+        arr[i].lo = arr[i].hi = -1
+    _check(lib.bout_b200_boundary_batch(C.byref(g.c), len(entries), arr, _stream()))
+
+
 def boundary_zerolaplace(g: Grid, side, f, dx, g11, g33, zlength, lo=-1, hi=-1):
     """In place.  BoundaryZeroLaplace on the xin / xout guard cells."""
     sd = {"xin": 0, "xout": 1}[side]

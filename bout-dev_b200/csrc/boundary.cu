@@ -26,9 +26,8 @@ struct BndryParams {
   int b;      // outward direction (-1 or +1)
 };
 
-__global__ void __launch_bounds__(256) k_boundary(const BndryParams p) {
+__device__ __forceinline__ void boundaryCell(const BndryParams& p, long long t) {
   const long long n = static_cast<long long>(p.hi - p.lo + 1) * p.nz;
-  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= n) {
     return;
   }
@@ -74,19 +73,46 @@ __global__ void __launch_bounds__(256) k_boundary(const BndryParams p) {
   }
 }
 
+__global__ void __launch_bounds__(256) k_boundary(const BndryParams p) {
+  boundaryCell(p, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
+
+// Several (field, side, condition) triples in ONE launch: blockIdx.y picks the entry.  The entries are reached
+// through a switch, not by indexing the parameter array with a run-time value (that would copy the whole struct to
+// local memory in every thread).  Entries do not depend on each other: a caller puts at most one entry per (field,
+// side) into a batch and keeps x sides (rows ystart..yend) apart from y sides that include their corner cells.
+constexpr int kMaxBndryBatch = 8;
+struct BndryBatch {
+  BndryParams s[kMaxBndryBatch];
+};
+__global__ void __launch_bounds__(256) k_boundary_batch(const BndryBatch b) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  switch (blockIdx.y) {
+  case 0: boundaryCell(b.s[0], t); break;
+  case 1: boundaryCell(b.s[1], t); break;
+  case 2: boundaryCell(b.s[2], t); break;
+  case 3: boundaryCell(b.s[3], t); break;
+  case 4: boundaryCell(b.s[4], t); break;
+  case 5: boundaryCell(b.s[5], t); break;
+  case 6: boundaryCell(b.s[6], t); break;
+  default: boundaryCell(b.s[7], t); break;
+  }
+}
+
 } // namespace b200
 
 using namespace b200;
 
-extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value,
-                                  const double* spacing2d, int lo, int hi, double* f, void* stream) {
+// fills p for one (field, side, condition); returns 1 when there is nothing to do on that side
+static int boundarySetup(const bout_b200_grid* g, int kind, int side, double value, const double* spacing2d, int lo,
+                         int hi, double* f, BndryParams& p) {
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
   B200_REQUIRE(f != nullptr && kind >= 0 && kind <= 5 && side >= 0 && side <= 3, BOUT_B200_ERR_ARG,
                "boundary: bad argument");
   B200_REQUIRE(kind != 1 || spacing2d != nullptr, BOUT_B200_ERR_ARG, "boundary: neumann needs the spacing");
-  BndryParams p{};
+  p = BndryParams{};
   p.f = f;
   p.spacing = spacing2d;
   p.val = value;
@@ -102,7 +128,7 @@ extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, d
   default: p.width = g->ny - g->yend - 1; p.first = g->ny - p.width; p.b = 1; break; // BoundaryRegionYUp
   }
   if (p.width <= 0) {
-    return 0; // no guard cells on this side
+    return 1; // no guard cells on this side
   }
   {
     const int interior = side < 2 ? g->xend - g->xstart + 1 : g->yend - g->ystart + 1;
@@ -115,7 +141,49 @@ extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, d
   }
   p.lo = lo;
   p.hi = hi;
-  const long long n = static_cast<long long>(hi - lo + 1) * g->nz;
+  return 0;
+}
+
+extern "C" int bout_b200_boundary_batch(const bout_b200_grid* g, int n, const bout_b200_bndry_spec* specs, void* stream) {
+  B200_REQUIRE(specs != nullptr && n >= 1, BOUT_B200_ERR_ARG, "boundary_batch: bad argument");
+  for (int i0 = 0; i0 < n; i0 += kMaxBndryBatch) {
+    BndryBatch b{};
+    int m = 0;
+    long long longest = 0;
+    for (int i = i0; i < n && i < i0 + kMaxBndryBatch; ++i) {
+      const bout_b200_bndry_spec& q = specs[i];
+      const int rc = boundarySetup(g, q.kind, q.side, q.value, q.spacing2d, q.lo, q.hi, q.f, b.s[m]);
+      if (rc < 0) {
+        return rc;
+      }
+      if (rc == 0) {
+        const long long cells = static_cast<long long>(b.s[m].hi - b.s[m].lo + 1) * g->nz;
+        longest = cells > longest ? cells : longest;
+        ++m;
+      }
+    }
+    if (m == 0) {
+      continue;
+    }
+    for (int i = m; i < kMaxBndryBatch; ++i) { // unused entries: empty ranges
+      b.s[i] = b.s[0];
+      b.s[i].hi = b.s[i].lo - 1;
+    }
+    const dim3 grid(static_cast<unsigned>((longest + 255) / 256), static_cast<unsigned>(m));
+    k_boundary_batch<<<grid, 256, 0, asStream(stream)>>>(b);
+    B200_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value,
+                                  const double* spacing2d, int lo, int hi, double* f, void* stream) {
+  BndryParams p{};
+  const int rc = boundarySetup(g, kind, side, value, spacing2d, lo, hi, f, p);
+  if (rc != 0) {
+    return rc < 0 ? rc : 0;
+  }
+  const long long n = static_cast<long long>(p.hi - p.lo + 1) * g->nz;
   k_boundary<<<static_cast<unsigned>((n + 255) / 256), 256, 0, asStream(stream)>>>(p);
   B200_LAUNCH_OK();
   return 0;

@@ -1373,12 +1373,13 @@ Field2D averageY(const Field2D& f) {
 
 // ---- boundaries ---------------------------------------------------------------------------------------
 namespace {
-void applyOne(Field3D& f, const std::string& cond_in, int side) {
+// The bout_b200_boundary arguments of one condition on one side of one field; false = nothing to apply.
+bool boundarySpec(Field3D& f, const std::string& cond_in, int side, bout_b200_bndry_spec& spec) {
   std::string cond = cond_in;
   cond.erase(std::remove_if(cond.begin(), cond.end(), [](unsigned char c) { return std::isspace(c); }), cond.end());
   std::transform(cond.begin(), cond.end(), cond.begin(), [](unsigned char c) { return std::tolower(c); });
   if (cond.empty() || cond == "none" || cond == "null") {
-    return;
+    return false;
   }
   if (cond.rfind("relax(", 0) == 0 && cond.back() == ')') {
     // relax(op[, rate]) (BoundaryRelax, boundary_standard.cxx:3599-3637): apply() is the wrapped condition's; the
@@ -1393,8 +1394,7 @@ void applyOne(Field3D& f, const std::string& cond_in, int side) {
         break;
       }
     }
-    applyOne(f, inner.substr(0, cut), side);
-    return;
+    return boundarySpec(f, inner.substr(0, cut), side, spec);
   }
   double value = 0.0;
   const auto paren = cond.find('(');
@@ -1429,11 +1429,23 @@ void applyOne(Field3D& f, const std::string& cond_in, int side) {
   } else {
     throw BoutException("Boundary condition '{}' is not available in the B200 host layer", cond);
   }
-  Mesh* m = f.getMesh();
-  Coordinates* c = m->getCoordinates();
-  const auto g = m->grid();
-  const double* spacing = side < 2 ? c->dx.dptr() : c->dy.dptr();
-  check(bout_b200_boundary(&g, kind, side, value, spacing, -1, -1, f.wptr(), nullptr));
+  Coordinates* c = f.getMesh()->getCoordinates();
+  spec = bout_b200_bndry_spec{};
+  spec.f = f.wptr();
+  spec.kind = kind;
+  spec.side = side;
+  spec.value = value;
+  spec.spacing2d = side < 2 ? c->dx.dptr() : c->dy.dptr();
+  spec.lo = -1;
+  spec.hi = -1;
+  return true;
+}
+void applyOne(Field3D& f, const std::string& cond, int side) {
+  bout_b200_bndry_spec q;
+  if (boundarySpec(f, cond, side, q)) {
+    const auto g = f.getMesh()->grid();
+    check(bout_b200_boundary(&g, q.kind, q.side, q.value, q.spacing2d, q.lo, q.hi, q.f, nullptr));
+  }
 }
 bool hasBoundary(Mesh* m, int side) {
   if (side < 2) {
@@ -2765,8 +2777,27 @@ void PhysicsModel::initialise(Solver* s) {
 }
 
 void Solver::pre_rhs() {
-  for (auto& f : f3d) {
-    f.var->applyBoundary();
+  // solver.cxx:1486-1500 applies every evolving field's conditions side by side; here all x sides go in ONE launch and
+  // all y sides (whose corner cells read what the x sides wrote) in a second one
+  if (f3d.empty()) {
+    return;
+  }
+  Mesh* m = f3d[0].var->getMesh();
+  const auto g = m->grid();
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<bout_b200_bndry_spec> specs;
+    for (auto& f : f3d) {
+      const auto& conds = f.var->bndry_conditions;
+      for (int s = 2 * pass; s < 2 * pass + 2 && s < static_cast<int>(conds.size()); ++s) {
+        bout_b200_bndry_spec q;
+        if (hasBoundary(m, s) && boundarySpec(*f.var, conds[s], s, q)) {
+          specs.push_back(q);
+        }
+      }
+    }
+    if (!specs.empty()) {
+      check(bout_b200_boundary_batch(&g, static_cast<int>(specs.size()), specs.data(), nullptr));
+    }
   }
 }
 void Solver::post_rhs() {

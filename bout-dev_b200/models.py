@@ -105,12 +105,13 @@ class HW3D:
     # -- one right-hand side on (n, vort) held in fields fn, fv
     def _pre_rhs(self, fn, fv):
         g = self.g
+        e = []
         if self.mesh is None or self.mesh.first_x:
-            capi.boundary(g, "dirichlet", "xin", fn)
-            capi.boundary(g, "dirichlet", "xin", fv)
+            e += [("dirichlet", "xin", fn), ("dirichlet", "xin", fv)]
         if self.mesh is None or self.mesh.last_x:
-            capi.boundary(g, "dirichlet", "xout", fn)
-            capi.boundary(g, "dirichlet", "xout", fv)
+            e += [("dirichlet", "xout", fn), ("dirichlet", "xout", fv)]
+        if e:
+            capi.boundary_batch(g, e)
 
     def _mark(self, name):
         """bench.py / tools: optional per-phase CUDA events (None = off, no overhead)."""
@@ -373,9 +374,8 @@ class ELMpb:
         else:
             self.mesh.communicate(fields)
 
-    def _bc_j(self, f):          # [J] bndry_core = neumann, rest dirichlet_o2
-        capi.boundary(self.g, "neumann", "xin", f, spacing=self.md["dx"])
-        capi.boundary(self.g, "dirichlet", "xout", f)
+    def _bc_j(self, f):          # [J] bndry_core = neumann, rest dirichlet_o2 (both sides in one launch)
+        capi.boundary_batch(self.g, [("neumann", "xin", f, 0.0, self.md["dx"]), ("dirichlet", "xout", f)])
 
     def _bc_psi(self, f):        # [Psi] zerolaplace on both X sides
         m = self.md
@@ -385,10 +385,9 @@ class ELMpb:
     def pre_rhs(self, U, P, Psi):
         """Solver::pre_rhs (solver.cxx:1486-1500): boundary conditions of the evolving fields."""
         g = self.g
-        capi.boundary(g, "dirichlet", "xin", U)
-        capi.boundary(g, "dirichlet", "xout", U)
-        capi.boundary(g, "neumann", "xin", P, spacing=self.md["dx"])      # [P] bndry_core = neumann
-        capi.boundary(g, "dirichlet", "xout", P)
+        capi.boundary_batch(g, [("dirichlet", "xin", U), ("dirichlet", "xout", U),
+                                ("neumann", "xin", P, 0.0, self.md["dx"]),      # [P] bndry_core = neumann
+                                ("dirichlet", "xout", P)])                      # one launch for the four
         self._bc_psi(Psi)
 
     def _grad_par_noslices(self, f):
@@ -448,8 +447,7 @@ class ELMpb:
             self.lap.solve(U, out=self.phi)
             ew(g, [(1.0, self.phi), (-0.5 * self.dnorm, P, None, self.B0)], out=self.phi)
             (sphi,) = self._comm_into([self.phi], ["phi"])
-            capi.boundary(g, "extend", "xin", self.phi)                           # :1498-1516
-            capi.boundary(g, "extend", "xout", self.phi)
+            capi.boundary_batch(g, [("extend", "xin", self.phi), ("extend", "xout", self.phi)])   # :1498-1516
         # The current chain (Delp2(Psi) -> BC -> communicate -> smooth_x -> ... -> row mode of Jpar: nine short launches
         # that depend on each other) is issued first; BOUT_B200_ELM_STREAMS=3 puts it on a third stream beside the
         # slice / row-mode kernels of the main one (no gain measured: the GPU is busy, not waiting)
@@ -647,11 +645,15 @@ class Blob2D:
         self.n.copy_(n)
         self.omega.copy_(omega)
 
-    def _bc(self, f):                          # bndry_all = neumann (Solver::pre_rhs)
-        if self.first_x:
-            capi.boundary(self.g, "neumann", "xin", f, spacing=self.md["dx"])
-        if self.last_x:
-            capi.boundary(self.g, "neumann", "xout", f, spacing=self.md["dx"])
+    def _bc(self, fields):                     # bndry_all = neumann (Solver::pre_rhs), one launch
+        e = []
+        for f in fields:
+            if self.first_x:
+                e.append(("neumann", "xin", f, 0.0, self.md["dx"]))
+            if self.last_x:
+                e.append(("neumann", "xout", f, 0.0, self.md["dx"]))
+        if e:
+            capi.boundary_batch(self.g, e)
 
     def _comm(self, fields):
         if self.mesh is not None:
@@ -662,8 +664,7 @@ class Blob2D:
         n = self.n if n is None else n
         omega = self.omega if omega is None else omega
         ew = capi.elementwise
-        self._bc(n)
-        self._bc(omega)
+        self._bc([n, omega])
         self._comm([n, omega])                                            # :169
         if not self.x_split:                                              # phi = phiSolver->solve(omega)  :181
             self.lap.solve(omega, out=self.phi)

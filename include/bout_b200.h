@@ -384,6 +384,18 @@ int bout_b200_where(const bout_b200_grid* g, const double* test, int test_is2d, 
  * (y for x sides, x for y sides); pass -1,-1 for the reference's default (ystart..yend / all x). */
 int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value,
                        const double* spacing2d, int lo, int hi, double* f, void* stream);
+/* Several boundary conditions in ONE launch (Solver::pre_rhs applies every evolving field's conditions on every side,
+ * src/solver/solver.cxx:1486-1500: up to 4 * nfields small passes in the reference).  Each entry is what one
+ * bout_b200_boundary call takes; entries must not depend on each other (at most one per field and side; x sides and
+ * y sides of one field only together when no entry's cells are another's inputs). */
+typedef struct bout_b200_bndry_spec {
+  double* f;
+  int kind, side;
+  double value;
+  const double* spacing2d;
+  int lo, hi;
+} bout_b200_bndry_spec;
+int bout_b200_boundary_batch(const bout_b200_grid* g, int n, const bout_b200_bndry_spec* specs, void* stream);
 /* zerolaplace (BoundaryZeroLaplace::apply(Field3D), src/mesh/boundary_standard.cxx:2630-2686): guard rows
  * continue the last interior row with the decaying solution of g11 d2f/dx2 - g33 kz^2 f = 0 per z mode and
  * a straight line for kz = 0.  X sides only (side 0 or 1); dx2d, g11, g33 Field2D; lo/hi as above. */

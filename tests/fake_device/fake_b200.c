@@ -222,6 +222,19 @@ int bout_b200_memcpy_d2h_async(void* dst, const void* src, size_t bytes, void* s
   return 0;
 }
 
+int bout_b200_boundary(const bout_b200_grid* g, int kind, int side, double value, const double* spacing2d, int lo,
+                       int hi, double* f, void* stream);
+int bout_b200_boundary_batch(const bout_b200_grid* g, int n, const bout_b200_bndry_spec* specs, void* stream) {
+  for (int i = 0; i < n; ++i) { /* one after the other: the entries of a batch are independent */
+    const int rc = bout_b200_boundary(g, specs[i].kind, specs[i].side, specs[i].value, specs[i].spacing2d, specs[i].lo,
+                                      specs[i].hi, specs[i].f, stream);
+    if (rc != 0) {
+      return rc;
+    }
+  }
+  return 0;
+}
+
 int bout_b200_where(const bout_b200_grid* g, const double* test, int test_is2d, const double* gt0, double gt0_value,
                     const double* le0, double le0_value, double* out, void* stream) {
   const long long n = (long long)g->nx * g->ny * g->nz;

@@ -105,9 +105,9 @@ def test_hw3d_guard_cells_written_by_the_producing_kernels(capi, gold, nz, monke
         assert torch.equal(a, b), name
     assert torch.isfinite(res["1"][0]).all() and float(res["1"][0].abs().max()) > 0.1
     if nz == 128:
-        # no boundary / exchange launches between the stages (the fused kernel itself is three launches: the edge
-        # rows apart from the rest)
-        assert res["1"][3] < res["0"][3] - 20
+        # no boundary / exchange launches between the stages: 12 right-hand sides of 4 solve launches + the fused kernel
+        # as three (the edge rows apart from the rest), plus the boundary / exchange launches of the very first state
+        assert res["1"][3] <= 12 * 7 + 4
 
 
 # ---- UNCHANGED reference models compiled against the C++ host layer -----------------------------------
