@@ -409,7 +409,7 @@ def boundary_batch(g: Grid, entries):
 
 def boundary_zerolaplace(g: Grid, side, f, dx, g11, g33, zlength, lo=-1, hi=-1):
     """In place.  BoundaryZeroLaplace on the xin / xout guard cells."""
-    sd = {"xin": 0, "xout": 1}[side]
+    sd = {"xin": 0, "xout": 1, "both": 2}[side]
     _check(lib.bout_b200_boundary_zerolaplace(C.byref(g.c), sd, _ptr(dx), _ptr(g11), _ptr(g33),
                                               C.c_double(zlength), lo, hi, _ptr(f), _stream()))
     return f

@@ -66,6 +66,9 @@ struct ZfftParams {
   const double* __restrict__ m_g11;
   const double* __restrict__ m_g33;
   int xin, bdir;
+  // Z_ZEROLAP on both X sides in one launch: zl_win >= 0 = number of inner guard rows; row groups 0 .. zl_win-1 are the
+  // inner guard cells (continued from zl_xstart inwards), the others the outer ones (from zl_xend outwards)
+  int zl_win, zl_xstart, zl_xend;
   double angle0, zlength0;
   int tpr, rows, pow2;
 };
@@ -89,10 +92,23 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
   const long long rowid = static_cast<long long>(blockIdx.x) * p.rows + rloc;
   const bool active = rowid < nrows;
   const long long rid = active ? rowid : nrows - 1; // idle groups redo the last row, never store
-  const int x = p.xs + static_cast<int>(rid / nyb);
+  int x = p.xs + static_cast<int>(rid / nyb);
+  int xin = p.xin, bdir = p.bdir;
+  if (p.mode == Z_ZEROLAP && p.zl_win >= 0) {
+    const int r = static_cast<int>(rid / nyb);
+    if (r < p.zl_win) {
+      x = r;
+      xin = p.zl_xstart;
+      bdir = -1;
+    } else {
+      x = p.zl_xend + 1 + (r - p.zl_win);
+      xin = p.zl_xend;
+      bdir = 1;
+    }
+  }
   const int y = p.ys + static_cast<int>(rid % nyb);
   const long long i2 = static_cast<long long>(x) * p.ny + y;
-  const long long isrc2 = p.mode == Z_ZEROLAP ? static_cast<long long>(p.xin) * p.ny + y : i2;
+  const long long isrc2 = p.mode == Z_ZEROLAP ? static_cast<long long>(xin) * p.ny + y : i2;
   const double* __restrict__ src = p.f + isrc2 * p.nz;
 
   // load the real row into A
@@ -111,7 +127,7 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
   cd* X = rfftForward(r);
   __shared__ double zsum[128];
   if (p.mode == Z_ZEROLAP) { // z-sum of the second interior row, all threads of the row group (uniform branch)
-    const double* __restrict__ in2 = p.f + (static_cast<long long>(p.xin - p.bdir) * p.ny + y) * p.nz;
+    const double* __restrict__ in2 = p.f + (static_cast<long long>(xin - bdir) * p.ny + y) * p.nz;
     double part = 0.0;
     for (int j = r.lane; j < p.nz; j += r.tpr) {
       part += __ldg(in2 + j);
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
       break;
     }
     case Z_ZEROLAP: { // BoundaryZeroLaplace::apply(Field3D), boundary_standard.cxx:2630-2686
-      const int steps = (x - p.xin) * p.bdir;
+      const int steps = (x - xin) * bdir;
       if (k == 0) { // straight line through the last two interior z-means
         double m2 = 0.0;
         for (int j = 0; j < p.tpr; ++j) {
@@ -191,7 +207,7 @@ __global__ void __launch_bounds__(128) k_zfft_rows(const ZfftParams p) {
       } else { // decaying solution of g11 d2f/dx2 - g33 kz^2 f = 0, applied guard cell by guard cell
         const double kwave = k * 2.0 * M_PI / p.zlength0;
         for (int s = 1; s <= steps; ++s) {
-          const long long ig = static_cast<long long>(p.xin + s * p.bdir) * p.ny + y;
+          const long long ig = static_cast<long long>(xin + s * bdir) * p.ny + y;
           const double coef = -1.0 * sqrt(__ldg(p.m_g33 + ig) / __ldg(p.m_g11 + ig)) * __ldg(p.m_dx + ig);
           const double e = exp(coef * kwave);
           v.re *= e;
@@ -819,9 +835,12 @@ extern "C" int bout_b200_boundary_zerolaplace(const bout_b200_grid* g, int side,
   if (checkGrid(g) != 0) {
     return BOUT_B200_ERR_ARG;
   }
-  B200_REQUIRE(f && dx2d && g11 && g33 && (side == 0 || side == 1), BOUT_B200_ERR_ARG,
-               "boundary_zerolaplace: bad argument (X boundaries only)");
-  const int width = side == 0 ? g->xstart : g->nx - 1 - g->xend;
+  B200_REQUIRE(f && dx2d && g11 && g33 && (side == 0 || side == 1 || side == 2), BOUT_B200_ERR_ARG,
+               "boundary_zerolaplace: bad argument (X boundaries only; 2 = both in one launch)");
+  if (side == 2 && (g->xstart == 0 || g->nx - 1 - g->xend == 0)) { // only one side has guard cells
+    side = g->xstart > 0 ? 0 : 1;
+  }
+  const int width = side == 0 ? g->xstart : (side == 1 ? g->nx - 1 - g->xend : g->xstart + g->nx - 1 - g->xend);
   if (width <= 0) {
     return 0;
   }
@@ -840,7 +859,14 @@ extern "C" int bout_b200_boundary_zerolaplace(const bout_b200_grid* g, int side,
   p.zlength0 = zlength;
   p.xin = side == 0 ? g->xstart : g->xend;
   p.bdir = side == 0 ? -1 : 1;
-  const Box b = side == 0 ? Box{0, g->xstart - 1, lo, hi} : Box{g->xend + 1, g->nx - 1, lo, hi};
+  p.zl_win = -1;
+  if (side == 2) { // row groups 0 .. width-1 cover the inner guard cells, then the outer ones
+    p.zl_win = g->xstart;
+    p.zl_xstart = g->xstart;
+    p.zl_xend = g->xend;
+  }
+  const Box b = side == 0 ? Box{0, g->xstart - 1, lo, hi}
+                          : (side == 1 ? Box{g->xend + 1, g->nx - 1, lo, hi} : Box{0, width - 1, lo, hi});
   return launchZfft(g, BOUT_B200_RGN_ALL, p, stream, &b);
 }
 

@@ -379,8 +379,7 @@ class ELMpb:
 
     def _bc_psi(self, f):        # [Psi] zerolaplace on both X sides
         m = self.md
-        capi.boundary_zerolaplace(self.g, "xin", f, m["dx"], m["g11"], m["g33"], self.zl)
-        capi.boundary_zerolaplace(self.g, "xout", f, m["dx"], m["g11"], m["g33"], self.zl)
+        capi.boundary_zerolaplace(self.g, "both", f, m["dx"], m["g11"], m["g33"], self.zl)   # one launch
 
     def pre_rhs(self, U, P, Psi):
         """Solver::pre_rhs (solver.cxx:1486-1500): boundary conditions of the evolving fields."""

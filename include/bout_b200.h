@@ -398,7 +398,8 @@ typedef struct bout_b200_bndry_spec {
 int bout_b200_boundary_batch(const bout_b200_grid* g, int n, const bout_b200_bndry_spec* specs, void* stream);
 /* zerolaplace (BoundaryZeroLaplace::apply(Field3D), src/mesh/boundary_standard.cxx:2630-2686): guard rows
  * continue the last interior row with the decaying solution of g11 d2f/dx2 - g33 kz^2 f = 0 per z mode and
- * a straight line for kz = 0.  X sides only (side 0 or 1); dx2d, g11, g33 Field2D; lo/hi as above. */
+ * a straight line for kz = 0.  X sides only (side 0 or 1; 2 = both sides in one launch); dx2d, g11, g33 Field2D;
+ * lo/hi as above. */
 int bout_b200_boundary_zerolaplace(const bout_b200_grid* g, int side, const double* dx2d,
                                    const double* g11, const double* g33, double zlength, int lo, int hi,
                                    double* f, void* stream);
