@@ -431,10 +431,10 @@ extern "C" int bout_b200_delp2_fft(const bout_b200_grid* g, const bout_b200_lapl
   }
   const bool fast_ok = aligned16(f) && aligned16(out) && getenv("BOUT_B200_NO_FAST_FFT") == nullptr;
   static const bool no_reg = getenv("BOUT_B200_DELP2_REG") != nullptr && getenv("BOUT_B200_DELP2_REG")[0] == '0';
-  // enough (y, x-tile) CTAs for the machine: the register path has no march, so 2-D (ny = 1) problems keep the
-  // marching kernel, whose tasks shrink with the problem
-  if (fast_ok && !no_reg && (g->nz == 128 || g->nz == 256 || g->nz == 512)
-      && static_cast<long long>(g->yend - g->ystart + 1) * (g->xend - g->xstart + 1) >= 148LL * 30) {
+  // the register-transform kernel for every problem size it supports: it has 2 / ROWS redundant transforms where a
+  // marching task has 2 per chunk, and on small 2-D grids (hasegawa-wakatani 256 x 256: four Delp2 per RHS) its one
+  // round of transforms is a third of the latency of a march (166 -> 148 us per RHS through the host layer)
+  if (fast_ok && !no_reg && (g->nz == 128 || g->nz == 256 || g->nz == 512)) {
     switch (g->nz / 2) {
     case 64: return launchDelp2Reg<64, 256>(p, s);
     case 128: return launchDelp2Reg<128, 256>(p, s);
