@@ -184,11 +184,16 @@ template <int N>
 int launchDelp2Fast(Delp2FftParams p, cudaStream_t s) {
   constexpr int TPR = FftShape<N>::TPR, ROWS_MAX = 256 / TPR;
   const int len = p.xe - p.xs + 1, nyb = p.ye - p.ys + 1;
-  // (y, x-chunk) tasks: enough of them to occupy the SMs; each chunk costs two extra forward transforms, so
-  // chunks shrink (down to 2 rows) only for small problems, where latency, not throughput, is the limit
+  // (y, x-chunk) tasks: enough of them to occupy the SMs; each chunk costs two extra forward transforms, so chunks
+  // shrink only for small problems and not below 4 rows (measured on blob2d's 1028 x 1 x 1024, the one shape this
+  // kernel still serves: 272 / 258 / 247 / 293 us per RHS with chunks of 1 / 2 / 4 / 8)
   int chunk = 32;
-  while (chunk > 2 && static_cast<long long>(nyb) * ((len + chunk - 1) / chunk) < 148LL * 4 * ROWS_MAX) {
+  while (chunk > 4 && static_cast<long long>(nyb) * ((len + chunk - 1) / chunk) < 148LL * 4 * ROWS_MAX) {
     chunk /= 2;
+  }
+  static const int chunk_env = getenv("BOUT_B200_DELP2_CHUNK") ? atoi(getenv("BOUT_B200_DELP2_CHUNK")) : 0;
+  if (chunk_env > 0) {
+    chunk = chunk_env;
   }
   p.chunk = chunk;
   p.nchunks = (len + chunk - 1) / chunk;
