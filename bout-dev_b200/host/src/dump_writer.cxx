@@ -426,13 +426,19 @@ void OutputPipeline::snapshot(double time, int iteration, const std::vector<cons
   cur.time = time;
   cur.iteration = iteration;
   cur.held.clear();
-  check(bout_b200_stream_wait(copy_stream, nullptr)); // the snapshot is complete once the compute stream gets here
+  // device pointers first: asking for one launches a field's pending (deferred) combination on the compute stream,
+  // and that launch has to be ahead of the point the copy stream waits for
+  std::vector<const double*> src(nfields);
   for (size_t f = 0; f < nfields; ++f) {
     if (!fields[f]->isAllocated()) {
       throw BoutException("OutputPipeline::snapshot: field {} has no data", f);
     }
     cur.held.push_back(*fields[f]); // copy-on-write handle: later steps cannot overwrite this block
-    check(bout_b200_memcpy_d2h_async(cur.staging + f * count, fields[f]->dptr(), count * sizeof(double), copy_stream));
+    src[f] = fields[f]->dptr();
+  }
+  check(bout_b200_stream_wait(copy_stream, nullptr)); // the snapshot is complete once the compute stream gets here
+  for (size_t f = 0; f < nfields; ++f) {
+    check(bout_b200_memcpy_d2h_async(cur.staging + f * count, src[f], count * sizeof(double), copy_stream));
   }
   cur.copying = true;
   ++next;
