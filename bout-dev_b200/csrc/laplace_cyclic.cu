@@ -427,6 +427,129 @@ __global__ void __launch_bounds__(LAP_PCR_NT) k_lap_pcr(const LapParams p) {
   }
 }
 
+// The same elimination with every thread's own rows (i = tid + k * 256, k < R) carried in REGISTERS from step to step:
+// a step then reads only the six neighbour values of a row from shared memory and stores its three new ones (six loads
+// + three stores where k_lap_pcr has nine + three through the pipe that bounds it).  Systems of up to 256 R rows.
+constexpr int LAP_PCRR_NT = 256;
+template <int R>
+__global__ void __launch_bounds__(LAP_PCRR_NT, 2) k_lap_pcr_reg(const LapParams p) {
+  extern __shared__ __align__(16) unsigned char pcr_raw[];
+  const int n = p.bd.xe - p.bd.xs + 1;
+  const bool periodic = p.bd.periodic_x != 0;
+  cd* const base = reinterpret_cast<cd*>(pcr_raw);
+  auto arr = [&](int h, int q) { return base + static_cast<size_t>(h * 3 + q) * n; };
+  const int nys = p.ye - p.ys + 1;
+  const int t = blockIdx.x;
+  const int iyl = t / p.nmode, kz = t % p.nmode;
+  const int jy = p.ys + iyl;
+  const long long xs = static_cast<long long>(nys) * p.nmode;
+  const double kwave = kz * 2.0 * M_PI / p.m.zlength;
+  const double* tab = p.table + (static_cast<long long>(jy) * p.nx + p.bd.xs) * LAP_NK;
+  cd* __restrict__ sp = p.spec + t;
+  const int tid = threadIdx.x;
+  bool bad = false;
+  cd ra[R], rc[R], rd[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int ix = tid + k * LAP_PCRR_NT;
+    ra[k] = rc[k] = rd[k] = cd{0.0, 0.0};
+    if (ix < n) {
+      cd a, b, c, r = ldcd(sp + ix * xs);
+      lapRow(p, tab, ix, jy, kz, kwave, a, b, c, r);
+      if (!periodic && ix == 0) {
+        a = {0.0, 0.0};
+      }
+      if (!periodic && ix == n - 1) {
+        c = {0.0, 0.0};
+      }
+      bad = bad || tiny(b);
+      const cd ib = crecip(b);
+      ra[k] = cmul(a, ib);
+      rc[k] = cmul(c, ib);
+      rd[k] = cmul(r, ib);
+      arr(0, 0)[ix] = ra[k];
+      arr(0, 1)[ix] = rc[k];
+      arr(0, 2)[ix] = rd[k];
+    }
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int sft = 1; sft < n; sft <<= 1) {
+    const cd* const ina = arr(cur, 0);
+    const cd* const inc = arr(cur, 1);
+    const cd* const ind = arr(cur, 2);
+    cd* const outa = arr(cur ^ 1, 0);
+    cd* const outc = arr(cur ^ 1, 1);
+    cd* const outd = arr(cur ^ 1, 2);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int i = tid + k * LAP_PCRR_NT;
+      if (i < n) {
+        int im = i - sft, ip = i + sft;
+        if (periodic) {
+          im &= n - 1;
+          ip &= n - 1;
+        } else { // a coupling that would leave the system is exactly zero: the clamped neighbour is multiplied by it
+          im = max(im, 0);
+          ip = min(ip, n - 1);
+        }
+        const cd a = ra[k], c = rc[k], d = rd[k];
+        const cd am = ina[im], cm = inc[im], dm = ind[im];
+        const cd ap = ina[ip], cp = inc[ip], dp = ind[ip];
+        const cd bb = csub(csub(cd{1.0, 0.0}, cmul(a, cm)), cmul(c, ap));
+        bad = bad || tiny(bb);
+        const cd ib = tiny(bb) ? crecip(bb) : crecipFast(bb);
+        const cd an = cmul(cmul(a, am), ib);
+        const cd cn = cmul(cmul(c, cp), ib);
+        ra[k] = {-an.re, -an.im};
+        rc[k] = {-cn.re, -cn.im};
+        rd[k] = cmul(csub(csub(d, cmul(a, dm)), cmul(c, dp)), ib);
+        outa[i] = ra[k];
+        outc[i] = rc[k];
+        outd[i] = rd[k];
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  // every row is decoupled: its remaining a and c multiply x_i itself (periodic, s = n) or are zero
+  __shared__ double psum[LAP_PCRR_NT];
+  double part = 0.0;
+  cd x[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = tid + k * LAP_PCRR_NT;
+    x[k] = {0.0, 0.0};
+    if (i < n) {
+      const cd b = cadd(cadd(ra[k], cd{1.0, 0.0}), rc[k]);
+      bad = bad || tiny(b);
+      x[k] = cmul(rd[k], crecip(b));
+      part += x[k].re;
+    }
+  }
+  double avg = 0.0;
+  if (periodic && kz == 0) { // subtract the x-average of the kz = 0 mode (cyclic_laplace.cxx:266-287); uniform branch
+    psum[tid] = part;
+    __syncthreads();
+    double sum = 0.0;
+    for (int q = 0; q < LAP_PCRR_NT; ++q) {
+      sum += psum[q];
+    }
+    avg = sum / static_cast<double>(n);
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = tid + k * LAP_PCRR_NT;
+    if (i < n) {
+      x[k].re -= avg;
+      sp[i * xs] = x[k];
+    }
+  }
+  if (bad) {
+    atomicExch(p.status, 1);
+  }
+}
+
 constexpr int LAP_PFC = 4; // coupled kernels carry two or three rings: keep them in registers
 
 // K2a (coupled systems): downward and upward elimination in one pass -> interface equations
@@ -1272,6 +1395,27 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
                                         static_cast<int>(pcr_smem)));
       pcr_attr = pcr_smem;
     }
+    static const bool pcr_noreg = getenv("BOUT_B200_PCR_REG") != nullptr && getenv("BOUT_B200_PCR_REG")[0] == '0';
+    const int rpt = (nrows_sys + LAP_PCRR_NT - 1) / LAP_PCRR_NT; // rows per thread of the register variant
+    if (!pcr_noreg && rpt <= 6 && 2 * (pcr_smem + 3072) <= 220 * 1024) {
+      auto launch = [&](auto kern) {
+        static size_t attr = 0; // (one static per instantiation)
+        if (pcr_smem > 48 * 1024 && pcr_smem > attr) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pcr_smem));
+          attr = pcr_smem;
+        }
+        kern<<<static_cast<unsigned>(plan.nsys), LAP_PCRR_NT, pcr_smem, s>>>(p);
+      };
+      switch (rpt) {
+      case 1: launch(k_lap_pcr_reg<1>); break;
+      case 2: launch(k_lap_pcr_reg<2>); break;
+      case 3: launch(k_lap_pcr_reg<3>); break;
+      case 4: launch(k_lap_pcr_reg<4>); break;
+      case 5: launch(k_lap_pcr_reg<5>); break;
+      default: launch(k_lap_pcr_reg<6>); break;
+      }
+      B200_LAUNCH_OK();
+    } else {
     // two 256-thread CTAs per SM while two systems fit into shared memory (measured at 1028 rows: 93 us per solve
     // against 107 us with one 512-thread CTA), one wide CTA beyond that; BOUT_B200_PCR_NT overrides
     static const int pcr_env = getenv("BOUT_B200_PCR_NT") ? atoi(getenv("BOUT_B200_PCR_NT")) : 0;
@@ -1281,6 +1425,7 @@ extern "C" int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bou
     }
     k_lap_pcr<<<static_cast<unsigned>(plan.nsys), pcr_nt, pcr_smem, s>>>(p);
     B200_LAUNCH_OK();
+    }
   } else if (!lapCoupled(L)) {
     k_lap_thomas<<<sblocks, 128, plan.tab_smem, s>>>(p, plan.tab_smem != 0);
     B200_LAUNCH_OK();
