@@ -262,6 +262,32 @@ B200_HD void regfftSplitWriteX(const cd (&v)[RegFft<N>::B], const cd (&pc)[RegFf
   }
 }
 
+// The same with a per-bin function applied to every spectrum value as it is written, mod(k, X[k]) -> stored value:
+// a kernel whose per-mode operation is a multiplier (z derivative, filters, phase shift) needs no separate pass over
+// the row buffer between the two transforms.
+template <int N, class Mod>
+B200_HD void regfftSplitWriteXMod(const cd (&v)[RegFft<N>::B], const cd (&pc)[RegFft<N>::B / 2 + 1], cd* X,
+                                  const cd* __restrict__ tw, int t, Mod mod) {
+  constexpr int T = RegFft<N>::T, B = RegFft<N>::B;
+  constexpr double sc = 0.5 / (2 * N);
+  const cd ws = ldtw(tw, t);
+#pragma unroll
+  for (int q = 0; q <= B / 2; ++q) {
+    if (q < B / 2 || t == 0) {
+      const int k = t + T * q;
+      const cd zk = v[q], zc = pc[q];
+      const cd e = cadd(zk, zc);
+      const cd dmi = csub(zk, zc);
+      const cd o = {dmi.im, -dmi.re}; // -i (zk - zc)
+      const cd wo = cmul(regfftSplitTw<N>(ws, q), o);
+      X[k] = mod(k, q, false, cscale(cadd(e, wo), sc));
+      if (q < B / 2) {
+        X[N - k] = mod(N - k, q, true, cscale(cconj(csub(e, wo)), sc));
+      }
+    }
+  }
+}
+
 // ---- real merge (backward): v[n2] = packed complex input element t + T n2 of the inverse transform -------------
 // X: the row buffer (spectrum); bins >= nmode, and the DC bin when zero_dc, read as zero.
 template <int N>

@@ -406,11 +406,27 @@ __global__ void __launch_bounds__(128, 4) k_zrows_reg(const ZfftParams p) {
     __syncwarp();
     regfftSplitWriteZ<N>(v, X, t);
     __syncwarp();
+    bool fused_mod = false; // the per-mode multiplier applied while the spectrum is written (single-output modes)
     {
       cd pc[B / 2 + 1];
       regfftSplitReadPartners<N>(pc, X, t);
       __syncwarp();
-      regfftSplitWriteX<N>(v, pc, X, p.tw, t);
+      if (!TWO && p.mode != Z_SHIFT && p.mode != Z_SLICE) {
+        fused_mod = true;
+        const int mode = p.mode, kmax = p.kmax, n0 = p.n0, keep_zonal = p.keep_zonal;
+        regfftSplitWriteXMod<N>(v, pc, X, p.tw, t, [&](int k, int, bool, cd w) -> cd {
+          const double kw = k * kfac;
+          switch (mode) {
+          case Z_DDZ1: return k <= kmax ? cd{-w.im * kw, w.re * kw} : cd{0.0, 0.0};
+          case Z_DDZ2: return cscale(w, -kw * kw);
+          case Z_FILTER: return k != n0 ? cd{0.0, 0.0} : w;
+          case Z_LOWPASS: return (k > kmax || (k == 0 && !keep_zonal)) ? cd{0.0, 0.0} : w;
+          default: return (k != n0 || k > kmax || (k == 0 && !keep_zonal)) ? cd{0.0, 0.0} : w; // Z_FILTER_LOWPASS
+          }
+        });
+      } else {
+        regfftSplitWriteX<N>(v, pc, X, p.tw, t);
+      }
     }
     __syncwarp();
 #pragma unroll
@@ -436,7 +452,9 @@ __global__ void __launch_bounds__(128, 4) k_zrows_reg(const ZfftParams p) {
         dstf = o == 0 ? p.out : p.out2;
       }
       // this thread's bins k = t + T q (and the Nyquist bin for t = 0): X -> D
-      if (mode == Z_SHIFT || mode == Z_SLICE) { // * exp(-i kwave ang), kwave = 2 pi k / zl
+      if (fused_mod) {
+        // already applied by regfftSplitWriteXMod (D is X)
+      } else if (mode == Z_SHIFT || mode == Z_SLICE) { // * exp(-i kwave ang), kwave = 2 pi k / zl
         const double th = 2.0 * M_PI / zl * ang;
         double sn, cs;
         sincos(th * t, &sn, &cs);
@@ -486,7 +504,9 @@ __global__ void __launch_bounds__(128, 4) k_zrows_reg(const ZfftParams p) {
           }
         }
       }
-      __syncwarp();
+      if (!fused_mod) {
+        __syncwarp();
+      }
       regfftMergeRead<N>(v, D, N + 1, false, p.tw, t);
       __syncwarp();
       regfftStage1<N, true>(v, p.tw, t);
