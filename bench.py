@@ -18,8 +18,12 @@ the same problem computed on one rank (<= 1e-12).
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
   python bench.py --workload elmpb [...]                        BASELINE configs[4]: elm-pb 3-field RHS, 512x64x256
                                                                 interior points per GPU (shifted metric), RK4
-The default (hw3d) line also carries "other": elm-pb RHS points/s at 1 GPU, LaplaceCyclic solves/s and the
-examples/performance microbenchmarks (BASELINE configs[1], 256x64x256) -- short extra measurements, N = 1 only.
+  python bench.py --workload blob2d [...]                       BASELINE configs[2]: blob2d 1024x1x1024 in total,
+                                                                X-decomposed over the GPUs (NXPE = N, strong scaling)
+The default (hw3d) line also carries "other": elm-pb RHS points/s at 1 GPU, LaplaceCyclic solves/s, the
+examples/performance microbenchmarks (BASELINE configs[1], 256x64x256; timed both after an L2 flush and in steady
+state over operand sets larger than L2) and the UNCHANGED reference sources (hasegawa-wakatani, blob2d,
+hasegawa-wakatani-3d) run through the C++ host layer -- short extra measurements, N = 1 only.
   python bench.py --impl reference [...]                        the reference's own CPU implementation of the
                                                                 same RHS (oracle/_ref, host cores, bounded slab)
 """
