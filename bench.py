@@ -289,6 +289,33 @@ def parity_gate_decomposed(torch, pkg, dev, rank, nxpe, nype):
                     f"problem on one rank"}
 
 
+
+def bind_to_gpu_numa_node(torch, local):
+    """Best effort, N > 1 only: run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host
+    buffer is allocated (first touch then places the e2e staging buffers next to that GPU's PCIe root instead of on
+    whichever node the launcher started the process).  Returns what was done, for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return {"gpu": bdf, "numa_node": node, "nodes": len(nodes), "bound": False}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu": bdf, "numa_node": node, "nodes": len(nodes), "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": bdf, "numa_node": node, "nodes": len(nodes), "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001 -- sysfs not visible in this container, old torch, ...
+        return {"bound": False, "why": repr(e)[:120]}
+
+
 def run_ours(args):
     import torch
     import __graft_entry__ as ge
@@ -307,6 +334,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: bout-dev_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if (world > 1 and os.environ.get("BOUT_B200_NUMA_BIND", "1") != "0") else None
     pkg = ge.load_package()
     capi, models = pkg.capi, pkg.models
     mesh = None
@@ -431,7 +459,7 @@ def run_ours(args):
         "e2e": {"value": npts * 4 * e2e_steps * world / e2e_secs, "unit": UNIT,
                 "h2d_bytes_per_step": 2 * field_bytes, "d2h_bytes_per_step": 2 * field_bytes,
                 "ms_per_step": e2e_secs / e2e_steps * 1e3, "result_equals_device_resident_step": e2e_ok,
-                "note": "state (n, vort) copied host->device from pinned memory and the result device->host every RK4 step; "
+                "host_numa_binding": numa, "note": "state (n, vort) copied host->device from pinned memory and the result device->host every RK4 step; "
                         "uploads / computation / downloads of neighbouring steps overlap on three streams (double-buffered)"},
         "roofline": {"bound": "hbm", "kernel": "k_hw3d_rhs<2> (fused RHS + RK stage update)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
