@@ -126,3 +126,26 @@ def test_rk_stage_updates(capi, orc, port):
     assert rel_err(got, 0.75 * s + 0.25 * k1 + 0.25 * dt * k2, I) < 1e-15
     got = capi.rk_stage(g, "rk3_stage3", dt, dev(s), dev(k1), dev(k2)).cpu().numpy()
     assert rel_err(got, (1. / 3) * s + (2. / 3.) * (k1 + dt * k2), I) < 1e-15
+
+
+def test_boundary_batch_equals_single_calls(capi):
+    """bout_b200_boundary_batch: several (field, side, condition) entries in one launch give bitwise what one
+    bout_b200_boundary call per entry gives (x sides in one batch, y sides -- whose corner cells read what the x sides
+    wrote -- in a second one, as Solver::pre_rhs of the host layer issues them); more entries than one launch holds."""
+    g = capi.Grid(11, 9, 12, 2, 2)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    fields = [torch.rand(g.shape3, dtype=torch.float64, device="cuda", generator=gen) for _ in range(5)]
+    dx = torch.rand(g.shape2, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    dy = torch.rand(g.shape2, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    kinds = ["dirichlet", "neumann", "free_o2", "free_o3", "extend"]
+    want = [f.clone() for f in fields]
+    for f, k in zip(want, kinds):
+        for side in ("xin", "xout"):
+            capi.boundary(g, k, side, f, value=0.3, spacing=dx)
+        for side in ("ydown", "yup"):
+            capi.boundary(g, k, side, f, value=0.3, spacing=dy)
+    got = [f.clone() for f in fields]
+    capi.boundary_batch(g, [(k, side, f, 0.3, dx) for f, k in zip(got, kinds) for side in ("xin", "xout")])     # 10 entries
+    capi.boundary_batch(g, [(k, side, f, 0.3, dy) for f, k in zip(got, kinds) for side in ("ydown", "yup")])
+    for a, b, k in zip(got, want, kinds):
+        assert torch.equal(a, b), k
