@@ -601,6 +601,8 @@ public:
   int geometry(); ///< g_ij, J, d1_dx from the contravariant metric (coordinates.cxx:932-1201; G1..G3 as given)
   /// cached reciprocal spacings used to fuse the "/dx" passes into the stencil kernels
   const Field2D& recip(const std::string& which);
+  const Field2D& invSg();                                         ///< 1 / sqrt(g_22) (coordinates.cxx:1879-1886)
+  const Field2D& Grad2_par2_DDY_invSg(const std::string& method); ///< DDY(invSg) invSg (coordinates.cxx:1888-1905)
   BoutReal zlength_ = 0.0;
 
 private:
@@ -659,6 +661,18 @@ Field3D D2DY2(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& meth
 Field3D D2DZ2(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT", const std::string& region = "RGN_NOBNDRY");
 Field3D VDDX(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT", const std::string& region = "RGN_NOBNDRY");
 Field3D VDDZ(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT", const std::string& region = "RGN_NOBNDRY");
+Field3D VDDY(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT", const std::string& region = "RGN_NOBNDRY");
+/// flux derivatives d/dx (v f) (derivs.cxx:501-600: the index operator divided by the spacing)
+Field3D FDDX(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT", const std::string& region = "RGN_NOBNDRY");
+Field3D FDDY(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT", const std::string& region = "RGN_NOBNDRY");
+Field3D FDDZ(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT", const std::string& region = "RGN_NOBNDRY");
+/// parallel operators with the identity parallel transform (coordinates.cxx:1517-1625, difops.cxx:46-180):
+/// Grad_par = DDY / sqrt(g_22), Vpar_Grad_par = VDDY / sqrt(g_22), Div_par(f) = Bxy Grad_par(f / Bxy),
+/// Grad2_par2 = DDY(1/sqrt(g_22))/sqrt(g_22) DDY(f) + D2DY2(f) / g_22
+Field3D Grad_par(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT");
+Field3D Vpar_Grad_par(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT");
+Field3D Div_par(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT");
+Field3D Grad2_par2(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT");
 Field3D bracket(const Field3D& f, const Field3D& g, BRACKET_METHOD method = BRACKET_STD, CELL_LOC = CELL_DEFAULT, Solver* = nullptr);
 Field3D bracket(const Field3D& f, const Field2D& g, BRACKET_METHOD method = BRACKET_STD, CELL_LOC = CELL_DEFAULT, Solver* = nullptr);
 Field3D bracket(const Field2D& f, const Field3D& g, BRACKET_METHOD method = BRACKET_STD, CELL_LOC = CELL_DEFAULT, Solver* = nullptr);

@@ -2083,6 +2083,109 @@ Field3D D2DZ2(const Field3D& f, CELL_LOC, const std::string& method, const std::
   }
   return stencil(f, nullptr, stencilOp("D2DX2", meth), BOUT_B200_Z, region, &m->getCoordinates()->recip("1/dz2"));
 }
+Field3D VDDY(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, &v, stencilOp("VDDX", pick(m, 'y', "upwind", method)), BOUT_B200_Y, region,
+                 &m->getCoordinates()->recip("1/dy"));
+}
+Field3D FDDX(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, &v, stencilOp("FDDX", pick(m, 'x', "flux", method)), BOUT_B200_X, region,
+                 &m->getCoordinates()->recip("1/dx"));
+}
+Field3D FDDY(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, &v, stencilOp("FDDX", pick(m, 'y', "flux", method)), BOUT_B200_Y, region,
+                 &m->getCoordinates()->recip("1/dy"));
+}
+Field3D FDDZ(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
+  Mesh* m = f.getMesh();
+  return stencil(f, &v, stencilOp("FDDX", pick(m, 'z', "flux", method)), BOUT_B200_Z, region,
+                 &m->getCoordinates()->recip("1/dz"));
+}
+
+// ---- parallel operators, identity parallel transform (coordinates.cxx:1517-1625) -------------------------------------
+const Field2D& Coordinates::invSg() {
+  CacheKey key;
+  key.blk[0] = g_22.block();
+  key.ver[0] = g_22.block() != nullptr ? g_22.block()->version : 0;
+  auto it = cache.find("invSg");
+  if (it != cache.end()) {
+    const CacheKey& k = cache_key["invSg"];
+    if (k.blk[0] == key.blk[0] && k.ver[0] == key.ver[0]) {
+      return it->second;
+    }
+    cache.erase(it);
+  }
+  cache_key["invSg"] = key;
+  const std::vector<double> g = g_22.getHost();
+  std::vector<double> v(g.size());
+  for (size_t i = 0; i < g.size(); ++i) {
+    v[i] = 1.0 / std::sqrt(g[i]);
+  }
+  Field2D r(localmesh);
+  r.setHost(v);
+  return cache.emplace("invSg", r).first->second;
+}
+const Field2D& Coordinates::Grad2_par2_DDY_invSg(const std::string& method) {
+  const std::string name = "G2P2:" + method;
+  CacheKey key;
+  key.blk[0] = g_22.block();
+  key.ver[0] = g_22.block() != nullptr ? g_22.block()->version : 0;
+  key.blk[1] = dy.block();
+  key.ver[1] = dy.block() != nullptr ? dy.block()->version : 0;
+  auto it = cache.find(name);
+  if (it != cache.end()) {
+    const CacheKey& k = cache_key[name];
+    if (k.blk[0] == key.blk[0] && k.ver[0] == key.ver[0] && k.blk[1] == key.blk[1] && k.ver[1] == key.ver[1]) {
+      return it->second;
+    }
+    cache.erase(it);
+  }
+  cache_key[name] = key;
+  // DDY of a Field2D over RGN_NOBNDRY with the mesh's first-derivative method, times invSg; the y guard cells of
+  // invSg are those of the metric itself (wrapped where y is periodic: what the reference's communicate gives)
+  const int nx = localmesh->LocalNx, ny = localmesh->LocalNy;
+  const std::vector<double> isg = invSg().getHost(), d = dy.getHost();
+  std::vector<double> v(isg.size(), 0.0);
+  const bool c4 = method == "C4";
+  if (!c4 && method != "C2") {
+    throw BoutException("Grad2_par2: first-derivative method '{}' is not available for Field2D on the B200 host layer", method);
+  }
+  for (int x = 0; x < nx; ++x) {
+    for (int y = localmesh->ystart; y <= localmesh->yend; ++y) {
+      const size_t i = static_cast<size_t>(x) * ny + y;
+      double dd;
+      if (c4) {
+        dd = (8.0 * isg[i + 1] - 8.0 * isg[i - 1] + isg[i - 2] - isg[i + 2]) / 12.0;
+      } else {
+        dd = 0.5 * (isg[i + 1] - isg[i - 1]);
+      }
+      v[i] = dd / d[i] * isg[i];
+    }
+  }
+  Field2D r(localmesh);
+  r.setHost(v);
+  return cache.emplace(name, r).first->second;
+}
+Field3D Grad_par(const Field3D& f, CELL_LOC loc, const std::string& method) {
+  return DDY(f, loc, method) * f.getMesh()->getCoordinates()->invSg();
+}
+Field3D Vpar_Grad_par(const Field3D& v, const Field3D& f, CELL_LOC loc, const std::string& method) {
+  return VDDY(v, f, loc, method) * f.getMesh()->getCoordinates()->invSg();
+}
+Field3D Div_par(const Field3D& f, CELL_LOC loc, const std::string& method) {
+  Coordinates* c = f.getMesh()->getCoordinates();
+  return c->Bxy * Grad_par(f / c->Bxy, loc, method);
+}
+Field3D Grad2_par2(const Field3D& f, CELL_LOC loc, const std::string& method) {
+  Mesh* m = f.getMesh();
+  Coordinates* c = m->getCoordinates();
+  const Field3D d1 = DDY(f, loc, method);
+  const Field3D r2 = D2DY2(f, loc, method) / c->g_22;
+  return c->Grad2_par2_DDY_invSg(pick(m, 'y', "first", method)) * d1 + r2;
+}
+
 Field3D VDDX(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
   Mesh* m = f.getMesh();
   return stencil(f, &v, stencilOp("VDDX", pick(m, 'x', "upwind", method)), BOUT_B200_X, region,

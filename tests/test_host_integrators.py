@@ -280,6 +280,20 @@ def test_vectors_grad_where_through_the_host_layer_host_logic(fake_device):
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
 
 
+def test_parallel_operators_and_flux_derivatives_host_logic(fake_device):
+    """tests/par_ops_check.py on CPU: the host layer's Grad_par, Vpar_Grad_par, Div_par, Grad2_par2 (identity parallel
+    transform), VDDY and FDDX / FDDY / FDDZ against the same model source run by the reference build on a mesh whose
+    g_22, dy and Bxy vary.  (On the device these are bout_b200_stencil calls in the Y direction and element-wise passes,
+    both covered by the -m gpu operator tests.)"""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "par_ops_check.py")],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
 def test_fieldperp_through_the_host_layer_host_logic(fake_device):
     """tests/perp_ops_check.py on CPU: the host layer's FieldPerp (sliceXZ, algebra, element access,
     Laplacian::solve(FieldPerp), Field3D = FieldPerp) against the same model source run by the reference build."""
