@@ -211,6 +211,16 @@ def test_vectors_grad_where_through_the_host_layer():
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
 
 
+def test_parallel_operators_and_flux_derivatives_through_the_host_layer():
+    """tests/models/par_ops.cxx on the device (tests/par_ops_check.py): Grad_par, Vpar_Grad_par, Div_par, Grad2_par2,
+    VDDY, FDDX / FDDY / FDDZ of the host layer against the reference build's run of the same source (1e-12)."""
+    import json, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, os.path.join(here, "par_ops_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
 def test_where_kernel(capi):
     """bout_b200_where against numpy (reference include/bout/where.hxx: test > 0 ? gt0 : le0), 3-D and 2-D tests,
     field and constant branches; bit-exact (a selection)."""
