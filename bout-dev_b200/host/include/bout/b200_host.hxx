@@ -673,6 +673,9 @@ Field3D Grad_par(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& m
 Field3D Vpar_Grad_par(const Field3D& v, const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT");
 Field3D Div_par(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT");
 Field3D Grad2_par2(const Field3D& f, CELL_LOC = CELL_DEFAULT, const std::string& method = "DEFAULT");
+/// Div_par(K Grad_par f) (difops.cxx:327-367): K Grad2_par2(f) [+ Div_par(K) Grad_par(f) for a field K]
+Field3D Div_par_K_Grad_par(BoutReal kY, const Field3D& f, CELL_LOC = CELL_DEFAULT);
+Field3D Div_par_K_Grad_par(const Field3D& kY, const Field3D& f, CELL_LOC = CELL_DEFAULT);
 Field3D bracket(const Field3D& f, const Field3D& g, BRACKET_METHOD method = BRACKET_STD, CELL_LOC = CELL_DEFAULT, Solver* = nullptr);
 Field3D bracket(const Field3D& f, const Field2D& g, BRACKET_METHOD method = BRACKET_STD, CELL_LOC = CELL_DEFAULT, Solver* = nullptr);
 Field3D bracket(const Field2D& f, const Field3D& g, BRACKET_METHOD method = BRACKET_STD, CELL_LOC = CELL_DEFAULT, Solver* = nullptr);

@@ -2186,6 +2186,11 @@ Field3D Grad2_par2(const Field3D& f, CELL_LOC loc, const std::string& method) {
   return c->Grad2_par2_DDY_invSg(pick(m, 'y', "first", method)) * d1 + r2;
 }
 
+Field3D Div_par_K_Grad_par(BoutReal kY, const Field3D& f, CELL_LOC loc) { return kY * Grad2_par2(f, loc); }
+Field3D Div_par_K_Grad_par(const Field3D& kY, const Field3D& f, CELL_LOC loc) {
+  return kY * Grad2_par2(f, loc) + Div_par(kY, loc) * Grad_par(f, loc);
+}
+
 Field3D VDDX(const Field3D& v, const Field3D& f, CELL_LOC, const std::string& method, const std::string& region) {
   Mesh* m = f.getMesh();
   return stencil(f, &v, stencilOp("VDDX", pick(m, 'x', "upwind", method)), BOUT_B200_X, region,

@@ -104,6 +104,27 @@ error_on_unused_options = false
 
 
 
+# examples/conduction/conduction.cxx (unchanged: ddt(T) = Div_par_K_Grad_par(chi, T)) on a periodic-y mesh whose dy and
+# g_22 vary along y; the shipped input (MXG = 0, one x point, dirichlet_o4 on open field lines, pvode) is not used.
+CONDUCTION_INI = make_ini(8, 16, 4, mxg=2, myg=2, dy="0.2*(1+0.1*cos(y))", mesh_extra="g22 = 1.1 + 0.05*sin(y)\nixseps1 = 8\nixseps2 = 8\n", extra="""
+[mesh:ddy]
+first = C2
+second = C2
+[conduction]
+chi = 0.7
+[all]
+scale = 0.0
+bndry_all = neumann
+[T]
+scale = 1.0
+function = gauss(y-pi, 0.4) * (1 + 0.1*cos(z))
+[solver]
+timestep = 0.005
+[input]
+error_on_unused_options = false
+""")
+
+
 def elmpb_ini(nx, ny, nz, timestep="1e-3", extra_highbeta=""):
     """examples/elm-pb/data/BOUT.inp (methods, solver flags, boundary conditions, [highbeta] switches as
     shipped) on a SYNTHETIC closed-form circular-cross-section tokamak grid given as mesh options (the
