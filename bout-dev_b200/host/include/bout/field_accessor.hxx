@@ -123,6 +123,8 @@ struct SIAssignTarget {
   void operator=(double v) const { *this = SIExpr::of(v); } // a boxed handle or a constant
   void operator+=(SIExpr e) const { bout::b200::si::Recorder::get().assigns.push_back({field, e.id, true}); }
   void operator+=(double v) const { *this += SIExpr::of(v); }
+  void operator-=(SIExpr e) const { *this += -e; }
+  void operator-=(double v) const { *this += SIExpr::of(-v); }
 };
 struct BoutRealArray {
   Field3D* field;

@@ -2380,11 +2380,14 @@ Recorder& Recorder::get() {
 }
 
 namespace {
-struct Term { // coef * prim(f, g); prim = CONST means the constant coef itself
+struct Term { // coef * prim(f, g) [* prim2(f2, g2)]; prim = CONST means the constant coef itself
   double coef;
   Kind prim;
   const Field3D* f;
   const Field3D* g;
+  Kind prim2 = CONST; // CONST = no second factor; else the term is the PRODUCT of two primitives (n[i] * phi[i] ...)
+  const Field3D* f2 = nullptr;
+  const Field3D* g2 = nullptr;
 };
 
 bool constantValue(const std::vector<Node>& nodes, int id, double* v) {
@@ -2416,7 +2419,14 @@ void linearise(const std::vector<Node>& nodes, int id, double scale, std::vector
   const Node& n = nodes[id];
   double c = 0.0;
   switch (n.kind) {
-  case CONST: out.push_back({scale * n.value, CONST, nullptr, nullptr}); return;
+  case CONST: {
+    Term t{};
+    t.coef = scale * n.value;
+    t.prim = CONST;
+    t.f = t.g = nullptr;
+    out.push_back(t);
+    return;
+  }
   case ADD:
     linearise(nodes, n.a, scale, out);
     linearise(nodes, n.b, scale, out);
@@ -2432,7 +2442,21 @@ void linearise(const std::vector<Node>& nodes, int id, double scale, std::vector
     } else if (constantValue(nodes, n.b, &c)) {
       linearise(nodes, n.a, scale * c, out);
     } else {
-      throw BoutException("BOUT_FOR_RAJA: a product of two field terms in a single-index loop is not implemented on the B200 path");
+      // two field-dependent factors: each must be ONE primitive (times a constant), their product becomes one term
+      std::vector<Term> ta, tb;
+      linearise(nodes, n.a, 1.0, ta);
+      linearise(nodes, n.b, 1.0, tb);
+      if (ta.size() != 1 || tb.size() != 1 || ta[0].prim == CONST || tb[0].prim == CONST || ta[0].prim2 != CONST
+          || tb[0].prim2 != CONST) {
+        throw BoutException("BOUT_FOR_RAJA: only products of two single operator terms are implemented in a single-index "
+                            "loop on the B200 path");
+      }
+      Term t = ta[0];
+      t.coef = scale * ta[0].coef * tb[0].coef;
+      t.prim2 = tb[0].prim;
+      t.f2 = tb[0].f;
+      t.g2 = tb[0].g;
+      out.push_back(t);
     }
     return;
   case DIV:
@@ -2441,7 +2465,15 @@ void linearise(const std::vector<Node>& nodes, int id, double scale, std::vector
     }
     linearise(nodes, n.a, scale / c, out);
     return;
-  default: out.push_back({scale, n.kind, n.f, n.g}); return;
+  default: {
+    Term t{};
+    t.coef = scale;
+    t.prim = n.kind;
+    t.f = n.f;
+    t.g = n.g;
+    out.push_back(t);
+    return;
+  }
   }
 }
 
@@ -2451,7 +2483,7 @@ std::vector<Term> merged(const std::vector<Term>& in) {
   for (const Term& t : in) {
     bool found = false;
     for (Term& o : out) {
-      if (o.prim == t.prim && o.f == t.f && o.g == t.g) {
+      if (o.prim == t.prim && o.f == t.f && o.g == t.g && o.prim2 == t.prim2 && o.f2 == t.f2 && o.g2 == t.g2) {
         o.coef += t.coef;
         found = true;
         break;
@@ -2466,7 +2498,7 @@ std::vector<Term> merged(const std::vector<Term>& in) {
 
 const Term* findTerm(const std::vector<Term>& ts, Kind prim, const Field3D* f = nullptr, const Field3D* g = nullptr) {
   for (const Term& t : ts) {
-    if (t.prim == prim && (f == nullptr || t.f == f) && (g == nullptr || t.g == g)) {
+    if (t.prim2 == CONST && t.prim == prim && (f == nullptr || t.f == f) && (g == nullptr || t.g == g)) {
       return &t;
     }
   }
@@ -2594,7 +2626,19 @@ bool tryHw3d(Mesh* mesh, const std::vector<std::pair<Field3D*, std::vector<Term>
 }
 
 // one kernel per operator: every primitive becomes a field, the assignment a linear combination over the region
+Field3D onePrimitive(Kind prim, const Field3D* f, const Field3D* g);
 Field3D primitiveField(const Term& t) {
+  if (t.prim2 != CONST) {
+    return onePrimitive(t.prim, t.f, t.g) * onePrimitive(t.prim2, t.f2, t.g2);
+  }
+  return onePrimitive(t.prim, t.f, t.g);
+}
+Field3D onePrimitive(Kind prim, const Field3D* f, const Field3D* g) {
+  struct {
+    Kind prim;
+    const Field3D* f;
+    const Field3D* g;
+  } t{prim, f, g};
   switch (t.prim) {
   case FIELD: return *t.f;
   case BRACKET: return ::bracket(*t.f, *t.g, BRACKET_ARAKAWA);
@@ -2629,8 +2673,17 @@ void dispatch(const Region<Ind3D>& region) {
       }
     }
     if (it == eqs.end()) {
-      if (a.accumulate) {
-        throw BoutException("BOUT_FOR_RAJA: ddt(f)[i] += ... before any assignment to it");
+      if (a.accumulate) { // `ddt(f)[i] += ...` in a loop of its own: on top of what an earlier loop (or statement) left
+        Field3D* cur = a.target->timeDeriv();
+        if (!cur->isAllocated()) {
+          throw BoutException("BOUT_FOR_RAJA: ddt(f)[i] += ... before any assignment to it");
+        }
+        Term t0{};
+        t0.coef = 1.0;
+        t0.prim = FIELD;
+        t0.f = cur;
+        t0.g = nullptr;
+        ts.insert(ts.begin(), t0);
       }
       eqs.push_back({a.target, ts});
     } else if (a.accumulate) {

@@ -7,6 +7,7 @@
  * BOUT_B200_ERR_CUDA.
  * The GPU tests run the same cases through the real kernels. */
 #define _GNU_SOURCE
+#include <stdio.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -57,6 +58,9 @@ int bout_b200_elementwise(const bout_b200_grid* g, int region, int nterms, const
   int xs, xe, ys, ye;
   (void)stream;
   if (nterms < 1 || nterms > 8 || box(g, region, &xs, &xe, &ys, &ye) != 0) {
+    if (getenv("B200_FAKE_TRACE")) {
+      fprintf(stderr, "fake bout_b200_elementwise: nterms = %d, region = %d\n", nterms, region);
+    }
     return BOUT_B200_ERR_ARG;
   }
   for (int x = xs; x <= xe; ++x) {
@@ -93,6 +97,9 @@ int bout_b200_lincomb(const bout_b200_grid* g, int region, int n, const double* 
   }
   for (int i = 0; i < n; ++i) {
     if (x[i] == NULL || x[i] == out) {
+      if (getenv("B200_FAKE_TRACE")) {
+        fprintf(stderr, "fake bout_b200_lincomb: operand %d of %d is %s\n", i, n, x[i] == NULL ? "NULL" : "the output");
+      }
       return BOUT_B200_ERR_ARG;
     }
     memset(&t[i], 0, sizeof(t[i]));
@@ -343,6 +350,10 @@ int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region, cons
   }
   free(t1);
   free(t2);
+  if (rc != 0 && getenv("B200_FAKE_TRACE")) {
+    fprintf(stderr, "fake bout_b200_stencil: oracle index derivative op=%d dir=%d op2=%d failed (%d) on %dx%dx%d\n", op, dir, op2,
+            rc, g->nx, g->ny, g->nz);
+  }
   return rc == 0 ? 0 : BOUT_B200_ERR_ARG;
 }
 
@@ -442,6 +453,37 @@ int bout_b200_dc(const bout_b200_grid* g, const double* f, double* out2d, void* 
   (void)stream;
   return fn ? fn(g, f, out2d) : BOUT_B200_ERR_UNSUPPORTED;
 }
+/* Coordinates::Delp2(f, useFFT = false) with C2 methods (coordinates.cxx:1701-1702):
+ * G1 DDX + G3 DDZ + g11 D2DX2 (+ the non-uniform d1_dx term of D2DX2) + g33 D2DZ2 + 2 g13 D2DXDZ over RGN_NOBNDRY */
+int bout_b200_delp2_fd(const bout_b200_grid* g, const double* f, const double* dx, const double* dz, const double* g11,
+                       const double* g33, const double* g13, const double* G1, const double* G3, const double* d1_dx,
+                       double* out, void* stream) {
+  const int ny = g->ny, nz = g->nz;
+  (void)stream;
+#define F3(x, y, z) f[((size_t)(x) * ny + (y)) * nz + (((z) % nz + nz) % nz)]
+  for (int x = g->xstart; x <= g->xend; ++x) {
+    for (int y = g->ystart; y <= g->yend; ++y) {
+      const size_t i2 = (size_t)x * ny + y;
+      const double rdx = 1.0 / dx[i2], rdz = 1.0 / dz[i2];
+      for (int z = 0; z < nz; ++z) {
+        const double ddx = (0.5 * (F3(x + 1, y, z) - F3(x - 1, y, z))) * rdx;
+        const double ddz = (0.5 * (F3(x, y, z + 1) - F3(x, y, z - 1))) * rdz;
+        double d2dx2 = (F3(x + 1, y, z) + F3(x - 1, y, z) - 2. * F3(x, y, z)) * (rdx * rdx);
+        if (d1_dx != NULL) {
+          d2dx2 += (d1_dx[i2] * (0.5 * (F3(x + 1, y, z) - F3(x - 1, y, z)))) * rdx;
+        }
+        const double d2dz2 = (F3(x, y, z + 1) + F3(x, y, z - 1) - 2. * F3(x, y, z)) * (rdz * rdz);
+        const double ddx_zp = (0.5 * (F3(x + 1, y, z + 1) - F3(x - 1, y, z + 1))) * rdx;
+        const double ddx_zm = (0.5 * (F3(x + 1, y, z - 1) - F3(x - 1, y, z - 1))) * rdx;
+        const double d2dxdz = (0.5 * (ddx_zp - ddx_zm)) * rdz;
+        out[i2 * nz + z] = G1[i2] * ddx + G3[i2] * ddz + g11[i2] * d2dx2 + g33[i2] * d2dz2 + 2 * g13[i2] * d2dxdz;
+      }
+    }
+  }
+#undef F3
+  return 0;
+}
+
 int bout_b200_delp2_fft(const bout_b200_grid* g, const bout_b200_laplace* L, const double* f, double* out,
                         void* stream) {
   typedef int (*fn_t)(const void*, const void*, const double*, double*);

@@ -237,7 +237,8 @@ from cases import HW_INI, HW3D_INI, BLOB_INI, ELMPB_INI, CONDUCTION_INI  # noqa:
 
 MODEL_CASES = {"hw": ("hw", HW_INI, "rk4", 5), "hw_rk3": ("hw", HW_INI, "rk3ssp", 5),
                "hw3d": ("hw3d", HW3D_INI, "rk4", 5), "blob2d": ("blob2d", BLOB_INI, "rk4", 5),
-               "conduction": ("conduction", CONDUCTION_INI, "rk4", 5)}
+               "conduction": ("conduction", CONDUCTION_INI, "rk4", 5),
+               "blob2d_outer": ("blob2d_outer", BLOB_INI, "rk4", 5)}
 
 
 SHIFTED_INI = orc.make_ini(12, 8, 16, mxg=2, myg=2, dx="0.2*(1+0.1*x)", dy="0.7+0.05*cos(2*pi*x)", dz="2*pi/16",

@@ -29,7 +29,8 @@ def main():
     for tag, model, solver, ini in (("hw", "hw", "rk4", cases.HW_INI), ("hw_rk3", "hw", "rk3ssp", cases.HW_INI),
                                     ("blob2d", "blob2d", "rk4", cases.BLOB_INI),
                                     ("hw3d", "hw3d", "rk4", cases.HW3D_INI),
-                                    ("conduction", "conduction", "rk4", cases.CONDUCTION_INI)):
+                                    ("conduction", "conduction", "rk4", cases.CONDUCTION_INI),
+                                    ("blob2d_outer", "blob2d_outer", "rk4", cases.BLOB_INI)):
         h = hostmod.Host(ini)
         try:
             names = h.model_create(model, solver)
