@@ -315,6 +315,25 @@ void releasePool();
 size_t poolAllocations(); ///< number of cudaMalloc calls so far (steady state: constant)
 size_t cowCopies();       ///< whole-block device copies made by copy-on-write so far (FieldBase::makeUnique)
 unsigned long long nextVersion();
+
+/// Y decomposition of the host layer's Mesh: NYPE ranks, NXPE = 1 (BoutMesh::setYDecompositionIndices,
+/// src/mesh/impls/bout/boutmesh.cxx:255-341, on an all-core topology).  One process per GPU; the process that owns
+/// the communicator (the Python harness with torch.distributed / NCCL, or any MPI-like host) fills this in BEFORE the
+/// mesh is created.  Mesh::communicate then packs the MYG lowest / highest interior rows of up to `capacity` doubles
+/// into send_lo / send_hi (bout_b200_halo_pack_y: pack_data, boutmesh.cxx:2400-2466), calls exchange(count) -- which
+/// must deliver send_lo to the recv_hi of rank yind - 1 and send_hi to the recv_lo of rank yind + 1 (periodic),
+/// ordered after the work already enqueued on the default stream and before work enqueued once it returns
+/// (sendY / wait, boutmesh.cxx:1245-1555) -- and unpacks recv_lo / recv_hi into the guard rows.
+struct YDecomposition {
+  int nype = 1, yind = 0;
+  int (*exchange)(size_t count, void* user) = nullptr;
+  /// global reduction of one host number over the ranks (op 0: sum, 1: max): the adaptive integrators' error norms
+  double (*allreduce)(double value, int op, void* user) = nullptr;
+  void* user = nullptr;
+  double *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr; ///< device buffers
+  size_t capacity = 0;                                                                   ///< doubles in each of them
+};
+YDecomposition& yDecomposition();
 } // namespace b200
 } // namespace bout
 
@@ -629,6 +648,13 @@ public:
   bool symmetricGlobalX = true, symmetricGlobalY = true; ///< mesh:symmetricGlobalX / Y (boutmesh.cxx:72-75)
   bool firstX() const { return true; }
   bool lastX() const { return true; }
+  int NYPE = 1, PE_YIND = 0; ///< bout::b200::yDecomposition() at construction (NXPE = 1)
+  int OffsetY = 0;           ///< global index of this rank's first interior row minus MYG (boutmesh.cxx:316-341)
+  int getNYPE() const { return NYPE; }
+  int getYProcIndex() const { return PE_YIND; }
+  int getGlobalYIndex(int jy) const { return jy + OffsetY; }
+  /// guard rows of a host-side [nx][ny] array from the neighbouring ranks (NYPE > 1)
+  void exchangeY2D(std::vector<double>& f);
   BoutReal GlobalX(int jx) const;
   BoutReal GlobalY(int jy) const;
   BoutReal GlobalZ(int jz) const;

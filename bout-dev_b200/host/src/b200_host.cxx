@@ -1340,6 +1340,9 @@ Field3D lowPass(const Field3D& f, int zmax, bool keep_zonal) {
 Field2D averageY(const Field2D& f) {
   requireData(f, "averageY");
   Mesh* m = f.getMesh();
+  if (m->NYPE > 1) {
+    throw BoutException("averageY: the sum over y crosses ranks; not available with NYPE > 1 in the B200 host layer");
+  }
   const int nyint = m->yend - m->ystart + 1;
   Field2D r(m);
   if (nyint == m->LocalNy) { // no y guards: every row is one contiguous run
@@ -1579,6 +1582,32 @@ Mesh::Mesh(Options& opts) : options(&opts) {
   LocalNx = nx;
   LocalNy = ny + 2 * MYG;
   LocalNz = nz;
+  {
+    // NYPE ranks along y, NXPE = 1 (boutmesh.cxx:255-341): equal slabs of ny / NYPE rows, rank PE_YIND holds global
+    // rows PE_YIND * MYSUB ... + MYSUB - 1 plus MYG guard rows either side
+    const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+    NYPE = yd.nype;
+    PE_YIND = yd.yind;
+    if (NYPE > 1) {
+      if (PE_YIND < 0 || PE_YIND >= NYPE || ny % NYPE != 0) {
+        throw BoutException("Mesh: ny = {} does not divide into NYPE = {} slabs (rank {})", ny, NYPE, PE_YIND);
+      }
+      const int mysub = ny / NYPE;
+      if (MYG < 1 || mysub < MYG) {
+        throw BoutException("Mesh: NYPE = {} needs MYG >= 1 and at least MYG rows per rank (ny / NYPE = {}, MYG = {})", NYPE,
+                            mysub, MYG);
+      }
+      if (!periodicY) {
+        throw BoutException("B200 host layer: NYPE > 1 is implemented for closed field lines (periodic y) only");
+      }
+      if (yd.exchange == nullptr || yd.send_lo == nullptr || yd.send_hi == nullptr || yd.recv_lo == nullptr
+          || yd.recv_hi == nullptr || yd.capacity < static_cast<size_t>(nx) * MYG * nz) {
+        throw BoutException("Mesh: NYPE = {} without an exchange function / buffers of at least nx MYG nz doubles", NYPE);
+      }
+      LocalNy = mysub + 2 * MYG;
+      OffsetY = PE_YIND * mysub;
+    }
+  }
   xstart = MXG;
   xend = nx - MXG - 1;
   ystart = MYG;
@@ -1630,10 +1659,68 @@ BoutReal Mesh::GlobalX(int jx) const {
 }
 BoutReal Mesh::GlobalY(int jy) const {
   const int ny = GlobalNy - 2 * MYG;
+  jy += OffsetY; // YGLOBAL (boutmesh.cxx:3192-3215): the same number on whichever rank holds the row
   if (!symmetricGlobalY) {
     return static_cast<BoutReal>(jy - MYG) / static_cast<BoutReal>(ny);
   }
   return (jy - MYG + 0.5) / static_cast<BoutReal>(ny);
+}
+
+namespace bout {
+namespace b200 {
+YDecomposition& yDecomposition() {
+  static YDecomposition yd;
+  return yd;
+}
+} // namespace b200
+} // namespace bout
+
+namespace {
+// Y guard rows of `n` device fields from the neighbouring ranks: pack -> exchange -> unpack, as many fields per round
+// as the exchange buffers hold.  All x (guard columns too): what the single-rank wrap copies (mesh.cxx:351-362).
+void exchangeYDevice(const bout_b200_grid& g, int myg, const std::vector<double*>& ptrs) {
+  const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+  const size_t per_field = static_cast<size_t>(g.nx) * myg * g.nz;
+  const size_t per_round = std::min<size_t>(8, yd.capacity / per_field);
+  for (size_t i = 0; i < ptrs.size(); i += per_round) {
+    const int n = static_cast<int>(std::min(per_round, ptrs.size() - i));
+    check(bout_b200_halo_pack_y(&g, n, ptrs.data() + i, g.ystart, myg, 0, g.nx - 1, yd.send_lo, nullptr));
+    check(bout_b200_halo_pack_y(&g, n, ptrs.data() + i, g.yend - myg + 1, myg, 0, g.nx - 1, yd.send_hi, nullptr));
+    if (yd.exchange(per_field * n, yd.user) != 0) {
+      throw BoutException("Mesh::communicate: the Y exchange between ranks failed (rank {} of {})", yd.yind, yd.nype);
+    }
+    check(bout_b200_halo_unpack_y(&g, n, ptrs.data() + i, g.ystart - myg, myg, 0, g.nx - 1, yd.recv_lo, nullptr));
+    check(bout_b200_halo_unpack_y(&g, n, ptrs.data() + i, g.yend + 1, myg, 0, g.nx - 1, yd.recv_hi, nullptr));
+  }
+}
+} // namespace
+
+// Metric arrays live on the host while the coordinates are set up: their guard rows take the same route as a field's
+// (through the exchange buffers), once per Coordinates::geometry(), not per step.
+void Mesh::exchangeY2D(std::vector<double>& f) {
+  const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+  const size_t n = static_cast<size_t>(LocalNx) * MYG;
+  std::vector<double> lo(n), hi(n);
+  for (int x = 0; x < LocalNx; ++x) {
+    for (int i = 0; i < MYG; ++i) {
+      lo[static_cast<size_t>(x) * MYG + i] = f[static_cast<size_t>(x) * LocalNy + ystart + i];
+      hi[static_cast<size_t>(x) * MYG + i] = f[static_cast<size_t>(x) * LocalNy + yend - MYG + 1 + i];
+    }
+  }
+  check(bout_b200_memcpy_h2d(yd.send_lo, lo.data(), n * sizeof(double), nullptr));
+  check(bout_b200_memcpy_h2d(yd.send_hi, hi.data(), n * sizeof(double), nullptr));
+  if (yd.exchange(n, yd.user) != 0) {
+    throw BoutException("Mesh: the Y exchange of a metric array between ranks failed (rank {} of {})", yd.yind, yd.nype);
+  }
+  check(bout_b200_memcpy_d2h(lo.data(), yd.recv_lo, n * sizeof(double), nullptr));
+  check(bout_b200_memcpy_d2h(hi.data(), yd.recv_hi, n * sizeof(double), nullptr));
+  check(bout_b200_stream_sync(nullptr));
+  for (int x = 0; x < LocalNx; ++x) {
+    for (int i = 0; i < MYG; ++i) {
+      f[static_cast<size_t>(x) * LocalNy + i] = lo[static_cast<size_t>(x) * MYG + i];
+      f[static_cast<size_t>(x) * LocalNy + yend + 1 + i] = hi[static_cast<size_t>(x) * MYG + i];
+    }
+  }
 }
 BoutReal Mesh::GlobalZ(int jz) const { return static_cast<BoutReal>(jz) / static_cast<BoutReal>(GlobalNz); }
 
@@ -1707,9 +1794,13 @@ void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
       k.b->block()->dependents.push_back(k.f->shared());
     }
   }
-  for (size_t i = 0; i < ptrs.size(); i += 8) { // the kernel takes up to 8 fields per launch
+  if (NYPE > 1) { // Y first, between ranks; then X (below) with the y guard rows just received (mesh.cxx:351-362)
+    exchangeYDevice(g, MYG, ptrs);
+  }
+  const int self_y = (periodicY && MYG > 0 && NYPE == 1) ? 1 : 0;
+  for (size_t i = 0; (self_y || periodicX) && i < ptrs.size(); i += 8) { // the kernel takes up to 8 fields per launch
     const int n = static_cast<int>(std::min<size_t>(8, ptrs.size() - i));
-    check(bout_b200_halo_self(&g, n, ptrs.data() + i, periodicX ? 1 : 0, (periodicY && MYG > 0) ? 1 : 0, nullptr));
+    check(bout_b200_halo_self(&g, n, ptrs.data() + i, periodicX ? 1 : 0, self_y, nullptr));
   }
   for (const Kept& k : kept) {
     bout::b200::Block::Recipe rec;
@@ -1750,7 +1841,9 @@ void fixGuards2D(Mesh* m, std::vector<double>& f, bool extrapolate) {
   const int nx = m->LocalNx, ny = m->LocalNy;
   auto at = [&](int x, int y) -> double& { return f[static_cast<size_t>(x) * ny + y]; };
   const int mx = m->xend - m->xstart + 1, my = m->yend - m->ystart + 1;
-  if (m->periodicY && m->MYG > 0) { // Y first, then X with the y guards included (mesh.cxx:351-362)
+  if (m->NYPE > 1) {
+    m->exchangeY2D(f);
+  } else if (m->periodicY && m->MYG > 0) { // Y first, then X with the y guards included (mesh.cxx:351-362)
     for (int x = 0; x < nx; ++x) {
       for (int i = 0; i < m->ystart; ++i) {
         at(x, i) = at(x, i + my);
@@ -2355,6 +2448,9 @@ Field3D InvertPar::solve(const Field3D& f) {
   ip.twist_shift = nullptr; // the host mesh has no twist shift (identity parallel transform)
   ip.zlength = c->zlength();
   ip.closed = localmesh->periodicY ? 1 : 0;
+  if (localmesh->NYPE > 1) {
+    throw BoutException("InvertPar: field lines cross ranks; not available with NYPE > 1 in the B200 host layer");
+  }
   const size_t need = bout_b200_invert_par_workspace(&g);
   if (need > workspace_bytes) {
     if (workspace != nullptr) {
@@ -3129,6 +3225,10 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   std::unique_ptr<bout::b200::OutputPipeline> dump;
   std::vector<const Field3D*> dump_fields;
   Options& oo = Options::root()["output"];
+  if ((oo.isSet("path") || !restart_path.empty()) && bout::globals::mesh->NYPE > 1) {
+    throw BoutException("[output] / [restart_file] path with NYPE > 1: per-rank dump files are not written by the B200 "
+                        "host layer (collect the slabs from the ranks instead)");
+  }
   if (oo.isSet("path") || !restart_path.empty()) {
     std::vector<std::string> names;
     for (const auto& f : f3d) {
@@ -3475,7 +3575,11 @@ public:
     double host = 0.0;
     check(bout_b200_memcpy_d2h(&host, result, sizeof(double), nullptr));
     check(bout_b200_stream_sync(nullptr));
-    const double neq = static_cast<double>(a.size()) * (g.xend - g.xstart + 1) * (g.yend - g.ystart + 1) * g.nz;
+    double neq = static_cast<double>(a.size()) * (g.xend - g.xstart + 1) * (g.yend - g.ystart + 1) * g.nz;
+    if (m->NYPE > 1) { // the reference sums error and neq over the ranks (rkscheme.cxx:155-163, MPI_Allreduce)
+      host = globalReduce(host, 0);
+      neq *= m->NYPE;
+    }
     return host / neq;
   }
 
@@ -3494,7 +3598,15 @@ public:
     double host = 0.0;
     check(bout_b200_memcpy_d2h(&host, result, sizeof(double), nullptr));
     check(bout_b200_stream_sync(nullptr));
-    return host;
+    return m->NYPE > 1 ? globalReduce(host, 1) : host;
+  }
+
+  static double globalReduce(double v, int op) {
+    const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+    if (yd.allreduce == nullptr) {
+      throw BoutException("adaptive time stepping on NYPE = {} ranks needs YDecomposition::allreduce", yd.nype);
+    }
+    return yd.allreduce(v, op, yd.user);
   }
 
 private:

@@ -44,6 +44,29 @@ void b200host_finalise() {
   }
 }
 
+// NYPE decomposition (bout::b200::YDecomposition): called before b200host_init; nype = 1 switches it off.  The
+// buffers are device memory of `capacity` doubles each, owned by the caller for the life of the mesh.
+int b200host_set_y_decomposition(int nype, int yind, int (*exchange)(size_t, void*), double (*allreduce)(double, int, void*),
+                                 void* user, double* send_lo, double* send_hi, double* recv_lo, double* recv_hi,
+                                 size_t capacity) {
+  return guarded([&]() {
+    bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+    yd = bout::b200::YDecomposition{};
+    if (nype > 1) {
+      yd.nype = nype;
+      yd.yind = yind;
+      yd.exchange = exchange;
+      yd.allreduce = allreduce;
+      yd.user = user;
+      yd.send_lo = send_lo;
+      yd.send_hi = send_hi;
+      yd.recv_lo = recv_lo;
+      yd.recv_hi = recv_hi;
+      yd.capacity = capacity;
+    }
+  });
+}
+
 // BoutInitialise: options from BOUT.inp text, mesh from options
 int b200host_init(const char* ini_text) {
   return guarded([&]() {

@@ -357,6 +357,37 @@ int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region, cons
   return rc == 0 ? 0 : BOUT_B200_ERR_ARG;
 }
 
+/* pack_data / unpack_data (boutmesh.cxx:2400-2466): rows y0..y0+nrows-1, x in [xlo,xhi] <-> [field][x][y][z] */
+int bout_b200_halo_pack_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0, int nrows, int xlo, int xhi,
+                          double* buf, void* stream) {
+  (void)stream;
+  size_t o = 0;
+  for (int k = 0; k < nfields; ++k) {
+    for (int x = xlo; x <= xhi; ++x) {
+      for (int y = y0; y < y0 + nrows; ++y) {
+        memcpy(buf + o, fields[k] + (((long long)x) * g->ny + y) * g->nz, sizeof(double) * g->nz);
+        o += g->nz;
+      }
+    }
+  }
+  return 0;
+}
+
+int bout_b200_halo_unpack_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0, int nrows, int xlo, int xhi,
+                            const double* buf, void* stream) {
+  (void)stream;
+  size_t o = 0;
+  for (int k = 0; k < nfields; ++k) {
+    for (int x = xlo; x <= xhi; ++x) {
+      for (int y = y0; y < y0 + nrows; ++y) {
+        memcpy(fields[k] + (((long long)x) * g->ny + y) * g->nz, buf + o, sizeof(double) * g->nz);
+        o += g->nz;
+      }
+    }
+  }
+  return 0;
+}
+
 int bout_b200_halo_self(const bout_b200_grid* g, int nfields, double* const* fields, int periodic_x, int periodic_y,
                         void* stream) {
   const int mx = g->xend - g->xstart + 1, my = g->yend - g->ystart + 1;

@@ -1,0 +1,130 @@
+"""The C++ host layer's Mesh decomposed in y over NYPE ranks (bout::b200::YDecomposition; the reference's BoutMesh with
+NXPE = 1, src/mesh/impls/bout/boutmesh.cxx:255-341, sendY / wait :1245-1555): one process per rank, launched by
+torch.distributed.run or by tests/test_host_integrators.py with RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT set.
+
+Every rank runs the UNCHANGED examples/hasegawa-wakatani-3d/hw.cxx (the headline workload) and examples/conduction/
+conduction.cxx (dy and g_22 vary along y: the metric's guard rows and d1_dy come from the neighbouring rank) on its
+slab and compares with the slab of the reference build's SINGLE-rank run (tests/golden/models.npz): initial profile
+(global y index in the expression evaluator), metric with its guard rows, one Solver::run_rhs (1e-10), the 5-step RK4
+trajectory (1e-8) -- results that must not depend on the decomposition.  Then an adaptive integrator (rkgeneric /
+cashkarp): the error norm is reduced over the ranks, so every rank must take the same number of RHS evaluations as
+the NYPE = 1 run each process makes first (same host layer, same device) and end on its slab of that run.
+
+On a GPU box: NCCL, real kernels.  On CPU: gloo and the host-memory test double (LD_PRELOAD=<libfake_b200.so>
+B200_FAKE_ORACLE_PORT=<liboracle_port.so>), which pins the HOST logic.  Rank 0 prints one JSON line; exit code 0 iff ok."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    import cases
+    hostmod = ge.load_package().host
+    rank, size = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl" if cuda else "gloo", rank=rank, world_size=size)
+    gold = np.load(os.path.join(HERE, "golden", "models.npz"))
+    res, bad = {"nype": size}, []
+    yr = hostmod.YRanks(1 << 16)
+    for tag, model, ini in (("hw3d", "hw3d", cases.HW3D_INI), ("conduction", "conduction", cases.CONDUCTION_INI)):
+        nx, ny, nz, mxg, myg = [int(v) for v in gold[tag + "_grid"]]
+        mysub = (ny - 2 * myg) // size
+        if myg == 0 or mysub * size != ny - 2 * myg or mysub < myg:
+            res[tag] = "skipped: ny does not decompose"
+            continue
+        sl = slice(myg + rank * mysub, myg + (rank + 1) * mysub)      # this rank's rows of the global array
+        own = lambda a: a[mxg:nx - mxg, sl]
+        loc = lambda a: a[mxg:nx - mxg, myg:myg + mysub]
+        h = hostmod.Host(ini, yranks=yr)
+        try:
+            names = h.model_create(model, "rk4")
+            assert h.shape3 == (nx, mysub + 2 * myg, nz), h.shape3
+            for v in names:
+                e = rel(loc(h.model_get(v)), own(gold[f"{tag}_init_{v}"]))
+                res[f"{tag}_init_{v}"] = e
+                if e > 1e-13:
+                    bad.append(f"{tag} init {v}")
+            for n in ("dx", "dy", "g11", "g33", "J", "g_22"):
+                # guard rows included: they come from the neighbouring rank (Mesh::exchangeY2D)
+                if not np.allclose(h.metric(n)[:, :], gold[f"{tag}_metric_{n}"][:, rank * mysub:rank * mysub + mysub + 2 * myg],
+                                   rtol=1e-14, atol=0):
+                    bad.append(f"{tag} metric {n}")
+            x0 = yr.exchanges
+            h.model_rhs(0.0)
+            res[f"{tag}_exchanges_per_rhs"] = yr.exchanges - x0
+            for v in names:
+                e = rel(loc(h.model_ddt(v)), own(gold[f"{tag}_ddt_{v}"]))
+                res[f"{tag}_ddt_{v}"] = e
+                if e > 1e-10:
+                    bad.append(f"{tag} ddt {v}")
+            dt, nsteps = gold[tag + "_dt_nsteps"]
+            for v in names:
+                a = np.zeros(h.shape3)
+                a[:, :, :] = gold[f"{tag}_init_{v}"][:, rank * mysub:rank * mysub + mysub + 2 * myg]
+                h.model_set(v, a)
+            h.model_solve(1, float(dt) * int(nsteps))
+            for v in names:
+                e = rel(loc(h.model_get(v)), own(gold[f"{tag}_final_{v}"]))
+                res[f"{tag}_final_{v}"] = e
+                if e > 1e-8:
+                    bad.append(f"{tag} final {v}")
+        finally:
+            h.close()
+    # adaptive integrator: global error norm.  Single-slab run first (every process makes it), then the decomposed one.
+    tag, ini = "hw3d", cases.HW3D_INI.replace("[solver]", "[solver]\nadaptive = true\nscheme = cashkarp\nrtol = 1e-6\natol = 1e-9")
+    nx, ny, nz, mxg, myg = [int(v) for v in gold[tag + "_grid"]]
+    mysub = (ny - 2 * myg) // size
+    h = hostmod.Host(ini)
+    try:
+        names = h.model_create("hw3d", "rkgeneric")
+        h.model_solve(1, 0.05)
+        single = {v: h.model_get(v) for v in names}
+        single_calls = h.rhs_calls()
+    finally:
+        h.close()
+    h = hostmod.Host(ini, yranks=yr)
+    try:
+        names = h.model_create("hw3d", "rkgeneric")
+        h.model_solve(1, 0.05)
+        calls = torch.tensor([h.rhs_calls()], dtype=torch.int64, device="cuda" if cuda else "cpu")
+        allc = [torch.zeros_like(calls) for _ in range(size)]
+        dist.all_gather(allc, calls)
+        res["adaptive_rhs_calls"] = [int(c.item()) for c in allc]
+        res["adaptive_rhs_calls_single"] = single_calls
+        if any(c != single_calls for c in res["adaptive_rhs_calls"]):
+            bad.append("adaptive rhs calls")
+        for v in names:
+            e = rel(h.model_get(v)[mxg:nx - mxg, myg:myg + mysub],
+                    single[v][mxg:nx - mxg, myg + rank * mysub:myg + (rank + 1) * mysub])
+            res[f"adaptive_final_{v}"] = e
+            if e > 1e-10:
+                bad.append(f"adaptive final {v}")
+    finally:
+        h.close()
+    flag = torch.tensor([len(bad)], dtype=torch.int64, device="cuda" if cuda else "cpu")
+    dist.all_reduce(flag)
+    res.update(ok=int(flag.item()) == 0, bad=bad)
+    if rank == 0 or bad:
+        print(json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -304,3 +304,36 @@ def test_fieldperp_through_the_host_layer_host_logic(fake_device):
                        timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
+@pytest.mark.parametrize("nype", [2, 4])
+def test_host_layer_mesh_decomposed_in_y_over_gloo_ranks(fake_device, nype):
+    """tests/host_ydecomp_check.py, world_size 2 and 4 over gloo: the C++ Mesh with NYPE ranks (global y index in
+    profiles and metric, guard rows of fields and of the y-varying metric from the neighbouring rank through
+    bout::b200::YDecomposition, error norms of the adaptive integrators reduced over the ranks) -- unchanged
+    hasegawa-wakatani-3d/hw.cxx and conduction.cxx against the reference build's single-rank run, slab by slab."""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(nype):
+        env = dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT, RANK=str(r), WORLD_SIZE=str(nype),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "host_ydecomp_check.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=900))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:] + e[-2000:]
+    res = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert res["ok"] and res["nype"] == nype, res
+    assert res["adaptive_rhs_calls"] == [res["adaptive_rhs_calls_single"]] * nype, res
