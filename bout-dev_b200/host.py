@@ -22,48 +22,74 @@ class HostError(RuntimeError):
     pass
 
 
-_EXCHANGE_T = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_void_p)
+_EXCHANGE_T = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_int, C.c_void_p)
+_ALLGATHER_T = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_void_p)
 _ALLREDUCE_T = C.CFUNCTYPE(C.c_double, C.c_double, C.c_int, C.c_void_p)
 
 
 class YRanks:
-    """The communicator side of the host layer's NYPE decomposition (bout::b200::YDecomposition, b200_host.hxx): one
+    """The communicator side of the host layer's decomposed Mesh (bout::b200::YDecomposition, b200_host.hxx): one
     process per GPU, `torch.distributed` already initialised (NCCL on GPUs; gloo with the CPU test double, whose
-    "device" memory is host memory).  Owns the four exchange buffers and the two callbacks the C++ Mesh calls:
-    exchange(count) = sendY / wait of boutmesh.cxx:1245-1555 (rows to the rank below and above, periodic), and
-    allreduce(value, op) for the adaptive integrators' error norms.  torch's P2P ops are ordered after the work already
-    on the current (= default) stream and their wait() orders later work on it after the receive, which is what
-    the C++ side's pack -> exchange -> unpack sequence needs."""
+    "device" memory is host memory).  direction "y": NYPE = the group's size (closed field lines, periodic);
+    direction "x": NXPE = the group's size (no wrap).  Owns the exchange buffers and the callbacks the C++ Mesh calls:
+    exchange(count, dir) = sendY / sendX / wait of boutmesh.cxx:1245-1555, allgather(count) for the interface rows
+    of an X-decomposed LaplaceCyclic solve (PE_XIND order), allreduce(value, op) for the adaptive integrators' error
+    norms.  torch's collectives are ordered after the work already on the current (= default) stream and their
+    wait() orders later work on it after the receive, which is what the C++ side's pack -> exchange -> unpack needs."""
 
-    def __init__(self, capacity_doubles: int, device=None, group=None):
+    def __init__(self, capacity_doubles: int, device=None, group=None, direction: str = "y"):
         import torch
         import torch.distributed as dist
-        self.dist, self.torch, self.group = dist, torch, group
+        if direction not in ("x", "y"):
+            raise ValueError("direction must be 'x' or 'y'")
+        self.dist, self.torch, self.group, self.direction = dist, torch, group, direction
         self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-        self.buf = torch.zeros(4, int(capacity_doubles), dtype=torch.float64, device=device)
         self.capacity = int(capacity_doubles)
+        self.buf = torch.zeros(4, self.capacity, dtype=torch.float64, device=device)
+        self.gather_send = torch.zeros(self.capacity, dtype=torch.float64, device=device)
+        self.gather_recv = torch.zeros(self.size * self.capacity if direction == "x" else 1, dtype=torch.float64, device=device)
         self.exchanges = 0
+        self.gathers = 0
         self.error = None
         grank = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
-        self.ydown, self.yup = grank((self.rank - 1) % self.size), grank((self.rank + 1) % self.size)
+        self.below, self.above = grank((self.rank - 1) % self.size), grank((self.rank + 1) % self.size)
         self._exchange = _EXCHANGE_T(self._do_exchange)
+        self._allgather = _ALLGATHER_T(self._do_allgather)
         self._allreduce = _ALLREDUCE_T(self._do_allreduce)
 
-    def _do_exchange(self, count, _user):
+    def _do_exchange(self, count, direction, _user):
         try:
             dist = self.dist
             send_lo, send_hi, recv_lo, recv_hi = (self.buf[i, :count] for i in range(4))
-            # with two ranks both neighbours are the same process: its first send (upwards) pairs with the first
+            up = direction == 0 or self.rank < self.size - 1     # x (1): no wrap at the ends of the row
+            down = direction == 0 or self.rank > 0
+            # with two ranks in y both neighbours are the same process: its first send (upwards) pairs with the first
             # receive posted here (from below), its second with the second
-            ops = [dist.P2POp(dist.isend, send_hi, self.yup, self.group), dist.P2POp(dist.irecv, recv_lo, self.ydown, self.group),
-                   dist.P2POp(dist.isend, send_lo, self.ydown, self.group), dist.P2POp(dist.irecv, recv_hi, self.yup, self.group)]
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            ops = []
+            if up:
+                ops.append(dist.P2POp(dist.isend, send_hi, self.above, self.group))
+            if down:
+                ops.append(dist.P2POp(dist.irecv, recv_lo, self.below, self.group))
+                ops.append(dist.P2POp(dist.isend, send_lo, self.below, self.group))
+            if up:
+                ops.append(dist.P2POp(dist.irecv, recv_hi, self.above, self.group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
             self.exchanges += 1
             return 0
         except Exception as e:   # an exception must not unwind through the C++ frames
+            self.error = e
+            return 1
+
+    def _do_allgather(self, count, _user):
+        try:
+            self.dist.all_gather_into_tensor(self.gather_recv[:self.size * count], self.gather_send[:count], group=self.group)
+            self.gathers += 1
+            return 0
+        except Exception as e:
             self.error = e
             return 1
 
@@ -76,7 +102,7 @@ class YRanks:
 
 class Host:
     """One live mesh/model at a time (like BOUT++ itself: global mesh, global options).  `yranks`: a YRanks for a mesh
-    decomposed in y over the ranks of its process group (this process holds slab yranks.rank of yranks.size)."""
+    decomposed in y or x over the ranks of its process group (this process holds slab yranks.rank of yranks.size)."""
 
     def __init__(self, ini_text: str, yranks: "YRanks | None" = None):
         if not os.path.exists(LIB_PATH):
@@ -90,15 +116,17 @@ class Host:
         L.b200host_model_rhs.argtypes = [C.c_double]
         L.b200host_model_solve.argtypes = [C.c_int, C.c_double]
         self.yranks = yranks
-        L.b200host_set_y_decomposition.argtypes = [C.c_int, C.c_int, _EXCHANGE_T, _ALLREDUCE_T, C.c_void_p] + [C.c_void_p] * 4 \
-            + [C.c_size_t]
+        L.b200host_set_decomposition.argtypes = [C.c_int] * 4 + [_EXCHANGE_T, _ALLGATHER_T, _ALLREDUCE_T, C.c_void_p] \
+            + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p, C.c_void_p]
         if yranks is not None and yranks.size > 1:
             b = yranks.buf
-            self._check(L.b200host_set_y_decomposition(yranks.size, yranks.rank, yranks._exchange, yranks._allreduce, None,
-                                                       b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
-                                                       yranks.capacity))
+            nx, ix, ny, iy = (yranks.size, yranks.rank, 1, 0) if yranks.direction == "x" else (1, 0, yranks.size, yranks.rank)
+            self._check(L.b200host_set_decomposition(nx, ix, ny, iy, yranks._exchange, yranks._allgather, yranks._allreduce, None,
+                                                     b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
+                                                     yranks.capacity, yranks.gather_send.data_ptr(), yranks.gather_recv.data_ptr()))
         else:
-            self._check(L.b200host_set_y_decomposition(1, 0, _EXCHANGE_T(), _ALLREDUCE_T(), None, None, None, None, None, 0))
+            self._check(L.b200host_set_decomposition(1, 0, 1, 0, _EXCHANGE_T(), _ALLGATHER_T(), _ALLREDUCE_T(), None, None, None,
+                                                     None, None, 0, None, None))
         self._check(L.b200host_init(ini_text.encode()))
         v = (C.c_int * 11)()
         self._check(L.b200host_mesh_info(v))

@@ -316,22 +316,31 @@ size_t poolAllocations(); ///< number of cudaMalloc calls so far (steady state: 
 size_t cowCopies();       ///< whole-block device copies made by copy-on-write so far (FieldBase::makeUnique)
 unsigned long long nextVersion();
 
-/// Y decomposition of the host layer's Mesh: NYPE ranks, NXPE = 1 (BoutMesh::setYDecompositionIndices,
-/// src/mesh/impls/bout/boutmesh.cxx:255-341, on an all-core topology).  One process per GPU; the process that owns
-/// the communicator (the Python harness with torch.distributed / NCCL, or any MPI-like host) fills this in BEFORE the
-/// mesh is created.  Mesh::communicate then packs the MYG lowest / highest interior rows of up to `capacity` doubles
-/// into send_lo / send_hi (bout_b200_halo_pack_y: pack_data, boutmesh.cxx:2400-2466), calls exchange(count) -- which
-/// must deliver send_lo to the recv_hi of rank yind - 1 and send_hi to the recv_lo of rank yind + 1 (periodic),
-/// ordered after the work already enqueued on the default stream and before work enqueued once it returns
-/// (sendY / wait, boutmesh.cxx:1245-1555) -- and unpacks recv_lo / recv_hi into the guard rows.
+/// Decomposition of the host layer's Mesh over ranks, along y (NYPE ranks, closed field lines) OR along x (NXPE
+/// ranks, non-periodic x): BoutMesh::setYDecompositionIndices / setXDecompositionIndices on an all-core topology
+/// (src/mesh/impls/bout/boutmesh.cxx:255-341).  One process per GPU; the process that owns the communicator (the
+/// Python harness with torch.distributed / NCCL, or any MPI-like host) fills this in BEFORE the mesh is created.
+/// Mesh::communicate copies the guard-cell sources of up to `capacity` doubles into send_lo / send_hi (y:
+/// bout_b200_halo_pack_y = pack_data, boutmesh.cxx:2400-2466; x: whole planes, contiguous), calls
+/// exchange(count, dir) -- which must deliver send_lo to the recv_hi of the rank below and send_hi to the recv_lo of
+/// the rank above (dir 0 = y, periodic; dir 1 = x, no wrap: the first rank has nothing below, the last nothing above),
+/// ordered after the work already enqueued on the default stream and before work enqueued once it returns (sendY /
+/// sendX / wait, boutmesh.cxx:1245-1555) -- and copies recv_lo / recv_hi into the guard cells.
+/// An X-decomposed LaplaceCyclic solve (CyclicReduce's distributed part, cyclic_reduction.hxx:169-440) is
+/// bout_b200_laplace_cyclic_reduce -> allgather(count): gather_send of every rank into gather_recv [nxpe][count] in
+/// PE_XIND order -> bout_b200_laplace_cyclic_finish.
 struct YDecomposition {
   int nype = 1, yind = 0;
-  int (*exchange)(size_t count, void* user) = nullptr;
+  int nxpe = 1, xind = 0;
+  int (*exchange)(size_t count, int dir, void* user) = nullptr;
+  int (*allgather)(size_t count, void* user) = nullptr;
   /// global reduction of one host number over the ranks (op 0: sum, 1: max): the adaptive integrators' error norms
   double (*allreduce)(double value, int op, void* user) = nullptr;
   void* user = nullptr;
   double *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr; ///< device buffers
   size_t capacity = 0;                                                                   ///< doubles in each of them
+  double *gather_send = nullptr, *gather_recv = nullptr; ///< device; capacity and nxpe * capacity doubles
+  int ranks() const { return nype * nxpe; }
 };
 YDecomposition& yDecomposition();
 } // namespace b200
@@ -646,10 +655,16 @@ public:
   int MXG, MYG;
   bool periodicX = false, periodicY = true; ///< periodicY: ixseps >= nx (all core)
   bool symmetricGlobalX = true, symmetricGlobalY = true; ///< mesh:symmetricGlobalX / Y (boutmesh.cxx:72-75)
-  bool firstX() const { return true; }
-  bool lastX() const { return true; }
-  int NYPE = 1, PE_YIND = 0; ///< bout::b200::yDecomposition() at construction (NXPE = 1)
+  bool firstX() const { return PE_XIND == 0; }
+  bool lastX() const { return PE_XIND == NXPE - 1; }
+  int NYPE = 1, PE_YIND = 0; ///< bout::b200::yDecomposition() at construction
+  int NXPE = 1, PE_XIND = 0;
   int OffsetY = 0;           ///< global index of this rank's first interior row minus MYG (boutmesh.cxx:316-341)
+  int OffsetX = 0;
+  int getNXPE() const { return NXPE; }
+  int getXProcIndex() const { return PE_XIND; }
+  int getGlobalXIndex(int jx) const { return jx + OffsetX; }
+  void exchangeX2D(std::vector<double>& f); ///< guard columns of a host-side [nx][ny] array (NXPE > 1)
   int getNYPE() const { return NYPE; }
   int getYProcIndex() const { return PE_YIND; }
   int getGlobalYIndex(int jy) const { return jy + OffsetY; }

@@ -1451,8 +1451,8 @@ void applyOne(Field3D& f, const std::string& cond, int side) {
   }
 }
 bool hasBoundary(Mesh* m, int side) {
-  if (side < 2) {
-    return !m->periodicX;
+  if (side < 2) { // only the ranks at the ends of an X row own a physical x boundary (boutmesh.cxx:1019-1059)
+    return !m->periodicX && (side == 0 ? m->firstX() : m->lastX());
   }
   return !m->periodicY;
 }
@@ -1607,9 +1607,33 @@ Mesh::Mesh(Options& opts) : options(&opts) {
       LocalNy = mysub + 2 * MYG;
       OffsetY = PE_YIND * mysub;
     }
+    NXPE = yd.nxpe;
+    PE_XIND = yd.xind;
+    if (NXPE > 1) {
+      const int mx = nx - 2 * MXG;
+      if (NYPE > 1) {
+        throw BoutException("B200 host layer: NXPE > 1 together with NYPE > 1 is not implemented (one direction at a time)");
+      }
+      if (PE_XIND < 0 || PE_XIND >= NXPE || MXG < 1 || mx % NXPE != 0 || mx / NXPE < MXG) {
+        throw BoutException("Mesh: nx - 2 MXG = {} does not divide into NXPE = {} slabs of at least MXG columns (rank {})",
+                            mx, NXPE, PE_XIND);
+      }
+      if (periodicX) {
+        throw BoutException("B200 host layer: NXPE > 1 with periodicX is not implemented");
+      }
+      const size_t plane = static_cast<size_t>(MXG) * LocalNy * nz;
+      if (yd.exchange == nullptr || yd.allgather == nullptr || yd.send_lo == nullptr || yd.send_hi == nullptr
+          || yd.recv_lo == nullptr || yd.recv_hi == nullptr || yd.gather_send == nullptr || yd.gather_recv == nullptr
+          || yd.capacity < plane) {
+        throw BoutException("Mesh: NXPE = {} without exchange / all-gather functions and buffers of at least MXG ny nz doubles",
+                            NXPE);
+      }
+      LocalNx = mx / NXPE + 2 * MXG;
+      OffsetX = PE_XIND * (mx / NXPE);
+    }
   }
   xstart = MXG;
-  xend = nx - MXG - 1;
+  xend = LocalNx - MXG - 1;
   ystart = MYG;
   yend = LocalNy - MYG - 1;
   zend = nz - 1;
@@ -1652,6 +1676,7 @@ std::string Mesh::method(char dir, const std::string& kind) const {
 // boutmesh.cxx:3159-3215 on one rank, all-core topology (jyseps1_1 = -1, no separatrix)
 BoutReal Mesh::GlobalX(int jx) const {
   const int MX = GlobalNx - 2 * MXG;
+  jx += OffsetX; // XGLOBAL (boutmesh.cxx:3159-3190)
   if (!symmetricGlobalX) {
     return static_cast<BoutReal>(jx) / static_cast<BoutReal>(MX);
   }
@@ -1686,7 +1711,7 @@ void exchangeYDevice(const bout_b200_grid& g, int myg, const std::vector<double*
     const int n = static_cast<int>(std::min(per_round, ptrs.size() - i));
     check(bout_b200_halo_pack_y(&g, n, ptrs.data() + i, g.ystart, myg, 0, g.nx - 1, yd.send_lo, nullptr));
     check(bout_b200_halo_pack_y(&g, n, ptrs.data() + i, g.yend - myg + 1, myg, 0, g.nx - 1, yd.send_hi, nullptr));
-    if (yd.exchange(per_field * n, yd.user) != 0) {
+    if (yd.exchange(per_field * n, 0, yd.user) != 0) {
       throw BoutException("Mesh::communicate: the Y exchange between ranks failed (rank {} of {})", yd.yind, yd.nype);
     }
     check(bout_b200_halo_unpack_y(&g, n, ptrs.data() + i, g.ystart - myg, myg, 0, g.nx - 1, yd.recv_lo, nullptr));
@@ -1694,6 +1719,54 @@ void exchangeYDevice(const bout_b200_grid& g, int myg, const std::vector<double*
   }
 }
 } // namespace
+
+namespace {
+// X guard planes of device fields from the neighbouring ranks (sendX / wait, boutmesh.cxx:1245-1340): planes are
+// contiguous ([x][y][z], x slowest), so "packing" is one device copy per field and side; all y (the y guard rows just
+// exchanged or wrapped travel with them: corner cells as in mesh.cxx:351-362).
+void exchangeXDevice(Mesh* m, const std::vector<double*>& ptrs) {
+  const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+  const size_t plane = static_cast<size_t>(m->MXG) * m->LocalNy * m->LocalNz;
+  const size_t per_round = std::max<size_t>(1, yd.capacity / plane);
+  const size_t bytes = plane * sizeof(double);
+  const size_t row = static_cast<size_t>(m->LocalNy) * m->LocalNz;
+  for (size_t i = 0; i < ptrs.size(); i += per_round) {
+    const size_t n = std::min(per_round, ptrs.size() - i);
+    for (size_t k = 0; k < n; ++k) {
+      check(bout_b200_memcpy_d2d(yd.send_lo + k * plane, ptrs[i + k] + m->xstart * row, bytes, nullptr));
+      check(bout_b200_memcpy_d2d(yd.send_hi + k * plane, ptrs[i + k] + (m->xend - m->MXG + 1) * row, bytes, nullptr));
+    }
+    if (yd.exchange(plane * n, 1, yd.user) != 0) {
+      throw BoutException("Mesh::communicate: the X exchange between ranks failed (rank {} of {})", yd.xind, yd.nxpe);
+    }
+    for (size_t k = 0; k < n; ++k) {
+      if (!m->firstX()) {
+        check(bout_b200_memcpy_d2d(ptrs[i + k], yd.recv_lo + k * plane, bytes, nullptr));
+      }
+      if (!m->lastX()) {
+        check(bout_b200_memcpy_d2d(ptrs[i + k] + (m->xend + 1) * row, yd.recv_hi + k * plane, bytes, nullptr));
+      }
+    }
+  }
+}
+} // namespace
+
+void Mesh::exchangeX2D(std::vector<double>& f) {
+  const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+  const size_t n = static_cast<size_t>(MXG) * LocalNy;
+  check(bout_b200_memcpy_h2d(yd.send_lo, f.data() + static_cast<size_t>(xstart) * LocalNy, n * sizeof(double), nullptr));
+  check(bout_b200_memcpy_h2d(yd.send_hi, f.data() + static_cast<size_t>(xend - MXG + 1) * LocalNy, n * sizeof(double), nullptr));
+  if (yd.exchange(n, 1, yd.user) != 0) {
+    throw BoutException("Mesh: the X exchange of a metric array between ranks failed (rank {} of {})", yd.xind, yd.nxpe);
+  }
+  if (!firstX()) {
+    check(bout_b200_memcpy_d2h(f.data(), yd.recv_lo, n * sizeof(double), nullptr));
+  }
+  if (!lastX()) {
+    check(bout_b200_memcpy_d2h(f.data() + static_cast<size_t>(xend + 1) * LocalNy, yd.recv_hi, n * sizeof(double), nullptr));
+  }
+  check(bout_b200_stream_sync(nullptr));
+}
 
 // Metric arrays live on the host while the coordinates are set up: their guard rows take the same route as a field's
 // (through the exchange buffers), once per Coordinates::geometry(), not per step.
@@ -1709,7 +1782,7 @@ void Mesh::exchangeY2D(std::vector<double>& f) {
   }
   check(bout_b200_memcpy_h2d(yd.send_lo, lo.data(), n * sizeof(double), nullptr));
   check(bout_b200_memcpy_h2d(yd.send_hi, hi.data(), n * sizeof(double), nullptr));
-  if (yd.exchange(n, yd.user) != 0) {
+  if (yd.exchange(n, 0, yd.user) != 0) {
     throw BoutException("Mesh: the Y exchange of a metric array between ranks failed (rank {} of {})", yd.yind, yd.nype);
   }
   check(bout_b200_memcpy_d2h(lo.data(), yd.recv_lo, n * sizeof(double), nullptr));
@@ -1797,7 +1870,16 @@ void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
   if (NYPE > 1) { // Y first, between ranks; then X (below) with the y guard rows just received (mesh.cxx:351-362)
     exchangeYDevice(g, MYG, ptrs);
   }
-  const int self_y = (periodicY && MYG > 0 && NYPE == 1) ? 1 : 0;
+  if (NXPE > 1) {
+    if (periodicY && MYG > 0) { // Y wrap on this rank first
+      for (size_t i = 0; i < ptrs.size(); i += 8) {
+        const int n = static_cast<int>(std::min<size_t>(8, ptrs.size() - i));
+        check(bout_b200_halo_self(&g, n, ptrs.data() + i, 0, 1, nullptr));
+      }
+    }
+    exchangeXDevice(this, ptrs);
+  }
+  const int self_y = (periodicY && MYG > 0 && NYPE == 1 && NXPE == 1) ? 1 : 0;
   for (size_t i = 0; (self_y || periodicX) && i < ptrs.size(); i += 8) { // the kernel takes up to 8 fields per launch
     const int n = static_cast<int>(std::min<size_t>(8, ptrs.size() - i));
     check(bout_b200_halo_self(&g, n, ptrs.data() + i, periodicX ? 1 : 0, self_y, nullptr));
@@ -1851,6 +1933,9 @@ void fixGuards2D(Mesh* m, std::vector<double>& f, bool extrapolate) {
       }
     }
   }
+  if (m->NXPE > 1) {
+    m->exchangeX2D(f);
+  }
   if (m->periodicX && m->MXG > 0) {
     for (int y = 0; y < ny; ++y) {
       for (int i = 0; i < m->xstart; ++i) {
@@ -1871,8 +1956,10 @@ void fixGuards2D(Mesh* m, std::vector<double>& f, bool extrapolate) {
       }
     }
   };
-  if (!m->periodicX && m->MXG > 0) {
+  if (!m->periodicX && m->MXG > 0 && m->firstX()) {
     outward(true, m->xstart - 1, -1, m->xstart, mx, m->ystart, m->yend);
+  }
+  if (!m->periodicX && m->MXG > 0 && m->lastX()) {
     outward(true, m->xend + 1, 1, nx - m->xend - 1, mx, m->ystart, m->yend);
   }
   if (!m->periodicY && m->MYG > 0) {
@@ -2371,6 +2458,9 @@ void LaplaceXZ::setCoefs(const Field2D& A2D, const Field2D& B2D) {
   B = B2D;
 }
 Field3D LaplaceXZ::solve(const Field3D& b, const Field3D& x0) {
+  if (localmesh->NXPE > 1) {
+    throw BoutException("LaplaceXZ: the x systems cross ranks; not available with NXPE > 1 in the B200 host layer");
+  }
   requireData(b, "LaplaceXZ::solve");
   requireData(x0, "LaplaceXZ::solve");
   Coordinates* c = localmesh->getCoordinates();
@@ -2904,8 +2994,8 @@ void Laplacian::fill(bout_b200_laplace& L) const {
   L.outer_boundary_flags = outer_boundary_flags;
   L.maxmode = maxmode;
   L.periodic_x = localmesh->periodicX ? 1 : 0;
-  L.first_x = 1;
-  L.last_x = 1;
+  L.first_x = localmesh->firstX() ? 1 : 0;
+  L.last_x = localmesh->lastX() ? 1 : 0;
   // cyclic_laplace.cxx:216-232: y guards are only solved where a y boundary exists
   L.include_yguards_lower = (include_yguards && !localmesh->periodicY) ? 1 : 0;
   L.include_yguards_upper = L.include_yguards_lower;
@@ -2934,12 +3024,33 @@ Field3D Laplacian::solve(const Field3D& b, const Field3D& x0) {
   Field3D x(localmesh);
   // cells the solve does not write keep the initial guess (cyclic_laplace.cxx:196 "x = x0" semantics
   // for boundary/guard cells are emptyFrom in the reference; zero-initialised pool blocks here)
+  if (localmesh->NXPE > 1) {
+    // the tridiagonal systems span the ranks of the X row: local elimination, one all-gather of the interface rows,
+    // interface system + back substitution (cyclic_reduction.hxx:169-440 without its gather / scatter of whole systems)
+    const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+    const size_t n = bout_b200_laplace_cyclic_iface_doubles(&g, &L);
+    if (n > yd.capacity) {
+      throw BoutException("Laplacian::solve with NXPE = {}: the interface record ({} doubles) exceeds the exchange buffers ({})",
+                          yd.nxpe, n, yd.capacity);
+    }
+    check(bout_b200_laplace_cyclic_reduce(&g, &L, b.dptr(), x0.isAllocated() ? x0.dptr() : nullptr, workspace, workspace_bytes,
+                                          yd.gather_send, nullptr));
+    if (yd.allgather(n, yd.user) != 0) {
+      throw BoutException("Laplacian::solve: the all-gather of the interface rows failed (rank {} of {})", yd.xind, yd.nxpe);
+    }
+    check(bout_b200_laplace_cyclic_finish(&g, &L, yd.gather_recv, yd.nxpe, yd.xind, x.wptr(), workspace, workspace_bytes,
+                                          nullptr));
+    return x;
+  }
   check(bout_b200_laplace_cyclic_solve(&g, &L, b.dptr(), x0.isAllocated() ? x0.dptr() : nullptr, x.wptr(), workspace,
                                        workspace_bytes, nullptr));
   return x;
 }
 
 FieldPerp Laplacian::solve(const FieldPerp& b, const FieldPerp& x0) {
+  if (localmesh->NXPE > 1) {
+    throw BoutException("Laplacian::solve(FieldPerp) is not available with NXPE > 1 in the B200 host layer");
+  }
   requireData(b, "Laplacian::solve(FieldPerp)");
   const int jy = b.getIndex();
   if (jy < 0 || jy >= localmesh->LocalNy) {
@@ -3225,8 +3336,8 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   std::unique_ptr<bout::b200::OutputPipeline> dump;
   std::vector<const Field3D*> dump_fields;
   Options& oo = Options::root()["output"];
-  if ((oo.isSet("path") || !restart_path.empty()) && bout::globals::mesh->NYPE > 1) {
-    throw BoutException("[output] / [restart_file] path with NYPE > 1: per-rank dump files are not written by the B200 "
+  if ((oo.isSet("path") || !restart_path.empty()) && bout::globals::mesh->NYPE * bout::globals::mesh->NXPE > 1) {
+    throw BoutException("[output] / [restart_file] path on a decomposed mesh: per-rank dump files are not written by the B200 "
                         "host layer (collect the slabs from the ranks instead)");
   }
   if (oo.isSet("path") || !restart_path.empty()) {
@@ -3576,9 +3687,9 @@ public:
     check(bout_b200_memcpy_d2h(&host, result, sizeof(double), nullptr));
     check(bout_b200_stream_sync(nullptr));
     double neq = static_cast<double>(a.size()) * (g.xend - g.xstart + 1) * (g.yend - g.ystart + 1) * g.nz;
-    if (m->NYPE > 1) { // the reference sums error and neq over the ranks (rkscheme.cxx:155-163, MPI_Allreduce)
+    if (m->NYPE * m->NXPE > 1) { // the reference sums error and neq over the ranks (rkscheme.cxx:155-163, MPI_Allreduce)
       host = globalReduce(host, 0);
-      neq *= m->NYPE;
+      neq *= m->NYPE * m->NXPE;
     }
     return host / neq;
   }
@@ -3598,13 +3709,13 @@ public:
     double host = 0.0;
     check(bout_b200_memcpy_d2h(&host, result, sizeof(double), nullptr));
     check(bout_b200_stream_sync(nullptr));
-    return m->NYPE > 1 ? globalReduce(host, 1) : host;
+    return m->NYPE * m->NXPE > 1 ? globalReduce(host, 1) : host;
   }
 
   static double globalReduce(double v, int op) {
     const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
     if (yd.allreduce == nullptr) {
-      throw BoutException("adaptive time stepping on NYPE = {} ranks needs YDecomposition::allreduce", yd.nype);
+      throw BoutException("adaptive time stepping on {} ranks needs YDecomposition::allreduce", yd.ranks());
     }
     return yd.allreduce(v, op, yd.user);
   }

@@ -44,18 +44,23 @@ void b200host_finalise() {
   }
 }
 
-// NYPE decomposition (bout::b200::YDecomposition): called before b200host_init; nype = 1 switches it off.  The
-// buffers are device memory of `capacity` doubles each, owned by the caller for the life of the mesh.
-int b200host_set_y_decomposition(int nype, int yind, int (*exchange)(size_t, void*), double (*allreduce)(double, int, void*),
-                                 void* user, double* send_lo, double* send_hi, double* recv_lo, double* recv_hi,
-                                 size_t capacity) {
+// Decomposition over ranks (bout::b200::YDecomposition): called before b200host_init; nxpe = nype = 1 switches it off.
+// The buffers are device memory (`capacity` doubles each, gather_recv nxpe * capacity), owned by the caller for the
+// life of the mesh.
+int b200host_set_decomposition(int nxpe, int xind, int nype, int yind, int (*exchange)(size_t, int, void*),
+                               int (*allgather)(size_t, void*), double (*allreduce)(double, int, void*), void* user,
+                               double* send_lo, double* send_hi, double* recv_lo, double* recv_hi, size_t capacity,
+                               double* gather_send, double* gather_recv) {
   return guarded([&]() {
     bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
     yd = bout::b200::YDecomposition{};
-    if (nype > 1) {
+    if (nxpe > 1 || nype > 1) {
+      yd.nxpe = nxpe;
+      yd.xind = xind;
       yd.nype = nype;
       yd.yind = yind;
       yd.exchange = exchange;
+      yd.allgather = allgather;
       yd.allreduce = allreduce;
       yd.user = user;
       yd.send_lo = send_lo;
@@ -63,6 +68,8 @@ int b200host_set_y_decomposition(int nype, int yind, int (*exchange)(size_t, voi
       yd.recv_lo = recv_lo;
       yd.recv_hi = recv_hi;
       yd.capacity = capacity;
+      yd.gather_send = gather_send;
+      yd.gather_recv = gather_recv;
     }
   });
 }

@@ -559,6 +559,106 @@ int bout_b200_laplace_cyclic_solve(const bout_b200_grid* g, const bout_b200_lapl
   return rc == 0 ? 0 : BOUT_B200_ERR_PIVOT;
 }
 
+/* ---- X-decomposed solve (bout_b200_laplace_cyclic_reduce / _finish), emulated: the test double has no distributed
+ * elimination.  The "interface record" a rank contributes is its whole slab -- right-hand side, initial guess, metric
+ * and coefficient arrays -- and _finish stitches the records of the X row into the global problem (interior columns from
+ * their owner, the boundary guard columns from the first / last rank), solves that with the single-rank routine above
+ * and keeps its own columns.  What this pins is the HOST side: record size, all-gather order (PE_XIND), first_x /
+ * last_x, which cells a rank receives.  The real kernels are checked against the oracle by tests/multigpu_check.py. */
+#define FAKE_IFACE_ARRAYS 12
+static const double* const* fake_lapl_arrays(const bout_b200_laplace* L, const double** a) {
+  a[0] = L->dx, a[1] = L->g11, a[2] = L->g33, a[3] = L->g13, a[4] = L->G1, a[5] = L->G3, a[6] = L->g_11, a[7] = L->g_22;
+  a[8] = L->A, a[9] = L->C1, a[10] = L->C2, a[11] = L->D;
+  return a;
+}
+size_t bout_b200_laplace_cyclic_iface_doubles(const bout_b200_grid* g, const bout_b200_laplace* L) {
+  (void)L;
+  const size_t n3 = (size_t)g->nx * g->ny * g->nz, n2 = (size_t)g->nx * g->ny;
+  return 2 * n3 + FAKE_IFACE_ARRAYS * n2 + FAKE_IFACE_ARRAYS + 1;
+}
+int bout_b200_laplace_cyclic_reduce(const bout_b200_grid* g, const bout_b200_laplace* L, const double* rhs, const double* x0,
+                                    void* workspace, size_t workspace_bytes, double* iface_out, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  (void)stream;
+  const size_t n3 = (size_t)g->nx * g->ny * g->nz, n2 = (size_t)g->nx * g->ny;
+  const double* a[FAKE_IFACE_ARRAYS];
+  fake_lapl_arrays(L, a);
+  double* p = iface_out;
+  memcpy(p, rhs, n3 * sizeof(double));
+  p += n3;
+  if (x0) {
+    memcpy(p, x0, n3 * sizeof(double));
+  } else {
+    memset(p, 0, n3 * sizeof(double));
+  }
+  p += n3;
+  for (int k = 0; k < FAKE_IFACE_ARRAYS; ++k, p += n2) {
+    if (a[k]) {
+      memcpy(p, a[k], n2 * sizeof(double));
+    } else {
+      memset(p, 0, n2 * sizeof(double));
+    }
+  }
+  for (int k = 0; k < FAKE_IFACE_ARRAYS; ++k) {
+    *p++ = a[k] ? 1.0 : 0.0;
+  }
+  *p = x0 ? 1.0 : 0.0;
+  return 0;
+}
+int bout_b200_laplace_cyclic_finish(const bout_b200_grid* g, const bout_b200_laplace* L, const double* iface_all, int nxpe,
+                                    int pe_xind, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  const int mxg = g->xstart, mxsub = g->nx - 2 * mxg, NX = nxpe * mxsub + 2 * mxg;
+  const size_t n3 = (size_t)g->nx * g->ny * g->nz, n2 = (size_t)g->nx * g->ny, rec = bout_b200_laplace_cyclic_iface_doubles(g, L);
+  const size_t row3 = (size_t)g->ny * g->nz, row2 = (size_t)g->ny;
+  bout_b200_grid G = *g;
+  G.nx = NX, G.xend = NX - mxg - 1;
+  double* f3[2];
+  double* f2[FAKE_IFACE_ARRAYS];
+  for (int k = 0; k < 2; ++k) {
+    f3[k] = (double*)calloc((size_t)NX * row3, sizeof(double));
+  }
+  for (int k = 0; k < FAKE_IFACE_ARRAYS; ++k) {
+    f2[k] = (double*)calloc((size_t)NX * row2, sizeof(double));
+  }
+  double* outG = (double*)calloc((size_t)NX * row3, sizeof(double));
+  for (int r = 0; r < nxpe; ++r) {
+    const double* R = iface_all + (size_t)r * rec;
+    const int lo = r == 0 ? 0 : mxg, hi = r == nxpe - 1 ? g->nx - 1 : g->nx - mxg - 1;
+    for (int lx = lo; lx <= hi; ++lx) {
+      const size_t gx = (size_t)r * mxsub + lx;
+      memcpy(f3[0] + gx * row3, R + (size_t)lx * row3, row3 * sizeof(double));
+      memcpy(f3[1] + gx * row3, R + n3 + (size_t)lx * row3, row3 * sizeof(double));
+      for (int k = 0; k < FAKE_IFACE_ARRAYS; ++k) {
+        memcpy(f2[k] + gx * row2, R + 2 * n3 + (size_t)k * n2 + (size_t)lx * row2, row2 * sizeof(double));
+      }
+    }
+  }
+  const double* flags = iface_all + (size_t)pe_xind * rec + 2 * n3 + FAKE_IFACE_ARRAYS * n2;
+  bout_b200_laplace LG = *L;
+#define PICK(k) (flags[k] != 0.0 ? f2[k] : NULL)
+  LG.dx = PICK(0), LG.g11 = PICK(1), LG.g33 = PICK(2), LG.g13 = PICK(3), LG.G1 = PICK(4), LG.G3 = PICK(5), LG.g_11 = PICK(6);
+  LG.g_22 = PICK(7), LG.A = PICK(8), LG.C1 = PICK(9), LG.C2 = PICK(10), LG.D = PICK(11);
+#undef PICK
+  LG.first_x = 1, LG.last_x = 1;
+  const int rc = bout_b200_laplace_cyclic_solve(&G, &LG, f3[0], flags[FAKE_IFACE_ARRAYS] != 0.0 ? f3[1] : NULL, outG, workspace,
+                                                workspace_bytes, stream);
+  if (rc == 0) {
+    const int lo = pe_xind == 0 ? 0 : mxg, hi = pe_xind == nxpe - 1 ? g->nx - 1 : g->nx - mxg - 1;
+    for (int lx = lo; lx <= hi; ++lx) {
+      memcpy(out + (size_t)lx * row3, outG + ((size_t)pe_xind * mxsub + lx) * row3, row3 * sizeof(double));
+    }
+  }
+  for (int k = 0; k < 2; ++k) {
+    free(f3[k]);
+  }
+  for (int k = 0; k < FAKE_IFACE_ARRAYS; ++k) {
+    free(f2[k]);
+  }
+  free(outG);
+  return rc;
+}
+
 /* ---- FieldPerp: plane copies, and the inversion of one plane through the full solve above ---------------------- */
 int bout_b200_copy_xz(const bout_b200_grid* g, int jy, double* field3d, double* perp, int to_perp, void* stream) {
   (void)stream;

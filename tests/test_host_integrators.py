@@ -306,12 +306,14 @@ def test_fieldperp_through_the_host_layer_host_logic(fake_device):
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
 
 
-@pytest.mark.parametrize("nype", [2, 4])
-def test_host_layer_mesh_decomposed_in_y_over_gloo_ranks(fake_device, nype):
-    """tests/host_ydecomp_check.py, world_size 2 and 4 over gloo: the C++ Mesh with NYPE ranks (global y index in
-    profiles and metric, guard rows of fields and of the y-varying metric from the neighbouring rank through
-    bout::b200::YDecomposition, error norms of the adaptive integrators reduced over the ranks) -- unchanged
-    hasegawa-wakatani-3d/hw.cxx and conduction.cxx against the reference build's single-rank run, slab by slab."""
+@pytest.mark.parametrize("direction,ranks", [("y", 2), ("y", 4), ("x", 2), ("x", 4)])
+def test_host_layer_mesh_decomposed_over_gloo_ranks(fake_device, direction, ranks):
+    """tests/host_ydecomp_check.py, world_size 2 and 4 over gloo: the C++ Mesh with NYPE or NXPE ranks (global index in
+    profiles and metric, guard cells of fields and of the metric from the neighbouring rank through
+    bout::b200::YDecomposition, x boundary conditions on the end ranks only, the X-decomposed LaplaceCyclic solve as
+    reduce -> all-gather -> finish, error norms of the adaptive integrators reduced over the ranks) -- unchanged
+    hasegawa-wakatani-3d/hw.cxx, conduction.cxx (y) and blob2d.cxx (x) against the reference build's single-rank run,
+    slab by slab.  (In the test double the distributed elimination is emulated: see fake_b200.c.)"""
     if not os.path.exists(PORT):
         pytest.skip("oracle/_ref/liboracle_port.so not built")
     import socket
@@ -319,10 +321,10 @@ def test_host_layer_mesh_decomposed_in_y_over_gloo_ranks(fake_device, nype):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     procs = []
-    for r in range(nype):
-        env = dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT, RANK=str(r), WORLD_SIZE=str(nype),
+    for r in range(ranks):
+        env = dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT, RANK=str(r), WORLD_SIZE=str(ranks),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
-        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "host_ydecomp_check.py")], env=env,
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "host_ydecomp_check.py"), direction], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
     try:
@@ -335,5 +337,7 @@ def test_host_layer_mesh_decomposed_in_y_over_gloo_ranks(fake_device, nype):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, o[-3000:] + e[-2000:]
     res = json.loads(outs[0][0].strip().splitlines()[-1])
-    assert res["ok"] and res["nype"] == nype, res
-    assert res["adaptive_rhs_calls"] == [res["adaptive_rhs_calls_single"]] * nype, res
+    assert res["ok"] and res["ranks"] == ranks and res["direction"] == direction, res
+    assert res["adaptive_rhs_calls"] == [res["adaptive_rhs_calls_single"]] * ranks, res
+    if direction == "x":
+        assert res["blob2d_gathers_per_rhs"] == 1 and res["hw3d_gathers_per_rhs"] == 1, res
