@@ -37,24 +37,42 @@ class YRanks:
     norms.  torch's collectives are ordered after the work already on the current (= default) stream and their
     wait() orders later work on it after the receive, which is what the C++ side's pack -> exchange -> unpack needs."""
 
-    def __init__(self, capacity_doubles: int, device=None, group=None, direction: str = "y"):
+    def __init__(self, capacity_doubles: int, device=None, group=None, direction: str = "y", nxpe: "int | None" = None):
         import torch
         import torch.distributed as dist
-        if direction not in ("x", "y"):
-            raise ValueError("direction must be 'x' or 'y'")
+        if direction not in ("x", "y", "xy"):
+            raise ValueError("direction must be 'x', 'y' or 'xy'")
         self.dist, self.torch, self.group, self.direction = dist, torch, group, direction
         self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        # BoutMesh's layout: rank = PE_YIND * NXPE + PE_XIND (boutmesh.cxx:255-341)
+        self.nxpe = {"x": self.size, "y": 1}.get(direction, nxpe)
+        if not self.nxpe or self.size % self.nxpe != 0:
+            raise ValueError(f"direction 'xy' needs nxpe dividing the {self.size} ranks")
+        self.nype = self.size // self.nxpe
+        self.xind, self.yind = self.rank % self.nxpe, self.rank // self.nxpe
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self.capacity = int(capacity_doubles)
         self.buf = torch.zeros(4, self.capacity, dtype=torch.float64, device=device)
         self.gather_send = torch.zeros(self.capacity, dtype=torch.float64, device=device)
-        self.gather_recv = torch.zeros(self.size * self.capacity if direction == "x" else 1, dtype=torch.float64, device=device)
+        self.gather_recv = torch.zeros(self.nxpe * self.capacity if self.nxpe > 1 else 1, dtype=torch.float64, device=device)
         self.exchanges = 0
         self.gathers = 0
         self.error = None
         grank = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
-        self.below, self.above = grank((self.rank - 1) % self.size), grank((self.rank + 1) % self.size)
+        at = lambda ix, iy: grank((iy % self.nype) * self.nxpe + ix)
+        # [dir][below, above]; None = no neighbour (the ends of an X row)
+        self.nbr = [(at(self.xind, self.yind - 1), at(self.xind, self.yind + 1)),
+                    (at(self.xind - 1, self.yind) if self.xind > 0 else None,
+                     at(self.xind + 1, self.yind) if self.xind < self.nxpe - 1 else None)]
+        # the ranks of one X row all-gather the interface rows of a LaplaceCyclic solve: one sub-group per row (every
+        # rank takes part in creating every group)
+        self.row_group = group
+        if self.nxpe > 1 and self.nype > 1:
+            for iy in range(self.nype):
+                gr = dist.new_group([at(ix, iy) for ix in range(self.nxpe)])
+                if iy == self.yind:
+                    self.row_group = gr
         self._exchange = _EXCHANGE_T(self._do_exchange)
         self._allgather = _ALLGATHER_T(self._do_allgather)
         self._allreduce = _ALLREDUCE_T(self._do_allreduce)
@@ -63,18 +81,18 @@ class YRanks:
         try:
             dist = self.dist
             send_lo, send_hi, recv_lo, recv_hi = (self.buf[i, :count] for i in range(4))
-            up = direction == 0 or self.rank < self.size - 1     # x (1): no wrap at the ends of the row
-            down = direction == 0 or self.rank > 0
+            below, above = self.nbr[1 if direction == 1 else 0]
+            up, down = above is not None, below is not None
             # with two ranks in y both neighbours are the same process: its first send (upwards) pairs with the first
             # receive posted here (from below), its second with the second
             ops = []
             if up:
-                ops.append(dist.P2POp(dist.isend, send_hi, self.above, self.group))
+                ops.append(dist.P2POp(dist.isend, send_hi, above, self.group))
             if down:
-                ops.append(dist.P2POp(dist.irecv, recv_lo, self.below, self.group))
-                ops.append(dist.P2POp(dist.isend, send_lo, self.below, self.group))
+                ops.append(dist.P2POp(dist.irecv, recv_lo, below, self.group))
+                ops.append(dist.P2POp(dist.isend, send_lo, below, self.group))
             if up:
-                ops.append(dist.P2POp(dist.irecv, recv_hi, self.above, self.group))
+                ops.append(dist.P2POp(dist.irecv, recv_hi, above, self.group))
             if ops:
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
@@ -86,7 +104,7 @@ class YRanks:
 
     def _do_allgather(self, count, _user):
         try:
-            self.dist.all_gather_into_tensor(self.gather_recv[:self.size * count], self.gather_send[:count], group=self.group)
+            self.dist.all_gather_into_tensor(self.gather_recv[:self.nxpe * count], self.gather_send[:count], group=self.row_group)
             self.gathers += 1
             return 0
         except Exception as e:
@@ -120,8 +138,7 @@ class Host:
             + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p, C.c_void_p]
         if yranks is not None and yranks.size > 1:
             b = yranks.buf
-            nx, ix, ny, iy = (yranks.size, yranks.rank, 1, 0) if yranks.direction == "x" else (1, 0, yranks.size, yranks.rank)
-            self._check(L.b200host_set_decomposition(nx, ix, ny, iy, yranks._exchange, yranks._allgather, yranks._allreduce, None,
+            self._check(L.b200host_set_decomposition(yranks.nxpe, yranks.xind, yranks.nype, yranks.yind, yranks._exchange, yranks._allgather, yranks._allreduce, None,
                                                      b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
                                                      yranks.capacity, yranks.gather_send.data_ptr(), yranks.gather_recv.data_ptr()))
         else:

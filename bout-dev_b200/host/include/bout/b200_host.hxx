@@ -316,8 +316,8 @@ size_t poolAllocations(); ///< number of cudaMalloc calls so far (steady state: 
 size_t cowCopies();       ///< whole-block device copies made by copy-on-write so far (FieldBase::makeUnique)
 unsigned long long nextVersion();
 
-/// Decomposition of the host layer's Mesh over ranks, along y (NYPE ranks, closed field lines) OR along x (NXPE
-/// ranks, non-periodic x): BoutMesh::setYDecompositionIndices / setXDecompositionIndices on an all-core topology
+/// Decomposition of the host layer's Mesh over NXPE x NYPE ranks (rank = PE_YIND * NXPE + PE_XIND), along y on closed
+/// field lines and along x when x is not periodic: BoutMesh::setYDecompositionIndices / setXDecompositionIndices on an all-core topology
 /// (src/mesh/impls/bout/boutmesh.cxx:255-341).  One process per GPU; the process that owns the communicator (the
 /// Python harness with torch.distributed / NCCL, or any MPI-like host) fills this in BEFORE the mesh is created.
 /// Mesh::communicate copies the guard-cell sources of up to `capacity` doubles into send_lo / send_hi (y:

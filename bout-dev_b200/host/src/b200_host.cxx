@@ -1611,9 +1611,6 @@ Mesh::Mesh(Options& opts) : options(&opts) {
     PE_XIND = yd.xind;
     if (NXPE > 1) {
       const int mx = nx - 2 * MXG;
-      if (NYPE > 1) {
-        throw BoutException("B200 host layer: NXPE > 1 together with NYPE > 1 is not implemented (one direction at a time)");
-      }
       if (PE_XIND < 0 || PE_XIND >= NXPE || MXG < 1 || mx % NXPE != 0 || mx / NXPE < MXG) {
         throw BoutException("Mesh: nx - 2 MXG = {} does not divide into NXPE = {} slabs of at least MXG columns (rank {})",
                             mx, NXPE, PE_XIND);
@@ -1871,7 +1868,7 @@ void Mesh::communicateFields(const std::vector<Field3D*>& fields) {
     exchangeYDevice(g, MYG, ptrs);
   }
   if (NXPE > 1) {
-    if (periodicY && MYG > 0) { // Y wrap on this rank first
+    if (periodicY && MYG > 0 && NYPE == 1) { // Y wrap on this rank first
       for (size_t i = 0; i < ptrs.size(); i += 8) {
         const int n = static_cast<int>(std::min<size_t>(8, ptrs.size() - i));
         check(bout_b200_halo_self(&g, n, ptrs.data() + i, 0, 1, nullptr));

@@ -44,24 +44,30 @@ def main():
     res, bad = {"ranks": size}, []
     direction = sys.argv[1] if len(sys.argv) > 1 else "y"
     res["direction"] = direction
-    yr = hostmod.YRanks(1 << 16, direction=direction)
+    yr = hostmod.YRanks(1 << 16, direction=direction, nxpe=2 if direction == "xy" else None)
+    res["nxpe"], res["nype"] = yr.nxpe, yr.nype
     todo = (("hw3d", "hw3d", cases.HW3D_INI), ("conduction", "conduction", cases.CONDUCTION_INI)) if direction == "y" else \
         (("hw3d", "hw3d", cases.HW3D_INI), ("blob2d", "blob2d", cases.BLOB_INI))   # (hw is periodic in x: NXPE > 1 refuses it)
+
+    def slabs(nx, ny, mxg, myg):
+        """(guards-included slab of a global array, interior of a local array) for this rank, or None"""
+        sx, sy = (nx - 2 * mxg) // yr.nxpe, (ny - 2 * myg) // yr.nype
+        if (yr.nxpe > 1 and (mxg == 0 or sx * yr.nxpe != nx - 2 * mxg or sx < mxg)) \
+                or (yr.nype > 1 and (myg == 0 or sy * yr.nype != ny - 2 * myg or sy < myg)):
+            return None
+        x0, y0 = yr.xind * sx, yr.yind * sy
+        slab = lambda a: a[x0:x0 + sx + 2 * mxg, y0:y0 + sy + 2 * myg]
+        inner = lambda a: a[mxg:mxg + sx, myg:myg + sy]
+        return slab, inner, (sx + 2 * mxg, sy + 2 * myg)
+
     for tag, model, ini in todo:
         nx, ny, nz, mxg, myg = [int(v) for v in gold[tag + "_grid"]]
-        n, g = (ny, myg) if direction == "y" else (nx, mxg)
-        sub = (n - 2 * g) // size
-        if g == 0 or sub * size != n - 2 * g or sub < g:
+        sl = slabs(nx, ny, mxg, myg)
+        if sl is None:
             res[tag] = "skipped: does not decompose"
             continue
-        if direction == "y":
-            slab = lambda a: a[:, rank * sub:rank * sub + sub + 2 * g]      # this rank's rows / columns, guards included
-            inner = lambda a: a[mxg:nx - mxg, g:g + sub]
-            shape = (nx, sub + 2 * g, nz)
-        else:
-            slab = lambda a: a[rank * sub:rank * sub + sub + 2 * g]
-            inner = lambda a: a[g:g + sub, myg:ny - myg]
-            shape = (sub + 2 * g, ny, nz)
+        slab, inner, shape2 = sl
+        shape = shape2 + (nz,)
         h = hostmod.Host(ini, yranks=yr)
         try:
             names = h.model_create(model, "rk4")
@@ -98,14 +104,8 @@ def main():
     # adaptive integrator: global error norm.  Single-slab run first (every process makes it), then the decomposed one.
     tag, ini = "hw3d", cases.HW3D_INI.replace("[solver]", "[solver]\nadaptive = true\nscheme = cashkarp\nrtol = 1e-6\natol = 1e-9")
     nx, ny, nz, mxg, myg = [int(v) for v in gold[tag + "_grid"]]
-    if direction == "y":
-        sub = (ny - 2 * myg) // size
-        mine = lambda a: a[mxg:nx - mxg, myg + rank * sub:myg + (rank + 1) * sub]
-        inner = lambda a: a[mxg:nx - mxg, myg:myg + sub]
-    else:
-        sub = (nx - 2 * mxg) // size
-        mine = lambda a: a[mxg + rank * sub:mxg + (rank + 1) * sub, myg:ny - myg]
-        inner = lambda a: a[mxg:mxg + sub, myg:ny - myg]
+    slab, inner, _ = slabs(nx, ny, mxg, myg)
+    mine = lambda a: inner(slab(a))
     h = hostmod.Host(ini)
     try:
         names = h.model_create("hw3d", "rkgeneric")

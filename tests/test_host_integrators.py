@@ -306,9 +306,9 @@ def test_fieldperp_through_the_host_layer_host_logic(fake_device):
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
 
 
-@pytest.mark.parametrize("direction,ranks", [("y", 2), ("y", 4), ("x", 2), ("x", 4)])
+@pytest.mark.parametrize("direction,ranks", [("y", 2), ("y", 4), ("x", 2), ("x", 4), ("xy", 4)])
 def test_host_layer_mesh_decomposed_over_gloo_ranks(fake_device, direction, ranks):
-    """tests/host_ydecomp_check.py, world_size 2 and 4 over gloo: the C++ Mesh with NYPE or NXPE ranks (global index in
+    """tests/host_ydecomp_check.py, world_size 2 and 4 over gloo: the C++ Mesh with NYPE, NXPE or 2 x 2 ranks (global index in
     profiles and metric, guard cells of fields and of the metric from the neighbouring rank through
     bout::b200::YDecomposition, x boundary conditions on the end ranks only, the X-decomposed LaplaceCyclic solve as
     reduce -> all-gather -> finish, error norms of the adaptive integrators reduced over the ranks) -- unchanged

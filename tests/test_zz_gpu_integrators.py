@@ -149,18 +149,18 @@ def test_free_boundaries_on_device(capi):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("direction,ranks", [("y", 2), ("y", 4), ("x", 2), ("x", 4)])
+@pytest.mark.parametrize("direction,ranks", [("y", 2), ("y", 4), ("x", 2), ("x", 4), ("xy", 4)])
 def test_host_layer_mesh_decomposed_over_nccl_ranks(direction, ranks):
     """tests/host_ydecomp_check.py on N GPUs (NCCL P2P between the pack and unpack steps of Mesh::communicate; NXPE: one
     all-gather between bout_b200_laplace_cyclic_reduce and _finish): the unchanged hasegawa-wakatani-3d/hw.cxx,
-    conduction.cxx and blob2d.cxx through the C++ host layer with NYPE = N or NXPE = N against the reference build's
+    conduction.cxx and blob2d.cxx through the C++ host layer with NYPE = N, NXPE = N or NXPE x NYPE = 2 x 2 against the reference build's
     single-rank run.  Skipped on a one-GPU box; the gloo run of tests/test_host_integrators.py covers the host logic on
     CPU."""
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < ranks:
         pytest.skip(f"needs {ranks} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr",
-           "127.0.0.1", "--master-port", str(29800 + ranks + (10 if direction == "x" else 0)),
+           "127.0.0.1", "--master-port", str(29800 + ranks + {"y": 0, "x": 10, "xy": 20}[direction]),
            os.path.join(HERE, "host_ydecomp_check.py"), direction]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
