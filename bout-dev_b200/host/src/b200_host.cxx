@@ -3333,11 +3333,29 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   std::unique_ptr<bout::b200::OutputPipeline> dump;
   std::vector<const Field3D*> dump_fields;
   Options& oo = Options::root()["output"];
-  if ((oo.isSet("path") || !restart_path.empty()) && bout::globals::mesh->NYPE * bout::globals::mesh->NXPE > 1) {
-    throw BoutException("[output] / [restart_file] path on a decomposed mesh: per-rank dump files are not written by the B200 "
-                        "host layer (collect the slabs from the ranks instead)");
+  std::string dump_path = oo.isSet("path") ? oo["path"].as<std::string>() : std::string();
+  {
+    Mesh* gm = bout::globals::mesh;
+    if (gm->NYPE * gm->NXPE > 1) {
+      if (!restart_path.empty()) {
+        throw BoutException("[restart_file] path on a decomposed mesh: per-rank restart files are not written by the B200 "
+                            "host layer");
+      }
+      if (!dump_path.empty()) {
+        // one file per rank, named like the reference's BOUT.dmp.<rank>.nc (rank = PE_YIND NXPE + PE_XIND): ".<rank>" goes
+        // in front of the extension, or replaces a ".0" already there
+        const int rank = gm->PE_YIND * gm->NXPE + gm->PE_XIND;
+        const size_t dot = dump_path.rfind('.');
+        std::string stem = dot == std::string::npos ? dump_path : dump_path.substr(0, dot);
+        const std::string ext = dot == std::string::npos ? std::string() : dump_path.substr(dot);
+        if (stem.size() >= 2 && stem.compare(stem.size() - 2, 2, ".0") == 0) {
+          stem.erase(stem.size() - 2);
+        }
+        dump_path = stem + "." + std::to_string(rank) + ext;
+      }
+    }
   }
-  if (oo.isSet("path") || !restart_path.empty()) {
+  if (!dump_path.empty() || !restart_path.empty()) {
     std::vector<std::string> names;
     for (const auto& f : f3d) {
       names.push_back(f.name);
@@ -3380,8 +3398,7 @@ int Solver::solve(int nout_in, BoutReal output_step) {
         once.push_back({kv.first, true, kv.second->getHost()});
       }
     }
-    dump = std::make_unique<bout::b200::OutputPipeline>(oo.isSet("path") ? oo["path"].as<std::string>() : std::string(),
-                                                        f3d[0].var->getMesh(), names, scalars, once, restart_path,
+    dump = std::make_unique<bout::b200::OutputPipeline>(dump_path, f3d[0].var->getMesh(), names, scalars, once, restart_path,
                                                         f3d.size());
     dump->snapshot(simtime, iteration0 - 1, dump_fields);
   }

@@ -351,8 +351,9 @@ OutputPipeline::OutputPipeline(const std::string& path, Mesh* mesh, const std::v
   count = static_cast<size_t>(g.nx) * g.ny * g.nz;
   std::vector<DumpScalar> scalars;
   const std::pair<const char*, int> ints[] = {
-      {"NXPE", 1}, {"NYPE", 1}, {"MXSUB", g.xend - g.xstart + 1}, {"MYSUB", g.yend - g.ystart + 1},
-      {"MXG", mesh->MXG}, {"MYG", mesh->MYG}, {"MZ", g.nz}, {"nx", g.nx}, {"ny", g.yend - g.ystart + 1}, {"nz", g.nz}};
+      {"NXPE", mesh->NXPE}, {"NYPE", mesh->NYPE}, {"MXSUB", g.xend - g.xstart + 1}, {"MYSUB", g.yend - g.ystart + 1},
+      {"MXG", mesh->MXG}, {"MYG", mesh->MYG}, {"MZ", g.nz}, {"nx", mesh->GlobalNx}, {"ny", mesh->GlobalNy - 2 * mesh->MYG},
+      {"nz", g.nz}, {"PE_XIND", mesh->PE_XIND}, {"PE_YIND", mesh->PE_YIND}}; // global sizes (boutdata.collect's stitching)
   for (const auto& kv : ints) {
     scalars.push_back({kv.first, false, kv.second, 0.0});
   }

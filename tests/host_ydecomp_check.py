@@ -132,6 +132,56 @@ def main():
                 bad.append(f"adaptive final {v}")
     finally:
         h.close()
+    # per-rank dump files (the reference's BOUT.dmp.<rank>.nc): stitched the way boutdata.collect does, they must be the
+    # records of the single-slab run's file
+    import tempfile
+    from scipy.io import netcdf_file
+    tmp = [tempfile.mkdtemp(prefix="b200_dump_") if rank == 0 else None]
+    dist.broadcast_object_list(tmp, src=0)
+    work = tmp[0]
+    out_ini = lambda path: cases.HW3D_INI + f"\n[output]\npath = {path}\n"
+    nx, ny, nz, mxg, myg = [int(v) for v in gold["hw3d_grid"]]
+    if rank == 0:
+        h = hostmod.Host(out_ini(os.path.join(work, "single.nc")))
+        try:
+            h.model_create("hw3d", "rk4")
+            h.model_solve(2, 0.02)
+        finally:
+            h.close()
+    h = hostmod.Host(out_ini(os.path.join(work, "BOUT.dmp.0.nc")), yranks=yr)
+    try:
+        h.model_create("hw3d", "rk4")
+        h.model_solve(2, 0.02)
+    finally:
+        h.close()
+    dist.barrier()
+    if rank == 0:
+        with netcdf_file(os.path.join(work, "single.nc"), "r", mmap=False) as nc:
+            want = {v: np.array(nc.variables[v][:]) for v in ("n", "vort")}
+            tw = np.array(nc.variables["t_array"][:])
+        got = {v: np.full_like(want[v], np.nan) for v in want}
+        for r in range(size):
+            with netcdf_file(os.path.join(work, f"BOUT.dmp.{r}.nc"), "r", mmap=False) as nc:
+                sc = {k: int(nc.variables[k].getValue()) for k in ("NXPE", "NYPE", "MXSUB", "MYSUB", "MXG", "MYG", "nx", "ny",
+                                                                   "PE_XIND", "PE_YIND")}
+                if (sc["NXPE"], sc["NYPE"], sc["nx"], sc["ny"]) != (yr.nxpe, yr.nype, nx, ny - 2 * myg) \
+                        or r != sc["PE_YIND"] * sc["NXPE"] + sc["PE_XIND"] or not np.array_equal(nc.variables["t_array"][:], tw):
+                    bad.append(f"dump scalars rank {r}")
+                x0, y0 = sc["PE_XIND"] * sc["MXSUB"], sc["PE_YIND"] * sc["MYSUB"]
+                for v in want:
+                    a = np.array(nc.variables[v][:])
+                    # boutdata.collect: interior cells from their owner, x boundary cells from the end ranks
+                    xl = 0 if sc["PE_XIND"] == 0 else mxg
+                    xh = a.shape[1] if sc["PE_XIND"] == sc["NXPE"] - 1 else a.shape[1] - mxg
+                    got[v][:, x0 + xl:x0 + xh, myg + y0:myg + y0 + sc["MYSUB"]] = a[:, xl:xh, myg:myg + sc["MYSUB"]]
+        for v in want:
+            I = (slice(None), slice(None), slice(myg, ny - myg))
+            e = float(np.nanmax(np.abs(got[v][I] - want[v][I])) / np.abs(want[v][I]).max()) if not np.isnan(got[v][I]).any() else 1.0
+            res[f"dump_collect_{v}"] = e
+            if e > 1e-12:
+                bad.append(f"dump collect {v}")
+        import shutil
+        shutil.rmtree(work, ignore_errors=True)
     flag = torch.tensor([len(bad)], dtype=torch.int64, device="cuda" if cuda else "cpu")
     dist.all_reduce(flag)
     res.update(ok=int(flag.item()) == 0, bad=bad)
