@@ -3303,7 +3303,24 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   // Restart (`restart = true`, file `[restart] path`): evolving variables, time and iteration of the latest output of
   // an earlier run (reference: Solver::add reads them from the restart options, solver.cxx:240-262; tt / hist_hi :694-697)
   Options& ro = Options::root()["restart_file"];
-  const std::string restart_path = ro.isSet("path") ? ro["path"].as<std::string>() : std::string();
+  // On a decomposed mesh every rank has files of its own, named like the reference's BOUT.dmp.<rank>.nc /
+  // BOUT.restart.<rank>.nc (rank = PE_YIND NXPE + PE_XIND): ".<rank>" goes in front of the extension, or replaces a
+  // ".0" already there
+  auto rankPath = [](std::string path) {
+    Mesh* gm = bout::globals::mesh;
+    if (path.empty() || gm->NYPE * gm->NXPE == 1) {
+      return path;
+    }
+    const int rank = gm->PE_YIND * gm->NXPE + gm->PE_XIND;
+    const size_t dot = path.rfind('.');
+    std::string stem = dot == std::string::npos ? path : path.substr(0, dot);
+    const std::string ext = dot == std::string::npos ? std::string() : path.substr(dot);
+    if (stem.size() >= 2 && stem.compare(stem.size() - 2, 2, ".0") == 0) {
+      stem.erase(stem.size() - 2);
+    }
+    return stem + "." + std::to_string(rank) + ext;
+  };
+  const std::string restart_path = rankPath(ro.isSet("path") ? ro["path"].as<std::string>() : std::string());
   int iteration0 = 0;
   if (Options::root()["restart"].withDefault(false)) {
     if (restart_path.empty()) {
@@ -3333,28 +3350,7 @@ int Solver::solve(int nout_in, BoutReal output_step) {
   std::unique_ptr<bout::b200::OutputPipeline> dump;
   std::vector<const Field3D*> dump_fields;
   Options& oo = Options::root()["output"];
-  std::string dump_path = oo.isSet("path") ? oo["path"].as<std::string>() : std::string();
-  {
-    Mesh* gm = bout::globals::mesh;
-    if (gm->NYPE * gm->NXPE > 1) {
-      if (!restart_path.empty()) {
-        throw BoutException("[restart_file] path on a decomposed mesh: per-rank restart files are not written by the B200 "
-                            "host layer");
-      }
-      if (!dump_path.empty()) {
-        // one file per rank, named like the reference's BOUT.dmp.<rank>.nc (rank = PE_YIND NXPE + PE_XIND): ".<rank>" goes
-        // in front of the extension, or replaces a ".0" already there
-        const int rank = gm->PE_YIND * gm->NXPE + gm->PE_XIND;
-        const size_t dot = dump_path.rfind('.');
-        std::string stem = dot == std::string::npos ? dump_path : dump_path.substr(0, dot);
-        const std::string ext = dot == std::string::npos ? std::string() : dump_path.substr(dot);
-        if (stem.size() >= 2 && stem.compare(stem.size() - 2, 2, ".0") == 0) {
-          stem.erase(stem.size() - 2);
-        }
-        dump_path = stem + "." + std::to_string(rank) + ext;
-      }
-    }
-  }
+  const std::string dump_path = rankPath(oo.isSet("path") ? oo["path"].as<std::string>() : std::string());
   if (!dump_path.empty() || !restart_path.empty()) {
     std::vector<std::string> names;
     for (const auto& f : f3d) {

@@ -154,6 +154,24 @@ def main():
         h.model_solve(2, 0.02)
     finally:
         h.close()
+    # restart files per rank: one output, then a restarted run of one more, ends bit-equal to the straight 2-output run
+    straight = None
+    for k, (nout, extra) in enumerate(((2, ""), (1, ""), (1, "restart = true\n"))):
+        rp = os.path.join(work, "BOUT.restart.nc" if k else "unused.restart.nc")
+        h = hostmod.Host(extra + cases.HW3D_INI + f"\n[restart_file]\npath = {rp}\n", yranks=yr)
+        try:
+            names = h.model_create("hw3d", "rk4")
+            h.model_solve(nout, 0.02)
+            final = {v: h.model_get(v) for v in names}
+        finally:
+            h.close()
+        straight = final if k == 0 else straight
+    if not os.path.exists(os.path.join(work, f"BOUT.restart.{rank}.nc")):
+        bad.append("restart file name")
+    for v in final:
+        res[f"restart_{v}_bit_equal"] = bool(np.array_equal(inner(final[v]), inner(straight[v])))
+        if not res[f"restart_{v}_bit_equal"]:
+            bad.append(f"restart {v}")
     dist.barrier()
     if rank == 0:
         with netcdf_file(os.path.join(work, "single.nc"), "r", mmap=False) as nc:
