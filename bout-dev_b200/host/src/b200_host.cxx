@@ -1518,7 +1518,17 @@ Field3D averageY(const Field3D& f) {
   if (m->LocalNy == 1) {
     return f;
   }
-  throw BoutException("averageY(Field3D) with ny > 1 is not available in the B200 host layer yet");
+  if (m->NYPE > 1) {
+    throw BoutException("averageY: the sum over y crosses ranks; not available with NYPE > 1 in the B200 host layer");
+  }
+  // mean over ystart..yend per (x, z), then every y row (guards included) set to it: two launches with the place for
+  // the all-reduce of a Y communicator between them (bout_b200.h)
+  const auto g = m->grid();
+  auto xz = bout::b200::acquire(static_cast<size_t>(m->LocalNx) * m->LocalNz);
+  Field3D r(m);
+  check(bout_b200_ymean(&g, f.dptr(), xz->ptr, nullptr));
+  check(bout_b200_yspread(&g, xz->ptr, 1.0, r.wptr(), nullptr));
+  return r;
 }
 
 // ======================================================================================================

@@ -60,6 +60,7 @@ std::unique_ptr<PhysicsModel> boutref_make_elem_access(); // tests/models/elem_a
 std::unique_ptr<PhysicsModel> boutref_make_perp_ops();    // tests/models/perp_ops.cxx
 std::unique_ptr<PhysicsModel> boutref_make_vec_ops();     // tests/models/vec_ops.cxx
 std::unique_ptr<PhysicsModel> boutref_make_par_ops();     // tests/models/par_ops.cxx
+std::unique_ptr<PhysicsModel> boutref_make_avg_ops();     // tests/models/avg_ops.cxx
 std::unique_ptr<PhysicsModel> boutref_make_conduction();  // examples/conduction/conduction.cxx (unchanged)
 std::unique_ptr<PhysicsModel> boutref_make_blob2d_outer(); // examples/blob2d-outerloop/blob2d.cxx (unchanged)
 int boutref_elmpb_get_impl(PhysicsModel* pm, const char* name, double* out, int* kind);
@@ -728,6 +729,8 @@ int boutref_model_create(const char* name, const char* solver) {
       model = boutref_make_vec_ops();
     } else if (n == "par_ops") {
       model = boutref_make_par_ops();
+    } else if (n == "avg_ops") {
+      model = boutref_make_avg_ops();
     } else if (n == "conduction") {
       model = boutref_make_conduction();
     } else if (n == "blob2d_outer") {

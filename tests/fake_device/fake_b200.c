@@ -357,6 +357,32 @@ int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region, cons
   return rc == 0 ? 0 : BOUT_B200_ERR_ARG;
 }
 
+/* averageY(Field3D) in its two halves (smoothing.cxx:272-323): mean over ystart..yend per (x, z); every y row set to it */
+int bout_b200_ymean(const bout_b200_grid* g, const double* f, double* xz, void* stream) {
+  (void)stream;
+  for (int x = 0; x < g->nx; ++x) {
+    for (int z = 0; z < g->nz; ++z) {
+      double acc = 0.0;
+      for (int y = g->ystart; y <= g->yend; ++y) {
+        acc += f[(((long long)x) * g->ny + y) * g->nz + z];
+      }
+      xz[(long long)x * g->nz + z] = acc / (g->yend - g->ystart + 1);
+    }
+  }
+  return 0;
+}
+int bout_b200_yspread(const bout_b200_grid* g, const double* xz, double scale, double* out, void* stream) {
+  (void)stream;
+  for (int x = 0; x < g->nx; ++x) {
+    for (int y = 0; y < g->ny; ++y) {
+      for (int z = 0; z < g->nz; ++z) {
+        out[(((long long)x) * g->ny + y) * g->nz + z] = scale * xz[(long long)x * g->nz + z];
+      }
+    }
+  }
+  return 0;
+}
+
 /* pack_data / unpack_data (boutmesh.cxx:2400-2466): rows y0..y0+nrows-1, x in [xlo,xhi] <-> [field][x][y][z] */
 int bout_b200_halo_pack_y(const bout_b200_grid* g, int nfields, double* const* fields, int y0, int nrows, int xlo, int xhi,
                           double* buf, void* stream) {

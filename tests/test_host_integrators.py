@@ -294,6 +294,18 @@ def test_parallel_operators_and_flux_derivatives_host_logic(fake_device):
     assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
 
 
+def test_average_y_through_the_host_layer_host_logic(fake_device):
+    """tests/avg_ops_check.py on CPU: the host layer's averageY(Field3D) (bout_b200_ymean + bout_b200_yspread),
+    averageY(Field2D) and DC against the same model source run by the reference build (tests/golden/avg_ops.npz)."""
+    if not os.path.exists(PORT):
+        pytest.skip("oracle/_ref/liboracle_port.so not built")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "avg_ops_check.py")],
+                       env=dict(os.environ, LD_PRELOAD=fake_device, B200_FAKE_ORACLE_PORT=PORT), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
 def test_fieldperp_through_the_host_layer_host_logic(fake_device):
     """tests/perp_ops_check.py on CPU: the host layer's FieldPerp (sliceXZ, algebra, element access,
     Laplacian::solve(FieldPerp), Field3D = FieldPerp) against the same model source run by the reference build."""
