@@ -25,6 +25,7 @@ class HostError(RuntimeError):
 _EXCHANGE_T = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_int, C.c_void_p)
 _ALLGATHER_T = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_void_p)
 _ALLREDUCE_T = C.CFUNCTYPE(C.c_double, C.c_double, C.c_int, C.c_void_p)
+_ALLREDUCE_Y_T = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_int, C.c_void_p)
 
 
 class YRanks:
@@ -73,8 +74,16 @@ class YRanks:
                 gr = dist.new_group([at(ix, iy) for ix in range(self.nxpe)])
                 if iy == self.yind:
                     self.row_group = gr
+        # ... and the ranks of one Y column all-reduce averageY's partial sums
+        self.col_group = group
+        if self.nxpe > 1 and self.nype > 1:
+            for ix in range(self.nxpe):
+                gr = dist.new_group([at(ix, iy) for iy in range(self.nype)])
+                if ix == self.xind:
+                    self.col_group = gr
         self._exchange = _EXCHANGE_T(self._do_exchange)
         self._allgather = _ALLGATHER_T(self._do_allgather)
+        self._allreduce_y = _ALLREDUCE_Y_T(self._do_allreduce_y)
         self._allreduce = _ALLREDUCE_T(self._do_allreduce)
 
     def _do_exchange(self, count, direction, _user):
@@ -111,6 +120,15 @@ class YRanks:
             self.error = e
             return 1
 
+    def _do_allreduce_y(self, count, op, _user):
+        try:
+            dist = self.dist
+            dist.all_reduce(self.gather_send[:count], op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM, group=self.col_group)
+            return 0
+        except Exception as e:
+            self.error = e
+            return 1
+
     def _do_allreduce(self, value, op, _user):
         dist, torch = self.dist, self.torch
         t = torch.tensor([value], dtype=torch.float64, device=self.buf.device)
@@ -134,15 +152,15 @@ class Host:
         L.b200host_model_rhs.argtypes = [C.c_double]
         L.b200host_model_solve.argtypes = [C.c_int, C.c_double]
         self.yranks = yranks
-        L.b200host_set_decomposition.argtypes = [C.c_int] * 4 + [_EXCHANGE_T, _ALLGATHER_T, _ALLREDUCE_T, C.c_void_p] \
+        L.b200host_set_decomposition.argtypes = [C.c_int] * 4 + [_EXCHANGE_T, _ALLGATHER_T, _ALLREDUCE_Y_T, _ALLREDUCE_T, C.c_void_p] \
             + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p, C.c_void_p]
         if yranks is not None and yranks.size > 1:
             b = yranks.buf
-            self._check(L.b200host_set_decomposition(yranks.nxpe, yranks.xind, yranks.nype, yranks.yind, yranks._exchange, yranks._allgather, yranks._allreduce, None,
+            self._check(L.b200host_set_decomposition(yranks.nxpe, yranks.xind, yranks.nype, yranks.yind, yranks._exchange, yranks._allgather, yranks._allreduce_y, yranks._allreduce, None,
                                                      b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
                                                      yranks.capacity, yranks.gather_send.data_ptr(), yranks.gather_recv.data_ptr()))
         else:
-            self._check(L.b200host_set_decomposition(1, 0, 1, 0, _EXCHANGE_T(), _ALLGATHER_T(), _ALLREDUCE_T(), None, None, None,
+            self._check(L.b200host_set_decomposition(1, 0, 1, 0, _EXCHANGE_T(), _ALLGATHER_T(), _ALLREDUCE_Y_T(), _ALLREDUCE_T(), None, None, None,
                                                      None, None, 0, None, None))
         self._check(L.b200host_init(ini_text.encode()))
         v = (C.c_int * 11)()

@@ -334,6 +334,9 @@ struct YDecomposition {
   int nxpe = 1, xind = 0;
   int (*exchange)(size_t count, int dir, void* user) = nullptr;
   int (*allgather)(size_t count, void* user) = nullptr;
+  /// all-reduce (op 0: sum, 1: max) of gather_send[0 .. count) in place over the ranks of one Y column (same PE_XIND):
+  /// averageY (smoothing.cxx:238-323, MPI_Allreduce over the y communicator)
+  int (*allreduce_y)(size_t count, int op, void* user) = nullptr;
   /// global reduction of one host number over the ranks (op 0: sum, 1: max): the adaptive integrators' error norms
   double (*allreduce)(double value, int op, void* user) = nullptr;
   void* user = nullptr;

@@ -1340,11 +1340,34 @@ Field3D lowPass(const Field3D& f, int zmax, bool keep_zonal) {
 Field2D averageY(const Field2D& f) {
   requireData(f, "averageY");
   Mesh* m = f.getMesh();
-  if (m->NYPE > 1) {
-    throw BoutException("averageY: the sum over y crosses ranks; not available with NYPE > 1 in the B200 host layer");
-  }
   const int nyint = m->yend - m->ystart + 1;
   Field2D r(m);
+  if (m->NYPE > 1) { // local sums per x, summed over the ranks of the Y column (smoothing.cxx:251-262)
+    const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+    const size_t nx = static_cast<size_t>(m->LocalNx);
+    if (yd.allreduce_y == nullptr || yd.gather_send == nullptr || yd.capacity < nx) {
+      throw BoutException("averageY on NYPE = {} ranks needs YDecomposition::allreduce_y and gather_send", yd.nype);
+    }
+    std::vector<double> h = f.getHost(), out(h.size()), s(nx, 0.0);
+    for (size_t x = 0; x < nx; ++x) {
+      for (int y = m->ystart; y <= m->yend; ++y) {
+        s[x] += h[x * m->LocalNy + y];
+      }
+    }
+    check(bout_b200_memcpy_h2d(yd.gather_send, s.data(), nx * sizeof(double), nullptr));
+    if (yd.allreduce_y(nx, 0, yd.user) != 0) {
+      throw BoutException("averageY: the all-reduce over the Y column failed");
+    }
+    check(bout_b200_memcpy_d2h(s.data(), yd.gather_send, nx * sizeof(double), nullptr));
+    check(bout_b200_stream_sync(nullptr));
+    for (size_t x = 0; x < nx; ++x) {
+      for (int y = 0; y < m->LocalNy; ++y) {
+        out[x * m->LocalNy + y] = s[x] / (nyint * m->NYPE);
+      }
+    }
+    r.setHost(out);
+    return r;
+  }
   if (nyint == m->LocalNy) { // no y guards: every row is one contiguous run
     bout_b200_grid g{m->LocalNx, 1, m->LocalNy, 0, m->LocalNx - 1, 0, 0};
     Field2D mean(m); // holds nx values in its first nx slots
@@ -1518,14 +1541,25 @@ Field3D averageY(const Field3D& f) {
   if (m->LocalNy == 1) {
     return f;
   }
-  if (m->NYPE > 1) {
-    throw BoutException("averageY: the sum over y crosses ranks; not available with NYPE > 1 in the B200 host layer");
-  }
   // mean over ystart..yend per (x, z), then every y row (guards included) set to it: two launches with the place for
   // the all-reduce of a Y communicator between them (bout_b200.h)
   const auto g = m->grid();
-  auto xz = bout::b200::acquire(static_cast<size_t>(m->LocalNx) * m->LocalNz);
+  const size_t nxz = static_cast<size_t>(m->LocalNx) * m->LocalNz;
   Field3D r(m);
+  if (m->NYPE > 1) {
+    const bout::b200::YDecomposition& yd = bout::b200::yDecomposition();
+    if (yd.allreduce_y == nullptr || yd.gather_send == nullptr || yd.capacity < nxz) {
+      throw BoutException("averageY on NYPE = {} ranks needs YDecomposition::allreduce_y and gather_send of nx nz doubles",
+                          yd.nype);
+    }
+    check(bout_b200_ymean(&g, f.dptr(), yd.gather_send, nullptr));
+    if (yd.allreduce_y(nxz, 0, yd.user) != 0) {
+      throw BoutException("averageY: the all-reduce over the Y column failed");
+    }
+    check(bout_b200_yspread(&g, yd.gather_send, 1.0 / m->NYPE, r.wptr(), nullptr));
+    return r;
+  }
+  auto xz = bout::b200::acquire(nxz);
   check(bout_b200_ymean(&g, f.dptr(), xz->ptr, nullptr));
   check(bout_b200_yspread(&g, xz->ptr, 1.0, r.wptr(), nullptr));
   return r;

@@ -48,7 +48,8 @@ void b200host_finalise() {
 // The buffers are device memory (`capacity` doubles each, gather_recv nxpe * capacity), owned by the caller for the
 // life of the mesh.
 int b200host_set_decomposition(int nxpe, int xind, int nype, int yind, int (*exchange)(size_t, int, void*),
-                               int (*allgather)(size_t, void*), double (*allreduce)(double, int, void*), void* user,
+                               int (*allgather)(size_t, void*), int (*allreduce_y)(size_t, int, void*),
+                               double (*allreduce)(double, int, void*), void* user,
                                double* send_lo, double* send_hi, double* recv_lo, double* recv_hi, size_t capacity,
                                double* gather_send, double* gather_recv) {
   return guarded([&]() {
@@ -61,6 +62,7 @@ int b200host_set_decomposition(int nxpe, int xind, int nype, int yind, int (*exc
       yd.yind = yind;
       yd.exchange = exchange;
       yd.allgather = allgather;
+      yd.allreduce_y = allreduce_y;
       yd.allreduce = allreduce;
       yd.user = user;
       yd.send_lo = send_lo;

@@ -101,6 +101,28 @@ def main():
                     bad.append(f"{tag} final {v}")
         finally:
             h.close()
+    # averageY on a decomposed mesh (partial sums all-reduced over the Y column): tests/models/avg_ops.cxx against the
+    # reference build's single-rank run
+    if yr.nype > 1:
+        ops = dict(np.load(os.path.join(HERE, "golden", "vec_ops.npz")))
+        ops.update(np.load(os.path.join(HERE, "golden", "avg_ops.npz")))
+        nx, ny, nz = ops["f0"].shape
+        sl = slabs(nx, ny, 2, 2)
+        if sl is not None:
+            slab, inner, _ = sl
+            h = hostmod.Host(cases.OPS_MESH_INI, yranks=yr)
+            try:
+                h.model_create("avg_ops", "rk4")
+                h.model_set("f", np.ascontiguousarray(slab(ops["f0"])))
+                h.model_set("g", np.ascontiguousarray(slab(ops["g0"])))
+                h.model_rhs(0.0)
+                for v in ("f", "g"):
+                    e = rel(inner(h.model_ddt(v)), inner(slab(ops["avg_ddt_" + v])), ops["avg_ddt_" + v])
+                    res[f"average_y_ddt_{v}"] = e
+                    if e > 1e-12:
+                        bad.append(f"averageY ddt {v}")
+            finally:
+                h.close()
     # adaptive integrator: global error norm.  Single-slab run first (every process makes it), then the decomposed one.
     tag, ini = "hw3d", cases.HW3D_INI.replace("[solver]", "[solver]\nadaptive = true\nscheme = cashkarp\nrtol = 1e-6\natol = 1e-9")
     nx, ny, nz, mxg, myg = [int(v) for v in gold[tag + "_grid"]]
