@@ -148,6 +148,15 @@ def test_free_boundaries_on_device(capi):
         capi.boundary(tiny, "free_o3", "xin", torch.zeros(6, 6, 4, dtype=torch.float64, device="cuda"))
 
 
+def test_average_y_through_the_host_layer():
+    """tests/models/avg_ops.cxx on the device (tests/avg_ops_check.py): averageY(Field3D) = bout_b200_ymean +
+    bout_b200_yspread, averageY(Field2D), DC of the host layer against the reference build's run of the same source
+    (1e-12)."""
+    p = subprocess.run([sys.executable, os.path.join(HERE, "avg_ops_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("direction,ranks", [("y", 2), ("y", 4), ("x", 2), ("x", 4), ("xy", 4)])
 def test_host_layer_mesh_decomposed_over_nccl_ranks(direction, ranks):
@@ -164,12 +173,3 @@ def test_host_layer_mesh_decomposed_over_nccl_ranks(direction, ranks):
            os.path.join(HERE, "host_ydecomp_check.py"), direction]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-
-
-def test_average_y_through_the_host_layer():
-    """tests/models/avg_ops.cxx on the device (tests/avg_ops_check.py): averageY(Field3D) = bout_b200_ymean +
-    bout_b200_yspread, averageY(Field2D), DC of the host layer against the reference build's run of the same source
-    (1e-12)."""
-    p = subprocess.run([sys.executable, os.path.join(HERE, "avg_ops_check.py")], capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert json.loads(p.stdout.strip().splitlines()[-1])["ok"]
