@@ -606,6 +606,7 @@ Field3D filter(const Field3D& f, int N0);       ///< field3d.cxx:620-661
 Field3D lowPass(const Field3D& f, int zmax, bool keep_zonal = true); ///< field3d.cxx:664-710
 Field2D averageY(const Field2D& f);             ///< smoothing.cxx:238-270
 Field3D averageY(const Field3D& f);             ///< smoothing.cxx:272-323
+Field3D smooth_x(const Field3D& f);             ///< smoothing.cxx:46-73 (1-2-1 filter in x, then communicate)
 inline Field3D emptyFrom(const Field3D& f) { return Field3D(f.getMesh()).allocate(); }
 /// where(test, gt0, le0): test > 0 ? gt0 : le0, element by element (reference include/bout/where.hxx:41-91)
 Field3D where(const Field3D& test, const Field3D& gt0, const Field3D& le0);

@@ -1565,6 +1565,18 @@ Field3D averageY(const Field3D& f) {
   return r;
 }
 
+Field3D smooth_x(const Field3D& f) {
+  // smoothing.cxx:46-73: 0.5 f + 0.25 (f(x-1) + f(x+1)) for 0 < x < LocalNx - 1 over all y, z; the two edge planes
+  // copied; then the guard cells of the result exchanged
+  requireData(f, "smooth_x");
+  Mesh* m = f.getMesh();
+  const auto g = m->grid();
+  Field3D r(m);
+  check(bout_b200_smooth_x(&g, f.dptr(), r.wptr(), nullptr));
+  m->communicate(r);
+  return r;
+}
+
 // ======================================================================================================
 // Mesh and Coordinates
 // ======================================================================================================

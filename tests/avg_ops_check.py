@@ -1,4 +1,4 @@
-"""tests/models/avg_ops.cxx through the C++ host layer (averageY of Field3D and Field2D, DC: smoothing.cxx:238-323)
+"""tests/models/avg_ops.cxx through the C++ host layer (averageY of Field3D and Field2D, DC, smooth_x: smoothing.cxx:46-73, 238-323)
 against the SAME source run by the reference build (tests/golden/avg_ops.npz, made by tests/golden/make_golden_avg.py)
 on the mesh of cases.OPS_MESH_INI with the input fields of vec_ops.npz.  Runs on the GPU, or on CPU with the test double
 (LD_PRELOAD=<libfake_b200.so> B200_FAKE_ORACLE_PORT=<liboracle_port.so>).  Prints one JSON line; exit code 0 iff ok."""

@@ -357,6 +357,20 @@ int bout_b200_stencil(const bout_b200_grid* g, int op, int dir, int region, cons
   return rc == 0 ? 0 : BOUT_B200_ERR_ARG;
 }
 
+/* smooth_x (smoothing.cxx:46-73) without its closing communicate */
+int bout_b200_smooth_x(const bout_b200_grid* g, const double* f, double* out, void* stream) {
+  (void)stream;
+  const size_t row = (size_t)g->ny * g->nz;
+  memcpy(out, f, row * sizeof(double));
+  memcpy(out + (size_t)(g->nx - 1) * row, f + (size_t)(g->nx - 1) * row, row * sizeof(double));
+  for (int x = 1; x < g->nx - 1; ++x) {
+    for (size_t i = 0; i < row; ++i) {
+      out[x * row + i] = 0.5 * f[x * row + i] + 0.25 * (f[(x - 1) * row + i] + f[(x + 1) * row + i]);
+    }
+  }
+  return 0;
+}
+
 /* averageY(Field3D) in its two halves (smoothing.cxx:272-323): mean over ystart..yend per (x, z); every y row set to it */
 int bout_b200_ymean(const bout_b200_grid* g, const double* f, double* xz, void* stream) {
   (void)stream;

@@ -1,4 +1,4 @@
-"""Golden values of tests/models/avg_ops.cxx (averageY of Field3D / Field2D, DC) from the REFERENCE build
+"""Golden values of tests/models/avg_ops.cxx (averageY of Field3D / Field2D, DC, smooth_x) from the REFERENCE build
 (oracle/_ref/libboutref.so: the same source compiled against the reference's own headers and sources) on the mesh of
 cases.OPS_MESH_INI, with the input fields of vec_ops.npz.  Writes avg_ops.npz.  Run in the build container (needs
 /root/reference for oracle/_ref); the GPU box only reads the .npz."""

@@ -17,7 +17,7 @@ protected:
   int rhs(BoutReal) override {
     mesh->communicate(f, g);
     ddt(f) = averageY(f) + 0.5 * averageY(f * g);
-    ddt(g) = g - averageY(g) + averageY(DC(f));
+    ddt(g) = g - averageY(g) + averageY(DC(f)) + smooth_x(f);
     return 0;
   }
 };

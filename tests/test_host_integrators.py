@@ -296,7 +296,7 @@ def test_parallel_operators_and_flux_derivatives_host_logic(fake_device):
 
 def test_average_y_through_the_host_layer_host_logic(fake_device):
     """tests/avg_ops_check.py on CPU: the host layer's averageY(Field3D) (bout_b200_ymean + bout_b200_yspread),
-    averageY(Field2D) and DC against the same model source run by the reference build (tests/golden/avg_ops.npz)."""
+    averageY(Field2D), DC and smooth_x against the same model source run by the reference build (tests/golden/avg_ops.npz)."""
     if not os.path.exists(PORT):
         pytest.skip("oracle/_ref/liboracle_port.so not built")
     p = subprocess.run([sys.executable, os.path.join(HERE, "avg_ops_check.py")],

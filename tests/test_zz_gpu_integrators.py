@@ -150,7 +150,7 @@ def test_free_boundaries_on_device(capi):
 
 def test_average_y_through_the_host_layer():
     """tests/models/avg_ops.cxx on the device (tests/avg_ops_check.py): averageY(Field3D) = bout_b200_ymean +
-    bout_b200_yspread, averageY(Field2D), DC of the host layer against the reference build's run of the same source
+    bout_b200_yspread, averageY(Field2D), DC and smooth_x of the host layer against the reference build's run of the same source
     (1e-12)."""
     p = subprocess.run([sys.executable, os.path.join(HERE, "avg_ops_check.py")], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
